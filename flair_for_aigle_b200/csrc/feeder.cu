@@ -1,0 +1,89 @@
+// Tile feeder kernels: boundless windowed read of the zone raster (zero fill) + normalisation.
+//
+// Replaces flair_zonal_detection/dataset.py:89-117 (_load_patch: rasterio boundless read,
+// fill_value=0), :119-124 + flair_hub/data/utils_data/norm.py:37-44 ((x-mean)/std in
+// float64 -> float32) and the per-window Python loop of the DataLoader workers.  The raster
+// stays resident in HBM as uint8; a tile is 1 byte/channel/pixel read.
+#include "common.h"
+#include "../../include/flair_zonal_b200.h"
+
+namespace fz {
+
+// out[t][c][y][x] = (raster[c][row0+y][col0+x] (0 outside) - mean[c]) / std[c]
+// One thread = 4 consecutive x of one (t, c, y): 4 byte loads (coalesced across the warp),
+// one float4 store.
+__global__ void gather_f32_kernel(const uint8_t* __restrict__ raster, int C, int H, int W,
+                                  const int32_t* __restrict__ origins, int P, const float* __restrict__ mean,
+                                  const float* __restrict__ stdv, float* __restrict__ out) {
+  const int t = blockIdx.z;
+  const int c = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over P*P/4
+  const int per_row = P / 4;
+  if (idx >= P * per_row) return;
+  const int y = idx / per_row;
+  const int x = (idx % per_row) * 4;
+  const int r = origins[2 * t] + y;
+  const int c0 = origins[2 * t + 1] + x;
+  // float64 like norm.py:40-43, rounded once to float32 (torch.tensor(..., float32))
+  const double m = static_cast<double>(mean[c]);
+  const double s = static_cast<double>(stdv[c]);
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cc = c0 + j;
+    const double px = (r >= 0 && r < H && cc >= 0 && cc < W)
+                          ? static_cast<double>(raster[(static_cast<size_t>(c) * H + r) * W + cc])
+                          : 0.0;
+    v[j] = static_cast<float>((px - m) / s);
+  }
+  float4* dst = reinterpret_cast<float4*>(out + ((static_cast<size_t>(t) * C + c) * P + y) * P + x);
+  *dst = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// out[t][y][x][0..3] = raster[c][row0+y][col0+x] (0 outside, 0 for c >= C)
+__global__ void gather_u8_kernel(const uint8_t* __restrict__ raster, int C, int H, int W,
+                                 const int32_t* __restrict__ origins, int P, uint8_t* __restrict__ out) {
+  const int t = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over P*P
+  if (idx >= P * P) return;
+  const int y = idx / P, x = idx % P;
+  const int r = origins[2 * t] + y;
+  const int cc = origins[2 * t + 1] + x;
+  uchar4 px = make_uchar4(0, 0, 0, 0);
+  if (r >= 0 && r < H && cc >= 0 && cc < W) {
+    const size_t o = static_cast<size_t>(r) * W + cc;
+    const size_t plane = static_cast<size_t>(H) * W;
+    px.x = raster[o];
+    if (C > 1) px.y = raster[plane + o];
+    if (C > 2) px.z = raster[2 * plane + o];
+    if (C > 3) px.w = raster[3 * plane + o];
+  }
+  reinterpret_cast<uchar4*>(out)[static_cast<size_t>(t) * P * P + idx] = px;
+}
+
+}  // namespace fz
+
+extern "C" int fz_gather_tiles_f32(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles,
+                                   int P, const float* mean, const float* stdv, float* out, void* stream) {
+  FZ_REQUIRE(C >= 1 && H > 0 && W > 0 && P > 0 && P % 4 == 0, "fz_gather_tiles_f32: bad shape C=%d H=%d W=%d P=%d", C, H,
+             W, P);
+  if (n_tiles <= 0) return 0;
+  const int threads = 256;
+  dim3 grid((P * (P / 4) + threads - 1) / threads, C, n_tiles);
+  fz::gather_f32_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(raster, C, H, W, origins, P, mean,
+                                                                                      stdv, out);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_gather_tiles_u8(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles,
+                                  int P, uint8_t* out, void* stream) {
+  FZ_REQUIRE(C >= 1 && C <= 4 && H > 0 && W > 0 && P > 0, "fz_gather_tiles_u8: bad shape C=%d H=%d W=%d P=%d", C, H, W,
+             P);
+  if (n_tiles <= 0) return 0;
+  const int threads = 256;
+  dim3 grid((P * P + threads - 1) / threads, n_tiles);
+  fz::gather_u8_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(raster, C, H, W, origins, P, out);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,348 @@
+// bf16 GEMM on tcgen05 / TMEM fed by TMA, with the fused epilogues the ConvNeXt-V2 / U-Net
+// forward needs.  C[m,n] = sum_k A[m,k] * B[b(m)][n,k]   (both operands K-major, i.e. the
+// activations as NHWC rows and nn.Linear / 1x1-conv weights as stored).
+//
+// Replaces the cuBLAS/cuDNN fp32 calls under flair_hub/models/flair_model.py:376 (timm
+// ConvNeXtBlock mlp.fc1 / mlp.fc2, stage downsample conv2x2) and :539-541 (FusionHandler 1x1).
+//
+// One CTA = one 128 x BN output tile.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer
+// (+ TMEM allocator), warps 2..5 epilogue (TMEM lanes 32*(warp%4)..).  3-stage smem ring,
+// two CTAs co-resident per SM so one CTA's epilogue overlaps the other's main loop.
+#include "common.h"
+#include "ptx.cuh"
+#include "../../include/flair_zonal_b200.h"
+
+namespace fz {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmParams {
+  int M, N, K;
+  int rows_per_sample;  // rows of A per sample (H*W); selects the B batch and the sumsq row
+  int b_batched;        // 1: B is [num_samples][N][K] and the tile uses batch m0 / rows_per_sample
+  const float* bias;    // [N] or nullptr
+  void* out;            // [M,N] bf16 or f32
+  const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
+  float* sumsq;         // [num_samples, N] f32 accumulators (FZ_EPI_GELU_SUMSQ)
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+  static constexpr int OFF_BIAS = OFF_B + STAGES * B_STAGE_BYTES;
+  static constexpr int OFF_SQ = OFF_BIAS + BN * 4;
+  static constexpr int OFF_BAR = OFF_SQ + BN * 4;
+  static constexpr int OFF_TSLOT = OFF_BAR + (2 * STAGES + 1) * 8;
+  static constexpr int BYTES = OFF_TSLOT + 16 + 1024;  // + worst-case alignment pad
+};
+
+// Column sums over the 32 lanes of a warp of a 32-vector held per lane (transpose-reduce):
+// on return s[0] of lane l is the sum over lanes of the input s[l].  31 shuffles.
+__device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float a = s[i], b = s[i + off];
+      const float send = upper ? a : b;
+      const float keep = upper ? b : a;
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(192, 2)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + L::OFF_B;
+  float* sBias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  float* sSq = reinterpret_cast<float*>(smem + L::OFF_SQ);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + L::OFF_TSLOT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = p.N / BN;
+  const int n0 = (blockIdx.x % n_tiles) * BN;
+  const int m0 = (blockIdx.x / n_tiles) * BM;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tslot, BN);
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      sBias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
+      sSq[i] = 0.0f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int bcoord = p.b_batched ? (m0 / p.rows_per_sample) : 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
+        tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
+        tma_load_3d(&tmB, &full[s], sB + s * L::B_STAGE_BYTES, kb * BK, n0, bcoord);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t ad = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES), 128);
+        const uint64_t bd = umma_smem_desc(smem_u32(sB + s * L::B_STAGE_BYTES), 128);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // +32 bytes (16 bf16) along K inside the 128B swizzle atom = +2 in the >>4 address field
+          umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tfull);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&sBias[c * 32 + j]);
+        v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
+        v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+        v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+      }
+      const size_t off = static_cast<size_t>(m) * p.N + n0 + c * 32;
+      if (MODE == FZ_EPI_GELU_SUMSQ) {
+        float s[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = gelu_erf_fast(v[j]);
+          s[j] = row_ok ? v[j] * v[j] : 0.0f;
+        }
+        warp_colsum32(s, lane);
+        atomicAdd(&sSq[c * 32 + lane], s[0]);
+      } else if (MODE == FZ_EPI_RELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      } else if (MODE == FZ_EPI_RESID_F32) {
+        if (row_ok) {
+          const float4* rp = reinterpret_cast<const float4*>(p.resid + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = rp[j];
+            v[4 * j + 0] += x.x;
+            v[4 * j + 1] += x.y;
+            v[4 * j + 2] += x.z;
+            v[4 * j + 3] += x.w;
+          }
+        }
+      }
+      if (row_ok) {
+        if (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+      }
+    }
+    if (MODE == FZ_EPI_GELU_SUMSQ) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int sample = m0 / p.rows_per_sample;
+      for (int i = threadIdx.x - 64; i < BN; i += 128)
+        atomicAdd(&p.sumsq[static_cast<size_t>(sample) * p.N + n0 + i], sSq[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, BN);
+}
+
+template <int BN, int STAGES, int MODE>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    FZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    configured = true;
+  }
+  const int grid = ((p.M + BM - 1) / BM) * (p.N / BN);
+  kern<<<grid, 192, L::BYTES, stream>>>(tmA, tmB, p);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+  switch (mode) {
+    case FZ_EPI_BF16: return launch_gemm<BN, 3, FZ_EPI_BF16>(a, b, p, st);
+    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, 3, FZ_EPI_GELU_SUMSQ>(a, b, p, st);
+    case FZ_EPI_RESID_F32: return launch_gemm<BN, 3, FZ_EPI_RESID_F32>(a, b, p, st);
+    case FZ_EPI_F32: return launch_gemm<BN, 3, FZ_EPI_F32>(a, b, p, st);
+    case FZ_EPI_RELU_BF16: return launch_gemm<BN, 3, FZ_EPI_RELU_BF16>(a, b, p, st);
+  }
+  set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
+  return -1;
+}
+
+}  // namespace fz
+
+extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid,
+                            float* sumsq, int M, int N, int K, int b_batch, int rows_per_sample, int mode,
+                            void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(M > 0 && N > 0 && K > 0, "fz_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  FZ_REQUIRE(K % BK == 0, "fz_gemm_bf16: K=%d must be a multiple of %d", K, BK);
+  FZ_REQUIRE(N % 64 == 0, "fz_gemm_bf16: N=%d must be a multiple of 64", N);
+  FZ_REQUIRE(b_batch >= 1, "fz_gemm_bf16: b_batch must be >= 1");
+  if (mode == FZ_EPI_GELU_SUMSQ || b_batch > 1)
+    FZ_REQUIRE(rows_per_sample > 0 && rows_per_sample % BM == 0,
+               "fz_gemm_bf16: rows_per_sample=%d must be a positive multiple of %d", rows_per_sample, BM);
+  FZ_REQUIRE(mode != FZ_EPI_GELU_SUMSQ || sumsq != nullptr, "fz_gemm_bf16: sumsq buffer required");
+  FZ_REQUIRE(mode != FZ_EPI_RESID_F32 || resid != nullptr, "fz_gemm_bf16: residual buffer required");
+  const int BN = (N % 128 == 0) ? 128 : 64;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {BK, BM};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)b_batch};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)N};
+    const uint32_t box[3] = {BK, (uint32_t)BN, 1};
+    int rc = make_tmap_bf16(&tmB, B, 3, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
+  p.b_batched = b_batch > 1 ? 1 : 0;
+  p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return BN == 128 ? dispatch_mode<128>(mode, tmA, tmB, p, st) : dispatch_mode<64>(mode, tmA, tmB, p, st);
+}
+
+// ----------------------------------------------------------------------------------------
+// Plain SIMT GEMM with the same contract (exact erff GELU).  Used by the GPU tests to check
+// the tcgen05 kernel independently of any library, and selectable with FZ_GEMM_IMPL=simt for
+// bring-up.  Not a fallback: the engine never selects it on its own.
+// ----------------------------------------------------------------------------------------
+namespace fz {
+template <int MODE>
+__global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                 GemmParams p) {
+  __shared__ float sa[16][17];
+  __shared__ float sb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int n = blockIdx.x * 16 + tx;
+  const int m = blockIdx.y * 16 + ty;
+  const int m_tile0 = blockIdx.y * 16;
+  const int bidx = p.b_batched ? (m_tile0 / p.rows_per_sample) : 0;
+  const __nv_bfloat16* Bb = B + static_cast<size_t>(bidx) * p.N * p.K;
+  float acc = 0.0f;
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    const int am = blockIdx.y * 16 + ty;
+    sa[ty][tx] = (am < p.M) ? __bfloat162float(A[static_cast<size_t>(am) * p.K + k0 + tx]) : 0.0f;
+    const int bn = blockIdx.x * 16 + ty;
+    sb[ty][tx] = (bn < p.N) ? __bfloat162float(Bb[static_cast<size_t>(bn) * p.K + k0 + tx]) : 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[tx][k], acc);
+    __syncthreads();
+  }
+  if (m >= p.M || n >= p.N) return;
+  float v = acc + (p.bias ? p.bias[n] : 0.0f);
+  const size_t off = static_cast<size_t>(m) * p.N + n;
+  if (MODE == FZ_EPI_GELU_SUMSQ) {
+    v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    atomicAdd(&p.sumsq[static_cast<size_t>(m / p.rows_per_sample) * p.N + n], v * v);
+  } else if (MODE == FZ_EPI_RELU_BF16) {
+    v = fmaxf(v, 0.0f);
+  } else if (MODE == FZ_EPI_RESID_F32) {
+    v += p.resid[off];
+  }
+  if (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32)
+    reinterpret_cast<float*>(p.out)[off] = v;
+  else
+    reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(v);
+}
+}  // namespace fz
+
+extern "C" int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const float* bias, const float* resid,
+                                 float* sumsq, int M, int N, int K, int b_batch, int rows_per_sample, int mode,
+                                 void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(M > 0 && N > 0 && K > 0 && K % 16 == 0, "fz_gemm_bf16_simt: bad shape M=%d N=%d K=%d", M, N, K);
+  if (b_batch > 1) FZ_REQUIRE(rows_per_sample % 16 == 0, "fz_gemm_bf16_simt: rows_per_sample %% 16 != 0");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
+  p.b_batched = b_batch > 1 ? 1 : 0;
+  p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq;
+  dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(B);
+  switch (mode) {
+    case FZ_EPI_BF16: gemm_simt_kernel<FZ_EPI_BF16><<<grid, block, 0, st>>>(a, b, p); break;
+    case FZ_EPI_GELU_SUMSQ: gemm_simt_kernel<FZ_EPI_GELU_SUMSQ><<<grid, block, 0, st>>>(a, b, p); break;
+    case FZ_EPI_RESID_F32: gemm_simt_kernel<FZ_EPI_RESID_F32><<<grid, block, 0, st>>>(a, b, p); break;
+    case FZ_EPI_F32: gemm_simt_kernel<FZ_EPI_F32><<<grid, block, 0, st>>>(a, b, p); break;
+    case FZ_EPI_RELU_BF16: gemm_simt_kernel<FZ_EPI_RELU_BF16><<<grid, block, 0, st>>>(a, b, p); break;
+    default: set_error("fz_gemm_bf16_simt: unknown mode %d", mode); return -1;
+  }
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

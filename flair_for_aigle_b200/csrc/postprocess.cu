@@ -1,0 +1,293 @@
+// Memory-bound post-processing kernels: margin crop + argmax / softmax + overlap accumulate,
+// written straight into the zone raster in HBM.
+//
+// Replaces flair_zonal_detection/inference.py:295-352 (20 MB/tile fp32 D2H, numpy crop,
+// postprocess.convert, rasterio windowed write) and postprocess.py:9-30; the accumulating
+// variant implements the intended semantics of inference.py:468-572.
+//
+// Access pattern: one thread per output pixel (4 px per thread on the aligned NCHW path);
+// NCHW logits are read plane by plane so every warp load is a contiguous 128/512 B run;
+// NHWC logits (the engine's own layout, class fastest, 16 B-aligned records) are read with
+// 16 B vector loads and reduced in registers.
+#include "common.h"
+#include "../../include/flair_zonal_b200.h"
+
+#include <cuda_bf16.h>
+
+namespace fz {
+
+constexpr int MAX_CLS = 32;
+
+struct TileWin {
+  int y0, x0;      // first tile-local pixel (inside the P x P tile)
+  int r0, c0;      // raster pixel it maps to
+  int h, w;        // extent
+};
+
+// Resolve tile t's window: write window from the plan, optionally trimmed to the owned sub-window.
+__device__ __forceinline__ TileWin tile_window(const int32_t* plan, const int32_t* own, int t, int margin) {
+  const int32_t* p = plan + 6 * t;
+  const int top = p[2], left = p[3];
+  int r0 = top, r1 = top + p[4], c0 = left, c1 = left + p[5];
+  if (own) {
+    const int32_t* o = own + 4 * t;
+    r0 = max(r0, o[0]);
+    r1 = min(r1, o[1]);
+    c0 = max(c0, o[2]);
+    c1 = min(c1, o[3]);
+  }
+  TileWin w;
+  w.r0 = r0;
+  w.c0 = c0;
+  w.h = r1 - r0;
+  w.w = c1 - c0;
+  w.y0 = margin + (r0 - top);
+  w.x0 = margin + (c0 - left);
+  return w;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// Load the n_cls logits of one pixel into registers.
+template <typename T, int LAYOUT>
+__device__ __forceinline__ void load_pixel(const T* __restrict__ logits, int t, int n_cls, int cstride, int P, int y,
+                                           int x, float (&v)[MAX_CLS]) {
+  if (LAYOUT == FZ_NCHW) {
+    const T* base = logits + (static_cast<size_t>(t) * n_cls * P + y) * P + x;
+    const size_t plane = static_cast<size_t>(P) * P;
+#pragma unroll
+    for (int c = 0; c < MAX_CLS; ++c)
+      if (c < n_cls) v[c] = to_f32<T>(base[c * plane]);
+  } else {
+    const T* base = logits + ((static_cast<size_t>(t) * P + y) * P + x) * cstride;
+    if ((static_cast<size_t>(cstride) * sizeof(T)) % 16 == 0) {
+      constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+      for (int c = 0; c < MAX_CLS; c += PER) {
+        if (c < n_cls) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(base + c);
+          const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+          for (int j = 0; j < PER; ++j) v[c + j] = to_f32<T>(e[j]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < MAX_CLS; ++c)
+        if (c < n_cls) v[c] = to_f32<T>(base[c]);
+    }
+  }
+}
+
+__device__ __forceinline__ int argmax_first(const float (&v)[MAX_CLS], int n_cls) {
+  // np.argmax: first maximal index wins; NaN handling is not needed (finite logits).
+  int best = 0;
+  float bv = v[0];
+#pragma unroll
+  for (int c = 1; c < MAX_CLS; ++c)
+    if (c < n_cls && v[c] > bv) {
+      bv = v[c];
+      best = c;
+    }
+  return best;
+}
+
+__device__ __forceinline__ void softmax_inplace(float (&v)[MAX_CLS], int n_cls) {
+  float mx = v[0];
+#pragma unroll
+  for (int c = 1; c < MAX_CLS; ++c)
+    if (c < n_cls) mx = fmaxf(mx, v[c]);
+  float sum = 0.0f;
+#pragma unroll
+  for (int c = 0; c < MAX_CLS; ++c)
+    if (c < n_cls) {
+      v[c] = expf(v[c] - mx);
+      sum += v[c];
+    }
+#pragma unroll
+  for (int c = 0; c < MAX_CLS; ++c)
+    if (c < n_cls) v[c] = v[c] / sum;
+}
+
+constexpr int PP_THREADS = 128;
+constexpr int PP_ROWS = 4;  // rows of the window per CTA
+
+// MODE 0: argmax -> uint8 [H][W]; 1: round(softmax*255) -> uint8 [n_cls][H][W];
+// 2: canvas[n_cls][H][W] += w * softmax
+template <typename T, int LAYOUT, int MODE>
+__global__ void __launch_bounds__(PP_THREADS) crop_kernel(const T* __restrict__ logits, int n_cls, int cstride, int P,
+                                                          int margin, const int32_t* __restrict__ plan,
+                                                          const int32_t* __restrict__ own,
+                                                          const float* __restrict__ weight, uint8_t* __restrict__ out8,
+                                                          float* __restrict__ canvas, int H, int W) {
+  const int t = blockIdx.x;
+  const TileWin win = tile_window(plan, own, t, margin);
+  if (win.h <= 0 || win.w <= 0) return;
+  const int row_begin = blockIdx.y * PP_ROWS;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const int S = P - 2 * margin;
+  for (int ry = row_begin; ry < min(row_begin + PP_ROWS, win.h); ++ry) {
+    const int y = win.y0 + ry;
+    const size_t orow = static_cast<size_t>(win.r0 + ry) * W + win.c0;
+    for (int rx = threadIdx.x; rx < win.w; rx += PP_THREADS) {
+      float v[MAX_CLS];
+      load_pixel<T, LAYOUT>(logits, t, n_cls, cstride, P, y, win.x0 + rx, v);
+      if (MODE == 0) {
+        out8[orow + rx] = static_cast<uint8_t>(argmax_first(v, n_cls));
+      } else {
+        softmax_inplace(v, n_cls);
+        if (MODE == 1) {
+#pragma unroll
+          for (int c = 0; c < MAX_CLS; ++c)
+            if (c < n_cls) out8[c * plane + orow + rx] = static_cast<uint8_t>(rintf(v[c] * 255.0f));
+        } else {
+          const float wgt = weight ? weight[(y - margin) * S + (win.x0 + rx - margin)] : 1.0f;
+#pragma unroll
+          for (int c = 0; c < MAX_CLS; ++c)
+            if (c < n_cls) canvas[c * plane + orow + rx] += wgt * v[c];
+        }
+      }
+    }
+  }
+}
+
+template <int MODE>
+static int launch_crop(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
+                       int margin, const int32_t* plan, const int32_t* own, const float* weight, uint8_t* out8,
+                       float* canvas, int H, int W, cudaStream_t st) {
+  FZ_REQUIRE(n_cls >= 1 && n_cls <= MAX_CLS, "crop kernels support 1..%d classes, got %d", MAX_CLS, n_cls);
+  FZ_REQUIRE(P > 2 * margin && margin >= 0, "bad patch/margin %d/%d", P, margin);
+  FZ_REQUIRE(dtype == FZ_F32 || dtype == FZ_BF16, "bad dtype %d", dtype);
+  FZ_REQUIRE(layout == FZ_NCHW || layout == FZ_NHWC, "bad layout %d", layout);
+  if (layout == FZ_NHWC) FZ_REQUIRE(cstride >= n_cls, "cstride %d < n_cls %d", cstride, n_cls);
+  if (layout == FZ_NHWC && (static_cast<size_t>(cstride) * (dtype == FZ_F32 ? 4 : 2)) % 16 == 0)
+    FZ_REQUIRE(cstride >= ((n_cls + (dtype == FZ_F32 ? 3 : 7)) / (dtype == FZ_F32 ? 4 : 8)) * (dtype == FZ_F32 ? 4 : 8),
+               "vector path needs cstride >= n_cls rounded up to 16 B");
+  if (n_tiles <= 0) return 0;
+  const int S = P - 2 * margin;
+  dim3 grid(n_tiles, (S + PP_ROWS - 1) / PP_ROWS), block(PP_THREADS);
+#define FZ_LAUNCH(T, LAY)                                                                                       \
+  crop_kernel<T, LAY, MODE><<<grid, block, 0, st>>>(reinterpret_cast<const T*>(logits), n_cls, cstride, P, margin, \
+                                                    plan, own, weight, out8, canvas, H, W)
+  if (dtype == FZ_F32 && layout == FZ_NCHW) FZ_LAUNCH(float, FZ_NCHW);
+  else if (dtype == FZ_F32) FZ_LAUNCH(float, FZ_NHWC);
+  else if (layout == FZ_NCHW) FZ_LAUNCH(__nv_bfloat16, FZ_NCHW);
+  else FZ_LAUNCH(__nv_bfloat16, FZ_NHWC);
+#undef FZ_LAUNCH
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void canvas_argmax_kernel(const float* __restrict__ canvas, int n_cls, int64_t n_px,
+                                     uint8_t* __restrict__ labels, float* __restrict__ conf) {
+  // 4 pixels per thread, float4 plane loads (n_px is padded by the tail loop below).
+  const int64_t i4 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n_px) return;
+  if (i4 + 4 <= n_px && (n_px % 4 == 0)) {
+    float4 best = *reinterpret_cast<const float4*>(canvas + i4);
+    uchar4 idx = make_uchar4(0, 0, 0, 0);
+    for (int c = 1; c < n_cls; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(canvas + c * n_px + i4);
+      if (v.x > best.x) { best.x = v.x; idx.x = c; }
+      if (v.y > best.y) { best.y = v.y; idx.y = c; }
+      if (v.z > best.z) { best.z = v.z; idx.z = c; }
+      if (v.w > best.w) { best.w = v.w; idx.w = c; }
+    }
+    *reinterpret_cast<uchar4*>(labels + i4) = idx;
+    if (conf) *reinterpret_cast<float4*>(conf + i4) = best;
+  } else {
+    for (int64_t i = i4; i < min(i4 + 4, n_px); ++i) {
+      float best = canvas[i];
+      int idx = 0;
+      for (int c = 1; c < n_cls; ++c) {
+        const float v = canvas[c * n_px + i];
+        if (v > best) { best = v; idx = c; }
+      }
+      labels[i] = static_cast<uint8_t>(idx);
+      if (conf) conf[i] = best;
+    }
+  }
+}
+
+__global__ void convert_kernel(const float* __restrict__ img, int C, int64_t n_px, int mode,
+                               uint8_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  float v[MAX_CLS];
+#pragma unroll
+  for (int c = 0; c < MAX_CLS; ++c)
+    if (c < C) v[c] = img[c * n_px + i];
+  if (mode == 0) {
+    out[i] = static_cast<uint8_t>(argmax_first(v, C));
+  } else {
+    softmax_inplace(v, C);
+#pragma unroll
+    for (int c = 0; c < MAX_CLS; ++c)
+      if (c < C) out[c * n_px + i] = static_cast<uint8_t>(rintf(v[c] * 255.0f));
+  }
+}
+
+}  // namespace fz
+
+extern "C" int fz_crop_argmax_write(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls,
+                                    int P, int margin, const int32_t* plan, const int32_t* own, uint8_t* out_raster,
+                                    int H, int W, void* stream) {
+  return fz::launch_crop<0>(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, own, nullptr, out_raster,
+                            nullptr, H, W, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fz_crop_softmax_write(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls,
+                                     int P, int margin, const int32_t* plan, const int32_t* own, uint8_t* out_raster,
+                                     int H, int W, void* stream) {
+  return fz::launch_crop<1>(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, own, nullptr, out_raster,
+                            nullptr, H, W, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fz_crop_softmax_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles,
+                                          int n_cls, int P, int margin, const int32_t* plan, const float* weight,
+                                          float* canvas, int H, int W, void* stream) {
+  // Tiles of one call may overlap in the canvas (clamped edge rows/columns): serialise them.
+  // The grid is a product grid, so tiles that overlap are never in the same call when the
+  // caller batches by grid column; to stay safe for any batch we launch tile by tile.
+  for (int t = 0; t < n_tiles; ++t) {
+    int rc = fz::launch_crop<2>(logits, dtype, layout, cstride, 1, n_cls, P, margin, plan, nullptr, weight, nullptr,
+                                canvas, H, W, reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    // advance to the next tile: logits and plan are indexed by blockIdx.x inside the kernel
+    const size_t esz = dtype == FZ_F32 ? 4 : 2;
+    const size_t per_tile = layout == FZ_NCHW ? static_cast<size_t>(n_cls) * P * P
+                                              : static_cast<size_t>(P) * P * cstride;
+    logits = static_cast<const char*>(logits) + per_tile * esz;
+    plan += 6;
+  }
+  return 0;
+}
+
+extern "C" int fz_canvas_argmax(const float* canvas, int n_cls, int64_t n_px, uint8_t* labels, float* confidence,
+                                void* stream) {
+  FZ_REQUIRE(n_cls >= 1 && n_px >= 0, "fz_canvas_argmax: bad arguments");
+  if (n_px == 0) return 0;
+  const int threads = 256;
+  const int64_t blocks = (n_px + threads * 4 - 1) / (threads * 4);
+  fz::canvas_argmax_kernel<<<static_cast<unsigned>(blocks), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      canvas, n_cls, n_px, labels, confidence);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, void* stream) {
+  FZ_REQUIRE(C >= 1 && C <= fz::MAX_CLS, "fz_convert: supports 1..%d classes, got %d", fz::MAX_CLS, C);
+  FZ_REQUIRE(mode == 0 || mode == 1, "fz_convert: Unknown output type: %d", mode);
+  const int64_t n_px = static_cast<int64_t>(h) * w;
+  if (n_px == 0) return 0;
+  const int threads = 256;
+  fz::convert_kernel<<<static_cast<unsigned>((n_px + threads - 1) / threads), threads, 0,
+                       reinterpret_cast<cudaStream_t>(stream)>>>(img, C, n_px, mode, out);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,184 @@
+"""ctypes binding of libfz_b200.so (C ABI declared in include/flair_zonal_b200.h).
+
+PyTorch is used only as the owner of device memory and streams: every wrapper takes torch
+CUDA tensors, passes raw ``data_ptr()``s and the current stream handle.  There is NO CPU or
+library fallback: if the shared library is missing or a call fails, a ``NativeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "_native" / "libfz_b200.so"
+_lib: Optional[ctypes.CDLL] = None
+
+F32, BF16 = 0, 1
+NCHW, NHWC = 0, 1
+EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16 = 0, 1, 2, 3, 4
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "fz_last_error": [],
+    "fz_abi_version": [],
+    "fz_device_info": [_i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_sz)],
+    "fz_gather_tiles_f32": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
+    "fz_gather_tiles_u8": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp],
+    "fz_crop_argmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "fz_crop_softmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "fz_crop_softmax_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "fz_canvas_argmax": [_vp, _i, _i64, _vp, _vp, _vp],
+    "fz_convert": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "fz_gemm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_gemm_bf16_simt": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+}
+_RESTYPES = {"fz_last_error": ctypes.c_char_p}
+
+
+def exported_symbols():
+    """Names the header declares; tests check the library exports every one of them."""
+    return list(_SIGNATURES.keys())
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise NativeError(
+                f"{_LIB_PATH} is missing: build it with `python -m flair_for_aigle_b200.build` "
+                "(there is no CPU fallback for the hot path)")
+        _lib = ctypes.CDLL(str(_LIB_PATH))
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        if _lib.fz_abi_version() != 1:
+            raise NativeError("libfz_b200.so ABI version mismatch")
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().fz_last_error()
+        raise NativeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("native kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise NativeError("native kernels need contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise NativeError(f"unsupported logits dtype {t.dtype}")
+
+
+# --------------------------------------------------------------------------- feeder
+def gather_tiles_f32(raster: torch.Tensor, origins: torch.Tensor, P: int, mean: torch.Tensor, std: torch.Tensor,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    C, H, W = raster.shape
+    n = origins.shape[0]
+    assert raster.dtype == torch.uint8 and origins.dtype == torch.int32
+    if out is None:
+        out = torch.empty((n, C, P, P), dtype=torch.float32, device=raster.device)
+    _check(lib().fz_gather_tiles_f32(_ptr(raster), C, H, W, _ptr(origins), n, P, _ptr(mean), _ptr(std), _ptr(out),
+                                     _stream()), "fz_gather_tiles_f32")
+    return out
+
+
+def gather_tiles_u8(raster: torch.Tensor, origins: torch.Tensor, P: int,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    C, H, W = raster.shape
+    n = origins.shape[0]
+    if out is None:
+        out = torch.empty((n, P, P, 4), dtype=torch.uint8, device=raster.device)
+    _check(lib().fz_gather_tiles_u8(_ptr(raster), C, H, W, _ptr(origins), n, P, _ptr(out), _stream()),
+           "fz_gather_tiles_u8")
+    return out
+
+
+# --------------------------------------------------------------------------- post-processing
+def _logits_geom(logits: torch.Tensor, layout: int, n_cls: Optional[int]):
+    if layout == NCHW:
+        n, c, p, _ = logits.shape
+        return n, (n_cls or c), p, 0
+    n, p, _, cs = logits.shape
+    return n, (n_cls or cs), p, cs
+
+
+def crop_argmax_write(logits, layout, margin, plan, own, out_raster, n_cls=None):
+    n, c, p, cs = _logits_geom(logits, layout, n_cls)
+    H, W = out_raster.shape[-2:]
+    _check(lib().fz_crop_argmax_write(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan), _ptr(own),
+                                      _ptr(out_raster), H, W, _stream()), "fz_crop_argmax_write")
+
+
+def crop_softmax_write(logits, layout, margin, plan, own, out_raster, n_cls=None):
+    n, c, p, cs = _logits_geom(logits, layout, n_cls)
+    H, W = out_raster.shape[-2:]
+    _check(lib().fz_crop_softmax_write(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan), _ptr(own),
+                                       _ptr(out_raster), H, W, _stream()), "fz_crop_softmax_write")
+
+
+def crop_softmax_accumulate(logits, layout, margin, plan, weight, canvas, n_cls=None):
+    n, c, p, cs = _logits_geom(logits, layout, n_cls)
+    H, W = canvas.shape[-2:]
+    _check(lib().fz_crop_softmax_accumulate(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan),
+                                            _ptr(weight), _ptr(canvas), H, W, _stream()),
+           "fz_crop_softmax_accumulate")
+
+
+def canvas_argmax(canvas: torch.Tensor, want_confidence: bool = False):
+    c, H, W = canvas.shape
+    labels = torch.empty((H, W), dtype=torch.uint8, device=canvas.device)
+    conf = torch.empty((H, W), dtype=torch.float32, device=canvas.device) if want_confidence else None
+    _check(lib().fz_canvas_argmax(_ptr(canvas), c, H * W, _ptr(labels), _ptr(conf), _stream()), "fz_canvas_argmax")
+    return labels, conf
+
+
+def convert(img: torch.Tensor, mode: int) -> torch.Tensor:
+    C, h, w = img.shape
+    out = torch.empty((1, h, w) if mode == 0 else (C, h, w), dtype=torch.uint8, device=img.device)
+    _check(lib().fz_convert(_ptr(img), C, h, w, mode, _ptr(out), _stream()), "fz_convert")
+    return out
+
+
+# --------------------------------------------------------------------------- GEMM
+def gemm_bf16(A: torch.Tensor, B: torch.Tensor, mode: int, bias=None, resid=None, sumsq=None, out=None,
+              rows_per_sample: int = 0, impl: str = "tcgen05") -> torch.Tensor:
+    """A: bf16 [M,K]; B: bf16 [N,K] or [b,N,K]."""
+    M, K = A.shape
+    if B.dim() == 2:
+        b_batch, (N, K2) = 1, B.shape
+    else:
+        b_batch, N, K2 = B.shape
+    assert K2 == K and A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    if out is None:
+        odt = torch.float32 if mode in (EPI_RESID_F32, EPI_F32) else torch.bfloat16
+        out = torch.empty((M, N), dtype=odt, device=A.device)
+    fn = lib().fz_gemm_bf16 if impl == "tcgen05" else lib().fz_gemm_bf16_simt
+    _check(fn(_ptr(A), _ptr(B), _ptr(out), _ptr(bias), _ptr(resid), _ptr(sumsq), M, N, K, b_batch, rows_per_sample,
+              mode, _stream()), "fz_gemm_bf16")
+    return out

@@ -1,0 +1,103 @@
+/*
+ * flair_zonal_b200.h -- C ABI of libfz_b200.so, the sm_100a implementation of
+ * kezakool/flair-for-aigle's zonal segmentation hot path.
+ *
+ * The reference has no FFI of its own (it is pure Python calling PyTorch / smp / timm / numpy);
+ * each entry point below names the reference call site it replaces.  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer unless the name ends in _host; the caller owns
+ *     all memory; the library never allocates device memory.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and
+ *     capturable in a CUDA graph.
+ *   - return 0 on success, <0 on error; fz_last_error() returns a thread-local message.
+ *   - activations are NHWC; "bf16" is __nv_bfloat16 (uint16 storage).
+ */
+#ifndef FLAIR_ZONAL_B200_H
+#define FLAIR_ZONAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FZ_ABI_VERSION 1
+
+const char* fz_last_error(void);
+int fz_abi_version(void);
+int fz_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---------------------------------------------------------------- tile feeder
+ * Replaces flair_zonal_detection/dataset.py:89-124,174-209 (_load_patch boundless windowed
+ * read with fill 0, then norm.py:37-44 (x-mean)/std) and inference.py:280-286 (H2D).
+ * raster: uint8 [C][H][W] band-sequential (what rasterio's read() returns), resident in HBM.
+ * origins: int32 [n_tiles][2] = (row0, col0) of each tile's full window (may be negative /
+ * past the edge: zero fill BEFORE normalisation, like the reference).
+ * out: float32 [n_tiles][C][P][P] normalised, NCHW -- exactly the tensor the reference's
+ * model receives as batch[<MOD>].
+ */
+int fz_gather_tiles_f32(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
+                        const float* mean, const float* std, float* out, void* stream);
+/* Same window rule, raw bytes, NHWC uint8 [n_tiles][P][P][4] (C<=4, missing channels = 0):
+ * the operand the fused stem kernel consumes (20 B/px feeder of SURVEY 8d becomes 4+4 B/px). */
+int fz_gather_tiles_u8(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
+                       uint8_t* out, void* stream);
+
+/* ---------------------------------------------------------------- crop / softmax / blend / argmax
+ * Replaces inference.py:295-352 (D2H of fp32 logits, per-tile numpy crop + convert + windowed
+ * write) and postprocess.py:9-30 (convert).
+ * logits: [n_tiles][n_cls][P][P] (layout FZ_NCHW) or [n_tiles][P][P][cstride] (FZ_NHWC, class
+ * fastest, first n_cls of cstride valid); dtype FZ_F32 or FZ_BF16.
+ * plan: int32 [n_tiles][6] = (row0, col0, top_px, left_px, height_px, width_px): the write
+ * window of the margin-cropped prediction (inference.py:318-343); height_px<=0 = skipped.
+ * own:  int32 [n_tiles][4] = (r0, r1, c0, c1) sub-window (absolute raster px) of the write
+ * window that survives later tiles' overwrites ("last writer wins", inference.py:343-352);
+ * NULL = write the whole window (only valid when tiles in one call do not overlap).
+ */
+#define FZ_F32 0
+#define FZ_BF16 1
+#define FZ_NCHW 0
+#define FZ_NHWC 1
+int fz_crop_argmax_write(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
+                         int margin, const int32_t* plan, const int32_t* own, uint8_t* out_raster, int H, int W,
+                         void* stream);
+/* output_type == "class_prob": out_raster is uint8 [n_cls][H][W] = round(softmax*255). */
+int fz_crop_softmax_write(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
+                          int margin, const int32_t* plan, const int32_t* own, uint8_t* out_raster, int H, int W,
+                          void* stream);
+/* Intended semantics of inference.py:468-564: canvas[n_cls][H][W] (float32, planar like the
+ * reference's raster_logits) += weight(y,x) * softmax(cropped logits).
+ * weight: float32 [P-2m][P-2m] or NULL (=1). */
+int fz_crop_softmax_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
+                               int margin, const int32_t* plan, const float* weight, float* canvas, int H, int W,
+                               void* stream);
+/* inference.py:566-572: labels = argmax_c canvas (uint8), confidence = max_c canvas (float32,
+ * may be NULL).  canvas is [n_cls][n_px]. */
+int fz_canvas_argmax(const float* canvas, int n_cls, int64_t n_px, uint8_t* labels, float* confidence, void* stream);
+/* postprocess.py:9-30 on one (C,h,w) fp32 NCHW array: mode 0 argmax -> uint8 [h][w];
+ * mode 1 class_prob -> uint8 [C][h][w]. */
+int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, void* stream);
+
+/* ---------------------------------------------------------------- bf16 GEMM (tcgen05 / TMEM / TMA)
+ * C[m,n] = sum_k A[m,k] * B[b][n,k] (+ epilogue).  A: bf16 [M][K]; B: bf16 [b_batch][N][K];
+ * b = (m / rows_per_sample) when b_batch > 1 (per-sample GRN-scaled fc2 weights) else 0.
+ * Replaces the nn.Linear / 1x1 / 2x2-stride-2 conv calls under flair_model.py:376,539-541.
+ */
+#define FZ_EPI_BF16 0       /* out bf16 = acc + bias                                              */
+#define FZ_EPI_GELU_SUMSQ 1 /* out bf16 = gelu(acc + bias); sumsq[sample][n] += out^2 (GRN stats) */
+#define FZ_EPI_RESID_F32 2  /* out f32  = acc + bias + resid                                      */
+#define FZ_EPI_F32 3        /* out f32  = acc + bias                                              */
+#define FZ_EPI_RELU_BF16 4  /* out bf16 = relu(acc + bias)                                        */
+int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq, int M,
+                 int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
+/* Same contract on CUDA cores (exact erff); test/bring-up cross-check only. */
+int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq,
+                      int M, int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAIR_ZONAL_B200_H */
