@@ -1,0 +1,544 @@
+// CUDA-core kernels around the tensor-core GEMMs of the ConvNeXt-V2 encoder and U-Net decoder:
+//   stem (conv4x4 s4 on raw uint8 with the normalisation folded in, + LayerNorm2d),
+//   depthwise 7x7 + LayerNorm fused, LayerNorm2d + space-to-depth for the 2x2/s2 downsample,
+//   GRN statistics -> per-sample scales, weight / activation scaling, nearest-up x2 + concat.
+// Activations are NHWC; the residual stream is fp32, GEMM operands are bf16.
+//
+// Replaces the timm ConvNeXtBlock / ConvNeXtStage arithmetic invoked from
+// flair_hub/models/flair_model.py:376 and smp UnetDecoder's interpolate+cat invoked from :418
+// (SURVEY.md K1/K4).
+#include "common.h"
+#include "../../include/flair_zonal_b200.h"
+
+#include <cuda_bf16.h>
+
+namespace fz {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------ stem
+// in  : uint8 [B][P][P][4]           (fz_gather_tiles_u8)
+// w   : float [64][C0], row k = ky*16 + kx*4 + c, already divided by std[c]
+// bias: float [C0] = conv bias - sum_k w[k][n] * mean[c(k)]
+// out : float [B][P/4][P/4][C0] = LayerNorm2d(conv)
+constexpr int STEM_PX = 32;        // output pixels per segment (8 per warp)
+constexpr int STEM_IN_STRIDE = 80; // floats per pixel row in smem (64 used; 80 keeps stores conflict-free)
+
+template <int CPL, bool F32IN>
+__global__ void __launch_bounds__(128) stem_ln_kernel(const void* __restrict__ in_raw, int Cin,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                      float* __restrict__ out, int P, float eps) {
+  constexpr int C0 = 32 * CPL;
+  extern __shared__ float smem_f[];
+  float* sW = smem_f;                 // [64][C0]
+  float* sIn = smem_f + 64 * C0;      // [STEM_PX][STEM_IN_STRIDE]
+  const int OW = P / 4;
+  const int segs = OW / STEM_PX;
+  const int oy = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < 64 * C0; i += 128) sW[i] = w[i];
+  float bz[CPL], gw[CPL], gb[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    bz[j] = bias[lane * CPL + j];
+    gw[j] = ln_w[lane * CPL + j];
+    gb[j] = ln_b[lane * CPL + j];
+  }
+
+  for (int seg = 0; seg < segs; ++seg) {
+    const int ox0 = seg * STEM_PX;
+    __syncthreads();
+    // 4 input rows x 128 input px: thread t loads px (4*ox0 + t) of each row
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (F32IN) {
+        // float32 NCHW [B][Cin][P][P]: one coalesced load per channel
+        const float* xin = reinterpret_cast<const float*>(in_raw);
+        const size_t o = (static_cast<size_t>(b) * Cin * P + (4 * oy + r)) * P + 4 * ox0 + tid;
+        const size_t plane = static_cast<size_t>(P) * P;
+        f.x = xin[o];
+        if (Cin > 1) f.y = xin[o + plane];
+        if (Cin > 2) f.z = xin[o + 2 * plane];
+        if (Cin > 3) f.w = xin[o + 3 * plane];
+      } else {
+        const uchar4 u =
+            reinterpret_cast<const uchar4*>(in_raw)[(static_cast<size_t>(b) * P + (4 * oy + r)) * P + 4 * ox0 + tid];
+        f = make_float4(u.x, u.y, u.z, u.w);
+      }
+      *reinterpret_cast<float4*>(&sIn[(tid >> 2) * STEM_IN_STRIDE + r * 16 + (tid & 3) * 4]) = f;
+    }
+    __syncthreads();
+
+    float acc[8][CPL];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc[i][j] = bz[j];
+
+#pragma unroll 4
+    for (int k = 0; k < 64; k += 4) {
+      float wv[4][CPL];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (CPL % 4 == 0) {
+#pragma unroll
+          for (int j = 0; j < CPL; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&sW[(k + kk) * C0 + lane * CPL + j]);
+            wv[kk][j] = t4.x; wv[kk][j + 1] = t4.y; wv[kk][j + 2] = t4.z; wv[kk][j + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) wv[kk][j] = sW[(k + kk) * C0 + lane * CPL + j];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 x4 = *reinterpret_cast<const float4*>(&sIn[(warp * 8 + i) * STEM_IN_STRIDE + k]);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          acc[i][j] = fmaf(x4.x, wv[0][j], acc[i][j]);
+          acc[i][j] = fmaf(x4.y, wv[1][j], acc[i][j]);
+          acc[i][j] = fmaf(x4.z, wv[2][j], acc[i][j]);
+          acc[i][j] = fmaf(x4.w, wv[3][j], acc[i][j]);
+        }
+      }
+    }
+    // LayerNorm2d over the C0 channels of each pixel (two-pass, fp32)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) s += acc[i][j];
+      const float mean = warp_sum(s) * (1.0f / C0);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const float d = acc[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / C0) + eps);
+      float* o = out + ((static_cast<size_t>(b) * OW + oy) * OW + ox0 + warp * 8 + i) * C0 + lane * CPL;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) o[j] = (acc[i][j] - mean) * rstd * gw[j] + gb[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ dwconv7x7 + LN
+// x  : float [B][H][W][C] residual stream;  wdw: float [49][C];  bdw: float [C]
+// out: bf16  [B][H][W][C] = LayerNorm_C(dwconv7x7(x) + bdw) * ln_w + ln_b
+template <int TH, int TW, int SH, int SW>
+__global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ wdw,
+                                                        const float* __restrict__ bdw, const float* __restrict__ ln_w,
+                                                        const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
+                                                        int H, int W, int C, float eps) {
+  static_assert((TH / SH) * (TW / SW) == 8, "8 warps, one sub-tile each");
+  constexpr int HH = TH + 6, HW = TW + 6;
+  extern __shared__ float smem_f[];
+  float* sHalo = smem_f;                  // [HH][HW][32]
+  float* sStage = smem_f + HH * HW * 32;  // [TH*TW][C]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+  const int sy0 = (warp / (TW / SW)) * SH, sx0 = (warp % (TW / SW)) * SW;
+  const float* xb = x + static_cast<size_t>(b) * H * W * C;
+
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    __syncthreads();  // previous chunk's reads of sHalo are done
+    for (int idx = tid; idx < HH * HW * 32; idx += 256) {
+      const int pix = idx >> 5;
+      const int gy = y0 - 3 + pix / HW, gx = x0 - 3 + pix % HW;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = xb[(static_cast<size_t>(gy) * W + gx) * C + c0 + (idx & 31)];
+      sHalo[idx] = v;
+    }
+    float wreg[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) wreg[t] = wdw[t * C + c0 + lane];
+    const float bias = bdw[c0 + lane];
+    __syncthreads();
+
+    float acc[SH][SW];
+#pragma unroll
+    for (int a = 0; a < SH; ++a)
+#pragma unroll
+      for (int c = 0; c < SW; ++c) acc[a][c] = bias;
+#pragma unroll
+    for (int iy = 0; iy < SH + 6; ++iy) {
+#pragma unroll
+      for (int ix = 0; ix < SW + 6; ++ix) {
+        const float v = sHalo[((sy0 + iy) * HW + sx0 + ix) * 32 + lane];
+#pragma unroll
+        for (int a = 0; a < SH; ++a) {
+#pragma unroll
+          for (int c = 0; c < SW; ++c) {
+            const int ky = iy - a, kx = ix - c;
+            if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) acc[a][c] = fmaf(v, wreg[ky * 7 + kx], acc[a][c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < SH; ++a)
+#pragma unroll
+      for (int c = 0; c < SW; ++c) sStage[((sy0 + a) * TW + sx0 + c) * C + c0 + lane] = acc[a][c];
+  }
+  __syncthreads();
+
+  // LayerNorm over channels, one warp per pixel
+  for (int p = warp; p < TH * TW; p += 8) {
+    const int gy = y0 + p / TW, gx = x0 + p % TW;
+    if (gy >= H || gx >= W) continue;
+    const float* row = sStage + p * C;
+    __nv_bfloat16* o = out + ((static_cast<size_t>(b) * H + gy) * W + gx) * C;
+    if ((C & 127) == 0) {
+      const int nj = C >> 7;
+      float4 v[8];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nj) {
+          v[j] = *reinterpret_cast<const float4*>(row + j * 128 + lane * 4);
+          s += v[j].x + v[j].y + v[j].z + v[j].w;
+        }
+      const float mean = warp_sum(s) / C;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nj) {
+          v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+          q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+        }
+      const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nj) {
+          const int c = j * 128 + lane * 4;
+          const float4 g = *reinterpret_cast<const float4*>(ln_w + c);
+          const float4 be = *reinterpret_cast<const float4*>(ln_b + c);
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v[j].x * rstd * g.x + be.x, v[j].y * rstd * g.y + be.y);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(v[j].z * rstd * g.z + be.z, v[j].w * rstd * g.w + be.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(o + c) = pk;
+        }
+    } else {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s += row[c];
+      const float mean = warp_sum(s) / C;
+      float q = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float d = row[c] - mean;
+        q = fmaf(d, d, q);
+      }
+      const float rstd = rsqrtf(warp_sum(q) / C + eps);
+      for (int c = lane; c < C; c += 32) o[c] = __float2bfloat16_rn((row[c] - mean) * rstd * ln_w[c] + ln_b[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ LN2d + space-to-depth
+// x: float [B][H][W][C] -> out: bf16 [B][H/2][W/2][4C], k = (y&1)*2C + (x&1)*C + c  (the K order of
+// the 2x2/s2 conv weights repacked as [N][ky][kx][c]).  One warp per pixel.
+__global__ void __launch_bounds__(256) ln2d_s2d_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
+                                                       const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
+                                                       int n_px, int H, int W, int C, float eps) {
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= n_px) return;
+  const int xw = p % W, yh = (p / W) % H, b = p / (W * H);
+  const float* row = x + static_cast<size_t>(p) * C;
+  __nv_bfloat16* o = out + ((static_cast<size_t>(b) * (H / 2) + yh / 2) * (W / 2) + xw / 2) * 4 * C +
+                     ((yh & 1) * 2 + (xw & 1)) * C;
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    s += v.x + v.y + v.z + v.w;
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    const float a = v.x - mean, bb = v.y - mean, cc = v.z - mean, d = v.w - mean;
+    q += a * a + bb * bb + cc * cc + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    const float4 g = *reinterpret_cast<const float4*>(ln_w + c);
+    const float4 be = *reinterpret_cast<const float4*>(ln_b + c);
+    __nv_bfloat162 lo = __floats2bfloat162_rn((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(o + c) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------ GRN
+// scale[b][k] = 1 + gamma[k] * Gx / (mean_k Gx + eps), Gx = sqrt(sumsq[b][k]); sumsq is zeroed
+// for its next use (timm GlobalResponseNorm; the beta term is folded into fc2's bias on the host).
+__global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ sumsq, const float* __restrict__ gamma,
+                                                        float* __restrict__ scale, int K, float eps) {
+  __shared__ float red[8];
+  __shared__ float s_mean;
+  const int b = blockIdx.x;
+  float* sq = sumsq + static_cast<size_t>(b) * K;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) s += sqrtf(sq[k]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    s_mean = t / K;
+  }
+  __syncthreads();
+  const float inv = 1.0f / (s_mean + eps);
+  for (int k = threadIdx.x; k < K; k += 256) {
+    scale[static_cast<size_t>(b) * K + k] = 1.0f + gamma[k] * sqrtf(sq[k]) * inv;
+    sq[k] = 0.f;
+  }
+}
+
+// out[b][n][k] = bf16(w[n][k] * scale[b][k])   (8 elements per thread)
+__global__ void __launch_bounds__(256) scale_weights_kernel(const __nv_bfloat16* __restrict__ w,
+                                                            const float* __restrict__ scale,
+                                                            __nv_bfloat16* __restrict__ out, int N, int K) {
+  const int b = blockIdx.y;
+  const size_t i8 = (static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i8 >= static_cast<size_t>(N) * K) return;
+  const int k = static_cast<int>(i8 % K);
+  const uint4 raw = *reinterpret_cast<const uint4*>(w + i8);
+  const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const float4 s0 = *reinterpret_cast<const float4*>(scale + static_cast<size_t>(b) * K + k);
+  const float4 s1 = *reinterpret_cast<const float4*>(scale + static_cast<size_t>(b) * K + k + 4);
+  uint4 o;
+  __nv_bfloat162 t;
+  float2 f;
+  f = __bfloat1622float2(wp[0]); t = __floats2bfloat162_rn(f.x * s0.x, f.y * s0.y); o.x = *reinterpret_cast<uint32_t*>(&t);
+  f = __bfloat1622float2(wp[1]); t = __floats2bfloat162_rn(f.x * s0.z, f.y * s0.w); o.y = *reinterpret_cast<uint32_t*>(&t);
+  f = __bfloat1622float2(wp[2]); t = __floats2bfloat162_rn(f.x * s1.x, f.y * s1.y); o.z = *reinterpret_cast<uint32_t*>(&t);
+  f = __bfloat1622float2(wp[3]); t = __floats2bfloat162_rn(f.x * s1.z, f.y * s1.w); o.w = *reinterpret_cast<uint32_t*>(&t);
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(b) * N * K + i8) = o;
+}
+
+// h[m][k] = bf16(h[m][k] * scale[m / rows_per_sample][k]) in place
+__global__ void __launch_bounds__(256) scale_rows_kernel(__nv_bfloat16* __restrict__ h, const float* __restrict__ scale,
+                                                         size_t total, int K, int rows_per_sample) {
+  const size_t i8 = (static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i8 >= total) return;
+  const size_t m = i8 / K;
+  const int k = static_cast<int>(i8 % K);
+  const size_t b = m / rows_per_sample;
+  uint4 raw = *reinterpret_cast<const uint4*>(h + i8);
+  __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&raw);
+  const float4 s0 = *reinterpret_cast<const float4*>(scale + b * K + k);
+  const float4 s1 = *reinterpret_cast<const float4*>(scale + b * K + k + 4);
+  float2 f;
+  f = __bfloat1622float2(hp[0]); hp[0] = __floats2bfloat162_rn(f.x * s0.x, f.y * s0.y);
+  f = __bfloat1622float2(hp[1]); hp[1] = __floats2bfloat162_rn(f.x * s0.z, f.y * s0.w);
+  f = __bfloat1622float2(hp[2]); hp[2] = __floats2bfloat162_rn(f.x * s1.x, f.y * s1.y);
+  f = __bfloat1622float2(hp[3]); hp[3] = __floats2bfloat162_rn(f.x * s1.z, f.y * s1.w);
+  *reinterpret_cast<uint4*>(h + i8) = raw;
+}
+
+// ------------------------------------------------------------------------------------ up x2 + concat
+// out[b][y][x][0:C1] = a[b][y/2][x/2][:] (nearest, smp DecoderBlock) ; out[..][C1:C1+C2] = s[b][y][x][:]
+// a / s are bf16 or fp32 (encoder features are fp32); out is bf16.  8 channels per thread.
+template <typename T>
+__device__ __forceinline__ uint4 load8_bf16(const T* p);
+template <>
+__device__ __forceinline__ uint4 load8_bf16<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return *reinterpret_cast<const uint4*>(p);
+}
+template <>
+__device__ __forceinline__ uint4 load8_bf16<float>(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&t0);
+  o.y = *reinterpret_cast<uint32_t*>(&t1);
+  o.z = *reinterpret_cast<uint32_t*>(&t2);
+  o.w = *reinterpret_cast<uint32_t*>(&t3);
+  return o;
+}
+
+template <typename TA, typename TS>
+__global__ void __launch_bounds__(256) upcat_kernel(const TA* __restrict__ a, const TS* __restrict__ s,
+                                                    __nv_bfloat16* __restrict__ out, size_t n_vec, int H, int W,
+                                                    int C1, int C2) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n_vec) return;
+  const int CT = C1 + C2;
+  const int vec_per_px = CT / 8;
+  const size_t px = i / vec_per_px;
+  const int c = static_cast<int>(i % vec_per_px) * 8;
+  const int xw = static_cast<int>(px % W), yh = static_cast<int>((px / W) % H);
+  const size_t b = px / (static_cast<size_t>(W) * H);
+  uint4 v;
+  if (c < C1) {
+    v = load8_bf16<TA>(a + ((b * (H / 2) + yh / 2) * (W / 2) + xw / 2) * C1 + c);
+  } else {
+    v = load8_bf16<TS>(s + px * C2 + (c - C1));
+  }
+  *reinterpret_cast<uint4*>(out + px * CT + c) = v;
+}
+
+}  // namespace fz
+
+// ============================================================================ C ABI
+namespace fz {
+template <bool F32IN>
+static int launch_stem(const void* in, int Cin, const float* w, const float* bias, const float* ln_w,
+                       const float* ln_b, float* out, int B, int P, int C0, float eps, cudaStream_t st) {
+  FZ_REQUIRE(P % 128 == 0, "fz_stem_ln: P=%d must be a multiple of 128", P);
+  FZ_REQUIRE(C0 % 32 == 0 && C0 >= 32 && C0 <= 384, "fz_stem_ln: C0=%d unsupported", C0);
+  FZ_REQUIRE(Cin >= 1 && Cin <= 4, "fz_stem_ln: Cin=%d must be 1..4", Cin);
+  if (B <= 0) return 0;
+  const size_t smem = (64 * static_cast<size_t>(C0) + STEM_PX * STEM_IN_STRIDE) * sizeof(float);
+  dim3 grid(P / 4, B);
+#define FZ_STEM(CPL)                                                                                           \
+  case CPL: {                                                                                                  \
+    static bool cfg = false;                                                                                   \
+    if (!cfg) {                                                                                                \
+      FZ_CHECK_CUDA(cudaFuncSetAttribute(stem_ln_kernel<CPL, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         static_cast<int>(smem)));                                             \
+      cfg = true;                                                                                              \
+    }                                                                                                          \
+    stem_ln_kernel<CPL, F32IN><<<grid, 128, smem, st>>>(in, Cin, w, bias, ln_w, ln_b, out, P, eps);            \
+    break;                                                                                                     \
+  }
+  switch (C0 / 32) {
+    FZ_STEM(1) FZ_STEM(2) FZ_STEM(3) FZ_STEM(4) FZ_STEM(6) FZ_STEM(8) FZ_STEM(11) FZ_STEM(12)
+    default: set_error("fz_stem_ln: C0=%d not instantiated", C0); return -1;
+  }
+#undef FZ_STEM
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace fz
+
+extern "C" int fz_stem_ln(const uint8_t* tiles_u8, const float* w, const float* bias, const float* ln_w,
+                          const float* ln_b, float* out, int B, int P, int C0, float eps, void* stream) {
+  return fz::launch_stem<false>(tiles_u8, 4, w, bias, ln_w, ln_b, out, B, P, C0, eps,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fz_stem_ln_f32(const float* x_nchw, int Cin, const float* w, const float* bias, const float* ln_w,
+                              const float* ln_b, float* out, int B, int P, int C0, float eps, void* stream) {
+  return fz::launch_stem<true>(x_nchw, Cin, w, bias, ln_w, ln_b, out, B, P, C0, eps,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+namespace fz {
+template <int TH, int TW, int SH, int SW>
+static int launch_dwconv(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
+                         __nv_bfloat16* out, int B, int H, int W, int C, float eps, cudaStream_t st) {
+  const size_t smem = (static_cast<size_t>(TH + 6) * (TW + 6) * 32 + static_cast<size_t>(TH) * TW * C) * sizeof(float);
+  FZ_REQUIRE(smem <= 227 * 1024, "fz_dwconv7_ln: C=%d needs %zu B of shared memory", C, smem);
+  auto kern = dwconv_ln_kernel<TH, TW, SH, SW>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    FZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);
+  kern<<<grid, 256, smem, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, C, eps);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace fz
+
+extern "C" int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
+                             void* out_bf16, int B, int H, int W, int C, float eps, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(C % 32 == 0 && C > 0, "fz_dwconv7_ln: C=%d must be a multiple of 32", C);
+  if (B <= 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  // pixels per CTA ~ 16384 / C so the fp32 staging tile stays ~64 KB
+  if (C <= 128) return launch_dwconv<8, 16, 4, 4>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+  if (C <= 256) return launch_dwconv<8, 8, 2, 4>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+  if (C <= 512) return launch_dwconv<4, 8, 2, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+  return launch_dwconv<4, 4, 1, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+}
+
+extern "C" int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, int B, int H, int W,
+                           int C, float eps, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "fz_ln2d_s2d: bad shape H=%d W=%d C=%d", H, W, C);
+  const int n_px = B * H * W;
+  if (n_px <= 0) return 0;
+  ln2d_s2d_kernel<<<(n_px + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(out_bf16), n_px, H, W, C, eps);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_grn_scale(float* sumsq, const float* gamma, float* scale, int B, int K, float eps, void* stream) {
+  using namespace fz;
+  if (B <= 0) return 0;
+  grn_scale_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sumsq, gamma, scale, K, eps);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_scale_weights(const void* w_bf16, const float* scale, void* out_bf16, int B, int N, int K,
+                                void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(K % 8 == 0, "fz_scale_weights: K=%d must be a multiple of 8", K);
+  if (B <= 0) return 0;
+  const size_t n8 = static_cast<size_t>(N) * K / 8;
+  dim3 grid(static_cast<unsigned>((n8 + 255) / 256), B);
+  scale_weights_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(w_bf16), scale, reinterpret_cast<__nv_bfloat16*>(out_bf16), N, K);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K, int rows_per_sample, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(K % 8 == 0 && rows_per_sample > 0, "fz_scale_rows: bad arguments");
+  const size_t total = static_cast<size_t>(M) * K;
+  if (total == 0) return 0;
+  scale_rows_kernel<<<static_cast<unsigned>((total / 8 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(h_bf16), scale, total, K, rows_per_sample);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_upsample2_concat(const void* a, int a_dtype, const void* s, int s_dtype, void* out_bf16, int B, int H,
+                                   int W, int C1, int C2, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0 && C2 >= 0, "fz_upsample2_concat: C1=%d C2=%d must be multiples of 8",
+             C1, C2);
+  FZ_REQUIRE(H % 2 == 0 && W % 2 == 0, "fz_upsample2_concat: output H, W must be even");
+  const size_t n_vec = static_cast<size_t>(B) * H * W * (C1 + C2) / 8;
+  if (n_vec == 0) return 0;
+  const unsigned grid = static_cast<unsigned>((n_vec + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  typedef __nv_bfloat16 bf;
+  if (a_dtype == FZ_BF16 && s_dtype == FZ_BF16)
+    upcat_kernel<bf, bf><<<grid, 256, 0, st>>>((const bf*)a, (const bf*)s, o, n_vec, H, W, C1, C2);
+  else if (a_dtype == FZ_BF16)
+    upcat_kernel<bf, float><<<grid, 256, 0, st>>>((const bf*)a, (const float*)s, o, n_vec, H, W, C1, C2);
+  else if (s_dtype == FZ_BF16)
+    upcat_kernel<float, bf><<<grid, 256, 0, st>>>((const float*)a, (const bf*)s, o, n_vec, H, W, C1, C2);
+  else
+    upcat_kernel<float, float><<<grid, 256, 0, st>>>((const float*)a, (const float*)s, o, n_vec, H, W, C1, C2);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,278 @@
+"""ConvNeXt-V2 encoder + U-Net decoder forward, driven kernel by kernel through the C ABI.
+
+This is the B200 execution plan for the model the reference builds with
+``smp.create_model(arch='unet', encoder_name='tu-convnextv2_*')`` and runs at
+``flair_hub/models/flair_model.py:376`` (encoder) and ``:417-419`` (decoder + head).  It owns
+the packed weights (bf16 GEMM operands in the K-major layouts the tcgen05 kernels read, fp32
+vectors for the CUDA-core kernels) and a workspace sized for ``max_batch`` tiles; PyTorch only
+provides the device buffers and the stream.
+
+Numerics: GEMM / conv operands bf16, fp32 accumulation in TMEM, fp32 residual stream, fp32
+LayerNorm / GRN statistics, eval-mode BatchNorm applied as an fp32 per-channel scale + bias in
+the conv epilogue.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from .. import native as nv
+
+
+@dataclass
+class ConvNeXtCfg:
+    depths: Sequence[int] = (3, 3, 27, 3)
+    dims: Sequence[int] = (128, 256, 512, 1024)
+    in_chans: int = 4
+    decoder_channels: Sequence[int] = (256, 128, 64, 32, 16)
+    n_classes: int = 19
+    patch: int = 512
+
+
+CONVNEXTV2_CFGS = {
+    "convnextv2_atto": ((2, 2, 6, 2), (40, 80, 160, 320)),
+    "convnextv2_femto": ((2, 2, 6, 2), (48, 96, 192, 384)),
+    "convnextv2_pico": ((2, 2, 6, 2), (64, 128, 256, 512)),
+    "convnextv2_nano": ((2, 2, 8, 2), (80, 160, 320, 640)),
+    "convnextv2_tiny": ((3, 3, 9, 3), (96, 192, 384, 768)),
+    "convnextv2_base": ((3, 3, 27, 3), (128, 256, 512, 1024)),
+    "convnextv2_large": ((3, 3, 27, 3), (192, 384, 768, 1536)),
+    "convnextv2_huge": ((3, 3, 27, 3), (352, 704, 1408, 2816)),
+}
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _bf16(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16).contiguous()
+
+
+class ConvNeXtV2UNetEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], enc_prefix: str, dec_prefix: str, cfg: ConvNeXtCfg,
+                 device: torch.device, max_batch: int = 16, norm_mean: Optional[Sequence[float]] = None,
+                 norm_std: Optional[Sequence[float]] = None, bn_eps: float = 1e-5):
+        if device.type != "cuda":
+            raise nv.NativeError("ConvNeXtV2UNetEngine needs a CUDA device (no CPU fallback)")
+        for d in cfg.dims:
+            if d % 128 != 0:
+                raise NotImplementedError(f"encoder width {d}: the sm_100a kernels are tiled for multiples of 128")
+        nv.lib()
+        self.cfg, self.dev, self.B = cfg, device, max_batch
+        self.gemm_impl = "tcgen05"
+        sd = state_dict
+        E, D, dev = enc_prefix, dec_prefix, device
+        C0 = cfg.dims[0]
+
+        # ---- stem: [C0, Cin, 4, 4] -> [64][C0], k = ky*16 + kx*4 + c (c padded to 4)
+        w = sd[E + "stem_0.weight"].float()
+        assert w.shape == (C0, cfg.in_chans, 4, 4), w.shape
+        wk = torch.zeros(4, 4, 4, C0, dtype=torch.float64)
+        wk[:, :, :cfg.in_chans, :] = w.double().permute(2, 3, 1, 0)
+        self.stem_w_f32 = _f32(wk.reshape(64, C0), dev)           # for already-normalised float input
+        self.stem_b_f32 = _f32(sd[E + "stem_0.bias"], dev)
+        if norm_mean is not None:
+            mean = torch.zeros(4, dtype=torch.float64)
+            std = torch.ones(4, dtype=torch.float64)
+            mean[:cfg.in_chans] = torch.tensor(list(norm_mean), dtype=torch.float64)
+            std[:cfg.in_chans] = torch.tensor(list(norm_std), dtype=torch.float64)
+            wf = wk / std.view(1, 1, 4, 1)
+            bf = sd[E + "stem_0.bias"].double() - (wf * mean.view(1, 1, 4, 1)).sum(dim=(0, 1, 2))
+            self.stem_w_u8 = _f32(wf.reshape(64, C0), dev)        # raw uint8 input, normalisation folded
+            self.stem_b_u8 = _f32(bf, dev)
+        else:
+            self.stem_w_u8 = self.stem_b_u8 = None
+        self.stem_ln_w = _f32(sd[E + "stem_1.weight"], dev)
+        self.stem_ln_b = _f32(sd[E + "stem_1.bias"], dev)
+
+        # ---- stages
+        self.stages: List[dict] = []
+        for i, (depth, C) in enumerate(zip(cfg.depths, cfg.dims)):
+            S = E + f"stages_{i}."
+            st = {"C": C, "blocks": []}
+            if i > 0:
+                Ci = cfg.dims[i - 1]
+                st["ds_ln_w"] = _f32(sd[S + "downsample.0.weight"], dev)
+                st["ds_ln_b"] = _f32(sd[S + "downsample.0.bias"], dev)
+                wd = sd[S + "downsample.1.weight"].float()          # [C, Ci, 2, 2] -> [C][ky][kx][Ci]
+                st["ds_w"] = _bf16(wd.permute(0, 2, 3, 1).reshape(C, 4 * Ci), dev)
+                st["ds_b"] = _f32(sd[S + "downsample.1.bias"], dev)
+            for j in range(depth):
+                Bk = S + f"blocks.{j}."
+                w2 = sd[Bk + "mlp.fc2.weight"].float()              # [C, 4C]
+                beta = sd[Bk + "mlp.grn.bias"].float()
+                blk = {
+                    "dw_w": _f32(sd[Bk + "conv_dw.weight"].float().reshape(C, 49).t(), dev),   # [49][C]
+                    "dw_b": _f32(sd[Bk + "conv_dw.bias"], dev),
+                    "ln_w": _f32(sd[Bk + "norm.weight"], dev),
+                    "ln_b": _f32(sd[Bk + "norm.bias"], dev),
+                    "fc1_w": _bf16(sd[Bk + "mlp.fc1.weight"], dev),                            # [4C, C]
+                    "fc1_b": _f32(sd[Bk + "mlp.fc1.bias"], dev),
+                    "grn_g": _f32(sd[Bk + "mlp.grn.weight"], dev),
+                    "fc2_w": _bf16(w2, dev),                                                   # [C, 4C]
+                    # GRN: fc2(x*s + beta) = (W2 diag(s)) x + (W2 beta + b2)
+                    "fc2_b": _f32(sd[Bk + "mlp.fc2.bias"].double() + w2.double() @ beta.double(), dev),
+                }
+                st["blocks"].append(blk)
+            self.stages.append(st)
+
+        # ---- decoder (smp UnetDecoder): channels per block
+        enc_ch = [cfg.in_chans, 0] + list(cfg.dims)
+        rev = enc_ch[1:][::-1]
+        in_ch = [rev[0]] + list(cfg.decoder_channels[:-1])
+        skip_ch = list(rev[1:]) + [0]
+        self.dec: List[dict] = []
+        for k, (ci, cs, co) in enumerate(zip(in_ch, skip_ch, cfg.decoder_channels)):
+            blk = {"cin": ci, "cskip": cs, "cout": co}
+            for name in ("conv1", "conv2"):
+                Kp = D + f"decoder.blocks.{k}.{name}."
+                w = sd[Kp + "0.weight"].float()                     # [co, cin_total, 3, 3]
+                g, b_ = sd[Kp + "1.weight"].double(), sd[Kp + "1.bias"].double()
+                mu, var = sd[Kp + "1.running_mean"].double(), sd[Kp + "1.running_var"].double()
+                scale = g / torch.sqrt(var + bn_eps)
+                blk[name + "_w"] = _bf16(w.permute(0, 2, 3, 1), dev)   # [co][3][3][cin]
+                blk[name + "_s"] = _f32(scale, dev)
+                blk[name + "_b"] = _f32(b_ - mu * scale, dev)
+            assert blk["conv1_w"].shape[-1] == ci + cs, (blk["conv1_w"].shape, ci, cs)
+            self.dec.append(blk)
+        wh = sd[D + "segmentation_head.0.weight"].float()           # [ncls, 16, 3, 3]
+        assert wh.shape[0] == cfg.n_classes and cfg.n_classes <= 32
+        whp = torch.zeros(32, 3, 3, wh.shape[1])
+        whp[:cfg.n_classes] = wh.permute(0, 2, 3, 1)
+        bh = torch.zeros(32)
+        bh[:cfg.n_classes] = sd[D + "segmentation_head.0.bias"].float()
+        self.head_w, self.head_b = _bf16(whp, dev), _f32(bh, dev)
+
+        self._alloc_workspace()
+
+    # ------------------------------------------------------------------------------ workspace
+    def _alloc_workspace(self):
+        cfg, B, dev = self.cfg, self.B, self.dev
+        P = cfg.patch
+        bf, f32 = torch.bfloat16, torch.float32
+        hw = [(P // 4) >> i for i in range(4)]
+        self.hw = hw
+        self.x = [torch.empty((B, h, h, c), dtype=f32, device=dev) for h, c in zip(hw, cfg.dims)]
+        max_y = max(h * h * c for h, c in zip(hw, cfg.dims))
+        self.y = torch.empty(B * max_y, dtype=bf, device=dev)            # dwconv+LN out / s2d operand
+        self.h = torch.empty(B * max_y * 4, dtype=bf, device=dev)        # MLP hidden
+        kmax = 4 * max(cfg.dims)
+        self.sumsq = torch.zeros((B, kmax), dtype=f32, device=dev)
+        self.scale = torch.empty((B, kmax), dtype=f32, device=dev)
+        # per-sample GRN-scaled fc2 weights where that is cheaper than scaling the hidden rows
+        self.use_wscale = [h * h > c for h, c in zip(hw, cfg.dims)]
+        wmax = max([4 * c * c for c, u in zip(cfg.dims, self.use_wscale) if u] + [0])
+        self.w2s = torch.empty(B * wmax, dtype=bf, device=dev) if wmax else None
+        # decoder
+        sizes = []
+        hd = hw[3]
+        for blk in self.dec:
+            hd *= 2
+            sizes.append(hd * hd * (blk["cin"] + blk["cskip"]))
+            sizes.append(hd * hd * blk["cout"])
+        self.cat = torch.empty(B * max(sizes[0::2]), dtype=bf, device=dev)
+        self.t1 = torch.empty(B * max(sizes[1::2]), dtype=bf, device=dev)
+        self.t2 = torch.empty(B * max(sizes[1::2]), dtype=bf, device=dev)
+
+    # ------------------------------------------------------------------------------ encoder
+    def _gemm(self, A, Bw, mode, **kw):
+        return nv.gemm_bf16(A, Bw, mode, impl=self.gemm_impl, **kw)
+
+    def _encode(self, n: int) -> None:
+        cfg = self.cfg
+        for i, st in enumerate(self.stages):
+            C, hwi = st["C"], self.hw[i]
+            rps = hwi * hwi
+            M = n * rps
+            x = self.x[i][:n]
+            if i > 0:
+                Ci = cfg.dims[i - 1]
+                s2d = self.y[:M * 4 * Ci].view(M, 4 * Ci)
+                nv.ln2d_s2d(self.x[i - 1][:n], st["ds_ln_w"], st["ds_ln_b"], s2d)
+                self._gemm(s2d, st["ds_w"], nv.EPI_F32, bias=st["ds_b"], out=x.view(M, C))
+            y = self.y[:M * C].view(n, hwi, hwi, C)
+            hbuf = self.h[:M * 4 * C].view(M, 4 * C)
+            sumsq = self.sumsq[:n, :4 * C]
+            scale = self.scale[:n, :4 * C]
+            if sumsq.stride(0) != 4 * C:
+                # kernels index [b][k] densely: use a dense view of the flat buffers
+                sumsq = self.sumsq.view(-1)[:n * 4 * C].view(n, 4 * C)
+                scale = self.scale.view(-1)[:n * 4 * C].view(n, 4 * C)
+            for blk in st["blocks"]:
+                nv.dwconv7_ln(x, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], y)
+                self._gemm(y.view(M, C), blk["fc1_w"], nv.EPI_GELU_SUMSQ, bias=blk["fc1_b"], sumsq=sumsq, out=hbuf,
+                           rows_per_sample=rps)
+                nv.grn_scale(sumsq, blk["grn_g"], scale)
+                if self.use_wscale[i]:
+                    w2s = self.w2s[:n * 4 * C * C].view(n, C, 4 * C)
+                    nv.scale_weights(blk["fc2_w"], scale, w2s)
+                    self._gemm(hbuf, w2s if n > 1 else w2s[0], nv.EPI_RESID_F32, bias=blk["fc2_b"], resid=x.view(M, C),
+                               out=x.view(M, C), rows_per_sample=rps)
+                else:
+                    nv.scale_rows(hbuf, scale, rps)
+                    self._gemm(hbuf, blk["fc2_w"], nv.EPI_RESID_F32, bias=blk["fc2_b"], resid=x.view(M, C),
+                               out=x.view(M, C), rows_per_sample=rps)
+
+    def encode_u8(self, tiles_u8: torch.Tensor) -> None:
+        if self.stem_w_u8 is None:
+            raise nv.NativeError("engine was built without normalisation constants: uint8 input unavailable")
+        n = tiles_u8.shape[0]
+        assert n <= self.B
+        # sumsq must start at zero (grn_scale re-zeroes it after every use)
+        nv.stem_ln(tiles_u8, self.stem_w_u8, self.stem_b_u8, self.stem_ln_w, self.stem_ln_b, self.x[0][:n])
+        self._encode(n)
+
+    def encode_f32(self, x_nchw: torch.Tensor) -> None:
+        n = x_nchw.shape[0]
+        assert n <= self.B and x_nchw.shape[1] == self.cfg.in_chans
+        nv.stem_ln_f32(x_nchw, self.stem_w_f32, self.stem_b_f32, self.stem_ln_w, self.stem_ln_b, self.x[0][:n])
+        self._encode(n)
+
+    def features(self, n: int) -> List[torch.Tensor]:
+        """Stage outputs (strides 4/8/16/32) as fp32 NHWC views."""
+        return [x[:n] for x in self.x]
+
+    # ------------------------------------------------------------------------------ decoder
+    def _decode_body(self, n: int) -> torch.Tensor:
+        a = self.x[3][:n]
+        skips = [self.x[2][:n], self.x[1][:n], self.x[0][:n], None, None]
+        hd = self.hw[3]
+        bufs = [self.t1, self.t2]
+        for k, blk in enumerate(self.dec):
+            hd *= 2
+            ct = blk["cin"] + blk["cskip"]
+            cat = self.cat[:n * hd * hd * ct].view(n, hd, hd, ct)
+            skip = skips[k] if blk["cskip"] > 0 else None
+            nv.upsample2_concat(a, skip, cat)
+            o1 = self.t1[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
+            nv.conv3x3(cat, blk["conv1_w"], blk["conv1_s"], blk["conv1_b"], nv.CONV_RELU_BF16, out=o1)
+            o2 = self.t2[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
+            nv.conv3x3(o1, blk["conv2_w"], blk["conv2_s"], blk["conv2_b"], nv.CONV_RELU_BF16, out=o2)
+            a = o2
+        return a
+
+    def decode_logits_nchw(self, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 logits [n, n_classes, P, P] -- the layout FLAIR_HUB_Model.forward returns."""
+        a = self._decode_body(n)
+        P, nc = self.cfg.patch, self.cfg.n_classes
+        if out is None:
+            out = torch.empty((n, nc, P, P), dtype=torch.float32, device=self.dev)
+        nv.conv3x3(a, self.head_w, None, self.head_b, nv.CONV_LOGITS_F32_NCHW, out=out, cout=nc)
+        return out
+
+    def decode_logits_nhwc(self, n: int, out: torch.Tensor) -> torch.Tensor:
+        a = self._decode_body(n)
+        nv.conv3x3(a, self.head_w, None, self.head_b, nv.CONV_LOGITS_F32, out=out, cout=self.cfg.n_classes,
+                   cstride=out.shape[-1])
+        return out
+
+    def decode_argmax_to_raster(self, n: int, plan: torch.Tensor, own: Optional[torch.Tensor], raster: torch.Tensor,
+                                margin: int) -> None:
+        """Head conv with the crop + argmax + last-writer-wins write fused into its epilogue
+        (inference.py:295-352): no logits leave the SM."""
+        a = self._decode_body(n)
+        nv.conv3x3(a, self.head_w, None, self.head_b, nv.CONV_ARGMAX_RASTER, cout=self.cfg.n_classes, plan=plan,
+                   own=own, raster=raster, margin=margin)

@@ -190,6 +190,10 @@ def tile_plan(tiles_gdf, image_bounds: Dict[str, float], ref_res: float, patch_s
             w = img_w - left_px
         if h <= 0 or w <= 0:
             h = w = 0
+        elif top_px < 0 or left_px < 0:
+            # the reference hands rasterio a window with a negative offset here, which fails
+            raise ValueError("raster is smaller than the tile's inner window "
+                             f"({patch_size}-2*{margin} px): negative write offset ({top_px}, {left_px})")
         plan[i, 2:6] = (top_px, left_px, h, w)
     return plan
 

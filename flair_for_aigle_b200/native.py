@@ -19,6 +19,7 @@ _lib: Optional[ctypes.CDLL] = None
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16 = 0, 1, 2, 3, 4
+CONV_RELU_BF16, CONV_LOGITS_F32, CONV_ARGMAX_RASTER, CONV_LOGITS_F32_NCHW = 0, 1, 2, 3
 
 
 class NativeError(RuntimeError):
@@ -41,6 +42,15 @@ _SIGNATURES = {
     "fz_convert": [_vp, _i, _i, _i, _i, _vp, _vp],
     "fz_gemm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_gemm_bf16_simt": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_stem_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_stem_ln_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_dwconv7_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_ln2d_s2d": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_grn_scale": [_vp, _vp, _vp, _i, _i, ctypes.c_float, _vp],
+    "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
+    "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_conv3x3_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
 }
 _RESTYPES = {"fz_last_error": ctypes.c_char_p}
 
@@ -181,4 +191,74 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, mode: int, bias=None, resid=None
     fn = lib().fz_gemm_bf16 if impl == "tcgen05" else lib().fz_gemm_bf16_simt
     _check(fn(_ptr(A), _ptr(B), _ptr(out), _ptr(bias), _ptr(resid), _ptr(sumsq), M, N, K, b_batch, rows_per_sample,
               mode, _stream()), "fz_gemm_bf16")
+    return out
+
+
+# --------------------------------------------------------------------------- ConvNeXt-V2 / U-Net ops
+def stem_ln(tiles_u8, w, bias, ln_w, ln_b, out, eps=1e-6):
+    B, P = tiles_u8.shape[0], tiles_u8.shape[1]
+    C0 = w.shape[1]
+    _check(lib().fz_stem_ln(_ptr(tiles_u8), _ptr(w), _ptr(bias), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, P, C0, eps,
+                            _stream()), "fz_stem_ln")
+    return out
+
+
+def stem_ln_f32(x_nchw, w, bias, ln_w, ln_b, out, eps=1e-6):
+    B, Cin, P, _ = x_nchw.shape
+    C0 = w.shape[1]
+    _check(lib().fz_stem_ln_f32(_ptr(x_nchw), Cin, _ptr(w), _ptr(bias), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, P, C0,
+                                eps, _stream()), "fz_stem_ln_f32")
+    return out
+
+
+def dwconv7_ln(x, wdw, bdw, ln_w, ln_b, out, eps=1e-6):
+    B, H, W, C = x.shape
+    _check(lib().fz_dwconv7_ln(_ptr(x), _ptr(wdw), _ptr(bdw), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, H, W, C, eps,
+                               _stream()), "fz_dwconv7_ln")
+    return out
+
+
+def ln2d_s2d(x, ln_w, ln_b, out, eps=1e-6):
+    B, H, W, C = x.shape
+    _check(lib().fz_ln2d_s2d(_ptr(x), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, H, W, C, eps, _stream()), "fz_ln2d_s2d")
+    return out
+
+
+def grn_scale(sumsq, gamma, scale, eps=1e-6):
+    B, K = sumsq.shape
+    _check(lib().fz_grn_scale(_ptr(sumsq), _ptr(gamma), _ptr(scale), B, K, eps, _stream()), "fz_grn_scale")
+    return scale
+
+
+def scale_weights(w, scale, out):
+    N, K = w.shape
+    B = scale.shape[0]
+    _check(lib().fz_scale_weights(_ptr(w), _ptr(scale), _ptr(out), B, N, K, _stream()), "fz_scale_weights")
+    return out
+
+
+def scale_rows(h, scale, rows_per_sample):
+    M, K = h.shape
+    _check(lib().fz_scale_rows(_ptr(h), _ptr(scale), M, K, rows_per_sample, _stream()), "fz_scale_rows")
+    return h
+
+
+def upsample2_concat(a, s, out):
+    B, H, W, CT = out.shape
+    C1 = a.shape[-1]
+    C2 = 0 if s is None else s.shape[-1]
+    assert C1 + C2 == CT
+    _check(lib().fz_upsample2_concat(_ptr(a), _dt(a), _ptr(s), _dt(s) if s is not None else BF16, _ptr(out), B, H, W,
+                                     C1, C2, _stream()), "fz_upsample2_concat")
+    return out
+
+
+def conv3x3(x, w, scale, bias, mode, out=None, cout=None, cstride=0, plan=None, own=None, raster=None, margin=0):
+    """x bf16 [B,H,W,Cin]; w bf16 [rows,3,3,Cin]; scale/bias f32 [rows] (scale may be None)."""
+    B, H, W, Cin = x.shape
+    rows = w.shape[0]
+    cout = rows if cout is None else cout
+    RH, RW = (raster.shape[-2], raster.shape[-1]) if raster is not None else (0, 0)
+    _check(lib().fz_conv3x3_bf16(_ptr(x), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), B, H, W, Cin, cout, rows, mode, cstride,
+                                 _ptr(plan), _ptr(own), _ptr(raster), RH, RW, margin, _stream()), "fz_conv3x3_bf16")
     return out

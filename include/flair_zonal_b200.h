@@ -97,6 +97,60 @@ int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, con
 int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq,
                       int M, int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
 
+/* ---------------------------------------------------------------- ConvNeXt-V2 encoder pieces
+ * (timm ConvNeXtV2 as wrapped by smp TimmUniversalEncoder; call site flair_model.py:376)
+ *
+ * fz_stem_ln: conv4x4 stride 4 (+bias) + LayerNorm2d on raw uint8 tiles [B][P][P][4]; the
+ *   (x-mean)/std normalisation of norm.py:37-44 is folded into w/bias by the host:
+ *   w float [64][C0] with row k = ky*16+kx*4+c = weight[n][c][ky][kx]/std[c];
+ *   bias[n] = conv_bias[n] - sum_k w[k][n]*mean[c(k)].  out float [B][P/4][P/4][C0].
+ * fz_dwconv7_ln: depthwise 7x7 (pad 3, bias) + LayerNorm over C; x float NHWC, wdw float
+ *   [49][C] (tap-major), out bf16 NHWC (the fc1 GEMM's A operand).
+ * fz_ln2d_s2d: LayerNorm2d + space-to-depth: out bf16 [B][H/2][W/2][4C] with
+ *   k = (y&1)*2C + (x&1)*C + c, the A operand of the 2x2/s2 downsample conv as a GEMM.
+ * fz_grn_scale: scale[b][k] = 1 + gamma[k]*Gx/(mean_k Gx + eps), Gx = sqrt(sumsq[b][k])
+ *   (timm GlobalResponseNorm); zeroes sumsq for its next use.
+ * fz_scale_weights: out[b][n][k] = bf16(w[n][k]*scale[b][k]) (GRN folded into fc2's weights);
+ * fz_scale_rows:    h[m][k] *= scale[m/rows_per_sample][k] (GRN applied to the activations).
+ */
+int fz_stem_ln(const uint8_t* tiles_u8, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+               float* out, int B, int P, int C0, float eps, void* stream);
+/* same on already-normalised float32 NCHW input [B][Cin<=4][P][P] (the tensor the reference's
+ * model receives); w rows for c >= Cin must be zero. */
+int fz_stem_ln_f32(const float* x_nchw, int Cin, const float* w, const float* bias, const float* ln_w,
+                   const float* ln_b, float* out, int B, int P, int C0, float eps, void* stream);
+int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
+                  void* out_bf16, int B, int H, int W, int C, float eps, void* stream);
+int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, int B, int H, int W, int C,
+                float eps, void* stream);
+int fz_grn_scale(float* sumsq, const float* gamma, float* scale, int B, int K, float eps, void* stream);
+int fz_scale_weights(const void* w_bf16, const float* scale, void* out_bf16, int B, int N, int K, void* stream);
+int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K, int rows_per_sample, void* stream);
+
+/* ---------------------------------------------------------------- U-Net decoder pieces
+ * (smp 0.4.0 UnetDecoder + SegmentationHead; call site flair_model.py:417-419)
+ *
+ * fz_upsample2_concat: out[b][y][x][0:C1] = a[b][y/2][x/2][:] (F.interpolate nearest x2),
+ *   out[..][C1:C1+C2] = s[b][y][x][:] (skip; C2 may be 0).  a/s dtype FZ_F32 or FZ_BF16,
+ *   out bf16 [B][H][W][C1+C2].
+ * fz_conv3x3_bf16: 3x3 pad 1 conv as implicit GEMM on tcgen05.  in bf16 [B][H][W][Cin];
+ *   w bf16 [w_rows][3][3][Cin] (rows zero-padded to the N tile); scale/bias float [w_rows]:
+ *   result = acc*scale + bias (eval BatchNorm folded into scale/bias; scale NULL = 1).  mode FZ_CONV_RELU_BF16: out bf16 [B][H][W][Cout] = relu(conv+bias);
+ *   FZ_CONV_LOGITS_F32: out float [B][H][W][cstride] (first Cout valid) = conv+bias;
+ *   FZ_CONV_ARGMAX_RASTER: no logits are stored -- argmax over the Cout classes is written
+ *   straight into raster[RH][RW] at the tile's margin-cropped window (plan/own as in
+ *   fz_crop_argmax_write; tile index = batch index).
+ */
+#define FZ_CONV_RELU_BF16 0
+#define FZ_CONV_LOGITS_F32 1
+#define FZ_CONV_ARGMAX_RASTER 2
+#define FZ_CONV_LOGITS_F32_NCHW 3 /* out float [B][Cout][H][W]: the reference's logits layout */
+int fz_upsample2_concat(const void* a, int a_dtype, const void* s, int s_dtype, void* out_bf16, int B, int H, int W,
+                        int C1, int C2, void* stream);
+int fz_conv3x3_bf16(const void* in, const void* w, const float* scale, const float* bias, void* out, int B, int H,
+                    int W, int Cin, int Cout, int w_rows, int mode, int cstride, const int32_t* plan,
+                    const int32_t* own, uint8_t* raster, int RH, int RW, int margin, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

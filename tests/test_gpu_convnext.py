@@ -1,0 +1,226 @@
+"""GPU parity of the ConvNeXt-V2 / U-Net kernels: each op against a plain fp32 torch reference of
+the same op, then the whole engine against the fp32 oracle (oracle/models.py).
+
+Tolerances (bf16 operands, fp32 accumulate): single ops are compared with operands already
+rounded to bf16, so only the accumulation order and the bf16 OUTPUT rounding (2^-9 relative)
+remain; the end-to-end logits tolerance is stated in test_engine_vs_oracle.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def test_stem_u8_and_f32(cuda):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(0)
+    B, P, C0 = 2, 256, 128
+    u8 = torch.randint(0, 256, (B, P, P, 4), dtype=torch.uint8, device=cuda)
+    mean = torch.tensor([105.66, 111.35, 102.18, 106.59], device=cuda)
+    std = torch.tensor([52.23, 45.62, 44.30, 39.78], device=cuda)
+    w = torch.randn(C0, 4, 4, 4, device=cuda) * 0.2
+    b = torch.randn(C0, device=cuda) * 0.1
+    g, be = torch.rand(C0, device=cuda) + 0.5, torch.randn(C0, device=cuda) * 0.1
+    xn = (u8.float().permute(0, 3, 1, 2) - mean.view(1, 4, 1, 1)) / std.view(1, 4, 1, 1)
+    ref = F.conv2d(xn, w, b, stride=4).permute(0, 2, 3, 1)
+    ref = F.layer_norm(ref, (C0,), g, be, 1e-6)
+    wk = w.permute(2, 3, 1, 0).reshape(64, C0).contiguous()
+    wf = (w / std.view(1, 4, 1, 1)).permute(2, 3, 1, 0).reshape(64, C0).contiguous()
+    bf = b - (w / std.view(1, 4, 1, 1) * mean.view(1, 4, 1, 1)).sum(dim=(1, 2, 3))
+    out = torch.empty(B, P // 4, P // 4, C0, device=cuda)
+    nv.stem_ln(u8, wf, bf, g, be, out)
+    out2 = torch.empty_like(out)
+    nv.stem_ln_f32(xn.contiguous(), wk, b, g, be, out2)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 2e-4
+    assert (out2 - ref).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("C,H", [(128, 128), (128, 32), (256, 64), (512, 32), (1024, 16), (256, 24)])
+def test_dwconv7_ln(cuda, C, H):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(C + H)
+    B = 2
+    x = torch.randn(B, H, H, C, device=cuda)
+    w = torch.randn(C, 1, 7, 7, device=cuda) * 0.15
+    b = torch.randn(C, device=cuda) * 0.1
+    g, be = torch.rand(C, device=cuda) + 0.5, torch.randn(C, device=cuda) * 0.1
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=3, groups=C).permute(0, 2, 3, 1)
+    ref = F.layer_norm(ref, (C,), g, be, 1e-6)
+    out = torch.empty(B, H, H, C, dtype=torch.bfloat16, device=cuda)
+    nv.dwconv7_ln(x, w.reshape(C, 49).t().contiguous(), b, g, be, out)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2 ** -8 * ref.abs().max().item() + 1e-3, err
+
+
+def test_downsample_ln_s2d_gemm(cuda):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(3)
+    B, H, C, Co = 2, 32, 128, 256
+    x = torch.randn(B, H, H, C, device=cuda)
+    g, be = torch.rand(C, device=cuda) + 0.5, torch.randn(C, device=cuda) * 0.1
+    w = (torch.randn(Co, C, 2, 2, device=cuda) / (4 * C) ** 0.5).bfloat16().float()
+    b = torch.randn(Co, device=cuda) * 0.1
+    s2d = torch.empty(B * (H // 2) ** 2, 4 * C, dtype=torch.bfloat16, device=cuda)
+    nv.ln2d_s2d(x, g, be, s2d)
+    out = nv.gemm_bf16(s2d, w.permute(0, 2, 3, 1).reshape(Co, 4 * C).contiguous().bfloat16(), nv.EPI_F32, bias=b)
+    torch.cuda.synchronize()
+    xn = F.layer_norm(x, (C,), g, be, 1e-6).bfloat16().float()
+    ref = F.conv2d(xn.permute(0, 3, 1, 2), w, b, stride=2).permute(0, 2, 3, 1).reshape(-1, Co)
+    assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+def test_grn_scale_and_scalers(cuda):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(4)
+    B, K, N, rps = 3, 512, 128, 256
+    h = torch.randn(B * rps, K, device=cuda).bfloat16()
+    sumsq = (h.float().view(B, rps, K) ** 2).sum(1).contiguous()
+    gamma = torch.randn(K, device=cuda) * 0.5
+    gx = sumsq.sqrt()
+    ref_scale = 1 + gamma * gx / (gx.mean(dim=1, keepdim=True) + 1e-6)
+    scale = torch.empty(B, K, device=cuda)
+    sq = sumsq.clone()
+    nv.grn_scale(sq, gamma, scale)
+    w = torch.randn(N, K, device=cuda).bfloat16()
+    ws = torch.empty(B, N, K, dtype=torch.bfloat16, device=cuda)
+    nv.scale_weights(w, scale, ws)
+    h2 = h.clone()
+    nv.scale_rows(h2, scale, rps)
+    torch.cuda.synchronize()
+    assert (scale - ref_scale).abs().max().item() < 1e-5
+    assert sq.abs().max().item() == 0.0
+    assert torch.equal(ws, (w.float()[None] * scale[:, None, :]).bfloat16())
+    assert torch.equal(h2, (h.float().view(B, rps, K) * scale[:, None, :]).bfloat16().view(-1, K))
+
+
+@pytest.mark.parametrize("ta,ts", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
+                                   (torch.bfloat16, None)])
+def test_upsample2_concat(cuda, ta, ts):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(5)
+    B, H, C1, C2 = 2, 16, 64, (32 if ts is not None else 0)
+    a = torch.randn(B, H // 2, H // 2, C1, device=cuda).to(ta)
+    s = torch.randn(B, H, H, C2, device=cuda).to(ts) if ts is not None else None
+    out = torch.empty(B, H, H, C1 + C2, dtype=torch.bfloat16, device=cuda)
+    nv.upsample2_concat(a, s, out)
+    torch.cuda.synchronize()
+    up = a.float().repeat_interleave(2, 1).repeat_interleave(2, 2)
+    ref = torch.cat([up] + ([s.float()] if s is not None else []), dim=-1).bfloat16()
+    assert torch.equal(out, ref)
+
+
+CONV_CASES = [  # (H, Cin, Cout)  -- every (tile shape, KC, BN) combination the U-Net decoder uses
+    (32, 1536, 256), (32, 256, 256), (64, 512, 128), (64, 128, 128), (128, 256, 64), (128, 64, 64),
+    (256, 64, 32), (256, 32, 32), (512, 32, 16), (512, 16, 16),
+]
+
+
+@pytest.mark.parametrize("H,Cin,Cout", CONV_CASES)
+def test_conv3x3_relu(cuda, H, Cin, Cout):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(H + Cin + Cout)
+    B = 2 if H <= 256 else 1
+    x = torch.randn(B, H, H, Cin, device=cuda).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device=cuda) / (9 * Cin) ** 0.5).bfloat16()
+    scale = torch.rand(Cout, device=cuda) + 0.5
+    bias = torch.randn(Cout, device=cuda) * 0.2
+    out = torch.empty(B, H, H, Cout, dtype=torch.bfloat16, device=cuda)
+    nv.conv3x3(x, w.permute(0, 2, 3, 1).contiguous(), scale, bias, nv.CONV_RELU_BF16, out=out)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, padding=1)
+    ref = torch.relu(ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2 ** -8 * ref.abs().max().item() + 1e-3, err
+
+
+def test_conv3x3_head_modes(cuda):
+    from flair_for_aigle_b200 import native as nv
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import ownership_windows
+    torch.manual_seed(9)
+    B, H, Cin, ncls, margin = 2, 256, 16, 19, 32
+    x = torch.randn(B, H, H, Cin, device=cuda).bfloat16()
+    w = (torch.randn(ncls, Cin, 3, 3, device=cuda) / 12).bfloat16()
+    bias = torch.randn(ncls, device=cuda) * 0.2
+    wp = torch.zeros(32, 3, 3, Cin, dtype=torch.bfloat16, device=cuda)
+    wp[:ncls] = w.permute(0, 2, 3, 1)
+    bp = torch.zeros(32, device=cuda)
+    bp[:ncls] = bias
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)       # [B, ncls, H, W]
+    nchw = torch.empty(B, ncls, H, H, device=cuda)
+    nv.conv3x3(x, wp, None, bp, nv.CONV_LOGITS_F32_NCHW, out=nchw, cout=ncls)
+    nhwc = torch.full((B, H, H, 20), 7.0, device=cuda)
+    nv.conv3x3(x, wp, None, bp, nv.CONV_LOGITS_F32, out=nhwc, cout=ncls, cstride=20)
+    # fused crop + argmax + last-writer-wins: two tiles overlapping by 40 columns
+    s = H - 2 * margin
+    plan = np.array([[0, 0, 0, 0, s, s], [0, 0, 0, s - 40, s, s]], np.int32)
+    own = ownership_windows(plan)
+    raster = torch.full((s, 2 * s - 40), 255, dtype=torch.uint8, device=cuda)
+    nv.conv3x3(x, wp, None, bp, nv.CONV_ARGMAX_RASTER, cout=ncls, plan=torch.from_numpy(plan).to(cuda),
+               own=torch.from_numpy(own).to(cuda), raster=raster, margin=margin)
+    torch.cuda.synchronize()
+    assert (nchw - ref).abs().max().item() < 1e-4
+    assert (nhwc[..., :ncls] - ref.permute(0, 2, 3, 1)).abs().max().item() < 1e-4
+    assert nhwc[..., 19].abs().max().item() == 0.0
+    am = nchw.argmax(1)[:, margin:H - margin, margin:H - margin].to(torch.uint8)    # from the kernel's own logits
+    expect = torch.empty_like(raster)
+    expect[:, :s] = am[0]
+    expect[:, s - 40:] = am[1]
+    assert torch.equal(raster, expect)
+
+
+def _build_pair(cuda, seed=2025, n_cls=19, in_ch=4):
+    from oracle.models import FlairHubOracle, randomize_
+    from flair_for_aigle_b200.engine.convnext_unet import ConvNeXtCfg, ConvNeXtV2UNetEngine
+    task = "AERIAL_LABEL-COSIA"
+    oracle = FlairHubOracle("convnextv2_base-unet", {"AERIAL_RGBI": in_ch}, {task: n_cls}).eval()
+    randomize_(oracle, seed=seed, bf16_exact=True)
+    sd = {k: v.clone() for k, v in oracle.state_dict().items()}
+    mean, std = [105.66, 111.35, 102.18, 106.59], [52.23, 45.62, 44.30, 39.78]
+    eng = ConvNeXtV2UNetEngine(sd, "encoders.AERIAL_RGBI.seg_model.model.", f"main_decoders.{task}.seg_model.",
+                               ConvNeXtCfg(in_chans=in_ch, n_classes=n_cls), cuda, max_batch=2,
+                               norm_mean=mean[:in_ch], norm_std=std[:in_ch])
+    return oracle.to(cuda), eng, task, mean, std
+
+
+def test_engine_vs_oracle(cuda):
+    """End to end on 2 tiles: fp32 oracle (torch eager on the GPU, TF32 off) vs the engine.
+    Stated tolerance (bf16 operands through 36 blocks + 11 convs): max |dlogit| <= 6% of the
+    logit standard deviation and mean |dlogit| <= 1%."""
+    from flair_for_aigle_b200.synthetic import synthetic_raster
+    oracle, eng, task, mean, std = _build_pair(cuda)
+    P = 512
+    raster = synthetic_raster(640, 1100, seed=2025)
+    u8 = torch.from_numpy(np.stack([raster[:, 0:P, 0:P], raster[:, 100:100 + P, 500:500 + P]])).to(cuda)
+    xn = ((u8.double() - torch.tensor(mean, device=cuda, dtype=torch.float64).view(1, 4, 1, 1)) /
+          torch.tensor(std, device=cuda, dtype=torch.float64).view(1, 4, 1, 1)).float()
+    with torch.no_grad():
+        ref, _ = oracle({"AERIAL_RGBI": xn, task: torch.zeros(2, 19, P, P, device=cuda)})
+        ref = ref[task]
+        feats_ref = oracle.encoders["AERIAL_RGBI"].seg_model(xn)[2:]
+    eng.encode_u8(u8.permute(0, 2, 3, 1).contiguous())
+    feats = [f.clone() for f in eng.features(2)]
+    out = eng.decode_logits_nchw(2)
+    torch.cuda.synchronize()
+    for i, (f, fr) in enumerate(zip(feats, feats_ref)):
+        rel = (f.permute(0, 3, 1, 2) - fr).abs().max().item() / fr.std().item()
+        assert rel < 0.08, f"stage {i} feature error {rel}"
+    sd_ = ref.std().item()
+    d = (out - ref).abs()
+    agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"logits: max|d|={d.max().item():.4f} mean|d|={d.mean().item():.5f} std={sd_:.3f} argmax agree={agree:.5f}")
+    assert d.max().item() < 0.06 * sd_ and d.mean().item() < 0.01 * sd_
+    # same engine, already-normalised float input path (the reference's model(inputs) contract)
+    eng.encode_f32(xn)
+    out2 = eng.decode_logits_nchw(2)
+    torch.cuda.synchronize()
+    assert (out2 - out).abs().max().item() < 0.02 * sd_

@@ -19,7 +19,7 @@ def _own(plan):
     return ownership_windows(plan)
 
 
-@pytest.mark.parametrize("W,H,margin", [(300, 217, 16), (256, 256, 32), (97, 411, 8)])
+@pytest.mark.parametrize("W,H,margin", [(300, 217, 16), (256, 256, 32), (140, 411, 8)])
 @pytest.mark.parametrize("layout,dtype", [("nchw", torch.float32), ("nhwc", torch.bfloat16), ("nhwc", torch.float32),
                                           ("nchw", torch.bfloat16)])
 def test_crop_argmax_last_writer(cuda, W, H, margin, layout, dtype):

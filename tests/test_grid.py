@@ -54,7 +54,7 @@ def _product_tiles(W, H, P, margin, res=RES, geozone=None, left=L, top=T):
     return r, generate_patches_from_reference(cfg, r, geozone)
 
 
-CASES = KNOWN[:3] + KNOWN[4:] + [(333, 512, 0, None), (512, 512, 100, None), (1500, 90, 31, None),
+CASES = KNOWN[:3] + KNOWN[4:] + [(700, 512, 0, None), (512, 512, 100, None), (1500, 90, 31, None),
                                  (5000, 3000, 17, None)]
 
 
@@ -110,7 +110,7 @@ def test_geozone_crop_and_miss():
 
 
 @pytest.mark.parametrize("W,H,margin,P", [(1000, 700, 64, 512), (2048, 2048, 128, 512), (777, 1300, 40, 512),
-                                          (300, 217, 16, 128), (97, 411, 8, 128), (256, 256, 32, 128)])
+                                          (300, 217, 16, 128), (140, 411, 8, 128), (256, 256, 32, 128)])
 def test_ownership_is_last_writer(W, H, margin, P):
     geo = Georef(L, T, RES, W, H)
     plan = oracle_plan(generate_patches(P, margin, RES, geo), geo, P, margin)
@@ -124,3 +124,11 @@ def test_ownership_is_last_writer(W, H, margin, P):
             assert (painted[o[0]:o[1], o[2]:o[3]] == -1).all()   # owned windows are disjoint
             painted[o[0]:o[1], o[2]:o[3]] = i
     assert np.array_equal(painted, owner)
+
+
+def test_raster_smaller_than_inner_tile_is_rejected():
+    # the reference would hand rasterio a window with a negative offset (inference.py:343)
+    r, gdf = _product_tiles(333, 512, 512, 0)
+    b = r.bounds
+    with pytest.raises(ValueError):
+        tile_plan(gdf, {"left": b.left, "bottom": b.bottom, "right": b.right, "top": b.top}, RES, 512, 0)
