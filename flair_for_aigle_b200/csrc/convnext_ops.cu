@@ -284,16 +284,26 @@ __global__ void __launch_bounds__(256) ln2d_s2d_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------ GRN
-// scale[b][k] = 1 + gamma[k] * Gx / (mean_k Gx + eps), Gx = sqrt(sumsq[b][k]); sumsq is zeroed
-// for its next use (timm GlobalResponseNorm; the beta term is folded into fc2's bias on the host).
-__global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ sumsq, const float* __restrict__ gamma,
-                                                        float* __restrict__ scale, int K, float eps) {
+// scale[b][k] = 1 + gamma[k] * Gx / (mean_k Gx + eps), Gx = sqrt(sum_t partial[b*tps + t][k]) where the
+// partials are the fc1 epilogue's per-row-tile sums of squares (fixed summation order: the result
+// does not depend on how tiles are batched).  timm GlobalResponseNorm; the beta term is folded
+// into fc2's bias on the host.
+__global__ void __launch_bounds__(256) grn_scale_kernel(const float* __restrict__ partial, int tps,
+                                                        const float* __restrict__ gamma, float* __restrict__ scale,
+                                                        int K, float eps) {
+  extern __shared__ float s_gx[];  // [K]
   __shared__ float red[8];
   __shared__ float s_mean;
   const int b = blockIdx.x;
-  float* sq = sumsq + static_cast<size_t>(b) * K;
+  const float* base = partial + static_cast<size_t>(b) * tps * K;
   float s = 0.f;
-  for (int k = threadIdx.x; k < K; k += 256) s += sqrtf(sq[k]);
+  for (int k = threadIdx.x; k < K; k += 256) {
+    float acc = 0.f;
+    for (int t = 0; t < tps; ++t) acc += base[static_cast<size_t>(t) * K + k];
+    const float g = sqrtf(acc);
+    s_gx[k] = g;
+    s += g;
+  }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -304,10 +314,7 @@ __global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ sums
   }
   __syncthreads();
   const float inv = 1.0f / (s_mean + eps);
-  for (int k = threadIdx.x; k < K; k += 256) {
-    scale[static_cast<size_t>(b) * K + k] = 1.0f + gamma[k] * sqrtf(sq[k]) * inv;
-    sq[k] = 0.f;
-  }
+  for (int k = threadIdx.x; k < K; k += 256) scale[static_cast<size_t>(b) * K + k] = 1.0f + gamma[k] * s_gx[k] * inv;
 }
 
 // out[b][n][k] = bf16(w[n][k] * scale[b][k])   (8 elements per thread)
@@ -487,10 +494,13 @@ extern "C" int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b,
   return 0;
 }
 
-extern "C" int fz_grn_scale(float* sumsq, const float* gamma, float* scale, int B, int K, float eps, void* stream) {
+extern "C" int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale, int B,
+                            int K, float eps, void* stream) {
   using namespace fz;
+  FZ_REQUIRE(tiles_per_sample >= 1 && K >= 1 && K <= 12288, "fz_grn_scale: bad arguments tps=%d K=%d", tiles_per_sample, K);
   if (B <= 0) return 0;
-  grn_scale_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sumsq, gamma, scale, K, eps);
+  grn_scale_kernel<<<B, 256, K * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(sumsq_partial, tiles_per_sample,
+                                                                                          gamma, scale, K, eps);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -25,7 +25,7 @@ struct GemmParams {
   const float* bias;    // [N] or nullptr
   void* out;            // [M,N] bf16 or f32
   const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
-  float* sumsq;         // [num_samples, N] f32 accumulators (FZ_EPI_GELU_SUMSQ)
+  float* sumsq;         // [ceil(M/128), N] f32 per-row-tile partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
 };
 
 template <int BN, int STAGES>
@@ -34,7 +34,7 @@ struct GemmSmem {
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
   static constexpr int OFF_BIAS = OFF_B + STAGES * B_STAGE_BYTES;
   static constexpr int OFF_SQ = OFF_BIAS + BN * 4;
-  static constexpr int OFF_BAR = OFF_SQ + BN * 4;
+  static constexpr int OFF_BAR = OFF_SQ + 4 * BN * 4;  // one sumsq row per epilogue warp
   static constexpr int OFF_TSLOT = OFF_BAR + (2 * STAGES + 1) * 8;
   static constexpr int BYTES = OFF_TSLOT + 16 + 1024;  // + worst-case alignment pad
 };
@@ -91,7 +91,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < BN; i += 128) {
       sBias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
-      sSq[i] = 0.0f;
     }
   }
   tc_fence_before();
@@ -162,7 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s[j] = row_ok ? v[j] * v[j] : 0.0f;
         }
         warp_colsum32(s, lane);
-        atomicAdd(&sSq[c * 32 + lane], s[0]);
+        sSq[q * BN + c * 32 + lane] = s[0];
       } else if (MODE == FZ_EPI_RELU_BF16) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -194,10 +193,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (MODE == FZ_EPI_GELU_SUMSQ) {
+      // deterministic: fixed-order sum of the four warps' column sums, one plain store per column
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int sample = m0 / p.rows_per_sample;
       for (int i = threadIdx.x - 64; i < BN; i += 128)
-        atomicAdd(&p.sumsq[static_cast<size_t>(sample) * p.N + n0 + i], sSq[i]);
+        p.sumsq[static_cast<size_t>(m0 / BM) * p.N + n0 + i] =
+            (sSq[i] + sSq[BN + i]) + (sSq[2 * BN + i] + sSq[3 * BN + i]);
     }
   }
   tc_fence_before();
@@ -243,7 +243,7 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   FZ_REQUIRE(K % BK == 0, "fz_gemm_bf16: K=%d must be a multiple of %d", K, BK);
   FZ_REQUIRE(N % 64 == 0, "fz_gemm_bf16: N=%d must be a multiple of 64", N);
   FZ_REQUIRE(b_batch >= 1, "fz_gemm_bf16: b_batch must be >= 1");
-  if (mode == FZ_EPI_GELU_SUMSQ || b_batch > 1)
+  if (b_batch > 1)
     FZ_REQUIRE(rows_per_sample > 0 && rows_per_sample % BM == 0,
                "fz_gemm_bf16: rows_per_sample=%d must be a positive multiple of %d", rows_per_sample, BM);
   FZ_REQUIRE(mode != FZ_EPI_GELU_SUMSQ || sumsq != nullptr, "fz_gemm_bf16: sumsq buffer required");
@@ -307,7 +307,7 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv
   const size_t off = static_cast<size_t>(m) * p.N + n;
   if (MODE == FZ_EPI_GELU_SUMSQ) {
     v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-    atomicAdd(&p.sumsq[static_cast<size_t>(m / p.rows_per_sample) * p.N + n], v * v);
+    atomicAdd(&p.sumsq[static_cast<size_t>(m / 128) * p.N + n], v * v);
   } else if (MODE == FZ_EPI_RELU_BF16) {
     v = fmaxf(v, 0.0f);
   } else if (MODE == FZ_EPI_RESID_F32) {
@@ -333,6 +333,8 @@ extern "C" int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const 
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq;
   dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (mode == FZ_EPI_GELU_SUMSQ)
+    FZ_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * static_cast<size_t>((M + 127) / 128) * N, st));
   const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
   const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(B);
   switch (mode) {

@@ -160,8 +160,9 @@ class ConvNeXtV2UNetEngine:
         self.y = torch.empty(B * max_y, dtype=bf, device=dev)            # dwconv+LN out / s2d operand
         self.h = torch.empty(B * max_y * 4, dtype=bf, device=dev)        # MLP hidden
         kmax = 4 * max(cfg.dims)
-        self.sumsq = torch.zeros((B, kmax), dtype=f32, device=dev)
-        self.scale = torch.empty((B, kmax), dtype=f32, device=dev)
+        # fc1 epilogue partials: one row of 4C sums per 128-row tile
+        self.sumsq = torch.zeros(B * max((h * h // 128) * 4 * c for h, c in zip(hw, cfg.dims)), dtype=f32, device=dev)
+        self.scale = torch.empty(B * kmax, dtype=f32, device=dev)
         # per-sample GRN-scaled fc2 weights where that is cheaper than scaling the hidden rows
         self.use_wscale = [h * h > c for h, c in zip(hw, cfg.dims)]
         wmax = max([4 * c * c for c, u in zip(cfg.dims, self.use_wscale) if u] + [0])
@@ -195,21 +196,18 @@ class ConvNeXtV2UNetEngine:
                 self._gemm(s2d, st["ds_w"], nv.EPI_F32, bias=st["ds_b"], out=x.view(M, C))
             y = self.y[:M * C].view(n, hwi, hwi, C)
             hbuf = self.h[:M * 4 * C].view(M, 4 * C)
-            sumsq = self.sumsq[:n, :4 * C]
-            scale = self.scale[:n, :4 * C]
-            if sumsq.stride(0) != 4 * C:
-                # kernels index [b][k] densely: use a dense view of the flat buffers
-                sumsq = self.sumsq.view(-1)[:n * 4 * C].view(n, 4 * C)
-                scale = self.scale.view(-1)[:n * 4 * C].view(n, 4 * C)
+            tps = rps // 128
+            sumsq = self.sumsq[:n * tps * 4 * C].view(n * tps, 4 * C)
+            scale = self.scale[:n * 4 * C].view(n, 4 * C)
             for blk in st["blocks"]:
                 nv.dwconv7_ln(x, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], y)
                 self._gemm(y.view(M, C), blk["fc1_w"], nv.EPI_GELU_SUMSQ, bias=blk["fc1_b"], sumsq=sumsq, out=hbuf,
                            rows_per_sample=rps)
-                nv.grn_scale(sumsq, blk["grn_g"], scale)
+                nv.grn_scale(sumsq, tps, blk["grn_g"], scale)
                 if self.use_wscale[i]:
                     w2s = self.w2s[:n * 4 * C * C].view(n, C, 4 * C)
                     nv.scale_weights(blk["fc2_w"], scale, w2s)
-                    self._gemm(hbuf, w2s if n > 1 else w2s[0], nv.EPI_RESID_F32, bias=blk["fc2_b"], resid=x.view(M, C),
+                    self._gemm(hbuf, w2s, nv.EPI_RESID_F32, bias=blk["fc2_b"], resid=x.view(M, C),
                                out=x.view(M, C), rows_per_sample=rps)
                 else:
                     nv.scale_rows(hbuf, scale, rps)
@@ -221,7 +219,6 @@ class ConvNeXtV2UNetEngine:
             raise nv.NativeError("engine was built without normalisation constants: uint8 input unavailable")
         n = tiles_u8.shape[0]
         assert n <= self.B
-        # sumsq must start at zero (grn_scale re-zeroes it after every use)
         nv.stem_ln(tiles_u8, self.stem_w_u8, self.stem_b_u8, self.stem_ln_w, self.stem_ln_b, self.x[0][:n])
         self._encode(n)
 

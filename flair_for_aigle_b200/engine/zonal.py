@@ -1,0 +1,103 @@
+"""Zonal runner: raster in HBM -> class raster in HBM, tile batches replayed as one CUDA graph.
+
+This is the device-side replacement of the reference's per-batch / per-tile loops
+(flair_zonal_detection/inference.py:278-352 and the DataLoader workers of dataset.py:174-209):
+
+  feeder kernel (boundless window gather, uint8)  ->  stem (normalisation folded)  ->
+  ConvNeXt-V2 stages  ->  U-Net decoder  ->  head conv with crop + argmax + last-writer-wins
+  write fused into its epilogue.
+
+One batch = ``batch`` tiles; the whole batch forward (~250 kernel launches) is captured once
+into a CUDA graph and replayed with the batch's (origins, plan, own) rows copied into static
+device buffers.  Host<->device traffic of the end-to-end path: the uint8 raster in (pinned,
+async, strip by strip on a copy stream) and the uint8 class raster out -- 4+1 bytes per pixel
+instead of the reference's 28.3 MB in / 19.9 MB out per tile.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import native as nv
+from .convnext_unet import ConvNeXtV2UNetEngine
+
+
+class ZonalRunner:
+    def __init__(self, engine: ConvNeXtV2UNetEngine, margin: int, use_graph: bool = True):
+        self.eng = engine
+        self.B = engine.B
+        self.P = engine.cfg.patch
+        self.margin = margin
+        self.dev = engine.dev
+        self.use_graph = use_graph
+        B, dev = self.B, self.dev
+        self.s_origins = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+        self.s_plan = torch.zeros((B, 6), dtype=torch.int32, device=dev)
+        self.s_own = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+        self.tiles_u8 = torch.empty((B, self.P, self.P, 4), dtype=torch.uint8, device=dev)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_key = None
+        self.launches_per_batch = 0
+
+    # one batch, all launches on the current stream (capturable)
+    def _batch_body(self, raster: torch.Tensor, out_raster: torch.Tensor) -> None:
+        nv.gather_tiles_u8(raster, self.s_origins, self.P, out=self.tiles_u8)
+        self.eng.encode_u8(self.tiles_u8)
+        self.eng.decode_argmax_to_raster(self.B, self.s_plan, self.s_own, out_raster, self.margin)
+
+    def count_launches(self) -> int:
+        """Kernel launches of one batch (for bench.py's gpu_launches)."""
+        cfg = self.eng.cfg
+        n = 2  # gather + stem
+        for i, d in enumerate(cfg.depths):
+            n += (2 if i > 0 else 0) + d * 5
+        n += len(self.eng.dec) * 3 + 1
+        return n
+
+    def _ensure_graph(self, raster: torch.Tensor, out_raster: torch.Tensor) -> None:
+        key = (raster.data_ptr(), tuple(raster.shape), out_raster.data_ptr(), tuple(out_raster.shape))
+        if self._graph is not None and self._graph_key == key:
+            return
+        # warm-up on a side stream (sets func attributes, touches every buffer), then capture
+        self.s_plan.zero_()      # height 0 => nothing is written during warm-up / capture
+        self.s_own.zero_()
+        self.s_origins.zero_()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self._batch_body(raster, out_raster)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._batch_body(raster, out_raster)
+        self._graph, self._graph_key = g, key
+
+    def run(self, raster: torch.Tensor, plan: np.ndarray, own: np.ndarray, out_raster: torch.Tensor) -> int:
+        """raster uint8 [C,H,W] (cuda), plan int32 (n,6), own int32 (n,4), out_raster uint8 [H,W]
+        (cuda).  Tiles are processed in enumeration order; returns the number of batches."""
+        n = plan.shape[0]
+        if n == 0:
+            return 0
+        B = self.B
+        nb = (n + B - 1) // B
+        pad = nb * B - n
+        plan_p = np.concatenate([plan, np.zeros((pad, 6), np.int32)]) if pad else plan
+        own_p = np.concatenate([own, np.zeros((pad, 4), np.int32)]) if pad else own
+        plan_d = torch.from_numpy(np.ascontiguousarray(plan_p)).to(self.dev, non_blocking=True)
+        own_d = torch.from_numpy(np.ascontiguousarray(own_p)).to(self.dev, non_blocking=True)
+        org_d = plan_d[:, :2].contiguous()
+        if self.use_graph:
+            self._ensure_graph(raster, out_raster)
+        for b in range(nb):
+            sl = slice(b * B, (b + 1) * B)
+            self.s_origins.copy_(org_d[sl])
+            self.s_plan.copy_(plan_d[sl])
+            self.s_own.copy_(own_d[sl])
+            if self.use_graph:
+                self._graph.replay()
+            else:
+                self._batch_body(raster, out_raster)
+        return nb

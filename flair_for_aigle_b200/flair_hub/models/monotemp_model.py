@@ -1,0 +1,107 @@
+"""Mono-temporal encoder / decoder descriptions: drop-in for flair_hub/models/monotemp_model.py.
+
+The reference's ``FLAIR_Monotemp`` (monotemp_model.py:34-97) asks ``smp.create_model`` for a
+full segmentation model and keeps either ``.encoder`` or ``DecoderWrapper(decoder, head)``.
+Here the "model" is a *parameter specification*: the exact state_dict keys and shapes that smp
+0.4.0 / timm would create, which ``FLAIR_HUB_Model`` registers as plain
+tensors and the sm_100a engine packs for its kernels.  No torch.nn compute modules are built.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Sequence, Tuple
+
+from ...engine.convnext_unet import CONVNEXTV2_CFGS
+
+# kind drives the random initialisation only
+Spec = "OrderedDict[str, Tuple[Tuple[int, ...], str]]"
+
+UNET_DECODER_CHANNELS = (256, 128, 64, 32, 16)
+
+
+def split_arch(arch: str) -> Tuple[str, str]:
+    """monotemp_model.py:64-65: "<encoder>-<decoder>"."""
+    parts = arch.split("-")
+    return parts[0], parts[1]
+
+
+def resolve_encoder(name: str) -> str:
+    """The smp lookup of monotemp_model.py:67-92: native encoder name first, then 'tu-'+name."""
+    base = name[3:] if name.startswith("tu-") else name
+    if base in CONVNEXTV2_CFGS:
+        return base
+    raise KeyError(
+        f"encoder '{name}' has no sm_100a execution plan yet (available: {sorted(CONVNEXTV2_CFGS)}); "
+        "there is no PyTorch fallback")
+
+
+def encoder_out_channels(name: str, in_channels: int) -> List[int]:
+    """smp ``encoder.out_channels``; timm-universal "transformer style": [C_in, 0, c4, c8, c16, c32]."""
+    _, dims = CONVNEXTV2_CFGS[resolve_encoder(name)]
+    return [in_channels, 0] + list(dims)
+
+
+def convnextv2_encoder_spec(name: str, in_channels: int):
+    """Keys below ``encoders.<MOD>.seg_model.`` (smp TimmUniversalEncoder.model = timm
+    FeatureListNet with flatten_sequential=True)."""
+    depths, dims = CONVNEXTV2_CFGS[resolve_encoder(name)]
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    s["model.stem_0.weight"] = ((dims[0], in_channels, 4, 4), "conv")
+    s["model.stem_0.bias"] = ((dims[0],), "bias")
+    s["model.stem_1.weight"] = ((dims[0],), "norm_w")
+    s["model.stem_1.bias"] = ((dims[0],), "bias")
+    prev = dims[0]
+    for i, (d, c) in enumerate(zip(depths, dims)):
+        p = f"model.stages_{i}."
+        if i > 0:
+            s[p + "downsample.0.weight"] = ((prev,), "norm_w")
+            s[p + "downsample.0.bias"] = ((prev,), "bias")
+            s[p + "downsample.1.weight"] = ((c, prev, 2, 2), "conv")
+            s[p + "downsample.1.bias"] = ((c,), "bias")
+        for j in range(d):
+            b = p + f"blocks.{j}."
+            s[b + "conv_dw.weight"] = ((c, 1, 7, 7), "conv")
+            s[b + "conv_dw.bias"] = ((c,), "bias")
+            s[b + "norm.weight"] = ((c,), "norm_w")
+            s[b + "norm.bias"] = ((c,), "bias")
+            s[b + "mlp.fc1.weight"] = ((4 * c, c), "linear")
+            s[b + "mlp.fc1.bias"] = ((4 * c,), "bias")
+            s[b + "mlp.grn.weight"] = ((4 * c,), "grn")
+            s[b + "mlp.grn.bias"] = ((4 * c,), "grn")
+            s[b + "mlp.fc2.weight"] = ((c, 4 * c), "linear")
+            s[b + "mlp.fc2.bias"] = ((c,), "bias")
+        prev = c
+    return s
+
+
+def unet_decoder_spec(encoder_channels: Sequence[int], classes: int,
+                      decoder_channels: Sequence[int] = UNET_DECODER_CHANNELS):
+    """Keys below ``main_decoders.<TASK>.seg_model.`` (smp 0.4.0 UnetDecoder + SegmentationHead)."""
+    enc = list(encoder_channels)[1:][::-1]
+    in_ch = [enc[0]] + list(decoder_channels[:-1])
+    skip_ch = list(enc[1:]) + [0]
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    for k, (ci, cs, co) in enumerate(zip(in_ch, skip_ch, decoder_channels)):
+        for name, cin in (("conv1", ci + cs), ("conv2", co)):
+            p = f"decoder.blocks.{k}.{name}."
+            s[p + "0.weight"] = ((co, cin, 3, 3), "conv_relu")
+            s[p + "1.weight"] = ((co,), "norm_w")
+            s[p + "1.bias"] = ((co,), "bias")
+            s[p + "1.running_mean"] = ((co,), "bn_mean")
+            s[p + "1.running_var"] = ((co,), "bn_var")
+            s[p + "1.num_batches_tracked"] = ((), "bn_count")
+    s["segmentation_head.0.weight"] = ((classes, decoder_channels[-1], 3, 3), "head")
+    s["segmentation_head.0.bias"] = ((classes,), "bias")
+    return s
+
+
+def encoder_spec(arch: str, in_channels: int):
+    enc, _ = split_arch(arch)
+    return convnextv2_encoder_spec(enc, in_channels)
+
+
+def decoder_spec(arch: str, in_channels: int, classes: int):
+    enc, dec = split_arch(arch)
+    if dec.lower() != "unet":
+        raise KeyError(f"decoder '{dec}' has no sm_100a execution plan yet (available: unet); no PyTorch fallback")
+    return unet_decoder_spec(encoder_out_channels(enc, in_channels), classes)

@@ -1,0 +1,298 @@
+"""Zonal inference pipeline: drop-in for flair_zonal_detection/inference.py.
+
+Same entry points and call order as the reference's working caller
+(scripts/run_fast_aigle_segmentation.py:75-119):
+
+    config  = prep_config(...) / initialize_geometry_and_resolutions(config)
+    sizes   = compute_patch_sizes(config)
+    model   = build_inference_model(config, sizes).to(config['device'])
+    tiles   = generate_patches_from_reference(config, img_path, geozone)
+    dataset = prep_dataset(config, tiles, sizes);  loader = DataLoader(dataset, batch_size=...)
+    outs, _ = init_outputs(config, ref_img, i)
+    inference_and_write(model, loader, tiles, config, outs, ref_img)
+
+What changes is where the work happens: the raster stays in HBM as uint8, tiles are gathered by
+a kernel, the encoder/decoder run on tcgen05, and the margin crop + argmax + windowed write of
+inference.py:297-352 is the head convolution's epilogue.  No logits cross PCIe.
+"""
+from __future__ import annotations
+
+import glob
+import logging
+import os
+import time
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+from .. import native as nv
+from ..engine.zonal import ZonalRunner
+from .config import config_recap_1, config_recap_2, load_config, validate_config
+from .dataset import MultiModalSlicedDataset
+from .model_utils import build_inference_model, compute_patch_sizes
+from .postprocess import convert  # noqa: F401  (re-exported like the reference)
+from .raster import RasterSink, ZoneRaster, open_raster
+from .slicing import generate_patches_from_reference, ownership_windows, tile_plan
+
+logger = logging.getLogger(__name__)
+
+RASTER_GLOBS = ("*.jp2", "*.tif", "*.tiff", "*.npy")
+
+
+def overwrite_config(config, model_ckpt_path, model_threshold_filepath, result_folder, log_folder) -> Dict:
+    """inference.py:42-51."""
+    config['model_weights'] = model_ckpt_path
+    config['model_threshold_filepath'] = model_threshold_filepath
+    config['output_path'] = result_folder
+    config['log_folder'] = log_folder
+    return config
+
+
+def list_rasters(images_folder: str):
+    files = []
+    for pat in RASTER_GLOBS:
+        files += sorted(glob.glob(os.path.join(images_folder, pat)))
+    return files
+
+
+def prep_config(config_path: str, model_ckpt_path: str = None, model_threshold_filepath: str = None,
+                result_folder: str = None, log_folder: str = None, images_folder: str = None) -> Dict:
+    """inference.py:54-73.  The five override arguments are optional here so that the intent of
+    the reference's stale ``run_inference(config_path)`` also works."""
+    config = load_config(config_path)
+    if images_folder is not None:
+        rasters = list_rasters(images_folder)
+        if not rasters:
+            raise FileNotFoundError(f"no raster found in {images_folder}")
+        config['modalities']['AERIAL_RGBI']['input_img_path'] = rasters[0]
+    if model_ckpt_path is not None:
+        config = overwrite_config(config, model_ckpt_path, model_threshold_filepath, result_folder, log_folder)
+    validate_config(config)
+    config.setdefault('output_type', 'argmax')
+    config_recap_1(config)
+    config = initialize_geometry_and_resolutions(config)
+    config_recap_2(config)
+    config['device'] = torch.device("cuda" if config.get("use_gpu", torch.cuda.is_available()) else "cpu")
+    config['output_type'] = config.get("output_type", "argmax")
+    return config
+
+
+def initialize_geometry_and_resolutions(config: Dict) -> Dict:
+    """inference.py:76-132 (same keys set, same bounds check, same "smallest m/px" reference rule)."""
+    modalities = config['modalities']
+    active = [m for m, on in modalities['inputs'].items() if on]
+    resolutions, bounds = {}, []
+    for mod in active:
+        src = open_raster(modalities[mod]['input_img_path'])
+        resolutions[mod] = round(src.res[0], 5)
+        bounds.append((mod, src.bounds))
+        if 'image_shape_px' not in config:
+            config['image_shape_px'] = {'height': src.height, 'width': src.width}
+    ref_mod, ref_bounds = bounds[0]
+    for mod, b in bounds[1:]:
+        if not np.allclose(b, ref_bounds, atol=1e-2):
+            raise ValueError(f"[✗] Bounds mismatch between '{ref_mod}' and '{mod}':\n  {ref_mod}: {ref_bounds}\n"
+                             f"  {mod}: {b}")
+    ref_mod, reference_resolution = min(resolutions.items(), key=lambda kv: kv[1])
+    config['reference_modality'] = ref_mod
+    config['reference_resolution'] = reference_resolution
+    config['modality_resolutions'] = resolutions
+    config['image_bounds'] = {'left': ref_bounds.left, 'bottom': ref_bounds.bottom, 'right': ref_bounds.right,
+                              'top': ref_bounds.top}
+    config['tile_size_m'] = round(config['img_pixels_detection'] * reference_resolution, 2)
+    config['margin_size_m'] = round(config['margin'] * reference_resolution, 2)
+    return config
+
+
+def prep_dataset(config: Dict, tiles_gdf, patch_sizes: Dict[str, int]) -> MultiModalSlicedDataset:
+    """inference.py:136-154."""
+    active = [m for m, on in config['modalities']['inputs'].items() if on]
+    modality_cfgs = {m: config['modalities'][m] for m in active}
+    config['labels'] = [t['name'] for t in config['tasks'] if t['active']]
+    config['labels_configs'] = {t['name']: {'value_name': t['class_names']} for t in config['tasks'] if t['active']}
+    return MultiModalSlicedDataset(dataframe=tiles_gdf, modality_cfgs=modality_cfgs, patch_size_dict=patch_sizes,
+                                   ref_date_str=config.get('multitemp_model_ref_date'), modalities_config=config)
+
+
+def init_outputs(config: Dict, ref_img, i=0) -> Tuple[Dict[str, RasterSink], Dict[str, str]]:
+    """inference.py:157-208: one uint8 output raster per active task (1 band for argmax, n_cls
+    bands for class_prob), rescaled grid when ``output_px_meters`` differs."""
+    ref_img = open_raster(ref_img)
+    output_files, temp_paths = {}, {}
+    output_type = config['output_type']
+    ref_res = config['reference_resolution']
+    out_res = config.get("output_px_meters", ref_res)
+    ib = config['image_bounds']
+    needs_rescale = abs(ref_res - out_res) > 1e-6
+    device = config.get('device', torch.device('cuda'))
+    for task in config['tasks']:
+        if not task['active']:
+            continue
+        n_cls = len(task['class_names'])
+        suffix = 'argmax' if output_type == 'argmax' else 'class-prob'
+        out_path = os.path.join(config['output_path'], f"{config['output_name']}_{task['name']}_{suffix}_i.tif")
+        if not needs_rescale:
+            h, w = ref_img.height, ref_img.width
+        else:
+            h = int(round((ib['top'] - ib['bottom']) / out_res))
+            w = int(round((ib['right'] - ib['left']) / out_res))
+        output_files[task['name']] = RasterSink(out_path, n_cls if output_type == "class_prob" else 1, h, w,
+                                                ib['left'], ib['top'], out_res, ref_img.crs, device=device)
+        temp_paths[task['name']] = out_path
+    return output_files, temp_paths
+
+
+def resample_prediction(prediction, scale: float):
+    """inference.py:212-226 (nearest zoom).  Only the identity is on the hot path."""
+    if abs(scale - 1.0) < 1e-9:
+        return prediction
+    raise NotImplementedError("output_px_meters != reference resolution: nearest-neighbour rescaling of the "
+                              "prediction is not implemented on the GPU path yet")
+
+
+def _check_same_grid(config):
+    ref_res = config['reference_resolution']
+    out_res = config.get('output_px_meters', ref_res)
+    if abs(ref_res - out_res) > 1e-6:
+        resample_prediction(None, ref_res / out_res)
+
+
+def _runner(model, config, margin: int) -> ZonalRunner:
+    key = "_zonal_runner"
+    task = config['labels'][0] if 'labels' in config else [t['name'] for t in config['tasks'] if t['active']][0]
+    eng = model.engine(task, max_batch=int(config.get('batch_size', model.max_batch)))
+    r = getattr(model, key, None)
+    if r is None or r.eng is not eng or r.margin != margin:
+        r = ZonalRunner(eng, margin, use_graph=bool(config.get('use_cuda_graph', True)))
+        setattr(model, key, r)
+    return r
+
+
+@torch.no_grad()
+def inference_and_write(model, dataloader, tiles_gdf, config: Dict, output_files: Dict[str, RasterSink],
+                        ref_img) -> None:
+    """inference.py:254-355.  Writes every tile's margin-cropped prediction into the task's output
+    raster (later tiles overwrite earlier ones) and closes the rasters."""
+    device = torch.device(config['device'])
+    if device.type != "cuda":
+        raise nv.NativeError("inference_and_write runs on CUDA only (no CPU fallback)")
+    margin = int(config['margin'])
+    P = int(config['img_pixels_detection'])
+    output_type = config['output_type']
+    _check_same_grid(config)
+    ref_img = open_raster(ref_img)
+    b = ref_img.bounds
+    ib = {'left': b.left, 'bottom': b.bottom, 'right': b.right, 'top': b.top}
+    ref_res = config['reference_resolution']
+    plan = tile_plan(tiles_gdf, ib, ref_res, P, margin, config.get('output_px_meters', ref_res))
+    own = ownership_windows(plan)
+    dataset = getattr(dataloader, 'dataset', dataloader)
+    tasks = [t['name'] for t in config['tasks'] if t['active']]
+
+    if isinstance(dataset, MultiModalSlicedDataset) and output_type == "argmax" and len(tasks) == 1:
+        # fused device path: feeder -> encoder/decoder -> head epilogue writes the class raster
+        mod = model.active_mono[0]
+        raster = dataset.device_raster(mod, device)
+        sink = output_files[tasks[0]]
+        _runner(model, config, margin).run(raster, plan, own, sink.device_array[0])
+    else:
+        # generic path (any iterable of reference-style batches, class_prob output, several tasks):
+        # model(inputs) -> logits stay on the device -> crop/convert/write kernels
+        plan_d = torch.from_numpy(plan).to(device)
+        own_d = torch.from_numpy(own).to(device)
+        for batch in _iter_batches(dataloader, dataset, model, config, device):
+            idx = batch.pop('index').to(device).flatten().long()
+            logits_tasks, _ = model(batch)
+            for task, logits in logits_tasks.items():
+                sink = output_files[task]
+                pl, ow = plan_d[idx].contiguous(), own_d[idx].contiguous()
+                if output_type == "argmax":
+                    nv.crop_argmax_write(logits, nv.NCHW, margin, pl, ow, sink.device_array[0])
+                else:
+                    nv.crop_softmax_write(logits, nv.NCHW, margin, pl, ow, sink.device_array)
+    torch.cuda.synchronize(device)
+    for dst in output_files.values():
+        dst.close()
+
+
+def _iter_batches(dataloader, dataset, model, config, device):
+    """Reference-style batches ({MOD: (B,C,P,P) fp32 normalised, 'index': ...}).  For our own
+    dataset the tensors are produced on the device by the feeder kernel."""
+    if not isinstance(dataset, MultiModalSlicedDataset):
+        for batch in dataloader:
+            yield {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()
+                   if not k.endswith('_RAW')}
+        return
+    mod = model.active_mono[0]
+    raster = dataset.device_raster(mod, device)
+    norm = dataset.modalities[mod].get('normalization', {}) or {}
+    C = raster.shape[0]
+    mean = torch.tensor(norm.get('means', [0.0] * C), dtype=torch.float32, device=device)
+    std = torch.tensor(norm.get('stds', [1.0] * C), dtype=torch.float32, device=device)
+    P = int(config['img_pixels_detection'])
+    plan = torch.from_numpy(dataset.plan()).to(device)
+    bs = int(config.get('batch_size', 8))
+    for s in range(0, len(dataset), bs):
+        idx = torch.arange(s, min(s + bs, len(dataset)), device=device)
+        x = nv.gather_tiles_f32(raster, plan[idx, :2].contiguous(), P, mean, std)
+        yield {mod: x, 'index': idx}
+
+
+@torch.no_grad()
+def inference(model, dataloader, tiles_gdf, config: Dict, raster_img):
+    """inference.py:468-564 with its intended semantics (wide accumulator instead of
+    the wrapping int8 one, the window of inference.py:318-321): softmax of every margin-cropped
+    tile accumulated into a (n_cls,H,W) float32 canvas on the device.  Returns (canvas, transform)."""
+    device = torch.device(config['device'])
+    if device.type != "cuda":
+        raise nv.NativeError("inference runs on CUDA only (no CPU fallback)")
+    margin = int(config['margin'])
+    P = int(config['img_pixels_detection'])
+    _check_same_grid(config)
+    raster_img = open_raster(raster_img)
+    b = raster_img.bounds
+    ib = {'left': b.left, 'bottom': b.bottom, 'right': b.right, 'top': b.top}
+    ref_res = config['reference_resolution']
+    plan = torch.from_numpy(tile_plan(tiles_gdf, ib, ref_res, P, margin, ref_res)).to(device)
+    canvas = torch.zeros((model.task_nclasses, raster_img.height, raster_img.width), dtype=torch.float32,
+                         device=device)
+    dataset = getattr(dataloader, 'dataset', dataloader)
+    for batch in _iter_batches(dataloader, dataset, model, config, device):
+        idx = batch.pop('index').to(device).flatten().long()
+        logits_tasks, _ = model(batch)
+        for _, logits in logits_tasks.items():
+            nv.crop_softmax_accumulate(logits, nv.NCHW, margin, plan[idx].contiguous(), None, canvas)
+    torch.cuda.synchronize(device)
+    return canvas, raster_img.profile['transform']
+
+
+def logits_to_labels_and_confidence(probs):
+    """inference.py:566-572 on the device canvas."""
+    if not torch.is_tensor(probs):
+        probs = torch.from_numpy(np.ascontiguousarray(probs))
+    if not probs.is_cuda:
+        if not torch.cuda.is_available():
+            raise nv.NativeError("logits_to_labels_and_confidence runs on CUDA only (no CPU fallback)")
+        probs = probs.cuda()
+    return nv.canvas_argmax(probs.float().contiguous(), want_confidence=True)
+
+
+def run_inference(config_path: str) -> Dict[str, str]:
+    """inference.py:644-674, repaired: config in -> rasters out.  Returns the
+    written paths per task."""
+    from torch.utils.data import DataLoader
+    t0 = time.time()
+    config = prep_config(config_path)
+    ref_path = config['modalities'][config['reference_modality']]['input_img_path']
+    tiles_gdf = generate_patches_from_reference(config, ref_path, None)
+    logger.info(f"[✓] Sliced into {len(tiles_gdf)} tiles")
+    patch_sizes = compute_patch_sizes(config)
+    model = build_inference_model(config, patch_sizes).to(config['device'])
+    dataset = prep_dataset(config, tiles_gdf, patch_sizes)
+    dataloader = DataLoader(dataset, batch_size=config.get('batch_size', 8), num_workers=0)
+    ref_img = open_raster(ref_path)
+    output_files, temp_paths = init_outputs(config, ref_img, 0)
+    inference_and_write(model, dataloader, tiles_gdf, config, output_files, ref_img)
+    logger.info(f"[✓] Total time: {time.time() - t0:.2f}s")
+    return {k: v.written_path for k, v in output_files.items()}

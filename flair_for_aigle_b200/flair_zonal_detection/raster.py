@@ -27,6 +27,16 @@ class ZoneRaster:
             array = array[None]
         self.array = array
         self.left, self.top, self.res_value, self.crs, self.name = float(left), float(top), float(res), crs, name
+        self.pinned_tensor = None   # set by from_pinned(): the same pixels as a pinned torch tensor
+
+    @classmethod
+    def from_pinned(cls, tensor, left: float, top: float, res: float, crs: Optional[str] = None,
+                    name: str = "<pinned>"):
+        """Raster whose pixels live in page-locked host memory (torch uint8 tensor (C,H,W)), so the
+        upload to HBM is a single asynchronous DMA."""
+        r = cls(tensor.numpy(), left, top, res, crs, name)
+        r.pinned_tensor = tensor
+        return r
 
     # -- rasterio.DatasetReader look-alikes ------------------------------------------------
     @property
@@ -101,3 +111,62 @@ def open_raster(path) -> ZoneRaster:
         raise FileNotFoundError(path)
     with rasterio.open(path) as src:  # pragma: no cover
         return ZoneRaster(src.read(), src.bounds.left, src.bounds.top, abs(src.res[0]), str(src.crs), name=path)
+
+
+class RasterSink:
+    """Output raster of ``init_outputs`` (inference.py:157-208): a uint8 (count,H,W) array that lives
+    on the GPU while tiles are written into it by the kernels, copied to the host once and stored
+    on ``close()``.  GeoTIFF/COG encoding belongs to the raster-I/O row of SURVEY.md 8(f); here the
+    array is written as LZW TIFF through Pillow for single-band rasters that fit its limits,
+    otherwise as ``.npy``; georeferencing goes to a ``.json`` sidecar either way."""
+
+    def __init__(self, path: str, count: int, height: int, width: int, left: float, top: float, res: float,
+                 crs=None, device=None):
+        import torch
+        self.name = path
+        self.count, self.height, self.width = count, height, width
+        self.left, self.top, self.res_value, self.crs = left, top, res, crs
+        if device is None or torch.device(device).type != "cuda":
+            raise RuntimeError("RasterSink needs a CUDA device: predictions are written by GPU kernels")
+        self.device_array = torch.zeros((count, height, width), dtype=torch.uint8, device=device)
+        self.host_array = None
+        self.closed = False
+
+    def to_host(self) -> np.ndarray:
+        if self.host_array is None:
+            import torch
+            pinned = torch.empty(self.device_array.shape, dtype=torch.uint8, pin_memory=True)
+            pinned.copy_(self.device_array, non_blocking=True)
+            torch.cuda.current_stream(self.device_array.device).synchronize()
+            self.host_array = pinned.numpy()
+        return self.host_array
+
+    write_files = True   # class-level switch: False = keep the result in host memory only
+
+    def close(self) -> None:
+        if self.closed:
+            return
+        arr = self.to_host()
+        if not self.write_files:
+            self.written_path = None
+            self.closed = True
+            return
+        meta = {"left": self.left, "top": self.top, "res": self.res_value, "crs": self.crs,
+                "count": self.count, "height": self.height, "width": self.width, "dtype": "uint8",
+                "compress": "lzw"}
+        written = None
+        if self.count == 1:
+            try:
+                from PIL import Image
+                Image.MAX_IMAGE_PIXELS = None
+                Image.fromarray(arr[0]).save(self.name, format="TIFF", compression="tiff_lzw")
+                written = self.name
+            except Exception:  # pragma: no cover - Pillow limits / missing codec
+                written = None
+        if written is None:
+            written = os.path.splitext(self.name)[0] + ".npy"
+            np.save(written, arr)
+        with open(written + ".json", "w") as f:
+            json.dump(meta, f)
+        self.written_path = written
+        self.closed = True

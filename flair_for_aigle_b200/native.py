@@ -26,6 +26,30 @@ class NativeError(RuntimeError):
     pass
 
 
+# Optional per-launch timing (bench.py's roofline leg): when PROFILE is a list, every kernel wrapper
+# brackets its launch with CUDA events on the launching stream and appends
+# (kernel_family, meta, start_event, end_event).  Never enabled inside CUDA-graph capture.
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, family: str, **meta):
+        self.family, self.meta = family, meta
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream())
+            PROFILE.append((self.family, self.meta, self.e0, self.e1))
+        return False
+
+
 _vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -46,7 +70,7 @@ _SIGNATURES = {
     "fz_stem_ln_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_dwconv7_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
     "fz_ln2d_s2d": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
-    "fz_grn_scale": [_vp, _vp, _vp, _i, _i, ctypes.c_float, _vp],
+    "fz_grn_scale": [_vp, _i, _vp, _vp, _i, _i, ctypes.c_float, _vp],
     "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
     "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
@@ -124,8 +148,9 @@ def gather_tiles_u8(raster: torch.Tensor, origins: torch.Tensor, P: int,
     n = origins.shape[0]
     if out is None:
         out = torch.empty((n, P, P, 4), dtype=torch.uint8, device=raster.device)
-    _check(lib().fz_gather_tiles_u8(_ptr(raster), C, H, W, _ptr(origins), n, P, _ptr(out), _stream()),
-           "fz_gather_tiles_u8")
+    with _Timed('gather_u8', n=n):
+        _check(lib().fz_gather_tiles_u8(_ptr(raster), C, H, W, _ptr(origins), n, P, _ptr(out), _stream()),
+               "fz_gather_tiles_u8")
     return out
 
 
@@ -189,8 +214,9 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, mode: int, bias=None, resid=None
         odt = torch.float32 if mode in (EPI_RESID_F32, EPI_F32) else torch.bfloat16
         out = torch.empty((M, N), dtype=odt, device=A.device)
     fn = lib().fz_gemm_bf16 if impl == "tcgen05" else lib().fz_gemm_bf16_simt
-    _check(fn(_ptr(A), _ptr(B), _ptr(out), _ptr(bias), _ptr(resid), _ptr(sumsq), M, N, K, b_batch, rows_per_sample,
-              mode, _stream()), "fz_gemm_bf16")
+    with _Timed("gemm_tcgen05" if impl == "tcgen05" else "gemm_simt", M=M, N=N, K=K, mode=mode):
+        _check(fn(_ptr(A), _ptr(B), _ptr(out), _ptr(bias), _ptr(resid), _ptr(sumsq), M, N, K, b_batch,
+                  rows_per_sample, mode, _stream()), "fz_gemm_bf16")
     return out
 
 
@@ -198,8 +224,9 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, mode: int, bias=None, resid=None
 def stem_ln(tiles_u8, w, bias, ln_w, ln_b, out, eps=1e-6):
     B, P = tiles_u8.shape[0], tiles_u8.shape[1]
     C0 = w.shape[1]
-    _check(lib().fz_stem_ln(_ptr(tiles_u8), _ptr(w), _ptr(bias), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, P, C0, eps,
-                            _stream()), "fz_stem_ln")
+    with _Timed('stem_ln', n=B):
+        _check(lib().fz_stem_ln(_ptr(tiles_u8), _ptr(w), _ptr(bias), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, P, C0, eps,
+                                _stream()), "fz_stem_ln")
     return out
 
 
@@ -213,33 +240,40 @@ def stem_ln_f32(x_nchw, w, bias, ln_w, ln_b, out, eps=1e-6):
 
 def dwconv7_ln(x, wdw, bdw, ln_w, ln_b, out, eps=1e-6):
     B, H, W, C = x.shape
-    _check(lib().fz_dwconv7_ln(_ptr(x), _ptr(wdw), _ptr(bdw), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, H, W, C, eps,
-                               _stream()), "fz_dwconv7_ln")
+    with _Timed('dwconv7_ln', B=B, H=H, C=C):
+        _check(lib().fz_dwconv7_ln(_ptr(x), _ptr(wdw), _ptr(bdw), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, H, W, C, eps,
+                                   _stream()), "fz_dwconv7_ln")
     return out
 
 
 def ln2d_s2d(x, ln_w, ln_b, out, eps=1e-6):
     B, H, W, C = x.shape
-    _check(lib().fz_ln2d_s2d(_ptr(x), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, H, W, C, eps, _stream()), "fz_ln2d_s2d")
+    with _Timed('ln2d_s2d', B=B, H=H, C=C):
+        _check(lib().fz_ln2d_s2d(_ptr(x), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, H, W, C, eps, _stream()), "fz_ln2d_s2d")
     return out
 
 
-def grn_scale(sumsq, gamma, scale, eps=1e-6):
-    B, K = sumsq.shape
-    _check(lib().fz_grn_scale(_ptr(sumsq), _ptr(gamma), _ptr(scale), B, K, eps, _stream()), "fz_grn_scale")
+def grn_scale(partial, tiles_per_sample, gamma, scale, eps=1e-6):
+    """partial: f32 [B*tiles_per_sample, K] (fc1 epilogue); scale: f32 [B, K]."""
+    B, K = scale.shape
+    with _Timed('grn_scale', B=B, K=K):
+        _check(lib().fz_grn_scale(_ptr(partial), tiles_per_sample, _ptr(gamma), _ptr(scale), B, K, eps, _stream()),
+               "fz_grn_scale")
     return scale
 
 
 def scale_weights(w, scale, out):
     N, K = w.shape
     B = scale.shape[0]
-    _check(lib().fz_scale_weights(_ptr(w), _ptr(scale), _ptr(out), B, N, K, _stream()), "fz_scale_weights")
+    with _Timed('scale_weights', B=B, N=N, K=K):
+        _check(lib().fz_scale_weights(_ptr(w), _ptr(scale), _ptr(out), B, N, K, _stream()), "fz_scale_weights")
     return out
 
 
 def scale_rows(h, scale, rows_per_sample):
     M, K = h.shape
-    _check(lib().fz_scale_rows(_ptr(h), _ptr(scale), M, K, rows_per_sample, _stream()), "fz_scale_rows")
+    with _Timed('scale_rows', M=M, K=K):
+        _check(lib().fz_scale_rows(_ptr(h), _ptr(scale), M, K, rows_per_sample, _stream()), "fz_scale_rows")
     return h
 
 
@@ -248,8 +282,9 @@ def upsample2_concat(a, s, out):
     C1 = a.shape[-1]
     C2 = 0 if s is None else s.shape[-1]
     assert C1 + C2 == CT
-    _check(lib().fz_upsample2_concat(_ptr(a), _dt(a), _ptr(s), _dt(s) if s is not None else BF16, _ptr(out), B, H, W,
-                                     C1, C2, _stream()), "fz_upsample2_concat")
+    with _Timed('upsample2_concat', B=B, H=H, C=CT):
+        _check(lib().fz_upsample2_concat(_ptr(a), _dt(a), _ptr(s), _dt(s) if s is not None else BF16, _ptr(out), B, H, W,
+                                         C1, C2, _stream()), "fz_upsample2_concat")
     return out
 
 
@@ -259,6 +294,7 @@ def conv3x3(x, w, scale, bias, mode, out=None, cout=None, cstride=0, plan=None, 
     rows = w.shape[0]
     cout = rows if cout is None else cout
     RH, RW = (raster.shape[-2], raster.shape[-1]) if raster is not None else (0, 0)
-    _check(lib().fz_conv3x3_bf16(_ptr(x), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), B, H, W, Cin, cout, rows, mode, cstride,
-                                 _ptr(plan), _ptr(own), _ptr(raster), RH, RW, margin, _stream()), "fz_conv3x3_bf16")
+    with _Timed('conv3x3_tcgen05', B=B, H=H, Cin=Cin, Cout=cout, mode=mode):
+        _check(lib().fz_conv3x3_bf16(_ptr(x), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), B, H, W, Cin, cout, rows, mode, cstride,
+                                     _ptr(plan), _ptr(own), _ptr(raster), RH, RW, margin, _stream()), "fz_conv3x3_bf16")
     return out

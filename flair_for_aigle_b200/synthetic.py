@@ -1,30 +1,79 @@
 """Seeded synthetic inputs shared by bench.py and the tests: a 4-band
 uint8 "aerial" raster made of low-resolution noise bilinearly upsampled (land-cover-like smooth
-regions) plus per-pixel noise, generated strip by strip so 60k x 60k never needs a float copy."""
+regions) plus per-pixel noise.  Any row range can be generated independently (each 512-row band
+has its own noise stream), so a rank generates only its strip of a 60k x 60k zone."""
 from __future__ import annotations
 
 import numpy as np
 
+_BAND = 512
 
-def synthetic_raster(height: int, width: int, bands: int = 4, seed: int = 2025, cell: int = 96,
-                     noise: float = 6.0) -> np.ndarray:
-    """uint8 (bands, height, width).  Deterministic in (shape, seed, cell, noise)."""
-    rng = np.random.default_rng(seed)
+
+def synthetic_raster(height: int, width: int, bands: int = 4, seed: int = 2025, cell: int = 96, noise: float = 6.0,
+                     row0: int = 0, rows: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    """uint8 (bands, rows, width): rows [row0, row0+rows) of the (height x width) zone.
+    Deterministic in (height, width, bands, seed, cell, noise) and independent of the row range."""
+    rows = height - row0 if rows is None else rows
     gh, gw = height // cell + 3, width // cell + 3
-    coarse = rng.uniform(20.0, 235.0, size=(bands, gh, gw)).astype(np.float32)
-    out = np.empty((bands, height, width), dtype=np.uint8)
+    coarse = np.random.default_rng(seed).uniform(20.0, 235.0, size=(bands, gh, gw)).astype(np.float32)
+    if out is None:
+        out = np.empty((bands, rows, width), dtype=np.uint8)
     xs = (np.arange(width, dtype=np.float32) + 0.5) / cell
     x0 = np.floor(xs).astype(np.int64)
     fx = (xs - x0).astype(np.float32)
-    strip = 512
-    for r0 in range(0, height, strip):
-        r1 = min(r0 + strip, height)
-        ys = (np.arange(r0, r1, dtype=np.float32) + 0.5) / cell
+    first_band = row0 // _BAND
+    last_band = (row0 + rows - 1) // _BAND
+    for band in range(first_band, last_band + 1):
+        b0 = band * _BAND
+        b1 = min(b0 + _BAND, height)
+        ys = (np.arange(b0, b1, dtype=np.float32) + 0.5) / cell
         y0 = np.floor(ys).astype(np.int64)
         fy = (ys - y0).astype(np.float32)[None, :, None]
-        top = coarse[:, y0][:, :, x0] * (1 - fx) + coarse[:, y0][:, :, x0 + 1] * fx
-        bot = coarse[:, y0 + 1][:, :, x0] * (1 - fx) + coarse[:, y0 + 1][:, :, x0 + 1] * fx
+        cy0, cy1 = coarse[:, y0], coarse[:, y0 + 1]
+        top = cy0[:, :, x0] * (1 - fx) + cy0[:, :, x0 + 1] * fx
+        bot = cy1[:, :, x0] * (1 - fx) + cy1[:, :, x0 + 1] * fx
         val = top * (1 - fy) + bot * fy
+        rng = np.random.default_rng([seed, band])
         val += rng.standard_normal(val.shape, dtype=np.float32) * noise
-        out[:, r0:r1] = np.clip(np.rint(val), 0, 255).astype(np.uint8)
+        u8 = np.clip(np.rint(val), 0, 255).astype(np.uint8)
+        lo, hi = max(b0, row0), min(b1, row0 + rows)
+        out[:, lo - row0:hi - row0] = u8[:, lo - b0:hi - b0]
     return out
+
+
+DEFAULT_MEANS = [105.66, 111.35, 102.18, 106.59]   # configs/config_model_zonal_segmentation.yaml:48 +
+DEFAULT_STDS = [52.23, 45.62, 44.30, 39.78]        # configs/train/config_modalities.yaml:55-56 (IR band)
+
+
+def randomize_state_(state_dict, seed: int = 2025, bf16_exact: bool = True) -> None:
+    """Fill a reference-layout state_dict with seeded random values that keep activations O(1)
+    through the network and leave no path numerically inert (GRN gamma/beta, biases, BatchNorm
+    statistics all non-trivial).  Values are snapped to bf16-representable numbers so the bf16
+    kernels and an fp32 evaluation see identical weights."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    for k in sorted(state_dict.keys()):
+        t = state_dict[k]
+        if not t.dtype.is_floating_point:
+            continue
+        shape = t.shape
+        if k.endswith("running_mean"):
+            v = torch.randn(shape, generator=g) * 0.1
+        elif k.endswith("running_var"):
+            v = torch.rand(shape, generator=g) + 0.5
+        elif ".grn." in k:
+            v = torch.randn(shape, generator=g) * (0.5 if k.endswith("weight") else 0.1)
+        elif k.endswith("bias"):
+            v = torch.randn(shape, generator=g) * 0.1
+        elif t.dim() == 1:                       # LayerNorm / BatchNorm scale
+            v = torch.rand(shape, generator=g) + 0.5
+        elif t.dim() == 2:                       # linear
+            v = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+            if "mlp.fc2" in k:
+                v = v * 0.5
+        else:                                    # conv
+            fan_in = shape[1] * shape[2] * shape[3]
+            v = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+        if bf16_exact:
+            v = v.to(torch.bfloat16).to(torch.float32)
+        t.copy_(v)

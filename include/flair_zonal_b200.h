@@ -87,7 +87,7 @@ int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, vo
  * Replaces the nn.Linear / 1x1 / 2x2-stride-2 conv calls under flair_model.py:376,539-541.
  */
 #define FZ_EPI_BF16 0       /* out bf16 = acc + bias                                              */
-#define FZ_EPI_GELU_SUMSQ 1 /* out bf16 = gelu(acc + bias); sumsq[sample][n] += out^2 (GRN stats) */
+#define FZ_EPI_GELU_SUMSQ 1 /* out bf16 = gelu(acc+bias); sumsq[m/128][n] = sum over the 128-row tile of out^2 */
 #define FZ_EPI_RESID_F32 2  /* out f32  = acc + bias + resid                                      */
 #define FZ_EPI_F32 3        /* out f32  = acc + bias                                              */
 #define FZ_EPI_RELU_BF16 4  /* out bf16 = relu(acc + bias)                                        */
@@ -108,8 +108,9 @@ int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const float* bias
  *   [49][C] (tap-major), out bf16 NHWC (the fc1 GEMM's A operand).
  * fz_ln2d_s2d: LayerNorm2d + space-to-depth: out bf16 [B][H/2][W/2][4C] with
  *   k = (y&1)*2C + (x&1)*C + c, the A operand of the 2x2/s2 downsample conv as a GEMM.
- * fz_grn_scale: scale[b][k] = 1 + gamma[k]*Gx/(mean_k Gx + eps), Gx = sqrt(sumsq[b][k])
- *   (timm GlobalResponseNorm); zeroes sumsq for its next use.
+ * fz_grn_scale: scale[b][k] = 1 + gamma[k]*Gx/(mean_k Gx + eps), Gx = sqrt(sum_t partial[b*tps+t][k])
+ *   (timm GlobalResponseNorm) from the fc1 epilogue's per-128-row-tile partial sums; fixed
+ *   summation order, so the result is independent of batching.
  * fz_scale_weights: out[b][n][k] = bf16(w[n][k]*scale[b][k]) (GRN folded into fc2's weights);
  * fz_scale_rows:    h[m][k] *= scale[m/rows_per_sample][k] (GRN applied to the activations).
  */
@@ -123,7 +124,8 @@ int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw, const floa
                   void* out_bf16, int B, int H, int W, int C, float eps, void* stream);
 int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, int B, int H, int W, int C,
                 float eps, void* stream);
-int fz_grn_scale(float* sumsq, const float* gamma, float* scale, int B, int K, float eps, void* stream);
+int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale, int B, int K,
+                 float eps, void* stream);
 int fz_scale_weights(const void* w_bf16, const float* scale, void* out_bf16, int B, int N, int K, void* stream);
 int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K, int rows_per_sample, void* stream);
 

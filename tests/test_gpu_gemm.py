@@ -17,8 +17,7 @@ def _ref(A, B, bias, mode, resid, rows_per_sample):
     sumsq = None
     if mode == nv.EPI_GELU_SUMSQ:
         v = torch.nn.functional.gelu(v)
-        ns = A.shape[0] // rows_per_sample
-        sumsq = (v.view(ns, rows_per_sample, -1) ** 2).sum(1)
+        sumsq = (v.view(A.shape[0] // 128, 128, -1) ** 2).sum(1)
     elif mode == nv.EPI_RELU_BF16:
         v = torch.relu(v)
     elif mode == nv.EPI_RESID_F32:
@@ -40,8 +39,7 @@ def test_gemm_modes(cuda, impl, M, N, K, rps, bb, mode):
     B = (torch.randn((bb, N, K) if bb > 1 else (N, K), device=cuda) / K ** 0.5).bfloat16()
     bias = torch.randn(N, device=cuda) * 0.1
     resid = torch.randn(M, N, device=cuda) if mode == nv.EPI_RESID_F32 else None
-    ns = M // rps
-    sumsq = torch.zeros(ns, N, device=cuda) if mode == nv.EPI_GELU_SUMSQ else None
+    sumsq = torch.full((M // 128, N), -1.0, device=cuda) if mode == nv.EPI_GELU_SUMSQ else None
     out = nv.gemm_bf16(A, B, mode, bias=bias, resid=resid, sumsq=sumsq, rows_per_sample=rps, impl=impl)
     torch.cuda.synchronize()
     ref, ref_sq = _ref(A, B, bias, mode, resid, rps)

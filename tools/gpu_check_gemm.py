@@ -66,7 +66,7 @@ def bench(M, N, K, mode, rps, iters=20):
     B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
     bias = torch.zeros(N, device=dev)
     resid = torch.zeros(M, N, device=dev) if mode == nv.EPI_RESID_F32 else None
-    sumsq = torch.zeros(M // rps, N, device=dev) if mode == nv.EPI_GELU_SUMSQ else None
+    sumsq = torch.zeros(M // 128, N, device=dev) if mode == nv.EPI_GELU_SUMSQ else None
     out = nv.gemm_bf16(A, B, mode, bias=bias, resid=resid, sumsq=sumsq, rows_per_sample=rps)
     for _ in range(3):
         nv.gemm_bf16(A, B, mode, bias=bias, resid=resid, sumsq=sumsq, rows_per_sample=rps, out=out)
