@@ -63,7 +63,7 @@ class ConvNeXtV2UNetEngine:
         nv.lib()
         self.cfg, self.dev, self.B = cfg, device, max_batch
         self.gemm_impl = "tcgen05"
-        sd = state_dict
+        sd = {k: v.detach().to('cpu') for k, v in state_dict.items()}   # pack on the host, upload once
         E, D, dev = enc_prefix, dec_prefix, device
         C0 = cfg.dims[0]
 
