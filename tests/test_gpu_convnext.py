@@ -218,8 +218,17 @@ def test_engine_vs_oracle(cuda):
     agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
     print(f"logits: max|d|={d.max().item():.4f} mean|d|={d.mean().item():.5f} std={sd_:.3f} argmax agree={agree:.5f}")
     assert d.max().item() < 0.15 * sd_ and d.mean().item() < 0.015 * sd_
-    # same engine, already-normalised float input path (the reference's model(inputs) contract)
+    # same engine, already-normalised float input path (the reference's model(inputs) contract).
+    # Its first layer differs from the uint8 path by ~1e-6 (normalisation folded or not); after a
+    # few layers the bf16 roundings of the two runs are decorrelated, so each is compared with the
+    # ORACLE at the same tolerance, not with the other.
     eng.encode_f32(xn)
     out2 = eng.decode_logits_nchw(2)
     torch.cuda.synchronize()
-    assert (out2 - out).abs().max().item() < 0.02 * sd_
+    d2 = (out2 - ref).abs()
+    assert d2.max().item() < 0.15 * sd_ and d2.mean().item() < 0.015 * sd_
+    # identical input, identical path: bit-identical output (no atomics / races anywhere)
+    eng.encode_f32(xn)
+    out3 = eng.decode_logits_nchw(2)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out3)

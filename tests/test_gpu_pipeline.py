@@ -102,8 +102,15 @@ def test_inference_and_write_matches_oracle(setup):
             return inf._iter_batches(None, ds, model, cfg2, cfg2["device"])
     inf.inference_and_write(model, Plain(), tiles, cfg2, outs2, "mem://z1")
     got2 = outs2[TASK].to_host()[0]
-    # same kernels up to the head; argmax of fp32 logits in both: identical class map
-    assert (got2 == got).mean() >= 0.9999
+    # the float-input stem differs from the folded uint8 stem by ~1e-6, which decorrelates the bf16
+    # roundings downstream: compare this path with the ORACLE too, at the same bar
+    agree2 = (got2 == ref).mean()
+    print(f"generic path agreement with the oracle pipeline: {agree2:.5f}; with the fused path {(got2 == got).mean():.5f}")
+    assert agree2 >= 0.985
+    # the fused path is deterministic: a second run reproduces the raster bit for bit
+    outs3, _ = inf.init_outputs(cfg, "mem://z1", 0)
+    inf.inference_and_write(model, loader, tiles, cfg, outs3, "mem://z1")
+    assert np.array_equal(outs3[TASK].to_host()[0], got)
 
     # margin-conditioned agreement from the oracle's own logits
     from oracle.grid import Georef, generate_patches, tile_plan
@@ -149,8 +156,23 @@ def test_class_prob_and_blend_modes(setup):
     s = canvas.sum(0)
     assert s.min().item() >= 0.999          # every pixel covered at least once
     assert labels.shape == (600, 700) and conf.max().item() <= s.max().item() + 1e-5
-    agree = (labels.cpu().numpy() == ref.argmax(0)).mean()
-    assert agree > 0.97
+    # oracle: intended inference.py:468-572 (float softmax accumulate, then argmax)
+    from oracle.convert import blend_accumulate
+    from oracle.grid import Georef, generate_patches, tile_plan as oplan
+    from oracle.pipeline import load_batch
+    from flair_for_aigle_b200.synthetic import DEFAULT_MEANS, DEFAULT_STDS
+    geo = Georef(L, T, RES, 700, 600)
+    plan = oplan(generate_patches(512, 100, RES, geo), geo, 512, 100)
+    canvas_ref = np.zeros((19, 600, 700), np.float32)
+    with torch.no_grad():
+        for i in range(plan.shape[0]):
+            b = load_batch(arr, plan, [i], 512, DEFAULT_MEANS, DEFAULT_STDS, TASK, 19)
+            lo = oracle({k: v.cuda() for k, v in b.items()})[0][TASK].cpu().numpy()
+            blend_accumulate(lo, plan[i:i + 1], 100, canvas_ref)
+    agree = (labels.cpu().numpy() == canvas_ref.argmax(0)).mean()
+    print(f"blend-mode class agreement with the oracle: {agree:.5f}")
+    assert agree >= 0.985
+    assert np.abs(canvas.cpu().numpy() - canvas_ref).mean() < 2e-3
 
 
 def test_strip_sharding_is_bit_exact(setup):

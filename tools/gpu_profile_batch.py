@@ -1,0 +1,60 @@
+"""Per-kernel timing table of one zonal batch (eager launches, CUDA events per launch).
+Writes gpurun_out/profile_batch.txt.  Diagnostic; numbers are warm-L2, back-to-back."""
+import os, sys, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from flair_for_aigle_b200 import native as nv
+from flair_for_aigle_b200.engine.convnext_unet import ConvNeXtCfg, ConvNeXtV2UNetEngine
+from flair_for_aigle_b200.engine.zonal import ZonalRunner
+from flair_for_aigle_b200.flair_hub.models.flair_model import FLAIR_HUB_Model
+from flair_for_aigle_b200.flair_zonal_detection.model_utils import prepare_model_config
+from flair_for_aigle_b200.synthetic import synthetic_raster, randomize_state_, DEFAULT_MEANS, DEFAULT_STDS
+
+B = int(os.environ.get("B", "16"))
+dev = torch.device("cuda:0")
+cfg = prepare_model_config(bench.zonal_config("w", "/tmp", "unused", B))
+m = FLAIR_HUB_Model(cfg, {"AERIAL_RGBI": 512}, max_batch=B)
+sd = m.state_dict(); randomize_state_(sd, 1)
+eng = ConvNeXtV2UNetEngine(sd, "encoders.AERIAL_RGBI.seg_model.model.", f"main_decoders.{bench.TASK}.seg_model.",
+                           ConvNeXtCfg(), dev, max_batch=B, norm_mean=DEFAULT_MEANS, norm_std=DEFAULT_STDS)
+r = torch.from_numpy(synthetic_raster(3000, 3000)).to(dev)
+plan = np.zeros((B, 6), np.int32)
+for i in range(B):
+    plan[i] = ((i // 4) * 384, (i % 4) * 384, (i // 4) * 384 + 64, (i % 4) * 384 + 64, 384, 384)
+own = np.stack([plan[:, 2], plan[:, 2] + 384, plan[:, 3], plan[:, 3] + 384], 1).astype(np.int32)
+out = torch.zeros((3000, 3000), dtype=torch.uint8, device=dev)
+run = ZonalRunner(eng, 64, use_graph=False)
+for _ in range(2):
+    run.run(r, plan, own, out)
+torch.cuda.synchronize()
+nv.PROFILE = []
+reps = 3
+for _ in range(reps):
+    run.run(r, plan, own, out)
+torch.cuda.synchronize()
+prof, nv.PROFILE = nv.PROFILE, None
+agg = collections.OrderedDict()
+for fam, meta, a, b in prof:
+    key = (fam, tuple(sorted(meta.items())))
+    t, c = agg.get(key, (0.0, 0))
+    agg[key] = (t + a.elapsed_time(b), c + 1)
+tot = sum(t for t, _ in agg.values()) / reps
+lines = [f"batch B={B}: total kernel time {tot:.3f} ms = {tot/B:.4f} ms/tile (eager, per-launch events)"]
+fam_tot = collections.Counter()
+for (fam, meta), (t, c) in agg.items():
+    fam_tot[fam] += t / reps
+    md = dict(meta)
+    extra = ""
+    if fam == "gemm_tcgen05":
+        extra = f" {2.0*md['M']*md['N']*md['K']/(t/c*1e-3)/1e12:7.1f} TFLOP/s"
+    if fam == "conv3x3_tcgen05":
+        fl = 2.0 * md['B'] * md['H'] * md['H'] * 9 * md['Cin'] * md['Cout']
+        extra = f" {fl/(t/c*1e-3)/1e12:7.1f} TFLOP/s"
+    lines.append(f"{fam:18s} x{c//reps:3d} avg {t/c*1e3:9.1f} us  sum/batch {t/reps:8.3f} ms {extra}  {md}")
+lines.append("--- by family (ms per batch, share)")
+for fam, t in fam_tot.most_common():
+    lines.append(f"{fam:18s} {t:8.3f} ms  {t/tot*100:5.1f}%")
+os.makedirs("gpurun_out", exist_ok=True)
+open("gpurun_out/profile_batch.txt", "w").write("\n".join(lines) + "\n")
+print("\n".join(lines))
