@@ -134,112 +134,128 @@ __global__ void __launch_bounds__(128) stem_ln_kernel(const void* __restrict__ i
 // ------------------------------------------------------------------------------------ dwconv7x7 + LN
 // x  : float [B][H][W][C] residual stream;  wdw: float [49][C];  bdw: float [C]
 // out: bf16  [B][H][W][C] = LayerNorm_C(dwconv7x7(x) + bdw) * ln_w + ln_b
-template <int TH, int TW, int SH, int SW>
-__global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ wdw,
-                                                        const float* __restrict__ bdw, const float* __restrict__ ln_w,
-                                                        const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
-                                                        int H, int W, int C, float eps) {
-  static_assert((TH / SH) * (TW / SW) == 8, "8 warps, one sub-tile each");
-  constexpr int HH = TH + 6, HW = TW + 6;
-  extern __shared__ float smem_f[];
-  float* sHalo = smem_f;                  // [HH][HW][32]
-  float* sStage = smem_f + HH * HW * 32;  // [TH*TW][C]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-  const int sy0 = (warp / (TW / SW)) * SH, sx0 = (warp % (TW / SW)) * SW;
+//
+// One CTA = one 4 x SW pixel tile, ALL channels: warp w owns channels [32w, 32w+32) (and, for
+// CPT = 2, the same range in the upper half of C), lane = channel, so every global access is a
+// coalesced 128 B row and no shared-memory staging of the input is needed.  Each thread keeps
+// the 4 x SW outputs of its channel(s) in registers and walks the (4+6) x (SW+6) input window
+// once (14 loads feed up to 224 FMAs).  LayerNorm statistics: a 31-shuffle transpose-reduce
+// gives per-pixel sums over the warp's channels, a tiny shared array combines the warps
+// (fixed order -> deterministic), two passes (mean, then centred variance) in fp32.
+template <int OFF>
+__device__ __forceinline__ void colsum32_step(float (&s)[32], int lane) {
+  const bool upper = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < OFF; ++i) {
+    const float a = s[i], b = s[i + OFF];
+    s[i] = (upper ? b : a) + __shfl_xor_sync(0xffffffffu, upper ? a : b, OFF);
+  }
+}
+// on return s[0] of lane l = sum over lanes of the input s[l]
+__device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
+  colsum32_step<16>(s, lane);
+  colsum32_step<8>(s, lane);
+  colsum32_step<4>(s, lane);
+  colsum32_step<2>(s, lane);
+  colsum32_step<1>(s, lane);
+}
+
+template <int NW, int CPT>
+__global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ wdw,
+                                                            const float* __restrict__ bdw,
+                                                            const float* __restrict__ ln_w,
+                                                            const float* __restrict__ ln_b,
+                                                            __nv_bfloat16* __restrict__ out, int H, int W, int C,
+                                                            float eps) {
+  constexpr int SH = 4;
+  constexpr int SW = 8 / CPT;      // 32 accumulators per thread either way
+  constexpr int NPX = SH * SW;     // pixels per tile (32 or 16)
+  __shared__ float red[NW][32];
+  __shared__ float s_stat[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * SW, y0 = blockIdx.y * SH, b = blockIdx.z;
   const float* xb = x + static_cast<size_t>(b) * H * W * C;
 
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    __syncthreads();  // previous chunk's reads of sHalo are done
-    for (int idx = tid; idx < HH * HW * 32; idx += 256) {
-      const int pix = idx >> 5;
-      const int gy = y0 - 3 + pix / HW, gx = x0 - 3 + pix % HW;
-      float v = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = xb[(static_cast<size_t>(gy) * W + gx) * C + c0 + (idx & 31)];
-      sHalo[idx] = v;
-    }
+  float acc[CPT][NPX];
+#pragma unroll
+  for (int cc = 0; cc < CPT; ++cc) {
+    const int c = cc * (C / CPT) + warp * 32 + lane;
     float wreg[49];
 #pragma unroll
-    for (int t = 0; t < 49; ++t) wreg[t] = wdw[t * C + c0 + lane];
-    const float bias = bdw[c0 + lane];
-    __syncthreads();
-
-    float acc[SH][SW];
+    for (int t = 0; t < 49; ++t) wreg[t] = wdw[t * C + c];
+    const float bias = bdw[c];
 #pragma unroll
-    for (int a = 0; a < SH; ++a)
-#pragma unroll
-      for (int c = 0; c < SW; ++c) acc[a][c] = bias;
+    for (int p = 0; p < NPX; ++p) acc[cc][p] = bias;
 #pragma unroll
     for (int iy = 0; iy < SH + 6; ++iy) {
+      const int gy = y0 - 3 + iy;
+      const bool row_ok = gy >= 0 && gy < H;
+      float in[SW + 6];
 #pragma unroll
       for (int ix = 0; ix < SW + 6; ++ix) {
-        const float v = sHalo[((sy0 + iy) * HW + sx0 + ix) * 32 + lane];
+        const int gx = x0 - 3 + ix;
+        in[ix] = (row_ok && gx >= 0 && gx < W) ? xb[(static_cast<size_t>(gy) * W + gx) * C + c] : 0.0f;
+      }
 #pragma unroll
-        for (int a = 0; a < SH; ++a) {
+      for (int oy = 0; oy < SH; ++oy) {
+        const int ky = iy - oy;
+        if (ky >= 0 && ky < 7) {
 #pragma unroll
-          for (int c = 0; c < SW; ++c) {
-            const int ky = iy - a, kx = ix - c;
-            if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) acc[a][c] = fmaf(v, wreg[ky * 7 + kx], acc[a][c]);
-          }
+          for (int ox = 0; ox < SW; ++ox)
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) acc[cc][oy * SW + ox] = fmaf(in[ox + kx], wreg[ky * 7 + kx], acc[cc][oy * SW + ox]);
         }
       }
     }
+  }
+
+  // ---- LayerNorm over C per pixel.  s[] layout: CPT == 1: s[p]; CPT == 2: s[cc*16 + p]
+  float s[32];
 #pragma unroll
-    for (int a = 0; a < SH; ++a)
+  for (int cc = 0; cc < CPT; ++cc)
 #pragma unroll
-      for (int c = 0; c < SW; ++c) sStage[((sy0 + a) * TW + sx0 + c) * C + c0 + lane] = acc[a][c];
+    for (int p = 0; p < NPX; ++p) s[cc * NPX + p] = acc[cc][p];
+  warp_colsum32(s, lane);
+  float part = s[0];
+  if (CPT == 2) part += __shfl_xor_sync(0xffffffffu, part, 16);   // lane l and l^16 hold the two channel halves
+  red[warp][lane] = part;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) t += red[w2][lane];
+    s_stat[lane] = t / C;                                           // mean of pixel (lane % NPX)
   }
   __syncthreads();
-
-  // LayerNorm over channels, one warp per pixel
-  for (int p = warp; p < TH * TW; p += 8) {
-    const int gy = y0 + p / TW, gx = x0 + p % TW;
-    if (gy >= H || gx >= W) continue;
-    const float* row = sStage + p * C;
-    __nv_bfloat16* o = out + ((static_cast<size_t>(b) * H + gy) * W + gx) * C;
-    if ((C & 127) == 0) {
-      const int nj = C >> 7;
-      float4 v[8];
-      float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nj) {
-          v[j] = *reinterpret_cast<const float4*>(row + j * 128 + lane * 4);
-          s += v[j].x + v[j].y + v[j].z + v[j].w;
-        }
-      const float mean = warp_sum(s) / C;
-      float q = 0.f;
+  for (int cc = 0; cc < CPT; ++cc)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nj) {
-          v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
-          q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
-        }
-      const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    for (int p = 0; p < NPX; ++p) {
+      acc[cc][p] -= s_stat[p];
+      s[cc * NPX + p] = acc[cc][p] * acc[cc][p];
+    }
+  warp_colsum32(s, lane);
+  part = s[0];
+  if (CPT == 2) part += __shfl_xor_sync(0xffffffffu, part, 16);
+  __syncthreads();                                                  // everyone has read the means
+  red[warp][lane] = part;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nj) {
-          const int c = j * 128 + lane * 4;
-          const float4 g = *reinterpret_cast<const float4*>(ln_w + c);
-          const float4 be = *reinterpret_cast<const float4*>(ln_b + c);
-          __nv_bfloat162 lo = __floats2bfloat162_rn(v[j].x * rstd * g.x + be.x, v[j].y * rstd * g.y + be.y);
-          __nv_bfloat162 hi = __floats2bfloat162_rn(v[j].z * rstd * g.z + be.z, v[j].w * rstd * g.w + be.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(o + c) = pk;
-        }
-    } else {
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) s += row[c];
-      const float mean = warp_sum(s) / C;
-      float q = 0.f;
-      for (int c = lane; c < C; c += 32) {
-        const float d = row[c] - mean;
-        q = fmaf(d, d, q);
-      }
-      const float rstd = rsqrtf(warp_sum(q) / C + eps);
-      for (int c = lane; c < C; c += 32) o[c] = __float2bfloat16_rn((row[c] - mean) * rstd * ln_w[c] + ln_b[c]);
+    for (int w2 = 0; w2 < NW; ++w2) t += red[w2][lane];
+    s_stat[lane] = rsqrtf(t / C + eps);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cc = 0; cc < CPT; ++cc) {
+    const int c = cc * (C / CPT) + warp * 32 + lane;
+    const float g = ln_w[c], be = ln_b[c];
+#pragma unroll
+    for (int p = 0; p < NPX; ++p) {
+      const int gy = y0 + p / SW, gx = x0 + p % SW;
+      if (gy < H && gx < W)
+        out[((static_cast<size_t>(b) * H + gy) * W + gx) * C + c] = __float2bfloat16_rn(acc[cc][p] * s_stat[p] * g + be);
     }
   }
 }
@@ -450,19 +466,12 @@ extern "C" int fz_stem_ln_f32(const float* x_nchw, int Cin, const float* w, cons
 }
 
 namespace fz {
-template <int TH, int TW, int SH, int SW>
+template <int NW, int CPT>
 static int launch_dwconv(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
                          __nv_bfloat16* out, int B, int H, int W, int C, float eps, cudaStream_t st) {
-  const size_t smem = (static_cast<size_t>(TH + 6) * (TW + 6) * 32 + static_cast<size_t>(TH) * TW * C) * sizeof(float);
-  FZ_REQUIRE(smem <= 227 * 1024, "fz_dwconv7_ln: C=%d needs %zu B of shared memory", C, smem);
-  auto kern = dwconv_ln_kernel<TH, TW, SH, SW>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    FZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
-  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);
-  kern<<<grid, 256, smem, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, C, eps);
+  constexpr int SW = 8 / CPT;
+  dim3 grid((W + SW - 1) / SW, (H + 3) / 4, B);
+  dwconv_ln_kernel<NW, CPT><<<grid, NW * 32, 0, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, C, eps);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -471,15 +480,22 @@ static int launch_dwconv(const float* x, const float* wdw, const float* bdw, con
 extern "C" int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
                              void* out_bf16, int B, int H, int W, int C, float eps, void* stream) {
   using namespace fz;
-  FZ_REQUIRE(C % 32 == 0 && C > 0, "fz_dwconv7_ln: C=%d must be a multiple of 32", C);
   if (B <= 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  // pixels per CTA ~ 16384 / C so the fp32 staging tile stays ~64 KB
-  if (C <= 128) return launch_dwconv<8, 16, 4, 4>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-  if (C <= 256) return launch_dwconv<8, 8, 2, 4>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-  if (C <= 512) return launch_dwconv<4, 8, 2, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-  return launch_dwconv<4, 4, 1, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+  switch (C) {   // one warp per 32 channels; above 512 channels each thread carries two
+    case 64: return launch_dwconv<2, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 96: return launch_dwconv<3, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 128: return launch_dwconv<4, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 192: return launch_dwconv<6, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 256: return launch_dwconv<8, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 384: return launch_dwconv<12, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 512: return launch_dwconv<16, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 768: return launch_dwconv<12, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 1024: return launch_dwconv<16, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+  }
+  set_error("fz_dwconv7_ln: C=%d has no instantiation (64,96,128,192,256,384,512,768,1024)", C);
+  return -1;
 }
 
 extern "C" int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, int B, int H, int W,
