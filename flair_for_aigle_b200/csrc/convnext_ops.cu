@@ -160,13 +160,13 @@ __device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
   colsum32_step<1>(s, lane);
 }
 
-template <int NW, int CPT>
+template <int NW, int CPT, int C>
 __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ wdw,
                                                             const float* __restrict__ bdw,
                                                             const float* __restrict__ ln_w,
                                                             const float* __restrict__ ln_b,
-                                                            __nv_bfloat16* __restrict__ out, int H, int W, int C,
-                                                            float eps) {
+                                                            __nv_bfloat16* __restrict__ out, int H, int W, float eps) {
+  static_assert(NW * 32 * CPT == C, "one lane per channel (two for CPT = 2)");
   constexpr int SH = 4;
   constexpr int SW = 8 / CPT;      // 32 accumulators per thread either way
   constexpr int NPX = SH * SW;     // pixels per tile (32 or 16)
@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * SW, y0 = blockIdx.y * SH, b = blockIdx.z;
   const float* xb = x + static_cast<size_t>(b) * H * W * C;
+  // CTA-uniform edge flags: out-of-image taps are zero (conv padding); no per-load predicate math
+  const bool left_edge = x0 < 3, right_edge = x0 + SW + 3 > W;
 
   float acc[CPT][NPX];
 #pragma unroll
@@ -189,21 +191,24 @@ __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restr
 #pragma unroll
     for (int iy = 0; iy < SH + 6; ++iy) {
       const int gy = y0 - 3 + iy;
-      const bool row_ok = gy >= 0 && gy < H;
+      if (gy < 0 || gy >= H) continue;                       // CTA-uniform
+      // C is a compile-time constant: every tap below is [row + immediate]
+      const float* row = xb + (static_cast<ptrdiff_t>(gy) * W + (x0 - 3)) * C + c;
       float in[SW + 6];
 #pragma unroll
       for (int ix = 0; ix < SW + 6; ++ix) {
-        const int gx = x0 - 3 + ix;
-        in[ix] = (row_ok && gx >= 0 && gx < W) ? xb[(static_cast<size_t>(gy) * W + gx) * C + c] : 0.0f;
+        if (ix < 3) in[ix] = (left_edge && x0 - 3 + ix < 0) ? 0.0f : row[ix * C];
+        else if (ix >= SW + 3) in[ix] = (right_edge && x0 - 3 + ix >= W) ? 0.0f : row[ix * C];
+        else in[ix] = row[ix * C];
       }
 #pragma unroll
       for (int oy = 0; oy < SH; ++oy) {
         const int ky = iy - oy;
         if (ky >= 0 && ky < 7) {
 #pragma unroll
-          for (int ox = 0; ox < SW; ++ox)
+          for (int kx = 0; kx < 7; ++kx)
 #pragma unroll
-            for (int kx = 0; kx < 7; ++kx) acc[cc][oy * SW + ox] = fmaf(in[ox + kx], wreg[ky * 7 + kx], acc[cc][oy * SW + ox]);
+            for (int ox = 0; ox < SW; ++ox) acc[cc][oy * SW + ox] = fmaf(in[ox + kx], wreg[ky * 7 + kx], acc[cc][oy * SW + ox]);
         }
       }
     }
@@ -254,8 +259,7 @@ __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restr
 #pragma unroll
     for (int p = 0; p < NPX; ++p) {
       const int gy = y0 + p / SW, gx = x0 + p % SW;
-      if (gy < H && gx < W)
-        out[((static_cast<size_t>(b) * H + gy) * W + gx) * C + c] = __float2bfloat16_rn(acc[cc][p] * s_stat[p] * g + be);
+      out[((static_cast<size_t>(b) * H + gy) * W + gx) * C + c] = __float2bfloat16_rn(acc[cc][p] * s_stat[p] * g + be);
     }
   }
 }
@@ -301,36 +305,39 @@ __global__ void __launch_bounds__(256) ln2d_s2d_kernel(const float* __restrict__
 
 // ------------------------------------------------------------------------------------ GRN
 // scale[b][k] = 1 + gamma[k] * Gx / (mean_k Gx + eps), Gx = sqrt(sum_t partial[b*tps + t][k]) where the
-// partials are the fc1 epilogue's per-row-tile sums of squares (fixed summation order: the result
-// does not depend on how tiles are batched).  timm GlobalResponseNorm; the beta term is folded
-// into fc2's bias on the host.
-__global__ void __launch_bounds__(256) grn_scale_kernel(const float* __restrict__ partial, int tps,
-                                                        const float* __restrict__ gamma, float* __restrict__ scale,
-                                                        int K, float eps) {
-  extern __shared__ float s_gx[];  // [K]
-  __shared__ float red[8];
-  __shared__ float s_mean;
-  const int b = blockIdx.x;
-  const float* base = partial + static_cast<size_t>(b) * tps * K;
-  float s = 0.f;
-  for (int k = threadIdx.x; k < K; k += 256) {
-    float acc = 0.f;
-    for (int t = 0; t < tps; ++t) acc += base[static_cast<size_t>(t) * K + k];
-    const float g = sqrtf(acc);
-    s_gx[k] = g;
-    s += g;
-  }
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+// partials are the fc1 epilogue's per-row-tile sums of squares.  Two small grid-parallel kernels, every
+// sum in a fixed order (the result does not depend on how tiles are batched, no atomics).  timm
+// GlobalResponseNorm; the beta term is folded into fc2's bias on the host.
+//   pass 1: grid (K/64, B), 256 threads = 64 channels x 4 row-tile groups -> Gx into scale[], block sum into psum
+//   pass 2: grid (ceil(K/256), B): mean from the K/64 block sums, scale in place
+__global__ void __launch_bounds__(256) grn_gx_kernel(const float* __restrict__ partial, int tps,
+                                                     float* __restrict__ gx_out, float* __restrict__ psum, int K) {
+  __shared__ float sm[4][64];
+  const int b = blockIdx.y, kk = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int k = blockIdx.x * 64 + kk;
+  const float* base = partial + static_cast<size_t>(b) * tps * K + k;
+  float acc = 0.f;
+  for (int t = g; t < tps; t += 4) acc += base[static_cast<size_t>(t) * K];
+  sm[g][kk] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    s_mean = t / K;
+  if (g == 0) {
+    const float gx = sqrtf((sm[0][kk] + sm[1][kk]) + (sm[2][kk] + sm[3][kk]));
+    gx_out[static_cast<size_t>(b) * K + k] = gx;
+    float s = warp_sum(gx);                       // shuffle tree: fixed order
+    if ((kk & 31) == 0) sm[0][kk >> 5] = s;
   }
   __syncthreads();
-  const float inv = 1.0f / (s_mean + eps);
-  for (int k = threadIdx.x; k < K; k += 256) scale[static_cast<size_t>(b) * K + k] = 1.0f + gamma[k] * s_gx[k] * inv;
+  if (threadIdx.x == 0) psum[b * gridDim.x + blockIdx.x] = sm[0][0] + sm[0][1];
+}
+
+__global__ void __launch_bounds__(256) grn_apply_kernel(float* __restrict__ scale, const float* __restrict__ psum,
+                                                        int nblk, const float* __restrict__ gamma, int K, float eps) {
+  const int b = blockIdx.y;
+  float tot = 0.f;
+  for (int i = 0; i < nblk; ++i) tot += psum[b * nblk + i];     // <= 64 values, same order in every thread
+  const float inv = 1.0f / (tot / K + eps);
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k < K) scale[static_cast<size_t>(b) * K + k] = 1.0f + gamma[k] * scale[static_cast<size_t>(b) * K + k] * inv;
 }
 
 // out[b][n][k] = bf16(w[n][k] * scale[b][k])   (8 elements per thread)
@@ -466,12 +473,13 @@ extern "C" int fz_stem_ln_f32(const float* x_nchw, int Cin, const float* w, cons
 }
 
 namespace fz {
-template <int NW, int CPT>
+template <int NW, int CPT, int C>
 static int launch_dwconv(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
-                         __nv_bfloat16* out, int B, int H, int W, int C, float eps, cudaStream_t st) {
+                         __nv_bfloat16* out, int B, int H, int W, float eps, cudaStream_t st) {
   constexpr int SW = 8 / CPT;
-  dim3 grid((W + SW - 1) / SW, (H + 3) / 4, B);
-  dwconv_ln_kernel<NW, CPT><<<grid, NW * 32, 0, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, C, eps);
+  FZ_REQUIRE(H % 4 == 0 && W % SW == 0, "fz_dwconv7_ln: H=%d W=%d must be multiples of 4 x %d", H, W, SW);
+  dim3 grid(W / SW, H / 4, B);
+  dwconv_ln_kernel<NW, CPT, C><<<grid, NW * 32, 0, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, eps);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -484,15 +492,15 @@ extern "C" int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   switch (C) {   // one warp per 32 channels; above 512 channels each thread carries two
-    case 64: return launch_dwconv<2, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-    case 96: return launch_dwconv<3, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-    case 128: return launch_dwconv<4, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-    case 192: return launch_dwconv<6, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-    case 256: return launch_dwconv<8, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-    case 384: return launch_dwconv<12, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-    case 512: return launch_dwconv<16, 1>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-    case 768: return launch_dwconv<12, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
-    case 1024: return launch_dwconv<16, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, C, eps, st);
+    case 64: return launch_dwconv<2, 1, 64>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+    case 96: return launch_dwconv<3, 1, 96>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+    case 128: return launch_dwconv<4, 1, 128>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+    case 192: return launch_dwconv<6, 1, 192>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+    case 256: return launch_dwconv<8, 1, 256>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+    case 384: return launch_dwconv<12, 1, 384>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+    case 512: return launch_dwconv<16, 1, 512>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+    case 768: return launch_dwconv<12, 2, 768>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+    case 1024: return launch_dwconv<16, 2, 1024>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
   }
   set_error("fz_dwconv7_ln: C=%d has no instantiation (64,96,128,192,256,384,512,768,1024)", C);
   return -1;
@@ -510,13 +518,16 @@ extern "C" int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b,
   return 0;
 }
 
-extern "C" int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale, int B,
-                            int K, float eps, void* stream) {
+extern "C" int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale,
+                            float* scratch, int B, int K, float eps, void* stream) {
   using namespace fz;
-  FZ_REQUIRE(tiles_per_sample >= 1 && K >= 1 && K <= 12288, "fz_grn_scale: bad arguments tps=%d K=%d", tiles_per_sample, K);
+  FZ_REQUIRE(tiles_per_sample >= 1 && K >= 64 && K % 64 == 0, "fz_grn_scale: bad arguments tps=%d K=%d (K %% 64)",
+             tiles_per_sample, K);
+  FZ_REQUIRE(scratch != nullptr, "fz_grn_scale: scratch (B*K/64 floats) required");
   if (B <= 0) return 0;
-  grn_scale_kernel<<<B, 256, K * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(sumsq_partial, tiles_per_sample,
-                                                                                          gamma, scale, K, eps);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  grn_gx_kernel<<<dim3(K / 64, B), 256, 0, st>>>(sumsq_partial, tiles_per_sample, scale, scratch, K);
+  grn_apply_kernel<<<dim3((K + 255) / 256, B), 256, 0, st>>>(scale, scratch, K / 64, gamma, K, eps);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -5,76 +5,88 @@
 // Replaces the cuBLAS/cuDNN fp32 calls under flair_hub/models/flair_model.py:376 (timm
 // ConvNeXtBlock mlp.fc1 / mlp.fc2, stage downsample conv2x2) and :539-541 (FusionHandler 1x1).
 //
-// One CTA = one 128 x BN output tile.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer
-// (+ TMEM allocator), warps 2..5 epilogue (TMEM lanes 32*(warp%4)..).  3-stage smem ring,
-// two CTAs co-resident per SM so one CTA's epilogue overlaps the other's main loop.
+// Persistent kernel, one CTA per SM, static tile schedule (tile = blockIdx.x + i*gridDim.x,
+// n fastest so CTAs running together share the A rows in L2).  A CTA tile is 256 x BN: two
+// M=128 UMMA accumulators that share one B tile, which raises the operand intensity to
+// 256*BN*64*2 / ((256+BN)*128) flop per smem byte (87 at BN=128, 131 at BN=256) -- the 128x128
+// tile of the first version measured exactly its L2->SM bandwidth bound (64 flop/B * 8.6 TB/s).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 4..11 epilogue
+// (warps 4-7 rows 0..127, warps 8-11 rows 128..255; TMEM lane quarter = warp % 4).
+// smem ring of STAGES k-blocks runs continuously across tiles; with BN=128 the accumulators
+// are double buffered in TMEM (2 x 256 columns) so tile i's epilogue overlaps tile i+1's MMAs.
 #include "common.h"
 #include "ptx.cuh"
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
 
-constexpr int BM = 128;
+constexpr int BM = 256;              // rows per CTA tile (two UMMA M=128 halves)
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
 
 struct GemmParams {
   int M, N, K;
-  int rows_per_sample;  // rows of A per sample (H*W); selects the B batch and the sumsq row
+  int rows_per_sample;  // rows of A per sample (H*W); selects the B batch
   int b_batched;        // 1: B is [num_samples][N][K] and the tile uses batch m0 / rows_per_sample
   const float* bias;    // [N] or nullptr
   void* out;            // [M,N] bf16 or f32
   const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
-  float* sumsq;         // [ceil(M/128), N] f32 per-row-tile partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
+  float* sumsq;         // [ceil(M/128), N] f32 per-128-row partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
 };
 
 template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
-  static constexpr int OFF_BIAS = OFF_B + STAGES * B_STAGE_BYTES;
-  static constexpr int OFF_SQ = OFF_BIAS + BN * 4;
-  static constexpr int OFF_BAR = OFF_SQ + 4 * BN * 4;  // one sumsq row per epilogue warp
-  static constexpr int OFF_TSLOT = OFF_BAR + (2 * STAGES + 1) * 8;
-  static constexpr int BYTES = OFF_TSLOT + 16 + 1024;  // + worst-case alignment pad
+  static constexpr int OFF_SQ = OFF_B + STAGES * B_STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_SQ + 8 * BN * 4;           // one sumsq row per epilogue warp
+  static constexpr int OFF_TSLOT = OFF_BAR + (2 * STAGES + 4) * 8;
+  static constexpr int BYTES = OFF_TSLOT + 16 + 1024;            // + worst-case alignment pad
 };
 
+template <int OFF>
+__device__ __forceinline__ void colsum32_step(float (&s)[32], int lane) {
+  const bool upper = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < OFF; ++i) {
+    const float a = s[i], b = s[i + OFF];
+    s[i] = (upper ? b : a) + __shfl_xor_sync(0xffffffffu, upper ? a : b, OFF);
+  }
+}
 // Column sums over the 32 lanes of a warp of a 32-vector held per lane (transpose-reduce):
 // on return s[0] of lane l is the sum over lanes of the input s[l].  31 shuffles.
 __device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float a = s[i], b = s[i + off];
-      const float send = upper ? a : b;
-      const float keep = upper ? b : a;
-      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
+  colsum32_step<16>(s, lane);
+  colsum32_step<8>(s, lane);
+  colsum32_step<4>(s, lane);
+  colsum32_step<2>(s, lane);
+  colsum32_step<1>(s, lane);
 }
 
-template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(192, 2)
+template <int BN, int STAGES, int ACC_STAGES, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using L = GemmSmem<BN, STAGES>;
+  static_assert(ACC_STAGES * 2 * BN <= 512, "TMEM has 512 columns");
+  constexpr int TCOLS = 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + L::OFF_B;
-  float* sBias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
   float* sSq = reinterpret_cast<float*>(smem + L::OFF_SQ);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* tfull = empty + STAGES;     // [2]
+  uint64_t* tempty = tfull + 2;         // [2]
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + L::OFF_TSLOT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = p.N / BN;
-  const int n0 = (blockIdx.x % n_tiles) * BN;
-  const int m0 = (blockIdx.x / n_tiles) * BM;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int total_tiles = n_tiles * m_tiles;
   const int num_kb = p.K / BK;
 
   if (warp == 0 && lane == 0) {
@@ -84,15 +96,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 8);        // one arrive per epilogue warp
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tslot, BN);
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
-      sBias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
-    }
-  }
+  if (warp == 1) tmem_alloc(tslot, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -100,134 +110,178 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      const int bcoord = p.b_batched ? (m0 / p.rows_per_sample) : 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
-        tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
-        tma_load_3d(&tmB, &full[s], sB + s * L::B_STAGE_BYTES, kb * BK, n0, bcoord);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t % n_tiles) * BN;
+        const int m0 = (t / n_tiles) * BM;
+        const int bcoord = p.b_batched ? (m0 / p.rows_per_sample) : 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
+          tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
+          tma_load_3d(&tmB, &full[s], sB + s * L::B_STAGE_BYTES, kb * BK, n0, bcoord);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const uint32_t as = lt % ACC_STAGES;
+        const uint32_t aph = (lt / ACC_STAGES) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);           // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint64_t ad = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES), 128);
-        const uint64_t bd = umma_smem_desc(smem_u32(sB + s * L::B_STAGE_BYTES), 128);
+        const uint32_t acc0 = tmem + as * (2 * BN);
+        const uint32_t acc1 = acc0 + BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t ad0 = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES), 128);
+          const uint64_t ad1 = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES + 128 * BK * 2), 128);
+          const uint64_t bd = umma_smem_desc(smem_u32(sB + s * L::B_STAGE_BYTES), 128);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // +32 bytes (16 bf16) along K inside the 128B swizzle atom = +2 in the >>4 address field
-          umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes (16 bf16) along K inside the 128B swizzle atom = +2 in the >>4 address field
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            umma_bf16(acc0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
+            umma_bf16(acc1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
+          }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&tfull[as]);
       }
-      umma_commit(tfull);
     }
     __syncwarp();
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < p.M;
-    mbar_wait(tfull, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      float v[32];
+  } else if (warp >= EPI_WARP0) {
+    const int ew = warp - EPI_WARP0;            // 0..7
+    const int half = ew >> 2;                   // which M=128 accumulator
+    const int q = warp & 3;                     // TMEM lane quarter this warp may read
+    const int row = half * 128 + q * 32 + lane;
+    const int bar_id = 1 + half;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int n0 = (t % n_tiles) * BN;
+      const int m0 = (t / n_tiles) * BM;
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+      const uint32_t as = lt % ACC_STAGES;
+      const uint32_t aph = (lt / ACC_STAGES) & 1;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + as * (2 * BN) + half * BN;
+      uint32_t r[2][32];
+      tmem_ld32(tbase, r[0]);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(&sBias[c * 32 + j]);
-        v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
-        v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-        v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-      }
-      const size_t off = static_cast<size_t>(m) * p.N + n0 + c * 32;
-      if (MODE == FZ_EPI_GELU_SUMSQ) {
-        float s[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < BN / 32) tmem_ld32(tbase + (c + 1) * 32, r[(c + 1) & 1]);   // overlaps the math below
+        float v[32];
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = gelu_erf_fast(v[j]);
-          s[j] = row_ok ? v[j] * v[j] : 0.0f;
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = p.bias ? __ldg(bp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * j + 0] = __uint_as_float(r[c & 1][4 * j + 0]) + b4.x;
+          v[4 * j + 1] = __uint_as_float(r[c & 1][4 * j + 1]) + b4.y;
+          v[4 * j + 2] = __uint_as_float(r[c & 1][4 * j + 2]) + b4.z;
+          v[4 * j + 3] = __uint_as_float(r[c & 1][4 * j + 3]) + b4.w;
         }
-        warp_colsum32(s, lane);
-        sSq[q * BN + c * 32 + lane] = s[0];
-      } else if (MODE == FZ_EPI_RELU_BF16) {
+        const size_t off = static_cast<size_t>(m) * p.N + n0 + c * 32;
+        if (MODE == FZ_EPI_GELU_SUMSQ) {
+          float s[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-      } else if (MODE == FZ_EPI_RESID_F32) {
+          for (int j = 0; j < 32; ++j) {
+            v[j] = gelu_erf_fast(v[j]);
+            s[j] = row_ok ? v[j] * v[j] : 0.0f;
+          }
+          warp_colsum32(s, lane);
+          sSq[ew * BN + c * 32 + lane] = s[0];
+        } else if (MODE == FZ_EPI_RELU_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (MODE == FZ_EPI_RESID_F32) {
+          if (row_ok) {
+            const float4* rp = reinterpret_cast<const float4*>(p.resid + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = rp[j];
+              v[4 * j + 0] += x.x;
+              v[4 * j + 1] += x.y;
+              v[4 * j + 2] += x.z;
+              v[4 * j + 3] += x.w;
+            }
+          }
+        }
         if (row_ok) {
-          const float4* rp = reinterpret_cast<const float4*>(p.resid + off);
+          if (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x = rp[j];
-            v[4 * j + 0] += x.x;
-            v[4 * j + 1] += x.y;
-            v[4 * j + 2] += x.z;
-            v[4 * j + 3] += x.w;
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
           }
         }
       }
-      if (row_ok) {
-        if (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32) {
-          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        }
+      // all TMEM reads of this stage are complete (last tmem_ld_wait above): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (MODE == FZ_EPI_GELU_SUMSQ) {
+        // deterministic: fixed-order sum of the half's four warps, one plain store per column
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const float* sq = sSq + half * 4 * BN;
+        if (m0 + half * 128 < p.M)
+          for (int i = q * 32 + lane; i < BN; i += 128)
+            p.sumsq[static_cast<size_t>(m0 / 128 + half) * p.N + n0 + i] =
+                (sq[i] + sq[BN + i]) + (sq[2 * BN + i] + sq[3 * BN + i]);
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
-    }
-    if (MODE == FZ_EPI_GELU_SUMSQ) {
-      // deterministic: fixed-order sum of the four warps' column sums, one plain store per column
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < BN; i += 128)
-        p.sumsq[static_cast<size_t>(m0 / BM) * p.N + n0 + i] =
-            (sSq[i] + sSq[BN + i]) + (sSq[2 * BN + i] + sSq[3 * BN + i]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, BN);
+  if (warp == 1) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int BN, int STAGES, int MODE>
+template <int BN, int STAGES, int ACC_STAGES, int MODE>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_bf16_kernel<BN, STAGES, MODE>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE>;
   static bool configured = false;
+  static int sm_count = 0;
   if (!configured) {
     FZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    int dev = 0;
+    FZ_CHECK_CUDA(cudaGetDevice(&dev));
+    FZ_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
-  const int grid = ((p.M + BM - 1) / BM) * (p.N / BN);
-  kern<<<grid, 192, L::BYTES, stream>>>(tmA, tmB, p);
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int grid = tiles < sm_count ? tiles : sm_count;
+  kern<<<grid, GEMM_THREADS, L::BYTES, stream>>>(tmA, tmB, p);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int BN>
+// BN = 128: 4 smem stages (48 KB each), accumulators double buffered.
+// BN = 256: 3 smem stages (64 KB each), single accumulator stage (light epilogue, long K).
+template <int BN, int STAGES, int ACC_STAGES>
 static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
   switch (mode) {
-    case FZ_EPI_BF16: return launch_gemm<BN, 3, FZ_EPI_BF16>(a, b, p, st);
-    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, 3, FZ_EPI_GELU_SUMSQ>(a, b, p, st);
-    case FZ_EPI_RESID_F32: return launch_gemm<BN, 3, FZ_EPI_RESID_F32>(a, b, p, st);
-    case FZ_EPI_F32: return launch_gemm<BN, 3, FZ_EPI_F32>(a, b, p, st);
-    case FZ_EPI_RELU_BF16: return launch_gemm<BN, 3, FZ_EPI_RELU_BF16>(a, b, p, st);
+    case FZ_EPI_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_BF16>(a, b, p, st);
+    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_SUMSQ>(a, b, p, st);
+    case FZ_EPI_RESID_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RESID_F32>(a, b, p, st);
+    case FZ_EPI_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_F32>(a, b, p, st);
+    case FZ_EPI_RELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RELU_BF16>(a, b, p, st);
   }
   set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
   return -1;
@@ -248,7 +302,15 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
                "fz_gemm_bf16: rows_per_sample=%d must be a positive multiple of %d", rows_per_sample, BM);
   FZ_REQUIRE(mode != FZ_EPI_GELU_SUMSQ || sumsq != nullptr, "fz_gemm_bf16: sumsq buffer required");
   FZ_REQUIRE(mode != FZ_EPI_RESID_F32 || resid != nullptr, "fz_gemm_bf16: residual buffer required");
-  const int BN = (N % 128 == 0) ? 128 : 64;
+  // tile width: 256 for the long-K / light-epilogue GEMMs when it still leaves enough tiles,
+  // 128 (double-buffered accumulators) otherwise, 64 for narrow outputs
+  int BN = (N % 128 == 0) ? 128 : 64;
+  const char* force = getenv("FZ_GEMM_BN");
+  if (force) BN = atoi(force);
+  else if (N % 256 == 0 && mode != FZ_EPI_GELU_SUMSQ && K >= 1024 &&
+           static_cast<long long>((M + BM - 1) / BM) * (N / 256) >= 128)
+    BN = 256;
+  FZ_REQUIRE((BN == 64 || BN == 128 || BN == 256) && N % BN == 0, "fz_gemm_bf16: bad tile width %d for N=%d", BN, N);
 
   CUtensorMap tmA, tmB;
   {
@@ -271,7 +333,9 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return BN == 128 ? dispatch_mode<128>(mode, tmA, tmB, p, st) : dispatch_mode<64>(mode, tmA, tmB, p, st);
+  if (BN == 256) return dispatch_mode<256, 3, 1>(mode, tmA, tmB, p, st);
+  if (BN == 128) return dispatch_mode<128, 4, 2>(mode, tmA, tmB, p, st);
+  return dispatch_mode<64, 4, 2>(mode, tmA, tmB, p, st);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -163,6 +163,7 @@ class ConvNeXtV2UNetEngine:
         # fc1 epilogue partials: one row of 4C sums per 128-row tile
         self.sumsq = torch.zeros(B * max((h * h // 128) * 4 * c for h, c in zip(hw, cfg.dims)), dtype=f32, device=dev)
         self.scale = torch.empty(B * kmax, dtype=f32, device=dev)
+        self.grn_scratch = torch.empty(B * kmax // 64, dtype=f32, device=dev)
         # per-sample GRN-scaled fc2 weights where that is cheaper than scaling the hidden rows
         self.use_wscale = [h * h > c for h, c in zip(hw, cfg.dims)]
         wmax = max([4 * c * c for c, u in zip(cfg.dims, self.use_wscale) if u] + [0])
@@ -203,7 +204,7 @@ class ConvNeXtV2UNetEngine:
                 nv.dwconv7_ln(x, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], y)
                 self._gemm(y.view(M, C), blk["fc1_w"], nv.EPI_GELU_SUMSQ, bias=blk["fc1_b"], sumsq=sumsq, out=hbuf,
                            rows_per_sample=rps)
-                nv.grn_scale(sumsq, tps, blk["grn_g"], scale)
+                nv.grn_scale(sumsq, tps, blk["grn_g"], scale, scratch=self.grn_scratch)
                 if self.use_wscale[i]:
                     w2s = self.w2s[:n * 4 * C * C].view(n, C, 4 * C)
                     nv.scale_weights(blk["fc2_w"], scale, w2s)

@@ -70,7 +70,7 @@ _SIGNATURES = {
     "fz_stem_ln_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_dwconv7_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
     "fz_ln2d_s2d": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
-    "fz_grn_scale": [_vp, _i, _vp, _vp, _i, _i, ctypes.c_float, _vp],
+    "fz_grn_scale": [_vp, _i, _vp, _vp, _vp, _i, _i, ctypes.c_float, _vp],
     "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
     "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
@@ -253,12 +253,14 @@ def ln2d_s2d(x, ln_w, ln_b, out, eps=1e-6):
     return out
 
 
-def grn_scale(partial, tiles_per_sample, gamma, scale, eps=1e-6):
-    """partial: f32 [B*tiles_per_sample, K] (fc1 epilogue); scale: f32 [B, K]."""
+def grn_scale(partial, tiles_per_sample, gamma, scale, eps=1e-6, scratch=None):
+    """partial: f32 [B*tiles_per_sample, K] (fc1 epilogue); scale: f32 [B, K]; scratch: f32 [B*K/64]."""
     B, K = scale.shape
+    if scratch is None:
+        scratch = torch.empty(B * K // 64, dtype=torch.float32, device=scale.device)
     with _Timed('grn_scale', B=B, K=K):
-        _check(lib().fz_grn_scale(_ptr(partial), tiles_per_sample, _ptr(gamma), _ptr(scale), B, K, eps, _stream()),
-               "fz_grn_scale")
+        _check(lib().fz_grn_scale(_ptr(partial), tiles_per_sample, _ptr(gamma), _ptr(scale), _ptr(scratch), B, K, eps,
+                                  _stream()), "fz_grn_scale")
     return scale
 
 

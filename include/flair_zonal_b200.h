@@ -124,8 +124,8 @@ int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw, const floa
                   void* out_bf16, int B, int H, int W, int C, float eps, void* stream);
 int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, int B, int H, int W, int C,
                 float eps, void* stream);
-int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale, int B, int K,
-                 float eps, void* stream);
+int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale, float* scratch,
+                 int B, int K, float eps, void* stream); /* scratch: B*K/64 floats */
 int fz_scale_weights(const void* w_bf16, const float* scale, void* out_bf16, int B, int N, int K, void* stream);
 int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K, int rows_per_sample, void* stream);
 
