@@ -10,8 +10,9 @@
 // M=128 UMMA accumulators that share one B tile, which raises the operand intensity to
 // 256*BN*64*2 / ((256+BN)*128) flop per smem byte (87 at BN=128, 131 at BN=256) -- the 128x128
 // tile of the first version measured exactly its L2->SM bandwidth bound (64 flop/B * 8.6 TB/s).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 4..11 epilogue
-// (warps 4-7 rows 0..127, warps 8-11 rows 128..255; TMEM lane quarter = warp % 4).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 4..19 epilogue:
+// 16 warps = 2 row halves x 4 TMEM lane quarters (= warp % 4) x 2 interleaved column groups, i.e.
+// four epilogue warps per SM sub-partition to hide the TMEM-load / SFU / global latencies.
 // smem ring of STAGES k-blocks runs continuously across tiles; with BN=128 the accumulators
 // are double buffered in TMEM (2 x 256 columns) so tile i's epilogue overlaps tile i+1's MMAs.
 #include "common.h"
@@ -23,7 +24,7 @@ namespace fz {
 constexpr int BM = 256;              // rows per CTA tile (two UMMA M=128 halves)
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_THREADS = 640;   // 4 control warps + 16 epilogue warps
 constexpr int EPI_WARP0 = 4;
 
 struct GemmParams {
@@ -41,7 +42,7 @@ struct GemmSmem {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
   static constexpr int OFF_SQ = OFF_B + STAGES * B_STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_SQ + 8 * BN * 4;           // one sumsq row per epilogue warp
+  static constexpr int OFF_BAR = OFF_SQ + 2 * 8 * BN * 4;       // [tile parity][half*4+quarter][BN] sumsq rows
   static constexpr int OFF_TSLOT = OFF_BAR + (2 * STAGES + 4) * 8;
   static constexpr int BYTES = OFF_TSLOT + 16 + 1024;            // + worst-case alignment pad
 };
@@ -98,7 +99,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 8);        // one arrive per epilogue warp
+      mbar_init(&tempty[s], 16);       // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -159,9 +160,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
-    const int ew = warp - EPI_WARP0;            // 0..7
-    const int half = ew >> 2;                   // which M=128 accumulator
+    const int ew = warp - EPI_WARP0;            // 0..15
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
+    const int half = (ew >> 2) & 1;             // which M=128 accumulator
+    const int colgrp = ew >> 3;                 // chunks colgrp, colgrp+2, ...
     const int row = half * 128 + q * 32 + lane;
     const int bar_id = 1 + half;
     uint32_t lt = 0;
@@ -172,26 +174,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = m < p.M;
       const uint32_t as = lt % ACC_STAGES;
       const uint32_t aph = (lt / ACC_STAGES) & 1;
+      float* sq_buf = sSq + (lt & 1) * 8 * BN;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + as * (2 * BN) + half * BN;
-      uint32_t r[2][32];
-      tmem_ld32(tbase, r[0]);
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        tmem_ld_wait();
-        if (c + 1 < BN / 32) tmem_ld32(tbase + (c + 1) * 32, r[(c + 1) & 1]);   // overlaps the math below
+#pragma unroll 1
+      for (int c = colgrp; c < BN / 32; c += 2) {
+        uint32_t r[32];
+        tmem_ld32(tbase + c * 32, r);
         float v[32];
         const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+        float4 b4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b4[j] = p.bias ? __ldg(bp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t off = static_cast<size_t>(m) * p.N + n0 + c * 32;
+        float4 res[8];
+        if (MODE == FZ_EPI_RESID_F32 && row_ok) {
+          const float4* rp = reinterpret_cast<const float4*>(p.resid + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[j] = rp[j];
+        }
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b4 = p.bias ? __ldg(bp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[4 * j + 0] = __uint_as_float(r[c & 1][4 * j + 0]) + b4.x;
-          v[4 * j + 1] = __uint_as_float(r[c & 1][4 * j + 1]) + b4.y;
-          v[4 * j + 2] = __uint_as_float(r[c & 1][4 * j + 2]) + b4.z;
-          v[4 * j + 3] = __uint_as_float(r[c & 1][4 * j + 3]) + b4.w;
+          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4[j].x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4[j].y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
         }
-        const size_t off = static_cast<size_t>(m) * p.N + n0 + c * 32;
         if (MODE == FZ_EPI_GELU_SUMSQ) {
           float s[32];
 #pragma unroll
@@ -200,20 +210,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             s[j] = row_ok ? v[j] * v[j] : 0.0f;
           }
           warp_colsum32(s, lane);
-          sSq[ew * BN + c * 32 + lane] = s[0];
+          sq_buf[(half * 4 + q) * BN + c * 32 + lane] = s[0];
         } else if (MODE == FZ_EPI_RELU_BF16) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         } else if (MODE == FZ_EPI_RESID_F32) {
           if (row_ok) {
-            const float4* rp = reinterpret_cast<const float4*>(p.resid + off);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 x = rp[j];
-              v[4 * j + 0] += x.x;
-              v[4 * j + 1] += x.y;
-              v[4 * j + 2] += x.z;
-              v[4 * j + 3] += x.w;
+              v[4 * j + 0] += res[j].x;
+              v[4 * j + 1] += res[j].y;
+              v[4 * j + 2] += res[j].z;
+              v[4 * j + 3] += res[j].w;
             }
           }
         }
@@ -231,19 +239,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      // all TMEM reads of this stage are complete (last tmem_ld_wait above): hand it back to the MMA warp
+      // all TMEM reads of this stage are complete (tmem_ld_wait above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (MODE == FZ_EPI_GELU_SUMSQ) {
-        // deterministic: fixed-order sum of the half's four warps, one plain store per column
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        const float* sq = sSq + half * 4 * BN;
+        // deterministic: fixed-order sum of the four lane-quarter warps, one plain store per column.
+        // sq_buf alternates with the tile parity, so one barrier per tile is enough.
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        const float* sq = sq_buf + half * 4 * BN;
         if (m0 + half * 128 < p.M)
-          for (int i = q * 32 + lane; i < BN; i += 128)
+          for (int i = (colgrp * 4 + q) * 32 + lane; i < BN; i += 256)
             p.sumsq[static_cast<size_t>(m0 / 128 + half) * p.N + n0 + i] =
                 (sq[i] + sq[BN + i]) + (sq[2 * BN + i] + sq[3 * BN + i]);
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
     }
   }
@@ -308,8 +316,8 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   const char* force = getenv("FZ_GEMM_BN");
   if (force) BN = atoi(force);
   else if (N % 256 == 0 && mode != FZ_EPI_GELU_SUMSQ && K >= 1024 &&
-           static_cast<long long>((M + BM - 1) / BM) * (N / 256) >= 128)
-    BN = 256;
+           static_cast<long long>((M + BM - 1) / BM) * (N / 256) >= 3 * 148)
+    BN = 256;   // only when every CTA gets >= 3 tiles: the single accumulator stage cannot overlap its epilogue
   FZ_REQUIRE((BN == 64 || BN == 128 || BN == 256) && N % BN == 0, "fz_gemm_bf16: bad tile width %d for N=%d", BN, N);
 
   CUtensorMap tmA, tmB;
