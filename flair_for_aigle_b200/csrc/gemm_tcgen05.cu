@@ -35,7 +35,14 @@ struct GemmParams {
   void* out;            // [M,N] bf16 or f32
   const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
   float* sumsq;         // [ceil(M/128), N] f32 per-128-row partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
+  unsigned long long* trace;  // optional: CTA 0 writes clock64 stamps [tile][8] (diagnostics, see fz_gemm_set_trace)
 };
+
+static unsigned long long* g_trace = nullptr;
+#define FZ_TRACE(slot)                                                          \
+  do {                                                                          \
+    if (p.trace && blockIdx.x == 0 && lt < 64) p.trace[lt * 8 + (slot)] = clock64(); \
+  } while (0)
 
 template <int BN, int STAGES>
 struct GemmSmem {
@@ -111,11 +118,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
         const int n0 = (t % n_tiles) * BN;
         const int m0 = (t / n_tiles) * BM;
         const int bcoord = p.b_batched ? (m0 / p.rows_per_sample) : 0;
+        FZ_TRACE(0);   // producer starts issuing this tile's loads
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -134,8 +142,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
         const uint32_t as = lt % ACC_STAGES;
         const uint32_t aph = (lt / ACC_STAGES) & 1;
+        FZ_TRACE(1);   // MMA warp reaches the tile
         mbar_wait(&tempty[as], aph ^ 1);           // epilogue has drained this accumulator stage
         tc_fence_after();
+        FZ_TRACE(2);   // accumulator stage free
         const uint32_t acc0 = tmem + as * (2 * BN);
         const uint32_t acc1 = acc0 + BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -143,6 +153,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (kb == 0) FZ_TRACE(3);   // first k-block landed
           const uint64_t ad0 = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES), 128);
           const uint64_t ad1 = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES + 128 * BK * 2), 128);
           const uint64_t bd = umma_smem_desc(smem_u32(sB + s * L::B_STAGE_BYTES), 128);
@@ -156,6 +167,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[as]);
+        FZ_TRACE(4);   // all MMAs of the tile issued
       }
     }
     __syncwarp();
@@ -175,18 +187,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t as = lt % ACC_STAGES;
       const uint32_t aph = (lt / ACC_STAGES) & 1;
       float* sq_buf = sSq + (lt & 1) * 8 * BN;
+      if (ew == 0 && lane == 0) FZ_TRACE(5);   // epilogue warp 0 waits for the accumulator
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      if (ew == 0 && lane == 0) FZ_TRACE(6);   // accumulator complete
       const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + as * (2 * BN) + half * BN;
 #pragma unroll 1
       for (int c = colgrp; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld32(tbase + c * 32, r);
         float v[32];
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);   // bias is never null (host check)
         float4 b4[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) b4[j] = p.bias ? __ldg(bp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 8; ++j) b4[j] = __ldg(bp + j);
         const size_t off = static_cast<size_t>(m) * p.N + n0 + c * 32;
         float4 res[8];
         if (MODE == FZ_EPI_RESID_F32 && row_ok) {
@@ -207,7 +221,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             v[j] = gelu_erf_fast(v[j]);
-            s[j] = row_ok ? v[j] * v[j] : 0.0f;
+            s[j] = v[j] * v[j];     // M is a multiple of 128 in this mode (host check): no row mask
           }
           warp_colsum32(s, lane);
           sq_buf[(half * 4 + q) * BN + c * 32 + lane] = s[0];
@@ -243,6 +257,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
+      if (ew == 0 && lane == 0) FZ_TRACE(7);   // epilogue warp 0 done with the tile
       if (MODE == FZ_EPI_GELU_SUMSQ) {
         // deterministic: fixed-order sum of the four lane-quarter warps, one plain store per column.
         // sq_buf alternates with the tile parity, so one barrier per tile is enough.
@@ -297,6 +312,11 @@ static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, c
 
 }  // namespace fz
 
+extern "C" int fz_gemm_set_trace(void* device_buffer_64x8_u64) {
+  fz::g_trace = reinterpret_cast<unsigned long long*>(device_buffer_64x8_u64);
+  return 0;
+}
+
 extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid,
                             float* sumsq, int M, int N, int K, int b_batch, int rows_per_sample, int mode,
                             void* stream) {
@@ -309,6 +329,8 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
     FZ_REQUIRE(rows_per_sample > 0 && rows_per_sample % BM == 0,
                "fz_gemm_bf16: rows_per_sample=%d must be a positive multiple of %d", rows_per_sample, BM);
   FZ_REQUIRE(mode != FZ_EPI_GELU_SUMSQ || sumsq != nullptr, "fz_gemm_bf16: sumsq buffer required");
+  FZ_REQUIRE(mode != FZ_EPI_GELU_SUMSQ || M % 128 == 0, "fz_gemm_bf16: M=%d must be a multiple of 128 with GELU_SUMSQ", M);
+  FZ_REQUIRE(bias != nullptr, "fz_gemm_bf16: bias is required (pass zeros)");
   FZ_REQUIRE(mode != FZ_EPI_RESID_F32 || resid != nullptr, "fz_gemm_bf16: residual buffer required");
   // tile width: 256 for the long-K / light-epilogue GEMMs when it still leaves enough tiles,
   // 128 (double-buffered accumulators) otherwise, 64 for narrow outputs
@@ -339,7 +361,7 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.M = M; p.N = N; p.K = K;
   p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
   p.b_batched = b_batch > 1 ? 1 : 0;
-  p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq;
+  p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = g_trace;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (BN == 256) return dispatch_mode<256, 3, 1>(mode, tmA, tmB, p, st);
   if (BN == 128) return dispatch_mode<128, 4, 2>(mode, tmA, tmB, p, st);
@@ -402,7 +424,7 @@ extern "C" int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const 
   p.M = M; p.N = N; p.K = K;
   p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
   p.b_batched = b_batch > 1 ? 1 : 0;
-  p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq;
+  p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = nullptr;
   dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == FZ_EPI_GELU_SUMSQ)

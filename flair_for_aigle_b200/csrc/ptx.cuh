@@ -168,23 +168,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ math helpers
-// GELU(erf) as x * sigmoid(h(x)), h = logit(Phi(x)) fitted by x*Q(x^2) (deg-4 Q, |err| < 4e-6 abs
-// over all x, checked against 0.5x(1+erf(x/sqrt2)) in fp64).  One ex2 + one rcp on the SFU, the
-// rest on the FMA pipe.  Coefficients are pre-multiplied by -log2(e).
+// GELU(erf) = x * Phi(x) = x * sigmoid(h(x)) with h = logit(Phi(x)) fitted by x*Q(x^2) (deg-4 Q, |err| < 4e-6
+// abs over all x against 0.5x(1+erf(x/sqrt2)) in fp64).  sigmoid(h) = 0.5*(1 + tanh(h/2)), so the whole
+// activation is ONE SFU op (tanh.approx, rel. err 2^-11) plus 9 FMA-pipe ops: the fc1 epilogue is bound by
+// the SFU/MIO queue, and the ex2+rcp form costs two SFU ops per element.  Coefficients below are Q/2.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float k = -1.4426950408889634f;
-  const float c0 = 1.59565515e+00f * k, c1 = 7.29398588e-02f * k, c2 = -2.50950395e-04f * k,
-              c3 = -6.09348226e-05f * k, c4 = 2.22528911e-06f * k;
+  const float c0 = 0.5f * 1.59565515e+00f, c1 = 0.5f * 7.29398588e-02f, c2 = 0.5f * -2.50950395e-04f,
+              c3 = 0.5f * -6.09348226e-05f, c4 = 0.5f * 2.22528911e-06f;
   const float u = x * x;
   float q = fmaf(c4, u, c3);
   q = fmaf(q, u, c2);
   q = fmaf(q, u, c1);
   q = fmaf(q, u, c0);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * q));
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return x * r;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "fz_canvas_argmax": [_vp, _i, _i64, _vp, _vp, _vp],
     "fz_convert": [_vp, _i, _i, _i, _i, _vp, _vp],
     "fz_gemm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_gemm_set_trace": [_vp],
     "fz_gemm_bf16_simt": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_stem_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_stem_ln_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
@@ -210,6 +211,8 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, mode: int, bias=None, resid=None
     else:
         b_batch, N, K2 = B.shape
     assert K2 == K and A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    if bias is None:
+        bias = torch.zeros(N, dtype=torch.float32, device=A.device)
     if out is None:
         odt = torch.float32 if mode in (EPI_RESID_F32, EPI_F32) else torch.bfloat16
         out = torch.empty((M, N), dtype=odt, device=A.device)

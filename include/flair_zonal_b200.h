@@ -93,6 +93,10 @@ int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, vo
 #define FZ_EPI_RELU_BF16 4  /* out bf16 = relu(acc + bias)                                        */
 int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq, int M,
                  int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
+/* Diagnostics: when set to a device buffer of 64*8 uint64, CTA 0 of every following fz_gemm_bf16 launch
+ * records clock64 stamps per tile (producer start, MMA arrive, accumulator free, first operands landed,
+ * MMAs issued, epilogue wait, accumulator complete, epilogue done).  NULL switches it off. */
+int fz_gemm_set_trace(void* device_buffer_64x8_u64);
 /* Same contract on CUDA cores (exact erff); test/bring-up cross-check only. */
 int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq,
                       int M, int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
