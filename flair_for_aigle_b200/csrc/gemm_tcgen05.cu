@@ -49,7 +49,8 @@ struct GemmSmem {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
   static constexpr int OFF_SQ = OFF_B + STAGES * B_STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_SQ + 2 * 8 * BN * 4;       // [tile parity][half*4+quarter][BN] sumsq rows
+  static constexpr int OFF_STG = OFF_SQ + 2 * 8 * BN * 4;       // [tile parity][half*4+quarter][BN] sumsq rows
+  static constexpr int OFF_BAR = OFF_STG + 16 * 4096;           // 4 KB store-staging tile per epilogue warp
   static constexpr int OFF_TSLOT = OFF_BAR + (2 * STAGES + 4) * 8;
   static constexpr int BYTES = OFF_TSLOT + 16 + 1024;            // + worst-case alignment pad
 };
@@ -176,82 +177,112 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
     const int half = (ew >> 2) & 1;             // which M=128 accumulator
     const int colgrp = ew >> 3;                 // chunks colgrp, colgrp+2, ...
-    const int row = half * 128 + q * 32 + lane;
     const int bar_id = 1 + half;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const int n0 = (t % n_tiles) * BN;
       const int m0 = (t / n_tiles) * BM;
-      const int m = m0 + row;
-      const bool row_ok = m < p.M;
       const uint32_t as = lt % ACC_STAGES;
       const uint32_t aph = (lt / ACC_STAGES) & 1;
       float* sq_buf = sSq + (lt & 1) * 8 * BN;
+      char* stg = reinterpret_cast<char*>(smem + L::OFF_STG) + ew * 4096;
       if (ew == 0 && lane == 0) FZ_TRACE(5);   // epilogue warp 0 waits for the accumulator
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       if (ew == 0 && lane == 0) FZ_TRACE(6);   // accumulator complete
       const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + as * (2 * BN) + half * BN;
+      // Each chunk is 128 B of output per row (32 fp32 or 64 bf16 columns).  Results go through a
+      // per-warp 32 x 128 B staging tile (16 B segments XOR-swizzled with row&7: conflict-free both
+      // row-per-lane and row-contiguous) so that every global access is a full 128 B line: a
+      // row-per-thread STG/LDG touches 32 lines per instruction and was the v2 epilogue's bottleneck.
+      constexpr bool F32OUT = (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32);
+      constexpr int CH_COLS = F32OUT ? 32 : 64;
+      constexpr int ESZ = F32OUT ? 4 : 2;
+      const int rsub = lane >> 3, seg = lane & 7;              // row-contiguous mapping: 4 rows x 8 segments
+      const size_t row_bytes = static_cast<size_t>(p.N) * ESZ;
 #pragma unroll 1
-      for (int c = colgrp; c < BN / 32; c += 2) {
-        uint32_t r[32];
-        tmem_ld32(tbase + c * 32, r);
-        float v[32];
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);   // bias is never null (host check)
-        float4 b4[8];
+      for (int c = colgrp; c < BN / CH_COLS; c += 2) {
+        const int col0 = n0 + c * CH_COLS;
+        char* gout = reinterpret_cast<char*>(p.out) + static_cast<size_t>(m0 + half * 128 + q * 32) * row_bytes +
+                     static_cast<size_t>(col0) * ESZ;
+        if (MODE == FZ_EPI_RESID_F32) {
+          // coalesced residual tile -> staging
+          const char* gres = reinterpret_cast<const char*>(p.resid) +
+                             static_cast<size_t>(m0 + half * 128 + q * 32) * row_bytes + static_cast<size_t>(col0) * 4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) b4[j] = __ldg(bp + j);
-        const size_t off = static_cast<size_t>(m) * p.N + n0 + c * 32;
-        float4 res[8];
-        if (MODE == FZ_EPI_RESID_F32 && row_ok) {
-          const float4* rp = reinterpret_cast<const float4*>(p.resid + off);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) res[j] = rp[j];
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4[j].x;
-          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4[j].y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
-          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
-        }
-        if (MODE == FZ_EPI_GELU_SUMSQ) {
-          float s[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = gelu_erf_fast(v[j]);
-            s[j] = v[j] * v[j];     // M is a multiple of 128 in this mode (host check): no row mask
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (m0 + half * 128 + q * 32 + rr < p.M)
+              x = *reinterpret_cast<const uint4*>(gres + static_cast<size_t>(rr) * row_bytes + seg * 16);
+            *reinterpret_cast<uint4*>(stg + rr * 128 + ((seg ^ (rr & 7)) << 4)) = x;
           }
-          warp_colsum32(s, lane);
-          sq_buf[(half * 4 + q) * BN + c * 32 + lane] = s[0];
-        } else if (MODE == FZ_EPI_RELU_BF16) {
+          __syncwarp();
+        }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        } else if (MODE == FZ_EPI_RESID_F32) {
-          if (row_ok) {
+        for (int h = 0; h < CH_COLS / 32; ++h) {
+          uint32_t r[32];
+          tmem_ld32(tbase + c * CH_COLS + h * 32, r);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + h * 32);   // never null (host check)
+          float4 b4[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b4[j] = __ldg(bp + j);
+          float v[32];
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4[j].x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4[j].y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
+          }
+          if (MODE == FZ_EPI_GELU_SUMSQ) {
+            float s[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = gelu_erf_fast(v[j]);
+              s[j] = v[j] * v[j];     // M is a multiple of 128 in this mode (host check): no row mask
+            }
+            warp_colsum32(s, lane);
+            sq_buf[(half * 4 + q) * BN + c * CH_COLS + h * 32 + lane] = s[0];
+          } else if (MODE == FZ_EPI_RELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (MODE == FZ_EPI_RESID_F32) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              v[4 * j + 0] += res[j].x;
-              v[4 * j + 1] += res[j].y;
-              v[4 * j + 2] += res[j].z;
-              v[4 * j + 3] += res[j].w;
+              const float4 x = *reinterpret_cast<const float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
+              v[4 * j + 0] += x.x;
+              v[4 * j + 1] += x.y;
+              v[4 * j + 2] += x.z;
+              v[4 * j + 3] += x.w;
             }
+            __syncwarp();   // everyone has read its residual row before the tile is overwritten
           }
-        }
-        if (row_ok) {
-          if (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+          // own row -> staging
+          if (F32OUT) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+              *reinterpret_cast<uint4*>(stg + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)) =
+                  make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
           }
         }
+        __syncwarp();
+        // staging -> global, 4 full 128 B lines per instruction
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rsub;
+          const uint4 x = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((seg ^ (rr & 7)) << 4));
+          if (m0 + half * 128 + q * 32 + rr < p.M)
+            *reinterpret_cast<uint4*>(gout + static_cast<size_t>(rr) * row_bytes + seg * 16) = x;
+        }
+        __syncwarp();       // staging is reused by the next chunk
       }
       // all TMEM reads of this stage are complete (tmem_ld_wait above): hand it back to the MMA warp
       tc_fence_before();
@@ -295,8 +326,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return 0;
 }
 
-// BN = 128: 4 smem stages (48 KB each), accumulators double buffered.
-// BN = 256: 3 smem stages (64 KB each), single accumulator stage (light epilogue, long K).
+// BN = 128: 3 smem stages (48 KB each) + 64 KB store staging, accumulators double buffered.
+// BN = 256: 2 smem stages (64 KB each), single accumulator stage (FZ_GEMM_BN=256 experiments only).
 template <int BN, int STAGES, int ACC_STAGES>
 static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
   switch (mode) {
@@ -363,9 +394,9 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = g_trace;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch_mode<256, 3, 1>(mode, tmA, tmB, p, st);
-  if (BN == 128) return dispatch_mode<128, 4, 2>(mode, tmA, tmB, p, st);
-  return dispatch_mode<64, 4, 2>(mode, tmA, tmB, p, st);
+  if (BN == 256) return dispatch_mode<256, 2, 1>(mode, tmA, tmB, p, st);
+  if (BN == 128) return dispatch_mode<128, 3, 2>(mode, tmA, tmB, p, st);
+  return dispatch_mode<64, 3, 2>(mode, tmA, tmB, p, st);
 }
 
 // ----------------------------------------------------------------------------------------
