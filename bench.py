@@ -209,7 +209,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("FZ_BENCH_BATCH", "16")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("FZ_BENCH_BATCH", "37")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
