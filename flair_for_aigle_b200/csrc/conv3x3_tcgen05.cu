@@ -234,6 +234,11 @@ static int dispatch_conv(int BN, int KC, const CUtensorMap& a, const CUtensorMap
   return -1;
 }
 
+bool conv_rows_applicable(int H, int W, int Cin, int Cout, int mode);
+int conv_rows_launch(const void* in, const void* w, const float* scale, const float* bias, void* out, int B, int H,
+                     int W, int Cin, int Cout, int w_rows, int mode, int cstride, const int32_t* plan,
+                     const int32_t* own, uint8_t* raster, int RH, int RW, int margin, cudaStream_t st);
+
 }  // namespace fz
 
 extern "C" int fz_conv3x3_bf16(const void* in, const void* w, const float* scale, const float* bias, void* out, int B,
@@ -243,6 +248,13 @@ extern "C" int fz_conv3x3_bf16(const void* in, const void* w, const float* scale
   using namespace fz;
   FZ_REQUIRE(B > 0 && H > 0 && W > 0, "fz_conv3x3_bf16: bad shape");
   FZ_REQUIRE(Cin % 16 == 0, "fz_conv3x3_bf16: Cin=%d must be a multiple of 16", Cin);
+  if (mode == FZ_CONV_ARGMAX_RASTER) FZ_REQUIRE(plan && raster, "fz_conv3x3_bf16: argmax mode needs plan and raster");
+  if (mode == FZ_CONV_LOGITS_F32)
+    FZ_REQUIRE(cstride % 4 == 0 && cstride >= Cout && cstride <= 32, "fz_conv3x3_bf16: bad cstride %d", cstride);
+  // HBM-bound tail layers (wide maps, few channels): row-streaming kernel, every input row read once
+  if (conv_rows_applicable(H, W, Cin, Cout, mode))
+    return conv_rows_launch(in, w, scale, bias, out, B, H, W, Cin, Cout, w_rows, mode, cstride, plan, own, raster, RH,
+                            RW, margin, reinterpret_cast<cudaStream_t>(stream));
   const int KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   int BN;
   if (mode == FZ_CONV_RELU_BF16) {
