@@ -257,9 +257,12 @@ static int launch_rows(const CUtensorMap& a, const CUtensorMap& b, const RowConv
     int dev = 0;
     FZ_CHECK_CUDA(cudaGetDevice(&dev));
     FZ_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    FZ_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 192, BYTES));
+    // co-resident CTAs hide the per-row latency chain; bounded by shared memory and by TMEM (512 columns)
+    per_sm = (227 * 1024) / (BYTES + 1024);
+    const int tcols = (ROW_AS * BN) < 32 ? 32 : (ROW_AS * BN);
+    if (per_sm > 512 / tcols) per_sm = 512 / tcols;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 6) per_sm = 6;
     configured = true;
   }
   const int items = p.B * (p.W / 128) * (p.H / p.R);
