@@ -188,19 +188,33 @@ __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restr
     const float bias = bdw[c];
 #pragma unroll
     for (int p = 0; p < NPX; ++p) acc[cc][p] = bias;
-#pragma unroll
-    for (int iy = 0; iy < SH + 6; ++iy) {
+    // software-pipelined rows: row iy+1 is in flight while row iy feeds the FMAs
+    float nxt[SW + 6];
+    // running row pointer: one 64-bit add per input row, every tap is [row + immediate] (C is constexpr)
+    const ptrdiff_t row_stride = static_cast<ptrdiff_t>(W) * C;
+    const float* row0 = xb + (static_cast<ptrdiff_t>(y0 - 3) * W + (x0 - 3)) * C + c;
+    auto load_row = [&](int iy, float (&dst)[SW + 6]) {
       const int gy = y0 - 3 + iy;
-      if (gy < 0 || gy >= H) continue;                       // CTA-uniform
-      // C is a compile-time constant: every tap below is [row + immediate]
-      const float* row = xb + (static_cast<ptrdiff_t>(gy) * W + (x0 - 3)) * C + c;
-      float in[SW + 6];
+      if (gy < 0 || gy >= H) {                               // CTA-uniform: zero padding row
+#pragma unroll
+        for (int ix = 0; ix < SW + 6; ++ix) dst[ix] = 0.0f;
+        return;
+      }
+      const float* row = row0 + iy * row_stride;
 #pragma unroll
       for (int ix = 0; ix < SW + 6; ++ix) {
-        if (ix < 3) in[ix] = (left_edge && x0 - 3 + ix < 0) ? 0.0f : row[ix * C];
-        else if (ix >= SW + 3) in[ix] = (right_edge && x0 - 3 + ix >= W) ? 0.0f : row[ix * C];
-        else in[ix] = row[ix * C];
+        if (ix < 3) dst[ix] = (left_edge && x0 - 3 + ix < 0) ? 0.0f : row[ix * C];
+        else if (ix >= SW + 3) dst[ix] = (right_edge && x0 - 3 + ix >= W) ? 0.0f : row[ix * C];
+        else dst[ix] = row[ix * C];
       }
+    };
+    load_row(0, nxt);
+#pragma unroll
+    for (int iy = 0; iy < SH + 6; ++iy) {
+      float in[SW + 6];
+#pragma unroll
+      for (int ix = 0; ix < SW + 6; ++ix) in[ix] = nxt[ix];
+      if (iy + 1 < SH + 6) load_row(iy + 1, nxt);
 #pragma unroll
       for (int oy = 0; oy < SH; ++oy) {
         const int ky = iy - oy;
@@ -256,10 +270,14 @@ __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restr
   for (int cc = 0; cc < CPT; ++cc) {
     const int c = cc * (C / CPT) + warp * 32 + lane;
     const float g = ln_w[c], be = ln_b[c];
+    __nv_bfloat16* o0 = out + ((static_cast<size_t>(b) * H + y0) * W + x0) * C + c;
+    const ptrdiff_t orow = static_cast<ptrdiff_t>(W) * C;
 #pragma unroll
-    for (int p = 0; p < NPX; ++p) {
-      const int gy = y0 + p / SW, gx = x0 + p % SW;
-      out[((static_cast<size_t>(b) * H + gy) * W + gx) * C + c] = __float2bfloat16_rn(acc[cc][p] * s_stat[p] * g + be);
+    for (int oy = 0; oy < SH; ++oy) {
+      __nv_bfloat16* orp = o0 + oy * orow;
+#pragma unroll
+      for (int ox = 0; ox < SW; ++ox)
+        orp[ox * C] = __float2bfloat16_rn(acc[cc][oy * SW + ox] * s_stat[oy * SW + ox] * g + be);
     }
   }
 }
