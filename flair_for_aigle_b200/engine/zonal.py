@@ -52,7 +52,9 @@ class ZonalRunner:
         cfg = self.eng.cfg
         n = 2  # gather + stem
         for i, d in enumerate(cfg.depths):
-            n += (2 if i > 0 else 0) + d * 6   # dwconv, fc1, grn (2 kernels), weight/row scaling, fc2
+            sub = self.eng.sub_batch[i] if self.eng.sub_batch[i] > 0 else self.B
+            nsub = (self.B + sub - 1) // sub
+            n += (2 if i > 0 else 0) + nsub * d * 6   # dwconv, fc1, grn (2 kernels), weight/row scaling, fc2
         n += len(self.eng.dec) * 3 + 1
         return n
 
