@@ -64,7 +64,7 @@ class ConvNeXtV2UNetEngine:
         self.cfg, self.dev, self.B = cfg, device, max_batch
         self.gemm_impl = "tcgen05"
         import os as _os
-        sb = _os.environ.get("FZ_SUBBATCH", "4,8,0,0").split(",")
+        sb = _os.environ.get("FZ_SUBBATCH", "0,0,0,0").split(",")
         self.sub_batch = [int(v) for v in sb]          # tiles per sub-batch in stages 0..3 (0 = whole batch)
         sd = {k: v.detach().to('cpu') for k, v in state_dict.items()}   # pack on the host, upload once
         E, D, dev = enc_prefix, dec_prefix, device
@@ -190,7 +190,9 @@ class ConvNeXtV2UNetEngine:
         """Stages 0..3.  Within a stage the blocks run over L2-sized SUB-BATCHES of tiles: GRN statistics are
         per sample, so a block can finish a few tiles at a time, and the dwconv output / MLP hidden tensors of a
         sub-batch (67 MB at 4 tiles in stage 0) are produced and consumed out of the 126 MB L2 instead of
-        round-tripping HBM (at 37 tiles stage 0 alone would move 2.5 GB per block)."""
+        round-tripping HBM.  Measured on B200 (tools/gpu_subbatch_sweep.py): every sub-batched setting was SLOWER
+        (0.49-0.64 vs 0.446 ms/tile) -- the kernels are not HBM-bound, smaller launches only add ramp/tail
+        time -- so the default is 0,0,0,0 (whole batch); FZ_SUBBATCH overrides."""
         cfg = self.cfg
         for i, st in enumerate(self.stages):
             C, hwi = st["C"], self.hw[i]
