@@ -37,7 +37,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, uint32_t swizzle_bytes) {
+                   const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -3;
   cuuint64_t gdims[5];
@@ -47,7 +47,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;

@@ -17,7 +17,9 @@
 namespace fz {
 
 struct ConvParams {
-  int B, H, W, Cin, Cout;   // Cout = channels actually stored / compared
+  int B, H, W, Cin, Cout;   // H, W = OUTPUT size; Cout = channels actually stored / compared
+  int stride;               // 1 or 2 (input is H*stride x W*stride)
+  const void* resid;        // ADD_RELU: bf16 [B,H,W,Cout] added before the ReLU (ResNet BasicBlock identity)
   int TW, TH;               // output tile (TW*TH = 128)
   const float* bias;        // [n_tiles_n * BN] (zero padded)
   const float* scale;       // [n_tiles_n * BN] per-channel multiplier (folded BatchNorm) or nullptr
@@ -102,7 +104,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ky = tap / 3, kx = tap % 3;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], L::A_BYTES + L::B_BYTES);
-        tma_load_4d(&tmA, &full[s], sA + s * L::A_BYTES, c0, x0 + kx - 1, y0 + ky - 1, b);
+        tma_load_4d(&tmA, &full[s], sA + s * L::A_BYTES, c0, x0 * p.stride + kx - 1, y0 * p.stride + ky - 1, b);
         tma_load_2d(&tmB, &full[s], sB + s * L::B_BYTES, tap * p.Cin + c0, n0);
       }
     }
@@ -132,7 +134,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
     const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
-    if (MODE == FZ_CONV_RELU_BF16) {
+    if (MODE == FZ_CONV_RELU_BF16 || MODE == FZ_CONV_ADD_RELU_BF16 || MODE == FZ_CONV_BF16) {
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
         uint32_t r[16];
@@ -140,8 +142,23 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = fmaxf(fmaf(__uint_as_float(r[j]), sScale[c * 16 + j], sBias[c * 16 + j]), 0.0f);
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), sScale[c * 16 + j], sBias[c * 16 + j]);
+        if (MODE == FZ_CONV_ADD_RELU_BF16 && n0 + c * 16 < p.Cout) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) +
+                                                           pix * p.Cout + n0 + c * 16);
+          const uint4 r0 = rp[0], r1 = rp[1];
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = __bfloat1622float2(h0[j]), bq = __bfloat1622float2(h1[j]);
+            v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += bq.x; v[8 + 2 * j + 1] += bq.y;
+          }
+        }
+        if (MODE != FZ_CONV_BF16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
         if (n0 + c * 16 < p.Cout) {
           uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0 + c * 16);
           op[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -226,6 +243,8 @@ static int dispatch_conv(int BN, int KC, const CUtensorMap& a, const CUtensorMap
   if (MODE == FZ_CONV_RELU_BF16) {
     FZ_CASE(128, 64) FZ_CASE(64, 64) FZ_CASE(32, 64) FZ_CASE(32, 32) FZ_CASE(16, 32) FZ_CASE(16, 16)
     FZ_CASE(128, 32) FZ_CASE(64, 32) FZ_CASE(128, 16) FZ_CASE(64, 16) FZ_CASE(32, 16) FZ_CASE(16, 64)
+  } else if (MODE == FZ_CONV_ADD_RELU_BF16 || MODE == FZ_CONV_BF16) {
+    FZ_CASE(128, 64) FZ_CASE(64, 64)
   } else {
     FZ_CASE(32, 16) FZ_CASE(32, 32) FZ_CASE(32, 64)
   }
@@ -241,23 +260,37 @@ int conv_rows_launch(const void* in, const void* w, const float* scale, const fl
 
 }  // namespace fz
 
+extern "C" int fz_conv3x3_ex(const void* in, const void* w, const float* scale, const float* bias, void* out,
+                             const void* resid, int B, int H, int W, int Cin, int Cout, int w_rows, int stride, int mode,
+                             int cstride, const int32_t* plan, const int32_t* own, uint8_t* raster, int RH, int RW,
+                             int margin, void* stream);
+
 extern "C" int fz_conv3x3_bf16(const void* in, const void* w, const float* scale, const float* bias, void* out, int B,
-                               int H, int W,
-                               int Cin, int Cout, int w_rows, int mode, int cstride, const int32_t* plan,
+                               int H, int W, int Cin, int Cout, int w_rows, int mode, int cstride, const int32_t* plan,
                                const int32_t* own, uint8_t* raster, int RH, int RW, int margin, void* stream) {
+  return fz_conv3x3_ex(in, w, scale, bias, out, nullptr, B, H, W, Cin, Cout, w_rows, 1, mode, cstride, plan, own, raster,
+                       RH, RW, margin, stream);
+}
+
+extern "C" int fz_conv3x3_ex(const void* in, const void* w, const float* scale, const float* bias, void* out,
+                             const void* resid, int B, int H, int W, int Cin, int Cout, int w_rows, int stride, int mode,
+                             int cstride, const int32_t* plan, const int32_t* own, uint8_t* raster, int RH, int RW,
+                             int margin, void* stream) {
   using namespace fz;
   FZ_REQUIRE(B > 0 && H > 0 && W > 0, "fz_conv3x3_bf16: bad shape");
+  FZ_REQUIRE(stride == 1 || stride == 2, "fz_conv3x3_ex: stride %d unsupported", stride);
+  FZ_REQUIRE(mode != FZ_CONV_ADD_RELU_BF16 || resid != nullptr, "fz_conv3x3_ex: residual required");
   FZ_REQUIRE(Cin % 16 == 0, "fz_conv3x3_bf16: Cin=%d must be a multiple of 16", Cin);
   if (mode == FZ_CONV_ARGMAX_RASTER) FZ_REQUIRE(plan && raster, "fz_conv3x3_bf16: argmax mode needs plan and raster");
   if (mode == FZ_CONV_LOGITS_F32)
     FZ_REQUIRE(cstride % 4 == 0 && cstride >= Cout && cstride <= 32, "fz_conv3x3_bf16: bad cstride %d", cstride);
   // HBM-bound tail layers (wide maps, few channels): row-streaming kernel, every input row read once
-  if (conv_rows_applicable(H, W, Cin, Cout, mode))
+  if (stride == 1 && conv_rows_applicable(H, W, Cin, Cout, mode))
     return conv_rows_launch(in, w, scale, bias, out, B, H, W, Cin, Cout, w_rows, mode, cstride, plan, own, raster, RH,
                             RW, margin, reinterpret_cast<cudaStream_t>(stream));
   const int KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   int BN;
-  if (mode == FZ_CONV_RELU_BF16) {
+  if (mode == FZ_CONV_RELU_BF16 || mode == FZ_CONV_ADD_RELU_BF16 || mode == FZ_CONV_BF16) {
     FZ_REQUIRE(Cout % 16 == 0, "fz_conv3x3_bf16: Cout=%d must be a multiple of 16", Cout);
     BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 16));
   } else {
@@ -278,10 +311,14 @@ extern "C" int fz_conv3x3_bf16(const void* in, const void* w, const float* scale
 
   CUtensorMap tmA, tmB;
   {
-    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)TW, (uint32_t)TH, 1};
-    int rc = make_tmap_bf16(&tmA, in, 4, dims, strides, box, KC * 2);
+    const uint64_t Wi = (uint64_t)W * stride, Hi = (uint64_t)H * stride;     // input extent
+    const uint64_t dims[4] = {(uint64_t)Cin, Wi, Hi, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, Wi * Cin * 2, Hi * Wi * Cin * 2};
+    // with element strides the box is given in traversed input elements: TW*stride -> TW pixels land in smem
+    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)(TW * stride), (uint32_t)(TH * stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    FZ_REQUIRE(TW * stride <= 256, "fz_conv3x3_ex: tile too wide for a strided TMA box");
+    int rc = make_tmap_bf16(&tmA, in, 4, dims, strides, box, KC * 2, estr);
     if (rc) return rc;
   }
   {
@@ -293,11 +330,14 @@ extern "C" int fz_conv3x3_bf16(const void* in, const void* w, const float* scale
   }
   ConvParams p;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.TW = TW; p.TH = TH;
+  p.stride = stride; p.resid = resid;
   p.bias = bias; p.scale = scale; p.out = out; p.cstride = cstride; p.plan = plan; p.own = own; p.raster = raster;
   p.RH = RH; p.RW = RW; p.margin = margin;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (mode) {
     case FZ_CONV_RELU_BF16: return dispatch_conv<FZ_CONV_RELU_BF16>(BN, KC, tmA, tmB, p, st);
+    case FZ_CONV_ADD_RELU_BF16: return dispatch_conv<FZ_CONV_ADD_RELU_BF16>(BN, KC, tmA, tmB, p, st);
+    case FZ_CONV_BF16: return dispatch_conv<FZ_CONV_BF16>(BN, KC, tmA, tmB, p, st);
     case FZ_CONV_LOGITS_F32: return dispatch_conv<FZ_CONV_LOGITS_F32>(BN, KC, tmA, tmB, p, st);
     case FZ_CONV_LOGITS_F32_NCHW: return dispatch_conv<FZ_CONV_LOGITS_F32_NCHW>(BN, KC, tmA, tmB, p, st);
     case FZ_CONV_ARGMAX_RASTER: return dispatch_conv<FZ_CONV_ARGMAX_RASTER>(BN, KC, tmA, tmB, p, st);

@@ -19,6 +19,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from .. import native as nv
+from .unet_decoder import UNetDecoderPlan
 
 
 @dataclass
@@ -122,33 +123,10 @@ class ConvNeXtV2UNetEngine:
                 st["blocks"].append(blk)
             self.stages.append(st)
 
-        # ---- decoder (smp UnetDecoder): channels per block
-        enc_ch = [cfg.in_chans, 0] + list(cfg.dims)
-        rev = enc_ch[1:][::-1]
-        in_ch = [rev[0]] + list(cfg.decoder_channels[:-1])
-        skip_ch = list(rev[1:]) + [0]
-        self.dec: List[dict] = []
-        for k, (ci, cs, co) in enumerate(zip(in_ch, skip_ch, cfg.decoder_channels)):
-            blk = {"cin": ci, "cskip": cs, "cout": co}
-            for name in ("conv1", "conv2"):
-                Kp = D + f"decoder.blocks.{k}.{name}."
-                w = sd[Kp + "0.weight"].float()                     # [co, cin_total, 3, 3]
-                g, b_ = sd[Kp + "1.weight"].double(), sd[Kp + "1.bias"].double()
-                mu, var = sd[Kp + "1.running_mean"].double(), sd[Kp + "1.running_var"].double()
-                scale = g / torch.sqrt(var + bn_eps)
-                blk[name + "_w"] = _bf16(w.permute(0, 2, 3, 1), dev)   # [co][3][3][cin]
-                blk[name + "_s"] = _f32(scale, dev)
-                blk[name + "_b"] = _f32(b_ - mu * scale, dev)
-            assert blk["conv1_w"].shape[-1] == ci + cs, (blk["conv1_w"].shape, ci, cs)
-            self.dec.append(blk)
-        wh = sd[D + "segmentation_head.0.weight"].float()           # [ncls, 16, 3, 3]
-        assert wh.shape[0] == cfg.n_classes and cfg.n_classes <= 32
-        whp = torch.zeros(32, 3, 3, wh.shape[1])
-        whp[:cfg.n_classes] = wh.permute(0, 2, 3, 1)
-        bh = torch.zeros(32)
-        bh[:cfg.n_classes] = sd[D + "segmentation_head.0.bias"].float()
-        self.head_w, self.head_b = _bf16(whp, dev), _f32(bh, dev)
-
+        # ---- decoder + head (smp UnetDecoder / SegmentationHead), shared with the other encoders
+        self.decoder = UNetDecoderPlan(sd, D, [cfg.in_chans, 0] + list(cfg.dims), cfg.n_classes, cfg.patch, max_batch,
+                                       dev, decoder_channels=cfg.decoder_channels, bn_eps=bn_eps)
+        self.dec = self.decoder.blocks
         self._alloc_workspace()
 
     # ------------------------------------------------------------------------------ workspace
@@ -171,16 +149,6 @@ class ConvNeXtV2UNetEngine:
         self.use_wscale = [h * h > c for h, c in zip(hw, cfg.dims)]
         wmax = max([4 * c * c for c, u in zip(cfg.dims, self.use_wscale) if u] + [0])
         self.w2s = torch.empty(B * wmax, dtype=bf, device=dev) if wmax else None
-        # decoder
-        sizes = []
-        hd = hw[3]
-        for blk in self.dec:
-            hd *= 2
-            sizes.append(hd * hd * (blk["cin"] + blk["cskip"]))
-            sizes.append(hd * hd * blk["cout"])
-        self.cat = torch.empty(B * max(sizes[0::2]), dtype=bf, device=dev)
-        self.t1 = torch.empty(B * max(sizes[1::2]), dtype=bf, device=dev)
-        self.t2 = torch.empty(B * max(sizes[1::2]), dtype=bf, device=dev)
 
     # ------------------------------------------------------------------------------ encoder
     def _gemm(self, A, Bw, mode, **kw):
@@ -247,43 +215,18 @@ class ConvNeXtV2UNetEngine:
         return [x[:n] for x in self.x]
 
     # ------------------------------------------------------------------------------ decoder
-    def _decode_body(self, n: int) -> torch.Tensor:
-        a = self.x[3][:n]
-        skips = [self.x[2][:n], self.x[1][:n], self.x[0][:n], None, None]
-        hd = self.hw[3]
-        bufs = [self.t1, self.t2]
-        for k, blk in enumerate(self.dec):
-            hd *= 2
-            ct = blk["cin"] + blk["cskip"]
-            cat = self.cat[:n * hd * hd * ct].view(n, hd, hd, ct)
-            skip = skips[k] if blk["cskip"] > 0 else None
-            nv.upsample2_concat(a, skip, cat)
-            o1 = self.t1[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
-            nv.conv3x3(cat, blk["conv1_w"], blk["conv1_s"], blk["conv1_b"], nv.CONV_RELU_BF16, out=o1)
-            o2 = self.t2[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
-            nv.conv3x3(o1, blk["conv2_w"], blk["conv2_s"], blk["conv2_b"], nv.CONV_RELU_BF16, out=o2)
-            a = o2
-        return a
+    def _feats_deep_first(self, n: int):
+        return [self.x[3][:n], self.x[2][:n], self.x[1][:n], self.x[0][:n]]
 
     def decode_logits_nchw(self, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """fp32 logits [n, n_classes, P, P] -- the layout FLAIR_HUB_Model.forward returns."""
-        a = self._decode_body(n)
-        P, nc = self.cfg.patch, self.cfg.n_classes
-        if out is None:
-            out = torch.empty((n, nc, P, P), dtype=torch.float32, device=self.dev)
-        nv.conv3x3(a, self.head_w, None, self.head_b, nv.CONV_LOGITS_F32_NCHW, out=out, cout=nc)
-        return out
+        return self.decoder.logits_nchw(self._feats_deep_first(n), n, out)
 
     def decode_logits_nhwc(self, n: int, out: torch.Tensor) -> torch.Tensor:
-        a = self._decode_body(n)
-        nv.conv3x3(a, self.head_w, None, self.head_b, nv.CONV_LOGITS_F32, out=out, cout=self.cfg.n_classes,
-                   cstride=out.shape[-1])
-        return out
+        return self.decoder.logits_nhwc(self._feats_deep_first(n), n, out)
 
     def decode_argmax_to_raster(self, n: int, plan: torch.Tensor, own: Optional[torch.Tensor], raster: torch.Tensor,
                                 margin: int) -> None:
         """Head conv with the crop + argmax + last-writer-wins write fused into its epilogue
         (inference.py:295-352): no logits leave the SM."""
-        a = self._decode_body(n)
-        nv.conv3x3(a, self.head_w, None, self.head_b, nv.CONV_ARGMAX_RASTER, cout=self.cfg.n_classes, plan=plan,
-                   own=own, raster=raster, margin=margin)
+        self.decoder.argmax_to_raster(self._feats_deep_first(n), n, plan, own, raster, margin)

@@ -25,7 +25,9 @@ from .convnext_unet import ConvNeXtV2UNetEngine
 
 
 class ZonalRunner:
-    def __init__(self, engine: ConvNeXtV2UNetEngine, margin: int, use_graph: bool = True):
+    def __init__(self, engine, margin: int, use_graph: bool = True, norm=None):
+        """norm = (means, stds): needed by engines whose first layer zero-pads the NORMALISED image
+        (ResNet conv1, pad 3) and therefore take float tiles instead of raw uint8."""
         self.eng = engine
         self.B = engine.B
         self.P = engine.cfg.patch
@@ -36,20 +38,36 @@ class ZonalRunner:
         self.s_origins = torch.zeros((B, 2), dtype=torch.int32, device=dev)
         self.s_plan = torch.zeros((B, 6), dtype=torch.int32, device=dev)
         self.s_own = torch.zeros((B, 4), dtype=torch.int32, device=dev)
-        self.tiles_u8 = torch.empty((B, self.P, self.P, 4), dtype=torch.uint8, device=dev)
+        self.float_input = not hasattr(engine, 'stem_w_u8')
+        if self.float_input:
+            if norm is None or norm[0] is None:
+                raise nv.NativeError('this engine needs the normalisation constants (means, stds)')
+            self.mean = torch.tensor(list(norm[0]), dtype=torch.float32, device=dev)
+            self.std = torch.tensor(list(norm[1]), dtype=torch.float32, device=dev)
+            self.tiles_f32 = torch.empty((B, engine.cfg.in_chans, self.P, self.P), dtype=torch.float32, device=dev)
+        else:
+            self.tiles_u8 = torch.empty((B, self.P, self.P, 4), dtype=torch.uint8, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_key = None
         self.launches_per_batch = 0
 
     # one batch, all launches on the current stream (capturable)
     def _batch_body(self, raster: torch.Tensor, out_raster: torch.Tensor) -> None:
-        nv.gather_tiles_u8(raster, self.s_origins, self.P, out=self.tiles_u8)
-        self.eng.encode_u8(self.tiles_u8)
+        if self.float_input:
+            nv.gather_tiles_f32(raster, self.s_origins, self.P, self.mean, self.std, out=self.tiles_f32)
+            self.eng.encode_f32(self.tiles_f32)
+        else:
+            nv.gather_tiles_u8(raster, self.s_origins, self.P, out=self.tiles_u8)
+            self.eng.encode_u8(self.tiles_u8)
         self.eng.decode_argmax_to_raster(self.B, self.s_plan, self.s_own, out_raster, self.margin)
 
     def count_launches(self) -> int:
         """Kernel launches of one batch (for bench.py's gpu_launches)."""
         cfg = self.eng.cfg
+        if not hasattr(cfg, 'depths'):          # ResNet: gather, conv1, maxpool, 2-3 convs per block, decoder
+            nblk = sum(cfg.layers)
+            nds = sum(1 for b in self.eng.blocks if b['wd'] is not None)
+            return 3 + 2 * nblk + nds + self.eng.decoder.launches()
         n = 2  # gather + stem
         for i, d in enumerate(cfg.depths):
             sub = self.eng.sub_batch[i] if self.eng.sub_batch[i] > 0 else self.B

@@ -26,6 +26,7 @@ import torch.nn as nn
 
 from ... import native as nv
 from ...engine.convnext_unet import CONVNEXTV2_CFGS, ConvNeXtCfg, ConvNeXtV2UNetEngine
+from ...engine.resnet_unet import RESNET_LAYERS, ResNetCfg, ResNetUNetEngine
 from . import monotemp_model as mm
 
 logger = logging.getLogger(__name__)
@@ -114,7 +115,7 @@ class FLAIR_HUB_Model(nn.Module):
         for mod in self.active_mono:
             for k, (shape, kind) in mm.encoder_spec(self.arch, self.channels_dict[mod]).items():
                 _register(self.encoders, f"{mod}.seg_model.{k}", _init_tensor(shape, kind, gen),
-                          buffer=False)
+                          buffer=kind.startswith("bn_"))
         first = self.active_mono[0]
         # flair_model.py:141-149 / :466-471: FusionHandler.conv_f is always built (one 1x1 conv per
         # stage), also when a single modality makes it a pass-through; checkpoints carry its weights
@@ -156,7 +157,7 @@ class FLAIR_HUB_Model(nn.Module):
         self._engines = {}
         return super().load_state_dict(*a, **k)
 
-    def engine(self, task: Optional[str] = None, max_batch: Optional[int] = None) -> ConvNeXtV2UNetEngine:
+    def engine(self, task: Optional[str] = None, max_batch: Optional[int] = None):
         """Packed-weight execution plan for ``task`` on the parameters' device."""
         task = task or self.config['labels'][0]
         mb = max_batch or self.max_batch
@@ -168,16 +169,23 @@ class FLAIR_HUB_Model(nn.Module):
                     "FLAIR_HUB_Model runs on hand-written sm_100a kernels only: move it to a CUDA device "
                     "(`.to('cuda')`); there is no CPU fallback")
             mod = self.active_mono[0]
-            depths, dims = CONVNEXTV2_CFGS[self.encoder_name]
             ncls = len(self.config['labels_configs'][task]['value_name'])
-            cfg = ConvNeXtCfg(depths=depths, dims=dims, in_chans=self.channels_dict[mod], n_classes=ncls,
-                              patch=int(self.img_input_sizes[mod]))
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             mean, std = self._norm if self._norm else (None, None)
             self._engines = {k: e for k, e in self._engines.items() if k.endswith(f":{mb}")}
-            self._engines[key] = ConvNeXtV2UNetEngine(
-                sd, f"encoders.{mod}.seg_model.model.", f"main_decoders.{task}.seg_model.", cfg, dev,
-                max_batch=mb, norm_mean=mean, norm_std=std)
+            if self.encoder_name in RESNET_LAYERS:
+                cfg = ResNetCfg(layers=RESNET_LAYERS[self.encoder_name], in_chans=self.channels_dict[mod],
+                                n_classes=ncls, patch=int(self.img_input_sizes[mod]))
+                self._engines[key] = ResNetUNetEngine(sd, f"encoders.{mod}.seg_model.",
+                                                      f"main_decoders.{task}.seg_model.", cfg, dev, max_batch=mb,
+                                                      norm_mean=mean, norm_std=std)
+            else:
+                depths, dims = CONVNEXTV2_CFGS[self.encoder_name]
+                cfg = ConvNeXtCfg(depths=depths, dims=dims, in_chans=self.channels_dict[mod], n_classes=ncls,
+                                  patch=int(self.img_input_sizes[mod]))
+                self._engines[key] = ConvNeXtV2UNetEngine(
+                    sd, f"encoders.{mod}.seg_model.model.", f"main_decoders.{task}.seg_model.", cfg, dev,
+                    max_batch=mb, norm_mean=mean, norm_std=std)
         return self._engines[key]
 
     # -------------------------------------------------------------------------------- forward

@@ -12,6 +12,7 @@ from collections import OrderedDict
 from typing import Dict, List, Sequence, Tuple
 
 from ...engine.convnext_unet import CONVNEXTV2_CFGS
+from ...engine.resnet_unet import RESNET_LAYERS
 
 # kind drives the random initialisation only
 Spec = "OrderedDict[str, Tuple[Tuple[int, ...], str]]"
@@ -28,16 +29,19 @@ def split_arch(arch: str) -> Tuple[str, str]:
 def resolve_encoder(name: str) -> str:
     """The smp lookup of monotemp_model.py:67-92: native encoder name first, then 'tu-'+name."""
     base = name[3:] if name.startswith("tu-") else name
-    if base in CONVNEXTV2_CFGS:
+    if base in CONVNEXTV2_CFGS or base in RESNET_LAYERS:
         return base
     raise KeyError(
-        f"encoder '{name}' has no sm_100a execution plan yet (available: {sorted(CONVNEXTV2_CFGS)}); "
-        "there is no PyTorch fallback")
+        f"encoder '{name}' has no sm_100a execution plan yet (available: "
+        f"{sorted(CONVNEXTV2_CFGS) + sorted(RESNET_LAYERS)}); there is no PyTorch fallback")
 
 
 def encoder_out_channels(name: str, in_channels: int) -> List[int]:
     """smp ``encoder.out_channels``; timm-universal "transformer style": [C_in, 0, c4, c8, c16, c32]."""
-    _, dims = CONVNEXTV2_CFGS[resolve_encoder(name)]
+    base = resolve_encoder(name)
+    if base in RESNET_LAYERS:
+        return [in_channels, 64, 64, 128, 256, 512]          # smp native ResNetEncoder
+    _, dims = CONVNEXTV2_CFGS[base]
     return [in_channels, 0] + list(dims)
 
 
@@ -95,8 +99,46 @@ def unet_decoder_spec(encoder_channels: Sequence[int], classes: int,
     return s
 
 
+def _bn_spec(s, prefix: str, c: int):
+    s[prefix + ".weight"] = ((c,), "norm_w")
+    s[prefix + ".bias"] = ((c,), "bias")
+    s[prefix + ".running_mean"] = ((c,), "bn_mean")
+    s[prefix + ".running_var"] = ((c,), "bn_var")
+    s[prefix + ".num_batches_tracked"] = ((), "bn_count")
+
+
+def resnet_encoder_spec(name: str, in_channels: int):
+    """Keys below ``encoders.<MOD>.seg_model.`` for smp's native ResNetEncoder (torchvision ResNet, BasicBlock,
+    no fc).  (If smp resolved the name through timm instead the keys would carry a ``model.`` prefix; SURVEY.md
+    appendix A -- the checkpoint loader is tolerant either way.)"""
+    layers = RESNET_LAYERS[resolve_encoder(name)]
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    s["conv1.weight"] = ((64, in_channels, 7, 7), "conv_relu")
+    _bn_spec(s, "bn1", 64)
+    inpl = 64
+    for li, (nb, planes) in enumerate(zip(layers, (64, 128, 256, 512))):
+        for j in range(nb):
+            stride = 2 if (j == 0 and li > 0) else 1
+            p = f"layer{li + 1}.{j}."
+            s[p + "conv1.weight"] = ((planes, inpl, 3, 3), "conv_relu")
+            _bn_spec(s, p + "bn1", planes)
+            s[p + "conv2.weight"] = ((planes, planes, 3, 3), "conv_relu")
+            _bn_spec(s, p + "bn2", planes)
+            if stride != 1 or inpl != planes:
+                s[p + "downsample.0.weight"] = ((planes, inpl, 1, 1), "conv_relu")
+                _bn_spec(s, p + "downsample.1", planes)
+            inpl = planes
+    return s
+
+
+def encoder_family(name: str) -> str:
+    return "resnet" if resolve_encoder(name) in RESNET_LAYERS else "convnextv2"
+
+
 def encoder_spec(arch: str, in_channels: int):
     enc, _ = split_arch(arch)
+    if encoder_family(enc) == "resnet":
+        return resnet_encoder_spec(enc, in_channels)
     return convnextv2_encoder_spec(enc, in_channels)
 
 

@@ -164,7 +164,7 @@ def _runner(model, config, margin: int) -> ZonalRunner:
     eng = model.engine(task, max_batch=int(config.get('batch_size', model.max_batch)))
     r = getattr(model, key, None)
     if r is None or r.eng is not eng or r.margin != margin:
-        r = ZonalRunner(eng, margin, use_graph=bool(config.get('use_cuda_graph', True)))
+        r = ZonalRunner(eng, margin, use_graph=bool(config.get('use_cuda_graph', True)), norm=model._norm)
         setattr(model, key, r)
     return r
 

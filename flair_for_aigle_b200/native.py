@@ -19,7 +19,7 @@ _lib: Optional[ctypes.CDLL] = None
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16 = 0, 1, 2, 3, 4
-CONV_RELU_BF16, CONV_LOGITS_F32, CONV_ARGMAX_RASTER, CONV_LOGITS_F32_NCHW = 0, 1, 2, 3
+CONV_RELU_BF16, CONV_LOGITS_F32, CONV_ARGMAX_RASTER, CONV_LOGITS_F32_NCHW, CONV_ADD_RELU_BF16, CONV_BF16 = 0, 1, 2, 3, 4, 5
 
 
 class NativeError(RuntimeError):
@@ -75,6 +75,9 @@ _SIGNATURES = {
     "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
     "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_conv7x7s2_bn_relu": [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "fz_maxpool3x3s2": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_conv3x3_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_conv3x3_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
 }
 _RESTYPES = {"fz_last_error": ctypes.c_char_p}
@@ -293,13 +296,36 @@ def upsample2_concat(a, s, out):
     return out
 
 
-def conv3x3(x, w, scale, bias, mode, out=None, cout=None, cstride=0, plan=None, own=None, raster=None, margin=0):
-    """x bf16 [B,H,W,Cin]; w bf16 [rows,3,3,Cin]; scale/bias f32 [rows] (scale may be None)."""
-    B, H, W, Cin = x.shape
+def conv3x3(x, w, scale, bias, mode, out=None, cout=None, cstride=0, plan=None, own=None, raster=None, margin=0,
+            stride=1, resid=None):
+    """x bf16 [B,Hin,Win,Cin]; w bf16 [rows,3,3,Cin]; scale/bias f32 [rows] (scale may be None); the output is
+    [B,Hin/stride,Win/stride,cout]; resid (bf16, output shape) is added before the ReLU in CONV_ADD_RELU_BF16."""
+    B, Hin, Win, Cin = x.shape
+    H, W = Hin // stride, Win // stride
     rows = w.shape[0]
     cout = rows if cout is None else cout
     RH, RW = (raster.shape[-2], raster.shape[-1]) if raster is not None else (0, 0)
     with _Timed('conv3x3_tcgen05', B=B, H=H, Cin=Cin, Cout=cout, mode=mode):
-        _check(lib().fz_conv3x3_bf16(_ptr(x), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), B, H, W, Cin, cout, rows, mode, cstride,
-                                     _ptr(plan), _ptr(own), _ptr(raster), RH, RW, margin, _stream()), "fz_conv3x3_bf16")
+        _check(lib().fz_conv3x3_ex(_ptr(x), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), _ptr(resid), B, H, W, Cin, cout,
+                                   rows, stride, mode, cstride, _ptr(plan), _ptr(own), _ptr(raster), RH, RW, margin,
+                                   _stream()), "fz_conv3x3_ex")
+    return out
+
+
+def conv7x7s2_bn_relu(x, w, scale, bias, out):
+    """x: uint8 [B,P,P,4] or float32 [B,Cin,P,P]; out bf16 [B,P/2,P/2,64]."""
+    if x.dtype == torch.uint8:
+        B, P, is_f32, cin = x.shape[0], x.shape[1], 0, 4
+    else:
+        B, cin, P, is_f32 = x.shape[0], x.shape[1], x.shape[2], 1
+    with _Timed('conv7x7s2', B=B, P=P):
+        _check(lib().fz_conv7x7s2_bn_relu(_ptr(x), is_f32, cin, _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), B, P,
+                                          _stream()), "fz_conv7x7s2_bn_relu")
+    return out
+
+
+def maxpool3x3s2(x, out):
+    B, H, W, C = x.shape
+    with _Timed('maxpool3x3s2', B=B, H=H, C=C):
+        _check(lib().fz_maxpool3x3s2(_ptr(x), _ptr(out), B, H, W, C, _stream()), "fz_maxpool3x3s2")
     return out

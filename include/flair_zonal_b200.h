@@ -151,11 +151,31 @@ int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K, int rows_p
 #define FZ_CONV_LOGITS_F32 1
 #define FZ_CONV_ARGMAX_RASTER 2
 #define FZ_CONV_LOGITS_F32_NCHW 3 /* out float [B][Cout][H][W]: the reference's logits layout */
+#define FZ_CONV_ADD_RELU_BF16 4   /* out bf16 = relu(conv*scale + bias + resid): torchvision BasicBlock tail */
+#define FZ_CONV_BF16 5            /* out bf16 = conv*scale + bias (no activation): BasicBlock downsample branch */
 int fz_upsample2_concat(const void* a, int a_dtype, const void* s, int s_dtype, void* out_bf16, int B, int H, int W,
                         int C1, int C2, void* stream);
 int fz_conv3x3_bf16(const void* in, const void* w, const float* scale, const float* bias, void* out, int B, int H,
                     int W, int Cin, int Cout, int w_rows, int mode, int cstride, const int32_t* plan,
                     const int32_t* own, uint8_t* raster, int RH, int RW, int margin, void* stream);
+
+/* ---------------------------------------------------------------- ResNet-34 encoder front end
+ * (smp native ResNetEncoder = torchvision ResNet without fc; `resnet34-unet`, BASELINE.json configs[0])
+ * fz_conv7x7s2_bn_relu: conv 7x7 stride 2 pad 3 + eval BatchNorm (scale/bias) + ReLU.  in: uint8 [B][P][P][4]
+ *   (in_is_f32 = 0; normalisation folded into w/bias by the host) or float [B][Cin][P][P] (in_is_f32 = 1);
+ *   w float [196][64] with row k = (ky*7+kx)*4 + c; out bf16 [B][P/2][P/2][64].
+ * fz_maxpool3x3s2: max-pool 3x3 stride 2 pad 1 on bf16 NHWC. */
+int fz_conv7x7s2_bn_relu(const void* in, int in_is_f32, int Cin, const float* w, const float* scale, const float* bias,
+                         void* out_bf16, int B, int P, void* stream);
+int fz_maxpool3x3s2(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, void* stream);
+
+/* fz_conv3x3_ex: fz_conv3x3_bf16 plus stride (1 | 2; H, W are the OUTPUT size, the input is H*stride x W*stride,
+ * padding 1) and a residual operand (bf16 [B][H][W][Cout]) for FZ_CONV_ADD_RELU_BF16.  Covers the smp/torchvision
+ * ResNet BasicBlock (conv3x3 s1|s2 + BN + ReLU, conv3x3 + BN, + identity, ReLU) called at flair_model.py:376 for
+ * `resnet34-unet`; the 1x1/s2 downsample conv is expressed as a 3x3 with only the centre tap non-zero. */
+int fz_conv3x3_ex(const void* in, const void* w, const float* scale, const float* bias, void* out, const void* resid,
+                  int B, int H, int W, int Cin, int Cout, int w_rows, int stride, int mode, int cstride,
+                  const int32_t* plan, const int32_t* own, uint8_t* raster, int RH, int RW, int margin, void* stream);
 
 #ifdef __cplusplus
 }

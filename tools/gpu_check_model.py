@@ -87,11 +87,11 @@ try:
     for k, blk in enumerate(eng.dec):
         hd *= 2
         ct = blk["cin"] + blk["cskip"]
-        cat = eng.cat[:n * hd * hd * ct].view(n, hd, hd, ct)
+        cat = eng.decoder.cat[:n * hd * hd * ct].view(n, hd, hd, ct)
         nv.upsample2_concat(a, skips[k] if blk["cskip"] > 0 else None, cat)
-        o1 = eng.t1[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
+        o1 = eng.decoder.t1[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
         nv.conv3x3(cat, blk["conv1_w"], blk["conv1_s"], blk["conv1_b"], nv.CONV_RELU_BF16, out=o1)
-        o2 = eng.t2[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
+        o2 = eng.decoder.t2[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
         nv.conv3x3(o1, blk["conv2_w"], blk["conv2_s"], blk["conv2_b"], nv.CONV_RELU_BF16, out=o2)
         torch.cuda.synchronize()
         cmp(f"dec{k}", o2, acts[f"dec{k}"])
