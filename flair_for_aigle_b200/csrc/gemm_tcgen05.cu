@@ -74,7 +74,10 @@ __device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
   colsum32_step<1>(s, lane);
 }
 
-template <int BN, int STAGES, int ACC_STAGES, int MODE>
+// CL = 2: the two CTAs of a cluster work on neighbouring N tiles of the SAME 256 rows; each loads one 128-row half
+// of the A stage and TMA-multicasts it into both CTAs' shared memory, so a CTA pulls 32 KB instead of 48 KB per
+// k-block through the L2 fabric (the 6.3 KB/clk L2->SM cap is what bounded the 256x128 tiles at ~0.83 PFLOP/s).
+template <int BN, int STAGES, int ACC_STAGES, int MODE, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using L = GemmSmem<BN, STAGES>;
@@ -97,13 +100,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int m_tiles = (p.M + BM - 1) / BM;
   const int total_tiles = n_tiles * m_tiles;
   const int num_kb = p.K / BK;
+  // persistent schedule: tile t -> (m = t / n_tiles, n = t % n_tiles).  With CL = 2 consecutive CTAs (a cluster)
+  // take consecutive tiles, i.e. the same m and neighbouring n (n_tiles is even: host check).
+  const int crank = CL == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int t_first = blockIdx.x, t_step = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);          // released by the MMA warp of every CTA that reads the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -115,12 +122,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL == 2) cluster_sync_all();       // the peer's barriers exist before anything is multicast at them
   const uint32_t tmem = *tslot;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
         const int n0 = (t % n_tiles) * BN;
         const int m0 = (t / n_tiles) * BM;
         const int bcoord = p.b_batched ? (m0 / p.rows_per_sample) : 0;
@@ -130,7 +138,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
-          tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
+          if (CL == 2)   // my 128-row half of the shared A stage, into both CTAs (tmA's box is 128 rows here)
+            tma_load_2d_mcast(&tmA, &full[s], sA + s * A_STAGE_BYTES + crank * (128 * BK * 2), kb * BK,
+                              m0 + crank * 128, 0x3);
+          else
+            tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
           tma_load_3d(&tmB, &full[s], sB + s * L::B_STAGE_BYTES, kb * BK, n0, bcoord);
         }
       }
@@ -140,7 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
         const uint32_t as = lt % ACC_STAGES;
         const uint32_t aph = (lt / ACC_STAGES) & 1;
         FZ_TRACE(1);   // MMA warp reaches the tile
@@ -165,7 +177,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_bf16(acc0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
             umma_bf16(acc1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
           }
-          umma_commit(&empty[s]);
+          if (CL == 2) umma_commit_mcast(&empty[s], 0x3);
+          else umma_commit(&empty[s]);
         }
         umma_commit(&tfull[as]);
         FZ_TRACE(4);   // all MMAs of the tile issued
@@ -179,7 +192,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int colgrp = ew >> 3;                 // chunks colgrp, colgrp+2, ...
     const int bar_id = 1 + half;
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+    for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
       const int n0 = (t % n_tiles) * BN;
       const int m0 = (t / n_tiles) * BM;
       const uint32_t as = lt % ACC_STAGES;
@@ -303,13 +316,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();       // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp == 1) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int BN, int STAGES, int ACC_STAGES, int MODE>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BN, int STAGES, int ACC_STAGES, int MODE, int CL>
+static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE, CL>;
   static bool configured = false;
   static int sm_count = 0;
   if (!configured) {
@@ -320,22 +334,42 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     configured = true;
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = tiles < sm_count ? tiles : sm_count;
-  kern<<<grid, GEMM_THREADS, L::BYTES, stream>>>(tmA, tmB, p);
-  FZ_CHECK_CUDA(cudaGetLastError());
+  int grid = tiles < sm_count ? tiles : sm_count;
+  if (CL == 2) grid &= ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = L::BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FZ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   return 0;
+}
+
+template <int BN, int STAGES, int ACC_STAGES, int MODE>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA128, const CUtensorMap& tmB, const GemmParams& p,
+                       bool cluster, cudaStream_t stream) {
+  if (cluster) return launch_gemm_cl<BN, STAGES, ACC_STAGES, MODE, 2>(tmA128, tmB, p, stream);
+  return launch_gemm_cl<BN, STAGES, ACC_STAGES, MODE, 1>(tmA, tmB, p, stream);
 }
 
 // BN = 128: 3 smem stages (48 KB each) + 64 KB store staging, accumulators double buffered.
 // BN = 256: 2 smem stages (64 KB each), single accumulator stage (FZ_GEMM_BN=256 experiments only).
 template <int BN, int STAGES, int ACC_STAGES>
-static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& a128, const CUtensorMap& b,
+                         const GemmParams& p, bool cl, cudaStream_t st) {
   switch (mode) {
-    case FZ_EPI_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_BF16>(a, b, p, st);
-    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_SUMSQ>(a, b, p, st);
-    case FZ_EPI_RESID_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RESID_F32>(a, b, p, st);
-    case FZ_EPI_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_F32>(a, b, p, st);
-    case FZ_EPI_RELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RELU_BF16>(a, b, p, st);
+    case FZ_EPI_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_BF16>(a, a128, b, p, cl, st);
+    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_SUMSQ>(a, a128, b, p, cl, st);
+    case FZ_EPI_RESID_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RESID_F32>(a, a128, b, p, cl, st);
+    case FZ_EPI_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_F32>(a, a128, b, p, cl, st);
+    case FZ_EPI_RELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RELU_BF16>(a, a128, b, p, cl, st);
   }
   set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
   return -1;
@@ -373,12 +407,22 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
     BN = 256;   // only when every CTA gets >= 3 tiles: the single accumulator stage cannot overlap its epilogue
   FZ_REQUIRE((BN == 64 || BN == 128 || BN == 256) && N % BN == 0, "fz_gemm_bf16: bad tile width %d for N=%d", BN, N);
 
-  CUtensorMap tmA, tmB;
+  // cluster-of-2 multicast needs an even number of N tiles and pairs of tiles that start together
+  static int cluster_env = -1;
+  if (cluster_env < 0) {
+    const char* e = getenv("FZ_GEMM_CLUSTER");
+    cluster_env = e ? atoi(e) : 0;
+  }
+  const bool cluster = cluster_env != 0 && ((N / BN) % 2 == 0);
+  CUtensorMap tmA, tmA128, tmB;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)K * 2};
     const uint32_t box[2] = {BK, BM};
     int rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box, 128);
+    if (rc) return rc;
+    const uint32_t box128[2] = {BK, 128};
+    rc = make_tmap_bf16(&tmA128, A, 2, dims, strides, box128, 128);
     if (rc) return rc;
   }
   {
@@ -394,9 +438,9 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = g_trace;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch_mode<256, 2, 1>(mode, tmA, tmB, p, st);
-  if (BN == 128) return dispatch_mode<128, 3, 2>(mode, tmA, tmB, p, st);
-  return dispatch_mode<64, 3, 2>(mode, tmA, tmB, p, st);
+  if (BN == 256) return dispatch_mode<256, 2, 1>(mode, tmA, tmA128, tmB, p, cluster, st);
+  if (BN == 128) return dispatch_mode<128, 3, 2>(mode, tmA, tmA128, tmB, p, cluster, st);
+  return dispatch_mode<64, 3, 2>(mode, tmA, tmA128, tmB, p, cluster, st);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -76,10 +76,19 @@ class ZonalRunner:
         n += len(self.eng.dec) * 3 + 1
         return n
 
-    def _ensure_graph(self, raster: torch.Tensor, out_raster: torch.Tensor) -> None:
+    def _ensure_graph(self, raster: torch.Tensor, out_raster: torch.Tensor):
+        """Returns the (raster, out) tensors the captured graph reads / writes.  A graph is tied to the addresses
+        it was captured with: when a new zone of the SAME shape arrives in different buffers (a fresh upload, a
+        fresh output raster) it is staged through the captured buffers with two device-to-device copies
+        (~0.2 ms for a 10k x 10k zone) instead of paying a ~100 ms re-capture."""
         key = (raster.data_ptr(), tuple(raster.shape), out_raster.data_ptr(), tuple(out_raster.shape))
-        if self._graph is not None and self._graph_key == key:
-            return
+        if self._graph is not None:
+            if self._graph_key == key:
+                return raster, out_raster
+            if self._graph_key[1] == key[1] and self._graph_key[3] == key[3]:
+                self._g_raster.copy_(raster, non_blocking=True)
+                self._g_out.copy_(out_raster, non_blocking=True)
+                return self._g_raster, self._g_out
         # warm-up on a side stream (sets func attributes, touches every buffer), then capture
         self.s_plan.zero_()      # height 0 => nothing is written during warm-up / capture
         self.s_own.zero_()
@@ -94,6 +103,8 @@ class ZonalRunner:
         with torch.cuda.graph(g):
             self._batch_body(raster, out_raster)
         self._graph, self._graph_key = g, key
+        self._g_raster, self._g_out = raster, out_raster      # keep the captured buffers alive
+        return raster, out_raster
 
     def run(self, raster: torch.Tensor, plan: np.ndarray, own: np.ndarray, out_raster: torch.Tensor) -> int:
         """raster uint8 [C,H,W] (cuda), plan int32 (n,6), own int32 (n,4), out_raster uint8 [H,W]
@@ -109,8 +120,7 @@ class ZonalRunner:
         plan_d = torch.from_numpy(np.ascontiguousarray(plan_p)).to(self.dev, non_blocking=True)
         own_d = torch.from_numpy(np.ascontiguousarray(own_p)).to(self.dev, non_blocking=True)
         org_d = plan_d[:, :2].contiguous()
-        if self.use_graph:
-            self._ensure_graph(raster, out_raster)
+        g_raster, g_out = (self._ensure_graph(raster, out_raster) if self.use_graph else (raster, out_raster))
         for b in range(nb):
             sl = slice(b * B, (b + 1) * B)
             self.s_origins.copy_(org_d[sl])
@@ -120,4 +130,6 @@ class ZonalRunner:
                 self._graph.replay()
             else:
                 self._batch_body(raster, out_raster)
+        if g_out is not out_raster:
+            out_raster.copy_(g_out, non_blocking=True)
         return nb

@@ -113,6 +113,9 @@ def open_raster(path) -> ZoneRaster:
         return ZoneRaster(src.read(), src.bounds.left, src.bounds.top, abs(src.res[0]), str(src.crs), name=path)
 
 
+_PINNED_POOL = {}
+
+
 class RasterSink:
     """Output raster of ``init_outputs`` (inference.py:157-208): a uint8 (count,H,W) array that lives
     on the GPU while tiles are written into it by the kernels, copied to the host once and stored
@@ -131,11 +134,23 @@ class RasterSink:
         self.device_array = torch.zeros((count, height, width), dtype=torch.uint8, device=device)
         self.host_array = None
         self.closed = False
+        self._pinned = None
+
+    def release(self) -> None:
+        """Give the page-locked host buffer back for the next zone of the same shape (the numpy view returned by
+        to_host() must not be used afterwards)."""
+        if self._pinned is not None:
+            _PINNED_POOL[tuple(self._pinned.shape)] = self._pinned
+            self._pinned, self.host_array = None, None
 
     def to_host(self) -> np.ndarray:
         if self.host_array is None:
             import torch
-            pinned = torch.empty(self.device_array.shape, dtype=torch.uint8, pin_memory=True)
+            key = tuple(self.device_array.shape)
+            pinned = _PINNED_POOL.pop(key, None)            # page-locking 100 MB costs tens of ms: reuse
+            if pinned is None:
+                pinned = torch.empty(self.device_array.shape, dtype=torch.uint8, pin_memory=True)
+            self._pinned = pinned
             pinned.copy_(self.device_array, non_blocking=True)
             torch.cuda.current_stream(self.device_array.device).synchronize()
             self.host_array = pinned.numpy()

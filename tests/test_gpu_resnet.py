@@ -102,3 +102,46 @@ def test_resnet34_unet_engine_vs_oracle(cuda):
           f"agree={same.float().mean().item():.5f} agree(confident)={same[conf].float().mean().item():.6f}")
     assert d.mean().item() < 0.015 * sd_ and d.max().item() < 0.15 * sd_
     assert same.float().mean().item() >= 0.98 and same[conf].float().mean().item() >= 0.999
+
+
+def test_resnet34_zone_through_public_api(cuda, tmp_path):
+    """configs[0] through the drop-in API (build_inference_model -> inference_and_write) vs the oracle pipeline."""
+    import bench
+    from safetensors.torch import load_file, save_file
+    from oracle.grid import Georef
+    from oracle.models import FlairHubOracle
+    from oracle.pipeline import run_zone
+    from flair_for_aigle_b200.flair_hub.models.flair_model import FLAIR_HUB_Model
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model, prepare_model_config
+    from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink, ZoneRaster, register_raster
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import generate_patches_from_reference
+    from flair_for_aigle_b200.synthetic import DEFAULT_MEANS, DEFAULT_STDS, randomize_state_, synthetic_raster
+    wpath = str(tmp_path / "resnet34_unet.safetensors")
+    c = bench.zonal_config(wpath, str(tmp_path), "mem://r34", 4)
+    c["monotemp_arch"] = "resnet34-unet"
+    sd = FLAIR_HUB_Model(prepare_model_config(dict(c, model_weights=wpath)), {"AERIAL_RGBI": 512}).state_dict()
+    randomize_state_(sd, seed=5)
+    # keep activations O(1): shrink the second conv of every BasicBlock
+    for k in sd:
+        if ".conv2.weight" in k and "layer" in k:
+            sd[k].mul_(0.25)
+    save_file({k: v.contiguous() for k, v in sd.items()}, wpath)
+    arr = synthetic_raster(700, 1000, seed=4)
+    register_raster("mem://r34", ZoneRaster(arr, 700000.0, 6600000.0, 0.2))
+    cfg = inf.initialize_geometry_and_resolutions(c)
+    cfg["device"] = cuda
+    model = build_inference_model(cfg, {"AERIAL_RGBI": 512}).to(cuda)
+    tiles = generate_patches_from_reference(cfg, "mem://r34", None)
+    ds = inf.prep_dataset(cfg, tiles, {"AERIAL_RGBI": 512})
+    RasterSink.write_files = False
+    outs, _ = inf.init_outputs(cfg, "mem://r34", 0)
+    inf.inference_and_write(model, ds, tiles, cfg, outs, "mem://r34")
+    got = outs[TASK].to_host()[0]
+    oracle = FlairHubOracle("resnet34-unet", {"AERIAL_RGBI": 4}, {TASK: 19}).eval()
+    oracle.load_state_dict(load_file(wpath), strict=True)
+    ref, _, _ = run_zone(oracle.to(cuda), arr, Georef(700000.0, 6600000.0, 0.2, 1000, 700), 512, 64, DEFAULT_MEANS,
+                         DEFAULT_STDS, TASK, 19, batch_size=2, device="cuda")
+    agree = (got == ref).mean()
+    print(f"resnet34-unet zone class agreement with the oracle pipeline: {agree:.5f}")
+    assert agree >= 0.98
