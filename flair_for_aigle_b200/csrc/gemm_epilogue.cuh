@@ -1,0 +1,144 @@
+// Epilogue shared by the one-SM (gemm_tcgen05.cu) and CTA-pair (gemm_tcgen05_2sm.cu) bf16 GEMM kernels:
+// one warp moves a 32-row x 128-byte chunk of the accumulator TMEM -> registers -> (+bias, activation,
+// residual) -> XOR-swizzled per-warp staging tile -> global memory in full 128 B lines.
+#pragma once
+#include "ptx.cuh"
+#include "../../include/flair_zonal_b200.h"
+
+namespace fz {
+
+struct GemmParams {
+  int M, N, K;
+  int rows_per_sample;  // rows of A per sample (H*W); selects the B batch
+  int b_batched;        // 1: B is [num_samples][N][K] and the tile uses batch m0 / rows_per_sample
+  const float* bias;    // [N], never null
+  void* out;            // [M,N] bf16 or f32
+  const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
+  float* sumsq;         // [ceil(M/128), N] f32 per-128-row partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
+  unsigned long long* trace;  // optional: CTA 0 writes clock64 stamps [tile][8] (diagnostics, see fz_gemm_set_trace)
+};
+
+template <int OFF>
+__device__ __forceinline__ void colsum32_step(float (&s)[32], int lane) {
+  const bool upper = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < OFF; ++i) {
+    const float a = s[i], b = s[i + OFF];
+    s[i] = (upper ? b : a) + __shfl_xor_sync(0xffffffffu, upper ? a : b, OFF);
+  }
+}
+// Column sums over the 32 lanes of a warp of a 32-vector held per lane (transpose-reduce):
+// on return s[0] of lane l is the sum over lanes of the input s[l].  31 shuffles.
+__device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
+  colsum32_step<16>(s, lane);
+  colsum32_step<8>(s, lane);
+  colsum32_step<4>(s, lane);
+  colsum32_step<2>(s, lane);
+  colsum32_step<1>(s, lane);
+}
+
+template <int MODE>
+struct EpiShape {
+  static constexpr bool F32OUT = (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32);
+  static constexpr int CH_COLS = F32OUT ? 32 : 64;   // 128 B of output per row
+  static constexpr int ESZ = F32OUT ? 4 : 2;
+};
+
+// taddr : TMEM address of the chunk's first column at the warp's lane base (lane quarter already applied)
+// row0  : global output row of the warp's first row (its 32 rows are row0 .. row0+31)
+// col0  : global output column of the chunk
+// stg   : this warp's 4 KB staging tile; 16 B segments XOR-swizzled with row&7 so that both the row-per-lane and
+//         the row-contiguous access patterns are bank-conflict free.  A row-per-thread STG/LDG would touch 32
+//         lines per instruction, which was the first epilogue's bottleneck.
+// sq_dst: (GELU_SUMSQ) where lane l stores the 32-row column sum of out^2 for column l (+32 for the second half)
+template <int MODE>
+__device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, int row0, int col0, char* stg, int lane,
+                                          float* sq_dst) {
+  constexpr bool F32OUT = EpiShape<MODE>::F32OUT;
+  constexpr int CH_COLS = EpiShape<MODE>::CH_COLS;
+  constexpr int ESZ = EpiShape<MODE>::ESZ;
+  const int rsub = lane >> 3, seg = lane & 7;              // row-contiguous mapping: 4 rows x 8 segments
+  const size_t row_bytes = static_cast<size_t>(p.N) * ESZ;
+  char* gout = reinterpret_cast<char*>(p.out) + static_cast<size_t>(row0) * row_bytes + static_cast<size_t>(col0) * ESZ;
+  if (MODE == FZ_EPI_RESID_F32) {
+    // coalesced residual tile -> staging
+    const char* gres = reinterpret_cast<const char*>(p.resid) + static_cast<size_t>(row0) * row_bytes +
+                       static_cast<size_t>(col0) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + rsub;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (row0 + rr < p.M) x = *reinterpret_cast<const uint4*>(gres + static_cast<size_t>(rr) * row_bytes + seg * 16);
+      *reinterpret_cast<uint4*>(stg + rr * 128 + ((seg ^ (rr & 7)) << 4)) = x;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int h = 0; h < CH_COLS / 32; ++h) {
+    uint32_t r[32];
+    tmem_ld32(taddr + h * 32, r);
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + h * 32);
+    float4 b4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b4[j] = __ldg(bp + j);
+    float v[32];
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4[j].x;
+      v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4[j].y;
+      v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
+      v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
+    }
+    if (MODE == FZ_EPI_GELU_SUMSQ) {
+      float s[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = gelu_erf_fast(v[j]);
+        s[j] = v[j] * v[j];     // M is a multiple of 128 in this mode (host check): no row mask
+      }
+      warp_colsum32(s, lane);
+      sq_dst[h * 32 + lane] = s[0];
+    } else if (MODE == FZ_EPI_RELU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    } else if (MODE == FZ_EPI_RESID_F32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
+        v[4 * j + 0] += x.x;
+        v[4 * j + 1] += x.y;
+        v[4 * j + 2] += x.z;
+        v[4 * j + 3] += x.w;
+      }
+      __syncwarp();   // everyone has read its residual row before the tile is overwritten
+    }
+    // own row -> staging
+    if (F32OUT) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stg + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)) =
+            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    }
+  }
+  __syncwarp();
+  // staging -> global, 4 full 128 B lines per instruction
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + rsub;
+    const uint4 x = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((seg ^ (rr & 7)) << 4));
+    if (row0 + rr < p.M) *reinterpret_cast<uint4*>(gout + static_cast<size_t>(rr) * row_bytes + seg * 16) = x;
+  }
+  __syncwarp();       // staging is reused by the next chunk
+}
+
+// launchers of the two kernels (defined in their .cu files)
+int gemm_pair_launch(const void* A, const void* B, const GemmParams& p, int b_batch, int mode, cudaStream_t stream);
+
+}  // namespace fz

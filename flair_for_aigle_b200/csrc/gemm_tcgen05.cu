@@ -17,6 +17,7 @@
 // are double buffered in TMEM (2 x 256 columns) so tile i's epilogue overlaps tile i+1's MMAs.
 #include "common.h"
 #include "ptx.cuh"
+#include "gemm_epilogue.cuh"
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
@@ -26,17 +27,6 @@ constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int GEMM_THREADS = 640;   // 4 control warps + 16 epilogue warps
 constexpr int EPI_WARP0 = 4;
-
-struct GemmParams {
-  int M, N, K;
-  int rows_per_sample;  // rows of A per sample (H*W); selects the B batch
-  int b_batched;        // 1: B is [num_samples][N][K] and the tile uses batch m0 / rows_per_sample
-  const float* bias;    // [N] or nullptr
-  void* out;            // [M,N] bf16 or f32
-  const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
-  float* sumsq;         // [ceil(M/128), N] f32 per-128-row partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
-  unsigned long long* trace;  // optional: CTA 0 writes clock64 stamps [tile][8] (diagnostics, see fz_gemm_set_trace)
-};
 
 static unsigned long long* g_trace = nullptr;
 #define FZ_TRACE(slot)                                                          \
@@ -54,25 +44,6 @@ struct GemmSmem {
   static constexpr int OFF_TSLOT = OFF_BAR + (2 * STAGES + 4) * 8;
   static constexpr int BYTES = OFF_TSLOT + 16 + 1024;            // + worst-case alignment pad
 };
-
-template <int OFF>
-__device__ __forceinline__ void colsum32_step(float (&s)[32], int lane) {
-  const bool upper = (lane & OFF) != 0;
-#pragma unroll
-  for (int i = 0; i < OFF; ++i) {
-    const float a = s[i], b = s[i + OFF];
-    s[i] = (upper ? b : a) + __shfl_xor_sync(0xffffffffu, upper ? a : b, OFF);
-  }
-}
-// Column sums over the 32 lanes of a warp of a 32-vector held per lane (transpose-reduce):
-// on return s[0] of lane l is the sum over lanes of the input s[l].  31 shuffles.
-__device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
-  colsum32_step<16>(s, lane);
-  colsum32_step<8>(s, lane);
-  colsum32_step<4>(s, lane);
-  colsum32_step<2>(s, lane);
-  colsum32_step<1>(s, lane);
-}
 
 // CL = 2: the two CTAs of a cluster work on neighbouring N tiles of the SAME 256 rows; each loads one 128-row half
 // of the A stage and TMA-multicasts it into both CTAs' shared memory, so a CTA pulls 32 KB instead of 48 KB per
@@ -204,99 +175,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (ew == 0 && lane == 0) FZ_TRACE(6);   // accumulator complete
       const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + as * (2 * BN) + half * BN;
-      // Each chunk is 128 B of output per row (32 fp32 or 64 bf16 columns).  Results go through a
-      // per-warp 32 x 128 B staging tile (16 B segments XOR-swizzled with row&7: conflict-free both
-      // row-per-lane and row-contiguous) so that every global access is a full 128 B line: a
-      // row-per-thread STG/LDG touches 32 lines per instruction and was the v2 epilogue's bottleneck.
-      constexpr bool F32OUT = (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32);
-      constexpr int CH_COLS = F32OUT ? 32 : 64;
-      constexpr int ESZ = F32OUT ? 4 : 2;
-      const int rsub = lane >> 3, seg = lane & 7;              // row-contiguous mapping: 4 rows x 8 segments
-      const size_t row_bytes = static_cast<size_t>(p.N) * ESZ;
+      constexpr int CH_COLS = EpiShape<MODE>::CH_COLS;
 #pragma unroll 1
-      for (int c = colgrp; c < BN / CH_COLS; c += 2) {
-        const int col0 = n0 + c * CH_COLS;
-        char* gout = reinterpret_cast<char*>(p.out) + static_cast<size_t>(m0 + half * 128 + q * 32) * row_bytes +
-                     static_cast<size_t>(col0) * ESZ;
-        if (MODE == FZ_EPI_RESID_F32) {
-          // coalesced residual tile -> staging
-          const char* gres = reinterpret_cast<const char*>(p.resid) +
-                             static_cast<size_t>(m0 + half * 128 + q * 32) * row_bytes + static_cast<size_t>(col0) * 4;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + rsub;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (m0 + half * 128 + q * 32 + rr < p.M)
-              x = *reinterpret_cast<const uint4*>(gres + static_cast<size_t>(rr) * row_bytes + seg * 16);
-            *reinterpret_cast<uint4*>(stg + rr * 128 + ((seg ^ (rr & 7)) << 4)) = x;
-          }
-          __syncwarp();
-        }
-#pragma unroll
-        for (int h = 0; h < CH_COLS / 32; ++h) {
-          uint32_t r[32];
-          tmem_ld32(tbase + c * CH_COLS + h * 32, r);
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + h * 32);   // never null (host check)
-          float4 b4[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) b4[j] = __ldg(bp + j);
-          float v[32];
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4[j].x;
-            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4[j].y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
-            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
-          }
-          if (MODE == FZ_EPI_GELU_SUMSQ) {
-            float s[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = gelu_erf_fast(v[j]);
-              s[j] = v[j] * v[j];     // M is a multiple of 128 in this mode (host check): no row mask
-            }
-            warp_colsum32(s, lane);
-            sq_buf[(half * 4 + q) * BN + c * CH_COLS + h * 32 + lane] = s[0];
-          } else if (MODE == FZ_EPI_RELU_BF16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-          } else if (MODE == FZ_EPI_RESID_F32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 x = *reinterpret_cast<const float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
-              v[4 * j + 0] += x.x;
-              v[4 * j + 1] += x.y;
-              v[4 * j + 2] += x.z;
-              v[4 * j + 3] += x.w;
-            }
-            __syncwarp();   // everyone has read its residual row before the tile is overwritten
-          }
-          // own row -> staging
-          if (F32OUT) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(stg + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)) =
-                  make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-          }
-        }
-        __syncwarp();
-        // staging -> global, 4 full 128 B lines per instruction
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rsub;
-          const uint4 x = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((seg ^ (rr & 7)) << 4));
-          if (m0 + half * 128 + q * 32 + rr < p.M)
-            *reinterpret_cast<uint4*>(gout + static_cast<size_t>(rr) * row_bytes + seg * 16) = x;
-        }
-        __syncwarp();       // staging is reused by the next chunk
-      }
+      for (int c = colgrp; c < BN / CH_COLS; c += 2)
+        epi_chunk<MODE>(p, tbase + c * CH_COLS, m0 + half * 128 + q * 32, n0 + c * CH_COLS, stg, lane,
+                        sq_buf + (half * 4 + q) * BN + c * CH_COLS);
       // all TMEM reads of this stage are complete (tmem_ld_wait above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -438,6 +321,14 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = g_trace;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // CTA-pair kernel (256x256 tile over two SMs, gemm_tcgen05_2sm.cu): wide outputs with enough tiles for 74 pairs.
+  // FZ_GEMM_PAIR=0 disables, =2 forces it whenever N % 256 == 0.
+  const char* pair_e = getenv("FZ_GEMM_PAIR");
+  const int pair_env = pair_e ? atoi(pair_e) : 1;
+  if (!force && pair_env != 0 && N % 256 == 0) {
+    const long long pair_tiles = static_cast<long long>((M + BM - 1) / BM) * (N / 256);
+    if (pair_env == 2 || pair_tiles >= 74) return gemm_pair_launch(A, B, p, b_batch, mode, st);
+  }
   if (BN == 256) return dispatch_mode<256, 2, 1>(mode, tmA, tmA128, tmB, p, cluster, st);
   if (BN == 128) return dispatch_mode<128, 3, 2>(mode, tmA, tmA128, tmB, p, cluster, st);
   return dispatch_mode<64, 3, 2>(mode, tmA, tmA128, tmB, p, cluster, st);

@@ -52,6 +52,38 @@ def test_gemm_modes(cuda, impl, M, N, K, rps, bb, mode):
         assert rel < 2e-3, f"sumsq rel err {rel}"
 
 
+@pytest.mark.parametrize("M,N,K,rps,bb", [
+    (512, 256, 128, 256, 1), (2048, 2048, 512, 1024, 1), (2048, 512, 2048, 1024, 2),
+    (1408, 512, 256, 1408, 1),          # last pair tile: only the leader's 128 rows exist
+    (10240, 1024, 256, 1024, 10),       # 160 pair tiles over 74 pairs: ring + TMEM double buffering across tiles
+])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_gemm_pair_kernel(cuda, monkeypatch, M, N, K, rps, bb, mode):
+    """cta_group::2 kernel (gemm_tcgen05_2sm.cu), forced for every N % 256 == 0 shape."""
+    from flair_for_aigle_b200 import native as nv
+    monkeypatch.setenv("FZ_GEMM_PAIR", "2")
+    torch.manual_seed(M + N + K + mode)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    A = (torch.randn(M, K, device=cuda) * 0.5).bfloat16()
+    B = (torch.randn((bb, N, K) if bb > 1 else (N, K), device=cuda) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=cuda) * 0.1
+    resid = torch.randn(M, N, device=cuda) if mode == nv.EPI_RESID_F32 else None
+    sumsq = torch.full((M // 128, N), -1.0, device=cuda) if mode == nv.EPI_GELU_SUMSQ else None
+    out = nv.gemm_bf16(A, B, mode, bias=bias, resid=resid, sumsq=sumsq, rows_per_sample=rps)
+    torch.cuda.synchronize()
+    ref, ref_sq = _ref(A, B, bias, mode, resid, rps)
+    err = (out.float() - ref).abs().max().item()
+    tol = 2e-2 if out.dtype == torch.bfloat16 else 2e-4
+    assert err < tol * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+    if sumsq is not None:
+        rel = ((sumsq - ref_sq).abs() / ref_sq.clamp_min(1e-3)).max().item()
+        assert rel < 2e-3, f"sumsq rel err {rel}"
+    # same inputs, same launch -> identical bits (no atomics anywhere)
+    out2 = nv.gemm_bf16(A, B, mode, bias=bias, resid=resid, sumsq=sumsq, rows_per_sample=rps)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
 def test_gemm_inplace_residual(cuda):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(0)
