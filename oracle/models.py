@@ -25,6 +25,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .swin_upernet import SWIN_CFGS, SwinUniversalEncoder, UPerNetDecoder, UPerNetHead, WindowAttention
+
 
 # --------------------------------------------------------------------------------------
 # timm pieces (ConvNeXt-V2)
@@ -294,12 +296,16 @@ def make_encoder(name: str, in_channels: int) -> nn.Module:
         return ResNetEncoder(in_channels, (3, 4, 6, 3))
     if base == "resnet18":
         return ResNetEncoder(in_channels, (2, 2, 2, 2))
+    if base in SWIN_CFGS:
+        return SwinUniversalEncoder(base, in_channels)
     raise KeyError(f"oracle: encoder '{name}' not restated")
 
 
 def make_decoder(arch: str, encoder_channels: Sequence[int], classes: int) -> DecoderWrapper:
     if arch.lower() == "unet":
         return DecoderWrapper(UnetDecoder(encoder_channels), SegmentationHead(16, classes, 3))
+    if arch.lower() == "upernet":
+        return DecoderWrapper(UPerNetDecoder(encoder_channels), UPerNetHead(64, classes))
     raise KeyError(f"oracle: decoder '{arch}' not restated")
 
 
@@ -428,6 +434,8 @@ def randomize_(module: nn.Module, seed: int = 2025, bf16_exact: bool = True) -> 
         elif isinstance(mod, GlobalResponseNorm):
             mod.weight.copy_(rn(mod.weight.shape, 0.5))
             mod.bias.copy_(rn(mod.bias.shape, 0.1))
+        elif isinstance(mod, WindowAttention):
+            mod.relative_position_bias_table.copy_(rn(mod.relative_position_bias_table.shape, 0.5))
     if bf16_exact:
         for p in list(module.parameters()) + [b for b in module.buffers() if b.dtype.is_floating_point]:
             p.copy_(p.to(torch.bfloat16).to(p.dtype))
