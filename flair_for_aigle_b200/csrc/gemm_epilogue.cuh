@@ -99,6 +99,9 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
       }
       warp_colsum32(s, lane);
       sq_dst[h * 32 + lane] = s[0];
+    } else if (MODE == FZ_EPI_GELU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
     } else if (MODE == FZ_EPI_RELU_BF16) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);

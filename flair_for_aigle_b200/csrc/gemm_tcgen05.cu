@@ -253,6 +253,7 @@ static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& a128
     case FZ_EPI_RESID_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RESID_F32>(a, a128, b, p, cl, st);
     case FZ_EPI_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_F32>(a, a128, b, p, cl, st);
     case FZ_EPI_RELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RELU_BF16>(a, a128, b, p, cl, st);
+    case FZ_EPI_GELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_BF16>(a, a128, b, p, cl, st);
   }
   set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
   return -1;
@@ -368,6 +369,8 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv
   if (MODE == FZ_EPI_GELU_SUMSQ) {
     v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     atomicAdd(&p.sumsq[static_cast<size_t>(m / 128) * p.N + n], v * v);
+  } else if (MODE == FZ_EPI_GELU_BF16) {
+    v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
   } else if (MODE == FZ_EPI_RELU_BF16) {
     v = fmaxf(v, 0.0f);
   } else if (MODE == FZ_EPI_RESID_F32) {
@@ -403,6 +406,7 @@ extern "C" int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const 
     case FZ_EPI_RESID_F32: gemm_simt_kernel<FZ_EPI_RESID_F32><<<grid, block, 0, st>>>(a, b, p); break;
     case FZ_EPI_F32: gemm_simt_kernel<FZ_EPI_F32><<<grid, block, 0, st>>>(a, b, p); break;
     case FZ_EPI_RELU_BF16: gemm_simt_kernel<FZ_EPI_RELU_BF16><<<grid, block, 0, st>>>(a, b, p); break;
+    case FZ_EPI_GELU_BF16: gemm_simt_kernel<FZ_EPI_GELU_BF16><<<grid, block, 0, st>>>(a, b, p); break;
     default: set_error("fz_gemm_bf16_simt: unknown mode %d", mode); return -1;
   }
   FZ_CHECK_CUDA(cudaGetLastError());

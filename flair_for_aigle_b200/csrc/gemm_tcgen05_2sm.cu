@@ -213,6 +213,7 @@ int gemm_pair_launch(const void* A, const void* B, const GemmParams& p, int b_ba
     case FZ_EPI_RESID_F32: return launch_pair<FZ_EPI_RESID_F32>(tmA, tmB, p, stream);
     case FZ_EPI_F32: return launch_pair<FZ_EPI_F32>(tmA, tmB, p, stream);
     case FZ_EPI_RELU_BF16: return launch_pair<FZ_EPI_RELU_BF16>(tmA, tmB, p, stream);
+    case FZ_EPI_GELU_BF16: return launch_pair<FZ_EPI_GELU_BF16>(tmA, tmB, p, stream);
   }
   set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
   return -1;

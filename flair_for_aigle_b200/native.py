@@ -18,7 +18,7 @@ _lib: Optional[ctypes.CDLL] = None
 
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
-EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16 = 0, 1, 2, 3, 4
+EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16, EPI_GELU_BF16 = 0, 1, 2, 3, 4, 5
 CONV_RELU_BF16, CONV_LOGITS_F32, CONV_ARGMAX_RASTER, CONV_LOGITS_F32_NCHW, CONV_ADD_RELU_BF16, CONV_BF16 = 0, 1, 2, 3, 4, 5
 
 
@@ -79,6 +79,14 @@ _SIGNATURES = {
     "fz_maxpool3x3s2": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fz_conv3x3_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_conv3x3_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "fz_layernorm_rows": [_vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
+    "fz_merge_ln": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_swin_window_attn": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_cast_f32_bf16": [_vp, _vp, _i64, _vp],
+    "fz_adaptive_avgpool": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_bilinear_slice": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_updown_slice": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_head_upsample4": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"fz_last_error": ctypes.c_char_p}
 
@@ -328,4 +336,71 @@ def maxpool3x3s2(x, out):
     B, H, W, C = x.shape
     with _Timed('maxpool3x3s2', B=B, H=H, C=C):
         _check(lib().fz_maxpool3x3s2(_ptr(x), _ptr(out), B, H, W, C, _stream()), "fz_maxpool3x3s2")
+    return out
+
+
+# --------------------------------------------------------------------------- Swin / UPerNet ops
+def layernorm_rows(x: torch.Tensor, w, b, out: torch.Tensor, eps: float = 1e-5):
+    """x float [..., C] (contiguous) -> out bf16, nn.LayerNorm over C."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    with _Timed("layernorm_rows", rows=rows, C=C):
+        _check(lib().fz_layernorm_rows(_ptr(x), _ptr(w), _ptr(b), _ptr(out), rows, C, eps, _stream()), "fz_layernorm_rows")
+    return out
+
+
+def merge_ln(x: torch.Tensor, w, b, out: torch.Tensor, eps: float = 1e-5):
+    """timm PatchMerging gather + LayerNorm(4C): x float [B,H,W,C] -> out bf16 [B,H/2,W/2,4C]."""
+    B, H, W, C = x.shape
+    with _Timed("merge_ln", n=B, H=H, C=C):
+        _check(lib().fz_merge_ln(_ptr(x), _ptr(w), _ptr(b), _ptr(out), B, H, W, C, eps, _stream()), "fz_merge_ln")
+    return out
+
+
+def swin_window_attn(qkv: torch.Tensor, qkv_bias_bf16, table, out: torch.Tensor, heads: int, window: int, shift: int,
+                     scale: float):
+    """qkv bf16 [B,H,W,3C] -> out bf16 [B,H,W,C] (see include/flair_zonal_b200.h)."""
+    B, H, W, C3 = qkv.shape
+    with _Timed("swin_window_attn", n=B, H=H, C=C3 // 3):
+        _check(lib().fz_swin_window_attn(_ptr(qkv), _ptr(qkv_bias_bf16), _ptr(table), _ptr(out), B, H, W, C3 // 3, heads,
+                                         window, shift, scale, _stream()), "fz_swin_window_attn")
+    return out
+
+
+def cast_f32_bf16(x: torch.Tensor, out: torch.Tensor):
+    with _Timed("cast_f32_bf16", n=x.numel()):
+        _check(lib().fz_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "fz_cast_f32_bf16")
+    return out
+
+
+def adaptive_avgpool(x: torch.Tensor, S: int, out: torch.Tensor):
+    B, H, W, C = x.shape
+    with _Timed("adaptive_avgpool", n=B, S=S):
+        _check(lib().fz_adaptive_avgpool(_ptr(x), _ptr(out), B, H, W, C, S, _stream()), "fz_adaptive_avgpool")
+    return out
+
+
+def bilinear_slice(x: torch.Tensor, out: torch.Tensor, c0: int = 0, add=None):
+    """out[..., c0:c0+C] = bilinear(x -> out's H,W; align_corners=False) (+ add)."""
+    B, h, w, C = x.shape
+    _, H, W, Ctot = out.shape
+    with _Timed("bilinear_slice", n=B, H=H, C=C):
+        _check(lib().fz_bilinear_slice(_ptr(x), _ptr(add), _ptr(out), B, h, w, H, W, C, Ctot, c0, _stream()),
+               "fz_bilinear_slice")
+    return out
+
+
+def updown_slice(x: torch.Tensor, out: torch.Tensor, c0: int = 0):
+    B, H, W, C = x.shape
+    Ctot = out.shape[-1]
+    with _Timed("updown_slice", n=B, H=H, C=C):
+        _check(lib().fz_updown_slice(_ptr(x), _ptr(out), B, H, W, C, Ctot, c0, _stream()), "fz_updown_slice")
+    return out
+
+
+def head_upsample4(logits: torch.Tensor, n_cls: int, out: torch.Tensor):
+    """logits float [B,h,w,cstride] -> out float [B,n_cls,4h,4w] (UpsamplingBilinear2d, align_corners=True)."""
+    B, h, w, cs = logits.shape
+    with _Timed("head_upsample4", n=B):
+        _check(lib().fz_head_upsample4(_ptr(logits), _ptr(out), B, h, w, cs, n_cls, _stream()), "fz_head_upsample4")
     return out

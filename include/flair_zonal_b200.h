@@ -91,6 +91,7 @@ int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, vo
 #define FZ_EPI_RESID_F32 2  /* out f32  = acc + bias + resid                                      */
 #define FZ_EPI_F32 3        /* out f32  = acc + bias                                              */
 #define FZ_EPI_RELU_BF16 4  /* out bf16 = relu(acc + bias)                                        */
+#define FZ_EPI_GELU_BF16 5  /* out bf16 = gelu(acc + bias)   (timm Mlp.fc1 + nn.GELU of a Swin block)       */
 int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq, int M,
                  int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
 /* Diagnostics: when set to a device buffer of 64*8 uint64, CTA 0 of every following fz_gemm_bf16 launch
@@ -176,6 +177,42 @@ int fz_maxpool3x3s2(const void* in_bf16, void* out_bf16, int B, int H, int W, in
 int fz_conv3x3_ex(const void* in, const void* w, const float* scale, const float* bias, void* out, const void* resid,
                   int B, int H, int W, int Cin, int Cout, int w_rows, int stride, int mode, int cstride,
                   const int32_t* plan, const int32_t* own, uint8_t* raster, int RH, int RW, int margin, void* stream);
+
+/* ---------------------------------------------------------------- Swin encoder pieces
+ * (timm SwinTransformer behind smp TimmUniversalEncoder, `swin_base_patch4_window12_384-upernet`, BASELINE.json
+ * configs[2]; call site flair_model.py:376).  The linears run through fz_gemm_bf16; patch embedding through
+ * fz_stem_ln / fz_stem_ln_f32 with eps = 1e-5.
+ * fz_layernorm_rows: nn.LayerNorm(C) of float rows [rows][C] -> bf16 (C in 128, 256, 512, 1024, 2048).
+ * fz_merge_ln: timm PatchMerging up to its Linear: x float [B][H][W][C] -> bf16 [B][H/2][W/2][4C], channel blocks
+ *   (h0w0, h1w0, h0w1, h1w1), LayerNorm over 4C.
+ * fz_swin_window_attn: timm SwinTransformerBlock._attn between the qkv and proj linears: cyclic shift (roll by
+ *   -shift), zero-pad bottom/right to a multiple of `window`, window partition, softmax(q k^T * scale +
+ *   relative-position bias + shift mask (-100, regions on the padded grid)) v, window reverse, crop, roll back.
+ *   qkv bf16 [B][H][W][3C] (q | k | v, channel = head*32 + d) in natural token order; qkv_bias bf16 [3C] = q/k/v of
+ *   a padded (zero) token; table float [heads][(2*window-1)^2]; out bf16 [B][H][W][C].  window <= 12, head dim 32.
+ * fz_cast_f32_bf16: stage outputs (float) -> decoder operands (bf16). */
+int fz_layernorm_rows(const float* x, const float* w, const float* b, void* out_bf16, int64_t rows, int C, float eps,
+                      void* stream);
+int fz_merge_ln(const float* x, const float* w, const float* b, void* out_bf16, int B, int H, int W, int C, float eps,
+                void* stream);
+int fz_swin_window_attn(const void* qkv_bf16, const void* qkv_bias_bf16, const float* table, void* out_bf16, int B,
+                        int H, int W, int C, int heads, int window, int shift, float scale, void* stream);
+int fz_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- UPerNet decoder pieces
+ * (smp 0.4.0 UPerNetDecoder + SegmentationHead(kernel_size=1, upsampling=4); call site flair_model.py:417-419)
+ * fz_adaptive_avgpool: nn.AdaptiveAvgPool2d(S) on bf16 NHWC -> bf16 [B][S][S][C].
+ * fz_bilinear_slice: out[b][y][x][c0:c0+C] = bilinear(in, size=(H,W), align_corners=False)[b][y][x][:] (+ add[b][y][x][:]
+ *   when add != NULL); in bf16 [B][h][w][C], add bf16 [B][H][W][C], out bf16 [B][H][W][Ctot].  h == H is a copy.
+ * fz_updown_slice: same destination convention for down2(up2(in)) at in's own size (the 0-channel FPN stage followed
+ *   by the resize back to H/4): separable [1/8, 3/4, 1/8] with replicated borders.
+ * fz_head_upsample4: nn.UpsamplingBilinear2d(scale_factor=4) (align_corners=True): logits float [B][h][w][cstride]
+ *   (first n_cls valid) -> float [B][n_cls][4h][4w]. */
+int fz_adaptive_avgpool(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, int S, void* stream);
+int fz_bilinear_slice(const void* in_bf16, const void* add_bf16, void* out_bf16, int B, int h, int w, int H, int W,
+                      int C, int Ctot, int c0, void* stream);
+int fz_updown_slice(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, int Ctot, int c0, void* stream);
+int fz_head_upsample4(const float* logits, float* out_nchw, int B, int h, int w, int cstride, int n_cls, void* stream);
 
 #ifdef __cplusplus
 }

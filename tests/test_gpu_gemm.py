@@ -18,6 +18,8 @@ def _ref(A, B, bias, mode, resid, rows_per_sample):
     if mode == nv.EPI_GELU_SUMSQ:
         v = torch.nn.functional.gelu(v)
         sumsq = (v.view(A.shape[0] // 128, 128, -1) ** 2).sum(1)
+    elif mode == nv.EPI_GELU_BF16:
+        v = torch.nn.functional.gelu(v)
     elif mode == nv.EPI_RELU_BF16:
         v = torch.relu(v)
     elif mode == nv.EPI_RESID_F32:
@@ -30,7 +32,7 @@ def _ref(A, B, bias, mode, resid, rows_per_sample):
     (256, 128, 64, 128, 1), (512, 256, 128, 256, 1), (1024, 512, 512, 256, 4),
     (2048, 2048, 512, 1024, 1), (384, 64, 192, 128, 1), (2048, 512, 2048, 1024, 2),
 ])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_gemm_modes(cuda, impl, M, N, K, rps, bb, mode):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(M + N + K + mode)
@@ -57,7 +59,7 @@ def test_gemm_modes(cuda, impl, M, N, K, rps, bb, mode):
     (1408, 512, 256, 1408, 1),          # last pair tile: only the leader's 128 rows exist
     (10240, 1024, 256, 1024, 10),       # 160 pair tiles over 74 pairs: ring + TMEM double buffering across tiles
 ])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_gemm_pair_kernel(cuda, monkeypatch, M, N, K, rps, bb, mode):
     """cta_group::2 kernel (gemm_tcgen05_2sm.cu), forced for every N % 256 == 0 shape."""
     from flair_for_aigle_b200 import native as nv

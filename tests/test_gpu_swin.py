@@ -1,0 +1,139 @@
+"""GPU parity of the Swin / UPerNet kernels (csrc/swin_ops.cu, csrc/upernet_ops.cu) against torch fp32 and the
+oracle's window helpers (oracle/swin_upernet.py)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,C", [(1000, 128), (513, 256), (64, 512), (77, 1024), (9, 2048)])
+def test_layernorm_rows(cuda, rows, C):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(C)
+    x = torch.randn(rows, C, device=cuda) * 3 + 1
+    w, b = torch.rand(C, device=cuda) + 0.5, torch.randn(C, device=cuda) * 0.1
+    out = torch.empty(rows, C, dtype=torch.bfloat16, device=cuda)
+    nv.layernorm_rows(x, w, b, out, eps=1e-5)
+    ref = F.layer_norm(x, (C,), w, b, 1e-5)
+    assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,C", [(2, 16, 128), (3, 8, 256), (1, 4, 512)])
+def test_merge_ln(cuda, B, H, C):
+    from flair_for_aigle_b200 import native as nv
+    from oracle.swin_upernet import PatchMerging
+    torch.manual_seed(H)
+    pm = PatchMerging(C, 2 * C).to(cuda)
+    with torch.no_grad():
+        pm.norm.weight.uniform_(0.5, 1.5)
+        pm.norm.bias.normal_(0, 0.1)
+        pm.reduction.weight.copy_(torch.eye(2 * C, 4 * C))     # look at the normalised gather itself
+    x = torch.randn(B, H, H, C, device=cuda)
+    out = torch.empty(B, H // 2, H // 2, 4 * C, dtype=torch.bfloat16, device=cuda)
+    nv.merge_ln(x, pm.norm.weight, pm.norm.bias, out, eps=1e-5)
+    with torch.no_grad():
+        xr = x.reshape(B, H // 2, 2, H // 2, 2, C).permute(0, 1, 3, 4, 2, 5).flatten(3)
+        ref = pm.norm(xr)
+    assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def _attn_reference(qkv, bias_bf, table, heads, ws, shift, scale):
+    """timm SwinTransformerBlock._attn between the qkv and proj linears, in fp32, on bf16-rounded q/k/v.
+    qkv: [B,H,W,3C] float (natural token order); padded tokens take `bias_bf` (what qkv(0) gives)."""
+    from oracle.swin_upernet import relative_position_index, shift_attn_mask, window_partition, window_reverse
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    sx = torch.roll(qkv, shifts=(-shift, -shift), dims=(1, 2)) if shift else qkv
+    ph, pw = (ws - H % ws) % ws, (ws - W % ws) % ws
+    Hp, Wp = H + ph, W + pw
+    full = bias_bf.view(1, 1, 1, C3).expand(B, Hp, Wp, C3).clone()
+    full[:, :H, :W] = sx
+    xw = window_partition(full, ws).view(-1, ws * ws, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = xw.unbind(0)
+    attn = (q * scale) @ k.transpose(-2, -1)
+    idx = relative_position_index(ws).to(qkv.device)
+    bias = table.t()[idx.view(-1)].view(ws * ws, ws * ws, heads).permute(2, 0, 1)      # table is [heads][(2ws-1)^2]
+    attn = attn + bias.unsqueeze(0)
+    if shift:
+        mask = shift_attn_mask(H, W, ws, shift).to(qkv.device)
+        nw = mask.shape[0]
+        attn = (attn.view(-1, nw, heads, ws * ws, ws * ws) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, ws * ws, ws * ws)
+    out = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, ws, ws, C)
+    out = window_reverse(out, ws, Hp, Wp)[:, :H, :W].contiguous()
+    return torch.roll(out, shifts=(shift, shift), dims=(1, 2)) if shift else out
+
+
+@pytest.mark.parametrize("B,H,W,heads,ws,shift", [
+    (2, 16, 16, 2, 12, 0), (2, 16, 16, 2, 12, 6), (1, 32, 32, 4, 12, 6), (3, 24, 24, 1, 12, 6),
+    (1, 128, 128, 4, 12, 6), (2, 14, 14, 3, 7, 3), (1, 20, 28, 2, 8, 4), (2, 12, 12, 8, 12, 0),
+])
+def test_window_attention(cuda, B, H, W, heads, ws, shift):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(H * 7 + shift)
+    C = heads * 32
+    qkv = (torch.randn(B, H, W, 3 * C, device=cuda) * 1.5).bfloat16()
+    bias_bf = (torch.randn(3 * C, device=cuda) * 0.5).bfloat16()
+    table = torch.randn(heads, (2 * ws - 1) ** 2, device=cuda) * 0.5
+    scale = 32 ** -0.5
+    out = torch.full((B, H, W, C), float("nan"), dtype=torch.bfloat16, device=cuda)
+    nv.swin_window_attn(qkv, bias_bf, table, out, heads, ws, shift, scale)
+    torch.cuda.synchronize()
+    ref = _attn_reference(qkv.float(), bias_bf.float(), table, heads, ws, shift, scale)
+    assert not torch.isnan(out.float()).any(), "some token was never written"
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2 * max(1.0, ref.abs().max().item()), err      # P and the output are rounded to bf16
+    out2 = torch.empty_like(out)
+    nv.swin_window_attn(qkv, bias_bf, table, out2, heads, ws, shift, scale)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("S", [1, 2, 3, 6])
+def test_adaptive_avgpool(cuda, S):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(S)
+    x = torch.randn(3, 16, 16, 64, device=cuda).bfloat16()
+    out = torch.empty(3, S, S, 64, dtype=torch.bfloat16, device=cuda)
+    nv.adaptive_avgpool(x, S, out)
+    ref = F.adaptive_avg_pool2d(x.float().permute(0, 3, 1, 2), S).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("h,H", [(1, 16), (2, 16), (3, 16), (6, 16), (16, 32), (16, 128), (32, 128), (64, 128), (128, 128)])
+def test_bilinear_slice(cuda, h, H):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(h * 131 + H)
+    C, Ctot, c0 = 32, 80, 24
+    x = torch.randn(2, h, h, C, device=cuda).bfloat16()
+    add = torch.randn(2, H, H, C, device=cuda).bfloat16()
+    out = torch.zeros(2, H, H, Ctot, dtype=torch.bfloat16, device=cuda)
+    nv.bilinear_slice(x, out, c0, add=add)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(H, H), mode="bilinear", align_corners=False)
+    ref = ref.permute(0, 2, 3, 1) + add.float()
+    got = out[..., c0:c0 + C].float()
+    assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert (out[..., :c0] == 0).all() and (out[..., c0 + C:] == 0).all()
+
+
+def test_updown_slice(cuda):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(5)
+    x = torch.randn(2, 32, 32, 64, device=cuda).bfloat16()
+    out = torch.zeros(2, 32, 32, 128, dtype=torch.bfloat16, device=cuda)
+    nv.updown_slice(x, out, 64)
+    xf = x.float().permute(0, 3, 1, 2)
+    up = F.interpolate(xf, size=(64, 64), mode="bilinear", align_corners=False)
+    ref = F.interpolate(up, size=(32, 32), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert (out[..., 64:].float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+def test_head_upsample4(cuda):
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(6)
+    lg = torch.randn(2, 32, 32, 64, device=cuda)
+    out = torch.empty(2, 19, 128, 128, device=cuda)
+    nv.head_upsample4(lg, 19, out)
+    ref = torch.nn.UpsamplingBilinear2d(scale_factor=4)(lg[..., :19].permute(0, 3, 1, 2))
+    assert (out - ref).abs().max().item() < 1e-4
