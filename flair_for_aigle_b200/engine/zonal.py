@@ -64,6 +64,8 @@ class ZonalRunner:
     def count_launches(self) -> int:
         """Kernel launches of one batch (for bench.py's gpu_launches)."""
         cfg = self.eng.cfg
+        if hasattr(self.eng, 'launch_count'):
+            return 1 + self.eng.launch_count()
         if not hasattr(cfg, 'depths'):          # ResNet: gather, conv1, maxpool, 2-3 convs per block, decoder
             nblk = sum(cfg.layers)
             nds = sum(1 for b in self.eng.blocks if b['wd'] is not None)

@@ -27,6 +27,7 @@ import torch.nn as nn
 from ... import native as nv
 from ...engine.convnext_unet import CONVNEXTV2_CFGS, ConvNeXtCfg, ConvNeXtV2UNetEngine
 from ...engine.resnet_unet import RESNET_LAYERS, ResNetCfg, ResNetUNetEngine
+from ...engine.swin_upernet import SWIN_CFGS, SwinCfg, SwinUPerNetEngine
 from . import monotemp_model as mm
 
 logger = logging.getLogger(__name__)
@@ -50,14 +51,14 @@ def _register(root: nn.Module, dotted: str, tensor: torch.Tensor, buffer: bool) 
 
 
 def _init_tensor(shape, kind: str, gen: torch.Generator) -> torch.Tensor:
-    if kind in ("conv", "linear"):
+    if kind in ("conv", "linear", "table"):
         return torch.nn.init.trunc_normal_(torch.empty(shape), std=0.02, generator=gen)   # timm default
     if kind == "conv_relu":
         fan_in = shape[1] * shape[2] * shape[3]
         bound = math.sqrt(6.0 / fan_in)                                                   # smp: kaiming_uniform
         return (torch.rand(shape, generator=gen) * 2 - 1) * bound
     if kind == "head":
-        fan_in, fan_out = shape[1] * 9, shape[0] * 9
+        fan_in, fan_out = shape[1] * shape[2] * shape[3], shape[0] * shape[2] * shape[3]
         bound = math.sqrt(6.0 / (fan_in + fan_out))                                       # smp: xavier_uniform
         return (torch.rand(shape, generator=gen) * 2 - 1) * bound
     if kind in ("norm_w", "bn_var"):
@@ -179,6 +180,13 @@ class FLAIR_HUB_Model(nn.Module):
                 self._engines[key] = ResNetUNetEngine(sd, f"encoders.{mod}.seg_model.",
                                                       f"main_decoders.{task}.seg_model.", cfg, dev, max_batch=mb,
                                                       norm_mean=mean, norm_std=std)
+            elif self.encoder_name in SWIN_CFGS:
+                dim, depths, heads, window = SWIN_CFGS[self.encoder_name]
+                cfg = SwinCfg(embed_dim=dim, depths=depths, heads=heads, window=window,
+                              in_chans=self.channels_dict[mod], n_classes=ncls, patch=int(self.img_input_sizes[mod]))
+                self._engines[key] = SwinUPerNetEngine(sd, f"encoders.{mod}.seg_model.model.model.",
+                                                       f"main_decoders.{task}.seg_model.", cfg, dev, max_batch=mb,
+                                                       norm_mean=mean, norm_std=std)
             else:
                 depths, dims = CONVNEXTV2_CFGS[self.encoder_name]
                 cfg = ConvNeXtCfg(depths=depths, dims=dims, in_chans=self.channels_dict[mod], n_classes=ncls,

@@ -137,3 +137,74 @@ def test_head_upsample4(cuda):
     nv.head_upsample4(lg, 19, out)
     ref = torch.nn.UpsamplingBilinear2d(scale_factor=4)(lg[..., :19].permute(0, 3, 1, 2))
     assert (out - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("M", [37, 148, 333])
+def test_gemm_fewer_rows_than_a_tile(cuda, M):
+    """PSP 1x1 convs see M = batch * s^2 rows (37 at s = 1): rows beyond M are TMA zero fill, never stored."""
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(M)
+    A = torch.randn(M, 1024, device=cuda).bfloat16()
+    W = (torch.randn(256, 1024, device=cuda) / 32).bfloat16()
+    bias = torch.randn(256, device=cuda)
+    guard = torch.full((M + 300, 256), 7.0, dtype=torch.bfloat16, device=cuda)
+    nv.gemm_bf16(A, W, nv.EPI_RELU_BF16, bias=bias, out=guard[:M])
+    torch.cuda.synchronize()
+    ref = torch.relu(A.float() @ W.float().t() + bias)
+    assert (guard[:M].float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    assert (guard[M:] == 7.0).all()
+
+
+def _swin_pair(cuda, n_tiles):
+    from flair_for_aigle_b200.engine.swin_upernet import SwinCfg, SwinUPerNetEngine
+    from oracle.models import FlairHubOracle, randomize_
+    task = "AERIAL_LABEL-COSIA"
+    oracle = FlairHubOracle("swin_base_patch4_window12_384-upernet", {"AERIAL_RGBI": 4}, {task: 19}).eval()
+    randomize_(oracle, seed=2025, bf16_exact=True)
+    sd = {k: v.clone() for k, v in oracle.state_dict().items()}
+    mean, std = [105.66, 111.35, 102.18, 106.59], [52.23, 45.62, 44.30, 39.78]
+    eng = SwinUPerNetEngine(sd, "encoders.AERIAL_RGBI.seg_model.model.model.", f"main_decoders.{task}.seg_model.",
+                            SwinCfg(), cuda, max_batch=n_tiles, norm_mean=mean, norm_std=std)
+    return oracle.to(cuda), eng, task, mean, std
+
+
+def test_swin_upernet_engine_vs_oracle(cuda):
+    """End to end on 2 tiles: fp32 oracle (torch eager on the GPU, TF32 off) vs the engine.  Stated tolerance (bf16
+    operands through 24 blocks + the decoder, fp32 accumulation and residual stream): stage features within 5 % of
+    their std (max), logits mean |d| <= 1.5 % and max |d| <= 15 % of the logit std."""
+    import numpy as np
+    from flair_for_aigle_b200.synthetic import synthetic_raster
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, eng, task, mean, std = _swin_pair(cuda, 2)
+    P = 512
+    raster = synthetic_raster(640, 1100, seed=2025)
+    u8 = torch.from_numpy(np.stack([raster[:, 0:P, 0:P], raster[:, 100:100 + P, 500:500 + P]])).to(cuda)
+    xn = ((u8.double() - torch.tensor(mean, device=cuda, dtype=torch.float64).view(1, 4, 1, 1)) /
+          torch.tensor(std, device=cuda, dtype=torch.float64).view(1, 4, 1, 1)).float()
+    with torch.no_grad():
+        ref, _ = oracle({"AERIAL_RGBI": xn, task: torch.zeros(2, 19, P, P, device=cuda)})
+        ref = ref[task]
+        feats_ref = oracle.encoders["AERIAL_RGBI"].seg_model(xn)[2:]
+    eng.encode_u8(u8.permute(0, 2, 3, 1).contiguous())
+    feats = [f.clone() for f in eng.features(2)]
+    out = eng.decode_logits_nchw(2)
+    torch.cuda.synchronize()
+    for i, (f, fr) in enumerate(zip(feats, feats_ref)):
+        rel = (f.permute(0, 3, 1, 2) - fr).abs().max().item() / fr.std().item()
+        print(f"stage {i}: max err / std = {rel:.4f}")
+        assert rel < 0.05, f"stage {i} feature error {rel}"
+    sd_ = ref.std().item()
+    d = (out - ref).abs()
+    agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"logits: max|d|={d.max().item():.4f} mean|d|={d.mean().item():.5f} std={sd_:.3f} argmax agree={agree:.5f}")
+    assert d.max().item() < 0.15 * sd_ and d.mean().item() < 0.015 * sd_
+    eng.encode_f32(xn)
+    out2 = eng.decode_logits_nchw(2)
+    torch.cuda.synchronize()
+    d2 = (out2 - ref).abs()
+    assert d2.max().item() < 0.15 * sd_ and d2.mean().item() < 0.015 * sd_
+    eng.encode_f32(xn)
+    out3 = eng.decode_logits_nchw(2)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out3)
