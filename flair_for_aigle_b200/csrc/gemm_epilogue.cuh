@@ -15,6 +15,7 @@ struct GemmParams {
   void* out;            // [M,N] bf16 or f32
   const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
   float* sumsq;         // [ceil(M/128), N] f32 per-128-row partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
+  int reverse;          // 1: walk the tile list backwards (consume a just-written operand newest-first, while it is in L2)
   unsigned long long* trace;  // optional: CTA 0 writes clock64 stamps [tile][8] (diagnostics, see fz_gemm_set_trace)
 };
 

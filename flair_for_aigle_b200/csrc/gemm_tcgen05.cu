@@ -100,8 +100,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
       for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
-        const int n0 = (t % n_tiles) * BN;
-        const int m0 = (t / n_tiles) * BM;
+        const int te = p.reverse ? total_tiles - 1 - t : t;
+        const int n0 = (te % n_tiles) * BN;
+        const int m0 = (te / n_tiles) * BM;
         const int bcoord = p.b_batched ? (m0 / p.rows_per_sample) : 0;
         FZ_TRACE(0);   // producer starts issuing this tile's loads
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -164,8 +165,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int bar_id = 1 + half;
     uint32_t lt = 0;
     for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
-      const int n0 = (t % n_tiles) * BN;
-      const int m0 = (t / n_tiles) * BM;
+      const int te = p.reverse ? total_tiles - 1 - t : t;
+      const int n0 = (te % n_tiles) * BN;
+      const int m0 = (te / n_tiles) * BM;
       const uint32_t as = lt % ACC_STAGES;
       const uint32_t aph = (lt / ACC_STAGES) & 1;
       float* sq_buf = sSq + (lt & 1) * 8 * BN;
@@ -270,6 +272,8 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
                             float* sumsq, int M, int N, int K, int b_batch, int rows_per_sample, int mode,
                             void* stream) {
   using namespace fz;
+  const int reverse = (mode & FZ_EPI_REVERSE_TILES) ? 1 : 0;
+  mode &= ~FZ_EPI_REVERSE_TILES;
   FZ_REQUIRE(M > 0 && N > 0 && K > 0, "fz_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
   FZ_REQUIRE(K % BK == 0, "fz_gemm_bf16: K=%d must be a multiple of %d", K, BK);
   FZ_REQUIRE(N % 64 == 0, "fz_gemm_bf16: N=%d must be a multiple of 64", N);
@@ -321,6 +325,7 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = g_trace;
+  p.reverse = reverse;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // CTA-pair kernel (256x256 tile over two SMs, gemm_tcgen05_2sm.cu): wide outputs with enough tiles for 74 pairs.
   // FZ_GEMM_PAIR=0 disables, =2 forces it whenever N % 256 == 0.
@@ -394,6 +399,8 @@ extern "C" int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const 
   p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = nullptr;
+  p.reverse = 0;
+  mode &= ~FZ_EPI_REVERSE_TILES;
   dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == FZ_EPI_GELU_SUMSQ)

@@ -79,8 +79,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
-        const int n0 = (t % n_tiles) * BN;
-        const int m0 = (t / n_tiles) * BM;
+        const int te = p.reverse ? total_tiles - 1 - t : t;
+        const int n0 = (te % n_tiles) * BN;
+        const int m0 = (te / n_tiles) * BM;
         const int bcoord = p.b_batched ? (m0 / p.rows_per_sample) : 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -129,8 +130,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     char* stg = reinterpret_cast<char*>(smem + OFF_STG) + ew * 4096;
     uint32_t lt = 0;
     for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
-      const int n0 = (t % n_tiles) * BN;
-      const int m0 = (t / n_tiles) * BM + rank * 128;
+      const int te = p.reverse ? total_tiles - 1 - t : t;
+      const int n0 = (te % n_tiles) * BN;
+      const int m0 = (te / n_tiles) * BM + rank * 128;
       const uint32_t as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       float* sq_buf = sSq + (lt & 1) * 4 * BN;

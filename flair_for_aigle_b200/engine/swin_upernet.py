@@ -192,13 +192,16 @@ class SwinUPerNetEngine:
             qkv = self.qkv[:T * 3 * C].view(n, hwi, hwi, 3 * C)
             a = self.a[:T * C].view(n, hwi, hwi, C)
             hbuf = self.h[:T * 4 * C].view(T, 4 * C)
+            R = nv.EPI_REVERSE_TILES
             for blk in st["blocks"]:
                 nv.layernorm_rows(xm, blk["n1_w"], blk["n1_b"], y)
-                nv.gemm_bf16(y, blk["qkv_w"], nv.EPI_BF16, bias=blk["qkv_b"], out=qkv.view(T, 3 * C))
+                # GEMMs that consume a tensor the previous kernel has just streamed out walk their tiles backwards
+                # (newest rows are still in L2) and leave the rows the next forward kernel starts with for last
+                nv.gemm_bf16(y, blk["qkv_w"], nv.EPI_BF16 | R, bias=blk["qkv_b"], out=qkv.view(T, 3 * C))
                 nv.swin_window_attn(qkv, blk["qkv_b_bf16"], blk["table"], a, nh, ws, blk["shift"], self.scale)
-                nv.gemm_bf16(a.view(T, C), blk["proj_w"], nv.EPI_RESID_F32, bias=blk["proj_b"], resid=xm, out=xm)
+                nv.gemm_bf16(a.view(T, C), blk["proj_w"], nv.EPI_RESID_F32 | R, bias=blk["proj_b"], resid=xm, out=xm)
                 nv.layernorm_rows(xm, blk["n2_w"], blk["n2_b"], y)
-                nv.gemm_bf16(y, blk["fc1_w"], nv.EPI_GELU_BF16, bias=blk["fc1_b"], out=hbuf)
+                nv.gemm_bf16(y, blk["fc1_w"], nv.EPI_GELU_BF16 | R, bias=blk["fc1_b"], out=hbuf)
                 nv.gemm_bf16(hbuf, blk["fc2_w"], nv.EPI_RESID_F32, bias=blk["fc2_b"], resid=xm, out=xm)
 
     def encode_u8(self, tiles_u8: torch.Tensor) -> None:

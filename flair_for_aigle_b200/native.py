@@ -19,6 +19,7 @@ _lib: Optional[ctypes.CDLL] = None
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16, EPI_GELU_BF16 = 0, 1, 2, 3, 4, 5
+EPI_REVERSE_TILES = 0x100
 CONV_RELU_BF16, CONV_LOGITS_F32, CONV_ARGMAX_RASTER, CONV_LOGITS_F32_NCHW, CONV_ADD_RELU_BF16, CONV_BF16 = 0, 1, 2, 3, 4, 5
 
 
@@ -225,7 +226,7 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, mode: int, bias=None, resid=None
     if bias is None:
         bias = torch.zeros(N, dtype=torch.float32, device=A.device)
     if out is None:
-        odt = torch.float32 if mode in (EPI_RESID_F32, EPI_F32) else torch.bfloat16
+        odt = torch.float32 if (mode & 0xff) in (EPI_RESID_F32, EPI_F32) else torch.bfloat16
         out = torch.empty((M, N), dtype=odt, device=A.device)
     fn = lib().fz_gemm_bf16 if impl == "tcgen05" else lib().fz_gemm_bf16_simt
     with _Timed("gemm_tcgen05" if impl == "tcgen05" else "gemm_simt", M=M, N=N, K=K, mode=mode):

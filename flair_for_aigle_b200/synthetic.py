@@ -63,6 +63,8 @@ def randomize_state_(state_dict, seed: int = 2025, bf16_exact: bool = True) -> N
             v = torch.rand(shape, generator=g) + 0.5
         elif ".grn." in k:
             v = torch.randn(shape, generator=g) * (0.5 if k.endswith("weight") else 0.1)
+        elif k.endswith("relative_position_bias_table"):
+            v = torch.randn(shape, generator=g) * 0.5
         elif k.endswith("bias"):
             v = torch.randn(shape, generator=g) * 0.1
         elif t.dim() == 1:                       # LayerNorm / BatchNorm scale

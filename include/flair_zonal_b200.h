@@ -91,6 +91,8 @@ int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, vo
 #define FZ_EPI_RESID_F32 2  /* out f32  = acc + bias + resid                                      */
 #define FZ_EPI_F32 3        /* out f32  = acc + bias                                              */
 #define FZ_EPI_RELU_BF16 4  /* out bf16 = relu(acc + bias)                                        */
+#define FZ_EPI_REVERSE_TILES 0x100 /* OR into mode: walk the tile list backwards, so that an A operand the previous
+                                    * kernel has just streamed out (larger than L2) is consumed newest-first */
 #define FZ_EPI_GELU_BF16 5  /* out bf16 = gelu(acc + bias)   (timm Mlp.fc1 + nn.GELU of a Swin block)       */
 int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq, int M,
                  int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);

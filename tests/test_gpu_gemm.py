@@ -116,3 +116,26 @@ def test_gelu_fast_matches_erf(cuda):
     torch.cuda.synchronize()
     ref = torch.nn.functional.gelu(bias).bfloat16().float()
     assert (out.float() - ref[None, :]).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("pair", ["0", "2"])
+def test_gemm_reverse_tile_order_is_bit_identical(cuda, monkeypatch, pair):
+    """FZ_EPI_REVERSE_TILES only changes which CTA computes which tile."""
+    from flair_for_aigle_b200 import native as nv
+    monkeypatch.setenv("FZ_GEMM_PAIR", pair)
+    torch.manual_seed(3)
+    M, N, K = 4096 + 128, 512, 512
+    A = torch.randn(M, K, device=cuda).bfloat16()
+    B = (torch.randn(N, K, device=cuda) / 20).bfloat16()
+    bias = torch.randn(N, device=cuda)
+    for mode in (nv.EPI_BF16, nv.EPI_GELU_BF16, nv.EPI_F32):
+        a = nv.gemm_bf16(A, B, mode, bias=bias)
+        b = nv.gemm_bf16(A, B, mode | nv.EPI_REVERSE_TILES, bias=bias)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+    sq1 = torch.zeros(M // 128, N, device=cuda)
+    sq2 = torch.zeros(M // 128, N, device=cuda)
+    nv.gemm_bf16(A, B, nv.EPI_GELU_SUMSQ, bias=bias, sumsq=sq1)
+    nv.gemm_bf16(A, B, nv.EPI_GELU_SUMSQ | nv.EPI_REVERSE_TILES, bias=bias, sumsq=sq2)
+    torch.cuda.synchronize()
+    assert torch.equal(sq1, sq2)

@@ -208,3 +208,43 @@ def test_swin_upernet_engine_vs_oracle(cuda):
     out3 = eng.decode_logits_nchw(2)
     torch.cuda.synchronize()
     assert torch.equal(out2, out3)
+
+
+def test_swin_upernet_zone_through_public_api(cuda, tmp_path):
+    """configs[2] through the drop-in API (build_inference_model -> inference_and_write) vs the oracle pipeline."""
+    import bench
+    from safetensors.torch import load_file, save_file
+    from oracle.grid import Georef
+    from oracle.models import FlairHubOracle
+    from oracle.pipeline import run_zone
+    from flair_for_aigle_b200.flair_hub.models.flair_model import FLAIR_HUB_Model
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model, prepare_model_config
+    from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink, ZoneRaster, register_raster
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import generate_patches_from_reference
+    from flair_for_aigle_b200.synthetic import DEFAULT_MEANS, DEFAULT_STDS, randomize_state_, synthetic_raster
+    task = bench.TASK
+    wpath = str(tmp_path / "swin_upernet.safetensors")
+    c = bench.zonal_config(wpath, str(tmp_path), "mem://swin", 4)
+    c["monotemp_arch"] = "swin_base_patch4_window12_384-upernet"
+    sd = FLAIR_HUB_Model(prepare_model_config(dict(c, model_weights=wpath)), {"AERIAL_RGBI": 512}).state_dict()
+    randomize_state_(sd, seed=7)
+    save_file({k: v.contiguous() for k, v in sd.items()}, wpath)
+    arr = synthetic_raster(700, 1000, seed=4)
+    register_raster("mem://swin", ZoneRaster(arr, 700000.0, 6600000.0, 0.2))
+    cfg = inf.initialize_geometry_and_resolutions(c)
+    cfg["device"] = cuda
+    model = build_inference_model(cfg, {"AERIAL_RGBI": 512}).to(cuda)
+    tiles = generate_patches_from_reference(cfg, "mem://swin", None)
+    ds = inf.prep_dataset(cfg, tiles, {"AERIAL_RGBI": 512})
+    RasterSink.write_files = False
+    outs, _ = inf.init_outputs(cfg, "mem://swin", 0)
+    inf.inference_and_write(model, ds, tiles, cfg, outs, "mem://swin")
+    got = outs[task].to_host()[0]
+    oracle = FlairHubOracle("swin_base_patch4_window12_384-upernet", {"AERIAL_RGBI": 4}, {task: 19}).eval()
+    oracle.load_state_dict(load_file(wpath), strict=True)
+    ref, _, _ = run_zone(oracle.to(cuda), arr, Georef(700000.0, 6600000.0, 0.2, 1000, 700), 512, 64, DEFAULT_MEANS,
+                         DEFAULT_STDS, task, 19, batch_size=2, device="cuda")
+    agree = (got == ref).mean()
+    print(f"swin-upernet zone class agreement with the oracle pipeline: {agree:.5f}")
+    assert agree >= 0.98

@@ -11,20 +11,24 @@ from flair_for_aigle_b200.flair_hub.models.flair_model import FLAIR_HUB_Model
 from flair_for_aigle_b200.flair_zonal_detection.model_utils import prepare_model_config
 from flair_for_aigle_b200.synthetic import synthetic_raster, randomize_state_, DEFAULT_MEANS, DEFAULT_STDS
 
-B = int(os.environ.get("B", "16"))
+B = int(os.environ.get("B", "37"))
+ARCH = os.environ.get("ARCH", bench.ARCH)
 dev = torch.device("cuda:0")
-cfg = prepare_model_config(bench.zonal_config("w", "/tmp", "unused", B))
+zc = bench.zonal_config("w", "/tmp", "unused", B)
+zc["monotemp_arch"] = ARCH
+cfg = prepare_model_config(zc)
 m = FLAIR_HUB_Model(cfg, {"AERIAL_RGBI": 512}, max_batch=B)
 sd = m.state_dict(); randomize_state_(sd, 1)
-eng = ConvNeXtV2UNetEngine(sd, "encoders.AERIAL_RGBI.seg_model.model.", f"main_decoders.{bench.TASK}.seg_model.",
-                           ConvNeXtCfg(), dev, max_batch=B, norm_mean=DEFAULT_MEANS, norm_std=DEFAULT_STDS)
+m.load_state_dict(sd)
+m._norm = (DEFAULT_MEANS, DEFAULT_STDS)
+eng = m.to(dev).engine(bench.TASK, max_batch=B)
 r = torch.from_numpy(synthetic_raster(3000, 3000)).to(dev)
 plan = np.zeros((B, 6), np.int32)
 for i in range(B):
     plan[i] = ((i // 4) * 384, (i % 4) * 384, (i // 4) * 384 + 64, (i % 4) * 384 + 64, 384, 384)
 own = np.stack([plan[:, 2], plan[:, 2] + 384, plan[:, 3], plan[:, 3] + 384], 1).astype(np.int32)
 out = torch.zeros((3000, 3000), dtype=torch.uint8, device=dev)
-run = ZonalRunner(eng, 64, use_graph=False)
+run = ZonalRunner(eng, 64, use_graph=False, norm=(DEFAULT_MEANS, DEFAULT_STDS))
 for _ in range(2):
     run.run(r, plan, own, out)
 torch.cuda.synchronize()
@@ -40,7 +44,7 @@ for fam, meta, a, b in prof:
     t, c = agg.get(key, (0.0, 0))
     agg[key] = (t + a.elapsed_time(b), c + 1)
 tot = sum(t for t, _ in agg.values()) / reps
-lines = [f"batch B={B}: total kernel time {tot:.3f} ms = {tot/B:.4f} ms/tile (eager, per-launch events)"]
+lines = [f"{ARCH} batch B={B}: total kernel time {tot:.3f} ms = {tot/B:.4f} ms/tile (eager, per-launch events)"]
 fam_tot = collections.Counter()
 for (fam, meta), (t, c) in agg.items():
     fam_tot[fam] += t / reps
@@ -56,5 +60,5 @@ lines.append("--- by family (ms per batch, share)")
 for fam, t in fam_tot.most_common():
     lines.append(f"{fam:18s} {t:8.3f} ms  {t/tot*100:5.1f}%")
 os.makedirs("gpurun_out", exist_ok=True)
-open("gpurun_out/profile_batch.txt", "w").write("\n".join(lines) + "\n")
+open(f"gpurun_out/profile_batch_{ARCH.split('_')[0].split('-')[0]}.txt", "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
