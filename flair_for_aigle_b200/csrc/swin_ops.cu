@@ -134,6 +134,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttnParams p) {
   __shared__ __align__(16) __nv_bfloat16 sQ[WA_N * WA_LD];
   __shared__ __align__(16) __nv_bfloat16 sK[WA_N * WA_LD];
@@ -175,21 +181,33 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
     sSrc[tid] = src;
     sInfo[tid] = info;
   }
-  for (int i = tid; i < span * span; i += WA_THREADS) sTab[i] = p.table[static_cast<size_t>(head) * span * span + i];
+  for (int i = tid; i < span * span; i += WA_THREADS)
+    sTab[i] = p.table[static_cast<size_t>(head) * span * span + i] * 1.4426950408889634f;   // log2 domain
   __syncthreads();
 
   {
+    // 144 tokens x (q,k,v) x 4 chunks of 16 B = 6 per thread: all six loads are in flight before the first store
+    // (one dependent L2/HBM round trip per CTA instead of six)
     const size_t tok0 = static_cast<size_t>(b) * p.H * p.W;
     const int C3 = 3 * p.C;
-    for (int i = tid; i < WA_N * 12; i += WA_THREADS) {
+    static_assert(WA_N * 12 == 6 * WA_THREADS, "load loop is unrolled for 6 chunks per thread");
+    uint4 val[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = tid + k * WA_THREADS;
       const int tok = i / 12, rem = i % 12, m = rem >> 2, ch = rem & 3;
       const int src = sSrc[tok];
-      uint4 val = make_uint4(0, 0, 0, 0);
       const int coff = m * p.C + head * WA_D + ch * 8;
-      if (src >= 0) val = __ldg(reinterpret_cast<const uint4*>(p.qkv + (tok0 + src) * C3 + coff));
-      else if (src == -1) val = __ldg(reinterpret_cast<const uint4*>(p.qkv_bias + coff));
+      const __nv_bfloat16* ptr = src >= 0 ? p.qkv + (tok0 + src) * C3 + coff : p.qkv_bias + coff;
+      val[k] = __ldg(reinterpret_cast<const uint4*>(ptr));
+      if (src == -2) val[k] = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = tid + k * WA_THREADS;
+      const int tok = i / 12, rem = i % 12, m = rem >> 2, ch = rem & 3;
       __nv_bfloat16* dst = (m == 0 ? sQ : (m == 1 ? sK : sV)) + tok * WA_LD + ch * 8;
-      *reinterpret_cast<uint4*>(dst) = val;
+      *reinterpret_cast<uint4*>(dst) = val[k];
     }
   }
   __syncthreads();
@@ -211,41 +229,63 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
     mma_bf16_16816(s[nt], qa[1], kb[2], kb[3]);
   }
 
-  // scale + relative position bias + shift mask, then softmax over the 144 key slots (unused slots excluded)
+  // scale + relative position bias + shift mask, then softmax over the 144 key slots (unused slots excluded).
+  // Everything is kept in the log2 domain (scale, table and mask pre-multiplied by log2 e) so that the
+  // exponential is one ex2.approx.  The mask / unused-slot handling is skipped (CTA-uniform branch) for the
+  // windows that cannot need it: un-shifted blocks, and interior windows of shifted blocks.
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float sl2 = p.scale * LOG2E;
   const int base = (ws - 1) * span + (ws - 1);
   const int info_lo = sInfo[r0 + lr], info_hi = sInfo[r0 + lr + 8];
   const int code_lo = (info_lo & 0xffff) + base, code_hi = (info_hi & 0xffff) + base;
-  const int reg_lo = (info_lo >> 16) & 0xff, reg_hi = (info_hi >> 16) & 0xff;
   float m_lo = -INFINITY, m_hi = -INFINITY;
+  const bool general = (p.shift > 0 && (wy == p.nwy - 1 || wx == p.nwx - 1)) || n_tok < WA_N;
+  if (!general) {
 #pragma unroll
-  for (int nt = 0; nt < 18; ++nt) {
+    for (int nt = 0; nt < 18; ++nt) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int ci = sInfo[nt * 8 + lc + e];
-      const int cc = ci & 0xffff, cr = (ci >> 16) & 0xff;
-      const bool unused = (ci >> 24) != 0;
-      float a = s[nt][e] * p.scale + sTab[code_lo - cc] + (cr != reg_lo ? -100.0f : 0.0f);
-      float c = s[nt][2 + e] * p.scale + sTab[code_hi - cc] + (cr != reg_hi ? -100.0f : 0.0f);
-      a = unused ? -INFINITY : a;
-      c = unused ? -INFINITY : c;
-      s[nt][e] = a;
-      s[nt][2 + e] = c;
-      m_lo = fmaxf(m_lo, a);
-      m_hi = fmaxf(m_hi, c);
+      for (int e = 0; e < 2; ++e) {
+        const int cc = sInfo[nt * 8 + lc + e] & 0xffff;
+        const float a = fmaf(s[nt][e], sl2, sTab[code_lo - cc]);
+        const float c = fmaf(s[nt][2 + e], sl2, sTab[code_hi - cc]);
+        s[nt][e] = a;
+        s[nt][2 + e] = c;
+        m_lo = fmaxf(m_lo, a);
+        m_hi = fmaxf(m_hi, c);
+      }
+    }
+  } else {
+    const int reg_lo = (info_lo >> 16) & 0xff, reg_hi = (info_hi >> 16) & 0xff;
+    constexpr float MASKED = -100.0f * LOG2E;
+#pragma unroll
+    for (int nt = 0; nt < 18; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ci = sInfo[nt * 8 + lc + e];
+        const int cc = ci & 0xffff, cr = (ci >> 16) & 0xff;
+        const bool unused = (ci >> 24) != 0;
+        float a = fmaf(s[nt][e], sl2, sTab[code_lo - cc]) + (cr != reg_lo ? MASKED : 0.0f);
+        float c = fmaf(s[nt][2 + e], sl2, sTab[code_hi - cc]) + (cr != reg_hi ? MASKED : 0.0f);
+        a = unused ? -INFINITY : a;
+        c = unused ? -INFINITY : c;
+        s[nt][e] = a;
+        s[nt][2 + e] = c;
+        m_lo = fmaxf(m_lo, a);
+        m_hi = fmaxf(m_hi, c);
+      }
     }
   }
   m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
   m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
   m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
   m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
-  constexpr float LOG2E = 1.4426950408889634f;
   float sum_lo = 0.f, sum_hi = 0.f;
 #pragma unroll
   for (int nt = 0; nt < 18; ++nt) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float a = exp2f((s[nt][e] - m_lo) * LOG2E);
-      const float c = exp2f((s[nt][2 + e] - m_hi) * LOG2E);
+      const float a = ex2_approx(s[nt][e] - m_lo);
+      const float c = ex2_approx(s[nt][2 + e] - m_hi);
       s[nt][e] = a;
       s[nt][2 + e] = c;
       sum_lo += a;
