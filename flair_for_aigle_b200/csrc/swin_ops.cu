@@ -116,7 +116,7 @@ struct WinAttnParams {
   const __nv_bfloat16* qkv_bias;  // [3C] bf16: q/k/v of a zero (padded) token
   const float* table;             // [heads][(2ws-1)^2] relative position bias
   __nv_bfloat16* out;             // [B][H][W][C]
-  int H, W, C, heads, ws, shift, nwy, nwx;
+  int H, W, C, heads, ws, shift, nwy, nwx, hgroup;
   float scale;
 };
 
@@ -140,19 +140,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+constexpr int WA_MAT = WA_N * WA_LD;                      // bf16 elements of one staged q, k or v matrix
+constexpr int WA_TAB = 23 * 23 + 3;                       // floats per staged bias table (padded to 16 B)
+constexpr int WA_SMEM = 2 * 3 * WA_MAT * 2 + 2 * WA_TAB * 4 + 2 * WA_N * 4;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One CTA = one window x `hgroup` consecutive heads.  The q/k/v rows of head i+1 stream into the second smem buffer
+// (cp.async) while head i is computed, so only the first head's load latency is exposed.
 __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttnParams p) {
-  __shared__ __align__(16) __nv_bfloat16 sQ[WA_N * WA_LD];
-  __shared__ __align__(16) __nv_bfloat16 sK[WA_N * WA_LD];
-  __shared__ __align__(16) __nv_bfloat16 sV[WA_N * WA_LD];
-  __shared__ float sTab[23 * 23];
-  __shared__ int sSrc[WA_N];      // source token (y*W+x) | -1 padded token | -2 unused slot
-  __shared__ int sInfo[WA_N];     // rel-pos code (ty*(2ws-1)+tx) | region << 16 | unused << 24
+  extern __shared__ __align__(16) uint8_t wa_smem[];
+  __nv_bfloat16* sBuf = reinterpret_cast<__nv_bfloat16*>(wa_smem);                 // [2][3][WA_MAT]
+  float* sTabs = reinterpret_cast<float*>(wa_smem + 2 * 3 * WA_MAT * 2);          // [2][WA_TAB]
+  int* sSrc = reinterpret_cast<int*>(sTabs + 2 * WA_TAB);   // source token (y*W+x) | -1 padded token | -2 unused slot
+  int* sInfo = sSrc + WA_N;                                 // rel-pos code (ty*(2ws-1)+tx) | region << 16 | unused << 24
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nw = p.nwy * p.nwx;
-  const int head = blockIdx.x % p.heads;
-  const int win = (blockIdx.x / p.heads) % nw;
-  const int b = blockIdx.x / (p.heads * nw);
+  const int ngrp = p.heads / p.hgroup;
+  const int head0 = (blockIdx.x % ngrp) * p.hgroup;
+  const int win = (blockIdx.x / ngrp) % nw;
+  const int b = blockIdx.x / (ngrp * nw);
   const int ws = p.ws, n_tok = ws * ws, span = 2 * ws - 1;
   const int wy = win / p.nwx, wx = win % p.nwx;
 
@@ -181,39 +193,61 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
     sSrc[tid] = src;
     sInfo[tid] = info;
   }
-  for (int i = tid; i < span * span; i += WA_THREADS)
-    sTab[i] = p.table[static_cast<size_t>(head) * span * span + i] * 1.4426950408889634f;   // log2 domain
   __syncthreads();
 
-  {
-    // 144 tokens x (q,k,v) x 4 chunks of 16 B = 6 per thread: all six loads are in flight before the first store
-    // (one dependent L2/HBM round trip per CTA instead of six)
-    const size_t tok0 = static_cast<size_t>(b) * p.H * p.W;
-    const int C3 = 3 * p.C;
-    static_assert(WA_N * 12 == 6 * WA_THREADS, "load loop is unrolled for 6 chunks per thread");
-    uint4 val[6];
+  // 144 tokens x (q,k,v) x 4 chunks of 16 B = 6 per thread.  The chunk -> (token, matrix) mapping and the global
+  // offsets are the same for every head; unused slots (window side < 12) are zeroed once in both buffers.
+  static_assert(WA_N * 12 == 6 * WA_THREADS, "load loop is unrolled for 6 chunks per thread");
+  const size_t tok0 = static_cast<size_t>(b) * p.H * p.W;
+  const int C3 = 3 * p.C;
+  const __nv_bfloat16* gsrc[6];
+  int soff[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int i = tid + k * WA_THREADS;
-      const int tok = i / 12, rem = i % 12, m = rem >> 2, ch = rem & 3;
-      const int src = sSrc[tok];
-      const int coff = m * p.C + head * WA_D + ch * 8;
-      const __nv_bfloat16* ptr = src >= 0 ? p.qkv + (tok0 + src) * C3 + coff : p.qkv_bias + coff;
-      val[k] = __ldg(reinterpret_cast<const uint4*>(ptr));
-      if (src == -2) val[k] = make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int i = tid + k * WA_THREADS;
-      const int tok = i / 12, rem = i % 12, m = rem >> 2, ch = rem & 3;
-      __nv_bfloat16* dst = (m == 0 ? sQ : (m == 1 ? sK : sV)) + tok * WA_LD + ch * 8;
-      *reinterpret_cast<uint4*>(dst) = val[k];
+  for (int k = 0; k < 6; ++k) {
+    const int i = tid + k * WA_THREADS;
+    const int tok = i / 12, rem = i % 12, m = rem >> 2, ch = rem & 3;
+    const int src = sSrc[tok];
+    const int coff = m * p.C + ch * 8;
+    soff[k] = m * WA_MAT + tok * WA_LD + ch * 8;
+    gsrc[k] = src >= 0 ? p.qkv + (tok0 + src) * C3 + coff : (src == -1 ? p.qkv_bias + coff : nullptr);
+    if (src == -2) {
+      *reinterpret_cast<uint4*>(sBuf + soff[k]) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sBuf + 3 * WA_MAT + soff[k]) = make_uint4(0, 0, 0, 0);
     }
   }
-  __syncthreads();
+#define FZ_WA_ISSUE_HEAD(head_, buf_)                                                                        \
+  do {                                                                                                         \
+    _Pragma("unroll") for (int k = 0; k < 6; ++k)                                                              \
+      if (gsrc[k] != nullptr) cp_async16(sBuf + (buf_) * 3 * WA_MAT + soff[k], gsrc[k] + (head_) * WA_D);      \
+    cp_async_commit();                                                                                         \
+  } while (0)
+  const int tab_n = span * span;
+  FZ_WA_ISSUE_HEAD(head0, 0);
+  for (int i = tid; i < tab_n; i += WA_THREADS)
+    sTabs[i] = p.table[static_cast<size_t>(head0) * tab_n + i] * 1.4426950408889634f;   // log2 domain
 
   const int r0 = warp * 16;
   const int lr = lane >> 2, lc = (lane & 3) * 2;
+  const bool general = (p.shift > 0 && (wy == p.nwy - 1 || wx == p.nwx - 1)) || n_tok < WA_N;
+
+  for (int hh = 0; hh < p.hgroup; ++hh) {
+    const int head = head0 + hh;
+    const int cur = hh & 1;
+    __nv_bfloat16* sQ = sBuf + cur * 3 * WA_MAT;
+    __nv_bfloat16* sK = sQ + WA_MAT;
+    __nv_bfloat16* sV = sK + WA_MAT;
+    const float* sTab = sTabs + cur * WA_TAB;
+    cp_async_wait_all();
+    __syncthreads();          // head's q/k/v + table visible; everyone is done with the other buffer
+    float tnext[2] = {0.f, 0.f};
+    const bool more = hh + 1 < p.hgroup;
+    if (more) {
+      FZ_WA_ISSUE_HEAD(head + 1, cur ^ 1);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (tid + k * WA_THREADS < tab_n) tnext[k] = __ldg(p.table + static_cast<size_t>(head + 1) * tab_n + tid + k * WA_THREADS);
+    }
+
   uint32_t qa[2][4];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
@@ -239,7 +273,6 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
   const int info_lo = sInfo[r0 + lr], info_hi = sInfo[r0 + lr + 8];
   const int code_lo = (info_lo & 0xffff) + base, code_hi = (info_hi & 0xffff) + base;
   float m_lo = -INFINITY, m_hi = -INFINITY;
-  const bool general = (p.shift > 0 && (wy == p.nwy - 1 || wx == p.nwx - 1)) || n_tok < WA_N;
   if (!general) {
 #pragma unroll
     for (int nt = 0; nt < 18; ++nt) {
@@ -324,7 +357,6 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
     *reinterpret_cast<uint32_t*>(&sQ[(r0 + lr + 8) * WA_LD + nt * 8 + lc]) = pack_bf16(o[nt][2] * inv_hi, o[nt][3] * inv_hi);
   }
   __syncwarp();
-  const size_t tok0 = static_cast<size_t>(b) * p.H * p.W;
 #pragma unroll
   for (int i = lane; i < 64; i += 32) {
     const int tok = r0 + (i >> 2), ch = i & 3;
@@ -333,6 +365,13 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
       *reinterpret_cast<uint4*>(p.out + (tok0 + src) * p.C + head * WA_D + ch * 8) =
           *reinterpret_cast<const uint4*>(&sQ[tok * WA_LD + ch * 8]);
   }
+    if (more) {   // next head's table (log2 domain); its previous user finished before this iteration's barrier
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (tid + k * WA_THREADS < tab_n) sTabs[(cur ^ 1) * WA_TAB + tid + k * WA_THREADS] = tnext[k] * 1.4426950408889634f;
+    }
+  }   // heads
+#undef FZ_WA_ISSUE_HEAD
 }
 
 }  // namespace fz
@@ -384,9 +423,15 @@ extern "C" int fz_swin_window_attn(const void* qkv_bf16, const void* qkv_bias_bf
   p.nwy = (H + window - 1) / window;
   p.nwx = (W + window - 1) / window;
   p.scale = scale;
-  const long long grid = static_cast<long long>(B) * p.nwy * p.nwx * heads;
+  p.hgroup = heads % 4 == 0 ? 4 : (heads % 2 == 0 ? 2 : 1);
+  const long long grid = static_cast<long long>(B) * p.nwy * p.nwx * (heads / p.hgroup);
   FZ_REQUIRE(grid < (1ll << 31), "fz_swin_window_attn: grid too large");
-  swin_window_attn_kernel<<<static_cast<unsigned>(grid), WA_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  static bool configured = false;
+  if (!configured) {
+    FZ_CHECK_CUDA(cudaFuncSetAttribute(swin_window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+    configured = true;
+  }
+  swin_window_attn_kernel<<<static_cast<unsigned>(grid), WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
