@@ -63,6 +63,26 @@ __device__ __forceinline__ void load_pixel(const T* __restrict__ logits, int t, 
 #pragma unroll
     for (int c = 0; c < MAX_CLS; ++c)
       if (c < n_cls) v[c] = to_f32<T>(base[c * plane]);
+  } else if (LAYOUT == FZ_NHWC_UP4) {
+    // logits live at quarter resolution [P/4][P/4][cstride]; nn.UpsamplingBilinear2d(scale_factor=4)
+    // (align_corners=True) of smp's UPerNet head is evaluated here, with fz_head_upsample4's exact arithmetic
+    const int h = P / 4;
+    const float sc = static_cast<float>(h - 1) / static_cast<float>(P - 1);
+    const float fy = y * sc, fx = x * sc;
+    int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    y0 = y0 > h - 1 ? h - 1 : y0;
+    x0 = x0 > h - 1 ? h - 1 : x0;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < h - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const T* tb = logits + static_cast<size_t>(t) * h * h * cstride;
+    const T* p00 = tb + (static_cast<size_t>(y0) * h + x0) * cstride;
+    const T* p01 = tb + (static_cast<size_t>(y0) * h + x1) * cstride;
+    const T* p10 = tb + (static_cast<size_t>(y1) * h + x0) * cstride;
+    const T* p11 = tb + (static_cast<size_t>(y1) * h + x1) * cstride;
+#pragma unroll
+    for (int c = 0; c < MAX_CLS; ++c)
+      if (c < n_cls)
+        v[c] = hy * (hx * to_f32<T>(p00[c]) + lx * to_f32<T>(p01[c])) + ly * (hx * to_f32<T>(p10[c]) + lx * to_f32<T>(p11[c]));
   } else {
     const T* base = logits + ((static_cast<size_t>(t) * P + y) * P + x) * cstride;
     if ((static_cast<size_t>(cstride) * sizeof(T)) % 16 == 0) {
@@ -163,7 +183,9 @@ static int launch_crop(const void* logits, int dtype, int layout, int cstride, i
   FZ_REQUIRE(n_cls >= 1 && n_cls <= MAX_CLS, "crop kernels support 1..%d classes, got %d", MAX_CLS, n_cls);
   FZ_REQUIRE(P > 2 * margin && margin >= 0, "bad patch/margin %d/%d", P, margin);
   FZ_REQUIRE(dtype == FZ_F32 || dtype == FZ_BF16, "bad dtype %d", dtype);
-  FZ_REQUIRE(layout == FZ_NCHW || layout == FZ_NHWC, "bad layout %d", layout);
+  FZ_REQUIRE(layout == FZ_NCHW || layout == FZ_NHWC || layout == FZ_NHWC_UP4, "bad layout %d", layout);
+  if (layout == FZ_NHWC_UP4)
+    FZ_REQUIRE(dtype == FZ_F32 && P % 4 == 0 && P >= 8 && cstride >= n_cls, "quarter-resolution logits: fp32, P %% 4 == 0");
   if (layout == FZ_NHWC) FZ_REQUIRE(cstride >= n_cls, "cstride %d < n_cls %d", cstride, n_cls);
   if (layout == FZ_NHWC && (static_cast<size_t>(cstride) * (dtype == FZ_F32 ? 4 : 2)) % 16 == 0)
     FZ_REQUIRE(cstride >= ((n_cls + (dtype == FZ_F32 ? 3 : 7)) / (dtype == FZ_F32 ? 4 : 8)) * (dtype == FZ_F32 ? 4 : 8),
@@ -174,7 +196,8 @@ static int launch_crop(const void* logits, int dtype, int layout, int cstride, i
 #define FZ_LAUNCH(T, LAY)                                                                                       \
   crop_kernel<T, LAY, MODE><<<grid, block, 0, st>>>(reinterpret_cast<const T*>(logits), n_cls, cstride, P, margin, \
                                                     plan, own, weight, out8, canvas, H, W)
-  if (dtype == FZ_F32 && layout == FZ_NCHW) FZ_LAUNCH(float, FZ_NCHW);
+  if (layout == FZ_NHWC_UP4) FZ_LAUNCH(float, FZ_NHWC_UP4);
+  else if (dtype == FZ_F32 && layout == FZ_NCHW) FZ_LAUNCH(float, FZ_NCHW);
   else if (dtype == FZ_F32) FZ_LAUNCH(float, FZ_NHWC);
   else if (layout == FZ_NCHW) FZ_LAUNCH(__nv_bfloat16, FZ_NCHW);
   else FZ_LAUNCH(__nv_bfloat16, FZ_NHWC);

@@ -224,8 +224,9 @@ class SwinUPerNetEngine:
         return [x[:n] for x in self.x]
 
     # ------------------------------------------------------------------------------ decoder
-    def _decode(self, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """-> fp32 logits [n, n_cls, P, P] (in ``out`` when given and contiguous, else in the engine's buffer)."""
+    def _decode(self, n: int, out: Optional[torch.Tensor] = None, quarter: bool = False) -> torch.Tensor:
+        """-> fp32 logits [n, n_cls, P, P] (in ``out`` when given and contiguous, else in the engine's buffer); with
+        ``quarter`` the head's x4 upsampling is left to the consumer: returns [n, P/4, P/4, 64] (first n_cls valid)."""
         cfg, hw, dims = self.cfg, self.hw, self.dims
         Pc = cfg.pyramid_channels
         fb = [t[:n] for t in self.fb]
@@ -261,6 +262,8 @@ class SwinUPerNetEngine:
         lq = self.logits_q[:n]
         nv.gemm_bf16(fused.view(-1, cfg.segmentation_channels), self.head_w, nv.EPI_F32, bias=self.head_b,
                      out=lq.view(-1, 64))
+        if quarter:
+            return lq
         direct = out is not None and out.is_contiguous() and out.dtype == torch.float32
         dst = out if direct else self.logits[:n]
         nv.head_upsample4(lq, cfg.n_classes, dst)
@@ -279,13 +282,14 @@ class SwinUPerNetEngine:
     def decode_argmax_to_raster(self, n: int, plan: torch.Tensor, own: Optional[torch.Tensor], raster: torch.Tensor,
                                 margin: int) -> None:
         """inference.py:295-352 on the interpolated logits (argmax must follow the x4 bilinear)."""
-        lg = self._decode(n)
-        nv.crop_argmax_write(lg, nv.NCHW, margin, plan[:n], own[:n] if own is not None else None, raster)
+        lq = self._decode(n, quarter=True)     # the full-resolution logits (737 MB per 37 tiles) are never stored
+        nv.crop_argmax_write(lq, nv.NHWC_UP4, margin, plan[:n], own[:n] if own is not None else None, raster,
+                             n_cls=self.cfg.n_classes)
 
     def launch_count(self) -> int:
         """Kernel launches of one batch after the tile gather (bench.py's gpu_launches)."""
         n = 1                                                   # patch embed
         for i, d in enumerate(self.cfg.depths):
             n += (2 if i > 0 else 0) + 7 * d
-        n += 4 + 1 + 3 * len(PSP_SIZES) + 1 + 2 * 3 + 5 + 1 + 1 + 1 + 1     # casts, PSP, FPN, resizes, fuse, head, x4, crop
+        n += 4 + 1 + 3 * len(PSP_SIZES) + 1 + 2 * 3 + 5 + 1 + 1 + 1         # casts, PSP, FPN, resizes, fuse, head, crop(x4)
         return n

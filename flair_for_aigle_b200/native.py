@@ -17,7 +17,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "_native" / "libfz_b200.so"
 _lib: Optional[ctypes.CDLL] = None
 
 F32, BF16 = 0, 1
-NCHW, NHWC = 0, 1
+NCHW, NHWC, NHWC_UP4 = 0, 1, 2
 EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16, EPI_GELU_BF16 = 0, 1, 2, 3, 4, 5
 EPI_REVERSE_TILES = 0x100
 CONV_RELU_BF16, CONV_LOGITS_F32, CONV_ARGMAX_RASTER, CONV_LOGITS_F32_NCHW, CONV_ADD_RELU_BF16, CONV_BF16 = 0, 1, 2, 3, 4, 5
@@ -173,6 +173,8 @@ def _logits_geom(logits: torch.Tensor, layout: int, n_cls: Optional[int]):
         n, c, p, _ = logits.shape
         return n, (n_cls or c), p, 0
     n, p, _, cs = logits.shape
+    if layout == NHWC_UP4:
+        p *= 4
     return n, (n_cls or cs), p, cs
 
 

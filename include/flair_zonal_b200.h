@@ -61,6 +61,8 @@ int fz_gather_tiles_u8(const uint8_t* raster, int C, int H, int W, const int32_t
 #define FZ_BF16 1
 #define FZ_NCHW 0
 #define FZ_NHWC 1
+#define FZ_NHWC_UP4 2 /* float logits at quarter resolution [n][P/4][P/4][cstride]; the x4 bilinear (align_corners=True)
+                       * of smp's UPerNet SegmentationHead is evaluated inside the crop kernels */
 int fz_crop_argmax_write(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
                          int margin, const int32_t* plan, const int32_t* own, uint8_t* out_raster, int H, int W,
                          void* stream);

@@ -248,3 +248,24 @@ def test_swin_upernet_zone_through_public_api(cuda, tmp_path):
     agree = (got == ref).mean()
     print(f"swin-upernet zone class agreement with the oracle pipeline: {agree:.5f}")
     assert agree >= 0.98
+
+
+def test_crop_argmax_on_quarter_resolution_logits(cuda):
+    """FZ_NHWC_UP4: crop/argmax with the UPerNet head's x4 bilinear evaluated in the kernel == upsample, then crop."""
+    import numpy as np
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(9)
+    n, P, m = 3, 128, 16
+    lq = torch.randn(n, P // 4, P // 4, 64, device=cuda)
+    full = torch.empty(n, 19, P, P, device=cuda)
+    nv.head_upsample4(lq, 19, full)
+    S = P - 2 * m
+    plan = torch.tensor([[0, 0, m, m, S, S], [0, S, m, S + m, S, S - 5], [S, 0, S + m, m, S - 7, S]], dtype=torch.int32,
+                        device=cuda)
+    own = torch.stack([plan[:, 2], plan[:, 2] + plan[:, 4], plan[:, 3], plan[:, 3] + plan[:, 5]], 1).contiguous()
+    a = torch.full((2 * P, 2 * P), 255, dtype=torch.uint8, device=cuda)
+    b = torch.full((2 * P, 2 * P), 255, dtype=torch.uint8, device=cuda)
+    nv.crop_argmax_write(full, nv.NCHW, m, plan, own, a)
+    nv.crop_argmax_write(lq, nv.NHWC_UP4, m, plan, own, b, n_cls=19)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and (a != 255).any()
