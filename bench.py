@@ -375,8 +375,18 @@ def main() -> None:
         pk, how = peaks()
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        traffic = None
+        try:        # dram read+write per launch of the dominant GEMM shape, from the committed ncu --set full capture
+            if ARCH == "convnextv2_base-unet":
+                with open(os.path.join(ROOT, "profiles", "r1_ncu_gemm_traffic.json")) as f:
+                    tj = json.load(f)
+                traffic = {"bytes_per_launch": tj["dram_bytes_per_launch"],
+                           "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"], "kernel": tj["kernel"],
+                           "source": tj["source"]}
+        except Exception:
+            traffic = None
         roof = {"bound": "tensor", "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(ach / peak, 4), "traffic": None,
+                "frac": round(ach / peak, 4), "traffic": traffic,
                 "kernel": f"gemm_bf16_kernel / gemm_bf16_pair_kernel (tcgen05, every linear / 1x1 GEMM of one {ARCH} batch)",
                 "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": gemm_n, "avg_launch_us": round(gemm_ms / gemm_n * 1e3, 2),
