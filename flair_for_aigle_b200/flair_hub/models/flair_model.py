@@ -26,6 +26,7 @@ import torch.nn as nn
 
 from ... import native as nv
 from ...engine.convnext_unet import CONVNEXTV2_CFGS, ConvNeXtCfg, ConvNeXtV2UNetEngine
+from ...engine.fusion import FusedEncodersUNet
 from ...engine.resnet_unet import RESNET_LAYERS, ResNetCfg, ResNetUNetEngine
 from ...engine.swin_upernet import SWIN_CFGS, SwinCfg, SwinUPerNetEngine
 from . import monotemp_model as mm
@@ -101,12 +102,14 @@ class FLAIR_HUB_Model(nn.Module):
 
         self.arch = config['models']['monotemp_model']['arch']
         self.active_mono = [m for m in self.mono_keys if inputs.get(m, False)]
-        if len(self.active_mono) != 1:
-            raise NotImplementedError(
-                f"{len(self.active_mono)} mono-temporal modalities active: only the single-modality path "
-                "(FusionHandler case 1) has an sm_100a plan in this round")
+        if len(self.active_mono) < 1:
+            raise NotImplementedError("no mono-temporal modality is active")
         enc_name, _ = mm.split_arch(self.arch)
         self.encoder_name = mm.resolve_encoder(enc_name)
+        if len(self.active_mono) > 1 and self.encoder_name not in CONVNEXTV2_CFGS:
+            raise NotImplementedError(
+                f"{len(self.active_mono)} mono-temporal modalities: FusionHandler's concat + 1x1 path has an sm_100a "
+                "plan for the convnextv2_*-unet family only")
 
         gen = torch.Generator().manual_seed(int(config.get('seed', 2025)))
         self.encoders = _Node()
@@ -163,6 +166,22 @@ class FLAIR_HUB_Model(nn.Module):
         task = task or self.config['labels'][0]
         mb = max_batch or self.max_batch
         key = f"{task}:{mb}"
+        if key not in self._engines and len(self.active_mono) > 1:
+            # flair_model.py:376 per modality, :410 FusionHandler (concat + conv_f), :417-419 decoder
+            dev = self._device()
+            if dev.type != "cuda":
+                raise nv.NativeError("FLAIR_HUB_Model runs on hand-written sm_100a kernels only (no CPU fallback)")
+            ncls = len(self.config['labels_configs'][task]['value_name'])
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            depths, dims = CONVNEXTV2_CFGS[self.encoder_name]
+            encs = {}
+            for mod in self.active_mono:
+                cfg = ConvNeXtCfg(depths=depths, dims=dims, in_chans=self.channels_dict[mod], n_classes=ncls,
+                                  patch=int(self.img_input_sizes[mod]))
+                encs[mod] = ConvNeXtV2UNetEngine(sd, f"encoders.{mod}.seg_model.model.",
+                                                 f"main_decoders.{task}.seg_model.", cfg, dev, max_batch=mb)
+            self._engines = {k: e for k, e in self._engines.items() if k.endswith(f":{mb}")}
+            self._engines[key] = FusedEncodersUNet(encs, sd, "fusion_handler.")
         if key not in self._engines:
             dev = self._device()
             if dev.type != "cuda":
@@ -198,10 +217,32 @@ class FLAIR_HUB_Model(nn.Module):
 
     # -------------------------------------------------------------------------------- forward
     @torch.no_grad()
+    def _forward_fused(self, batch: dict):
+        """flair_model.py:357-430 with >= 2 mono modalities (FusionHandler concat + 1x1, :503-547)."""
+        labels = self.config['labels']
+        x0 = batch[self.active_mono[0]]
+        img_size = batch[labels[0]].shape[-1] if labels[0] in batch else x0.shape[-1]
+        if img_size != x0.shape[-1]:
+            raise NotImplementedError("final bilinear resize (flair_model.py:327) other than the identity is not built")
+        logits_tasks = {}
+        for task in labels:
+            eng = self.engine(task)
+            n = x0.shape[0]
+            out = torch.empty((n, eng.cfg.n_classes, x0.shape[-2], x0.shape[-1]), dtype=torch.float32, device=x0.device)
+            for s in range(0, n, eng.B):
+                e = min(s + eng.B, n)
+                eng.encode({m: batch[m][s:e] for m in self.active_mono})
+                eng.decode_logits_nchw(e - s, out=out[s:e])
+            logits_tasks[task] = out
+        return logits_tasks, {}
+
+    @torch.no_grad()
     def forward(self, batch: dict, apply_mod_dropout: bool = False):
         """flair_model.py:357-430 for one mono modality: returns ({task: (B,n_cls,H,W) fp32}, {})."""
         if apply_mod_dropout:
             raise NotImplementedError("modality dropout is a training-time feature outside the zonal hot path")
+        if len(self.active_mono) > 1:
+            return self._forward_fused(batch)
         mod = self.active_mono[0]
         x = batch[mod]
         if not x.is_cuda:
