@@ -61,6 +61,10 @@ class ConvNeXtV2UNetEngine:
         for d in cfg.dims:
             if d % 128 != 0:
                 raise NotImplementedError(f"encoder width {d}: the sm_100a kernels are tiled for multiples of 128")
+        if cfg.patch % 512 != 0:
+            # the fc1 epilogue emits GRN partial sums per 128-row tile and tiles must not straddle samples:
+            # (patch/32)^2 rows per sample in the last stage have to be a multiple of 128
+            raise NotImplementedError(f"patch size {cfg.patch}: the ConvNeXt-V2 plan needs a multiple of 512")
         nv.lib()
         self.cfg, self.dev, self.B = cfg, device, max_batch
         self.gemm_impl = "tcgen05"

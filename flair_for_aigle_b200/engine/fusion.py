@@ -6,7 +6,8 @@ Per stage the reference concatenates the modalities' feature maps along channels
     fused_i = W_i [x_i^(1) ; x_i^(2) ; ...] + b_i = sum_m W_i[:, slice_m] x_i^(m) + b_i
 so no concatenated tensor is materialised: one tcgen05 GEMM per (stage, modality), the first with the bias epilogue
 (FZ_EPI_F32), the following ones accumulating through the fp32 residual epilogue (FZ_EPI_RESID_F32, in place).
-All modalities must share the patch size (the bilinear alignment of flair_model.py:523-529 is the identity then).
+A modality whose maps are smaller / larger than the first one's (another patch size, e.g. a coarser DEM) is aligned with
+the bilinear resize of flair_model.py:523-529 on its bf16 operand.
 """
 from __future__ import annotations
 
@@ -32,11 +33,9 @@ class FusedEncodersUNet:
         feats0 = first.features(1)
         self.stage_shapes = [tuple(f.shape[1:]) for f in feats0]                 # (h, w, C_target)
         chans = {m: [f.shape[-1] for f in encoders[m].features(1)] for m in self.mods}
-        for m in self.mods:
-            for f, (h, w, _) in zip(encoders[m].features(1), self.stage_shapes):
-                if f.shape[1] != h or f.shape[2] != w:
-                    raise NotImplementedError("modalities with different patch sizes need the bilinear feature "
-                                              "alignment of flair_model.py:523-529 (not built)")
+        # modalities at another patch size (e.g. a coarser DEM): their maps are resized to the first modality's
+        # (F.interpolate bilinear, align_corners=False; flair_model.py:523-529) on the bf16 operand
+        self.src_hw = {m: [tuple(f.shape[1:3]) for f in encoders[m].features(1)] for m in self.mods}
         self.w: List[List[torch.Tensor]] = []
         self.b: List[torch.Tensor] = []
         for i, (_, _, ct) in enumerate(self.stage_shapes):
@@ -53,6 +52,9 @@ class FusedEncodersUNet:
         self.fused = [torch.empty((B, h, w, c), dtype=torch.float32, device=dev) for h, w, c in self.stage_shapes]
         self.a_bufs = [torch.empty(B * h * w * max(chans[m][i] for m in self.mods), dtype=torch.bfloat16, device=dev)
                        for i, (h, w, _) in enumerate(self.stage_shapes)]
+        need = [max([sh[0] * sh[1] * chans[m][i] for m in self.mods
+                     for sh in [self.src_hw[m][i]] if sh != (h, w)] + [0]) for i, (h, w, _) in enumerate(self.stage_shapes)]
+        self.r_bufs = [torch.empty(B * n, dtype=torch.bfloat16, device=dev) if n else None for n in need]
 
     def encode(self, batch: Dict[str, torch.Tensor]) -> int:
         n = None
@@ -70,7 +72,13 @@ class FusedEncodersUNet:
                 f = self.enc[m].features(n)[i]
                 cm = f.shape[-1]
                 a = self.a_bufs[i][:T * cm].view(T, cm)
-                nv.cast_f32_bf16(f, a)
+                sh, sw = self.src_hw[m][i]
+                if (sh, sw) == (h, w):
+                    nv.cast_f32_bf16(f, a)
+                else:
+                    small = self.r_bufs[i][:n * sh * sw * cm].view(n, sh, sw, cm)
+                    nv.cast_f32_bf16(f, small)
+                    nv.bilinear_slice(small, a.view(n, h, w, cm), 0)
                 if k == 0:
                     nv.gemm_bf16(a, self.w[i][k], nv.EPI_F32, bias=self.b[i], out=out)
                 else:

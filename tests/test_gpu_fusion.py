@@ -6,7 +6,7 @@ import torch
 TASK = "AERIAL_LABEL-COSIA"
 
 
-def _config():
+def _config(dem_patch=512):
     import bench
     from flair_for_aigle_b200.flair_zonal_detection.model_utils import prepare_model_config
     c = bench.zonal_config("unused.safetensors", "/tmp", "unused", 2)
@@ -61,3 +61,34 @@ def test_two_modality_forward_vs_oracle(cuda):
     assert d.mean().item() < 0.015 * sd_ and d.max().item() < 0.15 * sd_
     out2, _ = m(batch)
     assert torch.equal(out, out2[TASK])
+
+
+@pytest.mark.gpu
+def test_two_modalities_of_different_patch_size(cuda):
+    """DEM at twice the aerial patch size: FusionHandler resizes its feature maps to the aerial ones (bilinear)."""
+    from flair_for_aigle_b200.flair_hub.models.flair_model import FLAIR_HUB_Model
+    from flair_for_aigle_b200.synthetic import randomize_state_
+    from oracle.models import FlairHubOracle
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = FLAIR_HUB_Model(_config(), {"AERIAL_RGBI": 512, "DEM_ELEV": 1024}, max_batch=1)
+    sd = m.state_dict()
+    randomize_state_(sd, seed=12)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    o = FlairHubOracle("convnextv2_base-unet", {"AERIAL_RGBI": 4, "DEM_ELEV": 1}, {TASK: 19}).eval()
+    o.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    o = o.to(cuda)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    batch = {"AERIAL_RGBI": torch.randn(1, 4, 512, 512, generator=g).to(cuda),
+             "DEM_ELEV": torch.randn(1, 1, 1024, 1024, generator=g).to(cuda),
+             TASK: torch.zeros(1, 19, 512, 512, device=cuda)}
+    with torch.no_grad():
+        ref, _ = o(batch)
+    out, _ = m(batch)
+    torch.cuda.synchronize()
+    ref, out = ref[TASK], out[TASK]
+    sd_ = ref.std().item()
+    d = (out - ref).abs()
+    print(f"mixed-size fusion: max|d|={d.max().item():.4f} mean|d|={d.mean().item():.5f} std={sd_:.3f}")
+    assert d.mean().item() < 0.015 * sd_ and d.max().item() < 0.15 * sd_
