@@ -90,8 +90,9 @@ def register_raster(path: str, raster: ZoneRaster) -> None:
 
 
 def open_raster(path) -> ZoneRaster:
-    """``rasterio.open(path)`` stand-in.  Accepts a ZoneRaster, a registered name, ``*.npy``
-    (with ``<path>.json`` = {left, top, res[, crs]}) or, if rasterio is importable, any raster."""
+    """``rasterio.open(path)`` stand-in.  Accepts a ZoneRaster, a registered name, ``*.npy`` (with ``<path>.json`` =
+    {left, top, res[, crs]}), an 8-bit north-up GeoTIFF (built-in reader, ``geotiff.py``) or, if rasterio is importable,
+    any raster."""
     if isinstance(path, ZoneRaster):
         return path
     if path in _REGISTRY:
@@ -101,6 +102,13 @@ def open_raster(path) -> ZoneRaster:
         with open(path + ".json") as f:
             meta = json.load(f)
         return ZoneRaster(arr, meta["left"], meta["top"], meta["res"], meta.get("crs"), name=path)
+    if isinstance(path, str) and path.lower().endswith((".tif", ".tiff")) and os.path.isfile(path):
+        try:
+            from .geotiff import read_geotiff
+            arr, left, top, res, crs = read_geotiff(path)
+            return ZoneRaster(arr, left, top, res, crs, name=path)
+        except ValueError:
+            pass            # not something the built-in reader handles: let rasterio try
     try:
         import rasterio  # type: ignore
     except ImportError as e:  # pragma: no cover - depends on the host image
@@ -119,9 +127,9 @@ _PINNED_POOL = {}
 class RasterSink:
     """Output raster of ``init_outputs`` (inference.py:157-208): a uint8 (count,H,W) array that lives
     on the GPU while tiles are written into it by the kernels, copied to the host once and stored
-    on ``close()``.  GeoTIFF/COG encoding belongs to the raster-I/O row of SURVEY.md 8(f); here the
-    array is written as LZW TIFF through Pillow for single-band rasters that fit its limits,
-    otherwise as ``.npy``; georeferencing goes to a ``.json`` sidecar either way."""
+    on ``close()`` as a GeoTIFF (``geotiff.write_geotiff``: LZW for the single-band argmax raster like the
+    reference's profile, Deflate planar for ``class_prob``), or as ``.npy`` when it exceeds classic TIFF;
+    the georeferencing also goes to a ``.json`` sidecar."""
 
     def __init__(self, path: str, count: int, height: int, width: int, left: float, top: float, res: float,
                  crs=None, device=None):
@@ -170,14 +178,11 @@ class RasterSink:
                 "count": self.count, "height": self.height, "width": self.width, "dtype": "uint8",
                 "compress": "lzw"}
         written = None
-        if self.count == 1:
-            try:
-                from PIL import Image
-                Image.MAX_IMAGE_PIXELS = None
-                Image.fromarray(arr[0]).save(self.name, format="TIFF", compression="tiff_lzw")
-                written = self.name
-            except Exception:  # pragma: no cover - Pillow limits / missing codec
-                written = None
+        try:
+            from .geotiff import write_geotiff
+            written = write_geotiff(self.name, arr, self.left, self.top, self.res_value, self.crs)
+        except Exception:  # pragma: no cover - Pillow limits / classic-TIFF 4 GB limit
+            written = None
         if written is None:
             written = os.path.splitext(self.name)[0] + ".npy"
             np.save(written, arr)

@@ -203,3 +203,44 @@ def test_strip_sharding_is_bit_exact(setup):
             parts.append(out)
         torch.cuda.synchronize()
         assert torch.equal(torch.cat(parts), full)
+
+
+def test_geotiff_in_geotiff_out(setup, tmp_path):
+    """The reference's file contract end to end: RGBI GeoTIFF on disk -> inference_and_write -> LZW GeoTIFF class raster
+    with the input's georeferencing; identical to the run from the in-memory raster."""
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.geotiff import read_geotiff, write_geotiff
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model, compute_patch_sizes
+    from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import generate_patches_from_reference
+    import bench
+    tmp, wpath, _ = setup
+    arr, cfg_mem = _zone(tmp, wpath, 1000, 700, 64, "mem://z_tif")
+    # a 4-band GeoTIFF written the way GIS tools do (pixel interleaved): use Pillow directly
+    from PIL import Image, TiffImagePlugin
+    ifd = TiffImagePlugin.ImageFileDirectory_v2()
+    ifd[33550] = (RES, RES, 0.0)
+    ifd.tagtype[33550] = 12
+    ifd[33922] = (0.0, 0.0, 0.0, L, T, 0.0)
+    ifd.tagtype[33922] = 12
+    src = str(tmp_path / "ortho.tif")
+    Image.fromarray(np.ascontiguousarray(arr.transpose(1, 2, 0)), mode="RGBA").save(src, format="TIFF",
+                                                                                    compression="tiff_lzw", tiffinfo=ifd)
+    out_dir = str(tmp_path / "out")
+    os.makedirs(out_dir)
+    cfg = bench.zonal_config(wpath, out_dir, src, 4)
+    cfg = inf.initialize_geometry_and_resolutions(cfg)
+    cfg["device"] = torch.device("cuda:0")
+    sizes = compute_patch_sizes(cfg)
+    model = build_inference_model(cfg, sizes).to(cfg["device"])
+    RasterSink.write_files = True
+    results = {}
+    for name, c, img in (("file", cfg, src), ("mem", cfg_mem, "mem://z_tif")):
+        tiles = generate_patches_from_reference(c, img, None)
+        ds = inf.prep_dataset(c, tiles, sizes)
+        outs, _ = inf.init_outputs(c, img, 0)
+        inf.inference_and_write(model, ds, tiles, c, outs, img)
+        results[name] = (outs[TASK].to_host()[0].copy(), outs[TASK].written_path)
+    assert np.array_equal(results["file"][0], results["mem"][0])
+    got, left, top, res, _ = read_geotiff(results["file"][1])
+    assert np.array_equal(got[0], results["file"][0]) and (left, top, res) == (L, T, RES)
