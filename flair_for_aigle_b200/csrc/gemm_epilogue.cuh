@@ -19,25 +19,6 @@ struct GemmParams {
   unsigned long long* trace;  // optional: CTA 0 writes clock64 stamps [tile][8] (diagnostics, see fz_gemm_set_trace)
 };
 
-template <int OFF>
-__device__ __forceinline__ void colsum32_step(float (&s)[32], int lane) {
-  const bool upper = (lane & OFF) != 0;
-#pragma unroll
-  for (int i = 0; i < OFF; ++i) {
-    const float a = s[i], b = s[i + OFF];
-    s[i] = (upper ? b : a) + __shfl_xor_sync(0xffffffffu, upper ? a : b, OFF);
-  }
-}
-// Column sums over the 32 lanes of a warp of a 32-vector held per lane (transpose-reduce):
-// on return s[0] of lane l is the sum over lanes of the input s[l].  31 shuffles.
-__device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
-  colsum32_step<16>(s, lane);
-  colsum32_step<8>(s, lane);
-  colsum32_step<4>(s, lane);
-  colsum32_step<2>(s, lane);
-  colsum32_step<1>(s, lane);
-}
-
 template <int MODE>
 struct EpiShape {
   static constexpr bool F32OUT = (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32);
@@ -51,7 +32,7 @@ struct EpiShape {
 // stg   : this warp's 4 KB staging tile; 16 B segments XOR-swizzled with row&7 so that both the row-per-lane and
 //         the row-contiguous access patterns are bank-conflict free.  A row-per-thread STG/LDG would touch 32
 //         lines per instruction, which was the first epilogue's bottleneck.
-// sq_dst: (GELU_SUMSQ) where lane l stores the 32-row column sum of out^2 for column l (+32 for the second half)
+// sq_dst: (GELU_SUMSQ) 64 floats: 32-row column sums of out^2 for the chunk's columns (8-byte aligned)
 template <int MODE>
 __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, int row0, int col0, char* stg, int lane,
                                           float* sq_dst) {
@@ -91,16 +72,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
       v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
       v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
     }
-    if (MODE == FZ_EPI_GELU_SUMSQ) {
-      float s[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = gelu_erf_fast(v[j]);
-        s[j] = v[j] * v[j];     // M is a multiple of 128 in this mode (host check): no row mask
-      }
-      warp_colsum32(s, lane);
-      sq_dst[h * 32 + lane] = s[0];
-    } else if (MODE == FZ_EPI_GELU_BF16) {
+    if (MODE == FZ_EPI_GELU_SUMSQ || MODE == FZ_EPI_GELU_BF16) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
     } else if (MODE == FZ_EPI_RELU_BF16) {
@@ -132,6 +104,22 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
     }
   }
   __syncwarp();
+  if (MODE == FZ_EPI_GELU_SUMSQ) {
+    // GRN statistics: column sums of out^2 over this warp's 32 rows, read back from the staged bf16 tile (the values
+    // fc2 will actually consume): lane l owns columns 2l, 2l+1 = one 32-bit word per row, conflict-free under the
+    // XOR swizzle.  2.5 instructions per element instead of 4.9 for the register transpose-reduce it replaces.
+    // M is a multiple of 128 in this mode (host check): no row mask.
+    float a0 = 0.f, a1 = 0.f;
+    const int sidx = lane >> 2, woff = (lane & 3) * 4;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((sidx ^ (r & 7)) << 4) + woff);
+      const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+      a0 = fmaf(lo, lo, a0);
+      a1 = fmaf(hi, hi, a1);
+    }
+    *reinterpret_cast<float2*>(sq_dst + 2 * lane) = make_float2(a0, a1);
+  }
   // staging -> global, 4 full 128 B lines per instruction
 #pragma unroll
   for (int i = 0; i < 8; ++i) {

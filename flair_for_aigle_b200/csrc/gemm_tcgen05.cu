@@ -373,7 +373,8 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv
   const size_t off = static_cast<size_t>(m) * p.N + n;
   if (MODE == FZ_EPI_GELU_SUMSQ) {
     v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-    atomicAdd(&p.sumsq[static_cast<size_t>(m / 128) * p.N + n], v * v);
+    const float vr = __bfloat162float(__float2bfloat16_rn(v));     // statistics of the stored (bf16) value
+    atomicAdd(&p.sumsq[static_cast<size_t>(m / 128) * p.N + n], vr * vr);
   } else if (MODE == FZ_EPI_GELU_BF16) {
     v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
   } else if (MODE == FZ_EPI_RELU_BF16) {

@@ -89,7 +89,8 @@ int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, vo
  * Replaces the nn.Linear / 1x1 / 2x2-stride-2 conv calls under flair_model.py:376,539-541.
  */
 #define FZ_EPI_BF16 0       /* out bf16 = acc + bias                                              */
-#define FZ_EPI_GELU_SUMSQ 1 /* out bf16 = gelu(acc+bias); sumsq[m/128][n] = sum over the 128-row tile of out^2 */
+#define FZ_EPI_GELU_SUMSQ 1 /* out bf16 = gelu(acc+bias); sumsq[m/128][n] = sum over the 128-row tile of out^2 (of the
+                             * bf16-rounded values, i.e. exactly what the next GEMM reads) */
 #define FZ_EPI_RESID_F32 2  /* out f32  = acc + bias + resid                                      */
 #define FZ_EPI_F32 3        /* out f32  = acc + bias                                              */
 #define FZ_EPI_RELU_BF16 4  /* out bf16 = relu(acc + bias)                                        */

@@ -43,6 +43,45 @@ for fam, meta, a, b in prof:
     key = (fam, tuple(sorted(meta.items())))
     t, c = agg.get(key, (0.0, 0))
     agg[key] = (t + a.elapsed_time(b), c + 1)
+PEAKS = bench.peaks()[0]
+TENSOR, HBM = PEAKS.get("bf16_tflops_sustained", 1354.0) * 1e12, PEAKS.get("hbm_gbs", 6530.0) * 1e9
+FMA = 148 * 128 * 2 * PEAKS.get("sm_max_mhz", 1965.0) * 1e6        # fp32 CUDA-core peak (flop/s)
+
+
+def cost(fam, md):
+    """-> (flop, pipe peak, algorithmic HBM bytes) of one launch; None where no model is written down."""
+    if fam == "gemm_tcgen05":
+        M, N, K, mode = md["M"], md["N"], md["K"], md["mode"]
+        out_b = 4 if mode in (2, 3) else 2
+        by = 2 * M * K + 2 * N * K * (M // 1024 if mode == 2 and "convnext" in ARCH and N * 4 == K else 1)
+        by += out_b * M * N + (4 * M * N if mode == 2 else 0)
+        return 2.0 * M * N * K, TENSOR, by
+    if fam == "conv3x3_tcgen05":
+        px = md["B"] * md["H"] * md["H"]
+        out_b = 1 if md["mode"] == 2 else 2
+        return 2.0 * px * 9 * md["Cin"] * md["Cout"], TENSOR, px * (2 * md["Cin"] + out_b * md["Cout"])
+    if fam == "dwconv7_ln":
+        n = md["B"] * md["H"] * md["H"] * md["C"]
+        return 2.0 * 49 * n, FMA, 6 * n
+    if fam in ("ln2d_s2d", "layernorm_rows", "merge_ln"):
+        n = md.get("rows", 0) * md.get("C", 0) if "rows" in md else md.get("B", md.get("n", 0)) * md["H"] * md["H"] * md["C"]
+        return 0.0, FMA, 6 * n
+    if fam == "stem_ln":
+        n = md["n"]
+        return 2.0 * 64 * n * 128 * 128 * 128, FMA, n * (4 * 512 * 512 + 4 * 128 * 128 * 128)
+    if fam == "scale_weights":
+        return 0.0, FMA, 2 * md["N"] * md["K"] * (md["B"] + 1)
+    if fam == "upsample2_concat":
+        return 0.0, FMA, 2 * md["B"] * md["H"] * md["H"] * md["C"] * 1.6     # write + (quarter-size input, skip) read
+    if fam == "cast_f32_bf16":
+        return 0.0, FMA, 6 * md["n"]
+    if fam == "swin_window_attn":
+        H, C, n = md["H"], md["C"], md["n"]
+        nw = ((H + 11) // 12) ** 2
+        return n * nw * (C // 32) * 4.0 * 144 * 144 * 32, TENSOR, n * H * H * C * 2 * 4
+    return None
+
+
 tot = sum(t for t, _ in agg.values()) / reps
 lines = [f"{ARCH} batch B={B}: total kernel time {tot:.3f} ms = {tot/B:.4f} ms/tile (eager, per-launch events)"]
 fam_tot = collections.Counter()
@@ -55,7 +94,14 @@ for (fam, meta), (t, c) in agg.items():
     if fam == "conv3x3_tcgen05":
         fl = 2.0 * md['B'] * md['H'] * md['H'] * 9 * md['Cin'] * md['Cout']
         extra = f" {fl/(t/c*1e-3)/1e12:7.1f} TFLOP/s"
-    lines.append(f"{fam:18s} x{c//reps:3d} avg {t/c*1e3:9.1f} us  sum/batch {t/reps:8.3f} ms {extra}  {md}")
+    roof = ""
+    cm = cost(fam, md)
+    if cm is not None:
+        fl, pk, by = cm
+        t_pipe, t_hbm, t_meas = fl / pk, by / HBM, t / c * 1e-3
+        bound = "tensor" if (pk == TENSOR and t_pipe >= t_hbm) else ("fma" if t_pipe >= t_hbm else "hbm")
+        roof = f"  | roofline {max(t_pipe, t_hbm)*1e6:7.1f} us ({bound}) = {max(t_pipe, t_hbm)/t_meas*100:4.0f}%  {by/1e6:7.1f} MB"
+    lines.append(f"{fam:18s} x{c//reps:3d} avg {t/c*1e3:9.1f} us  sum/batch {t/reps:8.3f} ms {extra}{roof}  {md}")
 lines.append("--- by family (ms per batch, share)")
 for fam, t in fam_tot.most_common():
     lines.append(f"{fam:18s} {t:8.3f} ms  {t/tot*100:5.1f}%")
