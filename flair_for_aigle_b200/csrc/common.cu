@@ -4,6 +4,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
@@ -17,6 +21,38 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+static std::mutex g_cfg_mutex;
+
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+  int dev = 0;
+  FZ_CHECK_CUDA(cudaGetDevice(&dev));
+  static std::vector<std::pair<const void*, int>> done;
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  for (const auto& e : done)
+    if (e.first == kernel && e.second == dev) return 0;
+  FZ_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.emplace_back(kernel, dev);
+  return 0;
+}
+
+int device_sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("cudaGetDevice failed");
+    return 0;
+  }
+  static int cache[64] = {0};
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    set_error("cudaDeviceGetAttribute(MultiProcessorCount) failed");
+    return 0;
+  }
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

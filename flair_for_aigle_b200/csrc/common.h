@@ -19,6 +19,16 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint64_t* strides_bytes, const uint32_t* box, uint32_t swizzle_bytes,
                    const uint32_t* elem_strides = nullptr);
 
+// One-time (per device, thread-safe) opt-in of a kernel to `bytes` of dynamic shared memory; 0 or -2 (error set).
+int ensure_dynamic_smem(const void* kernel, int bytes);
+// Multiprocessor count of the CURRENT device (cached per device); 0 on error (error set).
+int device_sm_count();
+
+#define FZ_ENSURE_SMEM(kernel, bytes)                                                        \
+  do {                                                                                       \
+    if (int _rc = fz::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (bytes))) return _rc; \
+  } while (0)
+
 #define FZ_CHECK_CUDA(expr)                                                                  \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \

@@ -250,21 +250,15 @@ static int launch_rows(const CUtensorMap& a, const CUtensorMap& b, const RowConv
   constexpr int OFF_ROWS = ((9 * WTAP_BYTES + 1023) / 1024) * 1024;
   constexpr int BYTES = OFF_ROWS + ROW_NR * L::SLOT_BYTES + (2 * ROW_NR + 2 * ROW_AS + 1) * 8 + 16 + 1024;
   auto kern = conv3x3_rows_kernel<CIN, BN, MODE>;
-  static bool configured = false;
-  static int sm_count = 0, per_sm = 1;
-  if (!configured) {
-    FZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES));
-    int dev = 0;
-    FZ_CHECK_CUDA(cudaGetDevice(&dev));
-    FZ_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    // co-resident CTAs hide the per-row latency chain; bounded by shared memory and by TMEM (512 columns)
-    per_sm = (227 * 1024) / (BYTES + 1024);
-    const int tcols = (ROW_AS * BN) < 32 ? 32 : (ROW_AS * BN);
-    if (per_sm > 512 / tcols) per_sm = 512 / tcols;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 6) per_sm = 6;
-    configured = true;
-  }
+  FZ_ENSURE_SMEM(kern, BYTES);
+  const int sm_count = device_sm_count();
+  if (sm_count <= 0) return -2;
+  // co-resident CTAs hide the per-row latency chain; bounded by shared memory and by TMEM (512 columns)
+  int per_sm = (227 * 1024) / (BYTES + 1024);
+  constexpr int tcols = (ROW_AS * BN) < 32 ? 32 : (ROW_AS * BN);
+  if (per_sm > 512 / tcols) per_sm = 512 / tcols;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 6) per_sm = 6;
   const int items = p.B * (p.W / 128) * (p.H / p.R);
   int grid = sm_count * per_sm;
   if (grid > items) grid = items;

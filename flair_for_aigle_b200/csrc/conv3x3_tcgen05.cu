@@ -223,11 +223,7 @@ template <int BN, int KC, int MODE>
 static int launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t st) {
   using L = ConvSmem<BN, KC, 4>;
   auto kern = conv3x3_kernel<BN, KC, MODE>;
-  static bool configured = false;
-  if (!configured) {
-    FZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    configured = true;
-  }
+  FZ_ENSURE_SMEM(kern, L::BYTES);
   const int n_tiles_n = (p.Cout + BN - 1) / BN;
   const long long grid = 1LL * p.B * (p.H / p.TH) * (p.W / p.TW) * n_tiles_n;
   kern<<<static_cast<unsigned>(grid), 192, L::BYTES, st>>>(a, b, p);

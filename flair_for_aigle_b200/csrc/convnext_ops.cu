@@ -459,12 +459,7 @@ static int launch_stem(const void* in, int Cin, const float* w, const float* bia
   dim3 grid(P / 4, B);
 #define FZ_STEM(CPL)                                                                                           \
   case CPL: {                                                                                                  \
-    static bool cfg = false;                                                                                   \
-    if (!cfg) {                                                                                                \
-      FZ_CHECK_CUDA(cudaFuncSetAttribute(stem_ln_kernel<CPL, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         static_cast<int>(smem)));                                             \
-      cfg = true;                                                                                              \
-    }                                                                                                          \
+    FZ_ENSURE_SMEM((stem_ln_kernel<CPL, F32IN>), static_cast<int>(smem));                                      \
     stem_ln_kernel<CPL, F32IN><<<grid, 128, smem, st>>>(in, Cin, w, bias, ln_w, ln_b, out, P, eps);            \
     break;                                                                                                     \
   }

@@ -209,15 +209,9 @@ template <int BN, int STAGES, int ACC_STAGES, int MODE, int CL>
 static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
   auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE, CL>;
-  static bool configured = false;
-  static int sm_count = 0;
-  if (!configured) {
-    FZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    int dev = 0;
-    FZ_CHECK_CUDA(cudaGetDevice(&dev));
-    FZ_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  FZ_ENSURE_SMEM(kern, L::BYTES);
+  const int sm_count = device_sm_count();
+  if (sm_count <= 0) return -2;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   int grid = tiles < sm_count ? tiles : sm_count;
   if (CL == 2) grid &= ~1;

@@ -165,15 +165,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 template <int MODE>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_bf16_pair_kernel<MODE>;
-  static bool configured = false;
-  static int sm_count = 0;
-  if (!configured) {
-    FZ_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_BYTES));
-    int dev = 0;
-    FZ_CHECK_CUDA(cudaGetDevice(&dev));
-    FZ_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  FZ_ENSURE_SMEM(kern, pair::SMEM_BYTES);
+  const int sm_count = device_sm_count();
+  if (sm_count <= 0) return -2;
   const int tiles = ((p.M + pair::BM - 1) / pair::BM) * (p.N / pair::BN);
   int grid = 2 * tiles < sm_count ? 2 * tiles : (sm_count & ~1);
   cudaLaunchConfig_t cfg = {};

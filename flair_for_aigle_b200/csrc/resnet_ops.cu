@@ -144,12 +144,8 @@ extern "C" int fz_conv7x7s2_bn_relu(const void* in, int in_is_f32, int Cin, cons
   FZ_REQUIRE(P % 64 == 0 && Cin >= 1 && Cin <= 4, "fz_conv7x7s2_bn_relu: bad shape P=%d Cin=%d", P, Cin);
   if (B <= 0) return 0;
   const size_t smem = (196 * 64 + 7 * (C7_INPX + 3) * 4) * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    FZ_CHECK_CUDA(cudaFuncSetAttribute(conv7x7s2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FZ_CHECK_CUDA(cudaFuncSetAttribute(conv7x7s2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cfg = true;
-  }
+  FZ_ENSURE_SMEM(conv7x7s2_kernel<true>, static_cast<int>(smem));
+  FZ_ENSURE_SMEM(conv7x7s2_kernel<false>, static_cast<int>(smem));
   dim3 grid(P / 2, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);

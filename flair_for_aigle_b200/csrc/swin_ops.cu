@@ -426,11 +426,7 @@ extern "C" int fz_swin_window_attn(const void* qkv_bf16, const void* qkv_bias_bf
   p.hgroup = heads % 4 == 0 ? 4 : (heads % 2 == 0 ? 2 : 1);
   const long long grid = static_cast<long long>(B) * p.nwy * p.nwx * (heads / p.hgroup);
   FZ_REQUIRE(grid < (1ll << 31), "fz_swin_window_attn: grid too large");
-  static bool configured = false;
-  if (!configured) {
-    FZ_CHECK_CUDA(cudaFuncSetAttribute(swin_window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
-    configured = true;
-  }
+  FZ_ENSURE_SMEM(swin_window_attn_kernel, WA_SMEM);
   swin_window_attn_kernel<<<static_cast<unsigned>(grid), WA_THREADS, WA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
