@@ -144,19 +144,30 @@ __global__ void __launch_bounds__(PP_THREADS) crop_kernel(const T* __restrict__ 
                                                           int margin, const int32_t* __restrict__ plan,
                                                           const int32_t* __restrict__ own,
                                                           const float* __restrict__ weight, uint8_t* __restrict__ out8,
-                                                          float* __restrict__ canvas, int H, int W) {
+                                                          float* __restrict__ canvas, int H, int W,
+                                                          const int32_t* __restrict__ zmap) {
   const int t = blockIdx.x;
   const TileWin win = tile_window(plan, own, t, margin);
   if (win.h <= 0 || win.w <= 0) return;
   const int row_begin = blockIdx.y * PP_ROWS;
   const size_t plane = static_cast<size_t>(H) * W;
   const int S = P - 2 * margin;
+  // zmap (output_px_meters != reference resolution): nearest-neighbour zoom of the cropped prediction,
+  // inference.py:212-226,303-312 -- output offset o inside the tile's window reads crop pixel zmap[o]
   for (int ry = row_begin; ry < min(row_begin + PP_ROWS, win.h); ++ry) {
-    const int y = win.y0 + ry;
+    const int zy = zmap ? zmap[win.y0 - margin + ry] : 0;     // < 0: scipy's constant fill (zero logits / label 0)
+    const int y = zmap ? margin + zy : win.y0 + ry;
     const size_t orow = static_cast<size_t>(win.r0 + ry) * W + win.c0;
     for (int rx = threadIdx.x; rx < win.w; rx += PP_THREADS) {
+      const int zx = zmap ? zmap[win.x0 - margin + rx] : 0;
+      const int xs = zmap ? margin + zx : win.x0 + rx;
       float v[MAX_CLS];
-      load_pixel<T, LAYOUT>(logits, t, n_cls, cstride, P, y, win.x0 + rx, v);
+      if (zy < 0 || zx < 0) {
+#pragma unroll
+        for (int c = 0; c < MAX_CLS; ++c) v[c] = 0.0f;
+      } else {
+        load_pixel<T, LAYOUT>(logits, t, n_cls, cstride, P, y, xs, v);
+      }
       if (MODE == 0) {
         out8[orow + rx] = static_cast<uint8_t>(argmax_first(v, n_cls));
       } else {
@@ -166,7 +177,7 @@ __global__ void __launch_bounds__(PP_THREADS) crop_kernel(const T* __restrict__ 
           for (int c = 0; c < MAX_CLS; ++c)
             if (c < n_cls) out8[c * plane + orow + rx] = static_cast<uint8_t>(rintf(v[c] * 255.0f));
         } else {
-          const float wgt = weight ? weight[(y - margin) * S + (win.x0 + rx - margin)] : 1.0f;
+          const float wgt = weight ? weight[(y - margin) * S + (xs - margin)] : 1.0f;
 #pragma unroll
           for (int c = 0; c < MAX_CLS; ++c)
             if (c < n_cls) canvas[c * plane + orow + rx] += wgt * v[c];
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(PP_THREADS) crop_kernel(const T* __restrict__ 
 template <int MODE>
 static int launch_crop(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
                        int margin, const int32_t* plan, const int32_t* own, const float* weight, uint8_t* out8,
-                       float* canvas, int H, int W, cudaStream_t st) {
+                       float* canvas, int H, int W, cudaStream_t st, const int32_t* zmap = nullptr, int zoomed = 0) {
   FZ_REQUIRE(n_cls >= 1 && n_cls <= MAX_CLS, "crop kernels support 1..%d classes, got %d", MAX_CLS, n_cls);
   FZ_REQUIRE(P > 2 * margin && margin >= 0, "bad patch/margin %d/%d", P, margin);
   FZ_REQUIRE(dtype == FZ_F32 || dtype == FZ_BF16, "bad dtype %d", dtype);
@@ -191,11 +202,12 @@ static int launch_crop(const void* logits, int dtype, int layout, int cstride, i
     FZ_REQUIRE(cstride >= ((n_cls + (dtype == FZ_F32 ? 3 : 7)) / (dtype == FZ_F32 ? 4 : 8)) * (dtype == FZ_F32 ? 4 : 8),
                "vector path needs cstride >= n_cls rounded up to 16 B");
   if (n_tiles <= 0) return 0;
-  const int S = P - 2 * margin;
+  const int S = zmap ? zoomed : P - 2 * margin;      // rows a tile's write window can have
+  FZ_REQUIRE(S >= 1, "bad zoomed window size %d", S);
   dim3 grid(n_tiles, (S + PP_ROWS - 1) / PP_ROWS), block(PP_THREADS);
 #define FZ_LAUNCH(T, LAY)                                                                                       \
   crop_kernel<T, LAY, MODE><<<grid, block, 0, st>>>(reinterpret_cast<const T*>(logits), n_cls, cstride, P, margin, \
-                                                    plan, own, weight, out8, canvas, H, W)
+                                                    plan, own, weight, out8, canvas, H, W, zmap)
   if (layout == FZ_NHWC_UP4) FZ_LAUNCH(float, FZ_NHWC_UP4);
   else if (dtype == FZ_F32 && layout == FZ_NCHW) FZ_LAUNCH(float, FZ_NCHW);
   else if (dtype == FZ_F32) FZ_LAUNCH(float, FZ_NHWC);
@@ -313,4 +325,20 @@ extern "C" int fz_convert(const float* img, int C, int h, int w, int mode, uint8
                        reinterpret_cast<cudaStream_t>(stream)>>>(img, C, n_px, mode, out);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int fz_crop_zoom_write(int mode, const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls,
+                                  int P, int margin, const int32_t* plan, const int32_t* own, const int32_t* zmap,
+                                  int zoomed, uint8_t* out_raster, int H, int W, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(zmap != nullptr && zoomed >= 1, "fz_crop_zoom_write: zoom map required");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (mode == 0)
+    return launch_crop<0>(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, own, nullptr, out_raster,
+                          nullptr, H, W, st, zmap, zoomed);
+  if (mode == 1)
+    return launch_crop<1>(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, own, nullptr, out_raster,
+                          nullptr, H, W, st, zmap, zoomed);
+  set_error("fz_crop_zoom_write: mode %d (0 argmax, 1 class_prob)", mode);
+  return -1;
 }

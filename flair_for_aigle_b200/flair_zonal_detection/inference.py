@@ -144,18 +144,28 @@ def init_outputs(config: Dict, ref_img, i=0) -> Tuple[Dict[str, RasterSink], Dic
 
 
 def resample_prediction(prediction, scale: float):
-    """inference.py:212-226 (nearest zoom).  Only the identity is on the hot path."""
+    """inference.py:212-226: nearest-neighbour zoom of a (H, W) or (C, H, W) prediction (scipy.ndimage.zoom, order 0),
+    as separable index gathers.  Host helper with the reference's signature; the zonal path applies the same index
+    map inside the crop kernels (fz_crop_zoom_write)."""
+    from .slicing import zoom_map
     if abs(scale - 1.0) < 1e-9:
         return prediction
-    raise NotImplementedError("output_px_meters != reference resolution: nearest-neighbour rescaling of the "
-                              "prediction is not implemented on the GPU path yet")
+    prediction = np.asarray(prediction)
+    if prediction.ndim not in (2, 3):
+        raise ValueError(f"Unexpected prediction shape: {prediction.shape}")
+    zy, zx = zoom_map(prediction.shape[-2], scale), zoom_map(prediction.shape[-1], scale)
+    out = prediction[..., np.maximum(zy, 0), :][..., np.maximum(zx, 0)]
+    out[..., zy < 0, :] = 0          # scipy's constant fill (see zoom_map)
+    out[..., zx < 0] = 0
+    return out
 
 
-def _check_same_grid(config):
+def _rescale(config):
+    """(needs_rescale, scale) of inference.py:299-303."""
     ref_res = config['reference_resolution']
     out_res = config.get('output_px_meters', ref_res)
-    if abs(ref_res - out_res) > 1e-6:
-        resample_prediction(None, ref_res / out_res)
+    needs = abs(ref_res - out_res) > 1e-6
+    return needs, (ref_res / out_res if needs else 1.0)
 
 
 def _runner(model, config, margin: int) -> ZonalRunner:
@@ -180,7 +190,7 @@ def inference_and_write(model, dataloader, tiles_gdf, config: Dict, output_files
     margin = int(config['margin'])
     P = int(config['img_pixels_detection'])
     output_type = config['output_type']
-    _check_same_grid(config)
+    needs_rescale, scale = _rescale(config)
     ref_img = open_raster(ref_img)
     b = ref_img.bounds
     ib = {'left': b.left, 'bottom': b.bottom, 'right': b.right, 'top': b.top}
@@ -189,8 +199,13 @@ def inference_and_write(model, dataloader, tiles_gdf, config: Dict, output_files
     own = ownership_windows(plan)
     dataset = getattr(dataloader, 'dataset', dataloader)
     tasks = [t['name'] for t in config['tasks'] if t['active']]
+    zmap_d = None
+    if needs_rescale:
+        from .slicing import zoom_map
+        zmap_d = torch.from_numpy(zoom_map(P - 2 * margin, scale)).to(device)
 
-    if isinstance(dataset, MultiModalSlicedDataset) and output_type == "argmax" and len(tasks) == 1:
+    if (isinstance(dataset, MultiModalSlicedDataset) and output_type == "argmax" and len(tasks) == 1
+            and not needs_rescale):
         # fused device path: feeder -> encoder/decoder -> head epilogue writes the class raster
         mod = model.active_mono[0]
         raster = dataset.device_raster(mod, device)
@@ -207,7 +222,12 @@ def inference_and_write(model, dataloader, tiles_gdf, config: Dict, output_files
             for task, logits in logits_tasks.items():
                 sink = output_files[task]
                 pl, ow = plan_d[idx].contiguous(), own_d[idx].contiguous()
-                if output_type == "argmax":
+                if needs_rescale:
+                    # inference.py:303-312: argmax first, then zoom the labels; class_prob zooms the logits first --
+                    # with a nearest-neighbour zoom both are the same gather, done inside the crop kernel
+                    nv.crop_zoom_write(0 if output_type == "argmax" else 1, logits, nv.NCHW, margin, pl, ow, zmap_d,
+                                       sink.device_array[0] if output_type == "argmax" else sink.device_array)
+                elif output_type == "argmax":
                     nv.crop_argmax_write(logits, nv.NCHW, margin, pl, ow, sink.device_array[0])
                 else:
                     nv.crop_softmax_write(logits, nv.NCHW, margin, pl, ow, sink.device_array)
@@ -249,7 +269,9 @@ def inference(model, dataloader, tiles_gdf, config: Dict, raster_img):
         raise nv.NativeError("inference runs on CUDA only (no CPU fallback)")
     margin = int(config['margin'])
     P = int(config['img_pixels_detection'])
-    _check_same_grid(config)
+    if _rescale(config)[0]:
+        raise NotImplementedError("inference(): the accumulating variant is built for output_px_meters == reference "
+                                  "resolution only (inference_and_write handles the rescaled grid)")
     raster_img = open_raster(raster_img)
     b = raster_img.bounds
     ib = {'left': b.left, 'bottom': b.bottom, 'right': b.right, 'top': b.top}

@@ -158,6 +158,25 @@ def generate_patches_from_reference(config: Dict, img_path, geozone_contour_geom
 # ------------------------------------------------------------------------------------------
 # integer plans for the device kernels
 # ------------------------------------------------------------------------------------------
+def zoom_map(size: int, scale: float) -> np.ndarray:
+    """Source index of every output pixel of ``scipy.ndimage.zoom(prediction, scale, order=0)`` along one axis
+    (inference.py:212-226 ``resample_prediction``); -1 where scipy writes its constant fill value 0 instead of a source
+    pixel (with mode='constant' the last output coordinate can land a rounding error beyond the last input pixel, e.g. at
+    scale 0.5 -- the reference's rasters carry that zero row/column per tile, and so do ours).  scipy itself computes the
+    map when present (it is a dependency of the reference), so it is the reference's by construction; otherwise the rule
+    is restated without that quirk: output length round(size*scale), corner-aligned coordinates o*(size-1)/(out-1),
+    nearest = floor(c + 0.5)."""
+    try:
+        from scipy.ndimage import zoom
+        return np.asarray(zoom(np.arange(1, size + 1, dtype=np.int64), scale, order=0), dtype=np.int32) - 1
+    except ImportError:  # pragma: no cover - scipy ships with this image
+        out = int(round(size * scale))
+        if out <= 1:
+            return np.zeros(max(out, 0), np.int32)
+        c = np.arange(out, dtype=np.float64) * ((size - 1) / (out - 1))
+        return np.clip(np.floor(c + 0.5), 0, size - 1).astype(np.int32)
+
+
 def tile_plan(tiles_gdf, image_bounds: Dict[str, float], ref_res: float, patch_size: int, margin: int,
               out_res: Optional[float] = None) -> np.ndarray:
     """int32 (n,6): [row0, col0, top_px, left_px, height_px, width_px].
@@ -168,6 +187,8 @@ def tile_plan(tiles_gdf, image_bounds: Dict[str, float], ref_res: float, patch_s
     the bottom/right raster edge; height_px = 0 marks a tile the reference skips)."""
     out_res = ref_res if out_res is None else out_res
     s = patch_size - 2 * margin
+    if abs(out_res - ref_res) > 1e-6:
+        s = len(zoom_map(s, ref_res / out_res))          # size of the zoomed prediction (inference.py:303-312)
     n = len(tiles_gdf)
     plan = np.zeros((n, 6), dtype=np.int32)
     if n == 0:

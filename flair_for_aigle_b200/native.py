@@ -63,6 +63,7 @@ _SIGNATURES = {
     "fz_crop_argmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "fz_crop_softmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "fz_crop_softmax_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "fz_crop_zoom_write": [_i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
     "fz_canvas_argmax": [_vp, _i, _i64, _vp, _vp, _vp],
     "fz_convert": [_vp, _i, _i, _i, _i, _vp, _vp],
     "fz_gemm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
@@ -190,6 +191,15 @@ def crop_softmax_write(logits, layout, margin, plan, own, out_raster, n_cls=None
     H, W = out_raster.shape[-2:]
     _check(lib().fz_crop_softmax_write(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan), _ptr(own),
                                        _ptr(out_raster), H, W, _stream()), "fz_crop_softmax_write")
+
+
+def crop_zoom_write(mode: int, logits, layout, margin, plan, own, zmap, out_raster, n_cls=None):
+    """argmax (mode 0) / class_prob (mode 1) write with the nearest-neighbour zoom of inference.py:212-226."""
+    n, c, p, cs = _logits_geom(logits, layout, n_cls)
+    H, W = out_raster.shape[-2:]
+    _check(lib().fz_crop_zoom_write(mode, _ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan), _ptr(own),
+                                    _ptr(zmap), int(zmap.numel()), _ptr(out_raster), H, W, _stream()),
+           "fz_crop_zoom_write")
 
 
 def crop_softmax_accumulate(logits, layout, margin, plan, weight, canvas, n_cls=None):

@@ -70,6 +70,14 @@ int fz_crop_argmax_write(const void* logits, int dtype, int layout, int cstride,
 int fz_crop_softmax_write(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
                           int margin, const int32_t* plan, const int32_t* own, uint8_t* out_raster, int H, int W,
                           void* stream);
+/* output_px_meters != reference resolution (inference.py:212-226,299-312): the cropped prediction of a tile is zoomed
+ * (nearest neighbour, scipy.ndimage.zoom order 0) before it is written.  zmap int32 [zoomed]: crop pixel read by output
+ * offset o, or -1 where scipy writes its constant fill 0 (host: slicing.zoom_map); plan / own are in OUTPUT pixels with
+ * window sizes <= zoomed.
+ * mode 0 = argmax -> uint8 [H][W], 1 = class_prob -> uint8 [n_cls][H][W]. */
+int fz_crop_zoom_write(int mode, const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
+                       int margin, const int32_t* plan, const int32_t* own, const int32_t* zmap, int zoomed,
+                       uint8_t* out_raster, int H, int W, void* stream);
 /* Intended semantics of inference.py:468-564: canvas[n_cls][H][W] (float32, planar like the
  * reference's raster_logits) += weight(y,x) * softmax(cropped logits).
  * weight: float32 [P-2m][P-2m] or NULL (=1). */

@@ -47,6 +47,26 @@ def write_tiles(logits: np.ndarray, plan: np.ndarray, margin: int, out: np.ndarr
             out[:, top_px:top_px + h, left_px:left_px + w] = pred
 
 
+def write_tiles_rescaled(logits: np.ndarray, plan: np.ndarray, margin: int, out: np.ndarray, output_type: str,
+                         scale: float) -> None:
+    """inference.py:297-352 with ``output_px_meters != reference_resolution``: ``resample_prediction``
+    (inference.py:212-226 = scipy.ndimage.zoom, order 0) on the labels for 'argmax', on the logits before
+    ``convert`` for 'class_prob'; plan is in OUTPUT pixels (oracle/grid.py tile_plan with out_res)."""
+    from scipy.ndimage import zoom
+    p = logits.shape[-1]
+    for i in range(logits.shape[0]):
+        top_px, left_px, h, w = (int(v) for v in plan[i, 2:6])
+        if h <= 0 or w <= 0:
+            continue
+        patch = logits[i, :, margin:p - margin, margin:p - margin]
+        if output_type == "argmax":
+            pred = zoom(convert(patch, "argmax"), zoom=(1, scale, scale), order=0)
+            out[top_px:top_px + h, left_px:left_px + w] = pred[0, :h, :w]
+        else:
+            pred = convert(zoom(patch, zoom=(1, scale, scale), order=0), output_type)
+            out[:, top_px:top_px + h, left_px:left_px + w] = pred[:, :h, :w]
+
+
 def blend_accumulate(logits: np.ndarray, plan: np.ndarray, margin: int, canvas: np.ndarray,
                      weights: Optional[np.ndarray] = None) -> None:
     """Intended semantics of inference.py:520-562: softmax over classes of the

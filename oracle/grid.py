@@ -175,6 +175,10 @@ def tile_plan(tiles: List[Dict], geo: Georef, patch_size: int, margin: int,
     left, bottom, right, top = geo.bounds
     ib = {"left": left, "bottom": bottom, "right": right, "top": top}
     s = patch_size - 2 * margin
+    if abs(out_res - geo.res) > 1e-6:
+        # inference.py:303-325: the window has the size of the ZOOMED prediction; scipy.ndimage.zoom's output shape
+        # is round(in * zoom)
+        s = int(round(s * (geo.res / out_res)))
     plan = np.zeros((len(tiles), 6), dtype=np.int32)
     for i, t in enumerate(tiles):
         row0, col0 = read_window_px(t, geo, patch_size)

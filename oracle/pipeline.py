@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from .convert import write_tiles
+from .convert import write_tiles, write_tiles_rescaled
 from .grid import Georef, generate_patches, read_tile, tile_plan
 
 
@@ -40,13 +40,17 @@ def load_batch(raster: np.ndarray, plan: np.ndarray, idx: Sequence[int], patch: 
 @torch.no_grad()
 def run_zone(model, raster: np.ndarray, geo: Georef, patch: int, margin: int, means, stds, task: str, n_cls: int,
              batch_size: int = 8, output_type: str = "argmax", tile_indices: Optional[Sequence[int]] = None,
-             device: str = "cpu"):
+             device: str = "cpu", out_res: Optional[float] = None):
     """Full zone (or the listed tiles only).  Returns (out_raster uint8, seconds spent in the
-    batch loop, n_tiles processed)."""
+    batch loop, n_tiles processed).  ``out_res`` = output_px_meters (inference.py:165-194,299-312)."""
     tiles = generate_patches(patch, margin, geo.res, geo)
-    plan = tile_plan(tiles, geo, patch, margin)
+    rescale = out_res is not None and abs(out_res - geo.res) > 1e-6
+    plan = tile_plan(tiles, geo, patch, margin, out_res if rescale else None)
     order = list(range(len(tiles))) if tile_indices is None else list(tile_indices)
     h, w = geo.height, geo.width
+    if rescale:
+        left, bottom, right, top = geo.bounds
+        h, w = int(round((top - bottom) / out_res)), int(round((right - left) / out_res))
     out = np.zeros((h, w), np.uint8) if output_type == "argmax" else np.zeros((n_cls, h, w), np.uint8)
     t0 = time.perf_counter()
     for s in range(0, len(order), batch_size):
@@ -56,5 +60,8 @@ def run_zone(model, raster: np.ndarray, geo: Georef, patch: int, margin: int, me
             batch = {k: v.to(device) for k, v in batch.items()}
         logits, _ = model(batch)
         logits = logits[task].cpu().numpy()
-        write_tiles(logits, plan[idx], margin, out, output_type)
+        if rescale:
+            write_tiles_rescaled(logits, plan[idx], margin, out, output_type, geo.res / out_res)
+        else:
+            write_tiles(logits, plan[idx], margin, out, output_type)
     return out, time.perf_counter() - t0, len(order)
