@@ -244,3 +244,56 @@ def test_geotiff_in_geotiff_out(setup, tmp_path):
     assert np.array_equal(results["file"][0], results["mem"][0])
     got, left, top, res, _ = read_geotiff(results["file"][1])
     assert np.array_equal(got[0], results["file"][0]) and (left, top, res) == (L, T, RES)
+
+
+def test_full_size_zone_properties(setup):
+    """BASELINE.json configs[1] at its real size (10 000 x 10 000 px, 729 tiles, batches of 37 replayed as a CUDA graph),
+    checked through size-independent properties: every pixel written exactly by its owner (no sentinel left, labels
+    < n_cls), a second run reproduces the raster bit for bit, two row strips run as separate jobs concatenate to it,
+    and the tiles sampled for the oracle agree with it like the small zones do."""
+    from flair_for_aigle_b200.engine.strips import shard_rows
+    from flair_for_aigle_b200.engine.zonal import ZonalRunner
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import (generate_patches_from_reference,
+                                                                    ownership_windows, tile_plan)
+    from flair_for_aigle_b200.synthetic import DEFAULT_MEANS, DEFAULT_STDS
+    from oracle.grid import Georef
+    from oracle.pipeline import run_zone
+    tmp, wpath, oracle = setup
+    W = H = 10000
+    arr, cfg = _zone(tmp, wpath, W, H, 64, "mem://z_full", batch=37)
+    dev = cfg["device"]
+    model = build_inference_model(cfg, {"AERIAL_RGBI": 512}).to(dev)
+    tiles = generate_patches_from_reference(cfg, "mem://z_full", None)
+    assert len(tiles) == 729
+    plan = tile_plan(tiles, cfg["image_bounds"], RES, 512, 64)
+    own = ownership_windows(plan)
+    assert int(((own[:, 1] - own[:, 0]).clip(0) * (own[:, 3] - own[:, 2]).clip(0)).sum()) == W * H   # a partition
+    raster = torch.from_numpy(arr).to(dev)
+    runner = ZonalRunner(model.engine(TASK, max_batch=37), 64, use_graph=True)
+    full = torch.full((H, W), 255, dtype=torch.uint8, device=dev)
+    runner.run(raster, plan, own, full)
+    torch.cuda.synchronize()
+    assert int(full.max()) < 19
+    again = torch.full((H, W), 255, dtype=torch.uint8, device=dev)
+    runner.run(raster, plan, own, again)
+    assert torch.equal(full, again)
+    parts = []
+    for sh in shard_rows(plan, own, 512, H, 2):
+        out = torch.full((sh.out_r1 - sh.out_r0, W), 255, dtype=torch.uint8, device=dev)
+        ZonalRunner(model.engine(TASK, max_batch=37), 64, use_graph=False).run(
+            raster[:, sh.in_r0:sh.in_r1].contiguous(), sh.plan, sh.own, out)
+        parts.append(out)
+    assert torch.equal(torch.cat(parts), full)
+    # oracle on a sample of tiles (first / middle / clamped last column and row)
+    sample = [0, 13, 364, 701, 728]
+    ref, _, _ = run_zone(oracle, arr, Georef(L, T, RES, W, H), 512, 64, DEFAULT_MEANS, DEFAULT_STDS, TASK, 19,
+                         batch_size=5, tile_indices=sample, device="cuda")
+    got = full.cpu().numpy()
+    agree = []
+    for i in sample:
+        r0, r1, c0, c1 = (int(v) for v in own[i])
+        if r1 > r0 and c1 > c0:
+            agree.append((got[r0:r1, c0:c1] == ref[r0:r1, c0:c1]).mean())
+    print("full-size zone: agreement with the oracle on sampled tiles", [f"{a:.4f}" for a in agree])
+    assert min(agree) >= 0.98
