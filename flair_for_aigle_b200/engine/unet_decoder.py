@@ -8,6 +8,7 @@ epilogue, so the bf16 weights are exactly the checkpoint's.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -44,6 +45,10 @@ class UNetDecoderPlan:
                 blk[name + "_s"] = _f32(scale, device)
                 blk[name + "_b"] = _f32(b_ - mu * scale, device)
             assert blk["conv1_w"].shape[-1] == ci + cs, (blk["conv1_w"].shape, ci, cs)
+            if cs == 0 and ci in (32, 64) and co in (16, 32) and os.environ.get("FZ_UPCONV", "1") != "0":
+                # no skip: conv3x3(nearest_up2(a)) straight from `a` with merged sub-pixel taps (csrc/upconv3x3_rows.cu)
+                w1 = sd[prefix + f"decoder.blocks.{k}.conv1.0.weight"]
+                blk["conv1_w16"] = _bf16(nv.merge_upconv_weights(w1), device)
             self.blocks.append(blk)
         wh = sd[prefix + "segmentation_head.0.weight"].float()      # [ncls, c_last, 3, 3]
         assert wh.shape[0] == n_classes and n_classes <= 32
@@ -73,11 +78,15 @@ class UNetDecoderPlan:
         for k, blk in enumerate(self.blocks):
             hd *= 2
             ct = blk["cin"] + blk["cskip"]
-            cat = self.cat[:n * hd * hd * ct].view(n, hd, hd, ct)
-            skip = skips[k] if blk["cskip"] > 0 else None
-            nv.upsample2_concat(a, skip, cat)
             o1 = self.t1[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
-            nv.conv3x3(cat, blk["conv1_w"], blk["conv1_s"], blk["conv1_b"], nv.CONV_RELU_BF16, out=o1)
+            hs = hd // 2
+            if ("conv1_w16" in blk and a.dtype == torch.bfloat16 and hs % 128 == 0 and a.is_contiguous()):
+                nv.upconv3x3_bn_relu(a, blk["conv1_w16"], blk["conv1_s"], blk["conv1_b"], o1)
+            else:
+                cat = self.cat[:n * hd * hd * ct].view(n, hd, hd, ct)
+                skip = skips[k] if blk["cskip"] > 0 else None
+                nv.upsample2_concat(a, skip, cat)
+                nv.conv3x3(cat, blk["conv1_w"], blk["conv1_s"], blk["conv1_b"], nv.CONV_RELU_BF16, out=o1)
             o2 = self.t2[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
             nv.conv3x3(o1, blk["conv2_w"], blk["conv2_s"], blk["conv2_b"], nv.CONV_RELU_BF16, out=o2)
             a = o2
@@ -102,4 +111,8 @@ class UNetDecoderPlan:
                    raster=raster, margin=margin)
 
     def launches(self) -> int:
-        return 3 * len(self.blocks) + 1
+        hd, n = self.deepest, 1
+        for blk in self.blocks:
+            hd *= 2
+            n += 2 if ("conv1_w16" in blk and (hd // 2) % 128 == 0) else 3
+        return n

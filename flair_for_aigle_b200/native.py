@@ -77,6 +77,7 @@ _SIGNATURES = {
     "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
     "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_upconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_conv7x7s2_bn_relu": [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "fz_maxpool3x3s2": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fz_conv3x3_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
@@ -330,6 +331,34 @@ def conv3x3(x, w, scale, bias, mode, out=None, cout=None, cstride=0, plan=None, 
         _check(lib().fz_conv3x3_ex(_ptr(x), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), _ptr(resid), B, H, W, Cin, cout,
                                    rows, stride, mode, cstride, _ptr(plan), _ptr(own), _ptr(raster), RH, RW, margin,
                                    _stream()), "fz_conv3x3_ex")
+    return out
+
+
+def merge_upconv_weights(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] conv weight -> [Cout, 16, Cin] merged sub-pixel taps of conv3x3(nearest_up2(.)) (fp32 sums),
+    tile order ((py*2+px)*2+ra)*2+ca as documented at fz_upconv3x3_bn_relu."""
+    groups = {(0, 0): (0,), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2,)}
+    w = w.float()
+    tiles = []
+    for py in range(2):
+        for px in range(2):
+            for ra in range(2):
+                for ca in range(2):
+                    acc = torch.zeros_like(w[:, :, 0, 0])
+                    for ky in groups[(py, ra)]:
+                        for kx in groups[(px, ca)]:
+                            acc = acc + w[:, :, ky, kx]
+                    tiles.append(acc)
+    return torch.stack(tiles, dim=1)
+
+
+def upconv3x3_bn_relu(x, w16, scale, bias, out):
+    """x bf16 [B,H,W,Cin] -> out bf16 [B,2H,2W,Cout] = relu(bn(conv3x3(nearest_up2(x)))); w16 bf16 [rows,16,Cin]."""
+    B, H, W, Cin = x.shape
+    cout = out.shape[-1]
+    with _Timed('upconv3x3_tcgen05', B=B, H=H, Cin=Cin, Cout=cout):
+        _check(lib().fz_upconv3x3_bn_relu(_ptr(x), _ptr(w16), _ptr(scale), _ptr(bias), _ptr(out), B, H, W, Cin, cout,
+                                          w16.shape[0], _stream()), "fz_upconv3x3_bn_relu")
     return out
 
 

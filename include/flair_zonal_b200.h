@@ -173,6 +173,15 @@ int fz_conv3x3_bf16(const void* in, const void* w, const float* scale, const flo
                     int W, int Cin, int Cout, int w_rows, int mode, int cstride, const int32_t* plan,
                     const int32_t* own, uint8_t* raster, int RH, int RW, int margin, void* stream);
 
+/* fz_upconv3x3_bn_relu: relu(bn(conv3x3(F.interpolate(a, scale_factor=2, mode='nearest')))) -- the first convolution of
+ * the smp U-Net decoder blocks without a skip connection -- computed from `a` directly (sub-pixel decomposition; the
+ * upsampled tensor is never built).  in bf16 [B][H][W][Cin] (SOURCE size, W % 128 == 0, H % 16 == 0, Cin 32|64);
+ * w16 bf16 [w_rows][16][Cin]: merged taps, tile ((py*2+px)*2+ra)*2+ca = sum of the 3x3 taps (ky, kx) with
+ * ky in G(py,ra), kx in G(px,ca), G(0,0)={0}, G(0,1)={1,2}, G(1,0)={0,1}, G(1,1)={2}; out bf16 [B][2H][2W][Cout],
+ * Cout 16|32; scale/bias as in fz_conv3x3_bf16. */
+int fz_upconv3x3_bn_relu(const void* in, const void* w16, const float* scale, const float* bias, void* out, int B, int H,
+                         int W, int Cin, int Cout, int w_rows, void* stream);
+
 /* ---------------------------------------------------------------- ResNet-34 encoder front end
  * (smp native ResNetEncoder = torchvision ResNet without fc; `resnet34-unet`, BASELINE.json configs[0])
  * fz_conv7x7s2_bn_relu: conv 7x7 stride 2 pad 3 + eval BatchNorm (scale/bias) + ReLU.  in: uint8 [B][P][P][4]

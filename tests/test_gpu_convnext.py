@@ -232,3 +232,42 @@ def test_engine_vs_oracle(cuda):
     out3 = eng.decode_logits_nchw(2)
     torch.cuda.synchronize()
     assert torch.equal(out2, out3)
+
+
+@pytest.mark.parametrize("H,Cin,Cout", [(128, 64, 32), (256, 32, 16), (16, 64, 16), (32, 32, 32)])
+def test_upconv3x3_subpixel(cuda, H, Cin, Cout):
+    """conv3x3(nearest_up2(a)) + BN + ReLU from `a` directly (merged sub-pixel taps) vs torch on the upsampled tensor."""
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(H + Cin)
+    B, W = 2, 128 if H <= 32 else H
+    x = torch.randn(B, H, W, Cin, device=cuda).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device=cuda) / (9 * Cin) ** 0.5).bfloat16()
+    scale = torch.rand(Cout, device=cuda) + 0.5
+    bias = torch.randn(Cout, device=cuda) * 0.1
+    w16 = nv.merge_upconv_weights(w).bfloat16().contiguous()
+    out = torch.empty(B, 2 * H, 2 * W, Cout, dtype=torch.bfloat16, device=cuda)
+    nv.upconv3x3_bn_relu(x, w16, scale, bias, out)
+    torch.cuda.synchronize()
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = torch.relu(F.conv2d(up, w.float(), padding=1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    # merged taps are rounded to bf16 once more (2^-9 relative per merged weight) on top of the bf16 output rounding
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+    # the same computation with the merged (rounded) weights in fp32: tight
+    wm = w16.float()
+    groups = {(0, 0): (0,), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2,)}
+    xin = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    ref2 = torch.zeros(B, Cout, 2 * H, 2 * W, device=cuda)
+    for py in range(2):
+        for px in range(2):
+            acc = torch.zeros(B, Cout, H, W, device=cuda)
+            for ra in range(2):
+                for ca in range(2):
+                    t = ((py * 2 + px) * 2 + ra) * 2 + ca
+                    src = xin[:, :, py + ra:py + ra + H, px + ca:px + ca + W]
+                    acc += torch.einsum("bchw,oc->bohw", src, wm[:, t])
+            ref2[:, :, py::2, px::2] = acc
+    ref2 = torch.relu(ref2 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    err2 = (out.float() - ref2).abs().max().item()
+    assert err2 < 2 ** -8 * max(1.0, ref2.abs().max().item()) + 1e-3, err2
