@@ -188,14 +188,17 @@ def run_reference(args, rank: int, world: int) -> None:
         if i >= args.warmup:
             per_tile.append(spt)
     spt = float(np.mean(per_tile))
-    n_tiles = 729
-    mpx_s = (ZONE_W * ZONE_H / 1e6) / (spt * n_tiles)
+    # the N-GPU arm works on a 10000 x (10000*N) zone (weak scaling): same zone here, same per-tile cost
+    from oracle.grid import Georef, generate_patches
+    zone_h = ZONE_H * max(1, world)
+    n_tiles = len(generate_patches(PATCH, MARGIN, RES, Georef(LEFT, TOP, RES, ZONE_W, zone_h)))
+    mpx_s = (ZONE_W * zone_h / 1e6) / (spt * n_tiles)
     cb["value"] = round(mpx_s, 4)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(mpx_s, 4), "unit": "Mpx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(spt * n_tiles * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{ARCH} zonal inference, synthetic {ZONE_W}x{ZONE_H}x4 uint8 @0.2m, tile {PATCH} "
+        "config": {"workload": f"{ARCH} zonal inference, synthetic {ZONE_W}x{zone_h}x4 uint8 @0.2m, tile {PATCH} "
                                f"margin {MARGIN} ({n_tiles} tiles), {N_CLS} classes; CPU oracle (the reference cannot be "
                                "imported: smp/timm/rasterio absent), each step = bounded tile sample extrapolated"},
         "cpu_baseline": cb,
