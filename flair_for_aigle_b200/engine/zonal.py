@@ -108,9 +108,50 @@ class ZonalRunner:
         self._g_raster, self._g_out = raster, out_raster      # keep the captured buffers alive
         return raster, out_raster
 
-    def run(self, raster: torch.Tensor, plan: np.ndarray, own: np.ndarray, out_raster: torch.Tensor) -> int:
+    def run_streamed(self, host_raster: torch.Tensor, plan: np.ndarray, own: np.ndarray,
+                     out_raster: torch.Tensor) -> int:
+        """Same result as ``run`` from a PINNED HOST raster, with the upload hidden behind the compute: tiles are
+        processed bottom-up by tile row (ownership windows make the order irrelevant to the result), and before each
+        batch only the raster rows it needs and that are not resident yet are sent on a copy stream (contiguous per
+        channel plane).  The first batch waits for ~2 tile rows instead of the whole raster."""
+        n = plan.shape[0]
+        if n == 0:
+            return 0
+        C, H, W = host_raster.shape
+        key = (C, H, W)
+        if getattr(self, "_stream_raster_key", None) != key:
+            self._stream_raster = torch.empty((C, H, W), dtype=torch.uint8, device=self.dev)
+            self._stream_raster_key = key
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        dev_raster, cs = self._stream_raster, self._copy_stream
+        order = np.argsort(-plan[:, 0].astype(np.int64), kind="stable")       # bottom rows of the raster first
+        plan_o, own_o = plan[order], own[order]
+        B = self.B
+        nb = (n + B - 1) // B
+        lows = [max(int(plan_o[b * B:(b + 1) * B, 0].min()), 0) for b in range(nb)]
+        cur = torch.cuda.current_stream(self.dev)
+        cs.wait_stream(cur)                       # the previous zone's kernels are done with the device raster
+        resident_lo = H
+
+        def before_batch(b: int) -> None:
+            nonlocal resident_lo
+            lo = lows[b] if b + 1 < nb else 0    # the last batch takes whatever is left (rows no tile reads included)
+            if lo < resident_lo:
+                with torch.cuda.stream(cs):
+                    for c in range(C):
+                        dev_raster[c, lo:resident_lo].copy_(host_raster[c, lo:resident_lo], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                cur.wait_event(ev)
+                resident_lo = lo
+
+        return self.run(dev_raster, plan_o, own_o, out_raster, before_batch=before_batch)
+
+    def run(self, raster: torch.Tensor, plan: np.ndarray, own: np.ndarray, out_raster: torch.Tensor,
+            before_batch=None) -> int:
         """raster uint8 [C,H,W] (cuda), plan int32 (n,6), own int32 (n,4), out_raster uint8 [H,W]
-        (cuda).  Tiles are processed in enumeration order; returns the number of batches."""
+        (cuda).  Tiles are processed in the given order; returns the number of batches.  ``before_batch(b)`` is
+        called on the host before batch b is enqueued (run_streamed's upload hook)."""
         n = plan.shape[0]
         if n == 0:
             return 0
@@ -125,6 +166,8 @@ class ZonalRunner:
         g_raster, g_out = (self._ensure_graph(raster, out_raster) if self.use_graph else (raster, out_raster))
         for b in range(nb):
             sl = slice(b * B, (b + 1) * B)
+            if before_batch is not None:
+                before_batch(b)
             self.s_origins.copy_(org_d[sl])
             self.s_plan.copy_(plan_d[sl])
             self.s_own.copy_(own_d[sl])

@@ -49,6 +49,27 @@ class MultiModalSlicedDataset(Dataset):
                                    cfg.get('output_px_meters', ref_res))
         return self._plan
 
+    def host_raster(self, mod: str) -> torch.Tensor:
+        """uint8 (C,H,W) in page-locked host memory: the channels listed in the modality config."""
+        key = f"{mod}@host"
+        if key not in self._device_rasters:
+            r = self.readers[mod]
+            chans = list(self.modalities[mod].get('channels') or range(1, r.count + 1))
+            arr = r.read() if chans == list(range(1, r.count + 1)) else r.read(chans)
+            if arr.dtype != np.uint8:
+                raise NotImplementedError(f"{mod}: only uint8 rasters are supported by the device feeder")
+            pinned = getattr(r, 'pinned_tensor', None)
+            if pinned is not None and arr is r.array:
+                host = pinned
+            else:
+                host = torch.from_numpy(np.ascontiguousarray(arr))
+                try:
+                    host = host.pin_memory()
+                except RuntimeError:  # pragma: no cover - pinning can fail on exotic hosts
+                    pass
+            self._device_rasters[key] = host
+        return self._device_rasters[key]
+
     def device_raster(self, mod: str, device) -> torch.Tensor:
         """uint8 (C,H,W) on ``device``: the channels listed in the modality config (1-based, like
         rasterio ``indexes``), uploaded once through pinned memory."""

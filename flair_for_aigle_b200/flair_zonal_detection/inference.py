@@ -208,9 +208,13 @@ def inference_and_write(model, dataloader, tiles_gdf, config: Dict, output_files
             and not needs_rescale):
         # fused device path: feeder -> encoder/decoder -> head epilogue writes the class raster
         mod = model.active_mono[0]
-        raster = dataset.device_raster(mod, device)
         sink = output_files[tasks[0]]
-        _runner(model, config, margin).run(raster, plan, own, sink.device_array[0])
+        runner = _runner(model, config, margin)
+        host = dataset.host_raster(mod)
+        if host.is_pinned() and bool(config.get('stream_upload', True)):
+            runner.run_streamed(host, plan, own, sink.device_array[0])     # upload overlapped with the forward
+        else:
+            runner.run(dataset.device_raster(mod, device), plan, own, sink.device_array[0])
     else:
         # generic path (any iterable of reference-style batches, class_prob output, several tasks):
         # model(inputs) -> logits stay on the device -> crop/convert/write kernels

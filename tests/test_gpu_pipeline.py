@@ -297,3 +297,27 @@ def test_full_size_zone_properties(setup):
             agree.append((got[r0:r1, c0:c1] == ref[r0:r1, c0:c1]).mean())
     print("full-size zone: agreement with the oracle on sampled tiles", [f"{a:.4f}" for a in agree])
     assert min(agree) >= 0.98
+
+
+def test_streamed_upload_equals_resident_run(setup):
+    """run_streamed (pinned host raster, bottom-up tile order, row slabs uploaded behind the compute) == run."""
+    from flair_for_aigle_b200.engine.zonal import ZonalRunner
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import (generate_patches_from_reference,
+                                                                    ownership_windows, tile_plan)
+    tmp, wpath, _ = setup
+    arr, cfg = _zone(tmp, wpath, 2100, 1900, 64, "mem://z_stream", batch=5)
+    dev = cfg["device"]
+    model = build_inference_model(cfg, {"AERIAL_RGBI": 512}).to(dev)
+    tiles = generate_patches_from_reference(cfg, "mem://z_stream", None)
+    plan = tile_plan(tiles, cfg["image_bounds"], RES, 512, 64)
+    own = ownership_windows(plan)
+    runner = ZonalRunner(model.engine(TASK, max_batch=5), 64, use_graph=True)
+    a = torch.full((1900, 2100), 255, dtype=torch.uint8, device=dev)
+    runner.run(torch.from_numpy(arr).to(dev), plan, own, a)
+    host = torch.from_numpy(arr).pin_memory()
+    for _ in range(2):                                  # second pass reuses the device buffer and the graph
+        b = torch.full((1900, 2100), 255, dtype=torch.uint8, device=dev)
+        runner.run_streamed(host, plan, own, b)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b) and int(a.max()) < 19
