@@ -109,11 +109,13 @@ class ZonalRunner:
         return raster, out_raster
 
     def run_streamed(self, host_raster: torch.Tensor, plan: np.ndarray, own: np.ndarray,
-                     out_raster: torch.Tensor) -> int:
+                     out_raster: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> int:
         """Same result as ``run`` from a PINNED HOST raster, with the upload hidden behind the compute: tiles are
         processed bottom-up by tile row (ownership windows make the order irrelevant to the result), and before each
         batch only the raster rows it needs and that are not resident yet are sent on a copy stream (contiguous per
-        channel plane).  The first batch waits for ~2 tile rows instead of the whole raster."""
+        channel plane).  The first batch waits for ~2 tile rows instead of the whole raster.  With ``out_host`` (pinned
+        uint8 [H,W]) the class raster is read back the same way: rows that no unprocessed tile owns any more are final
+        and leave on the copy stream while the next batches run; on return the caller only has to synchronise."""
         n = plan.shape[0]
         if n == 0:
             return 0
@@ -145,10 +147,32 @@ class ZonalRunner:
                 cur.wait_event(ev)
                 resident_lo = lo
 
-        return self.run(dev_raster, plan_o, own_o, out_raster, before_batch=before_batch)
+        after_batch = None
+        if out_host is not None:
+            OH = out_raster.shape[0]
+            r1 = own_o[:, 1].astype(np.int64)
+            # rows >= final_lo[b] are owned by tiles of batches <= b only (suffix maximum of the owners' bottom edges)
+            suffix = np.maximum.accumulate(np.concatenate([r1, [0]])[::-1])[::-1]
+            final_lo = [int(suffix[min((b + 1) * B, n)]) for b in range(nb)]
+            done_lo = [OH]
+
+            def after_batch(b: int) -> None:
+                lo = final_lo[b] if b + 1 < nb else 0
+                if lo < done_lo[0]:
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    cs.wait_event(ev)
+                    with torch.cuda.stream(cs):
+                        out_host[lo:done_lo[0]].copy_(out_raster[lo:done_lo[0]], non_blocking=True)
+                    done_lo[0] = lo
+
+        nbat = self.run(dev_raster, plan_o, own_o, out_raster, before_batch=before_batch, after_batch=after_batch)
+        if out_host is not None:
+            cur.wait_stream(cs)                   # a synchronize on the current stream now covers the read-back
+        return nbat
 
     def run(self, raster: torch.Tensor, plan: np.ndarray, own: np.ndarray, out_raster: torch.Tensor,
-            before_batch=None) -> int:
+            before_batch=None, after_batch=None) -> int:
         """raster uint8 [C,H,W] (cuda), plan int32 (n,6), own int32 (n,4), out_raster uint8 [H,W]
         (cuda).  Tiles are processed in the given order; returns the number of batches.  ``before_batch(b)`` is
         called on the host before batch b is enqueued (run_streamed's upload hook)."""
@@ -175,6 +199,10 @@ class ZonalRunner:
                 self._graph.replay()
             else:
                 self._batch_body(raster, out_raster)
+            if after_batch is not None and g_out is out_raster:
+                after_batch(b)
         if g_out is not out_raster:
             out_raster.copy_(g_out, non_blocking=True)
+            if after_batch is not None:          # staged through the captured buffer: read back in one piece
+                after_batch(nb - 1)
         return nb

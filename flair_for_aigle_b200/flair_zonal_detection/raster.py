@@ -151,15 +151,28 @@ class RasterSink:
             _PINNED_POOL[tuple(self._pinned.shape)] = self._pinned
             self._pinned, self.host_array = None, None
 
-    def to_host(self) -> np.ndarray:
-        if self.host_array is None:
+    def pinned_buffer(self):
+        """Page-locked host tensor of the raster's shape (reused across zones: page-locking 100 MB costs tens of ms)."""
+        if self._pinned is None:
             import torch
             key = tuple(self.device_array.shape)
-            pinned = _PINNED_POOL.pop(key, None)            # page-locking 100 MB costs tens of ms: reuse
+            pinned = _PINNED_POOL.pop(key, None)
             if pinned is None:
                 pinned = torch.empty(self.device_array.shape, dtype=torch.uint8, pin_memory=True)
             self._pinned = pinned
-            pinned.copy_(self.device_array, non_blocking=True)
+        return self._pinned
+
+    def mark_streamed(self) -> None:
+        """The kernels' results were already read back into pinned_buffer() on a stream the current stream has joined
+        (ZonalRunner.run_streamed): to_host() only synchronises."""
+        self._streamed = True
+
+    def to_host(self) -> np.ndarray:
+        if self.host_array is None:
+            import torch
+            pinned = self.pinned_buffer()
+            if not getattr(self, "_streamed", False):
+                pinned.copy_(self.device_array, non_blocking=True)
             torch.cuda.current_stream(self.device_array.device).synchronize()
             self.host_array = pinned.numpy()
         return self.host_array

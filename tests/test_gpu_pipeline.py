@@ -318,6 +318,8 @@ def test_streamed_upload_equals_resident_run(setup):
     host = torch.from_numpy(arr).pin_memory()
     for _ in range(2):                                  # second pass reuses the device buffer and the graph
         b = torch.full((1900, 2100), 255, dtype=torch.uint8, device=dev)
-        runner.run_streamed(host, plan, own, b)
+        back = torch.full((1900, 2100), 254, dtype=torch.uint8).pin_memory()
+        runner.run_streamed(host, plan, own, b, out_host=back)
         torch.cuda.synchronize()
         assert torch.equal(a, b) and int(a.max()) < 19
+        assert torch.equal(back, a.cpu())               # streamed read-back of the finished rows
