@@ -8,8 +8,9 @@
 // Persistent kernel, one CTA per SM, static tile schedule (tile = blockIdx.x + i*gridDim.x,
 // n fastest so CTAs running together share the A rows in L2).  A CTA tile is 256 x BN: two
 // M=128 UMMA accumulators that share one B tile, which raises the operand intensity to
-// 256*BN*64*2 / ((256+BN)*128) flop per smem byte (87 at BN=128, 131 at BN=256) -- the 128x128
-// tile of the first version measured exactly its L2->SM bandwidth bound (64 flop/B * 8.6 TB/s).
+// 256*BN*64*2 / ((256+BN)*128) flop per smem byte (87 at BN=128) -- the 128x128 tile of the first version measured
+// exactly its L2->SM bandwidth bound (64 flop/B * 8.6 TB/s).  Outputs with N % 256 == 0 go to the CTA-pair kernel
+// (gemm_tcgen05_2sm.cu), which gets 131 flop/B out of a 256x256 tile split over two SMs.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 4..19 epilogue:
 // 16 warps = 2 row halves x 4 TMEM lane quarters (= warp % 4) x 2 interleaved column groups, i.e.
 // four epilogue warps per SM sub-partition to hide the TMEM-load / SFU / global latencies.
@@ -45,10 +46,7 @@ struct GemmSmem {
   static constexpr int BYTES = OFF_TSLOT + 16 + 1024;            // + worst-case alignment pad
 };
 
-// CL = 2: the two CTAs of a cluster work on neighbouring N tiles of the SAME 256 rows; each loads one 128-row half
-// of the A stage and TMA-multicasts it into both CTAs' shared memory, so a CTA pulls 32 KB instead of 48 KB per
-// k-block through the L2 fabric (the 6.3 KB/clk L2->SM cap is what bounded the 256x128 tiles at ~0.83 PFLOP/s).
-template <int BN, int STAGES, int ACC_STAGES, int MODE, int CL>
+template <int BN, int STAGES, int ACC_STAGES, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using L = GemmSmem<BN, STAGES>;
@@ -71,9 +69,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int m_tiles = (p.M + BM - 1) / BM;
   const int total_tiles = n_tiles * m_tiles;
   const int num_kb = p.K / BK;
-  // persistent schedule: tile t -> (m = t / n_tiles, n = t % n_tiles).  With CL = 2 consecutive CTAs (a cluster)
-  // take consecutive tiles, i.e. the same m and neighbouring n (n_tiles is even: host check).
-  const int crank = CL == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  // persistent schedule: tile t -> (m = t / n_tiles, n = t % n_tiles)
   const int t_first = blockIdx.x, t_step = gridDim.x;
 
   if (warp == 0 && lane == 0) {
@@ -81,7 +77,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);          // released by the MMA warp of every CTA that reads the stage
+      mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -93,7 +89,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (CL == 2) cluster_sync_all();       // the peer's barriers exist before anything is multicast at them
   const uint32_t tmem = *tslot;
 
   if (warp == 0) {
@@ -110,11 +105,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
-          if (CL == 2)   // my 128-row half of the shared A stage, into both CTAs (tmA's box is 128 rows here)
-            tma_load_2d_mcast(&tmA, &full[s], sA + s * A_STAGE_BYTES + crank * (128 * BK * 2), kb * BK,
-                              m0 + crank * 128, 0x3);
-          else
-            tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
+          tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
           tma_load_3d(&tmB, &full[s], sB + s * L::B_STAGE_BYTES, kb * BK, n0, bcoord);
         }
       }
@@ -149,8 +140,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_bf16(acc0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
             umma_bf16(acc1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
           }
-          if (CL == 2) umma_commit_mcast(&empty[s], 0x3);
-          else umma_commit(&empty[s]);
+          umma_commit(&empty[s]);
         }
         umma_commit(&tfull[as]);
         FZ_TRACE(4);   // all MMAs of the tile issued
@@ -201,55 +191,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();       // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp == 1) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int BN, int STAGES, int ACC_STAGES, int MODE, int CL>
-static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BN, int STAGES, int ACC_STAGES, int MODE>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE, CL>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE>;
   FZ_ENSURE_SMEM(kern, L::BYTES);
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return -2;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  int grid = tiles < sm_count ? tiles : sm_count;
-  if (CL == 2) grid &= ~1;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = L::BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  FZ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  const int grid = tiles < sm_count ? tiles : sm_count;
+  kern<<<grid, GEMM_THREADS, L::BYTES, stream>>>(tmA, tmB, p);
+  FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int BN, int STAGES, int ACC_STAGES, int MODE>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA128, const CUtensorMap& tmB, const GemmParams& p,
-                       bool cluster, cudaStream_t stream) {
-  if (cluster) return launch_gemm_cl<BN, STAGES, ACC_STAGES, MODE, 2>(tmA128, tmB, p, stream);
-  return launch_gemm_cl<BN, STAGES, ACC_STAGES, MODE, 1>(tmA, tmB, p, stream);
-}
-
-// BN = 128: 3 smem stages (48 KB each) + 64 KB store staging, accumulators double buffered.
-// BN = 256: 2 smem stages (64 KB each), single accumulator stage (FZ_GEMM_BN=256 experiments only).
+// BN = 128: 3 smem stages (48 KB each) + 64 KB store staging, accumulators double buffered; BN = 64 for narrow outputs.
+// (Wide outputs, N % 256 == 0, go to the CTA-pair kernel in gemm_tcgen05_2sm.cu.)
 template <int BN, int STAGES, int ACC_STAGES>
-static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& a128, const CUtensorMap& b,
-                         const GemmParams& p, bool cl, cudaStream_t st) {
+static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
   switch (mode) {
-    case FZ_EPI_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_BF16>(a, a128, b, p, cl, st);
-    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_SUMSQ>(a, a128, b, p, cl, st);
-    case FZ_EPI_RESID_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RESID_F32>(a, a128, b, p, cl, st);
-    case FZ_EPI_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_F32>(a, a128, b, p, cl, st);
-    case FZ_EPI_RELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RELU_BF16>(a, a128, b, p, cl, st);
-    case FZ_EPI_GELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_BF16>(a, a128, b, p, cl, st);
+    case FZ_EPI_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_BF16>(a, b, p, st);
+    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_SUMSQ>(a, b, p, st);
+    case FZ_EPI_RESID_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RESID_F32>(a, b, p, st);
+    case FZ_EPI_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_F32>(a, b, p, st);
+    case FZ_EPI_RELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RELU_BF16>(a, b, p, st);
+    case FZ_EPI_GELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_BF16>(a, b, p, st);
   }
   set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
   return -1;
@@ -279,41 +248,6 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   FZ_REQUIRE(mode != FZ_EPI_GELU_SUMSQ || M % 128 == 0, "fz_gemm_bf16: M=%d must be a multiple of 128 with GELU_SUMSQ", M);
   FZ_REQUIRE(bias != nullptr, "fz_gemm_bf16: bias is required (pass zeros)");
   FZ_REQUIRE(mode != FZ_EPI_RESID_F32 || resid != nullptr, "fz_gemm_bf16: residual buffer required");
-  // tile width: 256 for the long-K / light-epilogue GEMMs when it still leaves enough tiles,
-  // 128 (double-buffered accumulators) otherwise, 64 for narrow outputs
-  int BN = (N % 128 == 0) ? 128 : 64;
-  const char* force = getenv("FZ_GEMM_BN");
-  if (force) BN = atoi(force);
-  else if (N % 256 == 0 && mode != FZ_EPI_GELU_SUMSQ && K >= 1024 &&
-           static_cast<long long>((M + BM - 1) / BM) * (N / 256) >= 3 * 148)
-    BN = 256;   // only when every CTA gets >= 3 tiles: the single accumulator stage cannot overlap its epilogue
-  FZ_REQUIRE((BN == 64 || BN == 128 || BN == 256) && N % BN == 0, "fz_gemm_bf16: bad tile width %d for N=%d", BN, N);
-
-  // cluster-of-2 multicast needs an even number of N tiles and pairs of tiles that start together
-  static int cluster_env = -1;
-  if (cluster_env < 0) {
-    const char* e = getenv("FZ_GEMM_CLUSTER");
-    cluster_env = e ? atoi(e) : 0;
-  }
-  const bool cluster = cluster_env != 0 && ((N / BN) % 2 == 0);
-  CUtensorMap tmA, tmA128, tmB;
-  {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-    const uint64_t strides[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {BK, BM};
-    int rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box, 128);
-    if (rc) return rc;
-    const uint32_t box128[2] = {BK, 128};
-    rc = make_tmap_bf16(&tmA128, A, 2, dims, strides, box128, 128);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)b_batch};
-    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)N};
-    const uint32_t box[3] = {BK, (uint32_t)BN, 1};
-    int rc = make_tmap_bf16(&tmB, B, 3, dims, strides, box, 128);
-    if (rc) return rc;
-  }
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
@@ -325,13 +259,29 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   // FZ_GEMM_PAIR=0 disables, =2 forces it whenever N % 256 == 0.
   const char* pair_e = getenv("FZ_GEMM_PAIR");
   const int pair_env = pair_e ? atoi(pair_e) : 1;
-  if (!force && pair_env != 0 && N % 256 == 0) {
+  if (pair_env != 0 && N % 256 == 0) {
     const long long pair_tiles = static_cast<long long>((M + BM - 1) / BM) * (N / 256);
     if (pair_env == 2 || pair_tiles >= 74) return gemm_pair_launch(A, B, p, b_batch, mode, st);
   }
-  if (BN == 256) return dispatch_mode<256, 2, 1>(mode, tmA, tmA128, tmB, p, cluster, st);
-  if (BN == 128) return dispatch_mode<128, 3, 2>(mode, tmA, tmA128, tmB, p, cluster, st);
-  return dispatch_mode<64, 3, 2>(mode, tmA, tmA128, tmB, p, cluster, st);
+  // one-SM kernel: 256 x 128 tiles (double-buffered accumulators), 256 x 64 for narrow outputs
+  const int BN = (N % 128 == 0) ? 128 : 64;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {BK, BM};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)b_batch};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)N};
+    const uint32_t box[3] = {BK, (uint32_t)BN, 1};
+    int rc = make_tmap_bf16(&tmB, B, 3, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  if (BN == 128) return dispatch_mode<128, 3, 2>(mode, tmA, tmB, p, st);
+  return dispatch_mode<64, 3, 2>(mode, tmA, tmB, p, st);
 }
 
 // ----------------------------------------------------------------------------------------
