@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(256) ln2d_s2d_kernel(const float* __restrict__
 template <int NV>
 __global__ void __launch_bounds__(256) ln2d_s2d_reg_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
                                                            const float* __restrict__ ln_b,
-                                                           __nv_bfloat16* __restrict__ out, int n_px, int H, int W,
+                                                           __nv_bfloat16* __restrict__ out,
+                                                           __nv_bfloat16* __restrict__ copy, int n_px, int H, int W,
                                                            float eps) {
   constexpr int C = NV * 128;
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -342,6 +343,17 @@ __global__ void __launch_bounds__(256) ln2d_s2d_reg_kernel(const float* __restri
   for (int i = 0; i < NV; ++i) {
     v[i] = __ldg(row + i * 32 + lane);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  if (copy != nullptr) {      // the un-normalised stage output as bf16: the decoder's skip operand, no extra read
+    uint2* cp = reinterpret_cast<uint2*>(copy + static_cast<size_t>(p) * C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x, v[i].y), hi = __floats2bfloat162_rn(v[i].z, v[i].w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      cp[i * 32 + lane] = pk;
+    }
   }
   const float mean = warp_sum(s) * (1.0f / C);
   float q = 0.f;
@@ -565,7 +577,15 @@ extern "C" int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw,
 
 extern "C" int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, int B, int H, int W,
                            int C, float eps, void* stream) {
+  return fz_ln2d_s2d_copy(x, ln_w, ln_b, out_bf16, nullptr, B, H, W, C, eps, stream);
+}
+
+extern "C" int fz_ln2d_s2d_copy(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, void* copy_bf16,
+                                int B, int H, int W, int C, float eps, void* stream) {
   using namespace fz;
+  FZ_REQUIRE(copy_bf16 == nullptr || C == 128 || C == 256 || C == 512,
+             "fz_ln2d_s2d_copy: the bf16 copy is built for C = 128, 256, 512 (got %d)", C);
+  __nv_bfloat16* cpy = reinterpret_cast<__nv_bfloat16*>(copy_bf16);
   FZ_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "fz_ln2d_s2d: bad shape H=%d W=%d C=%d", H, W, C);
   const int n_px = B * H * W;
   if (n_px <= 0) return 0;
@@ -573,9 +593,9 @@ extern "C" int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b,
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   const unsigned grid = (n_px + 7) / 8;
   switch (C) {
-    case 128: ln2d_s2d_reg_kernel<1><<<grid, 256, 0, st>>>(x, ln_w, ln_b, o, n_px, H, W, eps); break;
-    case 256: ln2d_s2d_reg_kernel<2><<<grid, 256, 0, st>>>(x, ln_w, ln_b, o, n_px, H, W, eps); break;
-    case 512: ln2d_s2d_reg_kernel<4><<<grid, 256, 0, st>>>(x, ln_w, ln_b, o, n_px, H, W, eps); break;
+    case 128: ln2d_s2d_reg_kernel<1><<<grid, 256, 0, st>>>(x, ln_w, ln_b, o, cpy, n_px, H, W, eps); break;
+    case 256: ln2d_s2d_reg_kernel<2><<<grid, 256, 0, st>>>(x, ln_w, ln_b, o, cpy, n_px, H, W, eps); break;
+    case 512: ln2d_s2d_reg_kernel<4><<<grid, 256, 0, st>>>(x, ln_w, ln_b, o, cpy, n_px, H, W, eps); break;
     default: ln2d_s2d_kernel<<<grid, 256, 0, st>>>(x, ln_w, ln_b, o, n_px, H, W, C, eps);
   }
   FZ_CHECK_CUDA(cudaGetLastError());

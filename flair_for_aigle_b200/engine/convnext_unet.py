@@ -142,6 +142,10 @@ class ConvNeXtV2UNetEngine:
         hw = [(P // 4) >> i for i in range(4)]
         self.hw = hw
         self.x = [torch.empty((B, h, h, c), dtype=f32, device=dev) for h, c in zip(hw, cfg.dims)]
+        # bf16 copies of the stage outputs = the decoder's operands (written by the downsample LayerNorm kernel while
+        # the rows are in registers; the last stage by a cast)
+        self.xb = [torch.empty((B, h, h, c), dtype=bf, device=dev) for h, c in zip(hw, cfg.dims)]
+        self.copy_ok = [c in (128, 256, 512) for c in cfg.dims]
         max_y = max(h * h * c for h, c in zip(hw, cfg.dims))
         self.y = torch.empty(B * max_y, dtype=bf, device=dev)            # dwconv+LN out / s2d operand
         self.h = torch.empty(B * max_y * 4, dtype=bf, device=dev)        # MLP hidden
@@ -174,7 +178,10 @@ class ConvNeXtV2UNetEngine:
                 Ci = cfg.dims[i - 1]
                 M = n * rps
                 s2d = self.y[:M * 4 * Ci].view(M, 4 * Ci)
-                nv.ln2d_s2d(self.x[i - 1][:n], st["ds_ln_w"], st["ds_ln_b"], s2d)
+                nv.ln2d_s2d(self.x[i - 1][:n], st["ds_ln_w"], st["ds_ln_b"], s2d,
+                            copy=self.xb[i - 1][:n] if self.copy_ok[i - 1] else None)
+                if not self.copy_ok[i - 1]:
+                    nv.cast_f32_bf16(self.x[i - 1][:n], self.xb[i - 1][:n])
                 self._gemm(s2d, st["ds_w"], nv.EPI_F32, bias=st["ds_b"], out=self.x[i][:n].view(M, C))
             sub = self.sub_batch[i] if self.sub_batch[i] > 0 else n
             tps = rps // 128
@@ -225,7 +232,8 @@ class ConvNeXtV2UNetEngine:
 
     # ------------------------------------------------------------------------------ decoder
     def _feats_deep_first(self, n: int):
-        return [self.x[3][:n], self.x[2][:n], self.x[1][:n], self.x[0][:n]]
+        nv.cast_f32_bf16(self.x[3][:n], self.xb[3][:n])
+        return [self.xb[3][:n], self.xb[2][:n], self.xb[1][:n], self.xb[0][:n]]
 
     def decode_logits_nchw(self, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """fp32 logits [n, n_classes, P, P] -- the layout FLAIR_HUB_Model.forward returns."""

@@ -45,6 +45,11 @@ class UNetDecoderPlan:
                 blk[name + "_s"] = _f32(scale, device)
                 blk[name + "_b"] = _f32(b_ - mu * scale, device)
             assert blk["conv1_w"].shape[-1] == ci + cs, (blk["conv1_w"].shape, ci, cs)
+            if (cs > 0 and ci % 64 == 0 and cs % 64 == 0 and co % 64 == 0
+                    and os.environ.get("FZ_CATCONV", "1") != "0"):
+                # skip block: conv3x3(cat(up2(a), skip)) as one implicit GEMM (csrc/catconv3x3_tcgen05.cu)
+                w1 = sd[prefix + f"decoder.blocks.{k}.conv1.0.weight"]
+                blk["conv1_w16a"] = _bf16(nv.merge_upconv_weights(w1[:, :ci]), device)
             if cs == 0 and ci in (32, 64) and co in (16, 32) and os.environ.get("FZ_UPCONV", "1") != "0":
                 # no skip: conv3x3(nearest_up2(a)) straight from `a` with merged sub-pixel taps (csrc/upconv3x3_rows.cu)
                 w1 = sd[prefix + f"decoder.blocks.{k}.conv1.0.weight"]
@@ -80,8 +85,13 @@ class UNetDecoderPlan:
             ct = blk["cin"] + blk["cskip"]
             o1 = self.t1[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
             hs = hd // 2
+            skip_k = skips[k] if blk["cskip"] > 0 else None
             if ("conv1_w16" in blk and a.dtype == torch.bfloat16 and hs % 128 == 0 and a.is_contiguous()):
                 nv.upconv3x3_bn_relu(a, blk["conv1_w16"], blk["conv1_s"], blk["conv1_b"], o1)
+            elif ("conv1_w16a" in blk and a.dtype == torch.bfloat16 and skip_k is not None
+                  and skip_k.dtype == torch.bfloat16 and hs * hs >= 128 and (hs >= 128 and hs % 128 == 0 or 128 % hs == 0)
+                  and a.is_contiguous() and skip_k.is_contiguous()):
+                nv.catconv3x3_bn_relu(a, skip_k, blk["conv1_w16a"], blk["conv1_w"], blk["conv1_s"], blk["conv1_b"], o1)
             else:
                 cat = self.cat[:n * hd * hd * ct].view(n, hd, hd, ct)
                 skip = skips[k] if blk["cskip"] > 0 else None
@@ -114,5 +124,8 @@ class UNetDecoderPlan:
         hd, n = self.deepest, 1
         for blk in self.blocks:
             hd *= 2
-            n += 2 if ("conv1_w16" in blk and (hd // 2) % 128 == 0) else 3
+            hs = hd // 2
+            fused = ("conv1_w16" in blk and hs % 128 == 0) or \
+                    ("conv1_w16a" in blk and hs * hs >= 128 and (hs % 128 == 0 or 128 % hs == 0))
+            n += 2 if fused else 3        # (up-)conv1 [+ upsample/concat], conv2 -- with bf16 feature maps
         return n

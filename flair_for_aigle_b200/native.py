@@ -73,10 +73,12 @@ _SIGNATURES = {
     "fz_stem_ln_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_dwconv7_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
     "fz_ln2d_s2d": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_ln2d_s2d_copy": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_scale": [_vp, _i, _vp, _vp, _vp, _i, _i, ctypes.c_float, _vp],
     "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
     "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_catconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fz_upconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_conv7x7s2_bn_relu": [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "fz_maxpool3x3s2": [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -274,10 +276,12 @@ def dwconv7_ln(x, wdw, bdw, ln_w, ln_b, out, eps=1e-6):
     return out
 
 
-def ln2d_s2d(x, ln_w, ln_b, out, eps=1e-6):
+def ln2d_s2d(x, ln_w, ln_b, out, eps=1e-6, copy=None):
+    """LayerNorm2d + space-to-depth; ``copy`` (bf16 [B,H,W,C]) additionally receives the un-normalised input."""
     B, H, W, C = x.shape
     with _Timed('ln2d_s2d', B=B, H=H, C=C):
-        _check(lib().fz_ln2d_s2d(_ptr(x), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, H, W, C, eps, _stream()), "fz_ln2d_s2d")
+        _check(lib().fz_ln2d_s2d_copy(_ptr(x), _ptr(ln_w), _ptr(ln_b), _ptr(out), _ptr(copy), B, H, W, C, eps,
+                                      _stream()), "fz_ln2d_s2d_copy")
     return out
 
 
@@ -359,6 +363,19 @@ def upconv3x3_bn_relu(x, w16, scale, bias, out):
     with _Timed('upconv3x3_tcgen05', B=B, H=H, Cin=Cin, Cout=cout):
         _check(lib().fz_upconv3x3_bn_relu(_ptr(x), _ptr(w16), _ptr(scale), _ptr(bias), _ptr(out), B, H, W, Cin, cout,
                                           w16.shape[0], _stream()), "fz_upconv3x3_bn_relu")
+    return out
+
+
+def catconv3x3_bn_relu(a, skip, w16a, w, scale, bias, out):
+    """a bf16 [B,Hs,Ws,C1], skip bf16 [B,2Hs,2Ws,C2] -> out bf16 [B,2Hs,2Ws,Cout] =
+    relu(bn(conv3x3(cat(nearest_up2(a), skip)))); w16a = merged taps of the first C1 channels, w = the conv's weights."""
+    B, Hs, Ws, C1 = a.shape
+    C2 = skip.shape[-1]
+    cout = out.shape[-1]
+    fl_equiv = 2.0 * B * 4 * Hs * Ws * (4 * C1 + 9 * C2) * cout
+    with _Timed('catconv3x3_tcgen05', B=B, H=2 * Hs, C1=C1, C2=C2, Cout=cout, flop=fl_equiv):
+        _check(lib().fz_catconv3x3_bn_relu(_ptr(a), _ptr(skip), _ptr(w16a), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), B,
+                                           Hs, Ws, C1, C2, cout, w.shape[0], _stream()), "fz_catconv3x3_bn_relu")
     return out
 
 

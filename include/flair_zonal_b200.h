@@ -142,6 +142,10 @@ int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw, const floa
                   void* out_bf16, int B, int H, int W, int C, float eps, void* stream);
 int fz_ln2d_s2d(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, int B, int H, int W, int C,
                 float eps, void* stream);
+/* same, and the un-normalised input as bf16 rows [B*H*W][C] into copy_bf16 (may be NULL): the U-Net decoder's skip
+ * operand comes for free while the stage output is in registers.  C = 128, 256, 512 when copy_bf16 is given. */
+int fz_ln2d_s2d_copy(const float* x, const float* ln_w, const float* ln_b, void* out_bf16, void* copy_bf16, int B, int H,
+                     int W, int C, float eps, void* stream);
 int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale, float* scratch,
                  int B, int K, float eps, void* stream); /* scratch: B*K/64 floats */
 int fz_scale_weights(const void* w_bf16, const float* scale, void* out_bf16, int B, int N, int K, void* stream);
@@ -181,6 +185,15 @@ int fz_conv3x3_bf16(const void* in, const void* w, const float* scale, const flo
  * Cout 16|32; scale/bias as in fz_conv3x3_bf16. */
 int fz_upconv3x3_bn_relu(const void* in, const void* w16, const float* scale, const float* bias, void* out, int B, int H,
                          int W, int Cin, int Cout, int w_rows, void* stream);
+
+/* fz_catconv3x3_bn_relu: relu(bn(conv3x3(cat(nearest_up2(a), skip)))) -- the first convolution of the smp U-Net decoder
+ * blocks WITH a skip connection -- as one implicit GEMM; the concatenated tensor is never built.  a bf16
+ * [B][Hs][Ws][C1]; skip bf16 [B][2Hs][2Ws][C2]; w16a bf16 [w_rows][16][C1] = merged sub-pixel taps of the first C1 input
+ * channels (layout as in fz_upconv3x3_bn_relu); w bf16 [w_rows][3][3][C1+C2] = the convolution's own weights (their
+ * skip-channel part is used); out bf16 [B][2Hs][2Ws][Cout].  C1, C2, Cout multiples of 64. */
+int fz_catconv3x3_bn_relu(const void* a, const void* skip, const void* w16a, const void* w, const float* scale,
+                          const float* bias, void* out, int B, int Hs, int Ws, int C1, int C2, int Cout, int w_rows,
+                          void* stream);
 
 /* ---------------------------------------------------------------- ResNet-34 encoder front end
  * (smp native ResNetEncoder = torchvision ResNet without fc; `resnet34-unet`, BASELINE.json configs[0])

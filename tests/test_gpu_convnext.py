@@ -271,3 +271,29 @@ def test_upconv3x3_subpixel(cuda, H, Cin, Cout):
     ref2 = torch.relu(ref2 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
     err2 = (out.float() - ref2).abs().max().item()
     assert err2 < 2 ** -8 * max(1.0, ref2.abs().max().item()) + 1e-3, err2
+
+
+@pytest.mark.parametrize("Hs,C1,C2,Cout", [(16, 128, 64, 64), (16, 1024, 512, 256), (32, 256, 256, 128), (64, 128, 128, 64),
+                                           (16, 64, 128, 128)])
+def test_catconv3x3_subpixel(cuda, Hs, C1, C2, Cout):
+    """conv3x3(cat(nearest_up2(a), skip)) + BN + ReLU as one implicit GEMM vs torch on the materialised concat."""
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(Hs + C1)
+    B = 2
+    a = torch.randn(B, Hs, Hs, C1, device=cuda).bfloat16()
+    skip = torch.randn(B, 2 * Hs, 2 * Hs, C2, device=cuda).bfloat16()
+    w = (torch.randn(Cout, C1 + C2, 3, 3, device=cuda) / (9 * (C1 + C2)) ** 0.5).bfloat16()
+    scale = torch.rand(Cout, device=cuda) + 0.5
+    bias = torch.randn(Cout, device=cuda) * 0.1
+    w16a = nv.merge_upconv_weights(w[:, :C1]).bfloat16().contiguous()
+    w_nhwc = w.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((B, 2 * Hs, 2 * Hs, Cout), float("nan"), dtype=torch.bfloat16, device=cuda)
+    nv.catconv3x3_bn_relu(a, skip, w16a, w_nhwc, scale, bias, out)
+    torch.cuda.synchronize()
+    up = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    cat = torch.cat([up, skip.float().permute(0, 3, 1, 2)], dim=1)
+    ref = torch.relu(F.conv2d(cat, w.float(), padding=1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    ref = ref.permute(0, 2, 3, 1)
+    assert not torch.isnan(out.float()).any()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
