@@ -238,6 +238,8 @@ def main() -> None:
     if use_dist:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep "NCCL version ..." off stdout: the JSON line stays alone there
         dist.init_process_group("nccl", device_id=dev)
 
     from flair_for_aigle_b200 import native as nv
