@@ -68,10 +68,6 @@ class ConvNeXtV2UNetEngine:
         nv.lib()
         self.cfg, self.dev, self.B = cfg, device, max_batch
         self.gemm_impl = "tcgen05"
-        import os as _os
-        sb = _os.environ.get("FZ_SUBBATCH", "0,0,0,0").split(",")
-        self.sub_batch = [int(v) for v in sb]          # tiles per sub-batch in stages 0..3 (0 = whole batch)
-        self.fc2_order = 0 if _os.environ.get("FZ_FC2_FORWARD") == "1" else nv.EPI_REVERSE_TILES
         sd = {k: v.detach().to('cpu') for k, v in state_dict.items()}   # pack on the host, upload once
         E, D, dev = enc_prefix, dec_prefix, device
         C0 = cfg.dims[0]
@@ -164,53 +160,45 @@ class ConvNeXtV2UNetEngine:
         return nv.gemm_bf16(A, Bw, mode, impl=self.gemm_impl, **kw)
 
     def _encode(self, n: int) -> None:
-        """Stages 0..3.  Within a stage the blocks run over L2-sized SUB-BATCHES of tiles: GRN statistics are
-        per sample, so a block can finish a few tiles at a time, and the dwconv output / MLP hidden tensors of a
-        sub-batch (67 MB at 4 tiles in stage 0) are produced and consumed out of the 126 MB L2 instead of
-        round-tripping HBM.  Measured on B200 (tools/gpu_subbatch_sweep.py): every sub-batched setting was SLOWER
-        (0.49-0.64 vs 0.446 ms/tile) -- the kernels are not HBM-bound, smaller launches only add ramp/tail
-        time -- so the default is 0,0,0,0 (whole batch); FZ_SUBBATCH overrides."""
+        """Stages 0..3 on the whole batch.  (Running the blocks over L2-sized sub-batches of tiles, so that the dwconv
+        output / hidden tensors never leave the 126 MB L2, was measured slower in every setting -- DESIGN.md section 4 --
+        and is gone.)"""
         cfg = self.cfg
         for i, st in enumerate(self.stages):
             C, hwi = st["C"], self.hw[i]
             rps = hwi * hwi
+            M = n * rps
             if i > 0:
                 Ci = cfg.dims[i - 1]
-                M = n * rps
                 s2d = self.y[:M * 4 * Ci].view(M, 4 * Ci)
                 nv.ln2d_s2d(self.x[i - 1][:n], st["ds_ln_w"], st["ds_ln_b"], s2d,
                             copy=self.xb[i - 1][:n] if self.copy_ok[i - 1] else None)
                 if not self.copy_ok[i - 1]:
                     nv.cast_f32_bf16(self.x[i - 1][:n], self.xb[i - 1][:n])
                 self._gemm(s2d, st["ds_w"], nv.EPI_F32, bias=st["ds_b"], out=self.x[i][:n].view(M, C))
-            sub = self.sub_batch[i] if self.sub_batch[i] > 0 else n
             tps = rps // 128
-            for s0 in range(0, n, sub):
-                m = min(sub, n - s0)
-                M = m * rps
-                x = self.x[i][s0:s0 + m]
-                xm = x.view(M, C)
-                y = self.y[:M * C].view(m, hwi, hwi, C)
-                hbuf = self.h[:M * 4 * C].view(M, 4 * C)
-                sumsq = self.sumsq[:m * tps * 4 * C].view(m * tps, 4 * C)
-                scale = self.scale[:m * 4 * C].view(m, 4 * C)
-                for blk in st["blocks"]:
-                    nv.dwconv7_ln(x, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], y)
-                    self._gemm(y.view(M, C), blk["fc1_w"], nv.EPI_GELU_SUMSQ, bias=blk["fc1_b"], sumsq=sumsq, out=hbuf,
-                               rows_per_sample=rps)
-                    nv.grn_scale(sumsq, tps, blk["grn_g"], scale, scratch=self.grn_scratch)
-                    # fc2 walks its tiles backwards: fc1 has just streamed the hidden tensor out (larger than L2 in
-                    # stages 0-2), so its newest rows are still cached; it then finishes on the rows the next
-                    # block's dwconv starts with.  Measured -11 % on the stage-2 fc1+fc2 pair.
-                    fc2_mode = nv.EPI_RESID_F32 | self.fc2_order
-                    if self.use_wscale[i]:
-                        w2s = self.w2s[:m * 4 * C * C].view(m, C, 4 * C)
-                        nv.scale_weights(blk["fc2_w"], scale, w2s)
-                        self._gemm(hbuf, w2s, fc2_mode, bias=blk["fc2_b"], resid=xm, out=xm, rows_per_sample=rps)
-                    else:
-                        nv.scale_rows(hbuf, scale, rps)
-                        self._gemm(hbuf, blk["fc2_w"], fc2_mode, bias=blk["fc2_b"], resid=xm, out=xm,
-                                   rows_per_sample=rps)
+            x = self.x[i][:n]
+            xm = x.view(M, C)
+            y = self.y[:M * C].view(n, hwi, hwi, C)
+            hbuf = self.h[:M * 4 * C].view(M, 4 * C)
+            sumsq = self.sumsq[:n * tps * 4 * C].view(n * tps, 4 * C)
+            scale = self.scale[:n * 4 * C].view(n, 4 * C)
+            for blk in st["blocks"]:
+                nv.dwconv7_ln(x, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], y)
+                self._gemm(y.view(M, C), blk["fc1_w"], nv.EPI_GELU_SUMSQ, bias=blk["fc1_b"], sumsq=sumsq, out=hbuf,
+                           rows_per_sample=rps)
+                nv.grn_scale(sumsq, tps, blk["grn_g"], scale, scratch=self.grn_scratch)
+                # fc2 walks its tiles backwards: fc1 has just streamed the hidden tensor out (larger than L2 in
+                # stages 0-2), so its newest rows are still cached; it then finishes on the rows the next
+                # block's dwconv starts with.  Measured -11 % on the stage-2 fc1+fc2 pair.
+                fc2_mode = nv.EPI_RESID_F32 | nv.EPI_REVERSE_TILES
+                if self.use_wscale[i]:
+                    w2s = self.w2s[:n * 4 * C * C].view(n, C, 4 * C)
+                    nv.scale_weights(blk["fc2_w"], scale, w2s)
+                    self._gemm(hbuf, w2s, fc2_mode, bias=blk["fc2_b"], resid=xm, out=xm, rows_per_sample=rps)
+                else:
+                    nv.scale_rows(hbuf, scale, rps)
+                    self._gemm(hbuf, blk["fc2_w"], fc2_mode, bias=blk["fc2_b"], resid=xm, out=xm, rows_per_sample=rps)
 
     def encode_u8(self, tiles_u8: torch.Tensor) -> None:
         if self.stem_w_u8 is None:

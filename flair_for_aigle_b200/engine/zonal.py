@@ -72,9 +72,7 @@ class ZonalRunner:
             return 3 + 2 * nblk + nds + self.eng.decoder.launches()
         n = 2  # gather + stem
         for i, d in enumerate(cfg.depths):
-            sub = self.eng.sub_batch[i] if self.eng.sub_batch[i] > 0 else self.B
-            nsub = (self.B + sub - 1) // sub
-            n += (2 if i > 0 else 0) + nsub * d * 6   # dwconv, fc1, grn (2 kernels), weight/row scaling, fc2
+            n += (2 if i > 0 else 0) + d * 6   # dwconv, fc1, grn (2 kernels), weight/row scaling, fc2
         n += 1 + self.eng.decoder.launches()      # + bf16 cast of the deepest stage output
         return n
 
