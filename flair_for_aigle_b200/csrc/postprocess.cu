@@ -283,24 +283,42 @@ extern "C" int fz_crop_softmax_write(const void* logits, int dtype, int layout, 
                             nullptr, H, W, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int fz_crop_softmax_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles,
-                                          int n_cls, int P, int margin, const int32_t* plan, const float* weight,
-                                          float* canvas, int H, int W, void* stream) {
-  // Tiles of one call may overlap in the canvas (clamped edge rows/columns): serialise them.
-  // The grid is a product grid, so tiles that overlap are never in the same call when the
-  // caller batches by grid column; to stay safe for any batch we launch tile by tile.
+namespace fz {
+// Tiles of one call may overlap in the canvas (clamped edge rows/columns): serialise them.
+// The grid is a product grid, so tiles that overlap are never in the same call when the
+// caller batches by grid column; to stay safe for any batch we launch tile by tile.
+static int accumulate_tiles(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
+                            int margin, const int32_t* plan, const float* weight, float* canvas, int H, int W,
+                            cudaStream_t st, const int32_t* zmap, int zoomed) {
   for (int t = 0; t < n_tiles; ++t) {
-    int rc = fz::launch_crop<2>(logits, dtype, layout, cstride, 1, n_cls, P, margin, plan, nullptr, weight, nullptr,
-                                canvas, H, W, reinterpret_cast<cudaStream_t>(stream));
+    int rc = launch_crop<2>(logits, dtype, layout, cstride, 1, n_cls, P, margin, plan, nullptr, weight, nullptr, canvas, H,
+                            W, st, zmap, zoomed);
     if (rc) return rc;
     // advance to the next tile: logits and plan are indexed by blockIdx.x inside the kernel
     const size_t esz = dtype == FZ_F32 ? 4 : 2;
     const size_t per_tile = layout == FZ_NCHW ? static_cast<size_t>(n_cls) * P * P
-                                              : static_cast<size_t>(P) * P * cstride;
+                            : layout == FZ_NHWC_UP4 ? static_cast<size_t>(P / 4) * (P / 4) * cstride
+                                                    : static_cast<size_t>(P) * P * cstride;
     logits = static_cast<const char*>(logits) + per_tile * esz;
     plan += 6;
   }
   return 0;
+}
+}  // namespace fz
+
+extern "C" int fz_crop_softmax_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles,
+                                          int n_cls, int P, int margin, const int32_t* plan, const float* weight,
+                                          float* canvas, int H, int W, void* stream) {
+  return fz::accumulate_tiles(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, weight, canvas, H, W,
+                              reinterpret_cast<cudaStream_t>(stream), nullptr, 0);
+}
+
+extern "C" int fz_crop_zoom_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls,
+                                       int P, int margin, const int32_t* plan, const int32_t* zmap, int zoomed,
+                                       float* canvas, int H, int W, void* stream) {
+  FZ_REQUIRE(zmap != nullptr && zoomed >= 1, "fz_crop_zoom_accumulate: zoom map required");
+  return fz::accumulate_tiles(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, nullptr, canvas, H, W,
+                              reinterpret_cast<cudaStream_t>(stream), zmap, zoomed);
 }
 
 extern "C" int fz_canvas_argmax(const float* canvas, int n_cls, int64_t n_px, uint8_t* labels, float* confidence,

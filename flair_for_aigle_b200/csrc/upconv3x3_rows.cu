@@ -73,7 +73,7 @@ upconv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int segs = p.W / 128;
-  const int runs = p.H / p.R;
+  const int runs = (p.H + p.R - 1) / p.R;   // the last run of an image may be shorter
   const int items = p.B * segs * runs;
 
   if (warp == 0 && lane == 0) {
@@ -103,9 +103,10 @@ upconv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int tap = 0; tap < 16; ++tap) tma_load_2d(&tmB, wfull, sW + tap * WTAP_BYTES, tap * CIN, 0);
       uint32_t g = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int run = it % runs, seg = (it / runs) % segs, b = it / (runs * segs);
+        const int seg = it % segs, run = (it / segs) % runs, b = it / (runs * segs);   // segments of a row run side by side
         const int y0 = run * p.R, x0 = seg * 128;
-        for (int r = 0; r < p.R + 2; ++r, ++g) {
+        const int Rn = min(p.R, p.H - y0);
+        for (int r = 0; r < Rn + 2; ++r, ++g) {
           const int s = g % UP_NR;
           const uint32_t ph = (g / UP_NR) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -123,7 +124,8 @@ upconv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(wfull, 0);
       uint32_t g = 0, ro = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        for (int j = 0; j < p.R; ++j, ++ro) {
+        const int Rn = min(p.R, p.H - ((it / segs) % runs) * p.R);
+        for (int j = 0; j < Rn; ++j, ++ro) {
           const int first = (j == 0) ? 0 : 2;       // source rows g+j .. g+j+2 (rows land in order)
           for (int d = first; d < 3; ++d) {
             const uint32_t gi = g + j + d;
@@ -158,9 +160,9 @@ upconv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           umma_commit(&tfull[as]);
           umma_commit(&empty[(g + j) % UP_NR]);
         }
-        umma_commit(&empty[(g + p.R) % UP_NR]);
-        umma_commit(&empty[(g + p.R + 1) % UP_NR]);
-        g += p.R + 2;
+        umma_commit(&empty[(g + Rn) % UP_NR]);
+        umma_commit(&empty[(g + Rn + 1) % UP_NR]);
+        g += Rn + 2;
       }
     }
     __syncwarp();
@@ -176,9 +178,10 @@ upconv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int OW = 2 * p.W;
     uint32_t ro = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int run = it % runs, seg = (it / runs) % segs, b = it / (runs * segs);
+      const int seg = it % segs, run = (it / segs) % runs, b = it / (runs * segs);   // segments of a row run side by side
       const int xs = seg * 128 + m;
-      for (int j = 0; j < p.R; ++j, ++ro) {
+      const int Rn = min(p.R, p.H - run * p.R);
+      for (int j = 0; j < Rn; ++j, ++ro) {
         const int ys = run * p.R + j;
         const uint32_t as = ro % AS;
         mbar_wait(&tfull[as], (ro / AS) & 1);
@@ -234,10 +237,24 @@ static int launch_upconv(const CUtensorMap& a, const CUtensorMap& b, const UpCon
   if (per_sm > 512 / tcols) per_sm = 512 / tcols;
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 6) per_sm = 6;
-  const int items = p.B * (p.W / 128) * (p.H / p.R);
-  int grid = sm_count * per_sm;
-  if (grid > items) grid = items;
-  kern<<<grid, 192, BYTES, st>>>(a, b, p);
+  // rows per work item: every item re-reads a 2-row halo and refills the row pipeline, so long runs win as long as
+  // every SM still holds >= 2 CTAs (measured at B = 37, 512^2, 16 -> 16: R = 16/32/64/128 -> 208/201/172/169 us; run
+  // lengths that are not a power of two are slower, R = 26 -> 250 us, so they are not considered)
+  UpConvParams q = p;
+  int grid = 0;
+  for (int R = 128; R >= 16; R >>= 1) {
+    if (R > p.H && R > 16) continue;
+    const int it = p.B * (p.W / 128) * ((p.H + R - 1) / R);
+    q.R = R;
+    grid = it < sm_count * per_sm ? it : sm_count * per_sm;
+    if (it >= 2 * sm_count) break;
+  }
+  if (const char* e = getenv("FZ_ROWS_R")) {   // experiment override
+    q.R = atoi(e);
+    const int it = p.B * (p.W / 128) * ((p.H + q.R - 1) / q.R);
+    grid = it < sm_count * per_sm ? it : sm_count * per_sm;
+  }
+  kern<<<grid, 192, BYTES, st>>>(a, b, q);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -270,7 +287,7 @@ extern "C" int fz_upconv3x3_bn_relu(const void* in, const void* w16, const float
   }
   UpConvParams p;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
-  p.R = (H % 32 == 0) ? 32 : 16;
+  p.R = 32;   // launch_rows picks the real value
   p.bias = bias; p.scale = scale;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

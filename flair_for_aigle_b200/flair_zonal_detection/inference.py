@@ -275,24 +275,38 @@ def inference(model, dataloader, tiles_gdf, config: Dict, raster_img):
         raise nv.NativeError("inference runs on CUDA only (no CPU fallback)")
     margin = int(config['margin'])
     P = int(config['img_pixels_detection'])
-    if _rescale(config)[0]:
-        raise NotImplementedError("inference(): the accumulating variant is built for output_px_meters == reference "
-                                  "resolution only (inference_and_write handles the rescaled grid)")
+    needs_rescale, scale = _rescale(config)
     raster_img = open_raster(raster_img)
     b = raster_img.bounds
     ib = {'left': b.left, 'bottom': b.bottom, 'right': b.right, 'top': b.top}
     ref_res = config['reference_resolution']
-    plan = torch.from_numpy(tile_plan(tiles_gdf, ib, ref_res, P, margin, ref_res)).to(device)
-    canvas = torch.zeros((model.task_nclasses, raster_img.height, raster_img.width), dtype=torch.float32,
-                         device=device)
+    out_res = config.get('output_px_meters', ref_res)
+    plan = torch.from_numpy(tile_plan(tiles_gdf, ib, ref_res, P, margin, out_res)).to(device)
+    if needs_rescale:
+        # inference.py:515-523,538-539: the zoomed tiles land on the out_res grid, whose size the reference computes at
+        # :538-539 (its canvas keeps the input shape, which only fits when out_res >= ref_res); the canvas here IS that grid
+        from .slicing import zoom_map
+        H = int(round((ib['top'] - ib['bottom']) / out_res))
+        W = int(round((ib['right'] - ib['left']) / out_res))
+        zmap_d = torch.from_numpy(zoom_map(P - 2 * margin, scale)).to(device)
+    else:
+        H, W, zmap_d = raster_img.height, raster_img.width, None
+    canvas = torch.zeros((model.task_nclasses, H, W), dtype=torch.float32, device=device)
     dataset = getattr(dataloader, 'dataset', dataloader)
     for batch in _iter_batches(dataloader, dataset, model, config, device):
         idx = batch.pop('index').to(device).flatten().long()
         logits_tasks, _ = model(batch)
         for _, logits in logits_tasks.items():
-            nv.crop_softmax_accumulate(logits, nv.NCHW, margin, plan[idx].contiguous(), None, canvas)
+            if needs_rescale:
+                nv.crop_zoom_accumulate(logits, nv.NCHW, margin, plan[idx].contiguous(), zmap_d, canvas)
+            else:
+                nv.crop_softmax_accumulate(logits, nv.NCHW, margin, plan[idx].contiguous(), None, canvas)
     torch.cuda.synchronize(device)
-    return canvas, raster_img.profile['transform']
+    transform = raster_img.profile['transform']
+    if needs_rescale:   # same origin, out_res pixels (init_outputs' profile, inference.py:186-194)
+        t = tuple(transform)
+        transform = (out_res, t[1], t[2], t[3], -out_res, t[5])
+    return canvas, transform
 
 
 def logits_to_labels_and_confidence(probs):

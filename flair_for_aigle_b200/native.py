@@ -63,6 +63,7 @@ _SIGNATURES = {
     "fz_crop_argmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "fz_crop_softmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "fz_crop_softmax_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "fz_crop_zoom_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp],
     "fz_crop_zoom_write": [_i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
     "fz_canvas_argmax": [_vp, _i, _i64, _vp, _vp, _vp],
     "fz_convert": [_vp, _i, _i, _i, _i, _vp, _vp],
@@ -211,6 +212,15 @@ def crop_softmax_accumulate(logits, layout, margin, plan, weight, canvas, n_cls=
     _check(lib().fz_crop_softmax_accumulate(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan),
                                             _ptr(weight), _ptr(canvas), H, W, _stream()),
            "fz_crop_softmax_accumulate")
+
+
+def crop_zoom_accumulate(logits, layout, margin, plan, zmap, canvas, n_cls=None):
+    """canvas += softmax(zoomed cropped logits): the accumulating variant on the rescaled grid (inference.py:515-562)."""
+    n, c, p, cs = _logits_geom(logits, layout, n_cls)
+    H, W = canvas.shape[-2:]
+    _check(lib().fz_crop_zoom_accumulate(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan), _ptr(zmap),
+                                         int(zmap.numel()), _ptr(canvas), H, W, _stream()),
+           "fz_crop_zoom_accumulate")
 
 
 def canvas_argmax(canvas: torch.Tensor, want_confidence: bool = False):

@@ -84,6 +84,12 @@ int fz_crop_zoom_write(int mode, const void* logits, int dtype, int layout, int 
 int fz_crop_softmax_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
                                int margin, const int32_t* plan, const float* weight, float* canvas, int H, int W,
                                void* stream);
+/* The same accumulation on the rescaled output grid (inference.py:515-523 then :525-562): the cropped logits are zoomed
+ * with zmap (see fz_crop_zoom_write; constant-fill pixels carry zero logits, i.e. a uniform softmax) before the softmax;
+ * plan is in OUTPUT pixels. */
+int fz_crop_zoom_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
+                            int margin, const int32_t* plan, const int32_t* zmap, int zoomed, float* canvas, int H, int W,
+                            void* stream);
 /* inference.py:566-572: labels = argmax_c canvas (uint8), confidence = max_c canvas (float32,
  * may be NULL).  canvas is [n_cls][n_px]. */
 int fz_canvas_argmax(const float* canvas, int n_cls, int64_t n_px, uint8_t* labels, float* confidence, void* stream);

@@ -84,6 +84,21 @@ def blend_accumulate(logits: np.ndarray, plan: np.ndarray, margin: int, canvas: 
         canvas[:, top_px:top_px + h, left_px:left_px + w] += prob
 
 
+def blend_accumulate_rescaled(logits: np.ndarray, plan: np.ndarray, margin: int, canvas: np.ndarray,
+                              scale: float) -> None:
+    """inference.py:515-562 with ``output_px_meters != reference_resolution`` and the wide accumulator:
+    ``resample_prediction`` (scipy.ndimage.zoom, order 0) on the cropped logits (:521-523), ``convert``-style softmax
+    (:525), accumulation at the out_res pixel position (:530-562).  plan is in OUTPUT pixels."""
+    from scipy.ndimage import zoom
+    p = logits.shape[-1]
+    for i in range(logits.shape[0]):
+        top_px, left_px, h, w = (int(v) for v in plan[i, 2:6])
+        if h <= 0 or w <= 0:
+            continue
+        patch = zoom(logits[i, :, margin:p - margin, margin:p - margin].astype(np.float32), zoom=(1, scale, scale), order=0)
+        canvas[:, top_px:top_px + h, left_px:left_px + w] += softmax(patch, axis=0)[:, :h, :w]
+
+
 def logits_to_labels_and_confidence(probs: np.ndarray):
     """inference.py:566-572."""
     labels = np.argmax(probs, axis=0).astype(np.uint8)

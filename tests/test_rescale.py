@@ -116,3 +116,67 @@ def test_zoom_write_is_bit_exact_on_identical_logits(cuda, out_res):
     nv.crop_zoom_write(0, torch.from_numpy(logits).to(cuda), nv.NCHW, m, torch.from_numpy(plan).to(cuda),
                        torch.from_numpy(ownership_windows(plan)).to(cuda), zm, got)
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out_res", [0.4, 0.5, 0.25])
+def test_zoom_accumulate_matches_oracle_on_identical_logits(cuda, out_res):
+    """fz_crop_zoom_accumulate vs the oracle's scipy zoom + softmax accumulation on the same logits: fp32, 1e-6 absolute
+    per contribution (expf ulp), clamped edge tiles overlapping their neighbours included."""
+    from oracle.convert import blend_accumulate_rescaled
+    from oracle.grid import Georef, generate_patches, tile_plan
+    from flair_for_aigle_b200 import native as nv
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import zoom_map
+    W, H, P, m = 1000, 700, 512, 64
+    geo = Georef(L, T, RES, W, H)
+    plan = tile_plan(generate_patches(P, m, RES, geo), geo, P, m, out_res)
+    rng = np.random.default_rng(int(out_res * 1000))
+    logits = (3 * rng.standard_normal((plan.shape[0], 19, P, P))).astype(np.float32)
+    oh, ow = int(round(H * RES / out_res)), int(round(W * RES / out_res))
+    want = np.zeros((19, oh, ow), np.float32)
+    blend_accumulate_rescaled(logits, plan, m, want, RES / out_res)
+    got = torch.zeros((19, oh, ow), dtype=torch.float32, device=cuda)
+    zm = torch.from_numpy(zoom_map(P - 2 * m, RES / out_res)).to(cuda)
+    nv.crop_zoom_accumulate(torch.from_numpy(logits).to(cuda), nv.NCHW, m, torch.from_numpy(plan).to(cuda), zm, got)
+    got = got.cpu().numpy()
+    cover = want.sum(axis=0)
+    assert cover.min() > 0.99 and np.allclose(cover, np.round(cover), atol=1e-4)       # every pixel covered 1..4 times
+    assert np.abs(got - want).max() < 4e-6
+
+
+@pytest.mark.gpu
+def test_inference_accumulating_variant_on_rescaled_grid(cuda, tmp_path):
+    """inference() (inference.py:468-564) at output_px_meters = 0.4: canvas on the out_res grid, its labels agree with
+    inference_and_write's raster wherever exactly one tile covers the pixel."""
+    import bench
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model, compute_patch_sizes
+    from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink, ZoneRaster, register_raster
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import generate_patches_from_reference
+    from flair_for_aigle_b200.synthetic import synthetic_raster
+    wpath = str(tmp_path / "w.safetensors")
+    bench.make_weights(wpath, seed=7)
+    arr = synthetic_raster(700, 1000, seed=11)
+    name = "mem://rescale_accumulate"
+    register_raster(name, ZoneRaster(arr, L, T, RES, name=name))
+    cfg = bench.zonal_config(wpath, str(tmp_path), name, 4)
+    cfg["output_px_meters"] = 0.4
+    cfg = inf.initialize_geometry_and_resolutions(cfg)
+    cfg["device"] = cuda
+    sizes = compute_patch_sizes(cfg)
+    model = build_inference_model(cfg, sizes).to(cuda)
+    tiles = generate_patches_from_reference(cfg, name, None)
+    ds = inf.prep_dataset(cfg, tiles, sizes)
+    canvas, transform = inf.inference(model, ds, tiles, cfg, name)
+    assert tuple(canvas.shape) == (19, 350, 500) and tuple(transform)[0] == 0.4 and tuple(transform)[4] == -0.4
+    cover = canvas.sum(dim=0)
+    assert float(cover.min()) > 0.99                                   # every output pixel received a tile
+    labels, conf = inf.logits_to_labels_and_confidence(canvas)
+    RasterSink.write_files = False
+    outs, _ = inf.init_outputs(cfg, name, 0)
+    inf.inference_and_write(model, ds, tiles, cfg, outs, name)
+    written = torch.from_numpy(outs[TASK].to_host()[0]).to(cuda)
+    once = cover < 1.5
+    assert float(once.float().mean()) > 0.5
+    assert bool((labels[once] == written[once]).all())
+    assert float(conf[once].max()) <= 1.0 + 1e-5
