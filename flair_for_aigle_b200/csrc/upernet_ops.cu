@@ -65,63 +65,200 @@ __device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int
   l1 = s - static_cast<float>(i0);
 }
 
-// MODE 0: bilinear resize (h,w)->(H,W); MODE 1: down2(up2(.)) at the same size (h == H, w == W)
+constexpr int PYR_ROWS = 8;
+
+// x-interpolated source row: hx * f[yy][x0] + lx * f[yy][x1]
+__device__ __forceinline__ void pyr_xlerp(const __nv_bfloat16* src, int yy, int w, int C, int x0, int x1, float hx, float lx,
+                                          float (&dst)[8]) {
+  float f0[8], f1[8];
+  unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(yy) * w + x0) * C), f0);
+  unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(yy) * w + x1) * C), f1);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[j] = hx * f0[j] + lx * f1[j];
+}
+// horizontally filtered source row of the down2(up2(.)) stencil: 0.125 f[x-1] + 0.75 f[x] + 0.125 f[x+1] (clamped)
+__device__ __forceinline__ void pyr_xtap3(const __nv_bfloat16* src, int yy, int w, int C, int xm, int x, int xp,
+                                          float (&dst)[8]) {
+  float f0[8], f1[8], f2[8];
+  unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(yy) * w + xm) * C), f0);
+  unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(yy) * w + x) * C), f1);
+  unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(yy) * w + xp) * C), f2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[j] = 0.125f * f0[j] + 0.75f * f1[j] + 0.125f * f2[j];
+}
+
+// MODE 0: bilinear resize (h,w)->(H,W) (+ add); MODE 1: down2(up2(.)) at the same size (h == H, w == W)
+// One CTA owns a (256 / vectors-per-pixel) x PYR_ROWS output patch of one sample and walks its rows: the row and sample are
+// CTA-uniform, index math is 32-bit, and both resamplings run separably with the x-filtered source rows kept in
+// registers across the output rows that share them (the first version decoded a flat 64-bit index per 16-byte vector
+// and re-fetched 4 / 9 source vectors per output: 218 us for a 310 MB slice).
 template <int MODE>
 __global__ void __launch_bounds__(256) resize_slice_kernel(const __nv_bfloat16* __restrict__ in,
                                                            const __nv_bfloat16* __restrict__ add,
-                                                           __nv_bfloat16* __restrict__ out, size_t n_vec, int h, int w,
-                                                           int H, int W, int C, int Ctot, int c0) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n_vec) return;
+                                                           __nv_bfloat16* __restrict__ out, int h, int w, int H, int W,
+                                                           int C, int Ctot, int c0) {
   const int vpp = C / 8;
-  const int c = static_cast<int>(i % vpp) * 8;
-  const size_t px = i / vpp;
-  const int x = static_cast<int>(px % W), y = static_cast<int>((px / W) % H);
-  const size_t b = px / (static_cast<size_t>(W) * H);
-  const __nv_bfloat16* src = in + b * h * w * C + c;
-  float acc[8];
-  if (MODE == 0) {
-    if (h == H && w == W) {
-      unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y) * w + x) * C), acc);
-    } else {
-      int y0, y1, x0, x1;
-      float ly, lx;
-      bilin_coord(y, static_cast<float>(h) / H, h, y0, y1, ly);
-      bilin_coord(x, static_cast<float>(w) / W, w, x0, x1, lx);
-      float f00[8], f01[8], f10[8], f11[8];
-      unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y0) * w + x0) * C), f00);
-      unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y0) * w + x1) * C), f01);
-      unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y1) * w + x0) * C), f10);
-      unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y1) * w + x1) * C), f11);
-      const float hy = 1.f - ly, hx = 1.f - lx;
+  const int vper = vpp < 256 ? vpp : 256;                   // vectors of one pixel handled side by side
+  const int xi = threadIdx.x / vper, v = threadIdx.x - xi * vper;
+  const int x = blockIdx.x * (256 / vper) + xi;
+  if (x >= W || xi >= 256 / vper) return;
+  const size_t b = blockIdx.z;
+  const int ya = blockIdx.y * PYR_ROWS, yb = min(ya + PYR_ROWS, H);
+  const size_t orow = static_cast<size_t>(W) * Ctot, arow = static_cast<size_t>(W) * C;
+  for (int c = v * 8; c < C; c += 256 * 8) {
+    const __nv_bfloat16* src = in + b * h * w * C + c;
+    __nv_bfloat16* o = out + ((b * H + ya) * W + x) * static_cast<size_t>(Ctot) + c0 + c;
+    const __nv_bfloat16* ad = add ? add + ((b * H + ya) * W + x) * static_cast<size_t>(C) + c : nullptr;
+    auto emit = [&](float (&acc)[8]) {
+      if (ad != nullptr) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(ad), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = hy * (hx * f00[j] + lx * f01[j]) + ly * (hx * f10[j] + lx * f11[j]);
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        ad += arow;
+      }
+      *reinterpret_cast<uint4*>(o) = pack8(acc);
+      o += orow;
+    };
+    if (MODE == 0 && h == H && w == W) {
+      for (int y = ya; y < yb; ++y) {
+        float acc[8];
+        unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y) * w + x) * C), acc);
+        emit(acc);
+      }
+    } else if (MODE == 0) {
+      int x0, x1, cy0 = -1, cy1 = -1;
+      float lx;
+      bilin_coord(x, static_cast<float>(w) / W, w, x0, x1, lx);
+      const float hx = 1.f - lx;
+      float top[8], bot[8];
+      for (int y = ya; y < yb; ++y) {                        // y0, y1 are CTA-uniform: no divergence
+        int y0, y1;
+        float ly;
+        bilin_coord(y, static_cast<float>(h) / H, h, y0, y1, ly);
+        if (y0 != cy0) {
+          if (y0 == cy1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) top[j] = bot[j];
+          } else {
+            pyr_xlerp(src, y0, w, C, x0, x1, hx, lx, top);
+          }
+          cy0 = y0;
+        }
+        if (y1 != cy1) {
+          if (y1 == y0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bot[j] = top[j];
+          } else {
+            pyr_xlerp(src, y1, w, C, x0, x1, hx, lx, bot);
+          }
+          cy1 = y1;
+        }
+        const float hy = 1.f - ly;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = hy * top[j] + ly * bot[j];
+        emit(acc);
+      }
+    } else {
+      const int xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
+      float rm[8], r0[8], rp[8];
+      pyr_xtap3(src, ya > 0 ? ya - 1 : 0, W, C, xm, x, xp, rm);
+      pyr_xtap3(src, ya, W, C, xm, x, xp, r0);
+      for (int y = ya; y < yb; ++y) {
+        pyr_xtap3(src, y < H - 1 ? y + 1 : H - 1, W, C, xm, x, xp, rp);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = 0.125f * rm[j] + 0.75f * r0[j] + 0.125f * rp[j];
+          rm[j] = r0[j];
+          r0[j] = rp[j];
+        }
+        emit(acc);
+      }
+    }
+  }
+}
+
+// The UPerNet fuse input in one launch: out [B][H][H][5C] = [bilinear(p0) | bilinear(p1) | bilinear(p2) | p3 | down2(up2(p3))]
+// (smp UPerNetDecoder: the four FPN maps resized to the stride-4 grid plus the unused fifth block's map).  The slice-by-
+// slice version ran at 1.4-1.7 TB/s of output because every output vector pulled its 4 (or 9) source vectors through
+// L2 -> SM again (~6 TB/s of gather traffic).  Here one CTA owns ONE slice of a PX x 4 pixel patch and walks its 4 rows
+// in turn: source vectors shared by neighbouring output pixels are L1 hits, and both resamplings run separably (x pass
+// per source row, kept in registers across the output rows that share it), which halves the arithmetic per output.
+__global__ void __launch_bounds__(256) pyramid_concat_kernel(const __nv_bfloat16* __restrict__ p0, int s0,
+                                                             const __nv_bfloat16* __restrict__ p1, int s1,
+                                                             const __nv_bfloat16* __restrict__ p2, int s2,
+                                                             const __nv_bfloat16* __restrict__ p3,
+                                                             __nv_bfloat16* __restrict__ out, int H, int C) {
+  const int vpp = C / 8;                                   // 16-byte vectors per pixel and slice; 256 % vpp == 0
+  const int xi = threadIdx.x / vpp, c = (threadIdx.x - xi * vpp) * 8;
+  const int x = blockIdx.x * (256 / vpp) + xi;
+  const int k = blockIdx.z % 5;                            // CTA-uniform slice
+  const size_t b = blockIdx.z / 5;
+  if (x >= H) return;
+  const __nv_bfloat16* in = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+  const int h = k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : H));
+  const __nv_bfloat16* src = in + b * h * h * C + c;
+  const int ya = blockIdx.y * PYR_ROWS, yb = min(ya + PYR_ROWS, H);
+  __nv_bfloat16* o = out + ((b * H + ya) * H + x) * (5 * static_cast<size_t>(C)) + k * C + c;
+  const size_t orow = static_cast<size_t>(H) * 5 * C;
+  if (k < 4 && h == H) {                                   // same size: copy
+    for (int y = ya; y < yb; ++y, o += orow)
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y) * h + x) * C);
+  } else if (k < 4) {
+    // bilinear, separable: the x-interpolated source rows y0 / y1 are kept while consecutive output rows share them
+    int x0, x1, cy0 = -1, cy1 = -1;
+    float lx;
+    bilin_coord(x, static_cast<float>(h) / H, h, x0, x1, lx);
+    const float hx = 1.f - lx;
+    float top[8], bot[8];
+    for (int y = ya; y < yb; ++y, o += orow) {             // y0, y1 are CTA-uniform: no divergence
+      int y0, y1;
+      float ly;
+      bilin_coord(y, static_cast<float>(h) / H, h, y0, y1, ly);
+      if (y0 != cy0) {
+        if (y0 == cy1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) top[j] = bot[j];
+        } else {
+          pyr_xlerp(src, y0, h, C, x0, x1, hx, lx, top);
+        }
+        cy0 = y0;
+      }
+      if (y1 != cy1) {
+        if (y1 == y0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bot[j] = top[j];
+        } else {
+          pyr_xlerp(src, y1, h, C, x0, x1, hx, lx, bot);
+        }
+        cy1 = y1;
+      }
+      const float hy = 1.f - ly;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = hy * top[j] + ly * bot[j];
+      *reinterpret_cast<uint4*>(o) = pack8(acc);
     }
   } else {
-    const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
-    const int xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
-    const int ys[3] = {ym, y, yp}, xs[3] = {xm, x, xp};
-    const float k[3] = {0.125f, 0.75f, 0.125f};
+    // down2(up2(.)) = the separable 3-tap stencil [1/8 3/4 1/8] with clamped borders: rolling window of filtered rows
+    const int xm = x > 0 ? x - 1 : 0, xp = x < H - 1 ? x + 1 : H - 1;
+    float rm[8], r0[8], rp[8];
+    pyr_xtap3(src, ya > 0 ? ya - 1 : 0, H, C, xm, x, xp, rm);
+    pyr_xtap3(src, ya, H, C, xm, x, xp, r0);
+    for (int y = ya; y < yb; ++y, o += orow) {
+      pyr_xtap3(src, y < H - 1 ? y + 1 : H - 1, H, C, xm, x, xp, rp);
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(ys[a]) * w + xs[e]) * C), f);
-        const float wt = k[a] * k[e];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += wt * f[j];
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = 0.125f * rm[j] + 0.75f * r0[j] + 0.125f * rp[j];
+        rm[j] = r0[j];
+        r0[j] = rp[j];
       }
+      *reinterpret_cast<uint4*>(o) = pack8(acc);
+    }
   }
-  if (add != nullptr) {
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(add + px * C + c), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += f[j];
-  }
-  *reinterpret_cast<uint4*>(out + px * Ctot + c0 + c) = pack8(acc);
 }
 
 // logits float [B][h][w][cstride] (first n_cls valid) -> float [B][n_cls][4h][4w], bilinear align_corners=True
@@ -169,14 +306,15 @@ static int resize_common(int mode, const void* in, const void* add, void* out, i
   FZ_REQUIRE(B >= 0 && h > 0 && w > 0 && H > 0 && W > 0, "fz_bilinear_slice: bad shape");
   FZ_REQUIRE(C % 8 == 0 && Ctot % 8 == 0 && c0 % 8 == 0 && c0 + C <= Ctot, "fz_bilinear_slice: bad channel slice");
   if (B == 0) return 0;
-  const size_t n_vec = static_cast<size_t>(B) * H * W * (C / 8);
-  const unsigned grid = static_cast<unsigned>((n_vec + 255) / 256);
+  FZ_REQUIRE(B <= 65535, "fz_bilinear_slice: B=%d exceeds the grid limit", B);
+  const int vpp = C / 8, vper = vpp < 256 ? vpp : 256, px = 256 / vper;
+  const dim3 grid((W + px - 1) / px, (H + PYR_ROWS - 1) / PYR_ROWS, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* i = reinterpret_cast<const __nv_bfloat16*>(in);
   const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(add);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (mode == 0) resize_slice_kernel<0><<<grid, 256, 0, st>>>(i, a, o, n_vec, h, w, H, W, C, Ctot, c0);
-  else resize_slice_kernel<1><<<grid, 256, 0, st>>>(i, a, o, n_vec, h, w, H, W, C, Ctot, c0);
+  if (mode == 0) resize_slice_kernel<0><<<grid, 256, 0, st>>>(i, a, o, h, w, H, W, C, Ctot, c0);
+  else resize_slice_kernel<1><<<grid, 256, 0, st>>>(i, a, o, h, w, H, W, C, Ctot, c0);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -189,6 +327,23 @@ extern "C" int fz_bilinear_slice(const void* in_bf16, const void* add_bf16, void
 extern "C" int fz_updown_slice(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, int Ctot, int c0,
                                void* stream) {
   return resize_common(1, in_bf16, nullptr, out_bf16, B, H, W, H, W, C, Ctot, c0, stream);
+}
+
+extern "C" int fz_pyramid_concat(const void* p0, int s0, const void* p1, int s1, const void* p2, int s2, const void* p3,
+                                 void* out_bf16, int B, int H, int C, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(B >= 0 && H > 0 && s0 > 0 && s1 > 0 && s2 > 0 && s0 <= H && s1 <= H && s2 <= H, "fz_pyramid_concat: bad sizes");
+  FZ_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "fz_pyramid_concat: C=%d: C/8 must divide 256", C);
+  FZ_REQUIRE(H <= 65535 * 4 && B * 5 <= 65535, "fz_pyramid_concat: H=%d B=%d exceed the grid limits", H, B);
+  if (B == 0) return 0;
+  const int px = 256 / (C / 8);
+  const dim3 grid((H + px - 1) / px, (H + PYR_ROWS - 1) / PYR_ROWS, B * 5);
+  pyramid_concat_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(p0), s0, reinterpret_cast<const __nv_bfloat16*>(p1), s1,
+      reinterpret_cast<const __nv_bfloat16*>(p2), s2, reinterpret_cast<const __nv_bfloat16*>(p3),
+      reinterpret_cast<__nv_bfloat16*>(out_bf16), H, C);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int fz_head_upsample4(const float* logits, float* out_nchw, int B, int h, int w, int cstride, int n_cls,

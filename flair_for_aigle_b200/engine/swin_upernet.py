@@ -254,9 +254,12 @@ class SwinUPerNetEngine:
             nv.bilinear_slice(p[k], p[k + 1], 0, add=lat)
         # five maps at H/4: P0..P3 resized, and down2(up2(P3)) for the 0-channel stage
         big = self.cat[:n]
-        for k in range(4):
-            nv.bilinear_slice(p[k], big, k * Pc)
-        nv.updown_slice(p[3], big, 4 * Pc)
+        if Pc % 8 == 0 and 256 % (Pc // 8) == 0:
+            nv.pyramid_concat(p[0], p[1], p[2], p[3], big)          # one contiguous write of all five slices
+        else:
+            for k in range(4):
+                nv.bilinear_slice(p[k], big, k * Pc)
+            nv.updown_slice(p[3], big, 4 * Pc)
         fused = self.fused[:n]
         nv.conv3x3(big, self.fuse_w, self.fuse_s, self.fuse_b, nv.CONV_RELU_BF16, out=fused)
         lq = self.logits_q[:n]
@@ -291,5 +294,6 @@ class SwinUPerNetEngine:
         n = 1                                                   # patch embed
         for i, d in enumerate(self.cfg.depths):
             n += (2 if i > 0 else 0) + 7 * d
-        n += 4 + 1 + 3 * len(PSP_SIZES) + 1 + 2 * 3 + 5 + 1 + 1 + 1         # casts, PSP, FPN, resizes, fuse, head, crop(x4)
+        resizes = 1 if 256 % max(self.cfg.pyramid_channels // 8, 1) == 0 else 5        # fused pyramid concat
+        n += 4 + 1 + 3 * len(PSP_SIZES) + 1 + 2 * 3 + resizes + 1 + 1 + 1   # casts, PSP, FPN, resizes, fuse, head, crop(x4)
         return n

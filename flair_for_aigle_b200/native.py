@@ -92,6 +92,7 @@ _SIGNATURES = {
     "fz_adaptive_avgpool": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_bilinear_slice": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fz_updown_slice": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_pyramid_concat": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp],
     "fz_head_upsample4": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"fz_last_error": ctypes.c_char_p}
@@ -464,6 +465,20 @@ def updown_slice(x: torch.Tensor, out: torch.Tensor, c0: int = 0):
     Ctot = out.shape[-1]
     with _Timed("updown_slice", n=B, H=H, C=C):
         _check(lib().fz_updown_slice(_ptr(x), _ptr(out), B, H, W, C, Ctot, c0, _stream()), "fz_updown_slice")
+    return out
+
+
+def pyramid_concat(p0, p1, p2, p3, out: torch.Tensor):
+    """out [B,H,H,5C] = [bilinear(p0) | bilinear(p1) | bilinear(p2) | p3 | down2(up2(p3))]: the UPerNet fuse input."""
+    B, H, _, C = p3.shape
+    for t in (p0, p1, p2, p3, out):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise NativeError("pyramid_concat: contiguous bf16 NHWC maps required")
+    if tuple(out.shape) != (B, H, H, 5 * C):
+        raise NativeError(f"pyramid_concat: out shape {tuple(out.shape)} != {(B, H, H, 5 * C)}")
+    with _Timed("pyramid_concat", n=B, H=H, C=C):
+        _check(lib().fz_pyramid_concat(_ptr(p0), p0.shape[1], _ptr(p1), p1.shape[1], _ptr(p2), p2.shape[1], _ptr(p3),
+                                       _ptr(out), B, H, C, _stream()), "fz_pyramid_concat")
     return out
 
 

@@ -240,6 +240,11 @@ int fz_swin_window_attn(const void* qkv_bf16, const void* qkv_bias_bf16, const f
                         int H, int W, int C, int heads, int window, int shift, float scale, void* stream);
 int fz_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 
+/* smp UPerNetDecoder fuse input in one pass (the five strided slice writes it replaces are the calls above):
+ * out bf16 [B][H][H][5C] = [bilinear(p0: s0^2 -> H^2) | bilinear(p1) | bilinear(p2) | p3 | down2(up2(p3))], all maps bf16
+ * NHWC with C channels, C / 8 a divisor of 256. */
+int fz_pyramid_concat(const void* p0, int s0, const void* p1, int s1, const void* p2, int s2, const void* p3,
+                      void* out_bf16, int B, int H, int C, void* stream);
 /* ---------------------------------------------------------------- UPerNet decoder pieces
  * (smp 0.4.0 UPerNetDecoder + SegmentationHead(kernel_size=1, upsampling=4); call site flair_model.py:417-419)
  * fz_adaptive_avgpool: nn.AdaptiveAvgPool2d(S) on bf16 NHWC -> bf16 [B][S][S][C].

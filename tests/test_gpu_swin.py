@@ -129,6 +129,32 @@ def test_updown_slice(cuda):
     assert (out[..., 64:].float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("H,C", [(32, 256), (24, 64), (128, 256)])
+def test_pyramid_concat(cuda, H, C):
+    """fz_pyramid_concat (one launch, separable resampling) against torch fp32 and against the slice-by-slice kernels
+    it replaces (same values up to the fp32 operation order, i.e. at most one bf16 ulp)."""
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(H + C)
+    B = 2
+    p = [torch.randn(B, H >> (3 - k), H >> (3 - k), C, device=cuda).bfloat16() for k in range(4)]
+    got = torch.full((B, H, H, 5 * C), 7.0, dtype=torch.bfloat16, device=cuda)
+    nv.pyramid_concat(p[0], p[1], p[2], p[3], got)
+    old = torch.zeros_like(got)
+    for k in range(4):
+        nv.bilinear_slice(p[k], old, k * C)
+    nv.updown_slice(p[3], old, 4 * C)
+    assert torch.equal(got[..., 3 * C:4 * C], p[3])
+    d = (got.float() - old.float()).abs()
+    assert d.max().item() <= 2.0 ** -7 * max(1.0, old.float().abs().max().item())
+    for k in range(3):
+        ref = F.interpolate(p[k].float().permute(0, 3, 1, 2), size=(H, H), mode="bilinear", align_corners=False)
+        assert (got[..., k * C:(k + 1) * C].float() - ref.permute(0, 2, 3, 1)).abs().max().item() < 2e-2 * ref.abs().max().item()
+    xf = p[3].float().permute(0, 3, 1, 2)
+    up = F.interpolate(xf, size=(2 * H, 2 * H), mode="bilinear", align_corners=False)
+    ref = F.interpolate(up, size=(H, H), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert (got[..., 4 * C:].float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
 def test_head_upsample4(cuda):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(6)
