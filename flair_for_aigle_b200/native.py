@@ -93,6 +93,11 @@ _SIGNATURES = {
     "fz_bilinear_slice": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fz_updown_slice": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_pyramid_concat": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp],
+    "fz_ccl_label": [_vp, _vp, _i, _i, _vp],
+    "fz_ccl_areas": [_vp, _vp, _vp, _i, _i, _vp],
+    "fz_ccl_table": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_trace_rings": [_vp, _i, _i, _vp, _i, ctypes.c_double, _vp, _vp],
+    "fz_trace_rings_fetch": [_vp, _vp, _vp, _vp],
     "fz_head_upsample4": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"fz_last_error": ctypes.c_char_p}
@@ -488,3 +493,60 @@ def head_upsample4(logits: torch.Tensor, n_cls: int, out: torch.Tensor):
     with _Timed("head_upsample4", n=B):
         _check(lib().fz_head_upsample4(_ptr(logits), _ptr(out), B, h, w, cs, n_cls, _stream()), "fz_head_upsample4")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ polygonisation
+def ccl_label(raster: torch.Tensor) -> torch.Tensor:
+    """uint8 class raster [H,W] on the device -> int32 labels [H,W]: 4-connected components of equal class, label =
+    smallest linear pixel index of the component (rasterio.features.shapes' connectivity, inference.py:366)."""
+    if raster.dtype != torch.uint8 or raster.dim() != 2 or not raster.is_contiguous():
+        raise NativeError("ccl_label: contiguous uint8 [H,W] raster required")
+    H, W = raster.shape
+    labels = torch.empty((H, W), dtype=torch.int32, device=raster.device)
+    with _Timed("ccl_label", H=H, W=W):
+        _check(lib().fz_ccl_label(_ptr(raster), _ptr(labels), H, W, _stream()), "fz_ccl_label")
+    return labels
+
+
+def ccl_components(raster: torch.Tensor, labels: torch.Tensor, min_area_px: int = 0, ignore_class: int = -1):
+    """-> (roots int32[n], areas int32[n], classes uint8[n]) as numpy arrays sorted by root (= by first pixel), for the
+    components with at least ``min_area_px`` pixels whose class is not ``ignore_class``; also returns nothing else: the
+    total component count is ``ccl_components.last_total``."""
+    import numpy as np
+    H, W = raster.shape
+    area = torch.zeros(H * W, dtype=torch.int32, device=raster.device)
+    counter = torch.zeros(3, dtype=torch.int32, device=raster.device)
+    _check(lib().fz_ccl_areas(_ptr(labels), _ptr(area), _ptr(counter), H, W, _stream()), "fz_ccl_areas")
+    cap = 1 << 16
+    while True:
+        rec = torch.empty((cap, 3), dtype=torch.int32, device=raster.device)
+        counter[1:].zero_()
+        _check(lib().fz_ccl_table(_ptr(raster), _ptr(labels), _ptr(area), _ptr(counter[1:]), _ptr(rec), cap,
+                                  int(min_area_px), int(ignore_class), H, W, _stream()), "fz_ccl_table")
+        total, n = (int(v) for v in counter[:2].tolist())
+        if n <= cap:
+            break
+        cap = n
+    ccl_components.last_total = total
+    rec = rec[:n].cpu().numpy()
+    rec = rec[np.argsort(rec[:, 0], kind="stable")]
+    return rec[:, 0].copy(), rec[:, 1].copy(), rec[:, 2].astype(np.uint8)
+
+
+def trace_rings(labels_host, keep_roots, simplify_px: float = 0.0):
+    """Host ring tracer on an int32 label image (numpy, C-contiguous).  -> (ring_root int32[r], ring_is_hole bool[r],
+    ring_offset int64[r+1], xy float64[p,2]) in pixel-corner coordinates, rings closed."""
+    import numpy as np
+    labels_host = np.ascontiguousarray(labels_host, dtype=np.int32)
+    keep = np.ascontiguousarray(np.sort(np.asarray(keep_roots, dtype=np.int32)))
+    H, W = labels_host.shape
+    nr, npnt = ctypes.c_int64(0), ctypes.c_int64(0)
+    _check(lib().fz_trace_rings(labels_host.ctypes.data, H, W, keep.ctypes.data if keep.size else None, int(keep.size),
+                                float(simplify_px), ctypes.addressof(nr), ctypes.addressof(npnt)), "fz_trace_rings")
+    ring_root = np.empty(nr.value, np.int32)
+    ring_hole = np.empty(nr.value, np.uint8)
+    ring_off = np.empty(nr.value + 1, np.int64)
+    xy = np.empty((npnt.value, 2), np.float64)
+    _check(lib().fz_trace_rings_fetch(ring_root.ctypes.data, ring_hole.ctypes.data, ring_off.ctypes.data, xy.ctypes.data),
+           "fz_trace_rings_fetch")
+    return ring_root, ring_hole.astype(bool), ring_off, xy

@@ -260,6 +260,27 @@ int fz_bilinear_slice(const void* in_bf16, const void* add_bf16, void* out_bf16,
 int fz_updown_slice(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, int Ctot, int c0, void* stream);
 int fz_head_upsample4(const float* logits, float* out_nchw, int B, int h, int w, int cstride, int n_cls, void* stream);
 
+/* ---- polygonisation of the class raster (inference.py:356-407, the consumer of inference_and_write's output in
+ * scripts/run_fast_aigle_segmentation.py:119) ----
+ * Connected components, 4-connectivity (rasterio.features.shapes' default), all classes at once: labels int32 [H][W],
+ * label = smallest linear pixel index of the component (order independent).  raster/labels on the device. */
+int fz_ccl_label(const uint8_t* raster, int32_t* labels, int H, int W, void* stream);
+/* area[root] += pixel count (area int32 [H*W], zeroed by the caller); *n_roots (zeroed) = number of components. */
+int fz_ccl_areas(const int32_t* labels, int32_t* area_zeroed, int32_t* n_roots_zeroed, int H, int W, void* stream);
+/* Compacted table of the components with area >= min_area_px and class != ignore_class (-1: none), arbitrary order:
+ * records int32 [capacity][3] = (root, area, class); *counter (zeroed) ends as their number -- when it exceeds capacity
+ * only the first `capacity` were stored: call again with a larger buffer. */
+int fz_ccl_table(const uint8_t* raster, const int32_t* labels, const int32_t* area, int32_t* counter_zeroed,
+                 int32_t* records, int capacity, int min_area_px, int ignore_class, int H, int W, void* stream);
+/* HOST side of the same stage: boundary rings of the components listed in keep_roots (sorted ascending) on a label image
+ * in host memory, in pixel-corner coordinates (x right, y down; vertex (x, y) = top-left corner of pixel (x, y)),
+ * closed (first point repeated), exterior rings and hole rings (flagged), Douglas-Peucker simplified with tolerance
+ * simplify_px (0 = corners only).  Results are held per thread until fz_trace_rings_fetch copies them out:
+ * ring_root int32 [n_rings], ring_is_hole uint8 [n_rings], ring_offset int64 [n_rings + 1], xy float64 [n_points][2]. */
+int fz_trace_rings(const int32_t* labels_host, int H, int W, const int32_t* keep_roots, int n_keep, double simplify_px,
+                   int64_t* n_rings, int64_t* n_points);
+int fz_trace_rings_fetch(int32_t* ring_root, uint8_t* ring_is_hole, int64_t* ring_offset, double* xy);
+
 #ifdef __cplusplus
 }
 #endif
