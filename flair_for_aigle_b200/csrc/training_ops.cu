@@ -1,0 +1,241 @@
+// Loss and optimizer kernels of the training step: FLAIRLosses' nn.CrossEntropyLoss(weight=w)
+// (flair_hub/tasks/module_setup.py:119-200) on (B, C, H, W) logits with the targets of tasks_module.py:153-154, its
+// gradient, the predictions of tasks_module.py:159, and torch.optim.AdamW's update (tasks_module.py:377-391).
+// All HBM-bound: the loss reads C*4 B per pixel once, the gradient reads and writes C*4 B per pixel, AdamW moves
+// 28 B per parameter (p, g, m, v read; p, m, v written).  The backward of the model itself is not built yet.
+#include "common.h"
+#include "../../include/flair_zonal_b200.h"
+
+namespace fz {
+
+constexpr int CE_MAX_CLS = 32;
+constexpr int CE_THREADS = 256;
+
+// targets[b][y][x] = argmax_c onehot[b][c][y][x] (first maximum), tasks_module.py:154
+__global__ void __launch_bounds__(CE_THREADS) onehot_argmax_kernel(const float* __restrict__ onehot, int32_t* __restrict__ tgt,
+                                                                   int C, int64_t plane, int64_t n_px) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * CE_THREADS + threadIdx.x;
+  if (i >= n_px) return;
+  const int64_t b = i / plane, p = i - b * plane;
+  const float* src = onehot + b * C * plane + p;
+  float bv = src[0];
+  int best = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = src[c * plane];
+    if (v > bv) {
+      bv = v;
+      best = c;
+    }
+  }
+  tgt[i] = best;
+}
+
+// per pixel: lse, prediction, and the block's partial sums of w[t] * nll and w[t] (fixed-order tree: deterministic).
+// grid = (blocks per sample, B): no 64-bit index division; MAXC = class count rounded up to 8 (19 -> 24 unrolled slots).
+template <int MAXC>
+__global__ void __launch_bounds__(CE_THREADS) ce_forward_kernel(const float* __restrict__ logits,
+                                                                const int32_t* __restrict__ tgt,
+                                                                const float* __restrict__ weight, float* __restrict__ lse,
+                                                                int32_t* __restrict__ preds, double* __restrict__ partials,
+                                                                int C, int plane) {
+  __shared__ double s_l[CE_THREADS / 32], s_w[CE_THREADS / 32];
+  const int p = blockIdx.x * CE_THREADS + threadIdx.x;
+  const int64_t b = blockIdx.y;
+  double wl = 0.0, ww = 0.0;
+  if (p < plane) {
+    const int64_t i = b * plane + p;
+    const float* src = logits + b * C * plane + p;
+    // all class planes are requested before the first use (the first version interleaved load and compare and paid one
+    // DRAM round trip per class: 305 us; long_scoreboard 16 per issue in ncu)
+    float v[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) v[c] = (c < C) ? __ldg(src + static_cast<int64_t>(c) * plane) : -INFINITY;
+    float mx = v[0];
+    int best = 0;
+#pragma unroll
+    for (int c = 1; c < MAXC; ++c)
+      if (v[c] > mx) {          // padding classes hold -inf: never selected, exp() = 0
+        mx = v[c];
+        best = c;
+      }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) sum += expf(v[c] - mx);
+    const float l = logf(sum) + mx;
+    lse[i] = l;
+    if (preds) preds[i] = best;                    // argmax(softmax(logits)) = argmax(logits), tasks_module.py:159
+    const int t = tgt[i];
+    float xt = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c == t) xt = v[c];
+    const float w = weight ? weight[t] : 1.0f;
+    wl = static_cast<double>(w) * static_cast<double>(l - xt);
+    ww = static_cast<double>(w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wl += __shfl_xor_sync(0xffffffffu, wl, o);
+    ww += __shfl_xor_sync(0xffffffffu, ww, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_l[warp] = wl;
+    s_w[warp] = ww;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b2 = 0.0;
+    for (int k = 0; k < CE_THREADS / 32; ++k) {
+      a += s_l[k];
+      b2 += s_w[k];
+    }
+    const int64_t blk = b * gridDim.x + blockIdx.x;
+    partials[2 * blk] = a;
+    partials[2 * blk + 1] = b2;
+  }
+}
+
+// out[0] = task_weight * sum(w * nll) / sum(w) (CrossEntropyLoss 'mean' with class weights), out[1] = sum(w)
+__global__ void __launch_bounds__(256) ce_reduce_kernel(const double* __restrict__ partials, int n_blocks, float task_weight,
+                                                        float* __restrict__ out) {
+  __shared__ double s_l[256], s_w[256];
+  double a = 0.0, b = 0.0;
+  for (int k = threadIdx.x; k < n_blocks; k += 256) {
+    a += partials[2 * k];
+    b += partials[2 * k + 1];
+  }
+  s_l[threadIdx.x] = a;
+  s_w[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_l[threadIdx.x] += s_l[threadIdx.x + o];
+      s_w[threadIdx.x] += s_w[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = static_cast<float>(task_weight * s_l[0] / s_w[0]);
+    out[1] = static_cast<float>(s_w[0]);
+  }
+}
+
+// dlogits[b][c][p] = grad_scale * task_weight / sum(w) * w[t] * (softmax_c - [c == t])
+__global__ void __launch_bounds__(CE_THREADS) ce_backward_kernel(const float* __restrict__ logits,
+                                                                 const int32_t* __restrict__ tgt,
+                                                                 const float* __restrict__ weight,
+                                                                 const float* __restrict__ lse,
+                                                                 const float* __restrict__ loss_out, float scale,
+                                                                 float* __restrict__ dlogits, int C, int64_t plane,
+                                                                 int64_t n_px) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * CE_THREADS + threadIdx.x;
+  if (i >= n_px) return;
+  const int64_t b = i / plane, p = i - b * plane;
+  const int t = tgt[i];
+  const float g = scale / loss_out[1] * (weight ? weight[t] : 1.0f);
+  const float l = lse[i];
+  const float* src = logits + b * C * plane + p;
+  float* dst = dlogits + b * C * plane + p;
+  for (int c0 = 0; c0 < C; c0 += 8) {               // 8 planes in flight per thread
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (c0 + j < C) ? __ldg(src + (c0 + j) * plane) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < C) dst[(c0 + j) * plane] = g * (expf(x[j] - l) - (c0 + j == t ? 1.0f : 0.0f));
+  }
+}
+
+// torch.optim.AdamW, single-tensor formulation (decoupled weight decay, bias-corrected step)
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, int64_t n, float decay, float one_minus_b1,
+                                                    float b2, float one_minus_b2, float step_size, float bc2_sqrt,
+                                                    float eps) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  float pi = p[i] * decay;                              // param.mul_(1 - lr * weight_decay)
+  float mi = m[i];
+  mi = mi + one_minus_b1 * (gi - mi);                   // exp_avg.lerp_(grad, 1 - beta1)
+  float vi = v[i] * b2;
+  vi = vi + one_minus_b2 * (gi * gi);                   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi = pi - step_size * (mi / denom);                   // param.addcdiv_(exp_avg, denom, value=-step_size)
+  p[i] = pi;
+  m[i] = mi;
+  v[i] = vi;
+}
+
+}  // namespace fz
+
+extern "C" int fz_onehot_argmax(const float* onehot, int32_t* targets, int B, int C, int H, int W, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(B >= 0 && C >= 1 && H > 0 && W > 0, "fz_onehot_argmax: bad shape");
+  const int64_t plane = static_cast<int64_t>(H) * W, n_px = plane * B;
+  if (n_px == 0) return 0;
+  onehot_argmax_kernel<<<static_cast<unsigned>((n_px + CE_THREADS - 1) / CE_THREADS), CE_THREADS, 0,
+                         reinterpret_cast<cudaStream_t>(stream)>>>(onehot, targets, C, plane, n_px);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t fz_ce_workspace_doubles(int B, int H, int W) {
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  return 2 * B * ((plane + fz::CE_THREADS - 1) / fz::CE_THREADS);
+}
+
+extern "C" int fz_ce_loss_forward(const float* logits, const int32_t* targets, const float* class_weight, float task_weight,
+                                  float* lse, int32_t* preds, double* workspace, float* loss_out, int B, int C, int H,
+                                  int W, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(B >= 1 && B <= 65535 && C >= 1 && C <= CE_MAX_CLS && H > 0 && W > 0,
+             "fz_ce_loss_forward: B=%d C=%d (1..65535 samples, 1..%d classes)", B, C, CE_MAX_CLS);
+  FZ_REQUIRE(logits && targets && lse && workspace && loss_out, "fz_ce_loss_forward: null pointer");
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  FZ_REQUIRE(plane < (1LL << 31), "fz_ce_loss_forward: H*W must fit int32");
+  const int per_sample = static_cast<int>((plane + CE_THREADS - 1) / CE_THREADS);
+  const int64_t blocks = static_cast<int64_t>(per_sample) * B;
+  FZ_REQUIRE(blocks < (1LL << 31), "fz_ce_loss_forward: too many pixels");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid(per_sample, B);
+#define FZ_CE(maxc)                                                                                                  \
+  ce_forward_kernel<maxc><<<grid, CE_THREADS, 0, st>>>(logits, targets, class_weight, lse, preds, workspace, C, \
+                                                       static_cast<int>(plane))
+  if (C <= 8) FZ_CE(8);
+  else if (C <= 16) FZ_CE(16);
+  else if (C <= 24) FZ_CE(24);
+  else FZ_CE(32);
+#undef FZ_CE
+  ce_reduce_kernel<<<1, 256, 0, st>>>(workspace, static_cast<int>(blocks), task_weight, loss_out);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_ce_loss_backward(const float* logits, const int32_t* targets, const float* class_weight, float task_weight,
+                                   const float* lse, const float* loss_out, float grad_scale, float* dlogits, int B, int C,
+                                   int H, int W, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(B >= 1 && C >= 1 && H > 0 && W > 0 && logits && targets && lse && loss_out && dlogits,
+             "fz_ce_loss_backward: bad arguments");
+  const int64_t plane = static_cast<int64_t>(H) * W, n_px = plane * B;
+  ce_backward_kernel<<<static_cast<unsigned>((n_px + CE_THREADS - 1) / CE_THREADS), CE_THREADS, 0,
+                       reinterpret_cast<cudaStream_t>(stream)>>>(logits, targets, class_weight, lse, loss_out,
+                                                                 grad_scale * task_weight, dlogits, C, plane, n_px);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                             double beta1, double beta2, double eps, double weight_decay, int step, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(n >= 0 && step >= 1 && param && grad && exp_avg && exp_avg_sq, "fz_adamw_step: bad arguments (step counts from 1)");
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+  adamw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, static_cast<float>(1.0 - lr * weight_decay), static_cast<float>(1.0 - beta1),
+      static_cast<float>(beta2), static_cast<float>(1.0 - beta2), static_cast<float>(lr / bc1),
+      static_cast<float>(sqrt(bc2)), static_cast<float>(eps));
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

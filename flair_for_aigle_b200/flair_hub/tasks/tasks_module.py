@@ -1,0 +1,95 @@
+"""``SegmentationTask``: the loss / prediction / optimizer side of flair_hub/tasks/tasks_module.py:133-167,377-391
+ on the CUDA kernels of csrc/training_ops.cu.
+
+Built: ``step(batch, training=False)`` -- the reference's validation step: forward (eval mode, the zonal engines),
+``targets = argmax(one-hot)``, weighted cross entropy times ``task_weight``, ``preds = argmax(softmax(logits))``;
+``loss_gradients()`` -- d loss / d logits per task, the seed of the backward pass; ``AdamW`` -- ``torch.optim.AdamW``'s
+update over a flat parameter arena (``_init_optimizer``).  NOT built: the backward of the encoders / decoder (no backward
+kernels exist yet), so ``step(batch, training=True)`` raises instead of silently skipping the gradient."""
+from typing import Dict, Iterable, List
+
+import torch
+
+from ... import native as nv
+from .module_setup import FLAIRLosses
+
+
+class AdamW:
+    """``torch.optim.AdamW(params, lr, weight_decay, betas)`` (tasks_module.py:385-389) as one fused kernel per step:
+    parameters, gradients and both moments live in flat fp32 arenas; ``params`` become views into the arena."""
+
+    def __init__(self, params: Iterable[torch.Tensor], lr: float, weight_decay: float = 0.01, betas=(0.9, 0.999),
+                 eps: float = 1e-8):
+        self.params: List[torch.Tensor] = [p for p in params]
+        if not self.params:
+            raise ValueError("optimizer got an empty parameter list")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise nv.NativeError("AdamW runs on CUDA only (no CPU fallback)")
+        self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay), tuple(betas), float(eps)
+        n = sum(p.numel() for p in self.params)
+        self.arena = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        off = 0
+        self.grads: List[torch.Tensor] = []
+        for p in self.params:
+            k = p.numel()
+            self.arena[off:off + k].copy_(p.detach().reshape(-1).float())
+            p.data = self.arena[off:off + k].view(p.shape)              # the parameter now aliases the arena
+            self.grads.append(self.grad[off:off + k].view(p.shape))
+            off += k
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+    def step(self) -> None:
+        self.step_count += 1
+        nv.adamw_step(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.weight_decay, self.step_count)
+
+
+def init_optimizer(cfg: dict, params: Iterable[torch.Tensor]) -> AdamW:
+    """tasks_module.py:377-391 (``_init_optimizer``): 'adamw' is built; 'sgd' / 'adam' raise."""
+    optim_type = cfg['optimizer']
+    if optim_type == 'adamw':
+        return AdamW(params, lr=cfg["learning_rate"], weight_decay=cfg['optim_weight_decay'], betas=tuple(cfg['optim_betas']))
+    if optim_type in ('sgd', 'adam'):
+        raise NotImplementedError(f"optimizer '{optim_type}': only the reference default 'adamw' has a kernel")
+    raise ValueError(f"Unsupported optimizer type: {optim_type}")
+
+
+class SegmentationTask:
+    def __init__(self, model, config: dict):
+        self.model, self.config = model, config
+        self.criterion = FLAIRLosses(config).get_losses()
+        self.mod_dropout = False
+
+    def forward(self, batch: Dict[str, torch.Tensor]):
+        return self.model(batch)
+
+    @torch.no_grad()
+    def step(self, batch: Dict[str, torch.Tensor], training: bool = False):
+        """tasks_module.py:133-167.  -> (loss, {task: preds int32 (B,H,W)}, {task: targets int32 (B,H,W)})."""
+        if training:
+            raise NotImplementedError("training step: the backward kernels of the encoders / decoder are not built yet "
+                                      "(SURVEY.md A11); loss, loss gradient and AdamW are")
+        dict_logits_task, _ = self.forward(batch)
+        loss_sum = None
+        all_preds, all_targets = {}, {}
+        for task, logits in dict_logits_task.items():
+            targets = batch[task].to(logits.device)
+            targets = nv.onehot_argmax(targets) if targets.ndim == 4 else targets.to(torch.int32)
+            task_weight = self.config['labels_configs'][task].get('task_weight', 1.0)
+            main_loss, preds = self.criterion[task](logits, targets, task_weight=task_weight, want_preds=True)
+            if not bool(torch.isfinite(main_loss)):
+                raise ValueError(f"Invalid loss for task {task}: {float(main_loss)}")           # tasks_module.py:157
+            loss_sum = main_loss if loss_sum is None else loss_sum + main_loss
+            all_preds[task], all_targets[task] = preds, targets
+        return loss_sum, all_preds, all_targets
+
+    def loss_gradients(self) -> Dict[str, torch.Tensor]:
+        """d loss_sum / d logits per task for the last ``step`` (fp32, (B,C,H,W))."""
+        return {task: crit.backward() for task, crit in self.criterion.items() if crit._saved is not None}

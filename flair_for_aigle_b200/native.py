@@ -98,9 +98,15 @@ _SIGNATURES = {
     "fz_ccl_table": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_trace_rings": [_vp, _i, _i, _vp, _i, ctypes.c_double, _vp, _vp],
     "fz_trace_rings_fetch": [_vp, _vp, _vp, _vp],
+    "fz_onehot_argmax": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_ce_workspace_doubles": [_i, _i, _i],
+    "fz_ce_loss_forward": [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_ce_loss_backward": [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _i, _i, _i, _i, _vp],
+    "fz_adamw_step": [_vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                      ctypes.c_double, _i, _vp],
     "fz_head_upsample4": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
-_RESTYPES = {"fz_last_error": ctypes.c_char_p}
+_RESTYPES = {"fz_last_error": ctypes.c_char_p, "fz_ce_workspace_doubles": ctypes.c_int64}
 
 
 def exported_symbols():
@@ -550,3 +556,50 @@ def trace_rings(labels_host, keep_roots, simplify_px: float = 0.0):
     _check(lib().fz_trace_rings_fetch(ring_root.ctypes.data, ring_hole.ctypes.data, ring_off.ctypes.data, xy.ctypes.data),
            "fz_trace_rings_fetch")
     return ring_root, ring_hole.astype(bool), ring_off, xy
+
+
+# ------------------------------------------------------------------------------------------------ training: loss, optimizer
+def onehot_argmax(onehot: torch.Tensor) -> torch.Tensor:
+    """tasks_module.py:154: (B,C,H,W) float one-hot labels -> int32 (B,H,W) class indices."""
+    B, C, H, W = onehot.shape
+    out = torch.empty((B, H, W), dtype=torch.int32, device=onehot.device)
+    _check(lib().fz_onehot_argmax(_ptr(onehot.float().contiguous()), _ptr(out), B, C, H, W, _stream()), "fz_onehot_argmax")
+    return out
+
+
+def ce_loss_forward(logits: torch.Tensor, targets: torch.Tensor, class_weight: Optional[torch.Tensor],
+                    task_weight: float = 1.0, want_preds: bool = True):
+    """-> (loss_out float[2] = {task_weight * CE, sum of w[t]}, lse (B,H,W), preds int32 (B,H,W) or None)."""
+    if logits.dtype != torch.float32 or logits.dim() != 4:
+        raise NativeError("ce_loss_forward: fp32 (B,C,H,W) logits required")
+    B, C, H, W = logits.shape
+    dev = logits.device
+    lse = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    preds = torch.empty((B, H, W), dtype=torch.int32, device=dev) if want_preds else None
+    ws = torch.empty(int(lib().fz_ce_workspace_doubles(B, H, W)), dtype=torch.float64, device=dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    with _Timed("ce_loss_forward", n=B, C=C, H=H):
+        _check(lib().fz_ce_loss_forward(_ptr(logits), _ptr(targets), _ptr(class_weight), float(task_weight), _ptr(lse),
+                                        _ptr(preds), _ptr(ws), _ptr(out), B, C, H, W, _stream()), "fz_ce_loss_forward")
+    return out, lse, preds
+
+
+def ce_loss_backward(logits, targets, class_weight, task_weight, lse, loss_out, grad_scale: float = 1.0, out=None):
+    B, C, H, W = logits.shape
+    dlogits = out if out is not None else torch.empty_like(logits)
+    with _Timed("ce_loss_backward", n=B, C=C, H=H):
+        _check(lib().fz_ce_loss_backward(_ptr(logits), _ptr(targets), _ptr(class_weight), float(task_weight), _ptr(lse),
+                                         _ptr(loss_out), float(grad_scale), _ptr(dlogits), B, C, H, W, _stream()),
+               "fz_ce_loss_backward")
+    return dlogits
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step: int):
+    """torch.optim.AdamW's update on flat contiguous fp32 buffers, in place."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or t.numel() != param.numel():
+            raise NativeError("adamw_step: fp32 buffers of one size required")
+    with _Timed("adamw_step", n=param.numel()):
+        _check(lib().fz_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
+                                   float(beta1), float(beta2), float(eps), float(weight_decay), int(step), _stream()),
+               "fz_adamw_step")

@@ -281,6 +281,25 @@ int fz_trace_rings(const int32_t* labels_host, int H, int W, const int32_t* keep
                    int64_t* n_rings, int64_t* n_points);
 int fz_trace_rings_fetch(int32_t* ring_root, uint8_t* ring_is_hole, int64_t* ring_offset, double* xy);
 
+/* ---- training step, loss and optimizer side (the model's backward is not built yet) ----
+ * tasks_module.py:153-154: targets int32 [B][H][W] = argmax over C of the one-hot float labels [B][C][H][W]. */
+int fz_onehot_argmax(const float* onehot, int32_t* targets, int B, int C, int H, int W, void* stream);
+/* nn.CrossEntropyLoss(weight=class_weight) of module_setup.py:155, 'mean' reduction = sum(w[t] nll) / sum(w[t]), times
+ * task_weight (tasks_module.py:162-163), on fp32 NCHW logits.  lse float [B][H][W] (kept for the backward), preds int32
+ * [B][H][W] = argmax(softmax(logits)) (tasks_module.py:159; may be NULL), workspace = fz_ce_workspace_doubles(B,H,W)
+ * doubles, loss_out float[2] = {loss, sum of w[t]}.  Deterministic (fixed-order reductions in double). */
+int64_t fz_ce_workspace_doubles(int B, int H, int W);
+int fz_ce_loss_forward(const float* logits, const int32_t* targets, const float* class_weight, float task_weight, float* lse,
+                       int32_t* preds, double* workspace, float* loss_out, int B, int C, int H, int W, void* stream);
+/* dlogits = grad_scale * d loss / d logits = grad_scale * task_weight * w[t] / sum(w) * (softmax - onehot(t)). */
+int fz_ce_loss_backward(const float* logits, const int32_t* targets, const float* class_weight, float task_weight,
+                        const float* lse, const float* loss_out, float grad_scale, float* dlogits, int B, int C, int H,
+                        int W, void* stream);
+/* torch.optim.AdamW (tasks_module.py:385-389: lr, weight_decay, betas from the config; eps 1e-8) on one flat fp32
+ * buffer, in place; step counts from 1. */
+int fz_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
