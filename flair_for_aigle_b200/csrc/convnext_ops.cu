@@ -160,12 +160,13 @@ __device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
   colsum32_step<1>(s, lane);
 }
 
-template <int NW, int CPT, int C>
-__global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ wdw,
+template <int NW, int CPT, int C, bool PERSIST>
+__global__ void __launch_bounds__(NW * 32, (512 / (NW * 32)) > 0 ? 512 / (NW * 32) : 1) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ wdw,
                                                             const float* __restrict__ bdw,
                                                             const float* __restrict__ ln_w,
                                                             const float* __restrict__ ln_b,
-                                                            __nv_bfloat16* __restrict__ out, int H, int W, float eps) {
+                                                            __nv_bfloat16* __restrict__ out, int H, int W, float eps,
+                                                            int tiles_x, int tiles_y, int n_tiles) {
   static_assert(NW * 32 * CPT == C, "one lane per channel (two for CPT = 2)");
   constexpr int SH = 4;
   constexpr int SW = 8 / CPT;      // 32 accumulators per thread either way
@@ -173,7 +174,22 @@ __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restr
   __shared__ float red[NW][32];
   __shared__ float s_stat[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * SW, y0 = blockIdx.y * SH, b = blockIdx.z;
+  // PERSIST (one channel per lane only): the CTA walks a list of tiles and loads the 49 taps + bias ONCE -- they were 26 %
+  // of all loads and a dependent prologue in front of each tile's first FMA (stage 2, C = 512: 86 -> 78 us; C = 128 with
+  // four small CTAs per SM measured slower, 271 -> 283 us, and stays one tile per CTA)
+  static_assert(!PERSIST || CPT == 1, "the persistent walk keeps one channel's taps in registers");
+  float wreg[49];
+  float bias = 0.f;
+  if (PERSIST) {
+    const int c = warp * 32 + lane;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) wreg[t] = wdw[t * C + c];
+    bias = bdw[c];
+  }
+  int tile = blockIdx.x;
+  do {
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+  const int x0 = tx * SW, y0 = ty * SH;
   const float* xb = x + static_cast<size_t>(b) * H * W * C;
   // CTA-uniform edge flags: out-of-image taps are zero (conv padding); no per-load predicate math
   const bool left_edge = x0 < 3, right_edge = x0 + SW + 3 > W;
@@ -182,10 +198,11 @@ __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restr
 #pragma unroll
   for (int cc = 0; cc < CPT; ++cc) {
     const int c = cc * (C / CPT) + warp * 32 + lane;
-    float wreg[49];
+    if (!PERSIST) {
 #pragma unroll
-    for (int t = 0; t < 49; ++t) wreg[t] = wdw[t * C + c];
-    const float bias = bdw[c];
+      for (int t = 0; t < 49; ++t) wreg[t] = wdw[t * C + c];
+      bias = bdw[c];
+    }
 #pragma unroll
     for (int p = 0; p < NPX; ++p) acc[cc][p] = bias;
     // software-pipelined rows: row iy+1 is in flight while row iy feeds the FMAs
@@ -280,6 +297,8 @@ __global__ void __launch_bounds__(NW * 32) dwconv_ln_kernel(const float* __restr
         orp[ox * C] = __float2bfloat16_rn(acc[cc][oy * SW + ox] * s_stat[oy * SW + ox] * g + be);
     }
   }
+    tile += gridDim.x;
+  } while (PERSIST && tile < n_tiles);   // the next tile's first __syncthreads orders its shared-memory writes after these reads
 }
 
 // ------------------------------------------------------------------------------------ LN2d + space-to-depth
@@ -547,8 +566,26 @@ static int launch_dwconv(const float* x, const float* wdw, const float* bdw, con
                          __nv_bfloat16* out, int B, int H, int W, float eps, cudaStream_t st) {
   constexpr int SW = 8 / CPT;
   FZ_REQUIRE(H % 4 == 0 && W % SW == 0, "fz_dwconv7_ln: H=%d W=%d must be multiples of 4 x %d", H, W, SW);
-  dim3 grid(W / SW, H / 4, B);
-  dwconv_ln_kernel<NW, CPT, C><<<grid, NW * 32, 0, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, eps);
+  const int tiles_x = W / SW, tiles_y = H / 4, n_tiles = tiles_x * tiles_y * B;
+  // persistent walk for the 16-warp one-channel-per-lane shape: one CTA per SM, x-fastest tile order (neighbouring
+  // tiles run concurrently on different SMs and share their halos in L2)
+  static int persist = -1;
+  if (persist < 0) {
+    const char* e = getenv("FZ_DWCONV_PERSIST");
+    persist = (e && e[0] == '0') ? 0 : 1;
+  }
+  if constexpr (NW == 16 && CPT == 1) {
+   if (persist) {
+    const int sm_count = device_sm_count();
+    if (sm_count <= 0) return -2;
+    const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+    dwconv_ln_kernel<NW, 1, C, true><<<grid, NW * 32, 0, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, eps, tiles_x, tiles_y, n_tiles);
+    FZ_CHECK_CUDA(cudaGetLastError());
+    return 0;
+   }
+  }
+  dwconv_ln_kernel<NW, CPT, C, false><<<n_tiles, NW * 32, 0, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, eps, tiles_x, tiles_y,
+                                                                   n_tiles);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

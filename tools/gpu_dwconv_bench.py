@@ -1,11 +1,11 @@
-"""Depthwise 7x7 + LayerNorm at the four ConvNeXt-V2-base stage shapes (B = 37): FZ_DWCONV_COL=0/1."""
+"""Depthwise 7x7 + LayerNorm at the four ConvNeXt-V2-base stage shapes (B = 37): FZ_DWCONV_PERSIST=0/1."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flair_for_aigle_b200 import native as nv
 dev = torch.device("cuda:0")
 B = 37
-print("FZ_DWCONV_COL =", os.environ.get("FZ_DWCONV_COL"))
+print("FZ_DWCONV_PERSIST =", os.environ.get("FZ_DWCONV_PERSIST"))
 for C, H in ((128, 128), (256, 64), (512, 32), (1024, 16)):
     x = torch.randn(B, H, H, C, device=dev)
     w = torch.randn(49, C, device=dev) * 0.1
