@@ -12,7 +12,8 @@ namespace fz {
 // out[t][c][y][x] = (raster[c][row0+y][col0+x] (0 outside) - mean[c]) / std[c]
 // One thread = 4 consecutive x of one (t, c, y): 4 byte loads (coalesced across the warp),
 // one float4 store.
-__global__ void gather_f32_kernel(const uint8_t* __restrict__ raster, int C, int H, int W,
+template <typename T>
+__global__ void gather_f32_kernel(const T* __restrict__ raster, int C, int H, int W,
                                   const int32_t* __restrict__ origins, int P, const float* __restrict__ mean,
                                   const float* __restrict__ stdv, float* __restrict__ out) {
   const int t = blockIdx.z;
@@ -63,17 +64,32 @@ __global__ void gather_u8_kernel(const uint8_t* __restrict__ raster, int C, int 
 
 }  // namespace fz
 
-extern "C" int fz_gather_tiles_f32(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles,
-                                   int P, const float* mean, const float* stdv, float* out, void* stream) {
+static int gather_f32_launch(const void* raster, int src_f32, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
+                             const float* mean, const float* stdv, float* out, void* stream) {
   FZ_REQUIRE(C >= 1 && H > 0 && W > 0 && P > 0 && P % 4 == 0, "fz_gather_tiles_f32: bad shape C=%d H=%d W=%d P=%d", C, H,
              W, P);
   if (n_tiles <= 0) return 0;
   const int threads = 256;
   dim3 grid((P * (P / 4) + threads - 1) / threads, C, n_tiles);
-  fz::gather_f32_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(raster, C, H, W, origins, P, mean,
-                                                                                      stdv, out);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (src_f32)
+    fz::gather_f32_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(raster), C, H, W, origins, P, mean, stdv,
+                                                           out);
+  else
+    fz::gather_f32_kernel<uint8_t><<<grid, threads, 0, st>>>(static_cast<const uint8_t*>(raster), C, H, W, origins, P, mean,
+                                                             stdv, out);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int fz_gather_tiles_f32(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles,
+                                   int P, const float* mean, const float* stdv, float* out, void* stream) {
+  return gather_f32_launch(raster, 0, C, H, W, origins, n_tiles, P, mean, stdv, out, stream);
+}
+
+extern "C" int fz_gather_tiles_f32_from_f32(const float* raster, int C, int H, int W, const int32_t* origins, int n_tiles,
+                                            int P, const float* mean, const float* stdv, float* out, void* stream) {
+  return gather_f32_launch(raster, 1, C, H, W, origins, n_tiles, P, mean, stdv, out, stream);
 }
 
 extern "C" int fz_gather_tiles_u8(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles,

@@ -71,8 +71,8 @@ class MultiModalSlicedDataset(Dataset):
         return self._device_rasters[key]
 
     def device_raster(self, mod: str, device) -> torch.Tensor:
-        """uint8 (C,H,W) on ``device``: the channels listed in the modality config (1-based, like
-        rasterio ``indexes``), uploaded once through pinned memory."""
+        """uint8 (imagery) or float32 (elevation) (C,H,W) on ``device``: the channels listed in the modality config
+        (1-based, like rasterio ``indexes``), uploaded once through pinned memory."""
         key = f"{mod}@{device}"
         if key not in self._device_rasters:
             r = self.readers[mod]
@@ -81,8 +81,8 @@ class MultiModalSlicedDataset(Dataset):
                 arr = r.read()                       # all bands in order: no host copy
             else:
                 arr = r.read(chans)
-            if arr.dtype != np.uint8:
-                raise NotImplementedError(f"{mod}: only uint8 rasters are supported by the device feeder")
+            if arr.dtype not in (np.uint8, np.float32):
+                raise NotImplementedError(f"{mod}: the device feeder reads uint8 or float32 rasters, got {arr.dtype}")
             pinned = getattr(r, 'pinned_tensor', None)
             if pinned is not None and arr is r.array:
                 host = pinned                        # raster was created in pinned memory
@@ -94,6 +94,31 @@ class MultiModalSlicedDataset(Dataset):
                     pass
             self._device_rasters[key] = host.to(device, non_blocking=True)
         return self._device_rasters[key]
+
+    def modality_origins(self, mod: str) -> np.ndarray:
+        """int32 [n,2] (row0, col0) of every tile's read window in ``mod``'s own pixel grid (dataset.py:101:
+        ``from_bounds(*bounds, transform=reader.transform)``).  The window of a tile spans P * ref_res metres; it is read
+        without resampling, so it has to cover exactly ``patch_sizes[mod]`` whole pixels of the modality and start on one
+        -- the resampled (bilinear, fractional window) read of rasterio is not built."""
+        cfg = self.modalities_config
+        ref_mod = cfg.get('reference_modality', next(iter(self.readers)))
+        plan = self.plan()
+        if mod == ref_mod:
+            return np.ascontiguousarray(plan[:, :2]).astype(np.int32)
+        ref, r = self.readers[ref_mod], self.readers[mod]
+        ref_res, res = float(cfg['reference_resolution']), float(r.res[0])
+        P = int(cfg['img_pixels_detection'])
+        if abs(self.patch_sizes[mod] * res - P * ref_res) > 1e-6 * P * ref_res:
+            raise NotImplementedError(f"{mod}: a {P * ref_res} m tile is not {self.patch_sizes[mod]} whole pixels at {res} m/px; "
+                                      "resampled modality windows are not built")
+        x_left = ref.bounds.left + plan[:, 1].astype(np.float64) * ref_res
+        y_top = ref.bounds.top - plan[:, 0].astype(np.float64) * ref_res
+        col = (x_left - r.bounds.left) / res
+        row = (r.bounds.top - y_top) / res
+        if np.abs(col - np.round(col)).max() > 1e-4 or np.abs(row - np.round(row)).max() > 1e-4:
+            raise NotImplementedError(f"{mod}: tile windows do not start on whole pixels of this raster; resampled modality "
+                                      "windows are not built")
+        return np.stack([np.round(row), np.round(col)], axis=1).astype(np.int32)
 
     def __len__(self) -> int:
         return len(self.df)

@@ -205,7 +205,7 @@ def inference_and_write(model, dataloader, tiles_gdf, config: Dict, output_files
         zmap_d = torch.from_numpy(zoom_map(P - 2 * margin, scale)).to(device)
 
     if (isinstance(dataset, MultiModalSlicedDataset) and output_type == "argmax" and len(tasks) == 1
-            and not needs_rescale):
+            and not needs_rescale and len(model.active_mono) == 1):
         # fused device path: feeder -> encoder/decoder -> head epilogue writes the class raster
         mod = model.active_mono[0]
         sink = output_files[tasks[0]]
@@ -252,19 +252,24 @@ def _iter_batches(dataloader, dataset, model, config, device):
             yield {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()
                    if not k.endswith('_RAW')}
         return
-    mod = model.active_mono[0]
-    raster = dataset.device_raster(mod, device)
-    norm = dataset.modalities[mod].get('normalization', {}) or {}
-    C = raster.shape[0]
-    mean = torch.tensor(norm.get('means', [0.0] * C), dtype=torch.float32, device=device)
-    std = torch.tensor(norm.get('stds', [1.0] * C), dtype=torch.float32, device=device)
-    P = int(config['img_pixels_detection'])
-    plan = torch.from_numpy(dataset.plan()).to(device)
+    # every active mono-temporal modality: its own raster, window origins in its own pixel grid and normalisation
+    # (dataset.py:174-209); a single modality is FusionHandler case 1, two or more go through conv_f (flair_model.py:473-547)
+    feeds = []
+    for mod in model.active_mono:
+        raster = dataset.device_raster(mod, device)
+        norm = dataset.modalities[mod].get('normalization', {}) or {}
+        C = raster.shape[0]
+        mean = torch.tensor(norm.get('means', [0.0] * C), dtype=torch.float32, device=device)
+        std = torch.tensor(norm.get('stds', [1.0] * C), dtype=torch.float32, device=device)
+        origins = torch.from_numpy(dataset.modality_origins(mod)).to(device)
+        feeds.append((mod, raster, mean, std, origins, int(dataset.patch_sizes.get(mod, config['img_pixels_detection']))))
     bs = int(config.get('batch_size', 8))
     for s in range(0, len(dataset), bs):
         idx = torch.arange(s, min(s + bs, len(dataset)), device=device)
-        x = nv.gather_tiles_f32(raster, plan[idx, :2].contiguous(), P, mean, std)
-        yield {mod: x, 'index': idx}
+        batch = {mod: nv.gather_tiles_f32(raster, origins[idx].contiguous(), ps, mean, std)
+                 for mod, raster, mean, std, origins, ps in feeds}
+        batch['index'] = idx
+        yield batch
 
 
 @torch.no_grad()

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "fz_abi_version": [],
     "fz_device_info": [_i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_sz)],
     "fz_gather_tiles_f32": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
+    "fz_gather_tiles_f32_from_f32": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "fz_gather_tiles_u8": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp],
     "fz_crop_argmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "fz_crop_softmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
@@ -164,11 +165,13 @@ def gather_tiles_f32(raster: torch.Tensor, origins: torch.Tensor, P: int, mean: 
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
     C, H, W = raster.shape
     n = origins.shape[0]
-    assert raster.dtype == torch.uint8 and origins.dtype == torch.int32
+    if raster.dtype not in (torch.uint8, torch.float32) or origins.dtype != torch.int32:
+        raise NativeError("gather_tiles_f32: uint8 or float32 raster and int32 origins required")
     if out is None:
         out = torch.empty((n, C, P, P), dtype=torch.float32, device=raster.device)
-    _check(lib().fz_gather_tiles_f32(_ptr(raster), C, H, W, _ptr(origins), n, P, _ptr(mean), _ptr(std), _ptr(out),
-                                     _stream()), "fz_gather_tiles_f32")
+    fn = lib().fz_gather_tiles_f32 if raster.dtype == torch.uint8 else lib().fz_gather_tiles_f32_from_f32
+    _check(fn(_ptr(raster), C, H, W, _ptr(origins), n, P, _ptr(mean), _ptr(std), _ptr(out), _stream()),
+           "fz_gather_tiles_f32")
     return out
 
 

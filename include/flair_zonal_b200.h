@@ -41,6 +41,10 @@ int fz_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size
  */
 int fz_gather_tiles_f32(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
                         const float* mean, const float* std, float* out, void* stream);
+/* The same window gather for a float32 raster (a DEM / elevation modality next to the uint8 imagery, dataset.py:89-124):
+ * raster float32 [C][H][W], zero fill outside, (x - mean) / std in float64 rounded once to float32. */
+int fz_gather_tiles_f32_from_f32(const float* raster, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
+                                 const float* mean, const float* stdv, float* out, void* stream);
 /* Same window rule, raw bytes, NHWC uint8 [n_tiles][P][P][4] (C<=4, missing channels = 0):
  * the operand the fused stem kernel consumes (20 B/px feeder of SURVEY 8d becomes 4+4 B/px). */
 int fz_gather_tiles_u8(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
