@@ -1,0 +1,374 @@
+// Training-mode forward pieces and the backward of one ConvNeXt-V2 block (first slice of the model backward):
+//   x -> dwconv7x7 (+b) -> LayerNorm -> fc1 -> GELU -> GRN -> fc2 -> + x
+// The two Linear layers run on the tcgen05 GEMM (fz_gemm_bf16, and native.linear_backward for their gradients); the
+// kernels here are the memory-bound rest, written for correctness first (one thread per element / one warp per row, fixed
+// reduction orders, no atomics): they are NOT tuned yet -- the depthwise weight gradient in particular walks all pixels
+// per (tap, 32 channels) block.  Saved tensors follow PyTorch's autograd of the same modules (oracle/models.py
+// ConvNeXtBlock): the LayerNorm input with its row statistics, the pre-GELU activations, the GRN input and its norms.
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "../../include/flair_zonal_b200.h"
+
+namespace fz {
+
+// ------------------------------------------------------------------------------------------------ depthwise 7x7, fp32
+// out[b,y,x,c] = bias[c] + sum_k in[b,y+ky-3,x+kx-3,c] * w[k][c]   (flip: w[48-k], i.e. the data gradient)
+__global__ void __launch_bounds__(256) dwconv7_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int H,
+                                                          int W, int C, int64_t n, int flip) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const int64_t px = i / C;
+  const int x = static_cast<int>(px % W), y = static_cast<int>((px / W) % H);
+  const int64_t b = px / (static_cast<int64_t>(W) * H);
+  float acc = bias ? bias[c] : 0.f;
+  for (int ky = 0; ky < 7; ++ky) {
+    const int iy = y + ky - 3;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < 7; ++kx) {
+      const int ix = x + kx - 3;
+      if (ix < 0 || ix >= W) continue;
+      const int k = ky * 7 + kx;
+      acc = fmaf(in[((b * H + iy) * W + ix) * C + c], w[(flip ? 48 - k : k) * C + c], acc);
+    }
+  }
+  out[i] = acc;
+}
+
+// dw[k][c] = sum_{b,y,x} du[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]  (k < 49);  k == 49: db[c] = sum du.   grid (50, C/32)
+__global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du,
+                                                            float* __restrict__ dw, float* __restrict__ db, int B, int H,
+                                                            int W, int C) {
+  __shared__ float red[8][32];
+  const int k = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+  const int ky = k / 7, kx = k % 7;
+  const int64_t npx = static_cast<int64_t>(B) * H * W;
+  float acc = 0.f;
+  if (c < C)
+    for (int64_t p = ty; p < npx; p += 8) {
+      const float g = du[p * C + c];
+      if (k == 49) {
+        acc += g;
+      } else {
+        const int xw = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const int iy = y + ky - 3, ix = xw + kx - 3;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) acc = fmaf(g, x[(p + static_cast<int64_t>(ky - 3) * W + (kx - 3)) * C + c], acc);
+      }
+    }
+  red[ty][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    if (k == 49) db[c] = t;
+    else dw[k * C + c] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm rows
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per row: out = (x - mean) * rstd * g + b (bf16), mean / rstd saved
+__global__ void __launch_bounds__(256) ln_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                           const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
+                                                           float* __restrict__ mean, float* __restrict__ rstd, int64_t M,
+                                                           int C, float eps) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= M) return;
+  const float* row = x + r * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += row[c];
+  const float mu = warp_sum(s) / C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = row[c] - mu;
+    v += d * d;
+  }
+  const float rs = rsqrtf(warp_sum(v) / C + eps);
+  for (int c = lane; c < C; c += 32) out[r * C + c] = __float2bfloat16_rn((row[c] - mu) * rs * g[c] + b[c]);
+  if (lane == 0) {
+    mean[r] = mu;
+    rstd[r] = rs;
+  }
+}
+
+// dx = rstd * (dy*g - mean_c(dy*g) - xhat * mean_c(dy*g*xhat));  partial[blk][0][c] = sum dy*xhat, [1][c] = sum dy over the
+// block's rows (block b's warp w walks rows (b*8 + w) + k * gridDim.x*8: fixed assignment, fixed order)
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ g, float* __restrict__ dx,
+                                                     float* __restrict__ partial, int64_t M, int C) {
+  extern __shared__ float sh[];                      // [8 warps][2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* mine = sh + static_cast<size_t>(warp) * 2 * C;
+  for (int c = lane; c < 2 * C; c += 32) mine[c] = 0.f;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + warp; r < M; r += static_cast<int64_t>(gridDim.x) * 8) {
+    const float mu = mean[r], rs = rstd[r];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (x[r * C + c] - mu) * rs, d = __bfloat162float(dy[r * C + c]), gg = d * g[c];
+      s1 += gg;
+      s2 += gg * xh;
+      mine[c] += d * xh;
+      mine[C + c] += d;
+    }
+    const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (x[r * C + c] - mu) * rs, gg = __bfloat162float(dy[r * C + c]) * g[c];
+      dx[r * C + c] = rs * (gg - m1 - xh * m2);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) t += sh[static_cast<size_t>(w2) * 2 * C + c];
+    partial[static_cast<size_t>(blockIdx.x) * 2 * C + c] = t;
+  }
+}
+
+// out[n] = sum_s partial[s][n], fixed order
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int N,
+                                                          int S) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < S; ++s) t += partial[static_cast<size_t>(s) * N + n];
+  out[n] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ GELU (erf)
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ g,
+                                                       int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n) g[i] = __float2bfloat16_rn(gelu_exact(__bfloat162float(h[i])));
+}
+
+// ------------------------------------------------------------------------------------------------ GRN
+// out[b][c] = sum_hw f(a, bb): mode 0 a*a, 1 a*bb, 2 a.   grid (C/32, B), 32 channels x 8 row lanes per block
+__global__ void __launch_bounds__(256) sample_colreduce_kernel(const __nv_bfloat16* __restrict__ a,
+                                                               const __nv_bfloat16* __restrict__ bb, float* __restrict__ out,
+                                                               int HW, int C, int mode) {
+  __shared__ float red[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+  const int64_t base = static_cast<int64_t>(blockIdx.y) * HW * C;
+  float acc = 0.f;
+  if (c < C)
+    for (int r = ty; r < HW; r += 8) {
+      const float v = __bfloat162float(a[base + static_cast<int64_t>(r) * C + c]);
+      acc += mode == 0 ? v * v : (mode == 1 ? v * __bfloat162float(bb[base + static_cast<int64_t>(r) * C + c]) : v);
+    }
+  red[ty][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    out[static_cast<size_t>(blockIdx.y) * C + c] = t;
+  }
+}
+
+// one block per sample: Gx = sqrt(sumsq), mu = mean_c Gx, Nx = Gx / (mu + eps)
+__global__ void __launch_bounds__(256) grn_norms_kernel(const float* __restrict__ sumsq, float* __restrict__ gx,
+                                                        float* __restrict__ nx, float* __restrict__ mu_out, int C, float eps) {
+  __shared__ float red[256];
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float v = sqrtf(sumsq[static_cast<size_t>(b) * C + c]);
+    gx[static_cast<size_t>(b) * C + c] = v;
+    s += v;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float mu = red[0] / C;
+  if (threadIdx.x == 0) mu_out[b] = mu;
+  for (int c = threadIdx.x; c < C; c += 256) nx[static_cast<size_t>(b) * C + c] = gx[static_cast<size_t>(b) * C + c] / (mu + eps);
+}
+
+// y = g * (1 + gamma * Nx[b]) + beta
+__global__ void __launch_bounds__(256) grn_apply_train_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ nx,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              __nv_bfloat16* __restrict__ y, int64_t per_sample, int C,
+                                                              int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const int64_t b = i / per_sample;
+  y[i] = __float2bfloat16_rn(__bfloat162float(g[i]) * (1.0f + gamma[c] * nx[b * C + c]) + beta[c]);
+}
+
+// one block per sample: coefA = 1 + gamma*Nx, coefB = dGx / Gx with
+// dGx = gamma*S1/(mu+eps) - (sum_c gamma*S1*Gx) / (C (mu+eps)^2)
+__global__ void __launch_bounds__(256) grn_bwd_coef_kernel(const float* __restrict__ s1, const float* __restrict__ gx,
+                                                           const float* __restrict__ nx, const float* __restrict__ mu,
+                                                           const float* __restrict__ gamma, float* __restrict__ coef_a,
+                                                           float* __restrict__ coef_b, int C, float eps) {
+  __shared__ float red[256];
+  const int b = blockIdx.x;
+  const size_t o = static_cast<size_t>(b) * C;
+  float t = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) t += gamma[c] * s1[o + c] * gx[o + c];
+  red[threadIdx.x] = t;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  const float d = mu[b] + eps, tb = red[0] / (static_cast<float>(C) * d * d);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    coef_a[o + c] = 1.0f + gamma[c] * nx[o + c];
+    const float dgx = gamma[c] * s1[o + c] / d - tb;
+    coef_b[o + c] = gx[o + c] > 0.f ? dgx / gx[o + c] : 0.f;
+  }
+}
+
+// dgamma[c] = sum_b Nx*S1, dbeta[c] = sum_b S0
+__global__ void __launch_bounds__(256) grn_param_grad_kernel(const float* __restrict__ s1, const float* __restrict__ s0,
+                                                             const float* __restrict__ nx, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int B, int C) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, bsum = 0.f;
+  for (int b = 0; b < B; ++b) {
+    a += nx[static_cast<size_t>(b) * C + c] * s1[static_cast<size_t>(b) * C + c];
+    bsum += s0[static_cast<size_t>(b) * C + c];
+  }
+  dgamma[c] = a;
+  dbeta[c] = bsum;
+}
+
+// dh = (dy * coefA[b] + g * coefB[b]) * GELU'(h)
+__global__ void __launch_bounds__(256) grn_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ g,
+                                                           const __nv_bfloat16* __restrict__ h, const float* __restrict__ coef_a,
+                                                           const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ dh,
+                                                           int64_t per_sample, int C, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const int64_t b = i / per_sample;
+  const float dg = __bfloat162float(dy[i]) * coef_a[b * C + c] + __bfloat162float(g[i]) * coef_b[b * C + c];
+  dh[i] = __float2bfloat16_rn(dg * gelu_grad(__bfloat162float(h[i])));
+}
+
+__global__ void __launch_bounds__(256) add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                      float* __restrict__ out, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+static inline unsigned blocks_for(int64_t n) { return static_cast<unsigned>((n + 255) / 256); }
+
+}  // namespace fz
+
+using namespace fz;
+#define ST(stream) reinterpret_cast<cudaStream_t>(stream)
+typedef const __nv_bfloat16* cbf;
+typedef __nv_bfloat16* bf;
+
+extern "C" int fz_dwconv7_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C,
+                              int flip, void* stream) {
+  FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && in && w && out, "fz_dwconv7_f32: bad arguments");
+  const int64_t n = static_cast<int64_t>(B) * H * W * C;
+  dwconv7_f32_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(in, w, bias, out, H, W, C, n, flip);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, float* db, int B, int H, int W, int C,
+                                void* stream) {
+  FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && x && du && dw && db, "fz_dwconv7_wgrad: bad arguments");
+  dwconv7_wgrad_kernel<<<dim3(50, (C + 31) / 32), 256, 0, ST(stream)>>>(x, du, dw, db, B, H, W, C);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, float* mean, float* rstd,
+                                      int64_t M, int C, float eps, void* stream) {
+  FZ_REQUIRE(M > 0 && C > 0 && x && g && b && out_bf16 && mean && rstd, "fz_layernorm_fwd_stats: bad arguments");
+  ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16), mean,
+                                                                                 rstd, M, C, eps);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* g,
+                                float* dx, float* partial, float* dgamma_dbeta, int64_t M, int C, int blocks, void* stream) {
+  FZ_REQUIRE(M > 0 && C > 0 && blocks >= 1 && C <= 2048, "fz_layernorm_bwd: M=%lld C=%d (C <= 2048)", (long long)M, C);
+  auto kern = ln_bwd_kernel;
+  const int smem = 8 * 2 * C * 4;
+  FZ_ENSURE_SMEM(kern, 8 * 2 * 2048 * 4);        // opt in once for the largest C (the attribute is set once per kernel)
+  kern<<<blocks, 256, smem, ST(stream)>>>(reinterpret_cast<cbf>(dy_bf16), x, mean, rstd, g, dx, partial, M, C);
+  reduce_rows_kernel<<<(2 * C + 255) / 256, 256, 0, ST(stream)>>>(partial, dgamma_dbeta, 2 * C, blocks);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_gelu_fwd(const void* h_bf16, void* g_bf16, int64_t n, void* stream) {
+  FZ_REQUIRE(n > 0 && h_bf16 && g_bf16, "fz_gelu_fwd: bad arguments");
+  gelu_fwd_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(h_bf16), reinterpret_cast<bf>(g_bf16), n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_sample_colreduce(const void* a_bf16, const void* b_bf16, float* out, int B, int HW, int C, int mode,
+                                   void* stream) {
+  FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && mode >= 0 && mode <= 2 && a_bf16 && out && (mode != 1 || b_bf16) && B <= 65535,
+             "fz_sample_colreduce: bad arguments");
+  sample_colreduce_kernel<<<dim3((C + 31) / 32, B), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(a_bf16),
+                                                                          reinterpret_cast<cbf>(b_bf16), out, HW, C, mode);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* gamma, const float* beta, float* gx,
+                                    float* nx, float* mu, void* y_bf16, int B, int HW, int C, float eps, void* stream) {
+  FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && g_bf16 && sumsq && gamma && beta && gx && nx && mu && y_bf16,
+             "fz_grn_train_forward: bad arguments");
+  grn_norms_kernel<<<B, 256, 0, ST(stream)>>>(sumsq, gx, nx, mu, C, eps);
+  const int64_t per = static_cast<int64_t>(HW) * C, n = per * B;
+  grn_apply_train_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(g_bf16), nx, gamma, beta,
+                                                                reinterpret_cast<bf>(y_bf16), per, C, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1,
+                                    const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
+                                    float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, int B, int HW,
+                                    int C, float eps, void* stream) {
+  FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && dy_bf16 && g_bf16 && h_bf16 && s1 && s0 && gx && nx && mu && gamma && coef_a &&
+                 coef_b && dgamma && dbeta && dh_bf16,
+             "fz_grn_gelu_backward: bad arguments");
+  grn_bwd_coef_kernel<<<B, 256, 0, ST(stream)>>>(s1, gx, nx, mu, gamma, coef_a, coef_b, C, eps);
+  grn_param_grad_kernel<<<(C + 255) / 256, 256, 0, ST(stream)>>>(s1, s0, nx, dgamma, dbeta, B, C);
+  const int64_t per = static_cast<int64_t>(HW) * C, n = per * B;
+  grn_gelu_bwd_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(g_bf16),
+                                                             reinterpret_cast<cbf>(h_bf16), coef_a, coef_b,
+                                                             reinterpret_cast<bf>(dh_bf16), per, C, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  FZ_REQUIRE(n > 0 && a && b && out, "fz_add_f32: bad arguments");
+  add_f32_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(a, b, out, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -3,6 +3,8 @@
 // gradient, the predictions of tasks_module.py:159, and torch.optim.AdamW's update (tasks_module.py:377-391).
 // All HBM-bound: the loss reads C*4 B per pixel once, the gradient reads and writes C*4 B per pixel, AdamW moves
 // 28 B per parameter (p, g, m, v read; p, m, v written).  The backward of the model itself is not built yet.
+#include <cuda_bf16.h>
+
 #include "common.h"
 #include "../../include/flair_zonal_b200.h"
 
@@ -167,6 +169,54 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   v[i] = vi;
 }
 
+// out[c][r] = in[r][c] (bf16), 32 x 32 tiles through padded shared memory: the operand transposes that let the K-major
+// tcgen05 GEMM compute dX = dY W and dW = dY^T X (first backward building block; an MN-major operand path would save them)
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
+                                                             __nv_bfloat16* __restrict__ out, int R, int C) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = r0 + ty + 8 * j, c = c0 + tx;
+    if (r < R && c < C) tile[ty + 8 * j][tx] = in[static_cast<size_t>(r) * C + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 8 * j, r = r0 + tx;
+    if (r < R && c < C) out[static_cast<size_t>(c) * R + r] = tile[tx][ty + 8 * j];
+  }
+}
+
+// partial[s][n] = sum over the rows of chunk s of in[m][n]; then out[n] = sum_s partial[s][n] in a fixed order
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ partial,
+                                                             int64_t M, int N, int rows_per_chunk) {
+  __shared__ float red[8][32];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk;
+  const int64_t m1 = m0 + rows_per_chunk < M ? m0 + rows_per_chunk : M;
+  float a = 0.f;
+  if (n < N)
+    for (int64_t m = m0 + ty; m < m1; m += 8) a += __bfloat162float(in[m * N + n]);
+  red[ty][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    partial[static_cast<size_t>(blockIdx.y) * N + n] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int N,
+                                                           int chunks) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < chunks; ++s) t += partial[static_cast<size_t>(s) * N + n];
+  out[n] = t;
+}
+
 }  // namespace fz
 
 extern "C" int fz_onehot_argmax(const float* onehot, int32_t* targets, int B, int C, int H, int W, void* stream) {
@@ -236,6 +286,29 @@ extern "C" int fz_adamw_step(float* param, const float* grad, float* exp_avg, fl
       param, grad, exp_avg, exp_avg_sq, n, static_cast<float>(1.0 - lr * weight_decay), static_cast<float>(1.0 - beta1),
       static_cast<float>(beta2), static_cast<float>(1.0 - beta2), static_cast<float>(lr / bc1),
       static_cast<float>(sqrt(bc2)), static_cast<float>(eps));
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_transpose_bf16(const void* in, void* out, int R, int C, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(R > 0 && C > 0 && in && out, "fz_transpose_bf16: bad arguments");
+  const dim3 grid((C + 31) / 32, (R + 31) / 32);
+  FZ_REQUIRE(grid.y <= 65535, "fz_transpose_bf16: R=%d exceeds %d rows per call", R, 65535 * 32);
+  transpose_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), R, C);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_colsum_bf16(const void* in, float* partial, float* out, int64_t M, int N, int chunks, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(M > 0 && N > 0 && chunks >= 1 && chunks <= 65535 && in && partial && out, "fz_colsum_bf16: bad arguments");
+  const int rows_per_chunk = static_cast<int>((M + chunks - 1) / chunks);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  colsum_partial_kernel<<<dim3((N + 31) / 32, chunks), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), partial, M, N,
+                                                                      rows_per_chunk);
+  colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, out, N, chunks);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,110 @@
+"""Training-mode forward and backward of one ConvNeXt-V2 block (first slice of the model backward):
+
+    x -> dwconv7x7 (+b) -> LayerNorm(1e-6) -> fc1 -> GELU(erf) -> GRN -> fc2 -> + x         (timm ConvNeXtBlock, use_grn)
+
+Parameters in the reference's layout (``conv_dw.{weight,bias}``, ``norm.{weight,bias}``, ``mlp.fc1/fc2.{weight,bias}``,
+``mlp.grn.{weight,bias}``); activations NHWC, fp32 residual stream, bf16 GEMM operands with fp32 accumulation -- the same
+number formats as the inference engine.  The Linear layers and their gradients run on the tcgen05 GEMM
+(``native.gemm_bf16`` / ``native.linear_backward``); everything else is csrc/backward_ops.cu.  Correctness first: these
+kernels are not tuned and the block is not yet wired into a model-level backward (decoder, BatchNorm in training mode, stem
+and downsample layers are still missing)."""
+from typing import Dict
+
+import torch
+
+from .. import native as nv
+
+_L = nv.lib
+_P = nv._ptr
+_S = nv._stream
+
+
+def _chk(rc: int, what: str) -> None:
+    nv._check(rc, what)
+
+
+class ConvNeXtBlockTrain:
+    def __init__(self, params: Dict[str, torch.Tensor], eps_ln: float = 1e-6, eps_grn: float = 1e-6):
+        dev = params["conv_dw.weight"].device
+        if dev.type != "cuda":
+            raise nv.NativeError("ConvNeXtBlockTrain runs on CUDA only (no CPU fallback)")
+        C = params["conv_dw.weight"].shape[0]
+        self.C, self.eps_ln, self.eps_grn = C, eps_ln, eps_grn
+        f32 = lambda t: t.detach().float().contiguous()
+        self.w_dw = f32(params["conv_dw.weight"].reshape(C, 49).t())            # [49][C]
+        self.b_dw = f32(params["conv_dw.bias"])
+        self.ln_w, self.ln_b = f32(params["norm.weight"]), f32(params["norm.bias"])
+        self.w1 = params["mlp.fc1.weight"].detach().to(torch.bfloat16).contiguous()      # [4C][C]
+        self.b1 = f32(params["mlp.fc1.bias"])
+        self.grn_w, self.grn_b = f32(params["mlp.grn.weight"]), f32(params["mlp.grn.bias"])
+        self.w2 = params["mlp.fc2.weight"].detach().to(torch.bfloat16).contiguous()      # [C][4C]
+        self.b2 = f32(params["mlp.fc2.bias"])
+        self.saved = None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x fp32 [B,H,W,C] -> y fp32 [B,H,W,C]; keeps what backward() needs."""
+        B, H, W, C = x.shape
+        M, C4, dev = B * H * W, 4 * C, x.device
+        x = x.contiguous()
+        u = torch.empty_like(x)
+        _chk(_L().fz_dwconv7_f32(_P(x), _P(self.w_dw), _P(self.b_dw), _P(u), B, H, W, C, 0, _S()), "fz_dwconv7_f32")
+        a1 = torch.empty((M, C), dtype=torch.bfloat16, device=dev)
+        mean = torch.empty(M, dtype=torch.float32, device=dev)
+        rstd = torch.empty(M, dtype=torch.float32, device=dev)
+        _chk(_L().fz_layernorm_fwd_stats(_P(u), _P(self.ln_w), _P(self.ln_b), _P(a1), _P(mean), _P(rstd), M, C, self.eps_ln,
+                                         _S()), "fz_layernorm_fwd_stats")
+        h = nv.gemm_bf16(a1, self.w1, nv.EPI_BF16, bias=self.b1)                          # pre-GELU, bf16 [M,4C]
+        g = torch.empty_like(h)
+        _chk(_L().fz_gelu_fwd(_P(h), _P(g), h.numel(), _S()), "fz_gelu_fwd")
+        sumsq = torch.empty((B, C4), dtype=torch.float32, device=dev)
+        _chk(_L().fz_sample_colreduce(_P(g), None, _P(sumsq), B, H * W, C4, 0, _S()), "fz_sample_colreduce")
+        gx, nx = torch.empty_like(sumsq), torch.empty_like(sumsq)
+        mu = torch.empty(B, dtype=torch.float32, device=dev)
+        a2 = torch.empty_like(g)
+        _chk(_L().fz_grn_train_forward(_P(g), _P(sumsq), _P(self.grn_w), _P(self.grn_b), _P(gx), _P(nx), _P(mu), _P(a2), B,
+                                       H * W, C4, self.eps_grn, _S()), "fz_grn_train_forward")
+        y = nv.gemm_bf16(a2, self.w2, nv.EPI_RESID_F32, bias=self.b2, resid=x.view(M, C))
+        self.saved = (x, u, a1, mean, rstd, h, g, gx, nx, mu, a2)
+        return y.view(B, H, W, C)
+
+    def backward(self, dy: torch.Tensor):
+        """dy fp32 [B,H,W,C] -> (dx fp32 [B,H,W,C], {parameter name: gradient in the parameter's own shape})."""
+        if self.saved is None:
+            raise RuntimeError("backward() before forward()")
+        x, u, a1, mean, rstd, h, g, gx, nx, mu, a2 = self.saved
+        B, H, W, C = x.shape
+        M, C4, dev = B * H * W, 4 * C, x.device
+        dy = dy.contiguous()
+        dyb = torch.empty((M, C), dtype=torch.bfloat16, device=dev)
+        nv.cast_f32_bf16(dy.view(M, C), dyb)
+        da2, dw2, db2 = nv.linear_backward(dyb, a2, self.w2)                              # fc2
+        s1 = torch.empty((B, C4), dtype=torch.float32, device=dev)
+        s0 = torch.empty_like(s1)
+        _chk(_L().fz_sample_colreduce(_P(da2), _P(g), _P(s1), B, H * W, C4, 1, _S()), "fz_sample_colreduce")
+        _chk(_L().fz_sample_colreduce(_P(da2), None, _P(s0), B, H * W, C4, 2, _S()), "fz_sample_colreduce")
+        ca, cb = torch.empty_like(s1), torch.empty_like(s1)
+        dgrn_w = torch.empty(C4, dtype=torch.float32, device=dev)
+        dgrn_b = torch.empty_like(dgrn_w)
+        dh = torch.empty_like(h)
+        _chk(_L().fz_grn_gelu_backward(_P(da2), _P(g), _P(h), _P(s1), _P(s0), _P(gx), _P(nx), _P(mu), _P(self.grn_w), _P(ca),
+                                       _P(cb), _P(dgrn_w), _P(dgrn_b), _P(dh), B, H * W, C4, self.eps_grn, _S()),
+             "fz_grn_gelu_backward")
+        da1, dw1, db1 = nv.linear_backward(dh, a1, self.w1)                               # fc1
+        blocks = max(1, min(592, (M + 7) // 8))
+        du = torch.empty_like(u)
+        partial = torch.empty((blocks, 2, C), dtype=torch.float32, device=dev)
+        dln = torch.empty((2, C), dtype=torch.float32, device=dev)
+        _chk(_L().fz_layernorm_bwd(_P(da1), _P(u), _P(mean), _P(rstd), _P(self.ln_w), _P(du), _P(partial), _P(dln), M, C,
+                                   blocks, _S()), "fz_layernorm_bwd")
+        dconv = torch.empty_like(x)
+        _chk(_L().fz_dwconv7_f32(_P(du), _P(self.w_dw), None, _P(dconv), B, H, W, C, 1, _S()), "fz_dwconv7_f32")
+        dw_dw = torch.empty((49, C), dtype=torch.float32, device=dev)
+        db_dw = torch.empty(C, dtype=torch.float32, device=dev)
+        _chk(_L().fz_dwconv7_wgrad(_P(x), _P(du), _P(dw_dw), _P(db_dw), B, H, W, C, _S()), "fz_dwconv7_wgrad")
+        dx = torch.empty_like(x)
+        _chk(_L().fz_add_f32(_P(dy), _P(dconv), _P(dx), dx.numel(), _S()), "fz_add_f32")
+        grads = {"conv_dw.weight": dw_dw.t().reshape(C, 1, 7, 7), "conv_dw.bias": db_dw,
+                 "norm.weight": dln[0], "norm.bias": dln[1],
+                 "mlp.fc1.weight": dw1, "mlp.fc1.bias": db1, "mlp.grn.weight": dgrn_w, "mlp.grn.bias": dgrn_b,
+                 "mlp.fc2.weight": dw2, "mlp.fc2.bias": db2}
+        return dx, grads

@@ -105,6 +105,17 @@ _SIGNATURES = {
     "fz_ce_loss_backward": [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _i, _i, _i, _i, _vp],
     "fz_adamw_step": [_vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                       ctypes.c_double, _i, _vp],
+    "fz_transpose_bf16": [_vp, _vp, _i, _i, _vp],
+    "fz_colsum_bf16": [_vp, _vp, _vp, _i64, _i, _i, _vp],
+    "fz_dwconv7_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_dwconv7_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_layernorm_fwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
+    "fz_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
+    "fz_gelu_fwd": [_vp, _vp, _i64, _vp],
+    "fz_sample_colreduce": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_grn_gelu_backward": [_vp] * 14 + [_i, _i, _i, ctypes.c_float, _vp],
+    "fz_add_f32": [_vp, _vp, _vp, _i64, _vp],
     "fz_head_upsample4": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"fz_last_error": ctypes.c_char_p, "fz_ce_workspace_doubles": ctypes.c_int64}
@@ -606,3 +617,36 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
         _check(lib().fz_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
                                    float(beta1), float(beta2), float(eps), float(weight_decay), int(step), _stream()),
                "fz_adamw_step")
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    """bf16 [R,C] -> contiguous bf16 [C,R]."""
+    if x.dtype != torch.bfloat16 or x.dim() != 2:
+        raise NativeError("transpose_bf16: bf16 [R,C] required")
+    R, C = x.shape
+    out = torch.empty((C, R), dtype=torch.bfloat16, device=x.device)
+    with _Timed("transpose_bf16", R=R, C=C):
+        _check(lib().fz_transpose_bf16(_ptr(x), _ptr(out), R, C, _stream()), "fz_transpose_bf16")
+    return out
+
+
+def colsum_bf16(x: torch.Tensor, chunks: int = 64) -> torch.Tensor:
+    """bf16 [M,N] -> float32 [N] column sums (deterministic two-stage reduction)."""
+    M, N = x.shape
+    chunks = max(1, min(chunks, M))
+    partial = torch.empty((chunks, N), dtype=torch.float32, device=x.device)
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    _check(lib().fz_colsum_bf16(_ptr(x), _ptr(partial), _ptr(out), M, N, chunks, _stream()), "fz_colsum_bf16")
+    return out
+
+
+def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
+    """Gradients of Y = X W^T + b (X bf16 [M,K], W bf16 [N,K], dY bf16 [M,N]) on the tcgen05 GEMM:
+    dX = dY W (bf16 [M,K]), dW = dY^T X (fp32 [N,K], fp32 accumulation over all M rows), db = column sums of dY."""
+    M, N = dY.shape
+    K = X.shape[1]
+    if X.shape[0] != M or tuple(W.shape) != (N, K):
+        raise NativeError("linear_backward: shape mismatch")
+    dX = gemm_bf16(dY, transpose_bf16(W), EPI_BF16)                               # [M,N] x [K,N]^T
+    dW = gemm_bf16(transpose_bf16(dY), transpose_bf16(X), EPI_F32)                # [N,M] x [K,M]^T
+    return dX, dW, colsum_bf16(dY)

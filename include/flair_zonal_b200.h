@@ -304,6 +304,40 @@ int fz_ce_loss_backward(const float* logits, const int32_t* targets, const float
 int fz_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, int step, void* stream);
 
+/* First building blocks of the model backward (a Linear layer's gradients through the K-major tcgen05 GEMM):
+ * out bf16 [C][R] = in bf16 [R][C]^T (R <= 2 097 120 rows per call); out float [N] = column sums of in bf16 [M][N]
+ * (bias gradient; partial = float [chunks][N] workspace, fixed summation order). */
+int fz_transpose_bf16(const void* in, void* out, int R, int C, void* stream);
+int fz_colsum_bf16(const void* in, float* partial, float* out, int64_t M, int N, int chunks, void* stream);
+
+/* ---- backward of one ConvNeXt-V2 block (flair_model.py:376 -> timm ConvNeXtBlock: dwconv7x7 -> LN -> fc1 -> GELU -> GRN ->
+ * fc2 -> + x), first slice of the model backward; correctness-first kernels (csrc/backward_ops.cu), the Linear layers go
+ * through fz_gemm_bf16 / the transposes above.  All activations NHWC = rows [B*H*W][C]. ----
+ * depthwise 7x7 in fp32: out = bias + sum_k in(shifted) * w[k][c]; flip = 1 uses w[48-k] (= the data gradient). */
+int fz_dwconv7_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C, int flip,
+                   void* stream);
+/* dw float [49][C], db float [C]: gradients of the depthwise weights / bias from x and the output gradient du. */
+int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, float* db, int B, int H, int W, int C, void* stream);
+/* LayerNorm over C with saved row statistics (training forward), and its backward: dx float [M][C]; dgamma_dbeta float [2][C]
+ * (partial = float [blocks][2][C] workspace; blocks fixes the reduction order). */
+int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, float* mean, float* rstd,
+                           int64_t M, int C, float eps, void* stream);
+int fz_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* g, float* dx,
+                     float* partial, float* dgamma_dbeta, int64_t M, int C, int blocks, void* stream);
+/* exact (erf) GELU on bf16. */
+int fz_gelu_fwd(const void* h_bf16, void* g_bf16, int64_t n, void* stream);
+/* out float [B][C] = sum over a sample's HW rows of a*a (mode 0), a*b (1) or a (2); a, b bf16 [B][HW][C]. */
+int fz_sample_colreduce(const void* a_bf16, const void* b_bf16, float* out, int B, int HW, int C, int mode, void* stream);
+/* GRN, training forward: gx = sqrt(sumsq), mu = mean_c gx, nx = gx / (mu + eps), y = g (1 + gamma nx) + beta. */
+int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* gamma, const float* beta, float* gx, float* nx,
+                         float* mu, void* y_bf16, int B, int HW, int C, float eps, void* stream);
+/* GRN + GELU backward: dy = gradient at the GRN output, g = GELU(h), s1 = sum_hw dy g, s0 = sum_hw dy (fz_sample_colreduce);
+ * dh bf16 = gradient at the pre-GELU activations; dgamma / dbeta float [C]; coef_a / coef_b float [B][C] workspaces. */
+int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1, const float* s0,
+                         const float* gx, const float* nx, const float* mu, const float* gamma, float* coef_a, float* coef_b,
+                         float* dgamma, float* dbeta, void* dh_bf16, int B, int HW, int C, float eps, void* stream);
+int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,3 +152,25 @@ def test_validation_step_against_the_oracle(cuda, tmp_path):
     grads = task.loss_gradients()[TASK]
     assert tuple(grads.shape) == (2, 19, 512, 512) and bool(torch.isfinite(grads).all())
     assert abs(float(grads.sum())) < 1e-3                                     # softmax - onehot sums to zero per pixel
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 128), (16384, 2048, 512), (1024, 128, 512), (640, 64, 64)])
+def test_linear_backward(cuda, M, N, K):
+    """dX, dW, db of a Linear layer (the ConvNeXt MLPs, 1x1 convolutions, fusion conv_f) on the tcgen05 GEMM through explicit
+    operand transposes, vs fp32 matmuls of the same bf16 operands: dX within bf16 rounding, dW / db fp32-accumulated."""
+    from flair_for_aigle_b200 import native as nv
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    X = torch.randn(M, K, generator=g).bfloat16().to(cuda)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(cuda)
+    dY = torch.randn(M, N, generator=g).bfloat16().to(cuda)
+    assert torch.equal(nv.transpose_bf16(X), X.t().contiguous())
+    dX, dW, db = nv.linear_backward(dY, X, W)
+    rX = dY.float() @ W.float()
+    rW = dY.float().t() @ X.float()
+    rb = dY.float().sum(0)
+    assert float((dX.float() - rX).abs().max()) <= 1e-2 * float(rX.abs().max())
+    assert float((dW - rW).abs().max()) <= 2e-3 * float(rW.abs().max())
+    assert float((db - rb).abs().max()) <= 1e-4 * max(1.0, float(rb.abs().max()))
+    dX2, dW2, db2 = nv.linear_backward(dY, X, W)
+    assert torch.equal(dW, dW2) and torch.equal(db, db2) and torch.equal(dX, dX2)      # deterministic
