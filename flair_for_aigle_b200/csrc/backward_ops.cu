@@ -78,8 +78,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // one warp per row: out = (x - mean) * rstd * g + b (bf16), mean / rstd saved
 __global__ void __launch_bounds__(256) ln_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                            const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
-                                                           float* __restrict__ mean, float* __restrict__ rstd, int64_t M,
-                                                           int C, float eps) {
+                                                           float* __restrict__ out_f32, float* __restrict__ mean,
+                                                           float* __restrict__ rstd, int64_t M, int C, float eps) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= M) return;
@@ -93,7 +93,11 @@ __global__ void __launch_bounds__(256) ln_fwd_stats_kernel(const float* __restri
     v += d * d;
   }
   const float rs = rsqrtf(warp_sum(v) / C + eps);
-  for (int c = lane; c < C; c += 32) out[r * C + c] = __float2bfloat16_rn((row[c] - mu) * rs * g[c] + b[c]);
+  for (int c = lane; c < C; c += 32) {
+    const float v2 = (row[c] - mu) * rs * g[c] + b[c];
+    if (out) out[r * C + c] = __float2bfloat16_rn(v2);
+    if (out_f32) out_f32[r * C + c] = v2;
+  }
   if (lane == 0) {
     mean[r] = mu;
     rstd[r] = rs;
@@ -273,6 +277,39 @@ __global__ void __launch_bounds__(256) add_f32_kernel(const float* __restrict__ 
   if (i < n) out[i] = a[i] + b[i];
 }
 
+// space-to-depth for a k x k / stride k convolution as a GEMM: out[b][y/s][x/s][(ky*s + kx)*C + c] = in[b][y][x][c]
+// (inverse: the same index map read the other way -- the data gradient of the gather)
+__global__ void __launch_bounds__(256) s2d_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                       int H, int W, int C, int s, int inverse, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;      // index into the [B][H][W][C] side
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const int64_t px = i / C;
+  const int x = static_cast<int>(px % W), y = static_cast<int>((px / W) % H);
+  const int64_t b = px / (static_cast<int64_t>(W) * H);
+  const int64_t j = (((b * (H / s) + y / s) * (W / s) + x / s) * (s * s) + (y % s) * s + (x % s)) * C + c;
+  if (inverse) out[i] = in[j];
+  else out[j] = in[i];
+}
+
+// stem patches: out bf16 [B*(P/4)^2][Kpad], k = (c*4 + ky)*4 + kx (the flattening of a [Cout][Cin][4][4] weight), zero padded
+__global__ void __launch_bounds__(256) patchify4_nchw_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                             int Cin, int P, int Kpad, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;      // over rows * Kpad
+  if (i >= n) return;
+  const int k = static_cast<int>(i % Kpad);
+  const int64_t row = i / Kpad;
+  const int q = P / 4;
+  const int px = static_cast<int>(row % q), py = static_cast<int>((row / q) % q);
+  const int64_t b = row / (static_cast<int64_t>(q) * q);
+  float v = 0.f;
+  if (k < Cin * 16) {
+    const int c = k / 16, ky = (k / 4) % 4, kx = k % 4;
+    v = in[((b * Cin + c) * P + py * 4 + ky) * P + px * 4 + kx];
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
 static inline unsigned blocks_for(int64_t n) { return static_cast<unsigned>((n + 255) / 256); }
 
 }  // namespace fz
@@ -302,8 +339,8 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
 extern "C" int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, float* mean, float* rstd,
                                       int64_t M, int C, float eps, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && x && g && b && out_bf16 && mean && rstd, "fz_layernorm_fwd_stats: bad arguments");
-  ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16), mean,
-                                                                                 rstd, M, C, eps);
+  ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
+                                                                                 nullptr, mean, rstd, M, C, eps);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -369,6 +406,32 @@ extern "C" int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, con
 extern "C" int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
   FZ_REQUIRE(n > 0 && a && b && out, "fz_add_f32: bad arguments");
   add_f32_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(a, b, out, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_layernorm_fwd_stats2(const float* x, const float* g, const float* b, void* out_bf16, float* out_f32,
+                                       float* mean, float* rstd, int64_t M, int C, float eps, void* stream) {
+  FZ_REQUIRE(M > 0 && C > 0 && x && g && b && (out_bf16 || out_f32) && mean && rstd, "fz_layernorm_fwd_stats2: bad arguments");
+  ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
+                                                                                 out_f32, mean, rstd, M, C, eps);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_s2d_bf16(const void* in, void* out, int B, int H, int W, int C, int s, int inverse, void* stream) {
+  FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && s >= 1 && H % s == 0 && W % s == 0 && in && out, "fz_s2d_bf16: bad arguments");
+  const int64_t n = static_cast<int64_t>(B) * H * W * C;
+  s2d_bf16_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(in), reinterpret_cast<bf>(out), H, W, C, s,
+                                                         inverse, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin, int P, int Kpad, void* stream) {
+  FZ_REQUIRE(B > 0 && Cin > 0 && P > 0 && P % 4 == 0 && Kpad >= Cin * 16 && in && out_bf16, "fz_patchify4_nchw: bad arguments");
+  const int64_t n = static_cast<int64_t>(B) * (P / 4) * (P / 4) * Kpad;
+  patchify4_nchw_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(in, reinterpret_cast<bf>(out_bf16), Cin, P, Kpad, n);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -108,3 +108,138 @@ class ConvNeXtBlockTrain:
                  "mlp.fc1.weight": dw1, "mlp.fc1.bias": db1, "mlp.grn.weight": dgrn_w, "mlp.grn.bias": dgrn_b,
                  "mlp.fc2.weight": dw2, "mlp.fc2.bias": db2}
         return dx, grads
+
+
+class _LayerNormTrain:
+    """LayerNorm over C of [M,C] fp32 rows with saved statistics; bf16 and/or fp32 output."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6):
+        self.w, self.b, self.eps = weight.detach().float().contiguous(), bias.detach().float().contiguous(), eps
+        self.saved = None
+
+    def forward(self, x: torch.Tensor, want_bf16: bool, want_f32: bool):
+        M, C = x.shape
+        dev = x.device
+        ob = torch.empty((M, C), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+        of = torch.empty((M, C), dtype=torch.float32, device=dev) if want_f32 else None
+        mean = torch.empty(M, dtype=torch.float32, device=dev)
+        rstd = torch.empty(M, dtype=torch.float32, device=dev)
+        _chk(_L().fz_layernorm_fwd_stats2(_P(x), _P(self.w), _P(self.b), _P(ob), _P(of), _P(mean), _P(rstd), M, C, self.eps,
+                                          _S()), "fz_layernorm_fwd_stats2")
+        self.saved = (x, mean, rstd)
+        return ob, of
+
+    def backward(self, dy_bf16: torch.Tensor):
+        """dy bf16 [M,C] -> (dx fp32 [M,C], dweight [C], dbias [C])."""
+        x, mean, rstd = self.saved
+        M, C = x.shape
+        blocks = max(1, min(592, (M + 7) // 8))
+        dx = torch.empty_like(x)
+        partial = torch.empty((blocks, 2, C), dtype=torch.float32, device=x.device)
+        d = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        _chk(_L().fz_layernorm_bwd(_P(dy_bf16), _P(x), _P(mean), _P(rstd), _P(self.w), _P(dx), _P(partial), _P(d), M, C,
+                                   blocks, _S()), "fz_layernorm_bwd")
+        return dx, d[0], d[1]
+
+
+def _to_bf16(x_f32: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(x_f32.shape, dtype=torch.bfloat16, device=x_f32.device)
+    nv.cast_f32_bf16(x_f32, out)
+    return out
+
+
+class ConvNeXtV2EncoderTrain:
+    """Training forward + backward of the whole ConvNeXt-V2 feature extractor (timm ``convnextv2_*`` under smp's
+    TimmUniversalEncoder: ``stem_0`` conv4x4/s4, ``stem_1`` LayerNorm2d, ``stages_i.downsample.{0,1}`` LayerNorm2d + conv2x2/s2,
+    ``stages_i.blocks.j``): fp32 NCHW normalised tiles in, the four stage outputs (fp32 NHWC) out; ``backward`` takes the
+    gradients at the four outputs and returns every parameter's gradient under the reference's state_dict keys."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], depths, dims):
+        self.depths, self.dims = tuple(depths), tuple(dims)
+        w = params["stem_0.weight"]
+        self.cin = w.shape[1]
+        self.kpad = ((self.cin * 16 + 63) // 64) * 64
+        dev = w.device
+        w2 = torch.zeros((dims[0], self.kpad), dtype=torch.bfloat16, device=dev)
+        w2[:, :self.cin * 16] = w.detach().reshape(dims[0], -1).to(torch.bfloat16)
+        self.stem_w, self.stem_b = w2.contiguous(), params["stem_0.bias"].detach().float().contiguous()
+        self.stem_ln = _LayerNormTrain(params["stem_1.weight"], params["stem_1.bias"])
+        self.down, self.blocks = [], []
+        for i, (d, c) in enumerate(zip(depths, dims)):
+            if i > 0:
+                p = f"stages_{i}.downsample."
+                wd = params[p + "1.weight"].detach()                                  # [c, c_prev, 2, 2]
+                self.down.append((_LayerNormTrain(params[p + "0.weight"], params[p + "0.bias"]),
+                                  wd.permute(0, 2, 3, 1).reshape(c, -1).to(torch.bfloat16).contiguous(),
+                                  params[p + "1.bias"].detach().float().contiguous()))
+            else:
+                self.down.append(None)
+            self.blocks.append([ConvNeXtBlockTrain({k[len(f"stages_{i}.blocks.{j}."):]: v for k, v in params.items()
+                                                    if k.startswith(f"stages_{i}.blocks.{j}.")}) for j in range(d)])
+        self.saved = None
+
+    def forward(self, x_nchw: torch.Tensor):
+        B, Cin, P, _ = x_nchw.shape
+        dev = x_nchw.device
+        q = P // 4
+        patches = torch.empty((B * q * q, self.kpad), dtype=torch.bfloat16, device=dev)
+        _chk(_L().fz_patchify4_nchw(_P(x_nchw.float().contiguous()), _P(patches), B, Cin, P, self.kpad, _S()),
+             "fz_patchify4_nchw")
+        u0 = nv.gemm_bf16(patches, self.stem_w, nv.EPI_F32, bias=self.stem_b)             # conv4x4/s4 as a GEMM, fp32
+        _, x = self.stem_ln.forward(u0, want_bf16=False, want_f32=True)
+        h = q
+        feats, geo = [], []
+        for i, c in enumerate(self.dims):
+            if i > 0:
+                ln, wd, bd = self.down[i]
+                cp = self.dims[i - 1]
+                a, _ = ln.forward(x.view(-1, cp), want_bf16=True, want_f32=False)
+                a4 = torch.empty((B * (h // 2) * (h // 2), 4 * cp), dtype=torch.bfloat16, device=dev)
+                _chk(_L().fz_s2d_bf16(_P(a), _P(a4), B, h, h, cp, 2, 0, _S()), "fz_s2d_bf16")
+                geo.append((h, cp, a4))
+                h //= 2
+                x = nv.gemm_bf16(a4, wd, nv.EPI_F32, bias=bd)
+            else:
+                geo.append(None)
+            x = x.view(B, h, h, c)
+            for blk in self.blocks[i]:
+                x = blk.forward(x)
+            feats.append(x)
+        self.saved = (B, patches, geo)
+        return feats
+
+    def backward(self, dfeats):
+        B, patches, geo = self.saved
+        grads: Dict[str, torch.Tensor] = {}
+        d = None
+        for i in reversed(range(len(self.dims))):
+            c = self.dims[i]
+            df = dfeats[i].contiguous()
+            if d is None:
+                d = df
+            else:
+                s = torch.empty_like(df)
+                _chk(_L().fz_add_f32(_P(d.contiguous()), _P(df), _P(s), s.numel(), _S()), "fz_add_f32")
+                d = s
+            for j in reversed(range(self.depths[i])):
+                d, g = self.blocks[i][j].backward(d)
+                for k, v in g.items():
+                    grads[f"stages_{i}.blocks.{j}.{k}"] = v
+            if i > 0:
+                ln, wd, bd = self.down[i]
+                h, cp, a4 = geo[i]
+                da4, dw, db = nv.linear_backward(_to_bf16(d.view(-1, c)), a4, wd)
+                grads[f"stages_{i}.downsample.1.weight"] = dw.view(c, 2, 2, cp).permute(0, 3, 1, 2).contiguous()
+                grads[f"stages_{i}.downsample.1.bias"] = db
+                da = torch.empty((B * h * h, cp), dtype=torch.bfloat16, device=da4.device)
+                _chk(_L().fz_s2d_bf16(_P(da4), _P(da), B, h, h, cp, 2, 1, _S()), "fz_s2d_bf16")
+                dx, dg, dbeta = ln.backward(da)
+                grads[f"stages_{i}.downsample.0.weight"], grads[f"stages_{i}.downsample.0.bias"] = dg, dbeta
+                d = dx.view(B, h, h, cp)
+        du0, dg, dbeta = self.stem_ln.backward(_to_bf16(d.view(-1, self.dims[0])))
+        grads["stem_1.weight"], grads["stem_1.bias"] = dg, dbeta
+        du0b = _to_bf16(du0)
+        dw = nv.gemm_bf16(nv.transpose_bf16(du0b), nv.transpose_bf16(patches), nv.EPI_F32)   # [C0, Kpad]
+        grads["stem_0.weight"] = dw[:, :self.cin * 16].reshape(self.dims[0], self.cin, 4, 4).contiguous()
+        grads["stem_0.bias"] = nv.colsum_bf16(du0b)
+        return grads

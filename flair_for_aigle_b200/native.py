@@ -116,6 +116,9 @@ _SIGNATURES = {
     "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_gelu_backward": [_vp] * 14 + [_i, _i, _i, ctypes.c_float, _vp],
     "fz_add_f32": [_vp, _vp, _vp, _i64, _vp],
+    "fz_layernorm_fwd_stats2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
+    "fz_s2d_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_patchify4_nchw": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fz_head_upsample4": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"fz_last_error": ctypes.c_char_p, "fz_ce_workspace_doubles": ctypes.c_int64}
@@ -648,5 +651,13 @@ def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
     if X.shape[0] != M or tuple(W.shape) != (N, K):
         raise NativeError("linear_backward: shape mismatch")
     dX = gemm_bf16(dY, transpose_bf16(W), EPI_BF16)                               # [M,N] x [K,N]^T
-    dW = gemm_bf16(transpose_bf16(dY), transpose_bf16(X), EPI_F32)                # [N,M] x [K,M]^T
+    if M % 64:                                                                    # the GEMM's reduction length is a multiple of 64
+        Mp = (M + 63) // 64 * 64
+        dYp = torch.zeros((Mp, N), dtype=dY.dtype, device=dY.device)
+        Xp = torch.zeros((Mp, K), dtype=X.dtype, device=X.device)
+        dYp[:M].copy_(dY)
+        Xp[:M].copy_(X)
+        dW = gemm_bf16(transpose_bf16(dYp), transpose_bf16(Xp), EPI_F32)
+    else:
+        dW = gemm_bf16(transpose_bf16(dY), transpose_bf16(X), EPI_F32)            # [N,M] x [K,M]^T
     return dX, dW, colsum_bf16(dY)

@@ -337,6 +337,14 @@ int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_
                          const float* gx, const float* nx, const float* mu, const float* gamma, float* coef_a, float* coef_b,
                          float* dgamma, float* dbeta, void* dh_bf16, int B, int HW, int C, float eps, void* stream);
 int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* Encoder plumbing of the same slice: LayerNorm with a bf16 and / or an fp32 output (LayerNorm2d of the stem feeds the fp32
+ * residual stream, the one in front of a downsample conv feeds a GEMM); space-to-depth for the 2x2/s2 convolutions as GEMMs,
+ * k = (ky*s + kx)*C + c, and its inverse (inverse = 1: `in` is the [B][H/s][W/s][s*s*C] side); the stem's 4x4/s4 patches of a
+ * normalised fp32 NCHW tile as bf16 rows [B*(P/4)^2][Kpad], k = (c*4 + ky)*4 + kx, zero padded to Kpad. */
+int fz_layernorm_fwd_stats2(const float* x, const float* g, const float* b, void* out_bf16, float* out_f32, float* mean,
+                            float* rstd, int64_t M, int C, float eps, void* stream);
+int fz_s2d_bf16(const void* in, void* out, int B, int H, int W, int C, int s, int inverse, void* stream);
+int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin, int P, int Kpad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,3 +65,51 @@ def test_convnext_block_forward_backward_vs_autograd(cuda, B, H, C):
     dx2, grads2 = eng.backward(dy)
     assert torch.equal(y, y2) and torch.equal(dx, dx2)
     assert all(torch.equal(grads[k], grads2[k]) for k in grads)
+
+
+@pytest.mark.parametrize("depths,B,P,cin", [((1, 1, 2, 1), 2, 128, 4), ((3, 3, 27, 3), 1, 128, 1)])
+def test_convnext_encoder_backward_vs_autograd(cuda, depths, B, P, cin):
+    """The whole ConvNeXt-V2 feature extractor (stem, 4 stages, downsample layers; base widths, the second case with the real
+    base depths and the 1-channel elevation stem): gradients of every parameter for a loss that touches all four outputs."""
+    from oracle.models import ConvNeXtV2Features
+    from flair_for_aigle_b200.engine.convnext_train import ConvNeXtV2EncoderTrain
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dims = (128, 256, 512, 1024)
+    torch.manual_seed(sum(depths) + cin)
+    enc = ConvNeXtV2Features(cin, depths, dims)
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if "grn" in n:
+                p.copy_(torch.randn_like(p) * 0.3)
+            elif n.endswith("norm.weight") or n.endswith("stem_1.weight") or n.endswith("downsample.0.weight"):
+                p.copy_(1.0 + 0.1 * torch.randn_like(p))
+            elif p.dim() == 1:
+                p.copy_(0.05 * torch.randn_like(p))
+            else:
+                fan_in = p[0].numel()
+                p.copy_(torch.randn_like(p) / fan_in ** 0.5)
+            p.copy_(p.bfloat16().float())
+    enc = enc.to(cuda)
+    x = torch.randn(B, cin, P, P, device=cuda)
+    feats_ref = enc(x)
+    dfe = [torch.randn_like(f) / f[0].numel() ** 0.5 for f in feats_ref]           # NCHW
+    torch.autograd.backward(feats_ref, dfe)
+
+    eng = ConvNeXtV2EncoderTrain({n: p.detach() for n, p in enc.named_parameters()}, depths, dims)
+    feats = eng.forward(x)
+    for f, r in zip(feats, feats_ref):
+        cos, err = _rel(f, r.detach().permute(0, 2, 3, 1))
+        assert cos > 0.999 and err < 6e-2, (cos, err)
+    grads = eng.backward([d.permute(0, 2, 3, 1).contiguous() for d in dfe])
+    torch.cuda.synchronize()
+    worst = (1.0, "", 0.0)
+    names = [n for n, _ in enc.named_parameters()]
+    assert sorted(grads) == sorted(names)
+    for n, p in enc.named_parameters():
+        cos, err = _rel(grads[n], p.grad)
+        if cos < worst[0]:
+            worst = (cos, n, err)
+        assert tuple(grads[n].shape) == tuple(p.grad.shape), n
+        assert cos > 0.99, (n, cos, err)
+    print(f"encoder depths {depths}: {len(names)} parameter gradients, worst cosine {worst[0]:.5f} at {worst[1]} (max rel err {worst[2]:.3f})")
