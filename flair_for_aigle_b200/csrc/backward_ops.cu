@@ -310,6 +310,143 @@ __global__ void __launch_bounds__(256) patchify4_nchw_kernel(const float* __rest
   out[i] = __float2bfloat16_rn(v);
 }
 
+// ------------------------------------------------------------------------------------------------ U-Net decoder
+// col[p][(ky*3+kx)*C + c] = in[p + (ky-1, kx-1)][c] (zero outside the image and in the K padding)
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ col,
+                                                        int H, int W, int C, int Kpad, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int k = static_cast<int>(i % Kpad);
+  const int64_t p = i / Kpad;
+  __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+  if (k < 9 * C) {
+    const int tap = k / C, c = k - tap * C, ky = tap / 3, kx = tap - ky * 3;
+    const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+    const int iy = y + ky - 1, ix = x + kx - 1;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in[(p + static_cast<int64_t>(ky - 1) * W + (kx - 1)) * C + c];
+  }
+  col[i] = v;
+}
+
+// dx[q][c] = sum_taps dcol[q - (ky-1, kx-1)][(ky*3+kx)*C + c]
+__global__ void __launch_bounds__(256) col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dx, int H,
+                                                        int W, int C, int Kpad, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const int64_t q = i / C;
+  const int x = static_cast<int>(q % W), y = static_cast<int>((q / W) % H);
+  float acc = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int py = y - (ky - 1), px = x - (kx - 1);
+      if (py >= 0 && py < H && px >= 0 && px < W)
+        acc += __bfloat162float(dcol[(q - static_cast<int64_t>(ky - 1) * W - (kx - 1)) * Kpad + (ky * 3 + kx) * C + c]);
+    }
+  dx[i] = acc;
+}
+
+// partial[s][0][c] = sum_rows f0, partial[s][1][c] = sum_rows f1 over row chunk s.   grid (C/32, chunks)
+//   mode 0 (BN forward, pass 1): f0 = x                      mode 1 (pass 2): f0 = (x - mean)^2
+//   mode 2 (BN+ReLU backward):   f0 = g, f1 = g * xhat with g = dy * (y > 0), xhat = (x - mean) * rstd
+__global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy,
+                                                         const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd, float* __restrict__ partial, int64_t M,
+                                                         int C, int rows_per_chunk, int mode) {
+  __shared__ float r0[8][32], r1[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk;
+  const int64_t m1 = m0 + rows_per_chunk < M ? m0 + rows_per_chunk : M;
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    const float mu = mode ? mean[c] : 0.f, rs = mode == 2 ? rstd[c] : 0.f;
+    for (int64_t m = m0 + ty; m < m1; m += 8) {
+      const float xv = x[m * ldx + c];
+      if (mode == 0) a += xv;
+      else if (mode == 1) a += (xv - mu) * (xv - mu);
+      else {
+        const float g = __bfloat162float(y[m * C + c]) > 0.f ? __bfloat162float(dy[m * C + c]) : 0.f;
+        a += g;
+        b += g * (xv - mu) * rs;
+      }
+    }
+  }
+  r0[ty][threadIdx.x & 31] = a;
+  r1[ty][threadIdx.x & 31] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      t0 += r0[j][threadIdx.x];
+      t1 += r1[j][threadIdx.x];
+    }
+    partial[(static_cast<size_t>(blockIdx.y) * 2) * C + c] = t0;
+    partial[(static_cast<size_t>(blockIdx.y) * 2 + 1) * C + c] = t1;
+  }
+}
+// mode 0: mean = sum / M; mode 1: rstd = rsqrt(sum / M + eps) (biased variance, what BatchNorm normalises with)
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ out, int C, float M,
+                                                          float eps, int mode) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) out[c] = mode == 0 ? sums[c] / M : rsqrtf(sums[c] / M + eps);
+}
+// y = relu((x - mean) * rstd * gamma + beta)
+__global__ void __launch_bounds__(256) bn_relu_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                            int C, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const int64_t m = i / C;
+  const float v = (x[m * ldx + c] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+  y[i] = __float2bfloat16_rn(v > 0.f ? v : 0.f);
+}
+// dx[m][c] = gamma * rstd * (g - dbeta / M - xhat * dgamma / M), written bf16 with row stride ldd (padding columns zero)
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __restrict__ x, int ldx,
+                                                                const __nv_bfloat16* __restrict__ dy,
+                                                                const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ dgb, __nv_bfloat16* __restrict__ dx,
+                                                                int ldd, int C, float invM, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;      // over M * ldd
+  if (i >= n) return;
+  const int c = static_cast<int>(i % ldd);
+  const int64_t m = i / ldd;
+  float v = 0.f;
+  if (c < C) {
+    const float g = __bfloat162float(y[m * C + c]) > 0.f ? __bfloat162float(dy[m * C + c]) : 0.f;
+    const float xh = (x[m * ldx + c] - mean[c]) * rstd[c];
+    v = gamma[c] * rstd[c] * (g - dgb[c] * invM - xh * dgb[C + c] * invM);      // dgb = [dbeta | dgamma]
+  }
+  dx[i] = __float2bfloat16_rn(v);
+}
+
+// nearest x2 upsample + concat, backward: da[b][y][x][c] = sum_{2x2} dcat[b][2y+i][2x+j][c] (c < C1);
+// dskip[b][Y][X][c] = dcat[b][Y][X][C1 + c]
+__global__ void __launch_bounds__(256) upcat_bwd_kernel(const float* __restrict__ dcat, float* __restrict__ da,
+                                                        float* __restrict__ dskip, int H, int W, int C1, int C2, int64_t n_a,
+                                                        int64_t n_s) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int CT = C1 + C2;
+  if (i < n_a) {
+    const int c = static_cast<int>(i % C1);
+    const int64_t p = i / C1;
+    const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+    const int64_t b = p / (static_cast<int64_t>(W) * H);
+    const int64_t base = ((b * 2 * H + 2 * y) * 2 * W + 2 * x) * CT + c;
+    da[i] = dcat[base] + dcat[base + CT] + dcat[base + static_cast<int64_t>(2 * W) * CT] +
+            dcat[base + static_cast<int64_t>(2 * W) * CT + CT];
+  } else if (i < n_a + n_s) {
+    const int64_t j = i - n_a;
+    const int c = static_cast<int>(j % C2);
+    dskip[j] = dcat[(j / C2) * CT + C1 + c];
+  }
+}
+
 static inline unsigned blocks_for(int64_t n) { return static_cast<unsigned>((n + 255) / 256); }
 
 }  // namespace fz
@@ -432,6 +569,74 @@ extern "C" int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin
   FZ_REQUIRE(B > 0 && Cin > 0 && P > 0 && P % 4 == 0 && Kpad >= Cin * 16 && in && out_bf16, "fz_patchify4_nchw: bad arguments");
   const int64_t n = static_cast<int64_t>(B) * (P / 4) * (P / 4) * Kpad;
   patchify4_nchw_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(in, reinterpret_cast<bf>(out_bf16), Cin, P, Kpad, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_im2col3x3_bf16(const void* in, void* col, int B, int H, int W, int C, int Kpad, void* stream) {
+  FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Kpad >= 9 * C && in && col, "fz_im2col3x3_bf16: bad arguments");
+  const int64_t n = static_cast<int64_t>(B) * H * W * Kpad;
+  im2col3x3_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(in), reinterpret_cast<bf>(col), H, W, C, Kpad, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_col2im3x3(const void* dcol_bf16, float* dx, int B, int H, int W, int C, int Kpad, void* stream) {
+  FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Kpad >= 9 * C && dcol_bf16 && dx, "fz_col2im3x3: bad arguments");
+  const int64_t n = static_cast<int64_t>(B) * H * W * C;
+  col2im3x3_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(dcol_bf16), dx, H, W, C, Kpad, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_bn_relu_train_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16,
+                                        float* mean, float* rstd, float* workspace, int64_t M, int C, int chunks, float eps,
+                                        void* stream) {
+  FZ_REQUIRE(M > 0 && C > 0 && ldx >= C && chunks >= 1 && chunks <= 65535 && x && gamma && beta && y_bf16 && mean && rstd &&
+                 workspace,
+             "fz_bn_relu_train_forward: bad arguments");
+  cudaStream_t st = ST(stream);
+  const int rpc = static_cast<int>((M + chunks - 1) / chunks);
+  float* partial = workspace;                                  // [chunks][2][C]
+  float* sums = workspace + static_cast<size_t>(chunks) * 2 * C;   // [2][C]
+  const dim3 grid((C + 31) / 32, chunks);
+  bn_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, partial, M, C, rpc, 0);
+  reduce_rows_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, sums, 2 * C, chunks);
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, mean, C, static_cast<float>(M), eps, 0);
+  bn_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, mean, nullptr, partial, M, C, rpc, 1);
+  reduce_rows_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, sums, 2 * C, chunks);
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, rstd, C, static_cast<float>(M), eps, 1);
+  const int64_t n = M * C;
+  bn_relu_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, reinterpret_cast<bf>(y_bf16), C, n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_bn_relu_backward(const float* x, int ldx, const void* dy_bf16, const void* y_bf16, const float* mean,
+                                   const float* rstd, const float* gamma, void* dx_bf16, int ldd, float* dbeta_dgamma,
+                                   float* workspace, int64_t M, int C, int chunks, void* stream) {
+  FZ_REQUIRE(M > 0 && C > 0 && ldx >= C && ldd >= C && chunks >= 1 && chunks <= 65535 && x && dy_bf16 && y_bf16 && mean && rstd &&
+                 gamma && dx_bf16 && dbeta_dgamma && workspace,
+             "fz_bn_relu_backward: bad arguments");
+  cudaStream_t st = ST(stream);
+  const int rpc = static_cast<int>((M + chunks - 1) / chunks);
+  bn_partial_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, st>>>(x, ldx, reinterpret_cast<cbf>(dy_bf16),
+                                                                 reinterpret_cast<cbf>(y_bf16), mean, rstd, workspace, M, C, rpc, 2);
+  reduce_rows_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(workspace, dbeta_dgamma, 2 * C, chunks);
+  const int64_t n = M * ldd;
+  bn_relu_bwd_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(y_bf16),
+                                                          mean, rstd, gamma, dbeta_dgamma, reinterpret_cast<bf>(dx_bf16), ldd, C,
+                                                          1.0f / static_cast<float>(M), n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_upsample2_concat_backward(const float* dcat, float* da, float* dskip, int B, int H, int W, int C1, int C2,
+                                            void* stream) {
+  FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0 && dcat && da && (C2 == 0 || dskip),
+             "fz_upsample2_concat_backward: bad arguments");
+  const int64_t n_a = static_cast<int64_t>(B) * H * W * C1, n_s = static_cast<int64_t>(B) * 4 * H * W * C2;
+  upcat_bwd_kernel<<<blocks_for(n_a + n_s), 256, 0, ST(stream)>>>(dcat, da, dskip, H, W, C1, C2, n_a, n_s);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -243,3 +243,132 @@ class ConvNeXtV2EncoderTrain:
         grads["stem_0.weight"] = dw[:, :self.cin * 16].reshape(self.dims[0], self.cin, 4, 4).contiguous()
         grads["stem_0.bias"] = nv.colsum_bf16(du0b)
         return grads
+
+
+def _ceil64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+class Conv3x3BnReluTrain:
+    """smp ``Conv2dReLU``: conv3x3 (no bias) -> BatchNorm2d with batch statistics -> ReLU, NHWC bf16 in / out.  The convolution
+    is a GEMM over an explicit im2col (correctness first); K and N are zero padded to the GEMM's multiples of 64.  With
+    ``bn=False`` it is the segmentation head: conv3x3 + bias, fp32 output, no normalisation."""
+
+    BN_EPS = 1e-5
+
+    def __init__(self, weight: torch.Tensor, bn_weight=None, bn_bias=None, bias=None):
+        self.cout, self.cin = weight.shape[0], weight.shape[1]
+        self.kpad, self.npad = _ceil64(9 * self.cin), _ceil64(self.cout)
+        dev = weight.device
+        w2 = torch.zeros((self.npad, self.kpad), dtype=torch.bfloat16, device=dev)
+        w2[:self.cout, :9 * self.cin] = weight.detach().permute(0, 2, 3, 1).reshape(self.cout, -1).to(torch.bfloat16)
+        self.w2 = w2.contiguous()
+        self.bn = bn_weight is not None
+        if self.bn:
+            self.g, self.b = bn_weight.detach().float().contiguous(), bn_bias.detach().float().contiguous()
+        else:
+            self.bias = torch.zeros(self.npad, dtype=torch.float32, device=dev)
+            self.bias[:self.cout] = bias.detach().float()
+        self.saved = None
+
+    def forward(self, x: torch.Tensor):
+        B, H, W, C = x.shape
+        M, dev = B * H * W, x.device
+        col = torch.empty((M, self.kpad), dtype=torch.bfloat16, device=dev)
+        _chk(_L().fz_im2col3x3_bf16(_P(x.contiguous()), _P(col), B, H, W, C, self.kpad, _S()), "fz_im2col3x3_bf16")
+        conv = nv.gemm_bf16(col, self.w2, nv.EPI_F32, bias=None if self.bn else self.bias)      # fp32 [M, npad]
+        if not self.bn:
+            self.saved = (col, (B, H, W))
+            return conv.view(B, H, W, self.npad)
+        chunks = max(1, min(256, M // 64))
+        y = torch.empty((M, self.cout), dtype=torch.bfloat16, device=dev)
+        mean = torch.empty(self.cout, dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        ws = torch.empty((chunks + 1) * 2 * self.cout, dtype=torch.float32, device=dev)
+        _chk(_L().fz_bn_relu_train_forward(_P(conv), self.npad, _P(self.g), _P(self.b), _P(y), _P(mean), _P(rstd), _P(ws), M,
+                                           self.cout, chunks, self.BN_EPS, _S()), "fz_bn_relu_train_forward")
+        self.saved = (col, conv, y, mean, rstd, chunks, (B, H, W))
+        return y.view(B, H, W, self.cout)
+
+    def backward(self, dy: torch.Tensor):
+        """BN variant: dy bf16 [B,H,W,cout]; head variant: dy bf16 [B,H,W,npad] (padding columns zero).
+        -> (dx fp32 [B,H,W,cin], {weight, bn_weight, bn_bias | bias})."""
+        grads = {}
+        if self.bn:
+            col, conv, y, mean, rstd, chunks, (B, H, W) = self.saved
+            M, dev = B * H * W, col.device
+            dconv = torch.empty((M, self.npad), dtype=torch.bfloat16, device=dev)
+            dgb = torch.empty((2, self.cout), dtype=torch.float32, device=dev)
+            ws = torch.empty((chunks + 1) * 2 * self.cout, dtype=torch.float32, device=dev)
+            _chk(_L().fz_bn_relu_backward(_P(conv), self.npad, _P(dy.contiguous()), _P(y), _P(mean), _P(rstd), _P(self.g),
+                                          _P(dconv), self.npad, _P(dgb), _P(ws), M, self.cout, chunks, _S()),
+                 "fz_bn_relu_backward")
+            grads["bn_bias"], grads["bn_weight"] = dgb[0], dgb[1]
+        else:
+            col, (B, H, W) = self.saved
+            dconv = dy.contiguous().view(-1, self.npad)
+        dcol, dw, db = nv.linear_backward(dconv, col, self.w2)
+        if not self.bn:
+            grads["bias"] = db[:self.cout]
+        grads["weight"] = dw[:self.cout, :9 * self.cin].reshape(self.cout, 3, 3, self.cin).permute(0, 3, 1, 2).contiguous()
+        dx = torch.empty((B, H, W, self.cin), dtype=torch.float32, device=dcol.device)
+        _chk(_L().fz_col2im3x3(_P(dcol), _P(dx), B, H, W, self.cin, self.kpad, _S()), "fz_col2im3x3")
+        return dx, grads
+
+
+class UnetDecoderTrain:
+    """smp 0.4.0 ``UnetDecoder`` + ``SegmentationHead`` in training mode for the transformer-style feature list
+    [x, 0-channel dummy, f4, f8, f16, f32]: five blocks (nearest x2, concat the skip when it exists, two conv-BN-ReLU), then
+    conv3x3 + bias to the class logits.  Parameters under ``decoder.blocks.i.conv{1,2}.{0,1}.*`` / ``segmentation_head.0.*``."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], n_blocks: int = 5):
+        self.blocks = []
+        for i in range(n_blocks):
+            p = f"decoder.blocks.{i}."
+            self.blocks.append(tuple(Conv3x3BnReluTrain(params[p + f"conv{k}.0.weight"], params[p + f"conv{k}.1.weight"],
+                                                        params[p + f"conv{k}.1.bias"]) for k in (1, 2)))
+        self.head = Conv3x3BnReluTrain(params["segmentation_head.0.weight"], bias=params["segmentation_head.0.bias"])
+        self.n_classes = params["segmentation_head.0.weight"].shape[0]
+        self.saved = None
+
+    def forward(self, feats):
+        """feats: [f4, f8, f16, f32] NHWC (fp32 or bf16) -> logits fp32 [B, n_classes, H, W]."""
+        skips = list(feats[:-1][::-1]) + [None] * (len(self.blocks) - len(feats) + 1)
+        x = feats[-1]
+        shapes = []
+        for (c1, c2), skip in zip(self.blocks, skips):
+            B, H, W, C1 = x.shape
+            C2 = 0 if skip is None else skip.shape[-1]
+            cat = torch.empty((B, 2 * H, 2 * W, C1 + C2), dtype=torch.bfloat16, device=x.device)
+            nv.upsample2_concat(x.contiguous(), None if skip is None else skip.contiguous(), cat)
+            shapes.append((B, H, W, C1, C2))
+            x = c2.forward(c1.forward(cat))
+        lg = self.head.forward(x)                                               # [B,H,W,npad] fp32
+        self.saved = shapes
+        return lg[..., :self.n_classes].permute(0, 3, 1, 2).contiguous()
+
+    def backward(self, dlogits: torch.Tensor):
+        """dlogits fp32 [B, n_classes, H, W] -> ([df4, df8, df16, df32] fp32 NHWC, parameter gradients)."""
+        shapes = self.saved
+        B, C, H, W = dlogits.shape
+        dl = torch.zeros((B, H, W, self.head.npad), dtype=torch.bfloat16, device=dlogits.device)
+        dl[..., :C] = dlogits.permute(0, 2, 3, 1).to(torch.bfloat16)
+        grads: Dict[str, torch.Tensor] = {}
+        d, g = self.head.backward(dl)
+        grads["segmentation_head.0.weight"], grads["segmentation_head.0.bias"] = g["weight"], g["bias"]
+        dskips = []
+        for i in reversed(range(len(self.blocks))):
+            c1, c2 = self.blocks[i]
+            for conv, k in ((c2, 2), (c1, 1)):
+                d, g = conv.backward(_to_bf16(d))
+                p = f"decoder.blocks.{i}.conv{k}."
+                grads[p + "0.weight"], grads[p + "1.weight"], grads[p + "1.bias"] = g["weight"], g["bn_weight"], g["bn_bias"]
+            Bq, Hq, Wq, C1, C2 = shapes[i]
+            da = torch.empty((Bq, Hq, Wq, C1), dtype=torch.float32, device=d.device)
+            ds = torch.empty((Bq, 2 * Hq, 2 * Wq, C2), dtype=torch.float32, device=d.device) if C2 else None
+            _chk(_L().fz_upsample2_concat_backward(_P(d.contiguous()), _P(da), _P(ds), Bq, Hq, Wq, C1, C2, _S()),
+                 "fz_upsample2_concat_backward")
+            if C2:
+                dskips.append(ds)
+            d = da
+        return dskips + [d], grads      # skips were collected from block 2 (f4) down to block 0 (f16); d is now df32

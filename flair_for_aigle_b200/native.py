@@ -119,6 +119,11 @@ _SIGNATURES = {
     "fz_layernorm_fwd_stats2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
     "fz_s2d_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_patchify4_nchw": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_im2col3x3_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_col2im3x3": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_bn_relu_train_forward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, ctypes.c_float, _vp],
+    "fz_bn_relu_backward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _vp],
+    "fz_upsample2_concat_backward": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_head_upsample4": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"fz_last_error": ctypes.c_char_p, "fz_ce_workspace_doubles": ctypes.c_int64}

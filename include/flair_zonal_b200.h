@@ -345,6 +345,21 @@ int fz_layernorm_fwd_stats2(const float* x, const float* g, const float* b, void
                             float* rstd, int64_t M, int C, float eps, void* stream);
 int fz_s2d_bf16(const void* in, void* out, int B, int H, int W, int C, int s, int inverse, void* stream);
 int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin, int P, int Kpad, void* stream);
+/* U-Net decoder, training mode (smp UnetDecoder block: nearest x2 -> concat skip -> [conv3x3 -> BatchNorm -> ReLU] x 2):
+ * the 3x3 convolutions run as GEMMs over an explicit im2col (correctness-first; col bf16 [B*H*W][Kpad], k = (ky*3+kx)*C + c)
+ * with col2im as the data gradient; BatchNorm uses the batch statistics (biased variance) and keeps mean / rstd; x is the
+ * convolution output, fp32 with row stride ldx (the GEMM's padded N).  workspace: (chunks + 1) * 2 * C floats.
+ * fz_bn_relu_backward: dx bf16 with row stride ldd (padding columns zeroed), dbeta_dgamma float [2][C]. */
+int fz_im2col3x3_bf16(const void* in, void* col, int B, int H, int W, int C, int Kpad, void* stream);
+int fz_col2im3x3(const void* dcol_bf16, float* dx, int B, int H, int W, int C, int Kpad, void* stream);
+int fz_bn_relu_train_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* mean,
+                             float* rstd, float* workspace, int64_t M, int C, int chunks, float eps, void* stream);
+int fz_bn_relu_backward(const float* x, int ldx, const void* dy_bf16, const void* y_bf16, const float* mean, const float* rstd,
+                        const float* gamma, void* dx_bf16, int ldd, float* dbeta_dgamma, float* workspace, int64_t M, int C,
+                        int chunks, void* stream);
+/* gradient of fz_upsample2_concat: da float [B][H][W][C1] (2x2 sums), dskip float [B][2H][2W][C2] from dcat float
+ * [B][2H][2W][C1+C2]. */
+int fz_upsample2_concat_backward(const float* dcat, float* da, float* dskip, int B, int H, int W, int C1, int C2, void* stream);
 
 #ifdef __cplusplus
 }
