@@ -1,0 +1,101 @@
+"""One training step of ``convnextv2_*-unet`` with one or more mono-temporal encoders (BASELINE.json configs[4]: AERIAL_RGBI
+4 ch + DEM_ELEV 1 ch; tasks_module.py:133-167 + :377-391): training-mode forward (BatchNorm on batch statistics), weighted
+cross entropy, the backward through head, decoder, FusionHandler (flair_model.py:473-547) and encoders, and AdamW.
+
+Everything numeric runs on the CUDA kernels behind the C ABI (engine/convnext_train.py, csrc/backward_ops.cu,
+csrc/training_ops.cu, the tcgen05 GEMM); torch supplies memory, views, concatenation / slicing copies and dtype casts.
+This is the correctness-first version of SURVEY A11: the memory-bound backward kernels and the im2col convolutions are not
+tuned, BatchNorm running statistics are not updated (they do not enter the training forward), gradients are not yet
+all-reduced across ranks."""
+from typing import Dict, List
+
+import torch
+
+from .. import native as nv
+from ..flair_hub.tasks.module_setup import WeightedCrossEntropy
+from ..flair_hub.tasks.tasks_module import AdamW
+from .convnext_train import ConvNeXtV2EncoderTrain, UnetDecoderTrain, _to_bf16
+
+
+class ConvNeXtUNetTrainer:
+    def __init__(self, state: Dict[str, torch.Tensor], depths, dims, modalities: List[str], task: str,
+                 class_weight: torch.Tensor, task_weight: float = 1.0, lr: float = 5e-5, weight_decay: float = 0.01,
+                 betas=(0.9, 0.999)):
+        """state: the model's parameters by state_dict name (fp32, CUDA); they become views into the optimizer's arena."""
+        self.depths, self.dims, self.mods, self.task, self.task_weight = depths, dims, list(modalities), task, task_weight
+        self.names = [k for k in state if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+        self.params = {k: state[k] for k in self.names}
+        self.opt = AdamW([self.params[k] for k in self.names], lr=lr, weight_decay=weight_decay, betas=betas)
+        self.criterion = WeightedCrossEntropy(class_weight)
+        self._build()
+
+    def _build(self) -> None:
+        """Engines hold bf16 / repacked copies of the weights: rebuilt after every optimizer step."""
+        p = self.params
+        self.enc = {}
+        for m in self.mods:
+            pre = f"encoders.{m}.seg_model.model."
+            self.enc[m] = ConvNeXtV2EncoderTrain({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}, self.depths,
+                                                 self.dims)
+        pre = f"main_decoders.{self.task}.seg_model."
+        self.dec = UnetDecoderTrain({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)})
+        self.fuse = None
+        if len(self.mods) > 1:
+            self.fuse = [(p[f"fusion_handler.conv_f.{i}.weight"].detach().reshape(c, -1).to(torch.bfloat16).contiguous(),
+                          p[f"fusion_handler.conv_f.{i}.bias"].detach().float().contiguous()) for i, c in enumerate(self.dims)]
+
+    def forward_backward(self, batch: Dict[str, torch.Tensor]):
+        """-> (loss 0-d tensor, preds int32 (B,H,W), {parameter name: gradient})."""
+        feats = {m: self.enc[m].forward(batch[m]) for m in self.mods}
+        cats = None
+        if self.fuse is None:
+            fused = feats[self.mods[0]]
+        else:
+            fused, cats = [], []
+            for i, (w, b) in enumerate(self.fuse):
+                cat = torch.cat([_to_bf16(feats[m][i]) for m in self.mods], dim=-1).contiguous()      # [B,h,h,sum C]
+                B, h, _, ct = cat.shape
+                cats.append(cat)
+                fused.append(nv.gemm_bf16(cat.view(-1, ct), w, nv.EPI_F32, bias=b).view(B, h, h, -1))
+        logits = self.dec.forward(fused)
+        targets = batch[self.task]
+        targets = nv.onehot_argmax(targets) if targets.dim() == 4 else targets.to(torch.int32)
+        loss, preds = self.criterion(logits, targets, task_weight=self.task_weight, want_preds=True)
+        dfused, grads = self.dec.backward(self.criterion.backward())
+        grads = {f"main_decoders.{self.task}.seg_model.{k}": v for k, v in grads.items()}
+        if self.fuse is None:
+            dfeats = {self.mods[0]: dfused}
+        else:
+            dfeats = {m: [] for m in self.mods}
+            for i, (w, b) in enumerate(self.fuse):
+                cat = cats[i]
+                B, h, _, ct = cat.shape
+                dcat, dw, db = nv.linear_backward(_to_bf16(dfused[i].reshape(-1, self.dims[i])), cat.view(-1, ct), w)
+                grads[f"fusion_handler.conv_f.{i}.weight"] = dw.view(self.dims[i], ct, 1, 1)
+                grads[f"fusion_handler.conv_f.{i}.bias"] = db
+                off = 0
+                for m in self.mods:
+                    c = feats[m][i].shape[-1]
+                    dfeats[m].append(dcat[:, off:off + c].float().reshape(B, h, h, c).contiguous())
+                    off += c
+        for m in self.mods:
+            g = self.enc[m].backward(dfeats[m])
+            grads.update({f"encoders.{m}.seg_model.model.{k}": v for k, v in g.items()})
+        return loss, preds, grads
+
+    def step(self, batch: Dict[str, torch.Tensor]):
+        """forward + backward + AdamW update; -> (loss before the update, preds)."""
+        loss, preds, grads = self.forward_backward(batch)
+        # parameters the forward never touches (fusion_handler.conv_f with a single modality) have no gradient: torch's AdamW
+        # leaves them alone (no weight decay either), so they are put back after the fused update
+        unused = {n: self.params[n].clone() for n in self.names if n not in grads}
+        for name, g in zip(self.names, self.opt.grads):
+            if name in grads:
+                g.copy_(grads[name].reshape(g.shape))
+            else:
+                g.zero_()
+        self.opt.step()
+        for n, v in unused.items():
+            self.params[n].copy_(v)
+        self._build()
+        return loss, preds

@@ -1,0 +1,73 @@
+"""The training step of BASELINE.json configs[4] (convnextv2_base-unet, AERIAL_RGBI 4 ch + DEM_ELEV 1 ch, weighted CE, AdamW;
+tasks_module.py:133-167,377-391) at a reduced tile size: loss, every parameter gradient and the loss trajectory of a few
+optimizer steps against torch autograd + torch.optim.AdamW on the oracle model (training mode)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TASK = "AERIAL_LABEL-COSIA"
+
+
+def _cos(a, b):
+    return torch.nn.functional.cosine_similarity(a.float().flatten(), b.float().flatten(), dim=0).item()
+
+
+@pytest.mark.parametrize("mods", [{"AERIAL_RGBI": 4}, {"AERIAL_RGBI": 4, "DEM_ELEV": 1}])
+def test_training_step_vs_oracle(cuda, mods):
+    from oracle.models import CONVNEXTV2_CFGS, FlairHubOracle, randomize_
+    from oracle.training import default_class_weights, init_optimizer, step as oracle_step
+    from flair_for_aigle_b200.engine.train_step import ConvNeXtUNetTrainer
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B, P = 2, 128
+    oracle = FlairHubOracle("convnextv2_base-unet", mods, {TASK: 19})
+    randomize_(oracle, seed=3)
+    oracle = oracle.to(cuda).train()
+    g = torch.Generator(device="cpu").manual_seed(17)
+    batch = {m: torch.randn(B, c, P, P, generator=g).to(cuda) for m, c in mods.items()}
+    batch[TASK] = torch.nn.functional.one_hot(torch.randint(0, 19, (B, P, P), generator=g), 19).permute(0, 3, 1, 2).float().to(cuda)
+    cfg = {"labels_configs": {TASK: {"value_name": list(range(19)), "task_weight": 1.0,
+                                     "value_weights": {"default": 1, "default_exceptions": {15: 0, 16: 0, 17: 0, 18: 0}}}}}
+    ocfg = {"optimizer": "adamw", "learning_rate": 5e-5, "optim_weight_decay": 0.01, "optim_betas": [0.9, 0.999]}
+    depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
+    state = {k: v.detach().clone() for k, v in oracle.state_dict().items()}
+    trainer = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, default_class_weights(cfg["labels_configs"][TASK]).to(cuda))
+    assert sorted(trainer.names) == sorted(n for n, _ in oracle.named_parameters())
+
+    ref_loss, ref_preds, _ = oracle_step(oracle, batch, cfg)
+    ref_loss.backward()
+    loss, preds, grads = trainer.forward_backward(batch)
+    torch.cuda.synchronize()
+    print(f"loss {float(loss):.5f} vs oracle {float(ref_loss):.5f}; predictions equal {(preds == ref_preds[TASK]).float().mean().item():.4f}")
+    assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss))
+    worst, tot_dot, tot_a, tot_b = (1.0, ""), 0.0, 0.0, 0.0
+    for n, p in oracle.named_parameters():
+        if p.grad is None:                      # fusion_handler.conv_f is unused with a single modality
+            assert n not in grads and n.startswith("fusion_handler.")
+            continue
+        assert tuple(grads[n].shape) == tuple(p.grad.shape), n
+        a, b = grads[n].float().flatten(), p.grad.float().flatten()
+        tot_dot += float(a @ b); tot_a += float(a @ a); tot_b += float(b @ b)
+        worst = min(worst, (_cos(a, b), n))
+    total = tot_dot / (tot_a ** 0.5 * tot_b ** 0.5)
+    print(f"{len(grads)} parameter gradients: whole-model cosine {total:.5f}, norm ratio {(tot_a / tot_b) ** 0.5:.4f}, "
+          f"worst tensor {worst[0]:.4f} at {worst[1]}")
+    assert total > 0.97 and 0.95 < (tot_a / tot_b) ** 0.5 < 1.05
+    assert worst[0] > 0.8
+
+    # a few optimizer steps on the same batch: both sides must go down the same way
+    opt = init_optimizer({**ocfg, "learning_rate": 2e-4}, oracle.parameters())
+    trainer.opt.lr = 2e-4
+    ours, theirs = [], []
+    for _ in range(4):
+        opt.zero_grad()
+        l, _, _ = oracle_step(oracle, batch, cfg)
+        l.backward()
+        opt.step()
+        theirs.append(float(l))
+        l2, _ = trainer.step(batch)
+        ours.append(float(l2))
+    print("loss trajectory  ours  :", " ".join(f"{v:.4f}" for v in ours))
+    print("loss trajectory  oracle:", " ".join(f"{v:.4f}" for v in theirs))
+    assert ours[-1] < ours[0] and theirs[-1] < theirs[0]
+    assert all(abs(a - b) <= 3e-2 * abs(b) for a, b in zip(ours, theirs))
