@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
                                                              __nv_bfloat16* __restrict__ out, int R, int C) {
   __shared__ __nv_bfloat16 tile[32][34];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;     // rows on grid.x: activations have millions of rows
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -293,8 +293,8 @@ extern "C" int fz_adamw_step(float* param, const float* grad, float* exp_avg, fl
 extern "C" int fz_transpose_bf16(const void* in, void* out, int R, int C, void* stream) {
   using namespace fz;
   FZ_REQUIRE(R > 0 && C > 0 && in && out, "fz_transpose_bf16: bad arguments");
-  const dim3 grid((C + 31) / 32, (R + 31) / 32);
-  FZ_REQUIRE(grid.y <= 65535, "fz_transpose_bf16: R=%d exceeds %d rows per call", R, 65535 * 32);
+  const dim3 grid((R + 31) / 32, (C + 31) / 32);
+  FZ_REQUIRE(grid.y <= 65535, "fz_transpose_bf16: C=%d exceeds %d columns", C, 65535 * 32);
   transpose_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), R, C);
   FZ_CHECK_CUDA(cudaGetLastError());

@@ -74,8 +74,9 @@ class SegmentationTask:
     def step(self, batch: Dict[str, torch.Tensor], training: bool = False):
         """tasks_module.py:133-167.  -> (loss, {task: preds int32 (B,H,W)}, {task: targets int32 (B,H,W)})."""
         if training:
-            raise NotImplementedError("training step: the backward kernels of the encoders / decoder are not built yet "
-                                      "(SURVEY.md A11); loss, loss gradient and AdamW are")
+            raise NotImplementedError("step(training=True) returns a loss for an external autograd / optimizer, which does not "
+                                      "exist here: use training_step(batch), which runs forward, backward and AdamW on the "
+                                      "CUDA kernels (engine/train_step.py)")
         dict_logits_task, _ = self.forward(batch)
         loss_sum = None
         all_preds, all_targets = {}, {}
@@ -89,6 +90,39 @@ class SegmentationTask:
             loss_sum = main_loss if loss_sum is None else loss_sum + main_loss
             all_preds[task], all_targets[task] = preds, targets
         return loss_sum, all_preds, all_targets
+
+    def configure_trainer(self, optim_cfg: dict):
+        """``_init_optimizer`` (tasks_module.py:377-391) + the training engine for ``convnextv2_*-unet`` models with one or more
+        mono-temporal encoders.  The model's parameters become views into the optimizer's flat arena."""
+        from ...engine.convnext_unet import CONVNEXTV2_CFGS
+        from ...engine.train_step import ConvNeXtUNetTrainer
+        arch = self.config['models']['monotemp_model']['arch'] if 'models' in self.config else self.config['monotemp_arch']
+        enc_name, dec_name = arch.rsplit('-', 1)
+        enc_name = enc_name[3:] if enc_name.startswith('tu-') else enc_name
+        if enc_name not in CONVNEXTV2_CFGS or dec_name.lower() != 'unet':
+            raise NotImplementedError(f"training engine: '{arch}' (built for convnextv2_*-unet)")
+        if optim_cfg['optimizer'] != 'adamw':
+            raise NotImplementedError(f"optimizer '{optim_cfg['optimizer']}': only the reference default 'adamw' has a kernel")
+        depths, dims = CONVNEXTV2_CFGS[enc_name]
+        task = self.config['labels'][0]
+        state = {k: v for k, v in self.model.state_dict(keep_vars=True).items()}
+        weight = self.criterion[task].weight
+        self.trainer = ConvNeXtUNetTrainer(state, depths, dims,            # the Parameter objects themselves: AdamW rebinds their .data
+                                           list(self.model.active_mono), task, weight.to(next(iter(state.values())).device),
+                                           task_weight=self.config['labels_configs'][task].get('task_weight', 1.0),
+                                           lr=optim_cfg['learning_rate'], weight_decay=optim_cfg['optim_weight_decay'],
+                                           betas=tuple(optim_cfg['optim_betas']))
+        return self.trainer
+
+    def training_step(self, batch: Dict[str, torch.Tensor]):
+        """tasks_module.py:196-207 (training_step -> step(training=True) -> backward -> optimizer.step) in one call.
+        -> (loss before the update, {task: preds})."""
+        if getattr(self, 'trainer', None) is None:
+            raise RuntimeError("call configure_trainer(optim_cfg) first")
+        loss, preds = self.trainer.step(batch)
+        if hasattr(self.model, '_engines'):
+            self.model._engines = {}                 # the inference engines hold repacked copies of the old weights
+        return loss, {self.trainer.task: preds}
 
     def loss_gradients(self) -> Dict[str, torch.Tensor]:
         """d loss_sum / d logits per task for the last ``step`` (fp32, (B,C,H,W))."""

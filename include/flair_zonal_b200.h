@@ -305,7 +305,7 @@ int fz_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   double beta2, double eps, double weight_decay, int step, void* stream);
 
 /* First building blocks of the model backward (a Linear layer's gradients through the K-major tcgen05 GEMM):
- * out bf16 [C][R] = in bf16 [R][C]^T (R <= 2 097 120 rows per call); out float [N] = column sums of in bf16 [M][N]
+ * out bf16 [C][R] = in bf16 [R][C]^T (C <= 2 097 120); out float [N] = column sums of in bf16 [M][N]
  * (bias gradient; partial = float [chunks][N] workspace, fixed summation order). */
 int fz_transpose_bf16(const void* in, void* out, int R, int C, void* stream);
 int fz_colsum_bf16(const void* in, float* partial, float* out, int64_t M, int N, int chunks, void* stream);

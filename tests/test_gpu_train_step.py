@@ -71,3 +71,42 @@ def test_training_step_vs_oracle(cuda, mods):
     print("loss trajectory  oracle:", " ".join(f"{v:.4f}" for v in theirs))
     assert ours[-1] < ours[0] and theirs[-1] < theirs[0]
     assert all(abs(a - b) <= 3e-2 * abs(b) for a, b in zip(ours, theirs))
+
+
+def test_segmentation_task_training_step(cuda, tmp_path):
+    """The drop-in surface: FLAIR_HUB_Model + SegmentationTask.configure_trainer / training_step (tasks_module.py:196-207,
+    377-391): the model's own parameters are updated in place (they alias the optimizer arena), the loss goes down, and the
+    zonal forward afterwards runs on the UPDATED weights."""
+    import bench
+    from flair_for_aigle_b200.flair_hub.tasks.tasks_module import SegmentationTask
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model, prepare_model_config
+    from flair_for_aigle_b200.flair_zonal_detection.raster import ZoneRaster, register_raster
+    from flair_for_aigle_b200.synthetic import synthetic_raster
+    wpath = str(tmp_path / "w.safetensors")
+    bench.make_weights(wpath, seed=7)
+    name = "mem://train_task"
+    register_raster(name, ZoneRaster(synthetic_raster(512, 512, seed=1), 700000.0, 6600000.0, 0.2, name=name))
+    cfg = inf.initialize_geometry_and_resolutions(bench.zonal_config(wpath, str(tmp_path), name, 2))
+    cfg["device"] = cuda
+    model = build_inference_model(cfg, {"AERIAL_RGBI": 512}).to(cuda)
+    mcfg = prepare_model_config(cfg)
+    mcfg["labels"] = [TASK]
+    mcfg["labels_configs"] = {TASK: {"value_name": list(range(19)), "task_weight": 1.0,
+                                     "value_weights": {"default": 1, "default_exceptions": {15: 0, 16: 0, 17: 0, 18: 0}}}}
+    mcfg.setdefault("modalities", {}).setdefault("aux_loss", {})
+    task = SegmentationTask(model, mcfg)
+    task.configure_trainer({"optimizer": "adamw", "learning_rate": 2e-4, "optim_weight_decay": 0.01, "optim_betas": [0.9, 0.999]})
+    g = torch.Generator(device="cpu").manual_seed(23)
+    batch = {"AERIAL_RGBI": torch.randn(2, 4, 256, 256, generator=g).to(cuda),
+             TASK: torch.nn.functional.one_hot(torch.randint(0, 19, (2, 256, 256), generator=g), 19).permute(0, 3, 1, 2).float().to(cuda)}
+    key = "encoders.AERIAL_RGBI.seg_model.model.stages_2.blocks.5.mlp.fc1.weight"
+    before = model.state_dict()[key].clone()
+    losses = [float(task.training_step(batch)[0]) for _ in range(3)]
+    print("training_step losses:", losses)
+    assert losses[-1] < losses[0]
+    after = model.state_dict()[key]
+    assert not torch.equal(before, after) and after.data_ptr() >= task.trainer.opt.arena.data_ptr()
+    x = torch.randn(1, 4, 512, 512, generator=g).to(cuda)
+    out, _ = model({"AERIAL_RGBI": x})
+    assert bool(torch.isfinite(out[TASK]).all())
