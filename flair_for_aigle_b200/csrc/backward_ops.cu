@@ -16,38 +16,42 @@ namespace fz {
 // out[b,y,x,c] = bias[c] + sum_k in[b,y+ky-3,x+kx-3,c] * w[k][c]   (flip: w[48-k], i.e. the data gradient)
 __global__ void __launch_bounds__(256) dwconv7_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                           const float* __restrict__ bias, float* __restrict__ out, int H,
-                                                          int W, int C, int64_t n, int flip) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
-  const int c = static_cast<int>(i % C);
-  const int64_t px = i / C;
-  const int x = static_cast<int>(px % W), y = static_cast<int>((px / W) % H);
-  const int64_t b = px / (static_cast<int64_t>(W) * H);
+                                                          int W, int C, int flip) {
+  // grid (ceil(W*C / 256), H, B): the row and the sample come from the grid, the rest is 32-bit index math
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= W * C) return;
+  const int x = t / C, c = t - x * C, y = blockIdx.y;
+  const size_t img = static_cast<size_t>(blockIdx.z) * H * W * C;
   float acc = bias ? bias[c] : 0.f;
+#pragma unroll
   for (int ky = 0; ky < 7; ++ky) {
     const int iy = y + ky - 3;
     if (iy < 0 || iy >= H) continue;
+    const float* row = in + img + static_cast<size_t>(iy) * W * C + c;
+#pragma unroll
     for (int kx = 0; kx < 7; ++kx) {
       const int ix = x + kx - 3;
       if (ix < 0 || ix >= W) continue;
       const int k = ky * 7 + kx;
-      acc = fmaf(in[((b * H + iy) * W + ix) * C + c], w[(flip ? 48 - k : k) * C + c], acc);
+      acc = fmaf(row[ix * C], w[(flip ? 48 - k : k) * C + c], acc);
     }
   }
-  out[i] = acc;
+  out[img + (static_cast<size_t>(y) * W + x) * C + c] = acc;
 }
 
-// dw[k][c] = sum_{b,y,x} du[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]  (k < 49);  k == 49: db[c] = sum du.   grid (50, C/32)
+// partial[z][k][c] = sum over pixel chunk z of du[p][c] * x[p + tap k][c]  (k < 49);  k == 49: sum du.   grid (50, C/32, S)
 __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du,
-                                                            float* __restrict__ dw, float* __restrict__ db, int B, int H,
-                                                            int W, int C) {
+                                                            float* __restrict__ partial, int B, int H, int W, int C,
+                                                            int px_per_chunk) {
   __shared__ float red[8][32];
   const int k = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
   const int ky = k / 7, kx = k % 7;
   const int64_t npx = static_cast<int64_t>(B) * H * W;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.z) * px_per_chunk;
+  const int64_t p1 = p0 + px_per_chunk < npx ? p0 + px_per_chunk : npx;
   float acc = 0.f;
   if (c < C)
-    for (int64_t p = ty; p < npx; p += 8) {
+    for (int64_t p = p0 + ty; p < p1; p += 8) {
       const float g = du[p * C + c];
       if (k == 49) {
         acc += g;
@@ -63,8 +67,7 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const float* __restr
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
-    if (k == 49) db[c] = t;
-    else dw[k * C + c] = t;
+    partial[(static_cast<size_t>(blockIdx.z) * 50 + k) * C + c] = t;
   }
 }
 
@@ -154,10 +157,35 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f +
 __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
 }
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(w[j] << 16);
+    v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 q;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = q;
+}
+// n is a multiple of 8 (C4 is a multiple of 8)
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ g,
                                                        int64_t n) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i < n) g[i] = __float2bfloat16_rn(gelu_exact(__bfloat162float(h[i])));
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i >= n) return;
+  float v[8];
+  load8(h + i, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = gelu_exact(v[j]);
+  store8(g + i, v);
 }
 
 // ------------------------------------------------------------------------------------------------ GRN
@@ -206,16 +234,19 @@ __global__ void __launch_bounds__(256) grn_norms_kernel(const float* __restrict_
   for (int c = threadIdx.x; c < C; c += 256) nx[static_cast<size_t>(b) * C + c] = gx[static_cast<size_t>(b) * C + c] / (mu + eps);
 }
 
-// y = g * (1 + gamma * Nx[b]) + beta
+// y = g * (1 + gamma * Nx[b]) + beta.   grid (ceil(per_sample / 2048), B), 8 channels per thread (C % 8 == 0)
 __global__ void __launch_bounds__(256) grn_apply_train_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ nx,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              __nv_bfloat16* __restrict__ y, int64_t per_sample, int C,
-                                                              int64_t n) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
-  const int c = static_cast<int>(i % C);
-  const int64_t b = i / per_sample;
-  y[i] = __float2bfloat16_rn(__bfloat162float(g[i]) * (1.0f + gamma[c] * nx[b * C + c]) + beta[c]);
+                                                              __nv_bfloat16* __restrict__ y, int per_sample, int C) {
+  const int e = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (e >= per_sample) return;
+  const int c = e % C;
+  const size_t b = blockIdx.y, i = b * per_sample + e;
+  float v[8];
+  load8(g + i, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = v[j] * (1.0f + gamma[c + j] * nx[b * C + c + j]) + beta[c + j];
+  store8(y + i, v);
 }
 
 // one block per sample: coefA = 1 + gamma*Nx, coefB = dGx / Gx with
@@ -258,17 +289,23 @@ __global__ void __launch_bounds__(256) grn_param_grad_kernel(const float* __rest
   dbeta[c] = bsum;
 }
 
-// dh = (dy * coefA[b] + g * coefB[b]) * GELU'(h)
+// dh = (dy * coefA[b] + g * coefB[b]) * GELU'(h).   grid (ceil(per_sample / 2048), B), 8 channels per thread
 __global__ void __launch_bounds__(256) grn_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ g,
                                                            const __nv_bfloat16* __restrict__ h, const float* __restrict__ coef_a,
                                                            const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ dh,
-                                                           int64_t per_sample, int C, int64_t n) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
-  const int c = static_cast<int>(i % C);
-  const int64_t b = i / per_sample;
-  const float dg = __bfloat162float(dy[i]) * coef_a[b * C + c] + __bfloat162float(g[i]) * coef_b[b * C + c];
-  dh[i] = __float2bfloat16_rn(dg * gelu_grad(__bfloat162float(h[i])));
+                                                           int per_sample, int C) {
+  const int e = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (e >= per_sample) return;
+  const int c = e % C;
+  const size_t b = blockIdx.y, i = b * per_sample + e;
+  float d[8], gg[8], hh[8];
+  load8(dy + i, d);
+  load8(g + i, gg);
+  load8(h + i, hh);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    d[j] = (d[j] * coef_a[b * C + c + j] + gg[j] * coef_b[b * C + c + j]) * gelu_grad(hh[j]);
+  store8(dh + i, d);
 }
 
 __global__ void __launch_bounds__(256) add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
@@ -459,8 +496,8 @@ typedef __nv_bfloat16* bf;
 extern "C" int fz_dwconv7_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C,
                               int flip, void* stream) {
   FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && in && w && out, "fz_dwconv7_f32: bad arguments");
-  const int64_t n = static_cast<int64_t>(B) * H * W * C;
-  dwconv7_f32_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(in, w, bias, out, H, W, C, n, flip);
+  FZ_REQUIRE(H <= 65535 && B <= 65535, "fz_dwconv7_f32: H=%d B=%d exceed the grid limits", H, B);
+  dwconv7_f32_kernel<<<dim3((W * C + 255) / 256, H, B), 256, 0, ST(stream)>>>(in, w, bias, out, H, W, C, flip);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -468,7 +505,29 @@ extern "C" int fz_dwconv7_f32(const float* in, const float* w, const float* bias
 extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, float* db, int B, int H, int W, int C,
                                 void* stream) {
   FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && x && du && dw && db, "fz_dwconv7_wgrad: bad arguments");
-  dwconv7_wgrad_kernel<<<dim3(50, (C + 31) / 32), 256, 0, ST(stream)>>>(x, du, dw, db, B, H, W, C);
+  // the pixel walk is split into chunks (grid.z) so that every SM has work and no thread chains thousands of dependent
+  // global loads; partial[chunk][50][C] lives in a per-device scratch buffer and is summed in a fixed order
+  const int64_t npx = static_cast<int64_t>(B) * H * W;
+  int chunks = static_cast<int>(npx / 2048);
+  chunks = chunks < 1 ? 1 : (chunks > 128 ? 128 : chunks);
+  const int ppc = static_cast<int>((npx + chunks - 1) / chunks);
+  static float* scratch[64] = {nullptr};
+  static size_t scratch_floats[64] = {0};
+  int dev = 0;
+  FZ_CHECK_CUDA(cudaGetDevice(&dev));
+  FZ_REQUIRE(dev >= 0 && dev < 64, "fz_dwconv7_wgrad: device index %d", dev);
+  const size_t need = static_cast<size_t>(chunks + 1) * 50 * C;
+  if (scratch_floats[dev] < need) {
+    if (scratch[dev]) cudaFree(scratch[dev]);
+    FZ_CHECK_CUDA(cudaMalloc(&scratch[dev], need * sizeof(float)));
+    scratch_floats[dev] = need;
+  }
+  float* partial = scratch[dev];
+  float* sums = partial + static_cast<size_t>(chunks) * 50 * C;
+  dwconv7_wgrad_kernel<<<dim3(50, (C + 31) / 32, chunks), 256, 0, ST(stream)>>>(x, du, partial, B, H, W, C, ppc);
+  reduce_rows_kernel<<<(50 * C + 255) / 256, 256, 0, ST(stream)>>>(partial, sums, 50 * C, chunks);
+  FZ_CHECK_CUDA(cudaMemcpyAsync(dw, sums, static_cast<size_t>(49) * C * sizeof(float), cudaMemcpyDeviceToDevice, ST(stream)));
+  FZ_CHECK_CUDA(cudaMemcpyAsync(db, sums + static_cast<size_t>(49) * C, C * sizeof(float), cudaMemcpyDeviceToDevice, ST(stream)));
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -496,7 +555,8 @@ extern "C" int fz_layernorm_bwd(const void* dy_bf16, const float* x, const float
 
 extern "C" int fz_gelu_fwd(const void* h_bf16, void* g_bf16, int64_t n, void* stream) {
   FZ_REQUIRE(n > 0 && h_bf16 && g_bf16, "fz_gelu_fwd: bad arguments");
-  gelu_fwd_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(h_bf16), reinterpret_cast<bf>(g_bf16), n);
+  FZ_REQUIRE(n % 8 == 0, "fz_gelu_fwd: n=%lld must be a multiple of 8", (long long)n);
+  gelu_fwd_kernel<<<blocks_for(n / 8), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(h_bf16), reinterpret_cast<bf>(g_bf16), n);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -516,9 +576,10 @@ extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, cons
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && g_bf16 && sumsq && gamma && beta && gx && nx && mu && y_bf16,
              "fz_grn_train_forward: bad arguments");
   grn_norms_kernel<<<B, 256, 0, ST(stream)>>>(sumsq, gx, nx, mu, C, eps);
-  const int64_t per = static_cast<int64_t>(HW) * C, n = per * B;
-  grn_apply_train_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(g_bf16), nx, gamma, beta,
-                                                                reinterpret_cast<bf>(y_bf16), per, C, n);
+  const int64_t per = static_cast<int64_t>(HW) * C;
+  FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_train_forward: C %% 8, HW*C < 2^31, B <= 65535");
+  grn_apply_train_kernel<<<dim3(static_cast<unsigned>((per / 8 + 255) / 256), B), 256, 0, ST(stream)>>>(
+      reinterpret_cast<cbf>(g_bf16), nx, gamma, beta, reinterpret_cast<bf>(y_bf16), static_cast<int>(per), C);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -532,10 +593,11 @@ extern "C" int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, con
              "fz_grn_gelu_backward: bad arguments");
   grn_bwd_coef_kernel<<<B, 256, 0, ST(stream)>>>(s1, gx, nx, mu, gamma, coef_a, coef_b, C, eps);
   grn_param_grad_kernel<<<(C + 255) / 256, 256, 0, ST(stream)>>>(s1, s0, nx, dgamma, dbeta, B, C);
-  const int64_t per = static_cast<int64_t>(HW) * C, n = per * B;
-  grn_gelu_bwd_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(g_bf16),
-                                                             reinterpret_cast<cbf>(h_bf16), coef_a, coef_b,
-                                                             reinterpret_cast<bf>(dh_bf16), per, C, n);
+  const int64_t per = static_cast<int64_t>(HW) * C;
+  FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_gelu_backward: C %% 8, HW*C < 2^31, B <= 65535");
+  grn_gelu_bwd_kernel<<<dim3(static_cast<unsigned>((per / 8 + 255) / 256), B), 256, 0, ST(stream)>>>(
+      reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(g_bf16), reinterpret_cast<cbf>(h_bf16), coef_a, coef_b,
+      reinterpret_cast<bf>(dh_bf16), static_cast<int>(per), C);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
