@@ -46,19 +46,20 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const float* __restr
   __shared__ float red[8][32];
   const int k = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
   const int ky = k / 7, kx = k % 7;
-  const int64_t npx = static_cast<int64_t>(B) * H * W;
-  const int64_t p0 = static_cast<int64_t>(blockIdx.z) * px_per_chunk;
-  const int64_t p1 = p0 + px_per_chunk < npx ? p0 + px_per_chunk : npx;
+  const int npx = B * H * W;                                   // < 2^31 (host check): 32-bit pixel arithmetic
+  const int p0 = blockIdx.z * px_per_chunk;
+  const int p1 = p0 + px_per_chunk < npx ? p0 + px_per_chunk : npx;
+  const int shift = (ky - 3) * W + (kx - 3);
   float acc = 0.f;
   if (c < C)
-    for (int64_t p = p0 + ty; p < p1; p += 8) {
-      const float g = du[p * C + c];
+    for (int p = p0 + ty; p < p1; p += 8) {
+      const float g = du[static_cast<size_t>(p) * C + c];
       if (k == 49) {
         acc += g;
       } else {
-        const int xw = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const int row = p / W, xw = p - row * W, y = row % H;
         const int iy = y + ky - 3, ix = xw + kx - 3;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) acc = fmaf(g, x[(p + static_cast<int64_t>(ky - 3) * W + (kx - 3)) * C + c], acc);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) acc = fmaf(g, x[static_cast<size_t>(p + shift) * C + c], acc);
       }
     }
   red[ty][threadIdx.x & 31] = acc;
@@ -508,6 +509,7 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
   // the pixel walk is split into chunks (grid.z) so that every SM has work and no thread chains thousands of dependent
   // global loads; partial[chunk][50][C] lives in a per-device scratch buffer and is summed in a fixed order
   const int64_t npx = static_cast<int64_t>(B) * H * W;
+  FZ_REQUIRE(npx < (1LL << 31), "fz_dwconv7_wgrad: B*H*W must fit int32");
   int chunks = static_cast<int>(npx / 2048);
   chunks = chunks < 1 ? 1 : (chunks > 128 ? 128 : chunks);
   const int ppc = static_cast<int>((npx + chunks - 1) / chunks);
@@ -699,6 +701,13 @@ extern "C" int fz_upsample2_concat_backward(const float* dcat, float* da, float*
              "fz_upsample2_concat_backward: bad arguments");
   const int64_t n_a = static_cast<int64_t>(B) * H * W * C1, n_s = static_cast<int64_t>(B) * 4 * H * W * C2;
   upcat_bwd_kernel<<<blocks_for(n_a + n_s), 256, 0, ST(stream)>>>(dcat, da, dskip, H, W, C1, C2, n_a, n_s);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* stream) {
+  FZ_REQUIRE(N > 0 && S >= 1 && partial && out, "fz_reduce_rows_f32: bad arguments");
+  reduce_rows_kernel<<<(N + 255) / 256, 256, 0, ST(stream)>>>(partial, out, N, S);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

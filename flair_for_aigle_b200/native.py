@@ -116,6 +116,7 @@ _SIGNATURES = {
     "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_gelu_backward": [_vp] * 14 + [_i, _i, _i, ctypes.c_float, _vp],
     "fz_add_f32": [_vp, _vp, _vp, _i64, _vp],
+    "fz_reduce_rows_f32": [_vp, _vp, _i, _i, _vp],
     "fz_layernorm_fwd_stats2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
     "fz_s2d_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_patchify4_nchw": [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -648,6 +649,16 @@ def colsum_bf16(x: torch.Tensor, chunks: int = 64) -> torch.Tensor:
     return out
 
 
+_STREAMS = {}
+
+
+def _stream_pool(device, n: int):
+    key = (device.index, n)
+    if key not in _STREAMS:
+        _STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return _STREAMS[key]
+
+
 def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
     """Gradients of Y = X W^T + b (X bf16 [M,K], W bf16 [N,K], dY bf16 [M,N]) on the tcgen05 GEMM:
     dX = dY W (bf16 [M,K]), dW = dY^T X (fp32 [N,K], fp32 accumulation over all M rows), db = column sums of dY."""
@@ -656,7 +667,32 @@ def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
     if X.shape[0] != M or tuple(W.shape) != (N, K):
         raise NativeError("linear_backward: shape mismatch")
     dX = gemm_bf16(dY, transpose_bf16(W), EPI_BF16)                               # [M,N] x [K,N]^T
-    if M % 64:                                                                    # the GEMM's reduction length is a multiple of 64
+    tiles = ((N + 127) // 128) * ((K + 63) // 64)
+    if tiles < 64 and M >= 1 << 18:
+        # few output tiles and a very long reduction (the decoder convolutions at full resolution: dW is 64 x 320 over 4 M
+        # rows): a handful of CTAs would stream gigabytes each.  Split the rows into chunks, run their GEMMs side by side on
+        # separate streams into partial sums, add the partials in a fixed order.
+        S = min(32, M // 65536)
+        rows = (M // S + 63) // 64 * 64
+        bounds = [(r, min(r + rows, M)) for r in range(0, M, rows)]
+        partial = torch.zeros((len(bounds), N, K), dtype=torch.float32, device=dY.device)
+        cur = torch.cuda.current_stream()
+        pool = _stream_pool(dY.device, 8)
+        for i, (r0, r1) in enumerate(bounds):
+            st = pool[i % len(pool)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                a, b = dY[r0:r1], X[r0:r1]
+                if (r1 - r0) % 64:
+                    pad = (r1 - r0 + 63) // 64 * 64
+                    a2 = torch.zeros((pad, N), dtype=dY.dtype, device=dY.device); a2[:r1 - r0].copy_(a); a = a2
+                    b2 = torch.zeros((pad, K), dtype=X.dtype, device=X.device); b2[:r1 - r0].copy_(b); b = b2
+                gemm_bf16(transpose_bf16(a), transpose_bf16(b), EPI_F32, out=partial[i])
+        for st in pool:
+            cur.wait_stream(st)
+        dW = torch.empty((N, K), dtype=torch.float32, device=dY.device)
+        _check(lib().fz_reduce_rows_f32(_ptr(partial), _ptr(dW), N * K, len(bounds), _stream()), "fz_reduce_rows_f32")
+    elif M % 64:                                                                  # the GEMM's reduction length is a multiple of 64
         Mp = (M + 63) // 64 * 64
         dYp = torch.zeros((Mp, N), dtype=dY.dtype, device=dY.device)
         Xp = torch.zeros((Mp, K), dtype=X.dtype, device=X.device)

@@ -337,6 +337,8 @@ int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_
                          const float* gx, const float* nx, const float* mu, const float* gamma, float* coef_a, float* coef_b,
                          float* dgamma, float* dbeta, void* dh_bf16, int B, int HW, int C, float eps, void* stream);
 int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* out float [N] = sum over s of partial float [S][N], in the order s = 0 .. S-1 (split reductions stay reproducible). */
+int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* stream);
 /* Encoder plumbing of the same slice: LayerNorm with a bf16 and / or an fp32 output (LayerNorm2d of the stem feeds the fp32
  * residual stream, the one in front of a downsample conv feeds a GEMM); space-to-depth for the 2x2/s2 convolutions as GEMMs,
  * k = (ky*s + kx)*C + c, and its inverse (inverse = 1: `in` is the [B][H/s][W/s][s*s*C] side); the stem's 4x4/s4 patches of a
