@@ -316,7 +316,8 @@ int fz_colsum_bf16(const void* in, float* partial, float* out, int64_t M, int N,
  * depthwise 7x7 in fp32: out = bias + sum_k in(shifted) * w[k][c]; flip = 1 uses w[48-k] (= the data gradient). */
 int fz_dwconv7_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C, int flip,
                    void* stream);
-/* dw float [49][C], db float [C]: gradients of the depthwise weights / bias from x and the output gradient du. */
+/* dw float [49][C], db float [C]: gradients of the depthwise weights / bias from x and the output gradient du.  The one entry
+ * point that owns device memory: a per-device scratch buffer for its fixed-order partial sums, grown on demand. */
 int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, float* db, int B, int H, int W, int C, void* stream);
 /* LayerNorm over C with saved row statistics (training forward), and its backward: dx float [M][C]; dgamma_dbeta float [2][C]
  * (partial = float [blocks][2][C] workspace; blocks fixes the reduction order). */
