@@ -586,6 +586,18 @@ __global__ void __launch_bounds__(256) upcat_bwd_kernel(const float* __restrict_
   }
 }
 
+// nn.BatchNorm2d's side effect in training mode: running = (1 - momentum) * running + momentum * batch statistic, with the
+// UNBIASED batch variance (var * M / (M - 1)); the biased variance is recovered from rstd = 1 / sqrt(var + eps)
+__global__ void __launch_bounds__(256) bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                int C, float M, float eps, float momentum) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const float var = 1.0f / (rstd[c] * rstd[c]) - eps;
+  running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean[c];
+  running_var[c] = (1.0f - momentum) * running_var[c] + momentum * var * (M / (M - 1.0f));
+}
+
 static inline unsigned blocks_for(int64_t n) { return static_cast<unsigned>((n + 255) / 256); }
 
 }  // namespace fz
@@ -823,6 +835,15 @@ extern "C" int fz_upsample2_concat_backward(const float* dcat, float* da, float*
 extern "C" int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* stream) {
   FZ_REQUIRE(N > 0 && S >= 1 && partial && out, "fz_reduce_rows_f32: bad arguments");
   reduce_rows_kernel<<<(N + 255) / 256, 256, 0, ST(stream)>>>(partial, out, N, S);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_bn_update_running(const float* mean, const float* rstd, float* running_mean, float* running_var, int C,
+                                    int64_t M, float eps, float momentum, void* stream) {
+  FZ_REQUIRE(C > 0 && M > 1 && mean && rstd && running_mean && running_var, "fz_bn_update_running: bad arguments");
+  bn_update_running_kernel<<<(C + 255) / 256, 256, 0, ST(stream)>>>(mean, rstd, running_mean, running_var, C,
+                                                                    static_cast<float>(M), eps, momentum);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -256,7 +256,9 @@ class Conv3x3BnReluTrain:
 
     BN_EPS = 1e-5
 
-    def __init__(self, weight: torch.Tensor, bn_weight=None, bn_bias=None, bias=None):
+    def __init__(self, weight: torch.Tensor, bn_weight=None, bn_bias=None, bias=None, running=None):
+        """running: optional (running_mean, running_var, num_batches_tracked) buffers, updated in place by forward()."""
+        self.running = running
         self.cout, self.cin = weight.shape[0], weight.shape[1]
         self.kpad, self.npad = _ceil64(9 * self.cin), _ceil64(self.cout)
         dev = weight.device
@@ -287,6 +289,12 @@ class Conv3x3BnReluTrain:
         ws = torch.empty((chunks + 1) * 2 * self.cout, dtype=torch.float32, device=dev)
         _chk(_L().fz_bn_relu_train_forward(_P(conv), self.npad, _P(self.g), _P(self.b), _P(y), _P(mean), _P(rstd), _P(ws), M,
                                            self.cout, chunks, self.BN_EPS, _S()), "fz_bn_relu_train_forward")
+        if self.running is not None:
+            rm, rv, nbt = self.running
+            _chk(_L().fz_bn_update_running(_P(mean), _P(rstd), _P(rm), _P(rv), self.cout, M, self.BN_EPS, 0.1, _S()),
+                 "fz_bn_update_running")
+            if nbt is not None:
+                nbt.add_(1)
         self.saved = (col, conv, y, mean, rstd, chunks, (B, H, W))
         return y.view(B, H, W, self.cout)
 
@@ -325,8 +333,13 @@ class UnetDecoderTrain:
         self.blocks = []
         for i in range(n_blocks):
             p = f"decoder.blocks.{i}."
+            def running(k):
+                q = p + f"conv{k}.1."
+                if q + "running_mean" not in params:
+                    return None
+                return (params[q + "running_mean"], params[q + "running_var"], params.get(q + "num_batches_tracked"))
             self.blocks.append(tuple(Conv3x3BnReluTrain(params[p + f"conv{k}.0.weight"], params[p + f"conv{k}.1.weight"],
-                                                        params[p + f"conv{k}.1.bias"]) for k in (1, 2)))
+                                                        params[p + f"conv{k}.1.bias"], running=running(k)) for k in (1, 2)))
         self.head = Conv3x3BnReluTrain(params["segmentation_head.0.weight"], bias=params["segmentation_head.0.bias"])
         self.n_classes = params["segmentation_head.0.weight"].shape[0]
         self.saved = None

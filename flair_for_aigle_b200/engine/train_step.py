@@ -5,8 +5,8 @@ cross entropy, the backward through head, decoder, FusionHandler (flair_model.py
 Everything numeric runs on the CUDA kernels behind the C ABI (engine/convnext_train.py, csrc/backward_ops.cu,
 csrc/training_ops.cu, the tcgen05 GEMM); torch supplies memory, views, concatenation / slicing copies and dtype casts.
 This is the correctness-first version of SURVEY A11: the memory-bound backward kernels and the im2col convolutions are not
-tuned, BatchNorm running statistics are not updated (they do not enter the training forward), gradients are not yet
-all-reduced across ranks."""
+tuned.  BatchNorm running statistics are updated in place like nn.BatchNorm2d does (momentum 0.1, unbiased variance); under
+torch.distributed the flat gradient arena is averaged with one NCCL all-reduce per step."""
 from typing import Dict, List
 
 import torch
@@ -25,6 +25,7 @@ class ConvNeXtUNetTrainer:
         self.depths, self.dims, self.mods, self.task, self.task_weight = depths, dims, list(modalities), task, task_weight
         self.names = [k for k in state if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
         self.params = {k: state[k] for k in self.names}
+        self.buffers = {k: state[k] for k in state if k not in self.params}       # BatchNorm running statistics
         self.opt = AdamW([self.params[k] for k in self.names], lr=lr, weight_decay=weight_decay, betas=betas)
         self.criterion = WeightedCrossEntropy(class_weight)
         self._build()
@@ -38,7 +39,8 @@ class ConvNeXtUNetTrainer:
             self.enc[m] = ConvNeXtV2EncoderTrain({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}, self.depths,
                                                  self.dims)
         pre = f"main_decoders.{self.task}.seg_model."
-        self.dec = UnetDecoderTrain({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)})
+        both = {**p, **self.buffers}
+        self.dec = UnetDecoderTrain({k[len(pre):]: v for k, v in both.items() if k.startswith(pre)})
         self.fuse = None
         if len(self.mods) > 1:
             self.fuse = [(p[f"fusion_handler.conv_f.{i}.weight"].detach().reshape(c, -1).to(torch.bfloat16).contiguous(),

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "fz_col2im3x3": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_bn_relu_train_forward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, ctypes.c_float, _vp],
     "fz_bn_relu_backward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _vp],
+    "fz_bn_update_running": [_vp, _vp, _vp, _vp, _i, _i64, ctypes.c_float, ctypes.c_float, _vp],
     "fz_upsample2_concat_backward": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_head_upsample4": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 }

@@ -360,6 +360,10 @@ int fz_bn_relu_train_forward(const float* x, int ldx, const float* gamma, const 
 int fz_bn_relu_backward(const float* x, int ldx, const void* dy_bf16, const void* y_bf16, const float* mean, const float* rstd,
                         const float* gamma, void* dx_bf16, int ldd, float* dbeta_dgamma, float* workspace, int64_t M, int C,
                         int chunks, void* stream);
+/* BatchNorm2d's running statistics after a training forward (momentum 0.1 in smp's decoder): running_mean / running_var are
+ * updated in place from the batch mean and rstd of fz_bn_relu_train_forward (unbiased variance, like PyTorch). */
+int fz_bn_update_running(const float* mean, const float* rstd, float* running_mean, float* running_var, int C, int64_t M,
+                         float eps, float momentum, void* stream);
 /* gradient of fz_upsample2_concat: da float [B][H][W][C1] (2x2 sums), dskip float [B][2H][2W][C2] from dcat float
  * [B][2H][2W][C1+C2]. */
 int fz_upsample2_concat_backward(const float* dcat, float* da, float* dskip, int B, int H, int W, int C1, int C2, void* stream);

