@@ -16,9 +16,11 @@
 // Host part: ring tracing on the label image (boundary following on the pixel-corner lattice, component on the right,
 // right turn first = 4-connectivity at saddle points), hole rings told from exterior rings by orientation, and a
 // Douglas-Peucker pass per ring.  It runs on the CPU because it is pointer chasing over the boundary only
-// (O(perimeter) after one O(H*W) scan); the O(H*W) labelling is what the GPU takes over.
+// (O(perimeter) after one O(H*W) scan), on host threads that each own a share of the components; the O(H*W) labelling is what the GPU takes over.
 #include <algorithm>
 #include <cmath>
+#include <functional>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(256) ccl_table_kernel(const uint8_t* __restric
 
 // ------------------------------------------------------------------------------------------------ host ring tracer
 struct RingStore {
+  std::vector<size_t> ring_start;     // linear index of the ring's first top edge (its position in a row-major scan)
   std::vector<int32_t> ring_root;
   std::vector<int64_t> ring_offset;   // n_rings + 1
   std::vector<uint8_t> ring_hole;
@@ -205,20 +208,19 @@ extern "C" int fz_ccl_table(const uint8_t* raster, const int32_t* labels, const 
   return 0;
 }
 
-extern "C" int fz_trace_rings(const int32_t* labels, int H, int W, const int32_t* keep_roots, int n_keep,
-                              double simplify_px, int64_t* n_rings, int64_t* n_points) {
-  using namespace fz;
-  FZ_REQUIRE(labels && H > 0 && W > 0 && n_keep >= 0 && n_rings && n_points, "fz_trace_rings: bad arguments");
-  RingStore& rs = g_rings;
-  rs.ring_root.clear();
+namespace fz {
+// Rings of the components owned by thread `tid` of `n_threads` (components are dealt to threads by a hash of their label, so
+// every ring -- exterior or hole -- is walked exactly once, by the thread that owns its component).  Each thread scans the
+// whole label image (cheap next to the walks) and records where each ring starts; the caller merges the threads' rings by
+// that position, which reproduces the order of a single row-major scan.
+static void trace_band(const int32_t* labels, int H, int W, const int32_t* keep_roots, int n_keep, double simplify_px,
+                       int tid, int n_threads, RingStore& rs) {
   rs.ring_offset.assign(1, 0);
-  rs.ring_hole.clear();
-  rs.xy.clear();
   auto kept = [&](int32_t r) { return std::binary_search(keep_roots, keep_roots + n_keep, r); };
   auto lab = [&](int x, int y) -> int32_t {          // -1 outside the raster
     return (x < 0 || y < 0 || x >= W || y >= H) ? -1 : labels[static_cast<size_t>(y) * W + x];
   };
-  // one bit per pixel: "the top edge of this pixel has been walked"
+  // one bit per pixel: "the top edge of this pixel has been walked" (by THIS thread)
   std::vector<uint8_t> seen((static_cast<size_t>(H) * W + 7) / 8, 0);
   std::vector<int32_t> vx, vy;
   std::vector<uint8_t> keep;
@@ -235,7 +237,8 @@ extern "C" int fz_trace_rings(const int32_t* labels, int H, int W, const int32_t
       if (seen[bit >> 3] & (1u << (bit & 7))) continue;
       if (L != last_lab) {
         last_lab = L;
-        last_keep = kept(L);
+        last_keep = (n_threads == 1 || static_cast<int>((static_cast<uint32_t>(L) * 2654435761u >> 16) % n_threads) == tid) &&
+                    kept(L);
       }
       if (!last_keep) continue;
       // walk the ring that contains the east-heading top edge of (x, y), starting at vertex (x, y)
@@ -302,10 +305,49 @@ extern "C" int fz_trace_rings(const int32_t* labels, int H, int W, const int32_t
           rs.xy.push_back(py[i]);
           ++emitted;
         }
+      rs.ring_start.push_back(bit);
       rs.ring_root.push_back(L);
       rs.ring_hole.push_back(area2 < 0 ? 1 : 0);     // y grows downwards: exterior rings (component on the right) have area2 > 0
       rs.ring_offset.push_back(rs.ring_offset.back() + static_cast<int64_t>(emitted));
     }
+}
+}  // namespace fz
+
+extern "C" int fz_trace_rings(const int32_t* labels, int H, int W, const int32_t* keep_roots, int n_keep,
+                              double simplify_px, int64_t* n_rings, int64_t* n_points) {
+  using namespace fz;
+  FZ_REQUIRE(labels && H > 0 && W > 0 && n_keep >= 0 && n_rings && n_points, "fz_trace_rings: bad arguments");
+  // host threads (FZ_TRACE_THREADS overrides), each with its own H*W-bit bitmap; small rasters stay on one thread
+  int threads = static_cast<int>(std::thread::hardware_concurrency());
+  if (const char* e = getenv("FZ_TRACE_THREADS")) threads = atoi(e);
+  else if (static_cast<int64_t>(H) * W < (1 << 20)) threads = 1;
+  threads = threads < 1 ? 1 : (threads > 32 ? 32 : threads);
+  std::vector<RingStore> parts(threads);
+  if (threads == 1) {
+    trace_band(labels, H, W, keep_roots, n_keep, simplify_px, 0, 1, parts[0]);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+      pool.emplace_back(trace_band, labels, H, W, keep_roots, n_keep, simplify_px, t, threads, std::ref(parts[t]));
+    for (auto& th : pool) th.join();
+  }
+  // merge by ring start = the order of one row-major scan (each part is already sorted)
+  std::vector<std::pair<size_t, std::pair<int, int>>> order;            // (start, (part, ring index))
+  for (int t = 0; t < threads; ++t)
+    for (size_t i = 0; i < parts[t].ring_start.size(); ++i) order.push_back({parts[t].ring_start[i], {t, static_cast<int>(i)}});
+  std::sort(order.begin(), order.end());
+  RingStore& rs = g_rings;
+  rs = RingStore();
+  rs.ring_offset.assign(1, 0);
+  for (const auto& o : order) {
+    const RingStore& p = parts[o.second.first];
+    const int i = o.second.second;
+    const int64_t a0 = p.ring_offset[i], a1 = p.ring_offset[i + 1];
+    rs.ring_root.push_back(p.ring_root[i]);
+    rs.ring_hole.push_back(p.ring_hole[i]);
+    rs.xy.insert(rs.xy.end(), p.xy.begin() + 2 * a0, p.xy.begin() + 2 * a1);
+    rs.ring_offset.push_back(rs.ring_offset.back() + (a1 - a0));
+  }
   *n_rings = static_cast<int64_t>(rs.ring_root.size());
   *n_points = rs.ring_offset.back();
   return 0;

@@ -155,3 +155,24 @@ def test_raster_to_polygons_end_to_end(cuda):
     n_full = sum(len(r) for g in table.geometry for r in g["coordinates"])
     n_simp = sum(len(r) for g in simplified.geometry for r in g["coordinates"])
     assert n_simp < n_full
+
+
+def test_ring_tracer_threads_give_the_sequential_result(monkeypatch):
+    """The host tracer deals the components to threads (every ring is walked once, by the owner of its component) and merges
+    the rings by their start position, so any thread count returns exactly the single-thread arrays (order included)."""
+    from flair_for_aigle_b200 import native as nv
+    rng = np.random.default_rng(77)
+    H, W = 700, 420
+    raster = rng.integers(0, 4, (H // 10, W // 10), dtype=np.uint8).repeat(10, axis=0).repeat(10, axis=1)
+    raster[rng.random((H, W)) < 0.03] = 5                                      # speckle: many small holes
+    raster[100:600, 200:210] = 6                                               # a tall component crossing every band
+    labels = label_components(raster)
+    roots, areas, classes = component_table(raster, labels)
+    keep = roots[areas >= 3]
+    monkeypatch.setenv("FZ_TRACE_THREADS", "1")
+    ref = nv.trace_rings(labels, keep, 0.5)
+    for t in ("2", "5", "10"):
+        monkeypatch.setenv("FZ_TRACE_THREADS", t)
+        got = nv.trace_rings(labels, keep, 0.5)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got)), t
+    assert ref[0].size > 1000
