@@ -76,19 +76,26 @@ class ZonalRunner:
         n += 1 + self.eng.decoder.launches()      # + bf16 cast of the deepest stage output
         return n
 
-    def _ensure_graph(self, raster: torch.Tensor, out_raster: torch.Tensor):
-        """Returns the (raster, out) tensors the captured graph reads / writes.  A graph is tied to the addresses
-        it was captured with: when a new zone of the SAME shape arrives in different buffers (a fresh upload, a
-        fresh output raster) it is staged through the captured buffers with two device-to-device copies
-        (~0.2 ms for a 10k x 10k zone) instead of paying a ~100 ms re-capture."""
-        key = (raster.data_ptr(), tuple(raster.shape), out_raster.data_ptr(), tuple(out_raster.shape))
+    def buffers(self, raster_shape, out_shape, dtype=torch.uint8):
+        """The runner-owned device buffers (raster uint8/float [C,H,W], class raster uint8 [OH,OW]) the CUDA graph is
+        captured on.  A graph is tied to the addresses it was captured with, so it is NEVER captured on caller tensors:
+        ``run`` stages a caller's raster / output through these buffers (two device-to-device copies, ~0.2 ms for a
+        10k x 10k zone, instead of a ~100 ms re-capture per zone), ``run_streamed`` uploads straight into them.  A caller
+        that wants to skip the staging copy can fill ``buffers(...)[0]`` itself and pass it to ``run``."""
+        key = (tuple(raster_shape), tuple(out_shape), dtype)
+        if getattr(self, "_buf_key", None) != key:
+            self._graph = None
+            self._g_raster = self._g_out = None          # free the previous zone shape before allocating the next
+            self._g_raster = torch.empty(tuple(raster_shape), dtype=dtype, device=self.dev)
+            self._g_out = torch.zeros(tuple(out_shape), dtype=torch.uint8, device=self.dev)
+            self._buf_key = key
+        return self._g_raster, self._g_out
+
+    def _ensure_graph(self, raster_shape, out_shape, dtype=torch.uint8):
+        """Captures one batch on the private buffers (once per zone shape)."""
+        g_raster, g_out = self.buffers(raster_shape, out_shape, dtype)
         if self._graph is not None:
-            if self._graph_key == key:
-                return raster, out_raster
-            if self._graph_key[1] == key[1] and self._graph_key[3] == key[3]:
-                self._g_raster.copy_(raster, non_blocking=True)
-                self._g_out.copy_(out_raster, non_blocking=True)
-                return self._g_raster, self._g_out
+            return g_raster, g_out
         # warm-up on a side stream (sets func attributes, touches every buffer), then capture
         self.s_plan.zero_()      # height 0 => nothing is written during warm-up / capture
         self.s_own.zero_()
@@ -96,34 +103,41 @@ class ZonalRunner:
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
-            self._batch_body(raster, out_raster)
+            self._batch_body(g_raster, g_out)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._batch_body(raster, out_raster)
-        self._graph, self._graph_key = g, key
-        self._g_raster, self._g_out = raster, out_raster      # keep the captured buffers alive
-        return raster, out_raster
+            self._batch_body(g_raster, g_out)
+        self._graph = g
+        return g_raster, g_out
 
     def run_streamed(self, host_raster: torch.Tensor, plan: np.ndarray, own: np.ndarray,
                      out_raster: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> int:
         """Same result as ``run`` from a PINNED HOST raster, with the upload hidden behind the compute: tiles are
         processed bottom-up by tile row (ownership windows make the order irrelevant to the result), and before each
         batch only the raster rows it needs and that are not resident yet are sent on a copy stream (contiguous per
-        channel plane).  The first batch waits for ~2 tile rows instead of the whole raster.  With ``out_host`` (pinned
-        uint8 [H,W]) the class raster is read back the same way: rows that no unprocessed tile owns any more are final
-        and leave on the copy stream while the next batches run; on return the caller only has to synchronise."""
+        channel plane) INTO the runner's own raster buffer -- the one the CUDA graph reads.  The first batch waits for
+        ~2 tile rows instead of the whole raster.  With ``out_host`` (pinned uint8 [H,W]) the class raster is read back
+        the same way: rows that no unprocessed tile owns any more are final and leave on the copy stream while the next
+        batches run; on return the caller only has to synchronise.  ``out_raster`` receives the finished class raster
+        (one device-to-device copy at the end); its previous content survives where no tile owns a pixel."""
         n = plan.shape[0]
         if n == 0:
             return 0
         C, H, W = host_raster.shape
-        key = (C, H, W)
-        if getattr(self, "_stream_raster_key", None) != key:
-            self._stream_raster = torch.empty((C, H, W), dtype=torch.uint8, device=self.dev)
-            self._stream_raster_key = key
+        if self.use_graph:
+            dev_raster, dev_out = self._ensure_graph((C, H, W), tuple(out_raster.shape), host_raster.dtype)
+            dev_out.copy_(out_raster, non_blocking=True)
+        else:
+            key = (C, H, W, host_raster.dtype)
+            if getattr(self, "_stream_raster_key", None) != key:
+                self._stream_raster = torch.empty((C, H, W), dtype=host_raster.dtype, device=self.dev)
+                self._stream_raster_key = key
+            dev_raster, dev_out = self._stream_raster, out_raster
+        if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
-        dev_raster, cs = self._stream_raster, self._copy_stream
+        cs = self._copy_stream
         order = np.argsort(-plan[:, 0].astype(np.int64), kind="stable")       # bottom rows of the raster first
         plan_o, own_o = plan[order], own[order]
         B = self.B
@@ -161,22 +175,38 @@ class ZonalRunner:
                     ev.record(cur)
                     cs.wait_event(ev)
                     with torch.cuda.stream(cs):
-                        out_host[lo:done_lo[0]].copy_(out_raster[lo:done_lo[0]], non_blocking=True)
+                        out_host[lo:done_lo[0]].copy_(dev_out[lo:done_lo[0]], non_blocking=True)
                     done_lo[0] = lo
 
-        nbat = self.run(dev_raster, plan_o, own_o, out_raster, before_batch=before_batch, after_batch=after_batch)
+        nbat = self._run_batches(dev_raster, dev_out, plan_o, own_o, before_batch, after_batch)
+        if dev_out is not out_raster:
+            out_raster.copy_(dev_out, non_blocking=True)
         if out_host is not None:
             cur.wait_stream(cs)                   # a synchronize on the current stream now covers the read-back
         return nbat
 
-    def run(self, raster: torch.Tensor, plan: np.ndarray, own: np.ndarray, out_raster: torch.Tensor,
-            before_batch=None, after_batch=None) -> int:
+    def run(self, raster: torch.Tensor, plan: np.ndarray, own: np.ndarray, out_raster: torch.Tensor) -> int:
         """raster uint8 [C,H,W] (cuda), plan int32 (n,6), own int32 (n,4), out_raster uint8 [H,W]
-        (cuda).  Tiles are processed in the given order; returns the number of batches.  ``before_batch(b)`` is
-        called on the host before batch b is enqueued (run_streamed's upload hook)."""
-        n = plan.shape[0]
-        if n == 0:
+        (cuda).  Tiles are processed in the given order; returns the number of batches.  With the CUDA graph the
+        caller's tensors are staged through the runner's private buffers (see ``buffers``); a raster that already IS
+        that buffer is not copied."""
+        if plan.shape[0] == 0:
             return 0
+        if not self.use_graph:
+            return self._run_batches(raster, out_raster, plan, own, None, None)
+        g_raster, g_out = self._ensure_graph(tuple(raster.shape), tuple(out_raster.shape), raster.dtype)
+        if raster.data_ptr() != g_raster.data_ptr():
+            g_raster.copy_(raster, non_blocking=True)
+        g_out.copy_(out_raster, non_blocking=True)
+        nb = self._run_batches(g_raster, g_out, plan, own, None, None)
+        out_raster.copy_(g_out, non_blocking=True)
+        return nb
+
+    def _run_batches(self, raster: torch.Tensor, out_raster: torch.Tensor, plan: np.ndarray, own: np.ndarray,
+                     before_batch, after_batch) -> int:
+        """``raster`` / ``out_raster`` are the graph's own buffers (graph mode) or any device tensors (eager mode).
+        ``before_batch(b)`` / ``after_batch(b)`` run on the host around the enqueue of batch b (upload / read-back hooks)."""
+        n = plan.shape[0]
         B = self.B
         nb = (n + B - 1) // B
         pad = nb * B - n
@@ -185,7 +215,6 @@ class ZonalRunner:
         plan_d = torch.from_numpy(np.ascontiguousarray(plan_p)).to(self.dev, non_blocking=True)
         own_d = torch.from_numpy(np.ascontiguousarray(own_p)).to(self.dev, non_blocking=True)
         org_d = plan_d[:, :2].contiguous()
-        g_raster, g_out = (self._ensure_graph(raster, out_raster) if self.use_graph else (raster, out_raster))
         for b in range(nb):
             sl = slice(b * B, (b + 1) * B)
             if before_batch is not None:
@@ -197,10 +226,6 @@ class ZonalRunner:
                 self._graph.replay()
             else:
                 self._batch_body(raster, out_raster)
-            if after_batch is not None and g_out is out_raster:
+            if after_batch is not None:
                 after_batch(b)
-        if g_out is not out_raster:
-            out_raster.copy_(g_out, non_blocking=True)
-            if after_batch is not None:          # staged through the captured buffer: read back in one piece
-                after_batch(nb - 1)
         return nb

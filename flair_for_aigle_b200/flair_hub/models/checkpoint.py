@@ -1,173 +1,201 @@
-"""Checkpoint loading: drop-in for flair_hub/models/checkpoint.py (same names, same behaviour).
+"""Checkpoint loading: drop-in for ``load_checkpoint`` of flair_hub/models/checkpoint.py:176-290.
 
-Behaviour kept from the reference (checkpoint.py:176-290):
-  * ``.safetensors`` via safetensors, anything else via ``torch.load(...)["state_dict"]`` (:206-212);
-  * a leading ``model.`` (Lightning) is stripped when the module's own keys have none (:134-173);
-  * per task, ``[model.]main_decoders.<task>.seg_model.segmentation_head.0.{weight,bias}`` is
-    re-initialised (Xavier / zeros) when missing or when its class count differs (:224-241, :87-131);
-  * any other shape mismatch: ``relative_position_bias_table`` is resized bicubically (:33-56),
-    everything else re-initialised (:265-274);
-  * ``load_state_dict(strict=False)`` (:278); invalid path -> ``SystemExit`` unless
-    ``exit_on_fail=False`` (:200-204).
+The reference patches the checkpoint's tensors until ``load_state_dict(strict=False)`` cannot fail, in a fixed
+order that matters because every re-initialisation draws from torch's global RNG.  Here the same behaviour is
+a short list of REPAIR PASSES over the loaded tensors, each pass a pure function of (checkpoint tensors, module
+tensors) that returns the replacements it wants; ``load_checkpoint`` applies them in the reference's order, so
+that under the same ``torch.manual_seed`` the loaded module is bit-identical to the reference's
+(``tests/test_reference_pin.py::test_load_checkpoint_*`` runs both on crafted checkpoints).
+
+  pass                    reference lines   rule
+  ----------------------  ----------------  ---------------------------------------------------------------
+  read                    :206-212          ``.safetensors`` -> safetensors, else ``torch.load(path)["state_dict"]``
+                                            (a bare state dict is accepted too); bad path -> ``SystemExit`` unless
+                                            ``exit_on_fail=False`` (:200-204)
+  lightning prefix        :134-173          drop a leading ``model.`` from checkpoint keys iff some checkpoint key
+                                            has it and NO module key has it
+  task heads              :224-241,:87-131  per task, the head ``main_decoders.<task>.seg_model.segmentation_head.0``
+                                            is looked up with and without ``model.``; a missing head or one with
+                                            another class count is re-initialised (weight, then bias)
+  auxiliary heads         :243-250          same for module keys under ``model.aux_decoders.``
+  criterion weights       :252-259          a class-weight vector of another length takes the module's
+  shape mismatches        :261-274          ``relative_position_bias_table`` -> bicubic resize of the square table
+                                            (:33-56); anything else -> re-initialised
+  load                    :278              ``load_state_dict(strict=False)``
+
+Re-initialisation (:11-31) goes by NAME: ``weight`` in the key -> Xavier-uniform (a 1-D tensor therefore raises
+``ValueError``, as in the reference); ``bias`` in the key -> zeros (this catches ``relative_position_bias_table``
+too); any other tensor (BatchNorm statistics) is left as ``torch.empty_like`` by the reference, i.e. undefined --
+zeros here.  Deviation, deliberate: the reference's ``@rank_zero_only`` makes every rank but 0 skip the load and
+rely on DDP's broadcast; the zonal strips have no DDP wrapper, so every rank loads.
 """
 from __future__ import annotations
 
 import logging
 import os
-from typing import Any, Dict, List, Optional, Set
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, Iterator, List, Optional, Set, Tuple
 
 import torch
 import torch.nn as nn
 
 logger = logging.getLogger(__name__)
 
+Tensors = Dict[str, torch.Tensor]
+HEAD = "seg_model.segmentation_head.0.weight"
 
-def reinit_param(state_dict: dict, model_dict: dict, key: str) -> bool:
-    if key not in model_dict:
-        return False
+
+@dataclass
+class LoadReport:
+    matched_tasks: Set[str] = field(default_factory=set)
+    reinit_tasks: Set[str] = field(default_factory=set)
+    reinit_tensors: int = 0
+    resized: List[str] = field(default_factory=list)
+    missing_keys: List[str] = field(default_factory=list)
+    unexpected_keys: List[str] = field(default_factory=list)
+
+
+def _fresh(module_t: Tensors, key: str) -> Optional[torch.Tensor]:
+    """The reference's name-based re-initialisation of ``key`` (None when the module has no such tensor)."""
+    if key not in module_t:
+        return None
+    t = torch.empty_like(module_t[key])
     with torch.no_grad():
-        fresh = torch.empty_like(model_dict[key])
-        if 'weight' in key:
-            if fresh.dim() >= 2:
-                nn.init.xavier_uniform_(fresh)
-            else:
-                fresh.fill_(1.0)
-        elif 'bias' in key:
-            fresh.zero_()
-        state_dict[key] = fresh
-    return True
+        if "weight" in key:
+            nn.init.xavier_uniform_(t)       # raises ValueError on 1-D tensors, like the reference
+        else:
+            t.zero_()                        # 'bias' -> zeros; anything else is undefined in the reference
+    return t
+
+
+def _spelled(key: str, ckpt: Tensors) -> Optional[str]:
+    """``key`` as the checkpoint spells it: as given, or with the ``model.`` prefix toggled (:62-84)."""
+    other = key[6:] if key.startswith("model.") else "model." + key
+    return key if key in ckpt else (other if other in ckpt else None)
 
 
 def interpolate_bias_table(ckpt_tensor: torch.Tensor, model_tensor: torch.Tensor) -> torch.Tensor:
-    """(N_old, heads) -> (N_new, heads), bicubic on the square table (checkpoint.py:33-56)."""
-    n_old, heads = ckpt_tensor.shape
-    n_new = model_tensor.shape[0]
+    """Swin relative-position table (N_old, heads) -> (N_new, heads): bicubic, ``align_corners=False``, on the
+    square (2w-1) x (2w-1) grid (:33-56).  Non-square lengths raise AssertionError."""
+    (n_old, heads), n_new = ckpt_tensor.shape, model_tensor.shape[0]
     if n_old == n_new:
         return ckpt_tensor
-    s_old, s_new = int(n_old ** 0.5), int(n_new ** 0.5)
-    assert s_old * s_old == n_old, f"Checkpoint bias table shape {n_old} is not square"
-    assert s_new * s_new == n_new, f"Model bias table shape {n_new} is not square"
-    t = ckpt_tensor.reshape(1, s_old, s_old, heads).permute(0, 3, 1, 2)
-    t = torch.nn.functional.interpolate(t, size=(s_new, s_new), mode='bicubic', align_corners=False)
-    return t.permute(0, 2, 3, 1).reshape(n_new, heads)
+    side = [int(n ** 0.5) for n in (n_old, n_new)]
+    assert side[0] ** 2 == n_old, f"Checkpoint bias table shape {n_old} is not square"
+    assert side[1] ** 2 == n_new, f"Model bias table shape {n_new} is not square"
+    grid = ckpt_tensor.reshape(1, side[0], side[0], heads).permute(0, 3, 1, 2)
+    grid = torch.nn.functional.interpolate(grid, size=(side[1], side[1]), mode="bicubic", align_corners=False)
+    return grid.permute(0, 2, 3, 1).reshape(n_new, heads)
 
 
-def get_task_name_from_aux_key(key: str) -> str:
-    return key.split(".")[2].split("__")[1]
-
-
-def resolve_key(key: str, state_dict: dict) -> Optional[str]:
-    alt = key[len("model."):] if key.startswith("model.") else f"model.{key}"
-    for k in (key, alt):
-        if k in state_dict:
-            return k
-    return None
-
-
-def check_and_reinit_layer(state_dict, model_dict, key_weight, key_bias, expected_classes, matched_tasks: Set[str],
-                           reinit_tasks: Set[str], task_label: str, reinit_counter: List[int]) -> None:
-    kw, kb = resolve_key(key_weight, state_dict), resolve_key(key_bias, state_dict)
-    if kw:
-        found = state_dict[kw].shape[0]
-        if found != expected_classes:
-            logger.info(f"→ Mismatch: {kw}: ckpt={found}, config={expected_classes}")
-            reinit_counter[0] += reinit_param(state_dict, model_dict, key_weight)
-            if kb:
-                reinit_counter[0] += reinit_param(state_dict, model_dict, key_bias)
-            reinit_tasks.add(task_label)
-        else:
-            matched_tasks.add(task_label)
-    else:
-        logger.info(f"→ Missing: {key_weight}")
-        if key_weight in model_dict:
-            reinit_counter[0] += reinit_param(state_dict, model_dict, key_weight)
-        if key_bias in model_dict:
-            reinit_counter[0] += reinit_param(state_dict, model_dict, key_bias)
-        reinit_tasks.add(task_label)
-
-
-def strip_model_prefix_if_needed(state_dict: Dict[str, torch.Tensor], model_dict: Dict[str, torch.Tensor],
-                                 verbose: bool = False) -> Dict[str, torch.Tensor]:
-    ckpt_has = any(k.startswith("model.") for k in state_dict)
-    model_has_none = all(not k.startswith("model.") for k in model_dict)
-    if not (ckpt_has and model_has_none):
+def strip_model_prefix_if_needed(state_dict: Tensors, model_dict: Tensors, verbose: bool = False) -> Tensors:
+    if not any(k.startswith("model.") for k in state_dict) or any(k.startswith("model.") for k in model_dict):
         logger.info("→ No prefix stripping needed.")
         return state_dict
-    out, n = {}, 0
-    for k, v in state_dict.items():
-        if k.startswith("model."):
-            out[k[len("model."):]] = v
-            n += 1
-        else:
-            out[k] = v
-    logger.info(f"→ Stripped 'model.' prefix from {n} keys.")
+    out = {(k[6:] if k.startswith("model.") else k): v for k, v in state_dict.items()}
+    logger.info(f"→ Stripped 'model.' prefix from {sum(k.startswith('model.') for k in state_dict)} keys.")
     return out
 
 
+def _read(path: str) -> Tensors:
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return dict(load_file(path))
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    return dict(blob.get("state_dict", blob))
+
+
+def _repair_head(ckpt: Tensors, module_t: Tensors, w_key: str, n_classes: int, label: str, rep: LoadReport) -> bool:
+    """One classification head under one spelling of its key.  True when the checkpoint's head fits."""
+    b_key = w_key.replace("weight", "bias")
+    found_w, found_b = _spelled(w_key, ckpt), _spelled(b_key, ckpt)
+    if found_w is not None and ckpt[found_w].shape[0] == n_classes:
+        rep.matched_tasks.add(label)
+        return True
+    if found_w is not None:
+        logger.info(f"→ Mismatch: {found_w}: ckpt={ckpt[found_w].shape[0]}, config={n_classes}")
+        wanted = [w_key] + ([b_key] if found_b is not None else [])
+    else:
+        logger.info(f"→ Missing: {w_key}")
+        wanted = [w_key, b_key]
+    for k in wanted:                      # weight first, then bias: the RNG order of the reference
+        t = _fresh(module_t, k)
+        if t is not None:
+            ckpt[k] = t
+            rep.reinit_tensors += 1
+    rep.reinit_tasks.add(label)
+    return False
+
+
+def _pass_task_heads(ckpt: Tensors, module_t: Tensors, conf: Dict[str, Any], rep: LoadReport) -> None:
+    for task in conf["labels"]:
+        n = len(conf["labels_configs"][task]["value_name"])
+        spellings = (f"model.main_decoders.{task}.{HEAD}", f"main_decoders.{task}.{HEAD}")
+        if not any(_repair_head(ckpt, module_t, k, n, task, rep) for k in spellings):
+            logger.info(f"No valid weights found for task '{task}', reinitialized.")
+
+
+def _pass_aux_heads(ckpt: Tensors, module_t: Tensors, conf: Dict[str, Any], rep: LoadReport) -> None:
+    for key in module_t:
+        if key.startswith("model.aux_decoders.") and HEAD in key:
+            task = key.split(".")[2].split("__")[1]            # model.aux_decoders.<MOD>__<TASK>.… (:59-60)
+            n = len(conf["labels_configs"].get(task, {}).get("value_name", []))
+            _repair_head(ckpt, module_t, key, n, task, rep)
+
+
+def _pass_criterion(ckpt: Tensors, module_t: Tensors, conf: Dict[str, Any], rep: LoadReport) -> None:
+    for task in conf["labels"]:
+        k = f"criterion.{task}.weight"
+        if k in ckpt and k in module_t and ckpt[k].shape != module_t[k].shape:
+            logger.info(f"→ Reinitializing criterion weights for {task}")
+            ckpt[k] = module_t[k].clone()
+            rep.reinit_tensors += 1
+
+
+def _pass_shapes(ckpt: Tensors, module_t: Tensors, conf: Dict[str, Any], rep: LoadReport) -> None:
+    for k in list(ckpt):
+        if k not in module_t or ckpt[k].shape == module_t[k].shape:
+            continue
+        if "relative_position_bias_table" in k:
+            logger.info(f"→ Interpolating {k}: {tuple(ckpt[k].shape)} → {tuple(module_t[k].shape)}")
+            try:
+                ckpt[k] = interpolate_bias_table(ckpt[k], module_t[k])
+                rep.resized.append(k)
+                continue
+            except Exception as e:  # noqa: BLE001 -- the reference catches everything here (:268-271)
+                logger.info(f"⚠️  Interpolation failed for {k}: {e}. Reinitializing instead.")
+        else:
+            logger.info(f"→ Shape mismatch for {k}: checkpoint {tuple(ckpt[k].shape)} vs model "
+                        f"{tuple(module_t[k].shape)}. Reinitializing...")
+        ckpt[k] = _fresh(module_t, k)
+        rep.reinit_tensors += 1
+
+
+REPAIR_PASSES: Tuple[Callable[[Tensors, Tensors, Dict[str, Any], LoadReport], None], ...] = (
+    _pass_task_heads, _pass_aux_heads, _pass_criterion, _pass_shapes)
+
+
 def load_checkpoint(conf: Dict[str, Any], seg_module: nn.Module, exit_on_fail: bool = True) -> None:
-    path = conf['paths']['ckpt_model_path']
+    """Same call and effect as the reference's: ``conf['paths']['ckpt_model_path']`` into ``seg_module`` in place.
+    The ``LoadReport`` is left on ``seg_module.last_load_report`` (the reference only logs it)."""
+    path = conf["paths"]["ckpt_model_path"]
     logger.info(f"→ Loading checkpoint from: {path}")
     if not path or not os.path.isfile(path):
         logger.info("❌ Invalid checkpoint path.")
         if exit_on_fail:
             raise SystemExit()
         return
-
-    if path.endswith(".safetensors"):
-        from safetensors.torch import load_file as safe_load_file
-        state_dict = safe_load_file(path)
-    else:
-        ckpt = torch.load(path, map_location="cpu", weights_only=False)
-        state_dict = ckpt.get("state_dict", ckpt)
-    logger.info(f"→ Original state dict keys: {len(state_dict)}")
-
-    state_dict = strip_model_prefix_if_needed(dict(state_dict), seg_module.state_dict())
-    model_dict = seg_module.state_dict()
-    tasks = conf["labels"]
-    matched, reinit, counter = set(), set(), [0]
-
-    for task in tasks:
-        n_classes = len(conf["labels_configs"][task]["value_name"])
-        ok = False
-        for w_key in (f"model.main_decoders.{task}.seg_model.segmentation_head.0.weight",
-                      f"main_decoders.{task}.seg_model.segmentation_head.0.weight"):
-            before = len(matched)
-            check_and_reinit_layer(state_dict, model_dict, w_key, w_key.replace("weight", "bias"), n_classes, matched,
-                                   reinit, task, counter)
-            if len(matched) > before:
-                ok = True
-                break
-        if not ok:
-            logger.info(f"No valid weights found for task '{task}', reinitialized.")
-
-    for key in model_dict:
-        if key.startswith("model.aux_decoders.") and "seg_model.segmentation_head.0.weight" in key:
-            task_id = get_task_name_from_aux_key(key)
-            n_classes = len(conf["labels_configs"].get(task_id, {}).get("value_name", []))
-            check_and_reinit_layer(state_dict, model_dict, key, key.replace("weight", "bias"), n_classes, matched,
-                                   reinit, task_id, counter)
-
-    for task in tasks:
-        ck = f"criterion.{task}.weight"
-        if ck in state_dict and ck in model_dict and state_dict[ck].shape != model_dict[ck].shape:
-            state_dict[ck] = model_dict[ck].clone()
-            counter[0] += 1
-
-    for k in list(state_dict):
-        if k in model_dict and state_dict[k].shape != model_dict[k].shape:
-            if "relative_position_bias_table" in k:
-                try:
-                    state_dict[k] = interpolate_bias_table(state_dict[k], model_dict[k])
-                except Exception as e:  # noqa: BLE001 - mirror the reference's catch-all
-                    logger.info(f"⚠️  Interpolation failed for {k}: {e}. Reinitializing instead.")
-                    counter[0] += reinit_param(state_dict, model_dict, k)
-            else:
-                logger.info(f"→ Shape mismatch for {k}: checkpoint {tuple(state_dict[k].shape)} vs model "
-                            f"{tuple(model_dict[k].shape)}. Reinitializing...")
-                counter[0] += reinit_param(state_dict, model_dict, k)
-
-    result = seg_module.load_state_dict(state_dict, strict=False)
-    logger.info(f"Checkpoint load summary: matched={sorted(matched)} reinitialised={sorted(reinit)} "
-                f"tensors_reinit={counter[0]} missing={len(result.missing_keys)} "
-                f"unexpected={len(result.unexpected_keys)}")
+    ckpt = _read(path)
+    logger.info(f"→ Original state dict keys: {len(ckpt)}")
+    ckpt = strip_model_prefix_if_needed(ckpt, seg_module.state_dict())
+    module_t = seg_module.state_dict()
+    rep = LoadReport()
+    for repair in REPAIR_PASSES:
+        repair(ckpt, module_t, conf, rep)
+    result = seg_module.load_state_dict(ckpt, strict=False)
+    rep.missing_keys, rep.unexpected_keys = list(result.missing_keys), list(result.unexpected_keys)
+    logger.info(f"Checkpoint load summary: matched={sorted(rep.matched_tasks)} reinitialised={sorted(rep.reinit_tasks)} "
+                f"tensors_reinit={rep.reinit_tensors} resized={len(rep.resized)} missing={len(rep.missing_keys)} "
+                f"unexpected={len(rep.unexpected_keys)}")
+    seg_module.last_load_report = rep
     seg_module.last_load_result = result

@@ -21,6 +21,7 @@ import logging
 import math
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -141,10 +142,11 @@ class FLAIR_HUB_Model(nn.Module):
 
     # -------------------------------------------------------------------------------- helpers
     def _normalisation(self, mod: str):
-        cfg = self.config['modalities'].get(mod, {}).get('normalization', {}) or {}
-        if cfg.get('type') == 'custom' and cfg.get('means') and len(cfg['means']) == self.channels_dict[mod]:
-            return list(cfg['means']), list(cfg['stds'])
-        return None
+        """(means, stds) the fused uint8 stem folds in: every normalisation type of norm.py, for 8-bit imagery (the only
+        raster type the fused feeder reads)."""
+        from ...flair_zonal_detection.dataset import normalization_affine
+        return normalization_affine(self.config['modalities'].get(mod, {}).get('normalization'), self.channels_dict[mod],
+                                    np.uint8)
 
     def _device(self) -> torch.device:
         return next(self.parameters()).device

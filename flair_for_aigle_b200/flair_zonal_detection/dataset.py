@@ -23,6 +23,40 @@ from .slicing import ownership_windows, tile_plan
 logger = logging.getLogger(__name__)
 
 
+def normalization_affine(norm_cfg: Optional[Dict[str, Any]], channels: int, dtype=np.uint8):
+    """(means, stds) such that ``(x - mean_c) / std_c`` is what the reference's ``_normalize_patch`` (dataset.py:119-124)
+    -> ``norm`` (flair_hub/data/utils_data/norm.py:8-52) does to a patch of ``dtype``:
+      no / empty ``normalization`` block -> identity;  ``custom`` -> the configured per-channel means / stds;
+      ``scaling`` -> ``skimage.img_as_float`` (x / dtype max for unsigned integers, identity for floats);
+      ``without`` -> identity.  An unknown type, or means / stds of different lengths, end the program like norm.py:33-40
+    (``sys.exit(1)``).  One helper for every consumer (generic batches, fused stem, float-tile engines)."""
+    ident = [0.0] * channels, [1.0] * channels
+    if not norm_cfg:
+        return ident
+    kind = norm_cfg.get("type")
+    if kind not in ("scaling", "custom", "without"):
+        logger.info("Error: Normalization argument should be 'scaling', 'custom', or 'without'.")
+        raise SystemExit(1)
+    if kind == "custom":
+        means, stds = list(norm_cfg.get("means") or []), list(norm_cfg.get("stds") or [])
+        if len(means) != len(stds):
+            logger.info("Error: If using 'custom', the provided means and stds must have the same length.")
+            raise SystemExit(1)
+        if len(means) < channels:
+            # norm.py:42-44 indexes means[i] for every channel: an IndexError caught by its blanket except -> exit
+            logger.info("Unexpected error during normalization: list index out of range")
+            raise SystemExit(1)
+        return [float(v) for v in means[:channels]], [float(v) for v in stds[:channels]]
+    if kind == "scaling":
+        dt = np.dtype(dtype)
+        if dt.kind == "u":
+            return [0.0] * channels, [float(np.iinfo(dt).max)] * channels
+        if dt.kind == "f":
+            return ident
+        raise NotImplementedError(f"'scaling' normalisation of {dt} rasters")
+    return ident
+
+
 class MultiModalSlicedDataset(Dataset):
     def __init__(self, dataframe, modality_cfgs: Dict[str, Dict[str, Any]], patch_size_dict: Dict[str, int],
                  ref_date_str: Optional[str], modalities_config: Dict[str, Any]) -> None:

@@ -29,7 +29,7 @@ import torch
 from .. import native as nv
 from ..engine.zonal import ZonalRunner
 from .config import config_recap_1, config_recap_2, load_config, validate_config
-from .dataset import MultiModalSlicedDataset
+from .dataset import MultiModalSlicedDataset, normalization_affine
 from .model_utils import build_inference_model, compute_patch_sizes
 from .postprocess import convert  # noqa: F401  (re-exported like the reference)
 from .raster import RasterSink, ZoneRaster, open_raster
@@ -257,10 +257,11 @@ def _iter_batches(dataloader, dataset, model, config, device):
     feeds = []
     for mod in model.active_mono:
         raster = dataset.device_raster(mod, device)
-        norm = dataset.modalities[mod].get('normalization', {}) or {}
         C = raster.shape[0]
-        mean = torch.tensor(norm.get('means', [0.0] * C), dtype=torch.float32, device=device)
-        std = torch.tensor(norm.get('stds', [1.0] * C), dtype=torch.float32, device=device)
+        means, stds = normalization_affine(dataset.modalities[mod].get('normalization'), C,
+                                           np.uint8 if raster.dtype == torch.uint8 else np.float32)
+        mean = torch.tensor(means, dtype=torch.float32, device=device)
+        std = torch.tensor(stds, dtype=torch.float32, device=device)
         origins = torch.from_numpy(dataset.modality_origins(mod)).to(device)
         feeds.append((mod, raster, mean, std, origins, int(dataset.patch_sizes.get(mod, config['img_pixels_detection']))))
     bs = int(config.get('batch_size', 8))

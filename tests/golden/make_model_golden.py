@@ -1,9 +1,10 @@
-"""Generates tests/golden/model_<arch>.npz from the fp32 ORACLE (oracle/models.py) on CPU: for one seeded 512x512
-tile and seeded bf16-exact random weights in the reference's state_dict layout, the central 256x256 of the class map,
-a bit mask of the pixels whose top-2 logit gap exceeds 5 % of the logit std ("confident" pixels) and a few logit
-statistics.  The reference itself cannot run here (smp / timm absent), so these pin the oracle against regressions and
-give the GPU tests a fixture that does not need the oracle at run time.
-Run:  python tests/golden/make_model_golden.py"""
+"""Generates tests/golden/model_<arch>.npz on CPU from the REFERENCE's ``FLAIR_HUB_Model.forward`` (flair_model.py:357-430,
+imported from /root/reference behind tests/reference_stubs.py; its smp / timm sub-modules, absent from the image, are the
+restated ones of oracle/models.py): for one seeded 512x512 tile and seeded bf16-exact random weights in the reference's
+state_dict layout, the central 256x256 of the class map, a bit mask of the pixels whose top-2 logit gap exceeds 5 % of
+the logit std ("confident" pixels) and a few logit statistics.  The CPU suite checks that the oracle reproduces them, the
+GPU suite checks the engines against them without the oracle at run time.
+Run:  python tests/golden/make_model_golden.py          (needs /root/reference)"""
 import os
 import sys
 
@@ -46,6 +47,20 @@ def oracle_logits(arch: str, sd, xn):
     return out[TASK][0]
 
 
+def reference_logits(arch: str, sd, xn):
+    """The reference's own model class and forward (needs /root/reference)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import reference_stubs as rs
+    rs.install()
+    import test_reference_pin as pin
+    from flair_hub.models.flair_model import FLAIR_HUB_Model as RefModel
+    m = RefModel(pin._model_cfg(arch, {"AERIAL_RGBI": 4}), {"AERIAL_RGBI": 512}).eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out, _ = m({"AERIAL_RGBI": xn, TASK: torch.zeros(1, 19, 512, 512)})
+    return out[TASK][0]
+
+
 def summarise(logits: torch.Tensor):
     c = logits[:, 128:384, 128:384]
     top2 = c.topk(2, dim=0).values
@@ -59,7 +74,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     for arch, seed in ARCHS.items():
         sd, tile, xn = golden_inputs(arch, seed)
-        g = summarise(oracle_logits(arch, sd, xn))
+        g = summarise(reference_logits(arch, sd, xn))
         path = os.path.join(HERE, f"model_{arch.split('-')[0]}.npz")
         np.savez_compressed(path, **g)
         print(arch, "->", path, os.path.getsize(path), "bytes; stats", g["stats"], "confident frac",

@@ -1,5 +1,6 @@
-"""CPU: committed golden fixtures (tests/golden, made by tests/golden/make_golden.py from the oracle at
-the SURVEY.md H7 known-answer cases) against the oracle AND the product's grid implementation."""
+"""CPU: committed golden fixtures (tests/golden, made by tests/golden/make_reference_golden.py by running the
+REFERENCE's own slicing / dataset / inference_and_write / convert code at the SURVEY.md H7 cases) against the oracle AND
+the product's grid implementation.  These travel to the GPU box, where /root/reference does not exist."""
 import json
 import os
 
@@ -18,7 +19,7 @@ H7 = {"1000x700_m64": 6, "2048x2048_m128": 64, "777x1300_m40": 8, "10000x10000_m
       "10000x10000_m128": 1600, "10000x10000_m40": 576, "20000x20000_m64": 2809}
 
 
-@pytest.mark.parametrize("key", sorted(PLANS))
+@pytest.mark.parametrize("key", sorted(k for k in PLANS if not k.startswith("_")))
 def test_grid_golden(key):
     g = PLANS[key]
     assert g["n_tiles"] == H7[key]                       # the survey's independently derived counts

@@ -323,3 +323,51 @@ def test_streamed_upload_equals_resident_run(setup):
         torch.cuda.synchronize()
         assert torch.equal(a, b) and int(a.max()) < 19
         assert torch.equal(back, a.cpu())               # streamed read-back of the finished rows
+
+
+def test_graph_runner_never_aliases_caller_buffers(setup):
+    """Round-1 advisor finding: the graph used to be captured on the FIRST caller's tensors, so (a) a streamed run after
+    a resident run replayed on a stale raster and (b) every later zone was written through the first zone's output tensor.
+    Two different rasters of the same shape through ONE graph runner, resident then streamed then resident, each checked
+    against an independent eager (use_graph=False) runner; earlier outputs must keep their content."""
+    from flair_for_aigle_b200.engine.zonal import ZonalRunner
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import (generate_patches_from_reference,
+                                                                    ownership_windows, tile_plan)
+    from flair_for_aigle_b200.synthetic import synthetic_raster
+    tmp, wpath, _ = setup
+    arr1, cfg = _zone(tmp, wpath, 1300, 1100, 64, "mem://z_alias", batch=4)
+    arr2 = synthetic_raster(1100, 1300, seed=99)
+    assert arr2.shape == arr1.shape and not np.array_equal(arr1, arr2)
+    dev = cfg["device"]
+    model = build_inference_model(cfg, {"AERIAL_RGBI": 512}).to(dev)
+    tiles = generate_patches_from_reference(cfg, "mem://z_alias", None)
+    plan = tile_plan(tiles, cfg["image_bounds"], RES, 512, 64)
+    own = ownership_windows(plan)
+    eng = model.engine(TASK, max_batch=4)
+
+    def eager(arr):
+        out = torch.full((1100, 1300), 255, dtype=torch.uint8, device=dev)
+        ZonalRunner(eng, 64, use_graph=False).run(torch.from_numpy(arr).to(dev), plan, own, out)
+        torch.cuda.synchronize()
+        return out.cpu()
+
+    want1, want2 = eager(arr1), eager(arr2)
+    assert float((want1 != want2).float().mean()) > 0.05          # the two zones really differ
+    runner = ZonalRunner(eng, 64, use_graph=True)
+    x1 = torch.from_numpy(arr1).to(dev)
+    o1 = torch.full((1100, 1300), 255, dtype=torch.uint8, device=dev)
+    runner.run(x1, plan, own, o1)                                  # resident, captures the graph
+    torch.cuda.synchronize()
+    assert torch.equal(o1.cpu(), want1)
+    o2 = torch.full((1100, 1300), 255, dtype=torch.uint8, device=dev)
+    back = torch.full((1100, 1300), 254, dtype=torch.uint8).pin_memory()
+    runner.run_streamed(torch.from_numpy(arr2).pin_memory(), plan, own, o2, out_host=back)   # streamed, other raster
+    torch.cuda.synchronize()
+    assert torch.equal(o2.cpu(), want2) and torch.equal(back, want2)
+    assert torch.equal(o1.cpu(), want1)                            # zone 1's output was not touched by zone 2
+    assert torch.equal(x1.cpu(), torch.from_numpy(arr1))           # nor was the caller's raster
+    o3 = torch.full((1100, 1300), 255, dtype=torch.uint8, device=dev)
+    runner.run(x1, plan, own, o3)                                  # resident again after the streamed run
+    torch.cuda.synchronize()
+    assert torch.equal(o3.cpu(), want1) and torch.equal(o2.cpu(), want2)
