@@ -77,6 +77,27 @@ def zonal_config(weights_path: str, out_dir: str, raster_name: str, batch: int) 
     }
 
 
+def random_state(mods: dict, seed: int = 2025, arch: str = ARCH) -> dict:
+    """Seeded random state_dict in the reference's layout for the modalities ``{MOD: channels}`` (product model class only;
+    the oracle is not involved)."""
+    from flair_for_aigle_b200.flair_hub.models.flair_model import FLAIR_HUB_Model
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import prepare_model_config
+    from flair_for_aigle_b200.synthetic import randomize_state_
+    c = zonal_config("unused", tempfile.gettempdir(), "unused", 1)
+    c["monotemp_arch"] = arch
+    for m, ch in mods.items():
+        c["modalities"]["inputs"][m] = True
+        c["modalities"].setdefault(m, {"input_img_path": "unused", "channels": list(range(1, ch + 1))})
+    if "DEM_ELEV" in mods:
+        c["modalities"]["DEM_ELEV"].update({"calc_elevation": True, "calc_elevation_stack_dsm": False})
+    for m in list(c["modalities"]["inputs"]):
+        if m not in mods:
+            c["modalities"]["inputs"][m] = False
+    sd = FLAIR_HUB_Model(prepare_model_config(c), {m: PATCH for m in mods}).state_dict()
+    randomize_state_(sd, seed)
+    return sd
+
+
 def make_weights(path: str, seed: int = 2025) -> None:
     """Random-init checkpoint in the reference's state_dict layout (.safetensors)."""
     from safetensors.torch import save_file

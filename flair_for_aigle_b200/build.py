@@ -41,24 +41,32 @@ def _newer(target: Path, deps) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> Path:
+def build_native(force: bool = False, verbose: bool = False, operands: str = "f16") -> Path:
+    """operands="f16": the product library (inference kernels store fp16 operands, csrc/operand.cuh).
+    operands="bf16": libfz_b200_bf16.so, the round-1 behaviour, for A/B measurements (FZ_OPERANDS=bf16 selects it)."""
+    if operands not in ("f16", "bf16"):
+        raise ValueError(operands)
     OUT_DIR.mkdir(exist_ok=True)
+    obj_dir = OUT_DIR if operands == "f16" else OUT_DIR / "bf16"
+    obj_dir.mkdir(exist_ok=True)
+    lib = LIB if operands == "f16" else OUT_DIR / "libfz_b200_bf16.so"
+    flags = NVCC_FLAGS + (["-DFZ_OPERANDS_BF16"] if operands == "bf16" else [])
     nvcc = _nvcc()
     sources = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h"))
     objs = []
     jobs = []
     for src in sources:
-        obj = OUT_DIR / (src.stem + ".o")
+        obj = obj_dir / (src.stem + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + headers):
             jobs.append((src, obj))
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *flags, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
-        log = OUT_DIR / (src.stem + ".ptxas.log")
+        log = obj_dir / (src.stem + ".ptxas.log")
         log.write_text(res.stdout + res.stderr)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stderr[-4000:]}")
@@ -69,15 +77,15 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
-    if jobs or force or not LIB.exists():
-        cmd = [nvcc, "-shared", "-o", str(LIB), *[str(o) for o in objs], "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    if jobs or force or not lib.exists():
+        cmd = [nvcc, "-shared", "-o", str(lib), *[str(o) for o in objs], "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stderr[-4000:]}")
         if verbose:
-            print(f"[build] linked {LIB}")
-    return LIB
+            print(f"[build] linked {lib}")
+    return lib
 
 
 if __name__ == "__main__":
-    build_native(force="--force" in sys.argv, verbose=True)
+    build_native(force="--force" in sys.argv, verbose=True, operands="bf16" if "--bf16" in sys.argv else "f16")

@@ -13,6 +13,7 @@
 // unit = the convolution's padding of the upsampled / skip image.  Everything accumulates into one TMEM tile.
 #include "common.h"
 #include "ptx.cuh"
+#include "operand.cuh"
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
@@ -23,7 +24,7 @@ struct CatConvParams {
   int TW, TH;               // source tile (TW*TH = 128)
   const float* bias;
   const float* scale;
-  __nv_bfloat16* out;       // [B][2Hs][2Ws][Cout]
+  op_t* out;       // [B][2Hs][2Ws][Cout]
 };
 
 template <int BN, int KC, int STAGES>
@@ -119,7 +120,7 @@ catconv3x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = umma_idesc16(128, BN, OP_F16);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -153,9 +154,9 @@ catconv3x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         v[j] = fmaxf(fmaf(__uint_as_float(r[j]), sScale[c * 16 + j], sBias[c * 16 + j]), 0.0f);
       if (n0 + c * 16 < p.Cout) {
         uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + n0 + c * 16);
-        op[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        op[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                           pack_bf16(v[14], v[15]));
+        op[0] = make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]), pack_op(v[6], v[7]));
+        op[1] = make_uint4(pack_op(v[8], v[9]), pack_op(v[10], v[11]), pack_op(v[12], v[13]),
+                           pack_op(v[14], v[15]));
       }
     }
   }
@@ -202,7 +203,7 @@ extern "C" int fz_catconv3x3_bn_relu(const void* a, const void* skip, const void
     const uint64_t dims[4] = {(uint64_t)C1, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)C1 * 2, (uint64_t)Ws * C1 * 2, (uint64_t)Hs * Ws * C1 * 2};
     const uint32_t box[4] = {KC, (uint32_t)TW, (uint32_t)TH, 1};
-    int rc = make_tmap_bf16(&tmA1, a, 4, dims, strides, box, KC * 2);
+    int rc = make_tmap16(&tmA1, a, 4, dims, strides, box, KC * 2);
     if (rc) return rc;
   }
   {
@@ -211,27 +212,27 @@ extern "C" int fz_catconv3x3_bn_relu(const void* a, const void* skip, const void
     const uint64_t strides[3] = {(uint64_t)C2 * 2, W2 * C2 * 2, H2 * W2 * C2 * 2};
     const uint32_t box[4] = {KC, (uint32_t)(2 * TW), (uint32_t)(2 * TH), 1};     // traversed elements; stride 2 -> TW x TH land
     const uint32_t estr[4] = {1, 2, 2, 1};
-    int rc = make_tmap_bf16(&tmA2, skip, 4, dims, strides, box, KC * 2, estr);
+    int rc = make_tmap16(&tmA2, skip, 4, dims, strides, box, KC * 2, estr);
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)16 * C1, (uint64_t)w_rows};
     const uint64_t strides[1] = {(uint64_t)16 * C1 * 2};
     const uint32_t box[2] = {KC, (uint32_t)BN};
-    int rc = make_tmap_bf16(&tmB1, w16a, 2, dims, strides, box, KC * 2);
+    int rc = make_tmap16(&tmB1, w16a, 2, dims, strides, box, KC * 2);
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)9 * (C1 + C2), (uint64_t)w_rows};
     const uint64_t strides[1] = {(uint64_t)9 * (C1 + C2) * 2};
     const uint32_t box[2] = {KC, (uint32_t)BN};
-    int rc = make_tmap_bf16(&tmB2, w, 2, dims, strides, box, KC * 2);
+    int rc = make_tmap16(&tmB2, w, 2, dims, strides, box, KC * 2);
     if (rc) return rc;
   }
   CatConvParams p;
   p.B = B; p.Hs = Hs; p.Ws = Ws; p.C1 = C1; p.C2 = C2; p.Cout = Cout; p.TW = TW; p.TH = TH;
   p.bias = bias; p.scale = scale;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.out = reinterpret_cast<op_t*>(out);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (BN == 128) return launch_catconv<128, KC>(tmA1, tmA2, tmB1, tmB2, p, st);
   return launch_catconv<64, KC>(tmA1, tmA2, tmB1, tmB2, p, st);

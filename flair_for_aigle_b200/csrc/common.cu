@@ -72,7 +72,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+int make_tmap16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -3;
@@ -108,6 +108,14 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 extern "C" const char* fz_last_error(void) { return fz::last_error(); }
 
 extern "C" int fz_abi_version(void) { return FZ_ABI_VERSION; }
+
+extern "C" int fz_operand_format(void) {
+#ifdef FZ_OPERANDS_BF16
+  return FZ_BF16;
+#else
+  return FZ_F16;
+#endif
+}
 
 extern "C" int fz_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
   cudaDeviceProp p;

@@ -15,7 +15,7 @@ const char* last_error();
 // cudaGetDriverEntryPoint, so the library does not link libcuda directly).
 // dims/strides are innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).
 // swizzle_bytes in {0 (none), 32, 64, 128}.
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+int make_tmap16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, uint32_t swizzle_bytes,
                    const uint32_t* elem_strides = nullptr);
 

@@ -14,6 +14,7 @@
 // the MMA warp runs ahead of the 4 epilogue warps.
 #include "common.h"
 #include "ptx.cuh"
+#include "operand.cuh"
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
@@ -123,7 +124,7 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = umma_idesc16(128, BN, OP_F16);
       mbar_wait(wfull, 0);
       uint32_t g = 0, ro = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -197,14 +198,14 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) mbar_arrive(&tempty[as]);
         const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
         if (MODE == FZ_CONV_RELU_BF16) {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout);
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<op_t*>(p.out) + pix * p.Cout);
 #pragma unroll
           for (int c = 0; c < BN / 8; ++c)
             if (c * 8 < p.Cout)
-              op[c] = make_uint4(pack_bf16(fmaxf(v[8 * c], 0.f), fmaxf(v[8 * c + 1], 0.f)),
-                                 pack_bf16(fmaxf(v[8 * c + 2], 0.f), fmaxf(v[8 * c + 3], 0.f)),
-                                 pack_bf16(fmaxf(v[8 * c + 4], 0.f), fmaxf(v[8 * c + 5], 0.f)),
-                                 pack_bf16(fmaxf(v[8 * c + 6], 0.f), fmaxf(v[8 * c + 7], 0.f)));
+              op[c] = make_uint4(pack_op(fmaxf(v[8 * c], 0.f), fmaxf(v[8 * c + 1], 0.f)),
+                                 pack_op(fmaxf(v[8 * c + 2], 0.f), fmaxf(v[8 * c + 3], 0.f)),
+                                 pack_op(fmaxf(v[8 * c + 4], 0.f), fmaxf(v[8 * c + 5], 0.f)),
+                                 pack_op(fmaxf(v[8 * c + 6], 0.f), fmaxf(v[8 * c + 7], 0.f)));
         } else if (MODE == FZ_CONV_LOGITS_F32) {
           float* op = reinterpret_cast<float*>(p.out) + pix * p.cstride;
 #pragma unroll
@@ -322,14 +323,14 @@ int conv_rows_launch(const void* in, const void* w, const float* scale, const fl
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     const uint32_t box[4] = {8, ROW_PX, 1, 1};
-    int rc = make_tmap_bf16(&tmA, in, 4, dims, strides, box, 0);
+    int rc = make_tmap16(&tmA, in, 4, dims, strides, box, 0);
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)w_rows};
     const uint64_t strides[1] = {(uint64_t)9 * Cin * 2};
     const uint32_t box[2] = {(uint32_t)Cin, (uint32_t)BN};
-    int rc = make_tmap_bf16(&tmB, w, 2, dims, strides, box, Cin * 2);
+    int rc = make_tmap16(&tmB, w, 2, dims, strides, box, Cin * 2);
     if (rc) return rc;
   }
   RowConvParams p;

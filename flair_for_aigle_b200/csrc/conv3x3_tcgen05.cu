@@ -12,6 +12,7 @@
 // writes the box as 128 K-major rows with the hardware swizzle the UMMA descriptor expects.
 #include "common.h"
 #include "ptx.cuh"
+#include "operand.cuh"
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
@@ -111,7 +112,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = umma_idesc16(128, BN, OP_F16);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -144,14 +145,14 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), sScale[c * 16 + j], sBias[c * 16 + j]);
         if (MODE == FZ_CONV_ADD_RELU_BF16 && n0 + c * 16 < p.Cout) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) +
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const op_t*>(p.resid) +
                                                            pix * p.Cout + n0 + c * 16);
           const uint4 r0 = rp[0], r1 = rp[1];
-          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+          const op2_t* h0 = reinterpret_cast<const op2_t*>(&r0);
+          const op2_t* h1 = reinterpret_cast<const op2_t*>(&r1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 a = __bfloat1622float2(h0[j]), bq = __bfloat1622float2(h1[j]);
+            const float2 a = op22ff(h0[j]), bq = op22ff(h1[j]);
             v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += bq.x; v[8 + 2 * j + 1] += bq.y;
           }
         }
@@ -160,10 +161,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
         if (n0 + c * 16 < p.Cout) {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0 + c * 16);
-          op[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          op[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                             pack_bf16(v[14], v[15]));
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<op_t*>(p.out) + pix * p.Cout + n0 + c * 16);
+          op[0] = make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]), pack_op(v[6], v[7]));
+          op[1] = make_uint4(pack_op(v[8], v[9]), pack_op(v[10], v[11]), pack_op(v[12], v[13]),
+                             pack_op(v[14], v[15]));
         }
       }
     } else {
@@ -314,14 +315,14 @@ extern "C" int fz_conv3x3_ex(const void* in, const void* w, const float* scale, 
     const uint32_t box[4] = {(uint32_t)KC, (uint32_t)(TW * stride), (uint32_t)(TH * stride), 1};
     const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     FZ_REQUIRE(TW * stride <= 256, "fz_conv3x3_ex: tile too wide for a strided TMA box");
-    int rc = make_tmap_bf16(&tmA, in, 4, dims, strides, box, KC * 2, estr);
+    int rc = make_tmap16(&tmA, in, 4, dims, strides, box, KC * 2, estr);
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)w_rows};
     const uint64_t strides[1] = {(uint64_t)9 * Cin * 2};
     const uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
-    int rc = make_tmap_bf16(&tmB, w, 2, dims, strides, box, KC * 2);
+    int rc = make_tmap16(&tmB, w, 2, dims, strides, box, KC * 2);
     if (rc) return rc;
   }
   ConvParams p;

@@ -10,7 +10,8 @@
 #include "common.h"
 #include "../../include/flair_zonal_b200.h"
 
-#include <cuda_bf16.h>
+#include "ptx.cuh"
+#include "operand.cuh"
 
 namespace fz {
 
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(NW * 32, (512 / (NW * 32)) > 0 ? 512 / (NW * 3
                                                             const float* __restrict__ bdw,
                                                             const float* __restrict__ ln_w,
                                                             const float* __restrict__ ln_b,
-                                                            __nv_bfloat16* __restrict__ out, int H, int W, float eps,
+                                                            op_t* __restrict__ out, int H, int W, float eps,
                                                             int tiles_x, int tiles_y, int n_tiles) {
   static_assert(NW * 32 * CPT == C, "one lane per channel (two for CPT = 2)");
   constexpr int SH = 4;
@@ -287,14 +288,14 @@ __global__ void __launch_bounds__(NW * 32, (512 / (NW * 32)) > 0 ? 512 / (NW * 3
   for (int cc = 0; cc < CPT; ++cc) {
     const int c = cc * (C / CPT) + warp * 32 + lane;
     const float g = ln_w[c], be = ln_b[c];
-    __nv_bfloat16* o0 = out + ((static_cast<size_t>(b) * H + y0) * W + x0) * C + c;
+    op_t* o0 = out + ((static_cast<size_t>(b) * H + y0) * W + x0) * C + c;
     const ptrdiff_t orow = static_cast<ptrdiff_t>(W) * C;
 #pragma unroll
     for (int oy = 0; oy < SH; ++oy) {
-      __nv_bfloat16* orp = o0 + oy * orow;
+      op_t* orp = o0 + oy * orow;
 #pragma unroll
       for (int ox = 0; ox < SW; ++ox)
-        orp[ox * C] = __float2bfloat16_rn(acc[cc][oy * SW + ox] * s_stat[oy * SW + ox] * g + be);
+        orp[ox * C] = f2op(acc[cc][oy * SW + ox] * s_stat[oy * SW + ox] * g + be);
     }
   }
     tile += gridDim.x;
@@ -305,14 +306,14 @@ __global__ void __launch_bounds__(NW * 32, (512 / (NW * 32)) > 0 ? 512 / (NW * 3
 // x: float [B][H][W][C] -> out: bf16 [B][H/2][W/2][4C], k = (y&1)*2C + (x&1)*C + c  (the K order of
 // the 2x2/s2 conv weights repacked as [N][ky][kx][c]).  One warp per pixel.
 __global__ void __launch_bounds__(256) ln2d_s2d_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
-                                                       const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
+                                                       const float* __restrict__ ln_b, op_t* __restrict__ out,
                                                        int n_px, int H, int W, int C, float eps) {
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (p >= n_px) return;
   const int xw = p % W, yh = (p / W) % H, b = p / (W * H);
   const float* row = x + static_cast<size_t>(p) * C;
-  __nv_bfloat16* o = out + ((static_cast<size_t>(b) * (H / 2) + yh / 2) * (W / 2) + xw / 2) * 4 * C +
+  op_t* o = out + ((static_cast<size_t>(b) * (H / 2) + yh / 2) * (W / 2) + xw / 2) * 4 * C +
                      ((yh & 1) * 2 + (xw & 1)) * C;
   float s = 0.f;
   for (int c = lane * 4; c < C; c += 128) {
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__(256) ln2d_s2d_kernel(const float* __restrict__
     const float4 v = *reinterpret_cast<const float4*>(row + c);
     const float4 g = *reinterpret_cast<const float4*>(ln_w + c);
     const float4 be = *reinterpret_cast<const float4*>(ln_b + c);
-    __nv_bfloat162 lo = __floats2bfloat162_rn((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y);
-    __nv_bfloat162 hi = __floats2bfloat162_rn((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w);
+    op2_t lo = ff2op2((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y);
+    op2_t hi = ff2op2((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w);
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&lo);
     pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(256) ln2d_s2d_kernel(const float* __restrict__
 template <int NV>
 __global__ void __launch_bounds__(256) ln2d_s2d_reg_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
                                                            const float* __restrict__ ln_b,
-                                                           __nv_bfloat16* __restrict__ out,
-                                                           __nv_bfloat16* __restrict__ copy, int n_px, int H, int W,
+                                                           op_t* __restrict__ out,
+                                                           op_t* __restrict__ copy, int n_px, int H, int W,
                                                            float eps) {
   constexpr int C = NV * 128;
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(256) ln2d_s2d_reg_kernel(const float* __restri
   if (p >= n_px) return;
   const int xw = p % W, yh = (p / W) % H, b = p / (W * H);
   const float4* row = reinterpret_cast<const float4*>(x + static_cast<size_t>(p) * C);
-  __nv_bfloat16* o = out + ((static_cast<size_t>(b) * (H / 2) + yh / 2) * (W / 2) + xw / 2) * 4 * C +
+  op_t* o = out + ((static_cast<size_t>(b) * (H / 2) + yh / 2) * (W / 2) + xw / 2) * 4 * C +
                      ((yh & 1) * 2 + (xw & 1)) * C;
   float4 v[NV];
   float s = 0.f;
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(256) ln2d_s2d_reg_kernel(const float* __restri
     uint2* cp = reinterpret_cast<uint2*>(copy + static_cast<size_t>(p) * C);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x, v[i].y), hi = __floats2bfloat162_rn(v[i].z, v[i].w);
+      op2_t lo = ff2op2(v[i].x, v[i].y), hi = ff2op2(v[i].z, v[i].w);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -387,8 +388,8 @@ __global__ void __launch_bounds__(256) ln2d_s2d_reg_kernel(const float* __restri
     const int idx = i * 32 + lane;
     const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w) + idx);
     const float4 be = __ldg(reinterpret_cast<const float4*>(ln_b) + idx);
-    __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
-    __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
+    op2_t lo = ff2op2((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
+    op2_t hi = ff2op2((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&lo);
     pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -434,29 +435,29 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(float* __restrict__ scal
 }
 
 // out[b][n][k] = bf16(w[n][k] * scale[b][k])   (8 elements per thread)
-__global__ void __launch_bounds__(256) scale_weights_kernel(const __nv_bfloat16* __restrict__ w,
+__global__ void __launch_bounds__(256) scale_weights_kernel(const op_t* __restrict__ w,
                                                             const float* __restrict__ scale,
-                                                            __nv_bfloat16* __restrict__ out, int N, int K) {
+                                                            op_t* __restrict__ out, int N, int K) {
   const int b = blockIdx.y;
   const size_t i8 = (static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x) * 8;
   if (i8 >= static_cast<size_t>(N) * K) return;
   const int k = static_cast<int>(i8 % K);
   const uint4 raw = *reinterpret_cast<const uint4*>(w + i8);
-  const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const op2_t* wp = reinterpret_cast<const op2_t*>(&raw);
   const float4 s0 = *reinterpret_cast<const float4*>(scale + static_cast<size_t>(b) * K + k);
   const float4 s1 = *reinterpret_cast<const float4*>(scale + static_cast<size_t>(b) * K + k + 4);
   uint4 o;
-  __nv_bfloat162 t;
+  op2_t t;
   float2 f;
-  f = __bfloat1622float2(wp[0]); t = __floats2bfloat162_rn(f.x * s0.x, f.y * s0.y); o.x = *reinterpret_cast<uint32_t*>(&t);
-  f = __bfloat1622float2(wp[1]); t = __floats2bfloat162_rn(f.x * s0.z, f.y * s0.w); o.y = *reinterpret_cast<uint32_t*>(&t);
-  f = __bfloat1622float2(wp[2]); t = __floats2bfloat162_rn(f.x * s1.x, f.y * s1.y); o.z = *reinterpret_cast<uint32_t*>(&t);
-  f = __bfloat1622float2(wp[3]); t = __floats2bfloat162_rn(f.x * s1.z, f.y * s1.w); o.w = *reinterpret_cast<uint32_t*>(&t);
+  f = op22ff(wp[0]); t = ff2op2(f.x * s0.x, f.y * s0.y); o.x = *reinterpret_cast<uint32_t*>(&t);
+  f = op22ff(wp[1]); t = ff2op2(f.x * s0.z, f.y * s0.w); o.y = *reinterpret_cast<uint32_t*>(&t);
+  f = op22ff(wp[2]); t = ff2op2(f.x * s1.x, f.y * s1.y); o.z = *reinterpret_cast<uint32_t*>(&t);
+  f = op22ff(wp[3]); t = ff2op2(f.x * s1.z, f.y * s1.w); o.w = *reinterpret_cast<uint32_t*>(&t);
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(b) * N * K + i8) = o;
 }
 
 // h[m][k] = bf16(h[m][k] * scale[m / rows_per_sample][k]) in place
-__global__ void __launch_bounds__(256) scale_rows_kernel(__nv_bfloat16* __restrict__ h, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256) scale_rows_kernel(op_t* __restrict__ h, const float* __restrict__ scale,
                                                          size_t total, int K, int rows_per_sample) {
   const size_t i8 = (static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x) * 8;
   if (i8 >= total) return;
@@ -464,43 +465,50 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(__nv_bfloat16* __restri
   const int k = static_cast<int>(i8 % K);
   const size_t b = m / rows_per_sample;
   uint4 raw = *reinterpret_cast<const uint4*>(h + i8);
-  __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&raw);
+  op2_t* hp = reinterpret_cast<op2_t*>(&raw);
   const float4 s0 = *reinterpret_cast<const float4*>(scale + b * K + k);
   const float4 s1 = *reinterpret_cast<const float4*>(scale + b * K + k + 4);
   float2 f;
-  f = __bfloat1622float2(hp[0]); hp[0] = __floats2bfloat162_rn(f.x * s0.x, f.y * s0.y);
-  f = __bfloat1622float2(hp[1]); hp[1] = __floats2bfloat162_rn(f.x * s0.z, f.y * s0.w);
-  f = __bfloat1622float2(hp[2]); hp[2] = __floats2bfloat162_rn(f.x * s1.x, f.y * s1.y);
-  f = __bfloat1622float2(hp[3]); hp[3] = __floats2bfloat162_rn(f.x * s1.z, f.y * s1.w);
+  f = op22ff(hp[0]); hp[0] = ff2op2(f.x * s0.x, f.y * s0.y);
+  f = op22ff(hp[1]); hp[1] = ff2op2(f.x * s0.z, f.y * s0.w);
+  f = op22ff(hp[2]); hp[2] = ff2op2(f.x * s1.x, f.y * s1.y);
+  f = op22ff(hp[3]); hp[3] = ff2op2(f.x * s1.z, f.y * s1.w);
   *reinterpret_cast<uint4*>(h + i8) = raw;
 }
 
 // ------------------------------------------------------------------------------------ up x2 + concat
 // out[b][y][x][0:C1] = a[b][y/2][x/2][:] (nearest, smp DecoderBlock) ; out[..][C1:C1+C2] = s[b][y][x][:]
-// a / s are bf16 or fp32 (encoder features are fp32); out is bf16.  8 channels per thread.
-template <typename T>
-__device__ __forceinline__ uint4 load8_bf16(const T* p);
+// a / s are 16-bit (copied bit for bit: they must already be in the output's format) or fp32 (encoder features, converted
+// to the output's 16-bit format: fp16 saturating, or bf16 for the training step).  8 channels per thread.
+struct Raw16 {};   // "some 16-bit format", moved without interpretation
+template <typename T, bool F16>
+__device__ __forceinline__ uint4 load8_16(const void* p, size_t idx);
 template <>
-__device__ __forceinline__ uint4 load8_bf16<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return *reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ uint4 load8_16<Raw16, true>(const void* p, size_t idx) {
+  return *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p) + idx);
 }
 template <>
-__device__ __forceinline__ uint4 load8_bf16<float>(const float* p) {
+__device__ __forceinline__ uint4 load8_16<Raw16, false>(const void* p, size_t idx) {
+  return *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p) + idx);
+}
+template <bool F16>
+__device__ __forceinline__ uint4 cvt8_16(const float* p) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   const float4 b = *reinterpret_cast<const float4*>(p + 4);
-  __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
-  __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
-  uint4 o;
-  o.x = *reinterpret_cast<uint32_t*>(&t0);
-  o.y = *reinterpret_cast<uint32_t*>(&t1);
-  o.z = *reinterpret_cast<uint32_t*>(&t2);
-  o.w = *reinterpret_cast<uint32_t*>(&t3);
-  return o;
+  return make_uint4(pack16<F16>(a.x, a.y), pack16<F16>(a.z, a.w), pack16<F16>(b.x, b.y), pack16<F16>(b.z, b.w));
+}
+template <>
+__device__ __forceinline__ uint4 load8_16<float, true>(const void* p, size_t idx) {
+  return cvt8_16<true>(reinterpret_cast<const float*>(p) + idx);
+}
+template <>
+__device__ __forceinline__ uint4 load8_16<float, false>(const void* p, size_t idx) {
+  return cvt8_16<false>(reinterpret_cast<const float*>(p) + idx);
 }
 
-template <typename TA, typename TS>
-__global__ void __launch_bounds__(256) upcat_kernel(const TA* __restrict__ a, const TS* __restrict__ s,
-                                                    __nv_bfloat16* __restrict__ out, size_t n_vec, int H, int W,
+template <typename TA, typename TS, bool F16>
+__global__ void __launch_bounds__(256) upcat_kernel(const void* __restrict__ a, const void* __restrict__ s,
+                                                    uint16_t* __restrict__ out, size_t n_vec, int H, int W,
                                                     int C1, int C2) {
   const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n_vec) return;
@@ -512,11 +520,20 @@ __global__ void __launch_bounds__(256) upcat_kernel(const TA* __restrict__ a, co
   const size_t b = px / (static_cast<size_t>(W) * H);
   uint4 v;
   if (c < C1) {
-    v = load8_bf16<TA>(a + ((b * (H / 2) + yh / 2) * (W / 2) + xw / 2) * C1 + c);
+    v = load8_16<TA, F16>(a, ((b * (H / 2) + yh / 2) * (W / 2) + xw / 2) * C1 + c);
   } else {
-    v = load8_bf16<TS>(s + px * C2 + (c - C1));
+    v = load8_16<TS, F16>(s, px * C2 + (c - C1));
   }
   *reinterpret_cast<uint4*>(out + px * CT + c) = v;
+}
+
+template <bool F16>
+static void launch_upcat(bool a16, bool s16, const void* a, const void* s, uint16_t* o, size_t n_vec, int H, int W, int C1,
+                         int C2, unsigned grid, cudaStream_t st) {
+  if (a16 && s16) upcat_kernel<Raw16, Raw16, F16><<<grid, 256, 0, st>>>(a, s, o, n_vec, H, W, C1, C2);
+  else if (a16) upcat_kernel<Raw16, float, F16><<<grid, 256, 0, st>>>(a, s, o, n_vec, H, W, C1, C2);
+  else if (s16) upcat_kernel<float, Raw16, F16><<<grid, 256, 0, st>>>(a, s, o, n_vec, H, W, C1, C2);
+  else upcat_kernel<float, float, F16><<<grid, 256, 0, st>>>(a, s, o, n_vec, H, W, C1, C2);
 }
 
 }  // namespace fz
@@ -563,7 +580,7 @@ extern "C" int fz_stem_ln_f32(const float* x_nchw, int Cin, const float* w, cons
 namespace fz {
 template <int NW, int CPT, int C>
 static int launch_dwconv(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
-                         __nv_bfloat16* out, int B, int H, int W, float eps, cudaStream_t st) {
+                         op_t* out, int B, int H, int W, float eps, cudaStream_t st) {
   constexpr int SW = 8 / CPT;
   FZ_REQUIRE(H % 4 == 0 && W % SW == 0, "fz_dwconv7_ln: H=%d W=%d must be multiples of 4 x %d", H, W, SW);
   const int tiles_x = W / SW, tiles_y = H / 4, n_tiles = tiles_x * tiles_y * B;
@@ -596,7 +613,7 @@ extern "C" int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw,
   using namespace fz;
   if (B <= 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  op_t* o = reinterpret_cast<op_t*>(out_bf16);
   switch (C) {   // one warp per 32 channels; above 512 channels each thread carries two
     case 64: return launch_dwconv<2, 1, 64>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
     case 96: return launch_dwconv<3, 1, 96>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
@@ -622,12 +639,12 @@ extern "C" int fz_ln2d_s2d_copy(const float* x, const float* ln_w, const float* 
   using namespace fz;
   FZ_REQUIRE(copy_bf16 == nullptr || C == 128 || C == 256 || C == 512,
              "fz_ln2d_s2d_copy: the bf16 copy is built for C = 128, 256, 512 (got %d)", C);
-  __nv_bfloat16* cpy = reinterpret_cast<__nv_bfloat16*>(copy_bf16);
+  op_t* cpy = reinterpret_cast<op_t*>(copy_bf16);
   FZ_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "fz_ln2d_s2d: bad shape H=%d W=%d C=%d", H, W, C);
   const int n_px = B * H * W;
   if (n_px <= 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  op_t* o = reinterpret_cast<op_t*>(out_bf16);
   const unsigned grid = (n_px + 7) / 8;
   switch (C) {
     case 128: ln2d_s2d_reg_kernel<1><<<grid, 256, 0, st>>>(x, ln_w, ln_b, o, cpy, n_px, H, W, eps); break;
@@ -661,7 +678,7 @@ extern "C" int fz_scale_weights(const void* w_bf16, const float* scale, void* ou
   const size_t n8 = static_cast<size_t>(N) * K / 8;
   dim3 grid(static_cast<unsigned>((n8 + 255) / 256), B);
   scale_weights_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(w_bf16), scale, reinterpret_cast<__nv_bfloat16*>(out_bf16), N, K);
+      reinterpret_cast<const op_t*>(w_bf16), scale, reinterpret_cast<op_t*>(out_bf16), N, K);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -672,31 +689,28 @@ extern "C" int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K,
   const size_t total = static_cast<size_t>(M) * K;
   if (total == 0) return 0;
   scale_rows_kernel<<<static_cast<unsigned>((total / 8 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(h_bf16), scale, total, K, rows_per_sample);
+      reinterpret_cast<op_t*>(h_bf16), scale, total, K, rows_per_sample);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int fz_upsample2_concat(const void* a, int a_dtype, const void* s, int s_dtype, void* out_bf16, int B, int H,
-                                   int W, int C1, int C2, void* stream) {
+extern "C" int fz_upsample2_concat(const void* a, int a_dtype, const void* s, int s_dtype, void* out16, int out_dtype,
+                                   int B, int H, int W, int C1, int C2, void* stream) {
   using namespace fz;
   FZ_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0 && C2 >= 0, "fz_upsample2_concat: C1=%d C2=%d must be multiples of 8",
              C1, C2);
   FZ_REQUIRE(H % 2 == 0 && W % 2 == 0, "fz_upsample2_concat: output H, W must be even");
+  FZ_REQUIRE(out_dtype == FZ_BF16 || out_dtype == FZ_F16, "fz_upsample2_concat: the output is FZ_BF16 or FZ_F16");
+  FZ_REQUIRE((a_dtype == FZ_F32 || a_dtype == out_dtype) && (C2 == 0 || s_dtype == FZ_F32 || s_dtype == out_dtype),
+             "fz_upsample2_concat: a 16-bit input must have the output's format (a %d, s %d, out %d)", a_dtype, s_dtype,
+             out_dtype);
   const size_t n_vec = static_cast<size_t>(B) * H * W * (C1 + C2) / 8;
   if (n_vec == 0) return 0;
   const unsigned grid = static_cast<unsigned>((n_vec + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  typedef __nv_bfloat16 bf;
-  if (a_dtype == FZ_BF16 && s_dtype == FZ_BF16)
-    upcat_kernel<bf, bf><<<grid, 256, 0, st>>>((const bf*)a, (const bf*)s, o, n_vec, H, W, C1, C2);
-  else if (a_dtype == FZ_BF16)
-    upcat_kernel<bf, float><<<grid, 256, 0, st>>>((const bf*)a, (const float*)s, o, n_vec, H, W, C1, C2);
-  else if (s_dtype == FZ_BF16)
-    upcat_kernel<float, bf><<<grid, 256, 0, st>>>((const float*)a, (const bf*)s, o, n_vec, H, W, C1, C2);
-  else
-    upcat_kernel<float, float><<<grid, 256, 0, st>>>((const float*)a, (const float*)s, o, n_vec, H, W, C1, C2);
+  uint16_t* o = reinterpret_cast<uint16_t*>(out16);
+  if (out_dtype == FZ_F16) launch_upcat<true>(a_dtype != FZ_F32, s_dtype != FZ_F32, a, s, o, n_vec, H, W, C1, C2, grid, st);
+  else launch_upcat<false>(a_dtype != FZ_F32, s_dtype != FZ_F32, a, s, o, n_vec, H, W, C1, C2, grid, st);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,7 @@ struct GemmParams {
   void* out;            // [M,N] bf16 or f32
   const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
   float* sumsq;         // [ceil(M/128), N] f32 per-128-row partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
+  int f16;              // 1: A, B and a 16-bit output are fp16 (FZ_EPI_OPERANDS_F16), 0: bf16
   int reverse;          // 1: walk the tile list backwards (consume a just-written operand newest-first, while it is in L2)
   unsigned long long* trace;  // optional: CTA 0 writes clock64 stamps [tile][8] (diagnostics, see fz_gemm_set_trace)
 };
@@ -33,7 +34,7 @@ struct EpiShape {
 //         the row-contiguous access patterns are bank-conflict free.  A row-per-thread STG/LDG would touch 32
 //         lines per instruction, which was the first epilogue's bottleneck.
 // sq_dst: (GELU_SUMSQ) 64 floats: 32-row column sums of out^2 for the chunk's columns (8-byte aligned)
-template <int MODE>
+template <int MODE, bool F16>
 __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, int row0, int col0, char* stg, int lane,
                                           float* sq_dst) {
   constexpr bool F32OUT = EpiShape<MODE>::F32OUT;
@@ -99,13 +100,13 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(stg + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)) =
-            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            make_uint4(pack16<F16>(v[8 * j], v[8 * j + 1]), pack16<F16>(v[8 * j + 2], v[8 * j + 3]),
+                       pack16<F16>(v[8 * j + 4], v[8 * j + 5]), pack16<F16>(v[8 * j + 6], v[8 * j + 7]));
     }
   }
   __syncwarp();
   if (MODE == FZ_EPI_GELU_SUMSQ) {
-    // GRN statistics: column sums of out^2 over this warp's 32 rows, read back from the staged bf16 tile (the values
+    // GRN statistics: column sums of out^2 over this warp's 32 rows, read back from the staged 16-bit tile (the values
     // fc2 will actually consume): lane l owns columns 2l, 2l+1 = one 32-bit word per row, conflict-free under the
     // XOR swizzle.  2.5 instructions per element instead of 4.9 for the register transpose-reduce it replaces.
     // M is a multiple of 128 in this mode (host check): no row mask.
@@ -114,9 +115,9 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
       const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((sidx ^ (r & 7)) << 4) + woff);
-      const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
-      a0 = fmaf(lo, lo, a0);
-      a1 = fmaf(hi, hi, a1);
+      const float2 f = unpack16<F16>(w);
+      a0 = fmaf(f.x, f.x, a0);
+      a1 = fmaf(f.y, f.y, a1);
     }
     *reinterpret_cast<float2*>(sq_dst + 2 * lane) = make_float2(a0, a1);
   }

@@ -46,7 +46,7 @@ struct GemmSmem {
   static constexpr int BYTES = OFF_TSLOT + 16 + 1024;            // + worst-case alignment pad
 };
 
-template <int BN, int STAGES, int ACC_STAGES, int MODE>
+template <int BN, int STAGES, int ACC_STAGES, int MODE, bool F16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using L = GemmSmem<BN, STAGES>;
@@ -113,7 +113,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = umma_idesc16(128, BN, F16);
       uint32_t it = 0, lt = 0;
       for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
         const uint32_t as = lt % ACC_STAGES;
@@ -170,7 +170,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr int CH_COLS = EpiShape<MODE>::CH_COLS;
 #pragma unroll 1
       for (int c = colgrp; c < BN / CH_COLS; c += 2)
-        epi_chunk<MODE>(p, tbase + c * CH_COLS, m0 + half * 128 + q * 32, n0 + c * CH_COLS, stg, lane,
+        epi_chunk<MODE, F16>(p, tbase + c * CH_COLS, m0 + half * 128 + q * 32, n0 + c * CH_COLS, stg, lane,
                         sq_buf + (half * 4 + q) * BN + c * CH_COLS);
       // all TMEM reads of this stage are complete (tmem_ld_wait above): hand it back to the MMA warp
       tc_fence_before();
@@ -194,10 +194,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int BN, int STAGES, int ACC_STAGES, int MODE>
+template <int BN, int STAGES, int ACC_STAGES, int MODE, bool F16>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE, F16>;
   FZ_ENSURE_SMEM(kern, L::BYTES);
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return -2;
@@ -210,18 +210,23 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 // BN = 128: 3 smem stages (48 KB each) + 64 KB store staging, accumulators double buffered; BN = 64 for narrow outputs.
 // (Wide outputs, N % 256 == 0, go to the CTA-pair kernel in gemm_tcgen05_2sm.cu.)
-template <int BN, int STAGES, int ACC_STAGES>
-static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+template <int BN, int STAGES, int ACC_STAGES, bool F16>
+static int dispatch_mode_fmt(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
   switch (mode) {
-    case FZ_EPI_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_BF16>(a, b, p, st);
-    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_SUMSQ>(a, b, p, st);
-    case FZ_EPI_RESID_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RESID_F32>(a, b, p, st);
-    case FZ_EPI_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_F32>(a, b, p, st);
-    case FZ_EPI_RELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RELU_BF16>(a, b, p, st);
-    case FZ_EPI_GELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_BF16>(a, b, p, st);
+    case FZ_EPI_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_BF16, F16>(a, b, p, st);
+    case FZ_EPI_GELU_SUMSQ: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_SUMSQ, F16>(a, b, p, st);
+    case FZ_EPI_RESID_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RESID_F32, F16>(a, b, p, st);
+    case FZ_EPI_F32: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_F32, F16>(a, b, p, st);
+    case FZ_EPI_RELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_RELU_BF16, F16>(a, b, p, st);
+    case FZ_EPI_GELU_BF16: return launch_gemm<BN, STAGES, ACC_STAGES, FZ_EPI_GELU_BF16, F16>(a, b, p, st);
   }
   set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
   return -1;
+}
+template <int BN, int STAGES, int ACC_STAGES>
+static int dispatch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+  return p.f16 ? dispatch_mode_fmt<BN, STAGES, ACC_STAGES, true>(mode, a, b, p, st)
+               : dispatch_mode_fmt<BN, STAGES, ACC_STAGES, false>(mode, a, b, p, st);
 }
 
 }  // namespace fz
@@ -236,7 +241,8 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
                             void* stream) {
   using namespace fz;
   const int reverse = (mode & FZ_EPI_REVERSE_TILES) ? 1 : 0;
-  mode &= ~FZ_EPI_REVERSE_TILES;
+  const int f16 = (mode & FZ_EPI_OPERANDS_F16) ? 1 : 0;
+  mode &= ~(FZ_EPI_REVERSE_TILES | FZ_EPI_OPERANDS_F16);
   FZ_REQUIRE(M > 0 && N > 0 && K > 0, "fz_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
   FZ_REQUIRE(K % BK == 0, "fz_gemm_bf16: K=%d must be a multiple of %d", K, BK);
   FZ_REQUIRE(N % 64 == 0, "fz_gemm_bf16: N=%d must be a multiple of 64", N);
@@ -254,6 +260,7 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = g_trace;
   p.reverse = reverse;
+  p.f16 = f16;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // CTA-pair kernel (256x256 tile over two SMs, gemm_tcgen05_2sm.cu): wide outputs with enough tiles for 74 pairs.
   // FZ_GEMM_PAIR=0 disables, =2 forces it whenever N % 256 == 0.
@@ -270,14 +277,14 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)K * 2};
     const uint32_t box[2] = {BK, BM};
-    int rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box, 128);
+    int rc = make_tmap16(&tmA, A, 2, dims, strides, box, 128);
     if (rc) return rc;
   }
   {
     const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)b_batch};
     const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)N};
     const uint32_t box[3] = {BK, (uint32_t)BN, 1};
-    int rc = make_tmap_bf16(&tmB, B, 3, dims, strides, box, 128);
+    int rc = make_tmap16(&tmB, B, 3, dims, strides, box, 128);
     if (rc) return rc;
   }
   if (BN == 128) return dispatch_mode<128, 3, 2>(mode, tmA, tmB, p, st);
@@ -290,9 +297,18 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
 // bring-up.  Not a fallback: the engine never selects it on its own.
 // ----------------------------------------------------------------------------------------
 namespace fz {
-template <int MODE>
-__global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
-                                 GemmParams p) {
+template <bool F16> struct Op16 { typedef __nv_bfloat16 T; };
+template <> struct Op16<true> { typedef __half T; };
+__device__ __forceinline__ float ld16(const __nv_bfloat16& x) { return __bfloat162float(x); }
+__device__ __forceinline__ float ld16(const __half& x) { return __half2float(x); }
+__device__ __forceinline__ void st16(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st16(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)); }
+
+template <int MODE, bool F16>
+__global__ void gemm_simt_kernel(const void* __restrict__ Av, const void* __restrict__ Bv, GemmParams p) {
+  typedef typename Op16<F16>::T T16;
+  const T16* A = reinterpret_cast<const T16*>(Av);
+  const T16* B = reinterpret_cast<const T16*>(Bv);
   __shared__ float sa[16][17];
   __shared__ float sb[16][17];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -300,13 +316,13 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv
   const int m = blockIdx.y * 16 + ty;
   const int m_tile0 = blockIdx.y * 16;
   const int bidx = p.b_batched ? (m_tile0 / p.rows_per_sample) : 0;
-  const __nv_bfloat16* Bb = B + static_cast<size_t>(bidx) * p.N * p.K;
+  const T16* Bb = B + static_cast<size_t>(bidx) * p.N * p.K;
   float acc = 0.0f;
   for (int k0 = 0; k0 < p.K; k0 += 16) {
     const int am = blockIdx.y * 16 + ty;
-    sa[ty][tx] = (am < p.M) ? __bfloat162float(A[static_cast<size_t>(am) * p.K + k0 + tx]) : 0.0f;
+    sa[ty][tx] = (am < p.M) ? ld16(A[static_cast<size_t>(am) * p.K + k0 + tx]) : 0.0f;
     const int bn = blockIdx.x * 16 + ty;
-    sb[ty][tx] = (bn < p.N) ? __bfloat162float(Bb[static_cast<size_t>(bn) * p.K + k0 + tx]) : 0.0f;
+    sb[ty][tx] = (bn < p.N) ? ld16(Bb[static_cast<size_t>(bn) * p.K + k0 + tx]) : 0.0f;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[tx][k], acc);
@@ -317,7 +333,9 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv
   const size_t off = static_cast<size_t>(m) * p.N + n;
   if (MODE == FZ_EPI_GELU_SUMSQ) {
     v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-    const float vr = __bfloat162float(__float2bfloat16_rn(v));     // statistics of the stored (bf16) value
+    T16 tmp;
+    st16(&tmp, v);
+    const float vr = ld16(tmp);     // statistics of the stored (16-bit) value
     atomicAdd(&p.sumsq[static_cast<size_t>(m / 128) * p.N + n], vr * vr);
   } else if (MODE == FZ_EPI_GELU_BF16) {
     v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
@@ -329,7 +347,7 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv
   if (MODE == FZ_EPI_RESID_F32 || MODE == FZ_EPI_F32)
     reinterpret_cast<float*>(p.out)[off] = v;
   else
-    reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(v);
+    st16(reinterpret_cast<T16*>(p.out) + off, v);
 }
 }  // namespace fz
 
@@ -345,22 +363,27 @@ extern "C" int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const 
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = nullptr;
   p.reverse = 0;
-  mode &= ~FZ_EPI_REVERSE_TILES;
+  p.f16 = (mode & FZ_EPI_OPERANDS_F16) ? 1 : 0;
+  mode &= ~(FZ_EPI_REVERSE_TILES | FZ_EPI_OPERANDS_F16);
   dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == FZ_EPI_GELU_SUMSQ)
     FZ_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * static_cast<size_t>((M + 127) / 128) * N, st));
-  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
-  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(B);
+#define FZ_SIMT_CASE(M)                                                     \
+  case M:                                                                  \
+    if (p.f16) gemm_simt_kernel<M, true><<<grid, block, 0, st>>>(A, B, p); \
+    else gemm_simt_kernel<M, false><<<grid, block, 0, st>>>(A, B, p);      \
+    break;
   switch (mode) {
-    case FZ_EPI_BF16: gemm_simt_kernel<FZ_EPI_BF16><<<grid, block, 0, st>>>(a, b, p); break;
-    case FZ_EPI_GELU_SUMSQ: gemm_simt_kernel<FZ_EPI_GELU_SUMSQ><<<grid, block, 0, st>>>(a, b, p); break;
-    case FZ_EPI_RESID_F32: gemm_simt_kernel<FZ_EPI_RESID_F32><<<grid, block, 0, st>>>(a, b, p); break;
-    case FZ_EPI_F32: gemm_simt_kernel<FZ_EPI_F32><<<grid, block, 0, st>>>(a, b, p); break;
-    case FZ_EPI_RELU_BF16: gemm_simt_kernel<FZ_EPI_RELU_BF16><<<grid, block, 0, st>>>(a, b, p); break;
-    case FZ_EPI_GELU_BF16: gemm_simt_kernel<FZ_EPI_GELU_BF16><<<grid, block, 0, st>>>(a, b, p); break;
+    FZ_SIMT_CASE(FZ_EPI_BF16)
+    FZ_SIMT_CASE(FZ_EPI_GELU_SUMSQ)
+    FZ_SIMT_CASE(FZ_EPI_RESID_F32)
+    FZ_SIMT_CASE(FZ_EPI_F32)
+    FZ_SIMT_CASE(FZ_EPI_RELU_BF16)
+    FZ_SIMT_CASE(FZ_EPI_GELU_BF16)
     default: set_error("fz_gemm_bf16_simt: unknown mode %d", mode); return -1;
   }
+#undef FZ_SIMT_CASE
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

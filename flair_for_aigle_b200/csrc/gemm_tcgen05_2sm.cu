@@ -33,7 +33,7 @@ constexpr int THREADS = 640;
 constexpr int EPI_WARP0 = 4;
 }  // namespace pair
 
-template <int MODE>
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(pair::THREADS, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using namespace pair;
@@ -98,7 +98,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncwarp();
   } else if (warp == 1) {
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = umma_idesc16(BM, BN, F16);
       uint32_t it = 0, lt = 0;
       for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
         const uint32_t as = lt & 1;
@@ -141,7 +141,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c = colgrp; c < BN / CH_COLS; c += 4)
-        epi_chunk<MODE>(p, tbase + c * CH_COLS, m0 + q * 32, n0 + c * CH_COLS, stg, lane,
+        epi_chunk<MODE, F16>(p, tbase + c * CH_COLS, m0 + q * 32, n0 + c * CH_COLS, stg, lane,
                         sq_buf + q * BN + c * CH_COLS);
       tc_fence_before();
       __syncwarp();
@@ -162,9 +162,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) tmem_dealloc_pair(tmem, 512);
 }
 
-template <int MODE>
+template <int MODE, bool F16>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_bf16_pair_kernel<MODE>;
+  auto kern = gemm_bf16_pair_kernel<MODE, F16>;
   FZ_ENSURE_SMEM(kern, pair::SMEM_BYTES);
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return -2;
@@ -193,23 +193,23 @@ int gemm_pair_launch(const void* A, const void* B, const GemmParams& p, int b_ba
     const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
     const uint64_t strides[1] = {(uint64_t)p.K * 2};
     const uint32_t box[2] = {pair::BK, 128};
-    int rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box, 128);
+    int rc = make_tmap16(&tmA, A, 2, dims, strides, box, 128);
     if (rc) return rc;
   }
   {
     const uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.N, (uint64_t)b_batch};
     const uint64_t strides[2] = {(uint64_t)p.K * 2, (uint64_t)p.K * 2 * (uint64_t)p.N};
     const uint32_t box[3] = {pair::BK, 128, 1};
-    int rc = make_tmap_bf16(&tmB, B, 3, dims, strides, box, 128);
+    int rc = make_tmap16(&tmB, B, 3, dims, strides, box, 128);
     if (rc) return rc;
   }
   switch (mode) {
-    case FZ_EPI_BF16: return launch_pair<FZ_EPI_BF16>(tmA, tmB, p, stream);
-    case FZ_EPI_GELU_SUMSQ: return launch_pair<FZ_EPI_GELU_SUMSQ>(tmA, tmB, p, stream);
-    case FZ_EPI_RESID_F32: return launch_pair<FZ_EPI_RESID_F32>(tmA, tmB, p, stream);
-    case FZ_EPI_F32: return launch_pair<FZ_EPI_F32>(tmA, tmB, p, stream);
-    case FZ_EPI_RELU_BF16: return launch_pair<FZ_EPI_RELU_BF16>(tmA, tmB, p, stream);
-    case FZ_EPI_GELU_BF16: return launch_pair<FZ_EPI_GELU_BF16>(tmA, tmB, p, stream);
+    case FZ_EPI_BF16: return p.f16 ? launch_pair<FZ_EPI_BF16, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_BF16, false>(tmA, tmB, p, stream);
+    case FZ_EPI_GELU_SUMSQ: return p.f16 ? launch_pair<FZ_EPI_GELU_SUMSQ, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_GELU_SUMSQ, false>(tmA, tmB, p, stream);
+    case FZ_EPI_RESID_F32: return p.f16 ? launch_pair<FZ_EPI_RESID_F32, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_RESID_F32, false>(tmA, tmB, p, stream);
+    case FZ_EPI_F32: return p.f16 ? launch_pair<FZ_EPI_F32, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_F32, false>(tmA, tmB, p, stream);
+    case FZ_EPI_RELU_BF16: return p.f16 ? launch_pair<FZ_EPI_RELU_BF16, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_RELU_BF16, false>(tmA, tmB, p, stream);
+    case FZ_EPI_GELU_BF16: return p.f16 ? launch_pair<FZ_EPI_GELU_BF16, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_GELU_BF16, false>(tmA, tmB, p, stream);
   }
   set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
   return -1;

@@ -13,6 +13,7 @@
 #include "../../include/flair_zonal_b200.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace fz {
 
@@ -52,6 +53,8 @@ template <>
 __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 
 // Load the n_cls logits of one pixel into registers.
 template <typename T, int LAYOUT>
@@ -193,7 +196,7 @@ static int launch_crop(const void* logits, int dtype, int layout, int cstride, i
                        float* canvas, int H, int W, cudaStream_t st, const int32_t* zmap = nullptr, int zoomed = 0) {
   FZ_REQUIRE(n_cls >= 1 && n_cls <= MAX_CLS, "crop kernels support 1..%d classes, got %d", MAX_CLS, n_cls);
   FZ_REQUIRE(P > 2 * margin && margin >= 0, "bad patch/margin %d/%d", P, margin);
-  FZ_REQUIRE(dtype == FZ_F32 || dtype == FZ_BF16, "bad dtype %d", dtype);
+  FZ_REQUIRE(dtype == FZ_F32 || dtype == FZ_BF16 || dtype == FZ_F16, "bad dtype %d", dtype);
   FZ_REQUIRE(layout == FZ_NCHW || layout == FZ_NHWC || layout == FZ_NHWC_UP4, "bad layout %d", layout);
   if (layout == FZ_NHWC_UP4)
     FZ_REQUIRE(dtype == FZ_F32 && P % 4 == 0 && P >= 8 && cstride >= n_cls, "quarter-resolution logits: fp32, P %% 4 == 0");
@@ -211,8 +214,10 @@ static int launch_crop(const void* logits, int dtype, int layout, int cstride, i
   if (layout == FZ_NHWC_UP4) FZ_LAUNCH(float, FZ_NHWC_UP4);
   else if (dtype == FZ_F32 && layout == FZ_NCHW) FZ_LAUNCH(float, FZ_NCHW);
   else if (dtype == FZ_F32) FZ_LAUNCH(float, FZ_NHWC);
-  else if (layout == FZ_NCHW) FZ_LAUNCH(__nv_bfloat16, FZ_NCHW);
-  else FZ_LAUNCH(__nv_bfloat16, FZ_NHWC);
+  else if (dtype == FZ_BF16 && layout == FZ_NCHW) FZ_LAUNCH(__nv_bfloat16, FZ_NCHW);
+  else if (dtype == FZ_BF16) FZ_LAUNCH(__nv_bfloat16, FZ_NHWC);
+  else if (layout == FZ_NCHW) FZ_LAUNCH(__half, FZ_NCHW);
+  else FZ_LAUNCH(__half, FZ_NHWC);
 #undef FZ_LAUNCH
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace fz {
@@ -124,14 +125,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t swiz
   return d;
 }
 
-// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, A/B = bf16 K-major, D = f32.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
-  return (1u << 4)            // c_format = F32
-         | (1u << 7)          // a_format = BF16
-         | (1u << 10)         // b_format = BF16
-         | ((n >> 3) << 17)   // N >> 3
-         | ((m >> 4) << 24);  // M >> 4
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, A/B K-major, D = f32.  kind::f16 takes
+// fp16 (format code 0) and bf16 (format code 1) operands at the same rate; `f16` selects which.
+__host__ __device__ constexpr uint32_t umma_idesc16(uint32_t m, uint32_t n, bool f16) {
+  return (1u << 4)                        // c_format = F32
+         | ((f16 ? 0u : 1u) << 7)         // a_format
+         | ((f16 ? 0u : 1u) << 10)        // b_format
+         | ((n >> 3) << 17)               // N >> 3
+         | ((m >> 4) << 24);              // M >> 4
 }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) { return umma_idesc16(m, n, false); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -252,6 +255,23 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// two floats -> packed fp16x2, round to nearest even, saturating to +-65504 instead of overflowing to inf
+// (one cvt instruction, like the bf16 pack)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+}
+// packed 16-bit pair -> two floats
+template <bool F16>
+__device__ __forceinline__ float2 unpack16(uint32_t w) {
+  if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
 }  // namespace fz

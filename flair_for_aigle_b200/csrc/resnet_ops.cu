@@ -6,7 +6,8 @@
 #include "common.h"
 #include "../../include/flair_zonal_b200.h"
 
-#include <cuda_bf16.h>
+#include "ptx.cuh"
+#include "operand.cuh"
 
 namespace fz {
 
@@ -20,7 +21,7 @@ template <bool F32IN>
 __global__ void __launch_bounds__(128) conv7x7s2_kernel(const void* __restrict__ in_raw, int Cin,
                                                         const float* __restrict__ w, const float* __restrict__ scale,
                                                         const float* __restrict__ bias,
-                                                        __nv_bfloat16* __restrict__ out, int P) {
+                                                        op_t* __restrict__ out, int P) {
   extern __shared__ float smem_f[];
   float* sW = smem_f;                        // [196][64]
   float* sIn = smem_f + 196 * 64;            // [7][C7_INPX + 3][4]
@@ -84,8 +85,8 @@ __global__ void __launch_bounds__(128) conv7x7s2_kernel(const void* __restrict__
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const int ox = ox0 + pg * 4 + a;
-      __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(acc[a][0] * sc[0] + bi[0], 0.f), fmaxf(acc[a][1] * sc[1] + bi[1], 0.f));
-      __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(acc[a][2] * sc[2] + bi[2], 0.f), fmaxf(acc[a][3] * sc[3] + bi[3], 0.f));
+      op2_t lo = ff2op2(fmaxf(acc[a][0] * sc[0] + bi[0], 0.f), fmaxf(acc[a][1] * sc[1] + bi[1], 0.f));
+      op2_t hi = ff2op2(fmaxf(acc[a][2] * sc[2] + bi[2], 0.f), fmaxf(acc[a][3] * sc[3] + bi[3], 0.f));
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(128) conv7x7s2_kernel(const void* __restrict__
 }
 
 // in bf16 [B][H][W][C] -> out bf16 [B][H/2][W/2][C]; 8 channels per thread; padding never wins (-inf)
-__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in,
-                                                           __nv_bfloat16* __restrict__ out, size_t n_vec, int H, int W,
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const op_t* __restrict__ in,
+                                                           op_t* __restrict__ out, size_t n_vec, int H, int W,
                                                            int C) {
   const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n_vec) return;
@@ -118,21 +119,21 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
       const int x = 2 * ox + dx;
       if (x < 0 || x >= W) continue;
       const uint4 raw = *reinterpret_cast<const uint4*>(in + ((b * H + y) * W + x) * C + c);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const op2_t* h = reinterpret_cast<const op2_t*>(&raw);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h[j]);
+        const float2 f = op22ff(h[j]);
         m[2 * j] = fmaxf(m[2 * j], f.x);
         m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
       }
     }
   }
   uint4 o;
-  __nv_bfloat162 t;
-  t = __floats2bfloat162_rn(m[0], m[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(m[2], m[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(m[4], m[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(m[6], m[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+  op2_t t;
+  t = ff2op2(m[0], m[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+  t = ff2op2(m[2], m[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+  t = ff2op2(m[4], m[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+  t = ff2op2(m[6], m[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
   *reinterpret_cast<uint4*>(out + px * C + c) = o;
 }
 
@@ -148,7 +149,7 @@ extern "C" int fz_conv7x7s2_bn_relu(const void* in, int in_is_f32, int Cin, cons
   FZ_ENSURE_SMEM(conv7x7s2_kernel<false>, static_cast<int>(smem));
   dim3 grid(P / 2, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  op_t* o = reinterpret_cast<op_t*>(out_bf16);
   if (in_is_f32) conv7x7s2_kernel<true><<<grid, 128, smem, st>>>(in, Cin, w, scale, bias, o, P);
   else conv7x7s2_kernel<false><<<grid, 128, smem, st>>>(in, 4, w, scale, bias, o, P);
   FZ_CHECK_CUDA(cudaGetLastError());
@@ -161,7 +162,7 @@ extern "C" int fz_maxpool3x3s2(const void* in_bf16, void* out_bf16, int B, int H
   const size_t n_vec = static_cast<size_t>(B) * (H / 2) * (W / 2) * (C / 8);
   if (n_vec == 0) return 0;
   maxpool3x3s2_kernel<<<static_cast<unsigned>((n_vec + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), n_vec, H, W, C);
+      reinterpret_cast<const op_t*>(in_bf16), reinterpret_cast<op_t*>(out_bf16), n_vec, H, W, C);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -14,7 +14,7 @@
 #include "ptx.cuh"
 #include "../../include/flair_zonal_b200.h"
 
-#include <cuda_bf16.h>
+#include "operand.cuh"
 
 namespace fz {
 
@@ -23,7 +23,7 @@ namespace fz {
 // different source rows (NSEG = 1: plain LayerNorm; NSEG = 4: patch merging).
 template <int NV, int NSEG>
 __global__ void __launch_bounds__(256) ln_gather_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ bvec, __nv_bfloat16* __restrict__ out,
+                                                        const float* __restrict__ bvec, op_t* __restrict__ out,
                                                         long long rows, int H, int W, int C, float eps) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -66,15 +66,15 @@ __global__ void __launch_bounds__(256) ln_gather_kernel(const float* __restrict_
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
   const float rstd = rsqrtf(var * (1.0f / CT) + eps);
-  __nv_bfloat16* orow = out + row * CT;
+  op_t* orow = out + row * CT;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int idx = i * 32 + lane;
     const float4 g = __ldg(reinterpret_cast<const float4*>(w) + idx);
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bvec) + idx);
     uint2 pk;
-    pk.x = pack_bf16((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
-    pk.y = pack_bf16((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+    pk.x = pack_op((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+    pk.y = pack_op((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
     reinterpret_cast<uint2*>(orow)[idx] = pk;
   }
 }
@@ -84,7 +84,7 @@ static int launch_ln(const float* x, const float* w, const float* b, void* out, 
                      float eps, cudaStream_t st) {
   const int ct = NSEG * C;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  op_t* o = reinterpret_cast<op_t*>(out);
   switch (ct / 128) {
     case 1: ln_gather_kernel<1, NSEG><<<grid, 256, 0, st>>>(x, w, b, o, rows, H, W, C, eps); break;
     case 2: ln_gather_kernel<2, NSEG><<<grid, 256, 0, st>>>(x, w, b, o, rows, H, W, C, eps); break;
@@ -97,12 +97,13 @@ static int launch_ln(const float* x, const float* w, const float* b, void* out, 
   return 0;
 }
 
-__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out,
-                                                            size_t n4) {
+template <bool F16>
+__global__ void __launch_bounds__(256) cast_f32_16_kernel(const float4* __restrict__ in, uint2* __restrict__ out,
+                                                          size_t n4) {
   const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n4) return;
   const float4 v = __ldg(in + i);
-  out[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  out[i] = make_uint2(pack16<F16>(v.x, v.y), pack16<F16>(v.z, v.w));
 }
 
 // ------------------------------------------------------------------------------------------------ window attention
@@ -112,10 +113,10 @@ constexpr int WA_THREADS = 288;  // 9 warps x 16 query rows
 constexpr int WA_D = 32;         // head dim (all timm Swin variants)
 
 struct WinAttnParams {
-  const __nv_bfloat16* qkv;       // [B][H][W][3C]: q | k | v, channel = head*32 + d
-  const __nv_bfloat16* qkv_bias;  // [3C] bf16: q/k/v of a zero (padded) token
+  const op_t* qkv;       // [B][H][W][3C]: q | k | v, channel = head*32 + d
+  const op_t* qkv_bias;  // [3C] bf16: q/k/v of a zero (padded) token
   const float* table;             // [heads][(2ws-1)^2] relative position bias
-  __nv_bfloat16* out;             // [B][H][W][C]
+  op_t* out;             // [B][H][W][C]
   int H, W, C, heads, ws, shift, nwy, nwx, hgroup;
   float scale;
 };
@@ -128,8 +129,13 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+// operands in the inference operand format (operand.cuh: fp16 unless built with FZ_OPERANDS_BF16), fp32 accumulate
+__device__ __forceinline__ void mma_op_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#ifdef FZ_OPERANDS_BF16
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#else
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#endif
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -154,7 +160,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // (cp.async) while head i is computed, so only the first head's load latency is exposed.
 __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttnParams p) {
   extern __shared__ __align__(16) uint8_t wa_smem[];
-  __nv_bfloat16* sBuf = reinterpret_cast<__nv_bfloat16*>(wa_smem);                 // [2][3][WA_MAT]
+  op_t* sBuf = reinterpret_cast<op_t*>(wa_smem);                 // [2][3][WA_MAT]
   float* sTabs = reinterpret_cast<float*>(wa_smem + 2 * 3 * WA_MAT * 2);          // [2][WA_TAB]
   int* sSrc = reinterpret_cast<int*>(sTabs + 2 * WA_TAB);   // source token (y*W+x) | -1 padded token | -2 unused slot
   int* sInfo = sSrc + WA_N;                                 // rel-pos code (ty*(2ws-1)+tx) | region << 16 | unused << 24
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
   static_assert(WA_N * 12 == 6 * WA_THREADS, "load loop is unrolled for 6 chunks per thread");
   const size_t tok0 = static_cast<size_t>(b) * p.H * p.W;
   const int C3 = 3 * p.C;
-  const __nv_bfloat16* gsrc[6];
+  const op_t* gsrc[6];
   int soff[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -233,9 +239,9 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
   for (int hh = 0; hh < p.hgroup; ++hh) {
     const int head = head0 + hh;
     const int cur = hh & 1;
-    __nv_bfloat16* sQ = sBuf + cur * 3 * WA_MAT;
-    __nv_bfloat16* sK = sQ + WA_MAT;
-    __nv_bfloat16* sV = sK + WA_MAT;
+    op_t* sQ = sBuf + cur * 3 * WA_MAT;
+    op_t* sK = sQ + WA_MAT;
+    op_t* sV = sK + WA_MAT;
     const float* sTab = sTabs + cur * WA_TAB;
     cp_async_wait_all();
     __syncthreads();          // head's q/k/v + table visible; everyone is done with the other buffer
@@ -259,8 +265,8 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
     s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
     uint32_t kb[4];
     ldsm_x4(kb, &sK[(nt * 8 + (lane & 7)) * WA_LD + (lane >> 3) * 8]);
-    mma_bf16_16816(s[nt], qa[0], kb[0], kb[1]);
-    mma_bf16_16816(s[nt], qa[1], kb[2], kb[3]);
+    mma_op_16816(s[nt], qa[0], kb[0], kb[1]);
+    mma_op_16816(s[nt], qa[1], kb[2], kb[3]);
   }
 
   // scale + relative position bias + shift mask, then softmax over the 144 key slots (unused slots excluded).
@@ -336,16 +342,16 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
 #pragma unroll
   for (int kk = 0; kk < 9; ++kk) {
     uint32_t pa[4];
-    pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-    pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-    pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    pa[0] = pack_op(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = pack_op(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = pack_op(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = pack_op(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
       uint32_t vb[4];
       ldsm_x4_t(vb, &sV[(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_LD + (np * 2 + (lane >> 4)) * 8]);
-      mma_bf16_16816(o[np * 2], pa, vb[0], vb[1]);
-      mma_bf16_16816(o[np * 2 + 1], pa, vb[2], vb[3]);
+      mma_op_16816(o[np * 2], pa, vb[0], vb[1]);
+      mma_op_16816(o[np * 2 + 1], pa, vb[2], vb[3]);
     }
   }
   const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
@@ -353,8 +359,8 @@ __global__ void __launch_bounds__(WA_THREADS, 2) swin_window_attn_kernel(WinAttn
   __syncwarp();
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    *reinterpret_cast<uint32_t*>(&sQ[(r0 + lr) * WA_LD + nt * 8 + lc]) = pack_bf16(o[nt][0] * inv_lo, o[nt][1] * inv_lo);
-    *reinterpret_cast<uint32_t*>(&sQ[(r0 + lr + 8) * WA_LD + nt * 8 + lc]) = pack_bf16(o[nt][2] * inv_hi, o[nt][3] * inv_hi);
+    *reinterpret_cast<uint32_t*>(&sQ[(r0 + lr) * WA_LD + nt * 8 + lc]) = pack_op(o[nt][0] * inv_lo, o[nt][1] * inv_lo);
+    *reinterpret_cast<uint32_t*>(&sQ[(r0 + lr + 8) * WA_LD + nt * 8 + lc]) = pack_op(o[nt][2] * inv_hi, o[nt][3] * inv_hi);
   }
   __syncwarp();
 #pragma unroll
@@ -394,15 +400,24 @@ extern "C" int fz_merge_ln(const float* x, const float* w, const float* b, void*
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int fz_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
+extern "C" int fz_cast_f32_16(const float* in, void* out16, int out_dtype, int64_t n, void* stream) {
   using namespace fz;
-  FZ_REQUIRE(n >= 0 && n % 4 == 0, "fz_cast_f32_bf16: n must be a multiple of 4");
+  FZ_REQUIRE(n >= 0 && n % 4 == 0, "fz_cast_f32_16: n must be a multiple of 4");
+  FZ_REQUIRE(out_dtype == FZ_BF16 || out_dtype == FZ_F16, "fz_cast_f32_16: the output is FZ_BF16 or FZ_F16");
   if (n == 0) return 0;
   const size_t n4 = static_cast<size_t>(n) / 4;
-  cast_f32_bf16_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out_bf16), n4);
+  const unsigned grid = static_cast<unsigned>((n4 + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_dtype == FZ_F16)
+    cast_f32_16_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out16), n4);
+  else
+    cast_f32_16_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out16), n4);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int fz_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
+  return fz_cast_f32_16(in, out_bf16, FZ_BF16, n, stream);
 }
 
 extern "C" int fz_swin_window_attn(const void* qkv_bf16, const void* qkv_bias_bf16, const float* table, void* out_bf16,
@@ -415,10 +430,10 @@ extern "C" int fz_swin_window_attn(const void* qkv_bf16, const void* qkv_bias_bf
   FZ_REQUIRE(shift >= 0 && shift < window, "fz_swin_window_attn: shift %d out of range", shift);
   if (B == 0) return 0;
   WinAttnParams p;
-  p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv_bf16);
-  p.qkv_bias = reinterpret_cast<const __nv_bfloat16*>(qkv_bias_bf16);
+  p.qkv = reinterpret_cast<const op_t*>(qkv_bf16);
+  p.qkv_bias = reinterpret_cast<const op_t*>(qkv_bias_bf16);
   p.table = table;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.out = reinterpret_cast<op_t*>(out_bf16);
   p.H = H; p.W = W; p.C = C; p.heads = heads; p.ws = window; p.shift = shift;
   p.nwy = (H + window - 1) / window;
   p.nwx = (W + window - 1) / window;

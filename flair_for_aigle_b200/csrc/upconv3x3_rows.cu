@@ -17,6 +17,7 @@
 // owns one source pixel and writes, per output row, the two adjacent output pixels (2*Cout bf16, contiguous).
 #include "common.h"
 #include "ptx.cuh"
+#include "operand.cuh"
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
@@ -26,7 +27,7 @@ struct UpConvParams {
   int R;                 // source rows per work item
   const float* bias;
   const float* scale;
-  __nv_bfloat16* out;    // [B][2H][2W][Cout]
+  op_t* out;    // [B][2H][2W][Cout]
 };
 
 constexpr int UP_PX = 130;
@@ -120,7 +121,7 @@ upconv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = umma_idesc16(128, BN, OP_F16);
       mbar_wait(wfull, 0);
       uint32_t g = 0, ro = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -190,7 +191,7 @@ upconv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int py = 0; py < 2; ++py) {
           // output pixels (2ys+py, 2xs) and (2ys+py, 2xs+1): 2*Cout bf16 contiguous
-          __nv_bfloat16* op = p.out + ((static_cast<size_t>(b) * 2 * p.H + 2 * ys + py) * OW + 2 * xs) * p.Cout;
+          op_t* op = p.out + ((static_cast<size_t>(b) * 2 * p.H + 2 * ys + py) * OW + 2 * xs) * p.Cout;
 #pragma unroll
           for (int px = 0; px < 2; ++px) {
             float v[BN];
@@ -206,8 +207,8 @@ upconv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             uint4* o4 = reinterpret_cast<uint4*>(op + px * p.Cout);
 #pragma unroll
             for (int c = 0; c < BN / 8; ++c)
-              o4[c] = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                                 pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+              o4[c] = make_uint4(pack_op(v[8 * c], v[8 * c + 1]), pack_op(v[8 * c + 2], v[8 * c + 3]),
+                                 pack_op(v[8 * c + 4], v[8 * c + 5]), pack_op(v[8 * c + 6], v[8 * c + 7]));
           }
         }
         tc_fence_before();
@@ -275,21 +276,21 @@ extern "C" int fz_upconv3x3_bn_relu(const void* in, const void* w16, const float
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     const uint32_t box[4] = {8, UP_PX, 1, 1};
-    int rc = make_tmap_bf16(&tmA, in, 4, dims, strides, box, 0);
+    int rc = make_tmap16(&tmA, in, 4, dims, strides, box, 0);
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)16 * Cin, (uint64_t)w_rows};
     const uint64_t strides[1] = {(uint64_t)16 * Cin * 2};
     const uint32_t box[2] = {(uint32_t)Cin, (uint32_t)Cout};
-    int rc = make_tmap_bf16(&tmB, w16, 2, dims, strides, box, Cin * 2);
+    int rc = make_tmap16(&tmB, w16, 2, dims, strides, box, Cin * 2);
     if (rc) return rc;
   }
   UpConvParams p;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
   p.R = 32;   // launch_rows picks the real value
   p.bias = bias; p.scale = scale;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.out = reinterpret_cast<op_t*>(out);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (Cin == 64 && Cout == 32) return launch_upconv<64, 32>(tmA, tmB, p, st);
   if (Cin == 64 && Cout == 16) return launch_upconv<64, 16>(tmA, tmB, p, st);

@@ -13,26 +13,27 @@
 #include "ptx.cuh"
 #include "../../include/flair_zonal_b200.h"
 
-#include <cuda_bf16.h>
+#include "ptx.cuh"
+#include "operand.cuh"
 
 namespace fz {
 
 __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const op2_t* h = reinterpret_cast<const op2_t*>(&raw);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 t = __bfloat1622float2(h[j]);
+    const float2 t = op22ff(h[j]);
     f[2 * j] = t.x;
     f[2 * j + 1] = t.y;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  return make_uint4(pack_op(f[0], f[1]), pack_op(f[2], f[3]), pack_op(f[4], f[5]), pack_op(f[6], f[7]));
 }
 
 // torch adaptive pooling bins: [floor(i*H/S), ceil((i+1)*H/S))
-__global__ void __launch_bounds__(128) adaptive_avgpool_kernel(const __nv_bfloat16* __restrict__ in,
-                                                               __nv_bfloat16* __restrict__ out, int H, int W, int C,
+__global__ void __launch_bounds__(128) adaptive_avgpool_kernel(const op_t* __restrict__ in,
+                                                               op_t* __restrict__ out, int H, int W, int C,
                                                                int S) {
   const int cell = blockIdx.x % (S * S);
   const int b = blockIdx.x / (S * S);
@@ -68,7 +69,7 @@ __device__ __forceinline__ void bilin_coord(int d, float scale, int in_size, int
 constexpr int PYR_ROWS = 8;
 
 // x-interpolated source row: hx * f[yy][x0] + lx * f[yy][x1]
-__device__ __forceinline__ void pyr_xlerp(const __nv_bfloat16* src, int yy, int w, int C, int x0, int x1, float hx, float lx,
+__device__ __forceinline__ void pyr_xlerp(const op_t* src, int yy, int w, int C, int x0, int x1, float hx, float lx,
                                           float (&dst)[8]) {
   float f0[8], f1[8];
   unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(yy) * w + x0) * C), f0);
@@ -77,7 +78,7 @@ __device__ __forceinline__ void pyr_xlerp(const __nv_bfloat16* src, int yy, int 
   for (int j = 0; j < 8; ++j) dst[j] = hx * f0[j] + lx * f1[j];
 }
 // horizontally filtered source row of the down2(up2(.)) stencil: 0.125 f[x-1] + 0.75 f[x] + 0.125 f[x+1] (clamped)
-__device__ __forceinline__ void pyr_xtap3(const __nv_bfloat16* src, int yy, int w, int C, int xm, int x, int xp,
+__device__ __forceinline__ void pyr_xtap3(const op_t* src, int yy, int w, int C, int xm, int x, int xp,
                                           float (&dst)[8]) {
   float f0[8], f1[8], f2[8];
   unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(yy) * w + xm) * C), f0);
@@ -93,9 +94,9 @@ __device__ __forceinline__ void pyr_xtap3(const __nv_bfloat16* src, int yy, int 
 // registers across the output rows that share them (the first version decoded a flat 64-bit index per 16-byte vector
 // and re-fetched 4 / 9 source vectors per output: 218 us for a 310 MB slice).
 template <int MODE>
-__global__ void __launch_bounds__(256) resize_slice_kernel(const __nv_bfloat16* __restrict__ in,
-                                                           const __nv_bfloat16* __restrict__ add,
-                                                           __nv_bfloat16* __restrict__ out, int h, int w, int H, int W,
+__global__ void __launch_bounds__(256) resize_slice_kernel(const op_t* __restrict__ in,
+                                                           const op_t* __restrict__ add,
+                                                           op_t* __restrict__ out, int h, int w, int H, int W,
                                                            int C, int Ctot, int c0) {
   const int vpp = C / 8;
   const int vper = vpp < 256 ? vpp : 256;                   // vectors of one pixel handled side by side
@@ -106,9 +107,9 @@ __global__ void __launch_bounds__(256) resize_slice_kernel(const __nv_bfloat16* 
   const int ya = blockIdx.y * PYR_ROWS, yb = min(ya + PYR_ROWS, H);
   const size_t orow = static_cast<size_t>(W) * Ctot, arow = static_cast<size_t>(W) * C;
   for (int c = v * 8; c < C; c += 256 * 8) {
-    const __nv_bfloat16* src = in + b * h * w * C + c;
-    __nv_bfloat16* o = out + ((b * H + ya) * W + x) * static_cast<size_t>(Ctot) + c0 + c;
-    const __nv_bfloat16* ad = add ? add + ((b * H + ya) * W + x) * static_cast<size_t>(C) + c : nullptr;
+    const op_t* src = in + b * h * w * C + c;
+    op_t* o = out + ((b * H + ya) * W + x) * static_cast<size_t>(Ctot) + c0 + c;
+    const op_t* ad = add ? add + ((b * H + ya) * W + x) * static_cast<size_t>(C) + c : nullptr;
     auto emit = [&](float (&acc)[8]) {
       if (ad != nullptr) {
         float f[8];
@@ -186,22 +187,22 @@ __global__ void __launch_bounds__(256) resize_slice_kernel(const __nv_bfloat16* 
 // L2 -> SM again (~6 TB/s of gather traffic).  Here one CTA owns ONE slice of a PX x 4 pixel patch and walks its 4 rows
 // in turn: source vectors shared by neighbouring output pixels are L1 hits, and both resamplings run separably (x pass
 // per source row, kept in registers across the output rows that share it), which halves the arithmetic per output.
-__global__ void __launch_bounds__(256) pyramid_concat_kernel(const __nv_bfloat16* __restrict__ p0, int s0,
-                                                             const __nv_bfloat16* __restrict__ p1, int s1,
-                                                             const __nv_bfloat16* __restrict__ p2, int s2,
-                                                             const __nv_bfloat16* __restrict__ p3,
-                                                             __nv_bfloat16* __restrict__ out, int H, int C) {
+__global__ void __launch_bounds__(256) pyramid_concat_kernel(const op_t* __restrict__ p0, int s0,
+                                                             const op_t* __restrict__ p1, int s1,
+                                                             const op_t* __restrict__ p2, int s2,
+                                                             const op_t* __restrict__ p3,
+                                                             op_t* __restrict__ out, int H, int C) {
   const int vpp = C / 8;                                   // 16-byte vectors per pixel and slice; 256 % vpp == 0
   const int xi = threadIdx.x / vpp, c = (threadIdx.x - xi * vpp) * 8;
   const int x = blockIdx.x * (256 / vpp) + xi;
   const int k = blockIdx.z % 5;                            // CTA-uniform slice
   const size_t b = blockIdx.z / 5;
   if (x >= H) return;
-  const __nv_bfloat16* in = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+  const op_t* in = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
   const int h = k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : H));
-  const __nv_bfloat16* src = in + b * h * h * C + c;
+  const op_t* src = in + b * h * h * C + c;
   const int ya = blockIdx.y * PYR_ROWS, yb = min(ya + PYR_ROWS, H);
-  __nv_bfloat16* o = out + ((b * H + ya) * H + x) * (5 * static_cast<size_t>(C)) + k * C + c;
+  op_t* o = out + ((b * H + ya) * H + x) * (5 * static_cast<size_t>(C)) + k * C + c;
   const size_t orow = static_cast<size_t>(H) * 5 * C;
   if (k < 4 && h == H) {                                   // same size: copy
     for (int y = ya; y < yb; ++y, o += orow)
@@ -295,7 +296,7 @@ extern "C" int fz_adaptive_avgpool(const void* in_bf16, void* out_bf16, int B, i
   FZ_REQUIRE(B >= 0 && H > 0 && W > 0 && S > 0 && S <= H && S <= W && C % 8 == 0, "fz_adaptive_avgpool: bad shape");
   if (B == 0) return 0;
   adaptive_avgpool_kernel<<<B * S * S, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), H, W, C, S);
+      reinterpret_cast<const op_t*>(in_bf16), reinterpret_cast<op_t*>(out_bf16), H, W, C, S);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -310,9 +311,9 @@ static int resize_common(int mode, const void* in, const void* add, void* out, i
   const int vpp = C / 8, vper = vpp < 256 ? vpp : 256, px = 256 / vper;
   const dim3 grid((W + px - 1) / px, (H + PYR_ROWS - 1) / PYR_ROWS, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const __nv_bfloat16* i = reinterpret_cast<const __nv_bfloat16*>(in);
-  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(add);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  const op_t* i = reinterpret_cast<const op_t*>(in);
+  const op_t* a = reinterpret_cast<const op_t*>(add);
+  op_t* o = reinterpret_cast<op_t*>(out);
   if (mode == 0) resize_slice_kernel<0><<<grid, 256, 0, st>>>(i, a, o, h, w, H, W, C, Ctot, c0);
   else resize_slice_kernel<1><<<grid, 256, 0, st>>>(i, a, o, h, w, H, W, C, Ctot, c0);
   FZ_CHECK_CUDA(cudaGetLastError());
@@ -339,9 +340,9 @@ extern "C" int fz_pyramid_concat(const void* p0, int s0, const void* p1, int s1,
   const int px = 256 / (C / 8);
   const dim3 grid((H + px - 1) / px, (H + PYR_ROWS - 1) / PYR_ROWS, B * 5);
   pyramid_concat_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(p0), s0, reinterpret_cast<const __nv_bfloat16*>(p1), s1,
-      reinterpret_cast<const __nv_bfloat16*>(p2), s2, reinterpret_cast<const __nv_bfloat16*>(p3),
-      reinterpret_cast<__nv_bfloat16*>(out_bf16), H, C);
+      reinterpret_cast<const op_t*>(p0), s0, reinterpret_cast<const op_t*>(p1), s1,
+      reinterpret_cast<const op_t*>(p2), s2, reinterpret_cast<const op_t*>(p3),
+      reinterpret_cast<op_t*>(out_bf16), H, C);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -49,7 +49,13 @@ def _f32(t, dev):
 
 
 def _bf16(t, dev):
-    return t.detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16).contiguous()
+    """fp32 -> the inference kernels' 16-bit operand format (nv.op_dtype(): float16, saturating; bfloat16 in the A/B
+    build), one rounding."""
+    t = t.detach().to(device=dev, dtype=torch.float32)
+    dt = nv.op_dtype()
+    if dt == torch.float16:
+        t = t.clamp(-65504.0, 65504.0)
+    return t.to(dt).contiguous()
 
 
 class ConvNeXtV2UNetEngine:
@@ -134,7 +140,7 @@ class ConvNeXtV2UNetEngine:
     def _alloc_workspace(self):
         cfg, B, dev = self.cfg, self.B, self.dev
         P = cfg.patch
-        bf, f32 = torch.bfloat16, torch.float32
+        bf, f32 = nv.op_dtype(), torch.float32
         hw = [(P // 4) >> i for i in range(4)]
         self.hw = hw
         self.x = [torch.empty((B, h, h, c), dtype=f32, device=dev) for h, c in zip(hw, cfg.dims)]

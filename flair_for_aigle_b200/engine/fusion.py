@@ -50,11 +50,11 @@ class FusedEncodersUNet:
             self.b.append(_f32(state_dict[f"{fusion_prefix}conv_f.{i}.bias"], dev))
         B = self.B
         self.fused = [torch.empty((B, h, w, c), dtype=torch.float32, device=dev) for h, w, c in self.stage_shapes]
-        self.a_bufs = [torch.empty(B * h * w * max(chans[m][i] for m in self.mods), dtype=torch.bfloat16, device=dev)
+        self.a_bufs = [torch.empty(B * h * w * max(chans[m][i] for m in self.mods), dtype=nv.op_dtype(), device=dev)
                        for i, (h, w, _) in enumerate(self.stage_shapes)]
         need = [max([sh[0] * sh[1] * chans[m][i] for m in self.mods
                      for sh in [self.src_hw[m][i]] if sh != (h, w)] + [0]) for i, (h, w, _) in enumerate(self.stage_shapes)]
-        self.r_bufs = [torch.empty(B * n, dtype=torch.bfloat16, device=dev) if n else None for n in need]
+        self.r_bufs = [torch.empty(B * n, dtype=nv.op_dtype(), device=dev) if n else None for n in need]
 
     def encode(self, batch: Dict[str, torch.Tensor]) -> int:
         n = None

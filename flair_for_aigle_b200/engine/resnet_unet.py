@@ -88,7 +88,7 @@ class ResNetUNetEngine:
         self.decoder = UNetDecoderPlan(sd, dec_prefix, [cfg.in_chans, 64, 64, 128, 256, 512], cfg.n_classes, cfg.patch,
                                        max_batch, dev, decoder_channels=cfg.decoder_channels)
         # workspace (bf16 NHWC)
-        P, B, bf = cfg.patch, max_batch, torch.bfloat16
+        P, B, bf = cfg.patch, max_batch, nv.op_dtype()
         self.xn = torch.empty((B, cfg.in_chans, P, P), dtype=torch.float32, device=dev)
         self.f1 = torch.empty((B, P // 2, P // 2, 64), dtype=bf, device=dev)
         self.feat = [torch.empty((B, P // s, P // s, c), dtype=bf, device=dev)

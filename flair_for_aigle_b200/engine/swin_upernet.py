@@ -156,7 +156,7 @@ class SwinUPerNetEngine:
     # ------------------------------------------------------------------------------ workspace
     def _alloc_workspace(self):
         cfg, B, dev = self.cfg, self.B, self.dev
-        bf, f32 = torch.bfloat16, torch.float32
+        bf, f32 = nv.op_dtype(), torch.float32
         hw, dims = self.hw, self.dims
         Pc, Sc = cfg.pyramid_channels, cfg.segmentation_channels
         self.x = [torch.empty((B, h, h, c), dtype=f32, device=dev) for h, c in zip(hw, dims)]

@@ -21,7 +21,13 @@ def _f32(t, dev):
 
 
 def _bf16(t, dev):
-    return t.detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16).contiguous()
+    """fp32 -> the inference kernels' 16-bit operand format (nv.op_dtype(): float16, saturating; bfloat16 in the A/B
+    build), one rounding."""
+    t = t.detach().to(device=dev, dtype=torch.float32)
+    dt = nv.op_dtype()
+    if dt == torch.float16:
+        t = t.clamp(-65504.0, 65504.0)
+    return t.to(dt).contiguous()
 
 
 class UNetDecoderPlan:
@@ -70,7 +76,7 @@ class UNetDecoderPlan:
             cat_sz.append(hd * hd * (blk["cin"] + blk["cskip"]))
             out_sz.append(hd * hd * blk["cout"])
         self.deepest = deepest
-        bf = torch.bfloat16
+        bf = nv.op_dtype()
         self.cat = torch.empty(max_batch * max(cat_sz), dtype=bf, device=device)
         self.t1 = torch.empty(max_batch * max(out_sz), dtype=bf, device=device)
         self.t2 = torch.empty(max_batch * max(out_sz), dtype=bf, device=device)
@@ -86,10 +92,10 @@ class UNetDecoderPlan:
             o1 = self.t1[:n * hd * hd * blk["cout"]].view(n, hd, hd, blk["cout"])
             hs = hd // 2
             skip_k = skips[k] if blk["cskip"] > 0 else None
-            if ("conv1_w16" in blk and a.dtype == torch.bfloat16 and hs % 128 == 0 and a.is_contiguous()):
+            if ("conv1_w16" in blk and a.dtype == nv.op_dtype() and hs % 128 == 0 and a.is_contiguous()):
                 nv.upconv3x3_bn_relu(a, blk["conv1_w16"], blk["conv1_s"], blk["conv1_b"], o1)
-            elif ("conv1_w16a" in blk and a.dtype == torch.bfloat16 and skip_k is not None
-                  and skip_k.dtype == torch.bfloat16 and hs * hs >= 128 and (hs >= 128 and hs % 128 == 0 or 128 % hs == 0)
+            elif ("conv1_w16a" in blk and a.dtype == nv.op_dtype() and skip_k is not None
+                  and skip_k.dtype == nv.op_dtype() and hs * hs >= 128 and (hs >= 128 and hs % 128 == 0 or 128 % hs == 0)
                   and a.is_contiguous() and skip_k.is_contiguous()):
                 nv.catconv3x3_bn_relu(a, skip_k, blk["conv1_w16a"], blk["conv1_w"], blk["conv1_s"], blk["conv1_b"], o1)
             else:

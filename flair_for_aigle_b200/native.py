@@ -13,10 +13,15 @@ from typing import Optional
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "_native" / "libfz_b200.so"
+# FZ_OPERANDS=bf16 selects the A/B build whose inference kernels store bf16 operands (round-1 behaviour, see
+# csrc/operand.cuh and build.py); the product library stores fp16.
+_LIB_PATH = Path(__file__).resolve().parent / "_native" / (
+    "libfz_b200_bf16.so" if os.environ.get("FZ_OPERANDS", "").lower() == "bf16" else "libfz_b200.so")
 _lib: Optional[ctypes.CDLL] = None
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
+ABI_VERSION = 2
+EPI_OPERANDS_F16 = 0x200
 NCHW, NHWC, NHWC_UP4 = 0, 1, 2
 EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16, EPI_GELU_BF16 = 0, 1, 2, 3, 4, 5
 EPI_REVERSE_TILES = 0x100
@@ -57,6 +62,7 @@ _vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_siz
 _SIGNATURES = {
     "fz_last_error": [],
     "fz_abi_version": [],
+    "fz_operand_format": [],
     "fz_device_info": [_i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_sz)],
     "fz_gather_tiles_f32": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "fz_gather_tiles_f32_from_f32": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
@@ -79,7 +85,7 @@ _SIGNATURES = {
     "fz_grn_scale": [_vp, _i, _vp, _vp, _vp, _i, _i, ctypes.c_float, _vp],
     "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
-    "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_catconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fz_upconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_conv7x7s2_bn_relu": [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
@@ -90,6 +96,7 @@ _SIGNATURES = {
     "fz_merge_ln": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
     "fz_swin_window_attn": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, ctypes.c_float, _vp],
     "fz_cast_f32_bf16": [_vp, _vp, _i64, _vp],
+    "fz_cast_f32_16": [_vp, _vp, _i, _i64, _vp],
     "fz_adaptive_avgpool": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_bilinear_slice": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fz_updown_slice": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
@@ -148,9 +155,22 @@ def lib() -> ctypes.CDLL:
             fn = getattr(_lib, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if _lib.fz_abi_version() != 1:
-            raise NativeError("libfz_b200.so ABI version mismatch")
+        if _lib.fz_abi_version() != ABI_VERSION:
+            raise NativeError(f"{_LIB_PATH.name} ABI version mismatch: rebuild with `python -m flair_for_aigle_b200.build`")
     return _lib
+
+
+def op_dtype() -> torch.dtype:
+    """torch dtype of the inference kernels' 16-bit operand format (FZ_OP16 of the header): float16 in the product
+    build, bfloat16 in the FZ_OPERANDS=bf16 A/B build.  Training tensors are bfloat16 in both."""
+    return torch.float16 if lib().fz_operand_format() == F16 else torch.bfloat16
+
+
+def _op16(*tensors) -> None:
+    want = op_dtype()
+    for t in tensors:
+        if t is not None and t.dtype != want:
+            raise NativeError(f"this kernel takes {want} operands (the library's inference operand format), got {t.dtype}")
 
 
 def _check(rc: int, what: str) -> None:
@@ -178,7 +198,9 @@ def _dt(t: torch.Tensor) -> int:
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
-    raise NativeError(f"unsupported logits dtype {t.dtype}")
+    if t.dtype == torch.float16:
+        return F16
+    raise NativeError(f"unsupported dtype {t.dtype}")
 
 
 # --------------------------------------------------------------------------- feeder
@@ -277,18 +299,25 @@ def convert(img: torch.Tensor, mode: int) -> torch.Tensor:
 # --------------------------------------------------------------------------- GEMM
 def gemm_bf16(A: torch.Tensor, B: torch.Tensor, mode: int, bias=None, resid=None, sumsq=None, out=None,
               rows_per_sample: int = 0, impl: str = "tcgen05") -> torch.Tensor:
-    """A: bf16 [M,K]; B: bf16 [N,K] or [b,N,K]."""
+    """A: 16-bit [M,K]; B: 16-bit [N,K] or [b,N,K], both float16 (inference) or both bfloat16 (training); a 16-bit
+    output has the operands' format.  The format travels to the kernel as FZ_EPI_OPERANDS_F16 in ``mode``."""
     M, K = A.shape
     if B.dim() == 2:
         b_batch, (N, K2) = 1, B.shape
     else:
         b_batch, N, K2 = B.shape
-    assert K2 == K and A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    if K2 != K or A.dtype != B.dtype or A.dtype not in (torch.bfloat16, torch.float16):
+        raise NativeError(f"gemm: operands must both be float16 or both bfloat16 with equal K (got {A.dtype} [{M},{K}], "
+                          f"{B.dtype} [..,{N},{K2}])")
+    f32_out = (mode & 0xff) in (EPI_RESID_F32, EPI_F32)
+    if A.dtype == torch.float16:
+        mode |= EPI_OPERANDS_F16
     if bias is None:
         bias = torch.zeros(N, dtype=torch.float32, device=A.device)
     if out is None:
-        odt = torch.float32 if (mode & 0xff) in (EPI_RESID_F32, EPI_F32) else torch.bfloat16
-        out = torch.empty((M, N), dtype=odt, device=A.device)
+        out = torch.empty((M, N), dtype=torch.float32 if f32_out else A.dtype, device=A.device)
+    elif out.dtype != (torch.float32 if f32_out else A.dtype):
+        raise NativeError(f"gemm: output dtype {out.dtype} does not match the epilogue / operand format")
     fn = lib().fz_gemm_bf16 if impl == "tcgen05" else lib().fz_gemm_bf16_simt
     with _Timed("gemm_tcgen05" if impl == "tcgen05" else "gemm_simt", M=M, N=N, K=K, mode=mode):
         _check(fn(_ptr(A), _ptr(B), _ptr(out), _ptr(bias), _ptr(resid), _ptr(sumsq), M, N, K, b_batch,
@@ -316,6 +345,7 @@ def stem_ln_f32(x_nchw, w, bias, ln_w, ln_b, out, eps=1e-6):
 
 def dwconv7_ln(x, wdw, bdw, ln_w, ln_b, out, eps=1e-6):
     B, H, W, C = x.shape
+    _op16(out)
     with _Timed('dwconv7_ln', B=B, H=H, C=C):
         _check(lib().fz_dwconv7_ln(_ptr(x), _ptr(wdw), _ptr(bdw), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, H, W, C, eps,
                                    _stream()), "fz_dwconv7_ln")
@@ -325,6 +355,7 @@ def dwconv7_ln(x, wdw, bdw, ln_w, ln_b, out, eps=1e-6):
 def ln2d_s2d(x, ln_w, ln_b, out, eps=1e-6, copy=None):
     """LayerNorm2d + space-to-depth; ``copy`` (bf16 [B,H,W,C]) additionally receives the un-normalised input."""
     B, H, W, C = x.shape
+    _op16(out, copy)
     with _Timed('ln2d_s2d', B=B, H=H, C=C):
         _check(lib().fz_ln2d_s2d_copy(_ptr(x), _ptr(ln_w), _ptr(ln_b), _ptr(out), _ptr(copy), B, H, W, C, eps,
                                       _stream()), "fz_ln2d_s2d_copy")
@@ -345,6 +376,7 @@ def grn_scale(partial, tiles_per_sample, gamma, scale, eps=1e-6, scratch=None):
 def scale_weights(w, scale, out):
     N, K = w.shape
     B = scale.shape[0]
+    _op16(w, out)
     with _Timed('scale_weights', B=B, N=N, K=K):
         _check(lib().fz_scale_weights(_ptr(w), _ptr(scale), _ptr(out), B, N, K, _stream()), "fz_scale_weights")
     return out
@@ -352,6 +384,7 @@ def scale_weights(w, scale, out):
 
 def scale_rows(h, scale, rows_per_sample):
     M, K = h.shape
+    _op16(h)
     with _Timed('scale_rows', M=M, K=K):
         _check(lib().fz_scale_rows(_ptr(h), _ptr(scale), M, K, rows_per_sample, _stream()), "fz_scale_rows")
     return h
@@ -363,8 +396,8 @@ def upsample2_concat(a, s, out):
     C2 = 0 if s is None else s.shape[-1]
     assert C1 + C2 == CT
     with _Timed('upsample2_concat', B=B, H=H, C=CT):
-        _check(lib().fz_upsample2_concat(_ptr(a), _dt(a), _ptr(s), _dt(s) if s is not None else BF16, _ptr(out), B, H, W,
-                                         C1, C2, _stream()), "fz_upsample2_concat")
+        _check(lib().fz_upsample2_concat(_ptr(a), _dt(a), _ptr(s), _dt(s) if s is not None else _dt(out), _ptr(out),
+                                         _dt(out), B, H, W, C1, C2, _stream()), "fz_upsample2_concat")
     return out
 
 
@@ -377,6 +410,7 @@ def conv3x3(x, w, scale, bias, mode, out=None, cout=None, cstride=0, plan=None, 
     rows = w.shape[0]
     cout = rows if cout is None else cout
     RH, RW = (raster.shape[-2], raster.shape[-1]) if raster is not None else (0, 0)
+    _op16(x, w, resid, out if mode in (CONV_RELU_BF16, CONV_ADD_RELU_BF16, CONV_BF16) else None)
     with _Timed('conv3x3_tcgen05', B=B, H=H, Cin=Cin, Cout=cout, mode=mode):
         _check(lib().fz_conv3x3_ex(_ptr(x), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), _ptr(resid), B, H, W, Cin, cout,
                                    rows, stride, mode, cstride, _ptr(plan), _ptr(own), _ptr(raster), RH, RW, margin,
@@ -406,6 +440,7 @@ def upconv3x3_bn_relu(x, w16, scale, bias, out):
     """x bf16 [B,H,W,Cin] -> out bf16 [B,2H,2W,Cout] = relu(bn(conv3x3(nearest_up2(x)))); w16 bf16 [rows,16,Cin]."""
     B, H, W, Cin = x.shape
     cout = out.shape[-1]
+    _op16(x, w16, out)
     with _Timed('upconv3x3_tcgen05', B=B, H=H, Cin=Cin, Cout=cout):
         _check(lib().fz_upconv3x3_bn_relu(_ptr(x), _ptr(w16), _ptr(scale), _ptr(bias), _ptr(out), B, H, W, Cin, cout,
                                           w16.shape[0], _stream()), "fz_upconv3x3_bn_relu")
@@ -419,6 +454,7 @@ def catconv3x3_bn_relu(a, skip, w16a, w, scale, bias, out):
     C2 = skip.shape[-1]
     cout = out.shape[-1]
     fl_equiv = 2.0 * B * 4 * Hs * Ws * (4 * C1 + 9 * C2) * cout
+    _op16(a, skip, w16a, w, out)
     with _Timed('catconv3x3_tcgen05', B=B, H=2 * Hs, C1=C1, C2=C2, Cout=cout, flop=fl_equiv):
         _check(lib().fz_catconv3x3_bn_relu(_ptr(a), _ptr(skip), _ptr(w16a), _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), B,
                                            Hs, Ws, C1, C2, cout, w.shape[0], _stream()), "fz_catconv3x3_bn_relu")
@@ -431,6 +467,7 @@ def conv7x7s2_bn_relu(x, w, scale, bias, out):
         B, P, is_f32, cin = x.shape[0], x.shape[1], 0, 4
     else:
         B, cin, P, is_f32 = x.shape[0], x.shape[1], x.shape[2], 1
+    _op16(out)
     with _Timed('conv7x7s2', B=B, P=P):
         _check(lib().fz_conv7x7s2_bn_relu(_ptr(x), is_f32, cin, _ptr(w), _ptr(scale), _ptr(bias), _ptr(out), B, P,
                                           _stream()), "fz_conv7x7s2_bn_relu")
@@ -439,6 +476,7 @@ def conv7x7s2_bn_relu(x, w, scale, bias, out):
 
 def maxpool3x3s2(x, out):
     B, H, W, C = x.shape
+    _op16(x, out)
     with _Timed('maxpool3x3s2', B=B, H=H, C=C):
         _check(lib().fz_maxpool3x3s2(_ptr(x), _ptr(out), B, H, W, C, _stream()), "fz_maxpool3x3s2")
     return out
@@ -449,6 +487,7 @@ def layernorm_rows(x: torch.Tensor, w, b, out: torch.Tensor, eps: float = 1e-5):
     """x float [..., C] (contiguous) -> out bf16, nn.LayerNorm over C."""
     C = x.shape[-1]
     rows = x.numel() // C
+    _op16(out)
     with _Timed("layernorm_rows", rows=rows, C=C):
         _check(lib().fz_layernorm_rows(_ptr(x), _ptr(w), _ptr(b), _ptr(out), rows, C, eps, _stream()), "fz_layernorm_rows")
     return out
@@ -457,6 +496,7 @@ def layernorm_rows(x: torch.Tensor, w, b, out: torch.Tensor, eps: float = 1e-5):
 def merge_ln(x: torch.Tensor, w, b, out: torch.Tensor, eps: float = 1e-5):
     """timm PatchMerging gather + LayerNorm(4C): x float [B,H,W,C] -> out bf16 [B,H/2,W/2,4C]."""
     B, H, W, C = x.shape
+    _op16(out)
     with _Timed("merge_ln", n=B, H=H, C=C):
         _check(lib().fz_merge_ln(_ptr(x), _ptr(w), _ptr(b), _ptr(out), B, H, W, C, eps, _stream()), "fz_merge_ln")
     return out
@@ -466,6 +506,7 @@ def swin_window_attn(qkv: torch.Tensor, qkv_bias_bf16, table, out: torch.Tensor,
                      scale: float):
     """qkv bf16 [B,H,W,3C] -> out bf16 [B,H,W,C] (see include/flair_zonal_b200.h)."""
     B, H, W, C3 = qkv.shape
+    _op16(qkv, qkv_bias_bf16, out)
     with _Timed("swin_window_attn", n=B, H=H, C=C3 // 3):
         _check(lib().fz_swin_window_attn(_ptr(qkv), _ptr(qkv_bias_bf16), _ptr(table), _ptr(out), B, H, W, C3 // 3, heads,
                                          window, shift, scale, _stream()), "fz_swin_window_attn")
@@ -473,13 +514,15 @@ def swin_window_attn(qkv: torch.Tensor, qkv_bias_bf16, table, out: torch.Tensor,
 
 
 def cast_f32_bf16(x: torch.Tensor, out: torch.Tensor):
+    """fp32 -> ``out``'s 16-bit format (float16: saturating; bfloat16), round to nearest even."""
     with _Timed("cast_f32_bf16", n=x.numel()):
-        _check(lib().fz_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "fz_cast_f32_bf16")
+        _check(lib().fz_cast_f32_16(_ptr(x), _ptr(out), _dt(out), x.numel(), _stream()), "fz_cast_f32_16")
     return out
 
 
 def adaptive_avgpool(x: torch.Tensor, S: int, out: torch.Tensor):
     B, H, W, C = x.shape
+    _op16(x, out)
     with _Timed("adaptive_avgpool", n=B, S=S):
         _check(lib().fz_adaptive_avgpool(_ptr(x), _ptr(out), B, H, W, C, S, _stream()), "fz_adaptive_avgpool")
     return out
@@ -489,6 +532,7 @@ def bilinear_slice(x: torch.Tensor, out: torch.Tensor, c0: int = 0, add=None):
     """out[..., c0:c0+C] = bilinear(x -> out's H,W; align_corners=False) (+ add)."""
     B, h, w, C = x.shape
     _, H, W, Ctot = out.shape
+    _op16(x, add, out)
     with _Timed("bilinear_slice", n=B, H=H, C=C):
         _check(lib().fz_bilinear_slice(_ptr(x), _ptr(add), _ptr(out), B, h, w, H, W, C, Ctot, c0, _stream()),
                "fz_bilinear_slice")
@@ -498,6 +542,7 @@ def bilinear_slice(x: torch.Tensor, out: torch.Tensor, c0: int = 0, add=None):
 def updown_slice(x: torch.Tensor, out: torch.Tensor, c0: int = 0):
     B, H, W, C = x.shape
     Ctot = out.shape[-1]
+    _op16(x, out)
     with _Timed("updown_slice", n=B, H=H, C=C):
         _check(lib().fz_updown_slice(_ptr(x), _ptr(out), B, H, W, C, Ctot, c0, _stream()), "fz_updown_slice")
     return out
@@ -507,8 +552,8 @@ def pyramid_concat(p0, p1, p2, p3, out: torch.Tensor):
     """out [B,H,H,5C] = [bilinear(p0) | bilinear(p1) | bilinear(p2) | p3 | down2(up2(p3))]: the UPerNet fuse input."""
     B, H, _, C = p3.shape
     for t in (p0, p1, p2, p3, out):
-        if t.dtype != torch.bfloat16 or not t.is_contiguous():
-            raise NativeError("pyramid_concat: contiguous bf16 NHWC maps required")
+        if t.dtype != op_dtype() or not t.is_contiguous():
+            raise NativeError("pyramid_concat: contiguous NHWC maps in the inference operand format required")
     if tuple(out.shape) != (B, H, H, 5 * C):
         raise NativeError(f"pyramid_concat: out shape {tuple(out.shape)} != {(B, H, H, 5 * C)}")
     with _Timed("pyramid_concat", n=B, H=H, C=C):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FZ_ABI_VERSION 1
+#define FZ_ABI_VERSION 2
 
 const char* fz_last_error(void);
 int fz_abi_version(void);
@@ -54,7 +54,7 @@ int fz_gather_tiles_u8(const uint8_t* raster, int C, int H, int W, const int32_t
  * Replaces inference.py:295-352 (D2H of fp32 logits, per-tile numpy crop + convert + windowed
  * write) and postprocess.py:9-30 (convert).
  * logits: [n_tiles][n_cls][P][P] (layout FZ_NCHW) or [n_tiles][P][P][cstride] (FZ_NHWC, class
- * fastest, first n_cls of cstride valid); dtype FZ_F32 or FZ_BF16.
+ * fastest, first n_cls of cstride valid); dtype FZ_F32, FZ_BF16 or FZ_F16.
  * plan: int32 [n_tiles][6] = (row0, col0, top_px, left_px, height_px, width_px): the write
  * window of the margin-cropped prediction (inference.py:318-343); height_px<=0 = skipped.
  * own:  int32 [n_tiles][4] = (r0, r1, c0, c1) sub-window (absolute raster px) of the write
@@ -63,6 +63,14 @@ int fz_gather_tiles_u8(const uint8_t* raster, int C, int H, int W, const int32_t
  */
 #define FZ_F32 0
 #define FZ_BF16 1
+#define FZ_F16 2
+/* FZ_OP16: the 16-bit OPERAND format of the inference kernels -- what they store between layers and feed to the tensor
+ * cores.  fp16 by default (11 significand bits; class-map agreement with the fp32 reference 99.0 % -> see DESIGN.md
+ * section 2), bf16 when the library is built with -DFZ_OPERANDS_BF16 (round-1 behaviour, A/B measurements).  Wherever an
+ * inference entry point below says "bf16" / "_bf16" for an activation or weight tensor, read "FZ_OP16"; fz_operand_format()
+ * returns which one this build uses.  The training entry points (backward / optimizer section) are always bf16, and
+ * fz_gemm_bf16 takes the format per call (FZ_EPI_OPERANDS_F16). */
+int fz_operand_format(void); /* FZ_F16 or FZ_BF16 */
 #define FZ_NCHW 0
 #define FZ_NHWC 1
 #define FZ_NHWC_UP4 2 /* float logits at quarter resolution [n][P/4][P/4][cstride]; the x4 bilinear (align_corners=True)
@@ -115,6 +123,9 @@ int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, vo
 #define FZ_EPI_REVERSE_TILES 0x100 /* OR into mode: walk the tile list backwards, so that an A operand the previous
                                     * kernel has just streamed out (larger than L2) is consumed newest-first */
 #define FZ_EPI_GELU_BF16 5  /* out bf16 = gelu(acc + bias)   (timm Mlp.fc1 + nn.GELU of a Swin block)       */
+#define FZ_EPI_OPERANDS_F16 0x200 /* OR into mode: A, B and a 16-bit output are IEEE fp16 instead of bf16 (same MMA rate,
+                                   * 3 more significand bits; outputs saturate at +-65504).  The inference engines use
+                                   * fp16 operands, the training step bf16 (see FZ_OP16 below). */
 int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq, int M,
                  int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
 /* Diagnostics: when set to a device buffer of 64*8 uint64, CTA 0 of every following fz_gemm_bf16 launch
@@ -181,7 +192,7 @@ int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K, int rows_p
 #define FZ_CONV_LOGITS_F32_NCHW 3 /* out float [B][Cout][H][W]: the reference's logits layout */
 #define FZ_CONV_ADD_RELU_BF16 4   /* out bf16 = relu(conv*scale + bias + resid): torchvision BasicBlock tail */
 #define FZ_CONV_BF16 5            /* out bf16 = conv*scale + bias (no activation): BasicBlock downsample branch */
-int fz_upsample2_concat(const void* a, int a_dtype, const void* s, int s_dtype, void* out_bf16, int B, int H, int W,
+int fz_upsample2_concat(const void* a, int a_dtype, const void* s, int s_dtype, void* out16, int out_dtype, int B, int H, int W,
                         int C1, int C2, void* stream);
 int fz_conv3x3_bf16(const void* in, const void* w, const float* scale, const float* bias, void* out, int B, int H,
                     int W, int Cin, int Cout, int w_rows, int mode, int cstride, const int32_t* plan,
@@ -243,6 +254,8 @@ int fz_merge_ln(const float* x, const float* w, const float* b, void* out_bf16, 
 int fz_swin_window_attn(const void* qkv_bf16, const void* qkv_bias_bf16, const float* table, void* out_bf16, int B,
                         int H, int W, int C, int heads, int window, int shift, float scale, void* stream);
 int fz_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+/* fp32 -> FZ_BF16 or FZ_F16 (round to nearest even; fp16 saturates at +-65504) */
+int fz_cast_f32_16(const float* in, void* out16, int out_dtype, int64_t n, void* stream);
 
 /* smp UPerNetDecoder fuse input in one pass (the five strided slice writes it replaces are the calls above):
  * out bf16 [B][H][H][5C] = [bilinear(p0: s0^2 -> H^2) | bilinear(p1) | bilinear(p2) | p3 | down2(up2(p3))], all maps bf16

@@ -11,6 +11,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+from flair_for_aigle_b200 import native as _nv  # noqa: E402
+OP = _nv.op_dtype()      # the inference kernels' 16-bit operand format (float16; bfloat16 in the A/B build)
 
 
 @pytest.fixture(autouse=True)
@@ -55,7 +57,7 @@ def test_dwconv7_ln(cuda, C, H):
     g, be = torch.rand(C, device=cuda) + 0.5, torch.randn(C, device=cuda) * 0.1
     ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=3, groups=C).permute(0, 2, 3, 1)
     ref = F.layer_norm(ref, (C,), g, be, 1e-6)
-    out = torch.empty(B, H, H, C, dtype=torch.bfloat16, device=cuda)
+    out = torch.empty(B, H, H, C, dtype=OP, device=cuda)
     nv.dwconv7_ln(x, w.reshape(C, 49).t().contiguous(), b, g, be, out)
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
@@ -68,13 +70,13 @@ def test_downsample_ln_s2d_gemm(cuda):
     B, H, C, Co = 2, 32, 128, 256
     x = torch.randn(B, H, H, C, device=cuda)
     g, be = torch.rand(C, device=cuda) + 0.5, torch.randn(C, device=cuda) * 0.1
-    w = (torch.randn(Co, C, 2, 2, device=cuda) / (4 * C) ** 0.5).bfloat16().float()
+    w = (torch.randn(Co, C, 2, 2, device=cuda) / (4 * C) ** 0.5).to(OP).float()
     b = torch.randn(Co, device=cuda) * 0.1
-    s2d = torch.empty(B * (H // 2) ** 2, 4 * C, dtype=torch.bfloat16, device=cuda)
+    s2d = torch.empty(B * (H // 2) ** 2, 4 * C, dtype=OP, device=cuda)
     nv.ln2d_s2d(x, g, be, s2d)
-    out = nv.gemm_bf16(s2d, w.permute(0, 2, 3, 1).reshape(Co, 4 * C).contiguous().bfloat16(), nv.EPI_F32, bias=b)
+    out = nv.gemm_bf16(s2d, w.permute(0, 2, 3, 1).reshape(Co, 4 * C).contiguous().to(OP), nv.EPI_F32, bias=b)
     torch.cuda.synchronize()
-    xn = F.layer_norm(x, (C,), g, be, 1e-6).bfloat16().float()
+    xn = F.layer_norm(x, (C,), g, be, 1e-6).to(OP).float()
     ref = F.conv2d(xn.permute(0, 3, 1, 2), w, b, stride=2).permute(0, 2, 3, 1).reshape(-1, Co)
     assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
 
@@ -83,37 +85,37 @@ def test_grn_scale_and_scalers(cuda):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(4)
     B, K, N, rps = 3, 512, 128, 256
-    h = torch.randn(B * rps, K, device=cuda).bfloat16()
+    h = torch.randn(B * rps, K, device=cuda).to(OP)
     partial = (h.float().view(B * rps // 128, 128, K) ** 2).sum(1).contiguous()   # what the fc1 epilogue emits
     gamma = torch.randn(K, device=cuda) * 0.5
     gx = partial.view(B, rps // 128, K).sum(1).sqrt()
     ref_scale = 1 + gamma * gx / (gx.mean(dim=1, keepdim=True) + 1e-6)
     scale = torch.empty(B, K, device=cuda)
     nv.grn_scale(partial, rps // 128, gamma, scale)
-    w = torch.randn(N, K, device=cuda).bfloat16()
-    ws = torch.empty(B, N, K, dtype=torch.bfloat16, device=cuda)
+    w = torch.randn(N, K, device=cuda).to(OP)
+    ws = torch.empty(B, N, K, dtype=OP, device=cuda)
     nv.scale_weights(w, scale, ws)
     h2 = h.clone()
     nv.scale_rows(h2, scale, rps)
     torch.cuda.synchronize()
     assert (scale - ref_scale).abs().max().item() < 1e-5
-    assert torch.equal(ws, (w.float()[None] * scale[:, None, :]).bfloat16())
-    assert torch.equal(h2, (h.float().view(B, rps, K) * scale[:, None, :]).bfloat16().view(-1, K))
+    assert torch.equal(ws, (w.float()[None] * scale[:, None, :]).to(OP))
+    assert torch.equal(h2, (h.float().view(B, rps, K) * scale[:, None, :]).to(OP).view(-1, K))
 
 
-@pytest.mark.parametrize("ta,ts", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
-                                   (torch.bfloat16, None)])
+@pytest.mark.parametrize("ta,ts", [(torch.float32, torch.float32), (OP, torch.float32),
+                                   (OP, None)])
 def test_upsample2_concat(cuda, ta, ts):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(5)
     B, H, C1, C2 = 2, 16, 64, (32 if ts is not None else 0)
     a = torch.randn(B, H // 2, H // 2, C1, device=cuda).to(ta)
     s = torch.randn(B, H, H, C2, device=cuda).to(ts) if ts is not None else None
-    out = torch.empty(B, H, H, C1 + C2, dtype=torch.bfloat16, device=cuda)
+    out = torch.empty(B, H, H, C1 + C2, dtype=OP, device=cuda)
     nv.upsample2_concat(a, s, out)
     torch.cuda.synchronize()
     up = a.float().repeat_interleave(2, 1).repeat_interleave(2, 2)
-    ref = torch.cat([up] + ([s.float()] if s is not None else []), dim=-1).bfloat16()
+    ref = torch.cat([up] + ([s.float()] if s is not None else []), dim=-1).to(OP)
     assert torch.equal(out, ref)
 
 
@@ -128,11 +130,11 @@ def test_conv3x3_relu(cuda, H, Cin, Cout):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(H + Cin + Cout)
     B = 2 if H <= 256 else 1
-    x = torch.randn(B, H, H, Cin, device=cuda).bfloat16()
-    w = (torch.randn(Cout, Cin, 3, 3, device=cuda) / (9 * Cin) ** 0.5).bfloat16()
+    x = torch.randn(B, H, H, Cin, device=cuda).to(OP)
+    w = (torch.randn(Cout, Cin, 3, 3, device=cuda) / (9 * Cin) ** 0.5).to(OP)
     scale = torch.rand(Cout, device=cuda) + 0.5
     bias = torch.randn(Cout, device=cuda) * 0.2
-    out = torch.empty(B, H, H, Cout, dtype=torch.bfloat16, device=cuda)
+    out = torch.empty(B, H, H, Cout, dtype=OP, device=cuda)
     nv.conv3x3(x, w.permute(0, 2, 3, 1).contiguous(), scale, bias, nv.CONV_RELU_BF16, out=out)
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, padding=1)
@@ -146,10 +148,10 @@ def test_conv3x3_head_modes(cuda):
     from flair_for_aigle_b200.flair_zonal_detection.slicing import ownership_windows
     torch.manual_seed(9)
     B, H, Cin, ncls, margin = 2, 256, 16, 19, 32
-    x = torch.randn(B, H, H, Cin, device=cuda).bfloat16()
-    w = (torch.randn(ncls, Cin, 3, 3, device=cuda) / 12).bfloat16()
+    x = torch.randn(B, H, H, Cin, device=cuda).to(OP)
+    w = (torch.randn(ncls, Cin, 3, 3, device=cuda) / 12).to(OP)
     bias = torch.randn(ncls, device=cuda) * 0.2
-    wp = torch.zeros(32, 3, 3, Cin, dtype=torch.bfloat16, device=cuda)
+    wp = torch.zeros(32, 3, 3, Cin, dtype=OP, device=cuda)
     wp[:ncls] = w.permute(0, 2, 3, 1)
     bp = torch.zeros(32, device=cuda)
     bp[:ncls] = bias
@@ -240,12 +242,12 @@ def test_upconv3x3_subpixel(cuda, H, Cin, Cout):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(H + Cin)
     B, W = 2, 128 if H <= 32 else H
-    x = torch.randn(B, H, W, Cin, device=cuda).bfloat16()
-    w = (torch.randn(Cout, Cin, 3, 3, device=cuda) / (9 * Cin) ** 0.5).bfloat16()
+    x = torch.randn(B, H, W, Cin, device=cuda).to(OP)
+    w = (torch.randn(Cout, Cin, 3, 3, device=cuda) / (9 * Cin) ** 0.5).to(OP)
     scale = torch.rand(Cout, device=cuda) + 0.5
     bias = torch.randn(Cout, device=cuda) * 0.1
-    w16 = nv.merge_upconv_weights(w).bfloat16().contiguous()
-    out = torch.empty(B, 2 * H, 2 * W, Cout, dtype=torch.bfloat16, device=cuda)
+    w16 = nv.merge_upconv_weights(w).to(OP).contiguous()
+    out = torch.empty(B, 2 * H, 2 * W, Cout, dtype=OP, device=cuda)
     nv.upconv3x3_bn_relu(x, w16, scale, bias, out)
     torch.cuda.synchronize()
     up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
@@ -280,14 +282,14 @@ def test_catconv3x3_subpixel(cuda, Hs, C1, C2, Cout):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(Hs + C1)
     B = 2
-    a = torch.randn(B, Hs, Hs, C1, device=cuda).bfloat16()
-    skip = torch.randn(B, 2 * Hs, 2 * Hs, C2, device=cuda).bfloat16()
-    w = (torch.randn(Cout, C1 + C2, 3, 3, device=cuda) / (9 * (C1 + C2)) ** 0.5).bfloat16()
+    a = torch.randn(B, Hs, Hs, C1, device=cuda).to(OP)
+    skip = torch.randn(B, 2 * Hs, 2 * Hs, C2, device=cuda).to(OP)
+    w = (torch.randn(Cout, C1 + C2, 3, 3, device=cuda) / (9 * (C1 + C2)) ** 0.5).to(OP)
     scale = torch.rand(Cout, device=cuda) + 0.5
     bias = torch.randn(Cout, device=cuda) * 0.1
-    w16a = nv.merge_upconv_weights(w[:, :C1]).bfloat16().contiguous()
+    w16a = nv.merge_upconv_weights(w[:, :C1]).to(OP).contiguous()
     w_nhwc = w.permute(0, 2, 3, 1).contiguous()
-    out = torch.full((B, 2 * Hs, 2 * Hs, Cout), float("nan"), dtype=torch.bfloat16, device=cuda)
+    out = torch.full((B, 2 * Hs, 2 * Hs, Cout), float("nan"), dtype=OP, device=cuda)
     nv.catconv3x3_bn_relu(a, skip, w16a, w_nhwc, scale, bias, out)
     torch.cuda.synchronize()
     up = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")

@@ -1,8 +1,12 @@
-"""GPU parity: tcgen05 GEMM (+ fused epilogues) vs an fp32 torch reference and the SIMT kernel."""
+"""GPU parity: tcgen05 GEMM (+ fused epilogues) vs an fp32 torch reference and the SIMT kernel, for both 16-bit operand
+formats the kernel takes per call (float16 = the inference engines, bfloat16 = the training step)."""
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+DTYPES = [torch.float16, torch.bfloat16]
+# 16-bit output rounding: 2^-11 relative for float16, 2^-8 for bfloat16 (x safety factor), else fp32 accumulation-order noise
+OUT_TOL = {torch.float16: 3e-3, torch.bfloat16: 2e-2, torch.float32: 2e-4}
 
 
 def _ref(A, B, bias, mode, resid, rows_per_sample):
@@ -18,7 +22,7 @@ def _ref(A, B, bias, mode, resid, rows_per_sample):
     if mode == nv.EPI_GELU_SUMSQ:
         v = torch.nn.functional.gelu(v)
         # GRN statistics are taken from the bf16 values fc2 will consume (the kernel re-reads its staged output tile)
-        sumsq = (v.bfloat16().float().view(A.shape[0] // 128, 128, -1) ** 2).sum(1)
+        sumsq = (v.to(A.dtype).float().view(A.shape[0] // 128, 128, -1) ** 2).sum(1)
     elif mode == nv.EPI_GELU_BF16:
         v = torch.nn.functional.gelu(v)
     elif mode == nv.EPI_RELU_BF16:
@@ -34,12 +38,13 @@ def _ref(A, B, bias, mode, resid, rows_per_sample):
     (2048, 2048, 512, 1024, 1), (384, 64, 192, 128, 1), (2048, 512, 2048, 1024, 2),
 ])
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
-def test_gemm_modes(cuda, impl, M, N, K, rps, bb, mode):
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gemm_modes(cuda, impl, M, N, K, rps, bb, mode, dt):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(M + N + K + mode)
     torch.backends.cuda.matmul.allow_tf32 = False
-    A = (torch.randn(M, K, device=cuda) * 0.5).bfloat16()
-    B = (torch.randn((bb, N, K) if bb > 1 else (N, K), device=cuda) / K ** 0.5).bfloat16()
+    A = (torch.randn(M, K, device=cuda) * 0.5).to(dt)
+    B = (torch.randn((bb, N, K) if bb > 1 else (N, K), device=cuda) / K ** 0.5).to(dt)
     bias = torch.randn(N, device=cuda) * 0.1
     resid = torch.randn(M, N, device=cuda) if mode == nv.EPI_RESID_F32 else None
     sumsq = torch.full((M // 128, N), -1.0, device=cuda) if mode == nv.EPI_GELU_SUMSQ else None
@@ -47,8 +52,8 @@ def test_gemm_modes(cuda, impl, M, N, K, rps, bb, mode):
     torch.cuda.synchronize()
     ref, ref_sq = _ref(A, B, bias, mode, resid, rps)
     err = (out.float() - ref).abs().max().item()
-    # tolerance: bf16 output rounding (2^-8 rel.) or fp32 accumulation-order noise
-    tol = 2e-2 if out.dtype == torch.bfloat16 else 2e-4
+    assert out.dtype == (torch.float32 if mode in (nv.EPI_RESID_F32, nv.EPI_F32) else dt)
+    tol = OUT_TOL[out.dtype]
     assert err < tol * max(1.0, ref.abs().max().item()), f"max abs err {err}"
     if sumsq is not None:
         rel = ((sumsq - ref_sq).abs() / ref_sq.clamp_min(1e-3)).max().item()
@@ -61,14 +66,15 @@ def test_gemm_modes(cuda, impl, M, N, K, rps, bb, mode):
     (10240, 1024, 256, 1024, 10),       # 160 pair tiles over 74 pairs: ring + TMEM double buffering across tiles
 ])
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
-def test_gemm_pair_kernel(cuda, monkeypatch, M, N, K, rps, bb, mode):
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gemm_pair_kernel(cuda, monkeypatch, M, N, K, rps, bb, mode, dt):
     """cta_group::2 kernel (gemm_tcgen05_2sm.cu), forced for every N % 256 == 0 shape."""
     from flair_for_aigle_b200 import native as nv
     monkeypatch.setenv("FZ_GEMM_PAIR", "2")
     torch.manual_seed(M + N + K + mode)
     torch.backends.cuda.matmul.allow_tf32 = False
-    A = (torch.randn(M, K, device=cuda) * 0.5).bfloat16()
-    B = (torch.randn((bb, N, K) if bb > 1 else (N, K), device=cuda) / K ** 0.5).bfloat16()
+    A = (torch.randn(M, K, device=cuda) * 0.5).to(dt)
+    B = (torch.randn((bb, N, K) if bb > 1 else (N, K), device=cuda) / K ** 0.5).to(dt)
     bias = torch.randn(N, device=cuda) * 0.1
     resid = torch.randn(M, N, device=cuda) if mode == nv.EPI_RESID_F32 else None
     sumsq = torch.full((M // 128, N), -1.0, device=cuda) if mode == nv.EPI_GELU_SUMSQ else None
@@ -76,7 +82,7 @@ def test_gemm_pair_kernel(cuda, monkeypatch, M, N, K, rps, bb, mode):
     torch.cuda.synchronize()
     ref, ref_sq = _ref(A, B, bias, mode, resid, rps)
     err = (out.float() - ref).abs().max().item()
-    tol = 2e-2 if out.dtype == torch.bfloat16 else 2e-4
+    tol = OUT_TOL[out.dtype]
     assert err < tol * max(1.0, ref.abs().max().item()), f"max abs err {err}"
     if sumsq is not None:
         rel = ((sumsq - ref_sq).abs() / ref_sq.clamp_min(1e-3)).max().item()
@@ -87,13 +93,14 @@ def test_gemm_pair_kernel(cuda, monkeypatch, M, N, K, rps, bb, mode):
     assert torch.equal(out, out2)
 
 
-def test_gemm_inplace_residual(cuda):
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gemm_inplace_residual(cuda, dt):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(0)
     torch.backends.cuda.matmul.allow_tf32 = False
     M, N, K = 1024, 256, 1024
-    A = torch.randn(M, K, device=cuda).bfloat16()
-    B = (torch.randn(N, K, device=cuda) / 32).bfloat16()
+    A = torch.randn(M, K, device=cuda).to(dt)
+    B = (torch.randn(N, K, device=cuda) / 32).to(dt)
     bias = torch.randn(N, device=cuda)
     x = torch.randn(M, N, device=cuda)
     ref = A.float() @ B.float().t() + bias + x
@@ -102,7 +109,8 @@ def test_gemm_inplace_residual(cuda):
     assert (x - ref).abs().max().item() < 1e-3
 
 
-def test_gelu_fast_matches_erf(cuda):
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gelu_fast_matches_erf(cuda, dt):
     """The epilogue's SFU GELU vs torch's erf GELU: K=64 identity-ish GEMM isolates it."""
     from flair_for_aigle_b200 import native as nv
     M, N, K = 4096, 64, 64
@@ -113,21 +121,47 @@ def test_gelu_fast_matches_erf(cuda):
     # acc = 0 -> value comes from the bias path only per column; use bias sweep instead
     bias = torch.linspace(-10, 10, N, device=cuda)
     sumsq = torch.zeros(M // 128, N, device=cuda)
-    out = nv.gemm_bf16(A.bfloat16(), B.bfloat16(), nv.EPI_GELU_SUMSQ, bias=bias, sumsq=sumsq, rows_per_sample=128)
+    out = nv.gemm_bf16(A.to(dt), B.to(dt), nv.EPI_GELU_SUMSQ, bias=bias, sumsq=sumsq, rows_per_sample=128)
     torch.cuda.synchronize()
-    ref = torch.nn.functional.gelu(bias).bfloat16().float()
-    assert (out.float() - ref[None, :]).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+    ref = torch.nn.functional.gelu(bias)
+    # fitted GELU (2.6e-5 abs) + tanh.approx (2^-11 rel.) + one output rounding
+    bound = (2 ** -8 if dt == torch.bfloat16 else 2 ** -10) * ref.abs().max().item()
+    assert (out.float() - ref[None, :]).abs().max().item() <= bound
+
+
+def test_fp16_output_saturates_instead_of_overflowing(cuda):
+    """|value| > 65504 is stored as +-65504 (cvt.rn.satfinite), never inf."""
+    from flair_for_aigle_b200 import native as nv
+    M, N, K = 256, 64, 64
+    A = torch.zeros(M, K, device=cuda, dtype=torch.float16)
+    B = torch.zeros(N, K, device=cuda, dtype=torch.float16)
+    bias = torch.linspace(-2.0e5, 2.0e5, N, device=cuda)
+    out = nv.gemm_bf16(A, B, nv.EPI_BF16, bias=bias)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert torch.equal(out[0].float(), bias.clamp(-65504.0, 65504.0).half().float())
+
+
+def test_gemm_rejects_mixed_operand_formats(cuda):
+    from flair_for_aigle_b200 import native as nv
+    A = torch.zeros(256, 64, device=cuda, dtype=torch.float16)
+    B = torch.zeros(64, 64, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(nv.NativeError):
+        nv.gemm_bf16(A, B, nv.EPI_BF16)
+    with pytest.raises(nv.NativeError):
+        nv.gemm_bf16(A, B.half(), nv.EPI_F32, out=torch.zeros(256, 64, device=cuda, dtype=torch.float16))
 
 
 @pytest.mark.parametrize("pair", ["0", "2"])
-def test_gemm_reverse_tile_order_is_bit_identical(cuda, monkeypatch, pair):
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gemm_reverse_tile_order_is_bit_identical(cuda, monkeypatch, pair, dt):
     """FZ_EPI_REVERSE_TILES only changes which CTA computes which tile."""
     from flair_for_aigle_b200 import native as nv
     monkeypatch.setenv("FZ_GEMM_PAIR", pair)
     torch.manual_seed(3)
     M, N, K = 4096 + 128, 512, 512
-    A = torch.randn(M, K, device=cuda).bfloat16()
-    B = (torch.randn(N, K, device=cuda) / 20).bfloat16()
+    A = torch.randn(M, K, device=cuda).to(dt)
+    B = (torch.randn(N, K, device=cuda) / 20).to(dt)
     bias = torch.randn(N, device=cuda)
     for mode in (nv.EPI_BF16, nv.EPI_GELU_BF16, nv.EPI_F32):
         a = nv.gemm_bf16(A, B, mode, bias=bias)

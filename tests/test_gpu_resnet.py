@@ -6,6 +6,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+from flair_for_aigle_b200 import native as _nv  # noqa: E402
+OP = _nv.op_dtype()      # the inference kernels' 16-bit operand format (float16; bfloat16 in the A/B build)
 TASK = "AERIAL_LABEL-COSIA"
 from parity import CLASS_AGREEMENT  # noqa: E402
 
@@ -22,17 +24,17 @@ def test_conv3x3_stride_and_residual(cuda, H, Cin, Cout, stride):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(H + Cin + stride)
     B = 2
-    x = torch.randn(B, H, H, Cin, device=cuda).bfloat16()
-    w = (torch.randn(Cout, Cin, 3, 3, device=cuda) / (9 * Cin) ** 0.5).bfloat16()
+    x = torch.randn(B, H, H, Cin, device=cuda).to(OP)
+    w = (torch.randn(Cout, Cin, 3, 3, device=cuda) / (9 * Cin) ** 0.5).to(OP)
     scale, bias = torch.rand(Cout, device=cuda) + 0.5, torch.randn(Cout, device=cuda) * 0.2
     Ho = H // stride
-    resid = torch.randn(B, Ho, Ho, Cout, device=cuda).bfloat16()
+    resid = torch.randn(B, Ho, Ho, Cout, device=cuda).to(OP)
     conv = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, stride=stride, padding=1)
     lin = (conv * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
     wp = w.permute(0, 2, 3, 1).contiguous()
     for mode, ref in ((nv.CONV_RELU_BF16, torch.relu(lin)), (nv.CONV_BF16, lin),
                       (nv.CONV_ADD_RELU_BF16, torch.relu(lin + resid.float()))):
-        out = torch.empty(B, Ho, Ho, Cout, dtype=torch.bfloat16, device=cuda)
+        out = torch.empty(B, Ho, Ho, Cout, dtype=OP, device=cuda)
         nv.conv3x3(x, wp, scale, bias, mode, out=out, stride=stride, resid=resid if mode == nv.CONV_ADD_RELU_BF16 else None)
         torch.cuda.synchronize()
         err = (out.float() - ref).abs().max().item()
@@ -53,9 +55,9 @@ def test_conv7x7_and_maxpool(cuda):
     scale, bias = torch.rand(64, device=cuda) + 0.5, torch.randn(64, device=cuda) * 0.1
     ref = torch.relu(F.conv2d(x, w, None, stride=2, padding=3) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
     wk = w.permute(2, 3, 1, 0).reshape(196, 64).contiguous()
-    out = torch.empty(B, P // 2, P // 2, 64, dtype=torch.bfloat16, device=cuda)
+    out = torch.empty(B, P // 2, P // 2, 64, dtype=OP, device=cuda)
     nv.conv7x7s2_bn_relu(x, wk, scale, bias, out)
-    mp = torch.empty(B, P // 4, P // 4, 64, dtype=torch.bfloat16, device=cuda)
+    mp = torch.empty(B, P // 4, P // 4, 64, dtype=OP, device=cuda)
     nv.maxpool3x3s2(out, mp)
     torch.cuda.synchronize()
     assert (out.float().permute(0, 3, 1, 2) - ref).abs().max().item() < 2 ** -8 * ref.abs().max().item() + 1e-3

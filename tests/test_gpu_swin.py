@@ -7,6 +7,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+from flair_for_aigle_b200 import native as _nv  # noqa: E402
+OP = _nv.op_dtype()      # the inference kernels' 16-bit operand format (float16; bfloat16 in the A/B build)
 
 
 @pytest.mark.parametrize("rows,C", [(1000, 128), (513, 256), (64, 512), (77, 1024), (9, 2048)])
@@ -15,7 +17,7 @@ def test_layernorm_rows(cuda, rows, C):
     torch.manual_seed(C)
     x = torch.randn(rows, C, device=cuda) * 3 + 1
     w, b = torch.rand(C, device=cuda) + 0.5, torch.randn(C, device=cuda) * 0.1
-    out = torch.empty(rows, C, dtype=torch.bfloat16, device=cuda)
+    out = torch.empty(rows, C, dtype=OP, device=cuda)
     nv.layernorm_rows(x, w, b, out, eps=1e-5)
     ref = F.layer_norm(x, (C,), w, b, 1e-5)
     assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
@@ -32,7 +34,7 @@ def test_merge_ln(cuda, B, H, C):
         pm.norm.bias.normal_(0, 0.1)
         pm.reduction.weight.copy_(torch.eye(2 * C, 4 * C))     # look at the normalised gather itself
     x = torch.randn(B, H, H, C, device=cuda)
-    out = torch.empty(B, H // 2, H // 2, 4 * C, dtype=torch.bfloat16, device=cuda)
+    out = torch.empty(B, H // 2, H // 2, 4 * C, dtype=OP, device=cuda)
     nv.merge_ln(x, pm.norm.weight, pm.norm.bias, out, eps=1e-5)
     with torch.no_grad():
         xr = x.reshape(B, H // 2, 2, H // 2, 2, C).permute(0, 1, 3, 4, 2, 5).flatten(3)
@@ -74,11 +76,11 @@ def test_window_attention(cuda, B, H, W, heads, ws, shift):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(H * 7 + shift)
     C = heads * 32
-    qkv = (torch.randn(B, H, W, 3 * C, device=cuda) * 1.5).bfloat16()
-    bias_bf = (torch.randn(3 * C, device=cuda) * 0.5).bfloat16()
+    qkv = (torch.randn(B, H, W, 3 * C, device=cuda) * 1.5).to(OP)
+    bias_bf = (torch.randn(3 * C, device=cuda) * 0.5).to(OP)
     table = torch.randn(heads, (2 * ws - 1) ** 2, device=cuda) * 0.5
     scale = 32 ** -0.5
-    out = torch.full((B, H, W, C), float("nan"), dtype=torch.bfloat16, device=cuda)
+    out = torch.full((B, H, W, C), float("nan"), dtype=OP, device=cuda)
     nv.swin_window_attn(qkv, bias_bf, table, out, heads, ws, shift, scale)
     torch.cuda.synchronize()
     ref = _attn_reference(qkv.float(), bias_bf.float(), table, heads, ws, shift, scale)
@@ -94,8 +96,8 @@ def test_window_attention(cuda, B, H, W, heads, ws, shift):
 def test_adaptive_avgpool(cuda, S):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(S)
-    x = torch.randn(3, 16, 16, 64, device=cuda).bfloat16()
-    out = torch.empty(3, S, S, 64, dtype=torch.bfloat16, device=cuda)
+    x = torch.randn(3, 16, 16, 64, device=cuda).to(OP)
+    out = torch.empty(3, S, S, 64, dtype=OP, device=cuda)
     nv.adaptive_avgpool(x, S, out)
     ref = F.adaptive_avg_pool2d(x.float().permute(0, 3, 1, 2), S).permute(0, 2, 3, 1)
     assert (out.float() - ref).abs().max().item() < 1e-2
@@ -106,9 +108,9 @@ def test_bilinear_slice(cuda, h, H):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(h * 131 + H)
     C, Ctot, c0 = 32, 80, 24
-    x = torch.randn(2, h, h, C, device=cuda).bfloat16()
-    add = torch.randn(2, H, H, C, device=cuda).bfloat16()
-    out = torch.zeros(2, H, H, Ctot, dtype=torch.bfloat16, device=cuda)
+    x = torch.randn(2, h, h, C, device=cuda).to(OP)
+    add = torch.randn(2, H, H, C, device=cuda).to(OP)
+    out = torch.zeros(2, H, H, Ctot, dtype=OP, device=cuda)
     nv.bilinear_slice(x, out, c0, add=add)
     ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(H, H), mode="bilinear", align_corners=False)
     ref = ref.permute(0, 2, 3, 1) + add.float()
@@ -120,8 +122,8 @@ def test_bilinear_slice(cuda, h, H):
 def test_updown_slice(cuda):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(5)
-    x = torch.randn(2, 32, 32, 64, device=cuda).bfloat16()
-    out = torch.zeros(2, 32, 32, 128, dtype=torch.bfloat16, device=cuda)
+    x = torch.randn(2, 32, 32, 64, device=cuda).to(OP)
+    out = torch.zeros(2, 32, 32, 128, dtype=OP, device=cuda)
     nv.updown_slice(x, out, 64)
     xf = x.float().permute(0, 3, 1, 2)
     up = F.interpolate(xf, size=(64, 64), mode="bilinear", align_corners=False)
@@ -136,8 +138,8 @@ def test_pyramid_concat(cuda, H, C):
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(H + C)
     B = 2
-    p = [torch.randn(B, H >> (3 - k), H >> (3 - k), C, device=cuda).bfloat16() for k in range(4)]
-    got = torch.full((B, H, H, 5 * C), 7.0, dtype=torch.bfloat16, device=cuda)
+    p = [torch.randn(B, H >> (3 - k), H >> (3 - k), C, device=cuda).to(OP) for k in range(4)]
+    got = torch.full((B, H, H, 5 * C), 7.0, dtype=OP, device=cuda)
     nv.pyramid_concat(p[0], p[1], p[2], p[3], got)
     old = torch.zeros_like(got)
     for k in range(4):
@@ -170,10 +172,10 @@ def test_gemm_fewer_rows_than_a_tile(cuda, M):
     """PSP 1x1 convs see M = batch * s^2 rows (37 at s = 1): rows beyond M are TMA zero fill, never stored."""
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(M)
-    A = torch.randn(M, 1024, device=cuda).bfloat16()
-    W = (torch.randn(256, 1024, device=cuda) / 32).bfloat16()
+    A = torch.randn(M, 1024, device=cuda).to(OP)
+    W = (torch.randn(256, 1024, device=cuda) / 32).to(OP)
     bias = torch.randn(256, device=cuda)
-    guard = torch.full((M + 300, 256), 7.0, dtype=torch.bfloat16, device=cuda)
+    guard = torch.full((M + 300, 256), 7.0, dtype=OP, device=cuda)
     nv.gemm_bf16(A, W, nv.EPI_RELU_BF16, bias=bias, out=guard[:M])
     torch.cuda.synchronize()
     ref = torch.relu(A.float() @ W.float().t() + bias)

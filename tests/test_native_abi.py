@@ -30,7 +30,8 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     # the ctypes binding covers the same set
     assert sorted(nv.exported_symbols()) == declared
-    assert nv.lib().fz_abi_version() == 1
+    assert nv.lib().fz_abi_version() == nv.ABI_VERSION == 2
+    assert nv.lib().fz_operand_format() == nv.F16 and nv.op_dtype() == torch.float16     # the product build stores fp16
 
 
 def test_argument_validation_without_gpu():
@@ -63,10 +64,11 @@ def test_no_cpu_fallback():
 
 
 def test_product_does_not_import_oracle():
-    """The oracle is test infrastructure: nothing under the package may import it."""
-    pkg = os.path.join(ROOT, "flair_for_aigle_b200")
-    for dp, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith(".py"):
-                src = open(os.path.join(dp, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+    """The oracle is test infrastructure: nothing under the package or tools/ may import it (only tests/,
+    __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs)."""
+    for top in ("flair_for_aigle_b200", "tools"):
+        for dp, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dp, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)

@@ -10,10 +10,10 @@ for i, (H, heads) in enumerate([(128, 4), (64, 8), (32, 16), (16, 32)]):
     if only is not None and int(only) != i:
         continue
     C = heads * 32
-    qkv = (torch.randn(B, H, H, 3 * C, device=dev)).bfloat16()
-    bias = torch.randn(3 * C, device=dev).bfloat16()
+    qkv = (torch.randn(B, H, H, 3 * C, device=dev)).to(nv.op_dtype())
+    bias = torch.randn(3 * C, device=dev).to(nv.op_dtype())
     table = torch.randn(heads, 529, device=dev) * 0.5
-    out = torch.empty(B, H, H, C, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(B, H, H, C, dtype=nv.op_dtype(), device=dev)
     for shift in (0, 6):
         for _ in range(2):
             nv.swin_window_attn(qkv, bias, table, out, heads, 12, shift, 32 ** -0.5)

@@ -28,8 +28,8 @@ ok = True
 for (M, N, K) in [(128, 128, 64), (128, 128, 128), (256, 128, 256), (1024, 512, 512), (4096, 2048, 512)]:
     try:
         torch.manual_seed(1)
-        A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
-        B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+        A = (torch.randn(M, K, device=dev) * 0.5).to(nv.op_dtype())
+        B = (torch.randn(N, K, device=dev) / K ** 0.5).to(nv.op_dtype())
         bias = torch.zeros(N, device=dev)
         ref = A.float() @ B.float().t()
         t0 = time.time()
@@ -62,8 +62,8 @@ for (M, N, K) in [(128, 128, 64), (128, 128, 128), (256, 128, 256), (1024, 512, 
 
 
 def bench(M, N, K, mode, rps, iters=20):
-    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
-    B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    A = (torch.randn(M, K, device=dev) * 0.5).to(nv.op_dtype())
+    B = (torch.randn(N, K, device=dev) / K ** 0.5).to(nv.op_dtype())
     bias = torch.zeros(N, device=dev)
     resid = torch.zeros(M, N, device=dev) if mode == nv.EPI_RESID_F32 else None
     sumsq = torch.zeros(M // 128, N, device=dev) if mode == nv.EPI_GELU_SUMSQ else None
@@ -78,7 +78,7 @@ def bench(M, N, K, mode, rps, iters=20):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    C = torch.empty(M, N, device=dev, dtype=nv.op_dtype())
     for _ in range(3):
         torch.matmul(A, B.t(), out=C)
     torch.cuda.synchronize()

@@ -10,7 +10,7 @@ for C, H in ((128, 128), (256, 64), (512, 32), (1024, 16)):
     x = torch.randn(B, H, H, C, device=dev)
     w = torch.randn(49, C, device=dev) * 0.1
     b = torch.randn(C, device=dev); g = torch.rand(C, device=dev) + 0.5; be = torch.randn(C, device=dev)
-    out = torch.empty(B, H, H, C, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(B, H, H, C, dtype=nv.op_dtype(), device=dev)
     for _ in range(3):
         nv.dwconv7_ln(x, w, b, g, be, out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -6,8 +6,8 @@ from flair_for_aigle_b200 import native as nv
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", "37"))
 def bench(M, N, K, mode, rps, iters=10):
-    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
-    Bw = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    A = (torch.randn(M, K, device=dev) * 0.5).to(nv.op_dtype())
+    Bw = (torch.randn(N, K, device=dev) / K ** 0.5).to(nv.op_dtype())
     bias = torch.zeros(N, device=dev)
     resid = torch.zeros(M, N, device=dev) if mode == nv.EPI_RESID_F32 else None
     sumsq = torch.zeros(M // 128, N, device=dev) if mode == nv.EPI_GELU_SUMSQ else None

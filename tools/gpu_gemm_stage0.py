@@ -6,11 +6,11 @@ from flair_for_aigle_b200 import native as nv
 dev = torch.device("cuda:0")
 B = 37
 for (M, N, K, rps) in ((B * 16384, 512, 128, 16384), (B * 4096, 1024, 256, 4096)):
-    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
-    W = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    A = (torch.randn(M, K, device=dev) * 0.5).to(nv.op_dtype())
+    W = (torch.randn(N, K, device=dev) / K ** 0.5).to(nv.op_dtype())
     bias = torch.zeros(N, device=dev)
     sq = torch.zeros(M // 128, N, device=dev)
-    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(M, N, dtype=nv.op_dtype(), device=dev)
     for _ in range(3):
         nv.gemm_bf16(A, W, nv.EPI_GELU_SUMSQ, bias=bias, sumsq=sq, out=out, rows_per_sample=rps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -7,12 +7,12 @@ from flair_for_aigle_b200 import native as nv
 dev = torch.device("cuda:0")
 B = 37
 M, C = B * 1024, 512
-y = (torch.randn(M, C, device=dev) * 0.5).bfloat16()
-w1 = (torch.randn(4 * C, C, device=dev) / C ** 0.5).bfloat16()
-w2 = (torch.randn(B, C, 4 * C, device=dev) / (4 * C) ** 0.5).bfloat16()
+y = (torch.randn(M, C, device=dev) * 0.5).to(nv.op_dtype())
+w1 = (torch.randn(4 * C, C, device=dev) / C ** 0.5).to(nv.op_dtype())
+w2 = (torch.randn(B, C, 4 * C, device=dev) / (4 * C) ** 0.5).to(nv.op_dtype())
 w2s = w2[0].contiguous()
 b1, b2 = torch.zeros(4 * C, device=dev), torch.zeros(C, device=dev)
-h = torch.empty(M, 4 * C, dtype=torch.bfloat16, device=dev)
+h = torch.empty(M, 4 * C, dtype=nv.op_dtype(), device=dev)
 x = torch.zeros(M, C, device=dev)
 sumsq = torch.zeros(M // 128, 4 * C, device=dev)
 iters = int(os.environ.get("ITERS", "300"))

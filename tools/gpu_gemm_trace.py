@@ -7,7 +7,7 @@ dev = torch.device("cuda:0")
 names = ["prod_start", "mma_arrive", "acc_free", "first_kb", "mma_issued", "epi_wait", "acc_done", "epi_done"]
 for (M, N, K, mode, rps) in ((16384, 2048, 512, nv.EPI_GELU_SUMSQ, 1024), (16384, 512, 2048, nv.EPI_RESID_F32, 1024),
                              (262144, 512, 128, nv.EPI_GELU_SUMSQ, 16384), (8192, 8192, 8192, nv.EPI_BF16, 8192)):
-    A = torch.randn(M, K, device=dev).bfloat16(); Bw = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    A = torch.randn(M, K, device=dev).to(nv.op_dtype()); Bw = (torch.randn(N, K, device=dev) / K ** 0.5).to(nv.op_dtype())
     bias = torch.zeros(N, device=dev)
     resid = torch.zeros(M, N, device=dev) if mode == nv.EPI_RESID_F32 else None
     sq = torch.zeros(M // 128, N, device=dev) if mode == nv.EPI_GELU_SUMSQ else None

@@ -5,11 +5,11 @@ import torch
 from flair_for_aigle_b200 import native as nv
 dev = torch.device("cuda:0")
 B, H = 37, 512
-x = torch.randn(B, H, H, 16, device=dev).bfloat16()
-w = (torch.randn(16, 3, 3, 16, device=dev) / 12).bfloat16()
-wh = torch.zeros(32, 3, 3, 16, device=dev).bfloat16(); wh[:19] = (torch.randn(19, 3, 3, 16, device=dev) / 12).bfloat16()
+x = torch.randn(B, H, H, 16, device=dev).to(nv.op_dtype())
+w = (torch.randn(16, 3, 3, 16, device=dev) / 12).to(nv.op_dtype())
+wh = torch.zeros(32, 3, 3, 16, device=dev).to(nv.op_dtype()); wh[:19] = (torch.randn(19, 3, 3, 16, device=dev) / 12).to(nv.op_dtype())
 s = torch.ones(32, device=dev); b = torch.zeros(32, device=dev)
-out = torch.empty(B, H, H, 16, dtype=torch.bfloat16, device=dev)
+out = torch.empty(B, H, H, 16, dtype=nv.op_dtype(), device=dev)
 plan = torch.zeros(B, 6, dtype=torch.int32, device=dev); plan[:, 4:] = 384
 for i in range(B):
     plan[i, 2] = (i // 8) * 384; plan[i, 3] = (i % 8) * 384

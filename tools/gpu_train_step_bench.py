@@ -12,17 +12,15 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-from oracle.models import CONVNEXTV2_CFGS, FlairHubOracle, randomize_     # only to get a random state_dict in the reference layout
+import bench
+from flair_for_aigle_b200.engine.convnext_unet import CONVNEXTV2_CFGS
 from flair_for_aigle_b200.engine.train_step import ConvNeXtUNetTrainer
 
 B = int(os.environ.get("B", "16"))
 P = int(os.environ.get("P", "512"))
 TASK = "AERIAL_LABEL-COSIA"
 mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
-m = FlairHubOracle("convnextv2_base-unet", mods, {TASK: 19})
-randomize_(m, seed=2025)
-state = {k: v.detach().to(dev) for k, v in m.state_dict().items()}
-del m
+state = {k: v.to(dev) for k, v in bench.random_state(mods, seed=2025).items()}
 depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
 w = torch.ones(19, device=dev); w[15:] = 0
 tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w)

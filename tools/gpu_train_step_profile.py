@@ -3,13 +3,13 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import ProfilerActivity, profile
-from oracle.models import CONVNEXTV2_CFGS, FlairHubOracle, randomize_
+import bench
+from flair_for_aigle_b200.engine.convnext_unet import CONVNEXTV2_CFGS
 from flair_for_aigle_b200.engine.train_step import ConvNeXtUNetTrainer
 dev = torch.device("cuda:0")
 B, P, TASK = int(os.environ.get("B", "16")), 512, "AERIAL_LABEL-COSIA"
 mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
-m = FlairHubOracle("convnextv2_base-unet", mods, {TASK: 19}); randomize_(m, seed=2025)
-state = {k: v.detach().to(dev) for k, v in m.state_dict().items()}; del m
+state = {k: v.to(dev) for k, v in bench.random_state(mods, seed=2025).items()}
 depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
 w = torch.ones(19, device=dev); w[15:] = 0
 tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w)
