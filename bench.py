@@ -7,8 +7,10 @@
 Workload (BASELINE.json configs[1]): ConvNeXtV2-base + U-Net, synthetic 4-band uint8 raster
 10000 x 10000 at 0.2 m/px, tile 512, margin 64 (overlap 128) -> 729 tiles, 19 classes, random-init
 weights in the reference's checkpoint layout loaded through build_inference_model().
-A step = one whole zone.  At N GPUs the zone is 10000 x (10000*N) and each rank owns one
-10000-row strip (weak scaling); value = all pixels / max-over-ranks time.
+A step = one whole zone.  At N > 1 GPUs the workload is configs[3]: ONE 60000 x 60000 zone (24 649 tiles) whose tile rows
+are dealt to the ranks as contiguous row strips (strong scaling, no data-path collective); value = zone pixels /
+max-over-ranks time, per-rank times are reported.  The line also carries a "train" block: the configs[4] training step
+(fwd + bwd + AdamW + DDP all-reduce), a few steps, samples/s.
 
 One JSON line on stdout (rank 0).  `value`: raster resident in HBM, CUDA-event timed.
 `e2e`: the same zone through inference_and_write() from pinned HOST memory to a HOST class raster
@@ -35,7 +37,6 @@ import numpy as np
 import torch
 
 PATCH, MARGIN, RES = 512, 64, 0.2
-ZONE_W, ZONE_H = 10000, 10000
 ARCH = "convnextv2_base-unet"
 TASK = "AERIAL_LABEL-COSIA"
 N_CLS = 19
@@ -191,37 +192,46 @@ def cpu_baseline_sample(weights_path: str, raster: np.ndarray, budget_s: float, 
                       f"torch {torch.__version__} fp32 eager, {threads} threads"}, s_per_tile
 
 
+def zone_side(args, world: int) -> int:
+    """N = 1: BASELINE.json configs[1] (10 000 x 10 000, the configuration the metric is quoted on).
+    N > 1: configs[3], ONE 60 000 x 60 000 zone (24 649 tiles, 157 tile rows) cut into N row strips -- strong scaling.
+    ``--zone`` / FZ_BENCH_ZONE override (e.g. the 60 k zone on one GPU, the strong-scaling base, profiles/)."""
+    if args.zone:
+        return args.zone
+    if os.environ.get("FZ_BENCH_ZONE"):
+        return int(os.environ["FZ_BENCH_ZONE"])
+    return 10000 if world == 1 else 60000
+
+
 def run_reference(args, rank: int, world: int) -> None:
+    """The reference's CPU path (the oracle pipeline: the reference cannot be installed here, smp / timm / rasterio are
+    absent) on the host cores, for our arm's zone.  Each step = a fixed sample of 32 tiles, extrapolated by tile count."""
     if rank != 0:
         return
     from flair_for_aigle_b200.synthetic import synthetic_raster
+    from oracle.grid import Georef, generate_patches
+    side = zone_side(args, world)
     tmp = tempfile.mkdtemp(prefix="fz_bench_ref_")
     wpath = os.path.join(tmp, "weights.safetensors")
     make_weights(wpath)
-    sample_h = 2048   # a 10000 x 2048 band of the zone holds plenty of tiles for the sample
-    raster = synthetic_raster(ZONE_H, ZONE_W, row0=0, rows=sample_h)
-    # tiles of the band are the zone's tiles (grid is bottom-anchored per raster; use the band as its own zone
-    # for the sample -- same tile size, margin, model: per-tile cost is identical)
-    vals, per_tile = [], []
-    total = args.steps + args.warmup
-    for i in range(total):
-        cb, spt = cpu_baseline_sample(wpath, raster, budget_s=max(4.0, 40.0 / total), max_tiles=8)
+    # a 10000 x 2048 band holds 162 tiles: plenty for the sample; same tile size, margin, model = same per-tile cost
+    raster = synthetic_raster(10000, 10000, row0=0, rows=2048)
+    per_tile, cb = [], None
+    for i in range(args.steps + args.warmup):
+        cb, spt = cpu_baseline_sample(wpath, raster, budget_s=1e9, max_tiles=32)
         if i >= args.warmup:
             per_tile.append(spt)
     spt = float(np.mean(per_tile))
-    # the N-GPU arm works on a 10000 x (10000*N) zone (weak scaling): same zone here, same per-tile cost
-    from oracle.grid import Georef, generate_patches
-    zone_h = ZONE_H * max(1, world)
-    n_tiles = len(generate_patches(PATCH, MARGIN, RES, Georef(LEFT, TOP, RES, ZONE_W, zone_h)))
-    mpx_s = (ZONE_W * zone_h / 1e6) / (spt * n_tiles)
+    n_tiles = len(generate_patches(PATCH, MARGIN, RES, Georef(LEFT, TOP, RES, side, side)))
+    mpx_s = (side * side / 1e6) / (spt * n_tiles)
     cb["value"] = round(mpx_s, 4)
+    cb["sample"] = (f"32 tiles per step, {args.steps} timed steps (spread {min(per_tile) * 1e3:.0f}-{max(per_tile) * 1e3:.0f} ms/tile), "
+                    + cb["sample"])
     line = {
         "impl": "reference", "metric": METRIC, "value": round(mpx_s, 4), "unit": "Mpx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(spt * n_tiles * 1e3, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{ARCH} zonal inference, synthetic {ZONE_W}x{zone_h}x4 uint8 @0.2m, tile {PATCH} "
-                               f"margin {MARGIN} ({n_tiles} tiles), {N_CLS} classes; CPU oracle (the reference cannot be "
-                               "imported: smp/timm/rasterio absent), each step = bounded tile sample extrapolated"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(side, n_tiles, world)},
         "cpu_baseline": cb,
         "e2e": {"value": round(mpx_s, 4), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -229,8 +239,74 @@ def run_reference(args, rank: int, world: int) -> None:
     print(json.dumps(line), flush=True)
 
 
+def workload_string(side: int, n_tiles: int, world: int) -> str:
+    return (f"{ARCH} zonal inference, synthetic {side}x{side}x4 uint8 @0.2m, tile {PATCH} margin {MARGIN} "
+            f"(overlap {2 * MARGIN}), {n_tiles} tiles, {N_CLS} classes, argmax raster"
+            + ("" if world == 1 else f"; ONE zone cut into {world} row strips (tile rows dealt contiguously, margin halo re-read)"))
+
+
+def train_block(dev, rank: int, world: int, steps: int, warmup: int):
+    """BASELINE.json configs[4]: convnextv2_base-unet, AERIAL_RGBI (16,4,512,512) + DEM_ELEV (16,1,512,512) per GPU, weighted
+    CE (classes 15-18 weight 0), AdamW(5e-5, wd 0.01), DDP gradient all-reduce (tasks_module.py:133-167,377-391;
+    trainers.py:81-91).  -> dict for the JSON line's "train" key (rank 0), None elsewhere."""
+    import torch.distributed as dist
+    from flair_for_aigle_b200.engine.convnext_unet import CONVNEXTV2_CFGS
+    from flair_for_aigle_b200.engine.train_step import ConvNeXtUNetTrainer
+    B, P = 16, PATCH
+    mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
+    state = {k: v.to(dev) for k, v in random_state(mods, seed=2025, arch="convnextv2_base-unet").items()}
+    depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
+    w = torch.ones(N_CLS, device=dev)
+    w[15:] = 0
+    tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w)
+    g = torch.Generator(device="cpu").manual_seed(2025 + rank)
+    host = {k: torch.randn(B, c, P, P, generator=g).pin_memory() for k, c in mods.items()}
+    host[TASK] = torch.randint(0, N_CLS, (B, P, P), generator=g, dtype=torch.int32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+
+    def one_step():
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}     # H2D of the step's inputs
+        loss, _ = tr.step(batch)
+        return float(loss)                                                     # D2H of the loss
+
+    losses = [one_step() for _ in range(max(1, warmup))]
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar = []
+    e0.record()
+    for _ in range(steps):
+        losses.append(one_step())
+        ar.append(getattr(tr, "last_allreduce_ms", 0.0))
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps, sum(ar) / max(len(ar), 1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step, ms_ar = float(ms[0]), float(ms[1])
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del tr, state
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    pk, how = peaks()
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    tflop_step = 1.063 * B                       # SURVEY 8(d): 177.2 GMAC fwd / sample, x3 fwd+bwd = 1.063 TFLOP / sample
+    return {"config": "configs[4]: convnextv2_base-unet, AERIAL_RGBI 4ch + DEM_ELEV 1ch, batch 16 x 512^2 per GPU, weighted CE, "
+                      "AdamW, DDP all-reduce of the gradient arena; inputs from pinned host memory every step, loss read back",
+            "samples_per_s": round(B * world / ms_step * 1e3, 2), "samples_per_s_per_gpu": round(B / ms_step * 1e3, 2),
+            "ms_per_step": round(ms_step, 2), "steps": steps, "warmup": max(1, warmup),
+            "allreduce_ms_exposed": round(ms_ar, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+            "loss_first_last": [round(losses[0], 4), round(losses[-1], 4)], "peak_memory_gib": round(peak_mem, 1),
+            "roofline": {"bound": "tensor", "achieved": round(tflop_step / (ms_step * 1e-3), 1), "peak": peak,
+                         "unit": "TFLOP/s", "frac": round(tflop_step / (ms_step * 1e-3) / peak, 4),
+                         "note": f"1.063 TFLOP per sample (fwd + bwd, SURVEY 8d) x {B} / step time; peak = {how} sustained bf16"},
+            "dtype": "bf16 operands, fp32 accumulate / master weights"}
+
+
 def main() -> None:
-    global ARCH, GFLOP_PER_TILE, ZONE_W, ZONE_H
+    global ARCH, GFLOP_PER_TILE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -238,11 +314,12 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("FZ_BENCH_BATCH", "37")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[4] training-step block")
     ap.add_argument("--arch", default=ARCH, choices=sorted(ARCH_GFLOP),
                     help="default = BASELINE.json's metric configuration; the others are measured for DESIGN.md only")
-    ap.add_argument("--zone", type=int, default=ZONE_W, help="zone side in pixels per GPU (default 10000)")
+    ap.add_argument("--zone", type=int, default=0, help="zone side in pixels (default: 10000 at 1 GPU, 60000 sharded at N > 1)")
     args = ap.parse_args()
-    ARCH, GFLOP_PER_TILE, ZONE_W, ZONE_H = args.arch, ARCH_GFLOP[args.arch], args.zone, args.zone
+    ARCH, GFLOP_PER_TILE = args.arch, ARCH_GFLOP[args.arch]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -267,18 +344,19 @@ def main() -> None:
     from flair_for_aigle_b200.engine.strips import shard_rows
     from flair_for_aigle_b200.engine.zonal import ZonalRunner
     from flair_for_aigle_b200.flair_zonal_detection import inference as inf
-    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model, compute_patch_sizes
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model
     from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink, ZoneRaster, register_raster
     from flair_for_aigle_b200.flair_zonal_detection.slicing import (generate_patches_from_reference,
                                                                     ownership_windows, tile_plan)
-    from flair_for_aigle_b200.synthetic import synthetic_raster
+    from flair_for_aigle_b200.synthetic import DEFAULT_MEANS, DEFAULT_STDS, synthetic_raster, synthetic_raster_to_pinned
 
     tmp = tempfile.mkdtemp(prefix=f"fz_bench_{rank}_")
     wpath = os.path.join(tmp, "weights.safetensors")
     make_weights(wpath)
 
-    # ---- global zone: 10000 x (10000 * world); rank r owns row strip r
-    gh, gw = ZONE_H * world, ZONE_W
+    # ---- ONE global zone; rank r owns row strip r of the global tile plan
+    side = zone_side(args, world)
+    gh = gw = side
     shape_only = ZoneRaster(np.broadcast_to(np.zeros((1, 1, 1), np.uint8), (4, gh, gw)), LEFT, TOP, RES)
     register_raster("synthetic://zone_shape", shape_only)
     cfg = zonal_config(wpath, tmp, "synthetic://zone_shape", args.batch)
@@ -295,19 +373,25 @@ def main() -> None:
     log(f"[rank {rank}] zone {gw}x{gh}: {len(tiles)} tiles, this rank {n_tiles_rank} tiles, input rows "
         f"[{shard.in_r0},{shard.in_r1}), output rows [{shard.out_r0},{shard.out_r1})")
 
-    # ---- this rank's input strip, generated straight into pinned host memory
+    # ---- this rank's input strip in pinned host memory (generated on the GPU in row chunks: the numpy generator makes
+    #      ~10 MB/s and the 60k zone is 14.4 GB; set-up, outside every timed region)
+    t_setup = time.perf_counter()
     host = torch.empty((4, in_rows, gw), dtype=torch.uint8, pin_memory=True)
-    synthetic_raster(gh, gw, row0=shard.in_r0, rows=in_rows, out=host.numpy())
+    synthetic_raster_to_pinned(gh, gw, host, dev, row0=shard.in_r0)
+    torch.cuda.synchronize(dev)
+    torch.cuda.empty_cache()
+    log(f"[rank {rank}] raster strip {host.numel() / 1e9:.2f} GB generated + pinned in {time.perf_counter() - t_setup:.1f} s")
     strip = ZoneRaster.from_pinned(host, LEFT, TOP - shard.in_r0 * RES, RES, name="synthetic://strip")
     register_raster("synthetic://strip", strip)
 
     patch_sizes = {"AERIAL_RGBI": PATCH}
     model = build_inference_model(cfg, patch_sizes).to(dev)
     eng = model.engine(TASK, max_batch=args.batch)
-    from flair_for_aigle_b200.synthetic import DEFAULT_MEANS, DEFAULT_STDS
     runner = ZonalRunner(eng, MARGIN, use_graph=True, norm=(DEFAULT_MEANS, DEFAULT_STDS))
 
-    raster_dev = host.to(dev, non_blocking=True)
+    # the raster is uploaded straight into the buffer the runner's CUDA graph reads (no second device copy of a 14 GB strip)
+    raster_dev, _ = runner.buffers((4, in_rows, gw), (out_rows, gw), torch.uint8)
+    raster_dev.copy_(host, non_blocking=True)
     out_dev = torch.zeros((out_rows, gw), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize(dev)
 
@@ -331,25 +415,33 @@ def main() -> None:
     e1.record()
     barrier()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
+    ms_rank = e0.elapsed_time(e1) / args.steps
+    rank_ms = [ms_rank]
+    rank_tiles = [n_tiles_rank]
     if use_dist:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    ms_per_step = ms / args.steps
+        t = torch.tensor([ms_rank, float(n_tiles_rank)], device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(x[0]) for x in allt]
+        rank_tiles = [int(x[1]) for x in allt]
+    ms_per_step = max(rank_ms)
     total_px = gw * gh
     value = total_px / 1e6 / (ms_per_step / 1e3)
     launches = nb * runner.count_launches()
     checksum = int(out_dev.to(torch.int64).sum().item())
 
-    # ---------------------------------------------------------------- e2e: public API, host buffers
+    # ---------------------------------------------------------------- e2e: public API on this rank's shard of the GLOBAL plan
     RasterSink.write_files = False
     cfg_e = dict(cfg)
     cfg_e["modalities"] = json.loads(json.dumps(cfg["modalities"]))
     cfg_e["modalities"]["AERIAL_RGBI"]["input_img_path"] = "synthetic://strip"
-    cfg_e = inf.initialize_geometry_and_resolutions(cfg_e)   # the strip as its own zone (this rank's work)
+    cfg_e = inf.initialize_geometry_and_resolutions(cfg_e)   # raster = this rank's strip (its input rows of the zone)
     cfg_e["device"] = dev
-    tiles_e = generate_patches_from_reference(cfg_e, "synthetic://strip", None)
+    # the rank's rows of the GLOBAL tile table (zone coordinates): the strip raster carries the zone's georeferencing, so
+    # the same tiles address the same pixels; a tile's ownership inside the shard equals its global ownership on the
+    # rows this rank owns (a global last writer that is in the shard is also the shard's last writer)
+    tiles_e = tiles.iloc[shard.tile_idx].reset_index(drop=True)
+    o0, o1 = shard.out_r0 - shard.in_r0, shard.out_r1 - shard.in_r0
 
     def e2e_step():
         ds = inf.prep_dataset(cfg_e, tiles_e, patch_sizes)           # fresh dataset: raster is uploaded again
@@ -357,23 +449,34 @@ def main() -> None:
         inf.inference_and_write(model, ds, tiles_e, cfg_e, outs, strip)   # H2D + compute + D2H (close())
         res = outs[TASK].to_host()
         nbytes = res.size
+        chk = int(res[0, o0:o1].astype(np.int64).sum()) if e2e_step.check else None
         outs[TASK].release()                                         # recycle the pinned result buffer
-        return nbytes
+        return nbytes, chk
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    e2e_step.check = True
+    _, chk = e2e_step()
+    e2e_same = bool(chk == checksum)
+    e2e_step.check = False
+    for _ in range(max(0, min(args.warmup, 2) - 1)):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res_bytes = e2e_step()
+        res_bytes, _ = e2e_step()
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / args.steps
     if use_dist:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-    e2e_px = gw * in_rows * world
-    e2e_val = e2e_px / 1e6 / e2e_s
+        t = torch.tensor([e2e_s, float(e2e_same)], device=dev)
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        e2e_s, e2e_same = float(tmax[0]), bool(tmin[1] > 0.5)
+        hb = torch.tensor([float(4 * in_rows * gw), float(res_bytes)], device=dev)
+        dist.all_reduce(hb)
+        h2d_total, d2h_total = int(hb[0]), int(hb[1])
+    else:
+        h2d_total, d2h_total = int(4 * in_rows * gw), int(res_bytes)
+    e2e_val = total_px / 1e6 / e2e_s
 
     # ---------------------------------------------------------------- roofline: GEMM launches of one batch, live
     roof = None
@@ -418,46 +521,74 @@ def main() -> None:
                            "source": tj["source"]}
         except Exception:
             traffic = None
+        per_batch = gemm_n // 3
         roof = {"bound": "tensor", "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s",
                 "frac": round(ach / peak, 4), "traffic": traffic,
-                "kernel": (f"gemm_bf16_kernel / gemm_bf16_pair_kernel (tcgen05, every linear / 1x1 GEMM of one {ARCH} batch)"
+                "kernel": (f"gemm_bf16_kernel / gemm_bf16_pair_kernel (tcgen05, all {per_batch} linear / 1x1 GEMM launches of one "
+                           f"{ARCH} batch of {args.batch} tiles, fp16 operands)"
                            if dom == "gemm_tcgen05" else
-                           f"conv3x3_kernel / conv3x3_rows_kernel (tcgen05 implicit GEMM, every 3x3 convolution of one {ARCH} batch)"),
-                "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
-                "launches_timed": gemm_n, "avg_launch_us": round(gemm_ms / gemm_n * 1e3, 2),
+                           f"conv3x3_kernel / conv3x3_rows_kernel (tcgen05 implicit GEMM, all {per_batch} 3x3 convolutions of one {ARCH} batch)"),
+                "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step; kind::f16 runs fp16 and bf16 at "
+                               "the same rate)",
+                "launches_timed": gemm_n, "launches_per_batch": per_batch, "avg_launch_us": round(gemm_ms / gemm_n * 1e3, 2),
                 "share_of_step_eager": breakdown.get(dom),
-                "model_flops_frac_of_peak": round(GFLOP_PER_TILE * 1e9 * n_tiles_rank / (ms_per_step * 1e-3) / 1e12 / peak, 4)}
+                "model_flops_frac_of_peak": round(GFLOP_PER_TILE * 1e9 * max(rank_tiles) / (ms_per_step * 1e-3) / 1e12 / peak, 4)}
+
+    # free the zone before the training block (the 60k strip and its graph buffers are tens of GB)
+    del runner, raster_dev, out_dev
+    if rank == 0:
+        del runner_e
+    torch.cuda.empty_cache()
+
+    train = None
+    if not args.no_train and ARCH == "convnextv2_base-unet":
+        try:
+            train = train_block(dev, rank, world, steps=min(args.steps, 5), warmup=2)
+        except Exception as ex:  # noqa: BLE001 -- the inference line must survive a training failure
+            train = {"error": repr(ex)} if rank == 0 else None
+            log(f"[rank {rank}] training block failed: {ex!r}")
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            band = synthetic_raster(ZONE_H, ZONE_W, row0=0, rows=2048)
-            cpu_base, _ = cpu_baseline_sample(wpath, band, budget_s=15.0, max_tiles=24)
+            band = synthetic_raster(10000, 10000, row0=0, rows=2048)
+            cpu_base, _ = cpu_baseline_sample(wpath, band, budget_s=20.0, max_tiles=32)
         except Exception as ex:  # noqa: BLE001
             cpu_base = {"value": None, "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port",
                         "sample": f"failed: {ex!r}"}
 
     if rank == 0:
+        strong = None
+        if world > 1:
+            strong = {"zone": f"{gw}x{gh}", "tiles": len(tiles), "tile_rows": int(len(np.unique(gplan[:, 2]))),
+                      "tiles_per_rank": rank_tiles, "ms_per_rank": [round(v, 2) for v in rank_ms],
+                      "imbalance_max_over_mean": round(max(rank_ms) / (sum(rank_ms) / len(rank_ms)), 4),
+                      "tiles_per_s_per_gpu": round(len(tiles) / world / (ms_per_step / 1e3), 1),
+                      "halo_rows_reread_per_strip": int(in_rows - out_rows),
+                      "note": "no data-path collective: every rank reads its rows (+ margin halo) of the zone and owns the "
+                              "output rows of its tile rows; 157 tile rows do not divide by 4 or 8, which is the imbalance; "
+                              "the 1-GPU value of THIS zone (strong-scaling base) is in profiles/r2_bench_60k_1gpu.json"}
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16" if nv.op_dtype() == torch.float16 else "bf16", "data": "synthetic",
             "config": {
-                "workload": f"{ARCH} zonal inference, synthetic {gw}x{gh}x4 uint8 @0.2m, tile {PATCH} margin {MARGIN} "
-                            f"(overlap {2*MARGIN}), {len(tiles)} tiles, {N_CLS} classes, argmax raster; "
-                            f"{world} row strip(s) of {ZONE_H} rows",
-                "batch_tiles": args.batch, "tiles_per_gpu": n_tiles_rank, "cuda_graph": True,
+                "workload": workload_string(side, len(tiles), world),
+                "batch_tiles": args.batch, "tiles_per_gpu": max(rank_tiles), "cuda_graph": True,
+                "operands": "fp16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 residual stream / statistics",
                 "l2": f"inputs larger than L2: {4 * in_rows * gw / 1e6:.0f} MB raster strip, >126 MB of activations per batch",
                 "tiles_per_s": round(len(tiles) / (ms_per_step / 1e3), 1), "class_raster_checksum": checksum},
-            "e2e": {"value": round(e2e_val, 2), "unit": "Mpx/s", "h2d_bytes_per_step": int(4 * in_rows * gw),
-                    "d2h_bytes_per_step": int(res_bytes),
-                    "note": "inference_and_write() on this rank's strip as a zone: pinned host raster -> HBM, fused "
-                            "forward, class raster -> pinned host; file encoding excluded"},
+            "e2e": {"value": round(e2e_val, 2), "unit": "Mpx/s", "h2d_bytes_per_step": h2d_total,
+                    "d2h_bytes_per_step": d2h_total, "same_result_as_value_leg": e2e_same,
+                    "note": "inference_and_write() on each rank's rows of the global tile table: pinned host raster strip -> "
+                            "HBM, fused forward, class raster -> pinned host (bytes summed over ranks); file encoding excluded"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu_base,
             "kernel_time_shares_eager": breakdown,
+            "strong_scaling": strong,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if use_dist:

@@ -238,18 +238,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------ math helpers
 // GELU(erf) = 0.5 x (1 + erf(x / sqrt 2)) = 0.5 x (1 + tanh(g(x))) with g = atanh(erf(x / sqrt 2)) fitted by x * Q(u),
-// u = min(x^2, 50), Q of degree 2: |err| < 2.6e-5 abs over all x in fp32 (the bf16 output rounding is 2e-3 relative, and
-// tanh.approx itself 5e-4); the clamp keeps Q positive so large |x| saturate to x / 0.  ONE SFU op + 7 FMA-pipe ops:
-// the fc1 epilogue is bound by issue slots, a degree-4 Q (err 3e-6) cost two more.
+// u = min(x^2, 50), Q of degree 2: |err| < 2.6e-5 abs over all x in fp32; the clamp keeps Q positive so large |x| saturate.
+// Evaluated as x * sigmoid(2 g) = x / (1 + 2^(-2 log2(e) x Q(u))) with ex2.approx (2^-22 rel.) and rcp.approx (1 ulp):
+// 2 SFU + 7 FMA-pipe ops.  Round 1 used tanh.approx.f32 (1 SFU + 7): its 2^-11 relative error is invisible under a bf16
+// output rounding (2^-9) but LARGER than the fp16 output rounding (2^-12) the inference path now stores, and it is
+// systematic, not random -- it was the largest unmodelled term of the precision budget (tests/error_budget.py).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float c0 = 7.97507880e-01f, c1 = 3.70056493e-02f, c2 = -3.51517274e-04f;
+  constexpr float S = -2.885390081777927f;     // -2 log2(e)
+  const float c0 = 7.97507880e-01f * S, c1 = 3.70056493e-02f * S, c2 = -3.51517274e-04f * S;
   const float u = fminf(x * x, 50.0f);
   float q = fmaf(c2, u, c1);
   q = fmaf(q, u, c0);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * q));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -79,3 +79,35 @@ def randomize_state_(state_dict, seed: int = 2025, bf16_exact: bool = True) -> N
         if bf16_exact:
             v = v.to(torch.bfloat16).to(torch.float32)
         t.copy_(v)
+
+
+def synthetic_raster_to_pinned(height: int, width: int, out, device, bands: int = 4, seed: int = 2025, cell: int = 96,
+                               noise: float = 6.0, row0: int = 0, chunk_rows: int = 1024) -> None:
+    """Same kind of content as ``synthetic_raster`` (smooth low-resolution field + per-pixel noise), generated on the
+    GPU in row chunks and downloaded into ``out`` = a PINNED HOST uint8 tensor (bands, rows, width) holding rows
+    [row0, row0+rows) of the zone.  The numpy generator makes ~10 MB/s; a 60 000 x 60 000 zone is 14.4 GB.
+    Deterministic in (height, width, bands, seed, cell, noise) and independent of the row range and of the chunking
+    (each chunk-aligned block of rows draws from its own seeded stream); NOT bit-identical to ``synthetic_raster``.
+    Set-up helper of bench.py: the timed regions start from the pinned host tensor."""
+    import torch
+    rows = out.shape[1]
+    gh, gw = height // cell + 3, width // cell + 3
+    coarse = torch.from_numpy(np.random.default_rng(seed).uniform(20.0, 235.0, size=(bands, gh, gw)).astype(np.float32)).to(device)
+    xs = (torch.arange(width, dtype=torch.float32, device=device) + 0.5) / cell
+    x0 = xs.floor().long()
+    fx = xs - x0
+    gen = torch.Generator(device=device)
+    blk0 = row0 // chunk_rows
+    blk1 = (row0 + rows - 1) // chunk_rows
+    for blk in range(blk0, blk1 + 1):
+        b0, b1 = blk * chunk_rows, min((blk + 1) * chunk_rows, height)
+        ys = (torch.arange(b0, b1, dtype=torch.float32, device=device) + 0.5) / cell
+        y0 = ys.floor().long()
+        fy = (ys - y0)[None, :, None]
+        rows_lo = coarse[:, y0] * (1 - fy) + coarse[:, y0 + 1] * fy              # (bands, n, gw)
+        val = rows_lo[:, :, x0] * (1 - fx) + rows_lo[:, :, x0 + 1] * fx          # (bands, n, width)
+        gen.manual_seed(seed * 1000003 + blk)
+        val += torch.randn(val.shape, generator=gen, device=device, dtype=torch.float32) * noise
+        u8 = val.round_().clamp_(0, 255).to(torch.uint8)
+        lo, hi = max(b0, row0), min(b1, row0 + rows)
+        out[:, lo - row0:hi - row0].copy_(u8[:, lo - b0:hi - b0], non_blocking=False)

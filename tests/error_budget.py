@@ -119,8 +119,8 @@ def _conv_bn_relu(seq, x, q, a_ch=None):
     return q["dec"](F.relu(y))
 
 
-def simulate(model, x, fmts: dict):
-    """fmts: {family: 'fp32'|'bf16'|'fp16'}.  Returns logits (B,n_cls,H,W) fp32."""
+def simulate(model, x, fmts: dict, want_feats: bool = False):
+    """fmts: {family: 'fp32'|'bf16'|'fp16'}.  Returns logits (B,n_cls,H,W) fp32 (and the four stage outputs)."""
     q = {f: rounder(fmts.get(f, "fp32")) for f in FAMILIES}
     g = fmts.get("gelu", "exact")
     q["gelu"] = F.gelu if g == "exact" else (lambda t: gelu_engine(t, g == "hw"))
@@ -133,7 +133,8 @@ def simulate(model, x, fmts: dict):
     for i, blk in enumerate(dec.decoder.blocks):
         a = _conv_bn_relu(blk.conv1, (a, sk[i]), q, a_ch=a.shape[1])
         a = _conv_bn_relu(blk.conv2, a, q)
-    return dec.segmentation_head(a)
+    logits = dec.segmentation_head(a)
+    return (logits, feats) if want_feats else logits
 
 
 def make_model(seed: int, arch: str = "convnextv2_base-unet", device="cpu"):
@@ -151,10 +152,17 @@ def make_tile(seed: int, P: int, device="cpu"):
     return ((t - mean) / std).float()[None].to(device)
 
 
+def no_tf32():
+    """fp32 means fp32: cuDNN / cuBLAS would otherwise run the oracle's convolutions and matmuls in TF32 on the GPU."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
 @torch.no_grad()
 def budget(P: int = 512, seeds=(1,), device="cpu", arch="convnextv2_base-unet"):
     """-> {row label: (class agreement, mean|d|/std, max|d|/std)} averaged over seeds."""
     rows = {}
+    no_tf32()
 
     def add(label, vals):
         rows.setdefault(label, []).append(vals)

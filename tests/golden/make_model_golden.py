@@ -38,6 +38,14 @@ def golden_inputs(arch: str, seed: int):
     return sd, tile, xn
 
 
+def zone_weights(path: str, arch: str = "resnet34-unet", seed: int = 31) -> None:
+    """Checkpoint (.safetensors, reference layout) of the small-zone golden (zone_small.npz): seeded, every parameter and
+    buffer randomised, activations O(1) -- shared by make_reference_golden.py and the GPU test."""
+    from safetensors.torch import save_file
+    sd, _, _ = golden_inputs(arch, seed)
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+
+
 def oracle_logits(arch: str, sd, xn):
     from oracle.models import FlairHubOracle
     o = FlairHubOracle(arch, {"AERIAL_RGBI": 4}, {TASK: 19}).eval()

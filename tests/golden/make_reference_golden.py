@@ -13,7 +13,7 @@ stand-in modules of tests/reference_stubs.py (rasterio / geopandas / shapely / s
   convert_small.json   postprocess.py:9-30 ``convert`` (argmax with ties, class_prob).
   zone_small.npz       class rasters (argmax) and class_prob planes written by the reference pipeline
                        (reference FLAIR_HUB_Model + load_checkpoint + dataset + inference_and_write) for
-                       resnet34-unet on a 1000 x 700 zone, margin 64 -- the product is compared with these on the GPU.
+                       convnextv2_base-unet on a 1000 x 700 zone, margin 64 -- the product is compared with these on the GPU.
   model_*.npz          see make_model_golden.py (logits of the reference FLAIR_HUB_Model.forward).
 """
 import json
@@ -35,6 +35,7 @@ L, T, RES = 700000.0, 6600000.0, 0.2
 TASK = "AERIAL_LABEL-COSIA"
 CASES = [(1000, 700, 64), (2048, 2048, 128), (777, 1300, 40), (10000, 10000, 64), (10000, 10000, 128),
          (10000, 10000, 40), (20000, 20000, 64)]
+ZONE_ARCH = "convnextv2_base-unet"      # the headline architecture; 6 tiles of 512 on the CPU
 MEANS, STDS = [105.66, 111.35, 102.18, 106.59], [52.23, 45.62, 44.30, 39.78]
 
 
@@ -125,11 +126,15 @@ def main():
     from flair_for_aigle_b200.synthetic import synthetic_raster
     tmp = tempfile.mkdtemp(prefix="fz_gold_")
     wpath = os.path.join(tmp, "w.safetensors")
-    pin._weights("resnet34-unet", {"AERIAL_RGBI": 4}, wpath, seed=31)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_model_golden", os.path.join(HERE, "make_model_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    mg.zone_weights(wpath, ZONE_ARCH, 31)
     arr = synthetic_raster(700, 1000, seed=11)
     out = {}
     for kind in ("argmax", "class_prob"):
-        canvas, tiles, _, _ = pin._reference_zone("resnet34-unet", arr, 64, kind, wpath, tmp, f"mem://gold_zone_{kind}")
+        canvas, tiles, _, _ = pin._reference_zone(ZONE_ARCH, arr, 64, kind, wpath, tmp, f"mem://gold_zone_{kind}")
         out[kind] = canvas
         print("zone_small", kind, canvas.shape, "tiles", len(tiles))
     np.savez_compressed(os.path.join(HERE, "zone_small.npz"), argmax=out["argmax"][0],

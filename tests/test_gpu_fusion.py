@@ -2,6 +2,8 @@
 configs[4] (AERIAL_RGBI 4 ch + DEM_ELEV 1 ch), forward, against the fp32 oracle."""
 import pytest
 import torch
+from parity import (CLASS_AGREEMENT, CLASS_AGREEMENT_CONFIDENT, CLASS_AGREEMENT_FUSED, LOGIT_MAX_ABS,  # noqa: E402,F401
+                    LOGIT_MEAN_ABS)
 
 TASK = "AERIAL_LABEL-COSIA"
 
@@ -58,7 +60,7 @@ def test_two_modality_forward_vs_oracle(cuda):
     d = (out - ref).abs()
     agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
     print(f"fused logits: max|d|={d.max().item():.4f} mean|d|={d.mean().item():.5f} std={sd_:.3f} agree={agree:.5f}")
-    assert d.mean().item() < 0.015 * sd_ and d.max().item() < 0.15 * sd_
+    assert d.mean().item() < LOGIT_MEAN_ABS * sd_ and d.max().item() < LOGIT_MAX_ABS * sd_
     out2, _ = m(batch)
     assert torch.equal(out, out2[TASK])
 
@@ -91,4 +93,4 @@ def test_two_modalities_of_different_patch_size(cuda):
     sd_ = ref.std().item()
     d = (out - ref).abs()
     print(f"mixed-size fusion: max|d|={d.max().item():.4f} mean|d|={d.mean().item():.5f} std={sd_:.3f}")
-    assert d.mean().item() < 0.015 * sd_ and d.max().item() < 0.15 * sd_
+    assert d.mean().item() < LOGIT_MEAN_ABS * sd_ and d.max().item() < LOGIT_MAX_ABS * sd_

@@ -13,6 +13,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+from parity import (CLASS_AGREEMENT, CLASS_AGREEMENT_CONFIDENT, CLASS_AGREEMENT_FUSED, LOGIT_MAX_ABS,  # noqa: E402,F401
+                    LOGIT_MEAN_ABS)
 
 TASK = "AERIAL_LABEL-COSIA"
 L, T, RES = 700000.0, 6600000.0, 0.2
@@ -87,7 +89,7 @@ def test_inference_and_write_matches_oracle(setup):
     assert os.path.exists(outs[TASK].written_path)
     agree = (got == ref).mean()
     print(f"class raster agreement with the oracle pipeline: {agree:.5f}")
-    assert agree >= 0.985
+    assert agree >= CLASS_AGREEMENT
 
     # generic path (reference-style batches produced by the feeder kernel, logits -> crop kernels)
     cfg2 = dict(cfg)
@@ -106,7 +108,7 @@ def test_inference_and_write_matches_oracle(setup):
     # roundings downstream: compare this path with the ORACLE too, at the same bar
     agree2 = (got2 == ref).mean()
     print(f"generic path agreement with the oracle pipeline: {agree2:.5f}; with the fused path {(got2 == got).mean():.5f}")
-    assert agree2 >= 0.985
+    assert agree2 >= CLASS_AGREEMENT
     # the fused path is deterministic: a second run reproduces the raster bit for bit
     outs3, _ = inf.init_outputs(cfg, "mem://z1", 0)
     inf.inference_and_write(model, loader, tiles, cfg, outs3, "mem://z1")
@@ -128,7 +130,7 @@ def test_inference_and_write_matches_oracle(setup):
     print(f"logits max|d| {(lo-lp).abs().max().item():.4f} mean|d| {(lo-lp).abs().mean().item():.5f} "
           f"std {lo.std().item():.3f}; confident px {confident.float().mean().item():.4f}, "
           f"agreement there {same[confident].float().mean().item():.6f}, overall {same.float().mean().item():.5f}")
-    assert same[confident].float().mean().item() >= 0.999
+    assert same[confident].float().mean().item() >= CLASS_AGREEMENT_CONFIDENT
 
 
 def test_class_prob_and_blend_modes(setup):
@@ -171,7 +173,7 @@ def test_class_prob_and_blend_modes(setup):
             blend_accumulate(lo, plan[i:i + 1], 100, canvas_ref)
     agree = (labels.cpu().numpy() == canvas_ref.argmax(0)).mean()
     print(f"blend-mode class agreement with the oracle: {agree:.5f}")
-    assert agree >= 0.985
+    assert agree >= CLASS_AGREEMENT
     assert np.abs(canvas.cpu().numpy() - canvas_ref).mean() < 2e-3
 
 
@@ -296,7 +298,7 @@ def test_full_size_zone_properties(setup):
         if r1 > r0 and c1 > c0:
             agree.append((got[r0:r1, c0:c1] == ref[r0:r1, c0:c1]).mean())
     print("full-size zone: agreement with the oracle on sampled tiles", [f"{a:.4f}" for a in agree])
-    assert min(agree) >= 0.98
+    assert min(agree) >= CLASS_AGREEMENT
 
 
 def test_streamed_upload_equals_resident_run(setup):
@@ -371,3 +373,44 @@ def test_graph_runner_never_aliases_caller_buffers(setup):
     runner.run(x1, plan, own, o3)                                  # resident again after the streamed run
     torch.cuda.synchronize()
     assert torch.equal(o3.cpu(), want1) and torch.equal(o2.cpu(), want2)
+
+
+def test_zone_against_reference_pipeline_golden(cuda, tmp_path):
+    """tests/golden/zone_small.npz was written by the REFERENCE's own pipeline (FLAIR_HUB_Model + load_checkpoint +
+    MultiModalSlicedDataset + inference_and_write, tests/golden/make_reference_golden.py) for this zone and these weights;
+    the product runs the same zone through its drop-in API.  argmax raster and class_prob planes."""
+    import os
+    import bench
+    from test_model_golden import mg
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model
+    from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink, ZoneRaster, register_raster
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import generate_patches_from_reference
+    from flair_for_aigle_b200.synthetic import synthetic_raster
+    ARCH = "convnextv2_base-unet"
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "zone_small.npz"))
+    wpath = str(tmp_path / "gold_zone.safetensors")
+    mg.zone_weights(wpath, ARCH, int(gold["weights_seed"]))
+    arr = synthetic_raster(700, 1000, seed=int(gold["raster_seed"]))
+    register_raster("mem://gold_zone", ZoneRaster(arr, 700000.0, 6600000.0, 0.2))
+    RasterSink.write_files = False
+    for kind in ("argmax", "class_prob"):
+        c = bench.zonal_config(wpath, str(tmp_path), "mem://gold_zone", 4)
+        c["monotemp_arch"] = ARCH
+        c["output_type"] = kind
+        cfg = inf.initialize_geometry_and_resolutions(c)
+        cfg["device"] = cuda
+        model = build_inference_model(cfg, {"AERIAL_RGBI": 512}).to(cuda)
+        tiles = generate_patches_from_reference(cfg, "mem://gold_zone", None)
+        ds = inf.prep_dataset(cfg, tiles, {"AERIAL_RGBI": 512})
+        outs, _ = inf.init_outputs(cfg, "mem://gold_zone", 0)
+        inf.inference_and_write(model, ds, tiles, cfg, outs, "mem://gold_zone")
+        got = outs[TASK].to_host()
+        if kind == "argmax":
+            agree = (got[0] == gold["argmax"]).mean()
+            print(f"{ARCH} zone vs the reference pipeline's raster: class agreement {agree:.5f}")
+            assert got[0].shape == gold["argmax"].shape and agree >= CLASS_AGREEMENT
+        else:
+            d = np.abs(got[:, 300:364, 400:528].astype(np.int32) - gold["class_prob"].astype(np.int32))
+            print(f"class_prob planes vs the reference pipeline: max |d| {d.max()} / 255, mean {d.mean():.4f}")
+            assert d.mean() < 0.3 and (d > 3).mean() < 1e-3

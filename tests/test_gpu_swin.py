@@ -7,6 +7,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+from parity import (CLASS_AGREEMENT, CLASS_AGREEMENT_CONFIDENT, CLASS_AGREEMENT_FUSED, LOGIT_MAX_ABS,  # noqa: E402,F401
+                    LOGIT_MEAN_ABS)
 from flair_for_aigle_b200 import native as _nv  # noqa: E402
 OP = _nv.op_dtype()      # the inference kernels' 16-bit operand format (float16; bfloat16 in the A/B build)
 
@@ -226,12 +228,12 @@ def test_swin_upernet_engine_vs_oracle(cuda):
     d = (out - ref).abs()
     agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
     print(f"logits: max|d|={d.max().item():.4f} mean|d|={d.mean().item():.5f} std={sd_:.3f} argmax agree={agree:.5f}")
-    assert d.max().item() < 0.15 * sd_ and d.mean().item() < 0.015 * sd_
+    assert d.max().item() < LOGIT_MAX_ABS * sd_ and d.mean().item() < LOGIT_MEAN_ABS * sd_
     eng.encode_f32(xn)
     out2 = eng.decode_logits_nchw(2)
     torch.cuda.synchronize()
     d2 = (out2 - ref).abs()
-    assert d2.max().item() < 0.15 * sd_ and d2.mean().item() < 0.015 * sd_
+    assert d2.max().item() < LOGIT_MAX_ABS * sd_ and d2.mean().item() < LOGIT_MEAN_ABS * sd_
     eng.encode_f32(xn)
     out3 = eng.decode_logits_nchw(2)
     torch.cuda.synchronize()
@@ -275,7 +277,7 @@ def test_swin_upernet_zone_through_public_api(cuda, tmp_path):
                          DEFAULT_STDS, task, 19, batch_size=2, device="cuda")
     agree = (got == ref).mean()
     print(f"swin-upernet zone class agreement with the oracle pipeline: {agree:.5f}")
-    assert agree >= 0.98
+    assert agree >= CLASS_AGREEMENT
 
 
 def test_crop_argmax_on_quarter_resolution_logits(cuda):

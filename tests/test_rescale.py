@@ -3,6 +3,8 @@ path on the GPU against the oracle pipeline (which calls scipy.ndimage.zoom like
 import numpy as np
 import pytest
 import torch
+from parity import (CLASS_AGREEMENT, CLASS_AGREEMENT_CONFIDENT, CLASS_AGREEMENT_FUSED, LOGIT_MAX_ABS,  # noqa: E402,F401
+                    LOGIT_MEAN_ABS)
 
 L, T, RES = 700000.0, 6600000.0, 0.2
 TASK = "AERIAL_LABEL-COSIA"
@@ -84,7 +86,7 @@ def test_zone_with_rescaled_output(cuda, tmp_path, out_res, output_type):
         assert got.shape == ref.shape == (int(round(700 * RES / out_res)), int(round(1000 * RES / out_res)))
         agree = (got == ref).mean()
         print(f"out_res {out_res}: class agreement with the oracle pipeline {agree:.5f}")
-        assert agree >= 0.985
+        assert agree >= CLASS_AGREEMENT
     else:
         assert got.shape == ref.shape
         d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
