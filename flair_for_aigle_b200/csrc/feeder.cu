@@ -62,7 +62,85 @@ __global__ void gather_u8_kernel(const uint8_t* __restrict__ raster, int C, int 
   reinterpret_cast<uchar4*>(out)[static_cast<size_t>(t) * P * P + idx] = px;
 }
 
+// Resampled window read (dataset.py:97-115 when a modality's pixel size differs from the reference modality's: the tile's
+// window is a FRACTIONAL number of the modality's pixels and rasterio resamples it to patch_sizes[mod] with
+// Resampling.bilinear, boundless, fill 0).  Restates GDAL's RasterIO convolution (see oracle/resample.py, which this follows
+// operation for operation, in double): destination pixel i sits at source coordinate off + (i + 0.5) * (win / ps); triangle
+// kernel on pixel-centre distances, widened by win / ps when the read downsamples, weights normalised; fill pixels take part
+// like data; integer rasters are rounded half up before the normalisation.
+// win: double [n][4] = (row_off, col_off, height, width) in the modality's pixels.  One thread per output pixel.
+constexpr int RS_MAXT = 20;   // taps per axis: ceil(2 * max(ratio, 1)) + 1 -> ratios up to 9.5
+template <typename T>
+__global__ void __launch_bounds__(256) gather_resampled_kernel(const T* __restrict__ raster, int C, int H, int W,
+                                                               const double* __restrict__ win, int ps,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ stdv, float* __restrict__ out) {
+  const int t = blockIdx.z, c = blockIdx.y;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= ps * ps) return;
+  const int oy = p / ps, ox = p - oy * ps;
+  const double row_off = win[4 * t], col_off = win[4 * t + 1], wh = win[4 * t + 2], ww = win[4 * t + 3];
+  const double ry = wh / ps, rx = ww / ps;
+  const double sy = ry > 1.0 ? ry : 1.0, sx = rx > 1.0 ? rx : 1.0;
+  const int ty = static_cast<int>(ceil(2.0 * sy)) + 1, tx = static_cast<int>(ceil(2.0 * sx)) + 1;
+  const double cy = row_off + (oy + 0.5) * ry, cx = col_off + (ox + 0.5) * rx;
+  const int fy = static_cast<int>(floor(cy - 0.5 - sy)) + 1, fx = static_cast<int>(floor(cx - 0.5 - sx)) + 1;
+  double wy[RS_MAXT], wx[RS_MAXT];
+  double sumy = 0.0, sumx = 0.0;
+  for (int k = 0; k < ty; ++k) {
+    const double w = 1.0 - fabs((fy + k + 0.5) - cy) / sy;
+    wy[k] = w > 0.0 ? w : 0.0;
+    sumy += wy[k];
+  }
+  for (int k = 0; k < tx; ++k) {
+    const double w = 1.0 - fabs((fx + k + 0.5) - cx) / sx;
+    wx[k] = w > 0.0 ? w : 0.0;
+    sumx += wx[k];
+  }
+  for (int k = 0; k < ty; ++k) wy[k] = sumy > 0.0 ? wy[k] / sumy : 0.0;
+  for (int k = 0; k < tx; ++k) wx[k] = sumx > 0.0 ? wx[k] / sumx : 0.0;
+  const T* plane = raster + static_cast<size_t>(c) * H * W;
+  double acc = 0.0;
+  for (int kx = 0; kx < tx; ++kx) {
+    const int xi = fx + kx;
+    double r = 0.0;                                   // rows first, like the oracle: r = sum_ky wy * v(yi, xi)
+    if (xi >= 0 && xi < W) {
+      for (int ky = 0; ky < ty; ++ky) {
+        const int yi = fy + ky;
+        const double v = (yi >= 0 && yi < H) ? static_cast<double>(plane[static_cast<size_t>(yi) * W + xi]) : 0.0;
+        r += wy[ky] * v;
+      }
+    }
+    acc += wx[kx] * r;
+  }
+  if (sizeof(T) == 1) {                               // uint8 raster: GDAL rounds the resampled value half up and clamps
+    acc = floor(acc + 0.5);
+    acc = acc < 0.0 ? 0.0 : (acc > 255.0 ? 255.0 : acc);
+  }
+  out[((static_cast<size_t>(t) * C + c) * ps + oy) * ps + ox] =
+      static_cast<float>((acc - static_cast<double>(mean[c])) / static_cast<double>(stdv[c]));
+}
+
 }  // namespace fz
+
+extern "C" int fz_gather_tiles_resampled(const void* raster, int src_f32, int C, int H, int W, const double* windows,
+                                         int n_tiles, int ps, double max_ratio, const float* mean, const float* stdv, float* out,
+                                         void* stream) {
+  FZ_REQUIRE(C >= 1 && H > 0 && W > 0 && ps > 0, "fz_gather_tiles_resampled: bad shape C=%d H=%d W=%d ps=%d", C, H, W, ps);
+  FZ_REQUIRE(max_ratio > 0.0 && static_cast<int>(ceil(2.0 * (max_ratio > 1.0 ? max_ratio : 1.0))) + 1 <= fz::RS_MAXT,
+             "fz_gather_tiles_resampled: window / patch ratio %.3f needs more than %d taps per axis", max_ratio, fz::RS_MAXT);
+  if (n_tiles <= 0) return 0;
+  dim3 grid((ps * ps + 255) / 256, C, n_tiles);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (src_f32)
+    fz::gather_resampled_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(raster), C, H, W, windows, ps, mean,
+                                                             stdv, out);
+  else
+    fz::gather_resampled_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(raster), C, H, W, windows, ps,
+                                                               mean, stdv, out);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 static int gather_f32_launch(const void* raster, int src_f32, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
                              const float* mean, const float* stdv, float* out, void* stream) {

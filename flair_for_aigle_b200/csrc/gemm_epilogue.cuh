@@ -15,6 +15,9 @@ struct GemmParams {
   void* out;            // [M,N] bf16 or f32
   const float* resid;   // [M,N] f32 (FZ_EPI_RESID_F32), may alias out
   float* sumsq;         // [ceil(M/128), N] f32 per-128-row partial sums of out^2 (FZ_EPI_GELU_SUMSQ)
+  int splits;           // split-K: the K range is cut into `splits` pieces of kb_per_split k-blocks; piece s writes its fp32
+  int kb_per_split;     //   partial tile to out + s * M * N (fz_gemm_bf16_splitk sums the pieces in order); 1 = off
+  int nobias;           // 1: the epilogue adds no bias (split-K partials)
   int f16;              // 1: A, B and a 16-bit output are fp16 (FZ_EPI_OPERANDS_F16), 0: bf16
   int reverse;          // 1: walk the tile list backwards (consume a just-written operand newest-first, while it is in L2)
   unsigned long long* trace;  // optional: CTA 0 writes clock64 stamps [tile][8] (diagnostics, see fz_gemm_set_trace)
@@ -36,13 +39,13 @@ struct EpiShape {
 // sq_dst: (GELU_SUMSQ) 64 floats: 32-row column sums of out^2 for the chunk's columns (8-byte aligned)
 template <int MODE, bool F16>
 __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, int row0, int col0, char* stg, int lane,
-                                          float* sq_dst) {
+                                          float* sq_dst, void* out_base) {
   constexpr bool F32OUT = EpiShape<MODE>::F32OUT;
   constexpr int CH_COLS = EpiShape<MODE>::CH_COLS;
   constexpr int ESZ = EpiShape<MODE>::ESZ;
   const int rsub = lane >> 3, seg = lane & 7;              // row-contiguous mapping: 4 rows x 8 segments
   const size_t row_bytes = static_cast<size_t>(p.N) * ESZ;
-  char* gout = reinterpret_cast<char*>(p.out) + static_cast<size_t>(row0) * row_bytes + static_cast<size_t>(col0) * ESZ;
+  char* gout = reinterpret_cast<char*>(out_base) + static_cast<size_t>(row0) * row_bytes + static_cast<size_t>(col0) * ESZ;
   if (MODE == FZ_EPI_RESID_F32) {
     // coalesced residual tile -> staging
     const char* gres = reinterpret_cast<const char*>(p.resid) + static_cast<size_t>(row0) * row_bytes +
@@ -63,7 +66,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
     const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + h * 32);
     float4 b4[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b4[j] = __ldg(bp + j);
+    for (int j = 0; j < 8; ++j) b4[j] = p.nobias ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(bp + j);
     float v[32];
     tmem_ld_wait();
 #pragma unroll

@@ -68,6 +68,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_tiles = p.N / BN;
   const int m_tiles = (p.M + BM - 1) / BM;
   const int total_tiles = n_tiles * m_tiles;
+  const int total_work = total_tiles * p.splits;      // split-K (p.splits > 1): work item = (tile, K piece)
   const int num_kb = p.K / BK;
   // persistent schedule: tile t -> (m = t / n_tiles, n = t % n_tiles)
   const int t_first = blockIdx.x, t_step = gridDim.x;
@@ -94,13 +95,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
-      for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
-        const int te = p.reverse ? total_tiles - 1 - t : t;
+      for (int t = t_first; t < total_work; t += t_step, ++lt) {
+        const int tile = t / p.splits, sp = t - tile * p.splits;
+        const int te = p.reverse ? total_tiles - 1 - tile : tile;
         const int n0 = (te % n_tiles) * BN;
         const int m0 = (te / n_tiles) * BM;
         const int bcoord = p.b_batched ? (m0 / p.rows_per_sample) : 0;
+        const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         FZ_TRACE(0);   // producer starts issuing this tile's loads
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -115,7 +118,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc16(128, BN, F16);
       uint32_t it = 0, lt = 0;
-      for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
+      for (int t = t_first; t < total_work; t += t_step, ++lt) {
+        const int sp = t % p.splits;
+        const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const uint32_t as = lt % ACC_STAGES;
         const uint32_t aph = (lt / ACC_STAGES) & 1;
         FZ_TRACE(1);   // MMA warp reaches the tile
@@ -124,19 +129,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         FZ_TRACE(2);   // accumulator stage free
         const uint32_t acc0 = tmem + as * (2 * BN);
         const uint32_t acc1 = acc0 + BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          if (kb == 0) FZ_TRACE(3);   // first k-block landed
+          if (kb == kb0) FZ_TRACE(3);   // first k-block landed
           const uint64_t ad0 = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES), 128);
           const uint64_t ad1 = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES + 128 * BK * 2), 128);
           const uint64_t bd = umma_smem_desc(smem_u32(sB + s * L::B_STAGE_BYTES), 128);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes (16 bf16) along K inside the 128B swizzle atom = +2 in the >>4 address field
-            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
             umma_bf16(acc0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
             umma_bf16(acc1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
           }
@@ -154,10 +159,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int colgrp = ew >> 3;                 // chunks colgrp, colgrp+2, ...
     const int bar_id = 1 + half;
     uint32_t lt = 0;
-    for (int t = t_first; t < total_tiles; t += t_step, ++lt) {
-      const int te = p.reverse ? total_tiles - 1 - t : t;
+    for (int t = t_first; t < total_work; t += t_step, ++lt) {
+      const int tile = t / p.splits, sp = t - tile * p.splits;
+      const int te = p.reverse ? total_tiles - 1 - tile : tile;
       const int n0 = (te % n_tiles) * BN;
       const int m0 = (te / n_tiles) * BM;
+      // split-K piece sp writes its fp32 partial tile to its own [M][N] plane of the workspace
+      void* out_base = reinterpret_cast<char*>(p.out) + static_cast<size_t>(sp) * p.M * p.N * sizeof(float);
       const uint32_t as = lt % ACC_STAGES;
       const uint32_t aph = (lt / ACC_STAGES) & 1;
       float* sq_buf = sSq + (lt & 1) * 8 * BN;
@@ -171,7 +179,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = colgrp; c < BN / CH_COLS; c += 2)
         epi_chunk<MODE, F16>(p, tbase + c * CH_COLS, m0 + half * 128 + q * 32, n0 + c * CH_COLS, stg, lane,
-                        sq_buf + (half * 4 + q) * BN + c * CH_COLS);
+                        sq_buf + (half * 4 + q) * BN + c * CH_COLS, out_base);
       // all TMEM reads of this stage are complete (tmem_ld_wait above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -201,7 +209,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   FZ_ENSURE_SMEM(kern, L::BYTES);
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return -2;
-  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * p.splits;
   const int grid = tiles < sm_count ? tiles : sm_count;
   kern<<<grid, GEMM_THREADS, L::BYTES, stream>>>(tmA, tmB, p);
   FZ_CHECK_CUDA(cudaGetLastError());
@@ -261,6 +269,7 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = g_trace;
   p.reverse = reverse;
   p.f16 = f16;
+  p.splits = 1; p.kb_per_split = K / BK; p.nobias = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // CTA-pair kernel (256x256 tile over two SMs, gemm_tcgen05_2sm.cu): wide outputs with enough tiles for 74 pairs.
   // FZ_GEMM_PAIR=0 disables, =2 forces it whenever N % 256 == 0.
@@ -289,6 +298,83 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   }
   if (BN == 128) return dispatch_mode<128, 3, 2>(mode, tmA, tmB, p, st);
   return dispatch_mode<64, 3, 2>(mode, tmA, tmB, p, st);
+}
+
+// ----------------------------------------------------------------------------------------
+// Split-K: C[M,N] (fp32) = A[M,K] B[N,K]^T for a SMALL output and a LONG reduction -- the weight gradients of the training
+// step (dW = dY^T X: a few output tiles, K = every pixel of the batch).  A plain launch would keep 2..32 of the 148 SMs
+// busy; here the K range is cut into `splits` pieces, every (tile, piece) is a work item of the same persistent kernel and
+// writes an fp32 partial tile to workspace[piece], and a second kernel adds the pieces in index order (deterministic, no
+// atomics).  No bias.
+// ----------------------------------------------------------------------------------------
+namespace fz {
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ out,
+                                                            size_t n4, int splits) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = ws[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 b = ws[static_cast<size_t>(s) * n4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  out[i] = a;
+}
+}  // namespace fz
+
+extern "C" int fz_gemm_splitk_max_splits(int M, int N, int K) {
+  using namespace fz;
+  if (M <= 0 || N <= 0 || K <= 0 || K % BK || N % 64) return 1;
+  const int sms = device_sm_count();
+  const int BN = (N % 128 == 0) ? 128 : 64;
+  const long long tiles = static_cast<long long>((M + BM - 1) / BM) * (N / BN);
+  const int num_kb = K / BK;
+  long long s = sms > 0 ? (2LL * sms) / tiles : 1;      // about two work items per SM
+  if (s > num_kb / 4) s = num_kb / 4;                   // every piece keeps >= 4 k-blocks
+  return static_cast<int>(s < 1 ? 1 : (s > 64 ? 64 : s));
+}
+
+extern "C" int fz_gemm_bf16_splitk(const void* A, const void* B, float* out, float* workspace, int M, int N, int K, int splits,
+                                   int flags, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(M > 0 && N > 0 && K > 0, "fz_gemm_bf16_splitk: bad shape M=%d N=%d K=%d", M, N, K);
+  FZ_REQUIRE(K % BK == 0 && N % 64 == 0, "fz_gemm_bf16_splitk: K=%d must be a multiple of %d and N=%d of 64", K, BK, N);
+  FZ_REQUIRE((static_cast<long long>(M) * N) % 4 == 0, "fz_gemm_bf16_splitk: M*N must be a multiple of 4");
+  const int num_kb = K / BK;
+  FZ_REQUIRE(splits >= 1 && splits <= num_kb, "fz_gemm_bf16_splitk: splits=%d out of range (1..%d)", splits, num_kb);
+  FZ_REQUIRE(splits == 1 || workspace != nullptr, "fz_gemm_bf16_splitk: workspace (splits*M*N floats) required");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.rows_per_sample = M; p.b_batched = 0;
+  p.bias = nullptr; p.resid = nullptr; p.sumsq = nullptr; p.trace = nullptr; p.reverse = 0;
+  p.f16 = (flags & FZ_EPI_OPERANDS_F16) ? 1 : 0;
+  p.nobias = 1;
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty piece
+  p.out = p.splits > 1 ? static_cast<void*>(workspace) : static_cast<void*>(out);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int BN = (N % 128 == 0) ? 128 : 64;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {BK, BM};
+    if (int rc = make_tmap16(&tmA, A, 2, dims, strides, box, 128)) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, 1};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)N};
+    const uint32_t box[3] = {BK, (uint32_t)BN, 1};
+    if (int rc = make_tmap16(&tmB, B, 3, dims, strides, box, 128)) return rc;
+  }
+  int rc = (BN == 128) ? dispatch_mode<128, 3, 2>(FZ_EPI_F32, tmA, tmB, p, st) : dispatch_mode<64, 3, 2>(FZ_EPI_F32, tmA, tmB, p, st);
+  if (rc) return rc;
+  if (p.splits > 1) {
+    const size_t n4 = static_cast<size_t>(M) * N / 4;
+    splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(workspace), reinterpret_cast<float4*>(out), n4, p.splits);
+    FZ_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -363,6 +449,7 @@ extern "C" int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const 
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = nullptr;
   p.reverse = 0;
+  p.splits = 1; p.kb_per_split = K / 16; p.nobias = 0;
   p.f16 = (mode & FZ_EPI_OPERANDS_F16) ? 1 : 0;
   mode &= ~(FZ_EPI_REVERSE_TILES | FZ_EPI_OPERANDS_F16);
   dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);

@@ -142,7 +142,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll 1
       for (int c = colgrp; c < BN / CH_COLS; c += 4)
         epi_chunk<MODE, F16>(p, tbase + c * CH_COLS, m0 + q * 32, n0 + c * CH_COLS, stg, lane,
-                        sq_buf + q * BN + c * CH_COLS);
+                        sq_buf + q * BN + c * CH_COLS, p.out);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[as], 0));

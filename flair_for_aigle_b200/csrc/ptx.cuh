@@ -239,11 +239,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------ math helpers
 // GELU(erf) = 0.5 x (1 + erf(x / sqrt 2)) = 0.5 x (1 + tanh(g(x))) with g = atanh(erf(x / sqrt 2)) fitted by x * Q(u),
 // u = min(x^2, 50), Q of degree 2: |err| < 2.6e-5 abs over all x in fp32; the clamp keeps Q positive so large |x| saturate.
-// Evaluated as x * sigmoid(2 g) = x / (1 + 2^(-2 log2(e) x Q(u))) with ex2.approx (2^-22 rel.) and rcp.approx (1 ulp):
-// 2 SFU + 7 FMA-pipe ops.  Round 1 used tanh.approx.f32 (1 SFU + 7): its 2^-11 relative error is invisible under a bf16
-// output rounding (2^-9) but LARGER than the fp16 output rounding (2^-12) the inference path now stores, and it is
-// systematic, not random -- it was the largest unmodelled term of the precision budget (tests/error_budget.py).
+// ONE SFU op (tanh.approx.f32, ~2^-11 relative) + 7 FMA-pipe ops: the fc1 epilogue is bound by issue slots.
+// Round 2 measured the exact alternative x / (1 + 2^(-2 log2(e) x Q(u))) (ex2.approx + rcp.approx, 2 SFU + 7, -DFZ_GELU_EXACT):
+// with it the engine's stage outputs equal the fp16-operand simulation to 1 % (profiles/r2_stage_errors.txt), but the class
+// agreement of the test zone moved only 0.99883 -> 0.99886 while the GEMM family slowed by 6 % -- the tanh.approx error is
+// below the fp16 operand rounding where it matters (tests/error_budget.py "gelu" rows), so the fast form stays.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
+#ifdef FZ_GELU_EXACT
   constexpr float S = -2.885390081777927f;     // -2 log2(e)
   const float c0 = 7.97507880e-01f * S, c1 = 3.70056493e-02f * S, c2 = -3.51517274e-04f * S;
   const float u = fminf(x * x, 50.0f);
@@ -253,6 +255,16 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * q));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
+#else
+  const float c0 = 7.97507880e-01f, c1 = 3.70056493e-02f, c2 = -3.51517274e-04f;
+  const float u = fminf(x * x, 50.0f);
+  float q = fmaf(c2, u, c1);
+  q = fmaf(q, u, c0);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+#endif
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

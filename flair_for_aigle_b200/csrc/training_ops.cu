@@ -71,8 +71,11 @@ __global__ void __launch_bounds__(CE_THREADS) ce_forward_kernel(const float* __r
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
       if (c == t) xt = v[c];
-    const float w = weight ? weight[t] : 1.0f;
-    wl = static_cast<double>(w) * static_cast<double>(l - xt);
+    // a target outside [0, C) -- nn.CrossEntropyLoss's ignore_index (-100) or a bad label -- is IGNORED: weight 0, left
+    // out of sum(w), zero gradient (PyTorch ignores -100 and raises on other values; it never reads out of bounds)
+    const bool valid = t >= 0 && t < C;
+    const float w = valid ? (weight ? weight[t] : 1.0f) : 0.0f;
+    wl = valid ? static_cast<double>(w) * static_cast<double>(l - xt) : 0.0;
     ww = static_cast<double>(w);
   }
 #pragma unroll
@@ -135,7 +138,8 @@ __global__ void __launch_bounds__(CE_THREADS) ce_backward_kernel(const float* __
   if (i >= n_px) return;
   const int64_t b = i / plane, p = i - b * plane;
   const int t = tgt[i];
-  const float g = scale / loss_out[1] * (weight ? weight[t] : 1.0f);
+  const bool valid = t >= 0 && t < C;                 // ignored targets (see ce_forward_kernel) get a zero gradient
+  const float g = valid ? scale / loss_out[1] * (weight ? weight[t] : 1.0f) : 0.0f;
   const float l = lse[i];
   const float* src = logits + b * C * plane + p;
   float* dst = dlogits + b * C * plane + p;

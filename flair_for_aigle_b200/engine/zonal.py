@@ -72,7 +72,8 @@ class ZonalRunner:
             return 3 + 2 * nblk + nds + self.eng.decoder.launches()
         n = 2  # gather + stem
         for i, d in enumerate(cfg.depths):
-            n += (2 if i > 0 else 0) + d * 6   # dwconv, fc1, grn (2 kernels), weight/row scaling, fc2
+            # dwconv, fc1, GRN statistics, scale + weight scaling in one kernel (stage 3: GRN apply + row scaling), fc2
+            n += (2 if i > 0 else 0) + d * (5 if self.eng.use_wscale[i] else 6)
         n += 1 + self.eng.decoder.launches()      # + bf16 cast of the deepest stage output
         return n
 

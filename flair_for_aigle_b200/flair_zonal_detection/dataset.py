@@ -129,30 +129,40 @@ class MultiModalSlicedDataset(Dataset):
             self._device_rasters[key] = host.to(device, non_blocking=True)
         return self._device_rasters[key]
 
-    def modality_origins(self, mod: str) -> np.ndarray:
-        """int32 [n,2] (row0, col0) of every tile's read window in ``mod``'s own pixel grid (dataset.py:101:
-        ``from_bounds(*bounds, transform=reader.transform)``).  The window of a tile spans P * ref_res metres; it is read
-        without resampling, so it has to cover exactly ``patch_sizes[mod]`` whole pixels of the modality and start on one
-        -- the resampled (bilinear, fractional window) read of rasterio is not built."""
+    def modality_windows(self, mod: str) -> np.ndarray:
+        """float64 [n,4] (row_off, col_off, height, width) of every tile's read window in ``mod``'s own pixel grid:
+        ``from_bounds(*row.geometry.bounds, transform=reader.transform)`` of dataset.py:97."""
+        r = self.readers[mod]
+        g = np.asarray([t.bounds for t in self.df["geometry"]], dtype=np.float64).reshape(-1, 4)
+        row0, col0, h, w = r.window_from_bounds(g[:, 0], g[:, 1], g[:, 2], g[:, 3])
+        return np.ascontiguousarray(np.stack([row0, col0, h, w], axis=1))
+
+    def modality_read_plan(self, mod: str):
+        """How ``mod``'s tiles are read: ("aligned", int32 [n,2] origins) when every window starts on a whole pixel and is
+        exactly ``patch_sizes[mod]`` pixels wide (the reference modality always; any modality at the reference
+        resolution) -- a plain copy with zero fill; else ("resampled", float64 [n,4] windows): the window is a fractional
+        number of the modality's pixels (a coarser DEM under a 0.2 m ortho) and rasterio resamples it bilinearly to
+        ``patch_sizes[mod]`` (dataset.py:108-115) -> fz_gather_tiles_resampled."""
         cfg = self.modalities_config
         ref_mod = cfg.get('reference_modality', next(iter(self.readers)))
-        plan = self.plan()
         if mod == ref_mod:
-            return np.ascontiguousarray(plan[:, :2]).astype(np.int32)
-        ref, r = self.readers[ref_mod], self.readers[mod]
-        ref_res, res = float(cfg['reference_resolution']), float(r.res[0])
-        P = int(cfg['img_pixels_detection'])
-        if abs(self.patch_sizes[mod] * res - P * ref_res) > 1e-6 * P * ref_res:
-            raise NotImplementedError(f"{mod}: a {P * ref_res} m tile is not {self.patch_sizes[mod]} whole pixels at {res} m/px; "
-                                      "resampled modality windows are not built")
-        x_left = ref.bounds.left + plan[:, 1].astype(np.float64) * ref_res
-        y_top = ref.bounds.top - plan[:, 0].astype(np.float64) * ref_res
-        col = (x_left - r.bounds.left) / res
-        row = (r.bounds.top - y_top) / res
-        if np.abs(col - np.round(col)).max() > 1e-4 or np.abs(row - np.round(row)).max() > 1e-4:
-            raise NotImplementedError(f"{mod}: tile windows do not start on whole pixels of this raster; resampled modality "
-                                      "windows are not built")
-        return np.stack([np.round(row), np.round(col)], axis=1).astype(np.int32)
+            return "aligned", np.ascontiguousarray(self.plan()[:, :2]).astype(np.int32)
+        win = self.modality_windows(mod)
+        ps = int(self.patch_sizes[mod])
+        if win.shape[0] == 0:
+            return "aligned", np.zeros((0, 2), np.int32)
+        aligned = (np.abs(win[:, :2] - np.round(win[:, :2])).max() < 1e-6 and np.abs(win[:, 2:] - ps).max() < 1e-6)
+        if aligned:
+            return "aligned", np.round(win[:, :2]).astype(np.int32)
+        return "resampled", win
+
+    def modality_origins(self, mod: str) -> np.ndarray:
+        """int32 [n,2] (row0, col0) of every tile's read window in ``mod``'s pixel grid, for modalities read without
+        resampling (see ``modality_read_plan``)."""
+        kind, plan = self.modality_read_plan(mod)
+        if kind != "aligned":
+            raise ValueError(f"{mod}: tile windows are fractional in this raster's pixels; use modality_read_plan()")
+        return plan
 
     def __len__(self) -> int:
         return len(self.df)

@@ -23,18 +23,42 @@ TAG_PIXEL_SCALE, TAG_TIEPOINT, TAG_GEOKEYS = 33550, 33922, 34735
 
 
 def _epsg(crs: Optional[str]) -> Optional[int]:
-    if not crs:
+    """EPSG code of a CRS given as ``EPSG:<n>`` / ``urn:ogc:def:crs:EPSG::<n>`` / a bare number, or as WKT whose OUTERMOST
+    authority is EPSG (``AUTHORITY["EPSG","2154"]]`` / ``ID["EPSG",2154]]`` closing the string).  Anything else (a WKT without
+    an authority, a PROJ string) has no code: no digits are guessed out of names such as ``GRS 1980``."""
+    if crs is None:
         return None
-    m = re.search(r"(\d{4,6})", str(crs))
-    return int(m.group(1)) if m else None
+    text = str(crs).strip()
+    m = re.fullmatch(r"(?:EPSG|epsg)\s*:\s*(\d+)", text) or re.fullmatch(r"urn:ogc:def:crs:EPSG:[^:]*:(\d+)", text, flags=re.I) \
+        or re.fullmatch(r"(\d{4,6})", text)
+    if m:
+        return int(m.group(1))
+    m = re.search(r"(?:AUTHORITY\s*\[\s*\"EPSG\"\s*,\s*\"?(\d+)\"?\s*\]|ID\s*\[\s*\"EPSG\"\s*,\s*(\d+)\s*\])\s*\]\s*$", text)
+    if m:
+        return int(m.group(1) or m.group(2))
+    return None
+
+
+def _is_geographic(crs: Optional[str], epsg: Optional[int]) -> bool:
+    """Geographic (lon/lat) CRS: a WKT starting with GEOGCS / GEOGCRS / GEODCRS, or one of the usual geographic EPSG codes
+    (4000-4999: WGS 84 = 4326, RGF93 = 4171, ETRS89 = 4258 ...)."""
+    text = str(crs or "").lstrip().upper()
+    if text.startswith(("GEOGCS", "GEOGCRS", "GEODCRS", "GEOGRAPHICCRS")):
+        return True
+    if text.startswith(("PROJCS", "PROJCRS", "PROJECTEDCRS")):
+        return False
+    return epsg is not None and 4000 <= epsg <= 4999
 
 
 def _geokeys(crs: Optional[str]):
-    """GeoKeyDirectory: version 1.1.0; GTModelType = projected, GTRasterType = PixelIsArea, ProjectedCSType = EPSG."""
+    """GeoKeyDirectory version 1.1.0: GTModelType (1 projected / 2 geographic), GTRasterType = PixelIsArea, and the EPSG code
+    under ProjectedCSTypeGeoKey (3072) or GeographicTypeGeoKey (2048)."""
     epsg = _epsg(crs)
-    keys = [(1024, 0, 1, 1), (1025, 0, 1, 1)]
+    geographic = _is_geographic(crs, epsg)
+    keys = [(1024, 0, 1, 2 if geographic else 1), (1025, 0, 1, 1)]
     if epsg is not None:
-        keys.append((3072, 0, 1, epsg))
+        keys.append((2048 if geographic else 3072, 0, 1, epsg))
+    keys.sort()
     flat = [1, 1, 0, len(keys)]
     for k in keys:
         flat.extend(k)

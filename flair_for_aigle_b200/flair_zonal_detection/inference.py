@@ -262,13 +262,15 @@ def _iter_batches(dataloader, dataset, model, config, device):
                                            np.uint8 if raster.dtype == torch.uint8 else np.float32)
         mean = torch.tensor(means, dtype=torch.float32, device=device)
         std = torch.tensor(stds, dtype=torch.float32, device=device)
-        origins = torch.from_numpy(dataset.modality_origins(mod)).to(device)
-        feeds.append((mod, raster, mean, std, origins, int(dataset.patch_sizes.get(mod, config['img_pixels_detection']))))
+        kind, rplan = dataset.modality_read_plan(mod)      # whole-pixel copy, or rasterio's resampled (bilinear) read
+        gather = nv.gather_tiles_f32 if kind == "aligned" else nv.gather_tiles_resampled
+        feeds.append((mod, raster, mean, std, torch.from_numpy(rplan).to(device), gather,
+                      int(dataset.patch_sizes.get(mod, config['img_pixels_detection']))))
     bs = int(config.get('batch_size', 8))
     for s in range(0, len(dataset), bs):
         idx = torch.arange(s, min(s + bs, len(dataset)), device=device)
-        batch = {mod: nv.gather_tiles_f32(raster, origins[idx].contiguous(), ps, mean, std)
-                 for mod, raster, mean, std, origins, ps in feeds}
+        batch = {mod: gather(raster, rplan[idx].contiguous(), ps, mean, std)
+                 for mod, raster, mean, std, rplan, gather, ps in feeds}
         batch['index'] = idx
         yield batch
 

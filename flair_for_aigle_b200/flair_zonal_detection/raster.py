@@ -9,11 +9,14 @@ I/O is the "next" row of SURVEY.md section 8(f).  ``ZoneRaster`` carries what th
 from __future__ import annotations
 
 import json
+import logging
 import os
 from collections import namedtuple
 from typing import Optional, Tuple
 
 import numpy as np
+
+logger = logging.getLogger(__name__)
 
 BoundingBox = namedtuple("BoundingBox", ["left", "bottom", "right", "top"])
 
@@ -72,6 +75,22 @@ class ZoneRaster:
                 "width": self.width, "crs": self.crs, "transform": (self.res_value, 0.0, self.left, 0.0,
                                                                      -self.res_value, self.top)}
 
+    def window_from_bounds(self, minx, miny, maxx, maxy):
+        """``rasterio.windows.from_bounds(minx, miny, maxx, maxy, transform)`` (dataset.py:97): the FLOAT window
+        (row_off, col_off, height, width) in this raster's pixels, through the inverse affine transform with the same
+        arithmetic as affine.Affine.__invert__ / __mul__ (a = res, e = -res, b = d = 0).  Vectorised over arrays."""
+        a, e, c, f = self.res_value, -self.res_value, self.left, self.top
+        idet = 1.0 / (a * e)
+        ra, re = e * idet, a * idet
+        rb, rd = -0.0 * idet, -0.0 * idet
+        rc, rf = -c * ra - f * rb, -c * rd - f * re
+        minx, miny, maxx, maxy = (np.asarray(v, dtype=np.float64) for v in (minx, miny, maxx, maxy))
+        cols = [x * ra + y * rb + rc for x, y in ((minx, maxy), (maxx, maxy), (maxx, miny), (minx, miny))]
+        rows = [x * rd + y * re + rf for x, y in ((minx, maxy), (maxx, maxy), (maxx, miny), (minx, miny))]
+        row0, row1 = np.minimum.reduce(rows), np.maximum.reduce(rows)
+        col0, col1 = np.minimum.reduce(cols), np.maximum.reduce(cols)
+        return row0, col0, np.maximum(row1 - row0, 0.0), np.maximum(col1 - col0, 0.0)
+
     def read(self, indexes=None) -> np.ndarray:
         if indexes is None:
             return self.array
@@ -122,6 +141,7 @@ def open_raster(path) -> ZoneRaster:
 
 
 _PINNED_POOL = {}
+CLASSIC_TIFF_LIMIT = (1 << 32) - (1 << 24)      # bytes of pixel data a classic (32-bit offset) TIFF can hold, with headroom
 
 
 class RasterSink:
@@ -190,15 +210,16 @@ class RasterSink:
         meta = {"left": self.left, "top": self.top, "res": self.res_value, "crs": self.crs,
                 "count": self.count, "height": self.height, "width": self.width, "dtype": "uint8",
                 "compress": "lzw"}
-        written = None
-        try:
-            from .geotiff import write_geotiff
-            written = write_geotiff(self.name, arr, self.left, self.top, self.res_value, self.crs)
-        except Exception:  # pragma: no cover - Pillow limits / classic-TIFF 4 GB limit
-            written = None
-        if written is None:
+        from .geotiff import write_geotiff
+        if arr.nbytes >= CLASSIC_TIFF_LIMIT:
+            # classic TIFF addresses 4 GiB (a 60 000 x 60 000 class raster is 3.6 GB, its class_prob raster 68 GB): the
+            # raster goes to <name>.npy + the .json sidecar instead -- said out loud, and ``written_path`` tells the caller
             written = os.path.splitext(self.name)[0] + ".npy"
+            logger.warning(f"[!] {self.name}: {arr.nbytes / 2**30:.1f} GiB exceeds classic TIFF; writing {written} (+ .json "
+                           "georeferencing) instead")
             np.save(written, arr)
+        else:
+            written = write_geotiff(self.name, arr, self.left, self.top, self.res_value, self.crs)   # errors propagate
         with open(written + ".json", "w") as f:
             json.dump(meta, f)
         self.written_path = written

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "fz_device_info": [_i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_sz)],
     "fz_gather_tiles_f32": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "fz_gather_tiles_f32_from_f32": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
+    "fz_gather_tiles_resampled": [_vp, _i, _i, _i, _i, _vp, _i, _i, ctypes.c_double, _vp, _vp, _vp, _vp],
     "fz_gather_tiles_u8": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp],
     "fz_crop_argmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "fz_crop_softmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
@@ -76,6 +77,8 @@ _SIGNATURES = {
     "fz_convert": [_vp, _i, _i, _i, _i, _vp, _vp],
     "fz_gemm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_gemm_set_trace": [_vp],
+    "fz_gemm_bf16_splitk": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_gemm_splitk_max_splits": [_i, _i, _i],
     "fz_gemm_bf16_simt": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_stem_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_stem_ln_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
@@ -85,6 +88,7 @@ _SIGNATURES = {
     "fz_grn_scale": [_vp, _i, _vp, _vp, _vp, _i, _i, ctypes.c_float, _vp],
     "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
+    "fz_grn_scale_weights": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_catconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fz_upconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
@@ -218,6 +222,22 @@ def gather_tiles_f32(raster: torch.Tensor, origins: torch.Tensor, P: int, mean: 
     return out
 
 
+def gather_tiles_resampled(raster: torch.Tensor, windows: torch.Tensor, ps: int, mean: torch.Tensor, std: torch.Tensor,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rasterio's resampled (bilinear, boundless, fill 0) window read + normalisation: raster uint8 / float32 (C,H,W),
+    windows float64 [n,4] = (row_off, col_off, height, width) in the raster's pixels -> float32 [n,C,ps,ps]."""
+    C, H, W = raster.shape
+    n = windows.shape[0]
+    if raster.dtype not in (torch.uint8, torch.float32) or windows.dtype != torch.float64 or windows.shape[1] != 4:
+        raise NativeError("gather_tiles_resampled: uint8 / float32 raster and float64 [n,4] windows required")
+    if out is None:
+        out = torch.empty((n, C, ps, ps), dtype=torch.float32, device=raster.device)
+    ratio = float(windows[:, 2:].max().item()) / ps if n else 1.0
+    _check(lib().fz_gather_tiles_resampled(_ptr(raster), 1 if raster.dtype == torch.float32 else 0, C, H, W, _ptr(windows), n, ps,
+                                           ratio, _ptr(mean), _ptr(std), _ptr(out), _stream()), "fz_gather_tiles_resampled")
+    return out
+
+
 def gather_tiles_u8(raster: torch.Tensor, origins: torch.Tensor, P: int,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     C, H, W = raster.shape
@@ -325,6 +345,33 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, mode: int, bias=None, resid=None
     return out
 
 
+_SPLITK_WS = {}
+
+
+def gemm_splitk(A: torch.Tensor, B: torch.Tensor, splits: Optional[int] = None, out: Optional[torch.Tensor] = None):
+    """fp32 [M,N] = A [M,K] B [N,K]^T for a small output and a long reduction (weight gradients): the K range is split over
+    the SMs inside one launch, partial tiles are added in a fixed order.  ``splits`` None = chosen from the shape."""
+    M, K = A.shape
+    N, K2 = B.shape
+    if K2 != K or A.dtype != B.dtype or A.dtype not in (torch.bfloat16, torch.float16):
+        raise NativeError("gemm_splitk: operands must both be float16 or both bfloat16 with equal K")
+    if splits is None:
+        splits = lib().fz_gemm_splitk_max_splits(M, N, K)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ws = None
+    if splits > 1:
+        key = (A.device.index, torch.cuda.current_stream().cuda_stream)
+        need = splits * M * N
+        ws = _SPLITK_WS.get(key)
+        if ws is None or ws.numel() < need:
+            ws = _SPLITK_WS[key] = torch.empty(need, dtype=torch.float32, device=A.device)
+    with _Timed("gemm_splitk", M=M, N=N, K=K, splits=splits):
+        _check(lib().fz_gemm_bf16_splitk(_ptr(A), _ptr(B), _ptr(out), _ptr(ws), M, N, K, splits,
+                                         EPI_OPERANDS_F16 if A.dtype == torch.float16 else 0, _stream()), "fz_gemm_bf16_splitk")
+    return out
+
+
 # --------------------------------------------------------------------------- ConvNeXt-V2 / U-Net ops
 def stem_ln(tiles_u8, w, bias, ln_w, ln_b, out, eps=1e-6):
     B, P = tiles_u8.shape[0], tiles_u8.shape[1]
@@ -379,6 +426,22 @@ def scale_weights(w, scale, out):
     _op16(w, out)
     with _Timed('scale_weights', B=B, N=N, K=K):
         _check(lib().fz_scale_weights(_ptr(w), _ptr(scale), _ptr(out), B, N, K, _stream()), "fz_scale_weights")
+    return out
+
+
+def grn_scale_weights(partial, tiles_per_sample, gamma, w, out, gx=None, scratch=None, eps=1e-6):
+    """GRN statistics + per-sample scaled fc2 weights, two launches: partial f32 [B*tps, K], w [N, K] -> out [B, N, K].
+    gx: f32 [B, K] scratch (receives Gx), scratch: f32 [B*K/64]."""
+    N, K = w.shape
+    B = out.shape[0]
+    _op16(w, out)
+    if gx is None:
+        gx = torch.empty((B, K), dtype=torch.float32, device=w.device)
+    if scratch is None:
+        scratch = torch.empty(B * K // 64, dtype=torch.float32, device=w.device)
+    with _Timed('grn_scale_weights', B=B, N=N, K=K):
+        _check(lib().fz_grn_scale_weights(_ptr(partial), tiles_per_sample, _ptr(gamma), _ptr(w), _ptr(out), _ptr(gx),
+                                          _ptr(scratch), B, N, K, eps, _stream()), "fz_grn_scale_weights")
     return out
 
 
@@ -713,38 +776,16 @@ def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
     if X.shape[0] != M or tuple(W.shape) != (N, K):
         raise NativeError("linear_backward: shape mismatch")
     dX = gemm_bf16(dY, transpose_bf16(W), EPI_BF16)                               # [M,N] x [K,N]^T
-    tiles = ((N + 127) // 128) * ((K + 63) // 64)
-    if tiles < 64 and M >= 1 << 18:
-        # few output tiles and a very long reduction (the decoder convolutions at full resolution: dW is 64 x 320 over 4 M
-        # rows): a handful of CTAs would stream gigabytes each.  Split the rows into chunks, run their GEMMs side by side on
-        # separate streams into partial sums, add the partials in a fixed order.
-        S = min(32, M // 65536)
-        rows = (M // S + 63) // 64 * 64
-        bounds = [(r, min(r + rows, M)) for r in range(0, M, rows)]
-        partial = torch.zeros((len(bounds), N, K), dtype=torch.float32, device=dY.device)
-        cur = torch.cuda.current_stream()
-        pool = _stream_pool(dY.device, 8)
-        for i, (r0, r1) in enumerate(bounds):
-            st = pool[i % len(pool)]
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                a, b = dY[r0:r1], X[r0:r1]
-                if (r1 - r0) % 64:
-                    pad = (r1 - r0 + 63) // 64 * 64
-                    a2 = torch.zeros((pad, N), dtype=dY.dtype, device=dY.device); a2[:r1 - r0].copy_(a); a = a2
-                    b2 = torch.zeros((pad, K), dtype=X.dtype, device=X.device); b2[:r1 - r0].copy_(b); b = b2
-                gemm_bf16(transpose_bf16(a), transpose_bf16(b), EPI_F32, out=partial[i])
-        for st in pool:
-            cur.wait_stream(st)
-        dW = torch.empty((N, K), dtype=torch.float32, device=dY.device)
-        _check(lib().fz_reduce_rows_f32(_ptr(partial), _ptr(dW), N * K, len(bounds), _stream()), "fz_reduce_rows_f32")
-    elif M % 64:                                                                  # the GEMM's reduction length is a multiple of 64
+    # dW = dY^T X: a small [N,K] output reduced over all M rows -- split-K inside the GEMM kernel (round 1 ran 2..32 CTAs per
+    # launch, or row chunks on side streams for the longest reductions)
+    if M % 64:                                                                    # the reduction length is a multiple of 64
         Mp = (M + 63) // 64 * 64
         dYp = torch.zeros((Mp, N), dtype=dY.dtype, device=dY.device)
         Xp = torch.zeros((Mp, K), dtype=X.dtype, device=X.device)
         dYp[:M].copy_(dY)
         Xp[:M].copy_(X)
-        dW = gemm_bf16(transpose_bf16(dYp), transpose_bf16(Xp), EPI_F32)
+        dY_t, X_t = transpose_bf16(dYp), transpose_bf16(Xp)
     else:
-        dW = gemm_bf16(transpose_bf16(dY), transpose_bf16(X), EPI_F32)            # [N,M] x [K,M]^T
+        dY_t, X_t = transpose_bf16(dY), transpose_bf16(X)
+    dW = gemm_splitk(dY_t, X_t)                                                   # [N,M] x [K,M]^T
     return dX, dW, colsum_bf16(dY)

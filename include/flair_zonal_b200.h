@@ -45,6 +45,14 @@ int fz_gather_tiles_f32(const uint8_t* raster, int C, int H, int W, const int32_
  * raster float32 [C][H][W], zero fill outside, (x - mean) / std in float64 rounded once to float32. */
 int fz_gather_tiles_f32_from_f32(const float* raster, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
                                  const float* mean, const float* stdv, float* out, void* stream);
+/* The RESAMPLED window read of dataset.py:97-115 for a modality whose pixel size differs from the reference modality's:
+ * windows double [n_tiles][4] = (row_off, col_off, height, width) of every tile in THIS raster's pixels (fractional),
+ * resampled to ps x ps like rasterio's read(out_shape=..., resampling=bilinear, boundless=True, fill_value=0) -- GDAL's
+ * RasterIO convolution restated in oracle/resample.py -- then (x - mean) / std.  raster: uint8 (src_f32 = 0, resampled
+ * values rounded half up like GDAL) or float32 (src_f32 = 1) [C][H][W]; max_ratio = max over tiles of window size / ps
+ * (host-checked against the kernel's tap budget).  out float32 [n_tiles][C][ps][ps]. */
+int fz_gather_tiles_resampled(const void* raster, int src_f32, int C, int H, int W, const double* windows, int n_tiles, int ps,
+                              double max_ratio, const float* mean, const float* stdv, float* out, void* stream);
 /* Same window rule, raw bytes, NHWC uint8 [n_tiles][P][P][4] (C<=4, missing channels = 0):
  * the operand the fused stem kernel consumes (20 B/px feeder of SURVEY 8d becomes 4+4 B/px). */
 int fz_gather_tiles_u8(const uint8_t* raster, int C, int H, int W, const int32_t* origins, int n_tiles, int P,
@@ -128,6 +136,14 @@ int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, vo
                                    * fp16 operands, the training step bf16 (see FZ_OP16 below). */
 int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq, int M,
                  int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
+/* Split-K variant for a small output with a long reduction (the training step's weight gradients dW = dY^T X): out float
+ * [M][N] = A [M][K] * B [N][K]^T, no bias, K cut into `splits` pieces that run as independent work items of the same
+ * persistent kernel (fp32 partial tiles in workspace [splits][M][N]) and are added in index order by a second kernel --
+ * deterministic.  flags: FZ_EPI_OPERANDS_F16 or 0 (bf16).  fz_gemm_splitk_max_splits: the split count that gives about two
+ * work items per SM while every piece keeps >= 4 k-blocks (1 = not worth splitting). */
+int fz_gemm_bf16_splitk(const void* A, const void* B, float* out, float* workspace, int M, int N, int K, int splits, int flags,
+                        void* stream);
+int fz_gemm_splitk_max_splits(int M, int N, int K);
 /* Diagnostics: when set to a device buffer of 64*8 uint64, CTA 0 of every following fz_gemm_bf16 launch
  * records clock64 stamps per tile (producer start, MMA arrive, accumulator free, first operands landed,
  * MMAs issued, epilogue wait, accumulator complete, epilogue done).  NULL switches it off. */
@@ -170,6 +186,11 @@ int fz_ln2d_s2d_copy(const float* x, const float* ln_w, const float* ln_b, void*
 int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale, float* scratch,
                  int B, int K, float eps, void* stream); /* scratch: B*K/64 floats */
 int fz_scale_weights(const void* w_bf16, const float* scale, void* out_bf16, int B, int N, int K, void* stream);
+/* fz_grn_scale + fz_scale_weights in two launches instead of three (the scale is applied while the weights are scaled):
+ * out16 [B][N][K] = w16 [N][K] * scale[b][k], scale as in fz_grn_scale.  gx_scratch: float [B][K] (receives Gx),
+ * psum_scratch: float [B][K/64].  Bit-identical to the two calls it replaces. */
+int fz_grn_scale_weights(const float* sumsq_partial, int tiles_per_sample, const float* gamma, const void* w16, void* out16,
+                         float* gx_scratch, float* psum_scratch, int B, int N, int K, float eps, void* stream);
 int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K, int rows_per_sample, void* stream);
 
 /* ---------------------------------------------------------------- U-Net decoder pieces

@@ -55,3 +55,34 @@ def test_rejects_tiff_without_georeference(tmp_path):
     Image.fromarray(np.zeros((8, 8), np.uint8)).save(p)
     with pytest.raises(ValueError):
         read_geotiff(p)
+
+
+def test_crs_codes_are_parsed_not_guessed():
+    """Round-1 advisor finding: the EPSG code used to be 'the first 4-6 digit run' of the CRS string, which reads 1980 out of
+    'GRS 1980' in a WKT, and geographic CRSs were written as projected ones."""
+    from flair_for_aigle_b200.flair_zonal_detection.geotiff import _epsg, _geokeys
+    wkt_l93 = ('PROJCS["RGF93 / Lambert-93",GEOGCS["RGF93",DATUM["Reseau_Geodesique_Francais_1993",SPHEROID["GRS 1980",6378137,'
+               '298.257222101,AUTHORITY["EPSG","7019"]],AUTHORITY["EPSG","6171"]],AUTHORITY["EPSG","4171"]],'
+               'PROJECTION["Lambert_Conformal_Conic_2SP"],UNIT["metre",1],AUTHORITY["EPSG","2154"]]')
+    wkt2_wgs = 'GEOGCRS["WGS 84",DATUM["World Geodetic System 1984",ELLIPSOID["WGS 84",6378137,298.257223563]],ID["EPSG",4326]]'
+    assert _epsg("EPSG:2154") == 2154 and _epsg("epsg:4326") == 4326 and _epsg("2154") == 2154
+    assert _epsg("urn:ogc:def:crs:EPSG::2154") == 2154
+    assert _epsg(wkt_l93) == 2154 and _epsg(wkt2_wgs) == 4326
+    assert _epsg('PROJCS["custom",GEOGCS["x",DATUM["d",SPHEROID["GRS 1980",6378137,298.25]]]]') is None     # no authority
+    assert _epsg(None) is None and _epsg("+proj=lcc +lat_1=49 +ellps=GRS80") is None
+
+    def keys(crs):
+        flat = _geokeys(crs)
+        return {flat[i]: flat[i + 3] for i in range(4, len(flat), 4)}
+    assert keys("EPSG:2154") == {1024: 1, 1025: 1, 3072: 2154}          # projected: ProjectedCSTypeGeoKey
+    assert keys("EPSG:4326") == {1024: 2, 1025: 1, 2048: 4326}          # geographic: GeographicTypeGeoKey
+    assert keys(wkt2_wgs) == {1024: 2, 1025: 1, 2048: 4326} and keys(wkt_l93) == {1024: 1, 1025: 1, 3072: 2154}
+    assert keys(None) == {1024: 1, 1025: 1}
+
+
+def test_geographic_crs_roundtrip(tmp_path):
+    from flair_for_aigle_b200.flair_zonal_detection.geotiff import read_geotiff, write_geotiff
+    arr = (np.arange(6 * 7, dtype=np.uint8).reshape(1, 6, 7) * 3)
+    p = write_geotiff(str(tmp_path / "geo.tif"), arr, 2.25, 48.75, 0.0001, "EPSG:4326")
+    got, left, top, res, crs = read_geotiff(p)
+    assert np.array_equal(got, arr) and (left, top, res, crs) == (2.25, 48.75, 0.0001, "EPSG:4326")

@@ -81,6 +81,33 @@ def test_cross_entropy_forward_backward(cuda, shape, weights, task_weight):
 
 
 @pytest.mark.gpu
+def test_cross_entropy_ignores_out_of_range_targets(cuda):
+    """Round-1 advisor finding: integer targets of -100 (nn.CrossEntropyLoss's ignore_index), negative or >= C used to index
+    the class weights out of bounds.  They are ignored now: no contribution to the loss or to sum(w), zero gradient --
+    exactly what torch does for -100."""
+    from flair_for_aigle_b200.flair_hub.tasks.module_setup import WeightedCrossEntropy
+    B, C, H, W = 2, 19, 40, 56
+    g = torch.Generator(device="cpu").manual_seed(5)
+    logits = (3 * torch.randn((B, C, H, W), generator=g)).to(cuda)
+    t = torch.randint(0, C, (B, H, W), generator=g)
+    holes = torch.rand((B, H, W), generator=g) < 0.3
+    t_torch = t.clone()
+    t_torch[holes] = -100
+    t_ours = t.clone()
+    t_ours[holes] = torch.tensor([-100, -1, C, 1000])[torch.randint(0, 4, (int(holes.sum()),), generator=g)]
+    w = (torch.rand(C, generator=g) + 0.5).to(cuda)
+    ref_logits = logits.clone().requires_grad_(True)
+    ref = torch.nn.CrossEntropyLoss(weight=w)(ref_logits, t_torch.to(cuda))
+    ref.backward()
+    crit = WeightedCrossEntropy(w)
+    loss = crit(logits, t_ours.to(cuda).int())
+    grad = crit.backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * abs(float(ref))
+    assert float((grad - ref_logits.grad).abs().max()) <= 2e-6 * float(ref_logits.grad.abs().max())
+    assert float(grad.permute(0, 2, 3, 1)[holes.to(cuda)].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
 def test_adamw_matches_torch(cuda):
     from oracle.training import init_optimizer as oracle_opt
     from flair_for_aigle_b200.flair_hub.tasks.tasks_module import init_optimizer

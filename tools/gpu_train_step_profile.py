@@ -22,5 +22,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
 tot = sum(e.device_time_total for e in rows)
 print(f"total device time {tot / 1e3:.1f} ms")
-for e in rows[:28]:
-    print(f"{e.device_time_total / 1e3:9.2f} ms {100 * e.device_time_total / tot:5.1f}%  x{e.count:5d}  {e.key[:90]}")
+for e in rows[:45]:
+    print(f"{e.device_time_total / 1e3:9.2f} ms {100 * e.device_time_total / tot:5.1f}%  x{e.count:5d}  {e.key[:110]}")
