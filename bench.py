@@ -514,7 +514,7 @@ def main() -> None:
         traffic = None
         try:        # dram read+write per launch of the dominant GEMM shape, from the committed ncu --set full capture
             if ARCH == "convnextv2_base-unet":
-                with open(os.path.join(ROOT, "profiles", "r1_ncu_gemm_traffic.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r2_ncu_gemm_traffic.json")) as f:
                     tj = json.load(f)
                 traffic = {"bytes_per_launch": tj["dram_bytes_per_launch"],
                            "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"], "kernel": tj["kernel"],

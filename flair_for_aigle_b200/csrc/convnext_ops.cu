@@ -456,61 +456,13 @@ __global__ void __launch_bounds__(256) scale_weights_kernel(const op_t* __restri
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(b) * N * K + i8) = o;
 }
 
-// grn_apply + scale_weights in one kernel: out[b][n][k] = w[n][k] * (1 + gamma[k] * Gx[b][k] * inv_b) with inv_b recomputed by
-// every thread from the <= 64 block sums of grn_gx_kernel (same order as grn_apply_kernel, so scale and weights are
-// bit-identical to the three-launch path).  One launch and one [B][K] round trip fewer per ConvNeXt block.
-// (A single-launch variant that also recomputed Gx per CTA from the fc1 partials was correct but 1.7x SLOWER than the
-// three kernels it replaced: the per-sample statistics are a serial chain of dependent loads, and the few large CTAs had
-// too little memory parallelism for the 77 MB of weights -- measured 12.6 % vs 7.6 % of the step, removed.)
-constexpr int GSW_U = 4;      // 16-byte chunks per thread: the per-CTA mean is amortised over 4 x 256 x 8 weights
-__global__ void __launch_bounds__(256) grn_apply_scale_weights_kernel(const op_t* __restrict__ w,
-                                                                      const float* __restrict__ gx,
-                                                                      const float* __restrict__ psum, int nblk,
-                                                                      const float* __restrict__ gamma, float eps,
-                                                                      op_t* __restrict__ out, int N, int K) {
-  __shared__ float s_inv;
-  const int b = blockIdx.y;
-  const size_t total = static_cast<size_t>(N) * K;
-  const size_t base = (static_cast<size_t>(blockIdx.x) * GSW_U * 256 + threadIdx.x) * 8;
-  // the operand loads go out first; one thread meanwhile adds the block sums in grn_apply_kernel's order
-  // (a first version had EVERY thread add them: 32 extra loads per 8 weights, 11 % of the step instead of 7.6 %)
-  uint4 raw[GSW_U];
-#pragma unroll
-  for (int u = 0; u < GSW_U; ++u) {
-    const size_t i8 = base + static_cast<size_t>(u) * 256 * 8;
-    raw[u] = i8 < total ? *reinterpret_cast<const uint4*>(w + i8) : make_uint4(0, 0, 0, 0);
-  }
-  if (threadIdx.x == 0) {
-    float tot = 0.f;
-    for (int i = 0; i < nblk; ++i) tot += psum[b * nblk + i];
-    s_inv = 1.0f / (tot / K + eps);
-  }
-  __syncthreads();
-  const float inv = s_inv;
-#pragma unroll
-  for (int u = 0; u < GSW_U; ++u) {
-    const size_t i8 = base + static_cast<size_t>(u) * 256 * 8;
-    if (i8 >= total) break;
-    const int k = static_cast<int>(i8 % K);
-    const float4 g0 = *reinterpret_cast<const float4*>(gx + static_cast<size_t>(b) * K + k);
-    const float4 g1 = *reinterpret_cast<const float4*>(gx + static_cast<size_t>(b) * K + k + 4);
-    const float4 m0 = __ldg(reinterpret_cast<const float4*>(gamma + k));
-    const float4 m1 = __ldg(reinterpret_cast<const float4*>(gamma + k + 4));
-    const float4 s0 = make_float4(1.0f + m0.x * g0.x * inv, 1.0f + m0.y * g0.y * inv, 1.0f + m0.z * g0.z * inv,
-                                  1.0f + m0.w * g0.w * inv);
-    const float4 s1 = make_float4(1.0f + m1.x * g1.x * inv, 1.0f + m1.y * g1.y * inv, 1.0f + m1.z * g1.z * inv,
-                                  1.0f + m1.w * g1.w * inv);
-    const op2_t* wp = reinterpret_cast<const op2_t*>(&raw[u]);
-    uint4 o;
-    op2_t t;
-    float2 f;
-    f = op22ff(wp[0]); t = ff2op2(f.x * s0.x, f.y * s0.y); o.x = *reinterpret_cast<uint32_t*>(&t);
-    f = op22ff(wp[1]); t = ff2op2(f.x * s0.z, f.y * s0.w); o.y = *reinterpret_cast<uint32_t*>(&t);
-    f = op22ff(wp[2]); t = ff2op2(f.x * s1.x, f.y * s1.y); o.z = *reinterpret_cast<uint32_t*>(&t);
-    f = op22ff(wp[3]); t = ff2op2(f.x * s1.z, f.y * s1.w); o.w = *reinterpret_cast<uint32_t*>(&t);
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(b) * total + i8) = o;
-  }
-}
+// Round 2 tried twice to shorten the GRN side path (grn_gx + grn_apply + scale_weights = 7.6 % of the step) and measured
+// both variants as no faster, so the three small kernels stay:
+//  (1) ONE launch that also recomputed Gx per CTA from the fc1 partials: bit-identical, but 12.6 % of the step -- the
+//      per-sample statistics are a serial chain of dependent loads, and a few large CTAs had too little memory parallelism
+//      for the 77 MB of scaled weights;
+//  (2) grn_apply folded into scale_weights (scale = 1 + gamma * Gx * inv computed per element): bit-identical, 8.1 % -- the
+//      kernel is bound by its 77 MB of writes (3.3 TB/s), and the extra Gx / gamma reads cost what the saved launch gave.
 
 // h[m][k] = bf16(h[m][k] * scale[m / rows_per_sample][k]) in place
 __global__ void __launch_bounds__(256) scale_rows_kernel(op_t* __restrict__ h, const float* __restrict__ scale,
@@ -735,24 +687,6 @@ extern "C" int fz_scale_weights(const void* w_bf16, const float* scale, void* ou
   dim3 grid(static_cast<unsigned>((n8 + 255) / 256), B);
   scale_weights_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const op_t*>(w_bf16), scale, reinterpret_cast<op_t*>(out_bf16), N, K);
-  FZ_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int fz_grn_scale_weights(const float* sumsq_partial, int tiles_per_sample, const float* gamma, const void* w16,
-                                    void* out16, float* gx_scratch, float* psum_scratch, int B, int N, int K, float eps,
-                                    void* stream) {
-  using namespace fz;
-  FZ_REQUIRE(tiles_per_sample >= 1 && K >= 64 && K % 64 == 0, "fz_grn_scale_weights: bad arguments tps=%d K=%d (K %% 64)",
-             tiles_per_sample, K);
-  FZ_REQUIRE(N >= 1 && gx_scratch != nullptr && psum_scratch != nullptr,
-             "fz_grn_scale_weights: scratch buffers (B*K and B*K/64 floats) required");
-  if (B <= 0) return 0;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  grn_gx_kernel<<<dim3(K / 64, B), 256, 0, st>>>(sumsq_partial, tiles_per_sample, gx_scratch, psum_scratch, K);
-  const size_t n8 = static_cast<size_t>(N) * K / 8;
-  grn_apply_scale_weights_kernel<<<dim3(static_cast<unsigned>((n8 + GSW_U * 256 - 1) / (GSW_U * 256)), B), 256, 0, st>>>(
-      reinterpret_cast<const op_t*>(w16), gx_scratch, psum_scratch, K / 64, gamma, eps, reinterpret_cast<op_t*>(out16), N, K);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

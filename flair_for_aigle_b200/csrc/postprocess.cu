@@ -120,25 +120,41 @@ __device__ __forceinline__ int argmax_first(const float (&v)[MAX_CLS], int n_cls
   return best;
 }
 
+// softmax over the classes of one pixel.  ex2.approx (2^-22 relative) and ONE reciprocal instead of 19 expf() + 19 IEEE
+// divisions: the class_prob / accumulate kernels were instruction-bound, not memory-bound (round 2: 576 GB/s with expf and
+// '/'), and the result feeds a uint8 (1/255 steps) or an fp32 canvas compared at 2e-6 absolute.
 __device__ __forceinline__ void softmax_inplace(float (&v)[MAX_CLS], int n_cls) {
   float mx = v[0];
 #pragma unroll
   for (int c = 1; c < MAX_CLS; ++c)
     if (c < n_cls) mx = fmaxf(mx, v[c]);
   float sum = 0.0f;
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float mxl = mx * LOG2E;
 #pragma unroll
   for (int c = 0; c < MAX_CLS; ++c)
     if (c < n_cls) {
-      v[c] = expf(v[c] - mx);
-      sum += v[c];
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v[c], LOG2E, -mxl)));
+      v[c] = e;
+      sum += e;
     }
+  const float inv = 1.0f / sum;
 #pragma unroll
   for (int c = 0; c < MAX_CLS; ++c)
-    if (c < n_cls) v[c] = v[c] / sum;
+    if (c < n_cls) v[c] = v[c] * inv;
 }
 
 constexpr int PP_THREADS = 128;
 constexpr int PP_ROWS = 4;  // rows of the window per CTA
+
+// Which tiles of the call a launch covers: n == 0 -> tile = blockIdx.x; else tile = idx[blockIdx.x] (a conflict-free group of
+// the accumulating variant, passed by value: no device-side index buffer, capturable in a CUDA graph).
+constexpr int TL_MAX = 96;
+struct TileList {
+  int n;
+  uint8_t idx[TL_MAX];
+};
 
 // MODE 0: argmax -> uint8 [H][W]; 1: round(softmax*255) -> uint8 [n_cls][H][W];
 // 2: canvas[n_cls][H][W] += w * softmax
@@ -148,8 +164,8 @@ __global__ void __launch_bounds__(PP_THREADS) crop_kernel(const T* __restrict__ 
                                                           const int32_t* __restrict__ own,
                                                           const float* __restrict__ weight, uint8_t* __restrict__ out8,
                                                           float* __restrict__ canvas, int H, int W,
-                                                          const int32_t* __restrict__ zmap) {
-  const int t = blockIdx.x;
+                                                          const int32_t* __restrict__ zmap, const TileList tl) {
+  const int t = tl.n ? tl.idx[blockIdx.x] : blockIdx.x;
   const TileWin win = tile_window(plan, own, t, margin);
   if (win.h <= 0 || win.w <= 0) return;
   const int row_begin = blockIdx.y * PP_ROWS;
@@ -190,10 +206,90 @@ __global__ void __launch_bounds__(PP_THREADS) crop_kernel(const T* __restrict__ 
   }
 }
 
+// fp32 logits, no zoom: 4 consecutive pixels per thread -- float4 loads of every class plane (NCHW) and 4-byte / 16-byte
+// stores per output plane instead of 19 single-byte (MODE 1) or 4-byte (MODE 2) accesses per pixel.  Round 2 measured the
+// one-pixel-per-thread kernel at 576 GB/s (class_prob planes) and 183 GB/s (accumulate, one launch per tile).
+// MODE 1: round(softmax * 255) -> uint8 [n_cls][H][W];  MODE 2: canvas[n_cls][H][W] += w * softmax.
+constexpr int PV_THREADS = 128;
+template <int LAYOUT, int MODE>
+__global__ void __launch_bounds__(PV_THREADS) crop_vec4_kernel(const float* __restrict__ logits, int n_cls, int cstride, int P,
+                                                               int margin, const int32_t* __restrict__ plan,
+                                                               const int32_t* __restrict__ own,
+                                                               const float* __restrict__ weight, uint8_t* __restrict__ out8,
+                                                               float* __restrict__ canvas, int H, int W, const TileList tl) {
+  const int t = tl.n ? tl.idx[blockIdx.x] : blockIdx.x;
+  const TileWin win = tile_window(plan, own, t, margin);
+  if (win.h <= 0 || win.w <= 0) return;
+  const int gw = (win.w + 3) >> 2;                      // groups of 4 pixels per row
+  const int g = blockIdx.y * PV_THREADS + threadIdx.x;
+  if (g >= gw * win.h) return;
+  const int ry = g / gw, rx = (g - ry * gw) * 4;
+  const int npx = min(4, win.w - rx);
+  const int y = win.y0 + ry, x = win.x0 + rx;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t opix = static_cast<size_t>(win.r0 + ry) * W + win.c0 + rx;
+  const int S = P - 2 * margin;
+  float v[4][MAX_CLS];
+  const size_t iplane = static_cast<size_t>(P) * P;
+  const float* ibase = logits + (static_cast<size_t>(t) * n_cls * P + y) * P + x;      // NCHW
+  const bool vec_in = LAYOUT == FZ_NCHW && npx == 4 && ((reinterpret_cast<uintptr_t>(ibase) & 15) == 0) && (iplane % 4 == 0);
+  if (vec_in) {
+#pragma unroll
+    for (int c = 0; c < MAX_CLS; ++c)
+      if (c < n_cls) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(ibase + c * iplane));
+        v[0][c] = q.x; v[1][c] = q.y; v[2][c] = q.z; v[3][c] = q.w;
+      }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < npx) load_pixel<float, LAYOUT>(logits, t, n_cls, cstride, P, y, x + j, v[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < npx) softmax_inplace(v[j], n_cls);
+  if (MODE == 1) {
+    const bool vec_out = npx == 4 && ((opix & 3) == 0) && (plane % 4 == 0);
+#pragma unroll
+    for (int c = 0; c < MAX_CLS; ++c)
+      if (c < n_cls) {
+        uint8_t* o = out8 + c * plane + opix;
+        if (vec_out) {
+          *reinterpret_cast<uchar4*>(o) = make_uchar4(static_cast<uint8_t>(rintf(v[0][c] * 255.0f)), static_cast<uint8_t>(rintf(v[1][c] * 255.0f)),
+                                                      static_cast<uint8_t>(rintf(v[2][c] * 255.0f)), static_cast<uint8_t>(rintf(v[3][c] * 255.0f)));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < npx) o[j] = static_cast<uint8_t>(rintf(v[j][c] * 255.0f));
+        }
+      }
+  } else {
+    float wg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wg[j] = (weight && j < npx) ? weight[(y - margin) * S + (x + j - margin)] : 1.0f;
+    const bool vec_out = npx == 4 && ((opix & 3) == 0) && (plane % 4 == 0);
+#pragma unroll
+    for (int c = 0; c < MAX_CLS; ++c)
+      if (c < n_cls) {
+        float* o = canvas + c * plane + opix;
+        if (vec_out) {
+          float4 a = *reinterpret_cast<float4*>(o);
+          a.x += wg[0] * v[0][c]; a.y += wg[1] * v[1][c]; a.z += wg[2] * v[2][c]; a.w += wg[3] * v[3][c];
+          *reinterpret_cast<float4*>(o) = a;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < npx) o[j] += wg[j] * v[j][c];
+        }
+      }
+  }
+}
+
 template <int MODE>
 static int launch_crop(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
                        int margin, const int32_t* plan, const int32_t* own, const float* weight, uint8_t* out8,
-                       float* canvas, int H, int W, cudaStream_t st, const int32_t* zmap = nullptr, int zoomed = 0) {
+                       float* canvas, int H, int W, cudaStream_t st, const int32_t* zmap = nullptr, int zoomed = 0,
+                       const TileList* tiles = nullptr) {
   FZ_REQUIRE(n_cls >= 1 && n_cls <= MAX_CLS, "crop kernels support 1..%d classes, got %d", MAX_CLS, n_cls);
   FZ_REQUIRE(P > 2 * margin && margin >= 0, "bad patch/margin %d/%d", P, margin);
   FZ_REQUIRE(dtype == FZ_F32 || dtype == FZ_BF16 || dtype == FZ_F16, "bad dtype %d", dtype);
@@ -207,10 +303,26 @@ static int launch_crop(const void* logits, int dtype, int layout, int cstride, i
   if (n_tiles <= 0) return 0;
   const int S = zmap ? zoomed : P - 2 * margin;      // rows a tile's write window can have
   FZ_REQUIRE(S >= 1, "bad zoomed window size %d", S);
-  dim3 grid(n_tiles, (S + PP_ROWS - 1) / PP_ROWS), block(PP_THREADS);
+  TileList tl;
+  tl.n = 0;
+  if (tiles) tl = *tiles;
+  const int n_launch = tl.n ? tl.n : n_tiles;
+  if ((MODE == 1 || MODE == 2) && dtype == FZ_F32 && zmap == nullptr && (layout == FZ_NCHW || layout == FZ_NHWC)) {
+    // fp32 logits without zoom: the 4-pixels-per-thread kernel
+    dim3 vgrid(n_launch, (((S + 3) / 4) * S + PV_THREADS - 1) / PV_THREADS);
+    if (layout == FZ_NCHW)
+      crop_vec4_kernel<FZ_NCHW, MODE><<<vgrid, PV_THREADS, 0, st>>>(static_cast<const float*>(logits), n_cls, cstride, P, margin,
+                                                                    plan, own, weight, out8, canvas, H, W, tl);
+    else
+      crop_vec4_kernel<FZ_NHWC, MODE><<<vgrid, PV_THREADS, 0, st>>>(static_cast<const float*>(logits), n_cls, cstride, P, margin,
+                                                                    plan, own, weight, out8, canvas, H, W, tl);
+    FZ_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  dim3 grid(n_launch, (S + PP_ROWS - 1) / PP_ROWS), block(PP_THREADS);
 #define FZ_LAUNCH(T, LAY)                                                                                       \
   crop_kernel<T, LAY, MODE><<<grid, block, 0, st>>>(reinterpret_cast<const T*>(logits), n_cls, cstride, P, margin, \
-                                                    plan, own, weight, out8, canvas, H, W, zmap)
+                                                    plan, own, weight, out8, canvas, H, W, zmap, tl)
   if (layout == FZ_NHWC_UP4) FZ_LAUNCH(float, FZ_NHWC_UP4);
   else if (dtype == FZ_F32 && layout == FZ_NCHW) FZ_LAUNCH(float, FZ_NCHW);
   else if (dtype == FZ_F32) FZ_LAUNCH(float, FZ_NHWC);
@@ -294,7 +406,38 @@ namespace fz {
 // caller batches by grid column; to stay safe for any batch we launch tile by tile.
 static int accumulate_tiles(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
                             int margin, const int32_t* plan, const float* weight, float* canvas, int H, int W,
-                            cudaStream_t st, const int32_t* zmap, int zoomed) {
+                            cudaStream_t st, const int32_t* zmap, int zoomed, const int32_t* plan_host) {
+  if (plan_host != nullptr && n_tiles > 1 && n_tiles <= TL_MAX) {
+    // Overlapping write windows must be accumulated one after the other (no atomics: the canvas is bit-reproducible), but
+    // most windows of a tile grid are disjoint.  Level the tiles: level(t) = 1 + max level of an EARLIER tile whose window
+    // intersects t's; tiles of one level never overlap and go into ONE launch, levels run in order -- so every pixel still
+    // receives its contributions in tile order, i.e. the result equals the one-launch-per-tile sequence bit for bit.
+    const int S = zmap ? zoomed : P - 2 * margin;
+    int level[TL_MAX], n_levels = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int32_t* pt = plan_host + 6 * t;
+      const int th = zmap ? pt[4] : (pt[4] < S ? pt[4] : S), tw = zmap ? pt[5] : (pt[5] < S ? pt[5] : S);
+      int lv = 0;
+      for (int u = 0; u < t; ++u) {
+        const int32_t* pu = plan_host + 6 * u;
+        const int uh = zmap ? pu[4] : (pu[4] < S ? pu[4] : S), uw = zmap ? pu[5] : (pu[5] < S ? pu[5] : S);
+        const bool apart = pt[2] + th <= pu[2] || pu[2] + uh <= pt[2] || pt[3] + tw <= pu[3] || pu[3] + uw <= pt[3];
+        if (!apart && th > 0 && tw > 0 && uh > 0 && uw > 0 && level[u] + 1 > lv) lv = level[u] + 1;
+      }
+      level[t] = lv;
+      if (lv + 1 > n_levels) n_levels = lv + 1;
+    }
+    for (int lv = 0; lv < n_levels; ++lv) {
+      TileList tl;
+      tl.n = 0;
+      for (int t = 0; t < n_tiles; ++t)
+        if (level[t] == lv) tl.idx[tl.n++] = static_cast<uint8_t>(t);
+      int rc = launch_crop<2>(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, nullptr, weight, nullptr, canvas,
+                              H, W, st, zmap, zoomed, &tl);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   for (int t = 0; t < n_tiles; ++t) {
     int rc = launch_crop<2>(logits, dtype, layout, cstride, 1, n_cls, P, margin, plan, nullptr, weight, nullptr, canvas, H,
                             W, st, zmap, zoomed);
@@ -312,18 +455,18 @@ static int accumulate_tiles(const void* logits, int dtype, int layout, int cstri
 }  // namespace fz
 
 extern "C" int fz_crop_softmax_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles,
-                                          int n_cls, int P, int margin, const int32_t* plan, const float* weight,
-                                          float* canvas, int H, int W, void* stream) {
+                                          int n_cls, int P, int margin, const int32_t* plan, const int32_t* plan_host,
+                                          const float* weight, float* canvas, int H, int W, void* stream) {
   return fz::accumulate_tiles(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, weight, canvas, H, W,
-                              reinterpret_cast<cudaStream_t>(stream), nullptr, 0);
+                              reinterpret_cast<cudaStream_t>(stream), nullptr, 0, plan_host);
 }
 
 extern "C" int fz_crop_zoom_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls,
-                                       int P, int margin, const int32_t* plan, const int32_t* zmap, int zoomed,
-                                       float* canvas, int H, int W, void* stream) {
+                                       int P, int margin, const int32_t* plan, const int32_t* plan_host, const int32_t* zmap,
+                                       int zoomed, float* canvas, int H, int W, void* stream) {
   FZ_REQUIRE(zmap != nullptr && zoomed >= 1, "fz_crop_zoom_accumulate: zoom map required");
   return fz::accumulate_tiles(logits, dtype, layout, cstride, n_tiles, n_cls, P, margin, plan, nullptr, canvas, H, W,
-                              reinterpret_cast<cudaStream_t>(stream), zmap, zoomed);
+                              reinterpret_cast<cudaStream_t>(stream), zmap, zoomed, plan_host);
 }
 
 extern "C" int fz_canvas_argmax(const float* canvas, int n_cls, int64_t n_px, uint8_t* labels, float* confidence,

@@ -193,17 +193,16 @@ class ConvNeXtV2UNetEngine:
                 nv.dwconv7_ln(x, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], y)
                 self._gemm(y.view(M, C), blk["fc1_w"], nv.EPI_GELU_SUMSQ, bias=blk["fc1_b"], sumsq=sumsq, out=hbuf,
                            rows_per_sample=rps)
+                nv.grn_scale(sumsq, tps, blk["grn_g"], scale, scratch=self.grn_scratch)
                 # fc2 walks its tiles backwards: fc1 has just streamed the hidden tensor out (larger than L2 in
                 # stages 0-2), so its newest rows are still cached; it then finishes on the rows the next
                 # block's dwconv starts with.  Measured -11 % on the stage-2 fc1+fc2 pair.
                 fc2_mode = nv.EPI_RESID_F32 | nv.EPI_REVERSE_TILES
                 if self.use_wscale[i]:
                     w2s = self.w2s[:n * 4 * C * C].view(n, C, 4 * C)
-                    # GRN statistics, then the scale applied while the per-sample weights are written: 2 launches (was 3)
-                    nv.grn_scale_weights(sumsq, tps, blk["grn_g"], blk["fc2_w"], w2s, gx=scale, scratch=self.grn_scratch)
+                    nv.scale_weights(blk["fc2_w"], scale, w2s)
                     self._gemm(hbuf, w2s, fc2_mode, bias=blk["fc2_b"], resid=xm, out=xm, rows_per_sample=rps)
                 else:
-                    nv.grn_scale(sumsq, tps, blk["grn_g"], scale, scratch=self.grn_scratch)
                     nv.scale_rows(hbuf, scale, rps)
                     self._gemm(hbuf, blk["fc2_w"], fc2_mode, bias=blk["fc2_b"], resid=xm, out=xm, rows_per_sample=rps)
 

@@ -291,7 +291,8 @@ def inference(model, dataloader, tiles_gdf, config: Dict, raster_img):
     ib = {'left': b.left, 'bottom': b.bottom, 'right': b.right, 'top': b.top}
     ref_res = config['reference_resolution']
     out_res = config.get('output_px_meters', ref_res)
-    plan = torch.from_numpy(tile_plan(tiles_gdf, ib, ref_res, P, margin, out_res)).to(device)
+    plan_np = tile_plan(tiles_gdf, ib, ref_res, P, margin, out_res)
+    plan = torch.from_numpy(plan_np).to(device)
     if needs_rescale:
         # inference.py:515-523,538-539: the zoomed tiles land on the out_res grid, whose size the reference computes at
         # :538-539 (its canvas keeps the input shape, which only fits when out_res >= ref_res); the canvas here IS that grid
@@ -306,11 +307,13 @@ def inference(model, dataloader, tiles_gdf, config: Dict, raster_img):
     for batch in _iter_batches(dataloader, dataset, model, config, device):
         idx = batch.pop('index').to(device).flatten().long()
         logits_tasks, _ = model(batch)
+        host_rows = plan_np[idx.cpu().numpy()]          # the batch's windows on the host: disjoint windows share a launch
         for _, logits in logits_tasks.items():
             if needs_rescale:
-                nv.crop_zoom_accumulate(logits, nv.NCHW, margin, plan[idx].contiguous(), zmap_d, canvas)
+                nv.crop_zoom_accumulate(logits, nv.NCHW, margin, plan[idx].contiguous(), zmap_d, canvas, plan_host=host_rows)
             else:
-                nv.crop_softmax_accumulate(logits, nv.NCHW, margin, plan[idx].contiguous(), None, canvas)
+                nv.crop_softmax_accumulate(logits, nv.NCHW, margin, plan[idx].contiguous(), None, canvas,
+                                           plan_host=host_rows)
     torch.cuda.synchronize(device)
     transform = raster_img.profile['transform']
     if needs_rescale:   # same origin, out_res pixels (init_outputs' profile, inference.py:186-194)

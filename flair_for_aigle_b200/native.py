@@ -70,8 +70,8 @@ _SIGNATURES = {
     "fz_gather_tiles_u8": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp],
     "fz_crop_argmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "fz_crop_softmax_write": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
-    "fz_crop_softmax_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
-    "fz_crop_zoom_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp],
+    "fz_crop_softmax_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "fz_crop_zoom_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
     "fz_crop_zoom_write": [_i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
     "fz_canvas_argmax": [_vp, _i, _i64, _vp, _vp, _vp],
     "fz_convert": [_vp, _i, _i, _i, _i, _vp, _vp],
@@ -88,7 +88,6 @@ _SIGNATURES = {
     "fz_grn_scale": [_vp, _i, _vp, _vp, _vp, _i, _i, ctypes.c_float, _vp],
     "fz_scale_weights": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_scale_rows": [_vp, _vp, _i64, _i, _i, _vp],
-    "fz_grn_scale_weights": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_upsample2_concat": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_catconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "fz_upconv3x3_bn_relu": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
@@ -284,19 +283,31 @@ def crop_zoom_write(mode: int, logits, layout, margin, plan, own, zmap, out_rast
            "fz_crop_zoom_write")
 
 
-def crop_softmax_accumulate(logits, layout, margin, plan, weight, canvas, n_cls=None):
+def _host_plan(plan_host, n):
+    """int32 [n,6] numpy copy of the plan for the host-side levelling of overlapping windows (None = one launch per tile)."""
+    if plan_host is None:
+        return None, None
+    import numpy as np
+    arr = np.ascontiguousarray(np.asarray(plan_host, dtype=np.int32).reshape(n, 6))
+    return arr, ctypes.c_void_p(arr.ctypes.data)
+
+
+def crop_softmax_accumulate(logits, layout, margin, plan, weight, canvas, n_cls=None, plan_host=None):
+    """plan_host: the same plan as a numpy array; with it, tiles whose windows do not overlap share a launch."""
     n, c, p, cs = _logits_geom(logits, layout, n_cls)
     H, W = canvas.shape[-2:]
-    _check(lib().fz_crop_softmax_accumulate(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan),
+    keep, php = _host_plan(plan_host, n)
+    _check(lib().fz_crop_softmax_accumulate(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan), php,
                                             _ptr(weight), _ptr(canvas), H, W, _stream()),
            "fz_crop_softmax_accumulate")
 
 
-def crop_zoom_accumulate(logits, layout, margin, plan, zmap, canvas, n_cls=None):
+def crop_zoom_accumulate(logits, layout, margin, plan, zmap, canvas, n_cls=None, plan_host=None):
     """canvas += softmax(zoomed cropped logits): the accumulating variant on the rescaled grid (inference.py:515-562)."""
     n, c, p, cs = _logits_geom(logits, layout, n_cls)
     H, W = canvas.shape[-2:]
-    _check(lib().fz_crop_zoom_accumulate(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan), _ptr(zmap),
+    keep, php = _host_plan(plan_host, n)
+    _check(lib().fz_crop_zoom_accumulate(_ptr(logits), _dt(logits), layout, cs, n, c, p, margin, _ptr(plan), php, _ptr(zmap),
                                          int(zmap.numel()), _ptr(canvas), H, W, _stream()),
            "fz_crop_zoom_accumulate")
 
@@ -426,22 +437,6 @@ def scale_weights(w, scale, out):
     _op16(w, out)
     with _Timed('scale_weights', B=B, N=N, K=K):
         _check(lib().fz_scale_weights(_ptr(w), _ptr(scale), _ptr(out), B, N, K, _stream()), "fz_scale_weights")
-    return out
-
-
-def grn_scale_weights(partial, tiles_per_sample, gamma, w, out, gx=None, scratch=None, eps=1e-6):
-    """GRN statistics + per-sample scaled fc2 weights, two launches: partial f32 [B*tps, K], w [N, K] -> out [B, N, K].
-    gx: f32 [B, K] scratch (receives Gx), scratch: f32 [B*K/64]."""
-    N, K = w.shape
-    B = out.shape[0]
-    _op16(w, out)
-    if gx is None:
-        gx = torch.empty((B, K), dtype=torch.float32, device=w.device)
-    if scratch is None:
-        scratch = torch.empty(B * K // 64, dtype=torch.float32, device=w.device)
-    with _Timed('grn_scale_weights', B=B, N=N, K=K):
-        _check(lib().fz_grn_scale_weights(_ptr(partial), tiles_per_sample, _ptr(gamma), _ptr(w), _ptr(out), _ptr(gx),
-                                          _ptr(scratch), B, N, K, eps, _stream()), "fz_grn_scale_weights")
     return out
 
 

@@ -102,14 +102,18 @@ int fz_crop_zoom_write(int mode, const void* logits, int dtype, int layout, int 
  * reference's raster_logits) += weight(y,x) * softmax(cropped logits).
  * weight: float32 [P-2m][P-2m] or NULL (=1). */
 int fz_crop_softmax_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
-                               int margin, const int32_t* plan, const float* weight, float* canvas, int H, int W,
-                               void* stream);
+                               int margin, const int32_t* plan, const int32_t* plan_host, const float* weight, float* canvas,
+                               int H, int W, void* stream);
+/* plan_host: the same plan in HOST memory, or NULL.  Overlapping write windows have to be accumulated one after the other (no
+ * atomics: the canvas is bit-reproducible).  Without the host copy every tile is its own launch; with it (n_tiles <= 96) the
+ * tiles are levelled on the host -- a tile's level is one more than the highest level of an earlier tile it overlaps -- and
+ * each level is ONE launch, so every pixel still receives its contributions in tile order: same bits, a few launches. */
 /* The same accumulation on the rescaled output grid (inference.py:515-523 then :525-562): the cropped logits are zoomed
  * with zmap (see fz_crop_zoom_write; constant-fill pixels carry zero logits, i.e. a uniform softmax) before the softmax;
  * plan is in OUTPUT pixels. */
 int fz_crop_zoom_accumulate(const void* logits, int dtype, int layout, int cstride, int n_tiles, int n_cls, int P,
-                            int margin, const int32_t* plan, const int32_t* zmap, int zoomed, float* canvas, int H, int W,
-                            void* stream);
+                            int margin, const int32_t* plan, const int32_t* plan_host, const int32_t* zmap, int zoomed,
+                            float* canvas, int H, int W, void* stream);
 /* inference.py:566-572: labels = argmax_c canvas (uint8), confidence = max_c canvas (float32,
  * may be NULL).  canvas is [n_cls][n_px]. */
 int fz_canvas_argmax(const float* canvas, int n_cls, int64_t n_px, uint8_t* labels, float* confidence, void* stream);
@@ -186,11 +190,6 @@ int fz_ln2d_s2d_copy(const float* x, const float* ln_w, const float* ln_b, void*
 int fz_grn_scale(const float* sumsq_partial, int tiles_per_sample, const float* gamma, float* scale, float* scratch,
                  int B, int K, float eps, void* stream); /* scratch: B*K/64 floats */
 int fz_scale_weights(const void* w_bf16, const float* scale, void* out_bf16, int B, int N, int K, void* stream);
-/* fz_grn_scale + fz_scale_weights in two launches instead of three (the scale is applied while the weights are scaled):
- * out16 [B][N][K] = w16 [N][K] * scale[b][k], scale as in fz_grn_scale.  gx_scratch: float [B][K] (receives Gx),
- * psum_scratch: float [B][K/64].  Bit-identical to the two calls it replaces. */
-int fz_grn_scale_weights(const float* sumsq_partial, int tiles_per_sample, const float* gamma, const void* w16, void* out16,
-                         float* gx_scratch, float* psum_scratch, int B, int N, int K, float eps, void* stream);
 int fz_scale_rows(void* h_bf16, const float* scale, int64_t M, int K, int rows_per_sample, void* stream);
 
 /* ---------------------------------------------------------------- U-Net decoder pieces

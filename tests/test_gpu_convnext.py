@@ -105,27 +105,6 @@ def test_grn_scale_and_scalers(cuda):
     assert torch.equal(h2, (h.float().view(B, rps, K) * scale[:, None, :]).to(OP).view(-1, K))
 
 
-@pytest.mark.parametrize("B,K,N,rps", [(3, 512, 128, 256), (37, 2048, 512, 1024), (5, 1024, 256, 4096), (2, 512, 128, 16384),
-                                       (1, 4096, 1024, 256), (4, 256, 64, 128 * 7)])
-def test_fused_grn_scale_weights_is_bit_identical_to_the_three_kernel_path(cuda, B, K, N, rps):
-    """fz_grn_scale_weights (Gx, then scale applied inside the weight scaler) == fz_grn_scale (two launches) +
-    fz_scale_weights, bit for bit."""
-    from flair_for_aigle_b200 import native as nv
-    torch.manual_seed(B + K)
-    tps = rps // 128
-    partial = (torch.rand(B * tps, K, device=cuda) * 300 + 1).contiguous()
-    gamma = torch.randn(K, device=cuda) * 0.5
-    w = torch.randn(N, K, device=cuda).to(OP)
-    scale = torch.empty(B, K, device=cuda)
-    nv.grn_scale(partial, tps, gamma, scale)
-    want = torch.empty(B, N, K, dtype=OP, device=cuda)
-    nv.scale_weights(w, scale, want)
-    got = torch.full((B, N, K), float("nan"), dtype=OP, device=cuda)
-    nv.grn_scale_weights(partial, tps, gamma, w, got)
-    torch.cuda.synchronize()
-    assert torch.equal(got, want)
-
-
 @pytest.mark.parametrize("ta,ts", [(torch.float32, torch.float32), (OP, torch.float32),
                                    (OP, None)])
 def test_upsample2_concat(cuda, ta, ts):

@@ -81,6 +81,8 @@ rows = [
     ("crop_softmax_write fp32 NCHW -> 19 uint8 planes (76 B + 19 B / output px)",
      lambda: nv.crop_softmax_write(l32, nv.NCHW, M, plan_d, own_d, out_planes), px_out * 95),
     ("crop_softmax_accumulate fp32 NCHW -> fp32 canvas (76 B + 76 B read + 76 B write / output px)",
+     lambda: nv.crop_softmax_accumulate(l32, nv.NCHW, M, plan_d, None, canvas, plan_host=plan), px_out * 228),
+    ("crop_softmax_accumulate, one launch per tile (no host plan: the round-1 behaviour)",
      lambda: nv.crop_softmax_accumulate(l32, nv.NCHW, M, plan_d, None, canvas), px_out * 228),
     ("canvas_argmax 19 x 10k x 10k fp32 -> uint8 + fp32 confidence (76 B + 5 B / px)",
      lambda: nv.canvas_argmax(canvas, want_confidence=True), ZONE * ZONE * 81),

@@ -7,7 +7,7 @@ from flair_for_aigle_b200 import native as nv
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-B = 16
+B = int(os.environ.get("B", "37"))
 if what in ("dwconv", "all"):
     for (C, H) in ((512, 32), (128, 128)):
         x = torch.randn(B, H, H, C, device=dev)
