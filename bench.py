@@ -285,6 +285,13 @@ def train_block(dev, rank: int, world: int, steps: int, warmup: int):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step, ms_ar = float(ms[0]), float(ms[1])
+    drift = 0.0
+    if world > 1:       # DDP invariant: after identical averaged updates every rank holds the same parameters
+        ref = tr.opt.arena.clone()
+        dist.broadcast(ref, 0)
+        d = (tr.opt.arena - ref).abs().max().reshape(1)
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        drift = float(d)
     peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     del tr, state
     torch.cuda.empty_cache()
@@ -297,7 +304,9 @@ def train_block(dev, rank: int, world: int, steps: int, warmup: int):
                       "AdamW, DDP all-reduce of the gradient arena; inputs from pinned host memory every step, loss read back",
             "samples_per_s": round(B * world / ms_step * 1e3, 2), "samples_per_s_per_gpu": round(B / ms_step * 1e3, 2),
             "ms_per_step": round(ms_step, 2), "steps": steps, "warmup": max(1, warmup),
-            "allreduce_ms_exposed": round(ms_ar, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+            "allreduce_ms_exposed": round(ms_ar, 3), "allreduce": "bucketed per backward group (decoder, fusion, encoder stages deepest "
+            "first), each bucket's NCCL all-reduce started on a side stream as its gradients land; exposed = what the compute "
+            "stream waited at the end", "max_parameter_difference_across_ranks": drift, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
             "loss_first_last": [round(losses[0], 4), round(losses[-1], 4)], "peak_memory_gib": round(peak_mem, 1),
             "roofline": {"bound": "tensor", "achieved": round(tflop_step / (ms_step * 1e-3), 1), "peak": peak,
                          "unit": "TFLOP/s", "frac": round(tflop_step / (ms_step * 1e-3) / peak, 4),

@@ -208,7 +208,10 @@ class ConvNeXtV2EncoderTrain:
         self.saved = (B, patches, geo)
         return feats
 
-    def backward(self, dfeats):
+    def backward(self, dfeats, emit=None):
+        """-> {parameter name: gradient}.  ``emit(group)`` (optional) is called with the gradients of each finished stage
+        (deepest first), then with the stem's: the trainer copies them into the gradient arena and starts that bucket's
+        all-reduce while the shallower stages are still running."""
         B, patches, geo = self.saved
         grads: Dict[str, torch.Tensor] = {}
         d = None
@@ -236,12 +239,16 @@ class ConvNeXtV2EncoderTrain:
                 dx, dg, dbeta = ln.backward(da)
                 grads[f"stages_{i}.downsample.0.weight"], grads[f"stages_{i}.downsample.0.bias"] = dg, dbeta
                 d = dx.view(B, h, h, cp)
+            if emit is not None:
+                emit({k: v for k, v in grads.items() if k.startswith(f"stages_{i}.")})
         du0, dg, dbeta = self.stem_ln.backward(_to_bf16(d.view(-1, self.dims[0])))
         grads["stem_1.weight"], grads["stem_1.bias"] = dg, dbeta
         du0b = _to_bf16(du0)
         dw = nv.gemm_bf16(nv.transpose_bf16(du0b), nv.transpose_bf16(patches), nv.EPI_F32)   # [C0, Kpad]
         grads["stem_0.weight"] = dw[:, :self.cin * 16].reshape(self.dims[0], self.cin, 4, 4).contiguous()
         grads["stem_0.bias"] = nv.colsum_bf16(du0b)
+        if emit is not None:
+            emit({k: v for k, v in grads.items() if k.startswith("stem_")})
         return grads
 
 

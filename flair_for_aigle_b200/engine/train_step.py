@@ -6,7 +6,10 @@ Everything numeric runs on the CUDA kernels behind the C ABI (engine/convnext_tr
 csrc/training_ops.cu, the tcgen05 GEMM); torch supplies memory, views, concatenation / slicing copies and dtype casts.
 This is the correctness-first version of SURVEY A11: the memory-bound backward kernels and the im2col convolutions are not
 tuned.  BatchNorm running statistics are updated in place like nn.BatchNorm2d does (momentum 0.1, unbiased variance); under
-torch.distributed the flat gradient arena is averaged with one NCCL all-reduce per step."""
+torch.distributed the gradients are averaged DDP-style (trainers.py:81-91): every finished group of the backward -- decoder,
+fusion convolutions, then each encoder stage, deepest first -- is copied into its (contiguous) range of the flat gradient
+arena and that range's NCCL all-reduce starts at once on a side stream, so only the last, smallest bucket (an encoder's stem)
+is exposed."""
 from typing import Dict, List
 
 import torch
@@ -28,6 +31,16 @@ class ConvNeXtUNetTrainer:
         self.buffers = {k: state[k] for k in state if k not in self.params}       # BatchNorm running statistics
         self.opt = AdamW([self.params[k] for k in self.names], lr=lr, weight_decay=weight_decay, betas=betas)
         self.criterion = WeightedCrossEntropy(class_weight)
+        self._slot = {}                                           # parameter name -> (offset, numel) in the arena
+        off = 0
+        for name in self.names:
+            k = self.params[name].numel()
+            self._slot[name] = (off, k)
+            off += k
+        self.names_index = {n: i for i, n in enumerate(self.names)}
+        self._comm_stream = None
+        self._works, self._reduced, self._leftover, self._filled, self._overlap = [], [], [], set(), False
+        self.last_allreduce_ms = 0.0
         self._build()
 
     def _build(self) -> None:
@@ -46,8 +59,44 @@ class ConvNeXtUNetTrainer:
             self.fuse = [(p[f"fusion_handler.conv_f.{i}.weight"].detach().reshape(c, -1).to(torch.bfloat16).contiguous(),
                           p[f"fusion_handler.conv_f.{i}.bias"].detach().float().contiguous()) for i, c in enumerate(self.dims)]
 
-    def forward_backward(self, batch: Dict[str, torch.Tensor]):
-        """-> (loss 0-d tensor, preds int32 (B,H,W), {parameter name: gradient})."""
+    # ------------------------------------------------------------------ gradient arena + bucketed all-reduce
+    def _distributed(self) -> bool:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _emit(self, group: Dict[str, torch.Tensor]) -> None:
+        """Copies a finished group of gradients into the arena; under torch.distributed starts the all-reduce (average) of
+        the arena range the group covers on the communication stream.  Groups cover contiguous ranges (parameters of a
+        module are adjacent in state_dict order); a group that does not is left to the final catch-all reduction."""
+        if not group:
+            return
+        lo, hi, tot = None, None, 0
+        for name, g in group.items():
+            off, k = self._slot[name]
+            self.opt.grads[self.names_index[name]].copy_(g.reshape(self.opt.grads[self.names_index[name]].shape))
+            lo = off if lo is None else min(lo, off)
+            hi = off + k if hi is None else max(hi, off + k)
+            tot += k
+            self._filled.add(name)
+        if not self._overlap:
+            return
+        if tot != hi - lo:
+            self._leftover.append((lo, hi))
+            return
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.opt.grad.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            self._works.append(dist.all_reduce(self.opt.grad[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
+        self._reduced.append((lo, hi))
+
+    def forward_backward(self, batch: Dict[str, torch.Tensor], into_arena: bool = False):
+        """-> (loss 0-d tensor, preds int32 (B,H,W), {parameter name: gradient}).  With ``into_arena`` the gradients are also
+        written to the optimizer's gradient arena group by group as the backward produces them (and all-reduced, see _emit)."""
+        emit = self._emit if into_arena else None
         feats = {m: self.enc[m].forward(batch[m]) for m in self.mods}
         cats = None
         if self.fuse is None:
@@ -65,6 +114,8 @@ class ConvNeXtUNetTrainer:
         loss, preds = self.criterion(logits, targets, task_weight=self.task_weight, want_preds=True)
         dfused, grads = self.dec.backward(self.criterion.backward())
         grads = {f"main_decoders.{self.task}.seg_model.{k}": v for k, v in grads.items()}
+        if emit:
+            emit(grads)
         if self.fuse is None:
             dfeats = {self.mods[0]: dfused}
         else:
@@ -80,33 +131,58 @@ class ConvNeXtUNetTrainer:
                     c = feats[m][i].shape[-1]
                     dfeats[m].append(dcat[:, off:off + c].float().reshape(B, h, h, c).contiguous())
                     off += c
+            if emit:
+                emit({k: v for k, v in grads.items() if k.startswith("fusion_handler.")})
         for m in self.mods:
-            g = self.enc[m].backward(dfeats[m])
-            grads.update({f"encoders.{m}.seg_model.model.{k}": v for k, v in g.items()})
+            pre = f"encoders.{m}.seg_model.model."
+            g = self.enc[m].backward(dfeats[m], emit=(lambda part, pre=pre: emit({pre + k: v for k, v in part.items()})) if emit else None)
+            grads.update({pre + k: v for k, v in g.items()})
         return loss, preds, grads
 
     def step(self, batch: Dict[str, torch.Tensor]):
-        """forward + backward + AdamW update; -> (loss before the update, preds)."""
-        loss, preds, grads = self.forward_backward(batch)
+        """forward + backward + (overlapped) gradient all-reduce + AdamW update; -> (loss before the update, preds)."""
+        self._filled, self._reduced, self._leftover, self._works = set(), [], [], []
+        self._overlap = self._distributed()
+        loss, preds, grads = self.forward_backward(batch, into_arena=True)
         # parameters the forward never touches (fusion_handler.conv_f with a single modality) have no gradient: torch's AdamW
         # leaves them alone (no weight decay either), so they are put back after the fused update
-        unused = {n: self.params[n].clone() for n in self.names if n not in grads}
-        for name, g in zip(self.names, self.opt.grads):
-            if name in grads:
-                g.copy_(grads[name].reshape(g.shape))
-            else:
-                g.zero_()
-        self.allreduce_gradients()
+        unused = {n: self.params[n].clone() for n in self.names if n not in self._filled}
+        for n in unused:
+            self.opt.grads[self.names_index[n]].zero_()
+        self._finish_allreduce()
         self.opt.step()
         for n, v in unused.items():
             self.params[n].copy_(v)
         self._build()
         return loss, preds
 
+    def _finish_allreduce(self) -> None:
+        """Waits for the buckets started during the backward and reduces whatever they did not cover (parameters without a
+        gradient, non-contiguous groups).  ``last_allreduce_ms`` = the time the compute stream had to wait, i.e. the EXPOSED
+        part of the gradient exchange."""
+        self.last_allreduce_ms = 0.0
+        if not self._overlap:
+            return
+        import torch.distributed as dist
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for w in self._works:
+            w.wait()                                  # the compute stream waits for NCCL's stream
+        covered = sorted(self._reduced)
+        pos, n = 0, self.opt.grad.numel()
+        for lo, hi in covered + [(n, n)]:
+            if lo > pos:                              # a gap no bucket covered: reduce it now (tiny: unused parameters)
+                dist.all_reduce(self.opt.grad[pos:lo], op=dist.ReduceOp.AVG)
+            pos = max(pos, hi)
+        e1.record(cur)
+        e1.synchronize()
+        self.last_allreduce_ms = e0.elapsed_time(e1)
+
     def allreduce_gradients(self) -> float:
-        """DDP (Lightning's strategy in the reference trainer): average the gradients over the ranks -- ONE NCCL all-reduce of
-        the flat gradient arena (183 M fp32 for configs[4]) over NVLink / NVSwitch.  Returns the milliseconds it took on this
-        rank (0.0 when not distributed).  Decoder BatchNorm statistics stay per-GPU (the reference uses no SyncBN)."""
+        """The un-overlapped exchange (round 1; kept for A/B): ONE blocking NCCL all-reduce of the whole gradient arena
+        (183 M fp32 for configs[4]).  Returns the milliseconds it took on this rank (0.0 when not distributed).  Decoder
+        BatchNorm statistics stay per-GPU (the reference uses no SyncBN)."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return 0.0

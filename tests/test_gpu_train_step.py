@@ -52,8 +52,10 @@ def test_training_step_vs_oracle(cuda, mods):
     total = tot_dot / (tot_a ** 0.5 * tot_b ** 0.5)
     print(f"{len(grads)} parameter gradients: whole-model cosine {total:.5f}, norm ratio {(tot_a / tot_b) ** 0.5:.4f}, "
           f"worst tensor {worst[0]:.4f} at {worst[1]}")
-    assert total > 0.97 and 0.95 < (tot_a / tot_b) ** 0.5 < 1.05
-    assert worst[0] > 0.8
+    # measured (bf16 operands, fp32 accumulate, split-K weight gradients): whole model 0.985 (one encoder) / 0.991 (two),
+    # norm ratio 1.002, worst single tensor 0.959 / 0.969 -- asserted with a small margin (round 1 asserted 0.97 / 0.8)
+    assert total > 0.98 and 0.98 < (tot_a / tot_b) ** 0.5 < 1.02
+    assert worst[0] > 0.94
 
     # a few optimizer steps on the same batch: both sides must go down the same way
     opt = init_optimizer({**ocfg, "learning_rate": 2e-4}, oracle.parameters())
@@ -89,11 +91,11 @@ def test_training_step_vs_oracle(cuda, mods):
             assert int(v) == int(sd[k]), (k, int(v), int(sd[k]))
     print(f"BatchNorm running statistics: worst |d mean| / std {worst_m:.4f} (first decoder conv {first_m:.4f}), "
           f"worst relative d var {worst_v:.4f}")
-    assert worst_m < 8e-2 and first_m < 0.6 and worst_v < 1.0
+    assert worst_m < 5e-2 and first_m < 0.4 and worst_v < 0.6            # measured 0.026 / 0.29 / 0.44
     print("loss trajectory  ours  :", " ".join(f"{v:.4f}" for v in ours))
     print("loss trajectory  oracle:", " ".join(f"{v:.4f}" for v in theirs))
     assert ours[-1] < ours[0] and theirs[-1] < theirs[0]
-    assert all(abs(a - b) <= 3e-2 * abs(b) for a, b in zip(ours, theirs))
+    assert all(abs(a - b) <= 1e-2 * abs(b) for a, b in zip(ours, theirs))        # measured <= 0.22 %
 
 
 def test_segmentation_task_training_step(cuda, tmp_path):
