@@ -245,6 +245,59 @@ def workload_string(side: int, n_tiles: int, world: int) -> str:
             + ("" if world == 1 else f"; ONE zone cut into {world} row strips (tile rows dealt contiguously, margin halo re-read)"))
 
 
+def other_config_block(dev, arch: str, side: int, steps: int, batch: int, label: str):
+    """One more BASELINE.json configuration on this GPU, device-timed like `value` (raster resident in HBM, CUDA graph, CUDA
+    events, inputs larger than L2): e.g. configs[2], Swin-base + UPerNet on a 20 000 x 20 000 zone."""
+    global ARCH
+    from flair_for_aigle_b200.engine.zonal import ZonalRunner
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model
+    from flair_for_aigle_b200.flair_zonal_detection.raster import ZoneRaster, register_raster
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import (generate_patches_from_reference, ownership_windows,
+                                                                    tile_plan)
+    from flair_for_aigle_b200.synthetic import DEFAULT_MEANS, DEFAULT_STDS, synthetic_raster_to_pinned
+    saved, ARCH = ARCH, arch
+    try:
+        tmp = tempfile.mkdtemp(prefix="fz_bench_other_")
+        wpath = os.path.join(tmp, "weights.safetensors")
+        make_weights(wpath)
+        name = f"synthetic://other_{side}"
+        register_raster(name, ZoneRaster(np.broadcast_to(np.zeros((1, 1, 1), np.uint8), (4, side, side)), LEFT, TOP, RES))
+        cfg = inf.initialize_geometry_and_resolutions(zonal_config(wpath, tmp, name, batch))
+        cfg["device"] = dev
+        tiles = generate_patches_from_reference(cfg, name, None)
+        plan = tile_plan(tiles, cfg["image_bounds"], RES, PATCH, MARGIN)
+        own = ownership_windows(plan)
+        model = build_inference_model(cfg, {"AERIAL_RGBI": PATCH}).to(dev)
+        runner = ZonalRunner(model.engine(TASK, max_batch=batch), MARGIN, use_graph=True, norm=(DEFAULT_MEANS, DEFAULT_STDS))
+        host = torch.empty((4, side, side), dtype=torch.uint8, pin_memory=True)
+        synthetic_raster_to_pinned(side, side, host, dev)
+        raster_dev, _ = runner.buffers((4, side, side), (side, side), torch.uint8)
+        raster_dev.copy_(host, non_blocking=True)
+        out = torch.zeros((side, side), dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            runner.run(raster_dev, plan, own, out)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            runner.run(raster_dev, plan, own, out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        pk, _ = peaks()
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        res = {"config": label, "value": round(side * side / 1e6 / (ms / 1e3), 2), "unit": "Mpx/s", "ms_per_step": round(ms, 2),
+               "steps": steps, "warmup": 2, "tiles": len(tiles), "tiles_per_s": round(len(tiles) / (ms / 1e3), 1),
+               "model_flops_frac_of_peak": round(ARCH_GFLOP[arch] * 1e9 * len(tiles) / (ms * 1e-3) / 1e12 / peak, 4),
+               "class_raster_checksum": int(out.to(torch.int64).sum().item())}
+        del runner, raster_dev, out, model, host
+        torch.cuda.empty_cache()
+        return res
+    finally:
+        ARCH = saved
+
+
 def train_block(dev, rank: int, world: int, steps: int, warmup: int):
     """BASELINE.json configs[4]: convnextv2_base-unet, AERIAL_RGBI (16,4,512,512) + DEM_ELEV (16,1,512,512) per GPU, weighted
     CE (classes 15-18 weight 0), AdamW(5e-5, wd 0.01), DDP gradient all-reduce (tasks_module.py:133-167,377-391;
@@ -549,6 +602,16 @@ def main() -> None:
         del runner_e
     torch.cuda.empty_cache()
 
+    others = None
+    if rank == 0 and world == 1 and not args.no_train and ARCH == "convnextv2_base-unet" and side == 10000:
+        try:    # BASELINE.json configs[2]: Swin-base + UPerNet, 20 000 x 20 000 zone (2809 tiles), device-timed
+            others = [other_config_block(dev, "swin_base_patch4_window12_384-upernet", 20000, 2, args.batch,
+                                         "configs[2]: swin_base_patch4_window12_384-upernet zonal inference, synthetic "
+                                         "20000x20000x4 uint8 @0.2m, tile 512 margin 64, 19 classes, argmax raster")]
+        except Exception as ex:  # noqa: BLE001
+            others = [{"error": repr(ex)}]
+            log(f"[rank {rank}] configs[2] block failed: {ex!r}")
+
     train = None
     if not args.no_train and ARCH == "convnextv2_base-unet":
         try:
@@ -597,6 +660,7 @@ def main() -> None:
             "cpu_baseline": cpu_base,
             "kernel_time_shares_eager": breakdown,
             "strong_scaling": strong,
+            "other_configs": others,
             "train": train,
         }
         print(json.dumps(line), flush=True)

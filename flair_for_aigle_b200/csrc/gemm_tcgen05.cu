@@ -157,7 +157,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
     const int half = (ew >> 2) & 1;             // which M=128 accumulator
     const int colgrp = ew >> 3;                 // chunks colgrp, colgrp+2, ...
-    const int bar_id = 1 + half;
+    const int bar_id = 1 + half * 2 + colgrp;   // named barriers 1..4: one per (row half, column group) of 4 warps
     uint32_t lt = 0;
     for (int t = t_first; t < total_work; t += t_step, ++lt) {
       const int tile = t / p.splits, sp = t - tile * p.splits;
@@ -188,12 +188,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (MODE == FZ_EPI_GELU_SUMSQ) {
         // deterministic: fixed-order sum of the four lane-quarter warps, one plain store per column.
         // sq_buf alternates with the tile parity, so one barrier per tile is enough.
-        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        // only the four warps sharing this (row half, column group) meet at the barrier
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         const float* sq = sq_buf + half * 4 * BN;
-        if (m0 + half * 128 < p.M)
-          for (int i = (colgrp * 4 + q) * 32 + lane; i < BN; i += 256)
+        if (m0 + half * 128 < p.M && q < CH_COLS / 32)
+          for (int c = colgrp; c < BN / CH_COLS; c += 2) {
+            const int i = c * CH_COLS + q * 32 + lane;
             p.sumsq[static_cast<size_t>(m0 / 128 + half) * p.N + n0 + i] =
                 (sq[i] + sq[BN + i]) + (sq[2 * BN + i] + sq[3 * BN + i]);
+          }
       }
     }
   }

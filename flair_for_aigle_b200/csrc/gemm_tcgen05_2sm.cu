@@ -147,12 +147,16 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
       if (MODE == FZ_EPI_GELU_SUMSQ) {
-        // deterministic: fixed-order sum of the four lane-quarter warps (same order as the one-SM kernel)
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (m0 < p.M)
-          for (int i = ew * 32 + lane; i < BN; i += 512)
+        // deterministic: fixed-order sum of the four lane-quarter warps (same order as the one-SM kernel).  Only the four
+        // warps that share this column group meet at the barrier (round 1 synchronised all 16 epilogue warps per tile:
+        // `barrier` was the largest stall reason of the fc1 launch, 1.4 warps per issue-active cycle).
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + colgrp) : "memory");
+        if (m0 < p.M && q < CH_COLS / 32)
+          for (int c = colgrp; c < BN / CH_COLS; c += 4) {
+            const int i = c * CH_COLS + q * 32 + lane;
             p.sumsq[static_cast<size_t>(m0 / 128) * p.N + n0 + i] =
                 (sq_buf[i] + sq_buf[BN + i]) + (sq_buf[2 * BN + i] + sq_buf[3 * BN + i]);
+          }
       }
     }
   }
