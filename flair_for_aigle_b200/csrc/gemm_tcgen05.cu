@@ -46,7 +46,9 @@ struct GemmSmem {
   static constexpr int BYTES = OFF_TSLOT + 16 + 1024;            // + worst-case alignment pad
 };
 
-template <int BN, int STAGES, int ACC_STAGES, int MODE, bool F16>
+// MNMAJOR: both operands are given transposed -- A as [K][M], B as [K][N], row-major (the weight-gradient GEMM dW = dY^T X reads
+// dY [rows][N_l] and X [rows][K_l] as they are, no transposed copies).  Each 64-wide block of M / N is its own TMA box.
+template <int BN, int STAGES, int ACC_STAGES, int MODE, bool F16, bool MNMAJOR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using L = GemmSmem<BN, STAGES>;
@@ -108,15 +110,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
-          tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
-          tma_load_3d(&tmB, &full[s], sB + s * L::B_STAGE_BYTES, kb * BK, n0, bcoord);
+          if (MNMAJOR) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES + j * (BK * 128), m0 + j * 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&tmB, &full[s], sB + s * L::B_STAGE_BYTES + j * (BK * 128), n0 + j * 64, kb * BK);
+          } else {
+            tma_load_2d(&tmA, &full[s], sA + s * A_STAGE_BYTES, kb * BK, m0);
+            tma_load_3d(&tmB, &full[s], sB + s * L::B_STAGE_BYTES, kb * BK, n0, bcoord);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc16(128, BN, F16);
+      constexpr uint32_t idesc = MNMAJOR ? umma_idesc16_mn(128, BN, F16) : umma_idesc16(128, BN, F16);
       uint32_t it = 0, lt = 0;
       for (int t = t_first; t < total_work; t += t_step, ++lt) {
         const int sp = t % p.splits;
@@ -135,15 +146,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full[s], ph);
           tc_fence_after();
           if (kb == kb0) FZ_TRACE(3);   // first k-block landed
-          const uint64_t ad0 = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES), 128);
-          const uint64_t ad1 = umma_smem_desc(smem_u32(sA + s * A_STAGE_BYTES + 128 * BK * 2), 128);
-          const uint64_t bd = umma_smem_desc(smem_u32(sB + s * L::B_STAGE_BYTES), 128);
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES), b_addr = smem_u32(sB + s * L::B_STAGE_BYTES);
+          // K-major: rows of 128 B, +32 bytes (16 elements) along K inside the swizzle atom = +2 in the >>4 address field.
+          // MN-major: 64-element MN blocks BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO); the second M = 128 half
+          // starts two MN blocks further; 16 k-rows = +2048 B = +128 in the address field.
+          const uint64_t ad0 = MNMAJOR ? umma_smem_desc_mn(a_addr, BK * 128, 1024) : umma_smem_desc(a_addr, 128);
+          const uint64_t ad1 = MNMAJOR ? umma_smem_desc_mn(a_addr + 2 * BK * 128, BK * 128, 1024)
+                                       : umma_smem_desc(a_addr + 128 * BK * 2, 128);
+          const uint64_t bd = MNMAJOR ? umma_smem_desc_mn(b_addr, BK * 128, 1024) : umma_smem_desc(b_addr, 128);
+          constexpr uint32_t KSTEP = MNMAJOR ? 128u : 2u;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes (16 bf16) along K inside the 128B swizzle atom = +2 in the >>4 address field
             const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
-            umma_bf16(acc0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
-            umma_bf16(acc1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
+            umma_bf16(acc0, ad0 + KSTEP * k, bd + KSTEP * k, idesc, accum);
+            umma_bf16(acc1, ad1 + KSTEP * k, bd + KSTEP * k, idesc, accum);
           }
           umma_commit(&empty[s]);
         }
@@ -205,10 +221,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int BN, int STAGES, int ACC_STAGES, int MODE, bool F16>
+template <int BN, int STAGES, int ACC_STAGES, int MODE, bool F16, bool MNMAJOR = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE, F16>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE, F16, MNMAJOR>;
   FZ_ENSURE_SMEM(kern, L::BYTES);
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return -2;
@@ -370,6 +386,58 @@ extern "C" int fz_gemm_bf16_splitk(const void* A, const void* B, float* out, flo
     if (int rc = make_tmap16(&tmB, B, 3, dims, strides, box, 128)) return rc;
   }
   int rc = (BN == 128) ? dispatch_mode<128, 3, 2>(FZ_EPI_F32, tmA, tmB, p, st) : dispatch_mode<64, 3, 2>(FZ_EPI_F32, tmA, tmB, p, st);
+  if (rc) return rc;
+  if (p.splits > 1) {
+    const size_t n4 = static_cast<size_t>(M) * N / 4;
+    splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(workspace), reinterpret_cast<float4*>(out), n4, p.splits);
+    FZ_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// Split-K with BOTH operands transposed in memory: out [M][N] = At^T Bt, At [K][M], Bt [K][N] row-major (MN-major UMMA
+// operands).  This is dW = dY^T X straight from dY [rows][N_l] and X [rows][K_l]: round 1 made transposed copies of both for
+// every layer and step (499 launches, 19 ms of the training step).
+extern "C" int fz_gemm_bf16_splitk_tn(const void* At, const void* Bt, float* out, float* workspace, int M, int N, int K,
+                                      int splits, int flags, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(M > 0 && N > 0 && K > 0, "fz_gemm_bf16_splitk_tn: bad shape M=%d N=%d K=%d", M, N, K);
+  FZ_REQUIRE(K % BK == 0 && N % 64 == 0 && M % 8 == 0,
+             "fz_gemm_bf16_splitk_tn: K=%d must be a multiple of %d, N=%d of 64, M=%d of 8", K, BK, N, M);
+  FZ_REQUIRE((static_cast<long long>(M) * N) % 4 == 0, "fz_gemm_bf16_splitk_tn: M*N must be a multiple of 4");
+  const int num_kb = K / BK;
+  FZ_REQUIRE(splits >= 1 && splits <= num_kb, "fz_gemm_bf16_splitk_tn: splits=%d out of range (1..%d)", splits, num_kb);
+  FZ_REQUIRE(splits == 1 || workspace != nullptr, "fz_gemm_bf16_splitk_tn: workspace (splits*M*N floats) required");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.rows_per_sample = M; p.b_batched = 0;
+  p.bias = nullptr; p.resid = nullptr; p.sumsq = nullptr; p.trace = nullptr; p.reverse = 0;
+  p.f16 = (flags & FZ_EPI_OPERANDS_F16) ? 1 : 0;
+  p.nobias = 1;
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.out = p.splits > 1 ? static_cast<void*>(workspace) : static_cast<void*>(out);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int BN = (N % 128 == 0) ? 128 : 64;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)M, (uint64_t)K};          // innermost = the GEMM's M index
+    const uint64_t strides[1] = {(uint64_t)M * 2};
+    const uint32_t box[2] = {64, BK};
+    if (int rc = make_tmap16(&tmA, At, 2, dims, strides, box, 128)) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
+    const uint64_t strides[1] = {(uint64_t)N * 2};
+    const uint32_t box[2] = {64, BK};
+    if (int rc = make_tmap16(&tmB, Bt, 2, dims, strides, box, 128)) return rc;
+  }
+  int rc;
+  if (BN == 128)
+    rc = p.f16 ? launch_gemm<128, 3, 2, FZ_EPI_F32, true, true>(tmA, tmB, p, st) : launch_gemm<128, 3, 2, FZ_EPI_F32, false, true>(tmA, tmB, p, st);
+  else
+    rc = p.f16 ? launch_gemm<64, 3, 2, FZ_EPI_F32, true, true>(tmA, tmB, p, st) : launch_gemm<64, 3, 2, FZ_EPI_F32, false, true>(tmA, tmB, p, st);
   if (rc) return rc;
   if (p.splits > 1) {
     const size_t n4 = static_cast<size_t>(M) * N / 4;

@@ -125,6 +125,21 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t swiz
   return d;
 }
 
+// MN-major operand tile (the operand's M or N index is the contiguous one in memory, e.g. A given as [K][M] row-major):
+// blocks of 64 MN-elements (one 128-byte swizzled row per k) x 8 k-rows; canonical layout ((8,8,m),(8,k)) :
+// ((1,8,LBO),(64,SBO)) in elements -- LBO = byte stride between 64-element MN blocks, SBO = byte stride between groups of
+// 8 k-rows.  This is what TMA boxes {64 MN-elements, BK k-rows} with CU_TENSOR_MAP_SWIZZLE_128B write when each MN block of
+// the tile is its own box (rows 128 B apart: SBO = 1024; boxes BK * 128 B apart: LBO = BK * 128).
+__device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                           // 128-byte swizzle
+  return d;
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, A/B K-major, D = f32.  kind::f16 takes
 // fp16 (format code 0) and bf16 (format code 1) operands at the same rate; `f16` selects which.
 __host__ __device__ constexpr uint32_t umma_idesc16(uint32_t m, uint32_t n, bool f16) {
@@ -135,6 +150,10 @@ __host__ __device__ constexpr uint32_t umma_idesc16(uint32_t m, uint32_t n, bool
          | ((m >> 4) << 24);              // M >> 4
 }
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) { return umma_idesc16(m, n, false); }
+// both operands MN-major (a_major = bit 15, b_major = bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc16_mn(uint32_t m, uint32_t n, bool f16) {
+  return umma_idesc16(m, n, f16) | (1u << 15) | (1u << 16);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

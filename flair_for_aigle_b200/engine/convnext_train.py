@@ -244,7 +244,7 @@ class ConvNeXtV2EncoderTrain:
         du0, dg, dbeta = self.stem_ln.backward(_to_bf16(d.view(-1, self.dims[0])))
         grads["stem_1.weight"], grads["stem_1.bias"] = dg, dbeta
         du0b = _to_bf16(du0)
-        dw = nv.gemm_bf16(nv.transpose_bf16(du0b), nv.transpose_bf16(patches), nv.EPI_F32)   # [C0, Kpad]
+        dw = nv.weight_gradient(du0b, patches)                                                # [C0, Kpad], operands read in place
         grads["stem_0.weight"] = dw[:, :self.cin * 16].reshape(self.dims[0], self.cin, 4, 4).contiguous()
         grads["stem_0.bias"] = nv.colsum_bf16(du0b)
         if emit is not None:

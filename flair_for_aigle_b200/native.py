@@ -79,6 +79,7 @@ _SIGNATURES = {
     "fz_gemm_set_trace": [_vp],
     "fz_gemm_bf16_splitk": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_gemm_splitk_max_splits": [_i, _i, _i],
+    "fz_gemm_bf16_splitk_tn": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_gemm_bf16_simt": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_stem_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_stem_ln_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
@@ -380,6 +381,31 @@ def gemm_splitk(A: torch.Tensor, B: torch.Tensor, splits: Optional[int] = None, 
     with _Timed("gemm_splitk", M=M, N=N, K=K, splits=splits):
         _check(lib().fz_gemm_bf16_splitk(_ptr(A), _ptr(B), _ptr(out), _ptr(ws), M, N, K, splits,
                                          EPI_OPERANDS_F16 if A.dtype == torch.float16 else 0, _stream()), "fz_gemm_bf16_splitk")
+    return out
+
+
+def gemm_splitk_tn(At: torch.Tensor, Bt: torch.Tensor, splits: Optional[int] = None, out: Optional[torch.Tensor] = None):
+    """fp32 [M,N] = At^T Bt with At [K,M] and Bt [K,N] (both row-major, i.e. transposed operands read in place: MN-major
+    tcgen05 descriptors).  dW = dY^T X without transposed copies.  K % 64 == 0, M % 8 == 0, N % 64 == 0."""
+    K, M = At.shape
+    K2, N = Bt.shape
+    if K2 != K or At.dtype != Bt.dtype or At.dtype not in (torch.bfloat16, torch.float16):
+        raise NativeError("gemm_splitk_tn: operands must both be float16 or both bfloat16 with equal K")
+    if splits is None:
+        splits = lib().fz_gemm_splitk_max_splits(M, N, K)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=At.device)
+    ws = None
+    if splits > 1:
+        key = (At.device.index, torch.cuda.current_stream().cuda_stream)
+        need = splits * M * N
+        ws = _SPLITK_WS.get(key)
+        if ws is None or ws.numel() < need:
+            ws = _SPLITK_WS[key] = torch.empty(need, dtype=torch.float32, device=At.device)
+    with _Timed("gemm_splitk_tn", M=M, N=N, K=K, splits=splits):
+        _check(lib().fz_gemm_bf16_splitk_tn(_ptr(At), _ptr(Bt), _ptr(out), _ptr(ws), M, N, K, splits,
+                                            EPI_OPERANDS_F16 if At.dtype == torch.float16 else 0, _stream()),
+               "fz_gemm_bf16_splitk_tn")
     return out
 
 
@@ -763,6 +789,24 @@ def _stream_pool(device, n: int):
     return _STREAMS[key]
 
 
+def weight_gradient(dY: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """fp32 [N,K] = dY^T X for dY [M,N] and X [M,K] (16-bit, same format): split-K, operands read in place.  Rows are padded
+    to a multiple of 64 (the reduction's k-block) only when needed; shapes the MN-major kernel does not take (N % 8 != 0 or
+    K % 64 != 0) go through transposed copies."""
+    M, N = dY.shape
+    K = X.shape[1]
+    if M % 64:
+        Mp = (M + 63) // 64 * 64
+        dYp = torch.zeros((Mp, N), dtype=dY.dtype, device=dY.device)
+        Xp = torch.zeros((Mp, K), dtype=X.dtype, device=X.device)
+        dYp[:M].copy_(dY)
+        Xp[:M].copy_(X)
+        dY, X = dYp, Xp
+    if N % 8 == 0 and K % 64 == 0:
+        return gemm_splitk_tn(dY, X)
+    return gemm_splitk(transpose_bf16(dY), transpose_bf16(X))
+
+
 def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
     """Gradients of Y = X W^T + b (X bf16 [M,K], W bf16 [N,K], dY bf16 [M,N]) on the tcgen05 GEMM:
     dX = dY W (bf16 [M,K]), dW = dY^T X (fp32 [N,K], fp32 accumulation over all M rows), db = column sums of dY."""
@@ -771,16 +815,8 @@ def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
     if X.shape[0] != M or tuple(W.shape) != (N, K):
         raise NativeError("linear_backward: shape mismatch")
     dX = gemm_bf16(dY, transpose_bf16(W), EPI_BF16)                               # [M,N] x [K,N]^T
-    # dW = dY^T X: a small [N,K] output reduced over all M rows -- split-K inside the GEMM kernel (round 1 ran 2..32 CTAs per
-    # launch, or row chunks on side streams for the longest reductions)
-    if M % 64:                                                                    # the reduction length is a multiple of 64
-        Mp = (M + 63) // 64 * 64
-        dYp = torch.zeros((Mp, N), dtype=dY.dtype, device=dY.device)
-        Xp = torch.zeros((Mp, K), dtype=X.dtype, device=X.device)
-        dYp[:M].copy_(dY)
-        Xp[:M].copy_(X)
-        dY_t, X_t = transpose_bf16(dYp), transpose_bf16(Xp)
-    else:
-        dY_t, X_t = transpose_bf16(dY), transpose_bf16(X)
-    dW = gemm_splitk(dY_t, X_t)                                                   # [N,M] x [K,M]^T
+    # dW = dY^T X: a small [N,K] output reduced over all M rows.  Split-K inside the GEMM kernel (round 1 ran 2..32 CTAs per
+    # launch, or row chunks on side streams), and both operands are read IN PLACE through MN-major tcgen05 descriptors
+    # (round 1 made transposed copies of dY and X for every layer: 499 launches, 19 ms per step)
+    dW = weight_gradient(dY, X)
     return dX, dW, colsum_bf16(dY)

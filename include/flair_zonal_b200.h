@@ -12,7 +12,9 @@
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and
  *     capturable in a CUDA graph.
  *   - return 0 on success, <0 on error; fz_last_error() returns a thread-local message.
- *   - activations are NHWC; "bf16" is __nv_bfloat16 (uint16 storage).
+ *   - activations are NHWC.  16-bit tensors of the INFERENCE entry points are in the library's operand format FZ_OP16
+ *     (IEEE fp16 in this build, see fz_operand_format() below) even where a parameter is still spelled "_bf16"; the
+ *     TRAINING entry points (backward / optimizer section) take __nv_bfloat16.
  */
 #ifndef FLAIR_ZONAL_B200_H
 #define FLAIR_ZONAL_B200_H
@@ -148,6 +150,10 @@ int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, con
 int fz_gemm_bf16_splitk(const void* A, const void* B, float* out, float* workspace, int M, int N, int K, int splits, int flags,
                         void* stream);
 int fz_gemm_splitk_max_splits(int M, int N, int K);
+/* The same with both operands TRANSPOSED in memory: out [M][N] = At^T Bt with At [K][M] and Bt [K][N] row-major (MN-major
+ * tcgen05 operands; M % 8 == 0).  dW = dY^T X reads dY [rows][N_l] and X [rows][K_l] as they are -- no transposed copies. */
+int fz_gemm_bf16_splitk_tn(const void* At, const void* Bt, float* out, float* workspace, int M, int N, int K, int splits,
+                           int flags, void* stream);
 /* Diagnostics: when set to a device buffer of 64*8 uint64, CTA 0 of every following fz_gemm_bf16 launch
  * records clock64 stamps per tile (producer start, MMA arrive, accumulator free, first operands landed,
  * MMAs issued, epilogue wait, accumulator complete, epilogue done).  NULL switches it off. */

@@ -203,3 +203,30 @@ def test_gemm_splitk(cuda, M, N, K, splits, dt):
     err_plain = (plain.double() - ref).abs().max().item()
     print(f"M={M} N={N} K={K} {dt}: split-K x{used} max err {err / sd:.2e} of the output spread, one chain {err_plain / sd:.2e}")
     assert err_plain < 2e-3 * sd
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(256, 128, 64, 1), (512, 128, 16384, None), (64, 320, 65536, None), (2048, 512, 16384, None),
+                                         (128, 64, 4096, 7), (16, 64, 262144, None), (72, 192, 640, 1), (1024, 256, 8192, 64)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gemm_splitk_transposed_operands_in_place(cuda, M, N, K, splits, dt):
+    """out = At^T Bt with At [K,M], Bt [K,N] read in place (MN-major tcgen05 descriptors): the weight-gradient GEMM dW = dY^T X
+    without transposed copies.  Same values as the K-major split-K kernel on explicitly transposed operands."""
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(M + N + 1)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    At = (torch.randn(K, M, device=cuda) * 0.5).to(dt)
+    Bt = (torch.randn(K, N, device=cuda) * 0.5).to(dt)
+    out = nv.gemm_splitk_tn(At, Bt, splits=splits)
+    torch.cuda.synchronize()
+    ref = At.double().t() @ Bt.double()
+    sd = ref.std().item()
+    assert (out.double() - ref).abs().max().item() < 5e-4 * sd
+    assert torch.equal(out, nv.gemm_splitk_tn(At, Bt, splits=splits))                      # deterministic
+    if M % 8 == 0 and K % 64 == 0:
+        used = splits if splits is not None else nv.lib().fz_gemm_splitk_max_splits(M, N, K)
+        same = nv.gemm_splitk(At.t().contiguous(), Bt.t().contiguous(), splits=used)      # K-major operands, same pieces
+        assert torch.equal(out, same)
+    # the helper the training step calls (pads the rows to a multiple of 64)
+    dW = nv.weight_gradient(At[:K - 3], Bt[:K - 3])
+    ref2 = At[:K - 3].double().t() @ Bt[:K - 3].double()
+    assert (dW.double() - ref2).abs().max().item() < 5e-4 * max(ref2.std().item(), 1e-6)
