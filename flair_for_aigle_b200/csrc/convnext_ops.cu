@@ -302,6 +302,153 @@ __global__ void __launch_bounds__(NW * 32, (512 / (NW * 32)) > 0 ? 512 / (NW * 3
   } while (PERSIST && tile < n_tiles);   // the next tile's first __syncthreads orders its shared-memory writes after these reads
 }
 
+// ------------------------------------------------------------------------------------ dwconv7x7 + LN, channel pairs
+// Round 2.  ncu on the kernel above (profiles/r2_ncu_dwconv_full_summary.txt): DRAM traffic = algorithmic, FMA pipe 43.6 %,
+// issue slots 63 %, and only 58 % of the 2690 instructions a thread executes for its 1568 FMAs ARE FMAs -- the rest is
+// per-channel overhead: 140 scalar loads, 32 two-byte stores, the LayerNorm shuffles.  Here a lane owns the channel PAIR
+// (2l, 2l+1) of its warp's 64 channels: every load is an 8-byte float2 (still a coalesced 256 B row per warp), every FMA is
+// Blackwell's packed fma.rn.f32x2 (two IEEE fp32 FMAs in one instruction: same bits as the scalar kernel, same summation
+// order), every store one packed 16-bit pair, and the LayerNorm statistics of the two channels share their shuffles.
+// Tile 2 x 8 pixels x 2 channels = 16 float2 accumulators (the 4 x 8 tile of the scalar kernel would need 150 registers and
+// halve the occupancy); the 49 x C taps live in shared memory (a lane reads its float2 per tap: 7 LDS.64 per input row and
+// output row), loaded once by the persistent CTA.
+template <int NW, int C, int SH>
+__global__ void __launch_bounds__(NW * 32, SH == 2 ? 512 / (NW * 32) : (NW >= 8 ? 1 : 256 / (NW * 32))) dwconv_ln_pair_kernel(const float* __restrict__ x, const float* __restrict__ wdw,
+                                                                 const float* __restrict__ bdw,
+                                                                 const float* __restrict__ ln_w,
+                                                                 const float* __restrict__ ln_b, op_t* __restrict__ out,
+                                                                 int H, int W, float eps, int tiles_x, int tiles_y,
+                                                                 int n_tiles) {
+  static_assert(NW * 64 == C, "one lane per channel pair");
+  static_assert(SH == 2 || SH == 4, "2 x 8 or 4 x 8 pixel tiles");
+  constexpr int SW = 8, NPX = SH * SW;
+  extern __shared__ float s_taps[];                    // [49][C]
+  __shared__ float red[NW][32];
+  __shared__ float s_stat[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x * 4; i < 49 * C; i += NW * 32 * 4)
+    *reinterpret_cast<float4*>(s_taps + i) = *reinterpret_cast<const float4*>(wdw + i);
+  const int c = warp * 64 + lane * 2;
+  const float2 bias = *reinterpret_cast<const float2*>(bdw + c);
+  const float2 g2 = *reinterpret_cast<const float2*>(ln_w + c), be2 = *reinterpret_cast<const float2*>(ln_b + c);
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int x0 = tx * SW, y0 = ty * SH;
+    const float* xb = x + static_cast<size_t>(b) * H * W * C;
+    const bool left_edge = x0 < 3, right_edge = x0 + SW + 3 > W;
+    float2 acc[NPX];
+#pragma unroll
+    for (int p = 0; p < NPX; ++p) acc[p] = bias;
+    float2 nxt[SW + 6];
+    const ptrdiff_t row_stride = static_cast<ptrdiff_t>(W) * C;
+    const float* row0 = xb + (static_cast<ptrdiff_t>(y0 - 3) * W + (x0 - 3)) * C + c;
+    auto load_row = [&](int iy, float2 (&dst)[SW + 6]) {
+      const int gy = y0 - 3 + iy;
+      if (gy < 0 || gy >= H) {                               // CTA-uniform: zero padding row
+#pragma unroll
+        for (int ix = 0; ix < SW + 6; ++ix) dst[ix] = make_float2(0.f, 0.f);
+        return;
+      }
+      const float* row = row0 + iy * row_stride;
+#pragma unroll
+      for (int ix = 0; ix < SW + 6; ++ix) {
+        const bool pad = (ix < 3 && left_edge && x0 - 3 + ix < 0) || (ix >= SW + 3 && right_edge && x0 - 3 + ix >= W);
+        dst[ix] = pad ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(row + ix * C);
+      }
+    };
+    load_row(0, nxt);
+#pragma unroll
+    for (int iy = 0; iy < SH + 6; ++iy) {
+      float2 in[SW + 6];
+#pragma unroll
+      for (int ix = 0; ix < SW + 6; ++ix) in[ix] = nxt[ix];
+      if (iy + 1 < SH + 6) load_row(iy + 1, nxt);
+#pragma unroll
+      for (int oy = 0; oy < SH; ++oy) {
+        const int ky = iy - oy;
+        if (ky >= 0 && ky < 7) {
+          float2 wk[7];
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) wk[kx] = *reinterpret_cast<const float2*>(s_taps + (ky * 7 + kx) * C + c);
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+            for (int ox = 0; ox < SW; ++ox) acc[oy * SW + ox] = __ffma2_rn(in[ox + kx], wk[kx], acc[oy * SW + ox]);
+        }
+      }
+    }
+    // ---- LayerNorm over C per pixel.  SH = 2: s[cc * 16 + p] = channel cc of the pair (like the CPT = 2 path above);
+    //      SH = 4: the pair is summed first, s[p] over 32 pixels
+    float s[32];
+    float part;
+    if (SH == 2) {
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        s[p] = acc[p].x;
+        s[16 + p] = acc[p].y;
+      }
+      warp_colsum32(s, lane);
+      part = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 16);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 32; ++p) s[p] = acc[p % NPX].x + acc[p % NPX].y;
+      warp_colsum32(s, lane);
+      part = s[0];
+    }
+    red[warp][lane] = part;
+    __syncthreads();
+    if (warp == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) t += red[w2][lane];
+      s_stat[lane] = t / C;                                           // mean of pixel (lane % NPX)
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < NPX; ++p) {
+      acc[p].x -= s_stat[p];
+      acc[p].y -= s_stat[p];
+    }
+    if (SH == 2) {
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        s[p] = acc[p].x * acc[p].x;
+        s[16 + p] = acc[p].y * acc[p].y;
+      }
+      warp_colsum32(s, lane);
+      part = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 16);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 32; ++p) s[p] = acc[p % NPX].x * acc[p % NPX].x + acc[p % NPX].y * acc[p % NPX].y;
+      warp_colsum32(s, lane);
+      part = s[0];
+    }
+    __syncthreads();                                                  // everyone has read the means
+    red[warp][lane] = part;
+    __syncthreads();
+    if (warp == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) t += red[w2][lane];
+      s_stat[lane] = rsqrtf(t / C + eps);
+    }
+    __syncthreads();
+    op_t* o0 = out + ((static_cast<size_t>(b) * H + y0) * W + x0) * C + c;
+    const ptrdiff_t orow = static_cast<ptrdiff_t>(W) * C;
+#pragma unroll
+    for (int oy = 0; oy < SH; ++oy) {
+      op_t* orp = o0 + oy * orow;
+#pragma unroll
+      for (int ox = 0; ox < SW; ++ox) {
+        const float r = s_stat[oy * SW + ox];
+        *reinterpret_cast<op2_t*>(orp + ox * C) = ff2op2(acc[oy * SW + ox].x * r * g2.x + be2.x, acc[oy * SW + ox].y * r * g2.y + be2.y);
+      }
+    }
+    // the next tile's first __syncthreads orders its shared-memory writes after these reads of s_stat
+  }
+}
+
 // ------------------------------------------------------------------------------------ LN2d + space-to-depth
 // x: float [B][H][W][C] -> out: bf16 [B][H/2][W/2][4C], k = (y&1)*2C + (x&1)*C + c  (the K order of
 // the 2x2/s2 conv weights repacked as [N][ky][kx][c]).  One warp per pixel.
@@ -616,12 +763,66 @@ static int launch_dwconv(const float* x, const float* wdw, const float* bdw, con
 }
 }  // namespace fz
 
+namespace fz {
+template <int NW, int C, int SH>
+static int launch_dwconv_pair(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
+                              op_t* out, int B, int H, int W, float eps, cudaStream_t st) {
+  FZ_REQUIRE(H % SH == 0 && W % 8 == 0, "fz_dwconv7_ln: H=%d W=%d must be multiples of %d x 8", H, W, SH);
+  const int tiles_x = W / 8, tiles_y = H / SH, n_tiles = tiles_x * tiles_y * B;
+  constexpr int SMEM = 49 * C * 4;
+  auto kern = dwconv_ln_pair_kernel<NW, C, SH>;
+  FZ_ENSURE_SMEM(kern, SMEM);
+  const int sm_count = device_sm_count();
+  if (sm_count <= 0) return -2;
+  // persistent CTAs: as many as fit per SM by shared memory (taps) and threads, x-fastest tile order
+  int per_sm = (220 * 1024) / (SMEM + 2048);
+  if (per_sm > 2048 / (NW * 32)) per_sm = 2048 / (NW * 32);
+  const int thread_cap = SH == 2 ? 512 : 256;                       // ~126 (2 x 8 tile) / ~170 (4 x 8) registers per thread
+  if (per_sm > thread_cap / (NW * 32)) per_sm = thread_cap / (NW * 32);
+  if (per_sm < 1) per_sm = 1;
+  const long long want = static_cast<long long>(sm_count) * per_sm;
+  const int grid = static_cast<int>(n_tiles < want ? n_tiles : want);
+  kern<<<grid, NW * 32, SMEM, st>>>(x, wdw, bdw, ln_w, ln_b, out, H, W, eps, tiles_x, tiles_y, n_tiles);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace fz
+
 extern "C" int fz_dwconv7_ln(const float* x, const float* wdw, const float* bdw, const float* ln_w, const float* ln_b,
                              void* out_bf16, int B, int H, int W, int C, float eps, void* stream) {
   using namespace fz;
   if (B <= 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   op_t* o = reinterpret_cast<op_t*>(out_bf16);
+  // Kernel choice, measured at B = 37 (profiles/r2_dwconv_pair_ab.txt): the one-channel-per-lane kernel, the channel-pair
+  // kernel with 2 x 8 tiles (40 % fewer instructions, 16 warps / SM) and with 4 x 8 tiles (half the L2 reads of the former,
+  // 8 warps / SM) all take the SAME time at C = 128 and 512 (264 / 267 / 274 us and 78.2 / 78.6 / 79.3 us): the kernel is
+  // bound by neither issue slots nor L2 traffic nor occupancy but by the fp32 FMA work itself under the power cap.  The pair
+  // kernels win where the scalar one had the wrong shape: C = 256 (4 x 8 tiles: 142 vs 149 us) and C = 1024 (2 x 8: 33.5 vs
+  // 43.7 us).  FZ_DWCONV_PAIR = 0 / 2 / 4 forces the scalar / 2 x 8 / 4 x 8 kernel everywhere (A/B measurements).
+  static int pair = -1;
+  if (pair < 0) {
+    const char* e = getenv("FZ_DWCONV_PAIR");
+    pair = e ? atoi(e) : 1;
+  }
+  const bool ok2 = H % 2 == 0 && W % 8 == 0, ok4 = H % 4 == 0 && W % 8 == 0;
+  if (ok4 && (pair == 4 || (pair == 1 && C == 256))) {
+    switch (C) {
+      case 128: return launch_dwconv_pair<2, 128, 4>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+      case 256: return launch_dwconv_pair<4, 256, 4>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+      case 512: return launch_dwconv_pair<8, 512, 4>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+      default: break;
+    }
+  }
+  if (ok2 && (pair == 2 || pair == 4 || (pair == 1 && C == 1024))) {
+    switch (C) {
+      case 128: return launch_dwconv_pair<2, 128, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+      case 256: return launch_dwconv_pair<4, 256, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+      case 512: return launch_dwconv_pair<8, 512, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+      case 1024: return launch_dwconv_pair<16, 1024, 2>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
+      default: break;
+    }
+  }
   switch (C) {   // one warp per 32 channels; above 512 channels each thread carries two
     case 64: return launch_dwconv<2, 1, 64>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
     case 96: return launch_dwconv<3, 1, 96>(x, wdw, bdw, ln_w, ln_b, o, B, H, W, eps, st);
