@@ -72,8 +72,23 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static int make_tmap_any(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, uint32_t swizzle_bytes,
+                         const uint32_t* elem_strides);
+
 int make_tmap16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides) {
+                const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides) {
+  return make_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle_bytes, elem_strides);
+}
+
+int make_tmap32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides) {
+  return make_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle_bytes, elem_strides);
+}
+
+static int make_tmap_any(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, uint32_t swizzle_bytes,
+                         const uint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -3;
   cuuint64_t gdims[5];
@@ -90,7 +105,7 @@ int make_tmap16(CUtensorMap* out, const void* base, int rank, const uint64_t* di
   if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
   else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
   else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+  CUresult r = enc(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

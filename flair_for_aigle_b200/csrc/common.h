@@ -11,13 +11,17 @@ namespace fz {
 void set_error(const char* fmt, ...);
 const char* last_error();
 
-// Encode a tiled tensor map over a bf16 tensor (driver entry point resolved lazily through
+// Encode a tiled tensor map over a 16-bit (bf16 / fp16: same element size, zero OOB fill) tensor (driver entry point resolved lazily through
 // cudaGetDriverEntryPoint, so the library does not link libcuda directly).
 // dims/strides are innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).
 // swizzle_bytes in {0 (none), 32, 64, 128}.
 int make_tmap16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, uint32_t swizzle_bytes,
                    const uint32_t* elem_strides = nullptr);
+
+// The same over a 32-bit (float) tensor: the TMA STORE of fp32 GEMM outputs.
+int make_tmap32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, uint32_t swizzle_bytes, const uint32_t* elem_strides = nullptr);
 
 // One-time (per device, thread-safe) opt-in of a kernel to `bytes` of dynamic shared memory; 0 or -2 (error set).
 int ensure_dynamic_smem(const void* kernel, int bytes);

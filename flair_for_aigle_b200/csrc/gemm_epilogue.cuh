@@ -18,6 +18,7 @@ struct GemmParams {
   int splits;           // split-K: the K range is cut into `splits` pieces of kb_per_split k-blocks; piece s writes its fp32
   int kb_per_split;     //   partial tile to out + s * M * N (fz_gemm_bf16_splitk sums the pieces in order); 1 = off
   int nobias;           // 1: the epilogue adds no bias (split-K partials)
+  int tma_store;        // 1: the staged 32 x 128 B chunk leaves through a TMA store (CTA-pair kernel; tmO is valid)
   int f16;              // 1: A, B and a 16-bit output are fp16 (FZ_EPI_OPERANDS_F16), 0: bf16
   int reverse;          // 1: walk the tile list backwards (consume a just-written operand newest-first, while it is in L2)
   unsigned long long* trace;  // optional: CTA 0 writes clock64 stamps [tile][8] (diagnostics, see fz_gemm_set_trace)
@@ -39,7 +40,7 @@ struct EpiShape {
 // sq_dst: (GELU_SUMSQ) 64 floats: 32-row column sums of out^2 for the chunk's columns (8-byte aligned)
 template <int MODE, bool F16>
 __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, int row0, int col0, char* stg, int lane,
-                                          float* sq_dst, void* out_base) {
+                                          float* sq_dst, void* out_base, const CUtensorMap* tmO = nullptr) {
   constexpr bool F32OUT = EpiShape<MODE>::F32OUT;
   constexpr int CH_COLS = EpiShape<MODE>::CH_COLS;
   constexpr int ESZ = EpiShape<MODE>::ESZ;
@@ -47,6 +48,10 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
   const size_t row_bytes = static_cast<size_t>(p.N) * ESZ;
   char* gout = reinterpret_cast<char*>(out_base) + static_cast<size_t>(row0) * row_bytes + static_cast<size_t>(col0) * ESZ;
   if (MODE == FZ_EPI_RESID_F32) {
+    if (tmO != nullptr) {          // the previous chunk's TMA store has read this staging tile
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
     // coalesced residual tile -> staging
     const char* gres = reinterpret_cast<const char*>(p.resid) + static_cast<size_t>(row0) * row_bytes +
                        static_cast<size_t>(col0) * 4;
@@ -94,6 +99,10 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
       __syncwarp();   // everyone has read its residual row before the tile is overwritten
     }
     // own row -> staging
+    if (tmO != nullptr && MODE != FZ_EPI_RESID_F32 && h == 0) {   // the previous chunk's TMA store has read this staging tile
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
     if (F32OUT) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -123,6 +132,18 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
       a1 = fmaf(f.y, f.y, a1);
     }
     *reinterpret_cast<float2*>(sq_dst + 2 * lane) = make_float2(a0, a1);
+  }
+  if (tmO != nullptr) {
+    // staging -> global as ONE TMA store of the 32-row x 128-byte box: the staging tile's XOR pattern (16-byte segment ^
+    // (row & 7), 4 KB-aligned) IS the 128-byte TMA swizzle; rows beyond M are clipped by the hardware.  Replaces 8 LDS.128 +
+    // 8 STG.128 per thread and chunk in the issue-bound epilogue.
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmO, stg, col0, row0);
+      tma_store_commit();
+    }
+    return;       // the staging tile is released by the wait at its next use
   }
   // staging -> global, 4 full 128 B lines per instruction
 #pragma unroll

@@ -50,7 +50,8 @@ struct GemmSmem {
 // dY [rows][N_l] and X [rows][K_l] as they are, no transposed copies).  Each 64-wide block of M / N is its own TMA box.
 template <int BN, int STAGES, int ACC_STAGES, int MODE, bool F16, bool MNMAJOR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, GemmParams p) {
   using L = GemmSmem<BN, STAGES>;
   static_assert(ACC_STAGES * 2 * BN <= 512, "TMEM has 512 columns");
   constexpr int TCOLS = 512;
@@ -195,7 +196,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = colgrp; c < BN / CH_COLS; c += 2)
         epi_chunk<MODE, F16>(p, tbase + c * CH_COLS, m0 + half * 128 + q * 32, n0 + c * CH_COLS, stg, lane,
-                        sq_buf + (half * 4 + q) * BN + c * CH_COLS, out_base);
+                        sq_buf + (half * 4 + q) * BN + c * CH_COLS, out_base, p.tma_store ? &tmO : nullptr);
       // all TMEM reads of this stage are complete (tmem_ld_wait above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -216,21 +217,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   }
+  if (p.tma_store && warp >= EPI_WARP0 && lane == 0) tma_store_wait_all();   // this warp's last TMA stores have landed
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, TCOLS);
 }
 
 template <int BN, int STAGES, int ACC_STAGES, int MODE, bool F16, bool MNMAJOR = false>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p0, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
+  // output map for the epilogue's TMA stores (box = one staged chunk: 32 rows x 128 bytes); not with split-K, whose pieces
+  // write row-offset planes of a workspace.  FZ_GEMM_TMA_STORE=0: the round-1 st.global path.
+  GemmParams p = p0;
+  CUtensorMap tmO = tmA;
+  p.tma_store = 0;
+  static int tma_store = -1;
+  if (tma_store < 0) {
+    const char* e = getenv("FZ_GEMM_TMA_STORE");
+    tma_store = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (tma_store && p.splits == 1 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+    constexpr bool F32OUT = EpiShape<MODE>::F32OUT;
+    const uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+    const uint64_t strides[1] = {(uint64_t)p.N * (F32OUT ? 4 : 2)};
+    const uint32_t box[2] = {F32OUT ? 32u : 64u, 32u};
+    if (int rc = F32OUT ? make_tmap32(&tmO, p.out, 2, dims, strides, box, 128) : make_tmap16(&tmO, p.out, 2, dims, strides, box, 128))
+      return rc;
+    p.tma_store = 1;
+  }
   auto kern = gemm_bf16_kernel<BN, STAGES, ACC_STAGES, MODE, F16, MNMAJOR>;
   FZ_ENSURE_SMEM(kern, L::BYTES);
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return -2;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * p.splits;
   const int grid = tiles < sm_count ? tiles : sm_count;
-  kern<<<grid, GEMM_THREADS, L::BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, GEMM_THREADS, L::BYTES, stream>>>(tmA, tmB, tmO, p);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -288,7 +309,7 @@ extern "C" int fz_gemm_bf16(const void* A, const void* B, void* out, const float
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = g_trace;
   p.reverse = reverse;
   p.f16 = f16;
-  p.splits = 1; p.kb_per_split = K / BK; p.nobias = 0;
+  p.splits = 1; p.kb_per_split = K / BK; p.nobias = 0; p.tma_store = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // CTA-pair kernel (256x256 tile over two SMs, gemm_tcgen05_2sm.cu): wide outputs with enough tiles for 74 pairs.
   // FZ_GEMM_PAIR=0 disables, =2 forces it whenever N % 256 == 0.
@@ -366,7 +387,7 @@ extern "C" int fz_gemm_bf16_splitk(const void* A, const void* B, float* out, flo
   p.rows_per_sample = M; p.b_batched = 0;
   p.bias = nullptr; p.resid = nullptr; p.sumsq = nullptr; p.trace = nullptr; p.reverse = 0;
   p.f16 = (flags & FZ_EPI_OPERANDS_F16) ? 1 : 0;
-  p.nobias = 1;
+  p.nobias = 1; p.tma_store = 0;
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty piece
   p.out = p.splits > 1 ? static_cast<void*>(workspace) : static_cast<void*>(out);
@@ -414,7 +435,7 @@ extern "C" int fz_gemm_bf16_splitk_tn(const void* At, const void* Bt, float* out
   p.rows_per_sample = M; p.b_batched = 0;
   p.bias = nullptr; p.resid = nullptr; p.sumsq = nullptr; p.trace = nullptr; p.reverse = 0;
   p.f16 = (flags & FZ_EPI_OPERANDS_F16) ? 1 : 0;
-  p.nobias = 1;
+  p.nobias = 1; p.tma_store = 0;
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.out = p.splits > 1 ? static_cast<void*>(workspace) : static_cast<void*>(out);
@@ -520,7 +541,7 @@ extern "C" int fz_gemm_bf16_simt(const void* A, const void* B, void* out, const 
   p.b_batched = b_batch > 1 ? 1 : 0;
   p.bias = bias; p.out = out; p.resid = resid; p.sumsq = sumsq; p.trace = nullptr;
   p.reverse = 0;
-  p.splits = 1; p.kb_per_split = K / 16; p.nobias = 0;
+  p.splits = 1; p.kb_per_split = K / 16; p.nobias = 0; p.tma_store = 0;
   p.f16 = (mode & FZ_EPI_OPERANDS_F16) ? 1 : 0;
   mode &= ~(FZ_EPI_REVERSE_TILES | FZ_EPI_OPERANDS_F16);
   dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);

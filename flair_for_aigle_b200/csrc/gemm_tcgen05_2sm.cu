@@ -35,7 +35,8 @@ constexpr int EPI_WARP0 = 4;
 
 template <int MODE, bool F16>
 __global__ void __launch_bounds__(pair::THREADS, 1)
-gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmO, GemmParams p) {
   using namespace pair;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -142,7 +143,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll 1
       for (int c = colgrp; c < BN / CH_COLS; c += 4)
         epi_chunk<MODE, F16>(p, tbase + c * CH_COLS, m0 + q * 32, n0 + c * CH_COLS, stg, lane,
-                        sq_buf + q * BN + c * CH_COLS, p.out);
+                        sq_buf + q * BN + c * CH_COLS, p.out, p.tma_store ? &tmO : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
@@ -160,6 +161,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   }
+  if (p.tma_store && warp >= EPI_WARP0 && lane == 0) tma_store_wait_all();   // this warp's last TMA stores have landed
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // the peer's smem / barriers / TMEM stay alive until both CTAs are done
@@ -167,7 +169,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 template <int MODE, bool F16>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
+                       cudaStream_t stream) {
   auto kern = gemm_bf16_pair_kernel<MODE, F16>;
   FZ_ENSURE_SMEM(kern, pair::SMEM_BYTES);
   const int sm_count = device_sm_count();
@@ -186,7 +189,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FZ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  FZ_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p));
   return 0;
 }
 
@@ -207,13 +210,32 @@ int gemm_pair_launch(const void* A, const void* B, const GemmParams& p, int b_ba
     int rc = make_tmap16(&tmB, B, 3, dims, strides, box, 128);
     if (rc) return rc;
   }
+  // output map for the epilogue's TMA stores: box = 32 rows x 128 bytes (one staged chunk), 128-byte swizzle.
+  // FZ_GEMM_TMA_STORE=0 keeps the round-1 register -> smem -> st.global path (A/B measurements).
+  GemmParams q = p;
+  static int tma_store = -1;
+  if (tma_store < 0) {
+    const char* e = getenv("FZ_GEMM_TMA_STORE");
+    tma_store = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool f32out = mode == FZ_EPI_RESID_F32 || mode == FZ_EPI_F32;
+  CUtensorMap tmO = tmA;     // placeholder when unused
+  q.tma_store = 0;
+  if (tma_store && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+    const uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+    const uint64_t strides[1] = {(uint64_t)p.N * (f32out ? 4 : 2)};
+    const uint32_t box[2] = {f32out ? 32u : 64u, 32u};
+    int rc = f32out ? make_tmap32(&tmO, p.out, 2, dims, strides, box, 128) : make_tmap16(&tmO, p.out, 2, dims, strides, box, 128);
+    if (rc) return rc;
+    q.tma_store = 1;
+  }
   switch (mode) {
-    case FZ_EPI_BF16: return p.f16 ? launch_pair<FZ_EPI_BF16, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_BF16, false>(tmA, tmB, p, stream);
-    case FZ_EPI_GELU_SUMSQ: return p.f16 ? launch_pair<FZ_EPI_GELU_SUMSQ, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_GELU_SUMSQ, false>(tmA, tmB, p, stream);
-    case FZ_EPI_RESID_F32: return p.f16 ? launch_pair<FZ_EPI_RESID_F32, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_RESID_F32, false>(tmA, tmB, p, stream);
-    case FZ_EPI_F32: return p.f16 ? launch_pair<FZ_EPI_F32, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_F32, false>(tmA, tmB, p, stream);
-    case FZ_EPI_RELU_BF16: return p.f16 ? launch_pair<FZ_EPI_RELU_BF16, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_RELU_BF16, false>(tmA, tmB, p, stream);
-    case FZ_EPI_GELU_BF16: return p.f16 ? launch_pair<FZ_EPI_GELU_BF16, true>(tmA, tmB, p, stream) : launch_pair<FZ_EPI_GELU_BF16, false>(tmA, tmB, p, stream);
+    case FZ_EPI_BF16: return q.f16 ? launch_pair<FZ_EPI_BF16, true>(tmA, tmB, tmO, q, stream) : launch_pair<FZ_EPI_BF16, false>(tmA, tmB, tmO, q, stream);
+    case FZ_EPI_GELU_SUMSQ: return q.f16 ? launch_pair<FZ_EPI_GELU_SUMSQ, true>(tmA, tmB, tmO, q, stream) : launch_pair<FZ_EPI_GELU_SUMSQ, false>(tmA, tmB, tmO, q, stream);
+    case FZ_EPI_RESID_F32: return q.f16 ? launch_pair<FZ_EPI_RESID_F32, true>(tmA, tmB, tmO, q, stream) : launch_pair<FZ_EPI_RESID_F32, false>(tmA, tmB, tmO, q, stream);
+    case FZ_EPI_F32: return q.f16 ? launch_pair<FZ_EPI_F32, true>(tmA, tmB, tmO, q, stream) : launch_pair<FZ_EPI_F32, false>(tmA, tmB, tmO, q, stream);
+    case FZ_EPI_RELU_BF16: return q.f16 ? launch_pair<FZ_EPI_RELU_BF16, true>(tmA, tmB, tmO, q, stream) : launch_pair<FZ_EPI_RELU_BF16, false>(tmA, tmB, tmO, q, stream);
+    case FZ_EPI_GELU_BF16: return q.f16 ? launch_pair<FZ_EPI_GELU_BF16, true>(tmA, tmB, tmO, q, stream) : launch_pair<FZ_EPI_GELU_BF16, false>(tmA, tmB, tmO, q, stream);
   }
   set_error("fz_gemm_bf16: unknown epilogue mode %d", mode);
   return -1;

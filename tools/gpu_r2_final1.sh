@@ -1,0 +1,10 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -s -p no:cacheprovider --maxfail=15 > gpurun_out/r2_pytest_gpu_final.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest_gpu_final.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1 | cut -c1-140
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1_final.json 2> gpurun_out/r2_bench_n1_final.err; echo "bench rc=$?"; head -c 260 gpurun_out/r2_bench_n1_final.json; echo
+BENCH="python bench.py --steps 1 --warmup 1 --no-train --no-cpu-baseline"
+$BENCH > gpurun_out/r2_ncu_plain_bench.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 2400 --csv --log-file gpurun_out/r2_ncu_launches.csv $BENCH > gpurun_out/r2_ncu_bench_under_ncu.log 2>&1
+echo "launch list rc=$?"
