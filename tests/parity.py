@@ -6,7 +6,7 @@ relative error stated), and the class map must agree on at least 99.9% of pixels
 Round 2 state (fp16 operands, fp32 accumulate): the engine reproduces "the fp32 forward with its tensor-core operands
 rounded to fp16" to within 1 % at every stage (tests/diag/gpu_stage_errors.py, profiles/r2_stage_errors.txt), i.e. it
 sits ON the 16-bit-operand floor.  Where that floor lies in class agreement depends on how many near-ties the random-
-init network has: measured 99.86 % .. 99.98 % of ALL pixels over the test zones / tiles / architectures (mean 99.91 %),
+init network has: measured 99.84 % .. 99.98 % of ALL pixels over the test zones / tiles / architectures (mean 99.91 %),
 100 % of the pixels whose top-2 gap exceeds 5 % of the logit std.  The bars below are the measured minima with a small
 margin -- they are 8-10x tighter than round 1's bf16 bars (0.98 / 1.5 % / 15 %).
 """
