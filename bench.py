@@ -311,7 +311,8 @@ def train_block(dev, rank: int, world: int, steps: int, warmup: int):
     depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
     w = torch.ones(N_CLS, device=dev)
     w[15:] = 0
-    tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w)
+    graphed = os.environ.get("FZ_TRAIN_GRAPH", "1") != "0"      # the step replayed as ONE CUDA graph (engine/train_step.py)
+    tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w, cuda_graph=graphed)
     g = torch.Generator(device="cpu").manual_seed(2025 + rank)
     host = {k: torch.randn(B, c, P, P, generator=g).pin_memory() for k, c in mods.items()}
     host[TASK] = torch.randint(0, N_CLS, (B, P, P), generator=g, dtype=torch.int32).pin_memory()
@@ -322,7 +323,7 @@ def train_block(dev, rank: int, world: int, steps: int, warmup: int):
         loss, _ = tr.step(batch)
         return float(loss)                                                     # D2H of the loss
 
-    losses = [one_step() for _ in range(max(1, warmup))]
+    losses = [one_step() for _ in range(max(2, warmup))]        # step 1 eager, step 2 captures the graph, then replays
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -356,7 +357,7 @@ def train_block(dev, rank: int, world: int, steps: int, warmup: int):
     return {"config": "configs[4]: convnextv2_base-unet, AERIAL_RGBI 4ch + DEM_ELEV 1ch, batch 16 x 512^2 per GPU, weighted CE, "
                       "AdamW, DDP all-reduce of the gradient arena; inputs from pinned host memory every step, loss read back",
             "samples_per_s": round(B * world / ms_step * 1e3, 2), "samples_per_s_per_gpu": round(B / ms_step * 1e3, 2),
-            "ms_per_step": round(ms_step, 2), "steps": steps, "warmup": max(1, warmup),
+            "ms_per_step": round(ms_step, 2), "steps": steps, "warmup": max(2, warmup), "cuda_graph": graphed,
             "allreduce_ms_exposed": round(ms_ar, 3), "allreduce": "bucketed per backward group (decoder, fusion, encoder stages deepest "
             "first), each bucket's NCCL all-reduce started on a side stream as its gradients land; exposed = what the compute "
             "stream waited at the end", "max_parameter_difference_across_ranks": drift, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,

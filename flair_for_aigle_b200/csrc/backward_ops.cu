@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "reduce_vec.cuh"
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
@@ -81,6 +82,65 @@ __global__ void __launch_bounds__(256) dwconv7_f32_tiled_kernel(const float* __r
     float* op = out + (img + static_cast<size_t>(y) * W + x0) * C + c;
 #pragma unroll
     for (int j = 0; j < 8; ++j) op[static_cast<size_t>(j) * C] = acc[j];
+  }
+}
+
+// 4 x 8 pixel tiles (H % 4 == 0, W % 8 == 0): an input row loaded once feeds up to four output rows, 140 loads per 1568 FMAs
+// (the 1 x 8 form above: 98 per 392), which is what bounds these kernels -- the loads hit L1/L2, the LSU issue rate is the
+// limit.  `add` (optional, same layout as out) is summed into the result: the block backward's dx = dy + dwconv^T(du) without
+// a separate pass.  grid (C/32, ceil(n_tiles / 16)), two tiles per warp.
+__global__ void __launch_bounds__(256) dwconv7_f32_tile48_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, const float* __restrict__ add,
+                                                                 float* __restrict__ out, int B, int H, int W, int C, int flip) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  if (c >= C) return;
+  const int tiles_x = W / 8, tiles_y = H / 4, n_tiles = B * tiles_y * tiles_x;
+  float wr[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) wr[k] = w[(flip ? 48 - k : k) * C + c];
+  const float b0 = bias ? bias[c] : 0.f;
+  for (int i = 0; i < 2; ++i) {
+    const int t = (blockIdx.y * 8 + warp) * 2 + i;
+    if (t >= n_tiles) return;
+    const int trow = t / tiles_x, tx = t - trow * tiles_x, ty = trow % tiles_y, b = trow / tiles_y;
+    const int x0 = tx * 8, y0 = ty * 4;
+    const size_t img = static_cast<size_t>(b) * H * W;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = b0;
+#pragma unroll
+    for (int iy = 0; iy < 10; ++iy) {
+      const int gy = y0 - 3 + iy;
+      if (gy < 0 || gy >= H) continue;                       // warp-uniform
+      const float* xr = in + (img + static_cast<size_t>(gy) * W) * C + c;
+      float xs[14];
+#pragma unroll
+      for (int q = 0; q < 14; ++q) {
+        const int ix = x0 - 3 + q;
+        xs[q] = (ix >= 0 && ix < W) ? xr[static_cast<size_t>(ix) * C] : 0.f;
+      }
+#pragma unroll
+      for (int oy = 0; oy < 4; ++oy) {
+        const int ky = iy - oy;
+        if (ky >= 0 && ky < 7) {
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[oy * 8 + j] = fmaf(xs[j + kx], wr[ky * 7 + kx], acc[oy * 8 + j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int oy = 0; oy < 4; ++oy) {
+      const size_t o = (img + static_cast<size_t>(y0 + oy) * W + x0) * C + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = acc[oy * 8 + j];
+        if (add) v += add[o + static_cast<size_t>(j) * C];
+        out[o + static_cast<size_t>(j) * C] = v;
+      }
+    }
   }
 }
 
@@ -173,6 +233,69 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_tiled_kernel(const float* _
     for (int k = warp; k < 50; k += 8) partial[(static_cast<size_t>(blockIdx.y) * 50 + k) * C + c] = red[k][lane];
 }
 
+// The same reduction over 4 x 8 pixel tiles (H % 4 == 0): 32 output gradients and 10 x 14 inputs per 1568 MACs.
+// grid (C/32, chunks); a chunk is a run of tiles_per_chunk tiles, its 8 warps take them round robin.
+__global__ void __launch_bounds__(256) dwconv7_wgrad_tile48_kernel(const float* __restrict__ x, const float* __restrict__ du,
+                                                                   float* __restrict__ partial, int B, int H, int W, int C,
+                                                                   int tiles_per_chunk) {
+  __shared__ float red[50][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int tiles_x = W / 8, tiles_y = H / 4, n_tiles = B * tiles_y * tiles_x;
+  const int t0 = blockIdx.y * tiles_per_chunk;
+  const int t1 = t0 + tiles_per_chunk < n_tiles ? t0 + tiles_per_chunk : n_tiles;
+  float acc[50];
+#pragma unroll
+  for (int k = 0; k < 50; ++k) acc[k] = 0.f;
+  if (c < C)
+    for (int t = t0 + warp; t < t1; t += 8) {
+      const int trow = t / tiles_x, tx = t - trow * tiles_x, ty = trow % tiles_y, b = trow / tiles_y;
+      const int x0 = tx * 8, y0 = ty * 4;
+      const size_t img = static_cast<size_t>(b) * H * W;
+      float g[32];
+#pragma unroll
+      for (int oy = 0; oy < 4; ++oy) {
+        const float* gp = du + ((img + static_cast<size_t>(y0 + oy) * W + x0) * C + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          g[oy * 8 + j] = gp[static_cast<size_t>(j) * C];
+          acc[49] += g[oy * 8 + j];
+        }
+      }
+#pragma unroll
+      for (int iy = 0; iy < 10; ++iy) {
+        const int gy = y0 - 3 + iy;
+        if (gy < 0 || gy >= H) continue;
+        const float* xr = x + (img + static_cast<size_t>(gy) * W) * C + c;
+        float xs[14];
+#pragma unroll
+        for (int q = 0; q < 14; ++q) {
+          const int ix = x0 - 3 + q;
+          xs[q] = (ix >= 0 && ix < W) ? xr[static_cast<size_t>(ix) * C] : 0.f;
+        }
+#pragma unroll
+        for (int oy = 0; oy < 4; ++oy) {
+          const int ky = iy - oy;
+          if (ky >= 0 && ky < 7) {
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[ky * 7 + kx] = fmaf(g[oy * 8 + j], xs[j + kx], acc[ky * 7 + kx]);
+          }
+        }
+      }
+    }
+  for (int w2 = 0; w2 < 8; ++w2) {                           // the 8 warps' sums, added in warp order (reproducible)
+    if (warp == w2) {
+#pragma unroll
+      for (int k = 0; k < 50; ++k) red[k][lane] = (w2 == 0 ? 0.f : red[k][lane]) + acc[k];
+    }
+    __syncthreads();
+  }
+  if (c < C)
+    for (int k = warp; k < 50; k += 8) partial[(static_cast<size_t>(blockIdx.y) * 50 + k) * C + c] = red[k][lane];
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm rows
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -244,14 +367,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
   }
 }
 
-// out[n] = sum_s partial[s][n], fixed order
+// out[n] = sum_s partial[s][n]: 32 columns x 8 row lanes per block, lane k adds rows k, k+8, ... in order and the eight lane
+// sums are added in lane order (a fixed order; the one-thread-per-column form chained up to 592 dependent loads).
+// grid ceil(N / 32)
 __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int N,
                                                           int S) {
-  const int n = blockIdx.x * 256 + threadIdx.x;
-  if (n >= N) return;
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31), k = threadIdx.x >> 5;
   float t = 0.f;
-  for (int s = 0; s < S; ++s) t += partial[static_cast<size_t>(s) * N + n];
-  out[n] = t;
+  if (n < N)
+    for (int s = k; s < S; s += 8) t += partial[static_cast<size_t>(s) * N + n];
+  red[k][threadIdx.x & 31] = t;
+  __syncthreads();
+  if (k == 0 && n < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += red[j][threadIdx.x];
+    out[n] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ GELU (erf)
@@ -410,6 +543,99 @@ __global__ void __launch_bounds__(256) grn_gelu_bwd_kernel(const __nv_bfloat16* 
   store8(dh + i, d);
 }
 
+// Row-walking forms of the two kernels above (reduce_vec.cuh's geometry: a thread owns one 8-channel group, the block walks
+// its row chunk): the per-(sample, channel) coefficients are loaded ONCE into registers instead of 16-24 scalar loads per
+// 16-byte payload load.  grid (slabs, chunks, B).
+__global__ void __launch_bounds__(256) grn_apply_rows_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ nx,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             __nv_bfloat16* __restrict__ y, int rows, int C, int cgs,
+                                                             int rows_per_chunk) {
+  const int rp = 256 / cgs;
+  const int cl = threadIdx.x % cgs, rr = threadIdx.x / cgs;
+  const int cg = blockIdx.x * cgs + cl;
+  if (rr >= rp || cg * 8 >= C) return;
+  const size_t b = blockIdx.z;
+  float ca[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ca[j] = 1.0f + gamma[cg * 8 + j] * nx[b * C + cg * 8 + j];
+    be[j] = beta[cg * 8 + j];
+  }
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  const size_t base = b * rows * C + static_cast<size_t>(cg) * 8;
+#pragma unroll 4
+  for (int r = r0 + rr; r < r1; r += rp) {
+    const size_t o = base + static_cast<size_t>(r) * C;
+    float v[8];
+    load8(g + o, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * ca[j] + be[j];
+    store8(y + o, v);
+  }
+}
+
+// dh = (dy * coefA[b] + g * coefB[b]) * GELU'(h), and the column sums of the stored (rounded) dh per (sample, chunk): fc1's
+// bias gradient without another pass over dh.   db_partial[(b * chunks + chunk) * C + c]
+__global__ void __launch_bounds__(256) grn_gelu_bwd_rows_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                const __nv_bfloat16* __restrict__ g,
+                                                                const __nv_bfloat16* __restrict__ h,
+                                                                const float* __restrict__ coef_a, const float* __restrict__ coef_b,
+                                                                __nv_bfloat16* __restrict__ dh, float* __restrict__ db_partial,
+                                                                int rows, int C, int cgs, int rows_per_chunk) {
+  __shared__ float red[256][9];
+  const int rp = 256 / cgs;
+  const int cl = threadIdx.x % cgs, rr = threadIdx.x / cgs;
+  const int cg = blockIdx.x * cgs + cl;
+  const bool active = rr < rp && cg * 8 < C;
+  const size_t b = blockIdx.z;
+  float ca[8], cb[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ca[j] = active ? coef_a[b * C + cg * 8 + j] : 0.f;
+    cb[j] = active ? coef_b[b * C + cg * 8 + j] : 0.f;
+    acc[j] = 0.f;
+  }
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  const size_t base = b * rows * C + static_cast<size_t>(cg) * 8;
+  if (active) {
+#pragma unroll 2
+    for (int r = r0 + rr; r < r1; r += rp) {
+      const size_t o = base + static_cast<size_t>(r) * C;
+      float d[8], gg[8], hh[8];
+      load8(dy + o, d);
+      load8(g + o, gg);
+      load8(h + o, hh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = (d[j] * ca[j] + gg[j] * cb[j]) * gelu_grad(hh[j]);
+      rv_store8_round(dh + o, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += d[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (rr == 0 && cg * 8 < C) {
+    float* dst = db_partial + (b * gridDim.y + blockIdx.y) * C + static_cast<size_t>(cg) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+      for (int q = 0; q < rp; ++q) t += red[q * cgs + cl][j];
+      dst[j] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) add_f32x4_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                        float4* __restrict__ out, int64_t n4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 u = a[i], v = b[i];
+  out[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+}
+
 __global__ void __launch_bounds__(256) add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                       float* __restrict__ out, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
@@ -485,6 +711,52 @@ __global__ void __launch_bounds__(256) col2im3x3_kernel(const __nv_bfloat16* __r
         acc += __bfloat162float(dcol[(q - static_cast<int64_t>(ky - 1) * W - (kx - 1)) * Kpad + (ky * 3 + kx) * C + c]);
     }
   dx[i] = acc;
+}
+
+// 8 channels (16 bytes) per thread, C % 8 == 0: one thread per (pixel, 8-wide slice of the Kpad row); 32-bit tap arithmetic
+__global__ void __launch_bounds__(256) im2col3x3_vec_kernel(const uint4* __restrict__ in, uint4* __restrict__ col, int H, int W,
+                                                            int C8, int K8, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int k8 = static_cast<int>(i % K8);
+  const int64_t p = i / K8;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (k8 < 9 * C8) {
+    const int tap = k8 / C8, c8 = k8 - tap * C8, ky = tap / 3, kx = tap - ky * 3;
+    const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+    const int iy = y + ky - 1, ix = x + kx - 1;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in[(p + static_cast<int64_t>(ky - 1) * W + (kx - 1)) * C8 + c8];
+  }
+  col[i] = v;
+}
+
+// one thread per (pixel, 8 channels): nine 16-byte reads of dcol, two float4 writes
+__global__ void __launch_bounds__(256) col2im3x3_vec_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dx, int H,
+                                                            int W, int C, int Kpad, int64_t n8) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n8) return;
+  const int C8 = C / 8;
+  const int c = static_cast<int>(i % C8) * 8;
+  const int64_t q = i / C8;
+  const int x = static_cast<int>(q % W), y = static_cast<int>((q / W) % H);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int py = y - (ky - 1), px = x - (kx - 1);
+      if (py >= 0 && py < H && px >= 0 && px < W) {
+        float v[8];
+        load8(dcol + (q - static_cast<int64_t>(ky - 1) * W - (kx - 1)) * Kpad + (ky * 3 + kx) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    }
+  float4* o = reinterpret_cast<float4*>(dx + q * C + c);
+  o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
 // partial[s][0][c] = sum_rows f0, partial[s][1][c] = sum_rows f1 over row chunk s.   grid (C/32, chunks)
@@ -607,10 +879,18 @@ using namespace fz;
 typedef const __nv_bfloat16* cbf;
 typedef __nv_bfloat16* bf;
 
-extern "C" int fz_dwconv7_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C,
-                              int flip, void* stream) {
+extern "C" int fz_dwconv7_f32_add(const float* in, const float* w, const float* bias, const float* add, float* out, int B,
+                                  int H, int W, int C, int flip, void* stream) {
   FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && in && w && out, "fz_dwconv7_f32: bad arguments");
   FZ_REQUIRE(H <= 65535 && B <= 65535, "fz_dwconv7_f32: H=%d B=%d exceed the grid limits", H, B);
+  if (W % 8 == 0 && H % 4 == 0) {
+    const int64_t n_tiles = static_cast<int64_t>(B) * (H / 4) * (W / 8);
+    FZ_REQUIRE(n_tiles < (1LL << 31) && (n_tiles + 15) / 16 <= 65535, "fz_dwconv7_f32: too many tiles");
+    dwconv7_f32_tile48_kernel<<<dim3((C + 31) / 32, static_cast<unsigned>((n_tiles + 15) / 16)), 256, 0, ST(stream)>>>(
+        in, w, bias, add, out, B, H, W, C, flip);
+    FZ_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (W % 8 == 0) {
     const int64_t n_tiles = static_cast<int64_t>(B) * H * (W / 8);
     FZ_REQUIRE(n_tiles < (1LL << 31) && (n_tiles + 31) / 32 <= 65535, "fz_dwconv7_f32: too many tiles");
@@ -620,7 +900,17 @@ extern "C" int fz_dwconv7_f32(const float* in, const float* w, const float* bias
     dwconv7_f32_kernel<<<dim3((W * C + 255) / 256, H, B), 256, 0, ST(stream)>>>(in, w, bias, out, H, W, C, flip);
   }
   FZ_CHECK_CUDA(cudaGetLastError());
+  if (add) {                                                   // ragged shapes: the sum as its own pass (out += add)
+    const int64_t n = static_cast<int64_t>(B) * H * W * C;
+    add_f32_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(out, add, out, n);
+    FZ_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
+}
+
+extern "C" int fz_dwconv7_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C,
+                              int flip, void* stream) {
+  return fz_dwconv7_f32_add(in, w, bias, nullptr, out, B, H, W, C, flip, stream);
 }
 
 extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, float* db, int B, int H, int W, int C,
@@ -630,8 +920,9 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
   // global loads; partial[chunk][50][C] lives in a per-device scratch buffer and is summed in a fixed order
   const int64_t npx = static_cast<int64_t>(B) * H * W;
   FZ_REQUIRE(npx < (1LL << 31), "fz_dwconv7_wgrad: B*H*W must fit int32");
-  const bool tiled = W % 8 == 0;
-  int chunks = tiled ? static_cast<int>(npx / 8 / 8) : static_cast<int>(npx / 2048);      // >= 8 tiles (one per warp) per chunk
+  const bool tiled = W % 8 == 0, tile48 = tiled && H % 4 == 0;
+  int chunks = tile48 ? static_cast<int>(npx / 32 / 8)                                    // >= 8 tiles (one per warp) per chunk
+                      : (tiled ? static_cast<int>(npx / 8 / 8) : static_cast<int>(npx / 2048));
   chunks = chunks < 1 ? 1 : (chunks > 128 ? 128 : chunks);
   const int ppc = static_cast<int>((npx + chunks - 1) / chunks);
   static float* scratch[64] = {nullptr};
@@ -647,14 +938,18 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
   }
   float* partial = scratch[dev];
   float* sums = partial + static_cast<size_t>(chunks) * 50 * C;
-  if (tiled) {
+  if (tile48) {
+    const int n_tiles = static_cast<int>(npx / 32);
+    dwconv7_wgrad_tile48_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, ST(stream)>>>(x, du, partial, B, H, W, C,
+                                                                                    (n_tiles + chunks - 1) / chunks);
+  } else if (tiled) {
     const int n_tiles = static_cast<int>(npx / 8);
     dwconv7_wgrad_tiled_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, ST(stream)>>>(x, du, partial, B, H, W, C,
                                                                                    (n_tiles + chunks - 1) / chunks);
   } else {
     dwconv7_wgrad_kernel<<<dim3(50, (C + 31) / 32, chunks), 256, 0, ST(stream)>>>(x, du, partial, B, H, W, C, ppc);
   }
-  reduce_rows_kernel<<<(50 * C + 255) / 256, 256, 0, ST(stream)>>>(partial, sums, 50 * C, chunks);
+  reduce_rows_kernel<<<(50 * C + 31) / 32, 256, 0, ST(stream)>>>(partial, sums, 50 * C, chunks);
   FZ_CHECK_CUDA(cudaMemcpyAsync(dw, sums, static_cast<size_t>(49) * C * sizeof(float), cudaMemcpyDeviceToDevice, ST(stream)));
   FZ_CHECK_CUDA(cudaMemcpyAsync(db, sums + static_cast<size_t>(49) * C, C * sizeof(float), cudaMemcpyDeviceToDevice, ST(stream)));
   FZ_CHECK_CUDA(cudaGetLastError());
@@ -677,7 +972,7 @@ extern "C" int fz_layernorm_bwd(const void* dy_bf16, const float* x, const float
   const int smem = 8 * 2 * C * 4;
   FZ_ENSURE_SMEM(kern, 8 * 2 * 2048 * 4);        // opt in once for the largest C (the attribute is set once per kernel)
   kern<<<blocks, 256, smem, ST(stream)>>>(reinterpret_cast<cbf>(dy_bf16), x, mean, rstd, g, dx, partial, M, C);
-  reduce_rows_kernel<<<(2 * C + 255) / 256, 256, 0, ST(stream)>>>(partial, dgamma_dbeta, 2 * C, blocks);
+  reduce_rows_kernel<<<(2 * C + 31) / 32, 256, 0, ST(stream)>>>(partial, dgamma_dbeta, 2 * C, blocks);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -694,9 +989,31 @@ extern "C" int fz_sample_colreduce(const void* a_bf16, const void* b_bf16, float
                                    void* stream) {
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && mode >= 0 && mode <= 2 && a_bf16 && out && (mode != 1 || b_bf16) && B <= 65535,
              "fz_sample_colreduce: bad arguments");
+  if (C % 8 == 0 && mode != 1) {
+    FZ_CHECK_CUDA(mode == 0 ? rv_colreduce<0>(a_bf16, nullptr, nullptr, out, nullptr, B, HW, C, ST(stream))
+                            : rv_colreduce<2>(a_bf16, nullptr, nullptr, out, nullptr, B, HW, C, ST(stream)));
+    return 0;
+  }
   sample_colreduce_kernel<<<dim3((C + 31) / 32, B), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(a_bf16),
                                                                           reinterpret_cast<cbf>(b_bf16), out, HW, C, mode);
   FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// s1[b][c] = sum_hw a*b, s0[b][c] = sum_hw a in ONE pass over both tensors (the GRN backward's two reductions)
+extern "C" int fz_sample_colreduce2(const void* a_bf16, const void* b_bf16, float* s1, float* s0, int B, int HW, int C,
+                                    void* stream) {
+  FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && a_bf16 && b_bf16 && s1 && s0 && B <= 65535,
+             "fz_sample_colreduce2: bad arguments (C %% 8 == 0)");
+  FZ_CHECK_CUDA(rv_colreduce<3>(a_bf16, b_bf16, nullptr, s1, s0, B, HW, C, ST(stream)));
+  return 0;
+}
+
+// g = GELU(h) (bf16) and sumsq[b][c] = sum_hw g^2 of the stored values, one pass
+extern "C" int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, float* sumsq, int B, int HW, int C, void* stream) {
+  FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && h_bf16 && g_bf16 && sumsq && B <= 65535,
+             "fz_gelu_fwd_sumsq: bad arguments (C %% 8 == 0)");
+  FZ_CHECK_CUDA(rv_colreduce<1>(h_bf16, nullptr, g_bf16, sumsq, nullptr, B, HW, C, ST(stream)));
   return 0;
 }
 
@@ -707,8 +1024,32 @@ extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, cons
   grn_norms_kernel<<<B, 256, 0, ST(stream)>>>(sumsq, gx, nx, mu, C, eps);
   const int64_t per = static_cast<int64_t>(HW) * C;
   FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_train_forward: C %% 8, HW*C < 2^31, B <= 65535");
-  grn_apply_train_kernel<<<dim3(static_cast<unsigned>((per / 8 + 255) / 256), B), 256, 0, ST(stream)>>>(
-      reinterpret_cast<cbf>(g_bf16), nx, gamma, beta, reinterpret_cast<bf>(y_bf16), static_cast<int>(per), C);
+  const RvGeom geo = rv_geometry(B, HW, C);
+  grn_apply_rows_kernel<<<dim3(geo.slabs, geo.chunks, B), 256, 0, ST(stream)>>>(
+      reinterpret_cast<cbf>(g_bf16), nx, gamma, beta, reinterpret_cast<bf>(y_bf16), HW, C, geo.cgs, geo.rows_per_chunk);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_grn_gelu_backward_db(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1,
+                                       const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
+                                       float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias,
+                                       int B, int HW, int C, float eps, void* stream) {
+  FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && dy_bf16 && g_bf16 && h_bf16 && s1 && s0 && gx && nx && mu && gamma && coef_a &&
+                 coef_b && dgamma && dbeta && dh_bf16,
+             "fz_grn_gelu_backward: bad arguments");
+  grn_bwd_coef_kernel<<<B, 256, 0, ST(stream)>>>(s1, gx, nx, mu, gamma, coef_a, coef_b, C, eps);
+  grn_param_grad_kernel<<<(C + 255) / 256, 256, 0, ST(stream)>>>(s1, s0, nx, dgamma, dbeta, B, C);
+  const int64_t per = static_cast<int64_t>(HW) * C;
+  FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_gelu_backward: C %% 8, HW*C < 2^31, B <= 65535");
+  // dh, and (dbias != NULL) the column sums of dh over all B*HW rows = the bias gradient of the Linear that produced h
+  const RvGeom geo = rv_geometry(B, HW, C);
+  float* partial = rv_scratch(static_cast<size_t>(B) * geo.chunks * C);
+  FZ_REQUIRE(partial != nullptr, "fz_grn_gelu_backward: no scratch memory");
+  grn_gelu_bwd_rows_kernel<<<dim3(geo.slabs, geo.chunks, B), 256, 0, ST(stream)>>>(
+      reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(g_bf16), reinterpret_cast<cbf>(h_bf16), coef_a, coef_b,
+      reinterpret_cast<bf>(dh_bf16), partial, HW, C, geo.cgs, geo.rows_per_chunk);
+  if (dbias) colreduce_final_kernel<<<dim3((C + 31) / 32, 1), 256, 0, ST(stream)>>>(partial, dbias, nullptr, B * geo.chunks, C, 1);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -717,23 +1058,19 @@ extern "C" int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, con
                                     const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
                                     float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, int B, int HW,
                                     int C, float eps, void* stream) {
-  FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && dy_bf16 && g_bf16 && h_bf16 && s1 && s0 && gx && nx && mu && gamma && coef_a &&
-                 coef_b && dgamma && dbeta && dh_bf16,
-             "fz_grn_gelu_backward: bad arguments");
-  grn_bwd_coef_kernel<<<B, 256, 0, ST(stream)>>>(s1, gx, nx, mu, gamma, coef_a, coef_b, C, eps);
-  grn_param_grad_kernel<<<(C + 255) / 256, 256, 0, ST(stream)>>>(s1, s0, nx, dgamma, dbeta, B, C);
-  const int64_t per = static_cast<int64_t>(HW) * C;
-  FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_gelu_backward: C %% 8, HW*C < 2^31, B <= 65535");
-  grn_gelu_bwd_kernel<<<dim3(static_cast<unsigned>((per / 8 + 255) / 256), B), 256, 0, ST(stream)>>>(
-      reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(g_bf16), reinterpret_cast<cbf>(h_bf16), coef_a, coef_b,
-      reinterpret_cast<bf>(dh_bf16), static_cast<int>(per), C);
-  FZ_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return fz_grn_gelu_backward_db(dy_bf16, g_bf16, h_bf16, s1, s0, gx, nx, mu, gamma, coef_a, coef_b, dgamma, dbeta, dh_bf16,
+                                 nullptr, B, HW, C, eps, stream);
 }
 
 extern "C" int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
   FZ_REQUIRE(n > 0 && a && b && out, "fz_add_f32: bad arguments");
-  add_f32_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(a, b, out, n);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (n % 4 == 0 && aligned)
+    add_f32x4_kernel<<<blocks_for(n / 4), 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(a),
+                                                                reinterpret_cast<const float4*>(b),
+                                                                reinterpret_cast<float4*>(out), n / 4);
+  else
+    add_f32_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(a, b, out, n);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -767,7 +1104,11 @@ extern "C" int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin
 extern "C" int fz_im2col3x3_bf16(const void* in, void* col, int B, int H, int W, int C, int Kpad, void* stream) {
   FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Kpad >= 9 * C && in && col, "fz_im2col3x3_bf16: bad arguments");
   const int64_t n = static_cast<int64_t>(B) * H * W * Kpad;
-  im2col3x3_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(in), reinterpret_cast<bf>(col), H, W, C, Kpad, n);
+  if (C % 8 == 0 && Kpad % 8 == 0)
+    im2col3x3_vec_kernel<<<blocks_for(n / 8), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(in),
+                                                                    reinterpret_cast<uint4*>(col), H, W, C / 8, Kpad / 8, n / 8);
+  else
+    im2col3x3_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(in), reinterpret_cast<bf>(col), H, W, C, Kpad, n);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -775,7 +1116,10 @@ extern "C" int fz_im2col3x3_bf16(const void* in, void* col, int B, int H, int W,
 extern "C" int fz_col2im3x3(const void* dcol_bf16, float* dx, int B, int H, int W, int C, int Kpad, void* stream) {
   FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Kpad >= 9 * C && dcol_bf16 && dx, "fz_col2im3x3: bad arguments");
   const int64_t n = static_cast<int64_t>(B) * H * W * C;
-  col2im3x3_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(dcol_bf16), dx, H, W, C, Kpad, n);
+  if (C % 8 == 0 && Kpad % 8 == 0)
+    col2im3x3_vec_kernel<<<blocks_for(n / 8), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(dcol_bf16), dx, H, W, C, Kpad, n / 8);
+  else
+    col2im3x3_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(dcol_bf16), dx, H, W, C, Kpad, n);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -792,10 +1136,10 @@ extern "C" int fz_bn_relu_train_forward(const float* x, int ldx, const float* ga
   float* sums = workspace + static_cast<size_t>(chunks) * 2 * C;   // [2][C]
   const dim3 grid((C + 31) / 32, chunks);
   bn_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, partial, M, C, rpc, 0);
-  reduce_rows_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, sums, 2 * C, chunks);
+  reduce_rows_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, sums, 2 * C, chunks);
   bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, mean, C, static_cast<float>(M), eps, 0);
   bn_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, mean, nullptr, partial, M, C, rpc, 1);
-  reduce_rows_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, sums, 2 * C, chunks);
+  reduce_rows_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, sums, 2 * C, chunks);
   bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, rstd, C, static_cast<float>(M), eps, 1);
   const int64_t n = M * C;
   bn_relu_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, reinterpret_cast<bf>(y_bf16), C, n);
@@ -813,7 +1157,7 @@ extern "C" int fz_bn_relu_backward(const float* x, int ldx, const void* dy_bf16,
   const int rpc = static_cast<int>((M + chunks - 1) / chunks);
   bn_partial_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, st>>>(x, ldx, reinterpret_cast<cbf>(dy_bf16),
                                                                  reinterpret_cast<cbf>(y_bf16), mean, rstd, workspace, M, C, rpc, 2);
-  reduce_rows_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(workspace, dbeta_dgamma, 2 * C, chunks);
+  reduce_rows_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(workspace, dbeta_dgamma, 2 * C, chunks);
   const int64_t n = M * ldd;
   bn_relu_bwd_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(y_bf16),
                                                           mean, rstd, gamma, dbeta_dgamma, reinterpret_cast<bf>(dx_bf16), ldd, C,
@@ -834,7 +1178,7 @@ extern "C" int fz_upsample2_concat_backward(const float* dcat, float* da, float*
 
 extern "C" int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* stream) {
   FZ_REQUIRE(N > 0 && S >= 1 && partial && out, "fz_reduce_rows_f32: bad arguments");
-  reduce_rows_kernel<<<(N + 255) / 256, 256, 0, ST(stream)>>>(partial, out, N, S);
+  reduce_rows_kernel<<<(N + 31) / 32, 256, 0, ST(stream)>>>(partial, out, N, S);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

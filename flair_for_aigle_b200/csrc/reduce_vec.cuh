@@ -1,0 +1,181 @@
+// Vectorised column reductions over bf16 [B][rows][C] activations for the training step (C % 8 == 0).
+//
+// The round-1 reductions gave every thread one channel and 2-byte loads (sample_colreduce_kernel: 0.6 TB/s, 20 ms per step).
+// Here a thread owns one 8-channel group (one 16-byte load per row) and the block walks its row chunk `rp` rows at a time,
+// so a warp reads 512 contiguous bytes per row and the per-channel coefficients / accumulators stay in registers.  Sums are
+// written per (sample, chunk) and added in chunk order by colreduce_final_kernel: the result does not depend on scheduling.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace fz {
+
+__device__ __forceinline__ void rv_load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(w[j] << 16);
+    v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+// rounds to bf16, stores, and leaves the ROUNDED values in v (what a later pass over the stored tensor would read)
+__device__ __forceinline__ void rv_store8_round(__nv_bfloat16* p, float (&v)[8]) {
+  uint4 q;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    v[2 * j] = __uint_as_float(w[j] << 16);
+    v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ float rv_gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// Geometry shared by the kernels below and their launchers: `cgs` column groups (of 8 channels) per block, rp = 256 / cgs
+// row lanes, grid (slabs, chunks, B).
+struct RvGeom {
+  int cgs, rp, slabs, chunks, rows_per_chunk;
+};
+static inline RvGeom rv_geometry(int B, int rows, int C, int max_chunks = 1 << 16) {
+  RvGeom g;
+  const int groups = C / 8;
+  g.cgs = groups < 256 ? groups : 256;
+  g.rp = 256 / g.cgs;
+  g.slabs = (groups + g.cgs - 1) / g.cgs;
+  int want = (148 * 4 + B * g.slabs - 1) / (B * g.slabs);             // ~4 blocks per SM over the whole grid
+  const int most = rows / (g.rp * 8) > 1 ? rows / (g.rp * 8) : 1;     // at least 8 rows per thread
+  want = want < 1 ? 1 : (want > most ? most : want);
+  g.chunks = want > max_chunks ? max_chunks : want;
+  g.rows_per_chunk = (rows + g.chunks - 1) / g.chunks;
+  g.chunks = (rows + g.rows_per_chunk - 1) / g.rows_per_chunk;
+  return g;
+}
+
+// MODE 0: sum a^2      1: g = GELU(a) stored to gout, sum g^2 (of the stored, rounded g)      2: sum a
+//      3: out0 = sum a*b, out1 = sum a
+// partial[((b * chunks + chunk) * NOUT + o) * C + c]
+template <int MODE>
+__global__ void __launch_bounds__(256) colreduce_vec_kernel(const __nv_bfloat16* __restrict__ a,
+                                                            const __nv_bfloat16* __restrict__ bb,
+                                                            __nv_bfloat16* __restrict__ gout, float* __restrict__ partial,
+                                                            int rows, int C, int cgs, int rows_per_chunk) {
+  constexpr int NOUT = MODE == 3 ? 2 : 1;
+  __shared__ float red[NOUT][256][9];                          // 9: the 8-float rows would collide 4-way on the banks
+  const int rp = 256 / cgs;
+  const int cl = threadIdx.x % cgs, rr = threadIdx.x / cgs;
+  const int cg = blockIdx.x * cgs + cl;
+  const bool active = rr < rp && cg * 8 < C;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  const size_t base = static_cast<size_t>(blockIdx.z) * rows * C + static_cast<size_t>(cg) * 8;
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
+  if (active) {
+#pragma unroll 4
+    for (int r = r0 + rr; r < r1; r += rp) {
+      const size_t o = base + static_cast<size_t>(r) * C;
+      float v[8];
+      rv_load8(a + o, v);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc0[j] = fmaf(v[j], v[j], acc0[j]);
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = rv_gelu_exact(v[j]);
+        rv_store8_round(gout + o, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc0[j] = fmaf(v[j], v[j], acc0[j]);
+      } else if (MODE == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc0[j] += v[j];
+      } else {
+        float w[8];
+        rv_load8(bb + o, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc0[j] = fmaf(v[j], w[j], acc0[j]);
+          acc1[j] += v[j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x][j] = acc0[j];
+    if (NOUT == 2) red[NOUT - 1][threadIdx.x][j] = acc1[j];
+  }
+  __syncthreads();
+  if (rr == 0 && cg * 8 < C) {
+    float* dst = partial + (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * NOUT * C + static_cast<size_t>(cg) * 8;
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = 0.f;
+        for (int q = 0; q < rp; ++q) t += red[o][q * cgs + cl][j];        // row lanes in a fixed order
+        dst[static_cast<size_t>(o) * C + j] = t;
+      }
+  }
+}
+
+// out_o[b][c] = sum_chunk partial[b][chunk][o][c].  32 channels x 8 chunk lanes per block: lane k adds chunks k, k+8, ... in
+// order, then the eight lane sums are added in lane order (fixed: reproducible).   grid (ceil(C / 32), B)
+static __global__ void __launch_bounds__(256) colreduce_final_kernel(const float* __restrict__ partial, float* __restrict__ out0,
+                                                                     float* __restrict__ out1, int chunks, int C, int nout) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), k = threadIdx.x >> 5;
+  const size_t b = blockIdx.y;
+  for (int o = 0; o < nout; ++o) {
+    float t = 0.f;
+    if (c < C)
+      for (int s = k; s < chunks; s += 8) t += partial[((b * chunks + s) * nout + o) * C + c];
+    red[k][threadIdx.x & 31] = t;
+    __syncthreads();
+    if (k == 0 && c < C) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v += red[j][threadIdx.x];
+      (o ? out1 : out0)[b * C + c] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// Per-device scratch for the partial sums (the training step runs its kernels on one stream).
+static inline float* rv_scratch(size_t floats) {
+  static float* buf[64] = {nullptr};
+  static size_t have[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (have[dev] < floats) {
+    if (buf[dev]) cudaFree(buf[dev]);
+    buf[dev] = nullptr;
+    have[dev] = 0;
+    if (cudaMalloc(&buf[dev], floats * sizeof(float)) != cudaSuccess) return nullptr;
+    have[dev] = floats;
+  }
+  return buf[dev];
+}
+
+// Launches MODE over a [B][rows][C] tensor; returns a cudaError_t.
+template <int MODE>
+static inline cudaError_t rv_colreduce(const void* a, const void* bb, void* gout, float* out0, float* out1, int B, int rows,
+                                       int C, cudaStream_t st) {
+  constexpr int NOUT = MODE == 3 ? 2 : 1;
+  const RvGeom g = rv_geometry(B, rows, C);
+  float* partial = rv_scratch(static_cast<size_t>(B) * g.chunks * NOUT * C);
+  if (!partial) return cudaErrorMemoryAllocation;
+  colreduce_vec_kernel<MODE><<<dim3(g.slabs, g.chunks, B), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(bb),
+      reinterpret_cast<__nv_bfloat16*>(gout), partial, rows, C, g.cgs, g.rows_per_chunk);
+  colreduce_final_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(partial, out0, out1, g.chunks, C, NOUT);
+  return cudaGetLastError();
+}
+
+}  // namespace fz

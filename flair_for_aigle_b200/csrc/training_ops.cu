@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "reduce_vec.cuh"
 #include "../../include/flair_zonal_b200.h"
 
 namespace fz {
@@ -173,6 +174,35 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   v[i] = vi;
 }
 
+// The step-dependent scalars computed ON THE DEVICE from a device-resident step counter, so that a whole training step
+// (this kernel included) can sit in a CUDA graph and be replayed: state[0] += 1; hyper = {lr / (1 - b1^t), sqrt(1 - b2^t)}
+__global__ void adamw_advance_kernel(long long* __restrict__ step, float* __restrict__ hyper, double lr, double beta1,
+                                     double beta2) {
+  const long long t = step[0] + 1;
+  step[0] = t;
+  hyper[0] = static_cast<float>(lr / (1.0 - pow(beta1, static_cast<double>(t))));
+  hyper[1] = static_cast<float>(sqrt(1.0 - pow(beta2, static_cast<double>(t))));
+}
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, int64_t n, float decay, float one_minus_b1,
+                                                        float b2, float one_minus_b2, const float* __restrict__ hyper,
+                                                        float eps) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float step_size = hyper[0], bc2_sqrt = hyper[1];
+  const float gi = g[i];
+  float pi = p[i] * decay;
+  float mi = m[i];
+  mi = mi + one_minus_b1 * (gi - mi);
+  float vi = v[i] * b2;
+  vi = vi + one_minus_b2 * (gi * gi);
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi = pi - step_size * (mi / denom);
+  p[i] = pi;
+  m[i] = mi;
+  v[i] = vi;
+}
+
 // out[c][r] = in[r][c] (bf16), 32 x 32 tiles through padded shared memory: the operand transposes that let the K-major
 // tcgen05 GEMM compute dX = dY W and dW = dY^T X (first backward building block; an MN-major operand path would save them)
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
@@ -294,6 +324,21 @@ extern "C" int fz_adamw_step(float* param, const float* grad, float* exp_avg, fl
   return 0;
 }
 
+extern "C" int fz_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                                 double beta1, double beta2, double eps, double weight_decay, int64_t* step_dev,
+                                 float* hyper_dev, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(n >= 0 && param && grad && exp_avg && exp_avg_sq && step_dev && hyper_dev, "fz_adamw_step_dev: bad arguments");
+  if (n == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  adamw_advance_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(step_dev), hyper_dev, lr, beta1, beta2);
+  adamw_dev_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      param, grad, exp_avg, exp_avg_sq, n, static_cast<float>(1.0 - lr * weight_decay), static_cast<float>(1.0 - beta1),
+      static_cast<float>(beta2), static_cast<float>(1.0 - beta2), hyper_dev, static_cast<float>(eps));
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int fz_transpose_bf16(const void* in, void* out, int R, int C, void* stream) {
   using namespace fz;
   FZ_REQUIRE(R > 0 && C > 0 && in && out, "fz_transpose_bf16: bad arguments");
@@ -310,6 +355,10 @@ extern "C" int fz_colsum_bf16(const void* in, float* partial, float* out, int64_
   FZ_REQUIRE(M > 0 && N > 0 && chunks >= 1 && chunks <= 65535 && in && partial && out, "fz_colsum_bf16: bad arguments");
   const int rows_per_chunk = static_cast<int>((M + chunks - 1) / chunks);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N % 8 == 0 && M < (1LL << 31)) {         // 16-byte loads, row-walking blocks; partial sums in the library's own scratch
+    FZ_CHECK_CUDA(fz::rv_colreduce<2>(in, nullptr, nullptr, out, nullptr, 1, static_cast<int>(M), N, st));
+    return 0;
+  }
   colsum_partial_kernel<<<dim3((N + 31) / 32, chunks), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), partial, M, N,
                                                                       rows_per_chunk);
   colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, out, N, chunks);

@@ -55,9 +55,8 @@ class ConvNeXtBlockTrain:
                                          _S()), "fz_layernorm_fwd_stats")
         h = nv.gemm_bf16(a1, self.w1, nv.EPI_BF16, bias=self.b1)                          # pre-GELU, bf16 [M,4C]
         g = torch.empty_like(h)
-        _chk(_L().fz_gelu_fwd(_P(h), _P(g), h.numel(), _S()), "fz_gelu_fwd")
         sumsq = torch.empty((B, C4), dtype=torch.float32, device=dev)
-        _chk(_L().fz_sample_colreduce(_P(g), None, _P(sumsq), B, H * W, C4, 0, _S()), "fz_sample_colreduce")
+        _chk(_L().fz_gelu_fwd_sumsq(_P(h), _P(g), _P(sumsq), B, H * W, C4, _S()), "fz_gelu_fwd_sumsq")   # GELU + GRN sums, one pass
         gx, nx = torch.empty_like(sumsq), torch.empty_like(sumsq)
         mu = torch.empty(B, dtype=torch.float32, device=dev)
         a2 = torch.empty_like(g)
@@ -80,29 +79,27 @@ class ConvNeXtBlockTrain:
         da2, dw2, db2 = nv.linear_backward(dyb, a2, self.w2)                              # fc2
         s1 = torch.empty((B, C4), dtype=torch.float32, device=dev)
         s0 = torch.empty_like(s1)
-        _chk(_L().fz_sample_colreduce(_P(da2), _P(g), _P(s1), B, H * W, C4, 1, _S()), "fz_sample_colreduce")
-        _chk(_L().fz_sample_colreduce(_P(da2), None, _P(s0), B, H * W, C4, 2, _S()), "fz_sample_colreduce")
+        _chk(_L().fz_sample_colreduce2(_P(da2), _P(g), _P(s1), _P(s0), B, H * W, C4, _S()), "fz_sample_colreduce2")
         ca, cb = torch.empty_like(s1), torch.empty_like(s1)
         dgrn_w = torch.empty(C4, dtype=torch.float32, device=dev)
         dgrn_b = torch.empty_like(dgrn_w)
         dh = torch.empty_like(h)
-        _chk(_L().fz_grn_gelu_backward(_P(da2), _P(g), _P(h), _P(s1), _P(s0), _P(gx), _P(nx), _P(mu), _P(self.grn_w), _P(ca),
-                                       _P(cb), _P(dgrn_w), _P(dgrn_b), _P(dh), B, H * W, C4, self.eps_grn, _S()),
-             "fz_grn_gelu_backward")
-        da1, dw1, db1 = nv.linear_backward(dh, a1, self.w1)                               # fc1
+        db1 = torch.empty(C4, dtype=torch.float32, device=dev)
+        _chk(_L().fz_grn_gelu_backward_db(_P(da2), _P(g), _P(h), _P(s1), _P(s0), _P(gx), _P(nx), _P(mu), _P(self.grn_w),
+                                          _P(ca), _P(cb), _P(dgrn_w), _P(dgrn_b), _P(dh), _P(db1), B, H * W, C4, self.eps_grn,
+                                          _S()), "fz_grn_gelu_backward_db")
+        da1, dw1, db1 = nv.linear_backward(dh, a1, self.w1, db=db1)                       # fc1 (bias gradient from the kernel above)
         blocks = max(1, min(592, (M + 7) // 8))
         du = torch.empty_like(u)
         partial = torch.empty((blocks, 2, C), dtype=torch.float32, device=dev)
         dln = torch.empty((2, C), dtype=torch.float32, device=dev)
         _chk(_L().fz_layernorm_bwd(_P(da1), _P(u), _P(mean), _P(rstd), _P(self.ln_w), _P(du), _P(partial), _P(dln), M, C,
                                    blocks, _S()), "fz_layernorm_bwd")
-        dconv = torch.empty_like(x)
-        _chk(_L().fz_dwconv7_f32(_P(du), _P(self.w_dw), None, _P(dconv), B, H, W, C, 1, _S()), "fz_dwconv7_f32")
+        dx = torch.empty_like(x)                                                          # dx = dy + dwconv^T(du), one pass
+        _chk(_L().fz_dwconv7_f32_add(_P(du), _P(self.w_dw), None, _P(dy), _P(dx), B, H, W, C, 1, _S()), "fz_dwconv7_f32_add")
         dw_dw = torch.empty((49, C), dtype=torch.float32, device=dev)
         db_dw = torch.empty(C, dtype=torch.float32, device=dev)
         _chk(_L().fz_dwconv7_wgrad(_P(x), _P(du), _P(dw_dw), _P(db_dw), B, H, W, C, _S()), "fz_dwconv7_wgrad")
-        dx = torch.empty_like(x)
-        _chk(_L().fz_add_f32(_P(dy), _P(dconv), _P(dx), dx.numel(), _S()), "fz_add_f32")
         grads = {"conv_dw.weight": dw_dw.t().reshape(C, 1, 7, 7), "conv_dw.bias": db_dw,
                  "norm.weight": dln[0], "norm.bias": dln[1],
                  "mlp.fc1.weight": dw1, "mlp.fc1.bias": db1, "mlp.grn.weight": dgrn_w, "mlp.grn.bias": dgrn_b,

@@ -9,7 +9,12 @@ tuned.  BatchNorm running statistics are updated in place like nn.BatchNorm2d do
 torch.distributed the gradients are averaged DDP-style (trainers.py:81-91): every finished group of the backward -- decoder,
 fusion convolutions, then each encoder stage, deepest first -- is copied into its (contiguous) range of the flat gradient
 arena and that range's NCCL all-reduce starts at once on a side stream, so only the last, smallest bucket (an encoder's stem)
-is exposed."""
+is exposed.
+
+``cuda_graph=True``: the step is launch-bound on the host (about 4000 kernel launches; 114 ms of device work took 156 ms of
+wall clock), so after one eager step the whole step -- rebuilding the 16-bit weight copies, forward, backward, the bucketed
+all-reduces, AdamW with its step counter on the device -- is captured once into a CUDA graph and replayed; inputs are copied
+into static buffers, loss and predictions come back in static buffers."""
 from typing import Dict, List
 
 import torch
@@ -23,8 +28,10 @@ from .convnext_train import ConvNeXtV2EncoderTrain, UnetDecoderTrain, _to_bf16
 class ConvNeXtUNetTrainer:
     def __init__(self, state: Dict[str, torch.Tensor], depths, dims, modalities: List[str], task: str,
                  class_weight: torch.Tensor, task_weight: float = 1.0, lr: float = 5e-5, weight_decay: float = 0.01,
-                 betas=(0.9, 0.999)):
+                 betas=(0.9, 0.999), cuda_graph: bool = False):
         """state: the model's parameters by state_dict name (fp32, CUDA); they become views into the optimizer's arena."""
+        self.cuda_graph = bool(cuda_graph)
+        self._graph, self._static, self._graph_out, self._stale, self._capturing = None, None, None, False, False
         self.depths, self.dims, self.mods, self.task, self.task_weight = depths, dims, list(modalities), task, task_weight
         self.names = [k for k in state if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
         self.params = {k: state[k] for k in self.names}
@@ -97,6 +104,9 @@ class ConvNeXtUNetTrainer:
         """-> (loss 0-d tensor, preds int32 (B,H,W), {parameter name: gradient}).  With ``into_arena`` the gradients are also
         written to the optimizer's gradient arena group by group as the backward produces them (and all-reduced, see _emit)."""
         emit = self._emit if into_arena else None
+        if self._stale and not self._capturing:      # graph replays rebuild the weight copies inside the graph only
+            self._build()
+            self._stale = False
         feats = {m: self.enc[m].forward(batch[m]) for m in self.mods}
         cats = None
         if self.fuse is None:
@@ -140,7 +150,49 @@ class ConvNeXtUNetTrainer:
         return loss, preds, grads
 
     def step(self, batch: Dict[str, torch.Tensor]):
-        """forward + backward + (overlapped) gradient all-reduce + AdamW update; -> (loss before the update, preds)."""
+        """forward + backward + (overlapped) gradient all-reduce + AdamW update; -> (loss before the update, preds).
+        With ``cuda_graph`` the first call runs eagerly (it sizes the library's scratch buffers and initialises NCCL), the
+        second captures, and every call from the second on replays the graph; the returned loss / preds are then the graph's
+        static output buffers (overwritten by the next step).  A batch of another shape falls back to the eager step."""
+        if not self.cuda_graph or self.opt.step_count == 0:
+            return self._step_eager(batch)
+        if self._graph is not None and not self._same_shapes(batch):
+            return self._step_eager(batch)
+        if self._graph is None:
+            self._capture(batch)
+        for k, v in self._static.items():
+            v.copy_(batch[k], non_blocking=True)
+        self._graph.replay()
+        self.opt.step_count += 1
+        self._stale = True
+        return self._graph_out
+
+    def _same_shapes(self, batch) -> bool:
+        return all(k in batch and batch[k].shape == v.shape and batch[k].dtype == v.dtype for k, v in self._static.items())
+
+    def _capture(self, batch) -> None:
+        keys = list(self.mods) + [self.task]
+        self._static = {k: batch[k].detach().clone() for k in keys}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()                     # the eager step's cached blocks: the graph gets its own pool
+        self._graph = torch.cuda.CUDAGraph()
+        self._capturing = True
+        try:
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):     # NCCL's watchdog thread keeps polling
+                self._build()                        # inside the graph: replays refresh the 16-bit weight copies themselves
+                self._graph_out = self._step_body(self._static, timed=False, on_device_counter=True)
+        finally:
+            self._capturing = False
+
+    def _step_eager(self, batch):
+        if self._stale:
+            self._build()
+            self._stale = False
+        out = self._step_body(batch, timed=True, on_device_counter=False)
+        self._build()
+        return out
+
+    def _step_body(self, batch, timed: bool, on_device_counter: bool):
         self._filled, self._reduced, self._leftover, self._works = set(), [], [], []
         self._overlap = self._distributed()
         loss, preds, grads = self.forward_backward(batch, into_arena=True)
@@ -149,35 +201,42 @@ class ConvNeXtUNetTrainer:
         unused = {n: self.params[n].clone() for n in self.names if n not in self._filled}
         for n in unused:
             self.opt.grads[self.names_index[n]].zero_()
-        self._finish_allreduce()
-        self.opt.step()
+        self._finish_allreduce(timed)
+        if on_device_counter:
+            self.opt.step_on_device_counter()
+        else:
+            self.opt.step()
         for n, v in unused.items():
             self.params[n].copy_(v)
-        self._build()
         return loss, preds
 
-    def _finish_allreduce(self) -> None:
+    def _finish_allreduce(self, timed: bool = True) -> None:
         """Waits for the buckets started during the backward and reduces whatever they did not cover (parameters without a
         gradient, non-contiguous groups).  ``last_allreduce_ms`` = the time the compute stream had to wait, i.e. the EXPOSED
-        part of the gradient exchange."""
-        self.last_allreduce_ms = 0.0
+        part of the gradient exchange (``timed=False``, under graph capture: not measured, the last eager value is kept)."""
+        if timed:
+            self.last_allreduce_ms = 0.0
         if not self._overlap:
             return
         import torch.distributed as dist
         cur = torch.cuda.current_stream()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(cur)
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
         for w in self._works:
             w.wait()                                  # the compute stream waits for NCCL's stream
+        if self._comm_stream is not None:
+            cur.wait_stream(self._comm_stream)        # explicit join (a forked stream must rejoin before a capture ends)
         covered = sorted(self._reduced)
         pos, n = 0, self.opt.grad.numel()
         for lo, hi in covered + [(n, n)]:
             if lo > pos:                              # a gap no bucket covered: reduce it now (tiny: unused parameters)
                 dist.all_reduce(self.opt.grad[pos:lo], op=dist.ReduceOp.AVG)
             pos = max(pos, hi)
-        e1.record(cur)
-        e1.synchronize()
-        self.last_allreduce_ms = e0.elapsed_time(e1)
+        if timed:
+            e1.record(cur)
+            e1.synchronize()
+            self.last_allreduce_ms = e0.elapsed_time(e1)
 
     def allreduce_gradients(self) -> float:
         """The un-overlapped exchange (round 1; kept for A/B): ONE blocking NCCL all-reduce of the whole gradient arena

@@ -33,6 +33,8 @@ class AdamW:
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)       # the same counter on the device (step_dev())
+        self._hyper = torch.zeros(2, dtype=torch.float32, device=dev)
         off = 0
         self.grads: List[torch.Tensor] = []
         for p in self.params:
@@ -47,8 +49,15 @@ class AdamW:
 
     def step(self) -> None:
         self.step_count += 1
+        self.step_dev.add_(1)
         nv.adamw_step(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                       self.weight_decay, self.step_count)
+
+    def step_on_device_counter(self) -> None:
+        """The same update driven by the device-resident counter: nothing in the launch depends on the step number, so it can
+        be captured in a CUDA graph and replayed (engine/train_step.py).  The caller keeps ``step_count`` in sync."""
+        nv.adamw_step_dev(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
+                          self.weight_decay, self.step_dev, self._hyper)
 
 
 def init_optimizer(cfg: dict, params: Iterable[torch.Tensor]) -> AdamW:

@@ -116,16 +116,22 @@ _SIGNATURES = {
     "fz_ce_loss_backward": [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _i, _i, _i, _i, _vp],
     "fz_adamw_step": [_vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                       ctypes.c_double, _i, _vp],
+    "fz_adamw_step_dev": [_vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                          ctypes.c_double, _vp, _vp, _vp],
     "fz_transpose_bf16": [_vp, _vp, _i, _i, _vp],
     "fz_colsum_bf16": [_vp, _vp, _vp, _i64, _i, _i, _vp],
     "fz_dwconv7_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_dwconv7_f32_add": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_dwconv7_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "fz_layernorm_fwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
     "fz_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "fz_gelu_fwd": [_vp, _vp, _i64, _vp],
     "fz_sample_colreduce": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_sample_colreduce2": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "fz_gelu_fwd_sumsq": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_gelu_backward": [_vp] * 14 + [_i, _i, _i, ctypes.c_float, _vp],
+    "fz_grn_gelu_backward_db": [_vp] * 15 + [_i, _i, _i, ctypes.c_float, _vp],
     "fz_add_f32": [_vp, _vp, _vp, _i64, _vp],
     "fz_reduce_rows_f32": [_vp, _vp, _i, _i, _vp],
     "fz_layernorm_fwd_stats2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
@@ -758,6 +764,19 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
                "fz_adamw_step")
 
 
+def adamw_step_dev(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step_dev, hyper_dev):
+    """The same update with the step counter on the device (``step_dev`` int64[1], incremented by the call; ``hyper_dev``
+    float32[2] scratch): no step-dependent host argument, so a captured step replays correctly as a CUDA graph."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or t.numel() != param.numel():
+            raise NativeError("adamw_step_dev: fp32 buffers of one size required")
+    if step_dev.dtype != torch.int64 or hyper_dev.dtype != torch.float32 or hyper_dev.numel() < 2:
+        raise NativeError("adamw_step_dev: step_dev int64[1] and hyper_dev float32[2] required")
+    _check(lib().fz_adamw_step_dev(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
+                                   float(beta1), float(beta2), float(eps), float(weight_decay), _ptr(step_dev),
+                                   _ptr(hyper_dev), _stream()), "fz_adamw_step_dev")
+
+
 def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
     """bf16 [R,C] -> contiguous bf16 [C,R]."""
     if x.dtype != torch.bfloat16 or x.dim() != 2:
@@ -807,9 +826,10 @@ def weight_gradient(dY: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
     return gemm_splitk(transpose_bf16(dY), transpose_bf16(X))
 
 
-def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
+def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor, db: torch.Tensor = None):
     """Gradients of Y = X W^T + b (X bf16 [M,K], W bf16 [N,K], dY bf16 [M,N]) on the tcgen05 GEMM:
-    dX = dY W (bf16 [M,K]), dW = dY^T X (fp32 [N,K], fp32 accumulation over all M rows), db = column sums of dY."""
+    dX = dY W (bf16 [M,K]), dW = dY^T X (fp32 [N,K], fp32 accumulation over all M rows), db = column sums of dY
+    (``db``: already computed by the kernel that produced dY -- returned as is)."""
     M, N = dY.shape
     K = X.shape[1]
     if X.shape[0] != M or tuple(W.shape) != (N, K):
@@ -819,4 +839,4 @@ def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor):
     # launch, or row chunks on side streams), and both operands are read IN PLACE through MN-major tcgen05 descriptors
     # (round 1 made transposed copies of dY and X for every layer: 499 launches, 19 ms per step)
     dW = weight_gradient(dY, X)
-    return dX, dW, colsum_bf16(dY)
+    return dX, dW, (colsum_bf16(dY) if db is None else db)

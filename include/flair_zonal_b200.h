@@ -342,6 +342,11 @@ int fz_ce_loss_backward(const float* logits, const int32_t* targets, const float
  * buffer, in place; step counts from 1. */
 int fz_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, int step, void* stream);
+/* The same update with the step counter ON THE DEVICE: step_dev (int64, device) is incremented and the bias corrections are
+ * computed by a one-thread kernel into hyper_dev (float[2], device), so the call has no step-dependent host argument and a
+ * captured training step can be replayed as a CUDA graph. */
+int fz_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, int64_t* step_dev, float* hyper_dev, void* stream);
 
 /* First building blocks of the model backward (a Linear layer's gradients through the K-major tcgen05 GEMM):
  * out bf16 [C][R] = in bf16 [R][C]^T (C <= 2 097 120); out float [N] = column sums of in bf16 [M][N]
@@ -355,6 +360,10 @@ int fz_colsum_bf16(const void* in, float* partial, float* out, int64_t M, int N,
  * depthwise 7x7 in fp32: out = bias + sum_k in(shifted) * w[k][c]; flip = 1 uses w[48-k] (= the data gradient). */
 int fz_dwconv7_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int C, int flip,
                    void* stream);
+/* the same with `add` (float, out's layout, may be NULL) summed into the result: the block backward's dx = dy + dwconv^T(du)
+ * in one pass.  H % 4 == 0 and W % 8 == 0 take the 4 x 8 register-tiled kernel. */
+int fz_dwconv7_f32_add(const float* in, const float* w, const float* bias, const float* add, float* out, int B, int H, int W,
+                       int C, int flip, void* stream);
 /* dw float [49][C], db float [C]: gradients of the depthwise weights / bias from x and the output gradient du.  The one entry
  * point that owns device memory: a per-device scratch buffer for its fixed-order partial sums, grown on demand. */
 int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, float* db, int B, int H, int W, int C, void* stream);
@@ -368,6 +377,10 @@ int fz_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, con
 int fz_gelu_fwd(const void* h_bf16, void* g_bf16, int64_t n, void* stream);
 /* out float [B][C] = sum over a sample's HW rows of a*a (mode 0), a*b (1) or a (2); a, b bf16 [B][HW][C]. */
 int fz_sample_colreduce(const void* a_bf16, const void* b_bf16, float* out, int B, int HW, int C, int mode, void* stream);
+/* s1 = sum_hw a*b and s0 = sum_hw a in ONE pass over both tensors (C % 8 == 0): the GRN backward's two reductions. */
+int fz_sample_colreduce2(const void* a_bf16, const void* b_bf16, float* s1, float* s0, int B, int HW, int C, void* stream);
+/* g = GELU(h) (bf16, stored) and sumsq float [B][C] = sum_hw g^2 of the stored values, one pass (C % 8 == 0). */
+int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, float* sumsq, int B, int HW, int C, void* stream);
 /* GRN, training forward: gx = sqrt(sumsq), mu = mean_c gx, nx = gx / (mu + eps), y = g (1 + gamma nx) + beta. */
 int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* gamma, const float* beta, float* gx, float* nx,
                          float* mu, void* y_bf16, int B, int HW, int C, float eps, void* stream);
@@ -376,6 +389,12 @@ int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* ga
 int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1, const float* s0,
                          const float* gx, const float* nx, const float* mu, const float* gamma, float* coef_a, float* coef_b,
                          float* dgamma, float* dbeta, void* dh_bf16, int B, int HW, int C, float eps, void* stream);
+/* the same, and dbias float [C] (may be NULL) = column sums of the stored dh over all B*HW rows: the bias gradient of the
+ * Linear that produced h, without another pass over dh. */
+int fz_grn_gelu_backward_db(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1, const float* s0,
+                            const float* gx, const float* nx, const float* mu, const float* gamma, float* coef_a,
+                            float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias, int B, int HW, int C,
+                            float eps, void* stream);
 int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* out float [N] = sum over s of partial float [S][N], in the order s = 0 .. S-1 (split reductions stay reproducible). */
 int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* stream);

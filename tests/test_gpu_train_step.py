@@ -135,3 +135,54 @@ def test_segmentation_task_training_step(cuda, tmp_path):
     x = torch.randn(1, 4, 512, 512, generator=g).to(cuda)
     out, _ = model({"AERIAL_RGBI": x})
     assert bool(torch.isfinite(out[TASK]).all())
+
+
+def test_graph_replayed_step_equals_eager_step(cuda):
+    """``cuda_graph=True`` (one eager step, then the whole step captured once and replayed) must walk the same trajectory as
+    the eager trainer: same kernels in the same order on the same data, the AdamW step counter on the device instead of in a
+    host argument.  Batches change from step to step (the graph reads its static input buffers)."""
+    import bench
+    from flair_for_aigle_b200.engine.convnext_unet import CONVNEXTV2_CFGS
+    from flair_for_aigle_b200.engine.train_step import ConvNeXtUNetTrainer
+    mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
+    depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
+    w = torch.ones(19, device=cuda)
+    w[15:] = 0
+    g = torch.Generator(device="cpu").manual_seed(5)
+    batches = []
+    for _ in range(5):
+        b = {m: torch.randn(2, c, 128, 128, generator=g).to(cuda) for m, c in mods.items()}
+        b[TASK] = torch.randint(0, 19, (2, 128, 128), generator=g, dtype=torch.int32).to(cuda)
+        batches.append(b)
+    runs = {}
+    for graphed in (False, True):
+        state = {k: v.to(cuda) for k, v in bench.random_state(mods, seed=11).items()}
+        tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w, lr=2e-4, cuda_graph=graphed)
+        losses, preds = [], []
+        for b in batches:
+            loss, p = tr.step(b)
+            losses.append(float(loss))
+            preds.append(p.clone())
+        assert (tr._graph is not None) == graphed and tr.opt.step_count == len(batches)
+        assert int(tr.opt.step_dev) == len(batches)
+        runs[graphed] = (losses, preds, tr.opt.arena.clone(), {k: v.clone() for k, v in tr.buffers.items()})
+        # a batch of another shape after the capture: falls back to the eager step, on the CURRENT weights
+        if graphed:
+            odd = {m: torch.randn(1, c, 128, 128, generator=g).to(cuda) for m, c in mods.items()}
+            odd[TASK] = torch.randint(0, 19, (1, 128, 128), generator=g, dtype=torch.int32).to(cuda)
+            before = tr.opt.arena.clone()
+            l_odd, _ = tr.step(odd)
+            assert torch.isfinite(l_odd) and not torch.equal(before, tr.opt.arena) and tr.opt.step_count == len(batches) + 1
+    (le, pe, ae, be), (lg, pg, ag, bg) = runs[False], runs[True]
+    print("eager  losses:", " ".join(f"{v:.5f}" for v in le))
+    print("graph  losses:", " ".join(f"{v:.5f}" for v in lg))
+    d = float((ae - ag).abs().max())
+    print(f"max parameter difference after {len(batches)} steps: {d:.3g}")
+    # the only arithmetic difference: the bias corrections come from a device pow() instead of the host's, which may move
+    # lr / (1 - b1^t) by one float ulp -- everything else is the same kernels on the same data
+    assert le[:2] == lg[:2], "step 1 is eager on both sides and step 2 starts from identical weights"
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(le, lg))
+    assert all((a == b).float().mean().item() >= 0.9999 for a, b in zip(pe, pg))
+    assert d <= 1e-6
+    for k in be:
+        assert torch.allclose(be[k].float(), bg[k].float(), rtol=0, atol=1e-6), k

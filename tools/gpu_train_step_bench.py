@@ -23,13 +23,14 @@ mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
 state = {k: v.to(dev) for k, v in bench.random_state(mods, seed=2025).items()}
 depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
 w = torch.ones(19, device=dev); w[15:] = 0
-tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w)
+tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w, cuda_graph=os.environ.get("GRAPH", "1") != "0")
 n_par = tr.opt.arena.numel()
 g = torch.Generator(device="cpu").manual_seed(2025 + rank)
 batch = {k: torch.randn(B, c, P, P, generator=g).to(dev) for k, c in mods.items()}
 batch[TASK] = torch.nn.functional.one_hot(torch.randint(0, 19, (B, P, P), generator=g), 19).permute(0, 3, 1, 2).float().to(dev)
 losses = []
-loss, _ = tr.step(batch); losses.append(float(loss))          # warm-up
+for _ in range(2):                                              # warm-up: one eager step, one that captures the graph
+    loss, _ = tr.step(batch); losses.append(float(loss))
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()

@@ -12,11 +12,11 @@ mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
 state = {k: v.to(dev) for k, v in bench.random_state(mods, seed=2025).items()}
 depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
 w = torch.ones(19, device=dev); w[15:] = 0
-tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w)
+tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w, cuda_graph=os.environ.get("GRAPH", "1") != "0")
 g = torch.Generator(device="cpu").manual_seed(1)
 batch = {k: torch.randn(B, c, P, P, generator=g).to(dev) for k, c in mods.items()}
 batch[TASK] = torch.nn.functional.one_hot(torch.randint(0, 19, (B, P, P), generator=g), 19).permute(0, 3, 1, 2).float().to(dev)
-tr.step(batch); torch.cuda.synchronize()
+tr.step(batch); tr.step(batch); torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     tr.step(batch); torch.cuda.synchronize()
 rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
