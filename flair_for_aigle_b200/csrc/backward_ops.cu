@@ -89,9 +89,13 @@ __global__ void __launch_bounds__(256) dwconv7_f32_tiled_kernel(const float* __r
 // (the 1 x 8 form above: 98 per 392), which is what bounds these kernels -- the loads hit L1/L2, the LSU issue rate is the
 // limit.  `add` (optional, same layout as out) is summed into the result: the block backward's dx = dy + dwconv^T(du) without
 // a separate pass.  grid (C/32, ceil(n_tiles / 16)), two tiles per warp.
+// CT: the channel count as a compile-time constant (0 = runtime): every tap address becomes [row pointer + immediate]
+// instead of a 64-bit multiply-add per load -- the instruction mix, not DRAM, bounds these kernels.
+template <int CT>
 __global__ void __launch_bounds__(256) dwconv7_f32_tile48_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, const float* __restrict__ add,
-                                                                 float* __restrict__ out, int B, int H, int W, int C, int flip) {
+                                                                 float* __restrict__ out, int B, int H, int W, int C_rt, int flip) {
+  const int C = CT ? CT : C_rt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   if (c >= C) return;
@@ -113,12 +117,13 @@ __global__ void __launch_bounds__(256) dwconv7_f32_tile48_kernel(const float* __
     for (int iy = 0; iy < 10; ++iy) {
       const int gy = y0 - 3 + iy;
       if (gy < 0 || gy >= H) continue;                       // warp-uniform
-      const float* xr = in + (img + static_cast<size_t>(gy) * W) * C + c;
+      const float* xr = in + (img + static_cast<size_t>(gy) * W + x0) * C + c;       // pixel x0 of the row
       float xs[14];
 #pragma unroll
       for (int q = 0; q < 14; ++q) {
-        const int ix = x0 - 3 + q;
-        xs[q] = (ix >= 0 && ix < W) ? xr[static_cast<size_t>(ix) * C] : 0.f;
+        // only the three halo pixels on either side can fall outside the row (W % 8 == 0)
+        const bool inside = q < 3 ? x0 - 3 + q >= 0 : (q >= 11 ? x0 - 3 + q < W : true);
+        xs[q] = inside ? xr[(q - 3) * C] : 0.f;
       }
 #pragma unroll
       for (int oy = 0; oy < 4; ++oy) {
@@ -137,8 +142,8 @@ __global__ void __launch_bounds__(256) dwconv7_f32_tile48_kernel(const float* __
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float v = acc[oy * 8 + j];
-        if (add) v += add[o + static_cast<size_t>(j) * C];
-        out[o + static_cast<size_t>(j) * C] = v;
+        if (add) v += add[o + j * C];
+        out[o + j * C] = v;
       }
     }
   }
@@ -235,9 +240,11 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_tiled_kernel(const float* _
 
 // The same reduction over 4 x 8 pixel tiles (H % 4 == 0): 32 output gradients and 10 x 14 inputs per 1568 MACs.
 // grid (C/32, chunks); a chunk is a run of tiles_per_chunk tiles, its 8 warps take them round robin.
+template <int CT>
 __global__ void __launch_bounds__(256) dwconv7_wgrad_tile48_kernel(const float* __restrict__ x, const float* __restrict__ du,
-                                                                   float* __restrict__ partial, int B, int H, int W, int C,
+                                                                   float* __restrict__ partial, int B, int H, int W, int C_rt,
                                                                    int tiles_per_chunk) {
+  const int C = CT ? CT : C_rt;
   __shared__ float red[50][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_tile48_kernel(const float* 
         const float* gp = du + ((img + static_cast<size_t>(y0 + oy) * W + x0) * C + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          g[oy * 8 + j] = gp[static_cast<size_t>(j) * C];
+          g[oy * 8 + j] = gp[j * C];
           acc[49] += g[oy * 8 + j];
         }
       }
@@ -266,12 +273,12 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_tile48_kernel(const float* 
       for (int iy = 0; iy < 10; ++iy) {
         const int gy = y0 - 3 + iy;
         if (gy < 0 || gy >= H) continue;
-        const float* xr = x + (img + static_cast<size_t>(gy) * W) * C + c;
+        const float* xr = x + (img + static_cast<size_t>(gy) * W + x0) * C + c;
         float xs[14];
 #pragma unroll
         for (int q = 0; q < 14; ++q) {
-          const int ix = x0 - 3 + q;
-          xs[q] = (ix >= 0 && ix < W) ? xr[static_cast<size_t>(ix) * C] : 0.f;
+          const bool inside = q < 3 ? x0 - 3 + q >= 0 : (q >= 11 ? x0 - 3 + q < W : true);
+          xs[q] = inside ? xr[(q - 3) * C] : 0.f;
         }
 #pragma unroll
         for (int oy = 0; oy < 4; ++oy) {
@@ -358,6 +365,127 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
       dx[r * C + c] = rs * (gg - m1 - xh * m2);
     }
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) t += sh[static_cast<size_t>(w2) * 2 * C + c];
+    partial[static_cast<size_t>(blockIdx.x) * 2 * C + c] = t;
+  }
+}
+
+__device__ __forceinline__ void load4_bf16(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 q = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(q.x << 16);
+  v[1] = __uint_as_float(q.x & 0xffff0000u);
+  v[2] = __uint_as_float(q.y << 16);
+  v[3] = __uint_as_float(q.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, const float (&v)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 q;
+  q.x = *reinterpret_cast<const uint32_t*>(&a);
+  q.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = q;
+}
+// ---- the same two kernels for C = 128 * NV: a lane owns NV float4 quads of the row (quad k*32 + lane) and keeps them in
+// registers, so the row is read from global memory once (the scalar forms re-read it for every pass, 4 bytes per load) and the
+// per-channel sums of the backward live in registers instead of a shared-memory read-modify-write per element.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
+                                                         float* __restrict__ out_f32, float* __restrict__ mean,
+                                                         float* __restrict__ rstd, int64_t M, float eps) {
+  constexpr int C = 128 * NV;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= M) return;
+  const float4* row = reinterpret_cast<const float4*>(x + r * C);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    v[k] = row[k * 32 + lane];
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  const float mu = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    v[k].x -= mu; v[k].y -= mu; v[k].z -= mu; v[k].w -= mu;
+    q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+  }
+  const float rs = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    const float4 gg = *reinterpret_cast<const float4*>(g + c), bb = *reinterpret_cast<const float4*>(b + c);
+    const float o[4] = {v[k].x * rs * gg.x + bb.x, v[k].y * rs * gg.y + bb.y, v[k].z * rs * gg.z + bb.z,
+                        v[k].w * rs * gg.w + bb.w};
+    if (out) store4_bf16(out + r * C + c, o);
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (lane == 0) {
+    mean[r] = mu;
+    rstd[r] = rs;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         const float* __restrict__ g, float* __restrict__ dx,
+                                                         float* __restrict__ partial, int64_t M) {
+  constexpr int C = 128 * NV;
+  extern __shared__ float sh[];                      // [8 warps][2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 gam[NV];
+  float a_dg[NV][4], a_db[NV][4];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    gam[k] = *reinterpret_cast<const float4*>(g + (k * 32 + lane) * 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a_dg[k][j] = a_db[k][j] = 0.f;
+  }
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + warp; r < M; r += static_cast<int64_t>(gridDim.x) * 8) {
+    const float mu = mean[r], rs = rstd[r];
+    float xh[NV][4], gg[NV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(x + r * C + c);
+      float d[4];
+      load4_bf16(dy + r * C + c, d);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float gs[4] = {gam[k].x, gam[k].y, gam[k].z, gam[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xh[k][j] = (xs[j] - mu) * rs;
+        gg[k][j] = d[j] * gs[j];
+        s1 += gg[k][j];
+        s2 += gg[k][j] * xh[k][j];
+        a_dg[k][j] += d[j] * xh[k][j];
+        a_db[k][j] += d[j];
+      }
+    }
+    const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(dx + r * C + c) =
+          make_float4(rs * (gg[k][0] - m1 - xh[k][0] * m2), rs * (gg[k][1] - m1 - xh[k][1] * m2),
+                      rs * (gg[k][2] - m1 - xh[k][2] * m2), rs * (gg[k][3] - m1 - xh[k][3] * m2));
+    }
+  }
+  float* mine = sh + static_cast<size_t>(warp) * 2 * C;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mine[(k * 32 + lane) * 4 + j] = a_dg[k][j];
+      mine[C + (k * 32 + lane) * 4 + j] = a_db[k][j];
+    }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += 256) {
     float t = 0.f;
@@ -582,7 +710,7 @@ __global__ void __launch_bounds__(256) grn_gelu_bwd_rows_kernel(const __nv_bfloa
                                                                 const __nv_bfloat16* __restrict__ h,
                                                                 const float* __restrict__ coef_a, const float* __restrict__ coef_b,
                                                                 __nv_bfloat16* __restrict__ dh, float* __restrict__ db_partial,
-                                                                int rows, int C, int cgs, int rows_per_chunk) {
+                                                                int rows, int C, int cgs, int rows_per_chunk, int h_is_dgelu) {
   __shared__ float red[256][9];
   const int rp = 256 / cgs;
   const int cl = threadIdx.x % cgs, rr = threadIdx.x / cgs;
@@ -608,7 +736,7 @@ __global__ void __launch_bounds__(256) grn_gelu_bwd_rows_kernel(const __nv_bfloa
       load8(g + o, gg);
       load8(h + o, hh);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = (d[j] * ca[j] + gg[j] * cb[j]) * gelu_grad(hh[j]);
+      for (int j = 0; j < 8; ++j) d[j] = (d[j] * ca[j] + gg[j] * cb[j]) * (h_is_dgelu ? hh[j] : rv_gelu_grad(hh[j]));
       rv_store8_round(dh + o, d);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += d[j];
@@ -653,6 +781,20 @@ __global__ void __launch_bounds__(256) s2d_bf16_kernel(const __nv_bfloat16* __re
   const int x = static_cast<int>(px % W), y = static_cast<int>((px / W) % H);
   const int64_t b = px / (static_cast<int64_t>(W) * H);
   const int64_t j = (((b * (H / s) + y / s) * (W / s) + x / s) * (s * s) + (y % s) * s + (x % s)) * C + c;
+  if (inverse) out[i] = in[j];
+  else out[j] = in[i];
+}
+
+// the same map moving 8 channels (16 bytes) per thread, C % 8 == 0
+__global__ void __launch_bounds__(256) s2d_bf16_vec_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W,
+                                                           int C8, int s, int inverse, int64_t n8) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;      // index into the [B][H][W][C/8] side
+  if (i >= n8) return;
+  const int c = static_cast<int>(i % C8);
+  const int64_t px = i / C8;
+  const int x = static_cast<int>(px % W), y = static_cast<int>((px / W) % H);
+  const int64_t b = px / (static_cast<int64_t>(W) * H);
+  const int64_t j = (((b * (H / s) + y / s) * (W / s) + x / s) * (s * s) + (y % s) * s + (x % s)) * C8 + c;
   if (inverse) out[i] = in[j];
   else out[j] = in[i];
 }
@@ -836,6 +978,119 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
   dx[i] = __float2bfloat16_rn(v);
 }
 
+// ---- the same three kernels, four channels (one float4 / one 8-byte bf16x4) per thread; C, ldx, ldd multiples of 4.
+// The scalar forms above move 4 bytes per thread per row and leave the 16-channel, 4-million-row layers of the decoder with
+// 256 blocks of work; here a thread owns one channel quad and the block walks its row chunk 256 / (C/4) rows at a time.
+// grid (slabs, chunks); partial[chunk][2][C] as above
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_partial_vec_kernel(const float* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy,
+                                                             const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, float* __restrict__ partial,
+                                                             int64_t M, int C, int cgs, int rows_per_chunk) {
+  __shared__ float red[2][256][5];
+  const int rp = 256 / cgs;
+  const int cl = threadIdx.x % cgs, rr = threadIdx.x / cgs;
+  const int c = (blockIdx.x * cgs + cl) * 4;
+  const bool active = rr < rp && c < C;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk;
+  const int64_t m1 = m0 + rows_per_chunk < M ? m0 + rows_per_chunk : M;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE >= 1) {
+      const float4 t = *reinterpret_cast<const float4*>(mean + c);
+      mu[0] = t.x; mu[1] = t.y; mu[2] = t.z; mu[3] = t.w;
+    }
+    if (MODE == 2) {
+      const float4 t = *reinterpret_cast<const float4*>(rstd + c);
+      rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w;
+    }
+#pragma unroll 4
+    for (int64_t m = m0 + rr; m < m1; m += rp) {
+      const float4 t = *reinterpret_cast<const float4*>(x + m * ldx + c);
+      const float xv[4] = {t.x, t.y, t.z, t.w};
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] += xv[j];
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] += (xv[j] - mu[j]) * (xv[j] - mu[j]);
+      } else {
+        float yv[4], dv[4];
+        load4_bf16(y + m * C + c, yv);
+        load4_bf16(dy + m * C + c, dv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float g = yv[j] > 0.f ? dv[j] : 0.f;
+          a[j] += g;
+          b[j] += g * (xv[j] - mu[j]) * rs[j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][threadIdx.x][j] = a[j];
+    red[1][threadIdx.x][j] = b[j];
+  }
+  __syncthreads();
+  if (rr == 0 && c < C) {
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = 0.f;
+        for (int q = 0; q < rp; ++q) t += red[o][q * cgs + cl][j];
+        partial[(static_cast<size_t>(blockIdx.y) * 2 + o) * C + c + j] = t;
+      }
+  }
+}
+__global__ void __launch_bounds__(256) bn_relu_apply_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                                int C4, int64_t n4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const int c = static_cast<int>(i % C4) * 4;
+  const int64_t m = i / C4;
+  const float4 xv = *reinterpret_cast<const float4*>(x + m * ldx + c);
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+  float v[4] = {(xv.x - mu.x) * rs.x * ga.x + be.x, (xv.y - mu.y) * rs.y * ga.y + be.y, (xv.z - mu.z) * rs.z * ga.z + be.z,
+                (xv.w - mu.w) * rs.w * ga.w + be.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+  store4_bf16(y + m * (C4 * 4) + c, v);
+}
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_vec_kernel(const float* __restrict__ x, int ldx,
+                                                                    const __nv_bfloat16* __restrict__ dy,
+                                                                    const __nv_bfloat16* __restrict__ y,
+                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ dgb,
+                                                                    __nv_bfloat16* __restrict__ dx, int ldd, int C, float invM,
+                                                                    int64_t n4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;      // over M * ldd / 4
+  if (i >= n4) return;
+  const int L4 = ldd / 4;
+  const int c = static_cast<int>(i % L4) * 4;
+  const int64_t m = i / L4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    float yv[4], dv[4];
+    load4_bf16(y + m * C + c, yv);
+    load4_bf16(dy + m * C + c, dv);
+    const float4 t = *reinterpret_cast<const float4*>(x + m * ldx + c);
+    const float xv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = yv[j] > 0.f ? dv[j] : 0.f;
+      const float xh = (xv[j] - mean[c + j]) * rstd[c + j];
+      v[j] = gamma[c + j] * rstd[c + j] * (g - dgb[c + j] * invM - xh * dgb[C + c + j] * invM);
+    }
+  }
+  store4_bf16(dx + m * ldd + c, v);
+}
+
 // nearest x2 upsample + concat, backward: da[b][y][x][c] = sum_{2x2} dcat[b][2y+i][2x+j][c] (c < C1);
 // dskip[b][Y][X][c] = dcat[b][Y][X][C1 + c]
 __global__ void __launch_bounds__(256) upcat_bwd_kernel(const float* __restrict__ dcat, float* __restrict__ da,
@@ -879,6 +1134,21 @@ using namespace fz;
 typedef const __nv_bfloat16* cbf;
 typedef __nv_bfloat16* bf;
 
+// C = 128 * NV rows: the register-resident LayerNorm forward; false = shape not covered (caller takes the scalar kernel)
+static bool launch_ln_fwd_vec(const float* x, const float* g, const float* b, bf out, float* out_f32, float* mean, float* rstd,
+                              int64_t M, int C, float eps, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+  switch (C % 128 == 0 ? C / 128 : 0) {
+    case 1: ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
+    case 2: ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
+    case 3: ln_fwd_vec_kernel<3><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
+    case 4: ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
+    case 6: ln_fwd_vec_kernel<6><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
+    case 8: ln_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
+    default: return false;
+  }
+}
+
 extern "C" int fz_dwconv7_f32_add(const float* in, const float* w, const float* bias, const float* add, float* out, int B,
                                   int H, int W, int C, int flip, void* stream) {
   FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && in && w && out, "fz_dwconv7_f32: bad arguments");
@@ -886,8 +1156,15 @@ extern "C" int fz_dwconv7_f32_add(const float* in, const float* w, const float* 
   if (W % 8 == 0 && H % 4 == 0) {
     const int64_t n_tiles = static_cast<int64_t>(B) * (H / 4) * (W / 8);
     FZ_REQUIRE(n_tiles < (1LL << 31) && (n_tiles + 15) / 16 <= 65535, "fz_dwconv7_f32: too many tiles");
-    dwconv7_f32_tile48_kernel<<<dim3((C + 31) / 32, static_cast<unsigned>((n_tiles + 15) / 16)), 256, 0, ST(stream)>>>(
-        in, w, bias, add, out, B, H, W, C, flip);
+    const dim3 grid((C + 31) / 32, static_cast<unsigned>((n_tiles + 15) / 16));
+#define FZ_DW_CASE(ct) \
+  case ct: dwconv7_f32_tile48_kernel<ct><<<grid, 256, 0, ST(stream)>>>(in, w, bias, add, out, B, H, W, C, flip); break;
+    switch (C) {                       // the ConvNeXt-V2 widths (tiny / base / large); anything else takes the runtime form
+      FZ_DW_CASE(96) FZ_DW_CASE(128) FZ_DW_CASE(192) FZ_DW_CASE(256) FZ_DW_CASE(384) FZ_DW_CASE(512) FZ_DW_CASE(768)
+      FZ_DW_CASE(1024) FZ_DW_CASE(1536)
+      default: dwconv7_f32_tile48_kernel<0><<<grid, 256, 0, ST(stream)>>>(in, w, bias, add, out, B, H, W, C, flip);
+    }
+#undef FZ_DW_CASE
     FZ_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -940,8 +1217,16 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
   float* sums = partial + static_cast<size_t>(chunks) * 50 * C;
   if (tile48) {
     const int n_tiles = static_cast<int>(npx / 32);
-    dwconv7_wgrad_tile48_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, ST(stream)>>>(x, du, partial, B, H, W, C,
-                                                                                    (n_tiles + chunks - 1) / chunks);
+    const dim3 grid((C + 31) / 32, chunks);
+    const int tpc = (n_tiles + chunks - 1) / chunks;
+#define FZ_DW_CASE(ct) \
+  case ct: dwconv7_wgrad_tile48_kernel<ct><<<grid, 256, 0, ST(stream)>>>(x, du, partial, B, H, W, C, tpc); break;
+    switch (C) {
+      FZ_DW_CASE(96) FZ_DW_CASE(128) FZ_DW_CASE(192) FZ_DW_CASE(256) FZ_DW_CASE(384) FZ_DW_CASE(512) FZ_DW_CASE(768)
+      FZ_DW_CASE(1024) FZ_DW_CASE(1536)
+      default: dwconv7_wgrad_tile48_kernel<0><<<grid, 256, 0, ST(stream)>>>(x, du, partial, B, H, W, C, tpc);
+    }
+#undef FZ_DW_CASE
   } else if (tiled) {
     const int n_tiles = static_cast<int>(npx / 8);
     dwconv7_wgrad_tiled_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, ST(stream)>>>(x, du, partial, B, H, W, C,
@@ -959,8 +1244,9 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
 extern "C" int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, float* mean, float* rstd,
                                       int64_t M, int C, float eps, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && x && g && b && out_bf16 && mean && rstd, "fz_layernorm_fwd_stats: bad arguments");
-  ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
-                                                                                 nullptr, mean, rstd, M, C, eps);
+  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), nullptr, mean, rstd, M, C, eps, ST(stream)))
+    ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
+                                                                                   nullptr, mean, rstd, M, C, eps);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -968,10 +1254,22 @@ extern "C" int fz_layernorm_fwd_stats(const float* x, const float* g, const floa
 extern "C" int fz_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* g,
                                 float* dx, float* partial, float* dgamma_dbeta, int64_t M, int C, int blocks, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && blocks >= 1 && C <= 2048, "fz_layernorm_bwd: M=%lld C=%d (C <= 2048)", (long long)M, C);
-  auto kern = ln_bwd_kernel;
   const int smem = 8 * 2 * C * 4;
-  FZ_ENSURE_SMEM(kern, 8 * 2 * 2048 * 4);        // opt in once for the largest C (the attribute is set once per kernel)
-  kern<<<blocks, 256, smem, ST(stream)>>>(reinterpret_cast<cbf>(dy_bf16), x, mean, rstd, g, dx, partial, M, C);
+#define FZ_LN_CASE(nv)                                                                                          \
+  case nv: {                                                                                                    \
+    auto kv = ln_bwd_vec_kernel<nv>;                                                                            \
+    FZ_ENSURE_SMEM(kv, 8 * 2 * 128 * nv * 4);                                                                   \
+    kv<<<blocks, 256, smem, ST(stream)>>>(reinterpret_cast<cbf>(dy_bf16), x, mean, rstd, g, dx, partial, M);    \
+  } break;
+  switch (C % 128 == 0 ? C / 128 : 0) {
+    FZ_LN_CASE(1) FZ_LN_CASE(2) FZ_LN_CASE(3) FZ_LN_CASE(4) FZ_LN_CASE(6) FZ_LN_CASE(8)
+    default: {
+      auto kern = ln_bwd_kernel;
+      FZ_ENSURE_SMEM(kern, 8 * 2 * 2048 * 4);        // opt in once for the largest C (the attribute is set once per kernel)
+      kern<<<blocks, 256, smem, ST(stream)>>>(reinterpret_cast<cbf>(dy_bf16), x, mean, rstd, g, dx, partial, M, C);
+    }
+  }
+#undef FZ_LN_CASE
   reduce_rows_kernel<<<(2 * C + 31) / 32, 256, 0, ST(stream)>>>(partial, dgamma_dbeta, 2 * C, blocks);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1010,10 +1308,11 @@ extern "C" int fz_sample_colreduce2(const void* a_bf16, const void* b_bf16, floa
 }
 
 // g = GELU(h) (bf16) and sumsq[b][c] = sum_hw g^2 of the stored values, one pass
-extern "C" int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, float* sumsq, int B, int HW, int C, void* stream) {
+extern "C" int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, void* dgelu_bf16, float* sumsq, int B, int HW, int C,
+                                 void* stream) {
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && h_bf16 && g_bf16 && sumsq && B <= 65535,
              "fz_gelu_fwd_sumsq: bad arguments (C %% 8 == 0)");
-  FZ_CHECK_CUDA(rv_colreduce<1>(h_bf16, nullptr, g_bf16, sumsq, nullptr, B, HW, C, ST(stream)));
+  FZ_CHECK_CUDA(rv_colreduce<1>(h_bf16, nullptr, g_bf16, sumsq, nullptr, B, HW, C, ST(stream), dgelu_bf16));
   return 0;
 }
 
@@ -1031,10 +1330,10 @@ extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, cons
   return 0;
 }
 
-extern "C" int fz_grn_gelu_backward_db(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1,
-                                       const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
-                                       float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias,
-                                       int B, int HW, int C, float eps, void* stream) {
+static int grn_gelu_backward_impl(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1,
+                                  const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
+                                  float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias,
+                                  int B, int HW, int C, float eps, void* stream, int h_is_dgelu) {
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && dy_bf16 && g_bf16 && h_bf16 && s1 && s0 && gx && nx && mu && gamma && coef_a &&
                  coef_b && dgamma && dbeta && dh_bf16,
              "fz_grn_gelu_backward: bad arguments");
@@ -1048,10 +1347,26 @@ extern "C" int fz_grn_gelu_backward_db(const void* dy_bf16, const void* g_bf16, 
   FZ_REQUIRE(partial != nullptr, "fz_grn_gelu_backward: no scratch memory");
   grn_gelu_bwd_rows_kernel<<<dim3(geo.slabs, geo.chunks, B), 256, 0, ST(stream)>>>(
       reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(g_bf16), reinterpret_cast<cbf>(h_bf16), coef_a, coef_b,
-      reinterpret_cast<bf>(dh_bf16), partial, HW, C, geo.cgs, geo.rows_per_chunk);
+      reinterpret_cast<bf>(dh_bf16), partial, HW, C, geo.cgs, geo.rows_per_chunk, h_is_dgelu);
   if (dbias) colreduce_final_kernel<<<dim3((C + 31) / 32, 1), 256, 0, ST(stream)>>>(partial, dbias, nullptr, B * geo.chunks, C, 1);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int fz_grn_gelu_backward_db(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1,
+                                       const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
+                                       float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias,
+                                       int B, int HW, int C, float eps, void* stream) {
+  return grn_gelu_backward_impl(dy_bf16, g_bf16, h_bf16, s1, s0, gx, nx, mu, gamma, coef_a, coef_b, dgamma, dbeta, dh_bf16,
+                                dbias, B, HW, C, eps, stream, 0);
+}
+
+extern "C" int fz_grn_gelu_backward_saved(const void* dy_bf16, const void* g_bf16, const void* dgelu_bf16, const float* s1,
+                                          const float* s0, const float* gx, const float* nx, const float* mu,
+                                          const float* gamma, float* coef_a, float* coef_b, float* dgamma, float* dbeta,
+                                          void* dh_bf16, float* dbias, int B, int HW, int C, float eps, void* stream) {
+  return grn_gelu_backward_impl(dy_bf16, g_bf16, dgelu_bf16, s1, s0, gx, nx, mu, gamma, coef_a, coef_b, dgamma, dbeta, dh_bf16,
+                                dbias, B, HW, C, eps, stream, 1);
 }
 
 extern "C" int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1,
@@ -1078,8 +1393,9 @@ extern "C" int fz_add_f32(const float* a, const float* b, float* out, int64_t n,
 extern "C" int fz_layernorm_fwd_stats2(const float* x, const float* g, const float* b, void* out_bf16, float* out_f32,
                                        float* mean, float* rstd, int64_t M, int C, float eps, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && x && g && b && (out_bf16 || out_f32) && mean && rstd, "fz_layernorm_fwd_stats2: bad arguments");
-  ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
-                                                                                 out_f32, mean, rstd, M, C, eps);
+  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), out_f32, mean, rstd, M, C, eps, ST(stream)))
+    ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
+                                                                                   out_f32, mean, rstd, M, C, eps);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1087,8 +1403,12 @@ extern "C" int fz_layernorm_fwd_stats2(const float* x, const float* g, const flo
 extern "C" int fz_s2d_bf16(const void* in, void* out, int B, int H, int W, int C, int s, int inverse, void* stream) {
   FZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && s >= 1 && H % s == 0 && W % s == 0 && in && out, "fz_s2d_bf16: bad arguments");
   const int64_t n = static_cast<int64_t>(B) * H * W * C;
-  s2d_bf16_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(in), reinterpret_cast<bf>(out), H, W, C, s,
-                                                         inverse, n);
+  if (C % 8 == 0)
+    s2d_bf16_vec_kernel<<<blocks_for(n / 8), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(in),
+                                                                   reinterpret_cast<uint4*>(out), H, W, C / 8, s, inverse, n / 8);
+  else
+    s2d_bf16_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(reinterpret_cast<cbf>(in), reinterpret_cast<bf>(out), H, W, C, s,
+                                                           inverse, n);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1134,15 +1454,23 @@ extern "C" int fz_bn_relu_train_forward(const float* x, int ldx, const float* ga
   const int rpc = static_cast<int>((M + chunks - 1) / chunks);
   float* partial = workspace;                                  // [chunks][2][C]
   float* sums = workspace + static_cast<size_t>(chunks) * 2 * C;   // [2][C]
-  const dim3 grid((C + 31) / 32, chunks);
-  bn_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, partial, M, C, rpc, 0);
+  const bool vec = C % 4 == 0 && ldx % 4 == 0;
+  const int groups = C / 4, cgs = vec ? (groups < 256 ? groups : 256) : 1;
+  const dim3 grid((C + 31) / 32, chunks), vgrid(vec ? (groups + cgs - 1) / cgs : 1, chunks);
+  if (vec) bn_partial_vec_kernel<0><<<vgrid, 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, partial, M, C, cgs, rpc);
+  else bn_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, partial, M, C, rpc, 0);
   reduce_rows_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, sums, 2 * C, chunks);
   bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, mean, C, static_cast<float>(M), eps, 0);
-  bn_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, mean, nullptr, partial, M, C, rpc, 1);
+  if (vec) bn_partial_vec_kernel<1><<<vgrid, 256, 0, st>>>(x, ldx, nullptr, nullptr, mean, nullptr, partial, M, C, cgs, rpc);
+  else bn_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, mean, nullptr, partial, M, C, rpc, 1);
   reduce_rows_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, sums, 2 * C, chunks);
   bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, rstd, C, static_cast<float>(M), eps, 1);
   const int64_t n = M * C;
-  bn_relu_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, reinterpret_cast<bf>(y_bf16), C, n);
+  if (vec)
+    bn_relu_apply_vec_kernel<<<blocks_for(n / 4), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, reinterpret_cast<bf>(y_bf16),
+                                                                C / 4, n / 4);
+  else
+    bn_relu_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, reinterpret_cast<bf>(y_bf16), C, n);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1155,13 +1483,24 @@ extern "C" int fz_bn_relu_backward(const float* x, int ldx, const void* dy_bf16,
              "fz_bn_relu_backward: bad arguments");
   cudaStream_t st = ST(stream);
   const int rpc = static_cast<int>((M + chunks - 1) / chunks);
-  bn_partial_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, st>>>(x, ldx, reinterpret_cast<cbf>(dy_bf16),
-                                                                 reinterpret_cast<cbf>(y_bf16), mean, rstd, workspace, M, C, rpc, 2);
+  const bool vec = C % 4 == 0 && ldx % 4 == 0 && ldd % 4 == 0;
+  const int groups = C / 4, cgs = vec ? (groups < 256 ? groups : 256) : 1;
+  if (vec)
+    bn_partial_vec_kernel<2><<<dim3((groups + cgs - 1) / cgs, chunks), 256, 0, st>>>(
+        x, ldx, reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(y_bf16), mean, rstd, workspace, M, C, cgs, rpc);
+  else
+    bn_partial_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, st>>>(x, ldx, reinterpret_cast<cbf>(dy_bf16),
+                                                                   reinterpret_cast<cbf>(y_bf16), mean, rstd, workspace, M, C, rpc, 2);
   reduce_rows_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(workspace, dbeta_dgamma, 2 * C, chunks);
   const int64_t n = M * ldd;
-  bn_relu_bwd_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(y_bf16),
-                                                          mean, rstd, gamma, dbeta_dgamma, reinterpret_cast<bf>(dx_bf16), ldd, C,
-                                                          1.0f / static_cast<float>(M), n);
+  if (vec)
+    bn_relu_bwd_apply_vec_kernel<<<blocks_for(n / 4), 256, 0, st>>>(
+        x, ldx, reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(y_bf16), mean, rstd, gamma, dbeta_dgamma,
+        reinterpret_cast<bf>(dx_bf16), ldd, C, 1.0f / static_cast<float>(M), n / 4);
+  else
+    bn_relu_bwd_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(y_bf16),
+                                                            mean, rstd, gamma, dbeta_dgamma, reinterpret_cast<bf>(dx_bf16), ldd, C,
+                                                            1.0f / static_cast<float>(M), n);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -34,7 +34,33 @@ __device__ __forceinline__ void rv_store8_round(__nv_bfloat16* p, float (&v)[8])
   }
   *reinterpret_cast<uint4*>(p) = q;
 }
-__device__ __forceinline__ float rv_gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Phi(x) = (1 + erf(x / sqrt 2)) / 2 and phi(x) = exp(-x^2 / 2) / sqrt(2 pi) from ONE exponential and one reciprocal
+// (Abramowitz & Stegun 7.1.26: erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), |error| <= 1.5e-7 -- below
+// fp32 resolution of erf near 1 and four orders below the bf16 rounding of the stored result).  erff() + expf() made the
+// GELU passes of the training step instruction-bound (2.8 TB/s for a read+write kernel); this form is ~15 instructions.
+// The negative tail is formed as poly * e / 2 directly, not as 1 - (1 - poly * e), so it keeps its relative accuracy.
+__device__ __forceinline__ void rv_gauss_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-z * z);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float tail = 0.5f * poly * t * e;                      // = (1 - erf(z)) / 2
+  cdf = x < 0.f ? tail : 1.0f - tail;
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float rv_gelu(float x) {
+  float cdf, pdf;
+  rv_gauss_cdf_pdf(x, cdf, pdf);
+  return x * cdf;
+}
+__device__ __forceinline__ float rv_gelu_grad(float x) {
+  float cdf, pdf;
+  rv_gauss_cdf_pdf(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
+}
 
 // Geometry shared by the kernels below and their launchers: `cgs` column groups (of 8 channels) per block, rp = 256 / cgs
 // row lanes, grid (slabs, chunks, B).
@@ -56,14 +82,15 @@ static inline RvGeom rv_geometry(int B, int rows, int C, int max_chunks = 1 << 1
   return g;
 }
 
-// MODE 0: sum a^2      1: g = GELU(a) stored to gout, sum g^2 (of the stored, rounded g)      2: sum a
-//      3: out0 = sum a*b, out1 = sum a
+// MODE 0: sum a^2      1: g = GELU(a) stored to gout, GELU'(a) stored to dout (when given), sum g^2 (of the stored,
+// rounded g)      2: sum a      3: out0 = sum a*b, out1 = sum a
 // partial[((b * chunks + chunk) * NOUT + o) * C + c]
 template <int MODE>
 __global__ void __launch_bounds__(256) colreduce_vec_kernel(const __nv_bfloat16* __restrict__ a,
                                                             const __nv_bfloat16* __restrict__ bb,
-                                                            __nv_bfloat16* __restrict__ gout, float* __restrict__ partial,
-                                                            int rows, int C, int cgs, int rows_per_chunk) {
+                                                            __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ dout,
+                                                            float* __restrict__ partial, int rows, int C, int cgs,
+                                                            int rows_per_chunk) {
   constexpr int NOUT = MODE == 3 ? 2 : 1;
   __shared__ float red[NOUT][256][9];                          // 9: the 8-float rows would collide 4-way on the banks
   const int rp = 256 / cgs;
@@ -86,8 +113,15 @@ __global__ void __launch_bounds__(256) colreduce_vec_kernel(const __nv_bfloat16*
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc0[j] = fmaf(v[j], v[j], acc0[j]);
       } else if (MODE == 1) {
+        float d[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = rv_gelu_exact(v[j]);
+        for (int j = 0; j < 8; ++j) {
+          float cdf, pdf;
+          rv_gauss_cdf_pdf(v[j], cdf, pdf);
+          d[j] = fmaf(v[j], pdf, cdf);                           // GELU'(a): the backward reads it instead of recomputing
+          v[j] *= cdf;
+        }
+        if (dout) rv_store8_round(dout + o, d);
         rv_store8_round(gout + o, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc0[j] = fmaf(v[j], v[j], acc0[j]);
@@ -166,14 +200,14 @@ static inline float* rv_scratch(size_t floats) {
 // Launches MODE over a [B][rows][C] tensor; returns a cudaError_t.
 template <int MODE>
 static inline cudaError_t rv_colreduce(const void* a, const void* bb, void* gout, float* out0, float* out1, int B, int rows,
-                                       int C, cudaStream_t st) {
+                                       int C, cudaStream_t st, void* dout = nullptr) {
   constexpr int NOUT = MODE == 3 ? 2 : 1;
   const RvGeom g = rv_geometry(B, rows, C);
   float* partial = rv_scratch(static_cast<size_t>(B) * g.chunks * NOUT * C);
   if (!partial) return cudaErrorMemoryAllocation;
   colreduce_vec_kernel<MODE><<<dim3(g.slabs, g.chunks, B), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(bb),
-      reinterpret_cast<__nv_bfloat16*>(gout), partial, rows, C, g.cgs, g.rows_per_chunk);
+      reinterpret_cast<__nv_bfloat16*>(gout), reinterpret_cast<__nv_bfloat16*>(dout), partial, rows, C, g.cgs, g.rows_per_chunk);
   colreduce_final_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(partial, out0, out1, g.chunks, C, NOUT);
   return cudaGetLastError();
 }

@@ -54,23 +54,23 @@ class ConvNeXtBlockTrain:
         _chk(_L().fz_layernorm_fwd_stats(_P(u), _P(self.ln_w), _P(self.ln_b), _P(a1), _P(mean), _P(rstd), M, C, self.eps_ln,
                                          _S()), "fz_layernorm_fwd_stats")
         h = nv.gemm_bf16(a1, self.w1, nv.EPI_BF16, bias=self.b1)                          # pre-GELU, bf16 [M,4C]
-        g = torch.empty_like(h)
+        g, dg = torch.empty_like(h), torch.empty_like(h)                  # GELU(h) and GELU'(h); h itself is not kept
         sumsq = torch.empty((B, C4), dtype=torch.float32, device=dev)
-        _chk(_L().fz_gelu_fwd_sumsq(_P(h), _P(g), _P(sumsq), B, H * W, C4, _S()), "fz_gelu_fwd_sumsq")   # GELU + GRN sums, one pass
+        _chk(_L().fz_gelu_fwd_sumsq(_P(h), _P(g), _P(dg), _P(sumsq), B, H * W, C4, _S()), "fz_gelu_fwd_sumsq")   # + GRN sums, one pass
         gx, nx = torch.empty_like(sumsq), torch.empty_like(sumsq)
         mu = torch.empty(B, dtype=torch.float32, device=dev)
         a2 = torch.empty_like(g)
         _chk(_L().fz_grn_train_forward(_P(g), _P(sumsq), _P(self.grn_w), _P(self.grn_b), _P(gx), _P(nx), _P(mu), _P(a2), B,
                                        H * W, C4, self.eps_grn, _S()), "fz_grn_train_forward")
         y = nv.gemm_bf16(a2, self.w2, nv.EPI_RESID_F32, bias=self.b2, resid=x.view(M, C))
-        self.saved = (x, u, a1, mean, rstd, h, g, gx, nx, mu, a2)
+        self.saved = (x, u, a1, mean, rstd, dg, g, gx, nx, mu, a2)
         return y.view(B, H, W, C)
 
     def backward(self, dy: torch.Tensor):
         """dy fp32 [B,H,W,C] -> (dx fp32 [B,H,W,C], {parameter name: gradient in the parameter's own shape})."""
         if self.saved is None:
             raise RuntimeError("backward() before forward()")
-        x, u, a1, mean, rstd, h, g, gx, nx, mu, a2 = self.saved
+        x, u, a1, mean, rstd, dg, g, gx, nx, mu, a2 = self.saved
         B, H, W, C = x.shape
         M, C4, dev = B * H * W, 4 * C, x.device
         dy = dy.contiguous()
@@ -83,11 +83,11 @@ class ConvNeXtBlockTrain:
         ca, cb = torch.empty_like(s1), torch.empty_like(s1)
         dgrn_w = torch.empty(C4, dtype=torch.float32, device=dev)
         dgrn_b = torch.empty_like(dgrn_w)
-        dh = torch.empty_like(h)
+        dh = torch.empty_like(g)
         db1 = torch.empty(C4, dtype=torch.float32, device=dev)
-        _chk(_L().fz_grn_gelu_backward_db(_P(da2), _P(g), _P(h), _P(s1), _P(s0), _P(gx), _P(nx), _P(mu), _P(self.grn_w),
-                                          _P(ca), _P(cb), _P(dgrn_w), _P(dgrn_b), _P(dh), _P(db1), B, H * W, C4, self.eps_grn,
-                                          _S()), "fz_grn_gelu_backward_db")
+        _chk(_L().fz_grn_gelu_backward_saved(_P(da2), _P(g), _P(dg), _P(s1), _P(s0), _P(gx), _P(nx), _P(mu), _P(self.grn_w),
+                                             _P(ca), _P(cb), _P(dgrn_w), _P(dgrn_b), _P(dh), _P(db1), B, H * W, C4, self.eps_grn,
+                                             _S()), "fz_grn_gelu_backward_saved")
         da1, dw1, db1 = nv.linear_backward(dh, a1, self.w1, db=db1)                       # fc1 (bias gradient from the kernel above)
         blocks = max(1, min(592, (M + 7) // 8))
         du = torch.empty_like(u)
@@ -286,7 +286,7 @@ class Conv3x3BnReluTrain:
         if not self.bn:
             self.saved = (col, (B, H, W))
             return conv.view(B, H, W, self.npad)
-        chunks = max(1, min(256, M // 64))
+        chunks = max(1, min(1184, M // 64))
         y = torch.empty((M, self.cout), dtype=torch.bfloat16, device=dev)
         mean = torch.empty(self.cout, dtype=torch.float32, device=dev)
         rstd = torch.empty_like(mean)

@@ -128,10 +128,11 @@ _SIGNATURES = {
     "fz_gelu_fwd": [_vp, _vp, _i64, _vp],
     "fz_sample_colreduce": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "fz_sample_colreduce2": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
-    "fz_gelu_fwd_sumsq": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "fz_gelu_fwd_sumsq": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_gelu_backward": [_vp] * 14 + [_i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_gelu_backward_db": [_vp] * 15 + [_i, _i, _i, ctypes.c_float, _vp],
+    "fz_grn_gelu_backward_saved": [_vp] * 15 + [_i, _i, _i, ctypes.c_float, _vp],
     "fz_add_f32": [_vp, _vp, _vp, _i64, _vp],
     "fz_reduce_rows_f32": [_vp, _vp, _i, _i, _vp],
     "fz_layernorm_fwd_stats2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],

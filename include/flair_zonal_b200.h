@@ -379,8 +379,9 @@ int fz_gelu_fwd(const void* h_bf16, void* g_bf16, int64_t n, void* stream);
 int fz_sample_colreduce(const void* a_bf16, const void* b_bf16, float* out, int B, int HW, int C, int mode, void* stream);
 /* s1 = sum_hw a*b and s0 = sum_hw a in ONE pass over both tensors (C % 8 == 0): the GRN backward's two reductions. */
 int fz_sample_colreduce2(const void* a_bf16, const void* b_bf16, float* s1, float* s0, int B, int HW, int C, void* stream);
-/* g = GELU(h) (bf16, stored) and sumsq float [B][C] = sum_hw g^2 of the stored values, one pass (C % 8 == 0). */
-int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, float* sumsq, int B, int HW, int C, void* stream);
+/* g = GELU(h) (bf16, stored), optionally GELU'(h) (bf16, stored; NULL = not wanted), and sumsq float [B][C] = sum_hw g^2 of
+ * the stored values, one pass (C % 8 == 0).  erf through Abramowitz-Stegun 7.1.26, |Phi error| <= 3e-7. */
+int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, void* dgelu_bf16, float* sumsq, int B, int HW, int C, void* stream);
 /* GRN, training forward: gx = sqrt(sumsq), mu = mean_c gx, nx = gx / (mu + eps), y = g (1 + gamma nx) + beta. */
 int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* gamma, const float* beta, float* gx, float* nx,
                          float* mu, void* y_bf16, int B, int HW, int C, float eps, void* stream);
@@ -395,6 +396,11 @@ int fz_grn_gelu_backward_db(const void* dy_bf16, const void* g_bf16, const void*
                             const float* gx, const float* nx, const float* mu, const float* gamma, float* coef_a,
                             float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias, int B, int HW, int C,
                             float eps, void* stream);
+/* the same with GELU'(h) as saved by fz_gelu_fwd_sumsq in place of h: no transcendental in the backward pass. */
+int fz_grn_gelu_backward_saved(const void* dy_bf16, const void* g_bf16, const void* dgelu_bf16, const float* s1,
+                               const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
+                               float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias, int B,
+                               int HW, int C, float eps, void* stream);
 int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* out float [N] = sum over s of partial float [S][N], in the order s = 0 .. S-1 (split reductions stay reproducible). */
 int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* stream);
