@@ -253,10 +253,19 @@ def _ceil64(n: int) -> int:
     return (n + 63) // 64 * 64
 
 
+def _ceil16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
 class Conv3x3BnReluTrain:
-    """smp ``Conv2dReLU``: conv3x3 (no bias) -> BatchNorm2d with batch statistics -> ReLU, NHWC bf16 in / out.  The convolution
-    is a GEMM over an explicit im2col (correctness first); K and N are zero padded to the GEMM's multiples of 64.  With
-    ``bn=False`` it is the segmentation head: conv3x3 + bias, fp32 output, no normalisation."""
+    """smp ``Conv2dReLU``: conv3x3 (no bias) -> BatchNorm2d with batch statistics -> ReLU, NHWC bf16 in / out.  With
+    ``bn=False`` it is the segmentation head: conv3x3 + bias, fp32 output, no normalisation.
+
+    Two convolution paths.  The wide, few-channel layers (16-64 channels in, <= 32 out, H % 8 == 0, W % 32 == 0: the 256^2 and
+    512^2 levels, where the layer is HBM-bound) run csrc/conv3x3_small.cu: forward, data gradient (the same kernel on the
+    flipped, transposed weights) and weight gradient from a halo'd tile staged once in shared memory -- no im2col matrix, the
+    output only as wide as the layer (``npad`` = 16 or 32).  Every other shape is a tcgen05 GEMM over an explicit im2col
+    (K and N zero padded to multiples of 64)."""
 
     BN_EPS = 1e-5
 
@@ -275,16 +284,39 @@ class Conv3x3BnReluTrain:
         else:
             self.bias = torch.zeros(self.npad, dtype=torch.float32, device=dev)
             self.bias[:self.cout] = bias.detach().float()
+        # the tile kernels' weights: [tap][co][ci] for the forward, [8 - tap][ci][co] for the data gradient
+        self.coutp = _ceil16(self.cout)
+        self.small_ok = self.cin in (16, 32, 48, 64) and self.coutp in (16, 32)
+        if self.small_ok:
+            wb = weight.detach().to(torch.bfloat16)
+            wf = torch.zeros((9, self.coutp, self.cin), dtype=torch.bfloat16, device=dev)
+            wf[:, :self.cout] = wb.permute(2, 3, 0, 1).reshape(9, self.cout, self.cin)
+            wd = torch.zeros((9, self.cin, self.coutp), dtype=torch.bfloat16, device=dev)
+            wd[:, :, :self.cout] = wb.flip(2, 3).permute(2, 3, 1, 0).reshape(9, self.cin, self.cout)
+            self.w_fwd, self.w_dgrad = wf.contiguous(), wd.contiguous()
         self.saved = None
+
+    def _small(self, H: int, W: int) -> bool:
+        return self.small_ok and bool(_L().fz_conv3x3_small_supported(H, W, self.cin, self.coutp))
 
     def forward(self, x: torch.Tensor):
         B, H, W, C = x.shape
         M, dev = B * H * W, x.device
-        col = torch.empty((M, self.kpad), dtype=torch.bfloat16, device=dev)
-        _chk(_L().fz_im2col3x3_bf16(_P(x.contiguous()), _P(col), B, H, W, C, self.kpad, _S()), "fz_im2col3x3_bf16")
-        conv = nv.gemm_bf16(col, self.w2, nv.EPI_F32, bias=None if self.bn else self.bias)      # fp32 [M, npad]
+        small = self._small(H, W)
+        self.npad = self.coutp if small else _ceil64(self.cout)               # width of the conv output / its gradient
+        x = x.contiguous()
+        if small:
+            col = None
+            conv = torch.empty((M, self.npad), dtype=torch.float32, device=dev)
+            _chk(_L().fz_conv3x3_small_forward(_P(x), _P(self.w_fwd), None if self.bn else _P(self.bias), _P(conv), 0, B, H, W,
+                                               C, self.npad, self.npad, self.npad, _S()), "fz_conv3x3_small_forward")
+        else:
+            col = torch.empty((M, self.kpad), dtype=torch.bfloat16, device=dev)
+            _chk(_L().fz_im2col3x3_bf16(_P(x), _P(col), B, H, W, C, self.kpad, _S()), "fz_im2col3x3_bf16")
+            conv = nv.gemm_bf16(col, self.w2, nv.EPI_F32, bias=None if self.bn else self.bias)      # fp32 [M, npad]
+        keep = x if small else col
         if not self.bn:
-            self.saved = (col, (B, H, W))
+            self.saved = (keep, small, (B, H, W))
             return conv.view(B, H, W, self.npad)
         chunks = max(1, min(1184, M // 64))
         y = torch.empty((M, self.cout), dtype=torch.bfloat16, device=dev)
@@ -299,7 +331,7 @@ class Conv3x3BnReluTrain:
                  "fz_bn_update_running")
             if nbt is not None:
                 nbt.add_(1)
-        self.saved = (col, conv, y, mean, rstd, chunks, (B, H, W))
+        self.saved = (keep, small, conv, y, mean, rstd, chunks, (B, H, W))
         return y.view(B, H, W, self.cout)
 
     def backward(self, dy: torch.Tensor):
@@ -307,8 +339,8 @@ class Conv3x3BnReluTrain:
         -> (dx fp32 [B,H,W,cin], {weight, bn_weight, bn_bias | bias})."""
         grads = {}
         if self.bn:
-            col, conv, y, mean, rstd, chunks, (B, H, W) = self.saved
-            M, dev = B * H * W, col.device
+            keep, small, conv, y, mean, rstd, chunks, (B, H, W) = self.saved
+            M, dev = B * H * W, keep.device
             dconv = torch.empty((M, self.npad), dtype=torch.bfloat16, device=dev)
             dgb = torch.empty((2, self.cout), dtype=torch.float32, device=dev)
             ws = torch.empty((chunks + 1) * 2 * self.cout, dtype=torch.float32, device=dev)
@@ -317,13 +349,23 @@ class Conv3x3BnReluTrain:
                  "fz_bn_relu_backward")
             grads["bn_bias"], grads["bn_weight"] = dgb[0], dgb[1]
         else:
-            col, (B, H, W) = self.saved
+            keep, small, (B, H, W) = self.saved
             dconv = dy.contiguous().view(-1, self.npad)
-        dcol, dw, db = nv.linear_backward(dconv, col, self.w2)
+        dx = torch.empty((B, H, W, self.cin), dtype=torch.float32, device=dconv.device)
+        if small:
+            dw = torch.empty((9, self.npad, self.cin), dtype=torch.float32, device=dconv.device)
+            _chk(_L().fz_conv3x3_small_wgrad(_P(keep), _P(dconv), self.npad, _P(dw), B, H, W, self.cin, self.npad, _S()),
+                 "fz_conv3x3_small_wgrad")
+            grads["weight"] = dw[:, :self.cout].permute(1, 2, 0).reshape(self.cout, self.cin, 3, 3).contiguous()
+            if not self.bn:
+                grads["bias"] = nv.colsum_bf16(dconv)[:self.cout]
+            _chk(_L().fz_conv3x3_small_forward(_P(dconv), _P(self.w_dgrad), None, _P(dx), 0, B, H, W, self.npad, self.cin,
+                                               self.cin, self.cin, _S()), "fz_conv3x3_small_forward")
+            return dx, grads
+        dcol, dw, db = nv.linear_backward(dconv, keep, self.w2)
         if not self.bn:
             grads["bias"] = db[:self.cout]
         grads["weight"] = dw[:self.cout, :9 * self.cin].reshape(self.cout, 3, 3, self.cin).permute(0, 3, 1, 2).contiguous()
-        dx = torch.empty((B, H, W, self.cin), dtype=torch.float32, device=dcol.device)
         _chk(_L().fz_col2im3x3(_P(dcol), _P(dx), B, H, W, self.cin, self.kpad, _S()), "fz_col2im3x3")
         return dx, grads
 

@@ -139,6 +139,9 @@ _SIGNATURES = {
     "fz_s2d_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_patchify4_nchw": [_vp, _vp, _i, _i, _i, _i, _vp],
     "fz_im2col3x3_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_conv3x3_small_supported": [_i, _i, _i, _i],
+    "fz_conv3x3_small_forward": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_conv3x3_small_wgrad": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_col2im3x3": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_bn_relu_train_forward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, ctypes.c_float, _vp],
     "fz_bn_relu_backward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _vp],

@@ -401,6 +401,18 @@ int fz_grn_gelu_backward_saved(const void* dy_bf16, const void* g_bf16, const vo
                                const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
                                float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias, int B,
                                int HW, int C, float eps, void* stream);
+/* ---- U-Net decoder convolutions of the training step without im2col (csrc/conv3x3_small.cu): 3x3 / pad 1 on bf16 NHWC maps
+ * with H % 8 == 0, W % 32 == 0 and 16 / 32 / 48 / 64 channels on either side (fz_conv3x3_small_supported: 1 / 0).
+ * forward: out[px][co] = bias[co] + sum_tap sum_ci in[px + tap][ci] * w[tap][co][ci], w bf16 [9][Cout][Cin], tap = ky*3 + kx;
+ * out fp32 (out_bf16 = 0) or bf16 [pixels][ldo], columns < n_store written.  The data gradient is the same call on the output
+ * gradient with w'[tap][ci][co] = w[8 - tap][co][ci].
+ * wgrad: dw float [9][Cout][Cin] = sum_px dconv[px][co] * x[px + tap][ci]; dconv bf16 [pixels][ldd]; Cout <= 32; partial sums
+ * live in a per-device scratch buffer grown on demand and are added in a fixed order. */
+int fz_conv3x3_small_supported(int H, int W, int Cin, int Cout);
+int fz_conv3x3_small_forward(const void* in_bf16, const void* w_bf16, const float* bias, void* out, int out_bf16, int B, int H,
+                             int W, int Cin, int Cout, int n_store, int ldo, void* stream);
+int fz_conv3x3_small_wgrad(const void* x_bf16, const void* dconv_bf16, int ldd, float* dw, int B, int H, int W, int Cin,
+                           int Cout, void* stream);
 int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* out float [N] = sum over s of partial float [S][N], in the order s = 0 .. S-1 (split reductions stay reproducible). */
 int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* stream);
