@@ -24,7 +24,9 @@ def _chk(rc: int, what: str) -> None:
 
 
 class ConvNeXtBlockTrain:
-    def __init__(self, params: Dict[str, torch.Tensor], eps_ln: float = 1e-6, eps_grn: float = 1e-6):
+    def __init__(self, params: Dict[str, torch.Tensor], eps_ln: float = 1e-6, eps_grn: float = 1e-6, params16=None):
+        """params16 (optional): bf16 copies of the same parameters under the same names (the trainer casts its whole arena in
+        one launch); the two Linear weights are then used as they are instead of being cast here."""
         dev = params["conv_dw.weight"].device
         if dev.type != "cuda":
             raise nv.NativeError("ConvNeXtBlockTrain runs on CUDA only (no CPU fallback)")
@@ -34,10 +36,12 @@ class ConvNeXtBlockTrain:
         self.w_dw = f32(params["conv_dw.weight"].reshape(C, 49).t())            # [49][C]
         self.b_dw = f32(params["conv_dw.bias"])
         self.ln_w, self.ln_b = f32(params["norm.weight"]), f32(params["norm.bias"])
-        self.w1 = params["mlp.fc1.weight"].detach().to(torch.bfloat16).contiguous()      # [4C][C]
+        p16 = params16 or {}
+        b16 = lambda k: p16[k] if k in p16 else params[k].detach().to(torch.bfloat16).contiguous()
+        self.w1 = b16("mlp.fc1.weight")                                                  # [4C][C]
         self.b1 = f32(params["mlp.fc1.bias"])
         self.grn_w, self.grn_b = f32(params["mlp.grn.weight"]), f32(params["mlp.grn.bias"])
-        self.w2 = params["mlp.fc2.weight"].detach().to(torch.bfloat16).contiguous()      # [C][4C]
+        self.w2 = b16("mlp.fc2.weight")                                                  # [C][4C]
         self.b2 = f32(params["mlp.fc2.bias"])
         self.saved = None
 
@@ -96,6 +100,8 @@ class ConvNeXtBlockTrain:
         _chk(_L().fz_layernorm_bwd(_P(da1), _P(u), _P(mean), _P(rstd), _P(self.ln_w), _P(du), _P(partial), _P(dln), M, C,
                                    blocks, _S()), "fz_layernorm_bwd")
         dx = torch.empty_like(x)                                                          # dx = dy + dwconv^T(du), one pass
+        # (a bf16 copy of dx written by the same kernel was tried: the extra stores cost the issue-bound kernel more than the
+        # cast pass of the next block saves)
         _chk(_L().fz_dwconv7_f32_add(_P(du), _P(self.w_dw), None, _P(dy), _P(dx), B, H, W, C, 1, _S()), "fz_dwconv7_f32_add")
         dw_dw = torch.empty((49, C), dtype=torch.float32, device=dev)
         db_dw = torch.empty(C, dtype=torch.float32, device=dev)
@@ -151,8 +157,9 @@ class ConvNeXtV2EncoderTrain:
     ``stages_i.blocks.j``): fp32 NCHW normalised tiles in, the four stage outputs (fp32 NHWC) out; ``backward`` takes the
     gradients at the four outputs and returns every parameter's gradient under the reference's state_dict keys."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], depths, dims):
+    def __init__(self, params: Dict[str, torch.Tensor], depths, dims, params16=None):
         self.depths, self.dims = tuple(depths), tuple(dims)
+        params16 = params16 or {}
         w = params["stem_0.weight"]
         self.cin = w.shape[1]
         self.kpad = ((self.cin * 16 + 63) // 64) * 64
@@ -171,8 +178,9 @@ class ConvNeXtV2EncoderTrain:
                                   params[p + "1.bias"].detach().float().contiguous()))
             else:
                 self.down.append(None)
-            self.blocks.append([ConvNeXtBlockTrain({k[len(f"stages_{i}.blocks.{j}."):]: v for k, v in params.items()
-                                                    if k.startswith(f"stages_{i}.blocks.{j}.")}) for j in range(d)])
+            sub = lambda src, pre: {k[len(pre):]: v for k, v in src.items() if k.startswith(pre)}
+            self.blocks.append([ConvNeXtBlockTrain(sub(params, f"stages_{i}.blocks.{j}."),
+                                                   params16=sub(params16, f"stages_{i}.blocks.{j}.")) for j in range(d)])
         self.saved = None
 
     def forward(self, x_nchw: torch.Tensor):

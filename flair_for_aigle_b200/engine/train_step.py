@@ -11,8 +11,8 @@ fusion convolutions, then each encoder stage, deepest first -- is copied into it
 arena and that range's NCCL all-reduce starts at once on a side stream, so only the last, smallest bucket (an encoder's stem)
 is exposed.
 
-``cuda_graph=True``: the step is launch-bound on the host (about 4000 kernel launches; 114 ms of device work took 156 ms of
-wall clock), so after one eager step the whole step -- rebuilding the 16-bit weight copies, forward, backward, the bucketed
+``cuda_graph=True`` (single process; under torch.distributed the step stays eager): the step is launch-bound on the host
+(about 4000 kernel launches), so after one eager step the whole step -- rebuilding the 16-bit weight copies, forward, backward, the bucketed
 all-reduces, AdamW with its step counter on the device -- is captured once into a CUDA graph and replayed; inputs are copied
 into static buffers, loss and predictions come back in static buffers."""
 from typing import Dict, List
@@ -46,6 +46,7 @@ class ConvNeXtUNetTrainer:
             off += k
         self.names_index = {n: i for i, n in enumerate(self.names)}
         self._comm_stream = None
+        self._arena16 = None
         self._works, self._reduced, self._leftover, self._filled, self._overlap = [], [], [], set(), False
         self.last_allreduce_ms = 0.0
         self._build()
@@ -53,11 +54,23 @@ class ConvNeXtUNetTrainer:
     def _build(self) -> None:
         """Engines hold bf16 / repacked copies of the weights: rebuilt after every optimizer step."""
         p = self.params
+        # the whole fp32 arena to bf16 in ONE launch; the Linear weights of the blocks (the bulk of the parameters) are views
+        # into it, the few tensors that need another layout (depthwise taps, convolutions) are still repacked one by one
+        if self._arena16 is None:
+            self._arena16 = torch.empty(self.opt.arena.shape, dtype=torch.bfloat16, device=self.opt.arena.device)
+        n4 = self.opt.arena.numel() // 4 * 4         # the cast kernel moves float4s; nothing that is used lives in the tail
+        nv.cast_f32_bf16(self.opt.arena[:n4], self._arena16[:n4])
+        p16 = {}
+        for name in self.names:
+            if name.endswith(("mlp.fc1.weight", "mlp.fc2.weight")):
+                off, k = self._slot[name]
+                if off % 8 == 0 and off + k <= n4:   # 16-byte aligned rows for the TMA descriptor
+                    p16[name] = self._arena16[off:off + k].view(p[name].shape)
         self.enc = {}
         for m in self.mods:
             pre = f"encoders.{m}.seg_model.model."
             self.enc[m] = ConvNeXtV2EncoderTrain({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}, self.depths,
-                                                 self.dims)
+                                                 self.dims, params16={k[len(pre):]: v for k, v in p16.items() if k.startswith(pre)})
         pre = f"main_decoders.{self.task}.seg_model."
         both = {**p, **self.buffers}
         self.dec = UnetDecoderTrain({k[len(pre):]: v for k, v in both.items() if k.startswith(pre)})
@@ -154,7 +167,10 @@ class ConvNeXtUNetTrainer:
         With ``cuda_graph`` the first call runs eagerly (it sizes the library's scratch buffers and initialises NCCL), the
         second captures, and every call from the second on replays the graph; the returned loss / preds are then the graph's
         static output buffers (overwritten by the next step).  A batch of another shape falls back to the eager step."""
-        if not self.cuda_graph or self.opt.step_count == 0:
+        # under torch.distributed the step stays eager: a capture that contains the bucketed NCCL all-reduces on the side
+        # stream did not come back on 2 GPUs (measured once, not debugged -- DESIGN.md section 8); eager costs ~8 ms of launch
+        # gaps per step there
+        if not self.cuda_graph or self.opt.step_count == 0 or self._distributed():
             return self._step_eager(batch)
         if self._graph is not None and not self._same_shapes(batch):
             return self._step_eager(batch)
