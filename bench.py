@@ -311,7 +311,8 @@ def train_block(dev, rank: int, world: int, steps: int, warmup: int):
     depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
     w = torch.ones(N_CLS, device=dev)
     w[15:] = 0
-    graphed = os.environ.get("FZ_TRAIN_GRAPH", "1") != "0"      # the step replayed as ONE CUDA graph (engine/train_step.py)
+    # the step replayed as a CUDA graph (one process) or a chain of graphs cut at the gradient buckets (torch.distributed)
+    graphed = os.environ.get("FZ_TRAIN_GRAPH", "1") != "0"
     tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w, cuda_graph=graphed)
     g = torch.Generator(device="cpu").manual_seed(2025 + rank)
     host = {k: torch.randn(B, c, P, P, generator=g).pin_memory() for k, c in mods.items()}

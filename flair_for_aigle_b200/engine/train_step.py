@@ -11,10 +11,11 @@ fusion convolutions, then each encoder stage, deepest first -- is copied into it
 arena and that range's NCCL all-reduce starts at once on a side stream, so only the last, smallest bucket (an encoder's stem)
 is exposed.
 
-``cuda_graph=True`` (single process; under torch.distributed the step stays eager): the step is launch-bound on the host
-(about 4000 kernel launches), so after one eager step the whole step -- rebuilding the 16-bit weight copies, forward, backward, the bucketed
+``cuda_graph=True``: the step is launch-bound on the host (about 4000 kernel launches), so after one eager step the whole
+step -- rebuilding the 16-bit weight copies, forward, backward, the bucketed
 all-reduces, AdamW with its step counter on the device -- is captured once into a CUDA graph and replayed; inputs are copied
-into static buffers, loss and predictions come back in static buffers."""
+into static buffers, loss and predictions come back in static buffers.  Under torch.distributed the capture is a chain of
+graphs cut at the gradient buckets, with the NCCL calls launched eagerly between the segments (_capture)."""
 from typing import Dict, List
 
 import torch
@@ -32,6 +33,7 @@ class ConvNeXtUNetTrainer:
         """state: the model's parameters by state_dict name (fp32, CUDA); they become views into the optimizer's arena."""
         self.cuda_graph = bool(cuda_graph)
         self._graph, self._static, self._graph_out, self._stale, self._capturing = None, None, None, False, False
+        self._segments, self._segmented, self._pool, self._cap_graph, self._graph_reduced = [], False, None, None, []
         self.depths, self.dims, self.mods, self.task, self.task_weight = depths, dims, list(modalities), task, task_weight
         self.names = [k for k in state if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
         self.params = {k: state[k] for k in self.names}
@@ -48,7 +50,7 @@ class ConvNeXtUNetTrainer:
         self._comm_stream = None
         self._arena16 = None
         self._works, self._reduced, self._leftover, self._filled, self._overlap = [], [], [], set(), False
-        self.last_allreduce_ms = 0.0
+        self._last_ar_ms, self._ar_events = 0.0, None
         self._build()
 
     def _build(self) -> None:
@@ -80,6 +82,19 @@ class ConvNeXtUNetTrainer:
                           p[f"fusion_handler.conv_f.{i}.bias"].detach().float().contiguous()) for i, c in enumerate(self.dims)]
 
     # ------------------------------------------------------------------ gradient arena + bucketed all-reduce
+    @property
+    def last_allreduce_ms(self) -> float:
+        """EXPOSED part of the last step's gradient exchange: what the compute stream waited for after the backward.  Graph
+        replays time it with a pair of events read back here, once they have completed (no host stall inside the step)."""
+        if self._ar_events is not None and self._ar_events[1].query():
+            self._last_ar_ms = self._ar_events[0].elapsed_time(self._ar_events[1])
+            self._ar_events = None
+        return self._last_ar_ms
+
+    @last_allreduce_ms.setter
+    def last_allreduce_ms(self, v: float) -> None:
+        self._last_ar_ms, self._ar_events = float(v), None
+
     def _distributed(self) -> bool:
         import torch.distributed as dist
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -98,11 +113,24 @@ class ConvNeXtUNetTrainer:
             hi = off + k if hi is None else max(hi, off + k)
             tot += k
             self._filled.add(name)
+        if self._capturing:
+            # graph capture: NCCL stays OUT of the graphs.  A contiguous bucket ends the current graph segment; the replay
+            # launches its all-reduce eagerly on the side stream between two segment replays (see _replay)
+            if self._segmented and tot == hi - lo:
+                self._seg_end(("reduce", lo, hi))
+                self._seg_begin()
+                self._reduced.append((lo, hi))
+            return
         if not self._overlap:
             return
         if tot != hi - lo:
             self._leftover.append((lo, hi))
             return
+        self._launch_allreduce(lo, hi)
+        self._reduced.append((lo, hi))
+
+    def _launch_allreduce(self, lo: int, hi: int) -> None:
+        """all-reduce (average) of grad[lo:hi] on the communication stream, ordered after everything already on the current one"""
         import torch.distributed as dist
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=self.opt.grad.device)
@@ -111,7 +139,6 @@ class ConvNeXtUNetTrainer:
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
             self._works.append(dist.all_reduce(self.opt.grad[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
-        self._reduced.append((lo, hi))
 
     def forward_backward(self, batch: Dict[str, torch.Tensor], into_arena: bool = False):
         """-> (loss 0-d tensor, preds int32 (B,H,W), {parameter name: gradient}).  With ``into_arena`` the gradients are also
@@ -167,10 +194,7 @@ class ConvNeXtUNetTrainer:
         With ``cuda_graph`` the first call runs eagerly (it sizes the library's scratch buffers and initialises NCCL), the
         second captures, and every call from the second on replays the graph; the returned loss / preds are then the graph's
         static output buffers (overwritten by the next step).  A batch of another shape falls back to the eager step."""
-        # under torch.distributed the step stays eager: a capture that contains the bucketed NCCL all-reduces on the side
-        # stream did not come back on 2 GPUs (measured once, not debugged -- DESIGN.md section 8); eager costs ~8 ms of launch
-        # gaps per step there
-        if not self.cuda_graph or self.opt.step_count == 0 or self._distributed():
+        if not self.cuda_graph or self.opt.step_count == 0:
             return self._step_eager(batch)
         if self._graph is not None and not self._same_shapes(batch):
             return self._step_eager(batch)
@@ -178,7 +202,7 @@ class ConvNeXtUNetTrainer:
             self._capture(batch)
         for k, v in self._static.items():
             v.copy_(batch[k], non_blocking=True)
-        self._graph.replay()
+        self._replay()
         self.opt.step_count += 1
         self._stale = True
         return self._graph_out
@@ -187,18 +211,68 @@ class ConvNeXtUNetTrainer:
         return all(k in batch and batch[k].shape == v.shape and batch[k].dtype == v.dtype for k, v in self._static.items())
 
     def _capture(self, batch) -> None:
+        """One graph in a single process.  Under torch.distributed (or FZ_TRAIN_SEGMENTS=1, which exercises the same code on
+        one GPU) the step is captured as a CHAIN of graphs sharing one memory pool, cut wherever a gradient bucket is complete
+        and once more in front of the optimizer: NCCL is never captured (a capture containing the side-stream all-reduces did
+        not come back on 2 GPUs); the replay launches each bucket's all-reduce eagerly between two segments, so the exchange
+        still overlaps the rest of the backward."""
+        import os
         keys = list(self.mods) + [self.task]
         self._static = {k: batch[k].detach().clone() for k in keys}
+        self._segmented = self._distributed() or os.environ.get("FZ_TRAIN_SEGMENTS", "0") == "1"
         torch.cuda.synchronize()
-        torch.cuda.empty_cache()                     # the eager step's cached blocks: the graph gets its own pool
-        self._graph = torch.cuda.CUDAGraph()
+        torch.cuda.empty_cache()                     # the eager step's cached blocks: the graphs get their own pool
+        self._segments, self._reduced = [], []
+        self._pool = torch.cuda.graph_pool_handle()
+        cap = torch.cuda.Stream(device=self.opt.grad.device)
+        cap.wait_stream(torch.cuda.current_stream())
         self._capturing = True
         try:
-            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):     # NCCL's watchdog thread keeps polling
+            with torch.cuda.stream(cap):
+                self._seg_begin()
                 self._build()                        # inside the graph: replays refresh the 16-bit weight copies themselves
                 self._graph_out = self._step_body(self._static, timed=False, on_device_counter=True)
+                self._seg_end(None)
         finally:
             self._capturing = False
+        torch.cuda.current_stream().wait_stream(cap)
+        self._graph = self._segments[0][0]
+        self._graph_reduced = sorted(self._reduced)
+
+    def _seg_begin(self) -> None:
+        self._cap_graph = torch.cuda.CUDAGraph()
+        self._cap_graph.capture_begin(pool=self._pool, capture_error_mode="thread_local")     # NCCL's watchdog thread keeps polling
+
+    def _seg_end(self, action) -> None:
+        self._cap_graph.capture_end()
+        self._segments.append((self._cap_graph, action))
+        self._cap_graph = None
+
+    def _replay(self) -> None:
+        import torch.distributed as dist
+        live = self._distributed()
+        self._works = []
+        for graph, action in self._segments:
+            graph.replay()
+            if action is None or not live:
+                continue
+            if action[0] == "reduce":
+                self._launch_allreduce(action[1], action[2])
+            elif action[0] == "finish":              # everything the buckets did not cover, then wait for the buckets
+                cur = torch.cuda.current_stream()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cur)
+                pos, n = 0, self.opt.grad.numel()
+                for lo, hi in self._graph_reduced + [(n, n)]:
+                    if lo > pos:
+                        dist.all_reduce(self.opt.grad[pos:lo], op=dist.ReduceOp.AVG)
+                    pos = max(pos, hi)
+                for w in self._works:
+                    w.wait()
+                if self._comm_stream is not None:
+                    cur.wait_stream(self._comm_stream)
+                e1.record(cur)
+                self._ar_events = (e0, e1)
 
     def _step_eager(self, batch):
         if self._stale:
@@ -230,6 +304,11 @@ class ConvNeXtUNetTrainer:
         """Waits for the buckets started during the backward and reduces whatever they did not cover (parameters without a
         gradient, non-contiguous groups).  ``last_allreduce_ms`` = the time the compute stream had to wait, i.e. the EXPOSED
         part of the gradient exchange (``timed=False``, under graph capture: not measured, the last eager value is kept)."""
+        if self._capturing:
+            if self._segmented:
+                self._seg_end(("finish",))
+                self._seg_begin()
+            return
         if timed:
             self.last_allreduce_ms = 0.0
         if not self._overlap:

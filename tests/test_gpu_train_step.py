@@ -137,10 +137,14 @@ def test_segmentation_task_training_step(cuda, tmp_path):
     assert bool(torch.isfinite(out[TASK]).all())
 
 
-def test_graph_replayed_step_equals_eager_step(cuda):
+@pytest.mark.parametrize("segments", [False, True])
+def test_graph_replayed_step_equals_eager_step(cuda, monkeypatch, segments):
     """``cuda_graph=True`` (one eager step, then the whole step captured once and replayed) must walk the same trajectory as
     the eager trainer: same kernels in the same order on the same data, the AdamW step counter on the device instead of in a
-    host argument.  Batches change from step to step (the graph reads its static input buffers)."""
+    host argument.  Batches change from step to step (the graph reads its static input buffers).  ``segments``: the chain of
+    graphs cut at the gradient buckets that torch.distributed runs use (NCCL launched between the segments), forced here on
+    one GPU."""
+    monkeypatch.setenv("FZ_TRAIN_SEGMENTS", "1" if segments else "0")
     import bench
     from flair_for_aigle_b200.engine.convnext_unet import CONVNEXTV2_CFGS
     from flair_for_aigle_b200.engine.train_step import ConvNeXtUNetTrainer
@@ -164,6 +168,9 @@ def test_graph_replayed_step_equals_eager_step(cuda):
             losses.append(float(loss))
             preds.append(p.clone())
         assert (tr._graph is not None) == graphed and tr.opt.step_count == len(batches)
+        if graphed:
+            print(f"graph segments: {len(tr._segments)}")
+            assert (len(tr._segments) > 5) == segments
         assert int(tr.opt.step_dev) == len(batches)
         runs[graphed] = (losses, preds, tr.opt.arena.clone(), {k: v.clone() for k, v in tr.buffers.items()})
         # a batch of another shape after the capture: falls back to the eager step, on the CURRENT weights
