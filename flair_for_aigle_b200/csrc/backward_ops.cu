@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) dwconv7_f32_tiled_kernel(const float* __r
 // CT: the channel count as a compile-time constant (0 = runtime): every tap address becomes [row pointer + immediate]
 // instead of a 64-bit multiply-add per load -- the instruction mix, not DRAM, bounds these kernels.
 template <int CT>
-__global__ void __launch_bounds__(256) dwconv7_f32_tile48_kernel(const float* __restrict__ in, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) dwconv7_f32_tile48_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, const float* __restrict__ add,
                                                                  float* __restrict__ out, int B, int H, int W, int C_rt, int flip) {
   const int C = CT ? CT : C_rt;
@@ -113,18 +113,31 @@ __global__ void __launch_bounds__(256) dwconv7_f32_tile48_kernel(const float* __
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = b0;
-#pragma unroll
-    for (int iy = 0; iy < 10; ++iy) {
+    // software-pipelined rows: row iy + 1 is in flight while row iy feeds the FMAs (16 resident warps per SM cannot hide the
+    // load latency on their own).  Rows outside the image are skipped, loads and FMAs both (warp-uniform).
+    const float* base = in + (img + static_cast<size_t>(y0 - 3) * W + x0) * C + c;      // pixel (y0 - 3, x0); only dereferenced inside
+    const ptrdiff_t row_stride = static_cast<ptrdiff_t>(W) * C;
+    auto load_row = [&](int iy, float (&dst)[14]) {
       const int gy = y0 - 3 + iy;
-      if (gy < 0 || gy >= H) continue;                       // warp-uniform
-      const float* xr = in + (img + static_cast<size_t>(gy) * W + x0) * C + c;       // pixel x0 of the row
-      float xs[14];
+      if (gy < 0 || gy >= H) return;
+      const float* xr = base + iy * row_stride;
 #pragma unroll
       for (int q = 0; q < 14; ++q) {
         // only the three halo pixels on either side can fall outside the row (W % 8 == 0)
         const bool inside = q < 3 ? x0 - 3 + q >= 0 : (q >= 11 ? x0 - 3 + q < W : true);
-        xs[q] = inside ? xr[(q - 3) * C] : 0.f;
+        dst[q] = inside ? xr[(q - 3) * C] : 0.f;
       }
+    };
+    float nxt[14];
+    load_row(0, nxt);
+#pragma unroll
+    for (int iy = 0; iy < 10; ++iy) {
+      float xs[14];
+#pragma unroll
+      for (int q = 0; q < 14; ++q) xs[q] = nxt[q];
+      if (iy + 1 < 10) load_row(iy + 1, nxt);
+      const int gy = y0 - 3 + iy;
+      if (gy < 0 || gy >= H) continue;                       // warp-uniform
 #pragma unroll
       for (int oy = 0; oy < 4; ++oy) {
         const int ky = iy - oy;
