@@ -33,6 +33,33 @@ __global__ void __launch_bounds__(CE_THREADS) onehot_argmax_kernel(const float* 
   tgt[i] = best;
 }
 
+// cm[t][p] += 1 for every pixel with 0 <= t, p < C (pixels whose label or prediction is out of range are skipped, like
+// sklearn's confusion_matrix(labels=range(C)) at prediction_writer.py:64 and torchmetrics' bincount of t * C + p).
+// Integer counting: per-block histogram in shared memory, lanes holding the same (t, p) elect one to add their count
+// (__match_any_sync: class rasters are spatially coherent, most warps hit one or two bins), one 64-bit global add per
+// non-empty bin per block.  Sums of integers: the result is exact and order independent.
+__global__ void __launch_bounds__(256) confusion_kernel(const int32_t* __restrict__ target, const int32_t* __restrict__ pred,
+                                                        int64_t n, int C, unsigned long long* __restrict__ cm) {
+  extern __shared__ unsigned int hist[];                       // [C * C]
+  for (int k = threadIdx.x; k < C * C; k += 256) hist[k] = 0u;
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+  // whole warps iterate together (the loop bound is rounded up to a multiple of the stride) so the match is convergent
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * 256; i0 < n; i0 += stride) {
+    const int64_t i = i0 + threadIdx.x;
+    int key = -1;
+    if (i < n) {
+      const int t = target[i], p = pred[i];
+      if (t >= 0 && t < C && p >= 0 && p < C) key = t * C + p;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[key], static_cast<unsigned>(__popc(peers)));
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < C * C; k += 256)
+    if (hist[k]) atomicAdd(&cm[k], static_cast<unsigned long long>(hist[k]));
+}
+
 // per pixel: lse, prediction, and the block's partial sums of w[t] * nll and w[t] (fixed-order tree: deterministic).
 // grid = (blocks per sample, B): no 64-bit index division; MAXC = class count rounded up to 8 (19 -> 24 unrolled slots).
 template <int MAXC>
@@ -260,6 +287,19 @@ extern "C" int fz_onehot_argmax(const float* onehot, int32_t* targets, int B, in
   if (n_px == 0) return 0;
   onehot_argmax_kernel<<<static_cast<unsigned>((n_px + CE_THREADS - 1) / CE_THREADS), CE_THREADS, 0,
                          reinterpret_cast<cudaStream_t>(stream)>>>(onehot, targets, C, plane, n_px);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fz_confusion_matrix(const int32_t* target, const int32_t* pred, int64_t n, int C, int64_t* cm, void* stream) {
+  using namespace fz;
+  FZ_REQUIRE(n >= 0 && C >= 1 && C <= 96 && cm && (n == 0 || (target && pred)), "fz_confusion_matrix: n=%lld C=%d (1..96 classes)",
+             (long long)n, C);
+  if (n == 0) return 0;
+  int64_t blocks = (n + 256 * 16 - 1) / (256 * 16);            // >= 16 pixels per thread before a block's global adds
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+  confusion_kernel<<<static_cast<unsigned>(blocks), 256, C * C * sizeof(unsigned int), reinterpret_cast<cudaStream_t>(stream)>>>(
+      target, pred, n, C, reinterpret_cast<unsigned long long*>(cm));
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

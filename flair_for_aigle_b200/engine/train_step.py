@@ -48,6 +48,7 @@ class ConvNeXtUNetTrainer:
             off += k
         self.names_index = {n: i for i, n in enumerate(self.names)}
         self._comm_stream = None
+        self.last_targets = None
         self._arena16 = None
         self._works, self._reduced, self._leftover, self._filled, self._overlap = [], [], [], set(), False
         self._last_ar_ms, self._ar_events = 0.0, None
@@ -161,6 +162,7 @@ class ConvNeXtUNetTrainer:
         logits = self.dec.forward(fused)
         targets = batch[self.task]
         targets = nv.onehot_argmax(targets) if targets.dim() == 4 else targets.to(torch.int32)
+        self.last_targets = targets                  # int32 (B,H,W): what the metrics compare the predictions with
         loss, preds = self.criterion(logits, targets, task_weight=self.task_weight, want_preds=True)
         dfused, grads = self.dec.backward(self.criterion.backward())
         grads = {f"main_decoders.{self.task}.seg_model.{k}": v for k, v in grads.items()}

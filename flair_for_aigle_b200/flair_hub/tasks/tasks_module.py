@@ -1,11 +1,13 @@
-"""``SegmentationTask``: the loss / prediction / optimizer side of flair_hub/tasks/tasks_module.py:133-167,377-391
- on the CUDA kernels of csrc/training_ops.cu.
+"""``SegmentationTask``: the loss / prediction / optimizer / metric side of flair_hub/tasks/tasks_module.py on
+the CUDA kernels of csrc/training_ops.cu and the training engine.
 
-Built: ``step(batch, training=False)`` -- the reference's validation step: forward (eval mode, the zonal engines),
+``step(batch, training=False)`` -- the reference's validation step (:133-167): forward (eval mode, the zonal engines),
 ``targets = argmax(one-hot)``, weighted cross entropy times ``task_weight``, ``preds = argmax(softmax(logits))``;
-``loss_gradients()`` -- d loss / d logits per task, the seed of the backward pass; ``AdamW`` -- ``torch.optim.AdamW``'s
-update over a flat parameter arena (``_init_optimizer``).  NOT built: the backward of the encoders / decoder (no backward
-kernels exist yet), so ``step(batch, training=True)`` raises instead of silently skipping the gradient."""
+``configure_trainer`` / ``training_step`` -- forward, backward and AdamW in one call (engine/train_step.py; :196-201,
+:377-391); ``validation_step`` and the two epoch-end hooks -- the reference's metric bookkeeping (:63-93, :196-201,
+:232-236, :268-276, :302-338: weighted mIoU for training and validation, per-class validation IoU, mean losses) on
+tasks/metrics.py, returning the values the reference hands to Lightning's ``self.log`` as a dict.  ``loss_gradients()`` --
+d loss / d logits per task.  Not built: auxiliary losses, modality dropout, schedulers, the per-class validation loss log."""
 from typing import Dict, Iterable, List
 
 import torch
@@ -75,6 +77,17 @@ class SegmentationTask:
         self.model, self.config = model, config
         self.criterion = FLAIRLosses(config).get_losses()
         self.mod_dropout = False
+        self._init_metrics()
+
+    def _init_metrics(self) -> None:
+        """tasks_module.py:63-93: weighted mean IoU (train, val), per-class IoU (val), mean loss (train, val), per task."""
+        from .metrics import MeanMetric, MulticlassJaccardIndex
+        labels = self.config.get('labels', [])
+        n_cls = {task: len(self.config['labels_configs'][task]['value_name']) for task in labels}
+        self.train_metrics = {task: MulticlassJaccardIndex(n_cls[task], average='weighted') for task in labels}
+        self.val_metrics = {task: MulticlassJaccardIndex(n_cls[task], average='weighted') for task in labels}
+        self.val_iou = {task: MulticlassJaccardIndex(n_cls[task], average=None) for task in labels}
+        self.train_loss, self.val_loss = MeanMetric(), MeanMetric()
 
     def forward(self, batch: Dict[str, torch.Tensor]):
         return self.model(batch)
@@ -131,7 +144,52 @@ class SegmentationTask:
         loss, preds = self.trainer.step(batch)
         if hasattr(self.model, '_engines'):
             self.model._engines = {}                 # the inference engines hold repacked copies of the old weights
-        return loss, {self.trainer.task: preds}
+        task = self.trainer.task
+        self.train_loss.update(loss)                                                  # tasks_module.py:198
+        if task in self.train_metrics and self.trainer.last_targets is not None:
+            self.train_metrics[task].update(preds, self.trainer.last_targets)         # :199-200
+        return loss, {task: preds}
+
+    def validation_step(self, batch: Dict[str, torch.Tensor]):
+        """tasks_module.py:268-276 without the per-class loss log: -> the step's loss."""
+        loss, all_preds, all_targets = self.step(batch, training=False)
+        self.val_loss.update(loss)
+        for task in all_preds:
+            self.val_metrics[task].update(all_preds[task], all_targets[task])
+            self.val_iou[task].update(all_preds[task], all_targets[task])
+        return loss
+
+    def on_train_epoch_end(self) -> Dict[str, float]:
+        """tasks_module.py:232-236,258-267: -> {'train_miou_<task suffix>': ..., 'train_loss': ...}; metrics are reset."""
+        out = {}
+        for task, metric in self.train_metrics.items():
+            if metric.confmat is not None:
+                out[f"train_miou_{task.split('-')[-1]}"] = float(metric.compute())
+            metric.reset()
+        if self.train_loss.total is not None:
+            out["train_loss"] = float(self.train_loss.compute())
+        self.train_loss.reset()
+        return out
+
+    def on_validation_epoch_end(self) -> Dict[str, float]:
+        """tasks_module.py:302-338: val_loss, val_miou_<task>, val_iou_<task>_<k>_<class name>, val_miou (mean over tasks)."""
+        out = {"val_loss": float(self.val_loss.compute())}
+        total = 0.0
+        for task in self.val_metrics:
+            suffix = task.split('-')[-1]
+            miou = float(self.val_metrics[task].compute())
+            total += miou
+            out[f"val_miou_{suffix}"] = miou
+            names = self.config['labels_configs'][task]['value_name']
+            per_class = torch.nan_to_num(self.val_iou[task].compute(), nan=0.0).tolist()
+            for k, iou in enumerate(per_class):
+                name = names.get(k, f"class_{k}") if isinstance(names, dict) else f"class_{k}"
+                out[f"val_iou_{suffix}_{k}_{name}"] = iou
+            self.val_metrics[task].reset()
+            self.val_iou[task].reset()
+        out["val_miou"] = total / max(1, len(self.val_metrics))
+        self.val_loss.reset()
+        return out
 
     def loss_gradients(self) -> Dict[str, torch.Tensor]:
         """d loss_sum / d logits per task for the last ``step`` (fp32, (B,C,H,W))."""

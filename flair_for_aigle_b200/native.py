@@ -114,6 +114,7 @@ _SIGNATURES = {
     "fz_ce_workspace_doubles": [_i, _i, _i],
     "fz_ce_loss_forward": [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "fz_ce_loss_backward": [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _i, _i, _i, _i, _vp],
+    "fz_confusion_matrix": [_vp, _vp, _i64, _i, _vp, _vp],
     "fz_adamw_step": [_vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                       ctypes.c_double, _i, _vp],
     "fz_adamw_step_dev": [_vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
@@ -727,6 +728,21 @@ def onehot_argmax(onehot: torch.Tensor) -> torch.Tensor:
     B, C, H, W = onehot.shape
     out = torch.empty((B, H, W), dtype=torch.int32, device=onehot.device)
     _check(lib().fz_onehot_argmax(_ptr(onehot.float().contiguous()), _ptr(out), B, C, H, W, _stream()), "fz_onehot_argmax")
+    return out
+
+
+def confusion_matrix(targets: torch.Tensor, preds: torch.Tensor, num_classes: int, out: Optional[torch.Tensor] = None):
+    """int64 [C][C] counts, rows = label, columns = prediction (sklearn / torchmetrics convention); labels or predictions
+    outside 0..C-1 are skipped.  ``out``: an existing matrix to accumulate into."""
+    if targets.shape != preds.shape:
+        raise NativeError(f"confusion_matrix: shapes {tuple(targets.shape)} vs {tuple(preds.shape)}")
+    t = targets.to(torch.int32).contiguous()
+    p = preds.to(torch.int32).contiguous()
+    if out is None:
+        out = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=t.device)
+    elif out.dtype != torch.int64 or tuple(out.shape) != (num_classes, num_classes):
+        raise NativeError("confusion_matrix: out must be int64 [C][C]")
+    _check(lib().fz_confusion_matrix(_ptr(t), _ptr(p), t.numel(), int(num_classes), _ptr(out), _stream()), "fz_confusion_matrix")
     return out
 
 

@@ -338,6 +338,11 @@ int fz_ce_loss_forward(const float* logits, const int32_t* targets, const float*
 int fz_ce_loss_backward(const float* logits, const int32_t* targets, const float* class_weight, float task_weight,
                         const float* lse, const float* loss_out, float grad_scale, float* dlogits, int B, int C, int H,
                         int W, void* stream);
+/* Confusion matrix of the training / validation metrics (tasks_module.py:74-90,212,274-275: torchmetrics
+ * MulticlassJaccardIndex; prediction_writer.py:64: sklearn confusion_matrix(labels=range(C))): cm int64 [C][C] (device),
+ * cm[t][p] += number of pixels with label t and prediction p; pixels with t or p outside 0..C-1 are skipped.  ACCUMULATES
+ * (zero cm first); exact integer counts, independent of scheduling.  C <= 96. */
+int fz_confusion_matrix(const int32_t* target, const int32_t* pred, int64_t n, int C, int64_t* cm, void* stream);
 /* torch.optim.AdamW (tasks_module.py:385-389: lr, weight_decay, betas from the config; eps 1e-8) on one flat fp32
  * buffer, in place; step counts from 1. */
 int fz_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,

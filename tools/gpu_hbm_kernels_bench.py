@@ -6,6 +6,7 @@ sizes: one batch of 37 tiles of 512^2, margin 64, 19 classes, on a 10 000 x 10 0
   crop_softmax_write         class_prob output: round(softmax * 255) -> 19 uint8 planes
   crop_softmax_accumulate    the accumulating variant (inference.py:468-564): fp32 canvas +=
   canvas_argmax              logits_to_labels_and_confidence (inference.py:566-572) over the 19 x 10k x 10k canvas
+  confusion_matrix           the metrics' label x prediction counts (tasks_module.py:212,274; prediction_writer.py:64)
 
 Algorithmic bytes = what the kernel must read + write once (stated per row below); time = CUDA events over 20 launches after
 3 warm-ups, the batch's tensors (>= 370 MB) far exceed nothing but L2 for the small ones, so a 256 MB buffer is written between
@@ -68,7 +69,16 @@ tiles_f32 = torch.empty((B, 4, P, P), dtype=torch.float32, device=dev)
 tiles_dem = torch.empty((B, 1, P, P), dtype=torch.float32, device=dev)
 mean4, std4 = torch.zeros(4, device=dev), torch.ones(4, device=dev)
 px_in, px_out = B * P * P, B * S * S
+# labels and predictions for the metric kernel: runs of one class, like a class raster (16 x 512^2 = one training batch; and
+# a 10k^2 zone's worth, what an evaluation over a predicted raster counts)
+lab16 = torch.randint(0, C, (16 * P * P // 64,), device=dev, dtype=torch.int32).repeat_interleave(64)
+prd16 = torch.where(torch.rand(lab16.shape, device=dev) < 0.8, lab16, torch.randint(0, C, lab16.shape, device=dev, dtype=torch.int32))
+labz = torch.randint(0, C, (ZONE * ZONE // 64,), device=dev, dtype=torch.int32).repeat_interleave(64)
+prdz = torch.where(torch.rand(labz.shape, device=dev) < 0.8, labz, torch.randint(0, C, labz.shape, device=dev, dtype=torch.int32))
+cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
 rows = [
+    ("confusion_matrix 16 x 512^2 int32 labels + predictions (8 B / px)", lambda: nv.confusion_matrix(lab16, prd16, C, out=cm), lab16.numel() * 8),
+    ("confusion_matrix 10k x 10k (8 B / px)", lambda: nv.confusion_matrix(labz, prdz, C, out=cm), labz.numel() * 8),
     ("gather_u8 (4 B read + 4 B write / input px)", lambda: nv.gather_tiles_u8(raster_u8, origins, P, out=tiles_u8), px_in * 8),
     ("gather_f32 from uint8 (4 B read + 16 B write / px)", lambda: nv.gather_tiles_f32(raster_u8, origins, P, mean4, std4, out=tiles_f32), px_in * 20),
     ("gather_f32 from float32 DEM (4 B + 4 B / px)", lambda: nv.gather_tiles_f32(raster_f32, origins, P, mean4[:1], std4[:1], out=tiles_dem), px_in * 8),
