@@ -29,9 +29,15 @@ from .convnext_train import ConvNeXtV2EncoderTrain, UnetDecoderTrain, _to_bf16
 class ConvNeXtUNetTrainer:
     def __init__(self, state: Dict[str, torch.Tensor], depths, dims, modalities: List[str], task: str,
                  class_weight: torch.Tensor, task_weight: float = 1.0, lr: float = 5e-5, weight_decay: float = 0.01,
-                 betas=(0.9, 0.999), cuda_graph: bool = False):
-        """state: the model's parameters by state_dict name (fp32, CUDA); they become views into the optimizer's arena."""
-        self.cuda_graph = bool(cuda_graph)
+                 betas=(0.9, 0.999), cuda_graph: bool = False, mod_dropout: bool = False):
+        """state: the model's parameters by state_dict name (fp32, CUDA); they become views into the optimizer's arena.
+        ``mod_dropout``: the reference's training-time modality dropout (flair_model.py:406-408, active with more than one
+        encoder): a dropped modality's feature maps are replaced by fresh noise, its encoder gets no gradient and -- like
+        torch.optim.AdamW with ``grad is None`` -- is left untouched by the update.  The random decisions change the work
+        from step to step, so such a trainer always steps eagerly."""
+        self.mod_dropout = bool(mod_dropout)
+        self.last_dropped: List[str] = []
+        self.cuda_graph = bool(cuda_graph) and not self.mod_dropout
         self._graph, self._static, self._graph_out, self._stale, self._capturing = None, None, None, False, False
         self._segments, self._segmented, self._pool, self._cap_graph, self._graph_reduced = [], False, None, None, []
         self.depths, self.dims, self.mods, self.task, self.task_weight = depths, dims, list(modalities), task, task_weight
@@ -148,7 +154,22 @@ class ConvNeXtUNetTrainer:
         if self._stale and not self._capturing:      # graph replays rebuild the weight copies inside the graph only
             self._build()
             self._stale = False
-        feats = {m: self.enc[m].forward(batch[m]) for m in self.mods}
+        dropped = {}
+        if self.mod_dropout and into_arena and len(self.mods) > 1:
+            from ..flair_hub.models.flair_model import draw_modality_dropout
+            shapes = {}
+            for m in self.mods:                      # smp's feature list for these encoders: x, 0-channel dummy, f4 .. f32
+                B, cin, P, _ = batch[m].shape
+                shapes[m] = [(B, cin, P, P), (B, 0, P // 2, P // 2)] + [(B, c, P // (4 << i), P // (4 << i))
+                                                                         for i, c in enumerate(self.dims)]
+            dropped = draw_modality_dropout(shapes, batch[self.mods[0]].device)
+        self.last_dropped = list(dropped)
+        feats = {}
+        for m in self.mods:
+            if m in dropped:                         # the encoder's output is discarded: its forward is skipped altogether
+                feats[m] = [t.permute(0, 2, 3, 1).contiguous() for t in dropped[m][2:]]
+            else:
+                feats[m] = self.enc[m].forward(batch[m])
         cats = None
         if self.fuse is None:
             fused = feats[self.mods[0]]
@@ -186,6 +207,8 @@ class ConvNeXtUNetTrainer:
             if emit:
                 emit({k: v for k, v in grads.items() if k.startswith("fusion_handler.")})
         for m in self.mods:
+            if m in dropped:                         # noise has no producer: no gradient for this encoder
+                continue
             pre = f"encoders.{m}.seg_model.model."
             g = self.enc[m].backward(dfeats[m], emit=(lambda part, pre=pre: emit({pre + k: v for k, v in part.items()})) if emit else None)
             grads.update({pre + k: v for k, v in g.items()})
@@ -286,18 +309,38 @@ class ConvNeXtUNetTrainer:
 
     def _step_body(self, batch, timed: bool, on_device_counter: bool):
         self._filled, self._reduced, self._leftover, self._works = set(), [], [], []
-        self._overlap = self._distributed()
+        # modality dropout is drawn per rank: which buckets exist would differ between ranks, so the exchange is then ONE
+        # all-reduce of the whole arena after the backward
+        self._overlap = self._distributed() and not self.mod_dropout
         loss, preds, grads = self.forward_backward(batch, into_arena=True)
         # parameters the forward never touches (fusion_handler.conv_f with a single modality) have no gradient: torch's AdamW
         # leaves them alone (no weight decay either), so they are put back after the fused update
-        unused = {n: self.params[n].clone() for n in self.names if n not in self._filled}
-        for n in unused:
-            self.opt.grads[self.names_index[n]].zero_()
-        self._finish_allreduce(timed)
+        dropped_everywhere = self.last_dropped
+        if self.mod_dropout and self._distributed():
+            # DDP semantics (find_unused_parameters): an encoder unused on SOME ranks still gets the averaged gradient of the
+            # others; only one that every rank dropped has no gradient at all
+            import torch.distributed as dist
+            used = torch.tensor([0.0 if m in self.last_dropped else 1.0 for m in self.mods], device=self.opt.grad.device)
+            dist.all_reduce(used)
+            dropped_everywhere = [m for m, u in zip(self.mods, used.tolist()) if u == 0]
+        skip = []
+        for m in dropped_everywhere:                 # a dropped encoder: one contiguous arena range the update leaves alone
+            pre = f"encoders.{m}."
+            offs = [self._slot[n] for n in self.names if n.startswith(pre)]
+            skip.append((min(o for o, _ in offs), max(o + k for o, k in offs)))
+        unused = {n: self.params[n].clone() for n in self.names
+                  if n not in self._filled and not any(lo <= self._slot[n][0] < hi for lo, hi in skip)}
+        for n in self.names:
+            if n not in self._filled:
+                self.opt.grads[self.names_index[n]].zero_()          # so that the averaged gradient of a skipped range is 0 too
+        if self.mod_dropout and self._distributed():
+            self.allreduce_gradients()
+        else:
+            self._finish_allreduce(timed)
         if on_device_counter:
             self.opt.step_on_device_counter()
         else:
-            self.opt.step()
+            self.opt.step(skip=skip)
         for n, v in unused.items():
             self.params[n].copy_(v)
         return loss, preds

@@ -13,7 +13,8 @@ PyTorch/CPU fallback.
 
 In scope: one mono-temporal modality (FusionHandler case 1,
 flair_model.py:488-490), U-Net decoder.  Out of scope and rejected loudly: Sentinel time-series
-encoders (UTAE), auxiliary decoders, modality dropout.
+encoders (UTAE), auxiliary decoders (dead code in the reference: their loss is identically zero); modality dropout lives in
+the training engine (``draw_modality_dropout`` below).
 """
 from __future__ import annotations
 
@@ -33,6 +34,30 @@ from ...engine.swin_upernet import SWIN_CFGS, SwinCfg, SwinUPerNetEngine
 from . import monotemp_model as mm
 
 logger = logging.getLogger(__name__)
+
+
+def draw_modality_dropout(feature_shapes: Dict[str, List[tuple]], device, dtype=torch.float32) -> Dict[str, List[torch.Tensor]]:
+    """The random part of the reference's training-time modality dropout (flair_model.py:406-408 and :330-354), draw for draw:
+    one ``random.uniform(0, 1)`` per modality in dict order (the dropout probability of THIS call -- the configured values
+    only switch the feature on, tasks_module.py:59-61), then per modality one ``torch.rand(1)`` against it, and for a dropped
+    modality every feature map of its list replaced by ``nn.init.xavier_uniform_`` noise of the same (B,C,h,w) shape (a
+    zero-channel dummy map draws nothing).  -> {dropped modality: [noise tensors, NCHW]}.  torch's own generators are used on
+    purpose: with the same seeds the draws equal the reference's (tests/test_reference_pin.py)."""
+    import random
+    import warnings
+    probs = {key: random.uniform(0, 1) for key in feature_shapes}
+    dropped: Dict[str, List[torch.Tensor]] = {}
+    for key, shapes in feature_shapes.items():
+        if torch.rand(1).item() < probs[key]:
+            maps = []
+            for shape in shapes:
+                t = torch.empty(tuple(shape), device=device, dtype=dtype)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")          # "Initializing zero-element tensors is a no-op"
+                    nn.init.xavier_uniform_(t)
+                maps.append(t)
+            dropped[key] = maps
+    return dropped
 
 
 class _Node(nn.Module):
@@ -242,7 +267,8 @@ class FLAIR_HUB_Model(nn.Module):
     def forward(self, batch: dict, apply_mod_dropout: bool = False):
         """flair_model.py:357-430 for one mono modality: returns ({task: (B,n_cls,H,W) fp32}, {})."""
         if apply_mod_dropout:
-            raise NotImplementedError("modality dropout is a training-time feature outside the zonal hot path")
+            raise NotImplementedError("modality dropout belongs to the training step: SegmentationTask.training_step / "
+                                      "engine.train_step.ConvNeXtUNetTrainer(mod_dropout=True) apply it (draw_modality_dropout)")
         if len(self.active_mono) > 1:
             return self._forward_fused(batch)
         mod = self.active_mono[0]

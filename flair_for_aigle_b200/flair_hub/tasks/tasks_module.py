@@ -7,7 +7,9 @@ the CUDA kernels of csrc/training_ops.cu and the training engine.
 :377-391); ``validation_step`` and the two epoch-end hooks -- the reference's metric bookkeeping (:63-93, :196-201,
 :232-236, :268-276, :302-338: weighted mIoU for training and validation, per-class validation IoU, mean losses) on
 tasks/metrics.py, returning the values the reference hands to Lightning's ``self.log`` as a dict.  ``loss_gradients()`` --
-d loss / d logits per task.  Not built: auxiliary losses, modality dropout, schedulers, the per-class validation loss log."""
+d loss / d logits per task.  Modality dropout (``config['modalities']['modality_dropout']``) is applied by the training engine.  Not built: the
+auxiliary decoders (their loss is identically zero in the reference, tests/test_reference_pin.py), schedulers, the per-class
+validation loss log."""
 from typing import Dict, Iterable, List
 
 import torch
@@ -37,6 +39,10 @@ class AdamW:
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)       # the same counter on the device (step_dev())
         self._hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        # torch keeps one step counter PER PARAMETER and leaves a parameter without a gradient untouched (moments, counter
+        # and weight decay included).  Here: arena segments [lo, hi) with their own counters; one segment until a step skips
+        # a range (modality dropout: a whole encoder has no gradient), then the segments split at that range's ends.
+        self._segments = [[0, n, 0]]
         off = 0
         self.grads: List[torch.Tensor] = []
         for p in self.params:
@@ -49,17 +55,41 @@ class AdamW:
     def zero_grad(self) -> None:
         self.grad.zero_()
 
-    def step(self) -> None:
+    def step(self, skip=()) -> None:
+        """``skip``: arena ranges [(lo, hi), ...] whose parameters received NO gradient this step: left exactly as they are,
+        like ``torch.optim.AdamW`` does for ``p.grad is None`` (no decay, no moment update, their step counter stands still)."""
         self.step_count += 1
         self.step_dev.add_(1)
-        nv.adamw_step(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
-                      self.weight_decay, self.step_count)
+        for lo, hi in skip:
+            self._split(lo)
+            self._split(hi)
+        for seg in self._segments:
+            lo, hi, _ = seg
+            if any(a <= lo and hi <= b for a, b in skip):
+                continue
+            seg[2] += 1
+            nv.adamw_step(self.arena[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr,
+                          self.betas[0], self.betas[1], self.eps, self.weight_decay, seg[2])
+
+    def _split(self, at: int) -> None:
+        for i, (lo, hi, k) in enumerate(self._segments):
+            if lo < at < hi:
+                self._segments[i:i + 1] = [[lo, at, k], [at, hi, k]]
+                return
+
+    @property
+    def uniform_steps(self) -> bool:
+        """True while every parameter has taken part in every step (the device-counter update assumes it)."""
+        return len(self._segments) == 1 and self._segments[0][2] == self.step_count
 
     def step_on_device_counter(self) -> None:
         """The same update driven by the device-resident counter: nothing in the launch depends on the step number, so it can
         be captured in a CUDA graph and replayed (engine/train_step.py).  The caller keeps ``step_count`` in sync."""
+        if len(self._segments) != 1:
+            raise RuntimeError("step_on_device_counter(): some parameters skipped earlier steps (per-segment counters)")
         nv.adamw_step_dev(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                           self.weight_decay, self.step_dev, self._hyper)
+        self._segments[0][2] += 1
 
 
 def init_optimizer(cfg: dict, params: Iterable[torch.Tensor]) -> AdamW:
@@ -76,7 +106,8 @@ class SegmentationTask:
     def __init__(self, model, config: dict):
         self.model, self.config = model, config
         self.criterion = FLAIRLosses(config).get_losses()
-        self.mod_dropout = False
+        # tasks_module.py:59-61: the configured probabilities only switch the feature on (the per-step probability is drawn)
+        self.mod_dropout = any(v > 0 for v in (self.config.get('modalities', {}).get('modality_dropout', {}) or {}).values())
         self._init_metrics()
 
     def _init_metrics(self) -> None:
@@ -133,7 +164,7 @@ class SegmentationTask:
                                            list(self.model.active_mono), task, weight.to(next(iter(state.values())).device),
                                            task_weight=self.config['labels_configs'][task].get('task_weight', 1.0),
                                            lr=optim_cfg['learning_rate'], weight_decay=optim_cfg['optim_weight_decay'],
-                                           betas=tuple(optim_cfg['optim_betas']))
+                                           betas=tuple(optim_cfg['optim_betas']), mod_dropout=self.mod_dropout)
         return self.trainer
 
     def training_step(self, batch: Dict[str, torch.Tensor]):

@@ -388,9 +388,29 @@ class FlairHubOracle(nn.Module):
             {t: FLAIRMonotemp(arch, 1, n, "decoder") for t, n in tasks.items()})
         self.aux_decoders = nn.ModuleDict()
 
-    def forward(self, batch: Dict[str, torch.Tensor]):
+    @staticmethod
+    def modality_dropout(feature_maps: Dict[str, list], probs: Dict[str, float]) -> Dict[str, list]:
+        """flair_model.py:330-354: per modality one ``torch.rand(1)`` against its probability; a dropped modality's maps are
+        replaced by xavier-uniform noise of the same shapes (fresh tensors: nothing upstream receives a gradient)."""
+        import warnings
+        for key in feature_maps.keys():
+            if torch.rand(1).item() < probs[key]:
+                noise = []
+                for t in feature_maps[key]:
+                    n = torch.empty_like(t)
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")              # zero-channel dummy map: initialisation is a no-op
+                        nn.init.xavier_uniform_(n)
+                    noise.append(n)
+                feature_maps[key] = noise
+        return feature_maps
+
+    def forward(self, batch: Dict[str, torch.Tensor], apply_mod_dropout: bool = False):
         img_size = batch[self.labels[0]].shape[-1]
         fmaps = {mod: enc.seg_model(batch[mod]) for mod, enc in self.encoders.items()}
+        if apply_mod_dropout and len(self.encoders) > 1:             # flair_model.py:406-408: the probabilities are drawn too
+            import random
+            fmaps = self.modality_dropout(fmaps, {key: random.uniform(0, 1) for key in fmaps.keys()})
         first = next(iter(self.encoders.keys()))
         fused = self.fusion_handler(fmaps, fmaps[first])
         logits = {}

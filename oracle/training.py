@@ -19,9 +19,11 @@ def default_class_weights(task_config: dict) -> torch.Tensor:
     return w
 
 
-def step(model: nn.Module, batch: Dict[str, torch.Tensor], config: dict):
-    """tasks_module.py:144-167 without auxiliary losses / modality dropout: -> (loss, preds, targets)."""
-    dict_logits_task, _ = model(batch)
+def step(model: nn.Module, batch: Dict[str, torch.Tensor], config: dict, apply_mod_dropout: bool = False):
+    """tasks_module.py:144-167: -> (loss, preds, targets).  The auxiliary loss is left out because it is identically zero in
+    the reference (tests/test_reference_pin.py::test_reference_aux_loss_is_identically_zero); ``apply_mod_dropout`` =
+    ``self.mod_dropout if training else False`` there (:145)."""
+    dict_logits_task, _ = model(batch, apply_mod_dropout) if apply_mod_dropout else model(batch)
     loss_sum = 0
     all_preds, all_targets = {}, {}
     for task, logits in dict_logits_task.items():

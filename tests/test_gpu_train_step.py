@@ -193,3 +193,79 @@ def test_graph_replayed_step_equals_eager_step(cuda, monkeypatch, segments):
     assert d <= 1e-6
     for k in be:
         assert torch.allclose(be[k].float(), bg[k].float(), rtol=0, atol=1e-6), k
+
+
+def test_modality_dropout_training_steps_vs_oracle(cuda):
+    """Training-time modality dropout (flair_model.py:406-408, :330-354; tasks_module.py:145): with the same seeds the trainer
+    and the oracle (torch autograd + torch.optim.AdamW) drop the same modalities and see the same noise features.  A dropped
+    encoder gets no gradient and is left untouched by AdamW -- weights, moments AND its step counter, so that its first real
+    update afterwards is a FIRST Adam step (|update| = lr), not a second one (0.74 lr)."""
+    import random
+    from oracle.models import CONVNEXTV2_CFGS, FlairHubOracle, randomize_
+    from oracle.training import default_class_weights, init_optimizer, step as oracle_step
+    from flair_for_aigle_b200.engine.train_step import ConvNeXtUNetTrainer
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
+
+    def decisions(seed, steps):
+        random.seed(seed)
+        torch.manual_seed(seed)
+        out = []
+        for _ in range(steps):
+            p = [random.uniform(0, 1) for _ in mods]
+            out.append([torch.rand(1).item() < q for q in p])
+        return out
+
+    seed = next(s for s in range(500) if decisions(s, 3)[:2] == [[False, True], [False, False]])
+    plan = decisions(seed, 3)
+    B, P, LR = 2, 128, 2e-4
+    oracle = FlairHubOracle("convnextv2_base-unet", mods, {TASK: 19})
+    randomize_(oracle, seed=3)
+    oracle = oracle.to(cuda).train()
+    cfg = {"labels_configs": {TASK: {"value_name": list(range(19)), "task_weight": 1.0,
+                                     "value_weights": {"default": 1, "default_exceptions": {15: 0, 16: 0, 17: 0, 18: 0}}}}}
+    depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
+    state = {k: v.detach().clone() for k, v in oracle.state_dict().items()}
+    g = torch.Generator(device="cpu").manual_seed(17)
+    batch = {m: torch.randn(B, c, P, P, generator=g).to(cuda) for m, c in mods.items()}
+    batch[TASK] = torch.nn.functional.one_hot(torch.randint(0, 19, (B, P, P), generator=g), 19).permute(0, 3, 1, 2).float().to(cuda)
+    dem = "encoders.DEM_ELEV.seg_model.model.stages_2.blocks.3.mlp.fc1.weight"
+
+    opt = init_optimizer({"optimizer": "adamw", "learning_rate": LR, "optim_weight_decay": 0.01, "optim_betas": [0.9, 0.999]},
+                         oracle.parameters())
+    random.seed(seed)
+    torch.manual_seed(seed)
+    theirs, their_dem = [], []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        l, _, _ = oracle_step(oracle, batch, cfg, apply_mod_dropout=True)
+        l.backward()
+        opt.step()
+        theirs.append(float(l))
+        their_dem.append(oracle.state_dict()[dem].detach().clone())
+
+    tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, default_class_weights(cfg["labels_configs"][TASK]).to(cuda),
+                             lr=LR, mod_dropout=True, cuda_graph=True)
+    assert tr.cuda_graph is False                                  # random per-step structure: always eager
+    random.seed(seed)
+    torch.manual_seed(seed)
+    ours, our_dem, dropped = [], [], []
+    init_dem = tr.params[dem].clone()
+    for _ in range(3):
+        l, _ = tr.step(batch)
+        ours.append(float(l))
+        our_dem.append(tr.params[dem].clone())
+        dropped.append([m in tr.last_dropped for m in mods])
+    print("dropped per step:", dropped, "losses ours", [round(v, 4) for v in ours], "oracle", [round(v, 4) for v in theirs])
+    assert dropped == plan
+    assert all(abs(a - b) <= 1e-2 * abs(b) for a, b in zip(ours, theirs))
+    # step 1: DEM_ELEV dropped on both sides -> its encoder is untouched
+    assert torch.equal(our_dem[0], init_dem) and torch.equal(their_dem[0], init_dem)
+    off, k = tr._slot[dem]
+    # step 2: its FIRST update: |delta| = lr (Adam's first step), on both sides
+    d_ours = float((our_dem[1] - our_dem[0]).abs().mean()) / LR
+    d_theirs = float((their_dem[1] - their_dem[0]).abs().mean()) / LR
+    print(f"first update of the once-skipped encoder: mean |delta| / lr ours {d_ours:.3f}, oracle {d_theirs:.3f}")
+    assert d_ours > 0.93 and abs(d_ours - d_theirs) < 0.03
+    assert len(tr.opt._segments) == 3 and sorted(s[2] for s in tr.opt._segments)[0] == (2 if not plan[2][1] else 1)

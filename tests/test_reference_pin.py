@@ -472,3 +472,63 @@ def test_training_step_loss_reference_vs_oracle():
     opt_o = init_optimizer(cfg["hyperparams"], model.parameters())
     assert type(opt_r) is type(opt_o) is torch.optim.AdamW
     assert {k: v for k, v in opt_r.defaults.items()} == {k: v for k, v in opt_o.defaults.items()}
+
+
+def test_reference_aux_loss_is_identically_zero():
+    """Why the training engine builds no auxiliary decoders: in the reference as it runs, ``_compute_aux_loss``
+    (tasks_module.py:169-194) looks for the TASK name among the keys of ``dict_logits_aux``, whose keys are
+    ``aux_<mod>_<task>`` (flair_model.py:384,402) -- the branch is never taken, the auxiliary logits never reach the loss and
+    the auxiliary decoders never receive a gradient.  Pinned here on the reference's own method with auxiliary losses switched
+    ON in the config and wildly wrong auxiliary logits."""
+    from flair_hub.tasks.module_setup import FLAIRLosses as RefLosses
+    from flair_hub.tasks.tasks_module import SegmentationTask
+    mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
+    cfg = {"labels": [TASK],
+           "labels_configs": {TASK: {"value_name": list(range(19)), "task_weight": 1.0,
+                                     "value_weights": {"default": 1, "default_exceptions": {}}}},
+           "modalities": {"inputs": {m: True for m in mods}, "aux_loss": {m: True for m in mods},
+                          "modality_dropout": {m: 0 for m in mods}, "aux_loss_weight": {m: 1.0 for m in mods}},
+           "hyperparams": {"optimizer": "adamw", "learning_rate": 5e-5, "optim_weight_decay": 0.01, "optim_betas": [0.9, 0.999]}}
+    task = SegmentationTask(torch.nn.Identity(), cfg, criterion=RefLosses(cfg).get_losses())
+    assert task.aux_loss_modalities == list(mods)                        # the auxiliary losses ARE configured
+    g = torch.Generator().manual_seed(4)
+    targets = torch.randint(0, 19, (2, 16, 16), generator=g)
+    aux = {f"aux_{m}_{TASK}": torch.randn(2, 19, 16, 16, generator=g) * 50 for m in mods}
+    out = task._compute_aux_loss(aux, TASK, targets)
+    assert float(out) == 0.0 and out.dtype == torch.float32
+
+
+def test_modality_dropout_draws_reference_vs_oracle_vs_product():
+    """flair_model.py:406-408 + :330-354 on the reference's own method: with the same seeds the oracle's restatement and the
+    product's ``draw_modality_dropout`` take the same decisions and produce the same noise (torch's generators on both
+    sides), over enough seeds that 'both kept', 'one dropped' and 'both dropped' all occur."""
+    import random
+    from flair_hub.models.flair_model import FLAIR_HUB_Model as RefModel
+    from oracle.models import FlairHubOracle
+    from flair_for_aigle_b200.flair_hub.models.flair_model import draw_modality_dropout
+    B, P, dims = 2, 64, (40, 80, 160, 320)
+    shapes = {"AERIAL_RGBI": [(B, 4, P, P), (B, 0, P // 2, P // 2)] + [(B, c, P // (4 << i), P // (4 << i)) for i, c in enumerate(dims)],
+              "DEM_ELEV": [(B, 1, P, P), (B, 0, P // 2, P // 2)] + [(B, c, P // (4 << i), P // (4 << i)) for i, c in enumerate(dims)]}
+    seen = set()
+    for seed in range(12):
+        outs = []
+        for which in ("reference", "oracle", "product"):
+            random.seed(seed)
+            torch.manual_seed(seed)
+            fmaps = {k: [torch.zeros(s) for s in v] for k, v in shapes.items()}
+            if which == "product":
+                dropped = draw_modality_dropout(shapes, "cpu")
+            else:
+                probs = {key: random.uniform(0, 1) for key in fmaps.keys()}               # flair_model.py:407
+                fn = RefModel.modality_dropout if which == "reference" else FlairHubOracle.modality_dropout
+                res = fn(None, fmaps, probs) if which == "reference" else fn(fmaps, probs)
+                dropped = {k: v for k, v in res.items() if any(t.abs().sum() > 0 for t in v)}
+            outs.append({k: [t.detach() for t in v] for k, v in dropped.items()})
+        ref, ora, prod = outs
+        assert set(ref) == set(ora) == set(prod)
+        seen.add(len(ref))
+        for k in ref:
+            assert all(torch.equal(a, b) and torch.equal(a, c) for a, b, c in zip(ref[k], ora[k], prod[k]))
+            bound = (6.0 / ((B + dims[0]) * (P // 4) ** 2)) ** 0.5                         # xavier: fan_in + fan_out = (C + B) h w
+            assert float(ref[k][2].abs().max()) <= bound and ref[k][1].numel() == 0
+    assert seen == {0, 1, 2}
