@@ -269,7 +269,10 @@ class ConvNeXtUNetTrainer:
         self._cap_graph.capture_begin(pool=self._pool, capture_error_mode="thread_local")     # NCCL's watchdog thread keeps polling
 
     def _seg_end(self, action) -> None:
-        self._cap_graph.capture_end()
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")          # two cuts in a row leave an empty segment: harmless, torch warns
+            self._cap_graph.capture_end()
         self._segments.append((self._cap_graph, action))
         self._cap_graph = None
 
