@@ -1213,6 +1213,10 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
   const bool tiled = W % 8 == 0, tile48 = tiled && H % 4 == 0;
   int chunks = tile48 ? static_cast<int>(npx / 32 / 8)                                    // >= 8 tiles (one per warp) per chunk
                       : (tiled ? static_cast<int>(npx / 8 / 8) : static_cast<int>(npx / 2048));
+  // the tile kernels hold 2 blocks of 128 registers per SM: size the grid to ONE wave of them (ncu: 1024 blocks with one
+  // tile per warp each spent their time in the 50-value block reduction, profiles/r2_ncu_train_bwd_summary.txt)
+  const int one_wave = 2 * 148 / ((C + 31) / 32);
+  if (tiled && chunks > one_wave) chunks = one_wave;
   chunks = chunks < 1 ? 1 : (chunks > 128 ? 128 : chunks);
   const int ppc = static_cast<int>((npx + chunks - 1) / chunks);
   static float* scratch[64] = {nullptr};
@@ -1336,7 +1340,7 @@ extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, cons
   grn_norms_kernel<<<B, 256, 0, ST(stream)>>>(sumsq, gx, nx, mu, C, eps);
   const int64_t per = static_cast<int64_t>(HW) * C;
   FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_train_forward: C %% 8, HW*C < 2^31, B <= 65535");
-  const RvGeom geo = rv_geometry(B, HW, C);
+  const RvGeom geo = rv_geometry(B, HW, C, rv_resident(grn_apply_rows_kernel));
   grn_apply_rows_kernel<<<dim3(geo.slabs, geo.chunks, B), 256, 0, ST(stream)>>>(
       reinterpret_cast<cbf>(g_bf16), nx, gamma, beta, reinterpret_cast<bf>(y_bf16), HW, C, geo.cgs, geo.rows_per_chunk);
   FZ_CHECK_CUDA(cudaGetLastError());
@@ -1355,7 +1359,7 @@ static int grn_gelu_backward_impl(const void* dy_bf16, const void* g_bf16, const
   const int64_t per = static_cast<int64_t>(HW) * C;
   FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_gelu_backward: C %% 8, HW*C < 2^31, B <= 65535");
   // dh, and (dbias != NULL) the column sums of dh over all B*HW rows = the bias gradient of the Linear that produced h
-  const RvGeom geo = rv_geometry(B, HW, C);
+  const RvGeom geo = rv_geometry(B, HW, C, rv_resident(grn_gelu_bwd_rows_kernel));
   float* partial = rv_scratch(static_cast<size_t>(B) * geo.chunks * C);
   FZ_REQUIRE(partial != nullptr, "fz_grn_gelu_backward: no scratch memory");
   grn_gelu_bwd_rows_kernel<<<dim3(geo.slabs, geo.chunks, B), 256, 0, ST(stream)>>>(

@@ -62,8 +62,11 @@ __device__ __forceinline__ void load_halo_tile(__nv_bfloat16* sX, const __nv_bfl
 // ------------------------------------------------------------------------------------------ forward / data gradient
 // 8 warps; warp w computes row w of the tile (32 pixels = two 16-pixel M blocks) for all COUT channels.
 // w: bf16 [9][COUT][CIN]; out: fp32 or bf16 [pixels][ldo], columns < n_store written (+ bias[col] when given).
+// The kernel is latency-bound between its load, compute and store phases (ncu, profiles/r2_ncu_train_conv_summary.txt: two
+// resident blocks per SM, issue slots 28 % busy, DRAM 29 %): the 16-output-channel variants (76 registers) are compiled for 3
+// resident blocks so that one block's loads overlap the others' MMAs and stores; grids are one wave of resident blocks.
 template <int CIN, int COUT, bool OUT16>
-__global__ void __launch_bounds__(256, 2) conv3x3_small_fwd_kernel(const __nv_bfloat16* __restrict__ in,
+__global__ void __launch_bounds__(256, COUT == 16 ? 3 : 2) conv3x3_small_fwd_kernel(const __nv_bfloat16* __restrict__ in,
                                                                    const __nv_bfloat16* __restrict__ w,
                                                                    const float* __restrict__ bias, void* __restrict__ out, int B,
                                                                    int H, int W, int n_store, int ldo) {
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_small_fwd_kernel(const __nv_bf
 // 9 warps, warp = tap.  Per tile the warp walks the 256 pixels in 16 chunks of 16 (K) and accumulates its [COUT][CIN] block in
 // registers over ALL the tiles of this CTA; partial[cta][tap][co][ci] is summed over CTAs in order by a second kernel.
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(288, 2) conv3x3_small_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(288, CIN * COUT <= 512 ? 3 : 2) conv3x3_small_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
                                                                      const __nv_bfloat16* __restrict__ dconv, int ldd,
                                                                      float* __restrict__ partial, int B, int H, int W) {
   using namespace cs;
@@ -233,33 +236,46 @@ static int sm_count() {
   return n;
 }
 
+// resident blocks per SM of a kernel at its launch configuration (asked once per kernel): persistent grids are one wave
+template <typename K>
+static int resident_blocks(K kernel, int threads, int smem) {
+  static int n = 0;
+  if (!n) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+  }
+  return n;
+}
+
 template <int CIN, int COUT>
 static int launch_fwd(const void* in, const void* w, const float* bias, void* out, int out16, int B, int H, int W, int n_store,
                       int ldo, cudaStream_t st) {
   constexpr int SMEM = (9 * COUT * (CIN + 8) + cs::HP * cs::WP * (CIN + 8)) * 2;
   const int n_tiles = B * (H / cs::TH) * (W / cs::TW);
-  const int grid = n_tiles < 2 * sm_count() ? n_tiles : 2 * sm_count();
   auto a = reinterpret_cast<const __nv_bfloat16*>(in);
   auto b = reinterpret_cast<const __nv_bfloat16*>(w);
   if (out16) {
     auto k = conv3x3_small_fwd_kernel<CIN, COUT, true>;
     FZ_ENSURE_SMEM(k, SMEM);
-    k<<<grid, 256, SMEM, st>>>(a, b, bias, out, B, H, W, n_store, ldo);
+    const int wave = resident_blocks(k, 256, SMEM) * sm_count();
+    k<<<n_tiles < wave ? n_tiles : wave, 256, SMEM, st>>>(a, b, bias, out, B, H, W, n_store, ldo);
   } else {
     auto k = conv3x3_small_fwd_kernel<CIN, COUT, false>;
     FZ_ENSURE_SMEM(k, SMEM);
-    k<<<grid, 256, SMEM, st>>>(a, b, bias, out, B, H, W, n_store, ldo);
+    const int wave = resident_blocks(k, 256, SMEM) * sm_count();
+    k<<<n_tiles < wave ? n_tiles : wave, 256, SMEM, st>>>(a, b, bias, out, B, H, W, n_store, ldo);
   }
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int CIN, int COUT>
-static int launch_wgrad(const void* x, const void* dconv, int ldd, float* dw, float* partial, int ctas, int B, int H, int W,
+static int launch_wgrad(const void* x, const void* dconv, int ldd, float* dw, float* partial, int max_ctas, int B, int H, int W,
                         cudaStream_t st) {
   constexpr int SMEM = (cs::HP * cs::WP * (CIN + 8) + cs::TH * cs::TW * (COUT + 8)) * 2;
   auto k = conv3x3_small_wgrad_kernel<CIN, COUT>;
   FZ_ENSURE_SMEM(k, SMEM);
+  const int wave = resident_blocks(k, 288, SMEM) * sm_count();
+  const int ctas = max_ctas < wave ? max_ctas : wave;                 // the scratch buffer is sized for max_ctas
   k<<<ctas, 288, SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dconv), ldd,
                              partial, B, H, W);
   const int n = 9 * COUT * CIN;
@@ -304,7 +320,7 @@ extern "C" int fz_conv3x3_small_wgrad(const void* x_bf16, const void* dconv_bf16
   FZ_REQUIRE(ldd >= Cout && ldd % 8 == 0, "fz_conv3x3_small_wgrad: ldd=%d (>= Cout, multiple of 8)", ldd);
   const int64_t n_tiles = static_cast<int64_t>(B) * (H / cs::TH) * (W / cs::TW);
   FZ_REQUIRE(n_tiles < (1LL << 31), "fz_conv3x3_small_wgrad: too many tiles");
-  const int ctas = n_tiles < 2 * sm_count() ? static_cast<int>(n_tiles) : 2 * sm_count();
+  const int ctas = n_tiles < 4 * sm_count() ? static_cast<int>(n_tiles) : 4 * sm_count();      // upper bound; launch_wgrad trims to one wave
   static float* scratch[64] = {nullptr};              // partial sums [ctas][9][Cout][Cin]: per-device, grown on demand
   static size_t have[64] = {0};
   int dev = 0;

@@ -67,13 +67,16 @@ __device__ __forceinline__ float rv_gelu_grad(float x) {
 struct RvGeom {
   int cgs, rp, slabs, chunks, rows_per_chunk;
 };
-static inline RvGeom rv_geometry(int B, int rows, int C, int max_chunks = 1 << 16) {
+// ctas_per_sm: how many 256-thread blocks of the kernel are resident on one SM (rv_resident).  The grid is sized to ONE wave of
+// resident blocks: ncu on the first version (profiles/r2_ncu_train_bwd_summary.txt) showed 592 blocks of a 76-register kernel,
+// of which only 3 x 148 were resident -- a second, one-third-full wave.
+static inline RvGeom rv_geometry(int B, int rows, int C, int ctas_per_sm = 4, int max_chunks = 1 << 16) {
   RvGeom g;
   const int groups = C / 8;
   g.cgs = groups < 256 ? groups : 256;
   g.rp = 256 / g.cgs;
   g.slabs = (groups + g.cgs - 1) / g.cgs;
-  int want = (148 * 4 + B * g.slabs - 1) / (B * g.slabs);             // ~4 blocks per SM over the whole grid
+  int want = (148 * ctas_per_sm) / (B * g.slabs);                     // one wave of resident blocks over the whole grid
   const int most = rows / (g.rp * 8) > 1 ? rows / (g.rp * 8) : 1;     // at least 8 rows per thread
   want = want < 1 ? 1 : (want > most ? most : want);
   g.chunks = want > max_chunks ? max_chunks : want;
@@ -181,6 +184,17 @@ static __global__ void __launch_bounds__(256) colreduce_final_kernel(const float
   }
 }
 
+// resident 256-thread blocks per SM of a kernel (register / shared-memory limited), asked once per kernel
+template <typename K>
+static inline int rv_resident(K kernel) {
+  static int n = 0;
+  if (!n) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, 0) != cudaSuccess || n < 1) n = 1;
+    if (n > 8) n = 8;
+  }
+  return n;
+}
+
 // Per-device scratch for the partial sums (the training step runs its kernels on one stream).
 static inline float* rv_scratch(size_t floats) {
   static float* buf[64] = {nullptr};
@@ -202,7 +216,7 @@ template <int MODE>
 static inline cudaError_t rv_colreduce(const void* a, const void* bb, void* gout, float* out0, float* out1, int B, int rows,
                                        int C, cudaStream_t st, void* dout = nullptr) {
   constexpr int NOUT = MODE == 3 ? 2 : 1;
-  const RvGeom g = rv_geometry(B, rows, C);
+  const RvGeom g = rv_geometry(B, rows, C, rv_resident(colreduce_vec_kernel<MODE>));
   float* partial = rv_scratch(static_cast<size_t>(B) * g.chunks * NOUT * C);
   if (!partial) return cudaErrorMemoryAllocation;
   colreduce_vec_kernel<MODE><<<dim3(g.slabs, g.chunks, B), 256, 0, st>>>(
