@@ -132,6 +132,113 @@ __global__ void __launch_bounds__(128) stem_ln_kernel(const void* __restrict__ i
   }
 }
 
+// ------------------------------------------------------------------------------------ stem on tensor cores (uint8 input)
+// ncu-level arithmetic: the stem is 64 x C0 MACs per output pixel = 9.9 GFLOP per batch of 37 tiles, which the fp32 FMA
+// kernel above executes at 33 TFLOP/s (295 us, 2.2 % of the step) while its HBM traffic (39 MB in, 310 MB out) needs 70 us.
+// Here the same sums run on mma.sync.m16n8k8 TF32 with the 3xTF32 split of the WEIGHTS (w = w_hi + w_lo, both TF32; the
+// uint8 inputs are exact in TF32), fp32 accumulation: every product is exact, the result differs from the fp32 kernel by
+// summation order only.  Block = one output row of one sample, 4 warps x 16 pixels per iteration (P % 256 == 0).
+constexpr int STEM_MMA_PX = 64;       // output pixels per block iteration
+constexpr int STEM_MMA_LDI = 68;      // floats per pixel row of the input tile (64 used; 68 = 4 mod 32: conflict-free A loads)
+
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NB>   // C0 = 8 * NB output channels
+__global__ void __launch_bounds__(128, 2) stem_ln_mma_kernel(const uchar4* __restrict__ in, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                             const float* __restrict__ ln_b, float* __restrict__ out, int P,
+                                                             float eps) {
+  constexpr int C0 = 8 * NB, LDW = C0 + 8;                       // LDW = 8 mod 32: conflict-free B loads
+  extern __shared__ float smem_f[];
+  float* sHi = smem_f;                                           // [64][LDW]
+  float* sLo = sHi + 64 * LDW;                                   // [64][LDW]
+  float* sIn = sLo + 64 * LDW;                                   // [STEM_MMA_PX][STEM_MMA_LDI]
+  float* sPar = sIn + STEM_MMA_PX * STEM_MMA_LDI;                // bias | ln_w | ln_b, C0 each
+  const int OW = P / 4;
+  const int oy = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 64 * C0; i += 128) {
+    const int k = i / C0, n = i - k * C0;
+    const float v = w[i];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);     // the TF32 part of the weight
+    sHi[k * LDW + n] = hi;
+    sLo[k * LDW + n] = v - hi;                                               // exact in fp32; its TF32 part is what the MMA reads
+  }
+  for (int i = tid; i < C0; i += 128) {
+    sPar[i] = bias[i];
+    sPar[C0 + i] = ln_w[i];
+    sPar[2 * C0 + i] = ln_b[i];
+  }
+  for (int ox0 = 0; ox0 < OW; ox0 += STEM_MMA_PX) {
+    __syncthreads();                                             // weights staged / previous iteration's reads done
+    // 4 input rows x 256 input pixels of 4 bytes: thread -> input pixels tid and tid + 128 of each row
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ip = tid + h * 128;                            // input pixel within the 256-pixel span
+        const uchar4 u = in[(static_cast<size_t>(b) * P + (4 * oy + r)) * P + 4 * ox0 + ip];
+        *reinterpret_cast<float4*>(&sIn[(ip >> 2) * STEM_MMA_LDI + r * 16 + (ip & 3) * 4]) = make_float4(u.x, u.y, u.z, u.w);
+      }
+    __syncthreads();
+    float acc[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      acc[nb][0] = acc[nb][2] = sPar[nb * 8 + 2 * t];
+      acc[nb][1] = acc[nb][3] = sPar[nb * 8 + 2 * t + 1];
+    }
+    const float* arow = sIn + (warp * 16 + g) * STEM_MMA_LDI + t;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t a[4];
+      a[0] = __float_as_uint(arow[ks * 8]);
+      a[1] = __float_as_uint(arow[8 * STEM_MMA_LDI + ks * 8]);
+      a[2] = __float_as_uint(arow[ks * 8 + 4]);
+      a[3] = __float_as_uint(arow[8 * STEM_MMA_LDI + ks * 8 + 4]);
+      const float* bh = sHi + (ks * 8 + t) * LDW + g;
+      const float* bl = sLo + (ks * 8 + t) * LDW + g;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        mma_tf32_1688(acc[nb], a, __float_as_uint(bh[nb * 8]), __float_as_uint(bh[4 * LDW + nb * 8]));
+        mma_tf32_1688(acc[nb], a, __float_as_uint(bl[nb * 8]), __float_as_uint(bl[4 * LDW + nb * 8]));
+      }
+    }
+    // LayerNorm2d over the C0 channels of each pixel: a pixel's channels sit in the 4 lanes of one g (rows g and g + 8)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float s = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) s += acc[nb][half * 2] + acc[nb][half * 2 + 1];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      const float mean = s * (1.0f / C0);
+      float q = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const float d0 = acc[nb][half * 2] - mean, d1 = acc[nb][half * 2 + 1] - mean;
+        q = fmaf(d0, d0, q);
+        q = fmaf(d1, d1, q);
+      }
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      const float rstd = rsqrtf(q * (1.0f / C0) + eps);
+      float* o = out + ((static_cast<size_t>(b) * OW + oy) * OW + ox0 + warp * 16 + g + half * 8) * C0 + 2 * t;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int c = nb * 8 + 2 * t;
+        *reinterpret_cast<float2*>(o + nb * 8) =
+            make_float2((acc[nb][half * 2] - mean) * rstd * sPar[C0 + c] + sPar[2 * C0 + c],
+                        (acc[nb][half * 2 + 1] - mean) * rstd * sPar[C0 + c + 1] + sPar[2 * C0 + c + 1]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ dwconv7x7 + LN
 // x  : float [B][H][W][C] residual stream;  wdw: float [49][C];  bdw: float [C]
 // out: bf16  [B][H][W][C] = LayerNorm_C(dwconv7x7(x) + bdw) * ln_w + ln_b
@@ -702,6 +809,27 @@ static int launch_stem(const void* in, int Cin, const float* w, const float* bia
   FZ_REQUIRE(C0 % 32 == 0 && C0 >= 32 && C0 <= 384, "fz_stem_ln: C0=%d unsupported", C0);
   FZ_REQUIRE(Cin >= 1 && Cin <= 4, "fz_stem_ln: Cin=%d must be 1..4", Cin);
   if (B <= 0) return 0;
+  // uint8 tiles, the common widths, P a multiple of 256: the tensor-core kernel (FZ_STEM_MMA=0 keeps the fp32 FMA kernel)
+  static int use_mma = -1;
+  if (use_mma < 0) {
+    const char* e = getenv("FZ_STEM_MMA");
+    use_mma = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!F32IN && use_mma && Cin == 4 && P % 256 == 0 && (C0 == 96 || C0 == 128 || C0 == 192)) {
+    const size_t sm = (2 * 64 * static_cast<size_t>(C0 + 8) + STEM_MMA_PX * STEM_MMA_LDI + 3 * C0) * sizeof(float);
+    dim3 g2(P / 4, B);
+    auto in4 = reinterpret_cast<const uchar4*>(in);
+#define FZ_STEM_MMA(NBV)                                                                         \
+  case NBV * 8: {                                                                                \
+    FZ_ENSURE_SMEM((stem_ln_mma_kernel<NBV>), static_cast<int>(sm));                             \
+    stem_ln_mma_kernel<NBV><<<g2, 128, sm, st>>>(in4, w, bias, ln_w, ln_b, out, P, eps);         \
+    break;                                                                                       \
+  }
+    switch (C0) { FZ_STEM_MMA(12) FZ_STEM_MMA(16) FZ_STEM_MMA(24) }
+#undef FZ_STEM_MMA
+    FZ_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = (64 * static_cast<size_t>(C0) + STEM_PX * STEM_IN_STRIDE) * sizeof(float);
   dim3 grid(P / 4, B);
 #define FZ_STEM(CPL)                                                                                           \

@@ -23,10 +23,13 @@ def _no_tf32():
     torch.backends.cudnn.allow_tf32 = False
 
 
-def test_stem_u8_and_f32(cuda):
+@pytest.mark.parametrize("P,C0", [(256, 128), (512, 96), (256, 192), (128, 128), (256, 64)])
+def test_stem_u8_and_f32(cuda, P, C0):
+    """uint8 tiles with P % 256 == 0 and C0 in {96, 128, 192} take the tensor-core stem (3xTF32 split of the weights: products
+    exact, fp32 accumulation); the other shapes and the float32 input the fp32 FMA kernel.  Same bound for both."""
     from flair_for_aigle_b200 import native as nv
     torch.manual_seed(0)
-    B, P, C0 = 2, 256, 128
+    B = 2
     u8 = torch.randint(0, 256, (B, P, P, 4), dtype=torch.uint8, device=cuda)
     mean = torch.tensor([105.66, 111.35, 102.18, 106.59], device=cuda)
     std = torch.tensor([52.23, 45.62, 44.30, 39.78], device=cuda)
@@ -44,8 +47,12 @@ def test_stem_u8_and_f32(cuda):
     out2 = torch.empty_like(out)
     nv.stem_ln_f32(xn.contiguous(), wk, b, g, be, out2)
     torch.cuda.synchronize()
+    ref64 = F.layer_norm(F.conv2d(xn.double(), w.double(), b.double(), stride=4).permute(0, 2, 3, 1), (C0,), g.double(), be.double(), 1e-6)
+    print(f"P={P} C0={C0}: max |err| vs float64: uint8 path {(out - ref64).abs().max().item():.2e}, float32 path "
+          f"{(out2 - ref64).abs().max().item():.2e}, torch fp32 {(ref - ref64).abs().max().item():.2e}")
     assert (out - ref).abs().max().item() < 2e-4
     assert (out2 - ref).abs().max().item() < 2e-4
+    assert (out - ref64).abs().max().item() < 5e-5               # fp32-grade on either kernel
 
 
 @pytest.mark.parametrize("C,H", [(128, 128), (128, 32), (256, 64), (512, 32), (1024, 16), (256, 24)])
