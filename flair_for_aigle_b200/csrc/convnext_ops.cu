@@ -151,7 +151,7 @@ template <int NB>   // C0 = 8 * NB output channels
 __global__ void __launch_bounds__(128, 2) stem_ln_mma_kernel(const uchar4* __restrict__ in, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                              const float* __restrict__ ln_b, float* __restrict__ out, int P,
-                                                             float eps) {
+                                                             int n_rows, float eps) {
   constexpr int C0 = 8 * NB, LDW = C0 + 8;                       // LDW = 8 mod 32: conflict-free B loads
   extern __shared__ float smem_f[];
   float* sHi = smem_f;                                           // [64][LDW]
@@ -159,9 +159,10 @@ __global__ void __launch_bounds__(128, 2) stem_ln_mma_kernel(const uchar4* __res
   float* sIn = sLo + 64 * LDW;                                   // [STEM_MMA_PX][STEM_MMA_LDI]
   float* sPar = sIn + STEM_MMA_PX * STEM_MMA_LDI;                // bias | ln_w | ln_b, C0 each
   const int OW = P / 4;
-  const int oy = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  // persistent blocks (one wave): the 64 x C0 weights are split and staged ONCE per block, not once per output row -- with
+  // a block per row the staging was most of the kernel (227 us for 4736 rows; ncu launch list of the bench)
   for (int i = tid; i < 64 * C0; i += 128) {
     const int k = i / C0, n = i - k * C0;
     const float v = w[i];
@@ -174,6 +175,8 @@ __global__ void __launch_bounds__(128, 2) stem_ln_mma_kernel(const uchar4* __res
     sPar[C0 + i] = ln_w[i];
     sPar[2 * C0 + i] = ln_b[i];
   }
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+  const int b = row / OW, oy = row - b * OW;                     // output maps are square: OH = OW
   for (int ox0 = 0; ox0 < OW; ox0 += STEM_MMA_PX) {
     __syncthreads();                                             // weights staged / previous iteration's reads done
     // 4 input rows x 256 input pixels of 4 bytes: thread -> input pixels tid and tid + 128 of each row
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(128, 2) stem_ln_mma_kernel(const uchar4* __res
                         (acc[nb][half * 2 + 1] - mean) * rstd * sPar[C0 + c + 1] + sPar[2 * C0 + c + 1]);
       }
     }
+  }
   }
 }
 
@@ -817,13 +821,14 @@ static int launch_stem(const void* in, int Cin, const float* w, const float* bia
   }
   if (!F32IN && use_mma && Cin == 4 && P % 256 == 0 && (C0 == 96 || C0 == 128 || C0 == 192)) {
     const size_t sm = (2 * 64 * static_cast<size_t>(C0 + 8) + STEM_MMA_PX * STEM_MMA_LDI + 3 * C0) * sizeof(float);
-    dim3 g2(P / 4, B);
+    const int n_rows = B * (P / 4);
+    const int g2 = n_rows < 2 * 148 ? n_rows : 2 * 148;          // two 89 KB blocks per SM
     auto in4 = reinterpret_cast<const uchar4*>(in);
-#define FZ_STEM_MMA(NBV)                                                                         \
-  case NBV * 8: {                                                                                \
-    FZ_ENSURE_SMEM((stem_ln_mma_kernel<NBV>), static_cast<int>(sm));                             \
-    stem_ln_mma_kernel<NBV><<<g2, 128, sm, st>>>(in4, w, bias, ln_w, ln_b, out, P, eps);         \
-    break;                                                                                       \
+#define FZ_STEM_MMA(NBV)                                                                                 \
+  case NBV * 8: {                                                                                        \
+    FZ_ENSURE_SMEM((stem_ln_mma_kernel<NBV>), static_cast<int>(sm));                                     \
+    stem_ln_mma_kernel<NBV><<<g2, 128, sm, st>>>(in4, w, bias, ln_w, ln_b, out, P, n_rows, eps);         \
+    break;                                                                                               \
   }
     switch (C0) { FZ_STEM_MMA(12) FZ_STEM_MMA(16) FZ_STEM_MMA(24) }
 #undef FZ_STEM_MMA

@@ -10,3 +10,8 @@ import json
 d = json.load(open("gpurun_out/r2_bench_n1_final.json"))
 print(json.dumps(d.get("train"), indent=None)[:900])
 PY
+BENCH="python bench.py --steps 1 --warmup 1 --no-train --no-cpu-baseline"
+$BENCH > gpurun_out/r2_ncu_plain_bench.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 2400 --csv --log-file gpurun_out/r2_ncu_launches.csv $BENCH > gpurun_out/r2_ncu_bench_under_ncu.log 2>&1
+echo "launch list rc=$?"
+timeout 300 python tools/gpu_hbm_kernels_bench.py 2>&1 | tail -16
