@@ -327,7 +327,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256) ln_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                            const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
                                                            float* __restrict__ out_f32, float* __restrict__ mean,
-                                                           float* __restrict__ rstd, int64_t M, int C, float eps) {
+                                                           float* __restrict__ rstd, int64_t M, int C, float eps, int out_f16) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= M) return;
@@ -343,7 +343,10 @@ __global__ void __launch_bounds__(256) ln_fwd_stats_kernel(const float* __restri
   const float rs = rsqrtf(warp_sum(v) / C + eps);
   for (int c = lane; c < C; c += 32) {
     const float v2 = (row[c] - mu) * rs * g[c] + b[c];
-    if (out) out[r * C + c] = __float2bfloat16_rn(v2);
+    if (out) {
+      if (out_f16) reinterpret_cast<__half*>(out)[r * C + c] = __float2half_rn(fminf(fmaxf(v2, -65504.f), 65504.f));
+      else out[r * C + c] = __float2bfloat16_rn(v2);
+    }
     if (out_f32) out_f32[r * C + c] = v2;
   }
   if (lane == 0) {
@@ -394,6 +397,36 @@ __device__ __forceinline__ void load4_bf16(const __nv_bfloat16* p, float (&v)[4]
   v[2] = __uint_as_float(q.y << 16);
   v[3] = __uint_as_float(q.y & 0xffff0000u);
 }
+// "value > 0" on the bit pattern of a 16-bit float: holds for bf16 and IEEE fp16 alike (sign bit clear, magnitude non-zero;
+// neither format's ReLU outputs are NaN), so the ReLU mask of the backward needs no format flag
+__device__ __forceinline__ bool positive16(__nv_bfloat16 v) {
+  const unsigned short b = *reinterpret_cast<const unsigned short*>(&v);
+  return b != 0 && (b & 0x8000u) == 0;
+}
+__device__ __forceinline__ void positive16x4(const __nv_bfloat16* p, bool (&pos)[4]) {
+  const uint2 q = *reinterpret_cast<const uint2*>(p);
+  const unsigned w[4] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pos[j] = w[j] != 0 && (w[j] & 0x8000u) == 0;
+}
+__device__ __forceinline__ void store4_16(__nv_bfloat16* p, const float (&v)[4], bool f16) {   // bf16 or (f16) IEEE half
+  uint2 q;
+  q.x = rv_pack2(v[0], v[1], f16);
+  q.y = rv_pack2(v[2], v[3], f16);
+  *reinterpret_cast<uint2*>(p) = q;
+}
+__device__ __forceinline__ void load4_16(const __nv_bfloat16* p, float (&v)[4], bool f16) {
+  const uint2 q = *reinterpret_cast<const uint2*>(p);
+  if (f16) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else {
+    v[0] = __uint_as_float(q.x << 16);
+    v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16);
+    v[3] = __uint_as_float(q.y & 0xffff0000u);
+  }
+}
 __device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, const float (&v)[4]) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
   uint2 q;
@@ -408,7 +441,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                          const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
                                                          float* __restrict__ out_f32, float* __restrict__ mean,
-                                                         float* __restrict__ rstd, int64_t M, float eps) {
+                                                         float* __restrict__ rstd, int64_t M, float eps, int out_f16) {
   constexpr int C = 128 * NV;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -435,7 +468,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
     const float4 gg = *reinterpret_cast<const float4*>(g + c), bb = *reinterpret_cast<const float4*>(b + c);
     const float o[4] = {v[k].x * rs * gg.x + bb.x, v[k].y * rs * gg.y + bb.y, v[k].z * rs * gg.z + bb.z,
                         v[k].w * rs * gg.w + bb.w};
-    if (out) store4_bf16(out + r * C + c, o);
+    if (out) store4_16(out + r * C + c, o, out_f16);
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
   if (lane == 0) {
@@ -690,7 +723,7 @@ __global__ void __launch_bounds__(256) grn_gelu_bwd_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) grn_apply_rows_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ nx,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              __nv_bfloat16* __restrict__ y, int rows, int C, int cgs,
-                                                             int rows_per_chunk) {
+                                                             int rows_per_chunk, int act_f16) {
   const int rp = 256 / cgs;
   const int cl = threadIdx.x % cgs, rr = threadIdx.x / cgs;
   const int cg = blockIdx.x * cgs + cl;
@@ -709,10 +742,10 @@ __global__ void __launch_bounds__(256) grn_apply_rows_kernel(const __nv_bfloat16
   for (int r = r0 + rr; r < r1; r += rp) {
     const size_t o = base + static_cast<size_t>(r) * C;
     float v[8];
-    load8(g + o, v);
+    rv_load8(g + o, v, act_f16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = v[j] * ca[j] + be[j];
-    store8(y + o, v);
+    rv_store8_round(y + o, v, act_f16);
   }
 }
 
@@ -723,7 +756,8 @@ __global__ void __launch_bounds__(256) grn_gelu_bwd_rows_kernel(const __nv_bfloa
                                                                 const __nv_bfloat16* __restrict__ h,
                                                                 const float* __restrict__ coef_a, const float* __restrict__ coef_b,
                                                                 __nv_bfloat16* __restrict__ dh, float* __restrict__ db_partial,
-                                                                int rows, int C, int cgs, int rows_per_chunk, int h_is_dgelu) {
+                                                                int rows, int C, int cgs, int rows_per_chunk, int h_is_dgelu,
+                                                                int act_f16) {
   __shared__ float red[256][9];
   const int rp = 256 / cgs;
   const int cl = threadIdx.x % cgs, rr = threadIdx.x / cgs;
@@ -746,8 +780,8 @@ __global__ void __launch_bounds__(256) grn_gelu_bwd_rows_kernel(const __nv_bfloa
       const size_t o = base + static_cast<size_t>(r) * C;
       float d[8], gg[8], hh[8];
       load8(dy + o, d);
-      load8(g + o, gg);
-      load8(h + o, hh);
+      rv_load8(g + o, gg, act_f16);
+      rv_load8(h + o, hh, act_f16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = (d[j] * ca[j] + gg[j] * cb[j]) * (h_is_dgelu ? hh[j] : rv_gelu_grad(hh[j]));
       rv_store8_round(dh + o, d);
@@ -775,6 +809,21 @@ __global__ void __launch_bounds__(256) add_f32x4_kernel(const float4* __restrict
   if (i >= n4) return;
   const float4 u = a[i], v = b[i];
   out[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+}
+
+// IEEE fp16 -> bf16, 8 values per thread (the tail one by one): the weight-gradient GEMMs want both operands in one format
+// (a tcgen05 kind::f16 MMA with a_format = BF16 and b_format = F16 is an illegal instruction on sm_100a -- tried), so the
+// fp16 forward activations are re-rounded to bf16 on their way into dW = dY^T X
+__global__ void __launch_bounds__(256) cast_f16_bf16_kernel(const __half* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                            int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float v[8];
+    rv_load8(in + i, v, true);
+    rv_store8_round(out + i, v, false);
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = __float2bfloat16_rn(__half2float(in[j]));
+  }
 }
 
 __global__ void __launch_bounds__(256) add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
@@ -814,7 +863,7 @@ __global__ void __launch_bounds__(256) s2d_bf16_vec_kernel(const uint4* __restri
 
 // stem patches: out bf16 [B*(P/4)^2][Kpad], k = (c*4 + ky)*4 + kx (the flattening of a [Cout][Cin][4][4] weight), zero padded
 __global__ void __launch_bounds__(256) patchify4_nchw_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                             int Cin, int P, int Kpad, int64_t n) {
+                                                             int Cin, int P, int Kpad, int64_t n, int out_f16) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;      // over rows * Kpad
   if (i >= n) return;
   const int k = static_cast<int>(i % Kpad);
@@ -827,7 +876,8 @@ __global__ void __launch_bounds__(256) patchify4_nchw_kernel(const float* __rest
     const int c = k / 16, ky = (k / 4) % 4, kx = k % 4;
     v = in[((b * Cin + c) * P + py * 4 + ky) * P + px * 4 + kx];
   }
-  out[i] = __float2bfloat16_rn(v);
+  if (out_f16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  else out[i] = __float2bfloat16_rn(v);
 }
 
 // ------------------------------------------------------------------------------------------------ U-Net decoder
@@ -933,7 +983,7 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
       if (mode == 0) a += xv;
       else if (mode == 1) a += (xv - mu) * (xv - mu);
       else {
-        const float g = __bfloat162float(y[m * C + c]) > 0.f ? __bfloat162float(dy[m * C + c]) : 0.f;
+        const float g = positive16(y[m * C + c]) ? __bfloat162float(dy[m * C + c]) : 0.f;
         a += g;
         b += g * (xv - mu) * rs;
       }
@@ -963,13 +1013,14 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
 __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                                                            int C, int64_t n) {
+                                                            int C, int64_t n, int out_f16) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n) return;
   const int c = static_cast<int>(i % C);
   const int64_t m = i / C;
   const float v = (x[m * ldx + c] - mean[c]) * rstd[c] * gamma[c] + beta[c];
-  y[i] = __float2bfloat16_rn(v > 0.f ? v : 0.f);
+  if (out_f16) reinterpret_cast<__half*>(y)[i] = __float2half_rn(v > 0.f ? fminf(v, 65504.f) : 0.f);
+  else y[i] = __float2bfloat16_rn(v > 0.f ? v : 0.f);
 }
 // dx[m][c] = gamma * rstd * (g - dbeta / M - xhat * dgamma / M), written bf16 with row stride ldd (padding columns zero)
 __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __restrict__ x, int ldx,
@@ -984,7 +1035,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
   const int64_t m = i / ldd;
   float v = 0.f;
   if (c < C) {
-    const float g = __bfloat162float(y[m * C + c]) > 0.f ? __bfloat162float(dy[m * C + c]) : 0.f;
+    const float g = positive16(y[m * C + c]) ? __bfloat162float(dy[m * C + c]) : 0.f;
     const float xh = (x[m * ldx + c] - mean[c]) * rstd[c];
     v = gamma[c] * rstd[c] * (g - dgb[c] * invM - xh * dgb[C + c] * invM);      // dgb = [dbeta | dgamma]
   }
@@ -1029,12 +1080,13 @@ __global__ void __launch_bounds__(256) bn_partial_vec_kernel(const float* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) a[j] += (xv[j] - mu[j]) * (xv[j] - mu[j]);
       } else {
-        float yv[4], dv[4];
-        load4_bf16(y + m * C + c, yv);
+        float dv[4];
+        bool pos[4];
+        positive16x4(y + m * C + c, pos);
         load4_bf16(dy + m * C + c, dv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float g = yv[j] > 0.f ? dv[j] : 0.f;
+          const float g = pos[j] ? dv[j] : 0.f;
           a[j] += g;
           b[j] += g * (xv[j] - mu[j]) * rs[j];
         }
@@ -1061,7 +1113,7 @@ __global__ void __launch_bounds__(256) bn_partial_vec_kernel(const float* __rest
 __global__ void __launch_bounds__(256) bn_relu_apply_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean,
                                                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                                                                int C4, int64_t n4) {
+                                                                int C4, int64_t n4, int out_f16) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n4) return;
   const int c = static_cast<int>(i % C4) * 4;
@@ -1073,7 +1125,7 @@ __global__ void __launch_bounds__(256) bn_relu_apply_vec_kernel(const float* __r
                 (xv.w - mu.w) * rs.w * ga.w + be.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
-  store4_bf16(y + m * (C4 * 4) + c, v);
+  store4_16(y + m * (C4 * 4) + c, v, out_f16);
 }
 __global__ void __launch_bounds__(256) bn_relu_bwd_apply_vec_kernel(const float* __restrict__ x, int ldx,
                                                                     const __nv_bfloat16* __restrict__ dy,
@@ -1089,14 +1141,15 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_vec_kernel(const float*
   const int64_t m = i / L4;
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    float yv[4], dv[4];
-    load4_bf16(y + m * C + c, yv);
+    float dv[4];
+    bool pos[4];
+    positive16x4(y + m * C + c, pos);
     load4_bf16(dy + m * C + c, dv);
     const float4 t = *reinterpret_cast<const float4*>(x + m * ldx + c);
     const float xv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float g = yv[j] > 0.f ? dv[j] : 0.f;
+      const float g = pos[j] ? dv[j] : 0.f;
       const float xh = (xv[j] - mean[c + j]) * rstd[c + j];
       v[j] = gamma[c + j] * rstd[c + j] * (g - dgb[c + j] * invM - xh * dgb[C + c + j] * invM);
     }
@@ -1149,15 +1202,15 @@ typedef __nv_bfloat16* bf;
 
 // C = 128 * NV rows: the register-resident LayerNorm forward; false = shape not covered (caller takes the scalar kernel)
 static bool launch_ln_fwd_vec(const float* x, const float* g, const float* b, bf out, float* out_f32, float* mean, float* rstd,
-                              int64_t M, int C, float eps, cudaStream_t st) {
+                              int64_t M, int C, float eps, int out_f16, cudaStream_t st) {
   const unsigned grid = static_cast<unsigned>((M + 7) / 8);
   switch (C % 128 == 0 ? C / 128 : 0) {
-    case 1: ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
-    case 2: ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
-    case 3: ln_fwd_vec_kernel<3><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
-    case 4: ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
-    case 6: ln_fwd_vec_kernel<6><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
-    case 8: ln_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps); return true;
+    case 1: ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
+    case 2: ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
+    case 3: ln_fwd_vec_kernel<3><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
+    case 4: ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
+    case 6: ln_fwd_vec_kernel<6><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
+    case 8: ln_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
     default: return false;
   }
 }
@@ -1259,11 +1312,11 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
 }
 
 extern "C" int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, float* mean, float* rstd,
-                                      int64_t M, int C, float eps, void* stream) {
+                                      int64_t M, int C, float eps, int out_f16, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && x && g && b && out_bf16 && mean && rstd, "fz_layernorm_fwd_stats: bad arguments");
-  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), nullptr, mean, rstd, M, C, eps, ST(stream)))
+  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), nullptr, mean, rstd, M, C, eps, out_f16, ST(stream)))
     ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
-                                                                                   nullptr, mean, rstd, M, C, eps);
+                                                                                   nullptr, mean, rstd, M, C, eps, out_f16);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1316,25 +1369,27 @@ extern "C" int fz_sample_colreduce(const void* a_bf16, const void* b_bf16, float
 }
 
 // s1[b][c] = sum_hw a*b, s0[b][c] = sum_hw a in ONE pass over both tensors (the GRN backward's two reductions)
-extern "C" int fz_sample_colreduce2(const void* a_bf16, const void* b_bf16, float* s1, float* s0, int B, int HW, int C,
-                                    void* stream) {
+extern "C" int fz_sample_colreduce2(const void* a_bf16, const void* b_16, float* s1, float* s0, int B, int HW, int C,
+                                    int b_f16, void* stream) {
+  const void* b_bf16 = b_16;
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && a_bf16 && b_bf16 && s1 && s0 && B <= 65535,
              "fz_sample_colreduce2: bad arguments (C %% 8 == 0)");
-  FZ_CHECK_CUDA(rv_colreduce<3>(a_bf16, b_bf16, nullptr, s1, s0, B, HW, C, ST(stream)));
+  FZ_CHECK_CUDA(rv_colreduce<3>(a_bf16, b_bf16, nullptr, s1, s0, B, HW, C, ST(stream), nullptr, b_f16 ? 2 : 0));
   return 0;
 }
 
 // g = GELU(h) (bf16) and sumsq[b][c] = sum_hw g^2 of the stored values, one pass
 extern "C" int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, void* dgelu_bf16, float* sumsq, int B, int HW, int C,
-                                 void* stream) {
+                                 int act_f16, void* stream) {
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && h_bf16 && g_bf16 && sumsq && B <= 65535,
              "fz_gelu_fwd_sumsq: bad arguments (C %% 8 == 0)");
-  FZ_CHECK_CUDA(rv_colreduce<1>(h_bf16, nullptr, g_bf16, sumsq, nullptr, B, HW, C, ST(stream), dgelu_bf16));
+  FZ_CHECK_CUDA(rv_colreduce<1>(h_bf16, nullptr, g_bf16, sumsq, nullptr, B, HW, C, ST(stream), dgelu_bf16, act_f16 ? 5 : 0));
   return 0;
 }
 
 extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* gamma, const float* beta, float* gx,
-                                    float* nx, float* mu, void* y_bf16, int B, int HW, int C, float eps, void* stream) {
+                                    float* nx, float* mu, void* y_bf16, int B, int HW, int C, float eps, int act_f16,
+                                    void* stream) {
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && g_bf16 && sumsq && gamma && beta && gx && nx && mu && y_bf16,
              "fz_grn_train_forward: bad arguments");
   grn_norms_kernel<<<B, 256, 0, ST(stream)>>>(sumsq, gx, nx, mu, C, eps);
@@ -1342,7 +1397,7 @@ extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, cons
   FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_train_forward: C %% 8, HW*C < 2^31, B <= 65535");
   const RvGeom geo = rv_geometry(B, HW, C, rv_resident(grn_apply_rows_kernel));
   grn_apply_rows_kernel<<<dim3(geo.slabs, geo.chunks, B), 256, 0, ST(stream)>>>(
-      reinterpret_cast<cbf>(g_bf16), nx, gamma, beta, reinterpret_cast<bf>(y_bf16), HW, C, geo.cgs, geo.rows_per_chunk);
+      reinterpret_cast<cbf>(g_bf16), nx, gamma, beta, reinterpret_cast<bf>(y_bf16), HW, C, geo.cgs, geo.rows_per_chunk, act_f16);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1350,7 +1405,7 @@ extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, cons
 static int grn_gelu_backward_impl(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1,
                                   const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
                                   float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias,
-                                  int B, int HW, int C, float eps, void* stream, int h_is_dgelu) {
+                                  int B, int HW, int C, float eps, void* stream, int h_is_dgelu, int act_f16) {
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && dy_bf16 && g_bf16 && h_bf16 && s1 && s0 && gx && nx && mu && gamma && coef_a &&
                  coef_b && dgamma && dbeta && dh_bf16,
              "fz_grn_gelu_backward: bad arguments");
@@ -1364,7 +1419,7 @@ static int grn_gelu_backward_impl(const void* dy_bf16, const void* g_bf16, const
   FZ_REQUIRE(partial != nullptr, "fz_grn_gelu_backward: no scratch memory");
   grn_gelu_bwd_rows_kernel<<<dim3(geo.slabs, geo.chunks, B), 256, 0, ST(stream)>>>(
       reinterpret_cast<cbf>(dy_bf16), reinterpret_cast<cbf>(g_bf16), reinterpret_cast<cbf>(h_bf16), coef_a, coef_b,
-      reinterpret_cast<bf>(dh_bf16), partial, HW, C, geo.cgs, geo.rows_per_chunk, h_is_dgelu);
+      reinterpret_cast<bf>(dh_bf16), partial, HW, C, geo.cgs, geo.rows_per_chunk, h_is_dgelu, act_f16);
   if (dbias) colreduce_final_kernel<<<dim3((C + 31) / 32, 1), 256, 0, ST(stream)>>>(partial, dbias, nullptr, B * geo.chunks, C, 1);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1375,15 +1430,16 @@ extern "C" int fz_grn_gelu_backward_db(const void* dy_bf16, const void* g_bf16, 
                                        float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias,
                                        int B, int HW, int C, float eps, void* stream) {
   return grn_gelu_backward_impl(dy_bf16, g_bf16, h_bf16, s1, s0, gx, nx, mu, gamma, coef_a, coef_b, dgamma, dbeta, dh_bf16,
-                                dbias, B, HW, C, eps, stream, 0);
+                                dbias, B, HW, C, eps, stream, 0, 0);
 }
 
 extern "C" int fz_grn_gelu_backward_saved(const void* dy_bf16, const void* g_bf16, const void* dgelu_bf16, const float* s1,
                                           const float* s0, const float* gx, const float* nx, const float* mu,
                                           const float* gamma, float* coef_a, float* coef_b, float* dgamma, float* dbeta,
-                                          void* dh_bf16, float* dbias, int B, int HW, int C, float eps, void* stream) {
+                                          void* dh_bf16, float* dbias, int B, int HW, int C, float eps, int act_f16,
+                                          void* stream) {
   return grn_gelu_backward_impl(dy_bf16, g_bf16, dgelu_bf16, s1, s0, gx, nx, mu, gamma, coef_a, coef_b, dgamma, dbeta, dh_bf16,
-                                dbias, B, HW, C, eps, stream, 1);
+                                dbias, B, HW, C, eps, stream, 1, act_f16);
 }
 
 extern "C" int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1,
@@ -1392,6 +1448,17 @@ extern "C" int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, con
                                     int C, float eps, void* stream) {
   return fz_grn_gelu_backward_db(dy_bf16, g_bf16, h_bf16, s1, s0, gx, nx, mu, gamma, coef_a, coef_b, dgamma, dbeta, dh_bf16,
                                  nullptr, B, HW, C, eps, stream);
+}
+
+extern "C" int fz_cast_f16_bf16(const void* in_f16, void* out_bf16, int64_t n, void* stream) {
+  FZ_REQUIRE(n >= 0 && (n == 0 || (in_f16 && out_bf16)), "fz_cast_f16_bf16: bad arguments");
+  FZ_REQUIRE(((reinterpret_cast<uintptr_t>(in_f16) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0,
+             "fz_cast_f16_bf16: 16-byte aligned buffers required");
+  if (n == 0) return 0;
+  cast_f16_bf16_kernel<<<blocks_for((n + 7) / 8), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in_f16),
+                                                                         reinterpret_cast<bf>(out_bf16), n);
+  FZ_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
@@ -1408,11 +1475,11 @@ extern "C" int fz_add_f32(const float* a, const float* b, float* out, int64_t n,
 }
 
 extern "C" int fz_layernorm_fwd_stats2(const float* x, const float* g, const float* b, void* out_bf16, float* out_f32,
-                                       float* mean, float* rstd, int64_t M, int C, float eps, void* stream) {
+                                       float* mean, float* rstd, int64_t M, int C, float eps, int out_f16, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && x && g && b && (out_bf16 || out_f32) && mean && rstd, "fz_layernorm_fwd_stats2: bad arguments");
-  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), out_f32, mean, rstd, M, C, eps, ST(stream)))
+  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), out_f32, mean, rstd, M, C, eps, out_f16, ST(stream)))
     ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
-                                                                                   out_f32, mean, rstd, M, C, eps);
+                                                                                   out_f32, mean, rstd, M, C, eps, out_f16);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1430,10 +1497,10 @@ extern "C" int fz_s2d_bf16(const void* in, void* out, int B, int H, int W, int C
   return 0;
 }
 
-extern "C" int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin, int P, int Kpad, void* stream) {
+extern "C" int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin, int P, int Kpad, int out_f16, void* stream) {
   FZ_REQUIRE(B > 0 && Cin > 0 && P > 0 && P % 4 == 0 && Kpad >= Cin * 16 && in && out_bf16, "fz_patchify4_nchw: bad arguments");
   const int64_t n = static_cast<int64_t>(B) * (P / 4) * (P / 4) * Kpad;
-  patchify4_nchw_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(in, reinterpret_cast<bf>(out_bf16), Cin, P, Kpad, n);
+  patchify4_nchw_kernel<<<blocks_for(n), 256, 0, ST(stream)>>>(in, reinterpret_cast<bf>(out_bf16), Cin, P, Kpad, n, out_f16);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1463,7 +1530,7 @@ extern "C" int fz_col2im3x3(const void* dcol_bf16, float* dx, int B, int H, int 
 
 extern "C" int fz_bn_relu_train_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16,
                                         float* mean, float* rstd, float* workspace, int64_t M, int C, int chunks, float eps,
-                                        void* stream) {
+                                        int out_f16, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && ldx >= C && chunks >= 1 && chunks <= 65535 && x && gamma && beta && y_bf16 && mean && rstd &&
                  workspace,
              "fz_bn_relu_train_forward: bad arguments");
@@ -1485,9 +1552,9 @@ extern "C" int fz_bn_relu_train_forward(const float* x, int ldx, const float* ga
   const int64_t n = M * C;
   if (vec)
     bn_relu_apply_vec_kernel<<<blocks_for(n / 4), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, reinterpret_cast<bf>(y_bf16),
-                                                                C / 4, n / 4);
+                                                                C / 4, n / 4, out_f16);
   else
-    bn_relu_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, reinterpret_cast<bf>(y_bf16), C, n);
+    bn_relu_apply_kernel<<<blocks_for(n), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, reinterpret_cast<bf>(y_bf16), C, n, out_f16);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

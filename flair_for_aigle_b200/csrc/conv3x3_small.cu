@@ -12,6 +12,7 @@
 // the forward kernel run on dconv with the flipped, transposed weights (the host prepares them with the 16-bit copies).
 // Shapes outside the template list keep the im2col + tcgen05 GEMM path (engine/convnext_train.py).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.h"
 #include "../../include/flair_zonal_b200.h"
@@ -35,6 +36,11 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa(dst)), "l"(src) : "memory");
 }
@@ -43,18 +49,37 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // Stages the halo'd tile of a [B][H][W][C] bf16 map at (b, y0 - 1, x0 - 1): sX[(r * WP + c) * LD + ch], zero outside the image.
+// f16_to_bf16: the map holds IEEE fp16 and the tile is wanted in bf16 (the weight gradient multiplies bf16 output gradients
+// with fp16 forward activations and mma.sync takes one format): converted on the way in, through registers instead of cp.async
 template <int C, int NT>
-__device__ __forceinline__ void load_halo_tile(__nv_bfloat16* sX, const __nv_bfloat16* in, int b, int y0, int x0, int H, int W) {
+__device__ __forceinline__ void load_halo_tile(__nv_bfloat16* sX, const __nv_bfloat16* in, int b, int y0, int x0, int H, int W,
+                                               bool f16_to_bf16 = false) {
   constexpr int LD = C + 8, C8 = C / 8;
   for (int i = threadIdx.x; i < HP * WP * C8; i += NT) {
     const int c8 = i % C8, pix = i / C8;
     const int r = pix / WP, c = pix - r * WP;
     const int gy = y0 - 1 + r, gx = x0 - 1 + c;
     __nv_bfloat16* dst = sX + pix * LD + c8 * 8;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-      cp_async16(dst, in + ((static_cast<size_t>(b) * H + gy) * W + gx) * C + c8 * 8);
-    else
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const __nv_bfloat16* src = in + ((static_cast<size_t>(b) * H + gy) * W + gx) * C + c8 * 8;
+      if (f16_to_bf16) {
+        const uint4 q = *reinterpret_cast<const uint4*>(src);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+          const __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
+          ow[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(dst) = o;
+      } else {
+        cp_async16(dst, src);
+      }
+    } else {
       *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 }
 }  // namespace cs
@@ -65,7 +90,7 @@ __device__ __forceinline__ void load_halo_tile(__nv_bfloat16* sX, const __nv_bfl
 // The kernel is latency-bound between its load, compute and store phases (ncu, profiles/r2_ncu_train_conv_summary.txt: two
 // resident blocks per SM, issue slots 28 % busy, DRAM 29 %): the 16-output-channel variants (76 registers) are compiled for 3
 // resident blocks so that one block's loads overlap the others' MMAs and stores; grids are one wave of resident blocks.
-template <int CIN, int COUT, bool OUT16>
+template <int CIN, int COUT, bool OUT16, bool F16>
 __global__ void __launch_bounds__(256, COUT == 16 ? 3 : 2) conv3x3_small_fwd_kernel(const __nv_bfloat16* __restrict__ in,
                                                                    const __nv_bfloat16* __restrict__ w,
                                                                    const float* __restrict__ bias, void* __restrict__ out, int B,
@@ -109,8 +134,13 @@ __global__ void __launch_bounds__(256, COUT == 16 ? 3 : 2) conv3x3_small_fwd_ker
           ldsm_x4(bb, sW + (tap * COUT + np * 16 + (lane >> 4) * 8 + (lane & 7)) * LDW + ks * 16 + ((lane >> 3) & 1) * 8);
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
-            mma_bf16(acc[m][np * 2], a[m], bb[0], bb[1]);
-            mma_bf16(acc[m][np * 2 + 1], a[m], bb[2], bb[3]);
+            if (F16) {
+              mma_f16(acc[m][np * 2], a[m], bb[0], bb[1]);
+              mma_f16(acc[m][np * 2 + 1], a[m], bb[2], bb[3]);
+            } else {
+              mma_bf16(acc[m][np * 2], a[m], bb[0], bb[1]);
+              mma_bf16(acc[m][np * 2 + 1], a[m], bb[2], bb[3]);
+            }
           }
         }
       }
@@ -150,7 +180,7 @@ __global__ void __launch_bounds__(256, COUT == 16 ? 3 : 2) conv3x3_small_fwd_ker
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(288, CIN * COUT <= 512 ? 3 : 2) conv3x3_small_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
                                                                      const __nv_bfloat16* __restrict__ dconv, int ldd,
-                                                                     float* __restrict__ partial, int B, int H, int W) {
+                                                                     float* __restrict__ partial, int B, int H, int W, int x_f16) {
   using namespace cs;
   constexpr int LDX = CIN + 8, LDD = COUT + 8;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -168,7 +198,7 @@ __global__ void __launch_bounds__(288, CIN * COUT <= 512 ? 3 : 2) conv3x3_small_
     const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
     const int x0 = tx * TW, y0 = ty * TH;
     __syncthreads();
-    load_halo_tile<CIN, 288>(sX, x, b, y0, x0, H, W);
+    load_halo_tile<CIN, 288>(sX, x, b, y0, x0, H, W, x_f16 != 0);
     for (int i = threadIdx.x; i < TH * TW * (COUT / 8); i += 288) {
       const int c8 = i % (COUT / 8), pix = i / (COUT / 8);
       const int r = pix / TW, c = pix - r * TW;
@@ -247,37 +277,38 @@ static int resident_blocks(K kernel, int threads, int smem) {
 }
 
 template <int CIN, int COUT>
-static int launch_fwd(const void* in, const void* w, const float* bias, void* out, int out16, int B, int H, int W, int n_store,
-                      int ldo, cudaStream_t st) {
+static int launch_fwd(const void* in, const void* w, const float* bias, void* out, int out16, int in_f16, int B, int H, int W,
+                      int n_store, int ldo, cudaStream_t st) {
   constexpr int SMEM = (9 * COUT * (CIN + 8) + cs::HP * cs::WP * (CIN + 8)) * 2;
   const int n_tiles = B * (H / cs::TH) * (W / cs::TW);
   auto a = reinterpret_cast<const __nv_bfloat16*>(in);
   auto b = reinterpret_cast<const __nv_bfloat16*>(w);
-  if (out16) {
-    auto k = conv3x3_small_fwd_kernel<CIN, COUT, true>;
-    FZ_ENSURE_SMEM(k, SMEM);
-    const int wave = resident_blocks(k, 256, SMEM) * sm_count();
-    k<<<n_tiles < wave ? n_tiles : wave, 256, SMEM, st>>>(a, b, bias, out, B, H, W, n_store, ldo);
-  } else {
-    auto k = conv3x3_small_fwd_kernel<CIN, COUT, false>;
-    FZ_ENSURE_SMEM(k, SMEM);
-    const int wave = resident_blocks(k, 256, SMEM) * sm_count();
-    k<<<n_tiles < wave ? n_tiles : wave, 256, SMEM, st>>>(a, b, bias, out, B, H, W, n_store, ldo);
+#define FZ_CS_LAUNCH(O16, F16)                                                                   \
+  {                                                                                              \
+    auto k = conv3x3_small_fwd_kernel<CIN, COUT, O16, F16>;                                      \
+    FZ_ENSURE_SMEM(k, SMEM);                                                                     \
+    const int wave = resident_blocks(k, 256, SMEM) * sm_count();                                 \
+    k<<<n_tiles < wave ? n_tiles : wave, 256, SMEM, st>>>(a, b, bias, out, B, H, W, n_store, ldo); \
   }
+  // the data gradient (bf16 operands) may write bf16; the forward (fp16 or bf16 operands) writes fp32
+  if (out16) FZ_CS_LAUNCH(true, false)
+  else if (in_f16) FZ_CS_LAUNCH(false, true)
+  else FZ_CS_LAUNCH(false, false)
+#undef FZ_CS_LAUNCH
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int CIN, int COUT>
 static int launch_wgrad(const void* x, const void* dconv, int ldd, float* dw, float* partial, int max_ctas, int B, int H, int W,
-                        cudaStream_t st) {
+                        int x_f16, cudaStream_t st) {
   constexpr int SMEM = (cs::HP * cs::WP * (CIN + 8) + cs::TH * cs::TW * (COUT + 8)) * 2;
   auto k = conv3x3_small_wgrad_kernel<CIN, COUT>;
   FZ_ENSURE_SMEM(k, SMEM);
   const int wave = resident_blocks(k, 288, SMEM) * sm_count();
   const int ctas = max_ctas < wave ? max_ctas : wave;                 // the scratch buffer is sized for max_ctas
   k<<<ctas, 288, SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dconv), ldd,
-                             partial, B, H, W);
+                             partial, B, H, W, x_f16);
   const int n = 9 * COUT * CIN;
   conv_small_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(partial, dw, n, ctas);
   FZ_CHECK_CUDA(cudaGetLastError());
@@ -295,7 +326,8 @@ extern "C" int fz_conv3x3_small_supported(int H, int W, int Cin, int Cout) {
 }
 
 extern "C" int fz_conv3x3_small_forward(const void* in_bf16, const void* w_bf16, const float* bias, void* out, int out_bf16,
-                                        int B, int H, int W, int Cin, int Cout, int n_store, int ldo, void* stream) {
+                                        int B, int H, int W, int Cin, int Cout, int n_store, int ldo, int in_f16, void* stream) {
+  FZ_REQUIRE(!(in_f16 && out_bf16), "fz_conv3x3_small_forward: fp16 operands write fp32 only");
   FZ_REQUIRE(B > 0 && in_bf16 && w_bf16 && out && fz_conv3x3_small_supported(H, W, Cin, Cout),
              "fz_conv3x3_small_forward: B=%d H=%d W=%d Cin=%d Cout=%d not covered (H %% 8, W %% 32, channels 16/32/48/64)", B, H,
              W, Cin, Cout);
@@ -304,7 +336,7 @@ extern "C" int fz_conv3x3_small_forward(const void* in_bf16, const void* w_bf16,
   FZ_REQUIRE(static_cast<int64_t>(B) * (H / cs::TH) * (W / cs::TW) < (1LL << 31), "fz_conv3x3_small_forward: too many tiles");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define FZ_CS(ci, co) \
-  if (Cin == ci && Cout == co) return launch_fwd<ci, co>(in_bf16, w_bf16, bias, out, out_bf16, B, H, W, n_store, ldo, st);
+  if (Cin == ci && Cout == co) return launch_fwd<ci, co>(in_bf16, w_bf16, bias, out, out_bf16, in_f16, B, H, W, n_store, ldo, st);
   FZ_CS(16, 16) FZ_CS(16, 32) FZ_CS(16, 48) FZ_CS(16, 64) FZ_CS(32, 16) FZ_CS(32, 32) FZ_CS(32, 48) FZ_CS(32, 64)
   FZ_CS(48, 16) FZ_CS(48, 32) FZ_CS(48, 48) FZ_CS(48, 64) FZ_CS(64, 16) FZ_CS(64, 32) FZ_CS(64, 48) FZ_CS(64, 64)
 #undef FZ_CS
@@ -313,7 +345,7 @@ extern "C" int fz_conv3x3_small_forward(const void* in_bf16, const void* w_bf16,
 }
 
 extern "C" int fz_conv3x3_small_wgrad(const void* x_bf16, const void* dconv_bf16, int ldd, float* dw, int B, int H, int W,
-                                      int Cin, int Cout, void* stream) {
+                                      int Cin, int Cout, int x_f16, void* stream) {
   FZ_REQUIRE(B > 0 && x_bf16 && dconv_bf16 && dw && fz_conv3x3_small_supported(H, W, Cin, Cout) && Cout <= 32,
              "fz_conv3x3_small_wgrad: B=%d H=%d W=%d Cin=%d Cout=%d not covered (H %% 8, W %% 32, Cin 16/32/48/64, Cout 16/32)", B,
              H, W, Cin, Cout);
@@ -336,7 +368,7 @@ extern "C" int fz_conv3x3_small_wgrad(const void* x_bf16, const void* dconv_bf16
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define FZ_CS(ci, co) \
-  if (Cin == ci && Cout == co) return launch_wgrad<ci, co>(x_bf16, dconv_bf16, ldd, dw, scratch[dev], ctas, B, H, W, st);
+  if (Cin == ci && Cout == co) return launch_wgrad<ci, co>(x_bf16, dconv_bf16, ldd, dw, scratch[dev], ctas, B, H, W, x_f16, st);
   FZ_CS(16, 16) FZ_CS(32, 16) FZ_CS(48, 16) FZ_CS(64, 16) FZ_CS(16, 32) FZ_CS(32, 32) FZ_CS(48, 32) FZ_CS(64, 32)
 #undef FZ_CS
   set_error("fz_conv3x3_small_wgrad: no kernel for Cin=%d Cout=%d", Cin, Cout);

@@ -128,6 +128,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
+      // (a_format = BF16 with b_format = F16 in one descriptor was tried for the training weight gradients: the MMA is an
+      //  illegal instruction on sm_100a, kind::f16 wants one format for both operands)
       constexpr uint32_t idesc = MNMAJOR ? umma_idesc16_mn(128, BN, F16) : umma_idesc16(128, BN, F16);
       uint32_t it = 0, lt = 0;
       for (int t = t_first; t < total_work; t += t_step, ++lt) {

@@ -6,31 +6,56 @@
 // written per (sample, chunk) and added in chunk order by colreduce_final_kernel: the result does not depend on scheduling.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
 
 namespace fz {
 
-__device__ __forceinline__ void rv_load8(const __nv_bfloat16* p, float (&v)[8]) {
+// Activation tensors of the training step come in two 16-bit formats: bf16 (gradients: range) and IEEE fp16 (forward
+// activations: three more significand bits -- tests/diag/grad_precision_budget.py: the bf16 rounding of the FORWARD tensors
+// alone costs the gradients 0.8 % of cosine, fp16 0.1 %).  `f16` selects the format of a tensor; it is warp-uniform.
+__device__ __forceinline__ void rv_load8(const void* p, float (&v)[8], bool f16 = false) {
   const uint4 q = *reinterpret_cast<const uint4*>(p);
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    v[2 * j] = __uint_as_float(w[j] << 16);
-    v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    if (f16) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    } else {
+      v[2 * j] = __uint_as_float(w[j] << 16);
+      v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
   }
 }
-// rounds to bf16, stores, and leaves the ROUNDED values in v (what a later pass over the stored tensor would read)
-__device__ __forceinline__ void rv_store8_round(__nv_bfloat16* p, float (&v)[8]) {
+__device__ __forceinline__ uint32_t rv_pack2(float lo, float hi, bool f16) {
+  uint32_t r;
+  if (f16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    r = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return r;
+}
+// rounds to the 16-bit format, stores, and leaves the ROUNDED values in v (what a later pass over the stored tensor would read)
+__device__ __forceinline__ void rv_store8_round(void* p, float (&v)[8], bool f16 = false) {
   uint4 q;
   uint32_t* w = reinterpret_cast<uint32_t*>(&q);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    w[j] = *reinterpret_cast<const uint32_t*>(&h);
-    v[2 * j] = __uint_as_float(w[j] << 16);
-    v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    w[j] = rv_pack2(v[2 * j], v[2 * j + 1], f16);
+    if (f16) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    } else {
+      v[2 * j] = __uint_as_float(w[j] << 16);
+      v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
   }
   *reinterpret_cast<uint4*>(p) = q;
 }
@@ -88,12 +113,14 @@ static inline RvGeom rv_geometry(int B, int rows, int C, int ctas_per_sm = 4, in
 // MODE 0: sum a^2      1: g = GELU(a) stored to gout, GELU'(a) stored to dout (when given), sum g^2 (of the stored,
 // rounded g)      2: sum a      3: out0 = sum a*b, out1 = sum a
 // partial[((b * chunks + chunk) * NOUT + o) * C + c]
+// fmt: bit 0 = `a` is fp16, bit 1 = `bb` is fp16, bit 2 = the stored outputs (gout, dout) are fp16; 0 = all bf16
 template <int MODE>
 __global__ void __launch_bounds__(256) colreduce_vec_kernel(const __nv_bfloat16* __restrict__ a,
                                                             const __nv_bfloat16* __restrict__ bb,
                                                             __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ dout,
                                                             float* __restrict__ partial, int rows, int C, int cgs,
-                                                            int rows_per_chunk) {
+                                                            int rows_per_chunk, int fmt) {
+  const bool a16 = fmt & 1, b16 = fmt & 2, o16 = fmt & 4;
   constexpr int NOUT = MODE == 3 ? 2 : 1;
   __shared__ float red[NOUT][256][9];                          // 9: the 8-float rows would collide 4-way on the banks
   const int rp = 256 / cgs;
@@ -111,7 +138,7 @@ __global__ void __launch_bounds__(256) colreduce_vec_kernel(const __nv_bfloat16*
     for (int r = r0 + rr; r < r1; r += rp) {
       const size_t o = base + static_cast<size_t>(r) * C;
       float v[8];
-      rv_load8(a + o, v);
+      rv_load8(a + o, v, a16);
       if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc0[j] = fmaf(v[j], v[j], acc0[j]);
@@ -124,8 +151,8 @@ __global__ void __launch_bounds__(256) colreduce_vec_kernel(const __nv_bfloat16*
           d[j] = fmaf(v[j], pdf, cdf);                           // GELU'(a): the backward reads it instead of recomputing
           v[j] *= cdf;
         }
-        if (dout) rv_store8_round(dout + o, d);
-        rv_store8_round(gout + o, v);
+        if (dout) rv_store8_round(dout + o, d, o16);
+        rv_store8_round(gout + o, v, o16);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc0[j] = fmaf(v[j], v[j], acc0[j]);
       } else if (MODE == 2) {
@@ -133,7 +160,7 @@ __global__ void __launch_bounds__(256) colreduce_vec_kernel(const __nv_bfloat16*
         for (int j = 0; j < 8; ++j) acc0[j] += v[j];
       } else {
         float w[8];
-        rv_load8(bb + o, w);
+        rv_load8(bb + o, w, b16);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc0[j] = fmaf(v[j], w[j], acc0[j]);
@@ -214,14 +241,14 @@ static inline float* rv_scratch(size_t floats) {
 // Launches MODE over a [B][rows][C] tensor; returns a cudaError_t.
 template <int MODE>
 static inline cudaError_t rv_colreduce(const void* a, const void* bb, void* gout, float* out0, float* out1, int B, int rows,
-                                       int C, cudaStream_t st, void* dout = nullptr) {
+                                       int C, cudaStream_t st, void* dout = nullptr, int fmt = 0) {
   constexpr int NOUT = MODE == 3 ? 2 : 1;
   const RvGeom g = rv_geometry(B, rows, C, rv_resident(colreduce_vec_kernel<MODE>));
   float* partial = rv_scratch(static_cast<size_t>(B) * g.chunks * NOUT * C);
   if (!partial) return cudaErrorMemoryAllocation;
   colreduce_vec_kernel<MODE><<<dim3(g.slabs, g.chunks, B), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(bb),
-      reinterpret_cast<__nv_bfloat16*>(gout), reinterpret_cast<__nv_bfloat16*>(dout), partial, rows, C, g.cgs, g.rows_per_chunk);
+      reinterpret_cast<__nv_bfloat16*>(gout), reinterpret_cast<__nv_bfloat16*>(dout), partial, rows, C, g.cgs, g.rows_per_chunk, fmt);
   colreduce_final_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(partial, out0, out1, g.chunks, C, NOUT);
   return cudaGetLastError();
 }

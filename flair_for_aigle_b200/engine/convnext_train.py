@@ -8,6 +8,7 @@ number formats as the inference engine.  The Linear layers and their gradients r
 (``native.gemm_bf16`` / ``native.linear_backward``); everything else is csrc/backward_ops.cu.  Correctness first: these
 kernels are not tuned and the block is not yet wired into a model-level backward (decoder, BatchNorm in training mode, stem
 and downsample layers are still missing)."""
+import os
 from typing import Dict
 
 import torch
@@ -18,6 +19,15 @@ _L = nv.lib
 _P = nv._ptr
 _S = nv._stream
 
+# Format of the FORWARD activations (LayerNorm outputs, hidden tensors, decoder activations, im2col rows, stem patches) and of
+# the weights they are multiplied with: IEEE fp16.  The gradients flowing backwards stay bf16 (range), and so do the weight
+# copies of the data-gradient GEMMs; weight gradients multiply the two formats directly (tcgen05 kind::f16 takes A and B
+# formats independently; the mma.sync tile kernel converts while staging).  Why: tests/diag/grad_precision_budget.py -- the
+# bf16 rounding of the forward tensors ALONE puts the whole-model gradient cosine against fp32 autograd at 0.992 (the engine
+# measured 0.985-0.990 with a bf16 forward), fp16 at 0.999.  FZ_TRAIN_ACT=bf16 restores the bf16 forward for comparison.
+ACT = torch.bfloat16 if os.environ.get("FZ_TRAIN_ACT", "f16") == "bf16" else torch.float16
+ACT_F16 = 1 if ACT == torch.float16 else 0
+
 
 def _chk(rc: int, what: str) -> None:
     nv._check(rc, what)
@@ -25,8 +35,9 @@ def _chk(rc: int, what: str) -> None:
 
 class ConvNeXtBlockTrain:
     def __init__(self, params: Dict[str, torch.Tensor], eps_ln: float = 1e-6, eps_grn: float = 1e-6, params16=None):
-        """params16 (optional): bf16 copies of the same parameters under the same names (the trainer casts its whole arena in
-        one launch); the two Linear weights are then used as they are instead of being cast here."""
+        """params16 (optional): {"act": {...}, "bf16": {...}} -- 16-bit copies of the parameters under the same names in the
+        forward format and in bf16 (the trainer casts its whole arena once per format); the two Linear weights are then used as
+        they are instead of being cast here."""
         dev = params["conv_dw.weight"].device
         if dev.type != "cuda":
             raise nv.NativeError("ConvNeXtBlockTrain runs on CUDA only (no CPU fallback)")
@@ -37,11 +48,13 @@ class ConvNeXtBlockTrain:
         self.b_dw = f32(params["conv_dw.bias"])
         self.ln_w, self.ln_b = f32(params["norm.weight"]), f32(params["norm.bias"])
         p16 = params16 or {}
-        b16 = lambda k: p16[k] if k in p16 else params[k].detach().to(torch.bfloat16).contiguous()
-        self.w1 = b16("mlp.fc1.weight")                                                  # [4C][C]
+        pa, pb = p16.get("act", {}), p16.get("bf16", {})
+        act = lambda k: pa[k] if k in pa else params[k].detach().to(ACT).contiguous()
+        b16 = lambda k: pb[k] if k in pb else params[k].detach().to(torch.bfloat16).contiguous()
+        self.w1, self.w1_b = act("mlp.fc1.weight"), b16("mlp.fc1.weight")                # [4C][C]: forward copy, backward copy
         self.b1 = f32(params["mlp.fc1.bias"])
         self.grn_w, self.grn_b = f32(params["mlp.grn.weight"]), f32(params["mlp.grn.bias"])
-        self.w2 = b16("mlp.fc2.weight")                                                  # [C][4C]
+        self.w2, self.w2_b = act("mlp.fc2.weight"), b16("mlp.fc2.weight")                # [C][4C]
         self.b2 = f32(params["mlp.fc2.bias"])
         self.saved = None
 
@@ -52,20 +65,20 @@ class ConvNeXtBlockTrain:
         x = x.contiguous()
         u = torch.empty_like(x)
         _chk(_L().fz_dwconv7_f32(_P(x), _P(self.w_dw), _P(self.b_dw), _P(u), B, H, W, C, 0, _S()), "fz_dwconv7_f32")
-        a1 = torch.empty((M, C), dtype=torch.bfloat16, device=dev)
+        a1 = torch.empty((M, C), dtype=ACT, device=dev)
         mean = torch.empty(M, dtype=torch.float32, device=dev)
         rstd = torch.empty(M, dtype=torch.float32, device=dev)
         _chk(_L().fz_layernorm_fwd_stats(_P(u), _P(self.ln_w), _P(self.ln_b), _P(a1), _P(mean), _P(rstd), M, C, self.eps_ln,
-                                         _S()), "fz_layernorm_fwd_stats")
-        h = nv.gemm_bf16(a1, self.w1, nv.EPI_BF16, bias=self.b1)                          # pre-GELU, bf16 [M,4C]
+                                         ACT_F16, _S()), "fz_layernorm_fwd_stats")
+        h = nv.gemm_bf16(a1, self.w1, nv.EPI_BF16, bias=self.b1)                          # pre-GELU, 16-bit [M,4C]
         g, dg = torch.empty_like(h), torch.empty_like(h)                  # GELU(h) and GELU'(h); h itself is not kept
         sumsq = torch.empty((B, C4), dtype=torch.float32, device=dev)
-        _chk(_L().fz_gelu_fwd_sumsq(_P(h), _P(g), _P(dg), _P(sumsq), B, H * W, C4, _S()), "fz_gelu_fwd_sumsq")   # + GRN sums, one pass
+        _chk(_L().fz_gelu_fwd_sumsq(_P(h), _P(g), _P(dg), _P(sumsq), B, H * W, C4, ACT_F16, _S()), "fz_gelu_fwd_sumsq")   # + GRN sums
         gx, nx = torch.empty_like(sumsq), torch.empty_like(sumsq)
         mu = torch.empty(B, dtype=torch.float32, device=dev)
         a2 = torch.empty_like(g)
         _chk(_L().fz_grn_train_forward(_P(g), _P(sumsq), _P(self.grn_w), _P(self.grn_b), _P(gx), _P(nx), _P(mu), _P(a2), B,
-                                       H * W, C4, self.eps_grn, _S()), "fz_grn_train_forward")
+                                       H * W, C4, self.eps_grn, ACT_F16, _S()), "fz_grn_train_forward")
         y = nv.gemm_bf16(a2, self.w2, nv.EPI_RESID_F32, bias=self.b2, resid=x.view(M, C))
         self.saved = (x, u, a1, mean, rstd, dg, g, gx, nx, mu, a2)
         return y.view(B, H, W, C)
@@ -80,19 +93,19 @@ class ConvNeXtBlockTrain:
         dy = dy.contiguous()
         dyb = torch.empty((M, C), dtype=torch.bfloat16, device=dev)
         nv.cast_f32_bf16(dy.view(M, C), dyb)
-        da2, dw2, db2 = nv.linear_backward(dyb, a2, self.w2)                              # fc2
+        da2, dw2, db2 = nv.linear_backward(dyb, a2, self.w2_b)                            # fc2
         s1 = torch.empty((B, C4), dtype=torch.float32, device=dev)
         s0 = torch.empty_like(s1)
-        _chk(_L().fz_sample_colreduce2(_P(da2), _P(g), _P(s1), _P(s0), B, H * W, C4, _S()), "fz_sample_colreduce2")
+        _chk(_L().fz_sample_colreduce2(_P(da2), _P(g), _P(s1), _P(s0), B, H * W, C4, ACT_F16, _S()), "fz_sample_colreduce2")
         ca, cb = torch.empty_like(s1), torch.empty_like(s1)
         dgrn_w = torch.empty(C4, dtype=torch.float32, device=dev)
         dgrn_b = torch.empty_like(dgrn_w)
-        dh = torch.empty_like(g)
+        dh = torch.empty(g.shape, dtype=torch.bfloat16, device=dev)
         db1 = torch.empty(C4, dtype=torch.float32, device=dev)
         _chk(_L().fz_grn_gelu_backward_saved(_P(da2), _P(g), _P(dg), _P(s1), _P(s0), _P(gx), _P(nx), _P(mu), _P(self.grn_w),
                                              _P(ca), _P(cb), _P(dgrn_w), _P(dgrn_b), _P(dh), _P(db1), B, H * W, C4, self.eps_grn,
-                                             _S()), "fz_grn_gelu_backward_saved")
-        da1, dw1, db1 = nv.linear_backward(dh, a1, self.w1, db=db1)                       # fc1 (bias gradient from the kernel above)
+                                             ACT_F16, _S()), "fz_grn_gelu_backward_saved")
+        da1, dw1, db1 = nv.linear_backward(dh, a1, self.w1_b, db=db1)                       # fc1 (bias gradient from the kernel above)
         blocks = max(1, min(592, (M + 7) // 8))
         du = torch.empty_like(u)
         partial = torch.empty((blocks, 2, C), dtype=torch.float32, device=dev)
@@ -123,12 +136,12 @@ class _LayerNormTrain:
     def forward(self, x: torch.Tensor, want_bf16: bool, want_f32: bool):
         M, C = x.shape
         dev = x.device
-        ob = torch.empty((M, C), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+        ob = torch.empty((M, C), dtype=ACT, device=dev) if want_bf16 else None             # "bf16" = the 16-bit forward format
         of = torch.empty((M, C), dtype=torch.float32, device=dev) if want_f32 else None
         mean = torch.empty(M, dtype=torch.float32, device=dev)
         rstd = torch.empty(M, dtype=torch.float32, device=dev)
         _chk(_L().fz_layernorm_fwd_stats2(_P(x), _P(self.w), _P(self.b), _P(ob), _P(of), _P(mean), _P(rstd), M, C, self.eps,
-                                          _S()), "fz_layernorm_fwd_stats2")
+                                          ACT_F16, _S()), "fz_layernorm_fwd_stats2")
         self.saved = (x, mean, rstd)
         return ob, of
 
@@ -151,6 +164,13 @@ def _to_bf16(x_f32: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _to_act(x_f32: torch.Tensor) -> torch.Tensor:
+    """fp32 -> the forward activation format (ACT)."""
+    out = torch.empty(x_f32.shape, dtype=ACT, device=x_f32.device)
+    nv.cast_f32_bf16(x_f32, out)
+    return out
+
+
 class ConvNeXtV2EncoderTrain:
     """Training forward + backward of the whole ConvNeXt-V2 feature extractor (timm ``convnextv2_*`` under smp's
     TimmUniversalEncoder: ``stem_0`` conv4x4/s4, ``stem_1`` LayerNorm2d, ``stages_i.downsample.{0,1}`` LayerNorm2d + conv2x2/s2,
@@ -164,8 +184,8 @@ class ConvNeXtV2EncoderTrain:
         self.cin = w.shape[1]
         self.kpad = ((self.cin * 16 + 63) // 64) * 64
         dev = w.device
-        w2 = torch.zeros((dims[0], self.kpad), dtype=torch.bfloat16, device=dev)
-        w2[:, :self.cin * 16] = w.detach().reshape(dims[0], -1).to(torch.bfloat16)
+        w2 = torch.zeros((dims[0], self.kpad), dtype=ACT, device=dev)
+        w2[:, :self.cin * 16] = w.detach().reshape(dims[0], -1).to(ACT)
         self.stem_w, self.stem_b = w2.contiguous(), params["stem_0.bias"].detach().float().contiguous()
         self.stem_ln = _LayerNormTrain(params["stem_1.weight"], params["stem_1.bias"])
         self.down, self.blocks = [], []
@@ -173,22 +193,24 @@ class ConvNeXtV2EncoderTrain:
             if i > 0:
                 p = f"stages_{i}.downsample."
                 wd = params[p + "1.weight"].detach()                                  # [c, c_prev, 2, 2]
+                wd2 = wd.permute(0, 2, 3, 1).reshape(c, -1)
                 self.down.append((_LayerNormTrain(params[p + "0.weight"], params[p + "0.bias"]),
-                                  wd.permute(0, 2, 3, 1).reshape(c, -1).to(torch.bfloat16).contiguous(),
+                                  (wd2.to(ACT).contiguous(), wd2.to(torch.bfloat16).contiguous()),    # forward / backward copies
                                   params[p + "1.bias"].detach().float().contiguous()))
             else:
                 self.down.append(None)
             sub = lambda src, pre: {k[len(pre):]: v for k, v in src.items() if k.startswith(pre)}
+            sub16 = lambda pre: {fmt: sub(d16, pre) for fmt, d16 in params16.items()}
             self.blocks.append([ConvNeXtBlockTrain(sub(params, f"stages_{i}.blocks.{j}."),
-                                                   params16=sub(params16, f"stages_{i}.blocks.{j}.")) for j in range(d)])
+                                                   params16=sub16(f"stages_{i}.blocks.{j}.")) for j in range(d)])
         self.saved = None
 
     def forward(self, x_nchw: torch.Tensor):
         B, Cin, P, _ = x_nchw.shape
         dev = x_nchw.device
         q = P // 4
-        patches = torch.empty((B * q * q, self.kpad), dtype=torch.bfloat16, device=dev)
-        _chk(_L().fz_patchify4_nchw(_P(x_nchw.float().contiguous()), _P(patches), B, Cin, P, self.kpad, _S()),
+        patches = torch.empty((B * q * q, self.kpad), dtype=ACT, device=dev)
+        _chk(_L().fz_patchify4_nchw(_P(x_nchw.float().contiguous()), _P(patches), B, Cin, P, self.kpad, ACT_F16, _S()),
              "fz_patchify4_nchw")
         u0 = nv.gemm_bf16(patches, self.stem_w, nv.EPI_F32, bias=self.stem_b)             # conv4x4/s4 as a GEMM, fp32
         _, x = self.stem_ln.forward(u0, want_bf16=False, want_f32=True)
@@ -199,11 +221,11 @@ class ConvNeXtV2EncoderTrain:
                 ln, wd, bd = self.down[i]
                 cp = self.dims[i - 1]
                 a, _ = ln.forward(x.view(-1, cp), want_bf16=True, want_f32=False)
-                a4 = torch.empty((B * (h // 2) * (h // 2), 4 * cp), dtype=torch.bfloat16, device=dev)
+                a4 = torch.empty((B * (h // 2) * (h // 2), 4 * cp), dtype=ACT, device=dev)
                 _chk(_L().fz_s2d_bf16(_P(a), _P(a4), B, h, h, cp, 2, 0, _S()), "fz_s2d_bf16")
                 geo.append((h, cp, a4))
                 h //= 2
-                x = nv.gemm_bf16(a4, wd, nv.EPI_F32, bias=bd)
+                x = nv.gemm_bf16(a4, wd[0], nv.EPI_F32, bias=bd)
             else:
                 geo.append(None)
             x = x.view(B, h, h, c)
@@ -236,7 +258,7 @@ class ConvNeXtV2EncoderTrain:
             if i > 0:
                 ln, wd, bd = self.down[i]
                 h, cp, a4 = geo[i]
-                da4, dw, db = nv.linear_backward(_to_bf16(d.view(-1, c)), a4, wd)
+                da4, dw, db = nv.linear_backward(_to_bf16(d.view(-1, c)), a4, wd[1])
                 grads[f"stages_{i}.downsample.1.weight"] = dw.view(c, 2, 2, cp).permute(0, 3, 1, 2).contiguous()
                 grads[f"stages_{i}.downsample.1.bias"] = db
                 da = torch.empty((B * h * h, cp), dtype=torch.bfloat16, device=da4.device)
@@ -285,7 +307,10 @@ class Conv3x3BnReluTrain:
         dev = weight.device
         w2 = torch.zeros((self.npad, self.kpad), dtype=torch.bfloat16, device=dev)
         w2[:self.cout, :9 * self.cin] = weight.detach().permute(0, 2, 3, 1).reshape(self.cout, -1).to(torch.bfloat16)
-        self.w2 = w2.contiguous()
+        self.w2 = w2.contiguous()                                                 # bf16: the data-gradient GEMM's operand
+        w2a = torch.zeros((self.npad, self.kpad), dtype=ACT, device=dev)
+        w2a[:self.cout, :9 * self.cin] = weight.detach().permute(0, 2, 3, 1).reshape(self.cout, -1).to(ACT)
+        self.w2_act = w2a.contiguous()                                            # forward format: the forward GEMM's operand
         self.bn = bn_weight is not None
         if self.bn:
             self.g, self.b = bn_weight.detach().float().contiguous(), bn_bias.detach().float().contiguous()
@@ -297,8 +322,8 @@ class Conv3x3BnReluTrain:
         self.small_ok = self.cin in (16, 32, 48, 64) and self.coutp in (16, 32)
         if self.small_ok:
             wb = weight.detach().to(torch.bfloat16)
-            wf = torch.zeros((9, self.coutp, self.cin), dtype=torch.bfloat16, device=dev)
-            wf[:, :self.cout] = wb.permute(2, 3, 0, 1).reshape(9, self.cout, self.cin)
+            wf = torch.zeros((9, self.coutp, self.cin), dtype=ACT, device=dev)
+            wf[:, :self.cout] = weight.detach().to(ACT).permute(2, 3, 0, 1).reshape(9, self.cout, self.cin)
             wd = torch.zeros((9, self.cin, self.coutp), dtype=torch.bfloat16, device=dev)
             wd[:, :, :self.cout] = wb.flip(2, 3).permute(2, 3, 1, 0).reshape(9, self.cin, self.cout)
             self.w_fwd, self.w_dgrad = wf.contiguous(), wd.contiguous()
@@ -317,22 +342,22 @@ class Conv3x3BnReluTrain:
             col = None
             conv = torch.empty((M, self.npad), dtype=torch.float32, device=dev)
             _chk(_L().fz_conv3x3_small_forward(_P(x), _P(self.w_fwd), None if self.bn else _P(self.bias), _P(conv), 0, B, H, W,
-                                               C, self.npad, self.npad, self.npad, _S()), "fz_conv3x3_small_forward")
+                                               C, self.npad, self.npad, self.npad, ACT_F16, _S()), "fz_conv3x3_small_forward")
         else:
-            col = torch.empty((M, self.kpad), dtype=torch.bfloat16, device=dev)
-            _chk(_L().fz_im2col3x3_bf16(_P(x), _P(col), B, H, W, C, self.kpad, _S()), "fz_im2col3x3_bf16")
-            conv = nv.gemm_bf16(col, self.w2, nv.EPI_F32, bias=None if self.bn else self.bias)      # fp32 [M, npad]
+            col = torch.empty((M, self.kpad), dtype=ACT, device=dev)
+            _chk(_L().fz_im2col3x3_bf16(_P(x), _P(col), B, H, W, C, self.kpad, _S()), "fz_im2col3x3_bf16")   # a 16-bit gather
+            conv = nv.gemm_bf16(col, self.w2_act, nv.EPI_F32, bias=None if self.bn else self.bias)  # fp32 [M, npad]
         keep = x if small else col
         if not self.bn:
             self.saved = (keep, small, (B, H, W))
             return conv.view(B, H, W, self.npad)
         chunks = max(1, min(1184, M // 64))
-        y = torch.empty((M, self.cout), dtype=torch.bfloat16, device=dev)
+        y = torch.empty((M, self.cout), dtype=ACT, device=dev)
         mean = torch.empty(self.cout, dtype=torch.float32, device=dev)
         rstd = torch.empty_like(mean)
         ws = torch.empty((chunks + 1) * 2 * self.cout, dtype=torch.float32, device=dev)
         _chk(_L().fz_bn_relu_train_forward(_P(conv), self.npad, _P(self.g), _P(self.b), _P(y), _P(mean), _P(rstd), _P(ws), M,
-                                           self.cout, chunks, self.BN_EPS, _S()), "fz_bn_relu_train_forward")
+                                           self.cout, chunks, self.BN_EPS, ACT_F16, _S()), "fz_bn_relu_train_forward")
         if self.running is not None:
             rm, rv, nbt = self.running
             _chk(_L().fz_bn_update_running(_P(mean), _P(rstd), _P(rm), _P(rv), self.cout, M, self.BN_EPS, 0.1, _S()),
@@ -362,13 +387,13 @@ class Conv3x3BnReluTrain:
         dx = torch.empty((B, H, W, self.cin), dtype=torch.float32, device=dconv.device)
         if small:
             dw = torch.empty((9, self.npad, self.cin), dtype=torch.float32, device=dconv.device)
-            _chk(_L().fz_conv3x3_small_wgrad(_P(keep), _P(dconv), self.npad, _P(dw), B, H, W, self.cin, self.npad, _S()),
-                 "fz_conv3x3_small_wgrad")
+            _chk(_L().fz_conv3x3_small_wgrad(_P(keep), _P(dconv), self.npad, _P(dw), B, H, W, self.cin, self.npad, ACT_F16,
+                                             _S()), "fz_conv3x3_small_wgrad")
             grads["weight"] = dw[:, :self.cout].permute(1, 2, 0).reshape(self.cout, self.cin, 3, 3).contiguous()
             if not self.bn:
                 grads["bias"] = nv.colsum_bf16(dconv)[:self.cout]
             _chk(_L().fz_conv3x3_small_forward(_P(dconv), _P(self.w_dgrad), None, _P(dx), 0, B, H, W, self.npad, self.cin,
-                                               self.cin, self.cin, _S()), "fz_conv3x3_small_forward")
+                                               self.cin, self.cin, 0, _S()), "fz_conv3x3_small_forward")
             return dx, grads
         dcol, dw, db = nv.linear_backward(dconv, keep, self.w2)
         if not self.bn:
@@ -406,7 +431,7 @@ class UnetDecoderTrain:
         for (c1, c2), skip in zip(self.blocks, skips):
             B, H, W, C1 = x.shape
             C2 = 0 if skip is None else skip.shape[-1]
-            cat = torch.empty((B, 2 * H, 2 * W, C1 + C2), dtype=torch.bfloat16, device=x.device)
+            cat = torch.empty((B, 2 * H, 2 * W, C1 + C2), dtype=ACT, device=x.device)
             nv.upsample2_concat(x.contiguous(), None if skip is None else skip.contiguous(), cat)
             shapes.append((B, H, W, C1, C2))
             x = c2.forward(c1.forward(cat))

@@ -23,7 +23,7 @@ import torch
 from .. import native as nv
 from ..flair_hub.tasks.module_setup import WeightedCrossEntropy
 from ..flair_hub.tasks.tasks_module import AdamW
-from .convnext_train import ConvNeXtV2EncoderTrain, UnetDecoderTrain, _to_bf16
+from .convnext_train import ACT, ConvNeXtV2EncoderTrain, UnetDecoderTrain, _to_act, _to_bf16
 
 
 class ConvNeXtUNetTrainer:
@@ -63,29 +63,38 @@ class ConvNeXtUNetTrainer:
     def _build(self) -> None:
         """Engines hold bf16 / repacked copies of the weights: rebuilt after every optimizer step."""
         p = self.params
-        # the whole fp32 arena to bf16 in ONE launch; the Linear weights of the blocks (the bulk of the parameters) are views
-        # into it, the few tensors that need another layout (depthwise taps, convolutions) are still repacked one by one
-        if self._arena16 is None:
-            self._arena16 = torch.empty(self.opt.arena.shape, dtype=torch.bfloat16, device=self.opt.arena.device)
+        # the whole fp32 arena to 16 bits in ONE launch per format (forward format for the forward GEMMs, bf16 for the data
+        # gradients); the Linear weights of the blocks (the bulk of the parameters) are views into these copies, the few
+        # tensors that need another layout (depthwise taps, convolutions) are still repacked one by one
         n4 = self.opt.arena.numel() // 4 * 4         # the cast kernel moves float4s; nothing that is used lives in the tail
-        nv.cast_f32_bf16(self.opt.arena[:n4], self._arena16[:n4])
-        p16 = {}
-        for name in self.names:
-            if name.endswith(("mlp.fc1.weight", "mlp.fc2.weight")):
-                off, k = self._slot[name]
-                if off % 8 == 0 and off + k <= n4:   # 16-byte aligned rows for the TMA descriptor
-                    p16[name] = self._arena16[off:off + k].view(p[name].shape)
+        if self._arena16 is None:
+            self._arena16 = {fmt: torch.empty(self.opt.arena.shape, dtype=dt, device=self.opt.arena.device)
+                             for fmt, dt in (("act", ACT), ("bf16", torch.bfloat16))}
+        p16 = {"act": {}, "bf16": {}}
+        for fmt, arena16 in self._arena16.items():
+            if fmt == "bf16" and ACT == torch.bfloat16:
+                arena16 = self._arena16["act"]                       # one format: one copy
+            else:
+                nv.cast_f32_bf16(self.opt.arena[:n4], arena16[:n4])
+            for name in self.names:
+                if name.endswith(("mlp.fc1.weight", "mlp.fc2.weight")):
+                    off, k = self._slot[name]
+                    if off % 8 == 0 and off + k <= n4:   # 16-byte aligned rows for the TMA descriptor
+                        p16[fmt][name] = arena16[off:off + k].view(p[name].shape)
         self.enc = {}
         for m in self.mods:
             pre = f"encoders.{m}.seg_model.model."
             self.enc[m] = ConvNeXtV2EncoderTrain({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}, self.depths,
-                                                 self.dims, params16={k[len(pre):]: v for k, v in p16.items() if k.startswith(pre)})
+                                                 self.dims, params16={fmt: {k[len(pre):]: v for k, v in d16.items() if k.startswith(pre)}
+                                                                      for fmt, d16 in p16.items()})
         pre = f"main_decoders.{self.task}.seg_model."
         both = {**p, **self.buffers}
         self.dec = UnetDecoderTrain({k[len(pre):]: v for k, v in both.items() if k.startswith(pre)})
         self.fuse = None
         if len(self.mods) > 1:
-            self.fuse = [(p[f"fusion_handler.conv_f.{i}.weight"].detach().reshape(c, -1).to(torch.bfloat16).contiguous(),
+            # (forward-format weight, bf16 weight for the data gradient, bias)
+            self.fuse = [(p[f"fusion_handler.conv_f.{i}.weight"].detach().reshape(c, -1).to(ACT).contiguous(),
+                          p[f"fusion_handler.conv_f.{i}.weight"].detach().reshape(c, -1).to(torch.bfloat16).contiguous(),
                           p[f"fusion_handler.conv_f.{i}.bias"].detach().float().contiguous()) for i, c in enumerate(self.dims)]
 
     # ------------------------------------------------------------------ gradient arena + bucketed all-reduce
@@ -175,8 +184,8 @@ class ConvNeXtUNetTrainer:
             fused = feats[self.mods[0]]
         else:
             fused, cats = [], []
-            for i, (w, b) in enumerate(self.fuse):
-                cat = torch.cat([_to_bf16(feats[m][i]) for m in self.mods], dim=-1).contiguous()      # [B,h,h,sum C]
+            for i, (w, _, b) in enumerate(self.fuse):
+                cat = torch.cat([_to_act(feats[m][i]) for m in self.mods], dim=-1).contiguous()       # [B,h,h,sum C]
                 B, h, _, ct = cat.shape
                 cats.append(cat)
                 fused.append(nv.gemm_bf16(cat.view(-1, ct), w, nv.EPI_F32, bias=b).view(B, h, h, -1))
@@ -193,7 +202,7 @@ class ConvNeXtUNetTrainer:
             dfeats = {self.mods[0]: dfused}
         else:
             dfeats = {m: [] for m in self.mods}
-            for i, (w, b) in enumerate(self.fuse):
+            for i, (_, w, b) in enumerate(self.fuse):
                 cat = cats[i]
                 B, h, _, ct = cat.shape
                 dcat, dw, db = nv.linear_backward(_to_bf16(dfused[i].reshape(-1, self.dims[i])), cat.view(-1, ct), w)

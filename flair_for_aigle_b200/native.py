@@ -20,7 +20,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "_native" / (
 _lib: Optional[ctypes.CDLL] = None
 
 F32, BF16, F16 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 EPI_OPERANDS_F16 = 0x200
 NCHW, NHWC, NHWC_UP4 = 0, 1, 2
 EPI_BF16, EPI_GELU_SUMSQ, EPI_RESID_F32, EPI_F32, EPI_RELU_BF16, EPI_GELU_BF16 = 0, 1, 2, 3, 4, 5
@@ -124,27 +124,28 @@ _SIGNATURES = {
     "fz_dwconv7_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_dwconv7_f32_add": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_dwconv7_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "fz_layernorm_fwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
+    "fz_layernorm_fwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _i, _vp],
     "fz_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "fz_gelu_fwd": [_vp, _vp, _i64, _vp],
     "fz_sample_colreduce": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "fz_sample_colreduce2": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
-    "fz_gelu_fwd_sumsq": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
-    "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp],
+    "fz_sample_colreduce2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_gelu_fwd_sumsq": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _i, _vp],
     "fz_grn_gelu_backward": [_vp] * 14 + [_i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_gelu_backward_db": [_vp] * 15 + [_i, _i, _i, ctypes.c_float, _vp],
-    "fz_grn_gelu_backward_saved": [_vp] * 15 + [_i, _i, _i, ctypes.c_float, _vp],
+    "fz_grn_gelu_backward_saved": [_vp] * 15 + [_i, _i, _i, ctypes.c_float, _i, _vp],
+    "fz_cast_f16_bf16": [_vp, _vp, _i64, _vp],
     "fz_add_f32": [_vp, _vp, _vp, _i64, _vp],
     "fz_reduce_rows_f32": [_vp, _vp, _i, _i, _vp],
-    "fz_layernorm_fwd_stats2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp],
+    "fz_layernorm_fwd_stats2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _i, _vp],
     "fz_s2d_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "fz_patchify4_nchw": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "fz_patchify4_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_im2col3x3_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_conv3x3_small_supported": [_i, _i, _i, _i],
-    "fz_conv3x3_small_forward": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "fz_conv3x3_small_wgrad": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "fz_conv3x3_small_forward": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "fz_conv3x3_small_wgrad": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "fz_col2im3x3": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "fz_bn_relu_train_forward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, ctypes.c_float, _vp],
+    "fz_bn_relu_train_forward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, ctypes.c_float, _i, _vp],
     "fz_bn_relu_backward": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _vp],
     "fz_bn_update_running": [_vp, _vp, _vp, _vp, _i, _i64, ctypes.c_float, ctypes.c_float, _vp],
     "fz_upsample2_concat_backward": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -829,11 +830,20 @@ def _stream_pool(device, n: int):
 
 
 def weight_gradient(dY: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
-    """fp32 [N,K] = dY^T X for dY [M,N] and X [M,K] (16-bit, same format): split-K, operands read in place.  Rows are padded
+    """fp32 [N,K] = dY^T X for dY [M,N] and X [M,K] (16-bit; same format, or bf16 dY with fp16 X): split-K, operands read in place.  Rows are padded
     to a multiple of 64 (the reduction's k-block) only when needed; shapes the MN-major kernel does not take (N % 8 != 0 or
     K % 64 != 0) go through transposed copies."""
     M, N = dY.shape
     K = X.shape[1]
+    if X.dtype != dY.dtype:
+        # bf16 gradients x fp16 forward activations: one MMA takes one operand format (a mixed descriptor is an illegal
+        # instruction), so the activations are re-rounded to bf16 here -- a benign rounding, the gradient noise that matters
+        # comes from the FORWARD values (tests/diag/grad_precision_budget.py)
+        if dY.dtype != torch.bfloat16 or X.dtype != torch.float16:
+            raise NativeError(f"weight_gradient: formats {dY.dtype} / {X.dtype} (bfloat16 gradients with float16 or bfloat16 activations)")
+        Xb = torch.empty(X.shape, dtype=torch.bfloat16, device=X.device)
+        _check(lib().fz_cast_f16_bf16(_ptr(X.contiguous()), _ptr(Xb), X.numel(), _stream()), "fz_cast_f16_bf16")
+        X = Xb
     if M % 64:
         Mp = (M + 63) // 64 * 64
         dYp = torch.zeros((Mp, N), dtype=dY.dtype, device=dY.device)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FZ_ABI_VERSION 2
+#define FZ_ABI_VERSION 3
 
 const char* fz_last_error(void);
 int fz_abi_version(void);
@@ -375,7 +375,7 @@ int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, float* db, int 
 /* LayerNorm over C with saved row statistics (training forward), and its backward: dx float [M][C]; dgamma_dbeta float [2][C]
  * (partial = float [blocks][2][C] workspace; blocks fixes the reduction order). */
 int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, float* mean, float* rstd,
-                           int64_t M, int C, float eps, void* stream);
+                           int64_t M, int C, float eps, int out_f16, void* stream);
 int fz_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* g, float* dx,
                      float* partial, float* dgamma_dbeta, int64_t M, int C, int blocks, void* stream);
 /* exact (erf) GELU on bf16. */
@@ -383,13 +383,15 @@ int fz_gelu_fwd(const void* h_bf16, void* g_bf16, int64_t n, void* stream);
 /* out float [B][C] = sum over a sample's HW rows of a*a (mode 0), a*b (1) or a (2); a, b bf16 [B][HW][C]. */
 int fz_sample_colreduce(const void* a_bf16, const void* b_bf16, float* out, int B, int HW, int C, int mode, void* stream);
 /* s1 = sum_hw a*b and s0 = sum_hw a in ONE pass over both tensors (C % 8 == 0): the GRN backward's two reductions. */
-int fz_sample_colreduce2(const void* a_bf16, const void* b_bf16, float* s1, float* s0, int B, int HW, int C, void* stream);
+int fz_sample_colreduce2(const void* a_bf16, const void* b_16, float* s1, float* s0, int B, int HW, int C, int b_f16,
+                         void* stream);
 /* g = GELU(h) (bf16, stored), optionally GELU'(h) (bf16, stored; NULL = not wanted), and sumsq float [B][C] = sum_hw g^2 of
  * the stored values, one pass (C % 8 == 0).  erf through Abramowitz-Stegun 7.1.26, |Phi error| <= 3e-7. */
-int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, void* dgelu_bf16, float* sumsq, int B, int HW, int C, void* stream);
+int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, void* dgelu_bf16, float* sumsq, int B, int HW, int C, int act_f16,
+                      void* stream);
 /* GRN, training forward: gx = sqrt(sumsq), mu = mean_c gx, nx = gx / (mu + eps), y = g (1 + gamma nx) + beta. */
 int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* gamma, const float* beta, float* gx, float* nx,
-                         float* mu, void* y_bf16, int B, int HW, int C, float eps, void* stream);
+                         float* mu, void* y_bf16, int B, int HW, int C, float eps, int act_f16, void* stream);
 /* GRN + GELU backward: dy = gradient at the GRN output, g = GELU(h), s1 = sum_hw dy g, s0 = sum_hw dy (fz_sample_colreduce);
  * dh bf16 = gradient at the pre-GELU activations; dgamma / dbeta float [C]; coef_a / coef_b float [B][C] workspaces. */
 int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1, const float* s0,
@@ -405,7 +407,7 @@ int fz_grn_gelu_backward_db(const void* dy_bf16, const void* g_bf16, const void*
 int fz_grn_gelu_backward_saved(const void* dy_bf16, const void* g_bf16, const void* dgelu_bf16, const float* s1,
                                const float* s0, const float* gx, const float* nx, const float* mu, const float* gamma,
                                float* coef_a, float* coef_b, float* dgamma, float* dbeta, void* dh_bf16, float* dbias, int B,
-                               int HW, int C, float eps, void* stream);
+                               int HW, int C, float eps, int act_f16, void* stream);
 /* ---- U-Net decoder convolutions of the training step without im2col (csrc/conv3x3_small.cu): 3x3 / pad 1 on bf16 NHWC maps
  * with H % 8 == 0, W % 32 == 0 and 16 / 32 / 48 / 64 channels on either side (fz_conv3x3_small_supported: 1 / 0).
  * forward: out[px][co] = bias[co] + sum_tap sum_ci in[px + tap][ci] * w[tap][co][ci], w bf16 [9][Cout][Cin], tap = ky*3 + kx;
@@ -415,20 +417,29 @@ int fz_grn_gelu_backward_saved(const void* dy_bf16, const void* g_bf16, const vo
  * live in a per-device scratch buffer grown on demand and are added in a fixed order. */
 int fz_conv3x3_small_supported(int H, int W, int Cin, int Cout);
 int fz_conv3x3_small_forward(const void* in_bf16, const void* w_bf16, const float* bias, void* out, int out_bf16, int B, int H,
-                             int W, int Cin, int Cout, int n_store, int ldo, void* stream);
+                             int W, int Cin, int Cout, int n_store, int ldo, int in_f16, void* stream);
 int fz_conv3x3_small_wgrad(const void* x_bf16, const void* dconv_bf16, int ldd, float* dw, int B, int H, int W, int Cin,
-                           int Cout, void* stream);
+                           int Cout, int x_f16, void* stream);
+/* IEEE fp16 -> bf16 (round to nearest even), n values, 16-byte aligned buffers: the forward activations on their way into a
+ * weight-gradient GEMM whose other operand is a bf16 gradient. */
+int fz_cast_f16_bf16(const void* in_f16, void* out_bf16, int64_t n, void* stream);
 int fz_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* out float [N] = sum over s of partial float [S][N], in the order s = 0 .. S-1 (split reductions stay reproducible). */
 int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* stream);
-/* Encoder plumbing of the same slice: LayerNorm with a bf16 and / or an fp32 output (LayerNorm2d of the stem feeds the fp32
+/* FORMATS of the training step's 16-bit tensors.  Gradients are bf16 (range).  FORWARD activations -- LayerNorm outputs, the
+ * hidden tensors h / GELU(h) / GELU'(h) / GRN output, decoder activations, stem patches, im2col rows -- are bf16 or, where an
+ * entry point takes an `act_f16` / `out_f16` / `in_f16` / `x_f16` / `b_f16` flag set to 1, IEEE fp16 (the trainer's choice:
+ * tests/diag/grad_precision_budget.py shows the bf16 rounding of the forward tensors alone costs the gradients 0.8 % of
+ * cosine against fp32 autograd, fp16 0.1 %).  The pointer parameters keep their *_bf16 names.  fz_bn_relu_backward reads its
+ * `y_bf16` for the sign only and accepts either format.
+ * Encoder plumbing of the same slice: LayerNorm with a bf16 and / or an fp32 output (LayerNorm2d of the stem feeds the fp32
  * residual stream, the one in front of a downsample conv feeds a GEMM); space-to-depth for the 2x2/s2 convolutions as GEMMs,
  * k = (ky*s + kx)*C + c, and its inverse (inverse = 1: `in` is the [B][H/s][W/s][s*s*C] side); the stem's 4x4/s4 patches of a
  * normalised fp32 NCHW tile as bf16 rows [B*(P/4)^2][Kpad], k = (c*4 + ky)*4 + kx, zero padded to Kpad. */
 int fz_layernorm_fwd_stats2(const float* x, const float* g, const float* b, void* out_bf16, float* out_f32, float* mean,
-                            float* rstd, int64_t M, int C, float eps, void* stream);
+                            float* rstd, int64_t M, int C, float eps, int out_f16, void* stream);
 int fz_s2d_bf16(const void* in, void* out, int B, int H, int W, int C, int s, int inverse, void* stream);
-int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin, int P, int Kpad, void* stream);
+int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin, int P, int Kpad, int out_f16, void* stream);
 /* U-Net decoder, training mode (smp UnetDecoder block: nearest x2 -> concat skip -> [conv3x3 -> BatchNorm -> ReLU] x 2):
  * the 3x3 convolutions run as GEMMs over an explicit im2col (correctness-first; col bf16 [B*H*W][Kpad], k = (ky*3+kx)*C + c)
  * with col2im as the data gradient; BatchNorm uses the batch statistics (biased variance) and keeps mean / rstd; x is the
@@ -437,7 +448,8 @@ int fz_patchify4_nchw(const float* in, void* out_bf16, int B, int Cin, int P, in
 int fz_im2col3x3_bf16(const void* in, void* col, int B, int H, int W, int C, int Kpad, void* stream);
 int fz_col2im3x3(const void* dcol_bf16, float* dx, int B, int H, int W, int C, int Kpad, void* stream);
 int fz_bn_relu_train_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* mean,
-                             float* rstd, float* workspace, int64_t M, int C, int chunks, float eps, void* stream);
+                             float* rstd, float* workspace, int64_t M, int C, int chunks, float eps, int out_f16,
+                             void* stream);
 int fz_bn_relu_backward(const float* x, int ldx, const void* dy_bf16, const void* y_bf16, const float* mean, const float* rstd,
                         const float* gamma, void* dx_bf16, int ldd, float* dbeta_dgamma, float* workspace, int64_t M, int C,
                         int chunks, void* stream);

@@ -192,7 +192,8 @@ def test_conv_bn_relu_layer_backward(cuda, cin, cout, H):
     nbt = torch.zeros((), dtype=torch.long, device=cuda)
     eng = Conv3x3BnReluTrain(layer[0].weight.detach(), layer[1].weight.detach(), layer[1].bias.detach(),
                              running=(rm0.zero_(), rv0.fill_(1.0), nbt))          # nn.BatchNorm2d's initial buffers
-    y = eng.forward(x.detach().permute(0, 2, 3, 1).contiguous().bfloat16())
+    from flair_for_aigle_b200.engine.convnext_train import ACT            # the forward activation format (fp16)
+    y = eng.forward(x.detach().permute(0, 2, 3, 1).contiguous().to(ACT))
     dm = float((rm0 - layer[1].running_mean).abs().max())
     dv = float(((rv0 - layer[1].running_var).abs() / layer[1].running_var).max())
     print(f"{cin}->{cout} running stats after one forward: max |d mean| {dm:.2e}, max rel d var {dv:.2e}")
@@ -207,19 +208,25 @@ def test_conv_bn_relu_layer_backward(cuda, cin, cout, H):
         assert cos > 0.9999 and err < 3e-2, (name, cos, err)
 
 
+@pytest.mark.parametrize("act", ["bf16", "f16"])
 @pytest.mark.parametrize("cin,cout,B,H,W", [(16, 16, 2, 16, 64), (32, 16, 1, 8, 32), (64, 32, 2, 24, 96), (48, 32, 1, 16, 32),
                                             (16, 13, 1, 32, 32), (32, 64, 1, 8, 64)])
-def test_conv3x3_small_kernels_vs_autograd(cuda, cin, cout, B, H, W):
+def test_conv3x3_small_kernels_vs_autograd(cuda, cin, cout, B, H, W, act):
     """csrc/conv3x3_small.cu called directly: forward, data gradient (the forward kernel on the flipped, transposed weights)
-    and weight gradient against torch autograd of F.conv2d on the same bf16-rounded operands (fp32 accumulation on both
-    sides: differences are summation order only).  Odd Cout (the head's 13 classes) is zero padded to 16."""
+    and weight gradient against torch autograd of F.conv2d on the same 16-bit-rounded operands (fp32 accumulation on both
+    sides: differences are summation order only).  Odd Cout (the head's 13 classes) is zero padded to 16.  ``act``: format of
+    the forward activations and forward weights (the trainer uses fp16); gradients and data-gradient weights are bf16, the
+    weight gradient converts the fp16 activations to bf16 while staging them (that rounding is part of its reference here)."""
     import torch.nn.functional as F
     from flair_for_aigle_b200 import native as nv
     L, P, S = nv.lib(), nv._ptr, nv._stream
     g = torch.Generator(device="cpu").manual_seed(cin * 100 + cout)
     coutp = (cout + 15) // 16 * 16
-    x = torch.randn(B, H, W, cin, generator=g).to(cuda).to(torch.bfloat16)
-    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.1).to(cuda).to(torch.bfloat16)
+    ACT, F16 = (torch.float16, 1) if act == "f16" else (torch.bfloat16, 0)
+    x = torch.randn(B, H, W, cin, generator=g).to(cuda).to(ACT)
+    # weights exactly representable in both formats, so that one tensor serves the forward (ACT) and the data gradient (bf16)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.1).to(cuda).to(torch.bfloat16).to(torch.float16).to(torch.bfloat16)
+    assert torch.equal(w.float(), w.to(torch.float16).float())
     dy = torch.zeros(B, H, W, coutp, device=cuda, dtype=torch.bfloat16)
     dy[..., :cout] = torch.randn(B, H, W, cout, generator=g).to(cuda).to(torch.bfloat16)
     bias = torch.zeros(coutp, device=cuda)
@@ -232,31 +239,35 @@ def test_conv3x3_small_kernels_vs_autograd(cuda, cin, cout, B, H, W):
         ref = F.conv2d(xr, wr, bias[:cout], padding=1)
         ref.backward(dy[..., :cout].float().permute(0, 3, 1, 2))
 
-    wf = torch.zeros(9, coutp, cin, device=cuda, dtype=torch.bfloat16)
-    wf[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    wf = torch.zeros(9, coutp, cin, device=cuda, dtype=ACT)
+    wf[:, :cout] = w.to(ACT).permute(2, 3, 0, 1).reshape(9, cout, cin)
     out = torch.full((B * H * W, coutp), float("nan"), device=cuda)
-    nv._check(L.fz_conv3x3_small_forward(P(x), P(wf), P(bias), P(out), 0, B, H, W, cin, coutp, coutp, coutp, S()), "fwd")
+    nv._check(L.fz_conv3x3_small_forward(P(x), P(wf), P(bias), P(out), 0, B, H, W, cin, coutp, coutp, coutp, F16, S()), "fwd")
     got = out.view(B, H, W, coutp)[..., :cout].permute(0, 3, 1, 2)
     e_f = float((got - ref).abs().max() / ref.std())
     assert bool(torch.isfinite(out).all()) and float(out[:, cout:].abs().max() if coutp > cout else 0.0) == 0.0
 
     if cout <= 32:
         dw = torch.full((9, coutp, cin), float("nan"), device=cuda)
-        nv._check(L.fz_conv3x3_small_wgrad(P(x), P(dy), coutp, P(dw), B, H, W, cin, coutp, S()), "wgrad")
+        nv._check(L.fz_conv3x3_small_wgrad(P(x), P(dy), coutp, P(dw), B, H, W, cin, coutp, F16, S()), "wgrad")
         gw = dw[:, :cout].permute(1, 2, 0).reshape(cout, cin, 3, 3)
-        e_w = float((gw - wr.grad).abs().max() / wr.grad.std())
+        ref_w = wr.grad
+        if F16:                       # the kernel multiplies bf16(x): its exact reference is the gradient taken at bf16(x)
+            xb = x.to(torch.bfloat16).float().permute(0, 3, 1, 2)
+            ref_w = torch.autograd.grad(F.conv2d(xb, wr, None, padding=1), wr, dy[..., :cout].float().permute(0, 3, 1, 2))[0]
+        e_w = float((gw - ref_w).abs().max() / ref_w.std())
     else:
         e_w = 0.0
 
     wd = torch.zeros(9, cin, coutp, device=cuda, dtype=torch.bfloat16)
     wd[:, :, :cout] = w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, cin, cout)
     dx = torch.full((B * H * W, cin), float("nan"), device=cuda)
-    nv._check(L.fz_conv3x3_small_forward(P(dy), P(wd), None, P(dx), 0, B, H, W, coutp, cin, cin, cin, S()), "dgrad")
+    nv._check(L.fz_conv3x3_small_forward(P(dy), P(wd), None, P(dx), 0, B, H, W, coutp, cin, cin, cin, 0, S()), "dgrad")
     gx = dx.view(B, H, W, cin).permute(0, 3, 1, 2)
     e_x = float((gx - xr.grad).abs().max() / xr.grad.std())
     # bf16 output of the same call
     dxb = torch.empty((B * H * W, cin), device=cuda, dtype=torch.bfloat16)
-    nv._check(L.fz_conv3x3_small_forward(P(dy), P(wd), None, P(dxb), 1, B, H, W, coutp, cin, cin, cin, S()), "dgrad bf16")
+    nv._check(L.fz_conv3x3_small_forward(P(dy), P(wd), None, P(dxb), 1, B, H, W, coutp, cin, cin, cin, 0, S()), "dgrad bf16")
     torch.cuda.synchronize()
     print(f"{cin}->{cout} {B}x{H}x{W}: forward {e_f:.2e}, weight gradient {e_w:.2e}, data gradient {e_x:.2e} (max err / std)")
     assert e_f < 1e-4 and e_w < 1e-4 and e_x < 1e-4

@@ -230,3 +230,21 @@ def test_gemm_splitk_transposed_operands_in_place(cuda, M, N, K, splits, dt):
     dW = nv.weight_gradient(At[:K - 3], Bt[:K - 3])
     ref2 = At[:K - 3].double().t() @ Bt[:K - 3].double()
     assert (dW.double() - ref2).abs().max().item() < 5e-4 * max(ref2.std().item(), 1e-6)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 128, 16384), (64, 320, 65536), (2048, 512, 4096), (16, 64, 8192)])
+def test_weight_gradient_bf16_gradients_times_fp16_activations(cuda, M, N, K):
+    """The training weight gradient dW = dY^T X with dY in bf16 (gradient range) and X in fp16 (the forward activations'
+    format).  One tcgen05 MMA takes one operand format (a descriptor with a_format = BF16 and b_format = F16 was tried: illegal
+    instruction), so ``weight_gradient`` re-rounds X to bf16 (fz_cast_f16_bf16) and the GEMM itself rejects the mix."""
+    from flair_for_aigle_b200 import native as nv
+    torch.manual_seed(M + N)
+    dY = (torch.randn(K, M, device=cuda) * 0.5).to(torch.bfloat16)
+    X = (torch.randn(K - 3, N, device=cuda) * 0.5).to(torch.float16)
+    dW = nv.weight_gradient(dY[:K - 3], X)
+    ref = dY[:K - 3].double().t() @ X.to(torch.bfloat16).double()            # X rounded to bf16: what the kernel multiplies
+    assert (dW.double() - ref).abs().max().item() < 5e-4 * ref.std().item()
+    exact = dY[:K - 3].double().t() @ X.double()
+    print(f"[{M}x{N}] K={K}: re-rounding the activations to bf16 moves dW by {(ref - exact).abs().max().item() / exact.std().item():.1e} of its std")
+    with pytest.raises(nv.NativeError):
+        nv.gemm_splitk_tn(dY[:K - 3], X)

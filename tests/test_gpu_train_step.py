@@ -39,7 +39,7 @@ def test_training_step_vs_oracle(cuda, mods):
     loss, preds, grads = trainer.forward_backward(batch)
     torch.cuda.synchronize()
     print(f"loss {float(loss):.5f} vs oracle {float(ref_loss):.5f}; predictions equal {(preds == ref_preds[TASK]).float().mean().item():.4f}")
-    assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss))
+    assert abs(float(loss) - float(ref_loss)) <= 1e-3 * abs(float(ref_loss))                 # measured 3e-6
     worst, tot_dot, tot_a, tot_b = (1.0, ""), 0.0, 0.0, 0.0
     for n, p in oracle.named_parameters():
         if p.grad is None:                      # fusion_handler.conv_f is unused with a single modality
@@ -52,10 +52,12 @@ def test_training_step_vs_oracle(cuda, mods):
     total = tot_dot / (tot_a ** 0.5 * tot_b ** 0.5)
     print(f"{len(grads)} parameter gradients: whole-model cosine {total:.5f}, norm ratio {(tot_a / tot_b) ** 0.5:.4f}, "
           f"worst tensor {worst[0]:.4f} at {worst[1]}")
-    # measured (bf16 operands, fp32 accumulate, split-K weight gradients): whole model 0.985 (one encoder) / 0.991 (two),
-    # norm ratio 1.002, worst single tensor 0.959 / 0.969 -- asserted with a small margin (round 1 asserted 0.97 / 0.8)
-    assert total > 0.98 and 0.98 < (tot_a / tot_b) ** 0.5 < 1.02
-    assert worst[0] > 0.94
+    # measured with the fp16 forward (fp16 activations and forward weights, bf16 gradients, fp32 accumulation, split-K weight
+    # gradients): whole model 0.9984 (one encoder) / 0.9987 (two), norm ratio 1.000, worst single tensor 0.9958 / 0.9953.
+    # With a bf16 forward the same engine measured 0.985 / 0.990 and 0.957 / 0.968: tests/diag/grad_precision_budget.py shows
+    # the forward rounding alone accounts for that.  Asserted with a small margin (the round-1 verdict asked for 0.995 / 0.95).
+    assert total > 0.997 and 0.99 < (tot_a / tot_b) ** 0.5 < 1.01
+    assert worst[0] > 0.99
 
     # a few optimizer steps on the same batch: both sides must go down the same way
     opt = init_optimizer({**ocfg, "learning_rate": 2e-4}, oracle.parameters())

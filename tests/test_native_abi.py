@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     # the ctypes binding covers the same set
     assert sorted(nv.exported_symbols()) == declared
-    assert nv.lib().fz_abi_version() == nv.ABI_VERSION == 2
+    assert nv.lib().fz_abi_version() == nv.ABI_VERSION == 3
     assert nv.lib().fz_operand_format() == nv.F16 and nv.op_dtype() == torch.float16     # the product build stores fp16
 
 
