@@ -327,7 +327,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256) ln_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                            const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
                                                            float* __restrict__ out_f32, float* __restrict__ mean,
-                                                           float* __restrict__ rstd, int64_t M, int C, float eps, int out_f16) {
+                                                           float* __restrict__ rstd, int64_t M, int C, float eps, int out_f16,
+                                                           __nv_bfloat16* __restrict__ out2) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= M) return;
@@ -348,6 +349,7 @@ __global__ void __launch_bounds__(256) ln_fwd_stats_kernel(const float* __restri
       else out[r * C + c] = __float2bfloat16_rn(v2);
     }
     if (out_f32) out_f32[r * C + c] = v2;
+    if (out2) out2[r * C + c] = __float2bfloat16_rn(v2);
   }
   if (lane == 0) {
     mean[r] = mu;
@@ -441,7 +443,8 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                          const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
                                                          float* __restrict__ out_f32, float* __restrict__ mean,
-                                                         float* __restrict__ rstd, int64_t M, float eps, int out_f16) {
+                                                         float* __restrict__ rstd, int64_t M, float eps, int out_f16,
+                                                         __nv_bfloat16* __restrict__ out2) {
   constexpr int C = 128 * NV;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -469,6 +472,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
     const float o[4] = {v[k].x * rs * gg.x + bb.x, v[k].y * rs * gg.y + bb.y, v[k].z * rs * gg.z + bb.z,
                         v[k].w * rs * gg.w + bb.w};
     if (out) store4_16(out + r * C + c, o, out_f16);
+    if (out2) store4_16(out2 + r * C + c, o, false);
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
   if (lane == 0) {
@@ -722,8 +726,8 @@ __global__ void __launch_bounds__(256) grn_gelu_bwd_kernel(const __nv_bfloat16* 
 // 16-byte payload load.  grid (slabs, chunks, B).
 __global__ void __launch_bounds__(256) grn_apply_rows_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ nx,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             __nv_bfloat16* __restrict__ y, int rows, int C, int cgs,
-                                                             int rows_per_chunk, int act_f16) {
+                                                             __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
+                                                             int rows, int C, int cgs, int rows_per_chunk, int act_f16) {
   const int rp = 256 / cgs;
   const int cl = threadIdx.x % cgs, rr = threadIdx.x / cgs;
   const int cg = blockIdx.x * cgs + cl;
@@ -745,7 +749,11 @@ __global__ void __launch_bounds__(256) grn_apply_rows_kernel(const __nv_bfloat16
     rv_load8(g + o, v, act_f16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = v[j] * ca[j] + be[j];
+    float v2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v2[j] = v[j];
     rv_store8_round(y + o, v, act_f16);
+    if (y2) rv_store8_round(y2 + o, v2, false);        // a bf16 copy of the same values: the weight gradient's operand
   }
 }
 
@@ -1202,15 +1210,15 @@ typedef __nv_bfloat16* bf;
 
 // C = 128 * NV rows: the register-resident LayerNorm forward; false = shape not covered (caller takes the scalar kernel)
 static bool launch_ln_fwd_vec(const float* x, const float* g, const float* b, bf out, float* out_f32, float* mean, float* rstd,
-                              int64_t M, int C, float eps, int out_f16, cudaStream_t st) {
+                              int64_t M, int C, float eps, int out_f16, bf out2, cudaStream_t st) {
   const unsigned grid = static_cast<unsigned>((M + 7) / 8);
   switch (C % 128 == 0 ? C / 128 : 0) {
-    case 1: ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
-    case 2: ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
-    case 3: ln_fwd_vec_kernel<3><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
-    case 4: ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
-    case 6: ln_fwd_vec_kernel<6><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
-    case 8: ln_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16); return true;
+    case 1: ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16, out2); return true;
+    case 2: ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16, out2); return true;
+    case 3: ln_fwd_vec_kernel<3><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16, out2); return true;
+    case 4: ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16, out2); return true;
+    case 6: ln_fwd_vec_kernel<6><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16, out2); return true;
+    case 8: ln_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(x, g, b, out, out_f32, mean, rstd, M, eps, out_f16, out2); return true;
     default: return false;
   }
 }
@@ -1311,12 +1319,13 @@ extern "C" int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, floa
   return 0;
 }
 
-extern "C" int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, float* mean, float* rstd,
-                                      int64_t M, int C, float eps, int out_f16, void* stream) {
+extern "C" int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, void* out2_bf16, float* mean,
+                                      float* rstd, int64_t M, int C, float eps, int out_f16, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && x && g && b && out_bf16 && mean && rstd, "fz_layernorm_fwd_stats: bad arguments");
-  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), nullptr, mean, rstd, M, C, eps, out_f16, ST(stream)))
-    ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
-                                                                                   nullptr, mean, rstd, M, C, eps, out_f16);
+  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), nullptr, mean, rstd, M, C, eps, out_f16,
+                         reinterpret_cast<bf>(out2_bf16), ST(stream)))
+    ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(
+        x, g, b, reinterpret_cast<bf>(out_bf16), nullptr, mean, rstd, M, C, eps, out_f16, reinterpret_cast<bf>(out2_bf16));
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1388,8 +1397,8 @@ extern "C" int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, void* dgelu_b
 }
 
 extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* gamma, const float* beta, float* gx,
-                                    float* nx, float* mu, void* y_bf16, int B, int HW, int C, float eps, int act_f16,
-                                    void* stream) {
+                                    float* nx, float* mu, void* y_bf16, void* y2_bf16, int B, int HW, int C, float eps,
+                                    int act_f16, void* stream) {
   FZ_REQUIRE(B > 0 && HW > 0 && C > 0 && g_bf16 && sumsq && gamma && beta && gx && nx && mu && y_bf16,
              "fz_grn_train_forward: bad arguments");
   grn_norms_kernel<<<B, 256, 0, ST(stream)>>>(sumsq, gx, nx, mu, C, eps);
@@ -1397,7 +1406,8 @@ extern "C" int fz_grn_train_forward(const void* g_bf16, const float* sumsq, cons
   FZ_REQUIRE(C % 8 == 0 && per < (1LL << 31) && B <= 65535, "fz_grn_train_forward: C %% 8, HW*C < 2^31, B <= 65535");
   const RvGeom geo = rv_geometry(B, HW, C, rv_resident(grn_apply_rows_kernel));
   grn_apply_rows_kernel<<<dim3(geo.slabs, geo.chunks, B), 256, 0, ST(stream)>>>(
-      reinterpret_cast<cbf>(g_bf16), nx, gamma, beta, reinterpret_cast<bf>(y_bf16), HW, C, geo.cgs, geo.rows_per_chunk, act_f16);
+      reinterpret_cast<cbf>(g_bf16), nx, gamma, beta, reinterpret_cast<bf>(y_bf16), reinterpret_cast<bf>(y2_bf16), HW, C,
+      geo.cgs, geo.rows_per_chunk, act_f16);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1477,9 +1487,9 @@ extern "C" int fz_add_f32(const float* a, const float* b, float* out, int64_t n,
 extern "C" int fz_layernorm_fwd_stats2(const float* x, const float* g, const float* b, void* out_bf16, float* out_f32,
                                        float* mean, float* rstd, int64_t M, int C, float eps, int out_f16, void* stream) {
   FZ_REQUIRE(M > 0 && C > 0 && x && g && b && (out_bf16 || out_f32) && mean && rstd, "fz_layernorm_fwd_stats2: bad arguments");
-  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), out_f32, mean, rstd, M, C, eps, out_f16, ST(stream)))
+  if (!launch_ln_fwd_vec(x, g, b, reinterpret_cast<bf>(out_bf16), out_f32, mean, rstd, M, C, eps, out_f16, nullptr, ST(stream)))
     ln_fwd_stats_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, ST(stream)>>>(x, g, b, reinterpret_cast<bf>(out_bf16),
-                                                                                   out_f32, mean, rstd, M, C, eps, out_f16);
+                                                                                   out_f32, mean, rstd, M, C, eps, out_f16, nullptr);
   FZ_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

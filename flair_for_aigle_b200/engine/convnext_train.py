@@ -65,11 +65,14 @@ class ConvNeXtBlockTrain:
         x = x.contiguous()
         u = torch.empty_like(x)
         _chk(_L().fz_dwconv7_f32(_P(x), _P(self.w_dw), _P(self.b_dw), _P(u), B, H, W, C, 0, _S()), "fz_dwconv7_f32")
+        # forward operands in ACT (used once, by the GEMM right after); what the backward keeps are bf16 copies written by the
+        # same kernels: the weight-gradient GEMMs multiply them with bf16 gradients and one MMA takes one operand format
         a1 = torch.empty((M, C), dtype=ACT, device=dev)
+        a1b = torch.empty((M, C), dtype=torch.bfloat16, device=dev) if ACT_F16 else None
         mean = torch.empty(M, dtype=torch.float32, device=dev)
         rstd = torch.empty(M, dtype=torch.float32, device=dev)
-        _chk(_L().fz_layernorm_fwd_stats(_P(u), _P(self.ln_w), _P(self.ln_b), _P(a1), _P(mean), _P(rstd), M, C, self.eps_ln,
-                                         ACT_F16, _S()), "fz_layernorm_fwd_stats")
+        _chk(_L().fz_layernorm_fwd_stats(_P(u), _P(self.ln_w), _P(self.ln_b), _P(a1), _P(a1b), _P(mean), _P(rstd), M, C,
+                                         self.eps_ln, ACT_F16, _S()), "fz_layernorm_fwd_stats")
         h = nv.gemm_bf16(a1, self.w1, nv.EPI_BF16, bias=self.b1)                          # pre-GELU, 16-bit [M,4C]
         g, dg = torch.empty_like(h), torch.empty_like(h)                  # GELU(h) and GELU'(h); h itself is not kept
         sumsq = torch.empty((B, C4), dtype=torch.float32, device=dev)
@@ -77,10 +80,11 @@ class ConvNeXtBlockTrain:
         gx, nx = torch.empty_like(sumsq), torch.empty_like(sumsq)
         mu = torch.empty(B, dtype=torch.float32, device=dev)
         a2 = torch.empty_like(g)
-        _chk(_L().fz_grn_train_forward(_P(g), _P(sumsq), _P(self.grn_w), _P(self.grn_b), _P(gx), _P(nx), _P(mu), _P(a2), B,
-                                       H * W, C4, self.eps_grn, ACT_F16, _S()), "fz_grn_train_forward")
+        a2b = torch.empty(g.shape, dtype=torch.bfloat16, device=dev) if ACT_F16 else None
+        _chk(_L().fz_grn_train_forward(_P(g), _P(sumsq), _P(self.grn_w), _P(self.grn_b), _P(gx), _P(nx), _P(mu), _P(a2),
+                                       _P(a2b), B, H * W, C4, self.eps_grn, ACT_F16, _S()), "fz_grn_train_forward")
         y = nv.gemm_bf16(a2, self.w2, nv.EPI_RESID_F32, bias=self.b2, resid=x.view(M, C))
-        self.saved = (x, u, a1, mean, rstd, dg, g, gx, nx, mu, a2)
+        self.saved = (x, u, a1b if ACT_F16 else a1, mean, rstd, dg, g, gx, nx, mu, a2b if ACT_F16 else a2)
         return y.view(B, H, W, C)
 
     def backward(self, dy: torch.Tensor):

@@ -124,13 +124,13 @@ _SIGNATURES = {
     "fz_dwconv7_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_dwconv7_f32_add": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "fz_dwconv7_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "fz_layernorm_fwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _i, _vp],
+    "fz_layernorm_fwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _i, _vp],
     "fz_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "fz_gelu_fwd": [_vp, _vp, _i64, _vp],
     "fz_sample_colreduce": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "fz_sample_colreduce2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "fz_gelu_fwd_sumsq": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _i, _vp],
+    "fz_grn_train_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _i, _vp],
     "fz_grn_gelu_backward": [_vp] * 14 + [_i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_gelu_backward_db": [_vp] * 15 + [_i, _i, _i, ctypes.c_float, _vp],
     "fz_grn_gelu_backward_saved": [_vp] * 15 + [_i, _i, _i, ctypes.c_float, _i, _vp],

@@ -374,8 +374,8 @@ int fz_dwconv7_f32_add(const float* in, const float* w, const float* bias, const
 int fz_dwconv7_wgrad(const float* x, const float* du, float* dw, float* db, int B, int H, int W, int C, void* stream);
 /* LayerNorm over C with saved row statistics (training forward), and its backward: dx float [M][C]; dgamma_dbeta float [2][C]
  * (partial = float [blocks][2][C] workspace; blocks fixes the reduction order). */
-int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, float* mean, float* rstd,
-                           int64_t M, int C, float eps, int out_f16, void* stream);
+int fz_layernorm_fwd_stats(const float* x, const float* g, const float* b, void* out_bf16, void* out2_bf16, float* mean,
+                           float* rstd, int64_t M, int C, float eps, int out_f16, void* stream);
 int fz_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* g, float* dx,
                      float* partial, float* dgamma_dbeta, int64_t M, int C, int blocks, void* stream);
 /* exact (erf) GELU on bf16. */
@@ -391,7 +391,7 @@ int fz_gelu_fwd_sumsq(const void* h_bf16, void* g_bf16, void* dgelu_bf16, float*
                       void* stream);
 /* GRN, training forward: gx = sqrt(sumsq), mu = mean_c gx, nx = gx / (mu + eps), y = g (1 + gamma nx) + beta. */
 int fz_grn_train_forward(const void* g_bf16, const float* sumsq, const float* gamma, const float* beta, float* gx, float* nx,
-                         float* mu, void* y_bf16, int B, int HW, int C, float eps, int act_f16, void* stream);
+                         float* mu, void* y_bf16, void* y2_bf16, int B, int HW, int C, float eps, int act_f16, void* stream);
 /* GRN + GELU backward: dy = gradient at the GRN output, g = GELU(h), s1 = sum_hw dy g, s0 = sum_hw dy (fz_sample_colreduce);
  * dh bf16 = gradient at the pre-GELU activations; dgamma / dbeta float [C]; coef_a / coef_b float [B][C] workspaces. */
 int fz_grn_gelu_backward(const void* dy_bf16, const void* g_bf16, const void* h_bf16, const float* s1, const float* s0,
@@ -431,7 +431,8 @@ int fz_reduce_rows_f32(const float* partial, float* out, int N, int S, void* str
  * entry point takes an `act_f16` / `out_f16` / `in_f16` / `x_f16` / `b_f16` flag set to 1, IEEE fp16 (the trainer's choice:
  * tests/diag/grad_precision_budget.py shows the bf16 rounding of the forward tensors alone costs the gradients 0.8 % of
  * cosine against fp32 autograd, fp16 0.1 %).  The pointer parameters keep their *_bf16 names.  fz_bn_relu_backward reads its
- * `y_bf16` for the sign only and accepts either format.
+ * `y_bf16` for the sign only and accepts either format.  out2_bf16 / y2_bf16 (may be NULL): a second copy of the output,
+ * always bf16 -- the operand of the weight-gradient GEMM, whose other operand is a bf16 gradient (one MMA, one format).
  * Encoder plumbing of the same slice: LayerNorm with a bf16 and / or an fp32 output (LayerNorm2d of the stem feeds the fp32
  * residual stream, the one in front of a downsample conv feeds a GEMM); space-to-depth for the 2x2/s2 convolutions as GEMMs,
  * k = (ky*s + kx)*C + c, and its inverse (inverse = 1: `in` is the [B][H/s][W/s][s*s*C] side); the stem's 4x4/s4 patches of a
