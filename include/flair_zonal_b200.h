@@ -139,7 +139,8 @@ int fz_convert(const float* img, int C, int h, int w, int mode, uint8_t* out, vo
 #define FZ_EPI_GELU_BF16 5  /* out bf16 = gelu(acc + bias)   (timm Mlp.fc1 + nn.GELU of a Swin block)       */
 #define FZ_EPI_OPERANDS_F16 0x200 /* OR into mode: A, B and a 16-bit output are IEEE fp16 instead of bf16 (same MMA rate,
                                    * 3 more significand bits; outputs saturate at +-65504).  The inference engines use
-                                   * fp16 operands, the training step bf16 (see FZ_OP16 below). */
+                                   * fp16 operands; the training step fp16 for its forward GEMMs and bf16 for its
+                                   * gradient GEMMs (see the format note at the training entry points). */
 int fz_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const float* resid, float* sumsq, int M,
                  int N, int K, int b_batch, int rows_per_sample, int mode, void* stream);
 /* Split-K variant for a small output with a long reduction (the training step's weight gradients dW = dY^T X): out float
