@@ -366,7 +366,7 @@ def train_block(dev, rank: int, world: int, steps: int, warmup: int):
             "roofline": {"bound": "tensor", "achieved": round(tflop_step / (ms_step * 1e-3), 1), "peak": peak,
                          "unit": "TFLOP/s", "frac": round(tflop_step / (ms_step * 1e-3) / peak, 4),
                          "note": f"1.063 TFLOP per sample (fwd + bwd, SURVEY 8d) x {B} / step time; peak = {how} sustained bf16"},
-            "dtype": "bf16 operands, fp32 accumulate / master weights"}
+            "dtype": "fp16 forward operands, bf16 gradient operands, fp32 accumulate / master weights"}
 
 
 def main() -> None:

@@ -1,13 +1,14 @@
-"""Training-mode forward and backward of one ConvNeXt-V2 block (first slice of the model backward):
+"""Training-mode forward and backward of the ConvNeXt-V2 encoder and the U-Net decoder.
 
-    x -> dwconv7x7 (+b) -> LayerNorm(1e-6) -> fc1 -> GELU(erf) -> GRN -> fc2 -> + x         (timm ConvNeXtBlock, use_grn)
+    block:  x -> dwconv7x7 (+b) -> LayerNorm(1e-6) -> fc1 -> GELU(erf) -> GRN -> fc2 -> + x         (timm ConvNeXtBlock, use_grn)
 
 Parameters in the reference's layout (``conv_dw.{weight,bias}``, ``norm.{weight,bias}``, ``mlp.fc1/fc2.{weight,bias}``,
-``mlp.grn.{weight,bias}``); activations NHWC, fp32 residual stream, bf16 GEMM operands with fp32 accumulation -- the same
-number formats as the inference engine.  The Linear layers and their gradients run on the tcgen05 GEMM
-(``native.gemm_bf16`` / ``native.linear_backward``); everything else is csrc/backward_ops.cu.  Correctness first: these
-kernels are not tuned and the block is not yet wired into a model-level backward (decoder, BatchNorm in training mode, stem
-and downsample layers are still missing)."""
+``mlp.grn.{weight,bias}``, smp's ``decoder.blocks.i.conv{1,2}.{0,1}.*``, ``segmentation_head.0.*``); activations NHWC, fp32
+residual stream and accumulation; 16-bit GEMM operands: fp16 for the forward products, bf16 for the gradient products (``ACT``
+below).  The Linear layers and their gradients run on the tcgen05 GEMM (``native.gemm_bf16`` / ``native.linear_backward``),
+the wide decoder convolutions on csrc/conv3x3_small.cu, everything else on csrc/backward_ops.cu.  ``ConvNeXtBlockTrain``,
+``ConvNeXtV2EncoderTrain``, ``Conv3x3BnReluTrain`` and ``UnetDecoderTrain`` each keep what their backward needs between the two
+calls; engine/train_step.py wires them into the model-level step."""
 import os
 from typing import Dict
 
