@@ -15,3 +15,7 @@ $BENCH > gpurun_out/r2_ncu_plain_bench.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 2400 --csv --log-file gpurun_out/r2_ncu_launches.csv $BENCH > gpurun_out/r2_ncu_bench_under_ncu.log 2>&1
 echo "launch list rc=$?"
 timeout 300 python tools/gpu_hbm_kernels_bench.py 2>&1 | tail -16
+echo "--- training step, fp16 forward (default) and bf16 forward (FZ_TRAIN_ACT=bf16)"
+STEPS=3 timeout 300 python tools/gpu_train_step_bench.py 2>&1 | tail -1 | cut -c1-260
+FZ_TRAIN_ACT=bf16 STEPS=3 timeout 300 python tools/gpu_train_step_bench.py 2>&1 | tail -1 | cut -c1-260
+GRAPH=0 timeout 600 python tools/gpu_train_step_profile.py > gpurun_out/r2_train_step_profile_b.txt 2>&1; echo "profile rc=$?"
