@@ -74,16 +74,31 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
     for (int j = 0; j < 8; ++j) b4[j] = p.nobias ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(bp + j);
     float v[32];
     tmem_ld_wait();
+    // packed fp32 adds / FMAs (add / fma.rn.f32x2: two IEEE operations per issue slot, same bits as the scalar forms) wherever
+    // the epilogue works on column pairs: the epilogue, not the MMA, bounds the K = 512 GEMMs
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4[j].x;
-      v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4[j].y;
-      v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
-      v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
+      const float2 lo = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])),
+                                   make_float2(b4[j].x, b4[j].y));
+      const float2 hi = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
+                                   make_float2(b4[j].z, b4[j].w));
+      v[4 * j + 0] = lo.x;
+      v[4 * j + 1] = lo.y;
+      v[4 * j + 2] = hi.x;
+      v[4 * j + 3] = hi.y;
     }
     if (MODE == FZ_EPI_GELU_SUMSQ || MODE == FZ_EPI_GELU_BF16) {
+#ifdef FZ_GELU_SCALAR                                      // A/B build: one column per instruction (round 2 before the packed form)
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+#else
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {                       // two columns per packed fp32 instruction (same bits as scalar)
+        const float2 g2 = gelu_erf_fast2(make_float2(v[2 * j], v[2 * j + 1]));
+        v[2 * j] = g2.x;
+        v[2 * j + 1] = g2.y;
+      }
+#endif
     } else if (MODE == FZ_EPI_RELU_BF16) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -91,10 +106,12 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 x = *reinterpret_cast<const float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
-        v[4 * j + 0] += x.x;
-        v[4 * j + 1] += x.y;
-        v[4 * j + 2] += x.z;
-        v[4 * j + 3] += x.w;
+        const float2 lo = __fadd2_rn(make_float2(v[4 * j + 0], v[4 * j + 1]), make_float2(x.x, x.y));
+        const float2 hi = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(x.z, x.w));
+        v[4 * j + 0] = lo.x;
+        v[4 * j + 1] = lo.y;
+        v[4 * j + 2] = hi.x;
+        v[4 * j + 3] = hi.y;
       }
       __syncwarp();   // everyone has read its residual row before the tile is overwritten
     }
@@ -122,16 +139,15 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, i
     // fc2 will actually consume): lane l owns columns 2l, 2l+1 = one 32-bit word per row, conflict-free under the
     // XOR swizzle.  2.5 instructions per element instead of 4.9 for the register transpose-reduce it replaces.
     // M is a multiple of 128 in this mode (host check): no row mask.
-    float a0 = 0.f, a1 = 0.f;
+    float2 acc = make_float2(0.f, 0.f);
     const int sidx = lane >> 2, woff = (lane & 3) * 4;
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
       const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((sidx ^ (r & 7)) << 4) + woff);
       const float2 f = unpack16<F16>(w);
-      a0 = fmaf(f.x, f.x, a0);
-      a1 = fmaf(f.y, f.y, a1);
+      acc = __ffma2_rn(f, f, acc);                          // both columns' sums in one packed FMA
     }
-    *reinterpret_cast<float2*>(sq_dst + 2 * lane) = make_float2(a0, a1);
+    *reinterpret_cast<float2*>(sq_dst + 2 * lane) = acc;
   }
   if (tmO != nullptr) {
     // staging -> global as ONE TMA store of the 32-row x 128-byte box: the staging tile's XOR pattern (16-byte segment ^

@@ -15,8 +15,10 @@ import torch
 
 # FZ_OPERANDS=bf16 selects the A/B build whose inference kernels store bf16 operands (round-1 behaviour, see
 # csrc/operand.cuh and build.py); the product library stores fp16.
+# FZ_LIB_VARIANT=<name> loads _native/libfz_b200_<name>.so: a hand-built A/B variant of the library (tools/build_variant.py).
 _LIB_PATH = Path(__file__).resolve().parent / "_native" / (
-    "libfz_b200_bf16.so" if os.environ.get("FZ_OPERANDS", "").lower() == "bf16" else "libfz_b200.so")
+    f"libfz_b200_{os.environ['FZ_LIB_VARIANT']}.so" if os.environ.get("FZ_LIB_VARIANT") else
+    ("libfz_b200_bf16.so" if os.environ.get("FZ_OPERANDS", "").lower() == "bf16" else "libfz_b200.so"))
 _lib: Optional[ctypes.CDLL] = None
 
 F32, BF16, F16 = 0, 1, 2
