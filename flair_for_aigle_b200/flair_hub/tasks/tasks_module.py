@@ -18,6 +18,40 @@ from ... import native as nv
 from .module_setup import FLAIRLosses
 
 
+class StepSegments:
+    """Adam step counters of a flat parameter arena.  torch keeps one counter PER PARAMETER and leaves a parameter without a
+    gradient untouched (moments, counter and weight decay included); here the arena [0, n) is covered by segments
+    [lo, hi, steps] -- one segment until a step skips a range (modality dropout: a whole encoder has no gradient), then the
+    segments split at that range's ends and count on their own.  Host bookkeeping only (tests/test_step_segments.py)."""
+
+    def __init__(self, n: int):
+        self.items = [[0, int(n), 0]]
+
+    def split(self, at: int) -> None:
+        for i, (lo, hi, k) in enumerate(self.items):
+            if lo < at < hi:
+                self.items[i:i + 1] = [[lo, at, k], [at, hi, k]]
+                return
+
+    def advance(self, skip=()):
+        """One optimizer step in which the ranges of ``skip`` [(lo, hi), ...] received no gradient: -> [(lo, hi, step)] of the
+        segments to update, ``step`` being that segment's own (already incremented) counter."""
+        for lo, hi in skip:
+            self.split(lo)
+            self.split(hi)
+        todo = []
+        for seg in self.items:
+            lo, hi, _ = seg
+            if any(a <= lo and hi <= b for a, b in skip):
+                continue
+            seg[2] += 1
+            todo.append((lo, hi, seg[2]))
+        return todo
+
+    def __len__(self) -> int:
+        return len(self.items)
+
+
 class AdamW:
     """``torch.optim.AdamW(params, lr, weight_decay, betas)`` (tasks_module.py:385-389) as one fused kernel per step:
     parameters, gradients and both moments live in flat fp32 arenas; ``params`` become views into the arena."""
@@ -39,10 +73,7 @@ class AdamW:
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)       # the same counter on the device (step_dev())
         self._hyper = torch.zeros(2, dtype=torch.float32, device=dev)
-        # torch keeps one step counter PER PARAMETER and leaves a parameter without a gradient untouched (moments, counter
-        # and weight decay included).  Here: arena segments [lo, hi) with their own counters; one segment until a step skips
-        # a range (modality dropout: a whole encoder has no gradient), then the segments split at that range's ends.
-        self._segments = [[0, n, 0]]
+        self._segs = StepSegments(n)                 # per-range step counters (torch: per parameter), see StepSegments
         off = 0
         self.grads: List[torch.Tensor] = []
         for p in self.params:
@@ -60,36 +91,27 @@ class AdamW:
         like ``torch.optim.AdamW`` does for ``p.grad is None`` (no decay, no moment update, their step counter stands still)."""
         self.step_count += 1
         self.step_dev.add_(1)
-        for lo, hi in skip:
-            self._split(lo)
-            self._split(hi)
-        for seg in self._segments:
-            lo, hi, _ = seg
-            if any(a <= lo and hi <= b for a, b in skip):
-                continue
-            seg[2] += 1
+        for lo, hi, k in self._segs.advance(skip):
             nv.adamw_step(self.arena[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.lr,
-                          self.betas[0], self.betas[1], self.eps, self.weight_decay, seg[2])
+                          self.betas[0], self.betas[1], self.eps, self.weight_decay, k)
 
-    def _split(self, at: int) -> None:
-        for i, (lo, hi, k) in enumerate(self._segments):
-            if lo < at < hi:
-                self._segments[i:i + 1] = [[lo, at, k], [at, hi, k]]
-                return
+    @property
+    def _segments(self):
+        return self._segs.items
 
     @property
     def uniform_steps(self) -> bool:
         """True while every parameter has taken part in every step (the device-counter update assumes it)."""
-        return len(self._segments) == 1 and self._segments[0][2] == self.step_count
+        return len(self._segs) == 1 and self._segs.items[0][2] == self.step_count
 
     def step_on_device_counter(self) -> None:
         """The same update driven by the device-resident counter: nothing in the launch depends on the step number, so it can
         be captured in a CUDA graph and replayed (engine/train_step.py).  The caller keeps ``step_count`` in sync."""
-        if len(self._segments) != 1:
+        if len(self._segs) != 1:
             raise RuntimeError("step_on_device_counter(): some parameters skipped earlier steps (per-segment counters)")
         nv.adamw_step_dev(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                           self.weight_decay, self.step_dev, self._hyper)
-        self._segments[0][2] += 1
+        self._segs.items[0][2] += 1
 
 
 def init_optimizer(cfg: dict, params: Iterable[torch.Tensor]) -> AdamW:

@@ -49,6 +49,19 @@ def test_argument_validation_without_gpu():
     rc = lib.fz_conv3x3_bf16(None, None, None, None, None, 1, 32, 32, 24, 16, 16, 0, 0, None, None, None, 0, 0, 0,
                              None)                                                               # Cin % 16 != 0
     assert rc == -1 and b"Cin=24" in lib.fz_last_error()
+    # the training step's tile convolutions: pure host predicate + shape checks
+    assert lib.fz_conv3x3_small_supported(512, 512, 32, 16) == 1 and lib.fz_conv3x3_small_supported(512, 512, 64, 32) == 1
+    assert lib.fz_conv3x3_small_supported(510, 512, 32, 16) == 0            # H % 8
+    assert lib.fz_conv3x3_small_supported(512, 500, 32, 16) == 0            # W % 32
+    assert lib.fz_conv3x3_small_supported(512, 512, 128, 16) == 0           # more than 64 channels: the im2col + GEMM path
+    rc = lib.fz_conv3x3_small_forward(None, None, None, None, 0, 1, 64, 64, 24, 16, 16, 16, 0, None)
+    assert rc == -1 and b"not covered" in lib.fz_last_error()
+    rc = lib.fz_conv3x3_small_wgrad(None, None, 64, None, 1, 64, 64, 32, 64, 0, None)          # Cout <= 32 only
+    assert rc == -1 and b"Cout=64" in lib.fz_last_error()
+    rc = lib.fz_confusion_matrix(None, None, 10, 200, None, None)                                # C <= 96
+    assert rc == -1 and b"C=200" in lib.fz_last_error()
+    rc = lib.fz_gelu_fwd_sumsq(None, None, None, None, 2, 64, 20, 1, None)                       # C % 8
+    assert rc == -1 and b"C % 8" in lib.fz_last_error()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
