@@ -1,10 +1,14 @@
-// Training-mode forward pieces and the backward of one ConvNeXt-V2 block (first slice of the model backward):
-//   x -> dwconv7x7 (+b) -> LayerNorm -> fc1 -> GELU -> GRN -> fc2 -> + x
-// The two Linear layers run on the tcgen05 GEMM (fz_gemm_bf16, and native.linear_backward for their gradients); the
-// kernels here are the memory-bound rest, written for correctness first (one thread per element / one warp per row, fixed
-// reduction orders, no atomics): they are NOT tuned yet -- the depthwise weight gradient in particular walks all pixels
-// per (tap, 32 channels) block.  Saved tensors follow PyTorch's autograd of the same modules (oracle/models.py
-// ConvNeXtBlock): the LayerNorm input with its row statistics, the pre-GELU activations, the GRN input and its norms.
+// Training-mode forward pieces and the backward of the ConvNeXt-V2 block, the encoder plumbing and the U-Net decoder:
+//   x -> dwconv7x7 (+b) -> LayerNorm -> fc1 -> GELU -> GRN -> fc2 -> + x;  stem / downsample LayerNorms, space-to-depth, patches;
+//   decoder: im2col / col2im for the deep layers, BatchNorm + ReLU on batch statistics, upsample-concat gradient.
+// The Linear layers run on the tcgen05 GEMM (fz_gemm_bf16, native.linear_backward), the wide decoder convolutions on
+// conv3x3_small.cu; the kernels here are the memory- and issue-bound rest.  Conventions: fixed reduction orders and no
+// floating-point atomics (gradients are bit-reproducible, graph replays equal eager steps); one thread per 8-channel group
+// with 16-byte accesses, blocks walking row chunks (reduce_vec.cuh); grids sized to one wave of resident blocks; forward
+// activations in bf16 or IEEE fp16 (flag per entry point), gradients in bf16.  Saved tensors follow PyTorch's autograd of the
+// same modules (oracle/models.py ConvNeXtBlock): the LayerNorm input with its row statistics, GELU(h) and GELU'(h), the GRN
+// norms.  The first, one-thread-per-element versions of several kernels are kept as the fallback for shapes the vector forms
+// do not take (channel counts that are not multiples of 8 / 4, ragged maps).
 #include <cuda_bf16.h>
 
 #include "common.h"
