@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NATIVE = os.path.join(ROOT, "flair_for_aigle_b200", "_native")
 OUT = os.path.join(ROOT, "profiles", "sass")
 PAT = re.compile(r"\b(UTC[A-Z]*MMA\S*|UTCBAR\S*|UTMA[A-Z]+\S*|LDTM\S*|STTM\S*|HMMA\S*|IMMA\S*|LDGSTS\S*|SYNCS\S*|F2FP\S*|MUFU\.\S+|"
-                 r"LDSM\S*|FFMA2?\b|HFMA2\S*|REDUX\S*|ATOM\S*|RED\.\S*)")
+                 r"LDSM\S*|FFMA2?\b|FMUL2\b|FADD2\b|HFMA2\S*|REDUX\S*|ATOM\S*|RED\.\S*)")
 KEY = ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "HMMA", "LDGSTS", "F2FP.SATFINITE.F16", "F2FP.BF16", "MUFU.EX2",
        "MUFU.RCP", "MUFU.TANH", "FFMA")
 
