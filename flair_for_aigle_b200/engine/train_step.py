@@ -238,7 +238,7 @@ class ConvNeXtUNetTrainer:
         for k, v in self._static.items():
             v.copy_(batch[k], non_blocking=True)
         self._replay()
-        self.opt.step_count += 1
+        self.opt.note_device_step()
         self._stale = True
         return self._graph_out
 

@@ -106,11 +106,17 @@ class AdamW:
 
     def step_on_device_counter(self) -> None:
         """The same update driven by the device-resident counter: nothing in the launch depends on the step number, so it can
-        be captured in a CUDA graph and replayed (engine/train_step.py).  The caller keeps ``step_count`` in sync."""
+        be captured in a CUDA graph and replayed (engine/train_step.py).  Host counters are NOT touched here (a capture does
+        not execute): the caller reports every executed step with ``note_device_step()``."""
         if len(self._segs) != 1:
             raise RuntimeError("step_on_device_counter(): some parameters skipped earlier steps (per-segment counters)")
         nv.adamw_step_dev(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                           self.weight_decay, self.step_dev, self._hyper)
+
+    def note_device_step(self) -> None:
+        """One step driven by the device counter has run (a graph replay): the host mirrors follow, so that an eager step
+        afterwards continues with the right bias corrections."""
+        self.step_count += 1
         self._segs.items[0][2] += 1
 
 

@@ -160,7 +160,7 @@ def test_graph_replayed_step_equals_eager_step(cuda, monkeypatch, segments):
         b = {m: torch.randn(2, c, 128, 128, generator=g).to(cuda) for m, c in mods.items()}
         b[TASK] = torch.randint(0, 19, (2, 128, 128), generator=g, dtype=torch.int32).to(cuda)
         batches.append(b)
-    runs = {}
+    runs, odd_runs = {}, {}
     for graphed in (False, True):
         state = {k: v.to(cuda) for k, v in bench.random_state(mods, seed=11).items()}
         tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w, lr=2e-4, cuda_graph=graphed)
@@ -175,13 +175,16 @@ def test_graph_replayed_step_equals_eager_step(cuda, monkeypatch, segments):
             assert (len(tr._segments) > 5) == segments
         assert int(tr.opt.step_dev) == len(batches)
         runs[graphed] = (losses, preds, tr.opt.arena.clone(), {k: v.clone() for k, v in tr.buffers.items()})
-        # a batch of another shape after the capture: falls back to the eager step, on the CURRENT weights
-        if graphed:
-            odd = {m: torch.randn(1, c, 128, 128, generator=g).to(cuda) for m, c in mods.items()}
-            odd[TASK] = torch.randint(0, 19, (1, 128, 128), generator=g, dtype=torch.int32).to(cuda)
-            before = tr.opt.arena.clone()
-            l_odd, _ = tr.step(odd)
-            assert torch.isfinite(l_odd) and not torch.equal(before, tr.opt.arena) and tr.opt.step_count == len(batches) + 1
+        # a batch of another shape after the capture: falls back to the eager step, on the CURRENT weights and with the step
+        # counters where the replays left them (same update as the all-eager trainer's sixth step)
+        go = torch.Generator(device="cpu").manual_seed(99)
+        odd = {m: torch.randn(1, c, 128, 128, generator=go).to(cuda) for m, c in mods.items()}
+        odd[TASK] = torch.randint(0, 19, (1, 128, 128), generator=go, dtype=torch.int32).to(cuda)
+        before = tr.opt.arena.clone()
+        l_odd, _ = tr.step(odd)
+        assert torch.isfinite(l_odd) and not torch.equal(before, tr.opt.arena) and tr.opt.step_count == len(batches) + 1
+        assert tr.opt._segments == [[0, tr.opt.arena.numel(), len(batches) + 1]] and int(tr.opt.step_dev) == len(batches) + 1
+        odd_runs[graphed] = (float(l_odd), tr.opt.arena.clone())
     (le, pe, ae, be), (lg, pg, ag, bg) = runs[False], runs[True]
     print("eager  losses:", " ".join(f"{v:.5f}" for v in le))
     print("graph  losses:", " ".join(f"{v:.5f}" for v in lg))
@@ -195,6 +198,7 @@ def test_graph_replayed_step_equals_eager_step(cuda, monkeypatch, segments):
     assert d <= 1e-6
     for k in be:
         assert torch.allclose(be[k].float(), bg[k].float(), rtol=0, atol=1e-6), k
+    assert odd_runs[False][0] == odd_runs[True][0] and float((odd_runs[False][1] - odd_runs[True][1]).abs().max()) <= 1e-6
 
 
 def test_modality_dropout_training_steps_vs_oracle(cuda):
