@@ -67,29 +67,27 @@ def cosine(a, b):
     return dot / (na * nb), worst
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--tile", type=int, default=128)
-    ap.add_argument("--batch", type=int, default=2)
-    ap.add_argument("--device", default="cpu")
-    a = ap.parse_args()
+CASES = (("bf16 activations + weights", torch.bfloat16, True, True), ("bf16 activations only", torch.bfloat16, False, True),
+         ("bf16 weights only", torch.bfloat16, True, False), ("fp16 activations + weights", torch.float16, True, True))
+
+
+def budget(arch: str = "convnextv2_base-unet", tile: int = 128, batch_size: int = 2, device: str = "cpu", cases=CASES):
+    """-> (loss of the unrounded run, [(label, loss, whole-model cosine, (worst cosine, tensor name))])."""
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    dev = torch.device(a.device)
+    dev = torch.device(device)
     mods = {"AERIAL_RGBI": 4, "DEM_ELEV": 1}
-    model = FlairHubOracle("convnextv2_base-unet", mods, {TASK: 19})
+    model = FlairHubOracle(arch, mods, {TASK: 19})
     randomize_(model, seed=3)
     model = model.to(dev).train()
     cfg = {"labels_configs": {TASK: {"value_name": list(range(19)), "task_weight": 1.0,
                                      "value_weights": {"default": 1, "default_exceptions": {15: 0, 16: 0, 17: 0, 18: 0}}}}}
     g = torch.Generator(device="cpu").manual_seed(17)
-    batch = {m: torch.randn(a.batch, c, a.tile, a.tile, generator=g).to(dev) for m, c in mods.items()}
-    batch[TASK] = torch.nn.functional.one_hot(torch.randint(0, 19, (a.batch, a.tile, a.tile), generator=g), 19).permute(0, 3, 1, 2).float().to(dev)
+    batch = {m: torch.randn(batch_size, c, tile, tile, generator=g).to(dev) for m, c in mods.items()}
+    batch[TASK] = torch.nn.functional.one_hot(torch.randint(0, 19, (batch_size, tile, tile), generator=g), 19).permute(0, 3, 1, 2).float().to(dev)
     ref, loss0 = grads(model, batch, cfg)
-    print(f"forward-only rounding (straight-through), convnextv2_base-unet 2 encoders, batch {a.batch} x {a.tile}^2, loss {loss0:.5f}")
-    print(f"{'rounded in the forward':44s} {'loss':>9s} {'whole-model cosine':>19s}   worst tensor")
-    for label, dt, w, ac in (("bf16 activations + weights", torch.bfloat16, True, True), ("bf16 activations only", torch.bfloat16, False, True),
-                             ("bf16 weights only", torch.bfloat16, True, False), ("fp16 activations + weights", torch.float16, True, True)):
+    rows = []
+    for label, dt, w, ac in cases:
         handles, saved = install(model, dt, w, ac)
         got, loss = grads(model, batch, cfg)
         for h in handles:
@@ -98,6 +96,21 @@ def main():
             if name in saved:
                 p.data = saved[name]
         c, worst = cosine(got, ref)
+        rows.append((label, loss, c, worst))
+    return loss0, rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tile", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--device", default="cpu")
+    ap.add_argument("--arch", default="convnextv2_base-unet")
+    a = ap.parse_args()
+    loss0, rows = budget(a.arch, a.tile, a.batch, a.device)
+    print(f"forward-only rounding (straight-through), {a.arch} 2 encoders, batch {a.batch} x {a.tile}^2, loss {loss0:.5f}")
+    print(f"{'rounded in the forward':44s} {'loss':>9s} {'whole-model cosine':>19s}   worst tensor")
+    for label, loss, c, worst in rows:
         print(f"{label:44s} {loss:9.5f} {c:19.5f}   {worst[0]:.4f} {worst[1]}")
 
 
