@@ -242,6 +242,15 @@ class ConvNeXtUNetTrainer:
         self._stale = True
         return self._graph_out
 
+    def set_lr(self, lr: float) -> None:
+        """New learning rate from a scheduler (flair_hub/tasks/schedulers.py).  The captured graphs carry the rate as a kernel
+        argument, so a change drops them and the next step captures again: fine for a plateau schedule that moves a few times
+        per run; a per-step schedule should run the trainer with ``cuda_graph=False``."""
+        lr = float(lr)
+        if lr != self.opt.lr:
+            self.opt.lr = lr
+            self._graph, self._segments, self._graph_out = None, [], None
+
     def _same_shapes(self, batch) -> bool:
         return all(k in batch and batch[k].shape == v.shape and batch[k].dtype == v.dtype for k, v in self._static.items())
 

@@ -7,9 +7,9 @@ the CUDA kernels of csrc/training_ops.cu and the training engine.
 :377-391); ``validation_step`` and the two epoch-end hooks -- the reference's metric bookkeeping (:63-93, :196-201,
 :232-236, :268-276, :302-338: weighted mIoU for training and validation, per-class validation IoU, mean losses) on
 tasks/metrics.py, returning the values the reference hands to Lightning's ``self.log`` as a dict.  ``loss_gradients()`` --
-d loss / d logits per task.  Modality dropout (``config['modalities']['modality_dropout']``) is applied by the training engine.  Not built: the
-auxiliary decoders (their loss is identically zero in the reference, tests/test_reference_pin.py), schedulers, the per-class
-validation loss log."""
+d loss / d logits per task.  Modality dropout (``config['modalities']['modality_dropout']``) is applied by the training engine.  ``configure_optimizers``
+adds the reference's learning-rate schedules (schedulers.py).  Not built: the auxiliary decoders (their loss is identically zero
+in the reference, tests/test_reference_pin.py), the per-class validation loss log."""
 from typing import Dict, Iterable, List
 
 import torch
@@ -195,6 +195,54 @@ class SegmentationTask:
                                            betas=tuple(optim_cfg['optim_betas']), mod_dropout=self.mod_dropout)
         return self.trainer
 
+    def configure_optimizers(self, total_steps: int):
+        """tasks_module.py:344-376 without Lightning: builds the trainer from ``config['hyperparams']`` (``configure_trainer``)
+        and the schedule it names -- 'reduce_on_plateau' (factor 0.5, ``plateau_patience``, cooldown 4, floor 1e-7; stepped by
+        ``on_validation_epoch_end`` with the validation loss), 'one_cycle_lr' (peak = ``learning_rate``, ``warmup_fraction`` of
+        ``total_steps`` rising from lr/1000; stepped after every training batch), 'cycle_then_plateau' (a one-cycle rise over
+        ``warmup_fraction * total_steps`` steps, then plateau halving with patience 10; :213-231, :311-314) or none.
+        ``total_steps`` is Lightning's ``trainer.estimated_stepping_batches``.  Returns what the reference returns, with this
+        package's optimizer / scheduler objects (flair_hub/tasks/schedulers.py)."""
+        from .schedulers import OneCycleLR, ReduceLROnPlateau
+        cfg = self.config['hyperparams']
+        if getattr(self, 'trainer', None) is None:
+            self.configure_trainer(cfg)
+        tr = self.trainer
+        self._scheduler_type = cfg.get("scheduler", None)
+        self._scheduler = self._warmup_scheduler = self._plateau_scheduler = None
+        self._using_plateau, self._global_step = False, 0
+        warmup_fraction = cfg.get("warmup_fraction", 0.0)
+        if self._scheduler_type == "reduce_on_plateau":
+            self._scheduler = ReduceLROnPlateau(tr.set_lr, tr.opt.lr, factor=0.5, patience=cfg['plateau_patience'], cooldown=4,
+                                                min_lr=1e-7)
+            return {"optimizer": tr.opt, "lr_scheduler": {"scheduler": self._scheduler, "monitor": "val_loss", "interval": "epoch"}}
+        if self._scheduler_type == "one_cycle_lr":
+            tr.cuda_graph = False                    # the rate changes every step: a captured graph would freeze it
+            self._scheduler = OneCycleLR(tr.set_lr, max_lr=cfg["learning_rate"], total_steps=total_steps,
+                                         pct_start=warmup_fraction, div_factor=1000)
+            return {"optimizer": tr.opt, "lr_scheduler": {"scheduler": self._scheduler, "interval": "step"}}
+        if self._scheduler_type == "cycle_then_plateau":
+            warmup_steps = int(warmup_fraction * total_steps)
+            self._warmup_scheduler = OneCycleLR(tr.set_lr, max_lr=cfg["learning_rate"], total_steps=warmup_steps, pct_start=1.0,
+                                                div_factor=1000, final_div_factor=1)
+            self._plateau_scheduler = ReduceLROnPlateau(tr.set_lr, cfg["learning_rate"], factor=0.5, patience=10, cooldown=4,
+                                                        min_lr=1e-7)
+            return {"optimizer": tr.opt}
+        return tr.opt
+
+    def _after_train_batch(self) -> None:
+        """What Lightning (interval 'step') and the reference's ``on_train_batch_end`` (:213-231) do after an optimizer step."""
+        self._global_step = getattr(self, '_global_step', 0) + 1
+        kind = getattr(self, '_scheduler_type', None)
+        if kind == "one_cycle_lr" and self._global_step < self._scheduler.total_steps:
+            self._scheduler.step()
+        elif kind == "cycle_then_plateau" and not self._using_plateau:
+            if self._global_step < self._warmup_scheduler.total_steps:
+                self._warmup_scheduler.step()
+            if self._global_step == self._warmup_scheduler.total_steps:
+                self._using_plateau = True
+                self._plateau_scheduler.lr = self.trainer.opt.lr      # the plateau phase starts from the rate the warm-up reached
+
     def training_step(self, batch: Dict[str, torch.Tensor]):
         """tasks_module.py:196-207 (training_step -> step(training=True) -> backward -> optimizer.step) in one call.
         -> (loss before the update, {task: preds})."""
@@ -207,6 +255,7 @@ class SegmentationTask:
         self.train_loss.update(loss)                                                  # tasks_module.py:198
         if task in self.train_metrics and self.trainer.last_targets is not None:
             self.train_metrics[task].update(preds, self.trainer.last_targets)         # :199-200
+        self._after_train_batch()
         return loss, {task: preds}
 
     def validation_step(self, batch: Dict[str, torch.Tensor]):
@@ -248,6 +297,11 @@ class SegmentationTask:
             self.val_iou[task].reset()
         out["val_miou"] = total / max(1, len(self.val_metrics))
         self.val_loss.reset()
+        kind = getattr(self, '_scheduler_type', None)                      # :311-314, and Lightning's epoch-interval monitor
+        if kind == "reduce_on_plateau":
+            self._scheduler.step(out["val_loss"])
+        elif kind == "cycle_then_plateau" and self._using_plateau:
+            self._plateau_scheduler.step(out["val_loss"])
         return out
 
     def loss_gradients(self) -> Dict[str, torch.Tensor]:

@@ -275,3 +275,31 @@ def test_modality_dropout_training_steps_vs_oracle(cuda):
     print(f"first update of the once-skipped encoder: mean |delta| / lr ours {d_ours:.3f}, oracle {d_theirs:.3f}")
     assert d_ours > 0.93 and abs(d_ours - d_theirs) < 0.03
     assert len(tr.opt._segments) == 3 and sorted(s[2] for s in tr.opt._segments)[0] == (2 if not plan[2][1] else 1)
+
+
+def test_set_lr_drops_and_recaptures_the_graph(cuda):
+    """A scheduler moving the learning rate (flair_hub/tasks/schedulers.py -> ConvNeXtUNetTrainer.set_lr): the captured graph
+    carries the rate as a kernel argument, so it is dropped and captured again; the trajectory equals the eager trainer's."""
+    import bench
+    from flair_for_aigle_b200.engine.convnext_unet import CONVNEXTV2_CFGS
+    from flair_for_aigle_b200.engine.train_step import ConvNeXtUNetTrainer
+    mods = {"AERIAL_RGBI": 4}
+    depths, dims = CONVNEXTV2_CFGS["convnextv2_base"]
+    w = torch.ones(19, device=cuda)
+    g = torch.Generator(device="cpu").manual_seed(8)
+    batch = {"AERIAL_RGBI": torch.randn(2, 4, 128, 128, generator=g).to(cuda),
+             TASK: torch.randint(0, 19, (2, 128, 128), generator=g, dtype=torch.int32).to(cuda)}
+    out = {}
+    for graphed in (False, True):
+        state = {k: v.to(cuda) for k, v in bench.random_state(mods, seed=4).items()}
+        tr = ConvNeXtUNetTrainer(state, depths, dims, list(mods), TASK, w, lr=2e-4, cuda_graph=graphed)
+        losses = []
+        for step in range(6):
+            if step == 3:
+                tr.set_lr(5e-5)
+                assert tr._graph is None
+            losses.append(float(tr.step(batch)[0]))
+        assert (tr._graph is not None) == graphed and tr.opt.lr == 5e-5
+        out[graphed] = (losses, tr.opt.arena.clone())
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(out[False][0], out[True][0]))
+    assert float((out[False][1] - out[True][1]).abs().max()) <= 1e-6
