@@ -53,7 +53,7 @@ def build_native(force: bool = False, verbose: bool = False, operands: str = "f1
     flags = NVCC_FLAGS + (["-DFZ_OPERANDS_BF16"] if operands == "bf16" else [])
     nvcc = _nvcc()
     sources = sorted(CSRC.glob("*.cu"))
-    headers = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h"))
+    headers = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [INCLUDE / "flair_zonal_b200.h"]
     objs = []
     jobs = []
     for src in sources:
@@ -87,5 +87,27 @@ def build_native(force: bool = False, verbose: bool = False, operands: str = "f1
     return lib
 
 
+RASTERIO_LIB = OUT_DIR / "libfz_rasterio.so"
+
+
+def build_rasterio(force: bool = False, verbose: bool = False) -> Path:
+    """libfz_rasterio.so: the host-only raster file I/O library (csrc/host/raster_io.cpp, include/flair_zonal_rasterio.h),
+    g++ + zlib, no CUDA."""
+    OUT_DIR.mkdir(exist_ok=True)
+    src = CSRC / "host" / "raster_io.cpp"
+    hdr = INCLUDE / "flair_zonal_rasterio.h"
+    if force or _newer(RASTERIO_LIB, [src, hdr]):
+        gxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+        cmd = [gxx, "-O3", "-std=c++17", "-Wall", "-fPIC", "-shared", "-pthread", "-I", str(INCLUDE), str(src), "-lz",
+               "-o", str(RASTERIO_LIB)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"g++ failed for {src.name}:\n{res.stderr[-4000:]}")
+        if verbose:
+            print(f"[build] linked {RASTERIO_LIB}")
+    return RASTERIO_LIB
+
+
 if __name__ == "__main__":
+    build_rasterio(force="--force" in sys.argv, verbose=True)
     build_native(force="--force" in sys.argv, verbose=True, operands="bf16" if "--bf16" in sys.argv else "f16")

@@ -31,7 +31,7 @@ from ..engine.zonal import ZonalRunner
 from .config import config_recap_1, config_recap_2, load_config, validate_config
 from .dataset import MultiModalSlicedDataset, normalization_affine
 from .model_utils import build_inference_model, compute_patch_sizes
-from .postprocess import convert  # noqa: F401  (re-exported like the reference)
+from .postprocess import convert, convert_to_cog  # noqa: F401  (re-exported like the reference)
 from .raster import RasterSink, ZoneRaster, open_raster
 from .slicing import generate_patches_from_reference, ownership_windows, tile_plan
 
@@ -333,6 +333,19 @@ def logits_to_labels_and_confidence(probs):
     return nv.canvas_argmax(probs.float().contiguous(), want_confidence=True)
 
 
+def postpro_outputs(temp_paths: Dict[str, str], config: Dict) -> Dict[str, str]:
+    """inference.py:633-641: with ``cog_conversion`` every output raster becomes ``<name>_COG.tif`` and the plain file is
+    removed.  Returns the paths that exist afterwards (the reference returns nothing)."""
+    final = dict(temp_paths)
+    if config.get("cog_conversion", False):
+        for task_name, temp_path in temp_paths.items():
+            cog_path = temp_path.replace(".tif", "_COG.tif")
+            convert_to_cog(temp_path, cog_path)
+            final[task_name] = cog_path
+            logger.info(f"\n[✓] Converted to COG: {cog_path}")
+    return final
+
+
 def run_inference(config_path: str) -> Dict[str, str]:
     """inference.py:644-674, repaired: config in -> rasters out.  Returns the
     written paths per task."""
@@ -349,5 +362,6 @@ def run_inference(config_path: str) -> Dict[str, str]:
     ref_img = open_raster(ref_path)
     output_files, temp_paths = init_outputs(config, ref_img, 0)
     inference_and_write(model, dataloader, tiles_gdf, config, output_files, ref_img)
+    written = postpro_outputs({k: v.written_path for k, v in output_files.items()}, config)       # inference.py:669
     logger.info(f"[✓] Total time: {time.time() - t0:.2f}s")
-    return {k: v.written_path for k, v in output_files.items()}
+    return written

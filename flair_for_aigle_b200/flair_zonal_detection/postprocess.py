@@ -1,9 +1,12 @@
-"""Drop-in for flair_zonal_detection/postprocess.py:9-30 (``convert``), computed on the GPU.
+"""Drop-in for flair_zonal_detection/postprocess.py: ``convert`` (:9-30), computed on the GPU, and ``convert_to_cog``
+(:33-52), the raster re-encoding step, on all host cores.
 
-Accepts what the reference accepts -- a (C,H,W) array of logits -- as numpy or torch; numpy in
+``convert`` accepts what the reference accepts -- a (C,H,W) array of logits -- as numpy or torch; numpy in
 gives numpy out.  There is no CPU implementation: without a CUDA device it raises.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -23,3 +26,15 @@ def convert(img, img_type: str):
     t = t.to(device="cuda", dtype=torch.float32).contiguous()
     out = nv.convert(t, 0 if img_type == "argmax" else 1)
     return out.cpu().numpy() if was_numpy else out
+
+
+def convert_to_cog(input_path: str, output_path: str) -> None:
+    """postprocess.py:33-52: GeoTIFF -> Cloud Optimized GeoTIFF with the reference's profile (LZW, blocksize 512, nearest
+    overviews, tiled), then the input file is removed.  The reference hands this to GDAL's COG driver through ``rio_copy``
+    (single-threaded); here ``libfz_rasterio.so`` decodes, builds the overview pyramid and encodes block-parallel
+    (include/flair_zonal_rasterio.h: fzio_convert_to_cog)."""
+    from .. import raster_io
+    if not os.path.isfile(input_path):
+        raise FileNotFoundError(f"Input file not found: {input_path}")
+    raster_io.convert_to_cog(input_path, output_path)
+    os.remove(input_path)
