@@ -369,6 +369,72 @@ def train_block(dev, rank: int, world: int, steps: int, warmup: int):
             "dtype": "fp16 forward operands, bf16 gradient operands, fp32 accumulate / master weights"}
 
 
+def file_io_block(inf, model, cfg, tiles, patch_sizes, host, tmp, dev, checksum, total_px) -> dict:
+    """SURVEY 8(f) rank 1, measured: the same zone FILE TO FILE through the public API -- a tiled LZW GeoTIFF of the RGBI zone on
+    disk (page cache warm) -> open_raster (libfz_rasterio.so decodes it block-parallel into page-locked memory) ->
+    inference_and_write -> the class raster as a tiled LZW GeoTIFF (the reference's profile) -> optional COG conversion
+    (postprocess.py:33-52).  Host work is on this box's cores; the reference does the same with one rasterio window read per
+    tile and one LZW window write per tile on one core."""
+    import torch
+    from flair_for_aigle_b200 import raster_io
+    from flair_for_aigle_b200.flair_zonal_detection.postprocess import convert_to_cog
+    from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink, open_raster
+    src = os.path.join(tmp, "zone_rgbi.tif")
+    t0 = time.perf_counter()
+    raster_io.write_geotiff(src, host.numpy(), LEFT, TOP, RES, epsg=2154, pixel_interleave=True, predictor=2)
+    make_ms = (time.perf_counter() - t0) * 1e3
+    cfg_f = dict(cfg)
+    cfg_f["modalities"] = json.loads(json.dumps(cfg["modalities"]))
+    cfg_f["modalities"]["AERIAL_RGBI"]["input_img_path"] = src
+    cfg_f.pop("image_shape_px", None)
+    out_dir = os.path.join(tmp, "file_io")
+    os.makedirs(out_dir, exist_ok=True)
+    cfg_f["output_path"] = out_dir
+    cfg_f = inf.initialize_geometry_and_resolutions(cfg_f)      # header only: no pixel is decoded for the geometry
+    cfg_f["device"] = dev
+    RasterSink.write_files = True
+    runs = []
+    written = None
+    for _ in range(2):                                          # the second run is the reported one
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        ref = open_raster(src)
+        ds = inf.prep_dataset(cfg_f, tiles, patch_sizes)
+        ds.host_raster("AERIAL_RGBI")                           # decode -> page-locked memory
+        t1 = time.perf_counter()
+        outs, _ = inf.init_outputs(cfg_f, ref, 0)
+        inf.inference_and_write(model, ds, tiles, cfg_f, outs, ref)      # H2D + forward + D2H + GeoTIFF written by close()
+        torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
+        written = outs[TASK].written_path
+        outs[TASK].release()
+        runs.append((t1 - t0, t2 - t1))
+        del ds, ref, outs
+    decode_s, infer_write_s = runs[-1]
+    got, info = raster_io.read_raster(written)
+    same = bool(int(got.astype(np.int64).sum()) == checksum)
+    t0 = time.perf_counter()
+    raster_io.write_geotiff(os.path.join(out_dir, "again.tif"), got, LEFT, TOP, RES, epsg=2154)
+    write_ms = (time.perf_counter() - t0) * 1e3
+    out_mb = os.path.getsize(written) / 1e6
+    t0 = time.perf_counter()
+    cog = written.replace(".tif", "_COG.tif")
+    convert_to_cog(written, cog)
+    cog_ms = (time.perf_counter() - t0) * 1e3
+    return {"value": round(total_px / 1e6 / (decode_s + infer_write_s), 2), "unit": "Mpx/s",
+            "ms": {"decode_input_geotiff_to_pinned": round(decode_s * 1e3, 1),
+                   "inference_and_write_incl_output_geotiff": round(infer_write_s * 1e3, 1),
+                   "of_which_encode_class_geotiff": round(write_ms, 1), "convert_to_cog_extra": round(cog_ms, 1),
+                   "make_input_file_setup": round(make_ms, 1)},
+            "input_file_mb": round(os.path.getsize(src) / 1e6, 1), "output_file_mb": round(out_mb, 2),
+            "output": {"tiled": info.tiled, "block": info.block_w, "compression": "lzw", "cog_overviews": raster_io.tiff_info(cog).overviews},
+            "same_result_as_value_leg": same, "host_cores": os.cpu_count(),
+            "note": "GeoTIFF on disk -> open_raster -> inference_and_write -> LZW GeoTIFF on disk, all through the public API; "
+                    "file codecs = libfz_rasterio.so, one 512x512 block per task on all host cores (profiles/r2_raster_io_bench.txt "
+                    "has the libtiff comparison); value = zone px / (decode + inference_and_write); COG conversion reported "
+                    "beside it, not inside"}
+
+
 def main() -> None:
     global ARCH, GFLOP_PER_TILE
     ap = argparse.ArgumentParser()
@@ -379,6 +445,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=int(os.environ.get("FZ_BENCH_BATCH", "37")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[4] training-step block")
+    ap.add_argument("--no-file-io", action="store_true", help="skip the GeoTIFF-in / GeoTIFF-out block")
     ap.add_argument("--arch", default=ARCH, choices=sorted(ARCH_GFLOP),
                     help="default = BASELINE.json's metric configuration; the others are measured for DESIGN.md only")
     ap.add_argument("--zone", type=int, default=0, help="zone side in pixels (default: 10000 at 1 GPU, 60000 sharded at N > 1)")
@@ -542,6 +609,16 @@ def main() -> None:
         h2d_total, d2h_total = int(4 * in_rows * gw), int(res_bytes)
     e2e_val = total_px / 1e6 / e2e_s
 
+    # ---------------------------------------------------------------- file to file, after the contract legs
+    file_io = None
+    if rank == 0 and world == 1 and side <= 20000 and not args.no_file_io:
+        try:
+            file_io = file_io_block(inf, model, cfg, tiles, patch_sizes, host, tmp, dev, checksum, total_px)
+        except Exception as ex:  # noqa: BLE001 -- the contract line must survive a failure of the extra block
+            file_io = {"error": repr(ex)}
+            log(f"[rank {rank}] file I/O block failed: {ex!r}")
+        RasterSink.write_files = False
+
     # ---------------------------------------------------------------- roofline: GEMM launches of one batch, live
     roof = None
     breakdown = {}
@@ -664,6 +741,7 @@ def main() -> None:
             "strong_scaling": strong,
             "other_configs": others,
             "train": train,
+            "file_io": file_io,
         }
         print(json.dumps(line), flush=True)
     if use_dist:

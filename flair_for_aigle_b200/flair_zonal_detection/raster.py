@@ -1,16 +1,18 @@
 """In-memory georeferenced raster: the part of ``rasterio.DatasetReader`` the hot path uses.
 
 The reference opens rasters with rasterio (flair_zonal_detection/dataset.py:44-46,
-inference.py:92-101, model_utils.py:11-16); this image has no rasterio/GDAL, and raster file
-I/O is the "next" row of SURVEY.md section 8(f).  ``ZoneRaster`` carries what the path needs
--- pixels (C,H,W), bounds, resolution -- and can be built from a numpy array, a ``.npy`` file
-(+ ``.json`` sidecar) or, when rasterio is installed, any GDAL-readable file.
+inference.py:92-101, model_utils.py:11-16); this image has no rasterio/GDAL.  ``ZoneRaster`` carries what the path needs
+-- pixels (C,H,W), bounds, resolution -- and can be built from a numpy array, a ``.npy`` file (+ ``.json`` sidecar), a
+GeoTIFF / BigTIFF (``geotiff.read_geotiff``: decoded block-parallel by libfz_rasterio.so, on a GPU host straight into
+page-locked memory so the upload to HBM needs no further copy), a JPEG-2000 file (``geotiff.read_jp2``) or, when rasterio
+is installed, any GDAL-readable file.
 """
 from __future__ import annotations
 
 import json
 import logging
 import os
+import weakref
 from collections import namedtuple
 from typing import Optional, Tuple
 
@@ -21,6 +23,7 @@ logger = logging.getLogger(__name__)
 BoundingBox = namedtuple("BoundingBox", ["left", "bottom", "right", "top"])
 
 _REGISTRY = {}
+_OPEN_FILES = weakref.WeakValueDictionary()     # (path, mtime, size) -> ZoneRaster, for as long as a caller holds it
 
 
 class ZoneRaster:
@@ -28,9 +31,10 @@ class ZoneRaster:
                  name: str = "<memory>"):
         if array.ndim == 2:
             array = array[None]
-        self.array = array
+        self._array, self._loader = array, None
+        self._shape, self._dtype = tuple(array.shape), array.dtype
         self.left, self.top, self.res_value, self.crs, self.name = float(left), float(top), float(res), crs, name
-        self.pinned_tensor = None   # set by from_pinned(): the same pixels as a pinned torch tensor
+        self.pinned_tensor = None   # set by from_pinned() / a lazy load: the same pixels as a pinned torch tensor
 
     @classmethod
     def from_pinned(cls, tensor, left: float, top: float, res: float, crs: Optional[str] = None,
@@ -41,18 +45,49 @@ class ZoneRaster:
         r.pinned_tensor = tensor
         return r
 
+    @classmethod
+    def lazy(cls, shape, dtype, loader, left: float, top: float, res: float, crs: Optional[str] = None,
+             name: str = "<file>"):
+        """Raster file opened the way ``rasterio.open`` opens it: size, type and georeferencing now, pixels when somebody
+        reads them.  ``loader() -> (array (C,H,W), pinned tensor or None)`` runs once, on the first access to ``array``:
+        the geometry-only callers of the path (slicing.py:20-49, inference.py:76-132,157-208) never decode the file."""
+        r = cls.__new__(cls)
+        r._array, r._loader = None, loader
+        r._shape, r._dtype = tuple(int(v) for v in shape), np.dtype(dtype)
+        r.left, r.top, r.res_value, r.crs, r.name = float(left), float(top), float(res), crs, name
+        r.pinned_tensor = None
+        return r
+
+    @property
+    def array(self) -> np.ndarray:
+        if self._array is None:
+            arr, pinned = self._loader()
+            if tuple(arr.shape) != self._shape:
+                raise ValueError(f"{self.name}: decoded {tuple(arr.shape)}, the header said {self._shape}")
+            self._array, self.pinned_tensor, self._loader, self._dtype = arr, pinned, None, arr.dtype
+        return self._array
+
+    @array.setter
+    def array(self, value: np.ndarray) -> None:
+        self._array, self._loader = value, None
+        self._shape, self._dtype = tuple(value.shape), value.dtype
+
+    @property
+    def loaded(self) -> bool:
+        return self._array is not None
+
     # -- rasterio.DatasetReader look-alikes ------------------------------------------------
     @property
     def count(self) -> int:
-        return self.array.shape[0]
+        return self._shape[0]
 
     @property
     def height(self) -> int:
-        return self.array.shape[1]
+        return self._shape[1]
 
     @property
     def width(self) -> int:
-        return self.array.shape[2]
+        return self._shape[2]
 
     @property
     def shape(self) -> Tuple[int, int]:
@@ -71,7 +106,7 @@ class ZoneRaster:
 
     @property
     def profile(self) -> dict:
-        return {"driver": "MEM", "dtype": str(self.array.dtype), "count": self.count, "height": self.height,
+        return {"driver": "MEM", "dtype": str(self._dtype), "count": self.count, "height": self.height,
                 "width": self.width, "crs": self.crs, "transform": (self.res_value, 0.0, self.left, 0.0,
                                                                      -self.res_value, self.top)}
 
@@ -110,8 +145,8 @@ def register_raster(path: str, raster: ZoneRaster) -> None:
 
 def open_raster(path) -> ZoneRaster:
     """``rasterio.open(path)`` stand-in.  Accepts a ZoneRaster, a registered name, ``*.npy`` (with ``<path>.json`` =
-    {left, top, res[, crs]}), an 8-bit north-up GeoTIFF (built-in reader, ``geotiff.py``) or, if rasterio is importable,
-    any raster."""
+    {left, top, res[, crs]}), a north-up GeoTIFF / BigTIFF or JPEG-2000 file (``geotiff.py``; decoded into page-locked
+    memory when the host has a CUDA device) or, if rasterio is importable, any raster."""
     if isinstance(path, ZoneRaster):
         return path
     if path in _REGISTRY:
@@ -121,13 +156,31 @@ def open_raster(path) -> ZoneRaster:
         with open(path + ".json") as f:
             meta = json.load(f)
         return ZoneRaster(arr, meta["left"], meta["top"], meta["res"], meta.get("crs"), name=path)
-    if isinstance(path, str) and path.lower().endswith((".tif", ".tiff")) and os.path.isfile(path):
+    if isinstance(path, str) and path.lower().endswith((".tif", ".tiff", ".jp2", ".j2k")) and os.path.isfile(path):
+        st = os.stat(path)
+        key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+        cached = _OPEN_FILES.get(key)
+        if cached is not None:
+            return cached                                 # same file, still held by somebody: one decode serves everyone
+        from . import geotiff
+        jp2 = path.lower().endswith((".jp2", ".j2k"))
+        header, reader = (geotiff.jp2_header, geotiff.read_jp2) if jp2 else (geotiff.geotiff_header, geotiff.read_geotiff)
         try:
-            from .geotiff import read_geotiff
-            arr, left, top, res, crs = read_geotiff(path)
-            return ZoneRaster(arr, left, top, res, crs, name=path)
-        except ValueError:
-            pass            # not something the built-in reader handles: let rasterio try
+            shape, dtype, left, top, res, crs = header(path)
+        except ValueError as e:
+            not_ours = e                                  # not something the built-in readers handle: let rasterio try
+        else:
+            def load():
+                holder = {}
+                arr = reader(path, alloc=lambda shp, dt: _pinned_array(shp, dt, holder))[0]
+                return arr, (holder.get("tensor") if arr is holder.get("array") else None)
+            raster = ZoneRaster.lazy(shape, dtype, load, left, top, res, crs, name=path)
+            _OPEN_FILES[key] = raster
+            return raster
+        try:
+            import rasterio  # type: ignore  # noqa: F401
+        except ImportError:
+            raise not_ours
     try:
         import rasterio  # type: ignore
     except ImportError as e:  # pragma: no cover - depends on the host image
@@ -140,16 +193,36 @@ def open_raster(path) -> ZoneRaster:
         return ZoneRaster(src.read(), src.bounds.left, src.bounds.top, abs(src.res[0]), str(src.crs), name=path)
 
 
+def _pinned_array(shape, dtype, holder: dict) -> np.ndarray:
+    """Array for a file reader to decode into: page-locked (a torch tensor's numpy view, kept in ``holder``) when the host
+    has a CUDA device and the dtype is one the feeder uploads, plain numpy otherwise."""
+    arr = None
+    if np.dtype(dtype) in (np.dtype(np.uint8), np.dtype(np.float32)):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                t = torch.empty(tuple(shape), dtype=torch.uint8 if np.dtype(dtype) == np.uint8 else torch.float32,
+                                pin_memory=True)
+                holder["tensor"] = t
+                arr = t.numpy()
+        except RuntimeError:  # pragma: no cover - page-locking can fail on exotic hosts
+            holder.pop("tensor", None)
+            arr = None
+    if arr is None:
+        arr = np.empty(tuple(shape), dtype)
+    holder["array"] = arr
+    return arr
+
+
 _PINNED_POOL = {}
-CLASSIC_TIFF_LIMIT = (1 << 32) - (1 << 24)      # bytes of pixel data a classic (32-bit offset) TIFF can hold, with headroom
 
 
 class RasterSink:
     """Output raster of ``init_outputs`` (inference.py:157-208): a uint8 (count,H,W) array that lives
     on the GPU while tiles are written into it by the kernels, copied to the host once and stored
-    on ``close()`` as a GeoTIFF (``geotiff.write_geotiff``: LZW for the single-band argmax raster like the
-    reference's profile, Deflate planar for ``class_prob``), or as ``.npy`` when it exceeds classic TIFF;
-    the georeferencing also goes to a ``.json`` sidecar."""
+    on ``close()`` as a tiled LZW GeoTIFF like the reference's profile (``geotiff.write_geotiff``: every 512 x 512 block
+    encoded on its own host core by libfz_rasterio.so; ``class_prob`` = one plane per class; BigTIFF when the file
+    outgrows 32-bit offsets); the georeferencing also goes to a ``.json`` sidecar."""
 
     def __init__(self, path: str, count: int, height: int, width: int, left: float, top: float, res: float,
                  crs=None, device=None):
@@ -211,15 +284,7 @@ class RasterSink:
                 "count": self.count, "height": self.height, "width": self.width, "dtype": "uint8",
                 "compress": "lzw"}
         from .geotiff import write_geotiff
-        if arr.nbytes >= CLASSIC_TIFF_LIMIT:
-            # classic TIFF addresses 4 GiB (a 60 000 x 60 000 class raster is 3.6 GB, its class_prob raster 68 GB): the
-            # raster goes to <name>.npy + the .json sidecar instead -- said out loud, and ``written_path`` tells the caller
-            written = os.path.splitext(self.name)[0] + ".npy"
-            logger.warning(f"[!] {self.name}: {arr.nbytes / 2**30:.1f} GiB exceeds classic TIFF; writing {written} (+ .json "
-                           "georeferencing) instead")
-            np.save(written, arr)
-        else:
-            written = write_geotiff(self.name, arr, self.left, self.top, self.res_value, self.crs)   # errors propagate
+        written = write_geotiff(self.name, arr, self.left, self.top, self.res_value, self.crs)   # errors propagate
         with open(written + ".json", "w") as f:
             json.dump(meta, f)
         self.written_path = written

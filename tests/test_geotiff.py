@@ -86,3 +86,171 @@ def test_geographic_crs_roundtrip(tmp_path):
     p = write_geotiff(str(tmp_path / "geo.tif"), arr, 2.25, 48.75, 0.0001, "EPSG:4326")
     got, left, top, res, crs = read_geotiff(p)
     assert np.array_equal(got, arr) and (left, top, res, crs) == (2.25, 48.75, 0.0001, "EPSG:4326")
+
+
+def test_outputs_are_tiled_lzw_and_the_geokeys_are_the_documented_ones(tmp_path):
+    """The writer is libfz_rasterio.so: 512 x 512 LZW tiles for the argmax raster AND the class_prob planes (the reference's
+    compress='lzw' profile for both, inference.py:182-203); the GeoKeyDirectory in the file is `_geokeys(crs)`."""
+    from PIL import Image
+    from flair_for_aigle_b200 import raster_io as rio
+    from flair_for_aigle_b200.flair_zonal_detection.geotiff import _geokeys
+    rng = np.random.default_rng(5)
+    for count, crs in ((1, "EPSG:2154"), (19, "EPSG:4326"), (1, None)):
+        arr = rng.integers(0, 19, (count, 600, 700), dtype=np.uint8)
+        p = write_geotiff(str(tmp_path / f"o{count}.tif"), arr, L, T, RES, crs)
+        info = rio.tiff_info(p)
+        assert info.tiled and (info.block_w, info.block_h) == (512, 512) and info.compression == rio.COMP_LZW
+        assert info.planar == (2 if count > 1 else 1) and info.count == count and not info.bigtiff
+        with Image.open(p) as im:
+            assert tuple(im.tag_v2[34735]) == _geokeys(crs)
+        got, left, top, res, crs_back = read_geotiff(p)
+        assert np.array_equal(got, arr) and (left, top, res, crs_back) == (L, T, RES, crs)
+
+
+def test_float32_elevation_geotiff_and_jpeg_in_tiff_fallback(tmp_path):
+    from PIL import Image, TiffImagePlugin
+    from flair_for_aigle_b200 import raster_io as rio
+    rng = np.random.default_rng(6)
+    dem = (rng.standard_normal((1, 300, 400)) * 30 + 250).astype(np.float32)
+    p = str(tmp_path / "dem.tif")
+    rio.write_geotiff(p, dem, L, T, 1.0, epsg=2154, compression="deflate")
+    r = open_raster(p)
+    assert r.read().dtype == np.float32 and np.array_equal(r.read(), dem) and r.res == (1.0, 1.0) and r.crs == "EPSG:2154"
+    # a codec the library does not implement (JPEG-in-TIFF): libtiff through Pillow decodes it
+    ifd = TiffImagePlugin.ImageFileDirectory_v2()
+    ifd[33550], ifd.tagtype[33550] = (RES, RES, 0.0), 12
+    ifd[33922], ifd.tagtype[33922] = (0.0, 0.0, 0.0, L, T, 0.0), 12
+    img = np.kron(rng.integers(0, 256, (20, 30, 3)).astype(np.uint8), np.ones((16, 16, 1), np.uint8))
+    p = str(tmp_path / "jpeg.tif")
+    Image.fromarray(img).save(p, format="TIFF", compression="jpeg", tiffinfo=ifd)
+    got, left, top, res, _ = read_geotiff(p)
+    with Image.open(p) as im:
+        want = np.asarray(im).transpose(2, 0, 1)
+    assert np.array_equal(got, want) and (left, top, res) == (L, T, RES)
+    assert np.abs(got.astype(int) - img.transpose(2, 0, 1)).mean() < 6          # lossy, but the right picture
+
+
+def _jp2_with_box(path, arr_hwc, box: bytes):
+    """Lossless JPEG 2000 written by OpenJPEG (Pillow), with one extra box spliced in front of the codestream."""
+    import struct
+    from PIL import Image
+    Image.fromarray(arr_hwc).save(path, format="JPEG2000", irreversible=False)
+    raw = open(path, "rb").read()
+    at = raw.index(b"jp2c") - 4
+    open(path, "wb").write(raw[:at] + box + raw[at:])
+
+
+def _geojp2_box(left, top, res, epsg, point=False):
+    import struct
+    scale = struct.pack("<3d", res, res, 0.0)
+    tie = struct.pack("<6d", 0.0, 0.0, 0.0, left + (0.5 * res if point else 0.0), top - (0.5 * res if point else 0.0), 0.0)
+    keys = struct.pack("<16H", 1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 2 if point else 1, 3072, 0, 1, epsg)
+    # degenerate 1 x 1 GeoTIFF, little endian: header, one pixel, out-of-line values, directory
+    body = b"\x00"
+    pos = 8 + len(body) + 1
+    offs = {}
+    blob = b""
+    for tag, b in ((33550, scale), (33922, tie), (34735, keys)):
+        offs[tag] = pos + len(blob)
+        blob += b
+    ents = [(256, 3, 1, struct.pack("<HH", 1, 0)), (257, 3, 1, struct.pack("<HH", 1, 0)), (258, 3, 1, struct.pack("<HH", 8, 0)),
+            (259, 3, 1, struct.pack("<HH", 1, 0)), (262, 3, 1, struct.pack("<HH", 1, 0)), (273, 4, 1, struct.pack("<I", 8)),
+            (277, 3, 1, struct.pack("<HH", 1, 0)), (278, 3, 1, struct.pack("<HH", 1, 0)), (279, 4, 1, struct.pack("<I", 1)),
+            (33550, 12, 3, struct.pack("<I", offs[33550])), (33922, 12, 6, struct.pack("<I", offs[33922])),
+            (34735, 3, 16, struct.pack("<I", offs[34735]))]
+    ifd_at = pos + len(blob)
+    tiff = b"II*\x00" + struct.pack("<I", ifd_at) + body + b"\x00" + blob
+    tiff += struct.pack("<H", len(ents)) + b"".join(struct.pack("<HHI", t, ty, n) + v for t, ty, n, v in ents) + struct.pack("<I", 0)
+    payload = bytes.fromhex("b14bf8bd083d4b43a5ae8cd7d5a6ce03") + tiff
+    return struct.pack(">I4s", 8 + len(payload), b"uuid") + payload
+
+
+def test_jpeg2000_inputs_with_geojp2_gmljp2_and_world_file(tmp_path):
+    """The reference's product script feeds *.jp2 orthos (inference.py:60, scripts/run_fast_aigle_segmentation.py:88)."""
+    import struct
+    from PIL import features
+    from flair_for_aigle_b200.flair_zonal_detection.geotiff import read_jp2
+    if not features.check("jpg_2000"):
+        pytest.skip("Pillow without OpenJPEG")
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (300, 420, 4), dtype=np.uint8)                 # RGBI
+    want = img.transpose(2, 0, 1)
+    p = str(tmp_path / "geojp2.jp2")
+    _jp2_with_box(p, img, _geojp2_box(L, T, RES, 2154))
+    got, left, top, res, crs = read_jp2(p)
+    assert np.array_equal(got, want) and (left, top, res, crs) == (L, T, RES, "EPSG:2154")
+    r = open_raster(p)                                                        # ... and through the rasterio.open stand-in
+    assert (r.count, r.height, r.width) == (4, 300, 420) and np.array_equal(r.read(), want) and r.bounds.left == L
+    p = str(tmp_path / "point.jp2")
+    _jp2_with_box(p, img, _geojp2_box(L, T, RES, 2154, point=True))           # PixelIsPoint tie point = pixel centre
+    _, left, top, res, _ = read_jp2(p)
+    assert abs(left - L) < 1e-9 and abs(top - T) < 1e-9
+    # GMLJP2: asoc(lbl, asoc(lbl, xml)) with a RectifiedGrid whose origin is the centre of the first pixel
+    gml = (f'<gml:FeatureCollection xmlns:gml="http://www.opengis.net/gml"><gml:featureMember><gml:RectifiedGridCoverage>'
+           f'<gml:rectifiedGridDomain><gml:RectifiedGrid dimension="2" srsName="urn:ogc:def:crs:EPSG::2154"><gml:limits><gml:GridEnvelope>'
+           f'<gml:low>0 0</gml:low><gml:high>419 299</gml:high></gml:GridEnvelope></gml:limits>'
+           f'<gml:origin><gml:Point srsName="urn:ogc:def:crs:EPSG::2154"><gml:pos>{L + RES / 2!r} {T - RES / 2!r}</gml:pos></gml:Point></gml:origin>'
+           f'<gml:offsetVector srsName="urn:ogc:def:crs:EPSG::2154">{RES} 0</gml:offsetVector>'
+           f'<gml:offsetVector srsName="urn:ogc:def:crs:EPSG::2154">0 -{RES}</gml:offsetVector>'
+           f'</gml:RectifiedGrid></gml:rectifiedGridDomain></gml:RectifiedGridCoverage></gml:featureMember></gml:FeatureCollection>').encode()
+
+    def box(kind, payload):
+        return struct.pack(">I4s", 8 + len(payload), kind) + payload
+    asoc = box(b"asoc", box(b"lbl ", b"gml.data") + box(b"asoc", box(b"lbl ", b"gml.root-instance") + box(b"xml ", gml)))
+    p = str(tmp_path / "gml.jp2")
+    _jp2_with_box(p, img[:, :, :3], asoc)
+    got, left, top, res, crs = read_jp2(p)
+    assert np.array_equal(got, want[:3]) and abs(left - L) < 1e-6 and abs(top - T) < 1e-6 and res == RES and crs == "EPSG:2154"
+    # world file
+    p = str(tmp_path / "wf.jp2")
+    _jp2_with_box(p, img[:, :, 0], b"")
+    with pytest.raises(ValueError, match="no georeferencing"):
+        read_jp2(p)
+    with pytest.raises(ValueError):                                           # open_raster: nothing else can read it either
+        open_raster(p)
+    open(str(tmp_path / "wf.j2w"), "w").write(f"{RES}\n0.0\n0.0\n-{RES}\n{L + RES / 2!r}\n{T - RES / 2!r}\n")
+    got, left, top, res, crs = read_jp2(p)
+    assert np.array_equal(got[0], img[:, :, 0]) and abs(left - L) < 1e-6 and abs(top - T) < 1e-6 and crs is None
+    bad = tmp_path / "bad.jp2"
+    bad.write_bytes(b"\x00" * 64)
+    with pytest.raises(ValueError, match="not a JP2"):
+        read_jp2(str(bad))
+
+
+def test_open_raster_is_lazy_shared_and_decodes_into_the_upload_buffer(tmp_path, monkeypatch):
+    """rasterio.open() semantics: geometry without touching pixels (slicing / init_outputs only need bounds), ONE decode
+    shared by everyone holding the file, and -- on a GPU host -- decoded straight into the page-locked tensor the dataset
+    uploads from (emulated here with an ordinary tensor: the control flow is the same)."""
+    import torch
+    from flair_for_aigle_b200 import raster_io as rio
+    from flair_for_aigle_b200.flair_zonal_detection import raster as raster_mod
+    rng = np.random.default_rng(8)
+    arr = rng.integers(0, 256, (4, 520, 700), dtype=np.uint8)
+    p = str(tmp_path / "ortho.tif")
+    rio.write_geotiff(p, arr, L, T, RES, epsg=2154, pixel_interleave=True, predictor=2)
+    calls = []
+    real_read = rio.read_window
+    monkeypatch.setattr(rio, "read_window", lambda *a, **k: (calls.append(1), real_read(*a, **k))[1])
+
+    def fake_pinned(shape, dtype, holder):
+        holder["tensor"] = torch.empty(tuple(shape), dtype=torch.uint8)
+        holder["array"] = holder["tensor"].numpy()
+        return holder["array"]
+    monkeypatch.setattr(raster_mod, "_pinned_array", fake_pinned)
+    r = open_raster(p)
+    assert (r.count, r.height, r.width, r.shape, r.res, r.crs) == (4, 520, 700, (520, 700), (RES, RES), "EPSG:2154")
+    assert r.bounds.left == L and r.profile["dtype"] == "uint8" and not r.loaded and calls == []      # no pixel decoded yet
+    assert open_raster(p) is r                                      # same file while somebody holds it
+    assert np.array_equal(r.read([4, 1]), arr[[3, 0]]) and r.loaded and calls == [1]
+    assert np.array_equal(open_raster(p).read(), arr) and calls == [1]                                # decoded once
+    assert r.pinned_tensor is not None and r.pinned_tensor.numpy().ctypes.data == r.array.ctypes.data
+    # the dataset hands exactly that tensor to the uploader (flair_zonal_detection/dataset.py: host_raster)
+    from flair_for_aigle_b200.flair_zonal_detection.dataset import MultiModalSlicedDataset
+    ds = MultiModalSlicedDataset.__new__(MultiModalSlicedDataset)
+    ds.readers, ds.modalities, ds._device_rasters = {"AERIAL_RGBI": r}, {"AERIAL_RGBI": {"channels": [1, 2, 3, 4]}}, {}
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: (_ for _ in ()).throw(AssertionError("copied")))
+    assert ds.host_raster("AERIAL_RGBI") is r.pinned_tensor
+    # a rewritten file is a different raster
+    rio.write_geotiff(p, arr[:, ::-1].copy(), L, T, RES, epsg=2154)
+    r2 = open_raster(p)
+    assert r2 is not r and np.array_equal(r2.read(), arr[:, ::-1])
