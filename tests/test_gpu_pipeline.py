@@ -248,6 +248,48 @@ def test_geotiff_in_geotiff_out(setup, tmp_path):
     assert np.array_equal(got[0], results["file"][0]) and (left, top, res) == (L, T, RES)
 
 
+def test_run_inference_jp2_in_cog_out(setup, tmp_path):
+    """The product script's file contract (scripts/run_fast_aigle_segmentation.py:75-119; inference.py:60 globs *.jp2):
+    a JPEG-2000 ortho with a GeoJP2 box + a config file -> ``run_inference`` -> the class raster as a COG (``cog_conversion``,
+    inference.py:633-641: LZW, 512 blocks, nearest overviews, the plain GeoTIFF removed), georeferenced like the input and
+    identical to the run from the in-memory raster."""
+    import json
+    import bench
+    from PIL import features
+    if not features.check("jpg_2000"):
+        pytest.skip("Pillow without OpenJPEG")
+    from test_geotiff import _geojp2_box, _jp2_with_box
+    from flair_for_aigle_b200 import raster_io
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model, compute_patch_sizes
+    from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import generate_patches_from_reference
+    tmp, wpath, _ = setup
+    arr, cfg_mem = _zone(tmp, wpath, 1000, 700, 64, "mem://z_jp2")
+    src = str(tmp_path / "ortho.jp2")
+    _jp2_with_box(src, np.ascontiguousarray(arr.transpose(1, 2, 0)), _geojp2_box(L, T, RES, 2154))     # lossless
+    cfg = bench.zonal_config(wpath, str(tmp_path / "out"), src, 4)
+    cfg["cog_conversion"] = True
+    cfg_path = str(tmp_path / "zone.json")
+    with open(cfg_path, "w") as f:
+        json.dump(cfg, f)
+    RasterSink.write_files = True
+    written = inf.run_inference(cfg_path)
+    cog = written[TASK]
+    assert cog.endswith("_COG.tif") and os.path.isfile(cog) and not os.path.exists(cog.replace("_COG.tif", ".tif"))
+    got, info = raster_io.read_raster(cog)
+    assert info.tiled and info.block_w == 512 and info.compression == raster_io.COMP_LZW and info.overviews == 1
+    assert (info.left, info.top, info.res_x, info.epsg) == (L, T, RES, 2154)
+    sizes = compute_patch_sizes(cfg_mem)
+    model = build_inference_model(cfg_mem, sizes).to(cfg_mem["device"])
+    tiles = generate_patches_from_reference(cfg_mem, "mem://z_jp2", None)
+    ds = inf.prep_dataset(cfg_mem, tiles, sizes)
+    outs, _ = inf.init_outputs(cfg_mem, "mem://z_jp2", 0)
+    inf.inference_and_write(model, ds, tiles, cfg_mem, outs, "mem://z_jp2")
+    assert np.array_equal(got[0], outs[TASK].to_host()[0])
+    assert np.array_equal(raster_io.read_raster(cog, level=1)[0][0], got[0][::2, ::2])        # nearest overview, even sizes
+
+
 def test_full_size_zone_properties(setup):
     """BASELINE.json configs[1] at its real size (10 000 x 10 000 px, 729 tiles, batches of 37 replayed as a CUDA graph),
     checked through size-independent properties: every pixel written exactly by its owner (no sentinel left, labels
