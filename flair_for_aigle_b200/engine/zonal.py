@@ -114,7 +114,7 @@ class ZonalRunner:
         return g_raster, g_out
 
     def run_streamed(self, host_raster: torch.Tensor, plan: np.ndarray, own: np.ndarray,
-                     out_raster: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> int:
+                     out_raster: torch.Tensor, out_host: Optional[torch.Tensor] = None, rows_ready=None) -> int:
         """Same result as ``run`` from a PINNED HOST raster, with the upload hidden behind the compute: tiles are
         processed bottom-up by tile row (ownership windows make the order irrelevant to the result), and before each
         batch only the raster rows it needs and that are not resident yet are sent on a copy stream (contiguous per
@@ -122,7 +122,10 @@ class ZonalRunner:
         ~2 tile rows instead of the whole raster.  With ``out_host`` (pinned uint8 [H,W]) the class raster is read back
         the same way: rows that no unprocessed tile owns any more are final and leave on the copy stream while the next
         batches run; on return the caller only has to synchronise.  ``out_raster`` receives the finished class raster
-        (one device-to-device copy at the end); its previous content survives where no tile owns a pixel."""
+        (one device-to-device copy at the end); its previous content survives where no tile owns a pixel.
+        ``rows_ready(lo, hi)``: called on the host before rows [lo, hi) are uploaded and returns when they hold valid pixels --
+        a raster FILE still being decoded into ``host_raster`` bottom-up (flair_zonal_detection/raster.py: ProgressiveLoad),
+        so the decode, too, hides behind the compute."""
         n = plan.shape[0]
         if n == 0:
             return 0
@@ -152,6 +155,8 @@ class ZonalRunner:
             nonlocal resident_lo
             lo = lows[b] if b + 1 < nb else 0    # the last batch takes whatever is left (rows no tile reads included)
             if lo < resident_lo:
+                if rows_ready is not None:
+                    rows_ready(lo, resident_lo)
                 with torch.cuda.stream(cs):
                     for c in range(C):
                         dev_raster[c, lo:resident_lo].copy_(host_raster[c, lo:resident_lo], non_blocking=True)

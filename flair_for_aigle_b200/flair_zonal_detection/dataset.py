@@ -69,6 +69,7 @@ class MultiModalSlicedDataset(Dataset):
             raise NotImplementedError("Sentinel time-series modalities are outside the zonal hot path")
         self.readers: Dict[str, ZoneRaster] = {m: open_raster(c['input_img_path']) for m, c in modality_cfgs.items()}
         self._device_rasters: Dict[str, torch.Tensor] = {}
+        self._rows_ready: Dict[str, Any] = {}
         self._plan = None
 
     # ---- integer plan shared by the feeder and the writer kernels
@@ -89,6 +90,13 @@ class MultiModalSlicedDataset(Dataset):
         if key not in self._device_rasters:
             r = self.readers[mod]
             chans = list(self.modalities[mod].get('channels') or range(1, r.count + 1))
+            begin = getattr(r, 'begin_progressive', None)
+            if begin is not None and chans == list(range(1, r.count + 1)) and r.profile['dtype'] == 'uint8':
+                prog = begin()                           # a file: decode it in the background, bottom rows first
+                if prog is not None and prog.tensor is not None:
+                    self._rows_ready[mod] = prog.wait_rows
+                    self._device_rasters[key] = prog.tensor
+                    return prog.tensor
             arr = r.read() if chans == list(range(1, r.count + 1)) else r.read(chans)
             if arr.dtype != np.uint8:
                 raise NotImplementedError(f"{mod}: only uint8 rasters are supported by the device feeder")
@@ -103,6 +111,11 @@ class MultiModalSlicedDataset(Dataset):
                     pass
             self._device_rasters[key] = host
         return self._device_rasters[key]
+
+    def host_rows_ready(self, mod: str):
+        """``wait(lo, hi)`` that returns once rows >= lo of ``host_raster(mod)`` hold decoded pixels, or None when they all
+        do already (the raster came from memory or was decoded in one go)."""
+        return self._rows_ready.get(mod)
 
     def device_raster(self, mod: str, device) -> torch.Tensor:
         """uint8 (imagery) or float32 (elevation) (C,H,W) on ``device``: the channels listed in the modality config

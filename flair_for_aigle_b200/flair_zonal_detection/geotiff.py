@@ -107,6 +107,17 @@ def geotiff_header(path: str):
     return (info.count, info.height, info.width), info.dtype, info.left, info.top, res, info.crs
 
 
+def streamable_info(path: str):
+    """TiffInfo when libfz_rasterio decodes this file itself (so it can be decoded slab by slab behind the upload), else None."""
+    try:
+        info = raster_io.tiff_info(path)
+    except raster_io.RasterIOError:
+        return None
+    ok = (info.compression in (raster_io.COMP_NONE, raster_io.COMP_LZW, raster_io.COMP_DEFLATE) and info.predictor in (1, 2)
+          and info.planar in (1, 2))
+    return info if ok else None
+
+
 def read_geotiff(path: str, alloc: Optional[Allocator] = None) -> Tuple[np.ndarray, float, float, float, Optional[str]]:
     """-> (array (count, H, W), left, top, res, crs).  ``alloc(shape, dtype)`` supplies the array to decode into (e.g. the
     numpy view of a page-locked tensor).  Strips or tiles, classic or BigTIFF, none / LZW / Deflate, predictor 2, 8 / 16 /

@@ -213,7 +213,8 @@ def inference_and_write(model, dataloader, tiles_gdf, config: Dict, output_files
         host = dataset.host_raster(mod)
         if host.is_pinned() and bool(config.get('stream_upload', True)):
             # upload and read-back overlapped with the forward
-            runner.run_streamed(host, plan, own, sink.device_array[0], out_host=sink.pinned_buffer()[0])
+            runner.run_streamed(host, plan, own, sink.device_array[0], out_host=sink.pinned_buffer()[0],
+                                rows_ready=dataset.host_rows_ready(mod))
             sink.mark_streamed()
         else:
             runner.run(dataset.device_raster(mod, device), plan, own, sink.device_array[0])

@@ -12,6 +12,7 @@ from __future__ import annotations
 import json
 import logging
 import os
+import threading
 import weakref
 from collections import namedtuple
 from typing import Optional, Tuple
@@ -24,6 +25,51 @@ BoundingBox = namedtuple("BoundingBox", ["left", "bottom", "right", "top"])
 
 _REGISTRY = {}
 _OPEN_FILES = weakref.WeakValueDictionary()     # (path, mtime, size) -> ZoneRaster, for as long as a caller holds it
+
+
+class ProgressiveLoad:
+    """A raster file being decoded on a background thread, bottom rows first, in slabs of whole block rows (each slab =
+    one block-parallel ``raster_io.read_window`` into the destination's rows).  The zonal runner processes tile rows
+    bottom-up and uploads only the rows the next batch needs (engine/zonal.py: run_streamed), so it calls
+    ``wait_rows(lo)`` before each upload and the rest of the file decodes behind the forward pass."""
+
+    def __init__(self, path: str, info, array: np.ndarray, tensor, slab_rows: int = 2048):
+        self.path, self.info, self.array, self.tensor = path, info, array, tensor
+        bh = max(1, int(info.block_h))
+        self.slab = max(bh, (slab_rows // bh) * bh)
+        self.lo = int(info.height)                       # rows [lo, H) are decoded
+        self.error: Optional[BaseException] = None
+        self._cv = threading.Condition()
+        self._thread = threading.Thread(target=self._run, name="fz-raster-decode", daemon=True)
+        self._thread.start()
+
+    def _run(self) -> None:
+        from .. import raster_io
+        try:
+            H, W = int(self.info.height), int(self.info.width)
+            hi = H
+            while hi > 0:
+                lo = ((hi - 1) // self.slab) * self.slab
+                raster_io.read_window(self.path, lo, 0, hi - lo, W, out=self.array[:, lo:hi], info=self.info)
+                with self._cv:
+                    self.lo = lo
+                    self._cv.notify_all()
+                hi = lo
+        except BaseException as e:  # noqa: BLE001 -- handed to whoever waits
+            with self._cv:
+                self.error = e
+                self._cv.notify_all()
+
+    def wait_rows(self, lo: int, hi: Optional[int] = None) -> None:
+        """Returns when every row >= lo is decoded (``hi`` is accepted for symmetry with the upload's row range)."""
+        with self._cv:
+            while self.lo > lo and self.error is None:
+                self._cv.wait()
+            if self.error is not None:
+                raise self.error
+
+    def wait_all(self) -> None:
+        self.wait_rows(0)
 
 
 class ZoneRaster:
@@ -47,7 +93,7 @@ class ZoneRaster:
 
     @classmethod
     def lazy(cls, shape, dtype, loader, left: float, top: float, res: float, crs: Optional[str] = None,
-             name: str = "<file>"):
+             name: str = "<file>", progressive=None):
         """Raster file opened the way ``rasterio.open`` opens it: size, type and georeferencing now, pixels when somebody
         reads them.  ``loader() -> (array (C,H,W), pinned tensor or None)`` runs once, on the first access to ``array``:
         the geometry-only callers of the path (slicing.py:20-49, inference.py:76-132,157-208) never decode the file."""
@@ -56,12 +102,28 @@ class ZoneRaster:
         r._shape, r._dtype = tuple(int(v) for v in shape), np.dtype(dtype)
         r.left, r.top, r.res_value, r.crs, r.name = float(left), float(top), float(res), crs, name
         r.pinned_tensor = None
+        r._progressive_start, r._progress = progressive, None
         return r
+
+    def begin_progressive(self) -> Optional["ProgressiveLoad"]:
+        """Starts (or returns) the background decode of a lazily opened file: the destination array exists at once, rows
+        become valid bottom-up (``ProgressiveLoad.wait_rows``).  None when the raster is already in memory or the file is not
+        one the block decoder streams (JPEG 2000, Pillow fallback)."""
+        if self._array is not None or getattr(self, "_progressive_start", None) is None:
+            return None
+        if self._progress is None:
+            self._progress = self._progressive_start()
+        return self._progress
 
     @property
     def array(self) -> np.ndarray:
         if self._array is None:
-            arr, pinned = self._loader()
+            prog = getattr(self, "_progress", None)
+            if prog is not None:                          # a background decode is under way: its array, once complete
+                prog.wait_all()
+                arr, pinned = prog.array, prog.tensor
+            else:
+                arr, pinned = self._loader()
             if tuple(arr.shape) != self._shape:
                 raise ValueError(f"{self.name}: decoded {tuple(arr.shape)}, the header said {self._shape}")
             self._array, self.pinned_tensor, self._loader, self._dtype = arr, pinned, None, arr.dtype
@@ -174,7 +236,17 @@ def open_raster(path) -> ZoneRaster:
                 holder = {}
                 arr = reader(path, alloc=lambda shp, dt: _pinned_array(shp, dt, holder))[0]
                 return arr, (holder.get("tensor") if arr is holder.get("array") else None)
-            raster = ZoneRaster.lazy(shape, dtype, load, left, top, res, crs, name=path)
+            progressive = None
+            if not jp2:
+                info = geotiff.streamable_info(path)
+
+                def progressive(info=info):
+                    holder = {}
+                    arr = _pinned_array(shape, dtype, holder)
+                    return ProgressiveLoad(path, info, arr, holder.get("tensor"))
+                if info is None:
+                    progressive = None
+            raster = ZoneRaster.lazy(shape, dtype, load, left, top, res, crs, name=path, progressive=progressive)
             _OPEN_FILES[key] = raster
             return raster
         try:

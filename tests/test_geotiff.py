@@ -180,6 +180,7 @@ def test_jpeg2000_inputs_with_geojp2_gmljp2_and_world_file(tmp_path):
     got, left, top, res, crs = read_jp2(p)
     assert np.array_equal(got, want) and (left, top, res, crs) == (L, T, RES, "EPSG:2154")
     r = open_raster(p)                                                        # ... and through the rasterio.open stand-in
+    assert r.begin_progressive() is None                                      # OpenJPEG decodes the image in one go
     assert (r.count, r.height, r.width) == (4, 300, 420) and np.array_equal(r.read(), want) and r.bounds.left == L
     p = str(tmp_path / "point.jp2")
     _jp2_with_box(p, img, _geojp2_box(L, T, RES, 2154, point=True))           # PixelIsPoint tie point = pixel centre
@@ -254,3 +255,75 @@ def test_open_raster_is_lazy_shared_and_decodes_into_the_upload_buffer(tmp_path,
     rio.write_geotiff(p, arr[:, ::-1].copy(), L, T, RES, epsg=2154)
     r2 = open_raster(p)
     assert r2 is not r and np.array_equal(r2.read(), arr[:, ::-1])
+
+
+def test_progressive_decode_bottom_up_behind_the_upload(tmp_path, monkeypatch):
+    """ProgressiveLoad: the file decodes on a background thread in slabs of whole block rows, bottom rows first;
+    ``wait_rows(lo)`` returns exactly when rows >= lo are valid (what run_streamed calls before uploading them); the result
+    is the one-shot decode; a decode error reaches the waiter; JPEG 2000 files are not streamed."""
+    import threading
+    import torch
+    from flair_for_aigle_b200 import raster_io as rio
+    from flair_for_aigle_b200.flair_zonal_detection import raster as raster_mod
+    rng = np.random.default_rng(9)
+    arr = rng.integers(0, 256, (4, 1500, 640), dtype=np.uint8)
+    p = str(tmp_path / "ortho.tif")
+    rio.write_geotiff(p, arr, L, T, RES, epsg=2154, pixel_interleave=True, block=128)
+
+    def fake_pinned(shape, dtype, holder):
+        holder["tensor"] = torch.zeros(tuple(shape), dtype=torch.uint8)
+        holder["array"] = holder["tensor"].numpy()
+        return holder["array"]
+    monkeypatch.setattr(raster_mod, "_pinned_array", fake_pinned)
+    gate = threading.Semaphore(0)
+    windows = []
+    real_read = rio.read_window
+
+    def gated_read(path, row0, col0, h, w, **kw):
+        gate.acquire()                                   # the test lets one slab through at a time
+        windows.append((row0, h))
+        return real_read(path, row0, col0, h, w, **kw)
+    monkeypatch.setattr(rio, "read_window", gated_read)
+    monkeypatch.setattr(raster_mod.ProgressiveLoad.__init__, "__defaults__", (512,))      # slab_rows: 4 slabs of 512 / 476
+    r = open_raster(p)
+    prog = r.begin_progressive()
+    assert prog is not None and prog.slab == 512 and r.begin_progressive() is prog and prog.lo == 1500 and not r.loaded
+    gate.release()
+    prog.wait_rows(1024)                                 # the bottom slab [1024, 1500)
+    assert prog.lo == 1024 and windows == [(1024, 476)]
+    assert np.array_equal(prog.array[:, 1024:], arr[:, 1024:]) and not prog.array[:, :1024].any()
+    waiter = threading.Thread(target=prog.wait_rows, args=(600,))
+    waiter.start()
+    waiter.join(0.2)
+    assert waiter.is_alive()                             # rows 600.. are not there yet
+    gate.release()
+    waiter.join(10)
+    assert not waiter.is_alive() and prog.lo == 512
+    for _ in range(2):
+        gate.release()
+    assert np.array_equal(r.read(), arr) and r.loaded    # .array waits for the rest
+    assert windows == [(1024, 476), (512, 512), (0, 512)][:len(windows)] and len(windows) == 3
+    assert r.pinned_tensor is prog.tensor and r.begin_progressive() is None
+    # the dataset streams it: host_raster returns the tensor at once, host_rows_ready is the wait function
+    monkeypatch.setattr(rio, "read_window", real_read)
+    p2 = str(tmp_path / "ortho2.tif")
+    rio.write_geotiff(p2, arr, L, T, RES, epsg=2154, pixel_interleave=True, block=128)
+    from flair_for_aigle_b200.flair_zonal_detection.dataset import MultiModalSlicedDataset
+    ds = MultiModalSlicedDataset.__new__(MultiModalSlicedDataset)
+    r2 = open_raster(p2)
+    ds.readers, ds.modalities, ds._device_rasters, ds._rows_ready = {"M": r2}, {"M": {"channels": None}}, {}, {}
+    host = ds.host_raster("M")
+    wait = ds.host_rows_ready("M")
+    assert wait is not None and host is r2.begin_progressive().tensor
+    wait(0, 1500)
+    assert np.array_equal(host.numpy(), arr)
+    # errors travel to the waiter
+    p3 = str(tmp_path / "trunc.tif")
+    rio.write_geotiff(p3, arr, L, T, RES, compression="none", block=128)
+    raw = open(p3, "rb").read()
+    open(p3, "wb").write(raw[:len(raw) // 3])
+    r3 = open_raster(p3)
+    with pytest.raises(rio.RasterIOError, match="outside the file"):
+        r3.begin_progressive().wait_all()
+    with pytest.raises(rio.RasterIOError):
+        r3.read()
