@@ -73,6 +73,44 @@ class PolygonTable:
                 json.dump(fc, f)
         return fc
 
+    def to_file(self, path: str, driver: str = "GPKG", layer: Optional[str] = None) -> str:
+        """``gdf_results.to_file(raster_results_filepath, driver="GPKG")`` (scripts/run_fast_aigle_segmentation.py:123): the
+        frame's two columns -- ``class_id`` and the polygon geometry -- as a GeoPackage layer in the table's CRS
+        (``gpkg.write_gpkg``); ``driver="GeoJSON"`` writes ``to_geojson``."""
+        if driver == "GeoJSON":
+            self.to_geojson(path)
+            return path
+        if driver != "GPKG":
+            raise ValueError(f"driver '{driver}': GPKG and GeoJSON are written")
+        from .gpkg import write_gpkg
+        geoms = self.geometry
+        rings = (geoms.rings(i) for i in range(len(geoms))) if isinstance(geoms, _Geometries) else \
+            ([np.asarray(r, dtype=np.float64) for r in g["coordinates"]] for g in geoms)
+        return write_gpkg(path, rings, {"class_id": np.asarray(self.class_id, dtype=np.int64)}, self.crs, layer)
+
+    @classmethod
+    def read_file(cls, path: str, layer: Optional[str] = None) -> "PolygonTable":
+        """``gpd.read_file(path)`` of a file written by ``to_file`` (scripts/run_fast_aigle_segmentation.py:131): class ids,
+        geometries and CRS; ``area`` is recomputed from the rings (shoelace, holes subtracted)."""
+        from .gpkg import read_gpkg
+        cols, geoms, crs = read_gpkg(path, layer)
+
+        def ring_area(r):
+            return 0.5 * abs(float(np.dot(r[:-1, 0], r[1:, 1]) - np.dot(r[1:, 0], r[:-1, 1])))
+        area = np.asarray([ring_area(g[0]) - sum(ring_area(h) for h in g[1:]) if g else 0.0 for g in geoms])
+        geometry = [{"type": "Polygon", "coordinates": [r.tolist() for r in g]} for g in geoms]
+        return cls(np.asarray(cols.get("class_id", np.zeros(len(geoms))), dtype=np.int64), area, geometry, crs)
+
+    @classmethod
+    def concat(cls, tables: List["PolygonTable"]) -> "PolygonTable":
+        """``pd.concat(gdf_results_list, ignore_index=True)`` (scripts/run_fast_aigle_segmentation.py:132)."""
+        tables = [t for t in tables if len(t)]
+        if not tables:
+            return cls(np.zeros(0, np.int64), np.zeros(0), [], None)
+        geometry = [g for t in tables for g in t.geometry]
+        return cls(np.concatenate([np.asarray(t.class_id, dtype=np.int64) for t in tables]),
+                   np.concatenate([np.asarray(t.area, dtype=np.float64) for t in tables]), geometry, tables[0].crs)
+
 
 def _device_raster(src, device):
     """-> (uint8 [H,W] CUDA tensor, left, top, res, crs) from a RasterSink, the {task: sink} dict the reference passes,

@@ -12,6 +12,7 @@ ownership windows implementing "last writer wins" of inference.py:343-352).
 """
 from __future__ import annotations
 
+import logging
 import math
 import os
 from typing import Dict, List, Optional, Sequence
@@ -19,6 +20,8 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from .raster import ZoneRaster, open_raster
+
+logger = logging.getLogger(__name__)
 
 try:  # pandas is the table type the reference's callers index (tiles_gdf.iloc[...])
     import pandas as pd
@@ -148,10 +151,16 @@ def generate_patches_from_reference(config: Dict, img_path, geozone_contour_geom
         return rows
     gdf = pd.DataFrame(rows)
     if config.get("write_dataframe", False) and len(gdf):
-        out = os.path.join(config["output_path"], output_name + "_slicing_job.csv")
-        gdf.drop(columns=["geometry"]).assign(
-            minx=[g.bounds[0] for g in gdf.geometry], miny=[g.bounds[1] for g in gdf.geometry],
-            maxx=[g.bounds[2] for g in gdf.geometry], maxy=[g.bounds[3] for g in gdf.geometry]).to_csv(out, index=False)
+        # slicing.py:116-119: the tile boxes and their columns as <output_name>_slicing_job.gpkg
+        from .gpkg import write_gpkg
+        out = os.path.join(config["output_path"], output_name + "_slicing_job.gpkg")
+
+        def box_ring(g):                                  # shapely.geometry.box's vertex order (counter-clockwise)
+            x0, y0, x1, y1 = g.bounds
+            return [np.asarray([(x1, y0), (x1, y1), (x0, y1), (x0, y0), (x1, y0)], dtype=np.float64)]
+        write_gpkg(out, (box_ring(g) for g in gdf.geometry),
+                   {c: gdf[c].to_numpy() for c in gdf.columns if c != "geometry"}, getattr(src, "crs", None))
+        logger.info(f"[✓] Saved Sliced Boxes: {out}")
     return gdf
 
 
