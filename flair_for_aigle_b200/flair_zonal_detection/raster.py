@@ -33,11 +33,16 @@ class ProgressiveLoad:
     bottom-up and uploads only the rows the next batch needs (engine/zonal.py: run_streamed), so it calls
     ``wait_rows(lo)`` before each upload and the rest of the file decodes behind the forward pass."""
 
-    def __init__(self, path: str, info, array: np.ndarray, tensor, slab_rows: int = 2048):
+    def __init__(self, path: str, info, array: np.ndarray, tensor, slab_rows: int = 2048, row0: int = 0,
+                 rows: Optional[int] = None):
+        """Decodes file rows [row0, row0 + rows) into ``array`` (C, rows, W): the whole raster by default, one rank's row strip
+        of it under multi-GPU sharding.  Row numbers of ``lo`` / ``wait_rows`` are relative to ``array``."""
         self.path, self.info, self.array, self.tensor = path, info, array, tensor
+        self.row0 = int(row0)
+        self.rows = int(info.height) - self.row0 if rows is None else int(rows)
         bh = max(1, int(info.block_h))
         self.slab = max(bh, (slab_rows // bh) * bh)
-        self.lo = int(info.height)                       # rows [lo, H) are decoded
+        self.lo = self.rows                              # rows [lo, rows) of the array are decoded
         self.error: Optional[BaseException] = None
         self._cv = threading.Condition()
         self._thread = threading.Thread(target=self._run, name="fz-raster-decode", daemon=True)
@@ -46,13 +51,14 @@ class ProgressiveLoad:
     def _run(self) -> None:
         from .. import raster_io
         try:
-            H, W = int(self.info.height), int(self.info.width)
-            hi = H
-            while hi > 0:
-                lo = ((hi - 1) // self.slab) * self.slab
-                raster_io.read_window(self.path, lo, 0, hi - lo, W, out=self.array[:, lo:hi], info=self.info)
+            W = int(self.info.width)
+            hi = self.row0 + self.rows                   # file rows; slab boundaries sit on whole block rows of the file
+            while hi > self.row0:
+                lo = max(self.row0, ((hi - 1) // self.slab) * self.slab)
+                raster_io.read_window(self.path, lo, 0, hi - lo, W, out=self.array[:, lo - self.row0:hi - self.row0],
+                                      info=self.info)
                 with self._cv:
-                    self.lo = lo
+                    self.lo = lo - self.row0
                     self._cv.notify_all()
                 hi = lo
         except BaseException as e:  # noqa: BLE001 -- handed to whoever waits
@@ -114,6 +120,39 @@ class ZoneRaster:
         if self._progress is None:
             self._progress = self._progressive_start()
         return self._progress
+
+    def row_strip(self, r0: int, r1: int, name: Optional[str] = None) -> "ZoneRaster":
+        """Rows [r0, r1) as a raster of their own (same columns, ``top`` moved down by r0 pixels): one rank's input strip of
+        a zone sharded over GPUs (engine/strips.py).  In memory: a view, no copy.  A file the block decoder streams: only
+        these rows are ever decoded (``fzio_read_window`` on the strip), lazily and progressively like the whole file."""
+        r0, r1 = max(0, int(r0)), min(self.height, int(r1))
+        if r1 <= r0:
+            raise ValueError(f"{self.name}: empty row strip [{r0}, {r1})")
+        top = self.top - r0 * self.res_value
+        name = name or f"{self.name}#rows{r0}-{r1}"
+        file = getattr(self, "_file", None)
+        if self._array is None and getattr(self, "_progress", None) is None and file is not None:
+            path, info = file
+            shape = (self._shape[0], r1 - r0, self._shape[2])
+
+            def load():
+                from .. import raster_io
+                holder = {}
+                arr = _pinned_array(shape, self._dtype, holder)
+                raster_io.read_window(path, r0, 0, r1 - r0, shape[2], out=arr, info=info)
+                return arr, holder.get("tensor")
+
+            def progressive():
+                holder = {}
+                arr = _pinned_array(shape, self._dtype, holder)
+                return ProgressiveLoad(path, info, arr, holder.get("tensor"), row0=r0, rows=r1 - r0)
+            return ZoneRaster.lazy(shape, self._dtype, load, self.left, top, self.res_value, self.crs, name=name,
+                                   progressive=progressive)
+        arr = self.array                                  # in memory (or any other source: decoded once, then sliced)
+        strip = ZoneRaster(arr[:, r0:r1], self.left, top, self.res_value, self.crs, name=name)
+        if self.pinned_tensor is not None:
+            strip.pinned_tensor = self.pinned_tensor[:, r0:r1]
+        return strip
 
     @property
     def array(self) -> np.ndarray:
@@ -247,6 +286,8 @@ def open_raster(path) -> ZoneRaster:
                 if info is None:
                     progressive = None
             raster = ZoneRaster.lazy(shape, dtype, load, left, top, res, crs, name=path, progressive=progressive)
+            if progressive is not None:
+                raster._file = (path, info)               # row_strip() reads windows of it
             _OPEN_FILES[key] = raster
             return raster
         try:

@@ -284,7 +284,7 @@ def test_progressive_decode_bottom_up_behind_the_upload(tmp_path, monkeypatch):
         windows.append((row0, h))
         return real_read(path, row0, col0, h, w, **kw)
     monkeypatch.setattr(rio, "read_window", gated_read)
-    monkeypatch.setattr(raster_mod.ProgressiveLoad.__init__, "__defaults__", (512,))      # slab_rows: 4 slabs of 512 / 476
+    monkeypatch.setattr(raster_mod.ProgressiveLoad.__init__, "__defaults__", (512, 0, None))      # slab_rows: 3 slabs of 476 / 512 / 512
     r = open_raster(p)
     prog = r.begin_progressive()
     assert prog is not None and prog.slab == 512 and r.begin_progressive() is prog and prog.lo == 1500 and not r.loaded

@@ -290,6 +290,55 @@ def test_run_inference_jp2_in_cog_out(setup, tmp_path):
     assert np.array_equal(raster_io.read_raster(cog, level=1)[0][0], got[0][::2, ::2])        # nearest overview, even sizes
 
 
+def test_zone_file_sharded_over_ranks_equals_single_run(setup, tmp_path):
+    """SURVEY 8(e) through the public API: ``shard_zone`` + ``run_zone_shard`` (what ``run_inference`` does per rank under
+    torch.distributed) on a GeoTIFF zone -- every rank decodes only its row strip of the file, runs it through
+    ``inference_and_write`` and returns the class-raster rows it owns; the ranks' rows stacked are the single-run raster bit
+    for bit.  (The ranks run one after the other on this GPU; tests/test_zone_shards.py moves the strips between gloo
+    processes with the job's send / recv.)"""
+    import bench
+    from flair_for_aigle_b200 import raster_io
+    from flair_for_aigle_b200.flair_zonal_detection import inference as inf
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import build_inference_model, compute_patch_sizes
+    from flair_for_aigle_b200.flair_zonal_detection.raster import RasterSink
+    from flair_for_aigle_b200.flair_zonal_detection.slicing import generate_patches_from_reference
+    from flair_for_aigle_b200.synthetic import synthetic_raster
+    tmp, wpath, _ = setup
+    arr = synthetic_raster(1500, 1000, seed=13)
+    src = str(tmp_path / "zone.tif")
+    raster_io.write_geotiff(src, arr, L, T, RES, epsg=2154, pixel_interleave=True, predictor=2, block=256)
+    out_dir = str(tmp_path / "out")
+    os.makedirs(out_dir)
+    cfg = bench.zonal_config(wpath, out_dir, src, 4)
+    cfg = inf.initialize_geometry_and_resolutions(cfg)
+    cfg["device"] = torch.device("cuda:0")
+    sizes = compute_patch_sizes(cfg)
+    model = build_inference_model(cfg, sizes).to(cfg["device"])
+    tiles = generate_patches_from_reference(cfg, src, None)
+    RasterSink.write_files = False
+    try:
+        ds = inf.prep_dataset(cfg, tiles, sizes)
+        outs, _ = inf.init_outputs(cfg, src, 0)
+        inf.inference_and_write(model, ds, tiles, cfg, outs, src)
+        whole = outs[TASK].to_host()[0].copy()
+        assert whole.shape == (1500, 1000) and whole.max() < 19
+        import gc
+        from flair_for_aigle_b200.flair_zonal_detection.raster import open_raster
+        del ds, outs
+        gc.collect()
+        assert not open_raster(src).loaded                   # nobody holds the decoded zone any more: ranks start from the file
+        for world in (2, 3):
+            parts = []
+            for rank in range(world):
+                sh = inf.shard_zone(cfg, tiles, rank, world)
+                owned = inf.run_zone_shard(model, sh, sizes)[TASK]
+                assert tuple(owned.shape) == (1, sh.out_rows[1] - sh.out_rows[0], 1000)
+                parts.append(owned[0].cpu().numpy())
+            assert np.array_equal(np.concatenate(parts), whole), world
+    finally:
+        RasterSink.write_files = True
+
+
 def test_full_size_zone_properties(setup):
     """BASELINE.json configs[1] at its real size (10 000 x 10 000 px, 729 tiles, batches of 37 replayed as a CUDA graph),
     checked through size-independent properties: every pixel written exactly by its owner (no sentinel left, labels
