@@ -57,7 +57,14 @@ std::string parallel_for(int64_t n, int threads, F&& fn) {
         for (;;) {
             int64_t i = next.fetch_add(1);
             if (i >= n || failed.load()) return;
-            std::string e = fn(i, worker);
+            std::string e;
+            try {
+                e = fn(i, worker);
+            } catch (const std::bad_alloc&) {             // an exception must not leave a worker thread
+                e = "out of memory";
+            } catch (const std::exception& ex) {
+                e = ex.what();
+            }
             if (!e.empty()) {
                 std::lock_guard<std::mutex> lock(mu);
                 if (first.empty()) first = e;
@@ -428,6 +435,13 @@ int check_supported(const char* path, const Dir& d) {
         return fail(-4, "%s: predictor %d is not supported (1, 2)", path, d.pred);
     if (d.planar != 1 && d.planar != 2) return fail(-4, "%s: PlanarConfiguration %d", path, d.planar);
     if (d.spp < 1 || d.spp > 4096) return fail(-4, "%s: %d samples per pixel", path, d.spp);
+    if (d.bw < 1 || d.bh < 1 || d.width > (1ll << 31) || d.height > (1ll << 31))
+        return fail(-3, "%s: implausible geometry (%lld x %lld, blocks %lld x %lld)", path, (long long)d.width, (long long)d.height,
+                    (long long)d.bw, (long long)d.bh);
+    const double block_bytes = (double)d.bw * (double)d.bh * (d.planar == 2 ? 1 : d.spp) * (d.bits / 8);
+    if (block_bytes > 1073741824.0)
+        return fail(-3, "%s: a %lld x %lld block of %.0f bytes is beyond what this reader decodes in one piece (1 GiB)", path,
+                    (long long)d.bw, (long long)d.bh, block_bytes);
     return 0;
 }
 
@@ -902,7 +916,14 @@ extern "C" {
 int fzio_abi_version(void) { return FZIO_ABI_VERSION; }
 const char* fzio_last_error(void) { return g_error.c_str(); }
 
+#define FZIO_GUARD_BEGIN try {
+#define FZIO_GUARD_END                                                         \
+    }                                                                          \
+    catch (const std::bad_alloc&) { return fail(-9, "out of memory"); }        \
+    catch (const std::exception& ex) { return fail(-9, "%s", ex.what()); }
+
 int fzio_tiff_info(const char* path, int level, fzio_info* out) {
+    FZIO_GUARD_BEGIN
     if (!path || !out) return fail(-1, "fzio_tiff_info: null argument");
     File f;
     int rc = open_file(path, f);
@@ -920,11 +941,13 @@ int fzio_tiff_info(const char* path, int level, fzio_info* out) {
     out->has_georef = g.ok ? 1 : 0; out->epsg = g.epsg; out->geographic = g.geographic ? 1 : 0;
     out->left = g.left; out->top = g.top; out->res_x = g.rx; out->res_y = g.ry;
     return 0;
+    FZIO_GUARD_END
 }
 
 int fzio_read_window(const char* path, int level, int64_t row0, int64_t col0, int64_t win_h, int64_t win_w,
                      const int32_t* bands, int32_t n_bands, void* dst, int64_t dst_band_stride, int64_t dst_row_stride,
                      int32_t threads) {
+    FZIO_GUARD_BEGIN
     if (!path || (!dst && win_h > 0 && win_w > 0)) return fail(-1, "fzio_read_window: null argument");
     File f;
     int rc = open_file(path, f);
@@ -935,18 +958,22 @@ int fzio_read_window(const char* path, int level, int64_t row0, int64_t col0, in
     rc = check_supported(path, d);
     if (rc) return rc;
     return read_window_impl(path, f, d, row0, col0, win_h, win_w, bands, n_bands, (uint8_t*)dst, dst_band_stride, dst_row_stride, threads);
+    FZIO_GUARD_END
 }
 
 int fzio_write_geotiff(const char* path, const void* data, int32_t count, int64_t height, int64_t width,
                        int64_t band_stride, int64_t row_stride, const fzio_write_opts* opts) {
+    FZIO_GUARD_BEGIN
     if (!path || !data) return fail(-1, "fzio_write_geotiff: null argument");
     fzio_write_opts o;
     memset(&o, 0, sizeof o);
     if (opts) o = *opts;
     return write_impl(path, (const uint8_t*)data, count, height, width, band_stride, row_stride, o);
+    FZIO_GUARD_END
 }
 
 int fzio_convert_to_cog(const char* src_path, const char* dst_path, int32_t threads) {
+    FZIO_GUARD_BEGIN
     if (!src_path || !dst_path) return fail(-1, "fzio_convert_to_cog: null argument");
     File f;
     int rc = open_file(src_path, f);
@@ -970,6 +997,7 @@ int fzio_convert_to_cog(const char* src_path, const char* dst_path, int32_t thre
         o.has_georef = 1; o.left = g.left; o.top = g.top; o.res = g.rx; o.epsg = g.epsg; o.geographic = g.geographic ? 1 : 0;
     }
     return write_impl(dst_path, pixels.data(), d.spp, d.height, d.width, 0, 0, o);
+    FZIO_GUARD_END
 }
 
 int64_t fzio_lzw_bound(int64_t n) { return lzw_bound(n); }

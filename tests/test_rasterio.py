@@ -343,3 +343,47 @@ def test_errors_are_loud(tmp_path):
     open(trunc, "wb").write(raw[:len(raw) // 2])
     with pytest.raises(rio.RasterIOError, match="outside the file"):
         rio.read_raster(trunc)
+
+
+def test_corrupted_files_never_crash_the_process(tmp_path):
+    """A file parser meets broken files: 400 random corruptions of valid TIFFs (bytes flipped in the header, the directory,
+    the block tables and the compressed data; truncations) either decode to SOMETHING of the right shape or raise
+    RasterIOError -- no crash, no hang, no out-of-bounds write (the destination carries guard rows)."""
+    rng = np.random.default_rng(12)
+    a = class_map(rng, 300, 260, 3)
+    seeds = []
+    for k, kw in enumerate((dict(compression="lzw", predictor=2, pixel_interleave=True, block=64),
+                            dict(compression="deflate", block=128, overviews=1), dict(compression="none", block=64, bigtiff=1))):
+        p = str(tmp_path / f"seed{k}.tif")
+        rio.write_geotiff(p, a, LEFT, TOP, RES, epsg=2154, **kw)
+        seeds.append(open(p, "rb").read())
+    outcomes = {"ok": 0, "error": 0}
+    victim = str(tmp_path / "victim.tif")
+    for trial in range(400):
+        raw = bytearray(seeds[trial % 3])
+        kind = trial % 4
+        if kind == 0:                                         # header + first directory region
+            for _ in range(int(rng.integers(1, 6))):
+                raw[int(rng.integers(0, min(400, len(raw))))] = int(rng.integers(0, 256))
+        elif kind == 1:                                       # anywhere
+            for _ in range(int(rng.integers(1, 40))):
+                raw[int(rng.integers(0, len(raw)))] = int(rng.integers(0, 256))
+        elif kind == 2:                                       # truncation
+            raw = raw[:int(rng.integers(8, len(raw)))]
+        else:                                                 # a run of garbage
+            at = int(rng.integers(0, len(raw) - 64))
+            raw[at:at + 64] = rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
+        with open(victim, "wb") as f:
+            f.write(bytes(raw))
+        try:
+            info = rio.tiff_info(victim)
+            if info.width * info.height * info.count * info.dtype.itemsize > 64 << 20:
+                raise rio.RasterIOError("implausibly large")  # a corrupted size field: the caller would refuse it as well
+            guard = np.full((info.count, info.height + 2, info.width), 0xAB, info.dtype.str.replace("f4", "u4"))
+            out = guard[:, 1:-1].view(info.dtype)
+            rio.read_window(victim, 0, 0, info.height, info.width, out=out, info=info)
+            assert (guard[:, 0].view(np.uint8) == 0xAB).all() and (guard[:, -1].view(np.uint8) == 0xAB).all()
+            outcomes["ok"] += 1
+        except rio.RasterIOError:
+            outcomes["error"] += 1
+    assert outcomes["ok"] + outcomes["error"] == 400 and outcomes["error"] > 50 and outcomes["ok"] > 20, outcomes
