@@ -90,10 +90,23 @@ constexpr int LZW_CODE_MAX = (1 << LZW_BITS_MAX) - 1;    // 4095
 int64_t lzw_bound(int64_t n) { return 2 * n + 64; }
 
 int64_t lzw_encode(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
-    // dictionary: open-addressing hash of (prefix code << 8 | byte) -> code
-    constexpr int HBITS = 14, HSIZE = 1 << HBITS;
-    static thread_local uint32_t keys[HSIZE];
-    static thread_local uint16_t vals[HSIZE];
+    // dictionary: child[code][byte] -> code, a direct 4096 x 256 table (2 MB per thread, allocated once).  One dependent load
+    // per input byte instead of a hash probe; only the <= 3837 entries made since the last ClearCode are non-zero, and a reset
+    // zeroes exactly those (their positions are remembered), never the whole table.
+    struct Dict {
+        std::vector<uint16_t> child;
+        std::vector<uint32_t> touched;
+        Dict() : child((size_t)4096 * 256, 0) { touched.reserve(4096); }
+        void reset() {
+            for (uint32_t t : touched) child[t] = 0;
+            touched.clear();
+        }
+    };
+    static thread_local std::unique_ptr<Dict> dict_holder;
+    if (!dict_holder) dict_holder.reset(new Dict());
+    Dict& dict = *dict_holder;
+    dict.reset();                                        // a previous call may have ended anywhere
+    uint16_t* const child = dict.child.data();
     uint64_t acc = 0;
     int nacc = 0;
     int64_t o = 0;
@@ -108,26 +121,19 @@ int64_t lzw_encode(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
         }
     };
     int nbits = LZW_BITS_MIN, maxcode = (1 << LZW_BITS_MIN) - 1, free_ent = LZW_FIRST;
-    memset(keys, 0, sizeof keys);
     put(LZW_CLEAR, nbits);
     if (n > 0) {
-        int ent = src[0];
+        uint32_t ent = src[0];
         for (int64_t i = 1; i < n; ++i) {
-            const int c = src[i];
-            const uint32_t key = ((uint32_t)ent << 8 | (uint32_t)c) + 1;            // 0 marks an empty slot
-            uint32_t h = (key * 2654435761u) >> (32 - HBITS);
-            bool found = false;
-            while (keys[h]) {
-                if (keys[h] == key) { ent = vals[h]; found = true; break; }
-                h = (h + 1) & (HSIZE - 1);
-            }
-            if (found) continue;
-            put(ent, nbits);
-            keys[h] = key;
-            vals[h] = (uint16_t)free_ent++;
-            ent = c;
+            const uint32_t slot = ent << 8 | src[i];
+            const uint32_t next = child[slot];
+            if (next) { ent = next; continue; }
+            put((int)ent, nbits);
+            child[slot] = (uint16_t)free_ent++;
+            dict.touched.push_back(slot);
+            ent = src[i];
             if (free_ent == LZW_CODE_MAX - 1) {                                     // table full: start over
-                memset(keys, 0, sizeof keys);
+                dict.reset();
                 free_ent = LZW_FIRST;
                 put(LZW_CLEAR, nbits);
                 nbits = LZW_BITS_MIN;
@@ -137,7 +143,7 @@ int64_t lzw_encode(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
                 maxcode = (1 << nbits) - 1;
             }
         }
-        put(ent, nbits);
+        put((int)ent, nbits);
         ++free_ent;                                     // the decoder adds an entry for this code too
         if (free_ent == LZW_CODE_MAX - 1) {
             put(LZW_CLEAR, nbits);
