@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <functional>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -132,12 +133,12 @@ struct RingStore {
   std::vector<uint8_t> ring_hole;
   std::vector<double> xy;
 };
-static thread_local RingStore g_rings;
+static thread_local std::vector<RingStore> g_parts;   // the bands' rings between fz_trace_rings and fz_trace_rings_fetch
 
 static void douglas_peucker(const std::vector<int32_t>& px, const std::vector<int32_t>& py, size_t a, size_t b, double tol2,
-                            std::vector<uint8_t>& keep) {
-  // iterative DP on the open chain a..b (both kept)
-  std::vector<std::pair<size_t, size_t>> stack;
+                            std::vector<uint8_t>& keep, std::vector<std::pair<size_t, size_t>>& stack) {
+  // iterative DP on the open chain a..b (both kept); `stack` is the caller's scratch (no allocation per ring)
+  stack.clear();
   stack.emplace_back(a, b);
   while (!stack.empty()) {
     const auto [s, e] = stack.back();
@@ -209,12 +210,19 @@ extern "C" int fz_ccl_table(const uint8_t* raster, const int32_t* labels, const 
 }
 
 namespace fz {
-// Rings of the components owned by thread `tid` of `n_threads` (components are dealt to threads by a hash of their label, so
-// every ring -- exterior or hole -- is walked exactly once, by the thread that owns its component).  Each thread scans the
-// whole label image (cheap next to the walks) and records where each ring starts; the caller merges the threads' rings by
-// that position, which reproduces the order of a single row-major scan.
+// Rings whose START lies in rows [y0, y1) of the label image.  A ring starts at its first east-heading top edge in row-major
+// order, which is where a single sequential scan would pick it up; the bands are dealt to threads, so the unit of parallel work
+// is the RING, not the component: one giant component (a background class with a million holes) spreads over all threads.
+// A thread walks every ring it meets in its band once (its own one-bit-per-pixel "top edge walked" map), notes the smallest
+// top-edge position on the way, and emits the ring only if that is the edge it started from -- otherwise the ring starts in
+// an earlier band and belongs to that band's thread (which also walks it: rings crossing k bands are walked k times, in
+// parallel; holes and small components, the bulk of the work, are walked once).  The owner's walk begins at the true start,
+// so vertex order, and after the caller's merge by start position the ring order, are those of the sequential scan for any
+// thread count.
 static void trace_band(const int32_t* labels, int H, int W, const int32_t* keep_roots, int n_keep, double simplify_px,
-                       int tid, int n_threads, RingStore& rs) {
+                       int y0, int y1, RingStore& out) {
+  RingStore rs;        // thread-local while tracing: the callers' stores sit side by side in one array, and growing vectors
+                       // whose headers share cache lines from several threads costs more than the walks themselves
   rs.ring_offset.assign(1, 0);
   auto kept = [&](int32_t r) { return std::binary_search(keep_roots, keep_roots + n_keep, r); };
   auto lab = [&](int x, int y) -> int32_t {          // -1 outside the raster
@@ -222,14 +230,17 @@ static void trace_band(const int32_t* labels, int H, int W, const int32_t* keep_
   };
   // one bit per pixel: "the top edge of this pixel has been walked" (by THIS thread)
   std::vector<uint8_t> seen((static_cast<size_t>(H) * W + 7) / 8, 0);
-  std::vector<int32_t> vx, vy;
+  std::vector<int32_t> vx, vy, px, py;
   std::vector<uint8_t> keep;
+  std::vector<std::pair<size_t, size_t>> dp_stack;
   const double tol2 = simplify_px * simplify_px;
   // direction d: 0 = east (+x), 1 = south (+y), 2 = west, 3 = north; component on the right-hand side
   static const int DX[4] = {1, 0, -1, 0}, DY[4] = {0, 1, 0, -1};
   int32_t last_lab = -2;
   bool last_keep = false;
-  for (int y = 0; y < H; ++y)
+  const auto t_band = std::chrono::steady_clock::now();
+  int64_t steps_mine = 0, steps_other = 0;
+  for (int y = y0; y < y1; ++y)
     for (int x = 0; x < W; ++x) {
       const int32_t L = labels[static_cast<size_t>(y) * W + x];
       if (y > 0 && labels[static_cast<size_t>(y - 1) * W + x] == L) continue;      // no boundary above this pixel
@@ -237,8 +248,7 @@ static void trace_band(const int32_t* labels, int H, int W, const int32_t* keep_
       if (seen[bit >> 3] & (1u << (bit & 7))) continue;
       if (L != last_lab) {
         last_lab = L;
-        last_keep = (n_threads == 1 || static_cast<int>((static_cast<uint32_t>(L) * 2654435761u >> 16) % n_threads) == tid) &&
-                    kept(L);
+        last_keep = kept(L);
       }
       if (!last_keep) continue;
       // walk the ring that contains the east-heading top edge of (x, y), starting at vertex (x, y)
@@ -246,10 +256,16 @@ static void trace_band(const int32_t* labels, int H, int W, const int32_t* keep_
       vy.clear();
       int cx = x, cy = y, d = 0;
       int64_t area2 = 0;
+      bool mine = true;                                   // until a top edge of this ring turns up BEFORE the one we started from
       do {
         if (d == 0) {
           const size_t b2 = static_cast<size_t>(cy) * W + cx;
           seen[b2 >> 3] |= static_cast<uint8_t>(1u << (b2 & 7));
+          if (b2 < bit && mine) {                         // the ring starts in an earlier band: finish marking, emit nothing
+            mine = false;
+            vx.clear();
+            vy.clear();
+          }
         }
         const int nx = cx + DX[d], ny = cy + DY[d];
         area2 += static_cast<int64_t>(cx) * ny - static_cast<int64_t>(nx) * cy;
@@ -268,16 +284,21 @@ static void trace_band(const int32_t* labels, int H, int W, const int32_t* keep_
         else if (lab(alx, aly) == L) nd = (d + 3) & 3;         // left turn
         else nd = d;
         if (nd != d) {
-          vx.push_back(cx);
-          vy.push_back(cy);
+          if (mine) {
+            vx.push_back(cx);
+            vy.push_back(cy);
+          }
           d = nd;
         }
+        ++(mine ? steps_mine : steps_other);
       } while (!(cx == x && cy == y && d == 0));
+      if (!mine) continue;
       // vertices hold every corner once (the start vertex is a corner: nothing of L lies above-left on its ring)
       const size_t nv = vx.size();
       if (nv < 4) continue;
       keep.assign(nv + 1, 0);
-      std::vector<int32_t> px(vx), py(vy);
+      px.assign(vx.begin(), vx.end());
+      py.assign(vy.begin(), vy.end());
       px.push_back(vx[0]);
       py.push_back(vy[0]);
       keep[0] = keep[nv] = 1;
@@ -293,8 +314,8 @@ static void trace_band(const int32_t* labels, int H, int W, const int32_t* keep_
           }
         }
         keep[far] = 1;
-        douglas_peucker(px, py, 0, far, tol2, keep);
-        douglas_peucker(px, py, far, nv, tol2, keep);
+        douglas_peucker(px, py, 0, far, tol2, keep, dp_stack);
+        douglas_peucker(px, py, far, nv, tol2, keep, dp_stack);
       } else {
         std::fill(keep.begin(), keep.end(), 1);
       }
@@ -310,6 +331,11 @@ static void trace_band(const int32_t* labels, int H, int W, const int32_t* keep_
       rs.ring_hole.push_back(area2 < 0 ? 1 : 0);     // y grows downwards: exterior rings (component on the right) have area2 > 0
       rs.ring_offset.push_back(rs.ring_offset.back() + static_cast<int64_t>(emitted));
     }
+  if (getenv("FZ_TRACE_TIMING"))
+    fprintf(stderr, "[trace_band] rows [%d,%d): %.1f ms, %zu rings, steps on own rings %lld, on rings of earlier bands %lld\n", y0, y1,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_band).count(), rs.ring_root.size(),
+            static_cast<long long>(steps_mine), static_cast<long long>(steps_other));
+  out = std::move(rs);
 }
 }  // namespace fz
 
@@ -317,50 +343,67 @@ extern "C" int fz_trace_rings(const int32_t* labels, int H, int W, const int32_t
                               double simplify_px, int64_t* n_rings, int64_t* n_points) {
   using namespace fz;
   FZ_REQUIRE(labels && H > 0 && W > 0 && n_keep >= 0 && n_rings && n_points, "fz_trace_rings: bad arguments");
-  // host threads (FZ_TRACE_THREADS overrides), each with its own H*W-bit bitmap; small rasters stay on one thread
+  const auto t_begin = std::chrono::steady_clock::now();
+  // host threads (FZ_TRACE_THREADS overrides), each with its own H*W-bit bitmap and its own band of rows; small rasters stay
+  // on one thread
   int threads = static_cast<int>(std::thread::hardware_concurrency());
   if (const char* e = getenv("FZ_TRACE_THREADS")) threads = atoi(e);
   else if (static_cast<int64_t>(H) * W < (1 << 20)) threads = 1;
-  threads = threads < 1 ? 1 : (threads > 32 ? 32 : threads);
+  threads = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+  if (threads > H) threads = H;
   std::vector<RingStore> parts(threads);
   if (threads == 1) {
-    trace_band(labels, H, W, keep_roots, n_keep, simplify_px, 0, 1, parts[0]);
+    trace_band(labels, H, W, keep_roots, n_keep, simplify_px, 0, H, parts[0]);
   } else {
     std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
-      pool.emplace_back(trace_band, labels, H, W, keep_roots, n_keep, simplify_px, t, threads, std::ref(parts[t]));
+    for (int t = 0; t < threads; ++t) {
+      const int y0 = static_cast<int>(static_cast<int64_t>(H) * t / threads), y1 = static_cast<int>(static_cast<int64_t>(H) * (t + 1) / threads);
+      pool.emplace_back(trace_band, labels, H, W, keep_roots, n_keep, simplify_px, y0, y1, std::ref(parts[t]));
+    }
     for (auto& th : pool) th.join();
   }
-  // merge by ring start = the order of one row-major scan (each part is already sorted)
-  std::vector<std::pair<size_t, std::pair<int, int>>> order;            // (start, (part, ring index))
-  for (int t = 0; t < threads; ++t)
-    for (size_t i = 0; i < parts[t].ring_start.size(); ++i) order.push_back({parts[t].ring_start[i], {t, static_cast<int>(i)}});
-  std::sort(order.begin(), order.end());
-  RingStore& rs = g_rings;
-  rs = RingStore();
-  rs.ring_offset.assign(1, 0);
-  for (const auto& o : order) {
-    const RingStore& p = parts[o.second.first];
-    const int i = o.second.second;
-    const int64_t a0 = p.ring_offset[i], a1 = p.ring_offset[i + 1];
-    rs.ring_root.push_back(p.ring_root[i]);
-    rs.ring_hole.push_back(p.ring_hole[i]);
-    rs.xy.insert(rs.xy.end(), p.xy.begin() + 2 * a0, p.xy.begin() + 2 * a1);
-    rs.ring_offset.push_back(rs.ring_offset.back() + (a1 - a0));
+  const auto t_traced = std::chrono::steady_clock::now();
+  // a band's rings all start inside the band, and the bands are ordered: concatenating the parts IS the order of one row-major
+  // scan.  Nothing is merged here; fz_trace_rings_fetch copies every part to its place in the caller's arrays, in parallel.
+  int64_t rings = 0, points = 0;
+  for (const RingStore& p : parts) {
+    rings += static_cast<int64_t>(p.ring_root.size());
+    points += p.ring_offset.back();
   }
-  *n_rings = static_cast<int64_t>(rs.ring_root.size());
-  *n_points = rs.ring_offset.back();
+  g_parts = std::move(parts);
+  *n_rings = rings;
+  *n_points = points;
+  if (getenv("FZ_TRACE_TIMING"))
+    fprintf(stderr, "[fz_trace_rings] %d threads: walk %.1f ms\n", threads,
+            std::chrono::duration<double, std::milli>(t_traced - t_begin).count());
   return 0;
 }
 
 extern "C" int fz_trace_rings_fetch(int32_t* ring_root, uint8_t* ring_is_hole, int64_t* ring_offset, double* xy) {
   using namespace fz;
-  RingStore& rs = g_rings;
   FZ_REQUIRE(ring_root && ring_is_hole && ring_offset && xy, "fz_trace_rings_fetch: null output");
-  std::copy(rs.ring_root.begin(), rs.ring_root.end(), ring_root);
-  std::copy(rs.ring_hole.begin(), rs.ring_hole.end(), ring_is_hole);
-  std::copy(rs.ring_offset.begin(), rs.ring_offset.end(), ring_offset);
-  std::copy(rs.xy.begin(), rs.xy.end(), xy);
-  rs = RingStore();
+  std::vector<RingStore> parts = std::move(g_parts);
+  g_parts.clear();
+  std::vector<int64_t> ring_base(parts.size() + 1, 0), point_base(parts.size() + 1, 0);
+  for (size_t t = 0; t < parts.size(); ++t) {
+    ring_base[t + 1] = ring_base[t] + static_cast<int64_t>(parts[t].ring_root.size());
+    point_base[t + 1] = point_base[t] + parts[t].ring_offset.back();
+  }
+  ring_offset[0] = 0;
+  auto copy_part = [&](size_t t) {
+    const RingStore& p = parts[t];
+    const int64_t rb = ring_base[t], pb = point_base[t];
+    std::copy(p.ring_root.begin(), p.ring_root.end(), ring_root + rb);
+    std::copy(p.ring_hole.begin(), p.ring_hole.end(), ring_is_hole + rb);
+    for (size_t i = 0; i < p.ring_root.size(); ++i) ring_offset[rb + 1 + static_cast<int64_t>(i)] = pb + p.ring_offset[i + 1];
+    std::copy(p.xy.begin(), p.xy.end(), xy + 2 * pb);
+  };
+  if (parts.size() <= 1) {
+    for (size_t t = 0; t < parts.size(); ++t) copy_part(t);
+  } else {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < parts.size(); ++t) pool.emplace_back(copy_part, t);
+    for (auto& th : pool) th.join();
+  }
   return 0;
 }
