@@ -107,15 +107,31 @@ def geotiff_header(path: str):
     return (info.count, info.height, info.width), info.dtype, info.left, info.top, res, info.crs
 
 
-def streamable_info(path: str):
-    """TiffInfo when libfz_rasterio decodes this file itself (so it can be decoded slab by slab behind the upload), else None."""
+def row_source(path: str):
+    """``raster.RowSource`` of a file whose rows can be decoded range by range -- so it can be decoded slab by slab behind the
+    upload, and strip by strip over several GPUs -- or None (the file is then decoded in one go).  GeoTIFF: when
+    libfz_rasterio decodes the file itself; JPEG 2000: when the OpenJPEG library can be driven directly."""
+    from .raster import RowSource
+    if path.lower().endswith((".jp2", ".j2k")):
+        from .. import openjpeg
+        try:
+            j = openjpeg.info(path)
+        except (openjpeg.OpenJPEGUnavailable, openjpeg.OpenJPEGError):
+            return None
+        def read_jp2_rows(lo: int, hi: int, out: np.ndarray) -> None:
+            openjpeg.read_rows(path, lo, hi, out=out)
+        return RowSource(read_jp2_rows, j.tile_h, j.height, j.width)
     try:
         info = raster_io.tiff_info(path)
     except raster_io.RasterIOError:
         return None
     ok = (info.compression in (raster_io.COMP_NONE, raster_io.COMP_LZW, raster_io.COMP_DEFLATE) and info.predictor in (1, 2)
           and info.planar in (1, 2))
-    return info if ok else None
+    if not ok:
+        return None
+    def read_tiff_rows(lo: int, hi: int, out: np.ndarray) -> None:
+        raster_io.read_window(path, lo, 0, hi - lo, info.width, out=out, info=info)
+    return RowSource(read_tiff_rows, info.block_h, info.height, info.width)
 
 
 def read_geotiff(path: str, alloc: Optional[Allocator] = None) -> Tuple[np.ndarray, float, float, float, Optional[str]]:
@@ -290,10 +306,20 @@ def jp2_header(path: str):
 
 def read_jp2(path: str, alloc: Optional[Allocator] = None) -> Tuple[np.ndarray, float, float, float, Optional[str]]:
     """JPEG-2000 raster (the reference's product inputs, inference.py:60 ``*.jp2``) -> (array (count, H, W) uint8, left, top,
-    res, crs).  Pixels: OpenJPEG through Pillow (the whole image once -- it becomes HBM-resident anyway -- instead of one
-    windowed decode per tile, dataset.py:108-115).  Georeferencing, in GDAL's order of preference: GeoJP2 uuid box, GMLJP2,
+    res, crs).  Pixels: the OpenJPEG library driven directly (``..openjpeg``: its worker threads on all cores, decoding into
+    the upload buffer; row ranges for strips and progressive loads), Pillow's one-thread path as the fallback -- the image is
+    decoded once, it becomes HBM-resident anyway, instead of one windowed decode per tile (dataset.py:108-115).  Georeferencing, in GDAL's order of preference: GeoJP2 uuid box, GMLJP2,
     world file."""
     left, top, res, crs = _jp2_georef(path)
+    from .. import openjpeg
+    try:                                                     # OpenJPEG driven directly: all cores, straight into the buffer
+        j = openjpeg.info(path)
+        shape = (j.count, j.height, j.width)
+        out = alloc(shape, np.dtype(np.uint8)) if alloc is not None else np.empty(shape, np.uint8)
+        openjpeg.read_rows(path, 0, j.height, out=out)
+        return out, left, top, res, crs
+    except (openjpeg.OpenJPEGUnavailable, openjpeg.OpenJPEGError):
+        pass                                                 # Pillow's one-thread path decodes what is left (or says why not)
     with _jp2_open(path) as im:
         a = np.asarray(im)
     if a.dtype != np.uint8:

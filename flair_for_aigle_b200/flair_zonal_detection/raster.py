@@ -15,7 +15,7 @@ import os
 import threading
 import weakref
 from collections import namedtuple
-from typing import Optional, Tuple
+from typing import Callable, NamedTuple, Optional, Tuple
 
 import numpy as np
 
@@ -27,20 +27,29 @@ _REGISTRY = {}
 _OPEN_FILES = weakref.WeakValueDictionary()     # (path, mtime, size) -> ZoneRaster, for as long as a caller holds it
 
 
+class RowSource(NamedTuple):
+    """A raster file that decodes any range of rows on request: ``read_rows(lo, hi, out)`` fills out (C, hi - lo, W).
+    GeoTIFF: libfz_rasterio's block-parallel window read; JPEG 2000: OpenJPEG's decode area + worker threads."""
+    read_rows: Callable[[int, int, np.ndarray], None]
+    block_h: int            # rows of one block / tile row of the file: slabs and strips decode whole block rows once
+    height: int
+    width: int
+
+
 class ProgressiveLoad:
     """A raster file being decoded on a background thread, bottom rows first, in slabs of whole block rows (each slab =
-    one block-parallel ``raster_io.read_window`` into the destination's rows).  The zonal runner processes tile rows
+    one ``RowSource.read_rows`` into the destination's rows, itself parallel over the slab's blocks).  The zonal runner processes tile rows
     bottom-up and uploads only the rows the next batch needs (engine/zonal.py: run_streamed), so it calls
     ``wait_rows(lo)`` before each upload and the rest of the file decodes behind the forward pass."""
 
-    def __init__(self, path: str, info, array: np.ndarray, tensor, slab_rows: int = 2048, row0: int = 0,
+    def __init__(self, source: "RowSource", array: np.ndarray, tensor, slab_rows: int = 2048, row0: int = 0,
                  rows: Optional[int] = None):
         """Decodes file rows [row0, row0 + rows) into ``array`` (C, rows, W): the whole raster by default, one rank's row strip
         of it under multi-GPU sharding.  Row numbers of ``lo`` / ``wait_rows`` are relative to ``array``."""
-        self.path, self.info, self.array, self.tensor = path, info, array, tensor
+        self.source, self.array, self.tensor = source, array, tensor
         self.row0 = int(row0)
-        self.rows = int(info.height) - self.row0 if rows is None else int(rows)
-        bh = max(1, int(info.block_h))
+        self.rows = int(source.height) - self.row0 if rows is None else int(rows)
+        bh = max(1, int(source.block_h))
         self.slab = max(bh, (slab_rows // bh) * bh)
         self.lo = self.rows                              # rows [lo, rows) of the array are decoded
         self.error: Optional[BaseException] = None
@@ -49,14 +58,11 @@ class ProgressiveLoad:
         self._thread.start()
 
     def _run(self) -> None:
-        from .. import raster_io
         try:
-            W = int(self.info.width)
             hi = self.row0 + self.rows                   # file rows; slab boundaries sit on whole block rows of the file
             while hi > self.row0:
                 lo = max(self.row0, ((hi - 1) // self.slab) * self.slab)
-                raster_io.read_window(self.path, lo, 0, hi - lo, W, out=self.array[:, lo - self.row0:hi - self.row0],
-                                      info=self.info)
+                self.source.read_rows(lo, hi, self.array[:, lo - self.row0:hi - self.row0])
                 with self._cv:
                     self.lo = lo - self.row0
                     self._cv.notify_all()
@@ -130,22 +136,20 @@ class ZoneRaster:
             raise ValueError(f"{self.name}: empty row strip [{r0}, {r1})")
         top = self.top - r0 * self.res_value
         name = name or f"{self.name}#rows{r0}-{r1}"
-        file = getattr(self, "_file", None)
-        if self._array is None and getattr(self, "_progress", None) is None and file is not None:
-            path, info = file
+        source = getattr(self, "_source", None)
+        if self._array is None and getattr(self, "_progress", None) is None and source is not None:
             shape = (self._shape[0], r1 - r0, self._shape[2])
 
             def load():
-                from .. import raster_io
                 holder = {}
                 arr = _pinned_array(shape, self._dtype, holder)
-                raster_io.read_window(path, r0, 0, r1 - r0, shape[2], out=arr, info=info)
+                source.read_rows(r0, r1, arr)
                 return arr, holder.get("tensor")
 
             def progressive():
                 holder = {}
                 arr = _pinned_array(shape, self._dtype, holder)
-                return ProgressiveLoad(path, info, arr, holder.get("tensor"), row0=r0, rows=r1 - r0)
+                return ProgressiveLoad(source, arr, holder.get("tensor"), row0=r0, rows=r1 - r0)
             return ZoneRaster.lazy(shape, self._dtype, load, self.left, top, self.res_value, self.crs, name=name,
                                    progressive=progressive)
         arr = self.array                                  # in memory (or any other source: decoded once, then sliced)
@@ -275,19 +279,15 @@ def open_raster(path) -> ZoneRaster:
                 holder = {}
                 arr = reader(path, alloc=lambda shp, dt: _pinned_array(shp, dt, holder))[0]
                 return arr, (holder.get("tensor") if arr is holder.get("array") else None)
+            source = geotiff.row_source(path)             # None: the file is decoded in one go (Pillow paths)
             progressive = None
-            if not jp2:
-                info = geotiff.streamable_info(path)
-
-                def progressive(info=info):
+            if source is not None:
+                def progressive():
                     holder = {}
                     arr = _pinned_array(shape, dtype, holder)
-                    return ProgressiveLoad(path, info, arr, holder.get("tensor"))
-                if info is None:
-                    progressive = None
+                    return ProgressiveLoad(source, arr, holder.get("tensor"))
             raster = ZoneRaster.lazy(shape, dtype, load, left, top, res, crs, name=path, progressive=progressive)
-            if progressive is not None:
-                raster._file = (path, info)               # row_strip() reads windows of it
+            raster._source = source                       # row_strip() decodes row ranges of it
             _OPEN_FILES[key] = raster
             return raster
         try:

@@ -180,7 +180,6 @@ def test_jpeg2000_inputs_with_geojp2_gmljp2_and_world_file(tmp_path):
     got, left, top, res, crs = read_jp2(p)
     assert np.array_equal(got, want) and (left, top, res, crs) == (L, T, RES, "EPSG:2154")
     r = open_raster(p)                                                        # ... and through the rasterio.open stand-in
-    assert r.begin_progressive() is None                                      # OpenJPEG decodes the image in one go
     assert (r.count, r.height, r.width) == (4, 300, 420) and np.array_equal(r.read(), want) and r.bounds.left == L
     p = str(tmp_path / "point.jp2")
     _jp2_with_box(p, img, _geojp2_box(L, T, RES, 2154, point=True))           # PixelIsPoint tie point = pixel centre
@@ -327,3 +326,71 @@ def test_progressive_decode_bottom_up_behind_the_upload(tmp_path, monkeypatch):
         r3.begin_progressive().wait_all()
     with pytest.raises(rio.RasterIOError):
         r3.read()
+
+
+def test_openjpeg_driven_directly_row_windows_threads_and_fallback(tmp_path, monkeypatch):
+    """flair_for_aigle_b200/openjpeg.py binds the libopenjp2 inside Pillow's wheel: row-window decodes (strips of a sharded
+    zone, progressive slabs) and OpenJPEG's worker threads.  Pinned against Pillow's own decode of the same files (lossless
+    AND lossy: same library, so the lossy pixels must be identical too); a JP2 zone decodes progressively and strip-wise like a
+    GeoTIFF; without the library the readers fall back to Pillow."""
+    from PIL import Image, features
+    if not features.check("jpg_2000"):
+        pytest.skip("Pillow without OpenJPEG")
+    from flair_for_aigle_b200 import openjpeg as oj
+    from flair_for_aigle_b200.flair_zonal_detection import geotiff, raster as raster_mod
+    rng = np.random.default_rng(10)
+    img = np.kron(rng.integers(0, 256, (40, 30, 4)).astype(np.uint8), np.ones((32, 32, 1), np.uint8))     # 1280 x 960 x 4
+    img[::7, ::5] += 3
+    want = img.transpose(2, 0, 1)
+    lossless, tiled, lossy, gray = (str(tmp_path / n) for n in ("a.jp2", "t.jp2", "l.jp2", "g.j2k"))
+    Image.fromarray(img).save(lossless, format="JPEG2000", irreversible=False)
+    Image.fromarray(img).save(tiled, format="JPEG2000", irreversible=False, tile_size=(256, 256))
+    Image.fromarray(img[:, :, :3]).save(lossy, format="JPEG2000", irreversible=True, quality_mode="rates", quality_layers=[20])
+    Image.fromarray(img[:, :, 0]).save(gray, format="JPEG2000", irreversible=False)                         # bare codestream
+    assert oj.info(lossless) == oj.JP2Info(960, 1280, 4, 960, 1280, oj.info(lossless).threads_supported)
+    assert oj.info(tiled)[:5] == (960, 1280, 4, 256, 256) and oj.info(gray)[:3] == (960, 1280, 1)
+    for path, ref in ((lossless, want), (tiled, want), (gray, want[:1])):
+        for threads in (1, 0):
+            assert np.array_equal(oj.read_rows(path, threads=threads), ref)
+        for r0, r1 in ((0, 1), (0, 256), (255, 257), (700, 1280), (1279, 1280)):
+            assert np.array_equal(oj.read_rows(path, r0, r1), ref[:, r0:r1]), (path, r0, r1)
+    with Image.open(lossy) as im:
+        pil = np.asarray(im).transpose(2, 0, 1)
+    assert np.array_equal(oj.read_rows(lossy), pil) and not np.array_equal(pil, want[:3])      # lossy, yet the same decoder
+    big = np.empty((4, 1400, 960), np.uint8)
+    oj.read_rows(tiled, 100, 1000, out=big[:, 200:1100])                       # into a row-strided slab of a larger buffer
+    assert np.array_equal(big[:, 200:1100], want[:, 100:1000])
+    with pytest.raises(oj.OpenJPEGError, match="outside"):
+        oj.read_rows(lossless, 10, 2000)
+    bad = tmp_path / "bad.jp2"
+    bad.write_bytes(b"\x00" * 100)
+    with pytest.raises(oj.OpenJPEGError, match="neither"):
+        oj.info(str(bad))
+    sixteen = str(tmp_path / "s.jp2")
+    Image.fromarray((img[:, :, 0].astype(np.uint16) * 200)).save(sixteen, format="JPEG2000", irreversible=False)
+    with pytest.raises(oj.OpenJPEGError, match="16-bit"):
+        oj.info(sixteen)
+    # a georeferenced JP2 zone: progressive (slabs on tile rows) and strip-wise, like a GeoTIFF
+    zone = str(tmp_path / "zone.jp2")
+    Image.fromarray(img).save(zone, format="JPEG2000", irreversible=False, tile_size=(256, 256))
+    raw = open(zone, "rb").read()
+    at = raw.index(b"jp2c") - 4
+    open(zone, "wb").write(raw[:at] + _geojp2_box(L, T, RES, 2154) + raw[at:])
+    monkeypatch.setattr(raster_mod.ProgressiveLoad.__init__, "__defaults__", (512, 0, None))
+    r = open_raster(zone)
+    prog = r.begin_progressive()
+    assert prog is not None and prog.slab == 512 and not r.loaded
+    prog.wait_rows(1024)
+    assert np.array_equal(prog.array[:, 1024:], want[:, 1024:])
+    assert np.array_equal(r.read(), want)
+    del r, prog
+    import gc
+    gc.collect()
+    strip = open_raster(zone).row_strip(300, 900)                             # nobody holds the decoded zone: rows only
+    assert not strip.loaded and strip.top == T - 300 * RES and np.array_equal(strip.read(), want[:, 300:900])
+    # no library -> Pillow decodes (one thread, whole image), nothing is streamed
+    monkeypatch.setattr(oj, "_lib", None)
+    monkeypatch.setattr(oj, "lib", lambda: (_ for _ in ()).throw(oj.OpenJPEGUnavailable("test")))
+    assert geotiff.row_source(zone) is None
+    got, left, top, res, crs = geotiff.read_jp2(zone)
+    assert np.array_equal(got, want) and (left, top, res, crs) == (L, T, RES, "EPSG:2154")

@@ -107,6 +107,28 @@ def main():
         t_win = (time.perf_counter() - t0) / 200
         say(f"  per-tile windows like the reference ({len(wins)} boundless 512 x 512 reads, 1 thread each): {t_win * 1e3:.2f} ms / window -> "
             f"{t_win * len(wins) * 1e3:.0f} ms per zone vs {t_n * 1e3:.0f} ms for ONE block-parallel pass into the upload buffer")
+        # ---------------------------------------------------------------- JPEG 2000 orthos (the reference's product inputs)
+        try:
+            from flair_for_aigle_b200 import openjpeg as oj
+            m = min(n, 4000)
+            crop = np.ascontiguousarray(ortho[:, :m, :m].transpose(1, 2, 0))
+            say("")
+            say(f"READ JPEG 2000 ortho ({m} x {m} x 4, tiles of 1024; OpenJPEG {oj.lib().opj_version().decode()} from Pillow's wheel)")
+            for label, kw in (("lossless (reversible 5/3)", dict(irreversible=False)),
+                              ("lossy 1:10 (irreversible 9/7)", dict(irreversible=True, quality_mode="rates", quality_layers=[10]))):
+                pj = os.path.join(tmp, "ortho.jp2")
+                Image.fromarray(crop).save(pj, format="JPEG2000", tile_size=(1024, 1024), **kw)
+                mbj = crop.nbytes / 1e6
+                t_pil = best(lambda: np.ascontiguousarray(np.asarray(Image.open(pj)).transpose(2, 0, 1)), 1)
+                dstj = np.empty((4, m, m), np.uint8)
+                t_1 = best(lambda: oj.read_rows(pj, out=dstj, threads=1), 1)
+                t_n = best(lambda: oj.read_rows(pj, out=dstj), 2)
+                t_strip = best(lambda: oj.read_rows(pj, m // 2, m // 2 + 1024), 2)
+                say(f"  {label:30s} file {os.path.getsize(pj) / 1e6:6.1f} MB: Pillow (1 thread, whole image) {t_pil * 1e3:7.0f} ms = {mbj / t_pil:5.0f} MB/s | "
+                    f"OpenJPEG direct 1 thread {t_1 * 1e3:7.0f} ms | {cores} threads {t_n * 1e3:7.0f} ms = {mbj / t_n:5.0f} MB/s | "
+                    f"one 1024-row strip {t_strip * 1e3:6.0f} ms")
+        except Exception as ex:  # noqa: BLE001
+            say(f"  JPEG 2000 section skipped: {ex!r}")
     if args.out:
         with open(args.out, "w") as f:
             f.write("\n".join(lines) + "\n")
