@@ -437,8 +437,10 @@ int check_supported(const char* path, const Dir& d) {
         return fail(-4, "%s: %d-bit samples are not supported (8, 16, 32)", path, d.bits);
     if (d.comp != 1 && d.comp != 5 && d.comp != 8)
         return fail(-4, "%s: TIFF compression %d is not supported (none, LZW, Deflate)", path, d.comp);
-    if (d.pred != 1 && d.pred != 2)
-        return fail(-4, "%s: predictor %d is not supported (1, 2)", path, d.pred);
+    if (d.pred != 1 && d.pred != 2 && d.pred != 3)
+        return fail(-4, "%s: predictor %d is not supported (1, 2, 3)", path, d.pred);
+    if (d.pred == 3 && (d.fmt != 3 || d.bits != 32))
+        return fail(-4, "%s: the floating-point predictor is decoded for 32-bit float samples only", path);
     if (d.planar != 1 && d.planar != 2) return fail(-4, "%s: PlanarConfiguration %d", path, d.planar);
     if (d.spp < 1 || d.spp > 4096) return fail(-4, "%s: %d samples per pixel", path, d.spp);
     if (d.bw < 1 || d.bh < 1 || d.width > (1ll << 31) || d.height > (1ll << 31))
@@ -519,6 +521,22 @@ std::string decode_block(const File& f, const Dir& d, int64_t idx, int64_t rows,
             got = (int64_t)len;
         }
         if (got < want) memset(buf + got, 0, want - got);
+    }
+    if (d.pred == 3 && d.comp != 1) {
+        // floating-point predictor (TIFF Technical Note 3; elevation rasters written with GDAL's PREDICTOR=3): every row holds
+        // the samples' bytes as planes, most significant byte first, differenced byte-wise along the whole row.  Undo the
+        // differences, then gather each sample's bytes (into native little-endian order) -- the row's own byte order does not
+        // matter, so the endian swap below is skipped.
+        const int64_t row_bytes = d.bw * sppb * bps, wc = d.bw * sppb;
+        std::vector<uint8_t> tmp((size_t)row_bytes);
+        for (int64_t r = 0; r < rows; ++r) {
+            uint8_t* row = buf + r * row_bytes;
+            for (int64_t i = sppb; i < row_bytes; ++i) row[i] = (uint8_t)(row[i] + row[i - sppb]);
+            memcpy(tmp.data(), row, (size_t)row_bytes);
+            for (int64_t k = 0; k < wc; ++k)
+                for (int b = 0; b < bps; ++b) row[bps * k + b] = tmp[(size_t)((bps - 1 - b) * wc + k)];
+        }
+        return "";
     }
     if (d.be && bps > 1) swap_samples(buf, rows * d.bw * sppb, bps);
     if (d.pred == 2 && d.comp != 1) {                   // libtiff applies the predictor inside the LZW / Deflate codecs only

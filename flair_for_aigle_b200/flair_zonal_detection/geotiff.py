@@ -125,7 +125,7 @@ def row_source(path: str):
         info = raster_io.tiff_info(path)
     except raster_io.RasterIOError:
         return None
-    ok = (info.compression in (raster_io.COMP_NONE, raster_io.COMP_LZW, raster_io.COMP_DEFLATE) and info.predictor in (1, 2)
+    ok = (info.compression in (raster_io.COMP_NONE, raster_io.COMP_LZW, raster_io.COMP_DEFLATE) and info.predictor in (1, 2, 3)
           and info.planar in (1, 2))
     if not ok:
         return None

@@ -13,7 +13,8 @@
  * raster is read ONCE, block by block on all host cores, straight into the (page-locked) array the GPU upload reads from,
  * and the class raster is encoded ONCE from the array the GPU read-back filled: 512 x 512 blocks, one block per task,
  * compressed in parallel, written in file order.  Classic TIFF and BigTIFF (chosen by size), strips or tiles,
- * uncompressed / LZW / Deflate, horizontal predictor, pixel- or band-interleaved, 8 / 16 / 32-bit samples.
+ * uncompressed / LZW / Deflate, horizontal predictor (and, reading, the floating-point predictor of elevation rasters),
+ * pixel- or band-interleaved, 8 / 16 / 32-bit samples.
  *
  * Conventions: plain pointers and sizes; every function returns 0 on success or a negative code and leaves a message in
  * fzio_last_error() (thread-local).  Arrays are band-sequential [count][height][width], as rasterio's read() returns them.

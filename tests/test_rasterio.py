@@ -151,6 +151,14 @@ def test_libtiff_predictor_uint16_float32(tmp_path):
     Image.fromarray(dem[0]).save(p, format="TIFF", compression="tiff_lzw")
     got, info = rio.read_raster(p)
     assert info.dtype == np.float32 and np.array_equal(got, dem)
+    # GDAL's PREDICTOR=3 for elevation rasters (floating-point predictor: byte planes + byte differences), libtiff-written
+    smooth = (np.cumsum(rng.standard_normal((1, 211, 333)), axis=2) * 3 + 400).astype(np.float32)
+    for comp in ("tiff_lzw", "tiff_adobe_deflate"):
+        p = str(tmp_path / "fp3.tif")
+        Image.fromarray(smooth[0]).save(p, format="TIFF", compression=comp, tiffinfo={317: 3})
+        got, info = rio.read_raster(p)
+        assert info.predictor == 3 and info.dtype == np.float32 and np.array_equal(got, smooth)
+        assert np.array_equal(rio.read_window(p, 100, -5, 50, 60)[0, :, 5:], smooth[0, 100:150, :55])
     # and written here (tiled float32 / uint16), read by libtiff
     for arr in (dem, a16):
         p = str(tmp_path / "w.tif")
