@@ -695,6 +695,11 @@ int write_impl(const char* path, const uint8_t* data, int count, int64_t height,
     if (o.bits == 0) o.bits = 8;
     if (count < 1 || height < 1 || width < 1) return fail(-1, "empty raster (%d x %lld x %lld)", count, (long long)height, (long long)width);
     if (o.block < 16 || o.block % 16) return fail(-1, "block=%d: TIFF tiles are multiples of 16", o.block);
+    if (o.block > 8192) return fail(-1, "block=%d: tiles above 8192 x 8192 are refused", o.block);
+    if (o.overview_resampling != FZIO_OVR_NEAREST && o.overview_resampling != FZIO_OVR_MODE)
+        return fail(-1, "overview_resampling=%d (0 nearest, 1 mode)", o.overview_resampling);
+    if (o.overview_resampling == FZIO_OVR_MODE && o.bits != 0 && o.bits != 8 && o.overviews != 0)
+        return fail(-1, "mode resampling of overviews is written for 8-bit (class) rasters only");
     if (o.compression != 1 && o.compression != 5 && o.compression != 8) return fail(-1, "compression=%d (1 none, 5 LZW, 8 Deflate)", o.compression);
     if (o.bits != 8 && o.bits != 16 && o.bits != 32) return fail(-1, "bits=%d (8, 16, 32)", o.bits);
     if (o.predictor != 1 && o.predictor != 2) return fail(-1, "predictor=%d (1, 2)", o.predictor);

@@ -90,6 +90,7 @@ class ZoneRaster:
         if array.ndim == 2:
             array = array[None]
         self._array, self._loader = array, None
+        self._progressive_start, self._progress, self._source = None, None, None
         self._shape, self._dtype = tuple(array.shape), array.dtype
         self.left, self.top, self.res_value, self.crs, self.name = float(left), float(top), float(res), crs, name
         self.pinned_tensor = None   # set by from_pinned() / a lazy load: the same pixels as a pinned torch tensor
@@ -105,7 +106,7 @@ class ZoneRaster:
 
     @classmethod
     def lazy(cls, shape, dtype, loader, left: float, top: float, res: float, crs: Optional[str] = None,
-             name: str = "<file>", progressive=None):
+             name: str = "<file>", progressive=None, source: Optional["RowSource"] = None):
         """Raster file opened the way ``rasterio.open`` opens it: size, type and georeferencing now, pixels when somebody
         reads them.  ``loader() -> (array (C,H,W), pinned tensor or None)`` runs once, on the first access to ``array``:
         the geometry-only callers of the path (slicing.py:20-49, inference.py:76-132,157-208) never decode the file."""
@@ -114,14 +115,14 @@ class ZoneRaster:
         r._shape, r._dtype = tuple(int(v) for v in shape), np.dtype(dtype)
         r.left, r.top, r.res_value, r.crs, r.name = float(left), float(top), float(res), crs, name
         r.pinned_tensor = None
-        r._progressive_start, r._progress = progressive, None
+        r._progressive_start, r._progress, r._source = progressive, None, source
         return r
 
     def begin_progressive(self) -> Optional["ProgressiveLoad"]:
         """Starts (or returns) the background decode of a lazily opened file: the destination array exists at once, rows
         become valid bottom-up (``ProgressiveLoad.wait_rows``).  None when the raster is already in memory or the file is not
         one the block decoder streams (JPEG 2000, Pillow fallback)."""
-        if self._array is not None or getattr(self, "_progressive_start", None) is None:
+        if self._array is not None or self._progressive_start is None:
             return None
         if self._progress is None:
             self._progress = self._progressive_start()
@@ -136,8 +137,8 @@ class ZoneRaster:
             raise ValueError(f"{self.name}: empty row strip [{r0}, {r1})")
         top = self.top - r0 * self.res_value
         name = name or f"{self.name}#rows{r0}-{r1}"
-        source = getattr(self, "_source", None)
-        if self._array is None and getattr(self, "_progress", None) is None and source is not None:
+        source = self._source
+        if self._array is None and self._progress is None and source is not None:
             shape = (self._shape[0], r1 - r0, self._shape[2])
 
             def load():
@@ -161,7 +162,7 @@ class ZoneRaster:
     @property
     def array(self) -> np.ndarray:
         if self._array is None:
-            prog = getattr(self, "_progress", None)
+            prog = self._progress
             if prog is not None:                          # a background decode is under way: its array, once complete
                 prog.wait_all()
                 arr, pinned = prog.array, prog.tensor
@@ -286,8 +287,8 @@ def open_raster(path) -> ZoneRaster:
                     holder = {}
                     arr = _pinned_array(shape, dtype, holder)
                     return ProgressiveLoad(source, arr, holder.get("tensor"))
-            raster = ZoneRaster.lazy(shape, dtype, load, left, top, res, crs, name=path, progressive=progressive)
-            raster._source = source                       # row_strip() decodes row ranges of it
+            raster = ZoneRaster.lazy(shape, dtype, load, left, top, res, crs, name=path, progressive=progressive,
+                                     source=source)       # row_strip() decodes row ranges of the source
             _OPEN_FILES[key] = raster
             return raster
         try:
