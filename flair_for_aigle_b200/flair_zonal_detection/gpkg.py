@@ -61,6 +61,9 @@ def write_gpkg(path: str, geometries: Iterable[Sequence[np.ndarray]], columns: D
     epsg = _epsg(crs)
     srs_id = epsg if epsg is not None else -1
     cols = {k: np.asarray(v) for k, v in columns.items()}
+    for k in cols:
+        if not isinstance(k, str) or not k or '"' in k or k.lower() in ("fid", "geom"):
+            raise ValueError(f"column name {k!r} cannot be used in a GeoPackage feature table")
     if os.path.exists(path):
         os.remove(path)
     con = sqlite3.connect(path)
@@ -121,14 +124,12 @@ def _parse_blob(blob: bytes) -> List[np.ndarray]:
     if blob[:2] != b"GP":
         raise ValueError("not a GeoPackageBinary geometry")
     flags = blob[3]
-    little = bool(flags & 1)
     env = (flags >> 1) & 7
     pos = 8 + {0: 0, 1: 32, 2: 48, 3: 48, 4: 64}[env]
     if flags & 0x10:
         return []                                    # empty geometry
     e = "<" if blob[pos] == 1 else ">"
     gtype = struct.unpack(e + "I", blob[pos + 1:pos + 5])[0]
-    del little
     if gtype % 1000 != 3:
         raise NotImplementedError(f"WKB geometry type {gtype} (only polygons are read)")
     dims = 2 + (1 if gtype // 1000 in (1, 3) else 0) + (1 if gtype // 1000 in (2, 3) else 0)

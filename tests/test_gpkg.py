@@ -143,3 +143,6 @@ def test_write_gpkg_argument_checks(tmp_path):
     assert crs is None and cols["score"].tolist() == [0.5] and cols["label"].tolist() == ["roof"] and len(geoms) == 1
     with pytest.raises(ValueError, match="no feature layer"):
         read_gpkg(p, layer="nope")
+    for bad in ('a"b', "fid", "GEOM", ""):
+        with pytest.raises(ValueError, match="column name"):
+            write_gpkg(str(tmp_path / "c.gpkg"), [[_square(0, 0, 1)]], {bad: [1]}, None)
