@@ -41,6 +41,13 @@ TASK = "AERIAL_LABEL-COSIA"
 def rounder(fmt: str):
     if fmt == "fp32":
         return lambda t: t
+    if fmt == "fp16x2":
+        # a hi / lo split of the operand (two fp16 values whose sum carries ~22 significand bits): what a tensor-core GEMM
+        # with its K dimension doubled would consume
+        def split(t):
+            hi = t.clamp(-65504.0, 65504.0).to(torch.float16).float()
+            return hi + (t - hi).to(torch.float16).float()
+        return split
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[fmt]
     if fmt == "fp16":
         return lambda t: t.clamp(-65504.0, 65504.0).to(dt).float()
@@ -137,10 +144,21 @@ def simulate(model, x, fmts: dict, want_feats: bool = False):
     return (logits, feats) if want_feats else logits
 
 
-def make_model(seed: int, arch: str = "convnextv2_base-unet", device="cpu"):
+def make_model(seed: int, arch: str = "convnextv2_base-unet", device="cpu", weights: str = "budget"):
+    """weights='budget': oracle.models.randomize_ (this tool's own draw); 'test': the checkpoint the GPU tests and the bench
+    use (bench.make_weights -> flair_for_aigle_b200.synthetic.randomize_state_), whose decoder amplifies rounding noise more."""
     from oracle.models import FlairHubOracle, randomize_
     m = FlairHubOracle(arch, {"AERIAL_RGBI": 4}, {TASK: 19})
-    randomize_(m, seed=seed)
+    if weights == "test":
+        import tempfile
+        import bench
+        from safetensors.torch import load_file
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "w.safetensors")
+            bench.make_weights(path, seed=seed)
+            m.load_state_dict(load_file(path), strict=True)
+    else:
+        randomize_(m, seed=seed)
     return m.eval().to(device)
 
 
@@ -202,6 +220,40 @@ def budget(P: int = 512, seeds=(1,), device="cpu", arch="convnextv2_base-unet"):
     return {k: tuple(sum(v[i] for v in vals) / len(vals) for i in range(3)) for k, vals in rows.items()}
 
 
+@torch.no_grad()
+def floor_table(P: int = 512, seeds=(7,), device="cpu", weights: str = "test"):
+    """Where the 16-bit-operand floor lies for a given weight draw, and what lifts it: every family fp16 (the engine), then
+    ONE group of families given more operand bits -- fp32, or the hi / lo fp16 split a doubled-K GEMM would carry."""
+    rows = {}
+    no_tf32()
+    dec_fams, enc_fams = ("skip", "dec", "wup"), ("y", "hidden", "w2s", "down")
+    for seed in seeds:
+        model = make_model(seed, device=device, weights=weights)
+        for tile in (100 + seed, 200 + seed):
+            x = make_tile(tile, P, device)
+            ref = simulate(model, x, {})
+            sd, cls = float(ref.std()), ref.argmax(1)
+
+            def score(fm):
+                out = simulate(model, x, fm)
+                d = (out - ref).abs()
+                return (float((out.argmax(1) == cls).float().mean()), float(d.mean()) / sd, float(d.max()) / sd)
+            base = {f: "fp16" for f in FAMILIES}
+            cases = [("all families fp16 (= the engine)", base),
+                     ("... decoder activations (dec) fp32", {**base, "dec": "fp32"}),
+                     ("... decoder activations (dec) fp16 hi/lo split", {**base, "dec": "fp16x2"}),
+                     ("... whole decoder (skip, dec, wup) fp32", {**base, **{f: "fp32" for f in dec_fams}}),
+                     ("... whole decoder fp16 hi/lo split", {**base, **{f: "fp16x2" for f in dec_fams}}),
+                     ("... whole encoder (y, hidden, w2s, down) fp32", {**base, **{f: "fp32" for f in enc_fams}}),
+                     ("all families fp16 hi/lo split", {f: "fp16x2" for f in FAMILIES})]
+            for label, fm in cases:
+                rows.setdefault(label, []).append(score(fm))
+            top2 = ref.topk(2, dim=1).values
+            gap = (top2[:, 0] - top2[:, 1]) / sd
+            rows.setdefault("(pixels with top-2 gap < 0.002 std)", []).append((float((gap < 0.002).float().mean()), 0.0, 0.0))
+    return {k: tuple(sum(v[i] for v in vals) / len(vals) for i in range(3)) for k, vals in rows.items()}
+
+
 def format_table(rows, P, seeds, arch):
     lines = [f"precision budget, {arch}, {len(seeds)} seeded tile(s) of {P}x{P}, random-init weights (every parameter randomised)",
              f"{'rounded tensors':48s} {'class agreement':>16s} {'mean|d|/std':>12s} {'max|d|/std':>11s}"]
@@ -216,6 +268,17 @@ if __name__ == "__main__":
     ap.add_argument("--seeds", type=int, default=2)
     ap.add_argument("--device", default="cpu")
     ap.add_argument("--arch", default="convnextv2_base-unet")
+    ap.add_argument("--floor", action="store_true", help="the 'what lifts the floor' table for both weight draws")
     a = ap.parse_args()
     seeds = tuple(range(1, a.seeds + 1))
-    print(format_table(budget(a.tile, seeds, a.device, a.arch), a.tile, seeds, a.arch))
+    if a.floor:
+        for weights, wseeds in (("test", (7,)), ("budget", (1,))):
+            rows = floor_table(a.tile, wseeds, a.device, weights)
+            print(f"what lifts the 16-bit floor, convnextv2_base-unet, weights = {weights} (seed {wseeds[0]}), 2 tiles of "
+                  f"{a.tile}x{a.tile}, simulation of the engine's rounding points on the fp32 oracle")
+            print(f"{'rounded tensors':52s} {'class agreement':>16s} {'mean|d|/std':>12s} {'max|d|/std':>11s}")
+            for k, (ag, m, x) in rows.items():
+                print(f"{k:52s} {ag:16.5f} {m:12.5f} {x:11.4f}")
+            print()
+    else:
+        print(format_table(budget(a.tile, seeds, a.device, a.arch), a.tile, seeds, a.arch))

@@ -33,3 +33,28 @@ def test_engine_gelu_matches_erf_gelu():
     x = torch.linspace(-12, 12, 200001)
     d = (eb.gelu_engine(x, hw=False) - torch.nn.functional.gelu(x.double()).float()).abs().max().item()
     assert d < 3e-5
+
+
+def test_what_lifts_the_floor_more_operand_bits_in_the_decoder():
+    """profiles/r2_precision_floor.txt at a reduced size: with every family in fp16 (the engine), a hi / lo fp16 split of the
+    decoder activations removes a third or more of the remaining logit error, the encoder's families much less, and a split
+    of every family leaves nothing -- the lever DESIGN.md section 2b / 8 names for >= 99.9 % on every weight draw."""
+    model = eb.make_model(1)
+    x = eb.make_tile(101, 128)
+    with torch.no_grad():
+        ref = eb.simulate(model, x, {})
+        sd = float(ref.std())
+        base = {f: "fp16" for f in eb.FAMILIES}
+
+        def err(fm):
+            return float((eb.simulate(model, x, fm) - ref).abs().mean()) / sd
+        e_all = err(base)
+        e_dec_split = err({**base, "dec": "fp16x2"})
+        e_dec_fp32 = err({**base, "dec": "fp32"})
+        e_enc_fp32 = err({**base, **{f: "fp32" for f in ("y", "hidden", "w2s", "down")}})
+        e_split = err({f: "fp16x2" for f in eb.FAMILIES})
+    print(f"mean|d|/std: all fp16 {e_all:.5f}, dec hi/lo {e_dec_split:.5f}, dec fp32 {e_dec_fp32:.5f}, encoder fp32 {e_enc_fp32:.5f}, "
+          f"all hi/lo {e_split:.6f}")
+    assert e_dec_split < 0.75 * e_all and abs(e_dec_split - e_dec_fp32) < 0.02 * e_all      # 22 bits are as good as fp32 here
+    assert e_enc_fp32 > e_dec_split                                                         # the decoder is the bigger lever
+    assert e_split < 0.01 * e_all
