@@ -395,3 +395,38 @@ def test_corrupted_files_never_crash_the_process(tmp_path):
         except rio.RasterIOError:
             outcomes["error"] += 1
     assert outcomes["ok"] + outcomes["error"] == 400 and outcomes["error"] > 50 and outcomes["ok"] > 20, outcomes
+
+
+def test_random_layouts_round_trip_and_decode_in_libtiff(tmp_path):
+    """Property test (hypothesis): any shape x band count x dtype x block size x codec x predictor x interleave x BigTIFF x
+    overview count round-trips bit for bit through the writer and the reader, windows included, and libtiff agrees on the
+    single-band / RGB cases it can open."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(h=st.integers(1, 300), w=st.integers(1, 300), count=st.sampled_from([1, 1, 2, 3, 4, 7]),
+           dtype=st.sampled_from(["u1", "u1", "u1", "u2", "f4", "i2"]), block=st.sampled_from([16, 32, 64, 128]),
+           comp=st.sampled_from(["lzw", "deflate", "none"]), pred2=st.booleans(), chunky=st.booleans(), big=st.booleans(),
+           ovr=st.integers(0, 2), seed=st.integers(0, 10 ** 6), smooth=st.booleans())
+    def check(h, w, count, dtype, block, comp, pred2, chunky, big, ovr, seed, smooth):
+        rng = np.random.default_rng(seed)
+        a = rng.integers(0, 200, (count, h, w)).astype(dtype)
+        if smooth:
+            a = np.sort(a, axis=2)
+        predictor = 2 if (pred2 and dtype == "u1" and comp != "none") else 1
+        p = str(tmp_path / "h.tif")
+        rio.write_geotiff(p, a, LEFT, TOP, RES, epsg=2154, compression=comp, predictor=predictor, block=block,
+                          pixel_interleave=chunky, bigtiff=int(big), overviews=ovr)
+        got, info = rio.read_raster(p)
+        assert np.array_equal(got, a) and info.dtype == a.dtype and info.bigtiff == big and info.count == count
+        assert info.overviews == min(ovr, sum(1 for k in range(ovr) if max((h + (1 << k) - 1) >> k, (w + (1 << k) - 1) >> k) > 1))
+        r0, c0 = int(rng.integers(-20, h)), int(rng.integers(-20, w))
+        hh, ww = int(rng.integers(1, h + 30)), int(rng.integers(1, w + 30))
+        pad = np.zeros((count, h + 800, w + 800), a.dtype)
+        pad[:, 400:400 + h, 400:400 + w] = a
+        assert np.array_equal(rio.read_window(p, r0, c0, hh, ww), pad[:, 400 + r0:400 + r0 + hh, 400 + c0:400 + c0 + ww])
+        if not big and dtype == "u1" and (count == 1 or (count == 3 and chunky)):
+            with Image.open(p) as im:
+                lib = np.asarray(im)
+            assert np.array_equal(lib if count == 1 else lib.transpose(2, 0, 1), a[0] if count == 1 else a)
+    check()
