@@ -258,6 +258,45 @@ def _world_file(path: str):
     return None
 
 
+def _tab_file(path: str):
+    """MapInfo .tab raster registration next to the image (how IGN delivers BD ORTHO tiles): control points
+    ``(x,y) (col,row) Label "Pt n"`` -- map coordinates of pixel CORNERS -- and optionally ``CoordSys Earth Projection ...``.
+    The points must describe a north-up, unrotated grid; the Lambert-93 definition is recognised, other projections leave
+    the CRS unknown."""
+    base = os.path.splitext(path)[0]
+    for cand in (base + ".tab", base + ".TAB"):
+        if not os.path.isfile(cand):
+            continue
+        text = open(cand, encoding="latin-1").read()
+        num = r"[-+]?[0-9]*\.?[0-9]+(?:[eE][-+]?[0-9]+)?"
+        pts = re.findall(rf"\(\s*({num})\s*,\s*({num})\s*\)\s*\(\s*({num})\s*,\s*({num})\s*\)\s*Label", text)
+        if len(pts) < 2:
+            continue
+        p = np.asarray(pts, dtype=np.float64)                 # x, y, col, row
+        cols, rows = p[:, 2], p[:, 3]
+        if np.ptp(cols) == 0 or np.ptp(rows) == 0:
+            continue
+        i0, i1 = int(np.argmin(cols)), int(np.argmax(cols))
+        j0, j1 = int(np.argmin(rows)), int(np.argmax(rows))
+        sx = (p[i1, 0] - p[i0, 0]) / (cols[i1] - cols[i0])
+        sy = (p[j0, 1] - p[j1, 1]) / (rows[j1] - rows[j0])
+        left, top = p[i0, 0] - cols[i0] * sx, p[j0, 1] + rows[j0] * sy
+        fit_x, fit_y = left + cols * sx, top - rows * sy
+        if sx <= 0 or sy <= 0 or np.abs(fit_x - p[:, 0]).max() > 1e-3 * sx or np.abs(fit_y - p[:, 1]).max() > 1e-3 * sy:
+            raise ValueError(f"{cand}: the control points do not describe a north-up, unrotated grid")
+        crs = None
+        m = re.search(r"CoordSys\s+Earth\s+Projection\s+([^\n]*)", text)
+        if m:
+            f = [t.strip().strip('"') for t in m.group(1).split(",")]
+            try:                                              # Lambert Conformal Conic, RGF93, 46.5 / 44 / 49, 700000 / 6600000
+                if int(f[0]) == 3 and int(f[1]) == 33 and [float(v) for v in f[3:9]] == [3.0, 46.5, 44.0, 49.0, 700000.0, 6600000.0]:
+                    crs = "EPSG:2154"
+            except (ValueError, IndexError):
+                pass
+        return float(left), float(top), float(sx), float(sy), crs
+    return None
+
+
 def _jp2_georef(path: str):
     with open(path, "rb") as f:
         head = f.read(12)
@@ -279,9 +318,9 @@ def _jp2_georef(path: str):
                 break
             body = f.read(size - 8 - len(ext))
             meta += hdr + ext + body
-    geo = _geojp2(bytes(meta)) or _gmljp2(bytes(meta)) or _world_file(path)
+    geo = _geojp2(bytes(meta)) or _gmljp2(bytes(meta)) or _world_file(path) or _tab_file(path)
     if geo is None:
-        raise ValueError(f"{path}: no georeferencing (GeoJP2 box, GMLJP2 box or world file)")
+        raise ValueError(f"{path}: no georeferencing (GeoJP2 box, GMLJP2 box, world file or MapInfo .tab)")
     left, top, sx, sy, crs = geo
     return left, top, _square_res(path, sx, sy), crs
 

@@ -215,6 +215,22 @@ def test_jpeg2000_inputs_with_geojp2_gmljp2_and_world_file(tmp_path):
     bad.write_bytes(b"\x00" * 64)
     with pytest.raises(ValueError, match="not a JP2"):
         read_jp2(str(bad))
+    # MapInfo .tab registration (IGN's BD ORTHO deliveries): corner control points + the Lambert-93 CoordSys clause
+    p = str(tmp_path / "tab.jp2")
+    _jp2_with_box(p, img[:, :, 0], b"")
+    right, bottom = L + 420 * RES, T - 300 * RES
+    open(str(tmp_path / "tab.tab"), "w", encoding="latin-1").write(
+        '!table\n!version 300\n!charset WindowsLatin1\n\nDefinition Table\n  File "tab.jp2"\n  Type "RASTER"\n'
+        f'  ({L!r},{T!r}) (0,0) Label "Pt 1",\n  ({right!r},{T!r}) (420,0) Label "Pt 2",\n'
+        f'  ({right!r},{bottom!r}) (420,300) Label "Pt 3",\n  ({L!r},{bottom!r}) (0,300) Label "Pt 4"\n'
+        '  CoordSys Earth Projection 3, 33, "m", 3, 46.5, 44, 49, 700000, 6600000\n  Units "m"\n')
+    got, left, top, res, crs = read_jp2(p)
+    assert np.array_equal(got[0], img[:, :, 0]) and abs(left - L) < 1e-6 and abs(top - T) < 1e-6 and abs(res - RES) < 1e-9
+    assert crs == "EPSG:2154"
+    open(str(tmp_path / "tab.tab"), "w").write('Definition Table\n  (0,0) (0,0) Label "a",\n  (10,1) (10,0) Label "b",\n'
+                                               '  (10,-10) (10,10) Label "c"\n')
+    with pytest.raises(ValueError, match="north-up"):
+        read_jp2(p)
 
 
 def test_open_raster_is_lazy_shared_and_decodes_into_the_upload_buffer(tmp_path, monkeypatch):
