@@ -199,3 +199,24 @@ def load_checkpoint(conf: Dict[str, Any], seg_module: nn.Module, exit_on_fail: b
                 f"unexpected={len(rep.unexpected_keys)}")
     seg_module.last_load_report = rep
     seg_module.last_load_result = result
+
+
+def save_checkpoint(path: str, seg_module: nn.Module, class_weights: Optional[Dict[str, torch.Tensor]] = None, epoch: int = 0,
+                    global_step: int = 0, extra: Optional[Dict[str, Any]] = None) -> str:
+    """The other direction of ``load_checkpoint``: the model's current weights in the layout the reference's training run
+    leaves on disk and its loader reads back (checkpoint.py:206-212) -- a Lightning ``.ckpt`` whose ``state_dict`` carries the
+    LightningModule's names, i.e. ``model.<key>`` for the segmentation model (tasks_module.py:49) and ``criterion.<task>.weight``
+    for the loss weights (tasks_module.py:56, module_setup.py:119-200) --, or, for a ``.safetensors`` path, the same tensors
+    without the pickle.  With the training engine the parameters are views into the optimizer's arena, so this is the
+    trained state.  ``extra``: further top-level entries of the ``.ckpt`` dict (optimizer / scheduler state for a resume)."""
+    tensors = {"model." + k: v.detach().to("cpu").contiguous().clone() for k, v in seg_module.state_dict().items()}
+    for task, w in (class_weights or {}).items():
+        tensors[f"criterion.{task}.weight"] = torch.as_tensor(w, dtype=torch.float32).detach().to("cpu").clone()
+    if path.endswith(".safetensors"):
+        from safetensors.torch import save_file
+        save_file(tensors, path)
+        return path
+    blob = {"epoch": int(epoch), "global_step": int(global_step), "pytorch-lightning_version": "2.5.1", "state_dict": tensors}
+    blob.update(extra or {})
+    torch.save(blob, path)
+    return path

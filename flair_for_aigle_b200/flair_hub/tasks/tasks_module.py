@@ -86,6 +86,28 @@ class AdamW:
     def zero_grad(self) -> None:
         self.grad.zero_()
 
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs besides the weights (those are the model's own state_dict): both moment arenas on
+        the CPU, the step counters (per arena segment, like torch's per-parameter ``step``) and the hyper-parameters."""
+        return {"exp_avg": self.exp_avg.detach().to("cpu").clone(), "exp_avg_sq": self.exp_avg_sq.detach().to("cpu").clone(),
+                "step_count": int(self.step_count), "segments": [list(map(int, seg)) for seg in self._segs.items],
+                "lr": self.lr, "weight_decay": self.weight_decay, "betas": tuple(self.betas), "eps": self.eps}
+
+    def load_state_dict(self, state: dict) -> None:
+        n = self.arena.numel()
+        if state["exp_avg"].numel() != n or state["exp_avg_sq"].numel() != n:
+            raise ValueError(f"optimizer state of {state['exp_avg'].numel()} values for an arena of {n}")
+        segs = [list(map(int, seg)) for seg in state["segments"]]
+        if not segs or segs[0][0] != 0 or segs[-1][1] != n or any(a[1] != b[0] for a, b in zip(segs, segs[1:])):
+            raise ValueError("optimizer state: the step-counter segments do not cover the arena")
+        self.exp_avg.copy_(state["exp_avg"].to(self.exp_avg.device))
+        self.exp_avg_sq.copy_(state["exp_avg_sq"].to(self.exp_avg_sq.device))
+        self.step_count = int(state["step_count"])
+        self.step_dev.fill_(self.step_count)
+        self._segs.items = segs
+        self.lr, self.weight_decay = float(state["lr"]), float(state["weight_decay"])
+        self.betas, self.eps = tuple(state["betas"]), float(state["eps"])
+
     def step(self, skip=()) -> None:
         """``skip``: arena ranges [(lo, hi), ...] whose parameters received NO gradient this step: left exactly as they are,
         like ``torch.optim.AdamW`` does for ``p.grad is None`` (no decay, no moment update, their step counter stands still)."""
@@ -194,6 +216,37 @@ class SegmentationTask:
                                            lr=optim_cfg['learning_rate'], weight_decay=optim_cfg['optim_weight_decay'],
                                            betas=tuple(optim_cfg['optim_betas']), mod_dropout=self.mod_dropout)
         return self.trainer
+
+    def save_checkpoint(self, path: str, epoch: int = 0) -> str:
+        """What Lightning's ModelCheckpoint leaves for this module (``model.*`` / ``criterion.*`` names in ``state_dict``;
+        flair_hub/models/checkpoint.py: save_checkpoint), readable by the reference's and this package's ``load_checkpoint``;
+        with a trainer the ``.ckpt`` also carries the optimizer's moments / step counters and the schedule position, which
+        ``load_training_state`` puts back for a resume."""
+        from ..models.checkpoint import save_checkpoint
+        weights = {t: c.weight for t, c in self.criterion.items() if getattr(c, 'weight', None) is not None}
+        extra = {}
+        tr = getattr(self, 'trainer', None)
+        if tr is not None and not path.endswith(".safetensors"):
+            extra["optimizer_states"] = [tr.opt.state_dict()]
+            extra["scheduler_position"] = {"global_step": int(getattr(self, '_global_step', 0)),
+                                           "using_plateau": bool(getattr(self, '_using_plateau', False))}
+        return save_checkpoint(path, self.model, weights, epoch=epoch, global_step=int(getattr(self, '_global_step', 0)),
+                               extra=extra)
+
+    def load_training_state(self, path: str) -> None:
+        """Resume: the optimizer state written by ``save_checkpoint`` back into the trainer (the weights are loaded the usual
+        way, ``load_checkpoint``, BEFORE ``configure_trainer``).  Captured CUDA graphs are dropped."""
+        blob = torch.load(path, map_location="cpu", weights_only=False)
+        tr = getattr(self, 'trainer', None)
+        if tr is None:
+            raise RuntimeError("load_training_state: call configure_trainer / configure_optimizers first")
+        if not blob.get("optimizer_states"):
+            raise ValueError(f"{path}: no optimizer state inside")
+        tr.opt.load_state_dict(blob["optimizer_states"][0])
+        tr.set_lr(tr.opt.lr)
+        tr._graph, tr._segments, tr._graph_out = None, [], None
+        pos = blob.get("scheduler_position", {})
+        self._global_step, self._using_plateau = int(pos.get("global_step", 0)), bool(pos.get("using_plateau", False))
 
     def configure_optimizers(self, total_steps: int):
         """tasks_module.py:344-376 without Lightning: builds the trainer from ``config['hyperparams']`` (``configure_trainer``)

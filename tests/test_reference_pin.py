@@ -408,6 +408,39 @@ def test_load_checkpoint_prefix_head_mismatch_and_torch_load(tmp_path):
         assert fn(bad, m, exit_on_fail=False) is None
 
 
+def test_saved_checkpoint_is_read_by_the_reference_loader(tmp_path):
+    """``save_checkpoint`` writes what a Lightning training run of the reference leaves on disk (``model.`` / ``criterion.``
+    names, ``state_dict`` inside a ``.ckpt``): the REFERENCE's ``load_checkpoint`` (checkpoint.py:176-290) loads it into the
+    reference model and gets the product model's tensors back, for both file types."""
+    from flair_for_aigle_b200.flair_hub.models.checkpoint import save_checkpoint
+    ref, prod, conf = _both_models("resnet34-unet", {"AERIAL_RGBI": 4}, n_cls=19)
+    trained = _random_state(prod, 5)
+    prod.load_state_dict(trained, strict=True)
+    for name in ("last.ckpt", "last.safetensors"):
+        p = save_checkpoint(str(tmp_path / name), prod, {TASK: torch.ones(19)}, epoch=3, global_step=1234,
+                            extra={"lr_schedulers": [{"last_epoch": 1234}]})
+        fresh_ref, fresh_prod, _ = _both_models("resnet34-unet", {"AERIAL_RGBI": 4}, n_cls=19)
+        out = _load_both(fresh_ref, fresh_prod, conf, p)
+        assert all(torch.equal(out[k], trained[k]) for k in trained)
+    blob = torch.load(str(tmp_path / "last.ckpt"), map_location="cpu", weights_only=False)
+    assert blob["epoch"] == 3 and blob["global_step"] == 1234 and blob["lr_schedulers"] == [{"last_epoch": 1234}]
+    # the task module's own save (no trainer: weights + the loss weights its criterion carries)
+    from flair_for_aigle_b200.flair_hub.tasks.tasks_module import SegmentationTask
+    cfg = {"labels": [TASK], "labels_configs": {TASK: {"value_name": list(range(19)), "task_weight": 1.0,
+                                                       "value_weights": {"default": 1, "default_exceptions": {18: 0}}}},
+           "modalities": {"inputs": {"AERIAL_RGBI": True}, "aux_loss": {"AERIAL_RGBI": False},
+                          "modality_dropout": {"AERIAL_RGBI": 0}, "aux_loss_weight": {"AERIAL_RGBI": 1.0}}}
+    task = SegmentationTask(prod, cfg)
+    p = task.save_checkpoint(str(tmp_path / "task.ckpt"), epoch=1)
+    tb = torch.load(p, map_location="cpu", weights_only=False)
+    w = tb["state_dict"][f"criterion.{TASK}.weight"]
+    assert w.shape == (19,) and float(w[18]) == 0.0 and float(w[:18].min()) == 1.0 and "optimizer_states" not in tb
+    fresh_ref, fresh_prod, _ = _both_models("resnet34-unet", {"AERIAL_RGBI": 4}, n_cls=19)
+    out = _load_both(fresh_ref, fresh_prod, conf, p)
+    assert all(torch.equal(out[k], trained[k]) for k in trained)
+    assert f"criterion.{TASK}.weight" in blob["state_dict"] and all(k.startswith(("model.", "criterion.")) for k in blob["state_dict"])
+
+
 def test_load_checkpoint_swin_bias_table_resize(tmp_path):
     """checkpoint.py:33-56,265-271: a window-7 checkpoint's (13*13, heads) tables resized bicubically to the
     window-12 model's (23*23, heads); a non-square table falls back to re-initialisation ('bias' in the name -> zeros)."""
