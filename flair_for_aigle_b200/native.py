@@ -40,11 +40,18 @@ class NativeError(RuntimeError):
 PROFILE = None
 
 
+# FZ_NVTX=1: every kernel wrapper also opens an NVTX range named after its kernel family (+ its shape), so that
+# `ncu --nvtx --nvtx-include "gemm_tcgen05/"` (or any NVTX-aware profiler) can select launches by what they compute.
+NVTX = os.environ.get("FZ_NVTX", "0") == "1"
+
+
 class _Timed:
     def __init__(self, family: str, **meta):
         self.family, self.meta = family, meta
 
     def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.family + ("/" + ",".join(f"{k}={v}" for k, v in self.meta.items()) if self.meta else ""))
         if PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
@@ -55,6 +62,8 @@ class _Timed:
         if PROFILE is not None:
             self.e1.record(torch.cuda.current_stream())
             PROFILE.append((self.family, self.meta, self.e0, self.e1))
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
         return False
 
 
