@@ -245,7 +245,8 @@ def inference_and_write(model, dataloader, tiles_gdf, config: Dict, output_files
         dst.close()
 
 
-from .polygonize import PolygonTable, raster_to_polygons  # noqa: E402,F401  (inference.py:375-407)
+from .polygonize import (PolygonTable, raster_to_polygons, vectorize_segmentation,  # noqa: E402,F401  (inference.py:375-407,
+                         vectorize_segmentation_parallel)                            # :574-632)
 
 def _iter_batches(dataloader, dataset, model, config, device):
     """Reference-style batches ({MOD: (B,C,P,P) fp32 normalised, 'index': ...}).  For our own

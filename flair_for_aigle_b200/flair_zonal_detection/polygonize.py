@@ -52,8 +52,9 @@ class PolygonTable:
     """Rows of {class_id, geometry}: ``geometry[i]`` is a GeoJSON-like dict (type Polygon, coordinates = [exterior,
     holes...], rings closed, CRS coordinates).  ``area`` holds each polygon's area in CRS units (pixel count * res^2)."""
 
-    def __init__(self, class_id: np.ndarray, area: np.ndarray, geometry, crs=None):
+    def __init__(self, class_id: np.ndarray, area: np.ndarray, geometry, crs=None, confidence: Optional[np.ndarray] = None):
         self.class_id, self.area, self.geometry, self.crs = class_id, area, geometry, crs
+        self.confidence = confidence     # optional third column (vectorize_segmentation: mean confidence of the row's class)
 
     def __len__(self) -> int:
         return len(self.geometry)
@@ -86,7 +87,10 @@ class PolygonTable:
         geoms = self.geometry
         rings = (geoms.rings(i) for i in range(len(geoms))) if isinstance(geoms, _Geometries) else \
             ([np.asarray(r, dtype=np.float64) for r in g["coordinates"]] for g in geoms)
-        return write_gpkg(path, rings, {"class_id": np.asarray(self.class_id, dtype=np.int64)}, self.crs, layer)
+        columns = {"class_id": np.asarray(self.class_id, dtype=np.int64)}
+        if self.confidence is not None:
+            columns["confidence"] = np.asarray(self.confidence, dtype=np.float64)
+        return write_gpkg(path, rings, columns, self.crs, layer)
 
     @classmethod
     def read_file(cls, path: str, layer: Optional[str] = None) -> "PolygonTable":
@@ -99,7 +103,8 @@ class PolygonTable:
             return 0.5 * abs(float(np.dot(r[:-1, 0], r[1:, 1]) - np.dot(r[1:, 0], r[:-1, 1])))
         area = np.asarray([ring_area(g[0]) - sum(ring_area(h) for h in g[1:]) if g else 0.0 for g in geoms])
         geometry = [{"type": "Polygon", "coordinates": [r.tolist() for r in g]} for g in geoms]
-        return cls(np.asarray(cols.get("class_id", np.zeros(len(geoms))), dtype=np.int64), area, geometry, crs)
+        conf = np.asarray(cols["confidence"], dtype=np.float64) if "confidence" in cols else None
+        return cls(np.asarray(cols.get("class_id", np.zeros(len(geoms))), dtype=np.int64), area, geometry, crs, conf)
 
     @classmethod
     def concat(cls, tables: List["PolygonTable"]) -> "PolygonTable":
@@ -108,8 +113,11 @@ class PolygonTable:
         if not tables:
             return cls(np.zeros(0, np.int64), np.zeros(0), [], None)
         geometry = [g for t in tables for g in t.geometry]
+        conf = None
+        if all(t.confidence is not None for t in tables):
+            conf = np.concatenate([np.asarray(t.confidence, dtype=np.float64) for t in tables])
         return cls(np.concatenate([np.asarray(t.class_id, dtype=np.int64) for t in tables]),
-                   np.concatenate([np.asarray(t.area, dtype=np.float64) for t in tables]), geometry, tables[0].crs)
+                   np.concatenate([np.asarray(t.area, dtype=np.float64) for t in tables]), geometry, tables[0].crs, conf)
 
 
 def _device_raster(src, device):
@@ -165,3 +173,39 @@ def raster_to_polygons(tiff_path, ignore_background: bool = True, background_val
     poly_ring_off = np.concatenate([[0], np.cumsum(np.bincount(ring_poly, minlength=order.size))])
     geometry = _Geometries(xy, ring_off, ring_perm, poly_ring_off)
     return PolygonTable(classes[order].astype(np.int64), areas[order].astype(np.float64) * (res * res), geometry, crs)
+
+
+def class_mean_confidence(labels: np.ndarray, confidence: np.ndarray, class_ids) -> np.ndarray:
+    """inference.py:588,610: ``confidence[labels == value].mean()`` -- the mean over ALL pixels of the class, which is what
+    every polygon of that class carries in the reference (not a per-polygon mean).  One bincount pass for all classes."""
+    lab = np.asarray(labels).reshape(-1).astype(np.int64)
+    n = int(lab.max()) + 1 if lab.size else 1
+    sums = np.bincount(lab, weights=np.asarray(confidence, dtype=np.float64).reshape(-1), minlength=n)
+    counts = np.bincount(lab, minlength=n)
+    ids = np.asarray(class_ids, dtype=np.int64)
+    return sums[ids] / np.maximum(counts[ids], 1)
+
+
+def vectorize_segmentation_parallel(labels, confidence, transform, n_jobs: int = 4, device=None, **kwargs) -> PolygonTable:
+    """inference.py:598-632 (and ``vectorize_segmentation``, :574-595): polygons of every class but 0 of the label map the
+    accumulating ``inference()`` returns, ``min_area`` (default 4.0 CRS units^2) and ``simplification_tolerance`` (default 1.0)
+    like the reference, each row carrying its class's mean confidence.  ``transform``: the raster's affine as
+    (a, b, c, d, e, f) or anything with those attributes (north-up: b = d = 0).  ``n_jobs`` is accepted and ignored (one GPU
+    labelling pass instead of a process per class)."""
+    t = tuple(transform)[:6] if not hasattr(transform, "a") else (transform.a, transform.b, transform.c, transform.d,
+                                                                   transform.e, transform.f)
+    a, b, c, d, e, f = (float(v) for v in t)
+    if b != 0.0 or d != 0.0 or abs(a + e) > 1e-9 * abs(a):
+        raise NotImplementedError("vectorize_segmentation: north-up rasters with square pixels only")
+    labels = np.asarray(labels)
+    table = raster_to_polygons((labels.astype(np.uint8), c, f, a, kwargs.get("crs", "EPSG:5490")), ignore_background=True,
+                               background_value=0, min_area=kwargs.get("min_area", 4.0),
+                               simplification=kwargs.get("simplification_tolerance", 1.0), n_jobs=n_jobs, device=device)
+    table.confidence = class_mean_confidence(labels, confidence, table.class_id) if len(table) else np.zeros(0)
+    return table
+
+
+def vectorize_segmentation(labels, confidence, transform, crs="EPSG:5490", simplification_tolerance=1.0, device=None) -> PolygonTable:
+    """inference.py:574-595: the same without an area filter."""
+    return vectorize_segmentation_parallel(labels, confidence, transform, crs=crs, min_area=0.0,
+                                           simplification_tolerance=simplification_tolerance, device=device)

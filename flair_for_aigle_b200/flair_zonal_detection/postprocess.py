@@ -38,3 +38,11 @@ def convert_to_cog(input_path: str, output_path: str) -> None:
         raise FileNotFoundError(f"Input file not found: {input_path}")
     raster_io.convert_to_cog(input_path, output_path)
     os.remove(input_path)
+
+
+def create_polygon_from_bounds(x_min: float, x_max: float, y_min: float, y_max: float) -> dict:
+    """postprocess.py:55-66: ``mapping(box(x_min, y_max, x_max, y_min))`` -- the GeoJSON-like polygon of a bounding box, with
+    the vertex order shapely's ``box`` gives for those arguments (its ``miny`` is y_max here) and tuples like ``mapping``."""
+    ring = ((float(x_max), float(y_max)), (float(x_max), float(y_min)), (float(x_min), float(y_min)),
+            (float(x_min), float(y_max)), (float(x_max), float(y_max)))
+    return {"type": "Polygon", "coordinates": (ring,)}

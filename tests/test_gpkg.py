@@ -146,3 +146,25 @@ def test_write_gpkg_argument_checks(tmp_path):
     for bad in ('a"b', "fid", "GEOM", ""):
         with pytest.raises(ValueError, match="column name"):
             write_gpkg(str(tmp_path / "c.gpkg"), [[_square(0, 0, 1)]], {bad: [1]}, None)
+
+
+def test_confidence_column_and_the_small_reference_helpers(tmp_path):
+    """vectorize_segmentation's third column (inference.py:588,610: every polygon carries the mean confidence of ALL pixels of
+    its class), carried through to_file / read_file / concat; create_polygon_from_bounds (postprocess.py:55-66)."""
+    from flair_for_aigle_b200.flair_zonal_detection.polygonize import class_mean_confidence
+    from flair_for_aigle_b200.flair_zonal_detection.postprocess import create_polygon_from_bounds
+    rng = np.random.default_rng(3)
+    labels, conf = rng.integers(0, 6, (80, 90)), rng.random((80, 90))
+    ids = np.asarray([5, 1, 1, 3])
+    got = class_mean_confidence(labels, conf, ids)
+    assert np.allclose(got, [conf[labels == v].mean() for v in ids], rtol=1e-12)
+    t = _table()
+    t.confidence = np.asarray([0.25, 0.25, 0.75])
+    back = PolygonTable.read_file(t.to_file(str(tmp_path / "c.gpkg")))
+    assert back.confidence.tolist() == [0.25, 0.25, 0.75] and back.class_id.tolist() == [6, 6, 12]
+    both = PolygonTable.concat([back, back])
+    assert both.confidence.tolist() == [0.25, 0.25, 0.75] * 2
+    assert PolygonTable.concat([back, _table()]).confidence is None          # a table without the column: dropped, not invented
+    # shapely: box(x_min, y_max, x_max, y_min) starts at (maxx, miny) = (x_max, y_max) and runs counter-clockwise in its own frame
+    assert create_polygon_from_bounds(0, 2, 1, 5) == {"type": "Polygon", "coordinates": (((2.0, 5.0), (2.0, 1.0), (0.0, 1.0),
+                                                                                       (0.0, 5.0), (2.0, 5.0)),)}
