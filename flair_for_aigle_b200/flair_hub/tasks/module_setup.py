@@ -1,4 +1,6 @@
-"""``FLAIRLosses``: drop-in for flair_hub/tasks/module_setup.py:119-200 on the training step's loss side.
+"""``FLAIRLosses``: drop-in for flair_hub/tasks/module_setup.py:119-200 on the training step's loss side, and
+the two factories in front of it: ``build_segmentation_module`` (:47-83) and ``get_input_img_sizes`` (:87-117).  The data
+module (``build_data_module``, :12-43: the FLAIR-HUB patch datasets and augmentations) is outside the scope of SURVEY 8.
 
 The reference builds one ``nn.CrossEntropyLoss(weight=w)`` per task (``_create_task_loss``, :155) with
 ``w = [value_weights.default] * n_classes`` overridden by ``value_weights.default_exceptions`` (:180-196), plus auxiliary
@@ -72,3 +74,26 @@ class FLAIRLosses:
 
     def get_losses(self) -> Dict[str, WeightedCrossEntropy]:
         return self.losses
+
+
+def build_segmentation_module(config: dict, in_img_sizes, stage: str = 'train'):
+    """module_setup.py:47-83: the model for ``in_img_sizes`` wrapped in a ``SegmentationTask`` -- with the losses for
+    'train', without for 'predict'."""
+    assert stage in ['train', 'predict'], "stage must be either 'train' or 'predict'"
+    from ..models.flair_model import FLAIR_HUB_Model
+    from .tasks_module import SegmentationTask
+    model = FLAIR_HUB_Model(config, in_img_sizes)
+    if stage == 'train':
+        return SegmentationTask(model=model, config=config, criterion=FLAIRLosses(config).get_losses())
+    return SegmentationTask(model=model, config=config)
+
+
+def get_input_img_sizes(config: dict, dm, stage: str = "fit") -> Dict[str, int]:
+    """module_setup.py:87-117: the last dimension of each active input modality in the first batch of the data module's
+    train / predict loader (any object with ``setup``, ``train_dataloader``, ``predict_dataloader``)."""
+    assert stage in {"fit", "predict"}, f"Unsupported stage '{stage}'"
+    dm.setup(stage)
+    dataloader = dm.train_dataloader() if stage == "fit" else dm.predict_dataloader()
+    monkeybatch = next(iter(dataloader))
+    return {modality: monkeybatch[modality][0].shape[-1] for modality, is_input in config['modalities']['inputs'].items()
+            if is_input and modality in monkeybatch}

@@ -153,9 +153,13 @@ def init_optimizer(cfg: dict, params: Iterable[torch.Tensor]) -> AdamW:
 
 
 class SegmentationTask:
-    def __init__(self, model, config: dict):
+    def __init__(self, model, config: dict, criterion=None):
+        """tasks_module.py:37-61.  ``criterion``: ``FLAIRLosses(config).get_losses()`` as module_setup.py:70-77 passes it for
+        training; built here when omitted (the reference's predict stage passes none and never needs one)."""
         self.model, self.config = model, config
-        self.criterion = FLAIRLosses(config).get_losses()
+        if criterion is None and all('value_weights' in config.get('labels_configs', {}).get(t, {}) for t in config.get('labels', [])):
+            criterion = FLAIRLosses(config).get_losses()
+        self.criterion = criterion                    # None: a predict-stage module (no class weights in its config)
         # tasks_module.py:59-61: the configured probabilities only switch the feature on (the per-step probability is drawn)
         self.mod_dropout = any(v > 0 for v in (self.config.get('modalities', {}).get('modality_dropout', {}) or {}).values())
         self._init_metrics()
@@ -223,7 +227,7 @@ class SegmentationTask:
         with a trainer the ``.ckpt`` also carries the optimizer's moments / step counters and the schedule position, which
         ``load_training_state`` puts back for a resume."""
         from ..models.checkpoint import save_checkpoint
-        weights = {t: c.weight for t, c in self.criterion.items() if getattr(c, 'weight', None) is not None}
+        weights = {t: c.weight for t, c in (self.criterion or {}).items() if getattr(c, 'weight', None) is not None}
         extra = {}
         tr = getattr(self, 'trainer', None)
         if tr is not None and not path.endswith(".safetensors"):

@@ -201,3 +201,35 @@ def test_linear_backward(cuda, M, N, K):
     assert float((db - rb).abs().max()) <= 1e-4 * max(1.0, float(rb.abs().max()))
     dX2, dW2, db2 = nv.linear_backward(dY, X, W)
     assert torch.equal(dW, dW2) and torch.equal(db, db2) and torch.equal(dX, dX2)      # deterministic
+
+
+def test_module_factories_like_the_reference():
+    """module_setup.py:47-117: ``build_segmentation_module`` (train: with the losses; predict: without, from a config that
+    carries no class weights) and ``get_input_img_sizes`` (first batch of the data module's loader)."""
+    import bench
+    from flair_for_aigle_b200.flair_hub.tasks.module_setup import build_segmentation_module, get_input_img_sizes
+    from flair_for_aigle_b200.flair_zonal_detection.model_utils import prepare_model_config
+    zc = bench.zonal_config("w", "/tmp", "unused", 1)
+    zc["monotemp_arch"] = "resnet34-unet"
+    cfg = prepare_model_config(zc)
+    task = build_segmentation_module(cfg, {"AERIAL_RGBI": 512}, "predict")
+    assert type(task).__name__ == "SegmentationTask" and type(task.model).__name__ == "FLAIR_HUB_Model" and task.criterion is None
+    label = cfg["labels"][0]
+    cfg["labels_configs"][label]["value_weights"] = {"default": 1, "default_exceptions": {18: 0}}
+    task = build_segmentation_module(cfg, {"AERIAL_RGBI": 512}, "train")
+    assert list(task.criterion) == [label] and float(task.criterion[label].weight[18]) == 0.0
+    with pytest.raises(AssertionError, match="stage"):
+        build_segmentation_module(cfg, {"AERIAL_RGBI": 512}, "fit")
+
+    class DM:
+        def setup(self, stage):
+            self.stage = stage
+
+        def train_dataloader(self):
+            return [{"AERIAL_RGBI": torch.zeros(2, 4, 512, 512), "DEM_ELEV": torch.zeros(2, 1, 128, 128), "other": 1}]
+
+        def predict_dataloader(self):
+            return [{"AERIAL_RGBI": torch.zeros(2, 4, 256, 256)}]
+    c = {"modalities": {"inputs": {"AERIAL_RGBI": True, "DEM_ELEV": True, "SPOT_RGBI": False}}}
+    assert get_input_img_sizes(c, DM(), "fit") == {"AERIAL_RGBI": 512, "DEM_ELEV": 128}
+    assert get_input_img_sizes(c, DM(), "predict") == {"AERIAL_RGBI": 256}
