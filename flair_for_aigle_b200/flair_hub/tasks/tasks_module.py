@@ -315,6 +315,15 @@ class SegmentationTask:
         self._after_train_batch()
         return loss, {task: preds}
 
+    @torch.no_grad()
+    def predict_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0, dataloader_idx: int = 0):
+        """tasks_module.py:337-342: ``{"preds_<task>": argmax over the classes}`` per task, int64 (B,H,W).  The softmax in
+        front of the reference's argmax is monotonic and is skipped; the argmax is the ``convert`` kernel (first maximum
+        wins, like torch.argmax), one sample at a time."""
+        dict_logits_task, _ = self.model(batch)
+        return {f"preds_{task}": torch.stack([nv.convert(sample.contiguous(), 0)[0] for sample in logits]).long()
+                for task, logits in dict_logits_task.items()}
+
     def validation_step(self, batch: Dict[str, torch.Tensor]):
         """tasks_module.py:268-276 without the per-class loss log: -> the step's loss."""
         loss, all_preds, all_targets = self.step(batch, training=False)
