@@ -23,6 +23,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -423,12 +424,18 @@ def file_io_block(inf, model, cfg, tiles, patch_sizes, host, tmp, dev, checksum,
     cog = written.replace(".tif", "_COG.tif")
     convert_to_cog(written, cog)
     cog_ms = (time.perf_counter() - t0) * 1e3
+    input_mb, cog_overviews = os.path.getsize(src) / 1e6, raster_io.tiff_info(cog).overviews
+    shutil.rmtree(out_dir, ignore_errors=True)                  # ~350 MB of scratch files: gone before the next block
+    try:
+        os.remove(src)
+    except OSError:
+        pass
     return {"value": round(total_px / 1e6 / zone_s, 2), "unit": "Mpx/s",
             "ms": {"file_to_file": round(zone_s * 1e3, 1), "decode_input_geotiff_to_pinned_alone": round(decode_s * 1e3, 1),
                    "encode_class_geotiff_alone": round(write_ms, 1), "convert_to_cog_extra": round(cog_ms, 1),
                    "make_input_file_setup": round(make_ms, 1)},
-            "input_file_mb": round(os.path.getsize(src) / 1e6, 1), "output_file_mb": round(out_mb, 2),
-            "output": {"tiled": info.tiled, "block": info.block_w, "compression": "lzw", "cog_overviews": raster_io.tiff_info(cog).overviews},
+            "input_file_mb": round(input_mb, 1), "output_file_mb": round(out_mb, 2),
+            "output": {"tiled": info.tiled, "block": info.block_w, "compression": "lzw", "cog_overviews": cog_overviews},
             "same_result_as_value_leg": same, "host_cores": os.cpu_count(),
             "note": "GeoTIFF on disk -> open_raster -> inference_and_write -> LZW GeoTIFF on disk, all through the public API; "
                     "file codecs = libfz_rasterio.so, one 512x512 block per task on all host cores (profiles/r2_raster_io_bench.txt "
