@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "gpu_next: GPU tests written after the round's GPU budget was spent -- not yet run on a "
+                                       "B200, deliberately outside `-m gpu` (tests/test_unverified_gpu.py)")
 
 
 @pytest.fixture(scope="session")
