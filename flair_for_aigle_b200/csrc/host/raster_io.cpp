@@ -645,7 +645,7 @@ Entry ent_doubles(int tag, const std::vector<double>& x) {
     return e;
 }
 
-void make_overview(const Level& src, Level& dst, int count, int bps, int resampling) {
+void make_overview(const Level& src, Level& dst, int count, int bps, int resampling, int threads) {
     dst.width = (src.width + 1) / 2;
     dst.height = (src.height + 1) / 2;
     dst.row_stride = dst.width * bps;
@@ -653,7 +653,7 @@ void make_overview(const Level& src, Level& dst, int count, int bps, int resampl
     dst.own.resize((size_t)dst.band_stride * count);
     dst.data = dst.own.data();
     const double rx = (double)src.width / (double)dst.width, ry = (double)src.height / (double)dst.height;
-    parallel_for(dst.height * count, 0, [&](int64_t i, int) -> std::string {
+    parallel_for(dst.height * count, threads, [&](int64_t i, int) -> std::string {
         const int64_t b = i / dst.height, y = i % dst.height;
         uint8_t* out = dst.own.data() + b * dst.band_stride + y * dst.row_stride;
         const uint8_t* plane = src.data + b * src.band_stride;
@@ -729,7 +729,7 @@ int write_impl(const char* path, const uint8_t* data, int count, int64_t height,
         const Level& prev = *levels.back();
         if (prev.width <= 1 && prev.height <= 1) break;
         std::unique_ptr<Level> next(new Level());
-        make_overview(prev, *next, count, bps, o.overview_resampling);
+        make_overview(prev, *next, count, bps, o.overview_resampling, o.threads);
         levels.push_back(std::move(next));
     }
 
