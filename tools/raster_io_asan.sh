@@ -1,7 +1,7 @@
 #!/bin/bash
 # The raster I/O library's tests (codec round trips, libtiff cross-checks, boundless windows, 400 corrupted files) under
 # AddressSanitizer + UndefinedBehaviorSanitizer.  Builds an instrumented libfz_rasterio.so in place, runs the CPU tests with
-# the sanitizer runtimes preloaded into python, restores the release build.  Last run: 35 passed, no report.
+# the sanitizer runtimes preloaded into python, restores the release build.  Last run (final code of round 2): 40 passed, no report.
 set -e
 cd "$(dirname "$0")/.."
 LIB=flair_for_aigle_b200/_native/libfz_rasterio.so
