@@ -137,7 +137,10 @@ class _Decoder:
             if not self.h.opj_setup_decoder(self.codec, params):
                 raise OpenJPEGError(f"{path}: opj_setup_decoder failed")
             if threads != 1 and self.h.opj_has_thread_support():
-                self.h.opj_codec_set_threads(self.codec, int(threads) if threads > 0 else (os.cpu_count() or 1))
+                from .raster_io import host_threads
+                n = host_threads(threads) or (os.cpu_count() or 1)      # this process's share of the cores under torchrun
+                if n > 1:
+                    self.h.opj_codec_set_threads(self.codec, n)
             if not self.h.opj_read_header(self.stream, self.codec, ctypes.byref(self.image)) or not self.image:
                 raise OpenJPEGError(f"{path}: {'; '.join(self.errors) or 'opj_read_header failed'}")
             im = self.image.contents

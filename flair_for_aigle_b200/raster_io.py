@@ -105,6 +105,21 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+def host_threads(threads: int = 0) -> int:
+    """Worker threads for one call: an explicit positive request wins; otherwise ``FZ_IO_THREADS``; otherwise, in a
+    one-process-per-GPU job (torchrun sets LOCAL_WORLD_SIZE), this process's share of the box's cores -- eight ranks each
+    decoding their strip of a zone must not start eight times the core count; otherwise 0 = all cores."""
+    if threads and threads > 0:
+        return int(threads)
+    env = os.environ.get("FZ_IO_THREADS", "")
+    if env.isdigit() and int(env) > 0:
+        return int(env)
+    local_world = os.environ.get("LOCAL_WORLD_SIZE", "")
+    if local_world.isdigit() and int(local_world) > 1:
+        return max(1, (os.cpu_count() or 1) // int(local_world))
+    return 0
+
+
 def _check(rc: int, what: str) -> None:
     if rc < 0:
         raise RasterIOError(f"{what}: {lib().fzio_last_error().decode(errors='replace')}")
@@ -154,7 +169,7 @@ def read_window(path: str, row0: int, col0: int, height: int, width: int, bands:
     band_arr = None if bands is None else (ctypes.c_int32 * n)(*[int(b) for b in bands])
     _check(lib().fzio_read_window(os.fsencode(path), int(level), int(row0), int(col0), int(height), int(width), band_arr, n,
                                   out.ctypes.data, out.strides[0] if out.size else 0, out.strides[1] if out.size else 0,
-                                  int(threads)), "read_window")
+                                  host_threads(threads)), "read_window")
     return out
 
 
@@ -185,7 +200,8 @@ def write_geotiff(path: str, arr: np.ndarray, left: Optional[float] = None, top:
         raise RasterIOError(f"overview_resampling '{overview_resampling}' (nearest, mode)")
     o = _WriteOpts()
     o.block, o.compression, o.predictor, o.deflate_level = int(block), _COMPRESSION[compression], int(predictor), int(deflate_level)
-    o.pixel_interleave, o.overviews, o.cog, o.bigtiff, o.threads = int(pixel_interleave), int(overviews), int(cog), int(bigtiff), int(threads)
+    o.pixel_interleave, o.overviews, o.cog, o.bigtiff = int(pixel_interleave), int(overviews), int(cog), int(bigtiff)
+    o.threads = host_threads(threads)
     o.overview_resampling = OVR_MODE if overview_resampling == "mode" else OVR_NEAREST
     o.sample_format, o.bits = fmt, bits
     if left is not None and top is not None and res is not None:
@@ -199,7 +215,7 @@ def write_geotiff(path: str, arr: np.ndarray, left: Optional[float] = None, top:
 
 def convert_to_cog(src_path: str, dst_path: str, threads: int = 0) -> str:
     """postprocess.py:33-52: GeoTIFF -> COG (LZW, 512 x 512 blocks, nearest overviews down to one block, IFDs first)."""
-    _check(lib().fzio_convert_to_cog(os.fsencode(src_path), os.fsencode(dst_path), int(threads)), "convert_to_cog")
+    _check(lib().fzio_convert_to_cog(os.fsencode(src_path), os.fsencode(dst_path), host_threads(threads)), "convert_to_cog")
     return dst_path
 
 

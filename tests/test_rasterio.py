@@ -430,3 +430,21 @@ def test_random_layouts_round_trip_and_decode_in_libtiff(tmp_path):
                 lib = np.asarray(im)
             assert np.array_equal(lib if count == 1 else lib.transpose(2, 0, 1), a[0] if count == 1 else a)
     check()
+
+
+def test_host_thread_share_in_a_multi_gpu_job(monkeypatch):
+    """One process per GPU: each rank's file codecs take their share of the cores, not all of them."""
+    import os
+    monkeypatch.delenv("FZ_IO_THREADS", raising=False)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    assert rio.host_threads(0) == 0 and rio.host_threads(3) == 3
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    monkeypatch.setattr(os, "cpu_count", lambda: 96)
+    assert rio.host_threads(0) == 12 and rio.host_threads(5) == 5
+    monkeypatch.setattr(os, "cpu_count", lambda: 4)
+    assert rio.host_threads(0) == 1
+    monkeypatch.setenv("FZ_IO_THREADS", "6")
+    assert rio.host_threads(0) == 6
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    monkeypatch.delenv("FZ_IO_THREADS")
+    assert rio.host_threads(0) == 0
