@@ -114,6 +114,8 @@ def row_source(path: str):
     from .raster import RowSource
     if path.lower().endswith((".jp2", ".j2k")):
         from .. import openjpeg
+        if os.environ.get("FZ_JP2_DECODER", "").lower() == "pillow":      # switch the direct OpenJPEG binding off
+            return None
         try:
             j = openjpeg.info(path)
         except Exception:  # noqa: BLE001 -- no library, a file it does not decode, a binding problem: Pillow's path takes over
@@ -352,6 +354,8 @@ def read_jp2(path: str, alloc: Optional[Allocator] = None) -> Tuple[np.ndarray, 
     left, top, res, crs = _jp2_georef(path)
     from .. import openjpeg
     try:                                                     # OpenJPEG driven directly: all cores, straight into the buffer
+        if os.environ.get("FZ_JP2_DECODER", "").lower() == "pillow":
+            raise openjpeg.OpenJPEGUnavailable("FZ_JP2_DECODER=pillow")
         j = openjpeg.info(path)
         shape = (j.count, j.height, j.width)
         out = alloc(shape, np.dtype(np.uint8)) if alloc is not None else np.empty(shape, np.uint8)
