@@ -448,3 +448,16 @@ def test_host_thread_share_in_a_multi_gpu_job(monkeypatch):
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
     monkeypatch.delenv("FZ_IO_THREADS")
     assert rio.host_threads(0) == 0
+
+
+def test_host_benchmark_tool_runs(tmp_path, monkeypatch):
+    """tools/raster_io_bench.py (the source of profiles/r2_raster_io_bench.txt) at a toy size: every leg runs and verifies
+    its own round trips."""
+    import runpy
+    import sys
+    out = str(tmp_path / "bench.txt")
+    monkeypatch.setattr(sys, "argv", ["raster_io_bench.py", "--size", "700", "--reps", "1", "--out", out])
+    runpy.run_path(os.path.join(ROOT, "tools", "raster_io_bench.py"), run_name="__main__")
+    text = open(out).read()
+    assert "WRITE argmax raster" in text and "READ 4-band uint8 ortho" in text and "READ JPEG 2000 ortho" in text
+    assert "skipped" not in text

@@ -123,7 +123,7 @@ def main():
                 dstj = np.empty((4, m, m), np.uint8)
                 t_1 = best(lambda: oj.read_rows(pj, out=dstj, threads=1), 1)
                 t_n = best(lambda: oj.read_rows(pj, out=dstj), 2)
-                t_strip = best(lambda: oj.read_rows(pj, m // 2, m // 2 + 1024), 2)
+                t_strip = best(lambda: oj.read_rows(pj, m // 2, min(m, m // 2 + 1024)), 2)
                 say(f"  {label:30s} file {os.path.getsize(pj) / 1e6:6.1f} MB: Pillow (1 thread, whole image) {t_pil * 1e3:7.0f} ms = {mbj / t_pil:5.0f} MB/s | "
                     f"OpenJPEG direct 1 thread {t_1 * 1e3:7.0f} ms | {cores} threads {t_n * 1e3:7.0f} ms = {mbj / t_n:5.0f} MB/s | "
                     f"one 1024-row strip {t_strip * 1e3:6.0f} ms")
