@@ -92,19 +92,25 @@ def _square_res(path: str, rx: float, ry: float) -> float:
 
 
 def _tiff_info(path: str):
+    """-> (TiffInfo, left, top, res, crs).  Georeferencing from the GeoTIFF tags or, for a plain TIFF, from a world file
+    (.tfw) or a MapInfo .tab registration next to it (GDAL's fallbacks; how IGN delivers some orthophoto tiles)."""
     try:
         info = raster_io.tiff_info(path)
     except raster_io.RasterIOError as e:
         raise ValueError(str(e)) from e
-    if not info.has_georef:
-        raise ValueError(f"{path}: no GeoTIFF georeferencing (ModelPixelScale / ModelTiepoint tags)")
-    return info, _square_res(path, info.res_x, info.res_y)
+    if info.has_georef:
+        return info, info.left, info.top, _square_res(path, info.res_x, info.res_y), info.crs
+    side = _world_file(path) or _tab_file(path)
+    if side is None:
+        raise ValueError(f"{path}: no GeoTIFF georeferencing (ModelPixelScale / ModelTiepoint tags), world file or .tab")
+    left, top, sx, sy, crs = side
+    return info, left, top, _square_res(path, sx, sy), crs
 
 
 def geotiff_header(path: str):
     """-> (shape (count, H, W), dtype, left, top, res, crs) from the directory alone: no pixel is decoded."""
-    info, res = _tiff_info(path)
-    return (info.count, info.height, info.width), info.dtype, info.left, info.top, res, info.crs
+    info, left, top, res, crs = _tiff_info(path)
+    return (info.count, info.height, info.width), info.dtype, left, top, res, crs
 
 
 def row_source(path: str):
@@ -140,7 +146,7 @@ def read_geotiff(path: str, alloc: Optional[Allocator] = None) -> Tuple[np.ndarr
     """-> (array (count, H, W), left, top, res, crs).  ``alloc(shape, dtype)`` supplies the array to decode into (e.g. the
     numpy view of a page-locked tensor).  Strips or tiles, classic or BigTIFF, none / LZW / Deflate, predictor 2, 8 / 16 /
     32-bit samples: decoded block-parallel by libfz_rasterio; any other libtiff codec: Pillow."""
-    info, res = _tiff_info(path)
+    info, left, top, res, crs = _tiff_info(path)
     shape = (info.count, info.height, info.width)
     try:
         out = alloc(shape, info.dtype) if alloc is not None else None
@@ -149,7 +155,7 @@ def read_geotiff(path: str, alloc: Optional[Allocator] = None) -> Tuple[np.ndarr
         if "is not supported" not in str(e):
             raise ValueError(str(e)) from e
         arr = _read_with_pillow(path)
-    return arr, info.left, info.top, res, info.crs
+    return arr, left, top, res, crs
 
 
 def _read_with_pillow(path: str) -> np.ndarray:

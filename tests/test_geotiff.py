@@ -1,4 +1,6 @@
 """GeoTIFF I/O at both ends of the path (flair_zonal_detection/geotiff.py) -- host code, no GPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -55,6 +57,19 @@ def test_rejects_tiff_without_georeference(tmp_path):
     Image.fromarray(np.zeros((8, 8), np.uint8)).save(p)
     with pytest.raises(ValueError):
         read_geotiff(p)
+    # ... unless a world file (pixel-centre convention) or a MapInfo .tab (pixel corners) sits next to it
+    open(str(tmp_path / "plain.tfw"), "w").write(f"{RES}\n0\n0\n-{RES}\n{L + RES / 2!r}\n{T - RES / 2!r}\n")
+    got, left, top, res, crs = read_geotiff(p)
+    assert got.shape == (1, 8, 8) and abs(left - L) < 1e-6 and abs(top - T) < 1e-6 and res == RES and crs is None
+    r = open_raster(p)
+    assert abs(r.bounds.left - L) < 1e-6 and abs(r.bounds.bottom - (T - 8 * RES)) < 1e-6
+    os.remove(str(tmp_path / "plain.tfw"))
+    open(str(tmp_path / "plain.tab"), "w").write(
+        f'Definition Table\n  File "plain.tif"\n  Type "RASTER"\n  ({L!r},{T!r}) (0,0) Label "Pt 1",\n'
+        f'  ({L + 8 * RES!r},{T!r}) (8,0) Label "Pt 2",\n  ({L!r},{T - 8 * RES!r}) (0,8) Label "Pt 3"\n'
+        '  CoordSys Earth Projection 3, 33, "m", 3, 46.5, 44, 49, 700000, 6600000\n')
+    _, left, top, res, crs = read_geotiff(p)
+    assert abs(left - L) < 1e-6 and abs(top - T) < 1e-6 and abs(res - RES) < 1e-9 and crs == "EPSG:2154"
 
 
 def test_crs_codes_are_parsed_not_guessed():
