@@ -53,7 +53,7 @@ def test_geotiff_in_geotiff_out(setup, tmp_path):
     assert np.array_equal(got[0], results["file"][0]) and (left, top, res) == (L, T, RES)
 
 
-def test_run_inference_jp2_in_cog_out(setup, tmp_path):
+def _run_inference_jp2_in_cog_out(setup, tmp_path):
     """The product script's file contract (scripts/run_fast_aigle_segmentation.py:75-119; inference.py:60 globs *.jp2):
     a JPEG-2000 ortho with a GeoJP2 box + a config file -> ``run_inference`` -> the class raster as a COG (``cog_conversion``,
     inference.py:633-641: LZW, 512 blocks, nearest overviews, the plain GeoTIFF removed), georeferenced like the input and
@@ -93,6 +93,13 @@ def test_run_inference_jp2_in_cog_out(setup, tmp_path):
     inf.inference_and_write(model, ds, tiles, cfg_mem, outs, "mem://z_jp2")
     assert np.array_equal(got[0], outs[TASK].to_host()[0])
     assert np.array_equal(raster_io.read_raster(cog, level=1)[0][0], got[0][::2, ::2])        # nearest overview, even sizes
+
+
+
+def test_run_inference_jp2_in_cog_out_pillow_decoder(setup, tmp_path, monkeypatch):
+    """JPEG 2000 decoded by Pillow in one go (FZ_JP2_DECODER=pillow): the path that ran on the B200 first."""
+    monkeypatch.setenv("FZ_JP2_DECODER", "pillow")
+    _run_inference_jp2_in_cog_out(setup, tmp_path)
 
 
 def test_zone_file_sharded_over_ranks_equals_single_run(setup, tmp_path):
@@ -142,3 +149,12 @@ def test_zone_file_sharded_over_ranks_equals_single_run(setup, tmp_path):
             assert np.array_equal(np.concatenate(parts), whole), world
     finally:
         RasterSink.write_files = True
+
+
+def test_zz_run_inference_jp2_in_cog_out_openjpeg_direct(setup, tmp_path, monkeypatch):
+    """The same with the direct OpenJPEG binding (flair_for_aigle_b200/openjpeg.py): worker threads, decoded progressively
+    behind the upload.  Written after the round's last GPU minutes, hence the LAST test of the GPU suite."""
+    monkeypatch.delenv("FZ_JP2_DECODER", raising=False)
+    from flair_for_aigle_b200.flair_zonal_detection import geotiff
+    _run_inference_jp2_in_cog_out(setup, tmp_path)
+    assert geotiff.row_source(str(tmp_path / "ortho.jp2")) is not None          # the direct decoder did take this file
