@@ -308,6 +308,11 @@ def _tab_file(path: str):
 def _jp2_georef(path: str):
     with open(path, "rb") as f:
         head = f.read(12)
+        if head[:4] == b"\xff\x4f\xff\x51":                  # a bare codestream (.j2k): no boxes, side files only
+            geo = _world_file(path) or _tab_file(path)
+            if geo is None:
+                raise ValueError(f"{path}: a JPEG 2000 codestream carries no georeferencing; no world file or .tab beside it")
+            return geo[0], geo[1], _square_res(path, geo[2], geo[3]), geo[4]
         if head[4:8] != b"jP  ":
             raise ValueError(f"{path}: not a JP2 file (no signature box)")
         # georeferencing boxes sit in front of the codestream: read up to it, not the pixels

@@ -230,6 +230,16 @@ def test_jpeg2000_inputs_with_geojp2_gmljp2_and_world_file(tmp_path):
     bad.write_bytes(b"\x00" * 64)
     with pytest.raises(ValueError, match="not a JP2"):
         read_jp2(str(bad))
+    # a bare codestream (.j2k) has no boxes: side files only
+    from PIL import Image
+    p = str(tmp_path / "raw.j2k")
+    Image.fromarray(img[:, :, 1]).save(p, format="JPEG2000", irreversible=False)
+    with pytest.raises(ValueError, match="codestream carries no georeferencing"):
+        read_jp2(p)
+    open(str(tmp_path / "raw.j2w"), "w").write(f"{RES}\n0.0\n0.0\n-{RES}\n{L + RES / 2!r}\n{T - RES / 2!r}\n")
+    got, left, top, res, crs = read_jp2(p)
+    assert np.array_equal(got[0], img[:, :, 1]) and abs(left - L) < 1e-6 and abs(top - T) < 1e-6
+    assert open_raster(p).shape == (300, 420)
     # MapInfo .tab registration (IGN's BD ORTHO deliveries): corner control points + the Lambert-93 CoordSys clause
     p = str(tmp_path / "tab.jp2")
     _jp2_with_box(p, img[:, :, 0], b"")
